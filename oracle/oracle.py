@@ -1,0 +1,262 @@
+"""ctypes binding of the CPU ORACLE (oracle/libqrl_oracle.so).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; the product package qradiolink_b200 never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# hier-block kinds (mirror qrl_oracle.h)
+DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB = 1, 2, 3, 4, 5, 6
+MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB = 101, 102, 103, 104, 105, 106
+WIN_HAMMING, WIN_HANN, WIN_BLACKMAN, WIN_RECT, WIN_KAISER, WIN_BLACKMAN_HARRIS = 0, 1, 2, 3, 4, 5
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libqrl_oracle.so")
+    src = os.path.join(_HERE, "qrl_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "libqrl_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        vp, f32p, u8p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint8)
+        L.qo_rx_create.restype = vp
+        L.qo_rx_create.argtypes = [C.c_int] * 6
+        L.qo_rx_destroy.argtypes = [vp]
+        L.qo_rx_work.argtypes = [vp, vp, C.c_long]
+        L.qo_rx_port_items.restype = C.c_long
+        L.qo_rx_port_items.argtypes = [vp, C.c_int]
+        L.qo_rx_port_data.restype = vp
+        L.qo_rx_port_data.argtypes = [vp, C.c_int]
+        L.qo_rx_port_clear.argtypes = [vp, C.c_int]
+        L.qo_rx_dbg_items.restype = C.c_long
+        L.qo_rx_dbg_items.argtypes = [vp, C.c_char_p]
+        L.qo_rx_dbg_data.restype = vp
+        L.qo_rx_dbg_data.argtypes = [vp, C.c_char_p]
+        L.qo_rx_ntaps.argtypes = [vp, C.c_int, vp, C.c_int]
+        L.qo_tx_create.restype = vp
+        L.qo_tx_create.argtypes = [C.c_int] * 6
+        L.qo_tx_destroy.argtypes = [vp]
+        L.qo_tx_set_bb_gain.argtypes = [vp, C.c_float]
+        L.qo_tx_work.argtypes = [vp, vp, C.c_long]
+        L.qo_tx_out_items.restype = C.c_long
+        L.qo_tx_out_items.argtypes = [vp]
+        L.qo_tx_out_data.restype = vp
+        L.qo_tx_out_data.argtypes = [vp]
+        L.qo_tx_out_clear.argtypes = [vp]
+        for name in ("qo_firdes_low_pass",):
+            getattr(L, name).argtypes = [C.c_double] * 4 + [C.c_int, vp, C.c_int]
+        L.qo_firdes_low_pass_2.argtypes = [C.c_double] * 5 + [C.c_int, vp, C.c_int]
+        L.qo_firdes_band_pass.argtypes = [C.c_double] * 5 + [C.c_int, vp, C.c_int]
+        L.qo_firdes_band_pass_2.argtypes = [C.c_double] * 6 + [C.c_int, vp, C.c_int]
+        L.qo_firdes_complex_band_pass.argtypes = [C.c_double] * 5 + [C.c_int, vp, C.c_int]
+        L.qo_firdes_complex_band_pass_2.argtypes = [C.c_double] * 6 + [C.c_int, vp, C.c_int]
+        L.qo_firdes_rrc.argtypes = [C.c_double] * 4 + [C.c_int, vp, C.c_int]
+        L.qo_deemph_taps.argtypes = [C.c_int, C.c_double, vp, vp]
+        L.qo_preemph_taps.argtypes = [C.c_int, C.c_double, C.c_double, vp, vp]
+        L.qo_sincosf.argtypes = [C.c_float, vp, vp]
+        L.qo_fast_atan2f.restype = C.c_float
+        L.qo_fast_atan2f.argtypes = [C.c_float, C.c_float]
+        L.qo_clock_loop_gains.argtypes = [C.c_float] * 3 + [vp, vp]
+        L.qo_control_loop_gains.argtypes = [C.c_float, vp, vp]
+        L.qo_fir_decim_ccf.restype = C.c_long
+        L.qo_fir_decim_ccf.argtypes = [vp, C.c_int, C.c_int, vp, C.c_long, vp]
+        L.qo_fir_fff.restype = C.c_long
+        L.qo_fir_fff.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_long, vp, C.c_long]
+        for name in ("qo_cc_encode", "qo_cc_decode"):
+            getattr(L, name).restype = C.c_long
+            getattr(L, name).argtypes = [vp, C.c_long, vp]
+        L.qo_scramble.argtypes = [vp, C.c_long, vp]
+        L.qo_descramble.argtypes = [vp, C.c_long, vp]
+        L.qo_find_frames.restype = C.c_long
+        L.qo_find_frames.argtypes = [vp, C.c_long, C.c_uint32, C.c_int, C.c_int, vp, C.c_long]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ------------------------------------------------------------------ design
+def _taps(fn, *args, complex_out=False, cap=1 << 15):
+    out = np.zeros(cap * (2 if complex_out else 1), np.float32)
+    n = fn(*args, _p(out), cap)
+    assert n > 0, n
+    if complex_out:
+        return out[: 2 * n].view(np.complex64).copy()
+    return out[:n].copy()
+
+
+def low_pass(gain, fs, fc, tw, win=WIN_HAMMING):
+    return _taps(lib().qo_firdes_low_pass, gain, fs, fc, tw, win)
+
+
+def low_pass_2(gain, fs, fc, tw, att, win=WIN_HAMMING):
+    return _taps(lib().qo_firdes_low_pass_2, gain, fs, fc, tw, att, win)
+
+
+def band_pass(gain, fs, lo, hi, tw, win=WIN_HAMMING):
+    return _taps(lib().qo_firdes_band_pass, gain, fs, lo, hi, tw, win)
+
+
+def complex_band_pass(gain, fs, lo, hi, tw, win=WIN_HAMMING):
+    return _taps(lib().qo_firdes_complex_band_pass, gain, fs, lo, hi, tw, win, complex_out=True)
+
+
+def rrc(gain, fs, symrate, alpha, ntaps):
+    return _taps(lib().qo_firdes_rrc, gain, fs, symrate, alpha, ntaps)
+
+
+def deemph_taps(fs, tau):
+    a = np.zeros(2); b = np.zeros(2)
+    lib().qo_deemph_taps(fs, tau, _p(a), _p(b))
+    return a, b
+
+
+def preemph_taps(fs, tau, fh=-1.0):
+    a = np.zeros(2); b = np.zeros(2)
+    lib().qo_preemph_taps(fs, tau, fh, _p(a), _p(b))
+    return a, b
+
+
+def table(name):
+    n = {"atan": 257, "mmse": 129 * 8, "tanh": 256, "fxpt_sine": 2048}[name]
+    out = np.zeros(n, np.float32)
+    getattr(lib(), "qo_%s_table" % name)(_p(out))
+    return out
+
+
+def sincosf(x):
+    x = np.asarray(x, np.float32).ravel()
+    s = np.zeros_like(x); c = np.zeros_like(x)
+    sv = C.c_float(); cv = C.c_float()
+    L = lib()
+    for i, v in enumerate(x):
+        L.qo_sincosf(float(v), C.byref(sv), C.byref(cv))
+        s[i] = sv.value; c[i] = cv.value
+    return s, c
+
+
+def fir_decim_ccf(h, D, x):
+    h = np.ascontiguousarray(h, np.float32); x = np.ascontiguousarray(x, np.complex64)
+    y = np.zeros(len(x) // D + 2, np.complex64)
+    n = lib().qo_fir_decim_ccf(_p(h), len(h), D, _p(x), len(x), _p(y))
+    return y[:n]
+
+
+def fir_fff(h, L_, M, x):
+    h = np.ascontiguousarray(h, np.float32); x = np.ascontiguousarray(x, np.float32)
+    cap = len(x) * L_ // M + 8
+    y = np.zeros(cap, np.float32)
+    n = lib().qo_fir_fff(_p(h), len(h), L_, M, _p(x), len(x), _p(y), cap)
+    return y[:n]
+
+
+def cc_encode(bits):
+    bits = np.ascontiguousarray(bits, np.uint8); out = np.zeros(2 * len(bits), np.uint8)
+    n = lib().qo_cc_encode(_p(bits), len(bits), _p(out)); return out[:n]
+
+
+def cc_decode(soft):
+    soft = np.ascontiguousarray(soft, np.uint8); out = np.zeros(len(soft) // 2 + 80, np.uint8)
+    n = lib().qo_cc_decode(_p(soft), len(soft), _p(out)); return out[:n]
+
+
+def scramble(bits):
+    bits = np.ascontiguousarray(bits, np.uint8); out = np.zeros_like(bits)
+    lib().qo_scramble(_p(bits), len(bits), _p(out)); return out
+
+
+def descramble(bits):
+    bits = np.ascontiguousarray(bits, np.uint8); out = np.zeros_like(bits)
+    lib().qo_descramble(_p(bits), len(bits), _p(out)); return out
+
+
+def find_frames(bits, sync, sync_bits, frame_len):
+    bits = np.ascontiguousarray(bits, np.uint8)
+    maxf = len(bits) // (8 * frame_len) + 1
+    out = np.zeros(maxf * frame_len, np.uint8)
+    n = lib().qo_find_frames(_p(bits), len(bits), sync, sync_bits, frame_len, _p(out), maxf)
+    return out[: n * frame_len].reshape(n, frame_len)
+
+
+# ------------------------------------------------------------------ chains
+class Rx:
+    """One channel of a reference demod hier-block (make_gr_demod_*), CPU oracle."""
+    PORT_DTYPES = {0: np.complex64, 2: np.uint8, 3: np.uint8}
+
+    def __init__(self, kind, sps, samp_rate, carrier_freq, filter_width, flag=0):
+        self.kind = kind
+        self.h = lib().qo_rx_create(kind, sps, samp_rate, carrier_freq, filter_width, int(flag))
+        if not self.h:
+            raise ValueError("oracle: unsupported demod kind %r" % kind)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().qo_rx_destroy(self.h); self.h = None
+
+    def work(self, iq):
+        iq = np.ascontiguousarray(iq, np.complex64)
+        rc = lib().qo_rx_work(self.h, _p(iq), len(iq))
+        assert rc == 0
+
+    def port(self, p, clear=True):
+        n = lib().qo_rx_port_items(self.h, p)
+        dt = self.PORT_DTYPES.get(p, np.float32 if self.kind in (DEMOD_NBFM, DEMOD_SSB) else np.complex64)
+        nbytes = n * np.dtype(dt).itemsize
+        if n == 0:
+            return np.zeros(0, dt)
+        buf = C.string_at(lib().qo_rx_port_data(self.h, p), nbytes)
+        out = np.frombuffer(buf, dt).copy()
+        if clear:
+            lib().qo_rx_port_clear(self.h, p)
+        return out
+
+    def dbg(self, name, dtype):
+        n = lib().qo_rx_dbg_items(self.h, name.encode())
+        if n <= 0:
+            return np.zeros(0, dtype)
+        buf = C.string_at(lib().qo_rx_dbg_data(self.h, name.encode()), n * np.dtype(dtype).itemsize)
+        return np.frombuffer(buf, dtype).copy()
+
+    def taps(self, which):
+        out = np.zeros(4096, np.float32)
+        n = lib().qo_rx_ntaps(self.h, which, _p(out), 4096)
+        return out[:n].copy()
+
+
+class Tx:
+    """One channel of a reference mod hier-block (make_gr_mod_*), CPU oracle."""
+
+    def __init__(self, kind, sps, samp_rate, carrier_freq, filter_width, flag=0):
+        self.h = lib().qo_tx_create(kind, sps, samp_rate, carrier_freq, filter_width, int(flag))
+        if not self.h:
+            raise ValueError("oracle: unsupported mod kind %r" % kind)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().qo_tx_destroy(self.h); self.h = None
+
+    def set_bb_gain(self, g):
+        lib().qo_tx_set_bb_gain(self.h, g)
+
+    def work(self, data):
+        data = np.ascontiguousarray(data)
+        rc = lib().qo_tx_work(self.h, _p(data), len(data))
+        assert rc == 0
+        n = lib().qo_tx_out_items(self.h)
+        buf = C.string_at(lib().qo_tx_out_data(self.h), n * 8)
+        lib().qo_tx_out_clear(self.h)
+        return np.frombuffer(buf, np.complex64).copy()

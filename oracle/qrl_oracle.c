@@ -1,0 +1,1335 @@
+/*
+ * qrl_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY; see qrl_oracle.h).
+ *
+ * Plain-C restatement of the GNU Radio 3.10 blocks the reference wires up in
+ *   /root/reference/src/gr/gr_demod_{nbfm,4fsk,qpsk}.cpp, gr_mod_{4fsk,qpsk}.cpp
+ * with the literal parameters of gr_demod_base.cpp:203-228 / gr_mod_base.cpp:155-180.
+ * Block semantics follow SURVEY.md Appendix A (GNU Radio / VOLK are not vendored by the
+ * reference and are absent here): PARITY UNPINNED against real GNU Radio.
+ *
+ * Numerics contract shared with the CUDA path (bit-exactness by construction):
+ *   - compiled with -ffp-contract=off; every fused multiply-add is an explicit fmaf();
+ *   - FIR dot products use ONE fixed order (fir_dot below): polyphase branches r = j mod D are
+ *     accumulated oldest-sample-first with fmaf into 32 "lane" partial sums (lane = r mod 32),
+ *     which are then combined by a fixed butterfly tree (offsets 16,8,4,2,1).  VOLK's real order
+ *     depends on the host SIMD width, so GNU Radio itself has no single bit-exact result; the
+ *     sequential order is kept (qo_set_fir_order(1)) so tests can bound the difference;
+ *   - sin/cos is qo_sincosf (Cody-Waite + Cephes polynomials in explicit fmaf steps), not libm;
+ *   - tables (atan, tanh, MMSE interpolator, fxpt sine) are generated here from closed forms.
+ */
+#define _GNU_SOURCE
+#include "qrl_oracle.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+static int g_fir_order = 0;
+static int g_fm_literal = 0;
+void qo_set_fir_order(int o) { g_fir_order = o; }
+void qo_set_fm_literal(int on) { g_fm_literal = on; }
+
+/* ------------------------------------------------------------------ growable vectors */
+typedef struct { unsigned char* d; size_t n, cap, isz; } qvec;
+static void qv_init(qvec* v, size_t isz) { v->d = NULL; v->n = 0; v->cap = 0; v->isz = isz; }
+static void qv_free(qvec* v) { free(v->d); v->d = NULL; v->n = v->cap = 0; }
+static void* qv_grow(qvec* v, size_t extra)
+{
+    if (v->n + extra > v->cap) {
+        size_t nc = v->cap ? v->cap : 1024;
+        while (nc < v->n + extra) nc *= 2;
+        v->d = (unsigned char*)realloc(v->d, nc * v->isz);
+        v->cap = nc;
+    }
+    return v->d + v->n * v->isz;
+}
+static void qv_push(qvec* v, const void* items, size_t n)
+{
+    if (!n) return;
+    void* p = qv_grow(v, n);
+    memcpy(p, items, n * v->isz);
+    v->n += n;
+}
+static void qv_push_zero(qvec* v, size_t n)
+{
+    if (!n) return;
+    void* p = qv_grow(v, n);
+    memset(p, 0, n * v->isz);
+    v->n += n;
+}
+static void qv_drop(qvec* v, size_t n)
+{
+    if (!n) return;
+    memmove(v->d, v->d + n * v->isz, (v->n - n) * v->isz);
+    v->n -= n;
+}
+static inline void qv_pushf(qvec* v, float x) { *(float*)qv_grow(v, 1) = x; v->n++; }
+static inline void qv_pushc(qvec* v, float re, float im) { float* p = (float*)qv_grow(v, 1); p[0] = re; p[1] = im; v->n++; }
+static inline void qv_pushb(qvec* v, unsigned char b) { *(unsigned char*)qv_grow(v, 1) = b; v->n++; }
+
+/* ------------------------------------------------------------------ design: windows / firdes (Appendix A1) */
+static double win_max_att(int win)
+{
+    switch (win) {
+    case QO_WIN_HAMMING: return 53; case QO_WIN_HANN: return 44; case QO_WIN_BLACKMAN: return 74;
+    case QO_WIN_RECT: return 21; case QO_WIN_BLACKMAN_HARRIS: return 92; default: return 53;
+    }
+}
+/* gr::fft::window::build: cosine windows evaluated in float (coswindow) */
+static void win_build(int win, int ntaps, float* w)
+{
+    float M = (float)(ntaps - 1);
+    for (int n = 0; n < ntaps; n++) {
+        switch (win) {
+        case QO_WIN_HAMMING:
+            w[n] = (float)(0.54 - 0.46 * cos((2 * M_PI * n) / M));
+            break;
+        case QO_WIN_HANN:
+            w[n] = (float)(0.5 - 0.5 * cos((2 * M_PI * n) / M));
+            break;
+        case QO_WIN_BLACKMAN: {
+            float c0 = 0.42f, c1 = 0.5f, c2 = 0.08f;
+            w[n] = c0 - c1 * cosf((float)((2.0 * M_PI * n) / M)) + c2 * cosf((float)((4.0 * M_PI * n) / M));
+            break; }
+        case QO_WIN_BLACKMAN_HARRIS: {
+            float c0 = 0.35875f, c1 = 0.48829f, c2 = 0.14128f, c3 = 0.01168f;
+            w[n] = c0 - c1 * cosf((float)((2.0 * M_PI * n) / M)) + c2 * cosf((float)((4.0 * M_PI * n) / M))
+                   - c3 * cosf((float)((6.0 * M_PI * n) / M));
+            break; }
+        default: w[n] = 1.0f;
+        }
+    }
+}
+static int compute_ntaps(double fs, double tw, int win)
+{
+    double a = win_max_att(win);
+    int ntaps = (int)(a * fs / (22.0 * tw));
+    if ((ntaps & 1) == 0) ntaps++;
+    return ntaps;
+}
+static int compute_ntaps_windes(double fs, double tw, double att)
+{
+    int ntaps = (int)(att * fs / (22.0 * tw));
+    if ((ntaps & 1) == 0) ntaps++;
+    return ntaps;
+}
+static int low_pass_n(double gain, double fs, double fc, int ntaps, int win, float* taps)
+{
+    float* w = (float*)malloc(sizeof(float) * ntaps);
+    win_build(win, ntaps, w);
+    int M = (ntaps - 1) / 2;
+    double fwT0 = 2 * M_PI * fc / fs;
+    for (int n = -M; n <= M; n++) {
+        if (n == 0) taps[n + M] = (float)(fwT0 / M_PI * w[n + M]);
+        else taps[n + M] = (float)(sin(n * fwT0) / (n * M_PI) * w[n + M]);
+    }
+    double fmax = taps[0 + M];
+    for (int n = 1; n <= M; n++) fmax += 2 * taps[n + M];
+    gain /= fmax;
+    for (int i = 0; i < ntaps; i++) taps[i] = (float)(taps[i] * gain);
+    free(w);
+    return ntaps;
+}
+int qo_firdes_low_pass(double gain, double fs, double fc, double tw, int win, float* out, int cap)
+{
+    int nt = compute_ntaps(fs, tw, win);
+    if (nt > cap) return -nt;
+    return low_pass_n(gain, fs, fc, nt, win, out);
+}
+int qo_firdes_low_pass_2(double gain, double fs, double fc, double tw, double att, int win, float* out, int cap)
+{
+    int nt = compute_ntaps_windes(fs, tw, att);
+    if (nt > cap) return -nt;
+    return low_pass_n(gain, fs, fc, nt, win, out);
+}
+static int band_pass_n(double gain, double fs, double lo, double hi, int ntaps, int win, float* taps)
+{
+    float* w = (float*)malloc(sizeof(float) * ntaps);
+    win_build(win, ntaps, w);
+    int M = (ntaps - 1) / 2;
+    double fwT0 = 2 * M_PI * lo / fs, fwT1 = 2 * M_PI * hi / fs;
+    for (int n = -M; n <= M; n++) {
+        if (n == 0) taps[n + M] = (float)((fwT1 - fwT0) / M_PI * w[n + M]);
+        else taps[n + M] = (float)((sin(n * fwT1) - sin(n * fwT0)) / (n * M_PI) * w[n + M]);
+    }
+    double fmax = taps[0 + M];
+    for (int n = 1; n <= M; n++) fmax += 2 * taps[n + M] * cos(n * (fwT0 + fwT1) * 0.5);
+    gain /= fmax;
+    for (int i = 0; i < ntaps; i++) taps[i] = (float)(taps[i] * gain);
+    free(w);
+    return ntaps;
+}
+int qo_firdes_band_pass(double gain, double fs, double lo, double hi, double tw, int win, float* out, int cap)
+{
+    int nt = compute_ntaps(fs, tw, win);
+    if (nt > cap) return -nt;
+    return band_pass_n(gain, fs, lo, hi, nt, win, out);
+}
+int qo_firdes_band_pass_2(double gain, double fs, double lo, double hi, double tw, double att, int win, float* out, int cap)
+{
+    int nt = compute_ntaps_windes(fs, tw, att);
+    if (nt > cap) return -nt;
+    return band_pass_n(gain, fs, lo, hi, nt, win, out);
+}
+/* firdes::complex_band_pass: low-pass prototype rotated to the band centre */
+static int complex_band_pass_n(double gain, double fs, double lo, double hi, int ntaps, int win, float* out_c)
+{
+    float* lp = (float*)malloc(sizeof(float) * ntaps);
+    low_pass_n(gain, fs, (hi - lo) / 2, ntaps, win, lp);
+    float freq = (float)(M_PI * (hi + lo) / fs);
+    float phase = 0;
+    if (ntaps & 1) phase = -freq * (float)(ntaps >> 1);
+    else phase = -freq / 2.0f * (float)((1 + 2 * ntaps) >> 1);
+    for (int i = 0; i < ntaps; i++) {
+        out_c[2 * i] = lp[i] * cosf(phase);
+        out_c[2 * i + 1] = lp[i] * sinf(phase);
+        phase += freq;
+    }
+    free(lp);
+    return ntaps;
+}
+int qo_firdes_complex_band_pass(double gain, double fs, double lo, double hi, double tw, int win, float* out_c, int cap)
+{
+    int nt = compute_ntaps(fs, tw, win);
+    if (nt > cap) return -nt;
+    return complex_band_pass_n(gain, fs, lo, hi, nt, win, out_c);
+}
+int qo_firdes_complex_band_pass_2(double gain, double fs, double lo, double hi, double tw, double att, int win, float* out_c, int cap)
+{
+    int nt = compute_ntaps_windes(fs, tw, att);
+    if (nt > cap) return -nt;
+    return complex_band_pass_n(gain, fs, lo, hi, nt, win, out_c);
+}
+int qo_firdes_rrc(double gain, double fs, double symrate, double alpha, int ntaps, float* taps, int cap)
+{
+    ntaps |= 1;
+    if (ntaps > cap) return -ntaps;
+    double spb = fs / symrate;
+    double scale = 0;
+    for (int i = 0; i < ntaps; i++) {
+        double x1, x2, x3, num, den;
+        double xindx = i - ntaps / 2;
+        x1 = M_PI * xindx / spb;
+        x2 = 4 * alpha * xindx / spb;
+        x3 = x2 * x2 - 1;
+        if (fabs(x3) >= 0.000001) {
+            if (i != ntaps / 2) num = cos((1 + alpha) * x1) + sin((1 - alpha) * x1) / (4 * alpha * xindx / spb);
+            else num = cos((1 + alpha) * x1) + (1 - alpha) * M_PI / (4 * alpha);
+            den = x3 * M_PI;
+        } else {
+            if (alpha == 1) { taps[i] = -1; scale += taps[i]; continue; }
+            x3 = (1 - alpha) * x1;
+            x2 = (1 + alpha) * x1;
+            num = (sin(x2) * (1 + alpha) * M_PI - cos(x3) * ((1 - alpha) * M_PI * spb) / (4 * alpha * xindx)
+                   + sin(x3) * spb * spb / (4 * alpha * xindx * xindx));
+            den = -32 * M_PI * alpha * alpha * xindx / spb;
+        }
+        taps[i] = (float)(4 * alpha * num / den);
+        scale += taps[i];
+    }
+    for (int i = 0; i < ntaps; i++) taps[i] = (float)(taps[i] * gain / scale);
+    return ntaps;
+}
+/* /root/reference/src/gr/emphasis.cpp:16-42 (note the float tanf inside double math) */
+void qo_deemph_taps(int sample_rate, double tau, double* a, double* b)
+{
+    double fs = (double)sample_rate;
+    double w_c = 1.0 / tau;
+    double w_ca = 2.0 * fs * tanf(w_c / (2.0 * fs));
+    double k = -w_ca / (2.0 * fs);
+    double z1 = -1.0;
+    double p1 = (1.0 + k) / (1.0 - k);
+    double b0 = -k / (1.0 - k);
+    b[0] = b0 * 1.0; b[1] = b0 * -z1;
+    a[0] = 1.0; a[1] = -p1;
+}
+/* /root/reference/src/gr/emphasis.cpp:44-88 */
+void qo_preemph_taps(int sample_rate, double tau, double fh, double* a, double* b)
+{
+    double fs = (double)sample_rate;
+    if (fh <= 0.0 || fh >= fs / 2.0) fh = 0.925 * fs / 2.0;
+    double w_cl = 1.0 / tau;
+    double w_ch = 2.0 * M_PI * fh;
+    double w_cla = 2.0 * fs * tanf(w_cl / (2.0 * fs));
+    double w_cha = 2.0 * fs * tanf(w_ch / (2.0 * fs));
+    double kl = -w_cla / (2.0 * fs);
+    double kh = -w_cha / (2.0 * fs);
+    double z1 = (1.0 + kl) / (1.0 - kl);
+    double p1 = (1.0 + kh) / (1.0 - kh);
+    double b0 = (1.0 - kl) / (1.0 - kh);
+    double w_0dB = 2.0 * M_PI * 0.0;
+    double g = fabs(1.0 - p1 * 1.0 * (cos(-w_0dB) + sin(-w_0dB))) / (b0 * fabs(1.0 - z1 * 1.0 * (cos(-w_0dB) + sin(-w_0dB))));
+    b[0] = g * b0 * 1.0; b[1] = g * b0 * -z1;
+    a[0] = 1.0; a[1] = -p1;
+}
+
+/* ------------------------------------------------------------------ tables */
+/* gr::fast_atan2f table: 257 entries of atan(i/255) as the 7-significant-digit literals GNU Radio prints */
+void qo_atan_table(float* t)
+{
+    char buf[64];
+    for (int i = 0; i < 256; i++) {
+        snprintf(buf, sizeof buf, "%e", atan((double)i / 255.0));
+        t[i] = strtof(buf, NULL);
+    }
+    t[256] = t[255];
+}
+/* blocks::tanhf_lut table: tanh((i-128)/64), 256 entries */
+void qo_tanh_table(float* t)
+{
+    for (int i = 0; i < 256; i++) t[i] = (float)tanh((double)(i - 128) / 64.0);
+}
+/* gr::fxpt sine table: 1024 (slope, intercept) pairs over u = (uint32 phase)>>1, f(u) = sin(u*pi/2^30) */
+void qo_fxpt_sine_table(float* t)
+{
+    const double scale = M_PI / 1073741824.0; /* pi / 2^30 */
+    const double inc = 2097152.0;             /* 2^21 */
+    for (int i = 0; i < 1024; i++) {
+        double a = i * inc, b = (i + 1) * inc;
+        double m = (sin(b * scale) - sin(a * scale)) / (b - a);
+        double c = sin(a * scale) - m * a;
+        t[2 * i] = (float)m;
+        t[2 * i + 1] = (float)c;
+    }
+}
+/* MMSE 8-tap fractional interpolator bank (gr::filter::mmse_fir_interpolator, interpolator_taps.h):
+ * regenerated from the MMSE criterion over |f| < 0.25 fs and rounded to the 6 significant digits the
+ * upstream header prints (rows checked against the upstream values in tests/test_oracle_design.py). */
+static void solve8(double A[8][9])
+{
+    for (int c = 0; c < 8; c++) {
+        int p = c;
+        for (int r = c + 1; r < 8; r++) if (fabs(A[r][c]) > fabs(A[p][c])) p = r;
+        if (p != c) for (int k = 0; k < 9; k++) { double t = A[c][k]; A[c][k] = A[p][k]; A[p][k] = t; }
+        for (int r = c + 1; r < 8; r++) {
+            double f = A[r][c] / A[c][c];
+            for (int k = c; k < 9; k++) A[r][k] -= f * A[c][k];
+        }
+    }
+    for (int r = 7; r >= 0; r--) {
+        double s = A[r][8];
+        for (int k = r + 1; k < 8; k++) s -= A[r][k] * A[k][8];
+        A[r][8] = s / A[r][r];
+    }
+}
+static double mmse_s(double d)
+{
+    const double B = 0.25;
+    if (fabs(d) < 1e-12) return 2 * B;
+    return sin(2 * M_PI * B * d) / (M_PI * d);
+}
+void qo_mmse_table(float* t)
+{
+    char buf[64];
+    for (int imu = 0; imu <= 128; imu++) {
+        double mu = imu / 128.0;
+        double A[8][9];
+        for (int a = 0; a < 8; a++) {
+            for (int b = 0; b < 8; b++) A[a][b] = mmse_s((double)(a - b));
+            A[a][8] = mmse_s((double)(a - 4) + mu);
+        }
+        solve8(A);
+        for (int k = 0; k < 8; k++) {
+            double v = A[k][8];
+            if (fabs(v) < 1e-9) v = 0.0;
+            snprintf(buf, sizeof buf, "%.5e", v);
+            t[imu * 8 + k] = strtof(buf, NULL);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ elementary functions */
+void qo_sincosf(float x, float* s, float* c)
+{
+    float k = rintf(x * 0.636619772f);
+    float r = fmaf(k, -1.5703125f, x);
+    r = fmaf(k, -4.837512969970703125e-4f, r);
+    r = fmaf(k, -7.54978995489188216e-8f, r);
+    int q = ((int)k) & 3;
+    float z = r * r;
+    float ps = fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f);
+    ps = fmaf(ps, z, -1.6666654611e-1f);
+    ps = ps * z;
+    float sn = fmaf(ps, r, r);
+    float pc = fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+    pc = fmaf(pc, z, 4.166664568298827e-2f);
+    pc = pc * z;
+    pc = pc * z;
+    float cs = fmaf(z, -0.5f, 1.0f);
+    cs = cs + pc;
+    switch (q) {
+    case 0: *s = sn; *c = cs; break;
+    case 1: *s = cs; *c = -sn; break;
+    case 2: *s = -sn; *c = -cs; break;
+    default: *s = -cs; *c = sn; break;
+    }
+}
+static float g_atan_tab[257];
+static float g_tanh_tab[256];
+static float g_mmse_tab[129 * 8];
+static float g_sine_tab[2048];
+static int g_tabs_ready = 0;
+static void tabs_init(void)
+{
+    if (g_tabs_ready) return;
+    qo_atan_table(g_atan_tab);
+    qo_tanh_table(g_tanh_tab);
+    qo_mmse_table(g_mmse_tab);
+    qo_fxpt_sine_table(g_sine_tab);
+    g_tabs_ready = 1;
+}
+/* gnuradio-runtime/lib/math/fast_atan2f.cc (Appendix A4) */
+float qo_fast_atan2f(float y, float x)
+{
+    tabs_init();
+    float x_abs, y_abs, z, alpha, angle, base_angle;
+    int index;
+    y_abs = fabsf(y);
+    x_abs = fabsf(x);
+    if (!((y_abs > 0.0f) || (x_abs > 0.0f))) return 0.0f;
+    if (y_abs < x_abs) z = y_abs / x_abs; else z = x_abs / y_abs;
+    if ((double)z < 0.003921569) base_angle = z;
+    else {
+        alpha = z * 255.0f;
+        index = ((int)alpha) & 0xff;
+        alpha -= (float)index;
+        base_angle = g_atan_tab[index];
+        base_angle += (g_atan_tab[index + 1] - g_atan_tab[index]) * alpha;
+    }
+    if (x_abs > y_abs) {
+        if (x >= 0.0f) { if (y >= 0.0f) angle = base_angle; else angle = -base_angle; }
+        else { angle = 3.14159265358979323846f; if (y >= 0.0f) angle -= base_angle; else angle = base_angle - angle; }
+    } else {
+        if (y >= 0.0f) { angle = 1.57079632679489661923f; if (x >= 0.0f) angle -= base_angle; else angle += base_angle; }
+        else { angle = -1.57079632679489661923f; if (x >= 0.0f) angle += base_angle; else angle -= base_angle; }
+    }
+    return angle;
+}
+static inline float tanhf_lut(float x)
+{
+    if (x > 2.0f) return 1.0f;
+    else if (x <= -2.0f) return -1.0f;
+    int index = (int)(128.0f + 64.0f * x);
+    if (index > 255) index = 255;
+    return g_tanh_tab[index];
+}
+static inline float clipf(float x, float lim)
+{
+    if (x > lim) return lim;
+    if (x < -lim) return -lim;
+    return x;
+}
+/* digital::clock_tracking_loop::update_gains */
+void qo_clock_loop_gains(float loop_bw, float damping, float ted_gain, float* alpha, float* beta)
+{
+    float omega_n_T = loop_bw, zeta = damping;
+    float k0 = 2.0f / ted_gain;
+    float k1 = expf(-zeta * omega_n_T);
+    float sh = sinhf(zeta * omega_n_T);
+    float cx;
+    if (zeta > 1.0f) cx = coshf(omega_n_T * sqrtf(zeta * zeta - 1.0f));
+    else if (zeta == 1.0f) cx = 1.0f;
+    else cx = cosf(omega_n_T * sqrtf(1.0f - zeta * zeta));
+    *alpha = k0 * k1 * sh;
+    *beta = k0 * (1.0f - k1 * (sh + cx));
+}
+/* blocks::control_loop::update_gains, damping sqrt(2)/2 */
+void qo_control_loop_gains(float loop_bw, float* alpha, float* beta)
+{
+    float damping = sqrtf(2.0f) / 2.0f;
+    float denom = (float)(1.0 + 2.0 * damping * loop_bw + loop_bw * loop_bw);
+    *alpha = (4 * damping * loop_bw) / denom;
+    *beta = (4 * loop_bw * loop_bw) / denom;
+}
+
+/* ------------------------------------------------------------------ THE FIR dot-product order */
+/* returns sum_j h[j] * x[-j*stride]  (x points at the newest sample; D = decimation of the filter) */
+static float fir_dot(const float* h, int ntaps, int D, const float* x, int stride)
+{
+    if (g_fir_order == 1) {
+        float s = 0.0f;
+        for (int j = ntaps - 1; j >= 0; j--) s = fmaf(h[j], x[-(long)j * stride], s);
+        return s;
+    }
+    float S[32];
+    for (int l = 0; l < 32; l++) S[l] = 0.0f;
+    for (int r = 0; r < D && r < ntaps; r++) {
+        float s = S[r & 31];
+        int qmax = (ntaps - 1 - r) / D;
+        for (int q = qmax; q >= 0; q--) {
+            int j = D * q + r;
+            s = fmaf(h[j], x[-(long)j * stride], s);
+        }
+        S[r & 31] = s;
+    }
+    for (int off = 16; off >= 1; off >>= 1)
+        for (int l = 0; l < off; l++) S[l] = S[l] + S[l + off];
+    return S[0];
+}
+
+/* ------------------------------------------------------------------ rational resampler / FIR (A2, A3) */
+typedef struct {
+    int ncomp;          /* 1 = float stream, 2 = complex stream */
+    int L, M;           /* interpolation, decimation */
+    int nt;             /* taps per arm */
+    float** arm;        /* L arms */
+    float* arm_store;
+    unsigned ctr;
+    size_t pos;         /* index in `in` of the newest sample for the next output */
+    qvec in;
+} resamp_t;
+
+static void resamp_init(resamp_t* r, int ncomp, int L, int M, const float* taps, int ntaps)
+{
+    int a = L, b = M; while (b) { int t = a % b; a = b; b = t; }
+    L /= a; M /= a;
+    r->ncomp = ncomp; r->L = L; r->M = M;
+    int padded = ((ntaps + L - 1) / L) * L;
+    r->nt = padded / L;
+    r->arm_store = (float*)calloc(padded, sizeof(float));
+    r->arm = (float**)malloc(sizeof(float*) * L);
+    for (int p = 0; p < L; p++) {
+        r->arm[p] = r->arm_store + (size_t)p * r->nt;
+        for (int k = 0; k < r->nt; k++) {
+            int j = p + k * L;
+            r->arm[p][k] = j < ntaps ? taps[j] : 0.0f;
+        }
+    }
+    r->ctr = 0;
+    qv_init(&r->in, sizeof(float) * ncomp);
+    qv_push_zero(&r->in, r->nt - 1);
+    r->pos = r->nt - 1;
+}
+static void resamp_free(resamp_t* r) { free(r->arm_store); free(r->arm); qv_free(&r->in); }
+static void resamp_work(resamp_t* r, const float* x, size_t n, qvec* out)
+{
+    qv_push(&r->in, x, n);
+    const float* b = (const float*)r->in.d;
+    int Drule = (r->L == 1) ? r->M : 1;
+    while (r->pos < r->in.n) {
+        const float* newest = b + r->pos * r->ncomp;
+        const float* h = r->arm[r->ctr];
+        if (r->ncomp == 2) {
+            float re = fir_dot(h, r->nt, Drule, newest, 2);
+            float im = fir_dot(h, r->nt, Drule, newest + 1, 2);
+            qv_pushc(out, re, im);
+        } else {
+            qv_pushf(out, fir_dot(h, r->nt, Drule, newest, 1));
+        }
+        r->ctr += r->M;
+        while (r->ctr >= (unsigned)r->L) { r->ctr -= r->L; r->pos++; }
+    }
+    size_t keep_from = r->pos - (r->nt - 1);
+    if (keep_from > 0) { qv_drop(&r->in, keep_from); r->pos -= keep_from; }
+}
+
+/* fft_filter_ccc restated in direct form: complex taps, complex stream */
+typedef struct { int nt; float* h; qvec in; size_t pos; } fircc_t;
+static void fircc_init(fircc_t* f, const float* taps_c, int nt)
+{
+    f->nt = nt; f->h = (float*)malloc(sizeof(float) * 2 * nt);
+    memcpy(f->h, taps_c, sizeof(float) * 2 * nt);
+    qv_init(&f->in, 8); qv_push_zero(&f->in, nt - 1); f->pos = nt - 1;
+}
+static void fircc_free(fircc_t* f) { free(f->h); qv_free(&f->in); }
+static void fircc_work(fircc_t* f, const float* x, size_t n, qvec* out)
+{
+    qv_push(&f->in, x, n);
+    const float* b = (const float*)f->in.d;
+    while (f->pos < f->in.n) {
+        float re = 0.0f, im = 0.0f;
+        for (int j = f->nt - 1; j >= 0; j--) {
+            float hr = f->h[2 * j], hi = f->h[2 * j + 1];
+            float xr = b[2 * (f->pos - j)], xi = b[2 * (f->pos - j) + 1];
+            re = fmaf(hr, xr, re); re = fmaf(-hi, xi, re);
+            im = fmaf(hr, xi, im); im = fmaf(hi, xr, im);
+        }
+        qv_pushc(out, re, im);
+        f->pos++;
+    }
+    size_t keep_from = f->pos - (f->nt - 1);
+    if (keep_from > 0) { qv_drop(&f->in, keep_from); f->pos -= keep_from; }
+}
+
+/* ------------------------------------------------------------------ analog blocks */
+/* analog::quadrature_demod_cf (A4) */
+typedef struct { float gain; float pr, pi; } qdemod_t;
+static void qdemod_init(qdemod_t* q, float gain) { q->gain = gain; q->pr = 0; q->pi = 0; }
+static void qdemod_work(qdemod_t* q, const float* x, size_t n, qvec* out)
+{
+    for (size_t i = 0; i < n; i++) {
+        float ar = x[2 * i], ai = x[2 * i + 1];
+        float re = ar * q->pr + ai * q->pi;      /* x[n] * conj(x[n-1]) */
+        float im = ai * q->pr - ar * q->pi;
+        qv_pushf(out, q->gain * qo_fast_atan2f(im, re));
+        q->pr = ar; q->pi = ai;
+    }
+}
+/* analog::pwr_squelch_cc / squelch_base_cc (A5) */
+typedef struct { double alpha, pwr, threshold; int ramp, ramped, state, gate; double envelope; } squelch_t;
+enum { SQ_MUTED, SQ_ATTACK, SQ_UNMUTED, SQ_DECAY };
+static void squelch_init(squelch_t* s, double db, double alpha, int ramp, int gate)
+{
+    s->alpha = alpha; s->pwr = 0; s->threshold = pow(10.0, db / 10.0); s->ramp = ramp; s->ramped = 0;
+    s->state = SQ_MUTED; s->gate = gate; s->envelope = ramp ? 0.0 : 1.0;
+}
+static void squelch_work(squelch_t* s, const float* x, size_t n, qvec* out)
+{
+    for (size_t i = 0; i < n; i++) {
+        float re = x[2 * i], im = x[2 * i + 1];
+        float mag2 = re * re + im * im;
+        s->pwr = s->alpha * (double)mag2 + (1.0 - s->alpha) * s->pwr;
+        int mute = s->pwr < s->threshold;
+        switch (s->state) {
+        case SQ_MUTED: if (!mute) s->state = s->ramp ? SQ_ATTACK : SQ_UNMUTED; break;
+        case SQ_UNMUTED: if (mute) s->state = s->ramp ? SQ_DECAY : SQ_MUTED; break;
+        case SQ_ATTACK:
+            s->envelope = 0.5 - cos(M_PI * (++s->ramped) / s->ramp) / 2.0;
+            if (s->ramped >= s->ramp) { s->state = SQ_UNMUTED; s->envelope = 1.0; }
+            break;
+        case SQ_DECAY:
+            s->envelope = 0.5 - cos(M_PI * (--s->ramped) / s->ramp) / 2.0;
+            if (s->ramped == 0) s->state = SQ_MUTED;
+            break;
+        }
+        if (s->state != SQ_MUTED) {
+            float e = (float)s->envelope;
+            qv_pushc(out, re * e, im * e);
+        } else if (!s->gate) qv_pushc(out, 0.0f, 0.0f);
+    }
+}
+/* filter::iir_filter_ffd, 2-tap ff / 2-tap fb, oldstyle=false (A6) */
+typedef struct { double b0, b1, a1; double x1, y1; } iir1_t;
+static void iir1_init(iir1_t* f, const double* b, const double* a) { f->b0 = b[0]; f->b1 = b[1]; f->a1 = a[1]; f->x1 = 0; f->y1 = 0; }
+static void iir1_work(iir1_t* f, const float* x, size_t n, qvec* out, float post_gain)
+{
+    for (size_t i = 0; i < n; i++) {
+        double xin = (double)x[i];
+        double acc = f->b0 * xin;
+        acc = acc + f->b1 * f->x1;
+        acc = acc - f->a1 * f->y1;
+        f->x1 = xin; f->y1 = acc;
+        qv_pushf(out, (float)acc * post_gain);
+    }
+}
+/* analog::agc2_cc (A7) */
+typedef struct { float attack, decay, ref, gain, max_gain; } agc2_t;
+static void agc2_init(agc2_t* a, float attack, float decay, float ref, float gain) { a->attack = attack; a->decay = decay; a->ref = ref; a->gain = gain; a->max_gain = 65536.0f; }
+static inline void agc2_step(agc2_t* a, float xr, float xi, float* yr, float* yi)
+{
+    float orr = xr * a->gain, oi = xi * a->gain;
+    float tmp = -a->ref + sqrtf(orr * orr + oi * oi);
+    float rate = a->decay;
+    if (fabsf(tmp) > a->gain) rate = a->attack;
+    a->gain -= tmp * rate;
+    if (a->gain < 0.0f) a->gain = 10e-5f;
+    if (a->max_gain > 0.0f && a->gain > a->max_gain) a->gain = a->max_gain;
+    *yr = orr; *yi = oi;
+}
+/* blocks::control_loop + digital::costas_loop_cc (A8) */
+typedef struct { float phase, freq, alpha, beta, max_freq, min_freq; int order, use_snr; } costas_t;
+static void costas_init(costas_t* c, float loop_bw, int order, int use_snr)
+{
+    tabs_init();
+    c->phase = 0; c->freq = 0; c->max_freq = 1.0f; c->min_freq = -1.0f; c->order = order; c->use_snr = use_snr;
+    qo_control_loop_gains(loop_bw, &c->alpha, &c->beta);
+}
+static inline void costas_step(costas_t* c, float xr, float xi, float* yr, float* yi)
+{
+    float sn, cs;
+    qo_sincosf(-c->phase, &sn, &cs);
+    float orr = xr * cs - xi * sn;
+    float oi = xr * sn + xi * cs;
+    float err;
+    if (c->order == 2) {
+        if (c->use_snr) { float snr = orr * orr + oi * oi; err = tanhf_lut(snr * orr) * oi; }
+        else err = orr * oi;
+    } else {
+        if (c->use_snr) {
+            float snr = orr * orr + oi * oi;
+            err = tanhf_lut(snr * orr) * oi - tanhf_lut(snr * oi) * orr;
+        } else {
+            err = (orr > 0.0f ? 1.0f : -1.0f) * oi - (oi > 0.0f ? 1.0f : -1.0f) * orr;
+        }
+    }
+    err = clipf(err, 1.0f);
+    c->freq = c->freq + c->beta * err;
+    c->phase = c->phase + c->freq + c->alpha * err;
+    while ((double)c->phase > 2.0 * M_PI) c->phase = (float)((double)c->phase - 2.0 * M_PI);
+    while ((double)c->phase < -2.0 * M_PI) c->phase = (float)((double)c->phase + 2.0 * M_PI);
+    if (c->freq > c->max_freq) c->freq = c->max_freq;
+    else if (c->freq < c->min_freq) c->freq = c->min_freq;
+    *yr = orr; *yi = oi;
+}
+
+/* ------------------------------------------------------------------ symbol_sync_{ff,cc} (A9) */
+enum { SL_RECT4 = 0, SL_DQPSK = 1, SL_BPSK = 2 };
+typedef struct {
+    int ncomp, slicer;
+    float sps, alpha, beta, max_period, min_period;
+    float avg_period, inst_period, mu;
+    float xr[3], xi[3], dr[3], di[3];
+    size_t ii;
+    int lookahead;
+    qvec in;
+} symsync_t;
+static void symsync_init(symsync_t* s, int ncomp, float sps, float loop_bw, float damping, float ted_gain, float max_dev, int slicer)
+{
+    tabs_init();
+    memset(s, 0, sizeof *s);
+    s->ncomp = ncomp; s->slicer = slicer; s->sps = sps;
+    qo_clock_loop_gains(loop_bw, damping, ted_gain, &s->alpha, &s->beta);
+    s->max_period = sps + max_dev; s->min_period = sps - max_dev;
+    s->avg_period = sps; s->inst_period = sps; s->mu = 0.0f; s->ii = 0;
+    s->lookahead = 8 + (int)ceilf(s->max_period) + 1;
+    qv_init(&s->in, sizeof(float) * ncomp);
+}
+static void symsync_free(symsync_t* s) { qv_free(&s->in); }
+static inline void slice(int slicer, float re, float im, float* dr, float* di)
+{
+    if (slicer == SL_RECT4) {
+        /* digital::constellation_rect(points {-1.5,-0.5,0.5,1.5}, real_sectors 4, width 1) */
+        int sec = (int)floorf(re + 2.0f);
+        if (sec < 0) sec = 0; if (sec > 3) sec = 3;
+        *dr = -1.5f + (float)sec; *di = 0.0f;
+    } else if (slicer == SL_DQPSK) {
+        *dr = re > 0.0f ? 0.707107f : -0.707107f;
+        *di = im > 0.0f ? 0.707107f : -0.707107f;
+    } else {
+        *dr = re > 0.0f ? 1.0f : -1.0f; *di = 0.0f;
+    }
+}
+/* 8-tap MMSE interpolation, oldest sample first: sum_k taps[imu][7-i] * in[i] */
+static inline float mmse_interp(const float* in, int stride, float mu)
+{
+    int imu = (int)rintf(mu * 128.0f);
+    const float* t = g_mmse_tab + imu * 8;
+    float acc = 0.0f;
+    for (int i = 0; i < 8; i++) acc = fmaf(t[7 - i], in[i * stride], acc);
+    return acc;
+}
+/* out: interpolated symbols (float or complex). */
+static void symsync_work(symsync_t* s, const float* x, size_t n, qvec* out)
+{
+    qv_push(&s->in, x, n);
+    const float* b = (const float*)s->in.d;
+    while (s->ii + (size_t)s->lookahead <= s->in.n) {
+        const float* p = b + s->ii * s->ncomp;
+        float yr, yi = 0.0f;
+        if (s->ncomp == 2) { yr = mmse_interp(p, 2, s->mu); yi = mmse_interp(p + 1, 2, s->mu); }
+        else yr = mmse_interp(p, 1, s->mu);
+        /* TED input */
+        s->xr[2] = s->xr[1]; s->xr[1] = s->xr[0]; s->xr[0] = yr;
+        s->xi[2] = s->xi[1]; s->xi[1] = s->xi[0]; s->xi[0] = yi;
+        s->dr[2] = s->dr[1]; s->dr[1] = s->dr[0];
+        s->di[2] = s->di[1]; s->di[1] = s->di[0];
+        slice(s->slicer, yr, yi, &s->dr[0], &s->di[0]);
+        float err;
+        if (s->ncomp == 2) {
+            /* TED_MOD_MUELLER_AND_MULLER complex: Re{(x0-x2) conj(d1) - (d0-d2) conj(x1)} */
+            float ar = s->xr[0] - s->xr[2], ai = s->xi[0] - s->xi[2];
+            float br = s->dr[0] - s->dr[2], bi = s->di[0] - s->di[2];
+            float u = (ar * s->dr[1] + ai * s->di[1]) - (br * s->xr[1] + bi * s->xi[1]);
+            err = clipf(u, 1.0f);
+        } else {
+            float u = (s->xr[0] - s->xr[2]) * s->dr[1] - (s->dr[0] - s->dr[2]) * s->xr[1];
+            err = clipf(u / 2.0f, 1.0f);
+        }
+        /* clock_tracking_loop::advance_loop */
+        s->avg_period = s->avg_period + s->beta * err;
+        if (s->avg_period > s->max_period) s->avg_period = s->max_period;
+        else if (s->avg_period < s->min_period) s->avg_period = s->min_period;
+        s->inst_period = s->avg_period + s->alpha * err;
+        if (s->inst_period <= 0.0f) s->inst_period = s->avg_period;
+        float ph = s->mu + s->inst_period;
+        float fl = floorf(ph);
+        s->mu = ph - fl;
+        s->ii += (size_t)(int)fl;
+        if (s->ncomp == 2) qv_pushc(out, yr, yi); else qv_pushf(out, yr);
+    }
+    /* drop consumed input */
+    if (s->ii > 0) {
+        size_t d = s->ii < s->in.n ? s->ii : s->in.n;
+        qv_drop(&s->in, d); s->ii -= d;
+    }
+}
+
+/* ------------------------------------------------------------------ FEC (A11) and LFSR (A12) */
+static inline int parity8(unsigned v) { v ^= v >> 4; v ^= v >> 2; v ^= v >> 1; return v & 1; }
+typedef struct { unsigned state; } ccenc_t;
+static void ccenc_work(ccenc_t* e, const uint8_t* bits, size_t n, qvec* out)
+{
+    for (size_t i = 0; i < n; i++) {
+        e->state = ((e->state << 1) | (bits[i] & 1)) & 0x7f;
+        qv_pushb(out, (uint8_t)parity8(e->state & 109));
+        qv_pushb(out, (uint8_t)parity8(e->state & 79));
+    }
+}
+/* fec::decoder(cc_decoder(80,7,2,{109,79},0,-1,CC_STREAMING)) : 8-bit metrics, generic VOLK butterfly */
+typedef struct { qvec in; int start_state; unsigned char branchtab[64]; } ccdec_t;
+static void ccdec_init(ccdec_t* d)
+{
+    qv_init(&d->in, 1);
+    qv_push_zero(&d->in, 12); /* history = rate*(k-1) zero items */
+    d->start_state = 0;
+    int polys[2] = { 109, 79 };
+    for (int st = 0; st < 32; st++)
+        for (int i = 0; i < 2; i++) d->branchtab[i * 32 + st] = parity8((2 * st) & polys[i]) ? 255 : 0;
+}
+static void ccdec_free(ccdec_t* d) { qv_free(&d->in); }
+static void ccdec_block(ccdec_t* d, const unsigned char* syms, unsigned char* out80)
+{
+    unsigned char m1[64], m2[64];
+    unsigned char* X = m1; unsigned char* Y = m2;
+    unsigned int dec[86][2];
+    memset(dec, 0, sizeof dec);
+    for (int i = 0; i < 64; i++) X[i] = 63;
+    X[d->start_state & 63] = 0;
+    for (int s = 0; s < 86; s++) {
+        for (int i = 0; i < 32; i++) {
+            unsigned char metric = 0, m0, mm1, mm2, m3;
+            for (int j = 0; j < 2; j++) metric += (d->branchtab[i + j * 32] ^ syms[s * 2 + j]) >> 2;
+            metric = metric >> 2;
+            const unsigned char max = ((2 * ((256 - 1) >> 2)) >> 2);
+            m0 = X[i] + metric;
+            mm1 = X[i + 32] + (max - metric);
+            mm2 = X[i] + (max - metric);
+            m3 = X[i + 32] + metric;
+            int decision0 = (signed int)(m0 - mm1) > 0;
+            int decision1 = (signed int)(mm2 - m3) > 0;
+            Y[2 * i] = decision0 ? mm1 : m0;
+            Y[2 * i + 1] = decision1 ? m3 : mm2;
+            dec[s][i / 16] |= (unsigned)(decision0 | decision1 << 1) << ((2 * i) & 31);
+        }
+        unsigned char min = Y[0];
+        for (int i = 0; i < 64; i++) if (min > Y[i]) min = Y[i];
+        for (int i = 0; i < 64; i++) Y[i] -= min;
+        unsigned char* t = X; X = Y; Y = t;
+    }
+    /* find_endstate: minimum final metric, first index on ties */
+    int endstate = 0; unsigned char best = X[0];
+    for (int i = 1; i < 64; i++) if (X[i] < best) { best = X[i]; endstate = i; }
+    /* chainback_viterbi(out, 80, endstate, tailsize 6) */
+    unsigned es = (unsigned)(endstate % 64) << 2;
+    int retval = 0;
+    int nbits = 80;
+    while (nbits-- > 80 - 6) {
+        unsigned st = es >> 2;
+        int k = (dec[nbits + 6][st / 32] >> (st % 32)) & 1;
+        es = (es >> 1) | ((unsigned)k << (7 - 2 + 2));
+        out80[nbits % 80] = (unsigned char)k;
+        retval = (int)es;
+    }
+    nbits += 1;
+    while (nbits-- != 0) {
+        unsigned st = es >> 2;
+        int k = (dec[nbits + 6][st / 32] >> (st % 32)) & 1;
+        es = (es >> 1) | ((unsigned)k << (7 - 2 + 2));
+        out80[nbits % 80] = (unsigned char)k;
+    }
+    d->start_state = retval >> 2;
+}
+static void ccdec_work(ccdec_t* d, const uint8_t* soft, size_t n, qvec* out)
+{
+    qv_push(&d->in, soft, n);
+    size_t off = 0;
+    while (d->in.n - off >= 172) {
+        unsigned char o[80];
+        ccdec_block(d, d->in.d + off, o);
+        qv_push(out, o, 80);
+        off += 160;
+    }
+    qv_drop(&d->in, off);
+}
+/* digital::lfsr(0x8A, 0x7F, 7) */
+typedef struct { unsigned reg; } lfsr_t;
+static void lfsr_init(lfsr_t* l) { l->reg = 0x7F; }
+static inline unsigned char lfsr_scramble(lfsr_t* l, unsigned char in)
+{
+    unsigned char out = l->reg & 1;
+    unsigned newbit = (parity8(l->reg & 0x8A) ^ (in & 1)) & 1;
+    l->reg = ((l->reg >> 1) | (newbit << 7)) & 0xff;
+    return out;
+}
+static inline unsigned char lfsr_descramble(lfsr_t* l, unsigned char in)
+{
+    unsigned char out = (unsigned char)(parity8(l->reg & 0x8A) ^ (in & 1));
+    l->reg = ((l->reg >> 1) | ((unsigned)(in & 1) << 7)) & 0xff;
+    return out;
+}
+/* blocks::float_to_uchar after multiply_const / add_const (A10) */
+static inline unsigned char soft_u8(float v, float scale)
+{
+    float t = v * scale;
+    t = t + 128.0f;
+    float r = rintf(t);
+    if (r < 0.0f) r = 0.0f; else if (r > 255.0f) r = 255.0f;
+    return (unsigned char)r;
+}
+
+/* ------------------------------------------------------------------ stand-alone helpers */
+long qo_fir_decim_ccf(const float* h, int ntaps, int D, const float* x, long n, float* y)
+{
+    resamp_t r; qvec out; qv_init(&out, 8);
+    resamp_init(&r, 2, 1, D, h, ntaps);
+    resamp_work(&r, x, (size_t)n, &out);
+    memcpy(y, out.d, out.n * 8);
+    long k = (long)out.n;
+    resamp_free(&r); qv_free(&out);
+    return k;
+}
+long qo_fir_fff(const float* h, int ntaps, int L, int M, const float* x, long n, float* y, long ycap)
+{
+    resamp_t r; qvec out; qv_init(&out, 4);
+    resamp_init(&r, 1, L, M, h, ntaps);
+    resamp_work(&r, x, (size_t)n, &out);
+    long k = (long)out.n; if (k > ycap) k = ycap;
+    memcpy(y, out.d, (size_t)k * 4);
+    resamp_free(&r); qv_free(&out);
+    return k;
+}
+long qo_cc_encode(const uint8_t* bits, long n, uint8_t* outb)
+{
+    ccenc_t e = { 0 }; qvec out; qv_init(&out, 1);
+    ccenc_work(&e, bits, (size_t)n, &out);
+    memcpy(outb, out.d, out.n); long k = (long)out.n; qv_free(&out); return k;
+}
+long qo_cc_decode(const uint8_t* soft, long n, uint8_t* outb)
+{
+    ccdec_t d; ccdec_init(&d); qvec out; qv_init(&out, 1);
+    ccdec_work(&d, soft, (size_t)n, &out);
+    memcpy(outb, out.d, out.n); long k = (long)out.n; qv_free(&out); ccdec_free(&d); return k;
+}
+void qo_scramble(const uint8_t* in, long n, uint8_t* out) { lfsr_t l; lfsr_init(&l); for (long i = 0; i < n; i++) out[i] = lfsr_scramble(&l, in[i]); }
+void qo_descramble(const uint8_t* in, long n, uint8_t* out) { lfsr_t l; lfsr_init(&l); for (long i = 0; i < n; i++) out[i] = lfsr_descramble(&l, in[i]); }
+
+/* ------------------------------------------------------------------ RX chains */
+struct qo_rx {
+    int kind, fm;
+    int sym_sps, tsr;
+    /* stages (not all used by every kind) */
+    resamp_t resamp;        /* stage-1 rational resampler (ccf) */
+    resamp_t filt;          /* fft_filter_ccf restated direct-form */
+    qdemod_t qd;
+    resamp_t shaping;       /* RRC (fff or ccf) */
+    symsync_t ss;
+    float pm_sens;
+    float soft_scale;
+    ccdec_t dec; lfsr_t descr;
+    /* nbfm */
+    squelch_t sq; resamp_t audio_rs; resamp_t audio_filt; iir1_t deemph;
+    /* qpsk */
+    agc2_t agc; costas_t pll, costas; float dp_r, dp_i; float rot_r, rot_i;
+    /* 4fsk non-fm */
+    fircc_t bp[4]; resamp_t symfilt;
+    /* scratch + ports */
+    qvec s_res, s_filt, s_dem, s_rrc, s_sym, s_soft, s_bits, s_tmp, s_tmp2, s_bp[4];
+    qvec port[4];
+    float taps_store[4][4096]; int ntaps_store[4];
+};
+
+static void rx_common_init(qo_rx* r)
+{
+    qv_init(&r->s_res, 8); qv_init(&r->s_filt, 8); qv_init(&r->s_dem, 4); qv_init(&r->s_rrc, 4);
+    qv_init(&r->s_sym, 4); qv_init(&r->s_soft, 1); qv_init(&r->s_bits, 1); qv_init(&r->s_tmp, 8); qv_init(&r->s_tmp2, 8);
+    for (int i = 0; i < 4; i++) qv_init(&r->s_bp[i], 8);
+    qv_init(&r->port[0], 8); qv_init(&r->port[1], 8); qv_init(&r->port[2], 1); qv_init(&r->port[3], 1);
+}
+
+qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag)
+{
+    (void)carrier_freq;
+    tabs_init();
+    qo_rx* r = (qo_rx*)calloc(1, sizeof *r);
+    r->kind = kind;
+    rx_common_init(r);
+    float* T0 = r->taps_store[0]; float* T1 = r->taps_store[1]; float* T2 = r->taps_store[2]; float* T3 = r->taps_store[3];
+    if (kind == QO_DEMOD_4FSK) {
+        /* /root/reference/src/gr/gr_demod_4fsk.cpp:32-205 */
+        int fm = flag; r->fm = fm;
+        int rs = 0, bw = 0, decimation = 1, interpolation = 1, nfilts = 0;
+        if (sps == 1) { r->tsr = 80000; r->sym_sps = sps * 8; decimation = 25; interpolation = 2; rs = 10000; bw = 4000; nfilts = 32 * r->sym_sps; }
+        if (sps == 5) { r->tsr = 20000; r->sym_sps = sps * 2; decimation = 50; interpolation = 1; rs = 2000; bw = 4000; nfilts = 25 * r->sym_sps; }
+        if (sps == 10) { r->tsr = 10000; r->sym_sps = sps; decimation = 100; interpolation = 1; rs = 1000; bw = 2000; nfilts = 25 * r->sym_sps; }
+        if (sps == 2) { interpolation = 1; decimation = 2; r->sym_sps = 5; r->tsr = 500000; nfilts = 50 * r->sym_sps; }
+        if ((nfilts % 2) == 0) nfilts += 1;
+        int n0 = qo_firdes_low_pass(interpolation, (double)interpolation * samp_rate, r->tsr / 2, r->tsr / 2, QO_WIN_BLACKMAN_HARRIS, T0, 4096);
+        r->ntaps_store[0] = n0;
+        resamp_init(&r->resamp, 2, interpolation, decimation, T0, n0);
+        int n1 = qo_firdes_low_pass(1, r->tsr, filter_width, filter_width / 2, QO_WIN_BLACKMAN_HARRIS, T1, 4096);
+        r->ntaps_store[1] = n1;
+        resamp_init(&r->filt, 2, 1, 1, T1, n1);
+        if (fm) {
+            qdemod_init(&r->qd, (float)(r->sym_sps / (1 * M_PI)));
+            int n2 = qo_firdes_rrc(1.5, r->tsr, r->tsr / r->sym_sps, 0.2, nfilts, T2, 4096);
+            r->ntaps_store[2] = n2;
+            resamp_init(&r->shaping, 1, 1, 1, T2, n2);
+            symsync_init(&r->ss, 1, (float)r->sym_sps, (float)(2 * M_PI / 200.0f), 1.0f, 0.2869f, 0.05f, SL_RECT4);
+        } else {
+            float tc[2 * 4096];
+            int fw = filter_width;
+            double lo[4] = { -fw, -fw + rs, 0, fw - rs }, hi[4] = { -fw + rs, 0, fw - rs, fw };
+            for (int i = 0; i < 4; i++) {
+                int n = qo_firdes_complex_band_pass(1, r->tsr, lo[i], hi[i], bw, QO_WIN_BLACKMAN_HARRIS, tc, 4096);
+                fircc_init(&r->bp[i], tc, n);
+            }
+            int n3 = qo_firdes_low_pass(1.0, r->tsr, r->tsr / r->sym_sps, r->tsr / r->sym_sps / 20, QO_WIN_BLACKMAN_HARRIS, T3, 4096);
+            r->ntaps_store[3] = n3;
+            resamp_init(&r->symfilt, 2, 1, 1, T3, n3);
+            symsync_init(&r->ss, 2, (float)r->sym_sps, (float)(2 * M_PI / 200.0f), 1.0f, 0.2869f, 0.05f, SL_RECT4);
+        }
+        r->pm_sens = (float)(M_PI / 2);
+        r->soft_scale = 128.0f;
+        ccdec_init(&r->dec); lfsr_init(&r->descr);
+    } else if (kind == QO_DEMOD_QPSK) {
+        /* /root/reference/src/gr/gr_demod_qpsk.cpp:33-159 */
+        int decimation, interpolation = 1; float costas_bw = (float)(M_PI / 200);
+        if (sps > 4 && sps < 125) { decimation = 25; r->sym_sps = sps * 4 / 25; r->tsr = 40000; }
+        else if (sps >= 125) { decimation = 100; r->sym_sps = sps / 25; r->tsr = 10000; }
+        else { decimation = 2; r->sym_sps = sps; r->tsr = 500000; costas_bw = (float)(M_PI / 400); }
+        int n0 = qo_firdes_low_pass_2(interpolation, (double)samp_rate * interpolation, r->tsr / 2, r->tsr / 10, 60, QO_WIN_BLACKMAN_HARRIS, T0, 4096);
+        r->ntaps_store[0] = n0;
+        resamp_init(&r->resamp, 2, interpolation, decimation, T0, n0);
+        int n1 = qo_firdes_rrc(r->sym_sps, r->sym_sps, 1, 0.35, 11 * r->sym_sps, T1, 4096);
+        r->ntaps_store[1] = n1;
+        resamp_init(&r->shaping, 2, 1, 1, T1, n1);
+        agc2_init(&r->agc, 1.0f, 1e-1f, 1.0f, 1.0f);
+        float symbol_rate = (float)r->tsr / (float)r->sym_sps;
+        float sps_dev = 200.0f / symbol_rate;
+        symsync_init(&r->ss, 2, (float)r->sym_sps, (float)(2 * M_PI / (symbol_rate / 10)), 1.0f, 0.2869f, sps_dev, SL_DQPSK);
+        costas_init(&r->pll, (float)(M_PI / 200 / r->sym_sps), 4, 1);
+        costas_init(&r->costas, costas_bw, 4, 1);
+        r->dp_r = 0; r->dp_i = 0;
+        float th = (float)(-3 * M_PI / 4);
+        r->rot_r = cosf(th); r->rot_i = sinf(th);
+        r->soft_scale = 48.0f;
+        ccdec_init(&r->dec); lfsr_init(&r->descr);
+        r->fm = (sps > 4); /* FLL in the chain: not restated yet */
+    } else if (kind == QO_DEMOD_NBFM) {
+        /* /root/reference/src/gr/gr_demod_nbfm.cpp:31-79 */
+        r->tsr = 20000;
+        double a[2], b[2];
+        qo_deemph_taps(r->tsr, 50e-6, a, b);
+        iir1_init(&r->deemph, b, a);
+        int n0 = qo_firdes_low_pass(1, samp_rate, r->tsr / 2, r->tsr / 2, QO_WIN_BLACKMAN_HARRIS, T0, 4096);
+        r->ntaps_store[0] = n0;
+        resamp_init(&r->resamp, 2, 1, 50, T0, n0);
+        int n1 = qo_firdes_low_pass_2(1, r->tsr, filter_width, 3500, 60, QO_WIN_BLACKMAN_HARRIS, T1, 4096);
+        r->ntaps_store[1] = n1;
+        resamp_init(&r->filt, 2, 1, 1, T1, n1);
+        int n2 = qo_firdes_low_pass_2(2, 2 * r->tsr, 3600, 250, 60, QO_WIN_BLACKMAN_HARRIS, T2, 4096);
+        r->ntaps_store[2] = n2;
+        resamp_init(&r->audio_rs, 1, 2, 5, T2, n2);
+        int n3 = qo_firdes_low_pass_2(1, 8000, 3500, 200, 35, QO_WIN_BLACKMAN_HARRIS, T3, 4096);
+        r->ntaps_store[3] = n3;
+        resamp_init(&r->audio_filt, 1, 1, 1, T3, n3);
+        qdemod_init(&r->qd, (float)(r->tsr / (4 * M_PI * filter_width)));
+        squelch_init(&r->sq, -140, 0.01, 320, 1);
+        r->port[1].isz = 4;
+    } else { free(r); return NULL; }
+    return r;
+}
+void qo_rx_destroy(qo_rx* r)
+{
+    if (!r) return;
+    /* leak-tolerant: test infrastructure; free the big ones */
+    qv_free(&r->s_res); qv_free(&r->s_filt); qv_free(&r->s_dem); qv_free(&r->s_rrc); qv_free(&r->s_sym);
+    qv_free(&r->s_soft); qv_free(&r->s_bits); qv_free(&r->s_tmp); qv_free(&r->s_tmp2);
+    for (int i = 0; i < 4; i++) { qv_free(&r->port[i]); qv_free(&r->s_bp[i]); }
+    free(r);
+}
+
+static void rx_fec_tail(qo_rx* r)
+{
+    /* soft -> decoder -> descrambler -> port2 */
+    size_t b0 = r->s_bits.n;
+    ccdec_work(&r->dec, r->s_soft.d, r->s_soft.n, &r->s_bits);
+    r->s_soft.n = 0;
+    for (size_t i = b0; i < r->s_bits.n; i++) qv_pushb(&r->port[2], lfsr_descramble(&r->descr, r->s_bits.d[i]));
+    r->s_bits.n = 0;
+}
+
+int qo_rx_work(qo_rx* r, const float* iq, long T)
+{
+    if (r->kind == QO_DEMOD_4FSK) {
+        r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
+        r->s_filt.n = 0; resamp_work(&r->filt, (const float*)r->s_res.d, r->s_res.n, &r->s_filt);
+        qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
+        r->s_sym.n = 0;
+        if (r->fm) {
+            r->s_dem.n = 0; qdemod_work(&r->qd, (const float*)r->s_filt.d, r->s_filt.n, &r->s_dem);
+            r->s_rrc.n = 0; resamp_work(&r->shaping, (const float*)r->s_dem.d, r->s_dem.n, &r->s_rrc);
+            r->s_sym.isz = 4;
+            symsync_work(&r->ss, (const float*)r->s_rrc.d, r->s_rrc.n, &r->s_sym);
+            const float* sy = (const float*)r->s_sym.d;
+            for (size_t i = 0; i < r->s_sym.n; i++) {
+                /* analog::phase_modulator_fc(pi/2) */
+                float ph = r->pm_sens * sy[i];
+                float sn, cs; qo_sincosf(ph, &sn, &cs);
+                qv_pushc(&r->port[1], cs, sn);
+                /* interleave: imag first, then real (gr_demod_4fsk.cpp:186-189) */
+                qv_pushb(&r->s_soft, soft_u8(sn, r->soft_scale));
+                qv_pushb(&r->s_soft, soft_u8(cs, r->soft_scale));
+            }
+        } else {
+            const float* f = (const float*)r->s_filt.d; size_t n = r->s_filt.n;
+            for (int i = 0; i < 4; i++) { r->s_bp[i].n = 0; fircc_work(&r->bp[i], f, n, &r->s_bp[i]); }
+            r->s_tmp.n = 0;
+            for (size_t i = 0; i < n; i++) {
+                float m[4];
+                for (int k = 0; k < 4; k++) { const float* c = (const float*)r->s_bp[k].d + 2 * i; m[k] = sqrtf(c[0] * c[0] + c[1] * c[1]); }
+                /* /root/reference/src/gr/gr_4fsk_discriminator.cpp:17-44 */
+                float orr = 0, oi = 0;
+                if ((m[0] > m[1]) && (m[0] > m[2]) && (m[0] > m[3])) { orr = (float)-0.707107; oi = (float)-0.707107; }
+                else if ((m[1] > m[0]) && (m[1] > m[2]) && (m[1] > m[3])) { orr = (float)-0.707107; oi = (float)0.707107; }
+                else if ((m[2] > m[1]) && (m[2] > m[0]) && (m[2] > m[3])) { orr = (float)0.707107; oi = (float)0.707107; }
+                else if ((m[3] > m[1]) && (m[3] > m[0]) && (m[3] > m[2])) { orr = (float)0.707107; oi = (float)-0.707107; }
+                qv_pushc(&r->s_tmp, orr, oi);
+            }
+            r->s_tmp2.n = 0; resamp_work(&r->symfilt, (const float*)r->s_tmp.d, r->s_tmp.n, &r->s_tmp2);
+            r->s_sym.isz = 8;
+            symsync_work(&r->ss, (const float*)r->s_tmp2.d, r->s_tmp2.n, &r->s_sym);
+            const float* sy = (const float*)r->s_sym.d;
+            for (size_t i = 0; i < r->s_sym.n; i++) {
+                qv_pushc(&r->port[1], sy[2 * i], sy[2 * i + 1]);
+                qv_pushb(&r->s_soft, soft_u8(sy[2 * i], r->soft_scale));
+                qv_pushb(&r->s_soft, soft_u8(sy[2 * i + 1], r->soft_scale));
+            }
+        }
+        rx_fec_tail(r);
+        return 0;
+    }
+    if (r->kind == QO_DEMOD_QPSK) {
+        r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
+        r->s_filt.n = 0; resamp_work(&r->shaping, (const float*)r->s_res.d, r->s_res.n, &r->s_filt);
+        qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
+        const float* f = (const float*)r->s_filt.d; size_t n = r->s_filt.n;
+        r->s_tmp.n = 0;
+        for (size_t i = 0; i < n; i++) {
+            float ar, ai, pr, pi;
+            agc2_step(&r->agc, f[2 * i], f[2 * i + 1], &ar, &ai);
+            costas_step(&r->pll, ar, ai, &pr, &pi);
+            qv_pushc(&r->s_tmp, pr, pi);
+        }
+        r->s_sym.isz = 8; r->s_sym.n = 0;
+        symsync_work(&r->ss, (const float*)r->s_tmp.d, r->s_tmp.n, &r->s_sym);
+        const float* sy = (const float*)r->s_sym.d;
+        for (size_t i = 0; i < r->s_sym.n; i++) {
+            float cr, ci;
+            costas_step(&r->costas, sy[2 * i], sy[2 * i + 1], &cr, &ci);
+            /* digital::diff_phasor_cc */
+            float dr = cr * r->dp_r + ci * r->dp_i;
+            float di = ci * r->dp_r - cr * r->dp_i;
+            r->dp_r = cr; r->dp_i = ci;
+            /* blocks::multiply_const_cc(exp(-j 3pi/4)) */
+            float orr = dr * r->rot_r - di * r->rot_i;
+            float oi = dr * r->rot_i + di * r->rot_r;
+            qv_pushc(&r->port[1], orr, oi);
+            qv_pushb(&r->s_soft, soft_u8(orr, r->soft_scale));
+            qv_pushb(&r->s_soft, soft_u8(oi, r->soft_scale));
+        }
+        rx_fec_tail(r);
+        return 0;
+    }
+    if (r->kind == QO_DEMOD_NBFM) {
+        r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
+        r->s_filt.n = 0; resamp_work(&r->filt, (const float*)r->s_res.d, r->s_res.n, &r->s_filt);
+        qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
+        r->s_tmp.n = 0; squelch_work(&r->sq, (const float*)r->s_filt.d, r->s_filt.n, &r->s_tmp);
+        r->s_dem.n = 0; qdemod_work(&r->qd, (const float*)r->s_tmp.d, r->s_tmp.n, &r->s_dem);
+        r->s_rrc.n = 0; resamp_work(&r->audio_rs, (const float*)r->s_dem.d, r->s_dem.n, &r->s_rrc);
+        r->s_sym.isz = 4; r->s_sym.n = 0; resamp_work(&r->audio_filt, (const float*)r->s_rrc.d, r->s_rrc.n, &r->s_sym);
+        iir1_work(&r->deemph, (const float*)r->s_sym.d, r->s_sym.n, &r->port[1], 2.0f);
+        return 0;
+    }
+    return -1;
+}
+long qo_rx_port_items(qo_rx* r, int port) { return (long)r->port[port].n; }
+const void* qo_rx_port_data(qo_rx* r, int port) { return r->port[port].d; }
+void qo_rx_port_clear(qo_rx* r, int port) { r->port[port].n = 0; }
+static qvec* rx_dbg(qo_rx* r, const char* name)
+{
+    if (!strcmp(name, "resamp")) return &r->s_res;
+    if (!strcmp(name, "filt")) return &r->s_filt;
+    if (!strcmp(name, "demod")) return &r->s_dem;
+    if (!strcmp(name, "rrc")) return &r->s_rrc;
+    if (!strcmp(name, "sym")) return &r->s_sym;
+    if (!strcmp(name, "tmp")) return &r->s_tmp;
+    return NULL;
+}
+long qo_rx_dbg_items(qo_rx* r, const char* name) { qvec* v = rx_dbg(r, name); return v ? (long)v->n : -1; }
+const void* qo_rx_dbg_data(qo_rx* r, const char* name) { qvec* v = rx_dbg(r, name); return v ? v->d : NULL; }
+int qo_rx_ntaps(qo_rx* r, int which, float* out, int cap)
+{
+    int n = r->ntaps_store[which];
+    if (out && n <= cap) memcpy(out, r->taps_store[which], sizeof(float) * n);
+    return n;
+}
+
+/* ------------------------------------------------------------------ TX chains */
+struct qo_tx {
+    int kind, fm, sps;
+    lfsr_t scr; ccenc_t enc;
+    resamp_t rrc; resamp_t interp;
+    float fm_sens, phase_f; uint32_t phase_q;
+    float amplif, bb_gain;
+    int pack_have; unsigned pack_acc;
+    unsigned diff_prev;
+    qvec s_bits, s_coded, s_sym, s_shaped, s_mod, out;
+};
+qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag)
+{
+    (void)carrier_freq;
+    tabs_init();
+    qo_tx* t = (qo_tx*)calloc(1, sizeof *t);
+    t->kind = kind; t->bb_gain = 1.0f;
+    lfsr_init(&t->scr);
+    qv_init(&t->s_bits, 1); qv_init(&t->s_coded, 1); qv_init(&t->s_sym, 4); qv_init(&t->s_shaped, 4);
+    qv_init(&t->s_mod, 8); qv_init(&t->out, 8);
+    static float taps[16384];
+    if (kind == QO_MOD_4FSK) {
+        /* /root/reference/src/gr/gr_mod_4fsk.cpp:27-117 */
+        int fm = flag; t->fm = fm;
+        int sym_sps = sps, nfilts = sym_sps * 10, second_interp = 20;
+        if (sps == 2) { sym_sps = 5; second_interp = 2; nfilts = 256; }
+        int spacing = 2; t->amplif = 0.8f;
+        if (fm) { t->amplif = 0.9f; spacing = 1; }
+        t->sps = sym_sps;
+        int n = qo_firdes_rrc(sym_sps, sym_sps, 1, 0.2, nfilts, taps, 16384);
+        resamp_init(&t->rrc, 1, sym_sps, 1, taps, n);
+        t->fm_sens = (float)((spacing * M_PI) / sym_sps);
+        n = qo_firdes_low_pass(second_interp, samp_rate, filter_width, filter_width, QO_WIN_HAMMING, taps, 16384);
+        resamp_init(&t->interp, 2, second_interp, 1, taps, n);
+        t->s_sym.isz = 4;
+    } else if (kind == QO_MOD_QPSK) {
+        /* /root/reference/src/gr/gr_mod_qpsk.cpp:26-90 */
+        int nfilts;
+        if (sps > 120) nfilts = 11; else if (sps > 10) nfilts = 13; else nfilts = 15;
+        t->sps = sps;
+        int n = qo_firdes_rrc(sps, sps, 1, 0.35, nfilts * sps, taps, 16384);
+        resamp_init(&t->rrc, 2, sps, 1, taps, n);
+        t->amplif = 0.6f;
+        t->s_sym.isz = 8;
+        (void)samp_rate; (void)filter_width;
+    } else { free(t); return NULL; }
+    return t;
+}
+void qo_tx_destroy(qo_tx* t)
+{
+    if (!t) return;
+    qv_free(&t->s_bits); qv_free(&t->s_coded); qv_free(&t->s_sym); qv_free(&t->s_shaped); qv_free(&t->s_mod); qv_free(&t->out);
+    free(t);
+}
+void qo_tx_set_bb_gain(qo_tx* t, float g) { t->bb_gain = g; }
+
+/* analog::frequency_modulator_fc (A13).  Default: Q32 fixed-point phase accumulator (prefix-sum friendly,
+ * documented deviation); literal: float accumulator + fmodf as GNU Radio does. */
+static void fm_mod(qo_tx* t, const float* x, size_t n, qvec* out, float post)
+{
+    for (size_t i = 0; i < n; i++) {
+        uint32_t ux;
+        if (g_fm_literal) {
+            const float F_PI = (float)M_PI;
+            t->phase_f = t->phase_f + t->fm_sens * x[i];
+            t->phase_f = fmodf(t->phase_f + F_PI, 2.0f * F_PI) - F_PI;
+            /* gr::fxpt::float_to_fixed */
+            float ph = t->phase_f;
+            int d = (int)floor(ph / 2 / M_PI + 0.5);
+            ph = (float)(ph - d * 2 * M_PI);
+            ux = (uint32_t)(int32_t)((float)ph * 2147483648.0f / (float)M_PI);
+        } else {
+            /* phase increment quantised once to Q32, accumulated exactly modulo 2^32 */
+            float inc = t->fm_sens * x[i];
+            double q = rint((double)inc * (2147483648.0 / M_PI));
+            t->phase_q += (uint32_t)(int32_t)(long long)q;
+            ux = t->phase_q;
+        }
+        /* gr::fxpt::sincos */
+        int si = ux >> 22;
+        float s = g_sine_tab[2 * si] * (float)(ux >> 1) + g_sine_tab[2 * si + 1];
+        uint32_t uc = ux + 0x40000000u;
+        int ci = uc >> 22;
+        float c = g_sine_tab[2 * ci] * (float)(uc >> 1) + g_sine_tab[2 * ci + 1];
+        qv_pushc(out, c * post, s * post);
+    }
+}
+
+int qo_tx_work(qo_tx* t, const void* in, long n)
+{
+    const uint8_t* bytes = (const uint8_t*)in;
+    if (t->kind == QO_MOD_4FSK || t->kind == QO_MOD_QPSK) {
+        /* packed_to_unpacked(1, MSB) -> scrambler -> cc_encoder */
+        t->s_bits.n = 0;
+        for (long i = 0; i < n; i++)
+            for (int b = 7; b >= 0; b--) qv_pushb(&t->s_bits, lfsr_scramble(&t->scr, (bytes[i] >> b) & 1));
+        t->s_coded.n = 0;
+        ccenc_work(&t->enc, t->s_bits.d, t->s_bits.n, &t->s_coded);
+        /* pack_k_bits(2) MSB first -> map {0,1,3,2} -> symbols */
+        static const int map[4] = { 0, 1, 3, 2 };
+        t->s_sym.n = 0;
+        for (size_t i = 0; i + 1 < t->s_coded.n; i += 2) {
+            int chunk = map[(t->s_coded.d[i] << 1) | t->s_coded.d[i + 1]];
+            if (t->kind == QO_MOD_4FSK) {
+                static const float lv[4] = { -1.5f, -0.5f, 0.5f, 1.5f };
+                qv_pushf(&t->s_sym, lv[chunk]);
+            } else {
+                /* digital::diff_encoder_bb(4) then chunks_to_symbols_bc */
+                t->diff_prev = (chunk + t->diff_prev) % 4;
+                static const float qr[4] = { -0.707f, -0.707f, 0.707f, 0.707f };
+                static const float qi[4] = { -0.707f, 0.707f, 0.707f, -0.707f };
+                qv_pushc(&t->s_sym, qr[t->diff_prev], qi[t->diff_prev]);
+            }
+        }
+        if (t->kind == QO_MOD_4FSK) {
+            t->s_shaped.n = 0;
+            if (t->fm) {
+                resamp_work(&t->rrc, (const float*)t->s_sym.d, t->s_sym.n, &t->s_shaped);
+                float* p = (float*)t->s_shaped.d;
+                for (size_t i = 0; i < t->s_shaped.n; i++) p[i] = p[i] * 0.66666666f;
+            } else {
+                const float* p = (const float*)t->s_sym.d;
+                for (size_t i = 0; i < t->s_sym.n; i++) for (int k = 0; k < t->sps; k++) qv_pushf(&t->s_shaped, p[i]);
+            }
+            t->s_mod.n = 0;
+            fm_mod(t, (const float*)t->s_shaped.d, t->s_shaped.n, &t->s_mod, 1.0f);
+            float* m = (float*)t->s_mod.d;
+            for (size_t i = 0; i < 2 * t->s_mod.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
+            resamp_work(&t->interp, m, t->s_mod.n, &t->out);
+        } else {
+            size_t o0 = t->out.n;
+            resamp_work(&t->rrc, (const float*)t->s_sym.d, t->s_sym.n, &t->out);
+            float* m = (float*)t->out.d;
+            for (size_t i = 2 * o0; i < 2 * t->out.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
+        }
+        return 0;
+    }
+    return -1;
+}
+long qo_tx_out_items(qo_tx* t) { return (long)t->out.n; }
+const float* qo_tx_out_data(qo_tx* t) { return (const float*)t->out.d; }
+void qo_tx_out_clear(qo_tx* t) { t->out.n = 0; }
+
+/* ------------------------------------------------------------------ framing (gr_modem.cpp:1119-1282 restated) */
+/* bit-serial shift-register sync search followed by frame_len bytes packed MSB first (packBytes, gr_modem.cpp:980-994) */
+long qo_find_frames(const uint8_t* bits, long nbits, uint32_t sync, int sync_bits, int frame_len, uint8_t* frames, long max_frames)
+{
+    uint64_t sh = 0; uint64_t mask = (sync_bits >= 64) ? ~0ull : ((1ull << sync_bits) - 1);
+    long found = 0; long i = 0;
+    while (i < nbits && found < max_frames) {
+        sh = ((sh << 1) | (bits[i] & 1)) & mask; i++;
+        if (sh == (uint64_t)sync) {
+            if (i + (long)frame_len * 8 > nbits) break;
+            for (int b = 0; b < frame_len; b++) {
+                int t = 0;
+                for (int k = 0; k < 8; k++) t = (t << 1) | (bits[i + b * 8 + k] & 1);
+                frames[found * frame_len + b] = (uint8_t)t;
+            }
+            found++; i += (long)frame_len * 8; sh = 0;
+        }
+    }
+    return found;
+}

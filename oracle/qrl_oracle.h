@@ -1,0 +1,101 @@
+/*
+ * qrl_oracle.h -- CPU ORACLE (TEST INFRASTRUCTURE ONLY) for the qradiolink IQ-stream DSP hot path.
+ *
+ * This is a from-scratch plain-C restatement of the GNU Radio 3.10 blocks that the reference
+ * wires together in src/gr/gr_demod_*.cpp / src/gr/gr_mod_*.cpp (see each function's citation in
+ * qrl_oracle.c).  It is the parity definition for the CUDA path in qradiolink_b200/.
+ *
+ * PARITY UNPINNED against real GNU Radio: the reference ships no tests / golden vectors and its
+ * arithmetic lives in GNU Radio + VOLK, which are not vendored.  The only piece
+ * of the path that compiles from the reference tree itself is src/gr/emphasis.cpp; oracle/_ref pins
+ * that one (tests/test_oracle_ref.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+ * load this library.  The product (qradiolink_b200/) never links, imports or calls it.
+ */
+#ifndef QRL_ORACLE_H
+#define QRL_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* window ids follow gr::fft::window::win_type */
+enum { QO_WIN_HAMMING = 0, QO_WIN_HANN = 1, QO_WIN_BLACKMAN = 2, QO_WIN_RECT = 3, QO_WIN_KAISER = 4,
+       QO_WIN_BLACKMAN_HARRIS = 5 };
+
+/* hier-block kinds (one per reference file) */
+enum { QO_DEMOD_NBFM = 1, QO_DEMOD_4FSK = 2, QO_DEMOD_QPSK = 3, QO_DEMOD_BPSK = 4, QO_DEMOD_2FSK = 5,
+       QO_DEMOD_SSB = 6,
+       QO_MOD_4FSK = 101, QO_MOD_QPSK = 102, QO_MOD_NBFM = 103, QO_MOD_BPSK = 104, QO_MOD_2FSK = 105,
+       QO_MOD_SSB = 106 };
+
+/* global numerics switches (used by tests to quantify the documented deviations) */
+void qo_set_fir_order(int order);      /* 0 = polyphase/32-lane tree (default, parity order), 1 = sequential oldest-first */
+void qo_set_fm_literal(int on);        /* 1 = float phase accumulator + fmodf (GNU Radio literal), 0 = Q32 fixed-point (default) */
+
+/* ---- design functions (firdes etc.) ---- */
+int  qo_firdes_low_pass(double gain, double fs, double fc, double tw, int win, float* out, int cap);
+int  qo_firdes_low_pass_2(double gain, double fs, double fc, double tw, double att_db, int win, float* out, int cap);
+int  qo_firdes_band_pass(double gain, double fs, double lo, double hi, double tw, int win, float* out, int cap);
+int  qo_firdes_band_pass_2(double gain, double fs, double lo, double hi, double tw, double att_db, int win, float* out, int cap);
+int  qo_firdes_complex_band_pass(double gain, double fs, double lo, double hi, double tw, int win, float* out_c, int cap);
+int  qo_firdes_complex_band_pass_2(double gain, double fs, double lo, double hi, double tw, double att_db, int win, float* out_c, int cap);
+int  qo_firdes_rrc(double gain, double fs, double symrate, double alpha, int ntaps, float* out, int cap);
+void qo_deemph_taps(int fs, double tau, double* a2, double* b2);
+void qo_preemph_taps(int fs, double tau, double fh, double* a2, double* b2);
+void qo_atan_table(float* t257);
+void qo_mmse_table(float* t129x8);
+void qo_tanh_table(float* t256);
+void qo_fxpt_sine_table(float* t1024x2);
+void qo_sincosf(float x, float* s, float* c);
+float qo_fast_atan2f(float y, float x);
+void qo_clock_loop_gains(float loop_bw, float damping, float ted_gain, float* alpha, float* beta);
+void qo_control_loop_gains(float loop_bw, float* alpha, float* beta);
+
+/* ---- stand-alone block helpers for unit tests (stateless, zero history) ---- */
+/* y[k] = sum_j h[j] x[D k - j], complex x (interleaved), real taps; returns number of outputs */
+long qo_fir_decim_ccf(const float* h, int ntaps, int D, const float* x, long n, float* y);
+long qo_fir_fff(const float* h, int ntaps, int L, int M, const float* x, long n, float* y, long ycap);
+long qo_cc_encode(const uint8_t* bits, long n, uint8_t* out);                 /* streaming K=7 r=1/2 {109,79}, state 0 */
+long qo_cc_decode(const uint8_t* soft, long n, uint8_t* out);                 /* fec::decoder(cc_decoder(80,7,2,{109,79})) stream semantics */
+void qo_scramble(const uint8_t* in, long n, uint8_t* out);
+void qo_descramble(const uint8_t* in, long n, uint8_t* out);
+
+/* ---- RX chains ---- */
+typedef struct qo_rx qo_rx;
+/* arguments exactly as the reference factories make_gr_demod_*(sps, samp_rate, carrier_freq, filter_width[, fm|sb]) */
+qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag);
+void   qo_rx_destroy(qo_rx*);
+/* feed T complex samples (interleaved float re,im) of ONE channel */
+int    qo_rx_work(qo_rx*, const float* iq, long T);
+/* ports: 0 = filtered IQ (complex), 1 = constellation (complex) or audio (float), 2 = bits, 3 = delayed bits */
+long   qo_rx_port_items(qo_rx*, int port);
+const void* qo_rx_port_data(qo_rx*, int port);
+void   qo_rx_port_clear(qo_rx*, int port);
+/* debug taps into intermediate streams (tests only): name in {"resamp","demod","rrc","sym","soft"} */
+long   qo_rx_dbg_items(qo_rx*, const char* name);
+const void* qo_rx_dbg_data(qo_rx*, const char* name);
+int    qo_rx_ntaps(qo_rx*, int which, float* out, int cap);
+
+/* ---- TX chains ---- */
+typedef struct qo_tx qo_tx;
+qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag);
+void   qo_tx_destroy(qo_tx*);
+void   qo_tx_set_bb_gain(qo_tx*, float g);
+/* digital: n bytes in; analog (NBFM/SSB): n float audio samples passed as bytes pointer to float */
+int    qo_tx_work(qo_tx*, const void* in, long n);
+long   qo_tx_out_items(qo_tx*);
+const float* qo_tx_out_data(qo_tx*);
+void   qo_tx_out_clear(qo_tx*);
+
+/* ---- host-side framing logic (gr_modem.cpp / gr_deframer_bb.cpp restatement) ---- */
+/* returns number of frames found; frames written back-to-back (frame_len bytes each) */
+long qo_find_frames(const uint8_t* bits, long nbits, uint32_t sync, int sync_bits, int frame_len_bytes,
+                    uint8_t* frames, long max_frames);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
