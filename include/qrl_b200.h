@@ -1,0 +1,123 @@
+/*
+ * qrl_b200.h -- C ABI of libqrl_b200.so: batched-channel, B200-native replacements for the per-mode
+ * GNU Radio hier-blocks that QRadioLink's gr_demod_base / gr_mod_base connect between the SDR
+ * source/sink and the gr_*_sink / gr_*_source boundary blocks.
+ *
+ * Every entry point returns 0 on success or a negative QRL_E* code; no C++ exception crosses the ABI.
+ * qrl_last_error() gives the message for the last failure on a handle (or the process-wide one for
+ * create failures when handle == NULL).  One caller thread per handle (same contract as a GNU Radio
+ * block's work(): /root/reference/src/gr/gr_bit_sink.h:36-38).
+ *
+ * What each entry point replaces in the reference:
+ *   qrl_rx_create      make_gr_demod_nbfm / make_gr_demod_4fsk / make_gr_demod_qpsk ... factories
+ *                      (src/gr/gr_demod_4fsk.h:51-53, gr_demod_qpsk.h:48-50, gr_demod_nbfm.h:38-39) as
+ *                      instantiated by gr_demod_base.cpp:203-228, for n_channels independent channels.
+ *   qrl_rx_work        the flattened hier-block's work()/general_work() calls for one chunk of the
+ *                      1 Msps gr_complex stream (gr_demod_base.cpp:180 "demod_valve" -> hier block),
+ *                      including the rotator_cc carrier shift (gr_demod_base.cpp:57,1220-1225).
+ *   qrl_rx_read_port   what gr_const_sink / gr_audio_sink / gr_bit_sink (src/gr/gr_bit_sink.cpp:45-84,
+ *                      gr_audio_sink.cpp:49-90) receive on output ports 0..3 of the hier block.
+ *   qrl_rx_set_param   set_squelch / set_filter_width / set_agc_attack ... (gr_demod_nbfm.h:47-49).
+ *   qrl_tx_create/work make_gr_mod_4fsk ... (src/gr/gr_mod_4fsk.h:46-48; gr_mod_base.cpp:155-180) fed by
+ *                      gr_byte_source (src/gr/gr_byte_source.cpp:54-106).
+ */
+#ifndef QRL_B200_H
+#define QRL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QRL_OK 0
+#define QRL_EINVAL (-22)      /* bad argument / unsupported mode */
+#define QRL_ENOMEM (-12)
+#define QRL_ECUDA (-5)        /* CUDA runtime error, see qrl_last_error */
+#define QRL_ERANGE (-34)      /* chunk larger than the handle was created for */
+#define QRL_ENODEV (-19)      /* no CUDA device: this library has no CPU fallback */
+
+/* hier-block kinds: one per reference file src/gr/gr_demod_<x>.cpp / gr_mod_<x>.cpp */
+enum qrl_kind {
+    QRL_DEMOD_NBFM = 1, QRL_DEMOD_4FSK = 2, QRL_DEMOD_QPSK = 3, QRL_DEMOD_BPSK = 4, QRL_DEMOD_2FSK = 5,
+    QRL_DEMOD_SSB = 6,
+    QRL_MOD_4FSK = 101, QRL_MOD_QPSK = 102, QRL_MOD_NBFM = 103, QRL_MOD_BPSK = 104, QRL_MOD_2FSK = 105,
+    QRL_MOD_SSB = 106
+};
+
+/* runtime parameters (qrl_rx_set_param / qrl_tx_set_param) */
+enum qrl_param {
+    QRL_PARAM_CARRIER_OFFSET_HZ = 1,  /* rotator_cc phase increment, gr_demod_base.cpp:1220-1225 */
+    QRL_PARAM_SQUELCH_DB = 2,         /* gr_demod_nbfm::set_squelch */
+    QRL_PARAM_FILTER_WIDTH = 3,       /* gr_demod_nbfm::set_filter_width */
+    QRL_PARAM_BB_GAIN = 4             /* gr_mod_*::set_bb_gain */
+};
+
+typedef struct qrl_rx qrl_rx;
+typedef struct qrl_tx qrl_tx;
+
+/* library / device */
+int  qrl_device_count(void);
+const char* qrl_version(void);
+const char* qrl_last_error(const void* handle);
+
+/* ---- RX ----
+ * kind, sps, samp_rate, carrier_freq, filter_width, flag: exactly the arguments of the reference factory
+ *   (flag = `fm` for 4FSK/2FSK, `sb` for SSB, ignored otherwise).
+ * n_channels independent channels; max_samples = largest T a single qrl_rx_work call will carry. */
+int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag,
+                  int n_channels, long max_samples, int device, qrl_rx** out);
+int qrl_rx_destroy(qrl_rx* h);
+/* run all kernels of this handle on an existing CUDA stream (cudaStream_t); NULL = the handle's own stream */
+int qrl_rx_set_stream(qrl_rx* h, void* cuda_stream);
+int qrl_rx_set_param(qrl_rx* h, int channel /* -1 = all */, int key, double value);
+int qrl_rx_reset(qrl_rx* h);
+/* iq: [n_channels][T] interleaved float (re,im) = gr_complex; channel stride = `stride` complex samples.
+ * on_device != 0: iq is a device pointer (already in HBM). Otherwise host memory (pinned or pageable);
+ * the copy to the device is part of the call.  Asynchronous on the handle's stream. */
+int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device);
+/* wait for everything submitted so far */
+int qrl_rx_sync(qrl_rx* h);
+/* number of output ports (2 for analog blocks, 3 for 4FSK/QPSK, 4 for BPSK/2FSK) and item size in bytes */
+int qrl_rx_num_ports(const qrl_rx* h);
+int qrl_rx_port_itemsize(const qrl_rx* h, int port);
+/* copy what the last qrl_rx_work call produced on `port` into dst[n_channels][cap] (items), and the
+ * per-channel item counts into counts[n_channels].  dst_on_device selects a device destination. Syncs. */
+int qrl_rx_read_port(qrl_rx* h, int port, void* dst, long cap, int* counts, int dst_on_device);
+/* device-resident view of a port (no copy): pointer to [n_channels][*cap] items and the int counts array */
+int qrl_rx_port_device(qrl_rx* h, int port, void** data, long* cap, int** counts);
+/* kernels launched by this handle so far (for bench accounting) */
+long qrl_rx_launch_count(const qrl_rx* h);
+
+/* ---- TX ---- */
+int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag,
+                  int n_channels, long max_items, int device, qrl_tx** out);
+int qrl_tx_destroy(qrl_tx* h);
+int qrl_tx_set_stream(qrl_tx* h, void* cuda_stream);
+int qrl_tx_set_param(qrl_tx* h, int channel, int key, double value);
+/* in: [n_channels][n] bytes (digital) ; produces [n_channels][n_out] gr_complex at 1 Msps */
+int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device);
+int qrl_tx_sync(qrl_tx* h);
+int qrl_tx_read(qrl_tx* h, float* dst, long cap, long* n_out, int dst_on_device);
+int qrl_tx_out_device(qrl_tx* h, float** data, long* stride, long* n_out);
+long qrl_tx_launch_count(const qrl_tx* h);
+
+/* ---- design helpers (host only; the gr::filter::firdes calls the reference makes at construction /
+ *      in set_filter_width, e.g. gr_demod_nbfm.cpp:82-90).  Return tap count or negative error. ---- */
+int qrl_firdes_low_pass(double gain, double fs, double fc, double tw, int window, float* out, int cap);
+int qrl_firdes_low_pass_2(double gain, double fs, double fc, double tw, double att_db, int window, float* out, int cap);
+int qrl_firdes_band_pass(double gain, double fs, double lo, double hi, double tw, int window, float* out, int cap);
+int qrl_firdes_complex_band_pass(double gain, double fs, double lo, double hi, double tw, int window, float* out, int cap);
+int qrl_firdes_root_raised_cosine(double gain, double fs, double symrate, double alpha, int ntaps, float* out, int cap);
+int qrl_design_table(const char* name /* "atan","tanh","mmse","fxpt_sine" */, float* out, int cap);
+int qrl_design_deemph(int fs, double tau, double* a2, double* b2);
+
+/* ---- stand-alone kernels exposed for tests / micro-benchmarks ---- */
+/* batched decimating FIR (stage 1 alone): x [C][T] device, y [C][ceil(T/D)] device; zero history */
+int qrl_fir_decim_ccf_device(const float* taps, int ntaps, int D, const float* x_dev, long T, long x_stride,
+                             float* y_dev, long y_stride, int C, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

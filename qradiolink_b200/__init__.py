@@ -1,0 +1,12 @@
+"""qradiolink_b200 -- B200-native batched-channel replacement for QRadioLink's per-mode GNU Radio
+demod/mod hier-blocks (src/gr/gr_demod_*.cpp, gr_mod_*.cpp).  The arithmetic runs in hand-written
+sm_100a CUDA kernels behind the C ABI in include/qrl_b200.h (libqrl_b200.so); this package is the
+Python host side: a ctypes binding plus mirrors of the reference's factory functions and sink blocks.
+
+There is no CPU fallback: importing works anywhere (so the CPU test tier can check the ABI), but
+creating a demodulator without a CUDA device raises.
+"""
+from .lib import (QrlError, load_library, device_count, KIND, PARAM)  # noqa: F401
+from .demod import (RxBlock, make_gr_demod_4fsk, make_gr_demod_qpsk, make_gr_demod_nbfm,  # noqa: F401
+                    gr_bit_sink, gr_audio_sink, gr_const_sink)
+from .mod import TxBlock, make_gr_mod_4fsk, make_gr_mod_qpsk  # noqa: F401

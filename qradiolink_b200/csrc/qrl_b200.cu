@@ -1,0 +1,520 @@
+// qrl_b200.cu -- handles, stage orchestration and the C ABI (include/qrl_b200.h) of libqrl_b200.so.
+//
+// One qrl_rx handle = n_channels independent instances of ONE reference demod hier-block
+// (/root/reference/src/gr/gr_demod_{nbfm,4fsk,qpsk}.cpp) running as batched CUDA kernels.  All
+// per-channel DSP state (FIR history, resampler phase, loop filters, Viterbi start state, LFSR)
+// lives in HBM between qrl_rx_work calls, so results do not depend on how the stream is chunked.
+// There is NO CPU fallback: without a CUDA device every create call fails with QRL_ENODEV.
+#include "../../include/qrl_b200.h"
+#include "qrl_design.hpp"
+#include "qrl_kernels.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace qrl;
+
+namespace {
+
+thread_local std::string g_err;
+std::once_flag g_tables_once[16];
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            set_err(h, std::string(#call) + ": " + cudaGetErrorString(e__));                         \
+            return QRL_ECUDA;                                                                        \
+        }                                                                                            \
+    } while (0)
+
+struct Ring {
+    void* d = nullptr;
+    unsigned mask = 0;
+    long long stride = 0;   // items per channel (= capacity)
+};
+
+unsigned pow2_at_least(long long n)
+{
+    unsigned long long c = 64;
+    while (c < static_cast<unsigned long long>(n)) c <<= 1;
+    return static_cast<unsigned>(c);
+}
+
+struct HandleBase {
+    std::string err;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    long launches = 0;
+    std::vector<void*> allocs;
+};
+
+void set_err(HandleBase* h, const std::string& s)
+{
+    g_err = s;
+    if (h) h->err = s;
+}
+
+int upload_tables(HandleBase* h)
+{
+    int rc = QRL_OK;
+    std::call_once(g_tables_once[h->device & 15], [&]() {
+        auto at = atan_table(); auto th = tanh_table(); auto mm = mmse_table(); auto sn = fxpt_sine_table();
+        cudaError_t e = cudaMemcpyToSymbol(d_atan_tab, at.data(), at.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(d_tanh_tab, th.data(), th.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(d_mmse_tab, mm.data(), mm.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(d_sine_tab, sn.data(), sn.size() * 4);
+        if (e != cudaSuccess) { set_err(h, std::string("table upload: ") + cudaGetErrorString(e)); rc = QRL_ECUDA; }
+    });
+    return rc;
+}
+
+template <class T>
+int dev_alloc(HandleBase* h, T** p, size_t n_items, bool zero = true)
+{
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(n_items * sizeof(T), 16);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) { set_err(h, std::string("cudaMalloc: ") + cudaGetErrorString(e)); return QRL_ENOMEM; }
+    if (zero) {
+        e = cudaMemsetAsync(q, 0, bytes, h->stream);
+        if (e != cudaSuccess) { set_err(h, std::string("cudaMemset: ") + cudaGetErrorString(e)); return QRL_ECUDA; }
+    }
+    h->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return QRL_OK;
+}
+
+int upload_floats(HandleBase* h, float** p, const std::vector<float>& v)
+{
+    int rc = dev_alloc(h, p, v.size(), false);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpy(*p, v.data(), v.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_err(h, std::string("tap upload: ") + cudaGetErrorString(e)); return QRL_ECUDA; }
+    return QRL_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+struct qrl_rx : HandleBase {
+    int kind = 0, sps = 0, samp_rate = 0, carrier_freq = 0, filter_width = 0, flag = 0, C = 0;
+    long Tmax = 0;
+    int nports = 3;
+    // stage 1 (rational_resampler_ccf(1, D))
+    int D1 = 1, Q1 = 1, ntaps1 = 0, H = 0, hist_cur = 0;
+    float* d_taps1 = nullptr;
+    float2* d_hist[2] = { nullptr, nullptr };
+    float2* d_in_staging = nullptr;
+    long long n_in = 0, n1 = 0;
+    Ring r1;
+    // stage 2: channel / shaping filter on the complex stream (port 0)
+    float* d_taps2 = nullptr; int ntaps2 = 0;
+    Ring r2;
+    float2* d_port0 = nullptr; long port0_cap = 0; long port0_n = 0;
+    // stage 3: quadrature demod + RRC (4FSK-FM)
+    float* d_taps3 = nullptr; int ntaps3 = 0; float qd_gain = 0;
+    Ring r4;
+    // symbol sync
+    SymSyncParams ssp{};
+    SymSyncState* d_ss = nullptr;
+    float2* d_port1 = nullptr; long port1_cap = 0; int* d_port1_cnt = nullptr;
+    Ring r5;   // soft bits (u8)
+    ViterbiState* d_vs = nullptr;
+    unsigned char* d_port2 = nullptr; long port2_cap = 0; int* d_port2_cnt = nullptr;
+    long n1max = 0;
+};
+
+namespace {
+
+template <int D, int Q, int K, int NOUT, int NWARPS>
+int launch_fir_poly(qrl_rx* h, const float2* iq, long long stride, long long T, long long k0, long long k1)
+{
+    constexpr int W = (NOUT + Q - 1) * D;
+    const size_t smem = sizeof(float2) * W;
+    static bool attr_done[16] = { false };
+    if (!attr_done[h->device & 15]) {
+        CK(cudaFuncSetAttribute(fir_decim_poly_kernel<D, Q, K, NOUT, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[h->device & 15] = true;
+    }
+    const long long nout = k1 - k0;
+    dim3 grid(static_cast<unsigned>((nout + NOUT - 1) / NOUT), h->C);
+    fir_decim_poly_kernel<D, Q, K, NOUT, NWARPS><<<grid, NWARPS * 32, smem, h->stream>>>(
+        iq, stride, T, h->d_hist[h->hist_cur], h->H, h->d_taps1,
+        static_cast<float2*>(h->r1.d), h->r1.mask, h->r1.stride, h->n_in, k0, k1);
+    h->launches++;
+    CK(cudaGetLastError());
+    return QRL_OK;
+}
+
+template <int NTP, int K, int NTHREADS>
+int launch_fir_d2(qrl_rx* h, const float2* iq, long long stride, long long T, long long k0, long long k1)
+{
+    constexpr int NOUT = NTHREADS * K;
+    constexpr int W = 2 * (NOUT - 1) + NTP;
+    const size_t smem = sizeof(float2) * (W + W / (2 * K) + 2);
+    const long long nout = k1 - k0;
+    dim3 grid(static_cast<unsigned>((nout + NOUT - 1) / NOUT), h->C);
+    fir_decim2_kernel<NTP, K, NTHREADS><<<grid, NTHREADS, smem, h->stream>>>(
+        iq, stride, T, h->d_hist[h->hist_cur], h->H, h->d_taps1,
+        static_cast<float2*>(h->r1.d), h->r1.mask, h->r1.stride, h->n_in, k0, k1);
+    h->launches++;
+    CK(cudaGetLastError());
+    return QRL_OK;
+}
+
+int stage1(qrl_rx* h, const float2* iq, long long stride, long long T, long long k0, long long k1)
+{
+    if (k1 <= k0) return QRL_OK;
+    if (h->D1 == 50 && h->Q1 == 9) return launch_fir_poly<50, 9, 8, 128, 8>(h, iq, stride, T, k0, k1);
+    if (h->D1 == 2 && h->ntaps1 <= 56) return launch_fir_d2<56, 8, 128>(h, iq, stride, T, k0, k1);
+    set_err(h, "stage-1 resampler shape not built (D=" + std::to_string(h->D1) + ", taps=" + std::to_string(h->ntaps1) + ")");
+    return QRL_EINVAL;
+}
+
+int make_ring(qrl_rx* h, Ring* r, size_t isz, long long min_items)
+{
+    unsigned cap = pow2_at_least(min_items);
+    r->mask = cap - 1;
+    r->stride = cap;
+    unsigned char* p = nullptr;
+    int rc = dev_alloc(h, &p, static_cast<size_t>(cap) * isz * h->C, true);
+    r->d = p;
+    return rc;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int qrl_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+const char* qrl_version(void) { return "qrl_b200 0.1 (sm_100a)"; }
+const char* qrl_last_error(const void* handle)
+{
+    if (handle) return static_cast<const HandleBase*>(handle)->err.c_str();
+    return g_err.c_str();
+}
+
+int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag,
+                  int n_channels, long max_samples, int device, qrl_rx** out)
+{
+    if (!out || n_channels <= 0 || max_samples <= 0) { set_err(nullptr, "qrl_rx_create: bad argument"); return QRL_EINVAL; }
+    *out = nullptr;
+    if (qrl_device_count() <= device) { set_err(nullptr, "qrl_rx_create: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
+    qrl_rx* h = new qrl_rx();
+    h->kind = kind; h->sps = sps; h->samp_rate = samp_rate; h->carrier_freq = carrier_freq;
+    h->filter_width = filter_width; h->flag = flag; h->C = n_channels; h->Tmax = max_samples; h->device = device;
+    auto fail = [&](int rc) { std::string e = h->err; qrl_rx_destroy(h); g_err = e; return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) { set_err(h, "cudaSetDevice failed"); return fail(QRL_ECUDA); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err(h, "stream create failed"); return fail(QRL_ECUDA); }
+    h->own_stream = true;
+    int rc = upload_tables(h);
+    if (rc) return fail(rc);
+
+    std::vector<float> taps1, taps2, taps3;
+    int tsr = 0, sym_sps = 0;
+    if (kind == QRL_DEMOD_4FSK) {
+        // gr_demod_4fsk.cpp:46-84 (sps ladder), :98-107 (resampler), :108-109 (filter), :125-131 (demod, RRC, sync)
+        int decimation = 1, interpolation = 1, nfilts = 0;
+        if (sps == 1) { tsr = 80000; sym_sps = sps * 8; decimation = 25; interpolation = 2; nfilts = 32 * sym_sps; }
+        else if (sps == 5) { tsr = 20000; sym_sps = sps * 2; decimation = 50; nfilts = 25 * sym_sps; }
+        else if (sps == 10) { tsr = 10000; sym_sps = sps; decimation = 100; nfilts = 25 * sym_sps; }
+        else if (sps == 2) { decimation = 2; sym_sps = 5; tsr = 500000; nfilts = 50 * sym_sps; }
+        else { set_err(h, "make_gr_demod_4fsk: unsupported sps"); return fail(QRL_EINVAL); }
+        if ((nfilts % 2) == 0) nfilts += 1;
+        if (!flag) { set_err(h, "4FSK non-FM discriminator variant not built yet"); return fail(QRL_EINVAL); }
+        if (interpolation != 1) { set_err(h, "4FSK 10k (2/25 resampler) not built yet"); return fail(QRL_EINVAL); }
+        taps1 = low_pass(interpolation, static_cast<double>(interpolation) * samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
+        h->D1 = decimation;
+        taps2 = low_pass(1, tsr, filter_width, filter_width / 2, WIN_BLACKMAN_HARRIS);
+        taps3 = root_raised_cosine(1.5, tsr, tsr / sym_sps, 0.2, nfilts);
+        h->qd_gain = static_cast<float>(sym_sps / (1 * kPi));
+        clock_loop_gains(static_cast<float>(2 * kPi / 200.0f), 1.0f, 0.2869f, h->ssp.alpha, h->ssp.beta);
+        h->ssp.sps = static_cast<float>(sym_sps);
+        h->ssp.max_period = h->ssp.sps + 0.05f; h->ssp.min_period = h->ssp.sps - 0.05f;
+        h->ssp.lookahead = 8 + static_cast<int>(ceilf(h->ssp.max_period)) + 1;
+        h->ssp.pm_sens = static_cast<float>(kPi / 2);
+        h->ssp.soft_scale = 128.0f;
+        h->nports = 3;
+    } else {
+        set_err(h, "qrl_rx_create: demod kind " + std::to_string(kind) + " not built");
+        return fail(QRL_EINVAL);
+    }
+
+    // ---- stage 1 buffers
+    h->ntaps1 = static_cast<int>(taps1.size());
+    h->Q1 = (h->ntaps1 + h->D1 - 1) / h->D1;
+    int padded = std::max(h->Q1 * h->D1, h->D1 == 2 ? 56 : 0);
+    std::vector<float> tp(padded, 0.0f);
+    std::copy(taps1.begin(), taps1.end(), tp.begin());
+    if ((rc = upload_floats(h, &h->d_taps1, tp))) return fail(rc);
+    h->H = padded;
+    if ((rc = dev_alloc(h, &h->d_hist[0], static_cast<size_t>(h->H) * h->C))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_hist[1], static_cast<size_t>(h->H) * h->C))) return fail(rc);
+    h->n1max = h->Tmax / h->D1 + 2;
+    // ---- rings
+    h->ntaps2 = static_cast<int>(taps2.size());
+    h->ntaps3 = static_cast<int>(taps3.size());
+    if ((rc = upload_floats(h, &h->d_taps2, taps2))) return fail(rc);
+    if ((rc = upload_floats(h, &h->d_taps3, taps3))) return fail(rc);
+    if ((rc = make_ring(h, &h->r1, sizeof(float2), h->n1max + h->ntaps2 + 8))) return fail(rc);
+    if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + h->ntaps3 + 8))) return fail(rc);
+    if ((rc = make_ring(h, &h->r4, sizeof(float), h->n1max + 64))) return fail(rc);
+    if ((rc = make_ring(h, &h->r5, 1, 2 * h->n1max + 1024))) return fail(rc);
+    h->port0_cap = h->n1max;
+    if ((rc = dev_alloc(h, &h->d_port0, static_cast<size_t>(h->port0_cap) * h->C))) return fail(rc);
+    h->port1_cap = h->n1max / std::max(1, sym_sps - 1) + 64;
+    if ((rc = dev_alloc(h, &h->d_port1, static_cast<size_t>(h->port1_cap) * h->C))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_port1_cnt, h->C))) return fail(rc);
+    h->port2_cap = h->port1_cap + 160;
+    if ((rc = dev_alloc(h, &h->d_port2, static_cast<size_t>(h->port2_cap) * h->C))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_port2_cnt, h->C))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_ss, h->C))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_vs, h->C))) return fail(rc);
+    if ((rc = qrl_rx_reset(h))) return fail(rc);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { set_err(h, "create sync failed"); return fail(QRL_ECUDA); }
+    *out = h;
+    return QRL_OK;
+}
+
+int qrl_rx_reset(qrl_rx* h)
+{
+    if (!h) return QRL_EINVAL;
+    // all-zero history / rings; loop states at their constructor values
+    std::vector<SymSyncState> ss(h->C);
+    std::vector<ViterbiState> vs(h->C);
+    for (int c = 0; c < h->C; c++) {
+        std::memset(&ss[c], 0, sizeof(SymSyncState));
+        ss[c].avg_period = h->ssp.sps; ss[c].inst_period = h->ssp.sps; ss[c].mu = 0.0f;
+        vs[c].rd = 0; vs[c].start_state = 0; vs[c].descr_reg = 0x7F;
+    }
+    CK(cudaMemcpyAsync(h->d_ss, ss.data(), sizeof(SymSyncState) * h->C, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_vs, vs.data(), sizeof(ViterbiState) * h->C, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_hist[0], 0, sizeof(float2) * h->H * h->C, h->stream));
+    CK(cudaMemsetAsync(h->d_hist[1], 0, sizeof(float2) * h->H * h->C, h->stream));
+    CK(cudaMemsetAsync(h->r1.d, 0, sizeof(float2) * h->r1.stride * h->C, h->stream));
+    CK(cudaMemsetAsync(h->r2.d, 0, sizeof(float2) * h->r2.stride * h->C, h->stream));
+    CK(cudaMemsetAsync(h->r4.d, 0, sizeof(float) * h->r4.stride * h->C, h->stream));
+    CK(cudaMemsetAsync(h->r5.d, 0, h->r5.stride * h->C, h->stream));
+    CK(cudaMemsetAsync(h->d_port1_cnt, 0, sizeof(int) * h->C, h->stream));
+    CK(cudaMemsetAsync(h->d_port2_cnt, 0, sizeof(int) * h->C, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // the staging vectors above go out of scope
+    h->n_in = 0; h->n1 = 0; h->hist_cur = 0; h->port0_n = 0;
+    return QRL_OK;
+}
+
+int qrl_rx_destroy(qrl_rx* h)
+{
+    if (!h) return QRL_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return QRL_OK;
+}
+
+int qrl_rx_set_stream(qrl_rx* h, void* s)
+{
+    if (!h) return QRL_EINVAL;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    if (s) h->stream = static_cast<cudaStream_t>(s);
+    else { CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    return QRL_OK;
+}
+
+int qrl_rx_set_param(qrl_rx* h, int, int key, double)
+{
+    if (!h) return QRL_EINVAL;
+    set_err(h, "qrl_rx_set_param: key " + std::to_string(key) + " not supported for this block yet");
+    return QRL_EINVAL;
+}
+
+int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
+{
+    if (!h || !iq || T < 0) return QRL_EINVAL;
+    if (T > h->Tmax) { set_err(h, "qrl_rx_work: T exceeds max_samples given at create"); return QRL_ERANGE; }
+    if (T == 0) return QRL_OK;
+    CK(cudaSetDevice(h->device));
+    const float2* x = reinterpret_cast<const float2*>(iq);
+    long long xstride = stride;
+    if (!on_device) {
+        if (!h->d_in_staging) {
+            int rc = dev_alloc(h, &h->d_in_staging, static_cast<size_t>(h->Tmax) * h->C, false);
+            if (rc) return rc;
+        }
+        CK(cudaMemcpy2DAsync(h->d_in_staging, sizeof(float2) * h->Tmax, iq, sizeof(float2) * stride,
+                             sizeof(float2) * T, h->C, cudaMemcpyHostToDevice, h->stream));
+        x = h->d_in_staging;
+        xstride = h->Tmax;
+    }
+    CK(cudaMemsetAsync(h->d_port1_cnt, 0, sizeof(int) * h->C, h->stream));
+    CK(cudaMemsetAsync(h->d_port2_cnt, 0, sizeof(int) * h->C, h->stream));
+
+    // ---- stage 1: decimating FIR; outputs k with D k <= last absolute input index
+    const long long N = h->n_in + T;
+    const long long k0 = h->n1;
+    const long long k1 = (N - 1) / h->D1 + 1;
+    int rc = stage1(h, x, xstride, T, k0, k1);
+    if (rc) return rc;
+    {
+        dim3 g((h->H + 127) / 128, h->C);
+        hist_update_kernel<<<g, 128, 0, h->stream>>>(x, xstride, T, h->d_hist[h->hist_cur], h->d_hist[h->hist_cur ^ 1], h->H);
+        h->launches++;
+        h->hist_cur ^= 1;
+    }
+    h->n_in = N; h->n1 = k1;
+    const long long n_new = k1 - k0;
+    h->port0_n = static_cast<long>(n_new);
+    if (n_new > 0) {
+        const int TB = 256;
+        dim3 g(static_cast<unsigned>((n_new + TB - 1) / TB), h->C);
+        // ---- stage 2: channel filter -> ring + port 0
+        fir_ccf_ring_kernel<<<g, TB, sizeof(float) * h->ntaps2, h->stream>>>(
+            static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
+            static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+            h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap);
+        h->launches++;
+        // ---- stage 3: quadrature demod + RRC
+        qdemod_fir_fff_kernel<<<g, TB, sizeof(float) * (2 * h->ntaps3 + TB), h->stream>>>(
+            static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+            static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
+            h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
+        h->launches++;
+    }
+    // ---- stage 4: symbol sync (+ phase mod + soft bits)
+    {
+        constexpr int CH = 256;
+        const int blocks = (h->C + 31) / 32;
+        const size_t smem = sizeof(float) * 32 * (CH * 1 + 1);
+        symsync_kernel<1, SL_RECT4, EPI_4FSK_FM, CH><<<blocks, 32, smem, h->stream>>>(
+            h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r4.d), h->r4.mask, h->r4.stride, k1,
+            h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
+            static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride);
+        h->launches++;
+    }
+    // ---- stage 5: Viterbi + descrambler
+    viterbi_k7_kernel<<<h->C, 32, 0, h->stream>>>(h->d_vs, h->d_ss, h->C,
+        static_cast<const unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride,
+        h->d_port2, h->port2_cap, h->d_port2_cnt, static_cast<int>(h->port2_cap));
+    h->launches++;
+    CK(cudaGetLastError());
+    return QRL_OK;
+}
+
+int qrl_rx_sync(qrl_rx* h)
+{
+    if (!h) return QRL_EINVAL;
+    CK(cudaStreamSynchronize(h->stream));
+    return QRL_OK;
+}
+
+int qrl_rx_num_ports(const qrl_rx* h) { return h ? h->nports : QRL_EINVAL; }
+int qrl_rx_port_itemsize(const qrl_rx* h, int port)
+{
+    if (!h || port < 0 || port >= h->nports) return QRL_EINVAL;
+    if (port == 0) return 8;
+    if (port == 1) return (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_SSB) ? 4 : 8;
+    return 1;
+}
+
+int qrl_rx_port_device(qrl_rx* h, int port, void** data, long* cap, int** counts)
+{
+    if (!h || port < 0 || port >= h->nports) return QRL_EINVAL;
+    if (port == 0) { *data = h->d_port0; *cap = h->port0_cap; *counts = nullptr; }
+    else if (port == 1) { *data = h->d_port1; *cap = h->port1_cap; *counts = h->d_port1_cnt; }
+    else { *data = h->d_port2; *cap = h->port2_cap; *counts = h->d_port2_cnt; }
+    return QRL_OK;
+}
+
+int qrl_rx_read_port(qrl_rx* h, int port, void* dst, long cap, int* counts, int dst_on_device)
+{
+    if (!h || port < 0 || port >= h->nports || !counts) return QRL_EINVAL;
+    void* src; long scap; int* dcnt;
+    int rc = qrl_rx_port_device(h, port, &src, &scap, &dcnt);
+    if (rc) return rc;
+    const int isz = qrl_rx_port_itemsize(h, port);
+    long maxn = 0;
+    if (dcnt) {
+        CK(cudaMemcpyAsync(counts, dcnt, sizeof(int) * h->C, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int c = 0; c < h->C; c++) { if (counts[c] > scap) counts[c] = static_cast<int>(scap); maxn = std::max<long>(maxn, counts[c]); }
+    } else {
+        for (int c = 0; c < h->C; c++) counts[c] = static_cast<int>(h->port0_n);
+        maxn = h->port0_n;
+    }
+    if (dst && maxn > 0) {
+        const long w = std::min(maxn, cap);
+        CK(cudaMemcpy2DAsync(dst, static_cast<size_t>(cap) * isz, src, static_cast<size_t>(scap) * isz, static_cast<size_t>(w) * isz, h->C,
+                             dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return QRL_OK;
+}
+
+long qrl_rx_launch_count(const qrl_rx* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------- TX (next milestone)
+struct qrl_tx : HandleBase {};
+int qrl_tx_create(int, int, int, int, int, int, int, long, int, qrl_tx** out)
+{
+    if (out) *out = nullptr;
+    set_err(nullptr, "qrl_tx_create: TX chains not built yet");
+    return QRL_EINVAL;
+}
+int qrl_tx_destroy(qrl_tx* h) { delete h; return QRL_OK; }
+int qrl_tx_set_stream(qrl_tx*, void*) { return QRL_EINVAL; }
+int qrl_tx_set_param(qrl_tx*, int, int, double) { return QRL_EINVAL; }
+int qrl_tx_work(qrl_tx*, const void*, long, long, int) { return QRL_EINVAL; }
+int qrl_tx_sync(qrl_tx*) { return QRL_EINVAL; }
+int qrl_tx_read(qrl_tx*, float*, long, long*, int) { return QRL_EINVAL; }
+int qrl_tx_out_device(qrl_tx*, float**, long*, long*) { return QRL_EINVAL; }
+long qrl_tx_launch_count(const qrl_tx*) { return 0; }
+
+// ---------------------------------------------------------------------------------------------- design helpers
+static int copy_out(const std::vector<float>& v, float* out, int cap, int per_item = 1)
+{
+    const int n = static_cast<int>(v.size()) / per_item;
+    if (n > cap) return -n;
+    if (out) std::memcpy(out, v.data(), v.size() * sizeof(float));
+    return n;
+}
+int qrl_firdes_low_pass(double gain, double fs, double fc, double tw, int window, float* out, int cap)
+{ return copy_out(low_pass(gain, fs, fc, tw, window), out, cap); }
+int qrl_firdes_low_pass_2(double gain, double fs, double fc, double tw, double att, int window, float* out, int cap)
+{ return copy_out(low_pass_2(gain, fs, fc, tw, att, window), out, cap); }
+int qrl_firdes_band_pass(double gain, double fs, double lo, double hi, double tw, int window, float* out, int cap)
+{ return copy_out(band_pass(gain, fs, lo, hi, tw, window), out, cap); }
+int qrl_firdes_complex_band_pass(double gain, double fs, double lo, double hi, double tw, int window, float* out, int cap)
+{ return copy_out(complex_band_pass(gain, fs, lo, hi, tw, window), out, cap, 2); }
+int qrl_firdes_root_raised_cosine(double gain, double fs, double symrate, double alpha, int ntaps, float* out, int cap)
+{ return copy_out(root_raised_cosine(gain, fs, symrate, alpha, ntaps), out, cap); }
+int qrl_design_table(const char* name, float* out, int cap)
+{
+    std::string n(name ? name : "");
+    if (n == "atan") return copy_out(atan_table(), out, cap);
+    if (n == "tanh") return copy_out(tanh_table(), out, cap);
+    if (n == "mmse") return copy_out(mmse_table(), out, cap);
+    if (n == "fxpt_sine") return copy_out(fxpt_sine_table(), out, cap);
+    return QRL_EINVAL;
+}
+int qrl_design_deemph(int fs, double tau, double* a2, double* b2) { deemph_taps(fs, tau, a2, b2); return QRL_OK; }
+
+int qrl_fir_decim_ccf_device(const float*, int, int, const float*, long, long, float*, long, int, void*)
+{
+    set_err(nullptr, "qrl_fir_decim_ccf_device: not built yet");
+    return QRL_EINVAL;
+}
+
+}  // extern "C"

@@ -1,0 +1,656 @@
+// qrl_kernels.cuh -- sm_100a device code for the batched-channel IQ DSP hot path.
+//
+// Numerics contract (see DESIGN.md "Numerics"): compiled with -fmad=false; every fused multiply-add is
+// an explicit fmaf(); FIR dot products follow ONE fixed order (polyphase branch r = j mod D accumulated
+// oldest-sample-first into lane r mod 32, lanes combined by an xor-butterfly 16,8,4,2,1); sin/cos is
+// qrl_sincosf below, never the CUDA libm one.  With that, integer outputs are bit-exact against the
+// CPU oracle and float outputs are bit-identical in practice.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qrl {
+
+// ------------------------------------------------------------------------------------------------
+// device tables (uploaded once per process by qrl_upload_tables)
+// ------------------------------------------------------------------------------------------------
+__device__ float d_atan_tab[257];
+__device__ float d_tanh_tab[256];
+__device__ float d_mmse_tab[129 * 8];
+__device__ float d_sine_tab[2048];
+
+// ------------------------------------------------------------------------------------------------
+// elementary functions shared by all loop kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void qrl_sincosf(float x, float& s, float& c)
+{
+    // Cody-Waite reduction by pi/2 (3 constants) + Cephes single-precision minimax polynomials
+    const float k = rintf(x * 0.636619772f);
+    float r = fmaf(k, -1.5703125f, x);
+    r = fmaf(k, -4.837512969970703125e-4f, r);
+    r = fmaf(k, -7.54978995489188216e-8f, r);
+    const int q = static_cast<int>(k) & 3;
+    const float z = r * r;
+    float ps = fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f);
+    ps = fmaf(ps, z, -1.6666654611e-1f);
+    ps = ps * z;
+    const float sn = fmaf(ps, r, r);
+    float pc = fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+    pc = fmaf(pc, z, 4.166664568298827e-2f);
+    pc = pc * z;
+    pc = pc * z;
+    float cs = fmaf(z, -0.5f, 1.0f);
+    cs = cs + pc;
+    switch (q) {
+    case 0: s = sn; c = cs; break;
+    case 1: s = cs; c = -sn; break;
+    case 2: s = -sn; c = -cs; break;
+    default: s = -cs; c = sn; break;
+    }
+}
+
+// gr::fast_atan2f restated (table + octant fix-up)
+__device__ __forceinline__ float qrl_fast_atan2f(float y, float x)
+{
+    const float y_abs = fabsf(y), x_abs = fabsf(x);
+    if (!((y_abs > 0.0f) || (x_abs > 0.0f))) return 0.0f;
+    const float z = (y_abs < x_abs) ? (y_abs / x_abs) : (x_abs / y_abs);
+    float base;
+    if (static_cast<double>(z) < 0.003921569) base = z;
+    else {
+        float alpha = z * 255.0f;
+        const int index = static_cast<int>(alpha) & 0xff;
+        alpha -= static_cast<float>(index);
+        base = d_atan_tab[index];
+        base += (d_atan_tab[index + 1] - d_atan_tab[index]) * alpha;
+    }
+    float angle;
+    if (x_abs > y_abs) {
+        if (x >= 0.0f) angle = (y >= 0.0f) ? base : -base;
+        else { angle = 3.14159265358979323846f; angle = (y >= 0.0f) ? (angle - base) : (base - angle); }
+    } else {
+        if (y >= 0.0f) { angle = 1.57079632679489661923f; angle = (x >= 0.0f) ? (angle - base) : (angle + base); }
+        else { angle = -1.57079632679489661923f; angle = (x >= 0.0f) ? (angle + base) : (angle - base); }
+    }
+    return angle;
+}
+
+__device__ __forceinline__ float qrl_tanhf_lut(float x)
+{
+    if (x > 2.0f) return 1.0f;
+    if (x <= -2.0f) return -1.0f;
+    int index = static_cast<int>(128.0f + 64.0f * x);
+    if (index > 255) index = 255;
+    return d_tanh_tab[index];
+}
+__device__ __forceinline__ float qrl_clip(float x, float lim) { return x > lim ? lim : (x < -lim ? -lim : x); }
+
+__device__ __forceinline__ unsigned char qrl_soft_u8(float v, float scale)
+{
+    float t = v * scale;
+    t = t + 128.0f;
+    float r = rintf(t);
+    r = r < 0.0f ? 0.0f : (r > 255.0f ? 255.0f : r);
+    return static_cast<unsigned char>(r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 1: batched polyphase decimating FIR  y[k] = sum_j h[j] x[D k - j]   (rational_resampler_ccf(1,D))
+//   grid  = (strips, channels); one CTA = NOUT consecutive outputs of one channel.
+//   lanes = polyphase branches: lane l owns branches r = l + 32*rho and keeps its Q taps per branch in
+//   registers; each lane computes K consecutive outputs from (K+Q-1) strided shared-memory samples per
+//   branch (register reuse 9K/(K+8) MAC per LDS.64); lane partials are combined with a transposed
+//   butterfly (16 SHFL for 2K=16 values) whose association order equals the plain xor-butterfly.
+//   Input samples are read once from HBM into shared memory (coalesced 8-byte loads); the previous
+//   call's tail (history) comes from a small per-channel buffer.
+// ------------------------------------------------------------------------------------------------
+template <int D, int Q, int K, int NOUT, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
+fir_decim_poly_kernel(const float2* __restrict__ iq, long long iq_stride, long long T,
+                      const float2* __restrict__ hist, int H,
+                      const float* __restrict__ taps_padded,   // Q*D floats, zero padded
+                      float2* __restrict__ out_ring, unsigned ring_mask, long long ring_stride,
+                      long long n_in_before, long long k0, long long k1)
+{
+    static_assert(K == 8, "transposed butterfly below is written for 2K = 16 values");
+    constexpr int R = (D + 31) / 32;                 // branch rounds per lane
+    constexpr int W = (NOUT + Q - 1) * D;            // samples in the strip window
+    extern __shared__ float2 xs[];
+
+    const int c = blockIdx.y;
+    const long long kbase = k0 + static_cast<long long>(blockIdx.x) * NOUT;
+    if (kbase >= k1) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // per-lane taps: tap[rho][q] = h[D q + r], r = lane + 32 rho (zero beyond the filter / beyond D)
+    float tap[R][Q];
+#pragma unroll
+    for (int rho = 0; rho < R; rho++) {
+        const int r = lane + 32 * rho;
+#pragma unroll
+        for (int q = 0; q < Q; q++) tap[rho][q] = (r < D) ? taps_padded[D * q + r] : 0.0f;
+    }
+
+    // window covers absolute samples [A0, A0 + W)
+    const long long A0 = D * kbase - (static_cast<long long>(Q) * D - 1);
+    const float2* iqc = iq + static_cast<long long>(c) * iq_stride;
+    const float2* hc = hist + static_cast<long long>(c) * H;
+    for (int idx = threadIdx.x; idx < W; idx += NWARPS * 32) {
+        const long long i = A0 + idx - n_in_before;   // index into this call's input
+        float2 v = make_float2(0.0f, 0.0f);
+        if (i >= 0) { if (i < T) v = __ldg(iqc + i); }
+        else if (H + i >= 0) v = hc[H + i];
+        xs[idx] = v;
+    }
+    __syncthreads();
+
+    float* outc = reinterpret_cast<float*>(out_ring + static_cast<long long>(c) * ring_stride);
+    for (int b = warp; b < NOUT / K; b += NWARPS) {
+        float ar[K], ai[K];
+#pragma unroll
+        for (int i = 0; i < K; i++) { ar[i] = 0.0f; ai[i] = 0.0f; }
+#pragma unroll
+        for (int rho = 0; rho < R; rho++) {
+            int r = lane + 32 * rho;
+            if (r > D - 1) r = D - 1;                 // idle lanes read a valid address, taps are zero
+            const float2* p = xs + D * K * b + (D - 1 - r);
+#pragma unroll
+            for (int ip = 0; ip < K + Q - 1; ip++) {  // ip = i - q + (Q-1): ascending = oldest sample first
+                const float2 x = p[D * ip];
+#pragma unroll
+                for (int i = 0; i < K; i++) {
+                    const int q = i + (Q - 1) - ip;
+                    if (q >= 0 && q < Q) {
+                        ar[i] = fmaf(tap[rho][q], x.x, ar[i]);
+                        ai[i] = fmaf(tap[rho][q], x.y, ai[i]);
+                    }
+                }
+            }
+        }
+        // transposed butterfly: value v = 2 i + comp; association order == xor-butterfly 16,8,4,2,1
+        float a[16];
+#pragma unroll
+        for (int i = 0; i < K; i++) { a[2 * i] = ar[i]; a[2 * i + 1] = ai[i]; }
+        {
+            const bool hi = lane & 16;
+#pragma unroll
+            for (int v = 0; v < 8; v++) {
+                const float send = hi ? a[v] : a[v + 8];
+                const float keep = hi ? a[v + 8] : a[v];
+                a[v] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+        }
+        {
+            const bool hi = lane & 8;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const float send = hi ? a[v] : a[v + 4];
+                const float keep = hi ? a[v + 4] : a[v];
+                a[v] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+        }
+        {
+            const bool hi = lane & 4;
+#pragma unroll
+            for (int v = 0; v < 2; v++) {
+                const float send = hi ? a[v] : a[v + 2];
+                const float keep = hi ? a[v + 2] : a[v];
+                a[v] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+        }
+        {
+            const bool hi = lane & 2;
+            const float send = hi ? a[0] : a[1];
+            const float keep = hi ? a[1] : a[0];
+            a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        a[0] = a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+        // lane l (even) now holds value v = l >> 1  -> output i = v >> 1, component v & 1
+        if ((lane & 1) == 0) {
+            const int v = lane >> 1;
+            const long long k = kbase + K * b + (v >> 1);
+            if (k < k1) outc[2 * (k & ring_mask) + (v & 1)] = a[0];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 1 for small decimations (QPSK-250k: D = 2): each thread owns K consecutive outputs and runs the
+// D branch chains itself over a sliding register window; y = tree(S_0..S_{D-1}) with D <= 2 here.
+// ------------------------------------------------------------------------------------------------
+template <int NTP /*padded taps, even*/, int K, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS)
+fir_decim2_kernel(const float2* __restrict__ iq, long long iq_stride, long long T,
+                  const float2* __restrict__ hist, int H,
+                  const float* __restrict__ taps_padded,   // NTP floats
+                  float2* __restrict__ out_ring, unsigned ring_mask, long long ring_stride,
+                  long long n_in_before, long long k0, long long k1)
+{
+    constexpr int D = 2;
+    constexpr int NOUT = NTHREADS * K;
+    constexpr int W = D * (NOUT - 1) + NTP;              // samples needed by the strip
+    constexpr int RUN = D * K;                           // samples per thread-run
+    constexpr int PITCH = RUN + 1;                       // +1 float2 pad: lane stride odd -> conflict-free LDS.64
+    extern __shared__ float2 xs[];
+    __shared__ float hs[NTP];
+    const int c = blockIdx.y;
+    const long long kbase = k0 + static_cast<long long>(blockIdx.x) * NOUT;
+    if (kbase >= k1) return;
+    for (int i = threadIdx.x; i < NTP; i += NTHREADS) hs[i] = taps_padded[i];
+    const long long A0 = D * kbase - (NTP - 1);
+    const float2* iqc = iq + static_cast<long long>(c) * iq_stride;
+    const float2* hc = hist + static_cast<long long>(c) * H;
+    for (int idx = threadIdx.x; idx < W; idx += NTHREADS) {
+        const long long i = A0 + idx - n_in_before;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (i >= 0) { if (i < T) v = __ldg(iqc + i); }
+        else if (H + i >= 0) v = hc[H + i];
+        xs[idx + idx / RUN] = v;                          // padded layout
+    }
+    __syncthreads();
+    // thread t: outputs kbase + K t + i ; newest sample of output i at window index (NTP-1) + D (K t + i)
+    float s0r[K], s0i[K], s1r[K], s1i[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) { s0r[i] = s0i[i] = s1r[i] = s1i[i] = 0.0f; }
+    const int t = threadIdx.x;
+    // walk window offsets w = 0 .. NTP-1 + D(K-1): sample index = D K t + w ; tap for output i: j = (NTP-1) + D i - w
+#pragma unroll
+    for (int w = 0; w < NTP + D * (K - 1); w++) {
+        const int idx = D * K * t + w;
+        const float2 x = xs[idx + idx / RUN];
+#pragma unroll
+        for (int i = 0; i < K; i++) {
+            const int j = (NTP - 1) + D * i - w;
+            if (j >= 0 && j < NTP) {
+                const float h = hs[j];
+                if ((j & 1) == 0) { s0r[i] = fmaf(h, x.x, s0r[i]); s0i[i] = fmaf(h, x.y, s0i[i]); }
+                else { s1r[i] = fmaf(h, x.x, s1r[i]); s1i[i] = fmaf(h, x.y, s1i[i]); }
+            }
+        }
+    }
+    float2* outc = out_ring + static_cast<long long>(c) * ring_stride;
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        const long long k = kbase + K * t + i;
+        if (k < k1) outc[k & ring_mask] = make_float2(s0r[i] + s1r[i], s0i[i] + s1i[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Low-rate stream stages (20 ksps .. 500 ksps): ring -> ring, one thread per output item, taps in smem,
+// sequential oldest-first accumulation (the D = 1 case of the FIR order).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxTapsSmem = 4096;
+
+// complex stream, real taps (fft_filter_ccf restated in direct form); optional linear copy (port 0)
+__global__ void fir_ccf_ring_kernel(const float2* __restrict__ in, unsigned in_mask, long long in_stride,
+                                    float2* __restrict__ out, unsigned out_mask, long long out_stride,
+                                    const float* __restrict__ taps, int ntaps, long long a0, long long a1,
+                                    float2* __restrict__ lin, long long lin_stride)
+{
+    extern __shared__ float hs_dyn[];
+    for (int i = threadIdx.x; i < ntaps; i += blockDim.x) hs_dyn[i] = taps[i];
+    __syncthreads();
+    const int c = blockIdx.y;
+    const long long a = a0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (a >= a1) return;
+    const float2* x = in + static_cast<long long>(c) * in_stride;
+    float re = 0.0f, im = 0.0f;
+    for (int j = ntaps - 1; j >= 0; j--) {
+        const float2 v = x[(a - j) & in_mask];
+        re = fmaf(hs_dyn[j], v.x, re);
+        im = fmaf(hs_dyn[j], v.y, im);
+    }
+    const float2 y = make_float2(re, im);
+    out[static_cast<long long>(c) * out_stride + (a & out_mask)] = y;
+    if (lin) lin[static_cast<long long>(c) * lin_stride + (a - a0)] = y;
+}
+
+// quadrature_demod_cf fused in front of a real FIR (RRC shaping filter): in = complex ring, out = float ring.
+// Each CTA demodulates its tile (+ntaps-1 halo) into shared memory, then filters from there.
+__global__ void qdemod_fir_fff_kernel(const float2* __restrict__ in, unsigned in_mask, long long in_stride,
+                                      float* __restrict__ out, unsigned out_mask, long long out_stride,
+                                      const float* __restrict__ taps, int ntaps, float gain,
+                                      long long a0, long long a1, float* __restrict__ demod_dbg, long long dbg_stride)
+{
+    extern __shared__ float sm_dyn[];
+    float* hs = sm_dyn;                 // ntaps
+    float* ds = sm_dyn + ntaps;         // blockDim.x + ntaps - 1 demodulated samples
+    for (int i = threadIdx.x; i < ntaps; i += blockDim.x) hs[i] = taps[i];
+    const int c = blockIdx.y;
+    const long long tile0 = a0 + static_cast<long long>(blockIdx.x) * blockDim.x;
+    const float2* x = in + static_cast<long long>(c) * in_stride;
+    const int span = blockDim.x + ntaps - 1;
+    for (int i = threadIdx.x; i < span; i += blockDim.x) {
+        const long long n = tile0 - (ntaps - 1) + i;       // absolute demod index
+        float d = 0.0f;
+        if (n >= 0 && n < a1) {
+            const float2 cur = x[n & in_mask];
+            float2 prev = make_float2(0.0f, 0.0f);
+            if (n >= 1) prev = x[(n - 1) & in_mask];
+            const float re = cur.x * prev.x + cur.y * prev.y;
+            const float im = cur.y * prev.x - cur.x * prev.y;
+            d = gain * qrl_fast_atan2f(im, re);
+        }
+        ds[i] = d;
+        if (demod_dbg && n >= a0 && n < a1 && i >= ntaps - 1) demod_dbg[static_cast<long long>(c) * dbg_stride + (n - a0)] = d;
+    }
+    __syncthreads();
+    const long long a = tile0 + threadIdx.x;
+    if (a >= a1) return;
+    float acc = 0.0f;
+    const float* p = ds + threadIdx.x + (ntaps - 1);       // newest sample of this output
+    for (int j = ntaps - 1; j >= 0; j--) acc = fmaf(hs[j], p[-j], acc);
+    out[static_cast<long long>(c) * out_stride + (a & out_mask)] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sequential loop stage: symbol_sync (PI clock loop, mod. Mueller&Muller TED, 8-tap MMSE interpolator)
+// One lane per channel; a warp stages 32 channels x CH samples in shared memory with coalesced loads,
+// then every lane runs its own loop from shared memory.  Epilogues:
+//   EPI_4FSK_FM : float symbols -> phase_modulator_fc(pi/2) -> port1, soft bits (imag, real)
+//   EPI_CPLX    : complex symbols -> port1, soft bits (real, imag)          (4FSK non-FM)
+//   EPI_QPSK    : complex symbols -> costas(4, snr) -> diff_phasor -> rotate -> port1, soft bits
+// ------------------------------------------------------------------------------------------------
+enum { SL_RECT4 = 0, SL_DQPSK = 1, SL_BPSK = 2 };
+enum { EPI_4FSK_FM = 0, EPI_CPLX = 1, EPI_QPSK = 2 };
+
+struct LoopState {               // control_loop (costas)
+    float phase, freq;
+};
+struct SymSyncState {
+    long long ii;                // absolute index of the first unconsumed input sample
+    long long n_sym;             // symbols produced so far (absolute)
+    long long n_soft;            // soft bits produced so far (absolute, = write index of the soft ring)
+    float avg_period, inst_period, mu;
+    float xr[3], xi[3], dr[3], di[3];
+    LoopState costas;            // second Costas loop (EPI_QPSK)
+    float dp_r, dp_i;            // diff_phasor memory
+};
+struct SymSyncParams {
+    float sps, alpha, beta, max_period, min_period;
+    int lookahead;
+    float pm_sens, soft_scale;
+    float costas_alpha, costas_beta;
+    float rot_r, rot_i;
+};
+
+__device__ __forceinline__ void qrl_slice(int slicer, float re, float im, float& dr, float& di)
+{
+    if (slicer == SL_RECT4) {
+        int sec = static_cast<int>(floorf(re + 2.0f));
+        sec = sec < 0 ? 0 : (sec > 3 ? 3 : sec);
+        dr = -1.5f + static_cast<float>(sec); di = 0.0f;
+    } else if (slicer == SL_DQPSK) {
+        dr = re > 0.0f ? 0.707107f : -0.707107f;
+        di = im > 0.0f ? 0.707107f : -0.707107f;
+    } else {
+        dr = re > 0.0f ? 1.0f : -1.0f; di = 0.0f;
+    }
+}
+
+__device__ __forceinline__ void qrl_costas_step(LoopState& st, float alpha, float beta, int order, bool use_snr,
+                                                float xr, float xi, float& yr, float& yi)
+{
+    float sn, cs;
+    qrl_sincosf(-st.phase, sn, cs);
+    const float orr = xr * cs - xi * sn;
+    const float oi = xr * sn + xi * cs;
+    float err;
+    if (order == 2) {
+        if (use_snr) { const float snr = orr * orr + oi * oi; err = qrl_tanhf_lut(snr * orr) * oi; }
+        else err = orr * oi;
+    } else {
+        if (use_snr) {
+            const float snr = orr * orr + oi * oi;
+            err = qrl_tanhf_lut(snr * orr) * oi - qrl_tanhf_lut(snr * oi) * orr;
+        } else {
+            err = (orr > 0.0f ? 1.0f : -1.0f) * oi - (oi > 0.0f ? 1.0f : -1.0f) * orr;
+        }
+    }
+    err = qrl_clip(err, 1.0f);
+    st.freq = st.freq + beta * err;
+    st.phase = st.phase + st.freq + alpha * err;
+    while (static_cast<double>(st.phase) > 2.0 * 3.14159265358979323846)
+        st.phase = static_cast<float>(static_cast<double>(st.phase) - 2.0 * 3.14159265358979323846);
+    while (static_cast<double>(st.phase) < -2.0 * 3.14159265358979323846)
+        st.phase = static_cast<float>(static_cast<double>(st.phase) + 2.0 * 3.14159265358979323846);
+    if (st.freq > 1.0f) st.freq = 1.0f;
+    else if (st.freq < -1.0f) st.freq = -1.0f;
+    yr = orr; yi = oi;
+}
+
+template <int NCOMP, int SLICER, int EPI, int CH>
+__global__ void __launch_bounds__(32)
+symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
+               const float* __restrict__ in, unsigned in_mask, long long in_stride /*items*/, long long avail_total,
+               float2* __restrict__ port1, long long port1_stride, int* __restrict__ port1_cnt, int port1_cap,
+               unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride)
+{
+    constexpr int PITCH = CH * NCOMP + 1;
+    extern __shared__ float stage[];                  // [32][PITCH]
+    const int lane = threadIdx.x;
+    const int c = blockIdx.x * 32 + lane;
+    const bool active = c < C;
+    SymSyncState st;
+    if (active) st = states[c];
+    else { st.ii = avail_total; }
+    int p1cnt = active ? port1_cnt[c] : 0;
+    float* mine = stage + lane * PITCH;
+
+    while (true) {
+        const bool can = active && (st.ii + p.lookahead <= avail_total);
+        if (!__any_sync(0xffffffffu, can)) break;
+        // cooperative staging: channel j of this warp, samples [ii_j, ii_j + CH)
+        for (int j = 0; j < 32; j++) {
+            const long long bj = __shfl_sync(0xffffffffu, st.ii, j);
+            const int cj = blockIdx.x * 32 + j;
+            if (cj >= C) continue;
+            const float* src = in + static_cast<long long>(cj) * in_stride * NCOMP;
+            float* dst = stage + j * PITCH;
+            for (int t = lane; t < CH * NCOMP; t += 32) {
+                const long long a = bj + t / NCOMP;
+                float v = 0.0f;
+                if (a < avail_total) v = src[(a & in_mask) * NCOMP + (t % NCOMP)];
+                dst[t] = v;
+            }
+        }
+        __syncwarp();
+        if (can) {
+            long long have = avail_total - st.ii;
+            const int lim = have < CH ? static_cast<int>(have) : CH;
+            int o = 0;
+            while (o + p.lookahead <= lim) {
+                // 8-tap MMSE interpolation, oldest sample first
+                const int imu = static_cast<int>(rintf(st.mu * 128.0f));
+                const float* tp = d_mmse_tab + imu * 8;
+                float yr = 0.0f, yi = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float tt = tp[7 - i];
+                    yr = fmaf(tt, mine[(o + i) * NCOMP], yr);
+                    if (NCOMP == 2) yi = fmaf(tt, mine[(o + i) * NCOMP + 1], yi);
+                }
+                st.xr[2] = st.xr[1]; st.xr[1] = st.xr[0]; st.xr[0] = yr;
+                st.xi[2] = st.xi[1]; st.xi[1] = st.xi[0]; st.xi[0] = yi;
+                st.dr[2] = st.dr[1]; st.dr[1] = st.dr[0];
+                st.di[2] = st.di[1]; st.di[1] = st.di[0];
+                qrl_slice(SLICER, yr, yi, st.dr[0], st.di[0]);
+                float err;
+                if (NCOMP == 2) {
+                    const float ar = st.xr[0] - st.xr[2], ai = st.xi[0] - st.xi[2];
+                    const float br = st.dr[0] - st.dr[2], bi = st.di[0] - st.di[2];
+                    const float u = (ar * st.dr[1] + ai * st.di[1]) - (br * st.xr[1] + bi * st.xi[1]);
+                    err = qrl_clip(u, 1.0f);
+                } else {
+                    const float u = (st.xr[0] - st.xr[2]) * st.dr[1] - (st.dr[0] - st.dr[2]) * st.xr[1];
+                    err = qrl_clip(u / 2.0f, 1.0f);
+                }
+                st.avg_period = st.avg_period + p.beta * err;
+                if (st.avg_period > p.max_period) st.avg_period = p.max_period;
+                else if (st.avg_period < p.min_period) st.avg_period = p.min_period;
+                st.inst_period = st.avg_period + p.alpha * err;
+                if (st.inst_period <= 0.0f) st.inst_period = st.avg_period;
+                const float ph = st.mu + st.inst_period;
+                const float fl = floorf(ph);
+                st.mu = ph - fl;
+                o += static_cast<int>(fl);
+
+                // ---- epilogue
+                float o_r, o_i;
+                unsigned char sb0, sb1;
+                if (EPI == EPI_4FSK_FM) {
+                    const float phs = p.pm_sens * yr;
+                    float sn, cs;
+                    qrl_sincosf(phs, sn, cs);
+                    o_r = cs; o_i = sn;
+                    sb0 = qrl_soft_u8(sn, p.soft_scale);       // interleave: imag first, then real
+                    sb1 = qrl_soft_u8(cs, p.soft_scale);
+                } else if (EPI == EPI_CPLX) {
+                    o_r = yr; o_i = yi;
+                    sb0 = qrl_soft_u8(yr, p.soft_scale);
+                    sb1 = qrl_soft_u8(yi, p.soft_scale);
+                } else {
+                    float cr, ci;
+                    qrl_costas_step(st.costas, p.costas_alpha, p.costas_beta, 4, true, yr, yi, cr, ci);
+                    const float dr = cr * st.dp_r + ci * st.dp_i;
+                    const float di = ci * st.dp_r - cr * st.dp_i;
+                    st.dp_r = cr; st.dp_i = ci;
+                    o_r = dr * p.rot_r - di * p.rot_i;
+                    o_i = dr * p.rot_i + di * p.rot_r;
+                    sb0 = qrl_soft_u8(o_r, p.soft_scale);
+                    sb1 = qrl_soft_u8(o_i, p.soft_scale);
+                }
+                if (p1cnt < port1_cap) port1[static_cast<long long>(c) * port1_stride + p1cnt] = make_float2(o_r, o_i);
+                p1cnt++;
+                unsigned char* sr = soft_ring + static_cast<long long>(c) * soft_stride;
+                sr[st.n_soft & soft_mask] = sb0;
+                sr[(st.n_soft + 1) & soft_mask] = sb1;
+                st.n_soft += 2;
+                st.n_sym += 1;
+            }
+            st.ii += o;
+        }
+        __syncwarp();
+    }
+    if (active) { states[c] = st; port1_cnt[c] = p1cnt; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CCSDS K=7 r=1/2 soft Viterbi, fec::decoder(cc_decoder(80,7,2,{109,79}, CC_STREAMING)) stream semantics,
+// + descrambler_bb(0x8A,0x7F,7).  One warp per channel: lane i = butterfly i (states 2i, 2i+1).
+// 32-bit path metrics without renormalisation are decision-equivalent to VOLK's 8-bit generic kernel
+// (which renormalises every step and never wraps: spread <= 6*31+31 < 256).
+// ------------------------------------------------------------------------------------------------
+struct ViterbiState {
+    long long rd;            // absolute soft-bit index of the next frame's first NEW symbol (frame start - 12 = rd - 12)
+    int start_state;
+    unsigned descr_reg;
+};
+
+__global__ void __launch_bounds__(32)
+viterbi_k7_kernel(ViterbiState* __restrict__ vstates, const SymSyncState* __restrict__ sstates, int C,
+                  const unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride,
+                  unsigned char* __restrict__ port2, long long port2_stride, int* __restrict__ port2_cnt, int port2_cap)
+{
+    __shared__ unsigned char syms[176];
+    __shared__ unsigned dec0[86], dec1[86];
+    __shared__ unsigned char obits[80];
+    const int c = blockIdx.x;
+    if (c >= C) return;
+    const int lane = threadIdx.x;
+    ViterbiState vs = vstates[c];
+    const long long avail = sstates[c].n_soft;
+    int cnt = port2_cnt[c];
+    const unsigned char* sr = soft_ring + static_cast<long long>(c) * soft_stride;
+    unsigned char* outp = port2 + static_cast<long long>(c) * port2_stride;
+
+    // Branchtab bits of butterfly `lane`: parity((2*lane) & poly)
+    const unsigned b0 = (__popc((2u * lane) & 109u) & 1u) ? 255u : 0u;
+    const unsigned b1 = (__popc((2u * lane) & 79u) & 1u) ? 255u : 0u;
+
+    while (vs.rd + 160 <= avail) {
+        // frame covers absolute soft indices [rd - 12, rd + 160); indices < 0 are the zero history
+        for (int i = lane; i < 172; i += 32) {
+            const long long a = vs.rd - 12 + i;
+            syms[i] = (a >= 0) ? sr[a & soft_mask] : 0;
+        }
+        __syncwarp();
+        // metrics: lane holds Y[2 lane] (lo 16 bits) and Y[2 lane + 1] (hi 16 bits)
+        unsigned ya = 63, yb = 63;
+        if ((vs.start_state & 63) == 2 * lane) ya = 0;
+        if ((vs.start_state & 63) == 2 * lane + 1) yb = 0;
+        for (int s = 0; s < 86; s++) {
+            const unsigned packed = ya | (yb << 16);
+            const unsigned pa = __shfl_sync(0xffffffffu, packed, lane >> 1);
+            const unsigned pb = __shfl_sync(0xffffffffu, packed, (lane >> 1) + 16);
+            const unsigned xi = (lane & 1) ? (pa >> 16) : (pa & 0xffffu);        // X[lane]
+            const unsigned xj = (lane & 1) ? (pb >> 16) : (pb & 0xffffu);        // X[lane + 32]
+            const unsigned s0 = syms[2 * s], s1 = syms[2 * s + 1];
+            const unsigned metric = (((b0 ^ s0) >> 2) + ((b1 ^ s1) >> 2)) >> 2;
+            const unsigned m0 = xi + metric, m1 = xj + (31u - metric);
+            const unsigned m2 = xi + (31u - metric), m3 = xj + metric;
+            const bool d0 = m0 > m1, d1 = m2 > m3;
+            ya = d0 ? m1 : m0;
+            yb = d1 ? m3 : m2;
+            const unsigned B0 = __ballot_sync(0xffffffffu, d0);
+            const unsigned B1 = __ballot_sync(0xffffffffu, d1);
+            if (lane == 0) { dec0[s] = B0; dec1[s] = B1; }
+        }
+        // best end state: minimum metric, lowest index on ties
+        unsigned key = (ya <= yb) ? ((ya << 6) | (2u * lane)) : ((yb << 6) | (2u * lane + 1u));
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const unsigned o = __shfl_xor_sync(0xffffffffu, key, off);
+            key = o < key ? o : key;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            unsigned st = key & 63u;
+            int next_start = 0;
+            for (int nb = 79; nb >= 0; nb--) {
+                const int s = nb + 6;
+                const unsigned k = (((st & 1u) ? dec1[s] : dec0[s]) >> (st >> 1)) & 1u;
+                st = (st >> 1) | (k << 5);
+                obits[nb] = static_cast<unsigned char>(k);
+                if (nb == 74) next_start = static_cast<int>(st);
+            }
+            vs.start_state = next_start;
+        }
+        vs.start_state = __shfl_sync(0xffffffffu, vs.start_state, 0);
+        __syncwarp();
+        // descrambler: out[n] = in[n] ^ in[n-1] ^ in[n-5] ^ in[n-7]; reg bit (8-d) holds in[n-d]
+        for (int i = lane; i < 80; i += 32) {
+            auto bit = [&](int n) -> unsigned {
+                return n >= 0 ? obits[n] : ((vs.descr_reg >> (8 + n)) & 1u);
+            };
+            const unsigned o = bit(i) ^ bit(i - 1) ^ bit(i - 5) ^ bit(i - 7);
+            if (cnt + i < port2_cap) outp[cnt + i] = static_cast<unsigned char>(o);
+        }
+        __syncwarp();
+        unsigned reg = 0;
+#pragma unroll
+        for (int d = 1; d <= 8; d++) reg |= static_cast<unsigned>(obits[80 - d]) << (8 - d);
+        vs.descr_reg = reg;
+        cnt += 80;
+        vs.rd += 160;
+        __syncwarp();
+    }
+    if (lane == 0) { vstates[c] = vs; port2_cnt[c] = cnt; }
+}
+
+// roll the stage-1 history: new_hist = last H samples of (old_hist ++ iq[0..T))
+__global__ void hist_update_kernel(const float2* __restrict__ iq, long long iq_stride, long long T,
+                                   const float2* __restrict__ old_hist, float2* __restrict__ new_hist, int H)
+{
+    const int c = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H) return;
+    const long long src = T - H + i;     // index into iq; negative -> old history
+    float2 v;
+    if (src >= 0) v = iq[static_cast<long long>(c) * iq_stride + src];
+    else v = old_hist[static_cast<long long>(c) * H + (H + src)];
+    new_hist[static_cast<long long>(c) * H + i] = v;
+}
+
+}  // namespace qrl

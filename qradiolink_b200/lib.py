@@ -1,0 +1,84 @@
+"""ctypes binding of libqrl_b200.so (C ABI: include/qrl_b200.h).  Fails loudly if the library is missing."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libqrl_b200.so")
+_LIB = None
+
+
+class QrlError(RuntimeError):
+    pass
+
+
+class KIND:
+    DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB = 1, 2, 3, 4, 5, 6
+    MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB = 101, 102, 103, 104, 105, 106
+
+
+class PARAM:
+    CARRIER_OFFSET_HZ, SQUELCH_DB, FILTER_WIDTH, BB_GAIN = 1, 2, 3, 4
+
+
+# every symbol include/qrl_b200.h declares: (restype, argtypes)
+_vp, _i, _l, _d = C.c_void_p, C.c_int, C.c_long, C.c_double
+SYMBOLS = {
+    "qrl_device_count": (_i, []),
+    "qrl_version": (C.c_char_p, []),
+    "qrl_last_error": (C.c_char_p, [_vp]),
+    "qrl_rx_create": (_i, [_i] * 7 + [_l, _i, C.POINTER(_vp)]),
+    "qrl_rx_destroy": (_i, [_vp]),
+    "qrl_rx_set_stream": (_i, [_vp, _vp]),
+    "qrl_rx_set_param": (_i, [_vp, _i, _i, _d]),
+    "qrl_rx_reset": (_i, [_vp]),
+    "qrl_rx_work": (_i, [_vp, _vp, _l, _l, _i]),
+    "qrl_rx_sync": (_i, [_vp]),
+    "qrl_rx_num_ports": (_i, [_vp]),
+    "qrl_rx_port_itemsize": (_i, [_vp, _i]),
+    "qrl_rx_read_port": (_i, [_vp, _i, _vp, _l, _vp, _i]),
+    "qrl_rx_port_device": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_l), C.POINTER(_vp)]),
+    "qrl_rx_launch_count": (_l, [_vp]),
+    "qrl_tx_create": (_i, [_i] * 7 + [_l, _i, C.POINTER(_vp)]),
+    "qrl_tx_destroy": (_i, [_vp]),
+    "qrl_tx_set_stream": (_i, [_vp, _vp]),
+    "qrl_tx_set_param": (_i, [_vp, _i, _i, _d]),
+    "qrl_tx_work": (_i, [_vp, _vp, _l, _l, _i]),
+    "qrl_tx_sync": (_i, [_vp]),
+    "qrl_tx_read": (_i, [_vp, _vp, _l, C.POINTER(_l), _i]),
+    "qrl_tx_out_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_l), C.POINTER(_l)]),
+    "qrl_tx_launch_count": (_l, [_vp]),
+    "qrl_firdes_low_pass": (_i, [_d] * 4 + [_i, _vp, _i]),
+    "qrl_firdes_low_pass_2": (_i, [_d] * 5 + [_i, _vp, _i]),
+    "qrl_firdes_band_pass": (_i, [_d] * 5 + [_i, _vp, _i]),
+    "qrl_firdes_complex_band_pass": (_i, [_d] * 5 + [_i, _vp, _i]),
+    "qrl_firdes_root_raised_cosine": (_i, [_d] * 4 + [_i, _vp, _i]),
+    "qrl_design_table": (_i, [C.c_char_p, _vp, _i]),
+    "qrl_design_deemph": (_i, [_i, _d, _vp, _vp]),
+    "qrl_fir_decim_ccf_device": (_i, [_vp, _i, _i, _vp, _l, _l, _vp, _l, _i, _vp]),
+}
+
+
+def load_library():
+    """Load libqrl_b200.so (built in-tree by __graft_entry__.build()).  No fallback of any kind."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_LIB_PATH):
+            raise QrlError("libqrl_b200.so is not built (%s missing): run `python __graft_entry__.py build`; "
+                           "qradiolink_b200 has no CPU fallback" % _LIB_PATH)
+        L = C.CDLL(_LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)     # AttributeError if the ABI lost a symbol
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def device_count():
+    return load_library().qrl_device_count()
+
+
+def check(rc, handle=None, what=""):
+    if rc != 0:
+        msg = load_library().qrl_last_error(handle)
+        raise QrlError("%s failed (%d): %s" % (what, rc, (msg or b"").decode()))

@@ -1,0 +1,69 @@
+"""Host-side mirror of the reference's TX operator surface: make_gr_mod_4fsk / make_gr_mod_qpsk
+(/root/reference/src/gr/gr_mod_4fsk.h:46-48, gr_mod_qpsk.h) batched over channels.  gr_byte_source
+(src/gr/gr_byte_source.cpp:54-106) hands the modulator a byte vector; `work(bytes)` is that hand-off."""
+import ctypes as C
+
+import numpy as np
+
+from .lib import KIND, PARAM, QrlError, check, load_library
+
+
+class TxBlock:
+    def __init__(self, kind, sps, samp_rate, carrier_freq, filter_width, flag=0, n_channels=1,
+                 max_items=1 << 12, device=0):
+        self._L = load_library()
+        self.n_channels, self.max_items = int(n_channels), int(max_items)
+        self._h = C.c_void_p()
+        rc = self._L.qrl_tx_create(kind, sps, samp_rate, carrier_freq, filter_width, int(flag),
+                                   self.n_channels, self.max_items, device, C.byref(self._h))
+        if rc != 0:
+            raise QrlError("qrl_tx_create failed (%d): %s" % (rc, (self._L.qrl_last_error(None) or b"").decode()))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.qrl_tx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_bb_gain(self, value):
+        check(self._L.qrl_tx_set_param(self._h, -1, PARAM.BB_GAIN, float(value)), self._h, "set_bb_gain")
+
+    def set_stream(self, cuda_stream_ptr):
+        check(self._L.qrl_tx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), self._h, "qrl_tx_set_stream")
+
+    def work(self, data):
+        """data: uint8 [n_channels, n] frame bytes -> complex64 [n_channels, n_out] at 1 Msps."""
+        data = np.ascontiguousarray(data, np.uint8)
+        if data.ndim == 1:
+            data = data[None, :]
+        n = data.shape[1]
+        check(self._L.qrl_tx_work(self._h, data.ctypes.data_as(C.c_void_p), n, n, 0), self._h, "qrl_tx_work")
+        dptr, stride, nout = C.c_void_p(), C.c_long(), C.c_long()
+        check(self._L.qrl_tx_out_device(self._h, C.byref(dptr), C.byref(stride), C.byref(nout)), self._h, "tx_out_device")
+        out = np.zeros((self.n_channels, nout.value), np.complex64)
+        n2 = C.c_long()
+        check(self._L.qrl_tx_read(self._h, out.ctypes.data_as(C.c_void_p), nout.value, C.byref(n2), 0), self._h, "qrl_tx_read")
+        return out[:, :n2.value]
+
+    def work_device(self, dev_ptr, n, stride):
+        check(self._L.qrl_tx_work(self._h, C.c_void_p(dev_ptr), n, stride, 1), self._h, "qrl_tx_work")
+
+    def sync(self):
+        check(self._L.qrl_tx_sync(self._h), self._h, "qrl_tx_sync")
+
+    @property
+    def launches(self):
+        return self._L.qrl_tx_launch_count(self._h)
+
+
+def make_gr_mod_4fsk(sps, samp_rate, carrier_freq, filter_width, fm, n_channels=1, **kw):
+    return TxBlock(KIND.MOD_4FSK, sps, samp_rate, carrier_freq, filter_width, int(bool(fm)), n_channels, **kw)
+
+
+def make_gr_mod_qpsk(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
+    return TxBlock(KIND.MOD_QPSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
