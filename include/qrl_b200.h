@@ -88,6 +88,12 @@ int qrl_rx_read_port(qrl_rx* h, int port, void* dst, long cap, int* counts, int 
 int qrl_rx_port_device(qrl_rx* h, int port, void** data, long* cap, int** counts);
 /* kernels launched by this handle so far (for bench accounting) */
 long qrl_rx_launch_count(const qrl_rx* h);
+/* per-stage device timing: when enabled, every qrl_rx_work brackets each stage's kernels with CUDA events on
+ * the handle's stream.  qrl_rx_profile_read syncs and returns the accumulated milliseconds and launch count of
+ * `stage` (0 = stage-1 decimating FIR, 1 = channel filter, 2 = demod/shaping, 3 = loops/symbol sync, 4 = FEC)
+ * since the last qrl_rx_profile(h, 1) call. */
+int qrl_rx_profile(qrl_rx* h, int enable);
+int qrl_rx_profile_read(qrl_rx* h, int stage, double* ms_total, long* n_launches);
 
 /* ---- TX ---- */
 int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag,

@@ -127,6 +127,25 @@ struct qrl_rx : HandleBase {
     ViterbiState* d_vs = nullptr;
     unsigned char* d_port2 = nullptr; long port2_cap = 0; int* d_port2_cnt = nullptr;
     long n1max = 0;
+    // optional per-stage device timing (qrl_rx_profile)
+    bool prof = false;
+    struct ProfRec { int stage; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs; size_t prof_used = 0;
+    double prof_ms[8] = { 0 }; long prof_n[8] = { 0 };
+    cudaEvent_t prof_begin(int stage)
+    {
+        if (!prof) return nullptr;
+        if (prof_used == prof_recs.size()) {
+            ProfRec r{ stage, nullptr, nullptr };
+            cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+            prof_recs.push_back(r);
+        }
+        ProfRec& r = prof_recs[prof_used];
+        r.stage = stage;
+        cudaEventRecord(r.a, stream);
+        return r.b;
+    }
+    void prof_end(cudaEvent_t b) { if (b) { cudaEventRecord(b, stream); prof_used++; } }
 };
 
 namespace {
@@ -366,7 +385,9 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
     const long long N = h->n_in + T;
     const long long k0 = h->n1;
     const long long k1 = (N - 1) / h->D1 + 1;
+    cudaEvent_t pe = h->prof_begin(0);
     int rc = stage1(h, x, xstride, T, k0, k1);
+    h->prof_end(pe);
     if (rc) return rc;
     {
         dim3 g((h->H + 127) / 128, h->C);
@@ -381,20 +402,25 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         const int TB = 256;
         dim3 g(static_cast<unsigned>((n_new + TB - 1) / TB), h->C);
         // ---- stage 2: channel filter -> ring + port 0
+        pe = h->prof_begin(1);
         fir_ccf_ring_kernel<<<g, TB, sizeof(float) * h->ntaps2, h->stream>>>(
             static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
             static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
             h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap);
         h->launches++;
+        h->prof_end(pe);
+        pe = h->prof_begin(2);
         // ---- stage 3: quadrature demod + RRC
         qdemod_fir_fff_kernel<<<g, TB, sizeof(float) * (2 * h->ntaps3 + TB), h->stream>>>(
             static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
             static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
             h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
         h->launches++;
+        h->prof_end(pe);
     }
     // ---- stage 4: symbol sync (+ phase mod + soft bits)
     {
+        pe = h->prof_begin(3);
         constexpr int CH = 256;
         const int blocks = (h->C + 31) / 32;
         const size_t smem = sizeof(float) * 32 * (CH * 1 + 1);
@@ -403,13 +429,42 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
             static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride);
         h->launches++;
+        h->prof_end(pe);
     }
     // ---- stage 5: Viterbi + descrambler
+    pe = h->prof_begin(4);
     viterbi_k7_kernel<<<h->C, 32, 0, h->stream>>>(h->d_vs, h->d_ss, h->C,
         static_cast<const unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride,
         h->d_port2, h->port2_cap, h->d_port2_cnt, static_cast<int>(h->port2_cap));
     h->launches++;
+    h->prof_end(pe);
     CK(cudaGetLastError());
+    return QRL_OK;
+}
+
+int qrl_rx_profile(qrl_rx* h, int enable)
+{
+    if (!h) return QRL_EINVAL;
+    CK(cudaStreamSynchronize(h->stream));
+    h->prof = enable != 0;
+    h->prof_used = 0;
+    for (int i = 0; i < 8; i++) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+    return QRL_OK;
+}
+
+int qrl_rx_profile_read(qrl_rx* h, int stage, double* ms_total, long* n_launches)
+{
+    if (!h || stage < 0 || stage >= 8) return QRL_EINVAL;
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < h->prof_used; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->prof_recs[i].a, h->prof_recs[i].b) == cudaSuccess) {
+            h->prof_ms[h->prof_recs[i].stage] += ms; h->prof_n[h->prof_recs[i].stage]++;
+        }
+    }
+    h->prof_used = 0;
+    if (ms_total) *ms_total = h->prof_ms[stage];
+    if (n_launches) *n_launches = h->prof_n[stage];
     return QRL_OK;
 }
 
