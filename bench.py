@@ -164,7 +164,8 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     blk = q.make_gr_demod_4fsk(5, 1000000, 1700, 3000, True, n_channels=C, max_samples=T, device=local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # a real (non-null) stream shared by torch events and the library
+    torch.cuda.set_stream(stream)
     blk.set_stream(stream.cuda_stream)
     L = q.load_library()
 

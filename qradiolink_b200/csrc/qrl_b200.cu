@@ -154,7 +154,7 @@ template <int D, int Q, int K, int NOUT, int NWARPS>
 int launch_fir_poly(qrl_rx* h, const float2* iq, long long stride, long long T, long long k0, long long k1)
 {
     constexpr int W = (NOUT + Q - 1) * D;
-    const size_t smem = sizeof(float2) * W;
+    const size_t smem = sizeof(float2) * (W + 2);
     static bool attr_done[16] = { false };
     if (!attr_done[h->device & 15]) {
         CK(cudaFuncSetAttribute(fir_decim_poly_kernel<D, Q, K, NOUT, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -288,7 +288,13 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     if ((rc = upload_floats(h, &h->d_taps3, taps3))) return fail(rc);
     if ((rc = make_ring(h, &h->r1, sizeof(float2), h->n1max + h->ntaps2 + 8))) return fail(rc);
     if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + h->ntaps3 + 8))) return fail(rc);
-    if ((rc = make_ring(h, &h->r4, sizeof(float), h->n1max + 64))) return fail(rc);
+    // r4 is channel-interleaved: [ceil(C/32)][slots][32]; allocate for the padded channel count
+    {
+        const int Csave = h->C; h->C = ((Csave + 31) / 32) * 32;
+        rc = make_ring(h, &h->r4, sizeof(float), h->n1max + 600);
+        h->C = Csave;
+        if (rc) return fail(rc);
+    }
     if ((rc = make_ring(h, &h->r5, 1, 2 * h->n1max + 1024))) return fail(rc);
     h->port0_cap = h->n1max;
     if ((rc = dev_alloc(h, &h->d_port0, static_cast<size_t>(h->port0_cap) * h->C))) return fail(rc);
@@ -323,7 +329,7 @@ int qrl_rx_reset(qrl_rx* h)
     CK(cudaMemsetAsync(h->d_hist[1], 0, sizeof(float2) * h->H * h->C, h->stream));
     CK(cudaMemsetAsync(h->r1.d, 0, sizeof(float2) * h->r1.stride * h->C, h->stream));
     CK(cudaMemsetAsync(h->r2.d, 0, sizeof(float2) * h->r2.stride * h->C, h->stream));
-    CK(cudaMemsetAsync(h->r4.d, 0, sizeof(float) * h->r4.stride * h->C, h->stream));
+    CK(cudaMemsetAsync(h->r4.d, 0, sizeof(float) * h->r4.stride * (((h->C + 31) / 32) * 32), h->stream));
     CK(cudaMemsetAsync(h->r5.d, 0, h->r5.stride * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_port1_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_port2_cnt, 0, sizeof(int) * h->C, h->stream));
@@ -423,7 +429,12 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         pe = h->prof_begin(3);
         constexpr int CH = 256;
         const int blocks = (h->C + 31) / 32;
-        const size_t smem = sizeof(float) * 32 * (CH * 1 + 1);
+        const size_t smem = sizeof(float) * (2 * CH * 32 + 129 * 8);
+        static bool ss_attr = false;
+        if (!ss_attr) {
+            CK(cudaFuncSetAttribute(symsync_kernel<1, SL_RECT4, EPI_4FSK_FM, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ss_attr = true;
+        }
         symsync_kernel<1, SL_RECT4, EPI_4FSK_FM, CH><<<blocks, 32, smem, h->stream>>>(
             h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r4.d), h->r4.mask, h->r4.stride, k1,
             h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),

@@ -20,6 +20,34 @@ __device__ float d_mmse_tab[129 * 8];
 __device__ float d_sine_tab[2048];
 
 // ------------------------------------------------------------------------------------------------
+// TMA 1-D bulk copy (cp.async.bulk -> UBLKCP) + mbarrier helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// ------------------------------------------------------------------------------------------------
 // elementary functions shared by all loop kernels
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void qrl_sincosf(float x, float& s, float& c)
@@ -115,7 +143,9 @@ fir_decim_poly_kernel(const float2* __restrict__ iq, long long iq_stride, long l
     static_assert(K == 8, "transposed butterfly below is written for 2K = 16 values");
     constexpr int R = (D + 31) / 32;                 // branch rounds per lane
     constexpr int W = (NOUT + Q - 1) * D;            // samples in the strip window
-    extern __shared__ float2 xs[];
+    static_assert((W & 1) == 0, "window must be an even number of samples (16-byte bulk copies)");
+    extern __shared__ __align__(128) float2 xs_raw[];   // W + 2 samples
+    __shared__ __align__(8) uint64_t fill_bar;
 
     const int c = blockIdx.y;
     const long long kbase = k0 + static_cast<long long>(blockIdx.x) * NOUT;
@@ -131,18 +161,35 @@ fir_decim_poly_kernel(const float2* __restrict__ iq, long long iq_stride, long l
         for (int q = 0; q < Q; q++) tap[rho][q] = (r < D) ? taps_padded[D * q + r] : 0.0f;
     }
 
-    // window covers absolute samples [A0, A0 + W)
+    // window covers absolute samples [A0, A0 + W); the copy starts one sample early when that makes the
+    // global source 16-byte aligned (S0 even relative to the 16-byte aligned channel base)
     const long long A0 = D * kbase - (static_cast<long long>(Q) * D - 1);
     const float2* iqc = iq + static_cast<long long>(c) * iq_stride;
     const float2* hc = hist + static_cast<long long>(c) * H;
-    for (int idx = threadIdx.x; idx < W; idx += NWARPS * 32) {
-        const long long i = A0 + idx - n_in_before;   // index into this call's input
-        float2 v = make_float2(0.0f, 0.0f);
-        if (i >= 0) { if (i < T) v = __ldg(iqc + i); }
-        else if (H + i >= 0) v = hc[H + i];
-        xs[idx] = v;
+    const long long i0 = A0 - n_in_before;                       // index of the window start in this call's input
+    const int shift = static_cast<int>(i0 & 1);                  // 1 -> start the bulk copy at i0 - 1
+    const float2* xs = xs_raw + shift;
+    const bool bulk = (i0 - shift >= 0) && (i0 - shift + W + 2 <= T) && ((iq_stride & 1) == 0) &&
+                      ((reinterpret_cast<unsigned long long>(iq) & 15ull) == 0);
+    if (bulk) {
+        if (threadIdx.x == 0) { mbar_init(&fill_bar, 1); mbar_fence_init(); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&fill_bar, (W + 2) * 8);
+            bulk_g2s(xs_raw, iqc + (i0 - shift), (W + 2) * 8, &fill_bar);
+        }
+        mbar_wait(&fill_bar, 0);
+    } else {
+        float2* xw = xs_raw + shift;
+        for (int idx = threadIdx.x; idx < W; idx += NWARPS * 32) {
+            const long long i = i0 + idx;
+            float2 v = make_float2(0.0f, 0.0f);
+            if (i >= 0) { if (i < T) v = __ldg(iqc + i); }
+            else if (H + i >= 0) v = hc[H + i];
+            xw[idx] = v;
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     float* outc = reinterpret_cast<float*>(out_ring + static_cast<long long>(c) * ring_stride);
     for (int b = warp; b < NOUT / K; b += NWARPS) {
@@ -341,7 +388,8 @@ __global__ void qdemod_fir_fff_kernel(const float2* __restrict__ in, unsigned in
     float acc = 0.0f;
     const float* p = ds + threadIdx.x + (ntaps - 1);       // newest sample of this output
     for (int j = ntaps - 1; j >= 0; j--) acc = fmaf(hs[j], p[-j], acc);
-    out[static_cast<long long>(c) * out_stride + (a & out_mask)] = acc;
+    // channel-interleaved ring: [c / 32][slot][c % 32]  (one warp of the symbol-sync kernel = one 128-byte row per time step)
+    out[(static_cast<long long>(c >> 5) * out_stride + (a & out_mask)) * 32 + (c & 31)] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -420,118 +468,160 @@ __device__ __forceinline__ void qrl_costas_step(LoopState& st, float alpha, floa
     yr = orr; yi = oi;
 }
 
+// exact threshold form of constellation_rect's floor(re + 2.0f) sector search (float addition rounds to nearest
+// even, so fl(re+2) >= 1,2,3  <=>  re >= -1, -2^-24, 1-2^-23; checked in tests/test_host_logic.py)
+__device__ __forceinline__ float qrl_slice_rect4(float re)
+{
+    return re >= 0.99999988079071044921875f ? 1.5f : (re >= -5.9604644775390625e-8f ? 0.5f : (re >= -1.0f ? -0.5f : -1.5f));
+}
+
+// Input ring layout: [group = channel / 32][slot][32 lanes][NCOMP] -- a time step of one warp's 32 channels is one
+// contiguous 128*NCOMP-byte row, so a CH-row window is ONE contiguous block: fetched with cp.async.bulk (TMA 1-D),
+// double buffered, while every lane reads column `lane` (bank = lane: conflict-free).
 template <int NCOMP, int SLICER, int EPI, int CH>
 __global__ void __launch_bounds__(32)
 symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
-               const float* __restrict__ in, unsigned in_mask, long long in_stride /*items*/, long long avail_total,
+               const float* __restrict__ in, unsigned in_mask, long long in_stride /*slots per group*/, long long avail_total,
                float2* __restrict__ port1, long long port1_stride, int* __restrict__ port1_cnt, int port1_cap,
                unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride)
 {
-    constexpr int PITCH = CH * NCOMP + 1;
-    extern __shared__ float stage[];                  // [32][PITCH]
+    constexpr int ROWF = 32 * NCOMP;                    // floats per row
+    constexpr int STRIDE = CH - 32;                     // window advance per chunk (lookahead <= 32)
+    extern __shared__ __align__(128) float sm_sync[];   // [2][CH][ROWF] + mmse table
+    __shared__ __align__(8) uint64_t bars[2];
+    float* stage0 = sm_sync;
+    float* mm = sm_sync + 2 * CH * ROWF;                // 129 * 8 floats
     const int lane = threadIdx.x;
-    const int c = blockIdx.x * 32 + lane;
+    const int g = blockIdx.x;
+    const int c = g * 32 + lane;
     const bool active = c < C;
+    for (int i = lane; i < 129 * 8; i += 32) mm[i] = d_mmse_tab[i];
+    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncwarp();
+
     SymSyncState st;
     if (active) st = states[c];
-    else { st.ii = avail_total; }
+    else { st.ii = 0x7fffffffffffffffLL; }
     int p1cnt = active ? port1_cnt[c] : 0;
-    float* mine = stage + lane * PITCH;
-
-    while (true) {
-        const bool can = active && (st.ii + p.lookahead <= avail_total);
-        if (!__any_sync(0xffffffffu, can)) break;
-        // cooperative staging: channel j of this warp, samples [ii_j, ii_j + CH)
-        for (int j = 0; j < 32; j++) {
-            const long long bj = __shfl_sync(0xffffffffu, st.ii, j);
-            const int cj = blockIdx.x * 32 + j;
-            if (cj >= C) continue;
-            const float* src = in + static_cast<long long>(cj) * in_stride * NCOMP;
-            float* dst = stage + j * PITCH;
-            for (int t = lane; t < CH * NCOMP; t += 32) {
-                const long long a = bj + t / NCOMP;
-                float v = 0.0f;
-                if (a < avail_total) v = src[(a & in_mask) * NCOMP + (t % NCOMP)];
-                dst[t] = v;
-            }
-        }
-        __syncwarp();
-        if (can) {
-            long long have = avail_total - st.ii;
-            const int lim = have < CH ? static_cast<int>(have) : CH;
-            int o = 0;
-            while (o + p.lookahead <= lim) {
-                // 8-tap MMSE interpolation, oldest sample first
-                const int imu = static_cast<int>(rintf(st.mu * 128.0f));
-                const float* tp = d_mmse_tab + imu * 8;
-                float yr = 0.0f, yi = 0.0f;
+    long long base = st.ii;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float tt = tp[7 - i];
-                    yr = fmaf(tt, mine[(o + i) * NCOMP], yr);
-                    if (NCOMP == 2) yi = fmaf(tt, mine[(o + i) * NCOMP + 1], yi);
-                }
-                st.xr[2] = st.xr[1]; st.xr[1] = st.xr[0]; st.xr[0] = yr;
-                st.xi[2] = st.xi[1]; st.xi[1] = st.xi[0]; st.xi[0] = yi;
-                st.dr[2] = st.dr[1]; st.dr[1] = st.dr[0];
-                st.di[2] = st.di[1]; st.di[1] = st.di[0];
-                qrl_slice(SLICER, yr, yi, st.dr[0], st.di[0]);
-                float err;
-                if (NCOMP == 2) {
-                    const float ar = st.xr[0] - st.xr[2], ai = st.xi[0] - st.xi[2];
-                    const float br = st.dr[0] - st.dr[2], bi = st.di[0] - st.di[2];
-                    const float u = (ar * st.dr[1] + ai * st.di[1]) - (br * st.xr[1] + bi * st.xi[1]);
-                    err = qrl_clip(u, 1.0f);
-                } else {
-                    const float u = (st.xr[0] - st.xr[2]) * st.dr[1] - (st.dr[0] - st.dr[2]) * st.xr[1];
-                    err = qrl_clip(u / 2.0f, 1.0f);
-                }
-                st.avg_period = st.avg_period + p.beta * err;
-                if (st.avg_period > p.max_period) st.avg_period = p.max_period;
-                else if (st.avg_period < p.min_period) st.avg_period = p.min_period;
-                st.inst_period = st.avg_period + p.alpha * err;
-                if (st.inst_period <= 0.0f) st.inst_period = st.avg_period;
-                const float ph = st.mu + st.inst_period;
-                const float fl = floorf(ph);
-                st.mu = ph - fl;
-                o += static_cast<int>(fl);
+    for (int off = 16; off >= 1; off >>= 1) {
+        const long long o = __shfl_xor_sync(0xffffffffu, base, off);
+        base = o < base ? o : base;
+    }
+    const float* ring = in + static_cast<long long>(g) * in_stride * ROWF;
+    const long long cap = static_cast<long long>(in_mask) + 1;
 
-                // ---- epilogue
-                float o_r, o_i;
-                unsigned char sb0, sb1;
-                if (EPI == EPI_4FSK_FM) {
-                    const float phs = p.pm_sens * yr;
-                    float sn, cs;
-                    qrl_sincosf(phs, sn, cs);
-                    o_r = cs; o_i = sn;
-                    sb0 = qrl_soft_u8(sn, p.soft_scale);       // interleave: imag first, then real
-                    sb1 = qrl_soft_u8(cs, p.soft_scale);
-                } else if (EPI == EPI_CPLX) {
-                    o_r = yr; o_i = yi;
-                    sb0 = qrl_soft_u8(yr, p.soft_scale);
-                    sb1 = qrl_soft_u8(yi, p.soft_scale);
-                } else {
-                    float cr, ci;
-                    qrl_costas_step(st.costas, p.costas_alpha, p.costas_beta, 4, true, yr, yi, cr, ci);
-                    const float dr = cr * st.dp_r + ci * st.dp_i;
-                    const float di = ci * st.dp_r - cr * st.dp_i;
-                    st.dp_r = cr; st.dp_i = ci;
-                    o_r = dr * p.rot_r - di * p.rot_i;
-                    o_i = dr * p.rot_i + di * p.rot_r;
-                    sb0 = qrl_soft_u8(o_r, p.soft_scale);
-                    sb1 = qrl_soft_u8(o_i, p.soft_scale);
+    auto issue = [&](int m) {           // lane 0: fetch rows [base + m*STRIDE, +CH) into buffer m & 1
+        const long long w0 = base + static_cast<long long>(m) * STRIDE;
+        float* dst = stage0 + (m & 1) * CH * ROWF;
+        const long long s0 = w0 & in_mask;
+        const long long first = (s0 + CH <= cap) ? CH : (cap - s0);
+        fence_proxy_async();
+        mbar_expect_tx(&bars[m & 1], CH * ROWF * 4);
+        bulk_g2s(dst, ring + s0 * ROWF, static_cast<uint32_t>(first * ROWF * 4), &bars[m & 1]);
+        if (first < CH) bulk_g2s(dst + first * ROWF, ring, static_cast<uint32_t>((CH - first) * ROWF * 4), &bars[m & 1]);
+    };
+
+    unsigned char* sr = soft_ring + static_cast<long long>(c) * soft_stride;
+    float2* p1 = port1 + static_cast<long long>(c) * port1_stride;
+    if (base + p.lookahead <= avail_total) {
+        if (lane == 0) issue(0);
+        for (int m = 0;; m++) {
+            const long long w0 = base + static_cast<long long>(m) * STRIDE;
+            const bool more = (w0 + STRIDE + p.lookahead <= avail_total);
+            if (more && lane == 0) issue(m + 1);
+            mbar_wait(&bars[m & 1], (m >> 1) & 1);
+            const float* buf = stage0 + (m & 1) * CH * ROWF + lane * NCOMP;
+            const long long wend = (w0 + CH < avail_total) ? (w0 + CH) : avail_total;
+            if (active) {
+                while (st.ii + p.lookahead <= wend) {
+                    const float* x = buf + (st.ii - w0) * ROWF;
+                    const int imu = static_cast<int>(rintf(st.mu * 128.0f));
+                    const float4 t0 = *reinterpret_cast<const float4*>(mm + imu * 8);
+                    const float4 t1 = *reinterpret_cast<const float4*>(mm + imu * 8 + 4);
+                    // 8-tap MMSE interpolation, oldest sample first: taps[7], taps[6], ...
+                    float yr, yi = 0.0f;
+                    yr = fmaf(t1.w, x[0 * ROWF], 0.0f);
+                    yr = fmaf(t1.z, x[1 * ROWF], yr);
+                    yr = fmaf(t1.y, x[2 * ROWF], yr);
+                    yr = fmaf(t1.x, x[3 * ROWF], yr);
+                    yr = fmaf(t0.w, x[4 * ROWF], yr);
+                    yr = fmaf(t0.z, x[5 * ROWF], yr);
+                    yr = fmaf(t0.y, x[6 * ROWF], yr);
+                    yr = fmaf(t0.x, x[7 * ROWF], yr);
+                    if (NCOMP == 2) {
+                        yi = fmaf(t1.w, x[0 * ROWF + 1], 0.0f);
+                        yi = fmaf(t1.z, x[1 * ROWF + 1], yi);
+                        yi = fmaf(t1.y, x[2 * ROWF + 1], yi);
+                        yi = fmaf(t1.x, x[3 * ROWF + 1], yi);
+                        yi = fmaf(t0.w, x[4 * ROWF + 1], yi);
+                        yi = fmaf(t0.z, x[5 * ROWF + 1], yi);
+                        yi = fmaf(t0.y, x[6 * ROWF + 1], yi);
+                        yi = fmaf(t0.x, x[7 * ROWF + 1], yi);
+                    }
+                    st.xr[2] = st.xr[1]; st.xr[1] = st.xr[0]; st.xr[0] = yr;
+                    st.xi[2] = st.xi[1]; st.xi[1] = st.xi[0]; st.xi[0] = yi;
+                    st.dr[2] = st.dr[1]; st.dr[1] = st.dr[0];
+                    st.di[2] = st.di[1]; st.di[1] = st.di[0];
+                    if (SLICER == SL_RECT4) { st.dr[0] = qrl_slice_rect4(yr); st.di[0] = 0.0f; }
+                    else qrl_slice(SLICER, yr, yi, st.dr[0], st.di[0]);
+                    float err;
+                    if (NCOMP == 2) {
+                        const float ar = st.xr[0] - st.xr[2], ai = st.xi[0] - st.xi[2];
+                        const float br = st.dr[0] - st.dr[2], bi = st.di[0] - st.di[2];
+                        const float u = (ar * st.dr[1] + ai * st.di[1]) - (br * st.xr[1] + bi * st.xi[1]);
+                        err = qrl_clip(u, 1.0f);
+                    } else {
+                        const float u = (st.xr[0] - st.xr[2]) * st.dr[1] - (st.dr[0] - st.dr[2]) * st.xr[1];
+                        err = qrl_clip(u / 2.0f, 1.0f);
+                    }
+                    st.avg_period = st.avg_period + p.beta * err;
+                    if (st.avg_period > p.max_period) st.avg_period = p.max_period;
+                    else if (st.avg_period < p.min_period) st.avg_period = p.min_period;
+                    st.inst_period = st.avg_period + p.alpha * err;
+                    if (st.inst_period <= 0.0f) st.inst_period = st.avg_period;
+                    const float ph = st.mu + st.inst_period;
+                    const float fl = floorf(ph);
+                    st.mu = ph - fl;
+                    st.ii += static_cast<int>(fl);
+
+                    // ---- epilogue (off the loop-carried path)
+                    float o_r, o_i;
+                    unsigned char sb0, sb1;
+                    if (EPI == EPI_4FSK_FM) {
+                        const float phs = p.pm_sens * yr;
+                        float sn, cs;
+                        qrl_sincosf(phs, sn, cs);
+                        o_r = cs; o_i = sn;
+                        sb0 = qrl_soft_u8(sn, p.soft_scale);       // interleave: imag first, then real
+                        sb1 = qrl_soft_u8(cs, p.soft_scale);
+                    } else if (EPI == EPI_CPLX) {
+                        o_r = yr; o_i = yi;
+                        sb0 = qrl_soft_u8(yr, p.soft_scale);
+                        sb1 = qrl_soft_u8(yi, p.soft_scale);
+                    } else {
+                        float cr, ci;
+                        qrl_costas_step(st.costas, p.costas_alpha, p.costas_beta, 4, true, yr, yi, cr, ci);
+                        const float dr = cr * st.dp_r + ci * st.dp_i;
+                        const float di = ci * st.dp_r - cr * st.dp_i;
+                        st.dp_r = cr; st.dp_i = ci;
+                        o_r = dr * p.rot_r - di * p.rot_i;
+                        o_i = dr * p.rot_i + di * p.rot_r;
+                        sb0 = qrl_soft_u8(o_r, p.soft_scale);
+                        sb1 = qrl_soft_u8(o_i, p.soft_scale);
+                    }
+                    if (p1cnt < port1_cap) p1[p1cnt] = make_float2(o_r, o_i);
+                    p1cnt++;
+                    sr[st.n_soft & soft_mask] = sb0;
+                    sr[(st.n_soft + 1) & soft_mask] = sb1;
+                    st.n_soft += 2;
+                    st.n_sym += 1;
                 }
-                if (p1cnt < port1_cap) port1[static_cast<long long>(c) * port1_stride + p1cnt] = make_float2(o_r, o_i);
-                p1cnt++;
-                unsigned char* sr = soft_ring + static_cast<long long>(c) * soft_stride;
-                sr[st.n_soft & soft_mask] = sb0;
-                sr[(st.n_soft + 1) & soft_mask] = sb1;
-                st.n_soft += 2;
-                st.n_sym += 1;
             }
-            st.ii += o;
+            __syncwarp();
+            if (!more) break;
         }
-        __syncwarp();
     }
     if (active) { states[c] = st; port1_cnt[c] = p1cnt; }
 }
