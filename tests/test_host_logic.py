@@ -1,0 +1,30 @@
+"""CPU tier: host-side logic and exact-equivalence arguments the CUDA kernels rely on."""
+import numpy as np
+
+
+def test_rect4_slicer_threshold_form_is_exact():
+    """kernels use re >= {-1, -2^-24, 1-2^-23} instead of clamp(floor(re + 2.0f), 0, 3) (constellation_rect
+    sector search): check equality on random floats and on every float near the three boundaries."""
+    rng = np.random.default_rng(0)
+    xs = [rng.standard_normal(2_000_000).astype(np.float32) * 2,
+          rng.uniform(-3, 3, 2_000_000).astype(np.float32)]
+    for centre in (-1.0, 0.0, 1.0, -2.0, 2.0):
+        v = np.float32(centre)
+        lo = [v]; hi = [v]
+        for _ in range(4096):
+            lo.append(np.nextafter(lo[-1], np.float32(-np.inf), dtype=np.float32))
+            hi.append(np.nextafter(hi[-1], np.float32(np.inf), dtype=np.float32))
+        xs.append(np.array(lo + hi, np.float32))
+    xs.append(np.array([0.0, -0.0, 1e-38, -1e-38, 1e-45, -1e-45, -5.9604645e-8, -5.9604652e-8, 0.99999994, 0.9999999], np.float32))
+    x = np.concatenate(xs)
+    sec = np.clip(np.floor((x + np.float32(2.0)).astype(np.float32)), 0, 3).astype(np.int32)
+    want = (np.float32(-1.5) + sec.astype(np.float32)).astype(np.float32)
+    t3, t2, t1 = np.float32(0.99999988079071044921875), np.float32(-5.9604644775390625e-8), np.float32(-1.0)
+    got = np.where(x >= t3, 1.5, np.where(x >= t2, 0.5, np.where(x >= t1, -0.5, -1.5))).astype(np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_viterbi_metric_spread_bound():
+    """32-bit metrics without renormalisation decide like VOLK's 8-bit kernel iff the 8-bit one never wraps:
+    worst case spread over K-1 = 6 steps of branch cost <= 31 plus one add stays below 256."""
+    assert 6 * 31 + 31 < 256 and 63 + 5 * 31 + 31 < 256
