@@ -92,6 +92,9 @@ long qrl_rx_launch_count(const qrl_rx* h);
  * the handle's stream.  qrl_rx_profile_read syncs and returns the accumulated milliseconds and launch count of
  * `stage` (0 = stage-1 decimating FIR, 1 = channel filter, 2 = demod/shaping, 3 = loops/symbol sync, 4 = FEC)
  * since the last qrl_rx_profile(h, 1) call. */
+/* SM partition in use: SMs reserved for the sequential loop/FEC kernels and SMs left to the parallel stages
+ * (both 0 when the driver refused green contexts and plain priority streams are used instead) */
+int qrl_rx_sm_partition(const qrl_rx* h, int* loop_sms, int* parallel_sms);
 int qrl_rx_profile(qrl_rx* h, int enable);
 int qrl_rx_profile_read(qrl_rx* h, int stage, double* ms_total, long* n_launches);
 

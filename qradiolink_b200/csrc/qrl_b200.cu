@@ -9,6 +9,8 @@
 #include "qrl_design.hpp"
 #include "qrl_kernels.cuh"
 
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstring>
 #include <mutex>
@@ -127,13 +129,29 @@ struct qrl_rx : HandleBase {
     ViterbiState* d_vs = nullptr;
     unsigned char* d_port2 = nullptr; long port2_cap = 0; int* d_port2_cnt = nullptr;
     long n1max = 0;
+    // software pipeline inside one work() call: parallel stages on `stream`, loop stages on s_loop, FEC on s_fec
+    static constexpr int kMaxSub = 16;
+    int nsub = 8;
+    cudaStream_t s_loop = nullptr, s_fec = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_a[kMaxSub] = { nullptr }, ev_b[kMaxSub] = { nullptr }, ev_loop_done = nullptr, ev_fec_done = nullptr;
+    long long* d_nsoft = nullptr;   // [kMaxSub][C] soft-bit write index snapshots
+    // static SM partition (CUDA green contexts): the sequential loop / FEC kernels get a small private set of SMs so
+    // their single dependent instruction streams never arbitrate with the FMA-bound FIR warps; the parallel stages
+    // run on the remaining SMs through s_par.  Falls back to plain streams when the driver refuses.
+    CUgreenCtx g_loop = nullptr, g_par = nullptr;
+    cudaStream_t s_par = nullptr;
+    cudaEvent_t ev_par_done = nullptr;
+    int sm_loop = 0, sm_par = 0;
+    cudaStream_t par() const { return s_par ? s_par : stream; }
     // optional per-stage device timing (qrl_rx_profile)
     bool prof = false;
     struct ProfRec { int stage; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_recs; size_t prof_used = 0;
     double prof_ms[8] = { 0 }; long prof_n[8] = { 0 };
-    cudaEvent_t prof_begin(int stage)
+    cudaStream_t prof_stream = nullptr;
+    cudaEvent_t prof_begin(int stage, cudaStream_t on = nullptr)
     {
+        prof_stream = on ? on : stream;
         if (!prof) return nullptr;
         if (prof_used == prof_recs.size()) {
             ProfRec r{ stage, nullptr, nullptr };
@@ -142,10 +160,10 @@ struct qrl_rx : HandleBase {
         }
         ProfRec& r = prof_recs[prof_used];
         r.stage = stage;
-        cudaEventRecord(r.a, stream);
+        cudaEventRecord(r.a, prof_stream);
         return r.b;
     }
-    void prof_end(cudaEvent_t b) { if (b) { cudaEventRecord(b, stream); prof_used++; } }
+    void prof_end(cudaEvent_t b) { if (b) { cudaEventRecord(b, prof_stream); prof_used++; } }
 };
 
 namespace {
@@ -162,7 +180,7 @@ int launch_fir_poly(qrl_rx* h, const float2* iq, long long stride, long long T, 
     }
     const long long nout = k1 - k0;
     dim3 grid(static_cast<unsigned>((nout + NOUT - 1) / NOUT), h->C);
-    fir_decim_poly_kernel<D, Q, K, NOUT, NWARPS><<<grid, NWARPS * 32, smem, h->stream>>>(
+    fir_decim_poly_kernel<D, Q, K, NOUT, NWARPS><<<grid, NWARPS * 32, smem, h->par()>>>(
         iq, stride, T, h->d_hist[h->hist_cur], h->H, h->d_taps1,
         static_cast<float2*>(h->r1.d), h->r1.mask, h->r1.stride, h->n_in, k0, k1);
     h->launches++;
@@ -178,7 +196,7 @@ int launch_fir_d2(qrl_rx* h, const float2* iq, long long stride, long long T, lo
     const size_t smem = sizeof(float2) * (W + W / (2 * K) + 2);
     const long long nout = k1 - k0;
     dim3 grid(static_cast<unsigned>((nout + NOUT - 1) / NOUT), h->C);
-    fir_decim2_kernel<NTP, K, NTHREADS><<<grid, NTHREADS, smem, h->stream>>>(
+    fir_decim2_kernel<NTP, K, NTHREADS><<<grid, NTHREADS, smem, h->par()>>>(
         iq, stride, T, h->d_hist[h->hist_cur], h->H, h->d_taps1,
         static_cast<float2*>(h->r1.d), h->r1.mask, h->r1.stride, h->n_in, k0, k1);
     h->launches++;
@@ -193,6 +211,45 @@ int stage1(qrl_rx* h, const float2* iq, long long stride, long long T, long long
     if (h->D1 == 2 && h->ntaps1 <= 56) return launch_fir_d2<56, 8, 128>(h, iq, stride, T, k0, k1);
     set_err(h, "stage-1 resampler shape not built (D=" + std::to_string(h->D1) + ", taps=" + std::to_string(h->ntaps1) + ")");
     return QRL_EINVAL;
+}
+
+template <class F>
+F drv(const char* name)
+{
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<F>(fn);
+}
+
+// split the device into {loop_sms} + {rest} and create the three internal streams; false -> caller falls back
+bool make_sm_partition(qrl_rx* h, unsigned loop_sms, int prio)
+{
+    if (const char* e = getenv("QRL_NO_SM_PARTITION")) { if (e[0] == '1') return false; }
+    auto pDeviceGet = drv<CUresult (*)(CUdevice*, int)>("cuDeviceGet");
+    auto pGetRes = drv<CUresult (*)(CUdevice, CUdevResource*, CUdevResourceType)>("cuDeviceGetDevResource");
+    auto pSplit = drv<CUresult (*)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int)>("cuDevSmResourceSplitByCount");
+    auto pDesc = drv<CUresult (*)(CUdevResourceDesc*, CUdevResource*, unsigned int)>("cuDevResourceGenerateDesc");
+    auto pCreate = drv<CUresult (*)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int)>("cuGreenCtxCreate");
+    auto pStream = drv<CUresult (*)(CUstream*, CUgreenCtx, unsigned int, int)>("cuGreenCtxStreamCreate");
+    if (!pDeviceGet || !pGetRes || !pSplit || !pDesc || !pCreate || !pStream) return false;
+    CUdevice dev;
+    if (pDeviceGet(&dev, h->device) != CUDA_SUCCESS) return false;
+    CUdevResource all{}, grp{}, rest{};
+    if (pGetRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    unsigned nb = 1;
+    if (pSplit(&grp, &nb, &all, &rest, 0, loop_sms) != CUDA_SUCCESS || nb < 1) return false;
+    CUdevResourceDesc d_loop, d_par;
+    if (pDesc(&d_loop, &grp, 1) != CUDA_SUCCESS || pDesc(&d_par, &rest, 1) != CUDA_SUCCESS) return false;
+    if (pCreate(&h->g_loop, d_loop, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    if (pCreate(&h->g_par, d_par, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    CUstream a = nullptr, b = nullptr, c = nullptr;
+    if (pStream(&a, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
+    if (pStream(&b, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
+    if (pStream(&c, h->g_par, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
+    h->s_loop = a; h->s_fec = b; h->s_par = c;
+    h->sm_loop = static_cast<int>(grp.sm.smCount); h->sm_par = static_cast<int>(rest.sm.smCount);
+    return true;
 }
 
 int make_ring(qrl_rx* h, Ring* r, size_t isz, long long min_items)
@@ -264,6 +321,8 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         h->ssp.lookahead = 8 + static_cast<int>(ceilf(h->ssp.max_period)) + 1;
         h->ssp.pm_sens = static_cast<float>(kPi / 2);
         h->ssp.soft_scale = 128.0f;
+        h->ssp.n0 = static_cast<int>(floorf(h->ssp.min_period - fabsf(h->ssp.alpha)));
+        h->ssp.fl0 = static_cast<float>(h->ssp.n0);
         h->nports = 3;
     } else {
         set_err(h, "qrl_rx_create: demod kind " + std::to_string(kind) + " not built");
@@ -306,6 +365,24 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     if ((rc = dev_alloc(h, &h->d_port2_cnt, h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_ss, h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_vs, h->C))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_nsoft, static_cast<size_t>(qrl_rx::kMaxSub) * h->C))) return fail(rc);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        bool ok = true;
+        if (!make_sm_partition(h, 8, hi)) {
+            h->s_par = nullptr; h->sm_loop = 0; h->sm_par = 0;
+            if (h->s_loop == nullptr)
+                ok = cudaStreamCreateWithPriority(&h->s_loop, cudaStreamNonBlocking, hi) == cudaSuccess;
+            if (h->s_fec == nullptr)
+                ok = ok && cudaStreamCreateWithPriority(&h->s_fec, cudaStreamNonBlocking, hi) == cudaSuccess;
+        }
+        auto mk = [&](cudaEvent_t* e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+        mk(&h->ev_start); mk(&h->ev_loop_done); mk(&h->ev_fec_done); mk(&h->ev_par_done);
+        for (int i = 0; i < qrl_rx::kMaxSub; i++) { mk(&h->ev_a[i]); mk(&h->ev_b[i]); }
+        if (!ok) { set_err(h, "stream/event creation failed"); return fail(QRL_ECUDA); }
+    }
+    if (const char* e = getenv("QRL_NSUB")) { int v = atoi(e); if (v >= 1 && v <= qrl_rx::kMaxSub) h->nsub = v; }
     if ((rc = qrl_rx_reset(h))) return fail(rc);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { set_err(h, "create sync failed"); return fail(QRL_ECUDA); }
     *out = h;
@@ -315,6 +392,9 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
 int qrl_rx_reset(qrl_rx* h)
 {
     if (!h) return QRL_EINVAL;
+    if (h->s_loop) CK(cudaStreamSynchronize(h->s_loop));
+    if (h->s_fec) CK(cudaStreamSynchronize(h->s_fec));
+    if (h->s_par) CK(cudaStreamSynchronize(h->s_par));
     // all-zero history / rings; loop states at their constructor values
     std::vector<SymSyncState> ss(h->C);
     std::vector<ViterbiState> vs(h->C);
@@ -343,6 +423,13 @@ int qrl_rx_destroy(qrl_rx* h)
     if (!h) return QRL_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->s_loop) { cudaStreamSynchronize(h->s_loop); cudaStreamDestroy(h->s_loop); }
+    if (h->s_fec) { cudaStreamSynchronize(h->s_fec); cudaStreamDestroy(h->s_fec); }
+    if (h->s_par) { cudaStreamSynchronize(h->s_par); cudaStreamDestroy(h->s_par); }
+    if (h->g_loop || h->g_par) {
+        auto pDestroy = drv<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
+        if (pDestroy) { if (h->g_loop) pDestroy(h->g_loop); if (h->g_par) pDestroy(h->g_par); }
+    }
     for (void* p : h->allocs) cudaFree(p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -387,68 +474,105 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
     CK(cudaMemsetAsync(h->d_port1_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_port2_cnt, 0, sizeof(int) * h->C, h->stream));
 
-    // ---- stage 1: decimating FIR; outputs k with D k <= last absolute input index
-    const long long N = h->n_in + T;
-    const long long k0 = h->n1;
-    const long long k1 = (N - 1) / h->D1 + 1;
-    cudaEvent_t pe = h->prof_begin(0);
-    int rc = stage1(h, x, xstride, T, k0, k1);
-    h->prof_end(pe);
-    if (rc) return rc;
-    {
-        dim3 g((h->H + 127) / 128, h->C);
-        hist_update_kernel<<<g, 128, 0, h->stream>>>(x, xstride, T, h->d_hist[h->hist_cur], h->d_hist[h->hist_cur ^ 1], h->H);
-        h->launches++;
-        h->hist_cur ^= 1;
-    }
-    h->n_in = N; h->n1 = k1;
-    const long long n_new = k1 - k0;
-    h->port0_n = static_cast<long>(n_new);
-    if (n_new > 0) {
-        const int TB = 256;
-        dim3 g(static_cast<unsigned>((n_new + TB - 1) / TB), h->C);
-        // ---- stage 2: channel filter -> ring + port 0
-        pe = h->prof_begin(1);
-        fir_ccf_ring_kernel<<<g, TB, sizeof(float) * h->ntaps2, h->stream>>>(
-            static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
-            static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-            h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap);
-        h->launches++;
+    // The call is cut into nsub time slices.  Per slice the parallel stages (decimating FIR, channel filter,
+    // demod + RRC) run on the caller's stream; the sequential loop stage of slice i runs on s_loop and the
+    // FEC stage on s_fec, overlapping the parallel stages of slices i+1.. (channels stay independent).
+    CK(cudaEventRecord(h->ev_start, h->stream));
+    CK(cudaStreamWaitEvent(h->s_loop, h->ev_start, 0));
+    CK(cudaStreamWaitEvent(h->s_fec, h->ev_start, 0));
+    if (h->s_par) CK(cudaStreamWaitEvent(h->s_par, h->ev_start, 0));
+    cudaStream_t sp = h->par();
+    int nsub = h->nsub;
+    if (T < 65536L * nsub) nsub = static_cast<int>(std::max<long>(1, T / 65536));
+    const long long k_call0 = h->n1;
+    h->port0_n = 0;
+    for (int i = 0; i < nsub; i++) {
+        const long long t0 = static_cast<long long>(T) * i / nsub, t1 = static_cast<long long>(T) * (i + 1) / nsub;
+        const long long Ti = t1 - t0;
+        const float2* xi = x + t0;
+        // ---- stage 1: decimating FIR; outputs k with D k <= last absolute input index
+        const long long N = h->n_in + Ti;
+        const long long k0 = h->n1;
+        const long long k1 = (N - 1) / h->D1 + 1;
+        cudaEvent_t pe = h->prof_begin(0, sp);
+        int rc = stage1(h, xi, xstride, Ti, k0, k1);
         h->prof_end(pe);
-        pe = h->prof_begin(2);
-        // ---- stage 3: quadrature demod + RRC
-        qdemod_fir_fff_kernel<<<g, TB, sizeof(float) * (2 * h->ntaps3 + TB), h->stream>>>(
-            static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-            static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
-            h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
-        h->launches++;
-        h->prof_end(pe);
-    }
-    // ---- stage 4: symbol sync (+ phase mod + soft bits)
-    {
-        pe = h->prof_begin(3);
-        constexpr int CH = 256;
-        const int blocks = (h->C + 31) / 32;
-        const size_t smem = sizeof(float) * (2 * CH * 32 + 129 * 8);
-        static bool ss_attr = false;
-        if (!ss_attr) {
-            CK(cudaFuncSetAttribute(symsync_kernel<1, SL_RECT4, EPI_4FSK_FM, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ss_attr = true;
+        if (rc) return rc;
+        {
+            dim3 g((h->H + 127) / 128, h->C);
+            hist_update_kernel<<<g, 128, 0, sp>>>(xi, xstride, Ti, h->d_hist[h->hist_cur], h->d_hist[h->hist_cur ^ 1], h->H);
+            h->launches++;
+            h->hist_cur ^= 1;
         }
-        symsync_kernel<1, SL_RECT4, EPI_4FSK_FM, CH><<<blocks, 32, smem, h->stream>>>(
-            h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r4.d), h->r4.mask, h->r4.stride, k1,
-            h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
-            static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride);
+        h->n_in = N; h->n1 = k1;
+        const long long n_new = k1 - k0;
+        h->port0_n += static_cast<long>(n_new);
+        if (n_new > 0) {
+            const int TB = 256;
+            dim3 g(static_cast<unsigned>((n_new + TB - 1) / TB), h->C);
+            // ---- stage 2: channel filter -> ring + port 0
+            pe = h->prof_begin(1, sp);
+            fir_ccf_ring_kernel<<<g, TB, sizeof(float) * h->ntaps2, sp>>>(
+                static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
+                static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0);
+            h->launches++;
+            h->prof_end(pe);
+            // ---- stage 3: quadrature demod + RRC
+            pe = h->prof_begin(2, sp);
+            qdemod_fir_fff_kernel<<<g, TB, sizeof(float) * (2 * h->ntaps3 + TB), sp>>>(
+                static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
+                h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
+            h->launches++;
+            h->prof_end(pe);
+        }
+        CK(cudaEventRecord(h->ev_a[i], sp));
+        // ---- stage 4: symbol sync (+ phase mod + soft bits) on the loop stream
+        CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
+        long long* nsoft_i = h->d_nsoft + static_cast<size_t>(i) * h->C;
+        {
+            pe = h->prof_begin(3, h->s_loop);
+            constexpr int CH = 256, NST = 3, NEPI = 2;
+            const int blocks = (h->C + 31) / 32;
+            const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
+            size_t smem = sizeof(float) * (NST * CH * 32 + 132 * 8 + 2 * maxs * 32) + sizeof(int) * 64;
+            // (asking for >= 176 KB to keep FIR CTAs off the loop CTA's SM was measured: the CTA then waits for
+            //  an SM to drain completely and the step gets slower: 3.2 ms vs 2.3 ms)
+            auto kern = symsync_kernel<1, SL_RECT4, EPI_4FSK_FM, CH, NST, NEPI>;
+            static bool ss_attr = false;
+            if (!ss_attr) {
+                CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                ss_attr = true;
+            }
+            kern<<<blocks, 64 + 32 * NEPI, smem, h->s_loop>>>(
+                h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r4.d), h->r4.mask, h->r4.stride, k1,
+                h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
+                static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i);
+            h->launches++;
+            h->prof_end(pe);
+        }
+        CK(cudaEventRecord(h->ev_b[i], h->s_loop));
+        // ---- stage 5: Viterbi + descrambler on the FEC stream
+        CK(cudaStreamWaitEvent(h->s_fec, h->ev_b[i], 0));
+        pe = h->prof_begin(4, h->s_fec);
+        constexpr int CPB = 4;    // 4 channels (8 warps) per CTA
+        static bool vit_attr = false;
+        if (!vit_attr) {
+            CK(cudaFuncSetAttribute(viterbi_k7_kernel<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+            vit_attr = true;
+        }
+        viterbi_k7_kernel<CPB><<<(h->C + CPB - 1) / CPB, 64 * CPB, 0, h->s_fec>>>(h->d_vs, nsoft_i, h->C,
+            static_cast<const unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride,
+            h->d_port2, h->port2_cap, h->d_port2_cnt, static_cast<int>(h->port2_cap));
         h->launches++;
         h->prof_end(pe);
     }
-    // ---- stage 5: Viterbi + descrambler
-    pe = h->prof_begin(4);
-    viterbi_k7_kernel<<<h->C, 32, 0, h->stream>>>(h->d_vs, h->d_ss, h->C,
-        static_cast<const unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride,
-        h->d_port2, h->port2_cap, h->d_port2_cnt, static_cast<int>(h->port2_cap));
-    h->launches++;
-    h->prof_end(pe);
+    CK(cudaEventRecord(h->ev_loop_done, h->s_loop));
+    CK(cudaEventRecord(h->ev_fec_done, h->s_fec));
+    if (h->s_par) { CK(cudaEventRecord(h->ev_par_done, h->s_par)); CK(cudaStreamWaitEvent(h->stream, h->ev_par_done, 0)); }
+    CK(cudaStreamWaitEvent(h->stream, h->ev_loop_done, 0));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_fec_done, 0));
     CK(cudaGetLastError());
     return QRL_OK;
 }
@@ -530,6 +654,13 @@ int qrl_rx_read_port(qrl_rx* h, int port, void* dst, long cap, int* counts, int 
 }
 
 long qrl_rx_launch_count(const qrl_rx* h) { return h ? h->launches : 0; }
+int qrl_rx_sm_partition(const qrl_rx* h, int* loop_sms, int* parallel_sms)
+{
+    if (!h) return QRL_EINVAL;
+    if (loop_sms) *loop_sms = h->sm_loop;
+    if (parallel_sms) *parallel_sms = h->sm_par;
+    return QRL_OK;
+}
 
 // ---------------------------------------------------------------------------------------------- TX (next milestone)
 struct qrl_tx : HandleBase {};

@@ -333,7 +333,7 @@ constexpr int kMaxTapsSmem = 4096;
 __global__ void fir_ccf_ring_kernel(const float2* __restrict__ in, unsigned in_mask, long long in_stride,
                                     float2* __restrict__ out, unsigned out_mask, long long out_stride,
                                     const float* __restrict__ taps, int ntaps, long long a0, long long a1,
-                                    float2* __restrict__ lin, long long lin_stride)
+                                    float2* __restrict__ lin, long long lin_stride, long long lin_base)
 {
     extern __shared__ float hs_dyn[];
     for (int i = threadIdx.x; i < ntaps; i += blockDim.x) hs_dyn[i] = taps[i];
@@ -350,7 +350,7 @@ __global__ void fir_ccf_ring_kernel(const float2* __restrict__ in, unsigned in_m
     }
     const float2 y = make_float2(re, im);
     out[static_cast<long long>(c) * out_stride + (a & out_mask)] = y;
-    if (lin) lin[static_cast<long long>(c) * lin_stride + (a - a0)] = y;
+    if (lin) lin[static_cast<long long>(c) * lin_stride + (a - lin_base)] = y;
 }
 
 // quadrature_demod_cf fused in front of a real FIR (RRC shaping filter): in = complex ring, out = float ring.
@@ -421,6 +421,7 @@ struct SymSyncParams {
     float pm_sens, soft_scale;
     float costas_alpha, costas_beta;
     float rot_r, rot_i;
+    float fl0; int n0;           // n0 = floor(min_period - |alpha|) as float / int (fast floor window)
 };
 
 __device__ __forceinline__ void qrl_slice(int slicer, float re, float im, float& dr, float& di)
@@ -470,160 +471,243 @@ __device__ __forceinline__ void qrl_costas_step(LoopState& st, float alpha, floa
 
 // exact threshold form of constellation_rect's floor(re + 2.0f) sector search (float addition rounds to nearest
 // even, so fl(re+2) >= 1,2,3  <=>  re >= -1, -2^-24, 1-2^-23; checked in tests/test_host_logic.py)
+__device__ __forceinline__ float qrl_ge1(float a, float b)     // (a >= b) ? 1.0f : 0.0f in one FSET, no predicate
+{
+    float r;
+    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 __device__ __forceinline__ float qrl_slice_rect4(float re)
 {
-    return re >= 0.99999988079071044921875f ? 1.5f : (re >= -5.9604644775390625e-8f ? 0.5f : (re >= -1.0f ? -0.5f : -1.5f));
+    // -1.5 + [re >= -1] + [re >= -2^-24] + [re >= 1 - 2^-23]  (all partial sums exact)
+    return ((-1.5f + qrl_ge1(re, -1.0f)) + qrl_ge1(re, -5.9604644775390625e-8f)) + qrl_ge1(re, 0.99999988079071044921875f);
+}
+// clip for non-NaN arguments: two FMNMX instead of compare + select
+__device__ __forceinline__ float qrl_clip1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // Input ring layout: [group = channel / 32][slot][32 lanes][NCOMP] -- a time step of one warp's 32 channels is one
-// contiguous 128*NCOMP-byte row, so a CH-row window is ONE contiguous block: fetched with cp.async.bulk (TMA 1-D),
-// double buffered, while every lane reads column `lane` (bank = lane: conflict-free).
-template <int NCOMP, int SLICER, int EPI, int CH>
-__global__ void __launch_bounds__(32)
+// contiguous 128*NCOMP-byte row, so a CH-row window is ONE contiguous block fetched with cp.async.bulk (TMA 1-D).
+// Warp-specialised CTA (one CTA per 32 channels):
+//   warp 1 (lane 0) : TMA producer, NST-stage ring of CH-row windows (mbarrier full/free)
+//   warp 0          : ONLY the loop-carried recurrence (interpolate -> TED -> PI loop -> next position); every lane
+//                     reads column `lane` of the window (bank = lane: conflict-free)
+//   warps 2..       : everything that does not feed back (phase modulator / 2nd Costas loop, soft bits, stores),
+//                     fed through a double-buffered shared-memory symbol hand-off (mbarrier full/empty)
+template <int NCOMP, int SLICER, int EPI, int CH, int NST, int NEPI>
+__global__ void __launch_bounds__(64 + 32 * NEPI)
 symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                const float* __restrict__ in, unsigned in_mask, long long in_stride /*slots per group*/, long long avail_total,
                float2* __restrict__ port1, long long port1_stride, int* __restrict__ port1_cnt, int port1_cap,
-               unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride)
+               unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride, int maxs,
+               long long* __restrict__ n_soft_out /* [C] snapshot of the soft-bit write index after this launch */)
 {
+    static_assert(EPI != EPI_QPSK || NEPI == 1, "the QPSK epilogue carries loop state: one epilogue warp");
     constexpr int ROWF = 32 * NCOMP;                    // floats per row
     constexpr int STRIDE = CH - 32;                     // window advance per chunk (lookahead <= 32)
-    extern __shared__ __align__(128) float sm_sync[];   // [2][CH][ROWF] + mmse table
-    __shared__ __align__(8) uint64_t bars[2];
+    extern __shared__ __align__(128) float sm_sync[];   // [NST][CH][ROWF] | mmse[129*8] | sym[2][maxs][ROWF] | cnt[2][32]
+    __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[2], bar_empty[2];
     float* stage0 = sm_sync;
-    float* mm = sm_sync + 2 * CH * ROWF;                // 129 * 8 floats
-    const int lane = threadIdx.x;
+    float* mm = sm_sync + NST * CH * ROWF;
+    float* symbuf = mm + 132 * 8;
+    int* cntbuf = reinterpret_cast<int*>(symbuf + 2 * maxs * ROWF);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
     const int c = g * 32 + lane;
     const bool active = c < C;
-    for (int i = lane; i < 129 * 8; i += 32) mm[i] = d_mmse_tab[i];
-    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
-    __syncwarp();
+    // tap-major copy of the MMSE bank: mm[k * 132 + imu] (a lane's 8 taps are 8 scalar loads in the order the
+    // oldest-first FMA chain consumes them; random imu across lanes spreads over all 32 banks)
+    for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) mm[(i & 7) * 132 + (i >> 3)] = d_mmse_tab[i];
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NST; b++) { mbar_init(&bar_in[b], 1); mbar_init(&bar_free[b], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&bar_full[b], 1); mbar_init(&bar_empty[b], NEPI); }
+        mbar_fence_init();
+    }
+    __syncthreads();
 
-    SymSyncState st;
-    if (active) st = states[c];
-    else { st.ii = 0x7fffffffffffffffLL; }
-    int p1cnt = active ? port1_cnt[c] : 0;
-    long long base = st.ii;
+    // every warp derives the same chunk schedule from the (uniform) minimum read position
+    long long my_ii = active ? states[c].ii : 0x7fffffffffffffffLL;
+    long long base = my_ii;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
         const long long o = __shfl_xor_sync(0xffffffffu, base, off);
         base = o < base ? o : base;
     }
-    const float* ring = in + static_cast<long long>(g) * in_stride * ROWF;
-    const long long cap = static_cast<long long>(in_mask) + 1;
+    if (warp == 2 && active) n_soft_out[c] = states[c].n_soft;
+    if (base + p.lookahead > avail_total) return;
+    const int nchunks = static_cast<int>((avail_total - p.lookahead - base) / STRIDE) + 1;
 
-    auto issue = [&](int m) {           // lane 0: fetch rows [base + m*STRIDE, +CH) into buffer m & 1
-        const long long w0 = base + static_cast<long long>(m) * STRIDE;
-        float* dst = stage0 + (m & 1) * CH * ROWF;
-        const long long s0 = w0 & in_mask;
-        const long long first = (s0 + CH <= cap) ? CH : (cap - s0);
-        fence_proxy_async();
-        mbar_expect_tx(&bars[m & 1], CH * ROWF * 4);
-        bulk_g2s(dst, ring + s0 * ROWF, static_cast<uint32_t>(first * ROWF * 4), &bars[m & 1]);
-        if (first < CH) bulk_g2s(dst + first * ROWF, ring, static_cast<uint32_t>((CH - first) * ROWF * 4), &bars[m & 1]);
-    };
-
-    unsigned char* sr = soft_ring + static_cast<long long>(c) * soft_stride;
-    float2* p1 = port1 + static_cast<long long>(c) * port1_stride;
-    if (base + p.lookahead <= avail_total) {
-        if (lane == 0) issue(0);
-        for (int m = 0;; m++) {
+    if (warp == 1) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const float* ring = in + static_cast<long long>(g) * in_stride * ROWF;
+            const long long cap = static_cast<long long>(in_mask) + 1;
+            for (int m = 0; m < nchunks; m++) {
+                const int st = m % NST, u = m / NST;
+                if (u > 0) mbar_wait(&bar_free[st], (u - 1) & 1);
+                const long long w0 = base + static_cast<long long>(m) * STRIDE;
+                float* dst = stage0 + st * CH * ROWF;
+                const long long s0 = w0 & in_mask;
+                const long long first = (s0 + CH <= cap) ? CH : (cap - s0);
+                fence_proxy_async();
+                mbar_expect_tx(&bar_in[st], CH * ROWF * 4);
+                bulk_g2s(dst, ring + s0 * ROWF, static_cast<uint32_t>(first * ROWF * 4), &bar_in[st]);
+                if (first < CH) bulk_g2s(dst + first * ROWF, ring, static_cast<uint32_t>((CH - first) * ROWF * 4), &bar_in[st]);
+            }
+        }
+    } else if (warp == 0) {
+        // ------------------------------------------------------------------ loop warp
+        float avg_period = 0, inst_period = 0, mu = 0, x0 = 0, x1 = 0, x2 = 0, y0i = 0, y1i = 0, y2i = 0;
+        float d0 = 0, d1 = 0, d2 = 0, e0 = 0, e1 = 0, e2 = 0;
+        if (active) {
+            const SymSyncState& st = states[c];
+            avg_period = st.avg_period; inst_period = st.inst_period; mu = st.mu;
+            x0 = st.xr[0]; x1 = st.xr[1]; x2 = st.xr[2]; y0i = st.xi[0]; y1i = st.xi[1]; y2i = st.xi[2];
+            d0 = st.dr[0]; d1 = st.dr[1]; d2 = st.dr[2]; e0 = st.di[0]; e1 = st.di[1]; e2 = st.di[2];
+        }
+        int o = 0;                                         // my read position relative to the current window
+        {
+            const long long d = my_ii - base;
+            o = d > 0x3fffffff ? 0x3fffffff : static_cast<int>(d);
+        }
+        const int la = p.lookahead;
+        // loop constants in registers (a constant-bank load inside the recurrence would sit on the critical path)
+        const float k_alpha = p.alpha, k_beta = p.beta, k_maxp = p.max_period, k_minp = p.min_period;
+        const float k_f0 = p.fl0, k_f1 = p.fl0 + 1.0f, k_f2 = p.fl0 + 2.0f, k_f3 = p.fl0 + 3.0f;
+        const int k_n0 = p.n0;
+        for (int m = 0; m < nchunks; m++) {
+            const int st = m % NST, b = m & 1;
+            if (m >= 2) mbar_wait(&bar_empty[b], ((m >> 1) - 1) & 1);    // epilogue released this hand-off buffer
+            mbar_wait(&bar_in[st], (m / NST) & 1);
+            const float* buf = stage0 + st * CH * ROWF + lane * NCOMP;
+            float* sy = symbuf + b * maxs * ROWF + lane * NCOMP;
             const long long w0 = base + static_cast<long long>(m) * STRIDE;
-            const bool more = (w0 + STRIDE + p.lookahead <= avail_total);
-            if (more && lane == 0) issue(m + 1);
-            mbar_wait(&bars[m & 1], (m >> 1) & 1);
-            const float* buf = stage0 + (m & 1) * CH * ROWF + lane * NCOMP;
-            const long long wend = (w0 + CH < avail_total) ? (w0 + CH) : avail_total;
+            const long long rem = avail_total - w0;
+            const int wlen = rem < CH ? static_cast<int>(rem) : CH;
+            int cnt = 0;
             if (active) {
-                while (st.ii + p.lookahead <= wend) {
-                    const float* x = buf + (st.ii - w0) * ROWF;
-                    const int imu = static_cast<int>(rintf(st.mu * 128.0f));
-                    const float4 t0 = *reinterpret_cast<const float4*>(mm + imu * 8);
-                    const float4 t1 = *reinterpret_cast<const float4*>(mm + imu * 8 + 4);
+                while (o + la <= wlen) {
+                    const float* x = buf + o * ROWF;
+                    // rintf(mu*128) without a conversion unit: adding 1.5*2^23 rounds to nearest-even at integer
+                    // granularity (same as rintf for 0 <= v < 2^22); the integer sits in the low mantissa bits
+                    const int imu = __float_as_int((mu * 128.0f) + 12582912.0f) & 0x3ff;
+                    const float* tp = mm + imu;
                     // 8-tap MMSE interpolation, oldest sample first: taps[7], taps[6], ...
-                    float yr, yi = 0.0f;
-                    yr = fmaf(t1.w, x[0 * ROWF], 0.0f);
-                    yr = fmaf(t1.z, x[1 * ROWF], yr);
-                    yr = fmaf(t1.y, x[2 * ROWF], yr);
-                    yr = fmaf(t1.x, x[3 * ROWF], yr);
-                    yr = fmaf(t0.w, x[4 * ROWF], yr);
-                    yr = fmaf(t0.z, x[5 * ROWF], yr);
-                    yr = fmaf(t0.y, x[6 * ROWF], yr);
-                    yr = fmaf(t0.x, x[7 * ROWF], yr);
-                    if (NCOMP == 2) {
-                        yi = fmaf(t1.w, x[0 * ROWF + 1], 0.0f);
-                        yi = fmaf(t1.z, x[1 * ROWF + 1], yi);
-                        yi = fmaf(t1.y, x[2 * ROWF + 1], yi);
-                        yi = fmaf(t1.x, x[3 * ROWF + 1], yi);
-                        yi = fmaf(t0.w, x[4 * ROWF + 1], yi);
-                        yi = fmaf(t0.z, x[5 * ROWF + 1], yi);
-                        yi = fmaf(t0.y, x[6 * ROWF + 1], yi);
-                        yi = fmaf(t0.x, x[7 * ROWF + 1], yi);
+                    float yr = 0.0f, yi = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float tt = tp[(7 - i) * 132];
+                        yr = fmaf(tt, x[i * ROWF], yr);
+                        if (NCOMP == 2) yi = fmaf(tt, x[i * ROWF + 1], yi);
                     }
-                    st.xr[2] = st.xr[1]; st.xr[1] = st.xr[0]; st.xr[0] = yr;
-                    st.xi[2] = st.xi[1]; st.xi[1] = st.xi[0]; st.xi[0] = yi;
-                    st.dr[2] = st.dr[1]; st.dr[1] = st.dr[0];
-                    st.di[2] = st.di[1]; st.di[1] = st.di[0];
-                    if (SLICER == SL_RECT4) { st.dr[0] = qrl_slice_rect4(yr); st.di[0] = 0.0f; }
-                    else qrl_slice(SLICER, yr, yi, st.dr[0], st.di[0]);
+                    x2 = x1; x1 = x0; x0 = yr;
+                    y2i = y1i; y1i = y0i; y0i = yi;
+                    d2 = d1; d1 = d0; e2 = e1; e1 = e0;
+                    if (SLICER == SL_RECT4) { d0 = qrl_slice_rect4(yr); e0 = 0.0f; }
+                    else qrl_slice(SLICER, yr, yi, d0, e0);
                     float err;
                     if (NCOMP == 2) {
-                        const float ar = st.xr[0] - st.xr[2], ai = st.xi[0] - st.xi[2];
-                        const float br = st.dr[0] - st.dr[2], bi = st.di[0] - st.di[2];
-                        const float u = (ar * st.dr[1] + ai * st.di[1]) - (br * st.xr[1] + bi * st.xi[1]);
-                        err = qrl_clip(u, 1.0f);
+                        const float ar = x0 - x2, ai = y0i - y2i;
+                        const float br = d0 - d2, bi = e0 - e2;
+                        const float u = (ar * d1 + ai * e1) - (br * x1 + bi * y1i);
+                        err = qrl_clip1(u);
                     } else {
-                        const float u = (st.xr[0] - st.xr[2]) * st.dr[1] - (st.dr[0] - st.dr[2]) * st.xr[1];
-                        err = qrl_clip(u / 2.0f, 1.0f);
+                        const float u = (x0 - x2) * d1 - (d0 - d2) * x1;
+                        err = qrl_clip1(u * 0.5f);
                     }
-                    st.avg_period = st.avg_period + p.beta * err;
-                    if (st.avg_period > p.max_period) st.avg_period = p.max_period;
-                    else if (st.avg_period < p.min_period) st.avg_period = p.min_period;
-                    st.inst_period = st.avg_period + p.alpha * err;
-                    if (st.inst_period <= 0.0f) st.inst_period = st.avg_period;
-                    const float ph = st.mu + st.inst_period;
-                    const float fl = floorf(ph);
-                    st.mu = ph - fl;
-                    st.ii += static_cast<int>(fl);
-
-                    // ---- epilogue (off the loop-carried path)
-                    float o_r, o_i;
-                    unsigned char sb0, sb1;
-                    if (EPI == EPI_4FSK_FM) {
-                        const float phs = p.pm_sens * yr;
-                        float sn, cs;
-                        qrl_sincosf(phs, sn, cs);
-                        o_r = cs; o_i = sn;
-                        sb0 = qrl_soft_u8(sn, p.soft_scale);       // interleave: imag first, then real
-                        sb1 = qrl_soft_u8(cs, p.soft_scale);
-                    } else if (EPI == EPI_CPLX) {
-                        o_r = yr; o_i = yi;
-                        sb0 = qrl_soft_u8(yr, p.soft_scale);
-                        sb1 = qrl_soft_u8(yi, p.soft_scale);
-                    } else {
-                        float cr, ci;
-                        qrl_costas_step(st.costas, p.costas_alpha, p.costas_beta, 4, true, yr, yi, cr, ci);
-                        const float dr = cr * st.dp_r + ci * st.dp_i;
-                        const float di = ci * st.dp_r - cr * st.dp_i;
-                        st.dp_r = cr; st.dp_i = ci;
-                        o_r = dr * p.rot_r - di * p.rot_i;
-                        o_i = dr * p.rot_i + di * p.rot_r;
-                        sb0 = qrl_soft_u8(o_r, p.soft_scale);
-                        sb1 = qrl_soft_u8(o_i, p.soft_scale);
-                    }
-                    if (p1cnt < port1_cap) p1[p1cnt] = make_float2(o_r, o_i);
-                    p1cnt++;
-                    sr[st.n_soft & soft_mask] = sb0;
-                    sr[(st.n_soft + 1) & soft_mask] = sb1;
-                    st.n_soft += 2;
-                    st.n_sym += 1;
+                    avg_period = avg_period + k_beta * err;
+                    avg_period = fminf(fmaxf(avg_period, k_minp), k_maxp);   // == the two-sided clamp (no NaNs here)
+                    inst_period = avg_period + k_alpha * err;
+                    inst_period = inst_period <= 0.0f ? avg_period : inst_period;
+                    const float ph = mu + inst_period;
+                    // floorf(ph): in lock ph lies in [n0, n0+3) (n0 = floor(min_period - |alpha|)): two compares and
+                    // selects replace FRND/F2I on the loop-carried path; anything else takes the generic route
+                    const bool g1 = ph >= k_f1, g2 = ph >= k_f2;
+                    float fl = g2 ? k_f2 : (g1 ? k_f1 : k_f0);
+                    int step = k_n0 + (g1 ? 1 : 0) + (g2 ? 1 : 0);
+                    if (__builtin_expect(!(ph >= k_f0 && ph < k_f3), 0)) { fl = floorf(ph); step = static_cast<int>(fl); }
+                    mu = ph - fl;
+                    o += step;
+                    sy[cnt * ROWF] = yr;
+                    if (NCOMP == 2) sy[cnt * ROWF + 1] = yi;
+                    cnt++;
                 }
             }
+            o -= STRIDE;                                   // next window starts STRIDE rows later
+            cntbuf[b * 32 + lane] = cnt;
             __syncwarp();
-            if (!more) break;
+            if (lane == 0) { mbar_arrive(&bar_free[st]); mbar_arrive(&bar_full[b]); }
+        }
+        if (active) {
+            SymSyncState& st = states[c];
+            st.ii = base + static_cast<long long>(nchunks) * STRIDE + o;
+            st.avg_period = avg_period; st.inst_period = inst_period; st.mu = mu;
+            st.xr[0] = x0; st.xr[1] = x1; st.xr[2] = x2; st.xi[0] = y0i; st.xi[1] = y1i; st.xi[2] = y2i;
+            st.dr[0] = d0; st.dr[1] = d1; st.dr[2] = d2; st.di[0] = e0; st.di[1] = e1; st.di[2] = e2;
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue warps
+        const int e = warp - 2;
+        long long n_sym = 0, n_soft = 0; LoopState costas{ 0.0f, 0.0f }; float dp_r = 0, dp_i = 0;
+        int p1cnt = 0;
+        if (active) {
+            const SymSyncState& st = states[c];
+            n_sym = st.n_sym; n_soft = st.n_soft; costas = st.costas; dp_r = st.dp_r; dp_i = st.dp_i;
+            p1cnt = port1_cnt[c];
+        }
+        unsigned char* sr = soft_ring + static_cast<long long>(c) * soft_stride;
+        float2* p1 = port1 + static_cast<long long>(c) * port1_stride;
+        for (int m = 0; m < nchunks; m++) {
+            const int b = m & 1;
+            mbar_wait(&bar_full[b], (m >> 1) & 1);
+            const int n = cntbuf[b * 32 + lane];
+            const float* sy = symbuf + b * maxs * ROWF + lane * NCOMP;
+            for (int s = e; s < n; s += NEPI) {
+                const float yr = sy[s * ROWF];
+                const float yi = (NCOMP == 2) ? sy[s * ROWF + 1] : 0.0f;
+                float o_r, o_i;
+                unsigned char sb0, sb1;
+                if (EPI == EPI_4FSK_FM) {
+                    const float phs = p.pm_sens * yr;
+                    float sn, cs;
+                    qrl_sincosf(phs, sn, cs);
+                    o_r = cs; o_i = sn;
+                    sb0 = qrl_soft_u8(sn, p.soft_scale);       // interleave: imag first, then real
+                    sb1 = qrl_soft_u8(cs, p.soft_scale);
+                } else if (EPI == EPI_CPLX) {
+                    o_r = yr; o_i = yi;
+                    sb0 = qrl_soft_u8(yr, p.soft_scale);
+                    sb1 = qrl_soft_u8(yi, p.soft_scale);
+                } else {
+                    float cr, ci;
+                    qrl_costas_step(costas, p.costas_alpha, p.costas_beta, 4, true, yr, yi, cr, ci);
+                    const float dr = cr * dp_r + ci * dp_i;
+                    const float di = ci * dp_r - cr * dp_i;
+                    dp_r = cr; dp_i = ci;
+                    o_r = dr * p.rot_r - di * p.rot_i;
+                    o_i = dr * p.rot_i + di * p.rot_r;
+                    sb0 = qrl_soft_u8(o_r, p.soft_scale);
+                    sb1 = qrl_soft_u8(o_i, p.soft_scale);
+                }
+                if (p1cnt + s < port1_cap) p1[p1cnt + s] = make_float2(o_r, o_i);
+                sr[(n_soft + 2 * s) & soft_mask] = sb0;
+                sr[(n_soft + 2 * s + 1) & soft_mask] = sb1;
+            }
+            p1cnt += n; n_soft += 2 * n; n_sym += n;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[b]);
+        }
+        if (active && e == 0) {
+            SymSyncState& st = states[c];
+            st.n_sym = n_sym; st.n_soft = n_soft; st.costas = costas; st.dp_r = dp_r; st.dp_i = dp_i;
+            port1_cnt[c] = p1cnt;
+            n_soft_out[c] = n_soft;
         }
     }
-    if (active) { states[c] = st; port1_cnt[c] = p1cnt; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -638,95 +722,145 @@ struct ViterbiState {
     unsigned descr_reg;
 };
 
-__global__ void __launch_bounds__(32)
-viterbi_k7_kernel(ViterbiState* __restrict__ vstates, const SymSyncState* __restrict__ sstates, int C,
+// Two warps per channel: warp 0 runs the add-compare-select recursion (lane i = butterfly i), finds the best end
+// state and walks back the 6 tail steps that fix the next frame's start state, then immediately starts the next
+// frame; warp 1 does the 80-step traceback, descrambling and the stores for the previous frame.  Decisions are
+// double buffered in shared memory (mbarrier full/empty); the next frame's soft symbols are prefetched into
+// registers during the current ACS.
+template <int CPB /* channels per CTA */>
+__global__ void __launch_bounds__(64 * CPB)
+viterbi_k7_kernel(ViterbiState* __restrict__ vstates, const long long* __restrict__ n_soft_avail, int C,
                   const unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride,
                   unsigned char* __restrict__ port2, long long port2_stride, int* __restrict__ port2_cnt, int port2_cap)
 {
-    __shared__ unsigned char syms[176];
-    __shared__ unsigned dec0[86], dec1[86];
-    __shared__ unsigned char obits[80];
-    const int c = blockIdx.x;
-    if (c >= C) return;
-    const int lane = threadIdx.x;
-    ViterbiState vs = vstates[c];
-    const long long avail = sstates[c].n_soft;
-    int cnt = port2_cnt[c];
-    const unsigned char* sr = soft_ring + static_cast<long long>(c) * soft_stride;
-    unsigned char* outp = port2 + static_cast<long long>(c) * port2_stride;
-
-    // Branchtab bits of butterfly `lane`: parity((2*lane) & poly)
-    const unsigned b0 = (__popc((2u * lane) & 109u) & 1u) ? 255u : 0u;
-    const unsigned b1 = (__popc((2u * lane) & 79u) & 1u) ? 255u : 0u;
-
-    while (vs.rd + 160 <= avail) {
-        // frame covers absolute soft indices [rd - 12, rd + 160); indices < 0 are the zero history
-        for (int i = lane; i < 172; i += 32) {
-            const long long a = vs.rd - 12 + i;
-            syms[i] = (a >= 0) ? sr[a & soft_mask] : 0;
-        }
-        __syncwarp();
-        // metrics: lane holds Y[2 lane] (lo 16 bits) and Y[2 lane + 1] (hi 16 bits)
-        unsigned ya = 63, yb = 63;
-        if ((vs.start_state & 63) == 2 * lane) ya = 0;
-        if ((vs.start_state & 63) == 2 * lane + 1) yb = 0;
-        for (int s = 0; s < 86; s++) {
-            const unsigned packed = ya | (yb << 16);
-            const unsigned pa = __shfl_sync(0xffffffffu, packed, lane >> 1);
-            const unsigned pb = __shfl_sync(0xffffffffu, packed, (lane >> 1) + 16);
-            const unsigned xi = (lane & 1) ? (pa >> 16) : (pa & 0xffffu);        // X[lane]
-            const unsigned xj = (lane & 1) ? (pb >> 16) : (pb & 0xffffu);        // X[lane + 32]
-            const unsigned s0 = syms[2 * s], s1 = syms[2 * s + 1];
-            const unsigned metric = (((b0 ^ s0) >> 2) + ((b1 ^ s1) >> 2)) >> 2;
-            const unsigned m0 = xi + metric, m1 = xj + (31u - metric);
-            const unsigned m2 = xi + (31u - metric), m3 = xj + metric;
-            const bool d0 = m0 > m1, d1 = m2 > m3;
-            ya = d0 ? m1 : m0;
-            yb = d1 ? m3 : m2;
-            const unsigned B0 = __ballot_sync(0xffffffffu, d0);
-            const unsigned B1 = __ballot_sync(0xffffffffu, d1);
-            if (lane == 0) { dec0[s] = B0; dec1[s] = B1; }
-        }
-        // best end state: minimum metric, lowest index on ties
-        unsigned key = (ya <= yb) ? ((ya << 6) | (2u * lane)) : ((yb << 6) | (2u * lane + 1u));
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            const unsigned o = __shfl_xor_sync(0xffffffffu, key, off);
-            key = o < key ? o : key;
-        }
-        __syncwarp();
-        if (lane == 0) {
-            unsigned st = key & 63u;
-            int next_start = 0;
-            for (int nb = 79; nb >= 0; nb--) {
-                const int s = nb + 6;
-                const unsigned k = (((st & 1u) ? dec1[s] : dec0[s]) >> (st >> 1)) & 1u;
-                st = (st >> 1) | (k << 5);
-                obits[nb] = static_cast<unsigned char>(k);
-                if (nb == 74) next_start = static_cast<int>(st);
-            }
-            vs.start_state = next_start;
-        }
-        vs.start_state = __shfl_sync(0xffffffffu, vs.start_state, 0);
-        __syncwarp();
-        // descrambler: out[n] = in[n] ^ in[n-1] ^ in[n-5] ^ in[n-7]; reg bit (8-d) holds in[n-d]
-        for (int i = lane; i < 80; i += 32) {
-            auto bit = [&](int n) -> unsigned {
-                return n >= 0 ? obits[n] : ((vs.descr_reg >> (8 + n)) & 1u);
-            };
-            const unsigned o = bit(i) ^ bit(i - 1) ^ bit(i - 5) ^ bit(i - 7);
-            if (cnt + i < port2_cap) outp[cnt + i] = static_cast<unsigned char>(o);
-        }
-        __syncwarp();
-        unsigned reg = 0;
-#pragma unroll
-        for (int d = 1; d <= 8; d++) reg |= static_cast<unsigned>(obits[80 - d]) << (8 - d);
-        vs.descr_reg = reg;
-        cnt += 80;
-        vs.rd += 160;
-        __syncwarp();
+    __shared__ unsigned char syms_all[CPB][2][176];
+    __shared__ unsigned dec0_all[CPB][2][86], dec1_all[CPB][2][86];
+    __shared__ unsigned endst_all[CPB][2];
+    __shared__ unsigned char obits_all[CPB][80];
+    __shared__ __align__(8) uint64_t bar_full_all[CPB][2], bar_empty_all[CPB][2];
+    const int slot = threadIdx.x >> 6;                       // channel slot inside the CTA (2 warps each)
+    const int c = blockIdx.x * CPB + slot;
+    const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 1;
+    unsigned char (*syms)[176] = syms_all[slot];
+    unsigned (*dec0)[86] = dec0_all[slot];
+    unsigned (*dec1)[86] = dec1_all[slot];
+    unsigned* endst = endst_all[slot];
+    unsigned char* obits = obits_all[slot];
+    uint64_t* bar_full = bar_full_all[slot];
+    uint64_t* bar_empty = bar_empty_all[slot];
+    if ((threadIdx.x & 63) == 0) {
+        for (int b = 0; b < 2; b++) { mbar_init(&bar_full[b], 1); mbar_init(&bar_empty[b], 1); }
+        mbar_fence_init();
     }
-    if (lane == 0) { vstates[c] = vs; port2_cnt[c] = cnt; }
+    __syncthreads();
+    if (c >= C) return;
+    const ViterbiState vs0 = vstates[c];
+    const long long avail = n_soft_avail[c];
+    const int nframes = (avail - vs0.rd) >= 160 ? static_cast<int>((avail - vs0.rd) / 160) : 0;
+    if (nframes == 0) return;
+    const unsigned char* sr = soft_ring + static_cast<long long>(c) * soft_stride;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- ACS warp
+        // Branchtab bits of butterfly `lane`: parity((2*lane) & poly)
+        const unsigned b0 = (__popc((2u * lane) & 109u) & 1u) ? 255u : 0u;
+        const unsigned b1 = (__popc((2u * lane) & 79u) & 1u) ? 255u : 0u;
+        int start_state = vs0.start_state;
+        // soft symbols of a frame: absolute indices [rd - 12, rd + 160); each lane carries bytes i = lane + 32 k
+        unsigned char pre[6];
+        auto fetch = [&](long long rd) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const int i = lane + 32 * k;
+                const long long a = rd - 12 + i;
+                pre[k] = (i < 172 && a >= 0) ? sr[a & soft_mask] : 0;
+            }
+        };
+        fetch(vs0.rd);
+        for (int f = 0; f < nframes; f++) {
+            const int b = f & 1;
+#pragma unroll
+            for (int k = 0; k < 6; k++) { const int i = lane + 32 * k; if (i < 172) syms[b][i] = pre[k]; }
+            if (f + 1 < nframes) fetch(vs0.rd + 160LL * (f + 1));      // latency hidden behind this frame's ACS
+            if (f >= 2) mbar_wait(&bar_empty[b], ((f >> 1) - 1) & 1);  // traceback warp released dec[b]
+            __syncwarp();
+            unsigned ya = 63, yb = 63;                                  // Y[2 lane], Y[2 lane + 1]
+            if ((start_state & 63) == 2 * lane) ya = 0;
+            if ((start_state & 63) == 2 * lane + 1) yb = 0;
+            const unsigned char* sy = syms[b];
+#pragma unroll 2
+            for (int s = 0; s < 86; s++) {
+                const unsigned xa0 = __shfl_sync(0xffffffffu, ya, lane >> 1);
+                const unsigned xb0 = __shfl_sync(0xffffffffu, yb, lane >> 1);
+                const unsigned xa1 = __shfl_sync(0xffffffffu, ya, (lane >> 1) + 16);
+                const unsigned xb1 = __shfl_sync(0xffffffffu, yb, (lane >> 1) + 16);
+                const unsigned xi = (lane & 1) ? xb0 : xa0;             // X[lane]
+                const unsigned xj = (lane & 1) ? xb1 : xa1;             // X[lane + 32]
+                const unsigned s0 = sy[2 * s], s1 = sy[2 * s + 1];
+                const unsigned metric = (((b0 ^ s0) >> 2) + ((b1 ^ s1) >> 2)) >> 2;
+                const unsigned m0 = xi + metric, m1 = xj + (31u - metric);
+                const unsigned m2 = xi + (31u - metric), m3 = xj + metric;
+                const bool d0 = m0 > m1, d1 = m2 > m3;
+                ya = d0 ? m1 : m0;
+                yb = d1 ? m3 : m2;
+                const unsigned B0 = __ballot_sync(0xffffffffu, d0);
+                const unsigned B1 = __ballot_sync(0xffffffffu, d1);
+                if (lane == 0) { dec0[b][s] = B0; dec1[b][s] = B1; }
+            }
+            // best end state: minimum metric, lowest index on ties
+            unsigned key = (ya <= yb) ? ((ya << 6) | (2u * lane)) : ((yb << 6) | (2u * lane + 1u));
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const unsigned o = __shfl_xor_sync(0xffffffffu, key, off);
+                key = o < key ? o : key;
+            }
+            __syncwarp();
+            // the first 6 traceback steps (bits 79..74) give the state the next frame starts from
+            unsigned st = key & 63u;
+#pragma unroll
+            for (int nb = 79; nb >= 74; nb--) {
+                const int s = nb + 6;
+                const unsigned k = (((st & 1u) ? dec1[b][s] : dec0[b][s]) >> (st >> 1)) & 1u;
+                st = (st >> 1) | (k << 5);
+            }
+            start_state = static_cast<int>(st);
+            if (lane == 0) { endst[b] = key & 63u; mbar_arrive(&bar_full[b]); }
+        }
+        if (lane == 0) { vstates[c].start_state = start_state; vstates[c].rd = vs0.rd + 160LL * nframes; }
+    } else {
+        // ---------------------------------------------------------------- traceback / output warp
+        unsigned descr_reg = vs0.descr_reg;
+        int cnt = port2_cnt[c];
+        unsigned char* outp = port2 + static_cast<long long>(c) * port2_stride;
+        for (int f = 0; f < nframes; f++) {
+            const int b = f & 1;
+            mbar_wait(&bar_full[b], (f >> 1) & 1);
+            if (lane == 0) {
+                unsigned st = endst[b];
+                for (int nb = 79; nb >= 0; nb--) {
+                    const int s = nb + 6;
+                    const unsigned k = (((st & 1u) ? dec1[b][s] : dec0[b][s]) >> (st >> 1)) & 1u;
+                    st = (st >> 1) | (k << 5);
+                    obits[nb] = static_cast<unsigned char>(k);
+                }
+                mbar_arrive(&bar_empty[b]);
+            }
+            __syncwarp();
+            // descrambler: out[n] = in[n] ^ in[n-1] ^ in[n-5] ^ in[n-7]; reg bit (8-d) holds in[n-d]
+            for (int i = lane; i < 80; i += 32) {
+                auto bit = [&](int n) -> unsigned { return n >= 0 ? obits[n] : ((descr_reg >> (8 + n)) & 1u); };
+                const unsigned o = bit(i) ^ bit(i - 1) ^ bit(i - 5) ^ bit(i - 7);
+                if (cnt + i < port2_cap) outp[cnt + i] = static_cast<unsigned char>(o);
+            }
+            unsigned reg = 0;
+#pragma unroll
+            for (int d = 1; d <= 8; d++) reg |= static_cast<unsigned>(obits[80 - d]) << (8 - d);
+            descr_reg = reg;
+            cnt += 80;
+            __syncwarp();
+        }
+        if (lane == 0) { vstates[c].descr_reg = descr_reg; port2_cnt[c] = cnt; }
+    }
 }
 
 // roll the stage-1 history: new_hist = last H samples of (old_hist ++ iq[0..T))

@@ -38,6 +38,7 @@ SYMBOLS = {
     "qrl_rx_read_port": (_i, [_vp, _i, _vp, _l, _vp, _i]),
     "qrl_rx_port_device": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_l), C.POINTER(_vp)]),
     "qrl_rx_launch_count": (_l, [_vp]),
+    "qrl_rx_sm_partition": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
     "qrl_rx_profile": (_i, [_vp, _i]),
     "qrl_rx_profile_read": (_i, [_vp, _i, C.POINTER(_d), C.POINTER(_l)]),
     "qrl_tx_create": (_i, [_i] * 7 + [_l, _i, C.POINTER(_vp)]),
