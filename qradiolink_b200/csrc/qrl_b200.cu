@@ -121,6 +121,12 @@ struct qrl_rx : HandleBase {
     // stage 3: quadrature demod + RRC (4FSK-FM)
     float* d_taps3 = nullptr; int ntaps3 = 0; float qd_gain = 0;
     Ring r4;
+    // PSK chains: agc2 + costas "PLL" loop stage (per sample), output ring r3 (interleaved)
+    AgcCostasParams acp{};
+    AgcCostasState* d_ac = nullptr;
+    Ring r3;
+    int sym_sps = 0;
+    std::vector<std::pair<void*, size_t>> zero_list;   // buffers qrl_rx_reset clears
     // symbol sync
     SymSyncParams ssp{};
     SymSyncState* d_ss = nullptr;
@@ -132,8 +138,9 @@ struct qrl_rx : HandleBase {
     // software pipeline inside one work() call: parallel stages on `stream`, loop stages on s_loop, FEC on s_fec
     static constexpr int kMaxSub = 16;
     int nsub = 8;
-    cudaStream_t s_loop = nullptr, s_fec = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_a[kMaxSub] = { nullptr }, ev_b[kMaxSub] = { nullptr }, ev_loop_done = nullptr, ev_fec_done = nullptr;
+    cudaStream_t s_loop = nullptr, s_loop2 = nullptr, s_fec = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_a[kMaxSub] = { nullptr }, ev_b[kMaxSub] = { nullptr }, ev_c[kMaxSub] = { nullptr },
+                ev_loop_done = nullptr, ev_loop2_done = nullptr, ev_fec_done = nullptr;
     long long* d_nsoft = nullptr;   // [kMaxSub][C] soft-bit write index snapshots
     // static SM partition (CUDA green contexts): the sequential loop / FEC kernels get a small private set of SMs so
     // their single dependent instruction streams never arbitrate with the FMA-bound FIR warps; the parallel stages
@@ -243,23 +250,28 @@ bool make_sm_partition(qrl_rx* h, unsigned loop_sms, int prio)
     if (pDesc(&d_loop, &grp, 1) != CUDA_SUCCESS || pDesc(&d_par, &rest, 1) != CUDA_SUCCESS) return false;
     if (pCreate(&h->g_loop, d_loop, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
     if (pCreate(&h->g_par, d_par, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
-    CUstream a = nullptr, b = nullptr, c = nullptr;
+    CUstream a = nullptr, b = nullptr, c = nullptr, d = nullptr;
     if (pStream(&a, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
     if (pStream(&b, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
+    if (pStream(&d, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
     if (pStream(&c, h->g_par, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
-    h->s_loop = a; h->s_fec = b; h->s_par = c;
+    h->s_loop = a; h->s_fec = b; h->s_par = c; h->s_loop2 = d;
     h->sm_loop = static_cast<int>(grp.sm.smCount); h->sm_par = static_cast<int>(rest.sm.smCount);
     return true;
 }
 
-int make_ring(qrl_rx* h, Ring* r, size_t isz, long long min_items)
+// interleaved = channel-interleaved layout [ceil(C/32)][slots][32] (allocated for the padded channel count)
+int make_ring(qrl_rx* h, Ring* r, size_t isz, long long min_items, bool interleaved = false)
 {
     unsigned cap = pow2_at_least(min_items);
     r->mask = cap - 1;
     r->stride = cap;
     unsigned char* p = nullptr;
-    int rc = dev_alloc(h, &p, static_cast<size_t>(cap) * isz * h->C, true);
+    const size_t nch = interleaved ? static_cast<size_t>((h->C + 31) / 32) * 32 : static_cast<size_t>(h->C);
+    const size_t bytes = static_cast<size_t>(cap) * isz * nch;
+    int rc = dev_alloc(h, &p, bytes, true);
     r->d = p;
+    if (!rc) h->zero_list.emplace_back(p, bytes);
     return rc;
 }
 
@@ -324,10 +336,35 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         h->ssp.n0 = static_cast<int>(floorf(h->ssp.min_period - fabsf(h->ssp.alpha)));
         h->ssp.fl0 = static_cast<float>(h->ssp.n0);
         h->nports = 3;
+    } else if (kind == QRL_DEMOD_QPSK) {
+        // gr_demod_qpsk.cpp:46-71 (sps ladder), :98-103 (resampler), :106-110 (RRC), :104,113-118 (agc, sync, costas)
+        if (sps > 4) { set_err(h, "QPSK 2k/20k (FLL band-edge) variants not built yet"); return fail(QRL_EINVAL); }
+        const int decimation = 2; sym_sps = sps; tsr = 500000;
+        const float costas_bw = static_cast<float>(kPi / 400);
+        taps1 = low_pass_2(1, static_cast<double>(samp_rate), tsr / 2, tsr / 10, 60, WIN_BLACKMAN_HARRIS);
+        h->D1 = decimation;
+        taps2 = root_raised_cosine(sym_sps, sym_sps, 1, 0.35, 11 * sym_sps);
+        h->acp.attack = 1.0f; h->acp.decay = 1e-1f; h->acp.ref = 1.0f; h->acp.max_gain = 65536.0f;
+        control_loop_gains(static_cast<float>(kPi / 200 / sym_sps), h->acp.alpha, h->acp.beta);
+        h->acp.order = 4; h->acp.use_snr = 1;
+        const float symbol_rate = static_cast<float>(tsr) / static_cast<float>(sym_sps);
+        const float sps_dev = 200.0f / symbol_rate;
+        clock_loop_gains(static_cast<float>(2 * kPi / (symbol_rate / 10)), 1.0f, 0.2869f, h->ssp.alpha, h->ssp.beta);
+        h->ssp.sps = static_cast<float>(sym_sps);
+        h->ssp.max_period = h->ssp.sps + sps_dev; h->ssp.min_period = h->ssp.sps - sps_dev;
+        h->ssp.lookahead = 8 + static_cast<int>(ceilf(h->ssp.max_period)) + 1;
+        control_loop_gains(costas_bw, h->ssp.costas_alpha, h->ssp.costas_beta);
+        const float th = static_cast<float>(-3 * kPi / 4);
+        h->ssp.rot_r = cosf(th); h->ssp.rot_i = sinf(th);
+        h->ssp.soft_scale = 48.0f;
+        h->ssp.n0 = static_cast<int>(floorf(h->ssp.min_period - fabsf(h->ssp.alpha)));
+        h->ssp.fl0 = static_cast<float>(h->ssp.n0);
+        h->nports = 3;
     } else {
         set_err(h, "qrl_rx_create: demod kind " + std::to_string(kind) + " not built");
         return fail(QRL_EINVAL);
     }
+    h->sym_sps = sym_sps;
 
     // ---- stage 1 buffers
     h->ntaps1 = static_cast<int>(taps1.size());
@@ -344,15 +381,15 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     h->ntaps2 = static_cast<int>(taps2.size());
     h->ntaps3 = static_cast<int>(taps3.size());
     if ((rc = upload_floats(h, &h->d_taps2, taps2))) return fail(rc);
-    if ((rc = upload_floats(h, &h->d_taps3, taps3))) return fail(rc);
+    if (!taps3.empty() && (rc = upload_floats(h, &h->d_taps3, taps3))) return fail(rc);
     if ((rc = make_ring(h, &h->r1, sizeof(float2), h->n1max + h->ntaps2 + 8))) return fail(rc);
-    if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + h->ntaps3 + 8))) return fail(rc);
-    // r4 is channel-interleaved: [ceil(C/32)][slots][32]; allocate for the padded channel count
-    {
-        const int Csave = h->C; h->C = ((Csave + 31) / 32) * 32;
-        rc = make_ring(h, &h->r4, sizeof(float), h->n1max + 600);
-        h->C = Csave;
-        if (rc) return fail(rc);
+    if (kind == QRL_DEMOD_4FSK) {
+        if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + h->ntaps3 + 8))) return fail(rc);
+        if ((rc = make_ring(h, &h->r4, sizeof(float), h->n1max + 600, true))) return fail(rc);
+    } else {   // QPSK: shaping-filter output and loop output are channel-interleaved complex rings
+        if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + 600, true))) return fail(rc);
+        if ((rc = make_ring(h, &h->r3, sizeof(float2), h->n1max + 600, true))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_ac, h->C))) return fail(rc);
     }
     if ((rc = make_ring(h, &h->r5, 1, 2 * h->n1max + 1024))) return fail(rc);
     h->port0_cap = h->n1max;
@@ -370,16 +407,22 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         bool ok = true;
-        if (!make_sm_partition(h, 8, hi)) {
+        // loop partition: one SM per big-shared-memory loop CTA (4FSK: symbol sync; QPSK: agc/costas + symbol sync)
+        const int groups = (h->C + 31) / 32;
+        const int big_ctas = (kind == QRL_DEMOD_QPSK) ? 2 * groups : groups;
+        unsigned loop_sms = static_cast<unsigned>(std::min(48, 8 * ((big_ctas + 4 + 7) / 8)));
+        if (!make_sm_partition(h, loop_sms, hi)) {
             h->s_par = nullptr; h->sm_loop = 0; h->sm_par = 0;
             if (h->s_loop == nullptr)
                 ok = cudaStreamCreateWithPriority(&h->s_loop, cudaStreamNonBlocking, hi) == cudaSuccess;
+            if (h->s_loop2 == nullptr)
+                ok = ok && cudaStreamCreateWithPriority(&h->s_loop2, cudaStreamNonBlocking, hi) == cudaSuccess;
             if (h->s_fec == nullptr)
                 ok = ok && cudaStreamCreateWithPriority(&h->s_fec, cudaStreamNonBlocking, hi) == cudaSuccess;
         }
         auto mk = [&](cudaEvent_t* e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
-        mk(&h->ev_start); mk(&h->ev_loop_done); mk(&h->ev_fec_done); mk(&h->ev_par_done);
-        for (int i = 0; i < qrl_rx::kMaxSub; i++) { mk(&h->ev_a[i]); mk(&h->ev_b[i]); }
+        mk(&h->ev_start); mk(&h->ev_loop_done); mk(&h->ev_loop2_done); mk(&h->ev_fec_done); mk(&h->ev_par_done);
+        for (int i = 0; i < qrl_rx::kMaxSub; i++) { mk(&h->ev_a[i]); mk(&h->ev_b[i]); mk(&h->ev_c[i]); }
         if (!ok) { set_err(h, "stream/event creation failed"); return fail(QRL_ECUDA); }
     }
     if (const char* e = getenv("QRL_NSUB")) { int v = atoi(e); if (v >= 1 && v <= qrl_rx::kMaxSub) h->nsub = v; }
@@ -394,6 +437,7 @@ int qrl_rx_reset(qrl_rx* h)
     if (!h) return QRL_EINVAL;
     if (h->s_loop) CK(cudaStreamSynchronize(h->s_loop));
     if (h->s_fec) CK(cudaStreamSynchronize(h->s_fec));
+    if (h->s_loop2) CK(cudaStreamSynchronize(h->s_loop2));
     if (h->s_par) CK(cudaStreamSynchronize(h->s_par));
     // all-zero history / rings; loop states at their constructor values
     std::vector<SymSyncState> ss(h->C);
@@ -407,10 +451,12 @@ int qrl_rx_reset(qrl_rx* h)
     CK(cudaMemcpyAsync(h->d_vs, vs.data(), sizeof(ViterbiState) * h->C, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->d_hist[0], 0, sizeof(float2) * h->H * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_hist[1], 0, sizeof(float2) * h->H * h->C, h->stream));
-    CK(cudaMemsetAsync(h->r1.d, 0, sizeof(float2) * h->r1.stride * h->C, h->stream));
-    CK(cudaMemsetAsync(h->r2.d, 0, sizeof(float2) * h->r2.stride * h->C, h->stream));
-    CK(cudaMemsetAsync(h->r4.d, 0, sizeof(float) * h->r4.stride * (((h->C + 31) / 32) * 32), h->stream));
-    CK(cudaMemsetAsync(h->r5.d, 0, h->r5.stride * h->C, h->stream));
+    for (auto& z : h->zero_list) CK(cudaMemsetAsync(z.first, 0, z.second, h->stream));
+    std::vector<AgcCostasState> ac(h->C);
+    if (h->d_ac) {
+        for (int c = 0; c < h->C; c++) { ac[c].pos = 0; ac[c].gain = 1.0f; ac[c].pll.phase = 0.0f; ac[c].pll.freq = 0.0f; }
+        CK(cudaMemcpyAsync(h->d_ac, ac.data(), sizeof(AgcCostasState) * h->C, cudaMemcpyHostToDevice, h->stream));
+    }
     CK(cudaMemsetAsync(h->d_port1_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_port2_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // the staging vectors above go out of scope
@@ -425,6 +471,7 @@ int qrl_rx_destroy(qrl_rx* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->s_loop) { cudaStreamSynchronize(h->s_loop); cudaStreamDestroy(h->s_loop); }
     if (h->s_fec) { cudaStreamSynchronize(h->s_fec); cudaStreamDestroy(h->s_fec); }
+    if (h->s_loop2) { cudaStreamSynchronize(h->s_loop2); cudaStreamDestroy(h->s_loop2); }
     if (h->s_par) { cudaStreamSynchronize(h->s_par); cudaStreamDestroy(h->s_par); }
     if (h->g_loop || h->g_par) {
         auto pDestroy = drv<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
@@ -479,6 +526,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
     // FEC stage on s_fec, overlapping the parallel stages of slices i+1.. (channels stay independent).
     CK(cudaEventRecord(h->ev_start, h->stream));
     CK(cudaStreamWaitEvent(h->s_loop, h->ev_start, 0));
+    CK(cudaStreamWaitEvent(h->s_loop2, h->ev_start, 0));
     CK(cudaStreamWaitEvent(h->s_fec, h->ev_start, 0));
     if (h->s_par) CK(cudaStreamWaitEvent(h->s_par, h->ev_start, 0));
     cudaStream_t sp = h->par();
@@ -507,61 +555,108 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         h->n_in = N; h->n1 = k1;
         const long long n_new = k1 - k0;
         h->port0_n += static_cast<long>(n_new);
-        if (n_new > 0) {
-            const int TB = 256;
-            dim3 g(static_cast<unsigned>((n_new + TB - 1) / TB), h->C);
-            // ---- stage 2: channel filter -> ring + port 0
-            pe = h->prof_begin(1, sp);
-            fir_ccf_ring_kernel<<<g, TB, sizeof(float) * h->ntaps2, sp>>>(
-                static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
-                static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-                h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0);
-            h->launches++;
-            h->prof_end(pe);
-            // ---- stage 3: quadrature demod + RRC
-            pe = h->prof_begin(2, sp);
-            qdemod_fir_fff_kernel<<<g, TB, sizeof(float) * (2 * h->ntaps3 + TB), sp>>>(
-                static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-                static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
-                h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
-            h->launches++;
-            h->prof_end(pe);
-        }
-        CK(cudaEventRecord(h->ev_a[i], sp));
-        // ---- stage 4: symbol sync (+ phase mod + soft bits) on the loop stream
-        CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
         long long* nsoft_i = h->d_nsoft + static_cast<size_t>(i) * h->C;
-        {
-            pe = h->prof_begin(3, h->s_loop);
-            constexpr int CH = 256, NST = 3, NEPI = 2;
-            const int blocks = (h->C + 31) / 32;
-            const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
-            size_t smem = sizeof(float) * (NST * CH * 32 + 132 * 8 + 2 * maxs * 32) + sizeof(int) * 64;
-            // (asking for >= 176 KB to keep FIR CTAs off the loop CTA's SM was measured: the CTA then waits for
-            //  an SM to drain completely and the step gets slower: 3.2 ms vs 2.3 ms)
-            auto kern = symsync_kernel<1, SL_RECT4, EPI_4FSK_FM, CH, NST, NEPI>;
-            static bool ss_attr = false;
-            if (!ss_attr) {
-                CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                ss_attr = true;
+        const int TB = 256;
+        dim3 gtile(static_cast<unsigned>((std::max<long long>(n_new, 1) + TB - 1) / TB), h->C);
+        const int groups = (h->C + 31) / 32;
+        if (h->kind == QRL_DEMOD_4FSK) {
+            if (n_new > 0) {
+                // ---- stage 2: channel filter -> ring + port 0
+                pe = h->prof_begin(1, sp);
+                fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->ntaps2, sp>>>(
+                    static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
+                    static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                    h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, 0);
+                h->launches++;
+                h->prof_end(pe);
+                // ---- stage 3: quadrature demod + RRC
+                pe = h->prof_begin(2, sp);
+                qdemod_fir_fff_kernel<<<gtile, TB, sizeof(float) * (2 * h->ntaps3 + TB), sp>>>(
+                    static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                    static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
+                    h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
+                h->launches++;
+                h->prof_end(pe);
             }
-            kern<<<blocks, 64 + 32 * NEPI, smem, h->s_loop>>>(
-                h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r4.d), h->r4.mask, h->r4.stride, k1,
-                h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
-                static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i);
-            h->launches++;
-            h->prof_end(pe);
+            CK(cudaEventRecord(h->ev_a[i], sp));
+            // ---- stage 4: symbol sync (+ phase mod + soft bits) on the loop stream
+            CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
+            {
+                pe = h->prof_begin(3, h->s_loop);
+                constexpr int CH = 256, NST = 3, NEPI = 2;
+                const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
+                const size_t smem = sizeof(float) * (NST * CH * 32 + 132 * 8 + 2 * maxs * 32) + sizeof(int) * 64;
+                auto kern = symsync_kernel<1, SL_RECT4, EPI_4FSK_FM, CH, NST, NEPI>;
+                static bool ss_attr = false;
+                if (!ss_attr) {
+                    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    ss_attr = true;
+                }
+                kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop>>>(
+                    h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r4.d), h->r4.mask, h->r4.stride, k1,
+                    h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
+                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i);
+                h->launches++;
+                h->prof_end(pe);
+            }
+            CK(cudaEventRecord(h->ev_b[i], h->s_loop));
+        } else {   // QRL_DEMOD_QPSK
+            if (n_new > 0) {
+                // ---- stage 2: RRC shaping filter -> interleaved ring + port 0
+                pe = h->prof_begin(1, sp);
+                fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->ntaps2, sp>>>(
+                    static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
+                    static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                    h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, 1);
+                h->launches++;
+                h->prof_end(pe);
+            }
+            CK(cudaEventRecord(h->ev_a[i], sp));
+            // ---- stage 3: agc2 + costas "PLL" per sample on the loop stream
+            CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
+            {
+                pe = h->prof_begin(2, h->s_loop);
+                constexpr int CH = 128, NST = 3;
+                const size_t smem = sizeof(float2) * (NST + 2) * CH * 32;
+                auto kern = agc_costas_kernel<CH, NST>;
+                static bool ac_attr = false;
+                if (!ac_attr) {
+                    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    ac_attr = true;
+                }
+                kern<<<groups, 96, smem, h->s_loop>>>(h->acp, h->d_ac, h->C,
+                    static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, k1,
+                    static_cast<float2*>(h->r3.d), h->r3.mask, h->r3.stride);
+                h->launches++;
+                h->prof_end(pe);
+            }
+            CK(cudaEventRecord(h->ev_c[i], h->s_loop));
+            // ---- stage 4: symbol sync + second Costas + diff phasor + soft bits on the second loop stream
+            CK(cudaStreamWaitEvent(h->s_loop2, h->ev_c[i], 0));
+            {
+                pe = h->prof_begin(3, h->s_loop2);
+                constexpr int CH = 128, NST = 3, NEPI = 1;
+                const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
+                const size_t smem = sizeof(float) * (NST * CH * 64 + 132 * 8 + 2 * maxs * 64) + sizeof(int) * 64;
+                auto kern = symsync_kernel<2, SL_DQPSK, EPI_QPSK, CH, NST, NEPI>;
+                static bool sq_attr = false;
+                if (!sq_attr) {
+                    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    sq_attr = true;
+                }
+                kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop2>>>(
+                    h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r3.d), h->r3.mask, h->r3.stride, k1,
+                    h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
+                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i);
+                h->launches++;
+                h->prof_end(pe);
+            }
+            CK(cudaEventRecord(h->ev_b[i], h->s_loop2));
         }
-        CK(cudaEventRecord(h->ev_b[i], h->s_loop));
         // ---- stage 5: Viterbi + descrambler on the FEC stream
         CK(cudaStreamWaitEvent(h->s_fec, h->ev_b[i], 0));
         pe = h->prof_begin(4, h->s_fec);
         constexpr int CPB = 4;    // 4 channels (8 warps) per CTA
-        static bool vit_attr = false;
-        if (!vit_attr) {
-            CK(cudaFuncSetAttribute(viterbi_k7_kernel<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
-            vit_attr = true;
-        }
         viterbi_k7_kernel<CPB><<<(h->C + CPB - 1) / CPB, 64 * CPB, 0, h->s_fec>>>(h->d_vs, nsoft_i, h->C,
             static_cast<const unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride,
             h->d_port2, h->port2_cap, h->d_port2_cnt, static_cast<int>(h->port2_cap));
@@ -569,6 +664,8 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         h->prof_end(pe);
     }
     CK(cudaEventRecord(h->ev_loop_done, h->s_loop));
+    CK(cudaEventRecord(h->ev_loop2_done, h->s_loop2));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_loop2_done, 0));
     CK(cudaEventRecord(h->ev_fec_done, h->s_fec));
     if (h->s_par) { CK(cudaEventRecord(h->ev_par_done, h->s_par)); CK(cudaStreamWaitEvent(h->stream, h->ev_par_done, 0)); }
     CK(cudaStreamWaitEvent(h->stream, h->ev_loop_done, 0));

@@ -38,6 +38,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t done;
@@ -333,7 +338,7 @@ constexpr int kMaxTapsSmem = 4096;
 __global__ void fir_ccf_ring_kernel(const float2* __restrict__ in, unsigned in_mask, long long in_stride,
                                     float2* __restrict__ out, unsigned out_mask, long long out_stride,
                                     const float* __restrict__ taps, int ntaps, long long a0, long long a1,
-                                    float2* __restrict__ lin, long long lin_stride, long long lin_base)
+                                    float2* __restrict__ lin, long long lin_stride, long long lin_base, int out_interleaved)
 {
     extern __shared__ float hs_dyn[];
     for (int i = threadIdx.x; i < ntaps; i += blockDim.x) hs_dyn[i] = taps[i];
@@ -349,7 +354,8 @@ __global__ void fir_ccf_ring_kernel(const float2* __restrict__ in, unsigned in_m
         im = fmaf(hs_dyn[j], v.y, im);
     }
     const float2 y = make_float2(re, im);
-    out[static_cast<long long>(c) * out_stride + (a & out_mask)] = y;
+    if (out_interleaved) out[(static_cast<long long>(c >> 5) * out_stride + (a & out_mask)) * 32 + (c & 31)] = y;
+    else out[static_cast<long long>(c) * out_stride + (a & out_mask)] = y;
     if (lin) lin[static_cast<long long>(c) * lin_stride + (a - lin_base)] = y;
 }
 
@@ -460,13 +466,131 @@ __device__ __forceinline__ void qrl_costas_step(LoopState& st, float alpha, floa
     err = qrl_clip(err, 1.0f);
     st.freq = st.freq + beta * err;
     st.phase = st.phase + st.freq + alpha * err;
-    while (static_cast<double>(st.phase) > 2.0 * 3.14159265358979323846)
+    // (double)phase > 2*pi  <=>  phase >= 6.28318548f (the float just above 2*pi): float compare on the hot path,
+    // the exact double subtraction only when a wrap really happens
+    while (st.phase >= 6.2831854820251465f)
         st.phase = static_cast<float>(static_cast<double>(st.phase) - 2.0 * 3.14159265358979323846);
-    while (static_cast<double>(st.phase) < -2.0 * 3.14159265358979323846)
+    while (st.phase <= -6.2831854820251465f)
         st.phase = static_cast<float>(static_cast<double>(st.phase) + 2.0 * 3.14159265358979323846);
     if (st.freq > 1.0f) st.freq = 1.0f;
     else if (st.freq < -1.0f) st.freq = -1.0f;
     yr = orr; yi = oi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sequential loop stage of the PSK chains: agc2_cc -> costas_loop_cc ("PLL" in gr_demod_qpsk.cpp:108-118), one
+// lane per channel, per SAMPLE.  The two recurrences are independent of each other, so they run in two warps:
+// warp 0 = AGC (gain recurrence), warp 2 = Costas (phase/frequency recurrence), connected by a double-buffered
+// shared-memory hand-off; warp 1 lane 0 = TMA producer.  Input and output rings are channel-interleaved.
+// ------------------------------------------------------------------------------------------------
+struct AgcCostasState {
+    long long pos;            // absolute index of the next input sample
+    float gain;               // agc2
+    LoopState pll;            // costas
+};
+struct AgcCostasParams {
+    float attack, decay, ref, max_gain;
+    float alpha, beta;
+    int order, use_snr;
+};
+
+template <int CH, int NST>
+__global__ void __launch_bounds__(96)
+agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
+                  const float2* __restrict__ in, unsigned in_mask, long long in_stride, long long avail_total,
+                  float2* __restrict__ out, unsigned out_mask, long long out_stride)
+{
+    extern __shared__ __align__(128) float2 sm_ac[];          // [NST][CH][32] | hand-off [2][CH][32]
+    __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[2], bar_empty[2];
+    float2* stage0 = sm_ac;
+    float2* hand = sm_ac + NST * CH * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x;
+    const int c = g * 32 + lane;
+    const bool active = c < C;
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NST; b++) { mbar_init(&bar_in[b], 1); mbar_init(&bar_free[b], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&bar_full[b], 1); mbar_init(&bar_empty[b], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // all channels of a handle advance in lock step (one output per input): the read position is uniform
+    const long long base = states[g * 32 < C ? g * 32 : 0].pos;
+    if (base >= avail_total) return;
+    const long long total = avail_total - base;
+    const int nchunks = static_cast<int>((total + CH - 1) / CH);
+
+    if (warp == 1) {
+        if (lane == 0) {
+            const float2* ring = in + static_cast<long long>(g) * in_stride * 32;
+            const long long cap = static_cast<long long>(in_mask) + 1;
+            for (int m = 0; m < nchunks; m++) {
+                const int st = m % NST, u = m / NST;
+                if (u > 0) mbar_wait(&bar_free[st], (u - 1) & 1);
+                const long long w0 = base + static_cast<long long>(m) * CH;
+                float2* dst = stage0 + st * CH * 32;
+                const long long s0 = w0 & in_mask;
+                const long long first = (s0 + CH <= cap) ? CH : (cap - s0);
+                fence_proxy_async();
+                mbar_expect_tx(&bar_in[st], CH * 256);
+                bulk_g2s(dst, ring + s0 * 32, static_cast<uint32_t>(first * 256), &bar_in[st]);
+                if (first < CH) bulk_g2s(dst + first * 32, ring, static_cast<uint32_t>((CH - first) * 256), &bar_in[st]);
+            }
+        }
+    } else if (warp == 0) {
+        // ---------------------------------------------------------------- AGC warp (agc2_cc::scale)
+        float gain = active ? states[c].gain : 1.0f;
+        const float k_att = p.attack, k_dec = p.decay, k_ref = p.ref, k_max = p.max_gain;
+        for (int m = 0; m < nchunks; m++) {
+            const int st = m % NST, b = m & 1;
+            if (m >= 2) mbar_wait(&bar_empty[b], ((m >> 1) - 1) & 1);
+            mbar_wait(&bar_in[st], (m / NST) & 1);
+            const float2* buf = stage0 + st * CH * 32 + lane;
+            float2* hb = hand + b * CH * 32 + lane;
+            const long long rem = total - static_cast<long long>(m) * CH;
+            const int n = rem < CH ? static_cast<int>(rem) : CH;
+            if (active) {
+                for (int i = 0; i < n; i++) {
+                    const float2 x = buf[i * 32];
+                    const float orr = x.x * gain, oi = x.y * gain;
+                    const float tmp = -k_ref + sqrtf(orr * orr + oi * oi);
+                    const float rate = (fabsf(tmp) > gain) ? k_att : k_dec;
+                    gain = gain - tmp * rate;
+                    if (gain < 0.0f) gain = 10e-5f;
+                    if (k_max > 0.0f && gain > k_max) gain = k_max;
+                    hb[i * 32] = make_float2(orr, oi);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&bar_free[st]); mbar_arrive(&bar_full[b]); }
+        }
+        if (active) states[c].gain = gain;
+    } else {
+        // ---------------------------------------------------------------- Costas warp
+        LoopState pll{ 0.0f, 0.0f };
+        if (active) pll = states[c].pll;
+        float2* oring = out + static_cast<long long>(g) * out_stride * 32 + lane;
+        const float k_a = p.alpha, k_b = p.beta;
+        for (int m = 0; m < nchunks; m++) {
+            const int b = m & 1;
+            mbar_wait(&bar_full[b], (m >> 1) & 1);
+            const float2* hb = hand + b * CH * 32 + lane;
+            const long long w0 = base + static_cast<long long>(m) * CH;
+            const long long rem = total - static_cast<long long>(m) * CH;
+            const int n = rem < CH ? static_cast<int>(rem) : CH;
+            if (active) {
+                for (int i = 0; i < n; i++) {
+                    const float2 x = hb[i * 32];
+                    float yr, yi;
+                    qrl_costas_step(pll, k_a, k_b, p.order, p.use_snr != 0, x.x, x.y, yr, yi);
+                    oring[((w0 + i) & out_mask) * 32] = make_float2(yr, yi);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[b]);
+        }
+        if (active) { states[c].pll = pll; states[c].pos = avail_total; }
+    }
 }
 
 // exact threshold form of constellation_rect's floor(re + 2.0f) sector search (float addition rounds to nearest
@@ -484,11 +608,6 @@ __device__ __forceinline__ float qrl_slice_rect4(float re)
 }
 // clip for non-NaN arguments: two FMNMX instead of compare + select
 __device__ __forceinline__ float qrl_clip1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // Input ring layout: [group = channel / 32][slot][32 lanes][NCOMP] -- a time step of one warp's 32 channels is one
 // contiguous 128*NCOMP-byte row, so a CH-row window is ONE contiguous block fetched with cp.async.bulk (TMA 1-D).
