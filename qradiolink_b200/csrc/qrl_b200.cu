@@ -126,6 +126,13 @@ struct qrl_rx : HandleBase {
     AgcCostasState* d_ac = nullptr;
     Ring r3;
     int sym_sps = 0;
+    // NBFM audio chain
+    NbfmParams nbp{};
+    NbfmState* d_nb = nullptr;
+    Ring rg, rd, rr;
+    float* d_env = nullptr; float* d_arm_taps = nullptr; float* d_audio_taps = nullptr;
+    float* d_port1f = nullptr;
+    int tsr = 0;
     std::vector<std::pair<void*, size_t>> zero_list;   // buffers qrl_rx_reset clears
     // symbol sync
     SymSyncParams ssp{};
@@ -360,11 +367,19 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         h->ssp.n0 = static_cast<int>(floorf(h->ssp.min_period - fabsf(h->ssp.alpha)));
         h->ssp.fl0 = static_cast<float>(h->ssp.n0);
         h->nports = 3;
+    } else if (kind == QRL_DEMOD_NBFM) {
+        // gr_demod_nbfm.cpp:39-66
+        tsr = 20000; sym_sps = 2;
+        taps1 = low_pass(1, samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
+        h->D1 = 50;
+        taps2 = low_pass_2(1, tsr, filter_width, 3500, 60, WIN_BLACKMAN_HARRIS);
+        h->qd_gain = static_cast<float>(tsr / (4 * kPi * filter_width));
+        h->nports = 2;
     } else {
         set_err(h, "qrl_rx_create: demod kind " + std::to_string(kind) + " not built");
         return fail(QRL_EINVAL);
     }
-    h->sym_sps = sym_sps;
+    h->sym_sps = sym_sps; h->tsr = tsr;
 
     // ---- stage 1 buffers
     h->ntaps1 = static_cast<int>(taps1.size());
@@ -380,10 +395,37 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     // ---- rings
     h->ntaps2 = static_cast<int>(taps2.size());
     h->ntaps3 = static_cast<int>(taps3.size());
-    if ((rc = upload_floats(h, &h->d_taps2, taps2))) return fail(rc);
+    {
+        std::vector<float> t2(std::max<size_t>(taps2.size(), 512), 0.0f);     // room for set_filter_width redesigns
+        std::copy(taps2.begin(), taps2.end(), t2.begin());
+        if ((rc = upload_floats(h, &h->d_taps2, t2))) return fail(rc);
+    }
     if (!taps3.empty() && (rc = upload_floats(h, &h->d_taps3, taps3))) return fail(rc);
-    if ((rc = make_ring(h, &h->r1, sizeof(float2), h->n1max + h->ntaps2 + 8))) return fail(rc);
-    if (kind == QRL_DEMOD_4FSK) {
+    if ((rc = make_ring(h, &h->r1, sizeof(float2), h->n1max + 512 + 8))) return fail(rc);
+    if (kind == QRL_DEMOD_NBFM) {
+        if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + 64))) return fail(rc);
+        std::vector<float> audio_rs = low_pass_2(2, 2 * tsr, 3600, 250, 60, WIN_BLACKMAN_HARRIS);
+        std::vector<float> audio_f = low_pass_2(1, 8000, 3500, 200, 35, WIN_BLACKMAN_HARRIS);
+        const int nt_arm = (static_cast<int>(audio_rs.size()) + 1) / 2;
+        std::vector<float> arms(2 * nt_arm, 0.0f);
+        for (int pp = 0; pp < 2; pp++)
+            for (int k = 0; k < nt_arm; k++) { const size_t j = pp + 2 * k; arms[pp * nt_arm + k] = j < audio_rs.size() ? audio_rs[j] : 0.0f; }
+        if ((rc = upload_floats(h, &h->d_arm_taps, arms))) return fail(rc);
+        if ((rc = upload_floats(h, &h->d_audio_taps, audio_f))) return fail(rc);
+        const int ramp = 320;
+        std::vector<float> env(ramp + 1);
+        for (int k = 0; k <= ramp; k++) env[k] = static_cast<float>(0.5 - std::cos(kPi * k / ramp) / 2.0);
+        if ((rc = upload_floats(h, &h->d_env, env))) return fail(rc);
+        double a[2], b[2];
+        deemph_taps(tsr, 50e-6, a, b);
+        h->nbp.sq_alpha = 0.01; h->nbp.sq_threshold = std::pow(10.0, -140 / 10.0); h->nbp.sq_ramp = ramp; h->nbp.sq_gate = 1;
+        h->nbp.qd_gain = h->qd_gain; h->nbp.nt_arm = nt_arm; h->nbp.nt_audio = static_cast<int>(audio_f.size());
+        h->nbp.b0 = b[0]; h->nbp.b1 = b[1]; h->nbp.a1 = a[1]; h->nbp.out_gain = 2.0f;
+        if ((rc = make_ring(h, &h->rg, sizeof(float2), h->n1max + 16))) return fail(rc);
+        if ((rc = make_ring(h, &h->rd, sizeof(float), h->n1max + nt_arm + 16))) return fail(rc);
+        if ((rc = make_ring(h, &h->rr, sizeof(float), h->n1max * 2 / 5 + h->nbp.nt_audio + 16))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_nb, h->C))) return fail(rc);
+    } else if (kind == QRL_DEMOD_4FSK) {
         if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + h->ntaps3 + 8))) return fail(rc);
         if ((rc = make_ring(h, &h->r4, sizeof(float), h->n1max + 600, true))) return fail(rc);
     } else {   // QPSK: shaping-filter output and loop output are channel-interleaved complex rings
@@ -396,6 +438,7 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     if ((rc = dev_alloc(h, &h->d_port0, static_cast<size_t>(h->port0_cap) * h->C))) return fail(rc);
     h->port1_cap = h->n1max / std::max(1, sym_sps - 1) + 64;
     if ((rc = dev_alloc(h, &h->d_port1, static_cast<size_t>(h->port1_cap) * h->C))) return fail(rc);
+    h->d_port1f = reinterpret_cast<float*>(h->d_port1);
     if ((rc = dev_alloc(h, &h->d_port1_cnt, h->C))) return fail(rc);
     h->port2_cap = h->port1_cap + 160;
     if ((rc = dev_alloc(h, &h->d_port2, static_cast<size_t>(h->port2_cap) * h->C))) return fail(rc);
@@ -452,6 +495,14 @@ int qrl_rx_reset(qrl_rx* h)
     CK(cudaMemsetAsync(h->d_hist[0], 0, sizeof(float2) * h->H * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_hist[1], 0, sizeof(float2) * h->H * h->C, h->stream));
     for (auto& z : h->zero_list) CK(cudaMemsetAsync(z.first, 0, z.second, h->stream));
+    std::vector<NbfmState> nb(h->C);
+    if (h->d_nb) {
+        for (int c = 0; c < h->C; c++) {
+            std::memset(&nb[c], 0, sizeof(NbfmState));
+            nb[c].sq_state = SQ_MUTED; nb[c].envelope = h->nbp.sq_ramp ? 0.0f : 1.0f;
+        }
+        CK(cudaMemcpyAsync(h->d_nb, nb.data(), sizeof(NbfmState) * h->C, cudaMemcpyHostToDevice, h->stream));
+    }
     std::vector<AgcCostasState> ac(h->C);
     if (h->d_ac) {
         for (int c = 0; c < h->C; c++) { ac[c].pos = 0; ac[c].gain = 1.0f; ac[c].pll.phase = 0.0f; ac[c].pll.freq = 0.0f; }
@@ -493,9 +544,25 @@ int qrl_rx_set_stream(qrl_rx* h, void* s)
     return QRL_OK;
 }
 
-int qrl_rx_set_param(qrl_rx* h, int, int key, double)
+int qrl_rx_set_param(qrl_rx* h, int, int key, double value)
 {
     if (!h) return QRL_EINVAL;
+    if (h->kind == QRL_DEMOD_NBFM && key == QRL_PARAM_SQUELCH_DB) {          // gr_demod_nbfm::set_squelch
+        h->nbp.sq_threshold = std::pow(10.0, value / 10.0);
+        return QRL_OK;
+    }
+    if (h->kind == QRL_DEMOD_NBFM && key == QRL_PARAM_FILTER_WIDTH) {        // gr_demod_nbfm::set_filter_width (:82-90)
+        const int fw = static_cast<int>(value);
+        std::vector<float> t = low_pass(1, h->tsr, fw, 1200, WIN_BLACKMAN_HARRIS);
+        if (t.size() > 512 || fw <= 0) { set_err(h, "set_filter_width: out of range"); return QRL_EINVAL; }
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(h->d_taps2, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+        h->ntaps2 = static_cast<int>(t.size());
+        h->filter_width = fw;
+        h->qd_gain = static_cast<float>(h->tsr / (4 * kPi * fw));
+        h->nbp.qd_gain = h->qd_gain;
+        return QRL_OK;
+    }
     set_err(h, "qrl_rx_set_param: key " + std::to_string(key) + " not supported for this block yet");
     return QRL_EINVAL;
 }
@@ -559,6 +626,29 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         const int TB = 256;
         dim3 gtile(static_cast<unsigned>((std::max<long long>(n_new, 1) + TB - 1) / TB), h->C);
         const int groups = (h->C + 31) / 32;
+        if (h->kind == QRL_DEMOD_NBFM) {
+            if (n_new > 0) {
+                pe = h->prof_begin(1, sp);
+                fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->ntaps2, sp>>>(
+                    static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
+                    static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                    h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, 0);
+                h->launches++;
+                h->prof_end(pe);
+            }
+            CK(cudaEventRecord(h->ev_a[i], sp));
+            CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
+            pe = h->prof_begin(3, h->s_loop);
+            nbfm_audio_kernel<<<h->C, 128, 0, h->s_loop>>>(h->nbp, h->d_nb,
+                static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, k1, h->d_env,
+                static_cast<float2*>(h->rg.d), h->rg.mask, h->rg.stride,
+                static_cast<float*>(h->rd.d), h->rd.mask, h->rd.stride,
+                static_cast<float*>(h->rr.d), h->rr.mask, h->rr.stride,
+                h->d_arm_taps, h->d_audio_taps, h->d_port1f, 2 * h->port1_cap, h->d_port1_cnt, static_cast<int>(2 * h->port1_cap));
+            h->launches++;
+            h->prof_end(pe);
+            continue;
+        }
         if (h->kind == QRL_DEMOD_4FSK) {
             if (n_new > 0) {
                 // ---- stage 2: channel filter -> ring + port 0
@@ -720,7 +810,10 @@ int qrl_rx_port_device(qrl_rx* h, int port, void** data, long* cap, int** counts
 {
     if (!h || port < 0 || port >= h->nports) return QRL_EINVAL;
     if (port == 0) { *data = h->d_port0; *cap = h->port0_cap; *counts = nullptr; }
-    else if (port == 1) { *data = h->d_port1; *cap = h->port1_cap; *counts = h->d_port1_cnt; }
+    else if (port == 1) {
+        *data = h->d_port1; *counts = h->d_port1_cnt;
+        *cap = (h->kind == QRL_DEMOD_NBFM) ? 2 * h->port1_cap : h->port1_cap;      // float view of the same buffer
+    }
     else { *data = h->d_port2; *cap = h->port2_cap; *counts = h->d_port2_cnt; }
     return QRL_OK;
 }

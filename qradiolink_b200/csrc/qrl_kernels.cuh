@@ -982,6 +982,150 @@ viterbi_k7_kernel(ViterbiState* __restrict__ vstates, const long long* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// NBFM audio chain after the channel filter (gr_demod_nbfm.cpp:68-76): pwr_squelch_cc(gate) -> quadrature_demod_cf
+// -> rational_resampler_fff(2,5) -> fft_filter_fff (audio LPF, direct form) -> iir_filter_ffd (de-emphasis) -> x2.
+// 20 ksps per channel: one CTA per channel; the two recurrences (squelch state machine with its double-precision
+// power IIR, de-emphasis IIR) run on thread 0, the FIR-type stages are spread over the CTA.  All streams are
+// small per-channel rings addressed by absolute item index, so chunking is invisible.
+// ------------------------------------------------------------------------------------------------
+struct NbfmState {
+    double pwr, iir_x1, iir_y1;
+    long long n_in;           // channel-filter items consumed
+    long long n_gate;         // items passed by the squelch (= demod stream length)
+    long long n_res;          // resampler outputs produced
+    long long n_aud;          // audio-filter / de-emphasis outputs produced
+    int sq_state, ramped;
+    float envelope;
+    float prev_r, prev_i;     // quadrature demod memory
+};
+struct NbfmParams {
+    double sq_alpha, sq_threshold;
+    int sq_ramp, sq_gate;
+    float qd_gain;
+    int nt_arm;               // taps per resampler arm (L = 2, M = 5)
+    int nt_audio;
+    double b0, b1, a1;
+    float out_gain;
+};
+enum { SQ_MUTED = 0, SQ_ATTACK = 1, SQ_UNMUTED = 2, SQ_DECAY = 3 };
+
+__global__ void __launch_bounds__(128)
+nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
+                  const float2* __restrict__ in, unsigned in_mask, long long in_stride, long long avail_in,
+                  const float* __restrict__ env_tab,            // sq_ramp + 1 envelope values
+                  float2* __restrict__ gate_ring, unsigned gate_mask, long long gate_stride,
+                  float* __restrict__ dem_ring, unsigned dem_mask, long long dem_stride,
+                  float* __restrict__ res_ring, unsigned res_mask, long long res_stride,
+                  const float* __restrict__ arm_taps,           // [2][nt_arm]
+                  const float* __restrict__ audio_taps,
+                  float* __restrict__ port1, long long port1_stride, int* __restrict__ port1_cnt, int port1_cap)
+{
+    const int c = blockIdx.x;
+    __shared__ NbfmState st;
+    if (threadIdx.x == 0) st = states[c];
+    __syncthreads();
+    const float2* x = in + static_cast<long long>(c) * in_stride;
+    float2* gr_ = gate_ring + static_cast<long long>(c) * gate_stride;
+    float* dr = dem_ring + static_cast<long long>(c) * dem_stride;
+    float* rr = res_ring + static_cast<long long>(c) * res_stride;
+    const long long gate0 = st.n_gate;
+
+    // ---- 1. squelch (sequential)
+    if (threadIdx.x == 0) {
+        double pwr = st.pwr; int state = st.sq_state, ramped = st.ramped; float env = st.envelope;
+        long long ng = st.n_gate;
+        for (long long a = st.n_in; a < avail_in; a++) {
+            const float2 v = x[a & in_mask];
+            const float mag2 = v.x * v.x + v.y * v.y;
+            pwr = p.sq_alpha * static_cast<double>(mag2) + (1.0 - p.sq_alpha) * pwr;
+            const bool mute = pwr < p.sq_threshold;
+            switch (state) {
+            case SQ_MUTED: if (!mute) state = p.sq_ramp ? SQ_ATTACK : SQ_UNMUTED; break;
+            case SQ_UNMUTED: if (mute) state = p.sq_ramp ? SQ_DECAY : SQ_MUTED; break;
+            case SQ_ATTACK:
+                env = env_tab[++ramped];
+                if (ramped >= p.sq_ramp) { state = SQ_UNMUTED; env = 1.0f; }
+                break;
+            case SQ_DECAY:
+                env = env_tab[--ramped];
+                if (ramped == 0) state = SQ_MUTED;
+                break;
+            }
+            if (state != SQ_MUTED) { gr_[ng & gate_mask] = make_float2(v.x * env, v.y * env); ng++; }
+            else if (!p.sq_gate) { gr_[ng & gate_mask] = make_float2(0.0f, 0.0f); ng++; }
+        }
+        st.pwr = pwr; st.sq_state = state; st.ramped = ramped; st.envelope = env; st.n_in = avail_in; st.n_gate = ng;
+    }
+    __syncthreads();
+    const long long gate1 = st.n_gate;
+    // ---- 2. quadrature demod over the gated stream
+    for (long long n = gate0 + threadIdx.x; n < gate1; n += blockDim.x) {
+        const float2 cur = gr_[n & gate_mask];
+        float2 prev;
+        if (n == gate0) prev = make_float2(st.prev_r, st.prev_i);
+        else prev = gr_[(n - 1) & gate_mask];
+        const float re = cur.x * prev.x + cur.y * prev.y;
+        const float im = cur.y * prev.x - cur.x * prev.y;
+        dr[n & dem_mask] = p.qd_gain * qrl_fast_atan2f(im, re);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && gate1 > gate0) { const float2 l = gr_[(gate1 - 1) & gate_mask]; st.prev_r = l.x; st.prev_i = l.y; }
+    // ---- 3. rational resampler 2/5: output i uses arm (5 i) mod 2 at input position floor(5 i / 2)
+    const long long res0 = st.n_res;
+    long long res1 = res0;
+    res1 = (2 * gate1 + 4) / 5;                                  // ceil(2 G / 5): outputs i with floor(5 i / 2) <= G - 1
+    if (res1 < res0) res1 = res0;
+    for (long long i = res0 + threadIdx.x; i < res1; i += blockDim.x) {
+        const long long pos = (5 * i) >> 1;
+        const float* h = arm_taps + ((5 * i) & 1) * p.nt_arm;
+        float acc = 0.0f;
+        for (int k = p.nt_arm - 1; k >= 0; k--) {
+            const long long n = pos - k;
+            const float v = n >= 0 ? dr[n & dem_mask] : 0.0f;
+            acc = fmaf(h[k], v, acc);
+        }
+        rr[i & res_mask] = acc;
+    }
+    __syncthreads();
+    // ---- 4. audio low-pass (direct form), into shared staging for the IIR
+    __shared__ float aud[2048];
+    const long long aud0 = st.n_aud;
+    const int n_aud = static_cast<int>(res1 - aud0);               // one output per resampler output
+    for (int base = 0; base < n_aud; base += 2048) {
+        const int nb = (n_aud - base) < 2048 ? (n_aud - base) : 2048;
+        for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+            const long long a = aud0 + base + j;
+            float acc = 0.0f;
+            for (int k = p.nt_audio - 1; k >= 0; k--) {
+                const long long n = a - k;
+                const float v = n >= 0 ? rr[n & res_mask] : 0.0f;
+                acc = fmaf(audio_taps[k], v, acc);
+            }
+            aud[j] = acc;
+        }
+        __syncthreads();
+        // ---- 5. de-emphasis IIR (double) + output gain (sequential)
+        if (threadIdx.x == 0) {
+            double x1 = st.iir_x1, y1 = st.iir_y1;
+            int cnt = port1_cnt[c];
+            float* o = port1 + static_cast<long long>(c) * port1_stride;
+            for (int j = 0; j < nb; j++) {
+                const double xin = static_cast<double>(aud[j]);
+                double acc = p.b0 * xin;
+                acc = acc + p.b1 * x1;
+                acc = acc - p.a1 * y1;
+                x1 = xin; y1 = acc;
+                if (cnt < port1_cap) o[cnt] = static_cast<float>(acc) * p.out_gain;
+                cnt++;
+            }
+            st.iir_x1 = x1; st.iir_y1 = y1; port1_cnt[c] = cnt;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { st.n_res = res1; st.n_aud = res1; states[c] = st; }
+}
+
 // roll the stage-1 history: new_hist = last H samples of (old_hist ++ iq[0..T))
 __global__ void hist_update_kernel(const float2* __restrict__ iq, long long iq_stride, long long T,
                                    const float2* __restrict__ old_hist, float2* __restrict__ new_hist, int H)

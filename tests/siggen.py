@@ -83,3 +83,20 @@ def count_good_frames(bits, sync, sync_bits, frame_len, payloads):
     fr = O.find_frames(bits, sync, sync_bits, frame_len)
     pl = set(payloads)
     return sum(1 for f in fr if f.tobytes() in pl), len(fr)
+
+
+def gen_nbfm_channels(n_channels, T, seed0=1, dev_hz=2000.0, snr_sigma=0.01, lead_zeros=0):
+    """FM-modulated two-tone audio (1 kHz + 2.2 kHz) at 1 Msps, amplitude 0.8, AWGN sigma."""
+    X = np.zeros((n_channels, T), np.complex64)
+    n = np.arange(T)
+    for c in range(n_channels):
+        rng = np.random.default_rng(seed0 + c)
+        f1, f2 = 1000.0 + 37.0 * c, 2200.0 - 11.0 * c
+        audio = 0.6 * np.sin(2 * np.pi * f1 * n / 1e6) + 0.4 * np.sin(2 * np.pi * f2 * n / 1e6 + 0.3)
+        phase = 2 * np.pi * dev_hz * np.cumsum(audio) / 1e6
+        x = 0.8 * np.exp(1j * (phase + 2 * np.pi * rng.uniform(-100, 100) * n / 1e6))
+        x = x + (rng.standard_normal(T) + 1j * rng.standard_normal(T)) * snr_sigma
+        if lead_zeros:
+            x[:lead_zeros] = 0
+        X[c] = x.astype(np.complex64)
+    return X
