@@ -852,22 +852,188 @@ int qrl_rx_sm_partition(const qrl_rx* h, int* loop_sms, int* parallel_sms)
     return QRL_OK;
 }
 
-// ---------------------------------------------------------------------------------------------- TX (next milestone)
-struct qrl_tx : HandleBase {};
-int qrl_tx_create(int, int, int, int, int, int, int, long, int, qrl_tx** out)
+// ---------------------------------------------------------------------------------------------- TX
+struct qrl_tx : HandleBase {
+    int kind = 0, sps = 0, samp_rate = 0, filter_width = 0, flag = 0, C = 0;
+    long max_items = 0;
+    int L1 = 1, nt1 = 0;            // first interpolation (RRC): L1 arms of nt1 taps
+    int L2 = 1, nt2 = 0;            // second interpolation (x20 low-pass), 4FSK only
+    float* d_arms1 = nullptr; float* d_arms2 = nullptr;
+    float fm_sens = 0, amplif = 0, bb_gain = 1.0f, pulse_scale = 0.66666666f;
+    int repeat_only = 0;
+    TxBitState* d_bits = nullptr;
+    unsigned char* d_in = nullptr;
+    float* d_sym = nullptr; unsigned sym_mask = 0; long long sym_stride = 0;    // float (4FSK) / float2 (QPSK)
+    float2* d_if = nullptr; unsigned if_mask = 0; long long if_stride = 0;
+    float2* d_out = nullptr; long long out_stride = 0; long n_out_last = 0;
+    long long n_sym = 0;           // symbols produced so far (absolute)
+};
+
+static std::vector<float> make_arms(const std::vector<float>& taps, int L, int nt)
 {
-    if (out) *out = nullptr;
-    set_err(nullptr, "qrl_tx_create: TX chains not built yet");
+    std::vector<float> a(static_cast<size_t>(L) * nt, 0.0f);
+    for (int p = 0; p < L; p++)
+        for (int k = 0; k < nt; k++) { const size_t j = p + static_cast<size_t>(k) * L; if (j < taps.size()) a[p * nt + k] = taps[j]; }
+    return a;
+}
+
+int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag,
+                  int n_channels, long max_items, int device, qrl_tx** out)
+{
+    (void)carrier_freq;
+    if (!out || n_channels <= 0 || max_items <= 0) { set_err(nullptr, "qrl_tx_create: bad argument"); return QRL_EINVAL; }
+    *out = nullptr;
+    if (qrl_device_count() <= device) { set_err(nullptr, "qrl_tx_create: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
+    qrl_tx* h = new qrl_tx();
+    h->kind = kind; h->sps = sps; h->samp_rate = samp_rate; h->filter_width = filter_width; h->flag = flag;
+    h->C = n_channels; h->max_items = max_items; h->device = device;
+    auto fail = [&](int rc) { std::string e = h->err; qrl_tx_destroy(h); g_err = e; return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) { set_err(h, "cudaSetDevice failed"); return fail(QRL_ECUDA); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err(h, "stream create failed"); return fail(QRL_ECUDA); }
+    h->own_stream = true;
+    int rc = upload_tables(h);
+    if (rc) return fail(rc);
+    std::vector<float> t1, t2;
+    if (kind == QRL_MOD_4FSK) {
+        // gr_mod_4fsk.cpp:55-92
+        int sym_sps = sps, nfilts = sym_sps * 10, second_interp = 20;
+        if (sps == 2) { sym_sps = 5; second_interp = 2; nfilts = 256; }
+        int spacing = 2; h->amplif = 0.8f;
+        if (flag) { h->amplif = 0.9f; spacing = 1; }
+        h->repeat_only = flag ? 0 : 1;
+        t1 = root_raised_cosine(sym_sps, sym_sps, 1, 0.2, nfilts);
+        h->L1 = sym_sps; h->nt1 = (static_cast<int>(t1.size()) + sym_sps - 1) / sym_sps;
+        h->fm_sens = static_cast<float>((spacing * kPi) / sym_sps);
+        t2 = low_pass(second_interp, samp_rate, filter_width, filter_width, WIN_HAMMING);
+        h->L2 = second_interp; h->nt2 = (static_cast<int>(t2.size()) + second_interp - 1) / second_interp;
+        if (h->L2 != 20 || h->nt2 > 35) { set_err(h, "make_gr_mod_4fsk: interpolator shape not built"); return fail(QRL_EINVAL); }
+        h->nt2 = 35;
+    } else if (kind == QRL_MOD_QPSK) {
+        // gr_mod_qpsk.cpp:58-75
+        int nfilts = sps > 120 ? 11 : (sps > 10 ? 13 : 15);
+        t1 = root_raised_cosine(sps, sps, 1, 0.35, nfilts * sps);
+        h->L1 = sps; h->nt1 = (static_cast<int>(t1.size()) + sps - 1) / sps;
+        if (h->L1 != 4 || h->nt1 > 16) { set_err(h, "make_gr_mod_qpsk: interpolator shape not built"); return fail(QRL_EINVAL); }
+        h->nt1 = 16;
+        h->amplif = 0.6f;
+    } else { set_err(h, "qrl_tx_create: mod kind " + std::to_string(kind) + " not built"); return fail(QRL_EINVAL); }
+    if ((rc = upload_floats(h, &h->d_arms1, make_arms(t1, h->L1, h->nt1)))) return fail(rc);
+    if (!t2.empty() && (rc = upload_floats(h, &h->d_arms2, make_arms(t2, h->L2, h->nt2)))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_bits, h->C))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_in, static_cast<size_t>(h->max_items) * h->C))) return fail(rc);
+    const long long max_sym = 8LL * max_items;
+    const bool qpsk = kind == QRL_MOD_QPSK;
+    { unsigned cap = pow2_at_least(max_sym + 64); h->sym_mask = cap - 1; h->sym_stride = cap;
+      if ((rc = dev_alloc(h, &h->d_sym, static_cast<size_t>(cap) * h->C * (qpsk ? 2 : 1)))) return fail(rc); }
+    if (!qpsk) {
+        unsigned cap = pow2_at_least(max_sym * h->L1 + 128); h->if_mask = cap - 1; h->if_stride = cap;
+        if ((rc = dev_alloc(h, &h->d_if, static_cast<size_t>(cap) * h->C))) return fail(rc);
+    }
+    h->out_stride = max_sym * h->L1 * (qpsk ? 1 : h->L2);
+    if ((rc = dev_alloc(h, &h->d_out, static_cast<size_t>(h->out_stride) * h->C, false))) return fail(rc);
+    std::vector<TxBitState> st(h->C);
+    for (auto& x : st) { x.scr_reg = 0x7F; x.enc_state = 0; x.diff_prev = 0; x.phase_q = 0; }
+    if (cudaMemcpy(h->d_bits, st.data(), sizeof(TxBitState) * h->C, cudaMemcpyHostToDevice) != cudaSuccess) { set_err(h, "state upload failed"); return fail(QRL_ECUDA); }
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { set_err(h, "create sync failed"); return fail(QRL_ECUDA); }
+    *out = h;
+    return QRL_OK;
+}
+int qrl_tx_destroy(qrl_tx* h)
+{
+    if (!h) return QRL_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return QRL_OK;
+}
+int qrl_tx_set_stream(qrl_tx* h, void* s)
+{
+    if (!h) return QRL_EINVAL;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    if (s) h->stream = static_cast<cudaStream_t>(s);
+    else { CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    return QRL_OK;
+}
+int qrl_tx_set_param(qrl_tx* h, int, int key, double value)
+{
+    if (!h) return QRL_EINVAL;
+    if (key == QRL_PARAM_BB_GAIN) { h->bb_gain = static_cast<float>(value); return QRL_OK; }   // gr_mod_4fsk::set_bb_gain
+    set_err(h, "qrl_tx_set_param: unsupported key");
     return QRL_EINVAL;
 }
-int qrl_tx_destroy(qrl_tx* h) { delete h; return QRL_OK; }
-int qrl_tx_set_stream(qrl_tx*, void*) { return QRL_EINVAL; }
-int qrl_tx_set_param(qrl_tx*, int, int, double) { return QRL_EINVAL; }
-int qrl_tx_work(qrl_tx*, const void*, long, long, int) { return QRL_EINVAL; }
-int qrl_tx_sync(qrl_tx*) { return QRL_EINVAL; }
-int qrl_tx_read(qrl_tx*, float*, long, long*, int) { return QRL_EINVAL; }
-int qrl_tx_out_device(qrl_tx*, float**, long*, long*) { return QRL_EINVAL; }
-long qrl_tx_launch_count(const qrl_tx*) { return 0; }
+int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
+{
+    if (!h || !in || n < 0) return QRL_EINVAL;
+    if (n > h->max_items) { set_err(h, "qrl_tx_work: n exceeds max_items given at create"); return QRL_ERANGE; }
+    h->n_out_last = 0;
+    if (n == 0) return QRL_OK;
+    CK(cudaSetDevice(h->device));
+    const unsigned char* b = static_cast<const unsigned char*>(in);
+    long long bstride = stride;
+    if (!on_device) {
+        CK(cudaMemcpy2DAsync(h->d_in, h->max_items, in, stride, n, h->C, cudaMemcpyHostToDevice, h->stream));
+        b = h->d_in; bstride = h->max_items;
+    }
+    const bool qpsk = h->kind == QRL_MOD_QPSK;
+    const long long sym0 = h->n_sym, nsym = 8LL * n;
+    if (qpsk) tx_bits_kernel<1><<<(h->C + 31) / 32, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
+    else tx_bits_kernel<0><<<(h->C + 31) / 32, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
+    h->launches++;
+    if (qpsk) {
+        constexpr int L = 4, NT = 16, MB = 8, MLEN = 64;
+        dim3 g(static_cast<unsigned>((nsym + MB * MLEN - 1) / (MB * MLEN)), h->C);
+        interp_fir_ccf_kernel<L, NT, MB, MLEN><<<g, L * MB, 0, h->stream>>>(
+            reinterpret_cast<const float2*>(h->d_sym), h->sym_mask, h->sym_stride, sym0, sym0 + nsym,
+            h->d_arms1, h->amplif, h->bb_gain, 1, h->d_out, h->out_stride, sym0 * L);
+        h->launches++;
+        h->n_out_last = static_cast<long>(nsym * L);
+    } else {
+        tx_shape_fm_kernel<256, 8><<<h->C, 256, 0, h->stream>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, sym0, nsym,
+            h->L1, h->nt1, h->d_arms1, h->repeat_only, h->pulse_scale, h->fm_sens, h->amplif, h->bb_gain,
+            h->d_if, h->if_mask, h->if_stride);
+        h->launches++;
+        constexpr int L = 20, NT = 35, MB = 8, MLEN = 70;
+        const long long m0 = sym0 * h->L1, m1 = (sym0 + nsym) * h->L1;
+        dim3 g(static_cast<unsigned>((m1 - m0 + MB * MLEN - 1) / (MB * MLEN)), h->C);
+        interp_fir_ccf_kernel<L, NT, MB, MLEN><<<g, L * MB, 0, h->stream>>>(
+            h->d_if, h->if_mask, h->if_stride, m0, m1, h->d_arms2, 1.0f, 1.0f, 0, h->d_out, h->out_stride, m0 * L);
+        h->launches++;
+        h->n_out_last = static_cast<long>((m1 - m0) * L);
+    }
+    h->n_sym += nsym;
+    CK(cudaGetLastError());
+    return QRL_OK;
+}
+int qrl_tx_sync(qrl_tx* h)
+{
+    if (!h) return QRL_EINVAL;
+    CK(cudaStreamSynchronize(h->stream));
+    return QRL_OK;
+}
+int qrl_tx_read(qrl_tx* h, float* dst, long cap, long* n_out, int dst_on_device)
+{
+    if (!h || !n_out) return QRL_EINVAL;
+    *n_out = h->n_out_last;
+    if (dst && h->n_out_last > 0) {
+        const long w = std::min(cap, h->n_out_last);
+        CK(cudaMemcpy2DAsync(dst, static_cast<size_t>(cap) * 8, h->d_out, static_cast<size_t>(h->out_stride) * 8, static_cast<size_t>(w) * 8, h->C,
+                             dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return QRL_OK;
+}
+int qrl_tx_out_device(qrl_tx* h, float** data, long* stride, long* n_out)
+{
+    if (!h) return QRL_EINVAL;
+    if (data) *data = reinterpret_cast<float*>(h->d_out);
+    if (stride) *stride = static_cast<long>(h->out_stride);
+    if (n_out) *n_out = h->n_out_last;
+    return QRL_OK;
+}
+long qrl_tx_launch_count(const qrl_tx* h) { return h ? h->launches : 0; }
 
 // ---------------------------------------------------------------------------------------------- design helpers
 static int copy_out(const std::vector<float>& v, float* out, int cap, int per_item = 1)

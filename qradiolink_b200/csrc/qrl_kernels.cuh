@@ -1140,4 +1140,179 @@ __global__ void hist_update_kernel(const float2* __restrict__ iq, long long iq_s
     new_hist[static_cast<long long>(c) * H + i] = v;
 }
 
+// ================================================================================================
+// TX chains (gr_mod_4fsk.cpp:95-115, gr_mod_qpsk.cpp:76-86)
+// ================================================================================================
+struct TxBitState {
+    unsigned scr_reg;      // scrambler_bb(0x8A, 0x7F, 7) register
+    unsigned enc_state;    // cc_encoder(80,7,2,{109,79}) CC_STREAMING shift register
+    unsigned diff_prev;    // diff_encoder_bb(4)
+    unsigned phase_q;      // Q32 phase accumulator of the frequency modulator
+};
+
+// bytes -> packed_to_unpacked(MSB) -> scrambler -> CC encoder -> pack_k_bits(2) -> map {0,1,3,2}
+//       -> chunks_to_symbols (4FSK: float level, QPSK: diff_encoder(4) + complex point)
+// one thread per channel (the scrambler is a feedback LFSR); 16 symbols per input byte... 8 per byte.
+template <int QPSK>
+__global__ void tx_bits_kernel(TxBitState* __restrict__ states, int C, const unsigned char* __restrict__ bytes, long long n, long long stride,
+                               float* __restrict__ sym_ring /* float or float2 */, unsigned sym_mask, long long sym_stride, long long sym0)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    TxBitState st = states[c];
+    const unsigned char* b = bytes + static_cast<long long>(c) * stride;
+    long long si = sym0;
+    for (long long i = 0; i < n; i++) {
+        const unsigned byte = b[i];
+        unsigned coded = 0;                       // 16 coded bits, first emitted = MSB
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            const unsigned in = (byte >> k) & 1u;
+            const unsigned out = st.scr_reg & 1u;
+            const unsigned nb = (__popc(st.scr_reg & 0x8Au) & 1u) ^ in;
+            st.scr_reg = ((st.scr_reg >> 1) | (nb << 7)) & 0xffu;
+            st.enc_state = ((st.enc_state << 1) | out) & 0x7fu;
+            coded = (coded << 2) | ((__popc(st.enc_state & 109u) & 1u) << 1) | (__popc(st.enc_state & 79u) & 1u);
+        }
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            const unsigned dibit = (coded >> (2 * k)) & 3u;
+            const unsigned chunk = dibit ^ (dibit >> 1);                  // map {0,1,3,2}
+            if (QPSK) {
+                st.diff_prev = (chunk + st.diff_prev) & 3u;
+                const float qr = (st.diff_prev >= 2u) ? 0.707f : -0.707f;
+                const float qi = (st.diff_prev == 1u || st.diff_prev == 2u) ? 0.707f : -0.707f;
+                reinterpret_cast<float2*>(sym_ring)[static_cast<long long>(c) * sym_stride + (si & sym_mask)] = make_float2(qr, qi);
+            } else {
+                sym_ring[static_cast<long long>(c) * sym_stride + (si & sym_mask)] = -1.5f + static_cast<float>(chunk);
+            }
+            si++;
+        }
+    }
+    states[c] = st;
+}
+
+// 4FSK-FM: rational_resampler_fff(L,1,RRC) -> x0.66666666 -> frequency_modulator_fc -> x amplif -> x bb_gain.
+// The phase accumulator is a Q32 integer (increment quantised once per sample, summed exactly mod 2^32), so the
+// per-channel phase is a prefix sum: one CTA per channel scans its samples block by block.
+template <int NTHREADS, int ITEMS>
+__global__ void __launch_bounds__(NTHREADS)
+tx_shape_fm_kernel(TxBitState* __restrict__ states, const float* __restrict__ sym_ring, unsigned sym_mask, long long sym_stride,
+                   long long sym0, long long nsym, int L, int nt_arm, const float* __restrict__ arms /* [L][nt_arm] */, int repeat_only,
+                   float pulse_scale, float fm_sens, float amplif, float bb_gain,
+                   float2* __restrict__ if_ring, unsigned if_mask, long long if_stride)
+{
+    const int c = blockIdx.x;
+    const float* sy = sym_ring + static_cast<long long>(c) * sym_stride;
+    float2* o = if_ring + static_cast<long long>(c) * if_stride;
+    __shared__ unsigned warp_sums[NTHREADS / 32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = states[c].phase_q;
+    __syncthreads();
+    const long long n0 = sym0 * L, n1 = (sym0 + nsym) * L;              // absolute IF sample range
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long blk = n0; blk < n1; blk += NTHREADS * ITEMS) {
+        unsigned inc[ITEMS];
+        unsigned local = 0;
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const long long a = blk + static_cast<long long>(threadIdx.x) * ITEMS + it;
+            unsigned q = 0;
+            if (a < n1) {
+                const long long m = a / L; const int ph = static_cast<int>(a - m * L);
+                float x;
+                if (repeat_only) x = sy[m & sym_mask];
+                else {
+                    const float* h = arms + ph * nt_arm;
+                    float acc = 0.0f;
+                    for (int k = nt_arm - 1; k >= 0; k--) acc = fmaf(h[k], sy[(m - k) & sym_mask], acc);
+                    x = acc * pulse_scale;
+                }
+                const float finc = fm_sens * x;
+                const double dq = rint(static_cast<double>(finc) * (2147483648.0 / 3.14159265358979323846));
+                q = static_cast<unsigned>(static_cast<int>(static_cast<long long>(dq)));
+            }
+            local += q;
+            inc[it] = local;                                             // inclusive prefix inside the thread
+        }
+        // block-wide exclusive scan of the per-thread totals
+        unsigned v = local;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += t; }
+        if (lane == 31) warp_sums[warp] = v;
+        __syncthreads();
+        unsigned wbase = 0;
+        for (int w = 0; w < warp; w++) wbase += warp_sums[w];
+        const unsigned excl = carry + wbase + (v - local);
+        unsigned total = 0;
+        for (int w = 0; w < NTHREADS / 32; w++) total += warp_sums[w];
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const long long a = blk + static_cast<long long>(threadIdx.x) * ITEMS + it;
+            if (a < n1) {
+                const unsigned ux = excl + inc[it];
+                const int si = ux >> 22;
+                const float sn = d_sine_tab[2 * si] * static_cast<float>(ux >> 1) + d_sine_tab[2 * si + 1];
+                const unsigned uc = ux + 0x40000000u;
+                const int ci = uc >> 22;
+                const float cs = d_sine_tab[2 * ci] * static_cast<float>(uc >> 1) + d_sine_tab[2 * ci + 1];
+                float re = cs * amplif, im = sn * amplif;
+                re = re * bb_gain; im = im * bb_gain;
+                o[a & if_mask] = make_float2(re, im);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) states[c].phase_q = carry;
+}
+
+// Interpolating FIR  y[L m + p] = sum_k arm[p][k] x[m - k]  (rational_resampler_ccf(L,1)), complex stream.
+// Thread = (m-block, phase p): its NT arm taps live in registers, its input window slides through registers
+// (one shared-memory load per m), 2 NT FFMA per output sample; L*MB threads keep every lane busy.
+template <int L, int NT, int MB, int MLEN>
+__global__ void __launch_bounds__(L * MB)
+interp_fir_ccf_kernel(const float2* __restrict__ in_ring, unsigned in_mask, long long in_stride, long long m0, long long m1,
+                      const float* __restrict__ arms /* [L][NT] */, float post_gain1, float post_gain2, int apply_gain,
+                      float2* __restrict__ out, long long out_stride, long long out_base /* absolute output index of out[c][0] */)
+{
+    static_assert(MLEN % NT == 0, "m-loop is unrolled in groups of NT");
+    __shared__ float2 xs[MB * MLEN + NT];
+    const int c = blockIdx.y;
+    const long long tile0 = m0 + static_cast<long long>(blockIdx.x) * (MB * MLEN);
+    if (tile0 >= m1) return;
+    const float2* x = in_ring + static_cast<long long>(c) * in_stride;
+    for (int i = threadIdx.x; i < MB * MLEN + NT - 1; i += L * MB) {
+        const long long m = tile0 - (NT - 1) + i;
+        xs[i] = (m < m1) ? x[m & in_mask] : make_float2(0.0f, 0.0f);
+    }
+    __syncthreads();
+    const int p = threadIdx.x % L, mb = threadIdx.x / L;
+    float h[NT];
+#pragma unroll
+    for (int k = 0; k < NT; k++) h[k] = arms[p * NT + k];
+    float2 w[NT];
+#pragma unroll
+    for (int j = 0; j < NT - 1; j++) w[j] = xs[mb * MLEN + j];
+    float2* oc = out + static_cast<long long>(c) * out_stride;
+    for (int g = 0; g < MLEN / NT; g++) {
+#pragma unroll
+        for (int i = 0; i < NT; i++) {
+            // window slot (NT-1+i) % NT receives the newest sample; sample m-k sits in slot (NT-1+i-k) % NT
+            w[(NT - 1 + i) % NT] = xs[mb * MLEN + g * NT + i + (NT - 1)];
+            float re = 0.0f, im = 0.0f;
+#pragma unroll
+            for (int k = NT - 1; k >= 0; k--) {
+                const float2 v = w[(NT - 1 + i - k + NT) % NT];
+                re = fmaf(h[k], v.x, re);
+                im = fmaf(h[k], v.y, im);
+            }
+            if (apply_gain) { re = re * post_gain1; im = im * post_gain1; re = re * post_gain2; im = im * post_gain2; }
+            const long long m = tile0 + mb * MLEN + g * NT + i;
+            if (m < m1) oc[(m * L + p) - out_base] = make_float2(re, im);
+        }
+    }
+}
+
 }  // namespace qrl
