@@ -255,10 +255,11 @@ def run_ours(args):
     launches_per_step = max(1, fir_n // args.steps)          # work() slices a step into several FIR launches
     alg_bytes = ALG_BYTES_PER_SAMPLE * C * T / launches_per_step
     achieved = alg_bytes / fir_avg_s / 1e9 if fir_avg_s > 0 else 0.0
+    launches_per_step = max(1, stage_ms[0][1] // args.steps)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "fir_traffic_bytes.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    if os.path.exists(tp):      # ncu --set full capture (profiles/): DRAM bytes per input sample x samples per launch
+        traffic = json.load(open(tp)).get("per_sample") * C * T / launches_per_step
 
     cpu_line = None
     if world == 1 and not args.no_cpu:

@@ -163,6 +163,13 @@ inline gr_demod_b200_sptr make_gr_demod_nbfm(int sps, int samp_rate, int carrier
                                              int n_channels = 1, long max_samples = 1 << 20, int device = 0)
 { return std::make_shared<gr_demod_b200>(QRL_DEMOD_NBFM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_samples, device); }
 
+inline gr_demod_b200_sptr make_gr_demod_bpsk(int sps, int samp_rate, int carrier_freq, int filter_width,
+                                             int n_channels = 1, long max_samples = 1 << 20, int device = 0)
+{ return std::make_shared<gr_demod_b200>(QRL_DEMOD_BPSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_samples, device); }
+inline gr_demod_b200_sptr make_gr_demod_2fsk(int sps, int samp_rate, int carrier_freq, int filter_width, bool fm,
+                                             int n_channels = 1, long max_samples = 1 << 20, int device = 0)
+{ return std::make_shared<gr_demod_b200>(QRL_DEMOD_2FSK, sps, samp_rate, carrier_freq, filter_width, fm ? 1 : 0, n_channels, max_samples, device); }
+
 // ---- batched modulator
 class gr_mod_b200 {
 public:

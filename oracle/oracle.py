@@ -195,7 +195,7 @@ def find_frames(bits, sync, sync_bits, frame_len):
 # ------------------------------------------------------------------ chains
 class Rx:
     """One channel of a reference demod hier-block (make_gr_demod_*), CPU oracle."""
-    PORT_DTYPES = {0: np.complex64, 2: np.uint8, 3: np.uint8}
+    PORT_DTYPES = {0: np.complex64, 2: np.uint8, 3: np.uint8}   # port 1: complex constellation or float audio
 
     def __init__(self, kind, sps, samp_rate, carrier_freq, filter_width, flag=0):
         self.kind = kind

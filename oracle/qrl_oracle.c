@@ -30,6 +30,8 @@
 
 static int g_fir_order = 0;
 static int g_fm_literal = 0;
+static int g_dbg_bypass_fll = 0;
+void qo_dbg_bypass_fll(int on) { g_dbg_bypass_fll = on; }
 void qo_set_fir_order(int o) { g_fir_order = o; }
 void qo_set_fm_literal(int on) { g_fm_literal = on; }
 
@@ -758,6 +760,108 @@ static void symsync_work(symsync_t* s, const float* x, size_t n, qvec* out)
     }
 }
 
+/* ------------------------------------------------------------------ fll_band_edge_cc (A8) */
+/* digital::fll_band_edge_cc(sps, rolloff, filter_size, bw): rotate by the NCO, band-edge filter pair on the rotated
+ * stream, error = |lower|^2 - |upper|^2 drives a second-order control loop (max/min freq = +-2*pi*2/sps).
+ * Dot products: taps index k ascending = oldest rotated sample first, complex multiply-accumulate in four fmaf chains. */
+typedef struct {
+    int N; float* lo; float* up;           /* complex taps, interleaved, stored reversed like d_taps_lower/upper */
+    float* hist;                            /* last N rotated outputs (complex), hist[N-1] newest */
+    float phase, freq, alpha, beta, max_freq, min_freq;
+} fll_t;
+static double fll_sinc(double x) { if (x == 0) return 1.0; return sin(M_PI * x) / (M_PI * x); }
+static void fll_init(fll_t* f, float sps, float rolloff, int N, float bw)
+{
+    f->N = N; f->lo = (float*)calloc(2 * N, 4); f->up = (float*)calloc(2 * N, 4); f->hist = (float*)calloc(2 * N, 4);
+    f->phase = 0; f->freq = 0;
+    qo_control_loop_gains(bw, &f->alpha, &f->beta);
+    f->max_freq = (float)(2.0 * M_PI * (2.0 / sps)); f->min_freq = -f->max_freq;
+    int M = (int)rint(N / sps);
+    float power = 0;
+    float* bb = (float*)malloc(sizeof(float) * N);
+    for (int i = 0; i < N; i++) {
+        float k = (float)(-M + i * 2.0 / sps);
+        float tap = (float)(fll_sinc(rolloff * k - 0.5) + fll_sinc(rolloff * k + 0.5));
+        power += tap; bb[i] = tap;
+    }
+    int Nh = (int)((N - 1.0) / 2.0);
+    for (int i = 0; i < N; i++) {
+        float tap = bb[i] / power;
+        float k = (float)((-Nh + i) / (2.0 * sps));
+        float ang = (float)(2.0 * M_PI * (1 + rolloff) * k);
+        f->lo[2 * (N - i - 1)] = tap * cosf(-ang); f->lo[2 * (N - i - 1) + 1] = tap * sinf(-ang);
+        f->up[2 * (N - i - 1)] = tap * cosf(ang);  f->up[2 * (N - i - 1) + 1] = tap * sinf(ang);
+    }
+    free(bb);
+}
+static void fll_free(fll_t* f) { free(f->lo); free(f->up); free(f->hist); }
+static inline void fll_step(fll_t* f, float xr, float xi, float* yr, float* yi)
+{
+    if (g_dbg_bypass_fll) { *yr = xr; *yi = xi; return; }
+    float sn, cs;
+    qo_sincosf(f->phase, &sn, &cs);
+    float orr = xr * cs - xi * sn, oi = xr * sn + xi * cs;
+    memmove(f->hist, f->hist + 2, sizeof(float) * 2 * (f->N - 1));
+    f->hist[2 * (f->N - 1)] = orr; f->hist[2 * (f->N - 1) + 1] = oi;
+    float ur = 0, ui = 0, lr = 0, li = 0;
+    for (int k = 0; k < f->N; k++) {
+        float hr = f->hist[2 * k], hi = f->hist[2 * k + 1];
+        ur = fmaf(f->up[2 * k], hr, ur); ur = fmaf(-f->up[2 * k + 1], hi, ur);
+        ui = fmaf(f->up[2 * k], hi, ui); ui = fmaf(f->up[2 * k + 1], hr, ui);
+        lr = fmaf(f->lo[2 * k], hr, lr); lr = fmaf(-f->lo[2 * k + 1], hi, lr);
+        li = fmaf(f->lo[2 * k], hi, li); li = fmaf(f->lo[2 * k + 1], hr, li);
+    }
+    float err = (lr * lr + li * li) - (ur * ur + ui * ui);
+    f->freq = f->freq + f->beta * err;
+    f->phase = f->phase + f->freq + f->alpha * err;
+    while ((double)f->phase > 2.0 * M_PI) f->phase = (float)((double)f->phase - 2.0 * M_PI);
+    while ((double)f->phase < -2.0 * M_PI) f->phase = (float)((double)f->phase + 2.0 * M_PI);
+    if (f->freq > f->max_freq) f->freq = f->max_freq;
+    else if (f->freq < f->min_freq) f->freq = f->min_freq;
+    *yr = orr; *yi = oi;
+}
+
+/* ------------------------------------------------------------------ clock_recovery_mm_cc (A9) */
+typedef struct {
+    float mu, omega, omega_mid, omega_lim, gain_omega, gain_mu;
+    float p0r, p0i, p1r, p1i, p2r, p2i, c0r, c0i, c1r, c1i, c2r, c2i;
+    size_t ii; qvec in;
+} crmm_t;
+static void crmm_init(crmm_t* c, float omega, float gain_omega, float mu, float gain_mu, float rel_lim)
+{
+    tabs_init();
+    memset(c, 0, sizeof *c);
+    c->mu = mu; c->omega = omega; c->omega_mid = omega; c->omega_lim = rel_lim * omega;
+    c->gain_omega = gain_omega; c->gain_mu = gain_mu;
+    qv_init(&c->in, 8);
+}
+static void crmm_work(crmm_t* c, const float* x, size_t n, qvec* out)
+{
+    qv_push(&c->in, x, n);
+    const float* b = (const float*)c->in.d;
+    while (c->ii + 24 <= c->in.n) {                     /* 8 interpolator taps + FUDGE 16 */
+        const float* p = b + 2 * c->ii;
+        c->p2r = c->p1r; c->p2i = c->p1i; c->p1r = c->p0r; c->p1i = c->p0i;
+        c->p0r = mmse_interp(p, 2, c->mu); c->p0i = mmse_interp(p + 1, 2, c->mu);
+        c->c2r = c->c1r; c->c2i = c->c1i; c->c1r = c->c0r; c->c1i = c->c0i;
+        c->c0r = c->p0r > 0.0f ? 1.0f : 0.0f; c->c0i = c->p0i > 0.0f ? 1.0f : 0.0f;   /* slicer_0deg */
+        /* x = (c0 - c2) * conj(p1);  y = (p0 - p2) * conj(c1);  mm = Re(y - x) */
+        float ar = c->c0r - c->c2r, ai = c->c0i - c->c2i;
+        float xr = ar * c->p1r + ai * c->p1i;
+        float br = c->p0r - c->p2r, bi = c->p0i - c->p2i;
+        float yr = br * c->c1r + bi * c->c1i;
+        float mm = clipf(yr - xr, 1.0f);
+        qv_pushc(out, c->p0r, c->p0i);
+        c->omega = c->omega + c->gain_omega * mm;
+        c->omega = c->omega_mid + clipf(c->omega - c->omega_mid, c->omega_lim);
+        c->mu = c->mu + c->omega + c->gain_mu * mm;
+        float fl = floorf(c->mu);
+        c->ii += (size_t)(int)fl;
+        c->mu = c->mu - fl;
+    }
+    if (c->ii > 0) { size_t d = c->ii < c->in.n ? c->ii : c->in.n; qv_drop(&c->in, d); c->ii -= d; }
+}
+
 /* ------------------------------------------------------------------ FEC (A11) and LFSR (A12) */
 static inline int parity8(unsigned v) { v ^= v >> 4; v ^= v >> 2; v ^= v >> 1; return v & 1; }
 typedef struct { unsigned state; } ccenc_t;
@@ -926,6 +1030,8 @@ struct qo_rx {
     agc2_t agc; costas_t pll, costas; float dp_r, dp_i; float rot_r, rot_i;
     /* 4fsk non-fm */
     fircc_t bp[4]; resamp_t symfilt;
+    /* bpsk / 2fsk */
+    fll_t fll; crmm_t crmm; ccdec_t dec2; lfsr_t descr2; int dec2_started;
     /* scratch + ports */
     qvec s_res, s_filt, s_dem, s_rrc, s_sym, s_soft, s_bits, s_tmp, s_tmp2, s_bp[4];
     qvec port[4];
@@ -1030,6 +1136,48 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         qdemod_init(&r->qd, (float)(r->tsr / (4 * M_PI * filter_width)));
         squelch_init(&r->sq, -140, 0.01, 320, 1);
         r->port[1].isz = 4;
+    } else if (kind == QO_DEMOD_2FSK) {
+        /* /root/reference/src/gr/gr_demod_2fsk.cpp:33-167 (fm variant; the band-filter variant is not restated yet) */
+        int decim, interp = 1, nfilts;
+        if (sps == 10) { r->tsr = 20000; r->sym_sps = sps; decim = 50; nfilts = 35 * r->sym_sps; }
+        else if (sps >= 5) { r->tsr = 40000; r->sym_sps = sps * 2; decim = 25; nfilts = 35 * r->sym_sps; }
+        else { free(r); return NULL; }
+        if (!flag) { free(r); return NULL; }
+        int spacing = 1;
+        if ((nfilts % 2) == 0) nfilts += 1;
+        int n0 = qo_firdes_low_pass(interp, (double)interp * samp_rate, r->tsr / 2, r->tsr / 2, QO_WIN_BLACKMAN_HARRIS, T0, 4096);
+        r->ntaps_store[0] = n0;
+        resamp_init(&r->resamp, 2, interp, decim, T0, n0);
+        fll_init(&r->fll, (float)r->sym_sps, 0.1f, 16, (float)(24 * M_PI / 100));
+        int n1 = qo_firdes_low_pass(1, r->tsr, filter_width, filter_width, QO_WIN_BLACKMAN_HARRIS, T1, 4096);
+        r->ntaps_store[1] = n1;
+        resamp_init(&r->filt, 2, 1, 1, T1, n1);
+        qdemod_init(&r->qd, (float)(r->sym_sps / (spacing * M_PI / 2)));
+        int n2 = qo_firdes_rrc(1, r->tsr, r->tsr / r->sym_sps, 0.2, nfilts, T2, 4096);
+        r->ntaps_store[2] = n2;
+        resamp_init(&r->shaping, 1, 1, 1, T2, n2);
+        float symbol_rate = (float)r->tsr / (float)r->sym_sps;
+        float sps_dev = 200.0f / symbol_rate;
+        symsync_init(&r->ss, 1, (float)r->sym_sps, (float)(2 * M_PI / (symbol_rate / 10)), 1.0f, 0.2869f, sps_dev, SL_BPSK);
+        r->soft_scale = 128.0f;
+        ccdec_init(&r->dec); lfsr_init(&r->descr); ccdec_init(&r->dec2); lfsr_init(&r->descr2);
+        r->fm = 1;
+    } else if (kind == QO_DEMOD_BPSK) {
+        /* /root/reference/src/gr/gr_demod_bpsk.cpp:33-105 */
+        r->tsr = 20000; r->sym_sps = sps;
+        int n0 = qo_firdes_low_pass(1, samp_rate, r->tsr / 2, r->tsr / 2, QO_WIN_BLACKMAN_HARRIS, T0, 4096);
+        r->ntaps_store[0] = n0;
+        resamp_init(&r->resamp, 2, 1, 50, T0, n0);
+        fll_init(&r->fll, (float)sps, 0.35f, 32, (float)(8 * M_PI / 100));
+        int n1 = qo_firdes_rrc(sps, sps, 1, 0.35, 15 * sps, T1, 4096);
+        r->ntaps_store[1] = n1;
+        resamp_init(&r->shaping, 2, 1, 1, T1, n1);
+        agc2_init(&r->agc, 1e-1f, 1e-1f, 1.0f, 1.0f);
+        float gain_mu = 0.05f, gain_omega = 0.005f;
+        crmm_init(&r->crmm, (float)sps, gain_omega * gain_omega, 0.5f, gain_mu, 0.001f);
+        costas_init(&r->costas, (float)(2 * M_PI / 200), 2, 0);
+        r->soft_scale = 64.0f;
+        ccdec_init(&r->dec); lfsr_init(&r->descr); ccdec_init(&r->dec2); lfsr_init(&r->descr2);
     } else { free(r); return NULL; }
     return r;
 }
@@ -1053,8 +1201,60 @@ static void rx_fec_tail(qo_rx* r)
     r->s_bits.n = 0;
 }
 
+/* two decoders on the same soft stream, the second one behind a delay(1) (gr_demod_bpsk.cpp:96-104) */
+static void rx_fec_tail_dual(qo_rx* r)
+{
+    size_t b0 = r->s_bits.n;
+    ccdec_work(&r->dec, r->s_soft.d, r->s_soft.n, &r->s_bits);
+    for (size_t i = b0; i < r->s_bits.n; i++) qv_pushb(&r->port[2], lfsr_descramble(&r->descr, r->s_bits.d[i]));
+    r->s_bits.n = 0;
+    if (!r->dec2_started) { unsigned char z = 0; ccdec_work(&r->dec2, &z, 1, &r->s_bits); r->dec2_started = 1; }
+    ccdec_work(&r->dec2, r->s_soft.d, r->s_soft.n, &r->s_bits);
+    for (size_t i = 0; i < r->s_bits.n; i++) qv_pushb(&r->port[3], lfsr_descramble(&r->descr2, r->s_bits.d[i]));
+    r->s_bits.n = 0;
+    r->s_soft.n = 0;
+}
+
 int qo_rx_work(qo_rx* r, const float* iq, long T)
 {
+    if (r->kind == QO_DEMOD_2FSK) {
+        r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
+        float* v = (float*)r->s_res.d;
+        for (size_t i = 0; i < r->s_res.n; i++) fll_step(&r->fll, v[2 * i], v[2 * i + 1], &v[2 * i], &v[2 * i + 1]);
+        r->s_filt.n = 0; resamp_work(&r->filt, v, r->s_res.n, &r->s_filt);
+        qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
+        r->s_dem.n = 0; qdemod_work(&r->qd, (const float*)r->s_filt.d, r->s_filt.n, &r->s_dem);
+        r->s_rrc.n = 0; resamp_work(&r->shaping, (const float*)r->s_dem.d, r->s_dem.n, &r->s_rrc);
+        r->s_sym.isz = 4; r->s_sym.n = 0;
+        symsync_work(&r->ss, (const float*)r->s_rrc.d, r->s_rrc.n, &r->s_sym);
+        const float* sy = (const float*)r->s_sym.d;
+        for (size_t i = 0; i < r->s_sym.n; i++) {
+            qv_pushc(&r->port[1], sy[i], 0.0f);                      /* float_to_complex, imag 0 */
+            qv_pushb(&r->s_soft, soft_u8(sy[i], r->soft_scale));
+        }
+        rx_fec_tail_dual(r);
+        return 0;
+    }
+    if (r->kind == QO_DEMOD_BPSK) {
+        r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
+        float* v = (float*)r->s_res.d;
+        for (size_t i = 0; i < r->s_res.n; i++) fll_step(&r->fll, v[2 * i], v[2 * i + 1], &v[2 * i], &v[2 * i + 1]);
+        r->s_filt.n = 0; resamp_work(&r->shaping, v, r->s_res.n, &r->s_filt);
+        qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
+        float* f = (float*)r->s_filt.d;
+        for (size_t i = 0; i < r->s_filt.n; i++) agc2_step(&r->agc, f[2 * i], f[2 * i + 1], &f[2 * i], &f[2 * i + 1]);
+        r->s_sym.isz = 8; r->s_sym.n = 0;
+        crmm_work(&r->crmm, f, r->s_filt.n, &r->s_sym);
+        const float* sy = (const float*)r->s_sym.d;
+        for (size_t i = 0; i < r->s_sym.n; i++) {
+            float cr, ci;
+            costas_step(&r->costas, sy[2 * i], sy[2 * i + 1], &cr, &ci);
+            qv_pushc(&r->port[1], cr, ci);
+            qv_pushb(&r->s_soft, soft_u8(cr, r->soft_scale));      /* complex_to_real */
+        }
+        rx_fec_tail_dual(r);
+        return 0;
+    }
     if (r->kind == QO_DEMOD_4FSK) {
         r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
         r->s_filt.n = 0; resamp_work(&r->filt, (const float*)r->s_res.d, r->s_res.n, &r->s_filt);
@@ -1215,6 +1415,25 @@ qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         t->amplif = 0.6f;
         t->s_sym.isz = 8;
         (void)samp_rate; (void)filter_width;
+    } else if (kind == QO_MOD_BPSK) {
+        /* /root/reference/src/gr/gr_mod_bpsk.cpp:27-69 */
+        t->sps = sps;
+        int n = qo_firdes_rrc(sps, sps, 1, 0.35, 11 * sps, taps, 16384);
+        resamp_init(&t->rrc, 2, sps, 1, taps, n);
+        t->amplif = 0.6f; t->s_sym.isz = 8;
+    } else if (kind == QO_MOD_2FSK) {
+        /* /root/reference/src/gr/gr_mod_2fsk.cpp:26-100 */
+        int fm = flag; t->fm = fm; t->sps = sps;
+        int nfilts = 25 * sps, spacing = 2; t->amplif = 0.8f;
+        if (fm) { spacing = 1; t->amplif = 0.9f; }
+        if (sps == 5) nfilts = nfilts * 5;
+        if ((nfilts % 2) == 0) nfilts += 1;
+        int n = qo_firdes_rrc(sps, sps, 1, 0.2, nfilts, taps, 16384);
+        resamp_init(&t->rrc, 1, sps, 1, taps, n);
+        t->fm_sens = (float)((spacing * M_PI / 2) / sps);
+        n = qo_firdes_low_pass(10, samp_rate, filter_width, filter_width, QO_WIN_HAMMING, taps, 16384);
+        resamp_init(&t->interp, 2, 10, 1, taps, n);
+        t->s_sym.isz = 4;
     } else { free(t); return NULL; }
     return t;
 }
@@ -1304,6 +1523,34 @@ int qo_tx_work(qo_tx* t, const void* in, long n)
             resamp_work(&t->rrc, (const float*)t->s_sym.d, t->s_sym.n, &t->out);
             float* m = (float*)t->out.d;
             for (size_t i = 2 * o0; i < 2 * t->out.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
+        }
+        return 0;
+    }
+    if (t->kind == QO_MOD_BPSK || t->kind == QO_MOD_2FSK) {
+        t->s_bits.n = 0;
+        for (long i = 0; i < n; i++)
+            for (int b = 7; b >= 0; b--) qv_pushb(&t->s_bits, lfsr_scramble(&t->scr, (bytes[i] >> b) & 1));
+        t->s_coded.n = 0;
+        ccenc_work(&t->enc, t->s_bits.d, t->s_bits.n, &t->s_coded);
+        t->s_sym.n = 0;
+        for (size_t i = 0; i < t->s_coded.n; i++) {
+            float lv = t->s_coded.d[i] ? 1.0f : -1.0f;
+            if (t->kind == QO_MOD_BPSK) qv_pushc(&t->s_sym, lv, 0.0f); else qv_pushf(&t->s_sym, lv);
+        }
+        if (t->kind == QO_MOD_BPSK) {
+            size_t o0 = t->out.n;
+            resamp_work(&t->rrc, (const float*)t->s_sym.d, t->s_sym.n, &t->out);
+            float* m = (float*)t->out.d;
+            for (size_t i = 2 * o0; i < 2 * t->out.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
+        } else {
+            t->s_shaped.n = 0;
+            if (t->fm) resamp_work(&t->rrc, (const float*)t->s_sym.d, t->s_sym.n, &t->s_shaped);
+            else { const float* p = (const float*)t->s_sym.d; for (size_t i = 0; i < t->s_sym.n; i++) for (int k = 0; k < t->sps; k++) qv_pushf(&t->s_shaped, p[i]); }
+            t->s_mod.n = 0;
+            fm_mod(t, (const float*)t->s_shaped.d, t->s_shaped.n, &t->s_mod, 1.0f);
+            float* m = (float*)t->s_mod.d;
+            for (size_t i = 0; i < 2 * t->s_mod.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
+            resamp_work(&t->interp, m, t->s_mod.n, &t->out);
         }
         return 0;
     }

@@ -126,6 +126,12 @@ struct qrl_rx : HandleBase {
     AgcCostasState* d_ac = nullptr;
     Ring r3;
     int sym_sps = 0;
+    // BPSK / 2FSK: fll_band_edge_cc + second (delayed) decoder
+    FllParams fllp{};
+    FllState* d_fll = nullptr; float2* d_fll_hist = nullptr; float* d_fll_taps = nullptr;
+    Ring rf;                       // FLL output (channel-major complex)
+    ViterbiState* d_vs2 = nullptr;
+    unsigned char* d_port3 = nullptr; int* d_port3_cnt = nullptr;
     // NBFM audio chain
     NbfmParams nbp{};
     NbfmState* d_nb = nullptr;
@@ -222,6 +228,9 @@ int stage1(qrl_rx* h, const float2* iq, long long stride, long long T, long long
 {
     if (k1 <= k0) return QRL_OK;
     if (h->D1 == 50 && h->Q1 == 9) return launch_fir_poly<50, 9, 8, 128, 8>(h, iq, stride, T, k0, k1);
+    if (h->D1 == 100 && h->Q1 == 9) return launch_fir_poly<100, 9, 8, 64, 8>(h, iq, stride, T, k0, k1);     // 837 taps (4FSK-1k, QPSK-2k shape)
+    if (h->D1 == 25 && h->Q1 == 9) return launch_fir_poly<25, 9, 8, 256, 8>(h, iq, stride, T, k0, k1);      // 209 taps (2FSK-2k)
+    if (h->D1 == 125 && h->Q1 == 9) return launch_fir_poly<125, 9, 8, 48, 6>(h, iq, stride, T, k0, k1);     // 1045 taps (SSB)
     if (h->D1 == 2 && h->ntaps1 <= 56) return launch_fir_d2<56, 8, 128>(h, iq, stride, T, k0, k1);
     set_err(h, "stage-1 resampler shape not built (D=" + std::to_string(h->D1) + ", taps=" + std::to_string(h->ntaps1) + ")");
     return QRL_EINVAL;
@@ -268,6 +277,29 @@ bool make_sm_partition(qrl_rx* h, unsigned loop_sms, int prio)
 }
 
 // interleaved = channel-interleaved layout [ceil(C/32)][slots][32] (allocated for the padded channel count)
+// digital::fll_band_edge_cc::design_filter restated: returns lower[2N] | upper[2N] (complex, stored reversed)
+std::vector<float> fll_design(float sps, float rolloff, int N)
+{
+    auto sinc = [](double x) { return x == 0 ? 1.0 : std::sin(kPi * x) / (kPi * x); };
+    std::vector<float> bb(N), t(4 * N);
+    const int M = static_cast<int>(std::rint(N / sps));
+    float power = 0;
+    for (int i = 0; i < N; i++) {
+        const float k = static_cast<float>(-M + i * 2.0 / sps);
+        const float tap = static_cast<float>(sinc(rolloff * k - 0.5) + sinc(rolloff * k + 0.5));
+        power += tap; bb[i] = tap;
+    }
+    const int Nh = static_cast<int>((N - 1.0) / 2.0);
+    for (int i = 0; i < N; i++) {
+        const float tap = bb[i] / power;
+        const float k = static_cast<float>((-Nh + i) / (2.0 * sps));
+        const float ang = static_cast<float>(2.0 * kPi * (1 + rolloff) * k);
+        t[2 * (N - i - 1)] = tap * cosf(-ang); t[2 * (N - i - 1) + 1] = tap * sinf(-ang);
+        t[2 * N + 2 * (N - i - 1)] = tap * cosf(ang); t[2 * N + 2 * (N - i - 1) + 1] = tap * sinf(ang);
+    }
+    return t;
+}
+
 int make_ring(qrl_rx* h, Ring* r, size_t isz, long long min_items, bool interleaved = false)
 {
     unsigned cap = pow2_at_least(min_items);
@@ -367,6 +399,53 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         h->ssp.n0 = static_cast<int>(floorf(h->ssp.min_period - fabsf(h->ssp.alpha)));
         h->ssp.fl0 = static_cast<float>(h->ssp.n0);
         h->nports = 3;
+    } else if (kind == QRL_DEMOD_2FSK) {
+        // gr_demod_2fsk.cpp:39-130 (fm variant)
+        int decim, nfilts;
+        if (sps == 10) { tsr = 20000; sym_sps = sps; decim = 50; nfilts = 35 * sym_sps; }
+        else if (sps >= 5) { tsr = 40000; sym_sps = sps * 2; decim = 25; nfilts = 35 * sym_sps; }
+        else { set_err(h, "make_gr_demod_2fsk: 10k (2/25 resampler) variant not built yet"); return fail(QRL_EINVAL); }
+        if (!flag) { set_err(h, "2FSK band-filter (non-FM) variant not built yet"); return fail(QRL_EINVAL); }
+        if ((nfilts % 2) == 0) nfilts += 1;
+        taps1 = low_pass(1, samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
+        h->D1 = decim;
+        taps2 = low_pass(1, tsr, filter_width, filter_width, WIN_BLACKMAN_HARRIS);
+        taps3 = root_raised_cosine(1, tsr, tsr / sym_sps, 0.2, nfilts);
+        h->qd_gain = static_cast<float>(sym_sps / (1 * kPi / 2));
+        const float symbol_rate = static_cast<float>(tsr) / static_cast<float>(sym_sps);
+        const float sps_dev = 200.0f / symbol_rate;
+        clock_loop_gains(static_cast<float>(2 * kPi / (symbol_rate / 10)), 1.0f, 0.2869f, h->ssp.alpha, h->ssp.beta);
+        h->ssp.sps = static_cast<float>(sym_sps);
+        h->ssp.max_period = h->ssp.sps + sps_dev; h->ssp.min_period = h->ssp.sps - sps_dev;
+        h->ssp.lookahead = 8 + static_cast<int>(ceilf(h->ssp.max_period)) + 1;
+        h->ssp.soft_scale = 128.0f;
+        h->ssp.n0 = static_cast<int>(floorf(h->ssp.min_period - fabsf(h->ssp.alpha)));
+        h->ssp.fl0 = static_cast<float>(h->ssp.n0);
+        h->fllp.N = 16;
+        control_loop_gains(static_cast<float>(24 * kPi / 100), h->fllp.alpha, h->fllp.beta);
+        h->fllp.max_freq = static_cast<float>(2.0 * kPi * (2.0 / sym_sps)); h->fllp.min_freq = -h->fllp.max_freq;
+        h->nports = 4;
+    } else if (kind == QRL_DEMOD_BPSK) {
+        // gr_demod_bpsk.cpp:40-76
+        tsr = 20000; sym_sps = sps;
+        taps1 = low_pass(1, samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
+        h->D1 = 50;
+        taps2 = root_raised_cosine(sps, sps, 1, 0.35, 15 * sps);
+        h->acp.attack = 1e-1f; h->acp.decay = 1e-1f; h->acp.ref = 1.0f; h->acp.max_gain = 65536.0f; h->acp.order = 0;
+        const float gain_mu = 0.05f, gain_omega = 0.005f;
+        h->ssp.loop_kind = LOOP_CRMM;
+        h->ssp.sps = static_cast<float>(sps);
+        h->ssp.gain_omega = gain_omega * gain_omega; h->ssp.gain_mu = gain_mu;
+        h->ssp.omega_mid = static_cast<float>(sps); h->ssp.omega_lim = 0.001f * static_cast<float>(sps);
+        h->ssp.lookahead = 24;
+        h->ssp.max_period = static_cast<float>(sps) + 1.0f; h->ssp.min_period = static_cast<float>(sps) - 1.0f;   // bounds for buffer sizing only
+        h->ssp.alpha = 0.0f;
+        control_loop_gains(static_cast<float>(2 * kPi / 200), h->ssp.costas_alpha, h->ssp.costas_beta);
+        h->ssp.soft_scale = 64.0f;
+        h->fllp.N = 32;
+        control_loop_gains(static_cast<float>(8 * kPi / 100), h->fllp.alpha, h->fllp.beta);
+        h->fllp.max_freq = static_cast<float>(2.0 * kPi * (2.0 / sps)); h->fllp.min_freq = -h->fllp.max_freq;
+        h->nports = 4;
     } else if (kind == QRL_DEMOD_NBFM) {
         // gr_demod_nbfm.cpp:39-66
         tsr = 20000; sym_sps = 2;
@@ -425,13 +504,24 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = make_ring(h, &h->rd, sizeof(float), h->n1max + nt_arm + 16))) return fail(rc);
         if ((rc = make_ring(h, &h->rr, sizeof(float), h->n1max * 2 / 5 + h->nbp.nt_audio + 16))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_nb, h->C))) return fail(rc);
-    } else if (kind == QRL_DEMOD_4FSK) {
+    } else if (kind == QRL_DEMOD_4FSK || kind == QRL_DEMOD_2FSK) {
         if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + h->ntaps3 + 8))) return fail(rc);
         if ((rc = make_ring(h, &h->r4, sizeof(float), h->n1max + 600, true))) return fail(rc);
-    } else {   // QPSK: shaping-filter output and loop output are channel-interleaved complex rings
+    } else {   // QPSK / BPSK: shaping-filter output and loop output are channel-interleaved complex rings
         if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + 600, true))) return fail(rc);
         if ((rc = make_ring(h, &h->r3, sizeof(float2), h->n1max + 600, true))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_ac, h->C))) return fail(rc);
+    }
+    if (kind == QRL_DEMOD_BPSK || kind == QRL_DEMOD_2FSK) {
+        const float fsps = static_cast<float>(sym_sps);
+        std::vector<float> ft = fll_design(fsps, kind == QRL_DEMOD_BPSK ? 0.35f : 0.1f, h->fllp.N);
+        if ((rc = upload_floats(h, &h->d_fll_taps, ft))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_fll, h->C))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_fll_hist, static_cast<size_t>(32) * h->C))) return fail(rc);
+        h->zero_list.emplace_back(h->d_fll_hist, sizeof(float2) * 32 * h->C);
+        h->zero_list.emplace_back(h->d_fll, sizeof(FllState) * h->C);
+        if ((rc = make_ring(h, &h->rf, sizeof(float2), h->n1max + 512 + 8))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_vs2, h->C))) return fail(rc);
     }
     if ((rc = make_ring(h, &h->r5, 1, 2 * h->n1max + 1024))) return fail(rc);
     h->port0_cap = h->n1max;
@@ -443,6 +533,10 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     h->port2_cap = h->port1_cap + 160;
     if ((rc = dev_alloc(h, &h->d_port2, static_cast<size_t>(h->port2_cap) * h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_port2_cnt, h->C))) return fail(rc);
+    if (h->nports == 4) {
+        if ((rc = dev_alloc(h, &h->d_port3, static_cast<size_t>(h->port2_cap) * h->C))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_port3_cnt, h->C))) return fail(rc);
+    }
     if ((rc = dev_alloc(h, &h->d_ss, h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_vs, h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_nsoft, static_cast<size_t>(qrl_rx::kMaxSub) * h->C))) return fail(rc);
@@ -487,11 +581,14 @@ int qrl_rx_reset(qrl_rx* h)
     std::vector<ViterbiState> vs(h->C);
     for (int c = 0; c < h->C; c++) {
         std::memset(&ss[c], 0, sizeof(SymSyncState));
-        ss[c].avg_period = h->ssp.sps; ss[c].inst_period = h->ssp.sps; ss[c].mu = 0.0f;
+        ss[c].avg_period = h->ssp.sps; ss[c].inst_period = h->ssp.sps;
+        ss[c].mu = (h->ssp.loop_kind == LOOP_CRMM) ? 0.5f : 0.0f;          // clock_recovery_mm_cc(omega, g_omega, mu = 0.5, ...)
         vs[c].rd = 0; vs[c].start_state = 0; vs[c].descr_reg = 0x7F;
     }
     CK(cudaMemcpyAsync(h->d_ss, ss.data(), sizeof(SymSyncState) * h->C, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_vs, vs.data(), sizeof(ViterbiState) * h->C, cudaMemcpyHostToDevice, h->stream));
+    if (h->d_vs2) CK(cudaMemcpyAsync(h->d_vs2, vs.data(), sizeof(ViterbiState) * h->C, cudaMemcpyHostToDevice, h->stream));
+    if (h->d_port3_cnt) CK(cudaMemsetAsync(h->d_port3_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_hist[0], 0, sizeof(float2) * h->H * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_hist[1], 0, sizeof(float2) * h->H * h->C, h->stream));
     for (auto& z : h->zero_list) CK(cudaMemsetAsync(z.first, 0, z.second, h->stream));
@@ -587,6 +684,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
     }
     CK(cudaMemsetAsync(h->d_port1_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_port2_cnt, 0, sizeof(int) * h->C, h->stream));
+    if (h->d_port3_cnt) CK(cudaMemsetAsync(h->d_port3_cnt, 0, sizeof(int) * h->C, h->stream));
 
     // The call is cut into nsub time slices.  Per slice the parallel stages (decimating FIR, channel filter,
     // demod + RRC) run on the caller's stream; the sequential loop stage of slice i runs on s_loop and the
@@ -646,6 +744,87 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 static_cast<float*>(h->rr.d), h->rr.mask, h->rr.stride,
                 h->d_arm_taps, h->d_audio_taps, h->d_port1f, 2 * h->port1_cap, h->d_port1_cnt, static_cast<int>(2 * h->port1_cap));
             h->launches++;
+            h->prof_end(pe);
+            continue;
+        }
+        if (h->kind == QRL_DEMOD_2FSK || h->kind == QRL_DEMOD_BPSK) {
+            const bool bpsk = h->kind == QRL_DEMOD_BPSK;
+            // ---- FLL (sequential, per sample) on the loop stream: r1 -> rf
+            CK(cudaEventRecord(h->ev_a[i], sp));
+            CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
+            pe = h->prof_begin(1, h->s_loop);
+            fll_kernel<32><<<groups, 32, 0, h->s_loop>>>(h->fllp, h->d_fll, h->d_fll_hist, h->C, h->d_fll_taps,
+                static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride, k1,
+                static_cast<float2*>(h->rf.d), h->rf.mask, h->rf.stride);
+            h->launches++;
+            h->prof_end(pe);
+            if (n_new > 0) {
+                // ---- channel filter / RRC on the FLL output -> port 0 (+ ring: channel-major for 2FSK, interleaved for BPSK)
+                pe = h->prof_begin(2, h->s_loop);
+                fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->ntaps2, h->s_loop>>>(
+                    static_cast<const float2*>(h->rf.d), h->rf.mask, h->rf.stride,
+                    static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                    h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, bpsk ? 1 : 0);
+                h->launches++;
+                if (!bpsk) {
+                    qdemod_fir_fff_kernel<<<gtile, TB, sizeof(float) * (2 * h->ntaps3 + TB), h->s_loop>>>(
+                        static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                        static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
+                        h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
+                    h->launches++;
+                }
+                h->prof_end(pe);
+            }
+            pe = h->prof_begin(3, h->s_loop);
+            if (bpsk) {
+                {   // agc2_cc (Costas bypassed): r2 -> r3
+                    constexpr int CH = 128, NST = 3;
+                    const size_t smem = sizeof(float2) * (NST + 2) * CH * 32;
+                    auto kern = agc_costas_kernel<CH, NST>;
+                    static bool a_attr = false;
+                    if (!a_attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a_attr = true; }
+                    kern<<<groups, 96, smem, h->s_loop>>>(h->acp, h->d_ac, h->C,
+                        static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, k1,
+                        static_cast<float2*>(h->r3.d), h->r3.mask, h->r3.stride);
+                    h->launches++;
+                }
+                constexpr int CH = 128, NST = 3, NEPI = 1;
+                const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period) + 3);
+                const size_t smem = sizeof(float) * (NST * CH * 64 + 132 * 8 + 2 * maxs * 64) + sizeof(int) * 64;
+                auto kern = symsync_kernel<2, SL_BPSK, EPI_BPSK, CH, NST, NEPI>;
+                static bool b_attr = false;
+                if (!b_attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); b_attr = true; }
+                kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop>>>(
+                    h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r3.d), h->r3.mask, h->r3.stride, k1,
+                    h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
+                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i);
+                h->launches++;
+            } else {
+                constexpr int CH = 256, NST = 3, NEPI = 2;
+                const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
+                const size_t smem = sizeof(float) * (NST * CH * 32 + 132 * 8 + 2 * maxs * 32) + sizeof(int) * 64;
+                auto kern = symsync_kernel<1, SL_BPSK, EPI_REAL1, CH, NST, NEPI>;
+                static bool f_attr = false;
+                if (!f_attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); f_attr = true; }
+                kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop>>>(
+                    h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r4.d), h->r4.mask, h->r4.stride, k1,
+                    h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
+                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i);
+                h->launches++;
+            }
+            h->prof_end(pe);
+            CK(cudaEventRecord(h->ev_b[i], h->s_loop));
+            // ---- two decoders on the same soft stream, the second behind delay(1)
+            CK(cudaStreamWaitEvent(h->s_fec, h->ev_b[i], 0));
+            pe = h->prof_begin(4, h->s_fec);
+            constexpr int CPB2 = 4;
+            viterbi_k7_kernel<CPB2><<<(h->C + CPB2 - 1) / CPB2, 64 * CPB2, 0, h->s_fec>>>(h->d_vs, nsoft_i, h->C,
+                static_cast<const unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride,
+                h->d_port2, h->port2_cap, h->d_port2_cnt, static_cast<int>(h->port2_cap), 0);
+            viterbi_k7_kernel<CPB2><<<(h->C + CPB2 - 1) / CPB2, 64 * CPB2, 0, h->s_fec>>>(h->d_vs2, nsoft_i, h->C,
+                static_cast<const unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride,
+                h->d_port3, h->port2_cap, h->d_port3_cnt, static_cast<int>(h->port2_cap), 1);
+            h->launches += 2;
             h->prof_end(pe);
             continue;
         }
@@ -749,7 +928,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         constexpr int CPB = 4;    // 4 channels (8 warps) per CTA
         viterbi_k7_kernel<CPB><<<(h->C + CPB - 1) / CPB, 64 * CPB, 0, h->s_fec>>>(h->d_vs, nsoft_i, h->C,
             static_cast<const unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride,
-            h->d_port2, h->port2_cap, h->d_port2_cnt, static_cast<int>(h->port2_cap));
+            h->d_port2, h->port2_cap, h->d_port2_cnt, static_cast<int>(h->port2_cap), 0);
         h->launches++;
         h->prof_end(pe);
     }
@@ -814,7 +993,8 @@ int qrl_rx_port_device(qrl_rx* h, int port, void** data, long* cap, int** counts
         *data = h->d_port1; *counts = h->d_port1_cnt;
         *cap = (h->kind == QRL_DEMOD_NBFM) ? 2 * h->port1_cap : h->port1_cap;      // float view of the same buffer
     }
-    else { *data = h->d_port2; *cap = h->port2_cap; *counts = h->d_port2_cnt; }
+    else if (port == 2) { *data = h->d_port2; *cap = h->port2_cap; *counts = h->d_port2_cnt; }
+    else { *data = h->d_port3; *cap = h->port2_cap; *counts = h->d_port3_cnt; }
     return QRL_OK;
 }
 

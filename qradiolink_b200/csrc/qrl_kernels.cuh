@@ -407,7 +407,8 @@ __global__ void qdemod_fir_fff_kernel(const float2* __restrict__ in, unsigned in
 //   EPI_QPSK    : complex symbols -> costas(4, snr) -> diff_phasor -> rotate -> port1, soft bits
 // ------------------------------------------------------------------------------------------------
 enum { SL_RECT4 = 0, SL_DQPSK = 1, SL_BPSK = 2 };
-enum { EPI_4FSK_FM = 0, EPI_CPLX = 1, EPI_QPSK = 2 };
+enum { EPI_4FSK_FM = 0, EPI_CPLX = 1, EPI_QPSK = 2, EPI_BPSK = 3, EPI_REAL1 = 4 };
+enum { LOOP_SYMSYNC = 0, LOOP_CRMM = 1 };
 
 struct LoopState {               // control_loop (costas)
     float phase, freq;
@@ -428,6 +429,9 @@ struct SymSyncParams {
     float costas_alpha, costas_beta;
     float rot_r, rot_i;
     float fl0; int n0;           // n0 = floor(min_period - |alpha|) as float / int (fast floor window)
+    int loop_kind;               // LOOP_SYMSYNC (symbol_sync_xx) or LOOP_CRMM (clock_recovery_mm_cc)
+    float gain_omega, gain_mu, omega_mid, omega_lim;      // clock_recovery_mm_cc
+    int costas_order;
 };
 
 __device__ __forceinline__ void qrl_slice(int slicer, float re, float im, float& dr, float& di)
@@ -475,6 +479,72 @@ __device__ __forceinline__ void qrl_costas_step(LoopState& st, float alpha, floa
     if (st.freq > 1.0f) st.freq = 1.0f;
     else if (st.freq < -1.0f) st.freq = -1.0f;
     yr = orr; yi = oi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fll_band_edge_cc (BPSK / 2FSK chains): per-sample NCO rotation + two N-tap complex band-edge filters on the
+// rotated stream + second-order loop.  One lane per channel, channel-major rings, rotated-sample window in shared
+// memory ([N][32] complex, bank = lane).  First correct version: the whole dot product sits in the sample loop
+// (only its last tap really depends on the current NCO phase -- hoisting the rest is the next optimisation).
+// ------------------------------------------------------------------------------------------------
+struct FllState { float phase, freq; long long pos; };
+struct FllParams { float alpha, beta, max_freq, min_freq; int N; };
+
+template <int NMAX>
+__global__ void __launch_bounds__(32)
+fll_kernel(FllParams p, FllState* __restrict__ states, float2* __restrict__ hist_g /* [C][NMAX] rotated-sample window */,
+           int C, const float* __restrict__ taps /* lower[2N] | upper[2N] */,
+           const float2* __restrict__ in, unsigned in_mask, long long in_stride, long long avail_total,
+           float2* __restrict__ out, unsigned out_mask, long long out_stride)
+{
+    __shared__ float2 win[NMAX][32];
+    __shared__ float tl[2 * NMAX], tu[2 * NMAX];
+    const int lane = threadIdx.x;
+    const int c = blockIdx.x * 32 + lane;
+    const int N = p.N;
+    for (int i = lane; i < 2 * N; i += 32) { tl[i] = taps[i]; tu[i] = taps[2 * N + i]; }
+    if (c < C) for (int k = 0; k < N; k++) win[k][lane] = hist_g[static_cast<long long>(c) * NMAX + k];
+    __syncwarp();
+    if (c >= C) return;
+    FllState st = states[c];
+    const float2* x = in + static_cast<long long>(c) * in_stride;
+    float2* y = out + static_cast<long long>(c) * out_stride;
+    int head = static_cast<int>(st.pos & (N - 1));            // slot of the OLDEST sample (N is a power of two)
+    for (long long a = st.pos; a < avail_total; a += 8) {
+        float2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = (a + j < avail_total) ? x[(a + j) & in_mask] : make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (a + j >= avail_total) break;
+            float sn, cs;
+            qrl_sincosf(st.phase, sn, cs);
+            const float orr = v[j].x * cs - v[j].y * sn, oi = v[j].x * sn + v[j].y * cs;
+            win[head][lane] = make_float2(orr, oi);            // overwrite the oldest: it becomes the newest
+            head = (head + 1) & (N - 1);                       // head is the oldest again
+            float ur = 0.0f, ui = 0.0f, lr = 0.0f, li = 0.0f;
+            for (int k = 0; k < N; k++) {
+                const float2 h = win[(head + k) & (N - 1)][lane];
+                ur = fmaf(tu[2 * k], h.x, ur); ur = fmaf(-tu[2 * k + 1], h.y, ur);
+                ui = fmaf(tu[2 * k], h.y, ui); ui = fmaf(tu[2 * k + 1], h.x, ui);
+                lr = fmaf(tl[2 * k], h.x, lr); lr = fmaf(-tl[2 * k + 1], h.y, lr);
+                li = fmaf(tl[2 * k], h.y, li); li = fmaf(tl[2 * k + 1], h.x, li);
+            }
+            const float err = (lr * lr + li * li) - (ur * ur + ui * ui);
+            st.freq = st.freq + p.beta * err;
+            st.phase = st.phase + st.freq + p.alpha * err;
+            while (st.phase >= 6.2831854820251465f) st.phase = static_cast<float>(static_cast<double>(st.phase) - 2.0 * 3.14159265358979323846);
+            while (st.phase <= -6.2831854820251465f) st.phase = static_cast<float>(static_cast<double>(st.phase) + 2.0 * 3.14159265358979323846);
+            if (st.freq > p.max_freq) st.freq = p.max_freq;
+            else if (st.freq < p.min_freq) st.freq = p.min_freq;
+            y[(a + j) & out_mask] = make_float2(orr, oi);
+        }
+    }
+    st.pos = avail_total;
+    states[c] = st;
+    // store the window oldest-first so that the next launch can start with head = pos & (N-1)
+    // (slot of sample index i is i & (N-1): already true for the circular buffer as laid out)
+    for (int k = 0; k < N; k++) hist_g[static_cast<long long>(c) * NMAX + k] = win[k][lane];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -581,8 +651,8 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
             if (active) {
                 for (int i = 0; i < n; i++) {
                     const float2 x = hb[i * 32];
-                    float yr, yi;
-                    qrl_costas_step(pll, k_a, k_b, p.order, p.use_snr != 0, x.x, x.y, yr, yi);
+                    float yr = x.x, yi = x.y;
+                    if (p.order != 0) qrl_costas_step(pll, k_a, k_b, p.order, p.use_snr != 0, x.x, x.y, yr, yi);
                     oring[((w0 + i) & out_mask) * 32] = make_float2(yr, yi);
                 }
             }
@@ -625,7 +695,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride, int maxs,
                long long* __restrict__ n_soft_out /* [C] snapshot of the soft-bit write index after this launch */)
 {
-    static_assert(EPI != EPI_QPSK || NEPI == 1, "the QPSK epilogue carries loop state: one epilogue warp");
+    static_assert((EPI != EPI_QPSK && EPI != EPI_BPSK) || NEPI == 1, "Costas epilogues carry loop state: one epilogue warp");
     constexpr int ROWF = 32 * NCOMP;                    // floats per row
     constexpr int STRIDE = CH - 32;                     // window advance per chunk (lookahead <= 32)
     extern __shared__ __align__(128) float sm_sync[];   // [NST][CH][ROWF] | mmse[129*8] | sym[2][maxs][ROWF] | cnt[2][32]
@@ -708,7 +778,39 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
             const long long rem = avail_total - w0;
             const int wlen = rem < CH ? static_cast<int>(rem) : CH;
             int cnt = 0;
-            if (active) {
+            if (active && p.loop_kind == LOOP_CRMM) {
+                // clock_recovery_mm_cc: avg_period holds omega, x*/y*i hold p_nT, d*/e* hold the 0/1 slicer outputs
+                while (o + la <= wlen) {
+                    const float* x = buf + o * ROWF;
+                    const int imu = __float_as_int((mu * 128.0f) + 12582912.0f) & 0x3ff;
+                    const float* tp = mm + imu;
+                    float yr = 0.0f, yi = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float tt = tp[(7 - i) * 132];
+                        yr = fmaf(tt, x[i * ROWF], yr);
+                        if (NCOMP == 2) yi = fmaf(tt, x[i * ROWF + 1], yi);
+                    }
+                    x2 = x1; x1 = x0; x0 = yr;
+                    y2i = y1i; y1i = y0i; y0i = yi;
+                    d2 = d1; d1 = d0; e2 = e1; e1 = e0;
+                    d0 = yr > 0.0f ? 1.0f : 0.0f; e0 = yi > 0.0f ? 1.0f : 0.0f;
+                    const float ar = d0 - d2, ai = e0 - e2;
+                    const float xr_ = ar * x1 + ai * y1i;
+                    const float br = x0 - x2, bi = y0i - y2i;
+                    const float yr_ = br * d1 + bi * e1;
+                    const float mmv = qrl_clip1(yr_ - xr_);
+                    avg_period = avg_period + p.gain_omega * mmv;
+                    avg_period = p.omega_mid + fminf(fmaxf(avg_period - p.omega_mid, -p.omega_lim), p.omega_lim);
+                    mu = mu + avg_period + p.gain_mu * mmv;
+                    const float fl = floorf(mu);
+                    o += static_cast<int>(fl);
+                    mu = mu - fl;
+                    sy[cnt * ROWF] = yr;
+                    if (NCOMP == 2) sy[cnt * ROWF + 1] = yi;
+                    cnt++;
+                }
+            } else if (active) {
                 while (o + la <= wlen) {
                     const float* x = buf + o * ROWF;
                     // rintf(mu*128) without a conversion unit: adding 1.5*2^23 rounds to nearest-even at integer
@@ -789,8 +891,15 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                 const float yr = sy[s * ROWF];
                 const float yi = (NCOMP == 2) ? sy[s * ROWF + 1] : 0.0f;
                 float o_r, o_i;
-                unsigned char sb0, sb1;
-                if (EPI == EPI_4FSK_FM) {
+                unsigned char sb0, sb1 = 0;
+                if (EPI == EPI_BPSK) {
+                    // costas_loop_cc(order 2) -> port 1; complex_to_real -> one soft bit per symbol
+                    qrl_costas_step(costas, p.costas_alpha, p.costas_beta, 2, false, yr, yi, o_r, o_i);
+                    sb0 = qrl_soft_u8(o_r, p.soft_scale);
+                } else if (EPI == EPI_REAL1) {
+                    o_r = yr; o_i = 0.0f;                      // float_to_complex(sym, 0)
+                    sb0 = qrl_soft_u8(yr, p.soft_scale);
+                } else if (EPI == EPI_4FSK_FM) {
                     const float phs = p.pm_sens * yr;
                     float sn, cs;
                     qrl_sincosf(phs, sn, cs);
@@ -813,10 +922,10 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                     sb1 = qrl_soft_u8(o_i, p.soft_scale);
                 }
                 if (p1cnt + s < port1_cap) p1[p1cnt + s] = make_float2(o_r, o_i);
-                sr[(n_soft + 2 * s) & soft_mask] = sb0;
-                sr[(n_soft + 2 * s + 1) & soft_mask] = sb1;
+                if (EPI == EPI_BPSK || EPI == EPI_REAL1) sr[(n_soft + s) & soft_mask] = sb0;
+                else { sr[(n_soft + 2 * s) & soft_mask] = sb0; sr[(n_soft + 2 * s + 1) & soft_mask] = sb1; }
             }
-            p1cnt += n; n_soft += 2 * n; n_sym += n;
+            p1cnt += n; n_soft += ((EPI == EPI_BPSK || EPI == EPI_REAL1) ? 1 : 2) * n; n_sym += n;
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[b]);
         }
@@ -850,7 +959,8 @@ template <int CPB /* channels per CTA */>
 __global__ void __launch_bounds__(64 * CPB)
 viterbi_k7_kernel(ViterbiState* __restrict__ vstates, const long long* __restrict__ n_soft_avail, int C,
                   const unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride,
-                  unsigned char* __restrict__ port2, long long port2_stride, int* __restrict__ port2_cnt, int port2_cap)
+                  unsigned char* __restrict__ port2, long long port2_stride, int* __restrict__ port2_cnt, int port2_cap,
+                  int delay /* blocks::delay(1) in front of the second decoder: stream index shifted by `delay` */)
 {
     __shared__ unsigned char syms_all[CPB][2][176];
     __shared__ unsigned dec0_all[CPB][2][86], dec1_all[CPB][2][86];
@@ -874,7 +984,7 @@ viterbi_k7_kernel(ViterbiState* __restrict__ vstates, const long long* __restric
     __syncthreads();
     if (c >= C) return;
     const ViterbiState vs0 = vstates[c];
-    const long long avail = n_soft_avail[c];
+    const long long avail = n_soft_avail[c] + delay;
     const int nframes = (avail - vs0.rd) >= 160 ? static_cast<int>((avail - vs0.rd) / 160) : 0;
     if (nframes == 0) return;
     const unsigned char* sr = soft_ring + static_cast<long long>(c) * soft_stride;
@@ -891,7 +1001,7 @@ viterbi_k7_kernel(ViterbiState* __restrict__ vstates, const long long* __restric
 #pragma unroll
             for (int k = 0; k < 6; k++) {
                 const int i = lane + 32 * k;
-                const long long a = rd - 12 + i;
+                const long long a = rd - 12 + i - delay;
                 pre[k] = (i < 172 && a >= 0) ? sr[a & soft_mask] : 0;
             }
         };

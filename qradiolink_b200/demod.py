@@ -113,6 +113,16 @@ def make_gr_demod_qpsk(sps, samp_rate, carrier_freq, filter_width, n_channels=1,
     return RxBlock(KIND.DEMOD_QPSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
 
 
+def make_gr_demod_bpsk(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
+    """src/gr/gr_demod_bpsk.h: 4 ports (IQ, constellation, bits, bits of the delayed decoder)."""
+    return RxBlock(KIND.DEMOD_BPSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
+
+
+def make_gr_demod_2fsk(sps, samp_rate, carrier_freq, filter_width, fm, n_channels=1, **kw):
+    """src/gr/gr_demod_2fsk.h: 4 ports (IQ, constellation, bits, bits of the delayed decoder)."""
+    return RxBlock(KIND.DEMOD_2FSK, sps, samp_rate, carrier_freq, filter_width, int(bool(fm)), n_channels, **kw)
+
+
 def make_gr_demod_nbfm(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
     return RxBlock(KIND.DEMOD_NBFM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
 

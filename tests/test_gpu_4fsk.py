@@ -98,3 +98,26 @@ def test_full_size_properties(qrl, oracle):
         rx = oracle.Rx(oracle.DEMOD_4FSK, 5, 1000000, 1700, 3000, 1)
         rx.work(X[c])
         assert np.array_equal(bits[c], rx.port(2))
+
+
+def test_4fsk_1k_fm_parity_d100(qrl, oracle):
+    """4FSK1KFM: make_gr_demod_4fsk(10,...,2000,true) -> /100 decimator with 837 taps (gr_demod_base.cpp:213)."""
+    C, T = 2, 1 << 19
+    rng = np.random.default_rng(77)
+    X = np.zeros((C, T), np.complex64)
+    for c in range(C):
+        data = rng.integers(0, 256, 120, dtype=np.uint8)
+        iq = oracle.Tx(oracle.MOD_4FSK, 50, 1000000, 1700, 2000, 1).work(data)
+        X[c] = siggen.channel(iq, rng, fo_hz=rng.uniform(-100, 100), delay=int(rng.integers(0, 300)), snr_db=20.0, total=T)
+    blk = qrl.make_gr_demod_4fsk(10, 1000000, 1700, 2000, True, n_channels=C, max_samples=T)
+    blk.work(X[:, :200001]); a = [blk.read_port(p) for p in range(3)]
+    blk.work(X[:, 200001:]); b = [blk.read_port(p) for p in range(3)]
+    for c in range(C):
+        rx = oracle.Rx(oracle.DEMOD_4FSK, 10, 1000000, 1700, 2000, 1)
+        rx.work(X[c])
+        for p in range(3):
+            got = np.concatenate([a[p][c], b[p][c]])
+            want = rx.port(p)
+            n = min(len(got), len(want))
+            assert n > 0 and len(want) - n <= 80
+            assert np.array_equal(got[:n], want[:n]), (c, p)
