@@ -107,6 +107,14 @@ def low_pass_2(gain, fs, fc, tw, att, win=WIN_HAMMING):
     return _taps(lib().qo_firdes_low_pass_2, gain, fs, fc, tw, att, win)
 
 
+def band_pass_2(gain, fs, lo, hi, tw, att, win=WIN_HAMMING):
+    return _taps(lib().qo_firdes_band_pass_2, gain, fs, lo, hi, tw, att, win)
+
+
+def complex_band_pass_2(gain, fs, lo, hi, tw, att, win=WIN_HAMMING):
+    return _taps(lib().qo_firdes_complex_band_pass_2, gain, fs, lo, hi, tw, att, win, complex_out=True)
+
+
 def band_pass(gain, fs, lo, hi, tw, win=WIN_HAMMING):
     return _taps(lib().qo_firdes_band_pass, gain, fs, lo, hi, tw, win)
 

@@ -1030,6 +1030,8 @@ struct qo_rx {
     agc2_t agc; costas_t pll, costas; float dp_r, dp_i; float rot_r, rot_i;
     /* 4fsk non-fm */
     fircc_t bp[4]; resamp_t symfilt;
+    /* ssb */
+    fircc_t ssb_bpf; resamp_t ssb_audio; float env_m2, env_m1; qvec s_clip; size_t st_pos;
     /* bpsk / 2fsk */
     fll_t fll; crmm_t crmm; ccdec_t dec2; lfsr_t descr2; int dec2_started;
     /* scratch + ports */
@@ -1136,6 +1138,24 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         qdemod_init(&r->qd, (float)(r->tsr / (4 * M_PI * filter_width)));
         squelch_init(&r->sq, -140, 0.01, 320, 1);
         r->port[1].isz = 4;
+    } else if (kind == QO_DEMOD_SSB) {
+        /* /root/reference/src/gr/gr_demod_ssb.cpp:31-86; flag = sb (0 = USB, 1 = LSB) */
+        r->tsr = 8000;
+        int n0 = qo_firdes_low_pass(1, samp_rate, r->tsr / 2, r->tsr / 2, QO_WIN_BLACKMAN_HARRIS, T0, 4096);
+        r->ntaps_store[0] = n0;
+        resamp_init(&r->resamp, 2, 1, sps, T0, n0);
+        float tc[2 * 4096];
+        int nb = flag ? qo_firdes_complex_band_pass_2(1, r->tsr, -filter_width, -200, 200, 90, QO_WIN_BLACKMAN_HARRIS, tc, 4096)
+                      : qo_firdes_complex_band_pass_2(1, r->tsr, 200, filter_width, 200, 90, QO_WIN_BLACKMAN_HARRIS, tc, 4096);
+        fircc_init(&r->ssb_bpf, tc, nb);
+        squelch_init(&r->sq, -140, 0.01, 0, 1);
+        agc2_init(&r->agc, 1e-1f, 1e-1f, 0.25f, 1.0f);
+        int n3 = qo_firdes_band_pass_2(1, r->tsr, 200, filter_width, 200, 90, QO_WIN_BLACKMAN_HARRIS, T3, 4096);
+        r->ntaps_store[3] = n3;
+        resamp_init(&r->ssb_audio, 1, 1, 1, T3, n3);
+        qv_init(&r->s_clip, 8);
+        r->env_m2 = 0; r->env_m1 = 0; r->st_pos = 0;
+        r->port[1].isz = 4;
     } else if (kind == QO_DEMOD_2FSK) {
         /* /root/reference/src/gr/gr_demod_2fsk.cpp:33-167 (fm variant; the band-filter variant is not restated yet) */
         int decim, interp = 1, nfilts;
@@ -1217,6 +1237,45 @@ static void rx_fec_tail_dual(qo_rx* r)
 
 int qo_rx_work(qo_rx* r, const float* iq, long T)
 {
+    if (r->kind == QO_DEMOD_SSB) {
+        r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
+        float* v = (float*)r->s_res.d;
+        for (size_t i = 0; i < 2 * r->s_res.n; i++) v[i] = v[i] * 0.9f;                 /* multiply_const_cc(0.9) */
+        r->s_filt.n = 0; fircc_work(&r->ssb_bpf, v, r->s_res.n, &r->s_filt);
+        qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
+        r->s_tmp.n = 0; squelch_work(&r->sq, (const float*)r->s_filt.d, r->s_filt.n, &r->s_tmp);
+        /* agc2_cc -> cessb::clipper_cc(0.95) (cessb/clipper_cc_impl.cc:65-95): magnitude clipped, phase kept */
+        const float* g = (const float*)r->s_tmp.d;
+        for (size_t i = 0; i < r->s_tmp.n; i++) {
+            float ar, ai;
+            agc2_step(&r->agc, g[2 * i], g[2 * i + 1], &ar, &ai);
+            float mag = sqrtf(ar * ar + ai * ai);
+            float ph = qo_fast_atan2f(ai, ar);
+            float cl = mag < 0.95f ? mag : 0.95f;
+            float sn, cs; qo_sincosf(ph, &sn, &cs);
+            qv_pushc(&r->s_clip, cs * cl, sn * cl);
+        }
+        /* cessb::stretcher_cc (stretcher_cc_impl.cc:70-110): 5-point envelope hold with a 2-sample look-ahead */
+        const float emax = (float)(1 / (sqrt(0.5) / 2));
+        const float* c = (const float*)r->s_clip.d;
+        r->s_rrc.n = 0;
+        while (r->st_pos + 2 < r->s_clip.n) {
+            size_t n = r->st_pos;
+            float e0 = sqrtf(c[2 * n] * c[2 * n] + c[2 * n + 1] * c[2 * n + 1]);
+            float e1 = sqrtf(c[2 * (n + 1)] * c[2 * (n + 1)] + c[2 * (n + 1) + 1] * c[2 * (n + 1) + 1]);
+            float e2 = sqrtf(c[2 * (n + 2)] * c[2 * (n + 2)] + c[2 * (n + 2) + 1] * c[2 * (n + 2) + 1]);
+            float h = e0;
+            h = fmaxf(h, r->env_m2); h = fmaxf(h, r->env_m1); h = fmaxf(h, e1); h = fmaxf(h, e2);
+            h = h * emax; h = fmaxf(h, 1.0f); h = h - 1.0f; h = h * 2.0f; h = h + 1.0f;
+            float re = c[2 * n] / h;
+            qv_pushf(&r->s_rrc, re * 1.333f);                                            /* complex_to_real, x1.333 */
+            r->env_m2 = r->env_m1; r->env_m1 = e0;
+            r->st_pos++;
+        }
+        if (r->st_pos > 0) { qv_drop(&r->s_clip, r->st_pos); r->st_pos = 0; }
+        resamp_work(&r->ssb_audio, (const float*)r->s_rrc.d, r->s_rrc.n, &r->port[1]);
+        return 0;
+    }
     if (r->kind == QO_DEMOD_2FSK) {
         r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
         float* v = (float*)r->s_res.d;

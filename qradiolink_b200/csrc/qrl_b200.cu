@@ -132,6 +132,11 @@ struct qrl_rx : HandleBase {
     Ring rf;                       // FLL output (channel-major complex)
     ViterbiState* d_vs2 = nullptr;
     unsigned char* d_port3 = nullptr; int* d_port3_cnt = nullptr;
+    // SSB audio chain
+    SsbParams ssbp{};
+    SsbState* d_ssb = nullptr;
+    Ring rclip, rstr;
+    float* d_taps2c = nullptr;     // complex side-band filter taps
     // NBFM audio chain
     NbfmParams nbp{};
     NbfmState* d_nb = nullptr;
@@ -446,6 +451,14 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         control_loop_gains(static_cast<float>(8 * kPi / 100), h->fllp.alpha, h->fllp.beta);
         h->fllp.max_freq = static_cast<float>(2.0 * kPi * (2.0 / sps)); h->fllp.min_freq = -h->fllp.max_freq;
         h->nports = 4;
+    } else if (kind == QRL_DEMOD_SSB) {
+        // gr_demod_ssb.cpp:37-61; flag = sb (0 USB, 1 LSB); sps = decimation (125)
+        tsr = 8000; sym_sps = 2;
+        taps1 = low_pass(1, samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
+        h->D1 = sps;
+        taps2 = flag ? complex_band_pass_2(1, tsr, -filter_width, -200, 200, 90, WIN_BLACKMAN_HARRIS)
+                     : complex_band_pass_2(1, tsr, 200, filter_width, 200, 90, WIN_BLACKMAN_HARRIS);
+        h->nports = 2;
     } else if (kind == QRL_DEMOD_NBFM) {
         // gr_demod_nbfm.cpp:39-66
         tsr = 20000; sym_sps = 2;
@@ -472,7 +485,7 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     if ((rc = dev_alloc(h, &h->d_hist[1], static_cast<size_t>(h->H) * h->C))) return fail(rc);
     h->n1max = h->Tmax / h->D1 + 2;
     // ---- rings
-    h->ntaps2 = static_cast<int>(taps2.size());
+    h->ntaps2 = static_cast<int>(taps2.size()) / (kind == QRL_DEMOD_SSB ? 2 : 1);
     h->ntaps3 = static_cast<int>(taps3.size());
     {
         std::vector<float> t2(std::max<size_t>(taps2.size(), 512), 0.0f);     // room for set_filter_width redesigns
@@ -481,7 +494,18 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     }
     if (!taps3.empty() && (rc = upload_floats(h, &h->d_taps3, taps3))) return fail(rc);
     if ((rc = make_ring(h, &h->r1, sizeof(float2), h->n1max + 512 + 8))) return fail(rc);
-    if (kind == QRL_DEMOD_NBFM) {
+    if (kind == QRL_DEMOD_SSB) {
+        if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + 64))) return fail(rc);
+        std::vector<float> audio_f = band_pass_2(1, tsr, 200, filter_width, 200, 90, WIN_BLACKMAN_HARRIS);
+        if ((rc = upload_floats(h, &h->d_audio_taps, audio_f))) return fail(rc);
+        h->ssbp.sq_alpha = 0.01; h->ssbp.sq_threshold = std::pow(10.0, -140 / 10.0);
+        h->ssbp.attack = 1e-1f; h->ssbp.decay = 1e-1f; h->ssbp.ref = 0.25f; h->ssbp.max_gain = 65536.0f;
+        h->ssbp.clip = 0.95f; h->ssbp.emax = static_cast<float>(1 / (std::sqrt(0.5) / 2)); h->ssbp.out_gain = 1.333f;
+        h->ssbp.nt_audio = static_cast<int>(audio_f.size());
+        if ((rc = make_ring(h, &h->rclip, sizeof(float2), h->n1max + 16))) return fail(rc);
+        if ((rc = make_ring(h, &h->rstr, sizeof(float), h->n1max + h->ssbp.nt_audio + 16))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_ssb, h->C))) return fail(rc);
+    } else if (kind == QRL_DEMOD_NBFM) {
         if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + 64))) return fail(rc);
         std::vector<float> audio_rs = low_pass_2(2, 2 * tsr, 3600, 250, 60, WIN_BLACKMAN_HARRIS);
         std::vector<float> audio_f = low_pass_2(1, 8000, 3500, 200, 35, WIN_BLACKMAN_HARRIS);
@@ -592,6 +616,11 @@ int qrl_rx_reset(qrl_rx* h)
     CK(cudaMemsetAsync(h->d_hist[0], 0, sizeof(float2) * h->H * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_hist[1], 0, sizeof(float2) * h->H * h->C, h->stream));
     for (auto& z : h->zero_list) CK(cudaMemsetAsync(z.first, 0, z.second, h->stream));
+    std::vector<SsbState> sb(h->C);
+    if (h->d_ssb) {
+        for (int c = 0; c < h->C; c++) { std::memset(&sb[c], 0, sizeof(SsbState)); sb[c].sq_state = SQ_MUTED; sb[c].gain = 1.0f; }
+        CK(cudaMemcpyAsync(h->d_ssb, sb.data(), sizeof(SsbState) * h->C, cudaMemcpyHostToDevice, h->stream));
+    }
     std::vector<NbfmState> nb(h->C);
     if (h->d_nb) {
         for (int c = 0; c < h->C; c++) {
@@ -724,6 +753,28 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         const int TB = 256;
         dim3 gtile(static_cast<unsigned>((std::max<long long>(n_new, 1) + TB - 1) / TB), h->C);
         const int groups = (h->C + 31) / 32;
+        if (h->kind == QRL_DEMOD_SSB) {
+            if (n_new > 0) {
+                pe = h->prof_begin(1, sp);
+                fir_ccc_ring_kernel<<<gtile, TB, sizeof(float) * 2 * h->ntaps2, sp>>>(
+                    static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
+                    static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                    h->d_taps2, h->ntaps2, 0.9f, k0, k1, h->d_port0, h->port0_cap, k_call0);
+                h->launches++;
+                h->prof_end(pe);
+            }
+            CK(cudaEventRecord(h->ev_a[i], sp));
+            CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
+            pe = h->prof_begin(3, h->s_loop);
+            ssb_audio_kernel<<<h->C, 128, 0, h->s_loop>>>(h->ssbp, h->d_ssb,
+                static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, k1,
+                static_cast<float2*>(h->rclip.d), h->rclip.mask, h->rclip.stride,
+                static_cast<float*>(h->rstr.d), h->rstr.mask, h->rstr.stride,
+                h->d_audio_taps, h->d_port1f, 2 * h->port1_cap, h->d_port1_cnt, static_cast<int>(2 * h->port1_cap));
+            h->launches++;
+            h->prof_end(pe);
+            continue;
+        }
         if (h->kind == QRL_DEMOD_NBFM) {
             if (n_new > 0) {
                 pe = h->prof_begin(1, sp);
@@ -991,7 +1042,7 @@ int qrl_rx_port_device(qrl_rx* h, int port, void** data, long* cap, int** counts
     if (port == 0) { *data = h->d_port0; *cap = h->port0_cap; *counts = nullptr; }
     else if (port == 1) {
         *data = h->d_port1; *counts = h->d_port1_cnt;
-        *cap = (h->kind == QRL_DEMOD_NBFM) ? 2 * h->port1_cap : h->port1_cap;      // float view of the same buffer
+        *cap = (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_SSB) ? 2 * h->port1_cap : h->port1_cap;      // float view of the same buffer
     }
     else if (port == 2) { *data = h->d_port2; *cap = h->port2_cap; *counts = h->d_port2_cnt; }
     else { *data = h->d_port3; *cap = h->port2_cap; *counts = h->d_port3_cnt; }

@@ -1236,6 +1236,139 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
     if (threadIdx.x == 0) { st.n_res = res1; st.n_aud = res1; states[c] = st; }
 }
 
+// complex stream, COMPLEX taps (fft_filter_ccc restated in direct form), optional input gain (multiply_const_cc in front)
+__global__ void fir_ccc_ring_kernel(const float2* __restrict__ in, unsigned in_mask, long long in_stride,
+                                    float2* __restrict__ out, unsigned out_mask, long long out_stride,
+                                    const float* __restrict__ taps_c /* interleaved */, int ntaps, float in_gain,
+                                    long long a0, long long a1, float2* __restrict__ lin, long long lin_stride, long long lin_base)
+{
+    extern __shared__ float hs_dyn[];
+    for (int i = threadIdx.x; i < 2 * ntaps; i += blockDim.x) hs_dyn[i] = taps_c[i];
+    __syncthreads();
+    const int c = blockIdx.y;
+    const long long a = a0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (a >= a1) return;
+    const float2* x = in + static_cast<long long>(c) * in_stride;
+    float re = 0.0f, im = 0.0f;
+    for (int j = ntaps - 1; j >= 0; j--) {
+        float2 v = x[(a - j) & in_mask];
+        v.x = v.x * in_gain; v.y = v.y * in_gain;
+        const float hr = hs_dyn[2 * j], hi = hs_dyn[2 * j + 1];
+        re = fmaf(hr, v.x, re); re = fmaf(-hi, v.y, re);
+        im = fmaf(hr, v.y, im); im = fmaf(hi, v.x, im);
+    }
+    const float2 y = make_float2(re, im);
+    out[static_cast<long long>(c) * out_stride + (a & out_mask)] = y;
+    if (lin) lin[static_cast<long long>(c) * lin_stride + (a - lin_base)] = y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SSB audio chain after the side-band filter (gr_demod_ssb.cpp:62-84): pwr_squelch_cc(gate, no ramp) -> agc2_cc ->
+// cessb::clipper_cc(0.95) -> cessb::stretcher_cc -> complex_to_real -> x1.333 -> audio band-pass (direct form).
+// 8 ksps per channel: one CTA per channel; squelch + AGC recurrences on thread 0, the rest spread over the CTA.
+// ------------------------------------------------------------------------------------------------
+struct SsbState {
+    double pwr;
+    long long n_in, n_gate, n_str, n_aud;
+    int sq_state; float gain;
+};
+struct SsbParams {
+    double sq_alpha, sq_threshold;
+    float attack, decay, ref, max_gain, clip, emax, out_gain;
+    int nt_audio;
+};
+
+__global__ void __launch_bounds__(128)
+ssb_audio_kernel(SsbParams p, SsbState* __restrict__ states,
+                 const float2* __restrict__ in, unsigned in_mask, long long in_stride, long long avail_in,
+                 float2* __restrict__ clip_ring, unsigned clip_mask, long long clip_stride,
+                 float* __restrict__ str_ring, unsigned str_mask, long long str_stride,
+                 const float* __restrict__ audio_taps,
+                 float* __restrict__ port1, long long port1_stride, int* __restrict__ port1_cnt, int port1_cap)
+{
+    const int c = blockIdx.x;
+    __shared__ SsbState st;
+    if (threadIdx.x == 0) st = states[c];
+    __syncthreads();
+    const float2* x = in + static_cast<long long>(c) * in_stride;
+    float2* cr = clip_ring + static_cast<long long>(c) * clip_stride;
+    float* sr = str_ring + static_cast<long long>(c) * str_stride;
+    const long long gate0 = st.n_gate;
+    // ---- 1. squelch + AGC (sequential); the AGC output is parked in the clip ring, clipped in place in step 2
+    if (threadIdx.x == 0) {
+        double pwr = st.pwr; int state = st.sq_state; float gain = st.gain; long long ng = st.n_gate;
+        for (long long a = st.n_in; a < avail_in; a++) {
+            const float2 v = x[a & in_mask];
+            const float mag2 = v.x * v.x + v.y * v.y;
+            pwr = p.sq_alpha * static_cast<double>(mag2) + (1.0 - p.sq_alpha) * pwr;
+            const bool mute = pwr < p.sq_threshold;
+            if (state == SQ_MUTED) { if (!mute) state = SQ_UNMUTED; }
+            else if (mute) state = SQ_MUTED;
+            if (state != SQ_MUTED) {
+                const float orr = v.x * gain, oi = v.y * gain;          // envelope is 1.0 without a ramp
+                const float tmp = -p.ref + sqrtf(orr * orr + oi * oi);
+                const float rate = (fabsf(tmp) > gain) ? p.attack : p.decay;
+                gain = gain - tmp * rate;
+                if (gain < 0.0f) gain = 10e-5f;
+                if (p.max_gain > 0.0f && gain > p.max_gain) gain = p.max_gain;
+                cr[ng & clip_mask] = make_float2(orr, oi);
+                ng++;
+            }
+        }
+        st.pwr = pwr; st.sq_state = state; st.gain = gain; st.n_in = avail_in; st.n_gate = ng;
+    }
+    __syncthreads();
+    const long long gate1 = st.n_gate;
+    // ---- 2. clipper: magnitude limited to `clip`, phase kept (fast_atan2f + sincos)
+    for (long long n = gate0 + threadIdx.x; n < gate1; n += blockDim.x) {
+        const float2 v = cr[n & clip_mask];
+        const float mag = sqrtf(v.x * v.x + v.y * v.y);
+        const float ph = qrl_fast_atan2f(v.y, v.x);
+        const float cl = mag < p.clip ? mag : p.clip;
+        float sn, cs;
+        qrl_sincosf(ph, sn, cs);
+        cr[n & clip_mask] = make_float2(cs * cl, sn * cl);
+    }
+    __syncthreads();
+    // ---- 3. stretcher: gain from the 5-point envelope maximum around n (needs n+2), real part x out_gain
+    const long long str0 = st.n_str;
+    const long long str1 = gate1 >= 2 ? gate1 - 2 : 0;
+    for (long long n = str0 + threadIdx.x; n < str1; n += blockDim.x) {
+        auto env = [&](long long k) -> float {
+            if (k < 0) return 0.0f;
+            const float2 v = cr[k & clip_mask];
+            return sqrtf(v.x * v.x + v.y * v.y);
+        };
+        float h = env(n);
+        h = fmaxf(h, env(n - 2)); h = fmaxf(h, env(n - 1)); h = fmaxf(h, env(n + 1)); h = fmaxf(h, env(n + 2));
+        h = h * p.emax; h = fmaxf(h, 1.0f); h = h - 1.0f; h = h * 2.0f; h = h + 1.0f;
+        const float re = cr[n & clip_mask].x / h;
+        sr[n & str_mask] = re * p.out_gain;
+    }
+    __syncthreads();
+    // ---- 4. audio band-pass (direct form), one output per stretcher output
+    const long long aud0 = st.n_aud;
+    int cnt0 = port1_cnt[c];
+    float* o = port1 + static_cast<long long>(c) * port1_stride;
+    const long long str1c = str1 > str0 ? str1 : str0;
+    for (long long a = aud0 + threadIdx.x; a < str1c; a += blockDim.x) {
+        float acc = 0.0f;
+        for (int k = p.nt_audio - 1; k >= 0; k--) {
+            const long long n = a - k;
+            const float v = n >= 0 ? sr[n & str_mask] : 0.0f;
+            acc = fmaf(audio_taps[k], v, acc);
+        }
+        const long long idx = cnt0 + (a - aud0);
+        if (idx < port1_cap) o[idx] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        port1_cnt[c] = cnt0 + static_cast<int>(str1c - aud0);
+        st.n_str = str1c; st.n_aud = str1c;
+        states[c] = st;
+    }
+}
+
 // roll the stage-1 history: new_hist = last H samples of (old_hist ++ iq[0..T))
 __global__ void hist_update_kernel(const float2* __restrict__ iq, long long iq_stride, long long T,
                                    const float2* __restrict__ old_hist, float2* __restrict__ new_hist, int H)

@@ -123,6 +123,11 @@ def make_gr_demod_2fsk(sps, samp_rate, carrier_freq, filter_width, fm, n_channel
     return RxBlock(KIND.DEMOD_2FSK, sps, samp_rate, carrier_freq, filter_width, int(bool(fm)), n_channels, **kw)
 
 
+def make_gr_demod_ssb(sps, samp_rate, carrier_freq, filter_width, sb, n_channels=1, **kw):
+    """src/gr/gr_demod_ssb.h: sb = 0 upper side band, 1 lower; ports (IQ, float audio)."""
+    return RxBlock(KIND.DEMOD_SSB, sps, samp_rate, carrier_freq, filter_width, int(sb), n_channels, **kw)
+
+
 def make_gr_demod_nbfm(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
     return RxBlock(KIND.DEMOD_NBFM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
 
