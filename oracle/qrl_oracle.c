@@ -1116,7 +1116,8 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         r->rot_r = cosf(th); r->rot_i = sinf(th);
         r->soft_scale = 48.0f;
         ccdec_init(&r->dec); lfsr_init(&r->descr);
-        r->fm = (sps > 4); /* FLL in the chain: not restated yet */
+        r->fm = (sps > 4); /* gr_demod_qpsk.cpp:130-138: the FLL is only connected for sps > 4 */
+        if (r->fm) fll_init(&r->fll, (float)r->sym_sps, 0.35f, 32, (float)(2 * M_PI / 100));
     } else if (kind == QO_DEMOD_NBFM) {
         /* /root/reference/src/gr/gr_demod_nbfm.cpp:31-79 */
         r->tsr = 20000;
@@ -1364,6 +1365,10 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
     }
     if (r->kind == QO_DEMOD_QPSK) {
         r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
+        if (r->fm) {
+            float* v = (float*)r->s_res.d;
+            for (size_t i = 0; i < r->s_res.n; i++) fll_step(&r->fll, v[2 * i], v[2 * i + 1], &v[2 * i], &v[2 * i + 1]);
+        }
         r->s_filt.n = 0; resamp_work(&r->shaping, (const float*)r->s_res.d, r->s_res.n, &r->s_filt);
         qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
         const float* f = (const float*)r->s_filt.d; size_t n = r->s_filt.n;

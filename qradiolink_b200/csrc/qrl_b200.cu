@@ -197,7 +197,7 @@ template <int D, int Q, int K, int NOUT, int NWARPS>
 int launch_fir_poly(qrl_rx* h, const float2* iq, long long stride, long long T, long long k0, long long k1)
 {
     constexpr int W = (NOUT + Q - 1) * D;
-    const size_t smem = sizeof(float2) * (W + 2);
+    const size_t smem = sizeof(float2) * ((W + 3) & ~1);
     static bool attr_done[16] = { false };
     if (!attr_done[h->device & 15]) {
         CK(cudaFuncSetAttribute(fir_decim_poly_kernel<D, Q, K, NOUT, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -236,6 +236,8 @@ int stage1(qrl_rx* h, const float2* iq, long long stride, long long T, long long
     if (h->D1 == 100 && h->Q1 == 9) return launch_fir_poly<100, 9, 8, 64, 8>(h, iq, stride, T, k0, k1);     // 837 taps (4FSK-1k, QPSK-2k shape)
     if (h->D1 == 25 && h->Q1 == 9) return launch_fir_poly<25, 9, 8, 256, 8>(h, iq, stride, T, k0, k1);      // 209 taps (2FSK-2k)
     if (h->D1 == 125 && h->Q1 == 9) return launch_fir_poly<125, 9, 8, 48, 6>(h, iq, stride, T, k0, k1);     // 1045 taps (SSB)
+    if (h->D1 == 25 && h->Q1 == 28) return launch_fir_poly<25, 28, 8, 192, 8>(h, iq, stride, T, k0, k1);    // 681 taps (QPSK-20k)
+    if (h->D1 == 100 && h->Q1 == 28) return launch_fir_poly<100, 28, 8, 32, 4>(h, iq, stride, T, k0, k1);   // 2727 taps (QPSK-2k)
     if (h->D1 == 2 && h->ntaps1 <= 56) return launch_fir_d2<56, 8, 128>(h, iq, stride, T, k0, k1);
     set_err(h, "stage-1 resampler shape not built (D=" + std::to_string(h->D1) + ", taps=" + std::to_string(h->ntaps1) + ")");
     return QRL_EINVAL;
@@ -382,9 +384,15 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         h->nports = 3;
     } else if (kind == QRL_DEMOD_QPSK) {
         // gr_demod_qpsk.cpp:46-71 (sps ladder), :98-103 (resampler), :106-110 (RRC), :104,113-118 (agc, sync, costas)
-        if (sps > 4) { set_err(h, "QPSK 2k/20k (FLL band-edge) variants not built yet"); return fail(QRL_EINVAL); }
-        const int decimation = 2; sym_sps = sps; tsr = 500000;
-        const float costas_bw = static_cast<float>(kPi / 400);
+        int decimation; float costas_bw = static_cast<float>(kPi / 200);
+        if (sps > 4 && sps < 125) { decimation = 25; sym_sps = sps * 4 / 25; tsr = 40000; }
+        else if (sps >= 125) { decimation = 100; sym_sps = sps / 25; tsr = 10000; }
+        else { decimation = 2; sym_sps = sps; tsr = 500000; costas_bw = static_cast<float>(kPi / 400); }
+        if (sps > 4) {      // gr_demod_qpsk.cpp:105,130-134: FLL between the resampler and the shaping filter
+            h->fllp.N = 32;
+            control_loop_gains(static_cast<float>(2 * kPi / 100), h->fllp.alpha, h->fllp.beta);
+            h->fllp.max_freq = static_cast<float>(2.0 * kPi * (2.0 / sym_sps)); h->fllp.min_freq = -h->fllp.max_freq;
+        }
         taps1 = low_pass_2(1, static_cast<double>(samp_rate), tsr / 2, tsr / 10, 60, WIN_BLACKMAN_HARRIS);
         h->D1 = decimation;
         taps2 = root_raised_cosine(sym_sps, sym_sps, 1, 0.35, 11 * sym_sps);
@@ -536,16 +544,17 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = make_ring(h, &h->r3, sizeof(float2), h->n1max + 600, true))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_ac, h->C))) return fail(rc);
     }
-    if (kind == QRL_DEMOD_BPSK || kind == QRL_DEMOD_2FSK) {
+    const bool has_fll = kind == QRL_DEMOD_BPSK || kind == QRL_DEMOD_2FSK || (kind == QRL_DEMOD_QPSK && sps > 4);
+    if (has_fll) {
         const float fsps = static_cast<float>(sym_sps);
-        std::vector<float> ft = fll_design(fsps, kind == QRL_DEMOD_BPSK ? 0.35f : 0.1f, h->fllp.N);
+        std::vector<float> ft = fll_design(fsps, kind == QRL_DEMOD_2FSK ? 0.1f : 0.35f, h->fllp.N);
         if ((rc = upload_floats(h, &h->d_fll_taps, ft))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_fll, h->C))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_fll_hist, static_cast<size_t>(32) * h->C))) return fail(rc);
         h->zero_list.emplace_back(h->d_fll_hist, sizeof(float2) * 32 * h->C);
         h->zero_list.emplace_back(h->d_fll, sizeof(FllState) * h->C);
         if ((rc = make_ring(h, &h->rf, sizeof(float2), h->n1max + 512 + 8))) return fail(rc);
-        if ((rc = dev_alloc(h, &h->d_vs2, h->C))) return fail(rc);
+        if (kind != QRL_DEMOD_QPSK && (rc = dev_alloc(h, &h->d_vs2, h->C))) return fail(rc);
     }
     if ((rc = make_ring(h, &h->r5, 1, 2 * h->n1max + 1024))) return fail(rc);
     h->port0_cap = h->n1max;
@@ -921,11 +930,24 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             }
             CK(cudaEventRecord(h->ev_b[i], h->s_loop));
         } else {   // QRL_DEMOD_QPSK
+            const float2* shaping_in = static_cast<const float2*>(h->r1.d);
+            unsigned shaping_mask = h->r1.mask; long long shaping_stride = h->r1.stride;
+            if (h->d_fll) {     // sps > 4: fll_band_edge_cc between resampler and shaping filter (sequential, on the loop stream)
+                CK(cudaEventRecord(h->ev_a[i], sp));
+                CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
+                fll_kernel<32><<<groups, 32, 0, h->s_loop>>>(h->fllp, h->d_fll, h->d_fll_hist, h->C, h->d_fll_taps,
+                    static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride, k1,
+                    static_cast<float2*>(h->rf.d), h->rf.mask, h->rf.stride);
+                h->launches++;
+                CK(cudaEventRecord(h->ev_c[i], h->s_loop));
+                CK(cudaStreamWaitEvent(sp, h->ev_c[i], 0));
+                shaping_in = static_cast<const float2*>(h->rf.d); shaping_mask = h->rf.mask; shaping_stride = h->rf.stride;
+            }
             if (n_new > 0) {
                 // ---- stage 2: RRC shaping filter -> interleaved ring + port 0
                 pe = h->prof_begin(1, sp);
                 fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->ntaps2, sp>>>(
-                    static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
+                    shaping_in, shaping_mask, shaping_stride,
                     static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
                     h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, 1);
                 h->launches++;

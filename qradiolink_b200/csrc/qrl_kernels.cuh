@@ -148,8 +148,8 @@ fir_decim_poly_kernel(const float2* __restrict__ iq, long long iq_stride, long l
     static_assert(K == 8, "transposed butterfly below is written for 2K = 16 values");
     constexpr int R = (D + 31) / 32;                 // branch rounds per lane
     constexpr int W = (NOUT + Q - 1) * D;            // samples in the strip window
-    static_assert((W & 1) == 0, "window must be an even number of samples (16-byte bulk copies)");
-    extern __shared__ __align__(128) float2 xs_raw[];   // W + 2 samples
+    constexpr int WC = (W + 3) & ~1;                 // bulk-copy length: even (16-byte multiple), >= W + 1
+    extern __shared__ __align__(128) float2 xs_raw[];   // WC samples
     __shared__ __align__(8) uint64_t fill_bar;
 
     const int c = blockIdx.y;
@@ -174,14 +174,14 @@ fir_decim_poly_kernel(const float2* __restrict__ iq, long long iq_stride, long l
     const long long i0 = A0 - n_in_before;                       // index of the window start in this call's input
     const int shift = static_cast<int>(i0 & 1);                  // 1 -> start the bulk copy at i0 - 1
     const float2* xs = xs_raw + shift;
-    const bool bulk = (i0 - shift >= 0) && (i0 - shift + W + 2 <= T) && ((iq_stride & 1) == 0) &&
+    const bool bulk = (i0 - shift >= 0) && (i0 - shift + WC <= T) && ((iq_stride & 1) == 0) &&
                       ((reinterpret_cast<unsigned long long>(iq) & 15ull) == 0);
     if (bulk) {
         if (threadIdx.x == 0) { mbar_init(&fill_bar, 1); mbar_fence_init(); }
         __syncthreads();
         if (threadIdx.x == 0) {
-            mbar_expect_tx(&fill_bar, (W + 2) * 8);
-            bulk_g2s(xs_raw, iqc + (i0 - shift), (W + 2) * 8, &fill_bar);
+            mbar_expect_tx(&fill_bar, WC * 8);
+            bulk_g2s(xs_raw, iqc + (i0 - shift), WC * 8, &fill_bar);
         }
         mbar_wait(&fill_bar, 0);
     } else {

@@ -60,3 +60,35 @@ def test_qpsk_chunked_stream(qrl, oracle):
         n1 = min(len(g1), len(w1)); n2 = min(len(g2), len(w2))
         assert n1 >= len(w1) - 8 and n2 >= len(w2) - 160
         assert np.array_equal(g1[:n1], w1[:n1]) and np.array_equal(g2[:n2], w2[:n2])
+
+
+@pytest.mark.parametrize("tx_sps,rx_sps,fw", [(100, 25, 6500), (500, 125, 1300)])
+def test_qpsk_fll_variants(qrl, oracle, tx_sps, rx_sps, fw):
+    """QPSK20K (make_gr_demod_qpsk(25,...,6500): /25, 681 taps) and QPSK2K (125,...,1300: /100, 2727 taps): both put a
+    fll_band_edge_cc between the resampler and the shaping filter (gr_demod_qpsk.cpp:130-134)."""
+    C, T = 2, 1 << 20
+    rng = np.random.default_rng(61)
+    X = np.zeros((C, T), np.complex64); payloads = []
+    for c in range(C):
+        data, pl = siggen.frames_4fsk(rng, 30 if tx_sps == 500 else 150)
+        iq = oracle.Tx(oracle.MOD_QPSK, tx_sps, 1000000, 1700, fw, 0).work(data)
+        X[c] = siggen.channel(iq, rng, fo_hz=rng.uniform(-40, 40), phase=rng.uniform(0, 6.28), delay=int(rng.integers(0, 200)),
+                              snr_db=18.0, amp=0.2, total=T)
+        payloads.append(pl)
+    blk = qrl.make_gr_demod_qpsk(rx_sps, 1000000, 1700, fw, n_channels=C, max_samples=600000)
+    acc = [[[] for _ in range(C)] for _ in range(3)]
+    for lo, hi in ((0, 600000), (600000, 600001), (600001, T)):
+        blk.work(X[:, lo:hi])
+        for p in range(3):
+            for c, v in enumerate(blk.read_port(p)):
+                acc[p][c].append(v)
+    for c in range(C):
+        rx = oracle.Rx(oracle.DEMOD_QPSK, rx_sps, 1000000, 1700, fw, 0)
+        rx.work(X[c])
+        for p in range(3):
+            got, want = np.concatenate(acc[p][c]), rx.port(p)
+            n = min(len(got), len(want))
+            assert n > 0 and len(want) - n <= 160, (p, len(got), len(want))
+            assert np.array_equal(got[:n], want[:n]), (c, p)
+        good, found = siggen.count_good_frames(np.concatenate(acc[2][c]), 0xED89AA, 24, 7, payloads[c])
+        assert good >= 10
