@@ -1163,8 +1163,7 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         if (sps == 10) { r->tsr = 20000; r->sym_sps = sps; decim = 50; nfilts = 35 * r->sym_sps; }
         else if (sps >= 5) { r->tsr = 40000; r->sym_sps = sps * 2; decim = 25; nfilts = 35 * r->sym_sps; }
         else { free(r); return NULL; }
-        if (!flag) { free(r); return NULL; }
-        int spacing = 1;
+        int spacing = flag ? 1 : 2;
         if ((nfilts % 2) == 0) nfilts += 1;
         int n0 = qo_firdes_low_pass(interp, (double)interp * samp_rate, r->tsr / 2, r->tsr / 2, QO_WIN_BLACKMAN_HARRIS, T0, 4096);
         r->ntaps_store[0] = n0;
@@ -1177,12 +1176,23 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         int n2 = qo_firdes_rrc(1, r->tsr, r->tsr / r->sym_sps, 0.2, nfilts, T2, 4096);
         r->ntaps_store[2] = n2;
         resamp_init(&r->shaping, 1, 1, 1, T2, n2);
+        if (!flag) {
+            /* band-filter variant (gr_demod_2fsk.cpp:88-100,137-149): upper = (-fw,0), lower = (0,fw), |upper|/|lower| */
+            float tc[2 * 4096];
+            int nb = qo_firdes_complex_band_pass(1, r->tsr, -filter_width, 0, filter_width, QO_WIN_BLACKMAN_HARRIS, tc, 4096);
+            fircc_init(&r->bp[0], tc, nb);                       /* _upper_filter */
+            nb = qo_firdes_complex_band_pass(1, r->tsr, 0, filter_width, filter_width, QO_WIN_BLACKMAN_HARRIS, tc, 4096);
+            fircc_init(&r->bp[1], tc, nb);                       /* _lower_filter */
+            int n3 = qo_firdes_low_pass(1.0, r->tsr, r->tsr / r->sym_sps, r->tsr / r->sym_sps, QO_WIN_HAMMING, T3, 4096);
+            r->ntaps_store[3] = n3;
+            resamp_init(&r->symfilt, 1, 1, 1, T3, n3);
+        }
         float symbol_rate = (float)r->tsr / (float)r->sym_sps;
         float sps_dev = 200.0f / symbol_rate;
         symsync_init(&r->ss, 1, (float)r->sym_sps, (float)(2 * M_PI / (symbol_rate / 10)), 1.0f, 0.2869f, sps_dev, SL_BPSK);
         r->soft_scale = 128.0f;
         ccdec_init(&r->dec); lfsr_init(&r->descr); ccdec_init(&r->dec2); lfsr_init(&r->descr2);
-        r->fm = 1;
+        r->fm = flag;
     } else if (kind == QO_DEMOD_BPSK) {
         /* /root/reference/src/gr/gr_demod_bpsk.cpp:33-105 */
         r->tsr = 20000; r->sym_sps = sps;
@@ -1283,8 +1293,26 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
         for (size_t i = 0; i < r->s_res.n; i++) fll_step(&r->fll, v[2 * i], v[2 * i + 1], &v[2 * i], &v[2 * i + 1]);
         r->s_filt.n = 0; resamp_work(&r->filt, v, r->s_res.n, &r->s_filt);
         qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
-        r->s_dem.n = 0; qdemod_work(&r->qd, (const float*)r->s_filt.d, r->s_filt.n, &r->s_dem);
-        r->s_rrc.n = 0; resamp_work(&r->shaping, (const float*)r->s_dem.d, r->s_dem.n, &r->s_rrc);
+        r->s_rrc.n = 0;
+        if (r->fm) {
+            r->s_dem.n = 0; qdemod_work(&r->qd, (const float*)r->s_filt.d, r->s_filt.n, &r->s_dem);
+            resamp_work(&r->shaping, (const float*)r->s_dem.d, r->s_dem.n, &r->s_rrc);
+        } else {
+            const float* f = (const float*)r->s_filt.d; size_t n = r->s_filt.n;
+            for (int k = 0; k < 2; k++) { r->s_bp[k].n = 0; fircc_work(&r->bp[k], f, n, &r->s_bp[k]); }
+            r->s_dem.n = 0;
+            for (size_t i = 0; i < n; i++) {
+                const float* u = (const float*)r->s_bp[0].d + 2 * i; const float* l = (const float*)r->s_bp[1].d + 2 * i;
+                float mu_ = sqrtf(u[0] * u[0] + u[1] * u[1]), ml = sqrtf(l[0] * l[0] + l[1] * l[1]);
+                float q = mu_ / ml;                                   /* blocks::divide_ff: upper / lower */
+                /* analog::rail_ff(0, 2).  0/0 at start-up gives NaN; the clamp is restated with IEEE fminf/fmaxf
+                 * (NaN -> the rail), which is what a SIMD min/max clamp does; std::min/max would let the NaN through
+                 * and poison the clock loop for ever. */
+                float t = fmaxf(fminf(q, 2.0f), 0.0f);
+                qv_pushf(&r->s_dem, t + -1.0f);                       /* add_const_ff(-1) */
+            }
+            resamp_work(&r->symfilt, (const float*)r->s_dem.d, r->s_dem.n, &r->s_rrc);
+        }
         r->s_sym.isz = 4; r->s_sym.n = 0;
         symsync_work(&r->ss, (const float*)r->s_rrc.d, r->s_rrc.n, &r->s_sym);
         const float* sy = (const float*)r->s_sym.d;

@@ -132,6 +132,10 @@ struct qrl_rx : HandleBase {
     Ring rf;                       // FLL output (channel-major complex)
     ViterbiState* d_vs2 = nullptr;
     unsigned char* d_port3 = nullptr; int* d_port3_cnt = nullptr;
+    // non-FM FSK detectors: band-pass bank + symbol filter
+    float* d_bank_taps = nullptr; int nt_bank = 0;
+    float* d_symf_taps = nullptr; int nt_symf = 0;
+    Ring rbank;                    // bank output (complex for 4FSK, float for 2FSK), channel-major
     // SSB audio chain
     SsbParams ssbp{};
     SsbState* d_ssb = nullptr;
@@ -366,7 +370,6 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         else if (sps == 2) { decimation = 2; sym_sps = 5; tsr = 500000; nfilts = 50 * sym_sps; }
         else { set_err(h, "make_gr_demod_4fsk: unsupported sps"); return fail(QRL_EINVAL); }
         if ((nfilts % 2) == 0) nfilts += 1;
-        if (!flag) { set_err(h, "4FSK non-FM discriminator variant not built yet"); return fail(QRL_EINVAL); }
         if (interpolation != 1) { set_err(h, "4FSK 10k (2/25 resampler) not built yet"); return fail(QRL_EINVAL); }
         taps1 = low_pass(interpolation, static_cast<double>(interpolation) * samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
         h->D1 = decimation;
@@ -382,6 +385,23 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         h->ssp.n0 = static_cast<int>(floorf(h->ssp.min_period - fabsf(h->ssp.alpha)));
         h->ssp.fl0 = static_cast<float>(h->ssp.n0);
         h->nports = 3;
+        if (!flag) {     // gr_demod_4fsk.cpp:110-124: four complex band-pass filters + discriminator + symbol filter
+            int rs = 0, bw = 0;
+            if (sps == 1) { rs = 10000; bw = 4000; } else if (sps == 5) { rs = 2000; bw = 4000; } else if (sps == 10) { rs = 1000; bw = 2000; }
+            else { set_err(h, "make_gr_demod_4fsk: non-FM variant needs sps 1, 5 or 10"); return fail(QRL_EINVAL); }
+            const int fw = filter_width;
+            const double lo[4] = { double(-fw), double(-fw + rs), 0.0, double(fw - rs) }, hi[4] = { double(-fw + rs), 0.0, double(fw - rs), double(fw) };
+            std::vector<float> bank;
+            for (int b = 0; b < 4; b++) {
+                std::vector<float> t = complex_band_pass(1, tsr, lo[b], hi[b], bw, WIN_BLACKMAN_HARRIS);
+                h->nt_bank = static_cast<int>(t.size() / 2);
+                bank.insert(bank.end(), t.begin(), t.end());
+            }
+            if ((rc = upload_floats(h, &h->d_bank_taps, bank))) return fail(rc);
+            std::vector<float> sf = low_pass(1.0, tsr, tsr / sym_sps, tsr / sym_sps / 20, WIN_BLACKMAN_HARRIS);
+            h->nt_symf = static_cast<int>(sf.size());
+            if ((rc = upload_floats(h, &h->d_symf_taps, sf))) return fail(rc);
+        }
     } else if (kind == QRL_DEMOD_QPSK) {
         // gr_demod_qpsk.cpp:46-71 (sps ladder), :98-103 (resampler), :106-110 (RRC), :104,113-118 (agc, sync, costas)
         int decimation; float costas_bw = static_cast<float>(kPi / 200);
@@ -418,8 +438,17 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if (sps == 10) { tsr = 20000; sym_sps = sps; decim = 50; nfilts = 35 * sym_sps; }
         else if (sps >= 5) { tsr = 40000; sym_sps = sps * 2; decim = 25; nfilts = 35 * sym_sps; }
         else { set_err(h, "make_gr_demod_2fsk: 10k (2/25 resampler) variant not built yet"); return fail(QRL_EINVAL); }
-        if (!flag) { set_err(h, "2FSK band-filter (non-FM) variant not built yet"); return fail(QRL_EINVAL); }
         if ((nfilts % 2) == 0) nfilts += 1;
+        if (!flag) {     // gr_demod_2fsk.cpp:88-100: upper (-fw,0) / lower (0,fw) band filters, ratio detector, symbol filter
+            std::vector<float> bank = complex_band_pass(1, tsr, -filter_width, 0, filter_width, WIN_BLACKMAN_HARRIS);
+            std::vector<float> lower = complex_band_pass(1, tsr, 0, filter_width, filter_width, WIN_BLACKMAN_HARRIS);
+            h->nt_bank = static_cast<int>(bank.size() / 2);
+            bank.insert(bank.end(), lower.begin(), lower.end());
+            if ((rc = upload_floats(h, &h->d_bank_taps, bank))) return fail(rc);
+            std::vector<float> sf = low_pass(1.0, tsr, tsr / sym_sps, tsr / sym_sps, WIN_HAMMING);
+            h->nt_symf = static_cast<int>(sf.size());
+            if ((rc = upload_floats(h, &h->d_symf_taps, sf))) return fail(rc);
+        }
         taps1 = low_pass(1, samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
         h->D1 = decim;
         taps2 = low_pass(1, tsr, filter_width, filter_width, WIN_BLACKMAN_HARRIS);
@@ -537,8 +566,12 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = make_ring(h, &h->rr, sizeof(float), h->n1max * 2 / 5 + h->nbp.nt_audio + 16))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_nb, h->C))) return fail(rc);
     } else if (kind == QRL_DEMOD_4FSK || kind == QRL_DEMOD_2FSK) {
-        if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + h->ntaps3 + 8))) return fail(rc);
+        if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + h->ntaps3 + 64))) return fail(rc);
         if ((rc = make_ring(h, &h->r4, sizeof(float), h->n1max + 600, true))) return fail(rc);
+        if (!flag) {
+            if ((rc = make_ring(h, &h->rbank, kind == QRL_DEMOD_4FSK ? sizeof(float2) : sizeof(float), h->n1max + h->nt_symf + 16))) return fail(rc);
+            if (kind == QRL_DEMOD_4FSK && (rc = make_ring(h, &h->r3, sizeof(float2), h->n1max + 600, true))) return fail(rc);
+        }
     } else {   // QPSK / BPSK: shaping-filter output and loop output are channel-interleaved complex rings
         if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + 600, true))) return fail(rc);
         if ((rc = make_ring(h, &h->r3, sizeof(float2), h->n1max + 600, true))) return fail(rc);
@@ -826,12 +859,20 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                     static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
                     h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, bpsk ? 1 : 0);
                 h->launches++;
-                if (!bpsk) {
+                if (!bpsk && h->flag) {
                     qdemod_fir_fff_kernel<<<gtile, TB, sizeof(float) * (2 * h->ntaps3 + TB), h->s_loop>>>(
                         static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
                         static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
                         h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
                     h->launches++;
+                } else if (!bpsk) {
+                    fsk_bank_kernel<2><<<gtile, TB, sizeof(float) * 4 * h->nt_bank, h->s_loop>>>(
+                        static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, h->d_bank_taps, h->nt_bank, k0, k1,
+                        static_cast<float*>(h->rbank.d), h->rbank.mask, h->rbank.stride);
+                    fir_fff_ring_kernel<<<gtile, TB, sizeof(float) * h->nt_symf, h->s_loop>>>(
+                        static_cast<const float*>(h->rbank.d), h->rbank.mask, h->rbank.stride,
+                        static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride, h->d_symf_taps, h->nt_symf, k0, k1);
+                    h->launches += 2;
                 }
                 h->prof_end(pe);
             }
@@ -898,19 +939,44 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                     h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, 0);
                 h->launches++;
                 h->prof_end(pe);
-                // ---- stage 3: quadrature demod + RRC
+                // ---- stage 3: quadrature demod + RRC   |   band-pass bank + discriminator + symbol filter
                 pe = h->prof_begin(2, sp);
-                qdemod_fir_fff_kernel<<<gtile, TB, sizeof(float) * (2 * h->ntaps3 + TB), sp>>>(
-                    static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-                    static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
-                    h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
-                h->launches++;
+                if (h->flag) {
+                    qdemod_fir_fff_kernel<<<gtile, TB, sizeof(float) * (2 * h->ntaps3 + TB), sp>>>(
+                        static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                        static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
+                        h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
+                    h->launches++;
+                } else {
+                    fsk_bank_kernel<4><<<gtile, TB, sizeof(float) * 8 * h->nt_bank, sp>>>(
+                        static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, h->d_bank_taps, h->nt_bank, k0, k1,
+                        static_cast<float*>(h->rbank.d), h->rbank.mask, h->rbank.stride);
+                    fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->nt_symf, sp>>>(
+                        static_cast<const float2*>(h->rbank.d), h->rbank.mask, h->rbank.stride,
+                        static_cast<float2*>(h->r3.d), h->r3.mask, h->r3.stride,
+                        h->d_symf_taps, h->nt_symf, k0, k1, nullptr, 0, 0, 1);
+                    h->launches += 2;
+                }
                 h->prof_end(pe);
             }
             CK(cudaEventRecord(h->ev_a[i], sp));
             // ---- stage 4: symbol sync (+ phase mod + soft bits) on the loop stream
             CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
-            {
+            if (!h->flag) {
+                pe = h->prof_begin(3, h->s_loop);
+                constexpr int CH = 128, NST = 3, NEPI = 2;
+                const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
+                const size_t smem = sizeof(float) * (NST * CH * 64 + 132 * 8 + 2 * maxs * 64) + sizeof(int) * 64;
+                auto kern = symsync_kernel<2, SL_RECT4, EPI_CPLX, CH, NST, NEPI>;
+                static bool sc_attr = false;
+                if (!sc_attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); sc_attr = true; }
+                kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop>>>(
+                    h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r3.d), h->r3.mask, h->r3.stride, k1,
+                    h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
+                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i);
+                h->launches++;
+                h->prof_end(pe);
+            } else {
                 pe = h->prof_begin(3, h->s_loop);
                 constexpr int CH = 256, NST = 3, NEPI = 2;
                 const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);

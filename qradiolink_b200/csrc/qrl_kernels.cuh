@@ -1369,6 +1369,69 @@ ssb_audio_kernel(SsbParams p, SsbState* __restrict__ states,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Non-FM FSK detectors: a bank of NB complex band-pass filters (fft_filter_ccc, direct form) on the channel-filter
+// output, complex_to_mag, then
+//   NB = 4: gr_4fsk_discriminator (strict-greater argmax -> +-0.707107 +-0.707107j, or 0)   gr_4fsk_discriminator.cpp:17-44
+//   NB = 2: divide_ff(upper / lower) -> rail_ff(0, 2) -> add_const_ff(-1)                     gr_demod_2fsk.cpp:137-148
+// one thread per sample, channel-major rings.
+// ------------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void fsk_bank_kernel(const float2* __restrict__ in, unsigned in_mask, long long in_stride,
+                                const float* __restrict__ taps_c /* [NB][2*ntaps] */, int ntaps, long long a0, long long a1,
+                                float* __restrict__ out /* float2 ring (NB=4) or float ring (NB=2) */, unsigned out_mask, long long out_stride)
+{
+    extern __shared__ float hs_dyn[];
+    for (int i = threadIdx.x; i < NB * 2 * ntaps; i += blockDim.x) hs_dyn[i] = taps_c[i];
+    __syncthreads();
+    const int c = blockIdx.y;
+    const long long a = a0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (a >= a1) return;
+    const float2* x = in + static_cast<long long>(c) * in_stride;
+    float m[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const float* h = hs_dyn + b * 2 * ntaps;
+        float re = 0.0f, im = 0.0f;
+        for (int j = ntaps - 1; j >= 0; j--) {
+            const float2 v = x[(a - j) & in_mask];
+            re = fmaf(h[2 * j], v.x, re); re = fmaf(-h[2 * j + 1], v.y, re);
+            im = fmaf(h[2 * j], v.y, im); im = fmaf(h[2 * j + 1], v.x, im);
+        }
+        m[b] = sqrtf(re * re + im * im);
+    }
+    if (NB == 4) {
+        float orr = 0.0f, oi = 0.0f;
+        const float P = static_cast<float>(0.707107), N = static_cast<float>(-0.707107);
+        if ((m[0] > m[1]) && (m[0] > m[2]) && (m[0] > m[3])) { orr = N; oi = N; }
+        else if ((m[1] > m[0]) && (m[1] > m[2]) && (m[1] > m[3])) { orr = N; oi = P; }
+        else if ((m[2] > m[1]) && (m[2] > m[0]) && (m[2] > m[3])) { orr = P; oi = P; }
+        else if ((m[3] > m[1]) && (m[3] > m[0]) && (m[3] > m[2])) { orr = P; oi = N; }
+        reinterpret_cast<float2*>(out)[static_cast<long long>(c) * out_stride + (a & out_mask)] = make_float2(orr, oi);
+    } else {
+        const float q = m[0] / m[1];
+        const float t = fmaxf(fminf(q, 2.0f), 0.0f);          // NaN (0/0 at start-up) -> the rail, like the oracle
+        out[static_cast<long long>(c) * out_stride + (a & out_mask)] = t + -1.0f;
+    }
+}
+
+// float stream, real taps (fft_filter_fff direct form): channel-major ring in, channel-interleaved ring out
+__global__ void fir_fff_ring_kernel(const float* __restrict__ in, unsigned in_mask, long long in_stride,
+                                    float* __restrict__ out, unsigned out_mask, long long out_stride,
+                                    const float* __restrict__ taps, int ntaps, long long a0, long long a1)
+{
+    extern __shared__ float hs_dyn[];
+    for (int i = threadIdx.x; i < ntaps; i += blockDim.x) hs_dyn[i] = taps[i];
+    __syncthreads();
+    const int c = blockIdx.y;
+    const long long a = a0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (a >= a1) return;
+    const float* x = in + static_cast<long long>(c) * in_stride;
+    float acc = 0.0f;
+    for (int j = ntaps - 1; j >= 0; j--) acc = fmaf(hs_dyn[j], x[(a - j) & in_mask], acc);
+    out[(static_cast<long long>(c >> 5) * out_stride + (a & out_mask)) * 32 + (c & 31)] = acc;
+}
+
 // roll the stage-1 history: new_hist = last H samples of (old_hist ++ iq[0..T))
 __global__ void hist_update_kernel(const float2* __restrict__ iq, long long iq_stride, long long T,
                                    const float2* __restrict__ old_hist, float2* __restrict__ new_hist, int H)

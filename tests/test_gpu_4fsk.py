@@ -121,3 +121,26 @@ def test_4fsk_1k_fm_parity_d100(qrl, oracle):
             n = min(len(got), len(want))
             assert n > 0 and len(want) - n <= 80
             assert np.array_equal(got[:n], want[:n]), (c, p)
+
+
+def test_4fsk_2k_discriminator_variant(qrl, oracle):
+    """4FSK2K (fm=false): four complex band-pass filters + gr_4fsk_discriminator + 837-tap symbol filter + symbol_sync_cc."""
+    C, T = 2, 1 << 20
+    X, payloads = siggen.gen_4fsk_channels(C, T, seed0=1300, fm=False)
+    blk = qrl.make_gr_demod_4fsk(5, 1000000, 1700, 4000, False, n_channels=C, max_samples=600000)
+    acc = [[[] for _ in range(C)] for _ in range(3)]
+    for lo, hi in ((0, 500000), (500000, 500003), (500003, T)):
+        blk.work(X[:, lo:hi])
+        for p in range(3):
+            for c, v in enumerate(blk.read_port(p)):
+                acc[p][c].append(v)
+    for c in range(C):
+        rx = oracle.Rx(oracle.DEMOD_4FSK, 5, 1000000, 1700, 4000, 0)
+        rx.work(X[c])
+        for p in range(3):
+            got, want = np.concatenate(acc[p][c]), rx.port(p)
+            n = min(len(got), len(want))
+            assert n > 0 and len(want) - n <= 80, (p, len(got), len(want))
+            assert np.array_equal(got[:n], want[:n]), (c, p)
+        good, found = siggen.count_good_frames(np.concatenate(acc[2][c]), 0xED89AA, 24, 7, payloads[c])
+        assert good >= len(payloads[c]) - 4

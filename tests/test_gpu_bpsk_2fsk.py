@@ -60,3 +60,17 @@ def test_bpsk_2k_parity(qrl, oracle):
     X, payloads = make_signals(oracle, "bpsk", C, T, 32)
     blk = qrl.make_gr_demod_bpsk(5, 1000000, 1700, 2400, n_channels=C, max_samples=400000)
     check(qrl, oracle, blk, oracle.DEMOD_BPSK, (5, 1000000, 1700, 2400, 0), X, payloads, [400000, 99999, 51])
+
+
+def test_2fsk_2k_band_filter_variant(qrl, oracle):
+    """2FSK2K (fm=false): upper/lower complex band filters, magnitude ratio, rail, symbol filter (gr_demod_2fsk.cpp:137-149)."""
+    C, T = 2, 1 << 20
+    rng = np.random.default_rng(35)
+    X = np.zeros((C, T), np.complex64); payloads = []
+    for c in range(C):
+        data, pl = siggen.frames_4fsk(rng, 20)
+        iq = oracle.Tx(oracle.MOD_2FSK, 25, 1000000, 1700, 4000, 0).work(data)
+        X[c] = siggen.channel(iq, rng, fo_hz=rng.uniform(-60, 60), delay=int(rng.integers(0, 300)), snr_db=20.0, amp=0.1, total=T)
+        payloads.append(pl)
+    blk = qrl.make_gr_demod_2fsk(5, 1000000, 1700, 4000, False, n_channels=C, max_samples=400000)
+    check(qrl, oracle, blk, oracle.DEMOD_2FSK, (5, 1000000, 1700, 4000, 0), X, payloads, [400000, 77777, 5])
