@@ -1162,6 +1162,7 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         int decim, interp = 1, nfilts;
         if (sps == 10) { r->tsr = 20000; r->sym_sps = sps; decim = 50; nfilts = 35 * r->sym_sps; }
         else if (sps >= 5) { r->tsr = 40000; r->sym_sps = sps * 2; decim = 25; nfilts = 35 * r->sym_sps; }
+        else if (sps == 1) { r->tsr = 80000; r->sym_sps = 4; decim = 25; interp = 2; nfilts = 125 * r->sym_sps; }
         else { free(r); return NULL; }
         int spacing = flag ? 1 : 2;
         if ((nfilts % 2) == 0) nfilts += 1;

@@ -108,7 +108,7 @@ struct qrl_rx : HandleBase {
     long Tmax = 0;
     int nports = 3;
     // stage 1 (rational_resampler_ccf(1, D))
-    int D1 = 1, Q1 = 1, ntaps1 = 0, H = 0, hist_cur = 0;
+    int D1 = 1, L1 = 1, Q1 = 1, ntaps1 = 0, H = 0, hist_cur = 0;
     float* d_taps1 = nullptr;
     float2* d_hist[2] = { nullptr, nullptr };
     float2* d_in_staging = nullptr;
@@ -233,9 +233,25 @@ int launch_fir_d2(qrl_rx* h, const float2* iq, long long stride, long long T, lo
     return QRL_OK;
 }
 
+int launch_fir_resamp_2_25(qrl_rx* h, const float2* iq, long long stride, long long T, long long k0, long long k1)
+{
+    constexpr int L = 2, M = 25, NT = 105, NOUT = 512;
+    constexpr int SPAN = (NOUT * M + L - 1) / L + NT + 1;
+    const size_t smem = sizeof(float2) * SPAN;
+    static bool attr_done = false;
+    if (!attr_done) { CK(cudaFuncSetAttribute(fir_resamp_ccf_kernel<L, M, NT, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    dim3 grid(static_cast<unsigned>((k1 - k0 + NOUT - 1) / NOUT), h->C);
+    fir_resamp_ccf_kernel<L, M, NT, NOUT><<<grid, 256, smem, h->par()>>>(iq, stride, T, h->d_hist[h->hist_cur], h->H, h->d_taps1,
+        static_cast<float2*>(h->r1.d), h->r1.mask, h->r1.stride, h->n_in, k0, k1);
+    h->launches++;
+    CK(cudaGetLastError());
+    return QRL_OK;
+}
+
 int stage1(qrl_rx* h, const float2* iq, long long stride, long long T, long long k0, long long k1)
 {
     if (k1 <= k0) return QRL_OK;
+    if (h->L1 == 2 && h->D1 == 25 && h->ntaps1 <= 210) return launch_fir_resamp_2_25(h, iq, stride, T, k0, k1);
     if (h->D1 == 50 && h->Q1 == 9) return launch_fir_poly<50, 9, 8, 128, 8>(h, iq, stride, T, k0, k1);
     if (h->D1 == 100 && h->Q1 == 9) return launch_fir_poly<100, 9, 8, 64, 8>(h, iq, stride, T, k0, k1);     // 837 taps (4FSK-1k, QPSK-2k shape)
     if (h->D1 == 25 && h->Q1 == 9) return launch_fir_poly<25, 9, 8, 256, 8>(h, iq, stride, T, k0, k1);      // 209 taps (2FSK-2k)
@@ -370,9 +386,8 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         else if (sps == 2) { decimation = 2; sym_sps = 5; tsr = 500000; nfilts = 50 * sym_sps; }
         else { set_err(h, "make_gr_demod_4fsk: unsupported sps"); return fail(QRL_EINVAL); }
         if ((nfilts % 2) == 0) nfilts += 1;
-        if (interpolation != 1) { set_err(h, "4FSK 10k (2/25 resampler) not built yet"); return fail(QRL_EINVAL); }
         taps1 = low_pass(interpolation, static_cast<double>(interpolation) * samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
-        h->D1 = decimation;
+        h->D1 = decimation; h->L1 = interpolation;
         taps2 = low_pass(1, tsr, filter_width, filter_width / 2, WIN_BLACKMAN_HARRIS);
         taps3 = root_raised_cosine(1.5, tsr, tsr / sym_sps, 0.2, nfilts);
         h->qd_gain = static_cast<float>(sym_sps / (1 * kPi));
@@ -434,10 +449,12 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         h->nports = 3;
     } else if (kind == QRL_DEMOD_2FSK) {
         // gr_demod_2fsk.cpp:39-130 (fm variant)
-        int decim, nfilts;
+        int decim, nfilts, interp = 1;
         if (sps == 10) { tsr = 20000; sym_sps = sps; decim = 50; nfilts = 35 * sym_sps; }
         else if (sps >= 5) { tsr = 40000; sym_sps = sps * 2; decim = 25; nfilts = 35 * sym_sps; }
-        else { set_err(h, "make_gr_demod_2fsk: 10k (2/25 resampler) variant not built yet"); return fail(QRL_EINVAL); }
+        else if (sps == 1) { tsr = 80000; sym_sps = 4; decim = 25; interp = 2; nfilts = 125 * sym_sps; }
+        else { set_err(h, "make_gr_demod_2fsk: unsupported sps"); return fail(QRL_EINVAL); }
+        h->L1 = interp;
         if ((nfilts % 2) == 0) nfilts += 1;
         if (!flag) {     // gr_demod_2fsk.cpp:88-100: upper (-fw,0) / lower (0,fw) band filters, ratio detector, symbol filter
             std::vector<float> bank = complex_band_pass(1, tsr, -filter_width, 0, filter_width, WIN_BLACKMAN_HARRIS);
@@ -449,7 +466,7 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
             h->nt_symf = static_cast<int>(sf.size());
             if ((rc = upload_floats(h, &h->d_symf_taps, sf))) return fail(rc);
         }
-        taps1 = low_pass(1, samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
+        taps1 = low_pass(interp, static_cast<double>(interp) * samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
         h->D1 = decim;
         taps2 = low_pass(1, tsr, filter_width, filter_width, WIN_BLACKMAN_HARRIS);
         taps3 = root_raised_cosine(1, tsr, tsr / sym_sps, 0.2, nfilts);
@@ -516,11 +533,17 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     int padded = std::max(h->Q1 * h->D1, h->D1 == 2 ? 56 : 0);
     std::vector<float> tp(padded, 0.0f);
     std::copy(taps1.begin(), taps1.end(), tp.begin());
+    if (h->L1 == 2) {       // rational_resampler arms: arm[p][k] = taps[p + k L], 105 taps per arm
+        const int nt = 105;
+        tp.assign(2 * nt, 0.0f);
+        for (int p = 0; p < 2; p++) for (int k = 0; k < nt; k++) { const size_t j = p + 2 * k; if (j < taps1.size()) tp[p * nt + k] = taps1[j]; }
+        padded = 128;       // history samples kept
+    }
     if ((rc = upload_floats(h, &h->d_taps1, tp))) return fail(rc);
     h->H = padded;
     if ((rc = dev_alloc(h, &h->d_hist[0], static_cast<size_t>(h->H) * h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_hist[1], static_cast<size_t>(h->H) * h->C))) return fail(rc);
-    h->n1max = h->Tmax / h->D1 + 2;
+    h->n1max = h->Tmax * h->L1 / h->D1 + 2;
     // ---- rings
     h->ntaps2 = static_cast<int>(taps2.size()) / (kind == QRL_DEMOD_SSB ? 2 : 1);
     h->ntaps3 = static_cast<int>(taps3.size());
@@ -777,7 +800,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         // ---- stage 1: decimating FIR; outputs k with D k <= last absolute input index
         const long long N = h->n_in + Ti;
         const long long k0 = h->n1;
-        const long long k1 = (N - 1) / h->D1 + 1;
+        const long long k1 = (N * h->L1 + h->D1 - 1) / h->D1;       // outputs i with floor(i M / L) <= N - 1
         cudaEvent_t pe = h->prof_begin(0, sp);
         int rc = stage1(h, xi, xstride, Ti, k0, k1);
         h->prof_end(pe);

@@ -329,6 +329,56 @@ fir_decim2_kernel(const float2* __restrict__ iq, long long iq_stride, long long 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stage 1 for the 10k modes: rational_resampler_ccf(L = 2, M = 25), 209 taps -> two arms of 105 taps.
+// output i uses arm (i M) mod L at input position floor(i M / L); each arm is accumulated oldest-first.
+// First version: one thread per output from a shared-memory window (cooperative fill).
+// ------------------------------------------------------------------------------------------------
+template <int L, int M, int NT /* taps per arm */, int NOUT>
+__global__ void __launch_bounds__(256)
+fir_resamp_ccf_kernel(const float2* __restrict__ iq, long long iq_stride, long long T,
+                      const float2* __restrict__ hist, int H,
+                      const float* __restrict__ arms /* [L][NT] */,
+                      float2* __restrict__ out_ring, unsigned ring_mask, long long ring_stride,
+                      long long n_in_before, long long k0, long long k1)
+{
+    constexpr int SPAN = (NOUT * M + L - 1) / L + NT + 1;      // input samples covering NOUT outputs
+    extern __shared__ float2 xs_rs[];
+    __shared__ float hs[L * NT];
+    const int c = blockIdx.y;
+    const long long kbase = k0 + static_cast<long long>(blockIdx.x) * NOUT;
+    if (kbase >= k1) return;
+    for (int i = threadIdx.x; i < L * NT; i += 256) hs[i] = arms[i];
+    const long long pos0 = (kbase * M) / L;                    // input position of the first output
+    const long long A0 = pos0 - (NT - 1);
+    const float2* iqc = iq + static_cast<long long>(c) * iq_stride;
+    const float2* hc = hist + static_cast<long long>(c) * H;
+    for (int idx = threadIdx.x; idx < SPAN; idx += 256) {
+        const long long i = A0 + idx - n_in_before;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (i >= 0) { if (i < T) v = __ldg(iqc + i); }
+        else if (H + i >= 0) v = hc[H + i];
+        xs_rs[idx] = v;
+    }
+    __syncthreads();
+    float2* outc = out_ring + static_cast<long long>(c) * ring_stride;
+    for (int o = threadIdx.x; o < NOUT; o += 256) {
+        const long long k = kbase + o;
+        if (k >= k1) break;
+        const long long pos = (k * M) / L;
+        const float* h = hs + static_cast<int>((k * M) % L) * NT;
+        const float2* p = xs_rs + (pos - A0);                 // newest sample of this output
+        float re = 0.0f, im = 0.0f;
+#pragma unroll 5
+        for (int j = NT - 1; j >= 0; j--) {
+            const float2 v = p[-j];
+            re = fmaf(h[j], v.x, re);
+            im = fmaf(h[j], v.y, im);
+        }
+        outc[k & ring_mask] = make_float2(re, im);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Low-rate stream stages (20 ksps .. 500 ksps): ring -> ring, one thread per output item, taps in smem,
 // sequential oldest-first accumulation (the D = 1 case of the FIR order).
 // ------------------------------------------------------------------------------------------------
