@@ -35,6 +35,7 @@ def lib():
         L.qo_rx_create.argtypes = [C.c_int] * 6
         L.qo_rx_destroy.argtypes = [vp]
         L.qo_rx_work.argtypes = [vp, vp, C.c_long]
+        L.qo_rx_set_carrier_offset.argtypes = [vp, C.c_double, C.c_double]
         L.qo_rx_port_items.restype = C.c_long
         L.qo_rx_port_items.argtypes = [vp, C.c_int]
         L.qo_rx_port_data.restype = vp
@@ -219,6 +220,9 @@ class Rx:
         iq = np.ascontiguousarray(iq, np.complex64)
         rc = lib().qo_rx_work(self.h, _p(iq), len(iq))
         assert rc == 0
+
+    def set_carrier_offset(self, hz, samp_rate=1e6):
+        lib().qo_rx_set_carrier_offset(self.h, float(hz), float(samp_rate))
 
     def port(self, p, clear=True):
         n = lib().qo_rx_port_items(self.h, p)

@@ -1034,6 +1034,8 @@ struct qo_rx {
     fircc_t ssb_bpf; resamp_t ssb_audio; float env_m2, env_m1; qvec s_clip; size_t st_pos;
     /* bpsk / 2fsk */
     fll_t fll; crmm_t crmm; ccdec_t dec2; lfsr_t descr2; int dec2_started;
+    /* front-end rotator (gr_demod_base.cpp:57,180,1220-1225): Q32 NCO, phase = base + inc * (n - n_base) */
+    uint32_t rot_inc, rot_base; long long rot_nbase, rot_n; qvec s_rot;
     /* scratch + ports */
     qvec s_res, s_filt, s_dem, s_rrc, s_sym, s_soft, s_bits, s_tmp, s_tmp2, s_bp[4];
     qvec port[4];
@@ -1247,8 +1249,34 @@ static void rx_fec_tail_dual(qo_rx* r)
     r->s_soft.n = 0;
 }
 
+/* blocks::rotator_cc restated with an exact Q32 phase (inc = rint(-offset/fs * 2^32)): y[n] = x[n] * exp(j*theta_n),
+ * theta_n = phase_n * pi / 2^31 (phase as signed 32-bit), sin/cos from qo_sincosf.  GNU Radio's rotator accumulates a
+ * float complex phasor (and renormalises every 512 samples); the two agree to ~1e-6. */
+void qo_rx_set_carrier_offset(qo_rx* r, double offset_hz, double samp_rate)
+{
+    r->rot_base = r->rot_base + r->rot_inc * (uint32_t)(r->rot_n - r->rot_nbase);
+    r->rot_nbase = r->rot_n;
+    r->rot_inc = (uint32_t)(int32_t)(long long)rint(-offset_hz / samp_rate * 4294967296.0);
+}
+static const float* rx_rotate(qo_rx* r, const float* iq, long T)
+{
+    if (r->rot_inc == 0 && r->rot_base == 0) { r->rot_n += T; return iq; }
+    if (!r->s_rot.isz) qv_init(&r->s_rot, 8);
+    r->s_rot.n = 0;
+    for (long i = 0; i < T; i++) {
+        uint32_t ph = r->rot_base + r->rot_inc * (uint32_t)(r->rot_n + i - r->rot_nbase);
+        float ang = (float)((double)(int32_t)ph * (M_PI / 2147483648.0));
+        float sn, cs; qo_sincosf(ang, &sn, &cs);
+        float xr = iq[2 * i], xi = iq[2 * i + 1];
+        qv_pushc(&r->s_rot, xr * cs - xi * sn, xr * sn + xi * cs);
+    }
+    r->rot_n += T;
+    return (const float*)r->s_rot.d;
+}
+
 int qo_rx_work(qo_rx* r, const float* iq, long T)
 {
+    iq = rx_rotate(r, iq, T);
     if (r->kind == QO_DEMOD_SSB) {
         r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
         float* v = (float*)r->s_res.d;

@@ -70,6 +70,8 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
 void   qo_rx_destroy(qo_rx*);
 /* feed T complex samples (interleaved float re,im) of ONE channel */
 int    qo_rx_work(qo_rx*, const float* iq, long T);
+/* gr_demod_base::set_carrier_offset: front-end rotator, phase increment 2*pi*(-offset)/samp_rate */
+void   qo_rx_set_carrier_offset(qo_rx*, double offset_hz, double samp_rate);
 /* ports: 0 = filtered IQ (complex), 1 = constellation (complex) or audio (float), 2 = bits, 3 = delayed bits */
 long   qo_rx_port_items(qo_rx*, int port);
 const void* qo_rx_port_data(qo_rx*, int port);

@@ -132,6 +132,8 @@ struct qrl_rx : HandleBase {
     Ring rf;                       // FLL output (channel-major complex)
     ViterbiState* d_vs2 = nullptr;
     unsigned char* d_port3 = nullptr; int* d_port3_cnt = nullptr;
+    // front-end rotator (carrier offset)
+    std::vector<RotState> rot; RotState* d_rot = nullptr; bool rot_active = false; float2* d_rot_buf = nullptr;
     // non-FM FSK detectors: band-pass bank + symbol filter
     float* d_bank_taps = nullptr; int nt_bank = 0;
     float* d_symf_taps = nullptr; int nt_symf = 0;
@@ -735,9 +737,27 @@ int qrl_rx_set_stream(qrl_rx* h, void* s)
     return QRL_OK;
 }
 
-int qrl_rx_set_param(qrl_rx* h, int, int key, double value)
+int qrl_rx_set_param(qrl_rx* h, int channel, int key, double value)
 {
     if (!h) return QRL_EINVAL;
+    if (key == QRL_PARAM_CARRIER_OFFSET_HZ) {        // gr_demod_base::set_carrier_offset (:1220-1225): phase inc = 2 pi (-offset) / fs
+        if (channel >= h->C) { set_err(h, "set_param: channel out of range"); return QRL_EINVAL; }
+        if (h->rot.empty()) h->rot.assign(h->C, RotState{ 0u, 0u, 0 });
+        const unsigned inc = static_cast<unsigned>(static_cast<int>(static_cast<long long>(std::rint(-value / h->samp_rate * 4294967296.0))));
+        for (int c = 0; c < h->C; c++) {
+            if (channel >= 0 && c != channel) continue;
+            RotState& r = h->rot[c];
+            r.base = r.base + r.inc * static_cast<unsigned>(h->n_in - r.n_base);     // keep the phase continuous
+            r.n_base = h->n_in;
+            r.inc = inc;
+        }
+        h->rot_active = false;
+        for (auto& r : h->rot) if (r.inc != 0 || r.base != 0) h->rot_active = true;
+        if (!h->d_rot) { int rc = dev_alloc(h, &h->d_rot, h->C); if (rc) return rc; }
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(h->d_rot, h->rot.data(), sizeof(RotState) * h->C, cudaMemcpyHostToDevice));
+        return QRL_OK;
+    }
     if (h->kind == QRL_DEMOD_NBFM && key == QRL_PARAM_SQUELCH_DB) {          // gr_demod_nbfm::set_squelch
         h->nbp.sq_threshold = std::pow(10.0, value / 10.0);
         return QRL_OK;
@@ -775,6 +795,13 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                              sizeof(float2) * T, h->C, cudaMemcpyHostToDevice, h->stream));
         x = h->d_in_staging;
         xstride = h->Tmax;
+    }
+    if (h->rot_active) {
+        if (!h->d_rot_buf) { int rc = dev_alloc(h, &h->d_rot_buf, static_cast<size_t>(h->Tmax) * h->C, false); if (rc) return rc; }
+        dim3 g(static_cast<unsigned>(std::min<long long>((T + 255) / 256, 4096)), h->C);
+        rotator_kernel<<<g, 256, 0, h->stream>>>(h->d_rot, x, xstride, h->d_rot_buf, h->Tmax, T, h->n_in);
+        h->launches++;
+        x = h->d_rot_buf; xstride = h->Tmax;
     }
     CK(cudaMemsetAsync(h->d_port1_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_port2_cnt, 0, sizeof(int) * h->C, h->stream));

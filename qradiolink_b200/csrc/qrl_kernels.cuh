@@ -1482,6 +1482,25 @@ __global__ void fir_fff_ring_kernel(const float* __restrict__ in, unsigned in_ma
     out[(static_cast<long long>(c >> 5) * out_stride + (a & out_mask)) * 32 + (c & 31)] = acc;
 }
 
+// Front-end rotator (gr_demod_base's rotator_cc, carrier offset): out[c][n] = in[c][n] * exp(j theta), exact Q32 phase
+// phase = base[c] + inc[c] * (n_abs - n_base[c]).  Only launched when some channel has a non-zero offset (the
+// reference default is 0); it costs one extra pass over the slab -- fusing it needs complex stage-1 taps (next).
+struct RotState { unsigned inc, base; long long n_base; };
+__global__ void rotator_kernel(const RotState* __restrict__ rs, const float2* __restrict__ in, long long in_stride,
+                               float2* __restrict__ out, long long out_stride, long long T, long long n_abs0)
+{
+    const int c = blockIdx.y;
+    const RotState r = rs[c];
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < T; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const unsigned ph = r.base + r.inc * static_cast<unsigned>(n_abs0 + i - r.n_base);
+        const float ang = static_cast<float>(static_cast<double>(static_cast<int>(ph)) * (3.14159265358979323846 / 2147483648.0));
+        float sn, cs;
+        qrl_sincosf(ang, sn, cs);
+        const float2 x = in[static_cast<long long>(c) * in_stride + i];
+        out[static_cast<long long>(c) * out_stride + i] = make_float2(x.x * cs - x.y * sn, x.x * sn + x.y * cs);
+    }
+}
+
 // roll the stage-1 history: new_hist = last H samples of (old_hist ++ iq[0..T))
 __global__ void hist_update_kernel(const float2* __restrict__ iq, long long iq_stride, long long T,
                                    const float2* __restrict__ old_hist, float2* __restrict__ new_hist, int H)

@@ -144,3 +144,34 @@ def test_4fsk_2k_discriminator_variant(qrl, oracle):
             assert np.array_equal(got[:n], want[:n]), (c, p)
         good, found = siggen.count_good_frames(np.concatenate(acc[2][c]), 0xED89AA, 24, 7, payloads[c])
         assert good >= len(payloads[c]) - 4
+
+
+def test_carrier_offset_rotator(qrl, oracle):
+    """gr_demod_base::set_carrier_offset: per-channel front-end rotator, changed mid-stream with continuous phase."""
+    C, T = 3, 300000
+    X, _ = siggen.gen_4fsk_channels(C, T, seed0=1500)
+    offs = [0.0, 1250.0, -2600.5]
+    n = np.arange(T)
+    for c in range(C):      # the signal sits `off` Hz above baseband; the receiver rotates it back down (phase inc = -2 pi off / fs)
+        X[c] = (X[c] * np.exp(2j * np.pi * offs[c] * n / 1e6)).astype(np.complex64)
+    blk = qrl.make_gr_demod_4fsk(5, 1000000, 1700, 3000, True, n_channels=C, max_samples=200000)
+    rxs = [oracle.Rx(oracle.DEMOD_4FSK, 5, 1000000, 1700, 3000, 1) for _ in range(C)]
+    for c in range(C):
+        blk.set_carrier_offset(offs[c], channel=c)
+        rxs[c].set_carrier_offset(offs[c])
+    acc = [[[] for _ in range(C)] for _ in range(3)]
+    for k, (lo, hi) in enumerate(((0, 150001), (150001, T))):
+        if k == 1:          # retune channel 1 mid-stream
+            blk.set_carrier_offset(1300.0, channel=1); rxs[1].set_carrier_offset(1300.0)
+        blk.work(X[:, lo:hi])
+        for c in range(C):
+            rxs[c].work(X[c, lo:hi])
+        for p in range(3):
+            for c, v in enumerate(blk.read_port(p)):
+                acc[p][c].append(v)
+    for c in range(C):
+        for p in range(3):
+            got, want = np.concatenate(acc[p][c]), rxs[c].port(p)
+            nmin = min(len(got), len(want))
+            assert nmin > 0 and len(want) - nmin <= 80
+            assert np.array_equal(got[:nmin], want[:nmin]), (c, p)
