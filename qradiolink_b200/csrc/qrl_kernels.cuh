@@ -74,12 +74,12 @@ __device__ __forceinline__ void qrl_sincosf(float x, float& s, float& c)
     pc = pc * z;
     float cs = fmaf(z, -0.5f, 1.0f);
     cs = cs + pc;
-    switch (q) {
-    case 0: s = sn; c = cs; break;
-    case 1: s = cs; c = -sn; break;
-    case 2: s = -sn; c = -cs; break;
-    default: s = -cs; c = sn; break;
-    }
+    // quadrant fix-up without branches (lanes are different channels: a switch would diverge 4 ways):
+    // q odd swaps sin/cos; sin is negated for q = 2,3, cos for q = 1,2 (sign-bit flips are exact)
+    const bool swap = q & 1;
+    const float s_ = swap ? cs : sn, c_ = swap ? sn : cs;
+    s = __int_as_float(__float_as_int(s_) ^ ((q & 2) << 30));
+    c = __int_as_float(__float_as_int(c_) ^ (((q + 1) & 2) << 30));
 }
 
 // gr::fast_atan2f restated (table + octant fix-up)
@@ -108,13 +108,13 @@ __device__ __forceinline__ float qrl_fast_atan2f(float y, float x)
     return angle;
 }
 
-__device__ __forceinline__ float qrl_tanhf_lut(float x)
+__device__ __forceinline__ float qrl_tanhf_lut(float x, const float* __restrict__ tab = d_tanh_tab)
 {
-    if (x > 2.0f) return 1.0f;
-    if (x <= -2.0f) return -1.0f;
-    int index = static_cast<int>(128.0f + 64.0f * x);
-    if (index > 255) index = 255;
-    return d_tanh_tab[index];
+    // x > 2 -> 1, x <= -2 -> -1, else table[(int)(128 + 64 x)] -- as selects, one table read
+    int index = static_cast<int>(128.0f + 64.0f * fminf(fmaxf(x, -2.0f), 2.0f));
+    index = index > 255 ? 255 : index;
+    const float t = tab[index];
+    return x > 2.0f ? 1.0f : (x <= -2.0f ? -1.0f : t);
 }
 __device__ __forceinline__ float qrl_clip(float x, float lim) { return x > lim ? lim : (x < -lim ? -lim : x); }
 
@@ -499,7 +499,8 @@ __device__ __forceinline__ void qrl_slice(int slicer, float re, float im, float&
 }
 
 __device__ __forceinline__ void qrl_costas_step(LoopState& st, float alpha, float beta, int order, bool use_snr,
-                                                float xr, float xi, float& yr, float& yi)
+                                                float xr, float xi, float& yr, float& yi,
+                                                const float* __restrict__ tanh_tab = d_tanh_tab)
 {
     float sn, cs;
     qrl_sincosf(-st.phase, sn, cs);
@@ -507,12 +508,12 @@ __device__ __forceinline__ void qrl_costas_step(LoopState& st, float alpha, floa
     const float oi = xr * sn + xi * cs;
     float err;
     if (order == 2) {
-        if (use_snr) { const float snr = orr * orr + oi * oi; err = qrl_tanhf_lut(snr * orr) * oi; }
+        if (use_snr) { const float snr = orr * orr + oi * oi; err = qrl_tanhf_lut(snr * orr, tanh_tab) * oi; }
         else err = orr * oi;
     } else {
         if (use_snr) {
             const float snr = orr * orr + oi * oi;
-            err = qrl_tanhf_lut(snr * orr) * oi - qrl_tanhf_lut(snr * oi) * orr;
+            err = qrl_tanhf_lut(snr * orr, tanh_tab) * oi - qrl_tanhf_lut(snr * oi, tanh_tab) * orr;
         } else {
             err = (orr > 0.0f ? 1.0f : -1.0f) * oi - (oi > 0.0f ? 1.0f : -1.0f) * orr;
         }
@@ -622,6 +623,8 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
 {
     extern __shared__ __align__(128) float2 sm_ac[];          // [NST][CH][32] | hand-off [2][CH][32]
     __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[2], bar_empty[2];
+    __shared__ float tanh_s[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tanh_s[i] = d_tanh_tab[i];
     float2* stage0 = sm_ac;
     float2* hand = sm_ac + NST * CH * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -702,7 +705,7 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
                 for (int i = 0; i < n; i++) {
                     const float2 x = hb[i * 32];
                     float yr = x.x, yi = x.y;
-                    if (p.order != 0) qrl_costas_step(pll, k_a, k_b, p.order, p.use_snr != 0, x.x, x.y, yr, yi);
+                    if (p.order != 0) qrl_costas_step(pll, k_a, k_b, p.order, p.use_snr != 0, x.x, x.y, yr, yi, tanh_s);
                     oring[((w0 + i) & out_mask) * 32] = make_float2(yr, yi);
                 }
             }
@@ -1191,32 +1194,42 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
     float* rr = res_ring + static_cast<long long>(c) * res_stride;
     const long long gate0 = st.n_gate;
 
-    // ---- 1. squelch (sequential)
-    if (threadIdx.x == 0) {
-        double pwr = st.pwr; int state = st.sq_state, ramped = st.ramped; float env = st.envelope;
-        long long ng = st.n_gate;
-        for (long long a = st.n_in; a < avail_in; a++) {
-            const float2 v = x[a & in_mask];
-            const float mag2 = v.x * v.x + v.y * v.y;
-            pwr = p.sq_alpha * static_cast<double>(mag2) + (1.0 - p.sq_alpha) * pwr;
-            const bool mute = pwr < p.sq_threshold;
-            switch (state) {
-            case SQ_MUTED: if (!mute) state = p.sq_ramp ? SQ_ATTACK : SQ_UNMUTED; break;
-            case SQ_UNMUTED: if (mute) state = p.sq_ramp ? SQ_DECAY : SQ_MUTED; break;
-            case SQ_ATTACK:
-                env = env_tab[++ramped];
-                if (ramped >= p.sq_ramp) { state = SQ_UNMUTED; env = 1.0f; }
-                break;
-            case SQ_DECAY:
-                env = env_tab[--ramped];
-                if (ramped == 0) state = SQ_MUTED;
-                break;
+    // ---- 1. squelch (sequential on thread 0; input tiles staged in shared memory by the whole CTA so the
+    //         recurrence never waits on a global load)
+    __shared__ float2 xin[2048];
+    for (long long tile0 = st.n_in; tile0 < avail_in; tile0 += 2048) {
+        const int nt = (avail_in - tile0) < 2048 ? static_cast<int>(avail_in - tile0) : 2048;
+        for (int j = threadIdx.x; j < nt; j += blockDim.x) xin[j] = x[(tile0 + j) & in_mask];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double pwr = st.pwr; int state = st.sq_state, ramped = st.ramped; float env = st.envelope;
+            long long ng = st.n_gate;
+            const double one_m_alpha = 1.0 - p.sq_alpha;
+            for (int j = 0; j < nt; j++) {
+                const float2 v = xin[j];
+                const float mag2 = v.x * v.x + v.y * v.y;
+                pwr = p.sq_alpha * static_cast<double>(mag2) + one_m_alpha * pwr;
+                const bool mute = pwr < p.sq_threshold;
+                switch (state) {
+                case SQ_MUTED: if (!mute) state = p.sq_ramp ? SQ_ATTACK : SQ_UNMUTED; break;
+                case SQ_UNMUTED: if (mute) state = p.sq_ramp ? SQ_DECAY : SQ_MUTED; break;
+                case SQ_ATTACK:
+                    env = env_tab[++ramped];
+                    if (ramped >= p.sq_ramp) { state = SQ_UNMUTED; env = 1.0f; }
+                    break;
+                case SQ_DECAY:
+                    env = env_tab[--ramped];
+                    if (ramped == 0) state = SQ_MUTED;
+                    break;
+                }
+                if (state != SQ_MUTED) { gr_[ng & gate_mask] = make_float2(v.x * env, v.y * env); ng++; }
+                else if (!p.sq_gate) { gr_[ng & gate_mask] = make_float2(0.0f, 0.0f); ng++; }
             }
-            if (state != SQ_MUTED) { gr_[ng & gate_mask] = make_float2(v.x * env, v.y * env); ng++; }
-            else if (!p.sq_gate) { gr_[ng & gate_mask] = make_float2(0.0f, 0.0f); ng++; }
+            st.pwr = pwr; st.sq_state = state; st.ramped = ramped; st.envelope = env; st.n_gate = ng;
         }
-        st.pwr = pwr; st.sq_state = state; st.ramped = ramped; st.envelope = env; st.n_in = avail_in; st.n_gate = ng;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) st.n_in = avail_in;
     __syncthreads();
     const long long gate1 = st.n_gate;
     // ---- 2. quadrature demod over the gated stream
