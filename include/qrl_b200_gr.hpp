@@ -205,4 +205,11 @@ inline gr_mod_b200_sptr make_gr_mod_qpsk(int sps, int samp_rate, int carrier_fre
                                          int n_channels = 1, long max_items = 4096, int device = 0)
 { return std::make_shared<gr_mod_b200>(QRL_MOD_QPSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_items, device); }
 
+inline gr_mod_b200_sptr make_gr_mod_bpsk(int sps, int samp_rate, int carrier_freq, int filter_width,
+                                         int n_channels = 1, long max_items = 4096, int device = 0)
+{ return std::make_shared<gr_mod_b200>(QRL_MOD_BPSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_items, device); }
+inline gr_mod_b200_sptr make_gr_mod_2fsk(int sps, int samp_rate, int carrier_freq, int filter_width, bool fm,
+                                         int n_channels = 1, long max_items = 4096, int device = 0)
+{ return std::make_shared<gr_mod_b200>(QRL_MOD_2FSK, sps, samp_rate, carrier_freq, filter_width, fm ? 1 : 0, n_channels, max_items, device); }
+
 }  // namespace qrl_gr

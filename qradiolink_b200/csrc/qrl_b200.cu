@@ -1275,23 +1275,40 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         h->fm_sens = static_cast<float>((spacing * kPi) / sym_sps);
         t2 = low_pass(second_interp, samp_rate, filter_width, filter_width, WIN_HAMMING);
         h->L2 = second_interp; h->nt2 = (static_cast<int>(t2.size()) + second_interp - 1) / second_interp;
-        if (h->L2 != 20 || h->nt2 > 35) { set_err(h, "make_gr_mod_4fsk: interpolator shape not built"); return fail(QRL_EINVAL); }
-        h->nt2 = 35;
+        if (h->L2 == 20 && h->nt2 <= 35) h->nt2 = 35;      // register-tiled instance <20, 35>
     } else if (kind == QRL_MOD_QPSK) {
         // gr_mod_qpsk.cpp:58-75
         int nfilts = sps > 120 ? 11 : (sps > 10 ? 13 : 15);
         t1 = root_raised_cosine(sps, sps, 1, 0.35, nfilts * sps);
         h->L1 = sps; h->nt1 = (static_cast<int>(t1.size()) + sps - 1) / sps;
-        if (h->L1 != 4 || h->nt1 > 16) { set_err(h, "make_gr_mod_qpsk: interpolator shape not built"); return fail(QRL_EINVAL); }
-        h->nt1 = 16;
+        if (h->L1 == 4 && h->nt1 <= 16) h->nt1 = 16;      // register-tiled instance <4, 16>
         h->amplif = 0.6f;
+    } else if (kind == QRL_MOD_BPSK) {
+        // gr_mod_bpsk.cpp:44-56
+        t1 = root_raised_cosine(sps, sps, 1, 0.35, 11 * sps);
+        h->L1 = sps; h->nt1 = (static_cast<int>(t1.size()) + sps - 1) / sps;
+        h->amplif = 0.6f;
+    } else if (kind == QRL_MOD_2FSK) {
+        // gr_mod_2fsk.cpp:43-76
+        int nfilts = 25 * sps, spacing = 2; h->amplif = 0.8f;
+        if (flag) { spacing = 1; h->amplif = 0.9f; }
+        if (sps == 5) nfilts = nfilts * 5;
+        if ((nfilts % 2) == 0) nfilts += 1;
+        h->repeat_only = flag ? 0 : 1;
+        h->pulse_scale = 1.0f;
+        t1 = root_raised_cosine(sps, sps, 1, 0.2, nfilts);
+        h->L1 = sps; h->nt1 = (static_cast<int>(t1.size()) + sps - 1) / sps;
+        h->fm_sens = static_cast<float>((spacing * kPi / 2) / sps);
+        t2 = low_pass(10, samp_rate, filter_width, filter_width, WIN_HAMMING);
+        h->L2 = 10; h->nt2 = (static_cast<int>(t2.size()) + 9) / 10;
     } else { set_err(h, "qrl_tx_create: mod kind " + std::to_string(kind) + " not built"); return fail(QRL_EINVAL); }
     if ((rc = upload_floats(h, &h->d_arms1, make_arms(t1, h->L1, h->nt1)))) return fail(rc);
     if (!t2.empty() && (rc = upload_floats(h, &h->d_arms2, make_arms(t2, h->L2, h->nt2)))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_bits, h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_in, static_cast<size_t>(h->max_items) * h->C))) return fail(rc);
-    const long long max_sym = 8LL * max_items;
-    const bool qpsk = kind == QRL_MOD_QPSK;
+    const bool one_per_bit = kind == QRL_MOD_BPSK || kind == QRL_MOD_2FSK;
+    const long long max_sym = (one_per_bit ? 16LL : 8LL) * max_items;
+    const bool qpsk = kind == QRL_MOD_QPSK || kind == QRL_MOD_BPSK;      // complex symbols, single interpolation stage
     { unsigned cap = pow2_at_least(max_sym + 64); h->sym_mask = cap - 1; h->sym_stride = cap;
       if ((rc = dev_alloc(h, &h->d_sym, static_cast<size_t>(cap) * h->C * (qpsk ? 2 : 1)))) return fail(rc); }
     if (!qpsk) {
@@ -1346,31 +1363,55 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
         CK(cudaMemcpy2DAsync(h->d_in, h->max_items, in, stride, n, h->C, cudaMemcpyHostToDevice, h->stream));
         b = h->d_in; bstride = h->max_items;
     }
-    const bool qpsk = h->kind == QRL_MOD_QPSK;
-    const long long sym0 = h->n_sym, nsym = 8LL * n;
-    if (qpsk) tx_bits_kernel<1><<<(h->C + 31) / 32, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
-    else tx_bits_kernel<0><<<(h->C + 31) / 32, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
-    h->launches++;
-    if (qpsk) {
-        constexpr int L = 4, NT = 16, MB = 8, MLEN = 64;
-        dim3 g(static_cast<unsigned>((nsym + MB * MLEN - 1) / (MB * MLEN)), h->C);
-        interp_fir_ccf_kernel<L, NT, MB, MLEN><<<g, L * MB, 0, h->stream>>>(
-            reinterpret_cast<const float2*>(h->d_sym), h->sym_mask, h->sym_stride, sym0, sym0 + nsym,
-            h->d_arms1, h->amplif, h->bb_gain, 1, h->d_out, h->out_stride, sym0 * L);
+    const bool cplx = h->kind == QRL_MOD_QPSK || h->kind == QRL_MOD_BPSK;
+    const bool one_per_bit = h->kind == QRL_MOD_BPSK || h->kind == QRL_MOD_2FSK;
+    const long long sym0 = h->n_sym, nsym = (one_per_bit ? 16LL : 8LL) * n;
+    {
+        dim3 g((h->C + 31) / 32);
+        if (h->kind == QRL_MOD_QPSK) tx_bits_kernel<TXM_QPSK><<<g, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
+        else if (h->kind == QRL_MOD_BPSK) tx_bits_kernel<TXM_BPSK><<<g, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
+        else if (h->kind == QRL_MOD_2FSK) tx_bits_kernel<TXM_2FSK><<<g, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
+        else tx_bits_kernel<TXM_4FSK><<<g, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
         h->launches++;
-        h->n_out_last = static_cast<long>(nsym * L);
+    }
+    auto generic_interp = [&](const float2* in, unsigned mask, long long stride_, long long m0, long long m1, const float* arms, int L, int NT,
+                              float g1, float g2, int apply) {
+        int MT = std::max(1, 4096 / L);
+        const size_t smem = sizeof(float) * ((L * NT + 1) & ~1) + sizeof(float2) * (MT + NT);
+        dim3 g(static_cast<unsigned>((m1 - m0 + MT - 1) / MT), h->C);
+        interp_fir_ccf_generic_kernel<<<g, 256, smem, h->stream>>>(in, mask, stride_, m0, m1, arms, L, NT, MT, g1, g2, apply,
+                                                                   h->d_out, h->out_stride, m0 * L);
+        h->launches++;
+    };
+    if (cplx) {
+        if (h->L1 == 4 && h->nt1 == 16) {
+            constexpr int L = 4, NT = 16, MB = 8, MLEN = 64;
+            dim3 g(static_cast<unsigned>((nsym + MB * MLEN - 1) / (MB * MLEN)), h->C);
+            interp_fir_ccf_kernel<L, NT, MB, MLEN><<<g, L * MB, 0, h->stream>>>(
+                reinterpret_cast<const float2*>(h->d_sym), h->sym_mask, h->sym_stride, sym0, sym0 + nsym,
+                h->d_arms1, h->amplif, h->bb_gain, 1, h->d_out, h->out_stride, sym0 * L);
+            h->launches++;
+        } else {
+            generic_interp(reinterpret_cast<const float2*>(h->d_sym), h->sym_mask, h->sym_stride, sym0, sym0 + nsym,
+                           h->d_arms1, h->L1, h->nt1, h->amplif, h->bb_gain, 1);
+        }
+        h->n_out_last = static_cast<long>(nsym * h->L1);
     } else {
         tx_shape_fm_kernel<256, 8><<<h->C, 256, 0, h->stream>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, sym0, nsym,
             h->L1, h->nt1, h->d_arms1, h->repeat_only, h->pulse_scale, h->fm_sens, h->amplif, h->bb_gain,
             h->d_if, h->if_mask, h->if_stride);
         h->launches++;
-        constexpr int L = 20, NT = 35, MB = 8, MLEN = 70;
         const long long m0 = sym0 * h->L1, m1 = (sym0 + nsym) * h->L1;
-        dim3 g(static_cast<unsigned>((m1 - m0 + MB * MLEN - 1) / (MB * MLEN)), h->C);
-        interp_fir_ccf_kernel<L, NT, MB, MLEN><<<g, L * MB, 0, h->stream>>>(
-            h->d_if, h->if_mask, h->if_stride, m0, m1, h->d_arms2, 1.0f, 1.0f, 0, h->d_out, h->out_stride, m0 * L);
-        h->launches++;
-        h->n_out_last = static_cast<long>((m1 - m0) * L);
+        if (h->L2 == 20 && h->nt2 == 35) {
+            constexpr int L = 20, NT = 35, MB = 8, MLEN = 70;
+            dim3 g(static_cast<unsigned>((m1 - m0 + MB * MLEN - 1) / (MB * MLEN)), h->C);
+            interp_fir_ccf_kernel<L, NT, MB, MLEN><<<g, L * MB, 0, h->stream>>>(
+                h->d_if, h->if_mask, h->if_stride, m0, m1, h->d_arms2, 1.0f, 1.0f, 0, h->d_out, h->out_stride, m0 * L);
+            h->launches++;
+        } else {
+            generic_interp(h->d_if, h->if_mask, h->if_stride, m0, m1, h->d_arms2, h->L2, h->nt2, 1.0f, 1.0f, 0);
+        }
+        h->n_out_last = static_cast<long>((m1 - m0) * h->L2);
     }
     h->n_sym += nsym;
     CK(cudaGetLastError());

@@ -1541,7 +1541,8 @@ struct TxBitState {
 // bytes -> packed_to_unpacked(MSB) -> scrambler -> CC encoder -> pack_k_bits(2) -> map {0,1,3,2}
 //       -> chunks_to_symbols (4FSK: float level, QPSK: diff_encoder(4) + complex point)
 // one thread per channel (the scrambler is a feedback LFSR); 16 symbols per input byte... 8 per byte.
-template <int QPSK>
+enum { TXM_4FSK = 0, TXM_QPSK = 1, TXM_BPSK = 2, TXM_2FSK = 3 };
+template <int MODE>
 __global__ void tx_bits_kernel(TxBitState* __restrict__ states, int C, const unsigned char* __restrict__ bytes, long long n, long long stride,
                                float* __restrict__ sym_ring /* float or float2 */, unsigned sym_mask, long long sym_stride, long long sym0)
 {
@@ -1562,11 +1563,22 @@ __global__ void tx_bits_kernel(TxBitState* __restrict__ states, int C, const uns
             st.enc_state = ((st.enc_state << 1) | out) & 0x7fu;
             coded = (coded << 2) | ((__popc(st.enc_state & 109u) & 1u) << 1) | (__popc(st.enc_state & 79u) & 1u);
         }
+        if (MODE == TXM_BPSK || MODE == TXM_2FSK) {
+            // one symbol per coded bit: chunks_to_symbols {-1, +1} (complex for BPSK, float for 2FSK)
+#pragma unroll
+            for (int k = 15; k >= 0; k--) {
+                const float lv = ((coded >> k) & 1u) ? 1.0f : -1.0f;
+                if (MODE == TXM_BPSK) reinterpret_cast<float2*>(sym_ring)[static_cast<long long>(c) * sym_stride + (si & sym_mask)] = make_float2(lv, 0.0f);
+                else sym_ring[static_cast<long long>(c) * sym_stride + (si & sym_mask)] = lv;
+                si++;
+            }
+            continue;
+        }
 #pragma unroll
         for (int k = 7; k >= 0; k--) {
             const unsigned dibit = (coded >> (2 * k)) & 3u;
             const unsigned chunk = dibit ^ (dibit >> 1);                  // map {0,1,3,2}
-            if (QPSK) {
+            if (MODE == TXM_QPSK) {
                 st.diff_prev = (chunk + st.diff_prev) & 3u;
                 const float qr = (st.diff_prev >= 2u) ? 0.707f : -0.707f;
                 const float qi = (st.diff_prev == 1u || st.diff_prev == 2u) ? 0.707f : -0.707f;
@@ -1700,6 +1712,42 @@ interp_fir_ccf_kernel(const float2* __restrict__ in_ring, unsigned in_mask, long
             const long long m = tile0 + mb * MLEN + g * NT + i;
             if (m < m1) oc[(m * L + p) - out_base] = make_float2(re, im);
         }
+    }
+}
+
+// Shape-generic interpolating FIR (any L, NT): one thread per output sample, arm taps and the input window in shared
+// memory.  Used for the TX shapes that have no register-tiled instance (QPSK x100/x500, BPSK x250/x500, 2FSK x10 ...).
+__global__ void __launch_bounds__(256)
+interp_fir_ccf_generic_kernel(const float2* __restrict__ in_ring, unsigned in_mask, long long in_stride, long long m0, long long m1,
+                              const float* __restrict__ arms /* [L][NT] */, int L, int NT, int MT /* m per CTA */,
+                              float post_gain1, float post_gain2, int apply_gain,
+                              float2* __restrict__ out, long long out_stride, long long out_base)
+{
+    extern __shared__ float sm_gi[];
+    float* hs = sm_gi;                                           // L*NT
+    float2* xs = reinterpret_cast<float2*>(sm_gi + ((L * NT + 1) & ~1));   // MT + NT - 1
+    const int c = blockIdx.y;
+    const long long tile0 = m0 + static_cast<long long>(blockIdx.x) * MT;
+    if (tile0 >= m1) return;
+    for (int i = threadIdx.x; i < L * NT; i += 256) hs[i] = arms[i];
+    const float2* x = in_ring + static_cast<long long>(c) * in_stride;
+    for (int i = threadIdx.x; i < MT + NT - 1; i += 256) {
+        const long long m = tile0 - (NT - 1) + i;
+        xs[i] = (m < m1) ? x[m & in_mask] : make_float2(0.0f, 0.0f);
+    }
+    __syncthreads();
+    float2* oc = out + static_cast<long long>(c) * out_stride;
+    const long long nout = static_cast<long long>(MT) * L;
+    for (long long o = threadIdx.x; o < nout; o += 256) {
+        const int ml = static_cast<int>(o / L), p = static_cast<int>(o - static_cast<long long>(ml) * L);
+        const long long m = tile0 + ml;
+        if (m >= m1) break;
+        const float* h = hs + p * NT;
+        const float2* w = xs + ml + (NT - 1);                    // newest sample of this output
+        float re = 0.0f, im = 0.0f;
+        for (int k = NT - 1; k >= 0; k--) { const float2 v = w[-k]; re = fmaf(h[k], v.x, re); im = fmaf(h[k], v.y, im); }
+        if (apply_gain) { re = re * post_gain1; im = im * post_gain1; re = re * post_gain2; im = im * post_gain2; }
+        oc[(m * L + p) - out_base] = make_float2(re, im);
     }
 }
 

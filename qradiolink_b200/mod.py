@@ -67,3 +67,13 @@ def make_gr_mod_4fsk(sps, samp_rate, carrier_freq, filter_width, fm, n_channels=
 
 def make_gr_mod_qpsk(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
     return TxBlock(KIND.MOD_QPSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
+
+
+def make_gr_mod_bpsk(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
+    """src/gr/gr_mod_bpsk.h (instances gr_mod_base.cpp:168-169)."""
+    return TxBlock(KIND.MOD_BPSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
+
+
+def make_gr_mod_2fsk(sps, samp_rate, carrier_freq, filter_width, fm, n_channels=1, **kw):
+    """src/gr/gr_mod_2fsk.h (instances gr_mod_base.cpp:155-159)."""
+    return TxBlock(KIND.MOD_2FSK, sps, samp_rate, carrier_freq, filter_width, int(bool(fm)), n_channels, **kw)

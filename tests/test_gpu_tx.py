@@ -65,3 +65,35 @@ def test_gpu_tx_to_gpu_rx_loopback(qrl):
     for c in range(C):
         good, found = siggen.count_good_frames(bits[c], 0xED89AA, 24, 7, payloads[c])
         assert good >= len(payloads[c]) - 4 and found - good <= 1, (c, good, found)
+
+
+TX_CASES = [
+    # name, python factory name, args (reference instances gr_mod_base.cpp:155-177), oracle kind, oracle args, bytes
+    ("4fsk1kfm", "make_gr_mod_4fsk", (50, 1000000, 1700, 2000, True), "MOD_4FSK", (50, 1000000, 1700, 2000, 1), 60),
+    ("4fsk10kfm", "make_gr_mod_4fsk", (5, 1000000, 1700, 20000, True), "MOD_4FSK", (5, 1000000, 1700, 20000, 1), 600),
+    ("4fsk2k", "make_gr_mod_4fsk", (25, 1000000, 1700, 4000, False), "MOD_4FSK", (25, 1000000, 1700, 4000, 0), 100),
+    ("4fsk100k", "make_gr_mod_4fsk", (2, 1000000, 1700, 125000, True), "MOD_4FSK", (2, 1000000, 1700, 125000, 1), 3000),
+    ("qpsk20k", "make_gr_mod_qpsk", (100, 1000000, 1700, 6500), "MOD_QPSK", (100, 1000000, 1700, 6500, 0), 300),
+    ("qpsk2k", "make_gr_mod_qpsk", (500, 1000000, 1700, 1300), "MOD_QPSK", (500, 1000000, 1700, 1300, 0), 60),
+    ("bpsk2k", "make_gr_mod_bpsk", (250, 1000000, 1700, 2800), "MOD_BPSK", (250, 1000000, 1700, 2800, 0), 60),
+    ("bpsk1k", "make_gr_mod_bpsk", (500, 1000000, 1700, 1500), "MOD_BPSK", (500, 1000000, 1700, 1500, 0), 40),
+    ("2fsk2kfm", "make_gr_mod_2fsk", (25, 1000000, 1700, 4000, True), "MOD_2FSK", (25, 1000000, 1700, 4000, 1), 100),
+    ("2fsk1kfm", "make_gr_mod_2fsk", (50, 1000000, 1700, 2500, True), "MOD_2FSK", (50, 1000000, 1700, 2500, 1), 60),
+    ("2fsk2k", "make_gr_mod_2fsk", (25, 1000000, 1700, 4000, False), "MOD_2FSK", (25, 1000000, 1700, 4000, 0), 100),
+    ("2fsk10kfm", "make_gr_mod_2fsk", (5, 1000000, 1700, 25000, True), "MOD_2FSK", (5, 1000000, 1700, 25000, 1), 600),
+]
+
+
+@pytest.mark.parametrize("name,factory,args,okind,oargs,nbytes", TX_CASES)
+def test_tx_all_digital_modes(qrl, oracle, name, factory, args, okind, oargs, nbytes):
+    C = 2
+    rng = np.random.default_rng(5200)
+    data = rng.integers(0, 256, (C, nbytes), dtype=np.uint8)
+    tx = getattr(qrl, factory)(*args, n_channels=C, max_items=nbytes)
+    cut = nbytes // 3
+    got = np.concatenate([tx.work(data[:, :cut]), tx.work(data[:, cut:])], axis=1)      # two calls: state carried
+    for c in range(C):
+        want = getattr(oracle, "Tx")(getattr(oracle, okind), *oargs).work(data[c])
+        assert got.shape[1] == len(want), (got.shape, len(want))
+        assert rel_rms(got[c], want) <= 1e-5
+        assert np.array_equal(got[c], want), name
