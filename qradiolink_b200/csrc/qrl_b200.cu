@@ -821,7 +821,12 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
     const long long k_call0 = h->n1;
     h->port0_n = 0;
     for (int i = 0; i < nsub; i++) {
-        const long long t0 = static_cast<long long>(T) * i / nsub, t1 = static_cast<long long>(T) * (i + 1) / nsub;
+        // slice boundaries on multiples of 2*D: the slice base stays 16-byte aligned (TMA bulk fill) and every slice
+        // produces the same number of stage-1 outputs
+        const long long q2d = 2LL * h->D1;
+        auto cut = [&](int j) { return j >= nsub ? static_cast<long long>(T) : (static_cast<long long>(T) * j / nsub) / q2d * q2d; };
+        const long long t0 = cut(i), t1 = cut(i + 1);
+        if (t1 <= t0) continue;
         const long long Ti = t1 - t0;
         const float2* xi = x + t0;
         // ---- stage 1: decimating FIR; outputs k with D k <= last absolute input index
