@@ -1500,6 +1500,8 @@ struct qo_tx {
     float amplif, bb_gain;
     int pack_have; unsigned pack_acc;
     unsigned diff_prev;
+    /* analog modulators */
+    resamp_t a_filt, a_rs, a_if; iir1_t preemph; fircc_t a_sb; float env_m2, env_m1; size_t st_pos; qvec s_aud, s_clip, s_c2;
     qvec s_bits, s_coded, s_sym, s_shaped, s_mod, out;
 };
 qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag)
@@ -1536,6 +1538,34 @@ qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         t->amplif = 0.6f;
         t->s_sym.isz = 8;
         (void)samp_rate; (void)filter_width;
+    } else if (kind == QO_MOD_NBFM) {
+        /* /root/reference/src/gr/gr_mod_nbfm.cpp:26-75 (CTCSS tone branch not connected by default) */
+        double a[2], b[2];
+        qo_preemph_taps(8000, 50e-6, -1.0, a, b);
+        iir1_init(&t->preemph, b, a);
+        int n = qo_firdes_low_pass_2(1, 8000, 3500, 200, 35, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&t->a_filt, 1, 1, 1, taps, n);
+        n = qo_firdes_low_pass_2(25, 50000 * 4, filter_width, 3500, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&t->a_rs, 1, 25, 4, taps, n);
+        t->fm_sens = (float)(4 * M_PI * filter_width / 50000.0f);
+        n = qo_firdes_low_pass_2(1, 50000, filter_width, 3500, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&t->a_if, 2, 1, 1, taps, n);
+        n = qo_firdes_low_pass_2(sps, samp_rate, filter_width, 3500, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&t->interp, 2, sps, 1, taps, n);
+        t->amplif = 0.8f;
+        qv_init(&t->s_aud, 4); qv_init(&t->s_clip, 8); qv_init(&t->s_c2, 8);
+    } else if (kind == QO_MOD_SSB) {
+        /* /root/reference/src/gr/gr_mod_ssb.cpp:28-82; flag = sb */
+        float tc[2 * 4096];
+        int n = qo_firdes_band_pass_2(1, 8000, 300, filter_width, 200, 90, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&t->a_filt, 1, 1, 1, taps, n);
+        n = flag ? qo_firdes_complex_band_pass_2(1, 8000, -filter_width, -200, 200, 90, QO_WIN_BLACKMAN_HARRIS, tc, 4096)
+                 : qo_firdes_complex_band_pass_2(1, 8000, 200, filter_width, 200, 90, QO_WIN_BLACKMAN_HARRIS, tc, 4096);
+        fircc_init(&t->a_sb, tc, n);
+        n = qo_firdes_low_pass_2(sps, samp_rate, filter_width, filter_width, 90, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&t->interp, 2, sps, 1, taps, n);
+        t->amplif = 0.9f;
+        qv_init(&t->s_aud, 4); qv_init(&t->s_clip, 8); qv_init(&t->s_c2, 8);
     } else if (kind == QO_MOD_BPSK) {
         /* /root/reference/src/gr/gr_mod_bpsk.cpp:27-69 */
         t->sps = sps;
@@ -1645,6 +1675,55 @@ int qo_tx_work(qo_tx* t, const void* in, long n)
             float* m = (float*)t->out.d;
             for (size_t i = 2 * o0; i < 2 * t->out.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
         }
+        return 0;
+    }
+    if (t->kind == QO_MOD_NBFM) {
+        /* n float audio samples at 8 ksps */
+        const float* au = (const float*)in;
+        t->s_aud.n = 0; resamp_work(&t->a_filt, au, (size_t)n, &t->s_aud);
+        float* a1 = (float*)t->s_aud.d;
+        for (size_t i = 0; i < t->s_aud.n; i++) a1[i] = a1[i] * 0.99f;                     /* multiply_const_ff(0.99) */
+        t->s_shaped.n = 0; iir1_work(&t->preemph, a1, t->s_aud.n, &t->s_shaped, 1.0f);
+        t->s_sym.isz = 4; t->s_sym.n = 0;
+        resamp_work(&t->a_rs, (const float*)t->s_shaped.d, t->s_shaped.n, &t->s_sym);       /* 8k -> 50k */
+        t->s_mod.n = 0; fm_mod(t, (const float*)t->s_sym.d, t->s_sym.n, &t->s_mod, 1.0f);
+        t->s_c2.n = 0; resamp_work(&t->a_if, (const float*)t->s_mod.d, t->s_mod.n, &t->s_c2);
+        float* m = (float*)t->s_c2.d;
+        for (size_t i = 0; i < 2 * t->s_c2.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
+        resamp_work(&t->interp, m, t->s_c2.n, &t->out);
+        return 0;
+    }
+    if (t->kind == QO_MOD_SSB) {
+        const float* au = (const float*)in;
+        t->s_aud.n = 0; resamp_work(&t->a_filt, au, (size_t)n, &t->s_aud);
+        const float* a1 = (const float*)t->s_aud.d;
+        for (size_t i = 0; i < t->s_aud.n; i++) {                                           /* float_to_complex -> clipper_cc(0.95) */
+            float mag = sqrtf(a1[i] * a1[i] + 0.0f * 0.0f);
+            float ph = qo_fast_atan2f(0.0f, a1[i]);
+            float cl = mag < 0.95f ? mag : 0.95f;
+            float sn, cs; qo_sincosf(ph, &sn, &cs);
+            qv_pushc(&t->s_clip, cs * cl, sn * cl);
+        }
+        const float emax = (float)(1 / (sqrt(0.5) / 2));
+        const float* c = (const float*)t->s_clip.d;
+        t->s_c2.n = 0;
+        while (t->st_pos + 2 < t->s_clip.n) {                                                /* stretcher_cc */
+            size_t k = t->st_pos;
+            float e0 = sqrtf(c[2 * k] * c[2 * k] + c[2 * k + 1] * c[2 * k + 1]);
+            float e1 = sqrtf(c[2 * (k + 1)] * c[2 * (k + 1)] + c[2 * (k + 1) + 1] * c[2 * (k + 1) + 1]);
+            float e2 = sqrtf(c[2 * (k + 2)] * c[2 * (k + 2)] + c[2 * (k + 2) + 1] * c[2 * (k + 2) + 1]);
+            float h = e0;
+            h = fmaxf(h, t->env_m2); h = fmaxf(h, t->env_m1); h = fmaxf(h, e1); h = fmaxf(h, e2);
+            h = h * emax; h = fmaxf(h, 1.0f); h = h - 1.0f; h = h * 2.0f; h = h + 1.0f;
+            qv_pushc(&t->s_c2, c[2 * k] / h, c[2 * k + 1] / h);
+            t->env_m2 = t->env_m1; t->env_m1 = e0;
+            t->st_pos++;
+        }
+        if (t->st_pos > 0) { qv_drop(&t->s_clip, t->st_pos); t->st_pos = 0; }
+        t->s_mod.n = 0; fircc_work(&t->a_sb, (const float*)t->s_c2.d, t->s_c2.n, &t->s_mod);
+        float* m = (float*)t->s_mod.d;
+        for (size_t i = 0; i < 2 * t->s_mod.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
+        resamp_work(&t->interp, m, t->s_mod.n, &t->out);
         return 0;
     }
     if (t->kind == QO_MOD_BPSK || t->kind == QO_MOD_2FSK) {

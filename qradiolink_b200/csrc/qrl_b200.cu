@@ -1241,6 +1241,16 @@ struct qrl_tx : HandleBase {
     float2* d_if = nullptr; unsigned if_mask = 0; long long if_stride = 0;
     float2* d_out = nullptr; long long out_stride = 0; long n_out_last = 0;
     long long n_sym = 0;           // symbols produced so far (absolute)
+    // analog modulators (NBFM / SSB)
+    TxAnalogState* d_an = nullptr;
+    float* d_ra = nullptr; unsigned ra_mask = 0; long long ra_stride = 0;          // audio ring
+    float* d_rb = nullptr;                                                         // filtered audio ring (same geometry)
+    float2* d_rc = nullptr; unsigned rc_mask = 0; long long rc_stride = 0;         // SSB clip ring / NBFM IF-filter ring
+    float2* d_rs2 = nullptr;                                                       // SSB stretcher ring (same geometry as rc)
+    float* d_lpf = nullptr; int nt_lpf = 0; float* d_cfilt = nullptr; int nt_cfilt = 0;
+    double pe_b0 = 0, pe_b1 = 0, pe_a1 = 0;
+    long long n_audio = 0, n_mid = 0;        // audio samples consumed / mid-rate items produced (host mirror of the device counters)
+    float* d_audio_in = nullptr;
 };
 
 static std::vector<float> make_arms(const std::vector<float>& taps, int L, int nt)
@@ -1288,6 +1298,36 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         h->L1 = sps; h->nt1 = (static_cast<int>(t1.size()) + sps - 1) / sps;
         if (h->L1 == 4 && h->nt1 <= 16) h->nt1 = 16;      // register-tiled instance <4, 16>
         h->amplif = 0.6f;
+    } else if (kind == QRL_MOD_NBFM) {
+        // gr_mod_nbfm.cpp:35-63 (sps = final interpolation, 20)
+        double a[2], b[2];
+        preemph_taps(8000, 50e-6, -1.0, a, b);
+        h->pe_b0 = b[0]; h->pe_b1 = b[1]; h->pe_a1 = a[1];
+        std::vector<float> lp = low_pass_2(1, 8000, 3500, 200, 35, WIN_BLACKMAN_HARRIS);
+        h->nt_lpf = static_cast<int>(lp.size());
+        if ((rc = upload_floats(h, &h->d_lpf, lp))) return fail(rc);
+        t1 = low_pass_2(25, 50000 * 4, filter_width, 3500, 60, WIN_BLACKMAN_HARRIS);          // 25/4 resampler arms
+        h->L1 = 25; h->nt1 = (static_cast<int>(t1.size()) + 24) / 25;
+        h->fm_sens = static_cast<float>(4 * kPi * filter_width / 50000.0f);
+        std::vector<float> ifl = low_pass_2(1, 50000, filter_width, 3500, 60, WIN_BLACKMAN_HARRIS);
+        h->nt_cfilt = static_cast<int>(ifl.size());
+        if ((rc = upload_floats(h, &h->d_cfilt, ifl))) return fail(rc);
+        t2 = low_pass_2(sps, samp_rate, filter_width, 3500, 60, WIN_BLACKMAN_HARRIS);
+        h->L2 = sps; h->nt2 = (static_cast<int>(t2.size()) + sps - 1) / sps;
+        h->amplif = 0.8f;
+    } else if (kind == QRL_MOD_SSB) {
+        // gr_mod_ssb.cpp:40-58 (sps = final interpolation, 125; flag = sb)
+        std::vector<float> bp = band_pass_2(1, 8000, 300, filter_width, 200, 90, WIN_BLACKMAN_HARRIS);
+        h->nt_lpf = static_cast<int>(bp.size());
+        if ((rc = upload_floats(h, &h->d_lpf, bp))) return fail(rc);
+        std::vector<float> sb = flag ? complex_band_pass_2(1, 8000, -filter_width, -200, 200, 90, WIN_BLACKMAN_HARRIS)
+                                     : complex_band_pass_2(1, 8000, 200, filter_width, 200, 90, WIN_BLACKMAN_HARRIS);
+        h->nt_cfilt = static_cast<int>(sb.size() / 2);
+        if ((rc = upload_floats(h, &h->d_cfilt, sb))) return fail(rc);
+        t2 = low_pass_2(sps, samp_rate, filter_width, filter_width, 90, WIN_BLACKMAN_HARRIS);
+        h->L2 = sps; h->nt2 = (static_cast<int>(t2.size()) + sps - 1) / sps;
+        h->L1 = 1; h->nt1 = 1; t1 = { 1.0f };
+        h->amplif = 0.9f;
     } else if (kind == QRL_MOD_BPSK) {
         // gr_mod_bpsk.cpp:44-56
         t1 = root_raised_cosine(sps, sps, 1, 0.35, 11 * sps);
@@ -1312,15 +1352,28 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     if ((rc = dev_alloc(h, &h->d_bits, h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_in, static_cast<size_t>(h->max_items) * h->C))) return fail(rc);
     const bool one_per_bit = kind == QRL_MOD_BPSK || kind == QRL_MOD_2FSK;
-    const long long max_sym = (one_per_bit ? 16LL : 8LL) * max_items;
+    const bool analog = kind == QRL_MOD_NBFM || kind == QRL_MOD_SSB;
+    long long max_sym = (one_per_bit ? 16LL : 8LL) * max_items;
+    if (kind == QRL_MOD_NBFM) max_sym = max_items * 25 / 4 + 8;        // 50 ksps items per call
+    if (kind == QRL_MOD_SSB) max_sym = max_items + 8;                  // 8 ksps complex items per call
+    if (analog) {
+        unsigned cap = pow2_at_least(max_items + 512); h->ra_mask = cap - 1; h->ra_stride = cap;
+        if ((rc = dev_alloc(h, &h->d_ra, static_cast<size_t>(cap) * h->C))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_rb, static_cast<size_t>(cap) * h->C))) return fail(rc);
+        unsigned cap2 = pow2_at_least(max_sym + 512); h->rc_mask = cap2 - 1; h->rc_stride = cap2;
+        if ((rc = dev_alloc(h, &h->d_rc, static_cast<size_t>(cap2) * h->C))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_rs2, static_cast<size_t>(cap2) * h->C))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_an, h->C))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_audio_in, static_cast<size_t>(max_items) * h->C))) return fail(rc);
+    }
     const bool qpsk = kind == QRL_MOD_QPSK || kind == QRL_MOD_BPSK;      // complex symbols, single interpolation stage
     { unsigned cap = pow2_at_least(max_sym + 64); h->sym_mask = cap - 1; h->sym_stride = cap;
       if ((rc = dev_alloc(h, &h->d_sym, static_cast<size_t>(cap) * h->C * (qpsk ? 2 : 1)))) return fail(rc); }
     if (!qpsk) {
-        unsigned cap = pow2_at_least(max_sym * h->L1 + 128); h->if_mask = cap - 1; h->if_stride = cap;
+        unsigned cap = pow2_at_least(max_sym * (analog ? 1 : h->L1) + 128); h->if_mask = cap - 1; h->if_stride = cap;
         if ((rc = dev_alloc(h, &h->d_if, static_cast<size_t>(cap) * h->C))) return fail(rc);
     }
-    h->out_stride = max_sym * h->L1 * (qpsk ? 1 : h->L2);
+    h->out_stride = analog ? max_sym * h->L2 : max_sym * h->L1 * (qpsk ? 1 : h->L2);
     if ((rc = dev_alloc(h, &h->d_out, static_cast<size_t>(h->out_stride) * h->C, false))) return fail(rc);
     std::vector<TxBitState> st(h->C);
     for (auto& x : st) { x.scr_reg = 0x7F; x.enc_state = 0; x.diff_prev = 0; x.phase_q = 0; }
@@ -1362,6 +1415,63 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
     h->n_out_last = 0;
     if (n == 0) return QRL_OK;
     CK(cudaSetDevice(h->device));
+    if (h->kind == QRL_MOD_NBFM || h->kind == QRL_MOD_SSB) {
+        // `in` = [C][n] float audio at 8 ksps
+        const float* au = static_cast<const float*>(in);
+        long long astride = stride;
+        if (!on_device) {
+            CK(cudaMemcpy2DAsync(h->d_audio_in, sizeof(float) * h->max_items, in, sizeof(float) * stride, sizeof(float) * n, h->C,
+                                 cudaMemcpyHostToDevice, h->stream));
+            au = h->d_audio_in; astride = h->max_items;
+        }
+        const int TB = 256;
+        if (h->kind == QRL_MOD_NBFM) {
+            tx_nbfm_front_kernel<<<h->C, 128, 0, h->stream>>>(h->d_an, au, n, astride, h->d_ra, h->ra_mask, h->ra_stride,
+                h->d_rb, h->ra_mask, h->ra_stride, h->d_lpf, h->nt_lpf, h->pe_b0, h->pe_b1, h->pe_a1, h->d_arms1, h->nt1,
+                h->d_sym, h->sym_mask, h->sym_stride);
+            const long long r0 = h->n_mid, r1 = ((h->n_audio + n) * 25 + 3) / 4;
+            static const float one = 1.0f; (void)one;
+            // frequency modulator (Q32 scan) on the 50 ksps stream: "RRC" stage degenerated to a pass-through arm {1}
+            tx_shape_fm_kernel<256, 8><<<h->C, 256, 0, h->stream>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, r0, r1 - r0,
+                1, 1, h->d_arms1, 1, 1.0f, h->fm_sens, 1.0f, 1.0f, h->d_if, h->if_mask, h->if_stride);
+            dim3 g(static_cast<unsigned>((r1 - r0 + TB - 1) / TB), h->C);
+            if (r1 > r0) {
+                fir_ccf_ring_kernel<<<g, TB, sizeof(float) * h->nt_cfilt, h->stream>>>(h->d_if, h->if_mask, h->if_stride,
+                    h->d_rc, h->rc_mask, h->rc_stride, h->d_cfilt, h->nt_cfilt, r0, r1, nullptr, 0, 0, 0);
+                scale2_ring_kernel<<<g, TB, 0, h->stream>>>(h->d_rc, h->rc_mask, h->rc_stride, r0, r1, h->amplif, h->bb_gain);
+                int MT = std::max(1, 4096 / h->L2);
+                const size_t smem = sizeof(float) * ((h->L2 * h->nt2 + 1) & ~1) + sizeof(float2) * (MT + h->nt2);
+                dim3 gi(static_cast<unsigned>((r1 - r0 + MT - 1) / MT), h->C);
+                interp_fir_ccf_generic_kernel<<<gi, 256, smem, h->stream>>>(h->d_rc, h->rc_mask, h->rc_stride, r0, r1, h->d_arms2, h->L2, h->nt2, MT,
+                                                                            1.0f, 1.0f, 0, h->d_out, h->out_stride, r0 * h->L2);
+            }
+            h->launches += 5;
+            h->n_out_last = static_cast<long>((r1 - r0) * h->L2);
+            h->n_mid = r1;
+        } else {
+            tx_ssb_front_kernel<<<h->C, 128, 0, h->stream>>>(h->d_an, au, n, astride, h->d_ra, h->ra_mask, h->ra_stride,
+                h->d_rc, h->rc_mask, h->rc_stride, h->d_lpf, h->nt_lpf, 0.95f, static_cast<float>(1 / (std::sqrt(0.5) / 2)),
+                h->d_rs2, h->rc_mask, h->rc_stride);
+            const long long s0 = h->n_mid, s1 = std::max<long long>(s0, h->n_audio + n - 2);
+            if (s1 > s0) {
+                dim3 g(static_cast<unsigned>((s1 - s0 + TB - 1) / TB), h->C);
+                fir_ccc_ring_kernel<<<g, TB, sizeof(float) * 2 * h->nt_cfilt, h->stream>>>(h->d_rs2, h->rc_mask, h->rc_stride,
+                    h->d_if, h->if_mask, h->if_stride, h->d_cfilt, h->nt_cfilt, 1.0f, s0, s1, nullptr, 0, 0);
+                scale2_ring_kernel<<<g, TB, 0, h->stream>>>(h->d_if, h->if_mask, h->if_stride, s0, s1, h->amplif, h->bb_gain);
+                int MT = std::max(1, 4096 / h->L2);
+                const size_t smem = sizeof(float) * ((h->L2 * h->nt2 + 1) & ~1) + sizeof(float2) * (MT + h->nt2);
+                dim3 gi(static_cast<unsigned>((s1 - s0 + MT - 1) / MT), h->C);
+                interp_fir_ccf_generic_kernel<<<gi, 256, smem, h->stream>>>(h->d_if, h->if_mask, h->if_stride, s0, s1, h->d_arms2, h->L2, h->nt2, MT,
+                                                                            1.0f, 1.0f, 0, h->d_out, h->out_stride, s0 * h->L2);
+            }
+            h->launches += 4;
+            h->n_out_last = static_cast<long>((s1 - s0) * h->L2);
+            h->n_mid = s1;
+        }
+        h->n_audio += n;
+        CK(cudaGetLastError());
+        return QRL_OK;
+    }
     const unsigned char* b = static_cast<const unsigned char*>(in);
     long long bstride = stride;
     if (!on_device) {

@@ -1751,4 +1751,114 @@ interp_fir_ccf_generic_kernel(const float2* __restrict__ in_ring, unsigned in_ma
     }
 }
 
+// ================================================================================================
+// Analog modulators (gr_mod_nbfm.cpp:26-75, gr_mod_ssb.cpp:28-82): 8 ksps float audio in.  One CTA per channel runs
+// the low-rate front part; the FM scan / IF filters / final interpolator reuse the digital TX kernels.
+// ================================================================================================
+struct TxAnalogState { long long n_in, n_rs, n_str; double iir_x1, iir_y1; };
+
+// NBFM: audio LPF -> x0.99 -> pre-emphasis IIR (double) -> rational_resampler_fff(25,4) -> float ring (FM input)
+__global__ void __launch_bounds__(128)
+tx_nbfm_front_kernel(TxAnalogState* __restrict__ states, const float* __restrict__ audio, long long n, long long a_stride,
+                     float* __restrict__ ra, unsigned ra_mask, long long ra_stride,      // audio ring
+                     float* __restrict__ rb, unsigned rb_mask, long long rb_stride,      // filtered + pre-emphasised
+                     const float* __restrict__ lpf, int nt_lpf, double b0, double b1, double a1,
+                     const float* __restrict__ arms /* [25][nt_arm] */, int nt_arm,
+                     float* __restrict__ rs_out, unsigned rs_mask, long long rs_stride)
+{
+    const int c = blockIdx.x;
+    __shared__ TxAnalogState st;
+    if (threadIdx.x == 0) st = states[c];
+    __syncthreads();
+    float* A = ra + static_cast<long long>(c) * ra_stride;
+    float* B = rb + static_cast<long long>(c) * rb_stride;
+    float* R = rs_out + static_cast<long long>(c) * rs_stride;
+    const long long a0 = st.n_in, a1n = st.n_in + n;
+    for (long long a = a0 + threadIdx.x; a < a1n; a += blockDim.x) A[a & ra_mask] = audio[static_cast<long long>(c) * a_stride + (a - a0)];
+    __syncthreads();
+    for (long long a = a0 + threadIdx.x; a < a1n; a += blockDim.x) {
+        float acc = 0.0f;
+        for (int k = nt_lpf - 1; k >= 0; k--) { const long long m = a - k; acc = fmaf(lpf[k], m >= 0 ? A[m & ra_mask] : 0.0f, acc); }
+        B[a & rb_mask] = acc * 0.99f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x1 = st.iir_x1, y1 = st.iir_y1;
+        for (long long a = a0; a < a1n; a++) {
+            const double xin = static_cast<double>(B[a & rb_mask]);
+            double acc = b0 * xin;
+            acc = acc + b1 * x1;
+            acc = acc - a1 * y1;
+            x1 = xin; y1 = acc;
+            B[a & rb_mask] = static_cast<float>(acc);
+        }
+        st.iir_x1 = x1; st.iir_y1 = y1;
+    }
+    __syncthreads();
+    // resampler 25/4: output i uses arm (4 i) mod 25 at input position floor(4 i / 25); available while pos <= a1n - 1
+    const long long r0 = st.n_rs, r1 = (a1n * 25 + 3) / 4;
+    for (long long i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+        const long long pos = (4 * i) / 25;
+        const float* h = arms + static_cast<int>((4 * i) % 25) * nt_arm;
+        float acc = 0.0f;
+        for (int k = nt_arm - 1; k >= 0; k--) { const long long m = pos - k; acc = fmaf(h[k], m >= 0 ? B[m & rb_mask] : 0.0f, acc); }
+        R[i & rs_mask] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { st.n_in = a1n; st.n_rs = r1; states[c] = st; }
+}
+
+// SSB: audio band-pass -> float_to_complex -> cessb::clipper_cc(0.95) -> cessb::stretcher_cc -> complex ring
+__global__ void __launch_bounds__(128)
+tx_ssb_front_kernel(TxAnalogState* __restrict__ states, const float* __restrict__ audio, long long n, long long a_stride,
+                    float* __restrict__ ra, unsigned ra_mask, long long ra_stride,
+                    float2* __restrict__ rclip, unsigned rc_mask, long long rc_stride,
+                    const float* __restrict__ bpf, int nt_bpf, float clip, float emax,
+                    float2* __restrict__ rstr, unsigned rs_mask, long long rs_stride)
+{
+    const int c = blockIdx.x;
+    __shared__ TxAnalogState st;
+    if (threadIdx.x == 0) st = states[c];
+    __syncthreads();
+    float* A = ra + static_cast<long long>(c) * ra_stride;
+    float2* Cc = rclip + static_cast<long long>(c) * rc_stride;
+    float2* S = rstr + static_cast<long long>(c) * rs_stride;
+    const long long a0 = st.n_in, a1n = st.n_in + n;
+    for (long long a = a0 + threadIdx.x; a < a1n; a += blockDim.x) A[a & ra_mask] = audio[static_cast<long long>(c) * a_stride + (a - a0)];
+    __syncthreads();
+    for (long long a = a0 + threadIdx.x; a < a1n; a += blockDim.x) {
+        float acc = 0.0f;
+        for (int k = nt_bpf - 1; k >= 0; k--) { const long long m = a - k; acc = fmaf(bpf[k], m >= 0 ? A[m & ra_mask] : 0.0f, acc); }
+        const float mag = sqrtf(acc * acc + 0.0f * 0.0f);
+        const float ph = qrl_fast_atan2f(0.0f, acc);
+        const float cl = mag < clip ? mag : clip;
+        float sn, cs;
+        qrl_sincosf(ph, sn, cs);
+        Cc[a & rc_mask] = make_float2(cs * cl, sn * cl);
+    }
+    __syncthreads();
+    const long long s0 = st.n_str, s1 = a1n >= 2 ? a1n - 2 : 0;
+    for (long long k = s0 + threadIdx.x; k < s1; k += blockDim.x) {
+        auto env = [&](long long j) -> float { if (j < 0) return 0.0f; const float2 v = Cc[j & rc_mask]; return sqrtf(v.x * v.x + v.y * v.y); };
+        float h = env(k);
+        h = fmaxf(h, env(k - 2)); h = fmaxf(h, env(k - 1)); h = fmaxf(h, env(k + 1)); h = fmaxf(h, env(k + 2));
+        h = h * emax; h = fmaxf(h, 1.0f); h = h - 1.0f; h = h * 2.0f; h = h + 1.0f;
+        const float2 v = Cc[k & rc_mask];
+        S[k & rs_mask] = make_float2(v.x / h, v.y / h);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { st.n_in = a1n; st.n_str = s1 > s0 ? s1 : s0; states[c] = st; }
+}
+
+// in-place x g1 x g2 on a channel-major complex ring segment (multiply_const_cc twice)
+__global__ void scale2_ring_kernel(float2* __restrict__ ring, unsigned mask, long long stride, long long a0, long long a1, float g1, float g2)
+{
+    const int c = blockIdx.y;
+    const long long a = a0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (a >= a1) return;
+    float2 v = ring[static_cast<long long>(c) * stride + (a & mask)];
+    v.x = v.x * g1; v.y = v.y * g1; v.x = v.x * g2; v.y = v.y * g2;
+    ring[static_cast<long long>(c) * stride + (a & mask)] = v;
+}
+
 }  // namespace qrl

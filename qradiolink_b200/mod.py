@@ -50,6 +50,20 @@ class TxBlock:
         check(self._L.qrl_tx_read(self._h, out.ctypes.data_as(C.c_void_p), nout.value, C.byref(n2), 0), self._h, "qrl_tx_read")
         return out[:, :n2.value]
 
+    def work_audio(self, audio):
+        """analog modulators (NBFM / SSB): float32 [n_channels, n] audio at 8 ksps -> complex64 [n_channels, n_out]."""
+        audio = np.ascontiguousarray(audio, np.float32)
+        if audio.ndim == 1:
+            audio = audio[None, :]
+        n = audio.shape[1]
+        check(self._L.qrl_tx_work(self._h, audio.ctypes.data_as(C.c_void_p), n, n, 0), self._h, "qrl_tx_work")
+        dptr, stride, nout = C.c_void_p(), C.c_long(), C.c_long()
+        check(self._L.qrl_tx_out_device(self._h, C.byref(dptr), C.byref(stride), C.byref(nout)), self._h, "tx_out_device")
+        out = np.zeros((self.n_channels, max(1, nout.value)), np.complex64)
+        n2 = C.c_long()
+        check(self._L.qrl_tx_read(self._h, out.ctypes.data_as(C.c_void_p), max(1, nout.value), C.byref(n2), 0), self._h, "qrl_tx_read")
+        return out[:, :n2.value]
+
     def work_device(self, dev_ptr, n, stride):
         check(self._L.qrl_tx_work(self._h, C.c_void_p(dev_ptr), n, stride, 1), self._h, "qrl_tx_work")
 
@@ -77,3 +91,13 @@ def make_gr_mod_bpsk(sps, samp_rate, carrier_freq, filter_width, n_channels=1, *
 def make_gr_mod_2fsk(sps, samp_rate, carrier_freq, filter_width, fm, n_channels=1, **kw):
     """src/gr/gr_mod_2fsk.h (instances gr_mod_base.cpp:155-159)."""
     return TxBlock(KIND.MOD_2FSK, sps, samp_rate, carrier_freq, filter_width, int(bool(fm)), n_channels, **kw)
+
+
+def make_gr_mod_nbfm(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
+    """src/gr/gr_mod_nbfm.h (instances gr_mod_base.cpp:171-172); feed with TxBlock.work_audio."""
+    return TxBlock(KIND.MOD_NBFM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
+
+
+def make_gr_mod_ssb(sps, samp_rate, carrier_freq, filter_width, sb, n_channels=1, **kw):
+    """src/gr/gr_mod_ssb.h (instances gr_mod_base.cpp:178-179); feed with TxBlock.work_audio."""
+    return TxBlock(KIND.MOD_SSB, sps, samp_rate, carrier_freq, filter_width, int(sb), n_channels, **kw)

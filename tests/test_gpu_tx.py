@@ -97,3 +97,26 @@ def test_tx_all_digital_modes(qrl, oracle, name, factory, args, okind, oargs, nb
         assert got.shape[1] == len(want), (got.shape, len(want))
         assert rel_rms(got[c], want) <= 1e-5
         assert np.array_equal(got[c], want), name
+
+
+@pytest.mark.parametrize("kind", ["nbfm2500", "nbfm5000", "usb", "lsb"])
+def test_tx_analog_modulators(qrl, oracle, kind):
+    """NBFM / SSB modulators (8 ksps float audio in) against the oracle, streamed in three uneven calls."""
+    C, n = 2, 4000
+    t = np.arange(n)
+    audio = np.stack([(0.5 * np.sin(2 * np.pi * (700 + 300 * c) * t / 8000) + 0.3 * np.sin(2 * np.pi * 1900 * t / 8000 + c)).astype(np.float32)
+                      for c in range(C)])
+    if kind.startswith("nbfm"):
+        fw = int(kind[4:])
+        tx = qrl.make_gr_mod_nbfm(20, 1000000, 1700, fw, n_channels=C, max_items=n)
+        okind, oargs = oracle.MOD_NBFM, (20, 1000000, 1700, fw, 0)
+    else:
+        sb = 1 if kind == "lsb" else 0
+        tx = qrl.make_gr_mod_ssb(125, 1000000, 1700, 2700, sb, n_channels=C, max_items=n)
+        okind, oargs = oracle.MOD_SSB, (125, 1000000, 1700, 2700, sb)
+    got = np.concatenate([tx.work_audio(audio[:, a:b]) for a, b in ((0, 1), (1, 1501), (1501, n))], axis=1)
+    for c in range(C):
+        want = oracle.Tx(okind, *oargs).work(audio[c])
+        assert got.shape[1] == len(want), (got.shape, len(want))
+        assert rel_rms(got[c], want) <= 1e-5
+        assert np.array_equal(got[c], want), kind
