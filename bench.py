@@ -202,7 +202,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = blk.launches - launches0
     stage_ms = []
-    for s in range(5):
+    for s in range(6):
         m, n = Ct.c_double(), Ct.c_long()
         L.qrl_rx_profile_read(blk._h, s, Ct.byref(m), Ct.byref(n))
         stage_ms.append((m.value, n.value))
@@ -284,7 +284,7 @@ def run_ours(args):
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fir_avg_s * 1e3,
                      "launches_per_step": launches_per_step},
-        "stage_ms_per_step": {n: (stage_ms[i][0] / args.steps) for i, n in enumerate(["fir_decim", "chan_filter", "demod_rrc", "symbol_sync", "viterbi"])},
+        "stage_ms_per_step": {n: (stage_ms[i][0] / args.steps) for i, n in enumerate(["fir_decim", "chan_filter", "demod_rrc", "symbol_sync", "viterbi", "soft_epilogue"])},
     }
     if cpu_line:
         line["cpu_baseline"] = cpu_line

@@ -112,7 +112,9 @@ struct qrl_rx : HandleBase {
     float* d_taps1 = nullptr;
     float2* d_hist[2] = { nullptr, nullptr };
     float2* d_in_staging = nullptr;
-    long long n_in = 0, n1 = 0;
+    long long n_in = 0, n1 = 0;       // stage-1 progress (absolute input samples consumed / outputs produced)
+    long long n_in_s = 0, n1_s = 0;   // progress of the per-slice stages behind it (equal to the above between calls)
+    int fir_group = 4;                 // stage-1 launches cover this many slices (bigger launches, same pipeline depth)
     Ring r1;
     // stage 2: channel / shaping filter on the complex stream (port 0)
     float* d_taps2 = nullptr; int ntaps2 = 0;
@@ -154,6 +156,8 @@ struct qrl_rx : HandleBase {
     // symbol sync
     SymSyncParams ssp{};
     SymSyncState* d_ss = nullptr;
+    float* d_ss_scratch = nullptr; int* d_ss_hdr = nullptr; long long ss_chunk_cap = 0, ss_chunk_off = 0;   // external symbol-sync epilogue
+    cudaStream_t s_epi = nullptr;                        // wide-partition stream of the external epilogue
     float2* d_port1 = nullptr; long port1_cap = 0; int* d_port1_cnt = nullptr;
     Ring r5;   // soft bits (u8)
     ViterbiState* d_vs = nullptr;
@@ -300,7 +304,9 @@ bool make_sm_partition(qrl_rx* h, unsigned loop_sms, int prio)
     if (pStream(&b, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
     if (pStream(&d, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
     if (pStream(&c, h->g_par, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
-    h->s_loop = a; h->s_fec = b; h->s_par = c; h->s_loop2 = d;
+    CUstream e2 = nullptr;
+    if (pStream(&e2, h->g_par, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
+    h->s_loop = a; h->s_fec = b; h->s_par = c; h->s_loop2 = d; h->s_epi = e2;
     h->sm_loop = static_cast<int>(grp.sm.smCount); h->sm_par = static_cast<int>(rest.sm.smCount);
     return true;
 }
@@ -593,6 +599,14 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     } else if (kind == QRL_DEMOD_4FSK || kind == QRL_DEMOD_2FSK) {
         if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + h->ntaps3 + 64))) return fail(rc);
         if ((rc = make_ring(h, &h->r4, sizeof(float), h->n1max + 600, true))) return fail(rc);
+        if (flag && kind == QRL_DEMOD_4FSK) {
+            // scratch of the external symbol-sync epilogue: [groups][chunks][maxs + 2][32] floats + a 128-int header per group
+            const int maxs = static_cast<int>((256 + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
+            h->ss_chunk_cap = h->n1max / (256 - 32) + 4 + 3 * qrl_rx::kMaxSub;
+            const size_t groups = (h->C + 31) / 32;
+            if ((rc = dev_alloc(h, &h->d_ss_scratch, groups * h->ss_chunk_cap * (maxs + 2) * 32))) return fail(rc);
+            if ((rc = dev_alloc(h, &h->d_ss_hdr, groups * 128 * qrl_rx::kMaxSub))) return fail(rc);
+        }
         if (!flag) {
             if ((rc = make_ring(h, &h->rbank, kind == QRL_DEMOD_4FSK ? sizeof(float2) : sizeof(float), h->n1max + h->nt_symf + 16))) return fail(rc);
             if (kind == QRL_DEMOD_4FSK && (rc = make_ring(h, &h->r3, sizeof(float2), h->n1max + 600, true))) return fail(rc);
@@ -639,6 +653,7 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         const int groups = (h->C + 31) / 32;
         const int big_ctas = (kind == QRL_DEMOD_QPSK) ? 2 * groups : groups;
         unsigned loop_sms = static_cast<unsigned>(std::min(48, 8 * ((big_ctas + 4 + 7) / 8)));
+        if (const char* e = getenv("QRL_LOOP_SMS")) { int v = atoi(e); if (v >= 8 && v <= 64) loop_sms = static_cast<unsigned>(v); }
         if (!make_sm_partition(h, loop_sms, hi)) {
             h->s_par = nullptr; h->sm_loop = 0; h->sm_par = 0;
             if (h->s_loop == nullptr)
@@ -647,6 +662,8 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
                 ok = ok && cudaStreamCreateWithPriority(&h->s_loop2, cudaStreamNonBlocking, hi) == cudaSuccess;
             if (h->s_fec == nullptr)
                 ok = ok && cudaStreamCreateWithPriority(&h->s_fec, cudaStreamNonBlocking, hi) == cudaSuccess;
+            if (h->s_epi == nullptr)
+                ok = ok && cudaStreamCreateWithPriority(&h->s_epi, cudaStreamNonBlocking, hi) == cudaSuccess;
         }
         auto mk = [&](cudaEvent_t* e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
         mk(&h->ev_start); mk(&h->ev_loop_done); mk(&h->ev_loop2_done); mk(&h->ev_fec_done); mk(&h->ev_par_done);
@@ -654,6 +671,7 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if (!ok) { set_err(h, "stream/event creation failed"); return fail(QRL_ECUDA); }
     }
     if (const char* e = getenv("QRL_NSUB")) { int v = atoi(e); if (v >= 1 && v <= qrl_rx::kMaxSub) h->nsub = v; }
+    if (const char* e = getenv("QRL_FIR_GROUP")) { int v = atoi(e); if (v >= 1 && v <= qrl_rx::kMaxSub) h->fir_group = v; }
     if ((rc = qrl_rx_reset(h))) return fail(rc);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { set_err(h, "create sync failed"); return fail(QRL_ECUDA); }
     *out = h;
@@ -666,6 +684,7 @@ int qrl_rx_reset(qrl_rx* h)
     if (h->s_loop) CK(cudaStreamSynchronize(h->s_loop));
     if (h->s_fec) CK(cudaStreamSynchronize(h->s_fec));
     if (h->s_loop2) CK(cudaStreamSynchronize(h->s_loop2));
+    if (h->s_epi) CK(cudaStreamSynchronize(h->s_epi));
     if (h->s_par) CK(cudaStreamSynchronize(h->s_par));
     // all-zero history / rings; loop states at their constructor values
     std::vector<SymSyncState> ss(h->C);
@@ -704,7 +723,7 @@ int qrl_rx_reset(qrl_rx* h)
     CK(cudaMemsetAsync(h->d_port1_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_port2_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // the staging vectors above go out of scope
-    h->n_in = 0; h->n1 = 0; h->hist_cur = 0; h->port0_n = 0;
+    h->n_in = 0; h->n1 = 0; h->n_in_s = 0; h->n1_s = 0; h->hist_cur = 0; h->port0_n = 0;
     return QRL_OK;
 }
 
@@ -716,6 +735,7 @@ int qrl_rx_destroy(qrl_rx* h)
     if (h->s_loop) { cudaStreamSynchronize(h->s_loop); cudaStreamDestroy(h->s_loop); }
     if (h->s_fec) { cudaStreamSynchronize(h->s_fec); cudaStreamDestroy(h->s_fec); }
     if (h->s_loop2) { cudaStreamSynchronize(h->s_loop2); cudaStreamDestroy(h->s_loop2); }
+    if (h->s_epi) { cudaStreamSynchronize(h->s_epi); cudaStreamDestroy(h->s_epi); }
     if (h->s_par) { cudaStreamSynchronize(h->s_par); cudaStreamDestroy(h->s_par); }
     if (h->g_loop || h->g_par) {
         auto pDestroy = drv<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
@@ -828,22 +848,30 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         const long long t0 = cut(i), t1 = cut(i + 1);
         if (t1 <= t0) continue;
         const long long Ti = t1 - t0;
-        const float2* xi = x + t0;
-        // ---- stage 1: decimating FIR; outputs k with D k <= last absolute input index
-        const long long N = h->n_in + Ti;
-        const long long k0 = h->n1;
-        const long long k1 = (N * h->L1 + h->D1 - 1) / h->D1;       // outputs i with floor(i M / L) <= N - 1
-        cudaEvent_t pe = h->prof_begin(0, sp);
-        int rc = stage1(h, xi, xstride, Ti, k0, k1);
-        h->prof_end(pe);
-        if (rc) return rc;
-        {
+        cudaEvent_t pe = nullptr;
+        // ---- stage 1: decimating FIR, one launch per group of slices (outputs k with D k <= last absolute input index)
+        if (i % h->fir_group == 0) {
+            const long long tg1 = cut(std::min(i + h->fir_group, nsub));
+            const long long Tg = tg1 - t0;
+            const float2* xg = x + t0;
+            const long long Ng = h->n_in + Tg;
+            const long long kg0 = h->n1;
+            const long long kg1 = (Ng * h->L1 + h->D1 - 1) / h->D1;       // outputs i with floor(i M / L) <= N - 1
+            pe = h->prof_begin(0, sp);
+            int rc = stage1(h, xg, xstride, Tg, kg0, kg1);
+            h->prof_end(pe);
+            if (rc) return rc;
             dim3 g((h->H + 127) / 128, h->C);
-            hist_update_kernel<<<g, 128, 0, sp>>>(xi, xstride, Ti, h->d_hist[h->hist_cur], h->d_hist[h->hist_cur ^ 1], h->H);
+            hist_update_kernel<<<g, 128, 0, sp>>>(xg, xstride, Tg, h->d_hist[h->hist_cur], h->d_hist[h->hist_cur ^ 1], h->H);
             h->launches++;
             h->hist_cur ^= 1;
+            h->n_in = Ng; h->n1 = kg1;
         }
-        h->n_in = N; h->n1 = k1;
+        // ---- the stages behind it advance slice by slice
+        const long long N = h->n_in_s + Ti;
+        const long long k0 = h->n1_s;
+        const long long k1 = (N * h->L1 + h->D1 - 1) / h->D1;
+        h->n_in_s = N; h->n1_s = k1;
         const long long n_new = k1 - k0;
         h->port0_n += static_cast<long>(n_new);
         long long* nsoft_i = h->d_nsoft + static_cast<size_t>(i) * h->C;
@@ -946,26 +974,26 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 }
                 constexpr int CH = 128, NST = 3, NEPI = 1;
                 const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period) + 3);
-                const size_t smem = sizeof(float) * (NST * CH * 64 + 132 * 8 + 2 * maxs * 64) + sizeof(int) * 64;
-                auto kern = symsync_kernel<2, SL_BPSK, EPI_BPSK, CH, NST, NEPI>;
+                const size_t smem = sizeof(float) * (NST * CH * 64 + SYMSYNC_TAB_FLOATS + 2 * maxs * 64) + sizeof(int) * 64;
+                auto kern = symsync_kernel<2, SL_BPSK, EPI_BPSK, CH, NST, NEPI, LOOP_CRMM>;
                 static bool b_attr = false;
                 if (!b_attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); b_attr = true; }
                 kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop>>>(
                     h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r3.d), h->r3.mask, h->r3.stride, k1,
                     h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
-                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i);
+                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i, nullptr, 0, 0, nullptr);
                 h->launches++;
             } else {
                 constexpr int CH = 256, NST = 3, NEPI = 2;
                 const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
-                const size_t smem = sizeof(float) * (NST * CH * 32 + 132 * 8 + 2 * maxs * 32) + sizeof(int) * 64;
+                const size_t smem = sizeof(float) * (NST * CH * 32 + SYMSYNC_TAB_FLOATS + 2 * maxs * 32) + sizeof(int) * 64;
                 auto kern = symsync_kernel<1, SL_BPSK, EPI_REAL1, CH, NST, NEPI>;
                 static bool f_attr = false;
                 if (!f_attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); f_attr = true; }
                 kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop>>>(
                     h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r4.d), h->r4.mask, h->r4.stride, k1,
                     h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
-                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i);
+                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i, nullptr, 0, 0, nullptr);
                 h->launches++;
             }
             h->prof_end(pe);
@@ -1017,39 +1045,64 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             CK(cudaEventRecord(h->ev_a[i], sp));
             // ---- stage 4: symbol sync (+ phase mod + soft bits) on the loop stream
             CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
+            bool ext_recorded = false;
             if (!h->flag) {
                 pe = h->prof_begin(3, h->s_loop);
                 constexpr int CH = 128, NST = 3, NEPI = 2;
                 const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
-                const size_t smem = sizeof(float) * (NST * CH * 64 + 132 * 8 + 2 * maxs * 64) + sizeof(int) * 64;
+                const size_t smem = sizeof(float) * (NST * CH * 64 + SYMSYNC_TAB_FLOATS + 2 * maxs * 64) + sizeof(int) * 64;
                 auto kern = symsync_kernel<2, SL_RECT4, EPI_CPLX, CH, NST, NEPI>;
                 static bool sc_attr = false;
                 if (!sc_attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); sc_attr = true; }
                 kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop>>>(
                     h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r3.d), h->r3.mask, h->r3.stride, k1,
                     h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
-                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i);
+                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i, nullptr, 0, 0, nullptr);
                 h->launches++;
                 h->prof_end(pe);
             } else {
                 pe = h->prof_begin(3, h->s_loop);
-                constexpr int CH = 256, NST = 3, NEPI = 2;
+                // real symbols: lean recurrence + external epilogue (symbols leave the SM by TMA bulk store; the phase
+                // modulator / soft-bit stores run on the wide partition behind it, same stream)
+                constexpr int CH = 256, NST = 3;
                 const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
-                const size_t smem = sizeof(float) * (NST * CH * 32 + 132 * 8 + 2 * maxs * 32) + sizeof(int) * 64;
-                auto kern = symsync_kernel<1, SL_RECT4, EPI_4FSK_FM, CH, NST, NEPI>;
-                static bool ss_attr = false;
-                if (!ss_attr) {
-                    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    ss_attr = true;
+                const size_t smem_base = sizeof(float) * (NST * CH * 32 + SYMSYNC_TAB_FLOATS + 2 * (maxs + 2) * 32) + sizeof(int) * 64;
+                const size_t smem_rep = smem_base + 129 * 512;          // + replicated (conflict-free) interpolator bank
+                const bool rep = smem_rep <= 220 * 1024;
+                const size_t smem = rep ? smem_rep : smem_base;
+                auto kern = rep ? symsync_kernel<1, SL_RECT4, EPI_EXT_4FSK_FM, CH, NST, 1, LOOP_SYMSYNC, 2>
+                                : symsync_kernel<1, SL_RECT4, EPI_EXT_4FSK_FM, CH, NST, 1, LOOP_SYMSYNC, 1>;
+                static bool ss_attr[2] = { false, false };
+                if (!ss_attr[rep]) {
+                    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+                    ss_attr[rep] = true;
                 }
-                kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop>>>(
+                // every slice of a call gets its own scratch region and header (the epilogue of slice i overlaps symsync i+1)
+                if (i == 0) h->ss_chunk_off = 0;
+                const int chunk_bound = static_cast<int>(std::min<long long>(h->ss_chunk_cap - h->ss_chunk_off, n_new / (CH - 32) + 3));
+                float* scratch_i = h->d_ss_scratch + static_cast<size_t>(h->ss_chunk_off) * (maxs + 2) * 32;
+                int* hdr_i = h->d_ss_hdr + static_cast<size_t>(i) * groups * 128;
+                h->ss_chunk_off += chunk_bound;
+                kern<<<groups, 96, smem, h->s_loop>>>(
                     h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r4.d), h->r4.mask, h->r4.stride, k1,
                     h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
-                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i);
+                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i,
+                    scratch_i, chunk_bound, static_cast<int>(h->ss_chunk_cap), hdr_i);
+                h->prof_end(pe);
+                cudaStream_t se = h->s_epi ? h->s_epi : h->s_loop;
+                if (se != h->s_loop) { CK(cudaEventRecord(h->ev_c[i], h->s_loop)); CK(cudaStreamWaitEvent(se, h->ev_c[i], 0)); }
+                pe = h->prof_begin(5, se);
+                if (chunk_bound > 0)
+                    symsync_ext_epilogue_kernel<<<dim3(chunk_bound, groups), dim3(32, 8), 0, se>>>(
+                        h->ssp, h->C, scratch_i, static_cast<int>(h->ss_chunk_cap), maxs, hdr_i,
+                        h->d_port1, h->port1_cap, static_cast<int>(h->port1_cap),
+                        static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride);
                 h->launches++;
                 h->prof_end(pe);
+                CK(cudaEventRecord(h->ev_b[i], se));
+                ext_recorded = true;
             }
-            CK(cudaEventRecord(h->ev_b[i], h->s_loop));
+            if (!ext_recorded) CK(cudaEventRecord(h->ev_b[i], h->s_loop));
         } else {   // QRL_DEMOD_QPSK
             const float2* shaping_in = static_cast<const float2*>(h->r1.d);
             unsigned shaping_mask = h->r1.mask; long long shaping_stride = h->r1.stride;
@@ -1100,7 +1153,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 pe = h->prof_begin(3, h->s_loop2);
                 constexpr int CH = 128, NST = 3, NEPI = 1;
                 const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
-                const size_t smem = sizeof(float) * (NST * CH * 64 + 132 * 8 + 2 * maxs * 64) + sizeof(int) * 64;
+                const size_t smem = sizeof(float) * (NST * CH * 64 + SYMSYNC_TAB_FLOATS + 2 * maxs * 64) + sizeof(int) * 64;
                 auto kern = symsync_kernel<2, SL_DQPSK, EPI_QPSK, CH, NST, NEPI>;
                 static bool sq_attr = false;
                 if (!sq_attr) {
@@ -1110,7 +1163,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop2>>>(
                     h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r3.d), h->r3.mask, h->r3.stride, k1,
                     h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
-                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i);
+                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i, nullptr, 0, 0, nullptr);
                 h->launches++;
                 h->prof_end(pe);
             }

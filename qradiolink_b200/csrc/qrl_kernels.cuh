@@ -7,6 +7,7 @@
 // CPU oracle and float outputs are bit-identical in practice.
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 #include <stdint.h>
 
 namespace qrl {
@@ -23,6 +24,17 @@ __device__ float d_sine_tab[2048];
 // TMA 1-D bulk copy (cp.async.bulk -> UBLKCP) + mbarrier helpers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// shared-memory access by 32-bit shared address + immediate offset (keeps the recurrence's address math in one IMAD)
+template <int OFF> __device__ __forceinline__ float lds_f32(uint32_t a)
+{
+    float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF)); return v;
+}
+template <int OFF> __device__ __forceinline__ float4 lds_f32x4(uint32_t a)
+{
+    float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -38,6 +50,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -457,7 +477,11 @@ __global__ void qdemod_fir_fff_kernel(const float2* __restrict__ in, unsigned in
 //   EPI_QPSK    : complex symbols -> costas(4, snr) -> diff_phasor -> rotate -> port1, soft bits
 // ------------------------------------------------------------------------------------------------
 enum { SL_RECT4 = 0, SL_DQPSK = 1, SL_BPSK = 2 };
-enum { EPI_4FSK_FM = 0, EPI_CPLX = 1, EPI_QPSK = 2, EPI_BPSK = 3, EPI_REAL1 = 4 };
+//   EPI_EXT_4FSK_FM : as EPI_4FSK_FM, but the symbols leave the SM as they are (TMA bulk store of each hand-off
+//                 block to a scratch buffer) and symsync_ext_epilogue_kernel does the phase modulator / soft bits
+//                 on the wide SM partition: the scattered per-channel stores no longer share the MIO queue with the
+//                 recurrence's shared-memory loads
+enum { EPI_4FSK_FM = 0, EPI_CPLX = 1, EPI_QPSK = 2, EPI_BPSK = 3, EPI_REAL1 = 4, EPI_EXT_4FSK_FM = 5 };
 enum { LOOP_SYMSYNC = 0, LOOP_CRMM = 1 };
 
 struct LoopState {               // control_loop (costas)
@@ -472,6 +496,7 @@ struct SymSyncState {
     LoopState costas;            // second Costas loop (EPI_QPSK)
     float dp_r, dp_i;            // diff_phasor memory
 };
+constexpr int SYMSYNC_TAB_FLOATS = 132 * 8 + 129 * 12 + 4;   // tap-major bank + entry-major bank (16-byte pitch multiple)
 struct SymSyncParams {
     float sps, alpha, beta, max_period, min_period;
     int lookahead;
@@ -732,6 +757,13 @@ __device__ __forceinline__ float qrl_slice_rect4(float re)
 // clip for non-NaN arguments: two FMNMX instead of compare + select
 __device__ __forceinline__ float qrl_clip1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
 
+// out-of-lock step of the lean symbol-sync loop (never inlined: keeps FRND off the predicated common path)
+__device__ __noinline__ float2 symsync_generic_step(float ph)
+{
+    const float fl = floorf(ph);
+    return make_float2(ph - fl, fl);
+}
+
 // Input ring layout: [group = channel / 32][slot][32 lanes][NCOMP] -- a time step of one warp's 32 channels is one
 // contiguous 128*NCOMP-byte row, so a CH-row window is ONE contiguous block fetched with cp.async.bulk (TMA 1-D).
 // Warp-specialised CTA (one CTA per 32 channels):
@@ -740,30 +772,52 @@ __device__ __forceinline__ float qrl_clip1(float x) { return fminf(fmaxf(x, -1.0
 //                     reads column `lane` of the window (bank = lane: conflict-free)
 //   warps 2..       : everything that does not feed back (phase modulator / 2nd Costas loop, soft bits, stores),
 //                     fed through a double-buffered shared-memory symbol hand-off (mbarrier full/empty)
-template <int NCOMP, int SLICER, int EPI, int CH, int NST, int NEPI>
+template <int NCOMP, int SLICER, int EPI, int CH, int NST, int NEPI, int LOOPK = LOOP_SYMSYNC, int VAR = 0>
 __global__ void __launch_bounds__(64 + 32 * NEPI)
 symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                const float* __restrict__ in, unsigned in_mask, long long in_stride /*slots per group*/, long long avail_total,
                float2* __restrict__ port1, long long port1_stride, int* __restrict__ port1_cnt, int port1_cap,
                unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride, int maxs,
-               long long* __restrict__ n_soft_out /* [C] snapshot of the soft-bit write index after this launch */)
+               long long* __restrict__ n_soft_out /* [C] snapshot of the soft-bit write index after this launch */,
+               float* __restrict__ ext_scratch = nullptr /* [groups][ext_chunk_cap][maxs + 2][32] (EPI_EXT_*) */,
+               int ext_chunk_cap = 0 /* chunks this launch may emit */, int ext_chunk_stride = 0 /* chunks per group in the scratch */,
+               int* __restrict__ ext_hdr = nullptr /* [groups][128] (EPI_EXT_*) */)
 {
     static_assert((EPI != EPI_QPSK && EPI != EPI_BPSK) || NEPI == 1, "Costas epilogues carry loop state: one epilogue warp");
+    constexpr bool EXT = (EPI == EPI_EXT_4FSK_FM);
+    static_assert(!EXT || (NEPI == 1 && NCOMP == 1), "external epilogue: one drain warp, real symbols");
     constexpr int ROWF = 32 * NCOMP;                    // floats per row
     constexpr int STRIDE = CH - 32;                     // window advance per chunk (lookahead <= 32)
     extern __shared__ __align__(128) float sm_sync[];   // [NST][CH][ROWF] | mmse[129*8] | sym[2][maxs][ROWF] | cnt[2][32]
     __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[2], bar_empty[2];
+    __shared__ volatile int lane_zero[32];
     float* stage0 = sm_sync;
     float* mm = sm_sync + NST * CH * ROWF;
-    float* symbuf = mm + 132 * 8;
-    int* cntbuf = reinterpret_cast<int*>(symbuf + 2 * maxs * ROWF);
+    float* mm2 = mm + 132 * 8;                          // entry-major copy (12-float pitch), taps reversed: two LDS.128
+    float* symbuf = mm + SYMSYNC_TAB_FLOATS;
+    const int blk_rows = EXT ? maxs + 2 : maxs;         // EXT: rows maxs / maxs+1 of a block hold the lane counts / lane bases
+    int* cntbuf = reinterpret_cast<int*>(symbuf + 2 * blk_rows * ROWF);
+    // VAR == 2: 16-fold replicated bank [imu][half][lane & 15][4] (129 * 512 bytes) behind everything else: the 8 lanes
+    // of an LDS.128 phase read 128 contiguous bytes, so the two tap loads of a symbol are conflict-free whatever imu is
+    constexpr bool REP = (VAR == 2);
+    float* mm3 = reinterpret_cast<float*>(cntbuf + 64);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
     const int c = g * 32 + lane;
     const bool active = c < C;
     // tap-major copy of the MMSE bank: mm[k * 132 + imu] (a lane's 8 taps are 8 scalar loads in the order the
     // oldest-first FMA chain consumes them; random imu across lanes spreads over all 32 banks)
-    for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) mm[(i & 7) * 132 + (i >> 3)] = d_mmse_tab[i];
+    for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) {
+        const float t = d_mmse_tab[i];
+        mm[(i & 7) * 132 + (i >> 3)] = t;
+        mm2[(i >> 3) * 12 + (7 - (i & 7))] = t;
+        if (REP) {
+            const int j = 7 - (i & 7);
+            float* q = mm3 + (i >> 3) * 128 + (j >> 2) * 64 + (j & 3);
+#pragma unroll
+            for (int r = 0; r < 16; r++) q[r * 4] = t;
+        }
+    }
     if (threadIdx.x == 0) {
         for (int b = 0; b < NST; b++) { mbar_init(&bar_in[b], 1); mbar_init(&bar_free[b], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&bar_full[b], 1); mbar_init(&bar_empty[b], NEPI); }
@@ -779,9 +833,21 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
         const long long o = __shfl_xor_sync(0xffffffffu, base, off);
         base = o < base ? o : base;
     }
-    if (warp == 2 && active) n_soft_out[c] = states[c].n_soft;
-    if (base + p.lookahead > avail_total) return;
-    const int nchunks = static_cast<int>((avail_total - p.lookahead - base) / STRIDE) + 1;
+    int nchunks = (base + p.lookahead > avail_total) ? 0 : static_cast<int>((avail_total - p.lookahead - base) / STRIDE) + 1;
+    if (EXT) {
+        // the launch's starting indices travel to the external epilogue in a header (this warp overwrites them at the end)
+        nchunks = nchunks < ext_chunk_cap ? nchunks : ext_chunk_cap;     // a clipped launch catches up on the next one
+        if (warp == 0) {
+            const long long ns0 = active ? states[c].n_soft : 0;
+            int* hdr = ext_hdr + g * 128;
+            hdr[lane] = active ? port1_cnt[c] : 0;
+            hdr[32 + lane] = static_cast<int>(ns0 & 0xffffffffLL);
+            hdr[64 + lane] = static_cast<int>(ns0 >> 32);
+            if (lane == 0) hdr[96] = nchunks;
+            if (active) n_soft_out[c] = ns0;
+        }
+    } else if (warp == 2 && active) n_soft_out[c] = states[c].n_soft;
+    if (nchunks == 0) return;
 
     if (warp == 1) {
         // ------------------------------------------------------------------ TMA producer
@@ -812,31 +878,46 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
             d0 = st.dr[0]; d1 = st.dr[1]; d2 = st.dr[2]; e0 = st.di[0]; e1 = st.di[1]; e2 = st.di[2];
         }
         int o = 0;                                         // my read position relative to the current window
+        int nsym_run = 0;                                  // EXT: symbols this lane has emitted so far in this launch
         {
             const long long d = my_ii - base;
             o = d > 0x3fffffff ? 0x3fffffff : static_cast<int>(d);
         }
         const int la = p.lookahead;
+        // a zero the compiler cannot see through (bounced through shared memory): pointers offset by it are
+        // per-lane registers to the compiler, so the recurrence addresses shared memory as [R+imm], not [R+UR+imm]
+        lane_zero[lane] = 0;
+        __syncwarp();
+        const int zoff = lane_zero[lane];
+        const float* mmp = mm + zoff;
+        const float* stp = stage0 + lane * NCOMP + zoff;
         // loop constants in registers (a constant-bank load inside the recurrence would sit on the critical path)
         const float k_alpha = p.alpha, k_beta = p.beta, k_maxp = p.max_period, k_minp = p.min_period;
         const float k_f0 = p.fl0, k_f1 = p.fl0 + 1.0f, k_f2 = p.fl0 + 2.0f, k_f3 = p.fl0 + 3.0f;
         const int k_n0 = p.n0;
+        // constants of the lean loop, made opaque (+0.0f the compiler cannot see) so they stay in plain registers
+        const float zf = __int_as_float(zoff);
+        const float k_hb = 0.5f * p.beta + zf, k_ha = 0.5f * p.alpha + zf, k128 = 128.0f + zf;
+        const float q_minp = p.min_period + zf, q_maxp = p.max_period + zf;
+        const float q_f0 = p.fl0 + zf, q_f1 = (p.fl0 + 1.0f) + zf, q_f2 = (p.fl0 + 2.0f) + zf;
+        const uint32_t mm2_b = REP ? smem_u32(mm3) + (lane & 15) * 16 - 0x4B400000u * 512u + static_cast<uint32_t>(zoff)
+                                   : smem_u32(mm2) - 0x4B400000u * 48u + static_cast<uint32_t>(zoff);
+        const bool lean_ok = p.min_period > fabsf(p.alpha) && p.fl0 >= 1.0f;
         for (int m = 0; m < nchunks; m++) {
             const int st = m % NST, b = m & 1;
             if (m >= 2) mbar_wait(&bar_empty[b], ((m >> 1) - 1) & 1);    // epilogue released this hand-off buffer
             mbar_wait(&bar_in[st], (m / NST) & 1);
-            const float* buf = stage0 + st * CH * ROWF + lane * NCOMP;
-            float* sy = symbuf + b * maxs * ROWF + lane * NCOMP;
+            const float* buf = stp + st * CH * ROWF;
+            float* sy = symbuf + b * blk_rows * ROWF + lane * NCOMP;
             const long long w0 = base + static_cast<long long>(m) * STRIDE;
             const long long rem = avail_total - w0;
             const int wlen = rem < CH ? static_cast<int>(rem) : CH;
             int cnt = 0;
-            if (active && p.loop_kind == LOOP_CRMM) {
+            if (active && LOOPK == LOOP_CRMM) {
                 // clock_recovery_mm_cc: avg_period holds omega, x*/y*i hold p_nT, d*/e* hold the 0/1 slicer outputs
                 while (o + la <= wlen) {
                     const float* x = buf + o * ROWF;
-                    const int imu = __float_as_int((mu * 128.0f) + 12582912.0f) & 0x3ff;
-                    const float* tp = mm + imu;
+                    const float* tp = mmp + (__float_as_int(fmaf(mu, 128.0f, 12582912.0f)) & 0x3ff);
                     float yr = 0.0f, yi = 0.0f;
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
@@ -863,13 +944,99 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                     if (NCOMP == 2) sy[cnt * ROWF + 1] = yi;
                     cnt++;
                 }
-            } else if (active) {
+            } else if (active && LOOPK == LOOP_SYMSYNC && NCOMP == 1 && SLICER == SL_RECT4 && VAR >= 1 && lean_ok) {
+                // Lean restatement of the real 4-level recurrence.  A lone warp pays ~1 cycle per issued instruction
+                // plus ~4 per dependent one, so the loop is written for instruction count.  Every rewrite is exact:
+                //  * err = clip(u/2, +-1) enters only as beta*err and alpha*err, formed as (beta/2)*clip(u, +-2)
+                //    (scaling by 1/2 commutes with rounding);
+                //  * the read position lives in a float as 2^23 + row (integer adds are exact, the row is the low
+                //    mantissa bits), so the stride floor(ph) = n0 + [ph >= n0+1] + [ph >= n0+2] never leaves the
+                //    float pipe and ph - floor(ph) is (ph - n0) minus the same two 0/1 terms (exact: integers
+                //    subtracted from a float of at least their magnitude);
+                //  * the TED history rotates through three registers (loop unrolled by 3) instead of being moved;
+                //  * inst_period <= 0 cannot happen when min_period > |alpha| (checked by lean_ok).
+                float ofm = 8388608.0f + static_cast<float>(o);
+                const float lim = 8388608.0f + static_cast<float>(wlen - la);
+                const uint32_t xb = smem_u32(buf) - (0x4B000000u << 7);
+                uint32_t syp = smem_u32(sy);
+                const uint32_t syp0 = syp;
+                float A = x0, B = x1, Cc = x2, dA = d0, dB = d1, dC = d2;
+                // one symbol; returns true when the lane fell out of the in-lock stride window (generic step taken)
+                auto body = [&](float& n, const float h1, const float h2, float& dn, const float dh1, const float dh2) -> bool {
+                    const uint32_t ta = mm2_b + __float_as_uint(fmaf(mu, k128, 12582912.0f)) * (REP ? 512u : 48u);
+                    const uint32_t xa = xb + (__float_as_uint(ofm) << 7);
+                    const float ofn = ofm + q_f0;
+                    const float kd = -1.5f - dh2;
+                    const float4 ta0 = lds_f32x4<0>(ta), ta1 = lds_f32x4<REP ? 256 : 16>(ta);   // taps[7..4], taps[3..0]
+                    float yr = fmaf(ta0.x, lds_f32<0>(xa), 0.0f);                 // oldest sample first
+                    yr = fmaf(ta0.y, lds_f32<ROWF * 4>(xa), yr);
+                    yr = fmaf(ta0.z, lds_f32<ROWF * 8>(xa), yr);
+                    yr = fmaf(ta0.w, lds_f32<ROWF * 12>(xa), yr);
+                    yr = fmaf(ta1.x, lds_f32<ROWF * 16>(xa), yr);
+                    yr = fmaf(ta1.y, lds_f32<ROWF * 20>(xa), yr);
+                    yr = fmaf(ta1.z, lds_f32<ROWF * 24>(xa), yr);
+                    yr = fmaf(ta1.w, lds_f32<ROWF * 28>(xa), yr);
+                    n = yr;
+                    // slicer levels are +-0.5, +-1.5: the sums below are exact in any order (two-level tree)
+                    const float s1 = qrl_ge1(yr, -1.0f), s23 = qrl_ge1(yr, -5.9604644775390625e-8f) + qrl_ge1(yr, 0.99999988079071044921875f);
+                    const float br = (s1 + kd) + s23;                             // dn - dh2
+                    dn = (s1 - 1.5f) + s23;
+                    const float u = (yr - h2) * dh1 - br * h1;
+                    const float e2x = fminf(fmaxf(u, -2.0f), 2.0f);               // 2 * err
+                    avg_period = avg_period + k_hb * e2x;
+                    avg_period = fminf(fmaxf(avg_period, q_minp), q_maxp);
+                    inst_period = avg_period + k_ha * e2x;
+                    const float ph = mu + inst_period;
+                    const float m0 = ph - q_f0;
+                    sts_f32(syp, yr);
+                    syp += ROWF * 4;
+                    const float s12 = qrl_ge1(m0, 1.0f) + qrl_ge1(m0, 2.0f);     // == [ph >= n0+1] + [ph >= n0+2] (m0 exact)
+                    mu = m0 - s12;
+                    ofm = ofn + s12;
+                    if (__builtin_expect(__float_as_uint(m0) >= 0x40400000u, 0)) {    // ph not in [n0, n0+3): generic floor
+                        const float2 g = symsync_generic_step(ph);
+                        mu = g.x;
+                        ofm = (ofn - q_f0) + g.y;
+                        return true;
+                    }
+                    return false;
+                };
+                // Trip counts are warp-uniform: in lock the stride is at most n0 + 2, so every lane can take
+                // floor(rows left / (n0 + 2)) + 1 symbols without looking at the window end; recomputed until no lane
+                // has a guaranteed symbol left, then each lane finishes under the exact per-lane check.
+                const unsigned amask = __activemask();
+                const float inv_s = 1.0f / static_cast<float>(k_n0 + 2);
+                for (;;) {
+                    const float left = lim - ofm;                      // exact (integers below 2^24)
+                    int ksafe = left >= 0.0f ? static_cast<int>(left * inv_s * 0.999f) + 1 : 0;   // never above the true quotient + 1
+                    ksafe = __reduce_min_sync(amask, ksafe);
+                    if (ksafe == 0) break;
+                    bool fell = false;
+                    for (; ksafe >= 3 && !fell; ksafe -= 3) {
+                        if (body(Cc, A, B, dC, dA, dB)) { const float t = Cc, dt = dC; Cc = B; B = A; A = t; dC = dB; dB = dA; dA = dt; fell = true; }
+                        else if (body(B, Cc, A, dB, dC, dA)) { const float t = B, dt = dB; B = Cc; Cc = A; A = t; dB = dC; dC = dA; dA = dt; fell = true; }
+                        else if (body(A, B, Cc, dA, dB, dC)) fell = true;
+                    }
+                    for (; ksafe >= 1 && !fell; ksafe--) {
+                        fell = body(Cc, A, B, dC, dA, dB);
+                        const float t = Cc, dt = dC; Cc = B; B = A; A = t; dC = dB; dB = dA; dA = dt;
+                    }
+                    if (__any_sync(amask, fell)) break;
+                }
+                while (ofm <= lim) {                                   // stragglers (and lanes that fell out of lock)
+                    body(Cc, A, B, dC, dA, dB);
+                    const float t = Cc, dt = dC; Cc = B; B = A; A = t; dC = dB; dB = dA; dA = dt;
+                }
+                x0 = A; x1 = B; x2 = Cc; d0 = dA; d1 = dB; d2 = dC;
+                o = static_cast<int>(ofm - 8388608.0f);
+                cnt = static_cast<int>((syp - syp0) / (ROWF * 4));
+            } else if (active && LOOPK == LOOP_SYMSYNC) {
                 while (o + la <= wlen) {
                     const float* x = buf + o * ROWF;
                     // rintf(mu*128) without a conversion unit: adding 1.5*2^23 rounds to nearest-even at integer
-                    // granularity (same as rintf for 0 <= v < 2^22); the integer sits in the low mantissa bits
-                    const int imu = __float_as_int((mu * 128.0f) + 12582912.0f) & 0x3ff;
-                    const float* tp = mm + imu;
+                    // granularity (mu*128 is exact, so the fused form rounds once); the integer sits in the low
+                    // mantissa bits
+                    const float* tp = mmp + (__float_as_int(fmaf(mu, 128.0f, 12582912.0f)) & 0x3ff);
                     // 8-tap MMSE interpolation, oldest sample first: taps[7], taps[6], ...
                     float yr = 0.0f, yi = 0.0f;
 #pragma unroll
@@ -879,17 +1046,19 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                         if (NCOMP == 2) yi = fmaf(tt, x[i * ROWF + 1], yi);
                     }
                     x2 = x1; x1 = x0; x0 = yr;
-                    y2i = y1i; y1i = y0i; y0i = yi;
-                    d2 = d1; d1 = d0; e2 = e1; e1 = e0;
-                    if (SLICER == SL_RECT4) { d0 = qrl_slice_rect4(yr); e0 = 0.0f; }
-                    else qrl_slice(SLICER, yr, yi, d0, e0);
+                    d2 = d1; d1 = d0;
+                    if (NCOMP == 2) { y2i = y1i; y1i = y0i; y0i = yi; e2 = e1; e1 = e0; }
                     float err;
                     if (NCOMP == 2) {
+                        if (SLICER == SL_RECT4) { d0 = qrl_slice_rect4(yr); e0 = 0.0f; }
+                        else qrl_slice(SLICER, yr, yi, d0, e0);
                         const float ar = x0 - x2, ai = y0i - y2i;
                         const float br = d0 - d2, bi = e0 - e2;
                         const float u = (ar * d1 + ai * e1) - (br * x1 + bi * y1i);
                         err = qrl_clip1(u);
                     } else {
+                        if (SLICER == SL_RECT4) d0 = qrl_slice_rect4(yr);
+                        else { float ee; qrl_slice(SLICER, yr, yi, d0, ee); }
                         const float u = (x0 - x2) * d1 - (d0 - d2) * x1;
                         err = qrl_clip1(u * 0.5f);
                     }
@@ -912,7 +1081,13 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                 }
             }
             o -= STRIDE;                                   // next window starts STRIDE rows later
-            cntbuf[b * 32 + lane] = cnt;
+            if (EXT) {
+                float* blk = symbuf + b * blk_rows * ROWF;
+                reinterpret_cast<int*>(blk)[maxs * 32 + lane] = cnt;
+                reinterpret_cast<int*>(blk)[(maxs + 1) * 32 + lane] = nsym_run;
+                nsym_run += cnt;
+                fence_proxy_async();                       // the drain warp's bulk store reads this block through the async proxy
+            } else cntbuf[b * 32 + lane] = cnt;
             __syncwarp();
             if (lane == 0) { mbar_arrive(&bar_free[st]); mbar_arrive(&bar_full[b]); }
         }
@@ -922,6 +1097,26 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
             st.avg_period = avg_period; st.inst_period = inst_period; st.mu = mu;
             st.xr[0] = x0; st.xr[1] = x1; st.xr[2] = x2; st.xi[0] = y0i; st.xi[1] = y1i; st.xi[2] = y2i;
             st.dr[0] = d0; st.dr[1] = d1; st.dr[2] = d2; st.di[0] = e0; st.di[1] = e1; st.di[2] = e2;
+            if (EXT) {
+                st.n_sym += nsym_run; st.n_soft += 2LL * nsym_run;
+                port1_cnt[c] += nsym_run;
+                n_soft_out[c] = st.n_soft;
+            }
+        }
+    } else if (EXT) {
+        // ------------------------------------------------------------------ drain warp: hand-off block -> scratch (TMA)
+        if (lane == 0) {
+            const size_t blk_floats = static_cast<size_t>(blk_rows) * ROWF;
+            float* dst0 = ext_scratch + static_cast<size_t>(g) * ext_chunk_stride * blk_floats;
+            for (int m = 0; m < nchunks; m++) {
+                const int b = m & 1;
+                mbar_wait(&bar_full[b], (m >> 1) & 1);
+                bulk_s2g(dst0 + static_cast<size_t>(m) * blk_floats, symbuf + b * blk_floats, static_cast<uint32_t>(blk_floats * 4));
+                bulk_commit();
+                bulk_wait_read0();                         // the block may be refilled once its bytes have been read
+                mbar_arrive(&bar_empty[b]);
+            }
+            bulk_wait_all0();
         }
     } else {
         // ------------------------------------------------------------------ epilogue warps
@@ -939,7 +1134,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
             const int b = m & 1;
             mbar_wait(&bar_full[b], (m >> 1) & 1);
             const int n = cntbuf[b * 32 + lane];
-            const float* sy = symbuf + b * maxs * ROWF + lane * NCOMP;
+            const float* sy = symbuf + b * blk_rows * ROWF + lane * NCOMP;
             for (int s = e; s < n; s += NEPI) {
                 const float yr = sy[s * ROWF];
                 const float yi = (NCOMP == 2) ? sy[s * ROWF + 1] : 0.0f;
@@ -988,6 +1183,38 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
             port1_cnt[c] = p1cnt;
             n_soft_out[c] = n_soft;
         }
+    }
+}
+
+// External epilogue of symsync_kernel<.., EPI_EXT_4FSK_FM, ..>: phase_modulator_fc(pi/2) -> port 1, soft bits (imag, real)
+// -> soft ring.  One block per (chunk, 32-channel group); x = channel lane (coalesced reads of the hand-off block),
+// y strides over the symbols of the chunk.  Same arithmetic as the in-kernel EPI_4FSK_FM branch.
+__global__ void __launch_bounds__(256)
+symsync_ext_epilogue_kernel(SymSyncParams p, int C, const float* __restrict__ scratch, int chunk_stride, int maxs,
+                            const int* __restrict__ hdr_all,
+                            float2* __restrict__ port1, long long port1_stride, int port1_cap,
+                            unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride)
+{
+    const int g = blockIdx.y, m = blockIdx.x, lane = threadIdx.x, c = g * 32 + lane;
+    const int* hdr = hdr_all + g * 128;
+    if (m >= hdr[96] || c >= C) return;
+    const size_t blk_floats = static_cast<size_t>(maxs + 2) * 32;
+    const float* blk = scratch + (static_cast<size_t>(g) * chunk_stride + m) * blk_floats;
+    const int cnt = reinterpret_cast<const int*>(blk)[maxs * 32 + lane];
+    const int sbase = reinterpret_cast<const int*>(blk)[(maxs + 1) * 32 + lane];
+    const int p1cnt0 = hdr[lane];
+    const long long n_soft0 = (static_cast<long long>(hdr[64 + lane]) << 32) | static_cast<unsigned>(hdr[32 + lane]);
+    unsigned char* sr = soft_ring + static_cast<long long>(c) * soft_stride;
+    float2* p1 = port1 + static_cast<long long>(c) * port1_stride;
+    for (int k = threadIdx.y; k < cnt; k += blockDim.y) {
+        const float yr = blk[k * 32 + lane];
+        float sn, cs;
+        qrl_sincosf(p.pm_sens * yr, sn, cs);
+        const int idx = sbase + k;
+        if (p1cnt0 + idx < port1_cap) p1[p1cnt0 + idx] = make_float2(cs, sn);
+        const long long so = n_soft0 + 2LL * idx;
+        sr[so & soft_mask] = qrl_soft_u8(sn, p.soft_scale);          // interleave: imag first, then real
+        sr[(so + 1) & soft_mask] = qrl_soft_u8(cs, p.soft_scale);
     }
 }
 
