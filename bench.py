@@ -45,6 +45,8 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.reasons = index, False, [], set()
         self.max_mhz = None
+        self.armed = False                 # only samples taken while armed (the timed region) count
+        self.ready = threading.Event()     # NVML is initialised: the first sample can be taken at once
 
     def run(self):
         try:
@@ -58,7 +60,11 @@ class ClockSampler(threading.Thread):
                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
             }
+            self.ready.set()
             while not self.stop_flag:
+                if not self.armed:
+                    time.sleep(0.0005)
+                    continue
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -67,9 +73,10 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.001)
         except Exception as e:  # noqa: BLE001
             self.reasons.add("sampler_error:%s" % type(e).__name__)
+            self.ready.set()
 
     def result(self):
         s = sorted(self.samples)
@@ -186,15 +193,18 @@ def run_ours(args):
     launches0 = blk.launches
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.ready.wait(10.0)
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.armed = True
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
     e1.record(stream)
     torch.cuda.synchronize()
+    sampler.armed = False
     if dist:
         dist.barrier()
     sampler.stop_flag = True

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 using namespace qrl;
@@ -158,6 +159,7 @@ struct qrl_rx : HandleBase {
     SymSyncState* d_ss = nullptr;
     float* d_ss_scratch = nullptr; int* d_ss_hdr = nullptr; long long ss_chunk_cap = 0, ss_chunk_off = 0;   // external symbol-sync epilogue
     cudaStream_t s_epi = nullptr;                        // wide-partition stream of the external epilogue
+    int ss_ch = 256;                                     // rows per symbol-sync window (256 x 3 stages or 512 x 2)
     float2* d_port1 = nullptr; long port1_cap = 0; int* d_port1_cnt = nullptr;
     Ring r5;   // soft bits (u8)
     ViterbiState* d_vs = nullptr;
@@ -165,7 +167,7 @@ struct qrl_rx : HandleBase {
     long n1max = 0;
     // software pipeline inside one work() call: parallel stages on `stream`, loop stages on s_loop, FEC on s_fec
     static constexpr int kMaxSub = 16;
-    int nsub = 8;
+    int nsub = 12;
     cudaStream_t s_loop = nullptr, s_loop2 = nullptr, s_fec = nullptr;
     cudaEvent_t ev_start = nullptr, ev_a[kMaxSub] = { nullptr }, ev_b[kMaxSub] = { nullptr }, ev_c[kMaxSub] = { nullptr },
                 ev_loop_done = nullptr, ev_loop2_done = nullptr, ev_fec_done = nullptr;
@@ -601,8 +603,15 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = make_ring(h, &h->r4, sizeof(float), h->n1max + 600, true))) return fail(rc);
         if (flag && kind == QRL_DEMOD_4FSK) {
             // scratch of the external symbol-sync epilogue: [groups][chunks][maxs + 2][32] floats + a 128-int header per group
-            const int maxs = static_cast<int>((256 + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
-            h->ss_chunk_cap = h->n1max / (256 - 32) + 4 + 3 * qrl_rx::kMaxSub;
+            // window size: 512 rows x 2 stages when the replicated interpolator bank still fits next to it, else 256 x 3
+            {
+                const int maxs512 = static_cast<int>((512 + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
+                const size_t need512 = sizeof(float) * (2 * 512 * 32 + SYMSYNC_TAB_FLOATS + 2 * (maxs512 + 2) * 32) + sizeof(int) * 64 + 129 * 512;
+                h->ss_ch = need512 <= 220 * 1024 ? 512 : 256;
+            }
+            if (const char* e = getenv("QRL_SS_CH")) { const int v = atoi(e); if (v == 512 || v == 256) h->ss_ch = v; }
+            const int maxs = static_cast<int>((h->ss_ch + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
+            h->ss_chunk_cap = h->n1max / (h->ss_ch - 32) + 4 + 3 * qrl_rx::kMaxSub;
             const size_t groups = (h->C + 31) / 32;
             if ((rc = dev_alloc(h, &h->d_ss_scratch, groups * h->ss_chunk_cap * (maxs + 2) * 32))) return fail(rc);
             if ((rc = dev_alloc(h, &h->d_ss_hdr, groups * 128 * qrl_rx::kMaxSub))) return fail(rc);
@@ -837,7 +846,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
     if (h->s_par) CK(cudaStreamWaitEvent(h->s_par, h->ev_start, 0));
     cudaStream_t sp = h->par();
     int nsub = h->nsub;
-    if (T < 65536L * nsub) nsub = static_cast<int>(std::max<long>(1, T / 65536));
+    if (T < 32768L * nsub) nsub = static_cast<int>(std::max<long>(1, T / 32768));
     const long long k_call0 = h->n1;
     h->port0_n = 0;
     for (int i = 0; i < nsub; i++) {
@@ -850,8 +859,11 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         const long long Ti = t1 - t0;
         cudaEvent_t pe = nullptr;
         // ---- stage 1: decimating FIR, one launch per group of slices (outputs k with D k <= last absolute input index)
-        if (i % h->fir_group == 0) {
-            const long long tg1 = cut(std::min(i + h->fir_group, nsub));
+        // stage-1 launch schedule: slice 0 alone (the loop stage starts as early as possible), then fir_group slices
+        // per launch (bigger launches run closer to the HBM roofline)
+        const bool fir_here = (i == 0) || ((i - 1) % h->fir_group == 0);
+        if (fir_here) {
+            const long long tg1 = cut(i == 0 ? 1 : std::min(i + h->fir_group, nsub));
             const long long Tg = tg1 - t0;
             const float2* xg = x + t0;
             const long long Ng = h->n_in + Tg;
@@ -1064,7 +1076,8 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 pe = h->prof_begin(3, h->s_loop);
                 // real symbols: lean recurrence + external epilogue (symbols leave the SM by TMA bulk store; the phase
                 // modulator / soft-bit stores run on the wide partition behind it, same stream)
-                constexpr int CH = 256, NST = 3;
+                auto run_ext = [&](auto ch_tag, auto nst_tag) -> int {
+                constexpr int CH = decltype(ch_tag)::value, NST = decltype(nst_tag)::value;
                 const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
                 const size_t smem_base = sizeof(float) * (NST * CH * 32 + SYMSYNC_TAB_FLOATS + 2 * (maxs + 2) * 32) + sizeof(int) * 64;
                 const size_t smem_rep = smem_base + 129 * 512;          // + replicated (conflict-free) interpolator bank
@@ -1072,7 +1085,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 const size_t smem = rep ? smem_rep : smem_base;
                 auto kern = rep ? symsync_kernel<1, SL_RECT4, EPI_EXT_4FSK_FM, CH, NST, 1, LOOP_SYMSYNC, 2>
                                 : symsync_kernel<1, SL_RECT4, EPI_EXT_4FSK_FM, CH, NST, 1, LOOP_SYMSYNC, 1>;
-                static bool ss_attr[2] = { false, false };
+                static bool ss_attr[2] = { false, false };   // per (CH, NST) instantiation of this lambda
                 if (!ss_attr[rep]) {
                     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
                     ss_attr[rep] = true;
@@ -1100,6 +1113,11 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 h->launches++;
                 h->prof_end(pe);
                 CK(cudaEventRecord(h->ev_b[i], se));
+                return QRL_OK;
+                };
+                const int rc_ext = h->ss_ch == 512 ? run_ext(std::integral_constant<int, 512>{}, std::integral_constant<int, 2>{})
+                                                   : run_ext(std::integral_constant<int, 256>{}, std::integral_constant<int, 3>{});
+                if (rc_ext) return rc_ext;
                 ext_recorded = true;
             }
             if (!ext_recorded) CK(cudaEventRecord(h->ev_b[i], h->s_loop));
