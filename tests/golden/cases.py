@@ -1,0 +1,112 @@
+"""Case definitions shared by tests/golden/make_golden.py (which freezes the answers) and tests/test_golden.py
+(which checks the oracle and the CUDA path against the frozen answers).  Test infrastructure only."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+EMPHASIS_CASES = ((20000, 50e-6), (8000, 50e-6), (48000, 75e-6), (8000, 75e-6))
+
+
+def load_ref_emphasis():
+    so = os.path.join(ROOT, "oracle", "_ref", "libqrl_ref_emphasis.so")
+    return C.CDLL(so) if os.path.exists(so) else None
+
+
+def ref_deemph(R, fs, tau):
+    a = np.zeros(2); b = np.zeros(2)
+    R.ref_deemph_taps(C.c_int(fs), C.c_double(tau), a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+    return list(a) + list(b)
+
+
+def ref_preemph(R, fs, tau):
+    a = np.zeros(2); b = np.zeros(2)
+    R.ref_preemph_taps(C.c_int(fs), C.c_double(tau), C.c_double(-1.0), a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+    return list(a) + list(b)
+
+
+# design functions with the argument lists the reference uses (SURVEY 8a tap counts: 419, 55, 251, 837, 1045, 689, 23)
+DESIGN_CASES = {
+    "lp_1e6_10k_10k_bh_419": lambda O: O.low_pass(1, 1e6, 10000, 10000, O.WIN_BLACKMAN_HARRIS),
+    "lp_20k_3000_1500_bh_55": lambda O: O.low_pass(1, 20000, 3000, 1500, O.WIN_BLACKMAN_HARRIS),
+    "rrc_1.5_20k_2k_0.2_251": lambda O: O.rrc(1.5, 20000, 2000, 0.2, 251),
+    "lp_20k_2000_100_bh_837": lambda O: O.low_pass(1, 20000, 2000, 100, O.WIN_BLACKMAN_HARRIS),
+    "lp_20_1e6_3500_3500_hamming_689": lambda O: O.low_pass(20, 1e6, 3500, 3500, O.WIN_HAMMING),
+    "rrc_2_2_1_0.35_23": lambda O: O.rrc(2, 2, 1, 0.35, 23),
+    "lp2_1e6_250k_50k_60_bh_55": lambda O: O.low_pass_2(1, 1e6, 250000, 50000, 60, O.WIN_BLACKMAN_HARRIS),
+    "table_atan": lambda O: O.table("atan"),
+    "table_mmse": lambda O: O.table("mmse"),
+    "table_tanh": lambda O: O.table("tanh"),
+}
+
+
+def _sig_4fsk(fm):
+    return lambda O, sg: sg.gen_4fsk_channels(2, 1 << 18, seed0=9100 if fm else 9200, fm=fm)[0]
+
+
+def _sig_qpsk(O, sg):
+    return sg.gen_qpsk_channels(1, 1 << 17, seed0=9300)[0]
+
+
+def _sig_nbfm(O, sg):
+    return sg.gen_nbfm_channels(1, 1 << 18, seed0=9400)
+
+
+def _sig_digital(kind):
+    def f(O, sg):
+        rng = np.random.default_rng(9500 + (1 if kind == "bpsk" else 2))
+        T = 1 << 18
+        data, _ = sg.frames_4fsk(rng, 4)
+        if kind == "bpsk":
+            iq = O.Tx(O.MOD_BPSK, 250, 1000000, 1700, 2800, 0).work(data)
+        else:
+            iq = O.Tx(O.MOD_2FSK, 25, 1000000, 1700, 4000, 1).work(data)
+        x = sg.channel(iq, rng, fo_hz=60.0, phase=1.0, delay=100, snr_db=18.0, amp=0.1, total=T)
+        return x[None, :]
+    return f
+
+
+def _sig_ssb(O, sg):
+    rng = np.random.default_rng(9600)
+    T = 1 << 18
+    n = np.arange(T)
+    x = 0.3 * np.exp(2j * np.pi * 1200.0 * n / 1e6) + 0.2 * np.exp(2j * np.pi * 700.0 * n / 1e6)
+    x = x + (rng.standard_normal(T) + 1j * rng.standard_normal(T)) * 0.005
+    return x.astype(np.complex64)[None, :]
+
+
+# name -> oracle kind, factory args (sps, samp_rate, carrier, filter_width, flag), ports, product factory name + args
+RX_CASES = {
+    "4fsk_2k_fm": dict(okind=2, args=(5, 1000000, 1700, 3000, 1), nports=3, signal=_sig_4fsk(True),
+                       factory="make_gr_demod_4fsk", fargs=(5, 1000000, 1700, 3000, True)),
+    "4fsk_2k": dict(okind=2, args=(5, 1000000, 1700, 4000, 0), nports=3, signal=_sig_4fsk(False),
+                    factory="make_gr_demod_4fsk", fargs=(5, 1000000, 1700, 4000, False)),
+    "qpsk_250k": dict(okind=3, args=(2, 1000000, 1700, 160000, 0), nports=3, signal=_sig_qpsk,
+                      factory="make_gr_demod_qpsk", fargs=(2, 1000000, 1700, 160000)),
+    "nbfm_2500": dict(okind=1, args=(125, 1000000, 1700, 2500, 0), nports=2, signal=_sig_nbfm,
+                      factory="make_gr_demod_nbfm", fargs=(125, 1000000, 1700, 2500)),
+    "bpsk_2k": dict(okind=4, args=(250, 1000000, 1700, 2800, 0), nports=4, signal=_sig_digital("bpsk"),
+                    factory="make_gr_demod_bpsk", fargs=(250, 1000000, 1700, 2800)),
+    "2fsk_2k_fm": dict(okind=5, args=(25, 1000000, 1700, 4000, 1), nports=4, signal=_sig_digital("2fsk"),
+                       factory="make_gr_demod_2fsk", fargs=(25, 1000000, 1700, 4000, True)),
+    "ssb_usb": dict(okind=6, args=(125, 1000000, 1700, 2700, 0), nports=2, signal=_sig_ssb,
+                    factory="make_gr_demod_ssb", fargs=(125, 1000000, 1700, 2700, 0)),
+}
+
+
+def _bytes(seed, n):
+    return lambda: np.random.default_rng(seed).integers(0, 256, n, dtype=np.uint8)
+
+
+TX_CASES = {
+    "tx_4fsk_2k_fm": dict(okind=101, args=(25, 1000000, 1700, 3500, 1), data=_bytes(9700, 24),
+                          factory="make_gr_mod_4fsk", fargs=(25, 1000000, 1700, 3500, True)),
+    "tx_qpsk_250k": dict(okind=102, args=(4, 1000000, 1700, 160000, 0), data=_bytes(9701, 600),
+                         factory="make_gr_mod_qpsk", fargs=(4, 1000000, 1700, 160000)),
+    "tx_bpsk_2k": dict(okind=104, args=(250, 1000000, 1700, 2800, 0), data=_bytes(9702, 12),
+                       factory="make_gr_mod_bpsk", fargs=(250, 1000000, 1700, 2800)),
+    "tx_2fsk_2k_fm": dict(okind=105, args=(25, 1000000, 1700, 4000, 1), data=_bytes(9703, 12),
+                          factory="make_gr_mod_2fsk", fargs=(25, 1000000, 1700, 4000, True)),
+}
