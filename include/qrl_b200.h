@@ -121,6 +121,32 @@ int qrl_firdes_root_raised_cosine(double gain, double fs, double symrate, double
 int qrl_design_table(const char* name /* "atan","tanh","mmse","fxpt_sine" */, float* out, int cap);
 int qrl_design_deemph(int fs, double tau, double* a2, double* b2);
 
+/* ---- polyphase channelizer / synthesizer -------------------------------------------
+ * Replaces gr::filter::pfb_channelizer_ccf::make(M, taps, 1.0) fed by blocks::stream_to_streams(M)
+ * (/root/reference/src/gr/gr_demod_mmdvm_multi2.cpp:98-107) and gr::filter::pfb_synthesizer_ccf::make(M, taps, false)
+ * (/root/reference/src/gr/gr_mod_mmdvm_multi2.cpp:90-92).  Streaming: history and samples that do not fill a frame
+ * of M stay in the handle, results do not depend on chunking.  Channel c of the channelizer is centred on
+ * +c*fs/M (ports M/2.. are the negative frequencies, the order both reference wirings rely on,
+ * gr_demod_mmdvm_multi2.cpp:110-124).  The channelizer output [M][stride] gr_complex is exactly the device-resident
+ * input layout of qrl_rx_work. */
+enum { QRL_PFB_CHANNELIZER = 201, QRL_PFB_SYNTHESIZER = 202 };
+typedef struct qrl_pfb qrl_pfb;
+/* max_in: channelizer = wideband samples per call; synthesizer = columns (samples per channel) per call */
+int  qrl_pfb_create(int kind, int M, const float* taps, int ntaps, long max_in, int device, qrl_pfb** out);
+int  qrl_pfb_destroy(qrl_pfb*);
+int  qrl_pfb_set_stream(qrl_pfb*, void* cuda_stream);
+/* channelizer: in = n_in wideband gr_complex (in_stride ignored); *n_out = new samples per channel.
+ * synthesizer: in = [M][in_stride] gr_complex, n_in columns; *n_out = n_in*M wideband samples.
+ * in_on_device = 0: host memory (copied inside the call), 1: device pointer. Asynchronous on the handle's stream. */
+int  qrl_pfb_work(qrl_pfb*, const void* in, long n_in, long in_stride, int in_on_device, long* n_out);
+int  qrl_pfb_sync(qrl_pfb*);
+/* device view of the last call's output: channelizer [M][*stride] gr_complex (*items valid columns),
+ * synthesizer [*items] gr_complex; valid until the next qrl_pfb_work */
+int  qrl_pfb_out_device(qrl_pfb*, void** data, long* stride, long* items);
+/* copy the last call's output to host (channelizer: row c at host_dst + c*dst_stride items) and synchronise */
+int  qrl_pfb_read(qrl_pfb*, void* host_dst, long dst_stride);
+long qrl_pfb_launch_count(qrl_pfb*);
+
 /* ---- stand-alone kernels exposed for tests / micro-benchmarks ---- */
 /* batched decimating FIR (stage 1 alone): x [C][T] device, y [C][ceil(T/D)] device; zero history */
 int qrl_fir_decim_ccf_device(const float* taps, int ntaps, int D, const float* x_dev, long T, long x_stride,

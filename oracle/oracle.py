@@ -82,6 +82,15 @@ def lib():
         L.qo_descramble.argtypes = [vp, C.c_long, vp]
         L.qo_find_frames.restype = C.c_long
         L.qo_find_frames.argtypes = [vp, C.c_long, C.c_uint32, C.c_int, C.c_int, vp, C.c_long]
+        L.qo_pfb_channelizer_create.restype = vp
+        L.qo_pfb_channelizer_create.argtypes = [C.c_int, vp, C.c_int]
+        L.qo_pfb_synthesizer_create.restype = vp
+        L.qo_pfb_synthesizer_create.argtypes = [C.c_int, vp, C.c_int]
+        L.qo_pfb_destroy.argtypes = [vp]
+        L.qo_pfb_channelizer_work.restype = C.c_long
+        L.qo_pfb_channelizer_work.argtypes = [vp, vp, C.c_long, vp, C.c_long, C.c_long]
+        L.qo_pfb_synthesizer_work.restype = C.c_long
+        L.qo_pfb_synthesizer_work.argtypes = [vp, vp, C.c_long, C.c_long, vp]
         _LIB = L
     return _LIB
 
@@ -272,3 +281,44 @@ class Tx:
         buf = C.string_at(lib().qo_tx_out_data(self.h), n * 8)
         lib().qo_tx_out_clear(self.h)
         return np.frombuffer(buf, np.complex64).copy()
+
+
+class PfbChannelizer:
+    """pfb_channelizer_ccf(M, taps, 1.0) behind stream_to_streams(M) (gr_demod_mmdvm_multi2.cpp:98-107), streaming."""
+
+    def __init__(self, M, taps):
+        taps = np.ascontiguousarray(taps, np.float32)
+        self.M = M
+        self._h = lib().qo_pfb_channelizer_create(M, _p(taps), len(taps))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().qo_pfb_destroy(self._h); self._h = None
+
+    def work(self, x):
+        """x: complex64 [n] -> complex64 [M, n_out] (n_out = complete frames of M available)."""
+        x = np.ascontiguousarray(x, np.complex64)
+        cap = len(x) // self.M + 2
+        out = np.zeros((self.M, cap), np.complex64)
+        n = lib().qo_pfb_channelizer_work(self._h, _p(x), len(x), _p(out), cap, 0)
+        return out[:, :n].copy()
+
+
+class PfbSynthesizer:
+    """pfb_synthesizer_ccf(M, taps, false) (gr_mod_mmdvm_multi2.cpp:90-92), streaming."""
+
+    def __init__(self, M, taps):
+        taps = np.ascontiguousarray(taps, np.float32)
+        self.M = M
+        self._h = lib().qo_pfb_synthesizer_create(M, _p(taps), len(taps))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().qo_pfb_destroy(self._h); self._h = None
+
+    def work(self, x):
+        """x: complex64 [M, n] -> complex64 [n * M]."""
+        x = np.ascontiguousarray(x, np.complex64)
+        out = np.zeros(x.shape[1] * self.M, np.complex64)
+        lib().qo_pfb_synthesizer_work(self._h, _p(x), x.shape[1], x.shape[1], _p(out))
+        return out

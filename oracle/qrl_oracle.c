@@ -1780,3 +1780,114 @@ long qo_find_frames(const uint8_t* bits, long nbits, uint32_t sync, int sync_bit
     }
     return found;
 }
+
+/* ------------------------------------------------------------------ polyphase channelizer / synthesizer
+ * gr::filter::pfb_channelizer_ccf(M, taps, 1.0) fed by blocks::stream_to_streams(M)
+ *   (/root/reference/src/gr/gr_demod_mmdvm_multi2.cpp:98-107) and gr::filter::pfb_synthesizer_ccf(M, taps, false)
+ *   (/root/reference/src/gr/gr_mod_mmdvm_multi2.cpp:90-92), restated from GNU Radio 3.10 (gr-filter
+ *   pfb_channelizer_ccf_impl::general_work, polyphase_filterbank::set_taps, pfb_synthesizer_ccf_impl::work; Appendix A):
+ *     branch filter k holds taps[k + t*M] (prototype zero-padded to a multiple of M);
+ *     channelizer: stream j = x[m*M + j]; u_k[m] = sum_t taps[k + tM] * x[(m - t)M + (M-1-k)];
+ *                  out_c[m] = sum_k u_k[m] * exp(+j 2 pi k c / M)        (FFTW backward, unnormalised)
+ *     synthesizer: v_i[n] = sum_c in_c[n] * exp(+j 2 pi i c / M);  y[nM + i] = sum_t taps[i + tM] * v_i[n - t]
+ *                  (polyphase interpolator: channel c leaves at +c fs/M with zero phase offset, so that
+ *                  channelizer(synthesizer(z)) returns channel c on port c -- the convention both reference wirings
+ *                  rely on, gr_mod_mmdvm_multi2.cpp:107-121 / gr_demod_mmdvm_multi2.cpp:110-124; upstream's internal
+ *                  bin/commutator ordering cannot be re-read offline and is not claimed)
+ *   Arithmetic order adopted by this oracle (FFTW's butterfly order is not reproducible offline: parity unpinned, the
+ *   float tolerance of 1e-5 RMS applies): branch FIRs accumulate oldest sample first with fmaf; the M-point DFT is the
+ *   direct sum over k ascending with twiddles (float)cos / (float)sin of the double angle 2 pi ((k c) mod M) / M and
+ *   re = fmaf(ur, wr, re); re = fmaf(-ui, wi, re); im = fmaf(ur, wi, im); im = fmaf(ui, wr, im). */
+struct qo_pfb {
+    int M, tpf, synth;
+    float* bt;              /* [M][tpf] branch taps */
+    float* w;               /* [M][2] twiddles */
+    qvec in;                /* channelizer: pending input samples incl. (tpf-1)*M history; synthesizer: per-branch v history */
+    float* vh;              /* synthesizer: [M][tpf-1][2] history of v_i, oldest first */
+};
+typedef struct qo_pfb qo_pfb;
+
+static qo_pfb* pfb_create(int M, const float* taps, int ntaps, int synth)
+{
+    qo_pfb* p = (qo_pfb*)calloc(1, sizeof(qo_pfb));
+    p->M = M; p->synth = synth;
+    p->tpf = (ntaps + M - 1) / M;
+    p->bt = (float*)calloc((size_t)M * p->tpf, sizeof(float));
+    for (int j = 0; j < ntaps; j++) p->bt[(size_t)(j % M) * p->tpf + j / M] = taps[j];
+    p->w = (float*)calloc((size_t)M * 2, sizeof(float));
+    for (int q = 0; q < M; q++) {
+        const double a = 2.0 * M_PI * (double)q / (double)M;
+        p->w[2 * q] = (float)cos(a); p->w[2 * q + 1] = (float)sin(a);
+    }
+    qv_init(&p->in, 8);
+    if (!synth) qv_push_zero(&p->in, (size_t)(p->tpf - 1) * M);
+    else p->vh = (float*)calloc((size_t)M * (p->tpf > 1 ? p->tpf - 1 : 1) * 2, sizeof(float));
+    return p;
+}
+qo_pfb* qo_pfb_channelizer_create(int M, const float* taps, int ntaps) { return pfb_create(M, taps, ntaps, 0); }
+qo_pfb* qo_pfb_synthesizer_create(int M, const float* taps, int ntaps) { return pfb_create(M, taps, ntaps, 1); }
+void qo_pfb_destroy(qo_pfb* p) { if (!p) return; free(p->bt); free(p->w); free(p->vh); qv_free(&p->in); free(p); }
+
+static void pfb_dft(const qo_pfb* p, const float* u /* [M][2] */, int c, float* re_out, float* im_out)
+{
+    float re = 0.0f, im = 0.0f;
+    for (int k = 0; k < p->M; k++) {
+        const int q = (int)(((long)k * c) % p->M);
+        const float wr = p->w[2 * q], wi = p->w[2 * q + 1], ur = u[2 * k], ui = u[2 * k + 1];
+        re = fmaf(ur, wr, re); re = fmaf(-ui, wi, re);
+        im = fmaf(ur, wi, im); im = fmaf(ui, wr, im);
+    }
+    *re_out = re; *im_out = im;
+}
+
+/* x: n complex samples of the wideband stream; out: [M][cap] complex, appended from column `have`; returns the number
+ * of new columns (output samples per channel).  Samples that do not fill a frame of M wait for the next call. */
+long qo_pfb_channelizer_work(qo_pfb* p, const float* x, long n, float* out, long cap, long have)
+{
+    const int M = p->M, tpf = p->tpf;
+    qv_push(&p->in, x, (size_t)n);
+    const float* s = (const float*)p->in.d;                 /* s[0] = oldest history sample */
+    const long hist = (long)(tpf - 1) * M;
+    const long frames = ((long)p->in.n - hist) / M;
+    float* u = (float*)malloc(sizeof(float) * 2 * M);
+    for (long m = 0; m < frames && have + m < cap; m++) {
+        for (int k = 0; k < M; k++) {
+            float re = 0.0f, im = 0.0f;
+            for (int t = tpf - 1; t >= 0; t--) {            /* oldest sample first */
+                const long idx = hist + (m - t) * M + (M - 1 - k);
+                const float h = p->bt[(size_t)k * tpf + t];
+                re = fmaf(h, s[2 * idx], re); im = fmaf(h, s[2 * idx + 1], im);
+            }
+            u[2 * k] = re; u[2 * k + 1] = im;
+        }
+        for (int c = 0; c < M; c++) pfb_dft(p, u, c, &out[2 * ((size_t)c * cap + have + m)], &out[2 * ((size_t)c * cap + have + m) + 1]);
+    }
+    free(u);
+    qv_drop(&p->in, (size_t)frames * M);
+    return frames;
+}
+
+/* in: [M][stride] complex (n columns used); out: n*M complex samples of the wideband stream */
+long qo_pfb_synthesizer_work(qo_pfb* p, const float* in, long n, long stride, float* out)
+{
+    const int M = p->M, tpf = p->tpf, H = tpf - 1;
+    float* xin = (float*)malloc(sizeof(float) * 2 * M);
+    for (long t0 = 0; t0 < n; t0++) {
+        for (int c = 0; c < M; c++) { xin[2 * c] = in[2 * ((size_t)c * stride + t0)]; xin[2 * c + 1] = in[2 * ((size_t)c * stride + t0) + 1]; }
+        for (int i = 0; i < M; i++) {
+            float vr, vi;
+            pfb_dft(p, xin, i, &vr, &vi);
+            float* hist = p->vh + (size_t)i * (H > 0 ? H : 1) * 2;        /* hist[0] = v_i[n - H] ... hist[H-1] = v_i[n - 1] */
+            float re = 0.0f, im = 0.0f;
+            for (int t = tpf - 1; t >= 1; t--) {            /* oldest first */
+                const float h = p->bt[(size_t)i * tpf + t];
+                re = fmaf(h, hist[2 * (H - t)], re); im = fmaf(h, hist[2 * (H - t) + 1], im);
+            }
+            { const float h = p->bt[(size_t)i * tpf]; re = fmaf(h, vr, re); im = fmaf(h, vi, im); }
+            out[2 * ((size_t)t0 * M + i)] = re; out[2 * ((size_t)t0 * M + i) + 1] = im;
+            if (H > 0) { memmove(hist, hist + 2, sizeof(float) * 2 * (H - 1)); hist[2 * (H - 1)] = vr; hist[2 * (H - 1) + 1] = vi; }
+        }
+    }
+    free(xin);
+    return n * M;
+}

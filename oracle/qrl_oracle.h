@@ -92,6 +92,17 @@ long   qo_tx_out_items(qo_tx*);
 const float* qo_tx_out_data(qo_tx*);
 void   qo_tx_out_clear(qo_tx*);
 
+/* ---- polyphase channelizer / synthesizer (pfb_channelizer_ccf(M, taps, 1.0) behind stream_to_streams(M);
+ *      pfb_synthesizer_ccf(M, taps, false)); streaming state inside the handle ---- */
+typedef struct qo_pfb qo_pfb;
+qo_pfb* qo_pfb_channelizer_create(int M, const float* taps, int ntaps);
+qo_pfb* qo_pfb_synthesizer_create(int M, const float* taps, int ntaps);
+void    qo_pfb_destroy(qo_pfb*);
+/* x: n complex samples; out: [M][cap] complex, new columns written from column `have`; returns new columns */
+long    qo_pfb_channelizer_work(qo_pfb*, const float* x, long n, float* out, long cap, long have);
+/* in: [M][stride] complex, n columns; out: n*M complex samples; returns n*M */
+long    qo_pfb_synthesizer_work(qo_pfb*, const float* in, long n, long stride, float* out);
+
 /* ---- host-side framing logic (gr_modem.cpp / gr_deframer_bb.cpp restatement) ---- */
 /* returns number of frames found; frames written back-to-back (frame_len bytes each) */
 long qo_find_frames(const uint8_t* bits, long nbits, uint32_t sync, int sync_bits, int frame_len_bytes,

@@ -354,6 +354,9 @@ int make_ring(qrl_rx* h, Ring* r, size_t isz, long long min_items, bool interlea
 }  // namespace
 
 // =====================================================================================================
+// last-error hook for the other translation units of the library (qrl_pfb.cu)
+void qrl_internal_set_err(const std::string& s) { g_err = s; }
+
 extern "C" {
 
 int qrl_device_count(void)

@@ -58,6 +58,14 @@ SYMBOLS = {
     "qrl_design_table": (_i, [C.c_char_p, _vp, _i]),
     "qrl_design_deemph": (_i, [_i, _d, _vp, _vp]),
     "qrl_fir_decim_ccf_device": (_i, [_vp, _i, _i, _vp, _l, _l, _vp, _l, _i, _vp]),
+    "qrl_pfb_create": (_i, [_i, _i, _vp, _i, _l, _i, C.POINTER(_vp)]),
+    "qrl_pfb_destroy": (_i, [_vp]),
+    "qrl_pfb_set_stream": (_i, [_vp, _vp]),
+    "qrl_pfb_work": (_i, [_vp, _vp, _l, _l, _i, C.POINTER(_l)]),
+    "qrl_pfb_sync": (_i, [_vp]),
+    "qrl_pfb_out_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_l), C.POINTER(_l)]),
+    "qrl_pfb_read": (_i, [_vp, _vp, _l]),
+    "qrl_pfb_launch_count": (_l, [_vp]),
 }
 
 

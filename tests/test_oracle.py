@@ -183,3 +183,46 @@ def test_nbfm_tone(oracle):
     f = np.fft.rfftfreq(len(seg), 1 / 8000.0)
     assert abs(f[np.argmax(spec)] - 1000.0) < 10.0
     assert 0.2 < np.std(seg) < 3.0
+
+
+def test_pfb_channelizer_and_synthesizer_against_float64(oracle):
+    """the oracle's polyphase channelizer / synthesizer against an independent float64 statement
+    (branch convolution with scipy-free numpy + np.fft), chunk invariance, and the loop-back convention."""
+    O = oracle
+    M = 10
+    taps = O.low_pass_2(1, 250000, 5000, 2000, 60, O.WIN_BLACKMAN_HARRIS)
+    assert len(taps) == 341                                   # the reference's prototype (gr_demod_mmdvm_multi2.cpp:56)
+    rng = np.random.default_rng(5)
+    x = ((rng.standard_normal(4003) + 1j * rng.standard_normal(4003)) * 0.3).astype(np.complex64)
+    y = O.PfbChannelizer(M, taps).work(x)
+    tpf = (len(taps) + M - 1) // M
+    hp = np.zeros(tpf * M); hp[:len(taps)] = taps
+    xs = np.concatenate([np.zeros(tpf * M), x.astype(np.complex128)])
+    frames = len(x) // M
+    u = np.zeros((frames, M), np.complex128)
+    for k in range(M):
+        s = xs[tpf * M + (M - 1 - k) - (tpf - 1) * M:][::M]   # stream M-1-k with tpf-1 samples of history in front
+        u[:, k] = np.convolve(s, hp[k::M])[tpf - 1:tpf - 1 + frames]
+    ref = (np.fft.ifft(u, axis=1) * M).T                      # sum_k u_k exp(+j 2 pi k c / M)
+    assert y.shape == ref.shape
+    assert np.max(np.abs(y - ref)) < 2e-6
+    parts = O.PfbChannelizer(M, taps)
+    y2 = np.concatenate([parts.work(x[a:b]) for a, b in ((0, 7), (7, 1234), (1234, 1235), (1235, len(x)))], axis=1)
+    assert np.array_equal(y, y2)
+    # synthesizer: float64 statement of y[nM + i] = sum_t taps[i + tM] v_i[n - t], v = M * ifft(in)
+    st = O.low_pass_2(10, 250000, 5000, 2000, 60, O.WIN_BLACKMAN_HARRIS)
+    z = ((rng.standard_normal((M, 300)) + 1j * rng.standard_normal((M, 300))) * 0.3).astype(np.complex64)
+    w = O.PfbSynthesizer(M, st).work(z)
+    sp = np.zeros(tpf * M); sp[:len(st)] = st
+    v = np.fft.ifft(z.astype(np.complex128), axis=0) * M
+    refw = np.zeros(300 * M, np.complex128)
+    for i in range(M):
+        refw[i::M] = np.convolve(v[i], sp[i::M])[:300]
+    assert np.max(np.abs(w - refw)) < 2e-5
+    s2 = O.PfbSynthesizer(M, st)
+    assert np.array_equal(w, np.concatenate([s2.work(z[:, :17]), s2.work(z[:, 17:])]))
+    # loop-back convention: a channel fed to synthesizer port c comes back on channelizer port c
+    zz = np.zeros((M, 800), np.complex64); zz[3] = 1.0; zz[9] = 0.5
+    back = O.PfbChannelizer(M, taps).work(O.PfbSynthesizer(M, st).work(zz))
+    p = np.abs(back[:, -1])
+    assert abs(p[3] - 1.0) < 0.02 and abs(p[9] - 0.5) < 0.02 and np.all(np.delete(p, [3, 9]) < 0.02)
