@@ -104,23 +104,24 @@ pfb_chan_kernel(const float* __restrict__ bt /*[M][TPF]*/, const float* __restri
         for (int r = 0; r < R; r++) ub[k * TMP + q * R + r] = make_float2(ar[r], ai[r]);
     }
     __syncthreads();
-    // ---- stage B
+    // ---- stage B: warp w owns channel c = w, w + nwarps, ...: its M twiddles stay in registers
     {
         const int warp = tid >> 5, lane = tid & 31, nwarps = (M * G) >> 5;
-        constexpr int CHUNKS = (TM + 31) / 32;
-        for (int task = warp; task < M * CHUNKS; task += nwarps) {
-            const int c = task / CHUNKS, m = (task % CHUNKS) * 32 + lane;
-            if (m < TM && m0 + m < frames) {
+        for (int c = warp; c < M; c += nwarps) {
+            float wr[M], wi[M];
+#pragma unroll
+            for (int k = 0; k < M; k++) { const int qd = (k * c) % M; wr[k] = w[2 * qd]; wi[k] = w[2 * qd + 1]; }
+            float2* orow = out + c * out_stride + m0;
+            for (int m = lane; m < TM; m += 32) {
+                if (m0 + m >= frames) break;
                 float re = 0.0f, im = 0.0f;
 #pragma unroll
                 for (int k = 0; k < M; k++) {
-                    const int qd = (k * c) % M;
-                    const float wr = w[2 * qd], wi = w[2 * qd + 1];
                     const float2 u = ub[k * TMP + m];
-                    re = fmaf(u.x, wr, re); re = fmaf(-u.y, wi, re);
-                    im = fmaf(u.x, wi, im); im = fmaf(u.y, wr, im);
+                    re = fmaf(u.x, wr[k], re); re = fmaf(-u.y, wi[k], re);
+                    im = fmaf(u.x, wi[k], im); im = fmaf(u.y, wr[k], im);
                 }
-                out[c * out_stride + m0 + m] = make_float2(re, im);
+                orow[m] = make_float2(re, im);
             }
         }
     }
@@ -199,18 +200,23 @@ pfb_synth_kernel(const float* __restrict__ bt, const float* __restrict__ w,
         xin[i] = n < 0 ? hist[c * (TPF - 1) + (TPF - 1) + n] : (n < n_cols ? in[c * in_stride + n] : make_float2(0.0f, 0.0f));
     }
     __syncthreads();
-    for (int i = tid; i < M * COLS; i += M * G) {
-        const int br = i / COLS, col = i % COLS;
-        float re = 0.0f, im = 0.0f;
+    {
+        const int warp = tid >> 5, lane = tid & 31, nwarps = (M * G) >> 5;
+        for (int br = warp; br < M; br += nwarps) {              // warp owns branch br: twiddles in registers
+            float wr[M], wi[M];
 #pragma unroll
-        for (int c = 0; c < M; c++) {
-            const int qd = (br * c) % M;
-            const float wr = w[2 * qd], wi = w[2 * qd + 1];
-            const float2 u = xin[c * COLS + col];
-            re = fmaf(u.x, wr, re); re = fmaf(-u.y, wi, re);
-            im = fmaf(u.x, wi, im); im = fmaf(u.y, wr, im);
+            for (int c = 0; c < M; c++) { const int qd = (br * c) % M; wr[c] = w[2 * qd]; wi[c] = w[2 * qd + 1]; }
+            for (int col = lane; col < COLS; col += 32) {
+                float re = 0.0f, im = 0.0f;
+#pragma unroll
+                for (int c = 0; c < M; c++) {
+                    const float2 u = xin[c * COLS + col];
+                    re = fmaf(u.x, wr[c], re); re = fmaf(-u.y, wi[c], re);
+                    im = fmaf(u.x, wi[c], im); im = fmaf(u.y, wr[c], im);
+                }
+                vb[br * VP + col] = make_float2(re, im);
+            }
         }
-        vb[br * VP + col] = make_float2(re, im);
     }
     __syncthreads();
     {
