@@ -147,6 +147,31 @@ int  qrl_pfb_out_device(qrl_pfb*, void** data, long* stride, long* items);
 int  qrl_pfb_read(qrl_pfb*, void* host_dst, long dst_stride);
 long qrl_pfb_launch_count(qrl_pfb*);
 
+/* ---- layer-1 deframer on the device -------------------------------------------------
+ * Replaces gr_modem::synchronize / findSync / packBytes (/root/reference/src/gr_modem.cpp:1119-1282, 980-994) for a
+ * batch of channels; sync words /root/reference/src/layer1framing.h:8-24.  sync_class: 1 = "1K" modes (0xB5),
+ * 2 = narrow modes (0xED89 voice + 24-bit text / proto / video / callsign / end), 3 = wide modes QPSK250K /
+ * QPSKVideo / 4FSK100K (IP / video / end).  bit_buf_len / rx_frame_length as gr_modem::toggleRxMode sets them
+ * (gr_modem.cpp:203-322), e.g. 64 / 7 for 4FSK-2k, 1517*8 / 1516 for QPSK-250k.  Input: one decoded bit per byte,
+ * [n_channels][stride] with a per-channel count -- exactly qrl_rx_port_device(handle, 2, ...).  Output: per channel
+ * up to max_frames records of qrl_deframer_record_bytes() bytes { uint32 frame_type (the sync word), uint32 nbytes,
+ * payload }, the arguments of gr_modem::processReceivedData.  State (partial frames, shift register, _modem_sync)
+ * carries across calls. */
+typedef struct qrl_deframer qrl_deframer;
+int  qrl_deframer_create(int sync_class, int bit_buf_len, int rx_frame_length, int n_channels, long max_bits, int max_frames,
+                         int device, qrl_deframer** out);
+int  qrl_deframer_destroy(qrl_deframer*);
+int  qrl_deframer_set_stream(qrl_deframer*, void* cuda_stream);
+/* bits [n_channels][stride], counts [n_channels]; on_device = 1: both are device pointers (e.g. from qrl_rx_port_device) */
+int  qrl_deframer_work(qrl_deframer*, const unsigned char* bits, const int* counts, long stride, int on_device);
+int  qrl_deframer_record_bytes(qrl_deframer*);
+/* records_host [n_channels][max_frames][record_bytes] (may be NULL), frame_counts_host [n_channels],
+ * modem_sync_host [n_channels] (may be NULL); synchronises */
+int  qrl_deframer_read(qrl_deframer*, unsigned char* records_host, int* frame_counts_host, int* modem_sync_host);
+int  qrl_deframer_out_device(qrl_deframer*, void** records, int** frame_counts);
+int  qrl_deframer_sync(qrl_deframer*);
+long qrl_deframer_launch_count(qrl_deframer*);
+
 /* ---- stand-alone kernels exposed for tests / micro-benchmarks ---- */
 /* batched decimating FIR (stage 1 alone): x [C][T] device, y [C][ceil(T/D)] device; zero history */
 int qrl_fir_decim_ccf_device(const float* taps, int ntaps, int D, const float* x_dev, long T, long x_stride,

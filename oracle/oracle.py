@@ -82,6 +82,12 @@ def lib():
         L.qo_descramble.argtypes = [vp, C.c_long, vp]
         L.qo_find_frames.restype = C.c_long
         L.qo_find_frames.argtypes = [vp, C.c_long, C.c_uint32, C.c_int, C.c_int, vp, C.c_long]
+        L.qo_deframer_create.restype = vp
+        L.qo_deframer_create.argtypes = [C.c_int] * 3
+        L.qo_deframer_destroy.argtypes = [vp]
+        L.qo_deframer_work.restype = C.c_long
+        L.qo_deframer_work.argtypes = [vp, vp, C.c_long, vp, C.c_int, C.c_long]
+        L.qo_deframer_modem_sync.argtypes = [vp]
         L.qo_pfb_channelizer_create.restype = vp
         L.qo_pfb_channelizer_create.argtypes = [C.c_int, vp, C.c_int]
         L.qo_pfb_synthesizer_create.restype = vp
@@ -322,3 +328,31 @@ class PfbSynthesizer:
         out = np.zeros(x.shape[1] * self.M, np.complex64)
         lib().qo_pfb_synthesizer_work(self._h, _p(x), x.shape[1], x.shape[1], _p(out))
         return out
+
+
+class Deframer:
+    """gr_modem::synchronize / findSync / packBytes (gr_modem.cpp:1119-1282), one channel, streaming.
+    work(bits) -> list of (frame_type, payload bytes)."""
+
+    def __init__(self, sync_class, bit_buf_len, rx_frame_length):
+        self.rec_bytes = 8 + (bit_buf_len + 7) // 8 + 8
+        self._h = lib().qo_deframer_create(sync_class, bit_buf_len, rx_frame_length)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().qo_deframer_destroy(self._h); self._h = None
+
+    def work(self, bits):
+        bits = np.ascontiguousarray(bits, np.uint8)
+        cap = len(bits) // 8 + 2
+        rec = np.zeros((cap, self.rec_bytes), np.uint8)
+        n = lib().qo_deframer_work(self._h, _p(bits), len(bits), _p(rec), self.rec_bytes, cap)
+        out = []
+        for r in rec[:n]:
+            ty, nb = int(r[:4].view(np.uint32)[0]), int(r[4:8].view(np.uint32)[0])
+            out.append((ty, r[8:8 + nb].tobytes()))
+        return out
+
+    @property
+    def modem_sync(self):
+        return lib().qo_deframer_modem_sync(self._h)

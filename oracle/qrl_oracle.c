@@ -1891,3 +1891,90 @@ long qo_pfb_synthesizer_work(qo_pfb* p, const float* in, long n, long stride, fl
     free(xin);
     return n * M;
 }
+
+/* ------------------------------------------------------------------ layer-1 deframer
+ * gr_modem::synchronize + findSync + packBytes (/root/reference/src/gr_modem.cpp:1119-1282, 980-994) restated bit for
+ * bit: a shift register searches the sync words of layer1framing.h:8-24; once one is found the next bit_len bits are
+ * collected, packed MSB first and handed on with the frame type; then the shift register is cleared.
+ * sync_class selects the findSync branch: 1 = "1K" modes (8-bit 0xB5 only; gr_modem.cpp:1208-1221),
+ * 2 = narrow modes (16-bit voice 0xED89, 24-bit text / proto / video / callsign / end; :1222-1257),
+ * 3 = wide modes QPSK250K / QPSKVideo / 4FSK100K (24-bit IP / video / end; :1258-1274).
+ * Lengths follow synchronize(): for classes 2, 3 a voice frame takes bit_buf_len bits into rx_frame_length + 1 bytes,
+ * any other frame bit_buf_len - 8 bits into rx_frame_length bytes; class 1 always bit_buf_len bits (:1146-1167). */
+enum { QO_FT_NONE = 0, QO_FT_VOICE = 0xED89, QO_FT_VOICE1 = 0xB5, QO_FT_TEXT = 0x89EDAA, QO_FT_IP = 0xDE98AA, QO_FT_VIDEO = 0x98DEAA,
+       QO_FT_CALLSIGN = 0x8CC8DD, QO_FT_PROTO = 0xED77AA, QO_FT_END = 0x4C8A2B };
+struct qo_deframer {
+    int sync_class, bit_buf_len, rx_frame_length;
+    uint64_t shift_reg; int sync_found; uint32_t cur_type; int bit_idx; int modem_sync;
+    uint8_t* bit_buf;
+};
+typedef struct qo_deframer qo_deframer;
+
+qo_deframer* qo_deframer_create(int sync_class, int bit_buf_len, int rx_frame_length)
+{
+    qo_deframer* d = (qo_deframer*)calloc(1, sizeof(qo_deframer));
+    d->sync_class = sync_class; d->bit_buf_len = bit_buf_len; d->rx_frame_length = rx_frame_length;
+    d->bit_buf = (uint8_t*)calloc((size_t)bit_buf_len + 8, 1);
+    return d;
+}
+void qo_deframer_destroy(qo_deframer* d) { if (d) { free(d->bit_buf); free(d); } }
+int qo_deframer_modem_sync(const qo_deframer* d) { return d->modem_sync; }
+
+static uint32_t deframer_find_sync(qo_deframer* d, unsigned bit)
+{
+    d->shift_reg = (d->shift_reg << 1) | (bit & 1u);
+    uint64_t t;
+    if (d->sync_class == 1) {
+        t = d->shift_reg & 0xFF;
+        if (t == QO_FT_VOICE1) { d->sync_found = 1; return QO_FT_VOICE1; }
+        return QO_FT_NONE;
+    }
+    if (d->sync_class == 2) {
+        t = d->shift_reg & 0xFFFF;
+        if (t == QO_FT_VOICE) { d->sync_found = 1; return QO_FT_VOICE; }
+        t = d->shift_reg & 0xFFFFFF;
+        if (t == QO_FT_TEXT || t == QO_FT_PROTO || t == QO_FT_VIDEO || t == QO_FT_CALLSIGN || t == QO_FT_END) { d->sync_found = 1; return (uint32_t)t; }
+        return QO_FT_NONE;
+    }
+    t = d->shift_reg & 0xFFFFFF;
+    if (t == QO_FT_IP || t == QO_FT_VIDEO || t == QO_FT_END) { d->sync_found = 1; return (uint32_t)t; }
+    return QO_FT_NONE;
+}
+
+/* bits: one bit per byte.  records: max_frames records of rec_bytes each = { u32 type, u32 nbytes, payload... };
+ * returns the number of frames completed by this call (state carries over). */
+long qo_deframer_work(qo_deframer* d, const uint8_t* bits, long n, uint8_t* records, int rec_bytes, long max_frames)
+{
+    long found = 0;
+    for (long i = 0; i < n; i++) {
+        if (!d->sync_found) {
+            d->cur_type = deframer_find_sync(d, bits[i]);
+            if (d->sync_found) { d->bit_idx = 0; if (d->modem_sync < 32) d->modem_sync += 8; continue; }
+            else if (d->modem_sync > 0) d->modem_sync -= 1;
+        }
+        if (d->sync_found) {
+            d->bit_buf[d->bit_idx++] = bits[i] & 1;
+            int frame_length = d->rx_frame_length, bit_len = d->bit_buf_len;
+            if (d->sync_class != 1) {
+                if (d->cur_type == QO_FT_VOICE) frame_length++;     /* reserved byte */
+                else bit_len = d->bit_buf_len - 8;
+            }
+            if (d->bit_idx >= bit_len) {
+                if (found < max_frames) {
+                    uint8_t* r = records + (size_t)found * rec_bytes;
+                    memset(r, 0, (size_t)rec_bytes);
+                    const uint32_t ty = d->cur_type, nb = (uint32_t)frame_length;
+                    memcpy(r, &ty, 4); memcpy(r + 4, &nb, 4);
+                    for (int b = 0; b * 8 < bit_len && 8 + b < rec_bytes; b++) {
+                        int t = 0;
+                        for (int k = 0; k < 8; k++) t = (t << 1) | (d->bit_buf[b * 8 + k] & 1);
+                        r[8 + b] = (uint8_t)t;
+                    }
+                    found++;
+                }
+                d->sync_found = 0; d->shift_reg = 0; d->bit_idx = 0;
+            }
+        }
+    }
+    return found;
+}

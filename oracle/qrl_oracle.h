@@ -108,6 +108,15 @@ long    qo_pfb_synthesizer_work(qo_pfb*, const float* in, long n, long stride, f
 long qo_find_frames(const uint8_t* bits, long nbits, uint32_t sync, int sync_bits, int frame_len_bytes,
                     uint8_t* frames, long max_frames);
 
+/* ---- layer-1 deframer: gr_modem::synchronize / findSync / packBytes restated (gr_modem.cpp:1119-1282).
+ *      sync_class 1 = "1K" modes (0xB5), 2 = narrow modes (0xED89 + 24-bit words), 3 = wide modes (IP / video / end).
+ *      records: { u32 type, u32 nbytes, payload } of rec_bytes each; returns frames completed by this call ---- */
+typedef struct qo_deframer qo_deframer;
+qo_deframer* qo_deframer_create(int sync_class, int bit_buf_len, int rx_frame_length);
+void  qo_deframer_destroy(qo_deframer*);
+long  qo_deframer_work(qo_deframer*, const uint8_t* bits, long n, uint8_t* records, int rec_bytes, long max_frames);
+int   qo_deframer_modem_sync(const qo_deframer*);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,275 @@
+// qrl_deframer.cu -- layer-1 deframer on the device, part of libqrl_b200.so.
+//
+// Replaces the bit-serial CPU loop gr_modem::synchronize + findSync + packBytes
+// (/root/reference/src/gr_modem.cpp:1119-1282, 980-994; sync words /root/reference/src/layer1framing.h:8-24) for a batch
+// of channels: the decoded bits (one per byte, port 2 / 3 of the demodulators) never leave the GPU, only packed frames
+// { type, length, payload } do.  Semantics are the reference's, bit for bit (oracle: qo_deframer_work):
+//   * a shift register searches for a sync word; class 1 ("1K" modes) 8-bit 0xB5; class 2 (narrow modes) 16-bit 0xED89
+//     first, then the 24-bit text / proto / video / callsign / end words; class 3 (QPSK250K, QPSKVideo, 4FSK100K) the
+//     24-bit IP / video / end words;
+//   * after a sync the next bit_len bits are collected and packed MSB first; classes 2, 3: voice frames take
+//     bit_buf_len bits into rx_frame_length + 1 bytes, all others bit_buf_len - 8 bits into rx_frame_length bytes;
+//   * then the shift register is cleared (a sync word cannot straddle the end of a frame);
+//   * _modem_sync: +8 (below 32) on a sync, -1 (above 0) per searched bit without one.
+// One warp per channel: 32 bit positions are tested at once (the lane's shift register is rebuilt from a ballot of
+// the 32 bits and the carried register), frames are packed a byte per lane.  State carries across calls.
+#include "../../include/qrl_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+extern "C" int qrl_device_count(void);
+void qrl_internal_set_err(const std::string& s);
+
+namespace {
+
+enum : uint32_t { FT_VOICE = 0xED89, FT_VOICE1 = 0xB5, FT_TEXT = 0x89EDAA, FT_IP = 0xDE98AA, FT_VIDEO = 0x98DEAA,
+                  FT_CALLSIGN = 0x8CC8DD, FT_PROTO = 0xED77AA, FT_END = 0x4C8A2B };
+
+struct DeframerState {
+    uint32_t shift_reg;
+    int sync_found;
+    uint32_t cur_type;
+    int bit_idx;
+    int modem_sync;
+};
+
+__device__ __forceinline__ uint32_t match_sync(int sync_class, uint32_t sr)
+{
+    if (sync_class == 1) return (sr & 0xFFu) == FT_VOICE1 ? FT_VOICE1 : 0u;
+    const uint32_t t24 = sr & 0xFFFFFFu;
+    if (sync_class == 2) {
+        if ((sr & 0xFFFFu) == FT_VOICE) return FT_VOICE;
+        if (t24 == FT_TEXT || t24 == FT_PROTO || t24 == FT_VIDEO || t24 == FT_CALLSIGN || t24 == FT_END) return t24;
+        return 0u;
+    }
+    if (t24 == FT_IP || t24 == FT_VIDEO || t24 == FT_END) return t24;
+    return 0u;
+}
+
+__global__ void __launch_bounds__(128)
+deframer_kernel(int C, int sync_class, int bit_buf_len, int rx_frame_length,
+                const unsigned char* __restrict__ bits, long long bits_stride, const int* __restrict__ counts, int fixed_count,
+                DeframerState* __restrict__ states, unsigned char* __restrict__ bit_buf /*[C][bit_buf_len]*/,
+                unsigned char* __restrict__ records, int rec_bytes, int max_frames, int* __restrict__ frame_counts)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= C) return;
+    const int c = warp;
+    const unsigned char* b = bits + static_cast<long long>(c) * bits_stride;
+    const int n = counts ? counts[c] : fixed_count;
+    DeframerState st = states[c];
+    unsigned char* bb = bit_buf + static_cast<long long>(c) * bit_buf_len;
+    unsigned char* rec = records + static_cast<long long>(c) * max_frames * rec_bytes;
+    int found = 0;
+    int pos = 0;
+    while (pos < n) {
+        if (!st.sync_found) {
+            const int v = min(32, n - pos);
+            const unsigned bit = (lane < v) ? (b[pos + lane] & 1u) : 0u;
+            const uint32_t wr = __brev(__ballot_sync(0xffffffffu, bit));      // bit 31 = the bit at pos
+            // my shift register after consuming bits pos .. pos + lane
+            const uint32_t sr = (lane == 31 ? 0u : (st.shift_reg << (lane + 1))) | (wr >> (31 - lane));
+            const uint32_t ty = (lane < v) ? match_sync(sync_class, sr) : 0u;
+            const unsigned hit = __ballot_sync(0xffffffffu, ty != 0u);
+            if (hit == 0u) {
+                st.shift_reg = __shfl_sync(0xffffffffu, sr, v - 1);
+                st.modem_sync = max(0, st.modem_sync - v);
+                pos += v;
+            } else {
+                const int f = __ffs(hit) - 1;
+                st.cur_type = __shfl_sync(0xffffffffu, ty, f);
+                st.shift_reg = __shfl_sync(0xffffffffu, sr, f);
+                st.modem_sync = max(0, st.modem_sync - f);
+                if (st.modem_sync < 32) st.modem_sync += 8;
+                st.sync_found = 1; st.bit_idx = 0;
+                pos += f + 1;
+            }
+        } else {
+            int frame_length = rx_frame_length, bit_len = bit_buf_len;
+            if (sync_class != 1) {
+                if (st.cur_type == FT_VOICE) frame_length++;
+                else bit_len = bit_buf_len - 8;
+            }
+            const int take = min(bit_len - st.bit_idx, n - pos);
+            const bool complete = st.bit_idx + take >= bit_len;
+            if (complete && found < max_frames) {
+                unsigned char* r = rec + static_cast<long long>(found) * rec_bytes;
+                for (int i = lane; i < rec_bytes; i += 32) r[i] = 0;
+                __syncwarp();
+                if (lane == 0) {
+                    reinterpret_cast<uint32_t*>(r)[0] = st.cur_type;
+                    reinterpret_cast<uint32_t*>(r)[1] = static_cast<uint32_t>(frame_length);
+                }
+                // byte j of the frame = bits 8j .. 8j+7: the first bit_idx bits are staged in bb, the rest come from b
+                for (int j = lane; j * 8 < bit_len && 8 + j < rec_bytes; j += 32) {
+                    int t = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int q = j * 8 + k;
+                        const unsigned bit = q < st.bit_idx ? bb[q] : b[pos + q - st.bit_idx];
+                        t = (t << 1) | (bit & 1u);
+                    }
+                    r[8 + j] = static_cast<unsigned char>(t);
+                }
+            } else if (!complete) {
+                for (int i = lane; i < take; i += 32) bb[st.bit_idx + i] = b[pos + i] & 1u;
+            }
+            __syncwarp();
+            pos += take;
+            if (complete) {
+                if (found < max_frames) found++;
+                st.sync_found = 0; st.shift_reg = 0; st.bit_idx = 0;
+            } else st.bit_idx += take;
+        }
+    }
+    if (lane == 0) { states[c] = st; frame_counts[c] = found; }
+}
+
+}  // namespace
+
+struct qrl_deframer {
+    std::string err;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    long launches = 0;
+    std::vector<void*> allocs;
+    int sync_class = 0, bit_buf_len = 0, rx_frame_length = 0, C = 0, max_frames = 0, rec_bytes = 0;
+    long max_bits = 0;
+    DeframerState* d_state = nullptr;
+    unsigned char *d_bit_buf = nullptr, *d_records = nullptr, *d_stage = nullptr;
+    int *d_counts = nullptr, *d_stage_counts = nullptr;
+};
+
+#define CKD(call)                                                                                    \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                            \
+            qrl_internal_set_err(h->err);                                                            \
+            return QRL_ECUDA;                                                                        \
+        }                                                                                            \
+    } while (0)
+
+extern "C" {
+
+int qrl_deframer_destroy(qrl_deframer* h)
+{
+    if (!h) return QRL_EINVAL;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return QRL_OK;
+}
+
+int qrl_deframer_create(int sync_class, int bit_buf_len, int rx_frame_length, int n_channels, long max_bits, int max_frames,
+                        int device, qrl_deframer** out)
+{
+    if (!out || sync_class < 1 || sync_class > 3 || bit_buf_len < 16 || (bit_buf_len & 7) || rx_frame_length < 1 || n_channels < 1 ||
+        max_bits < 1 || max_frames < 1) {
+        qrl_internal_set_err("qrl_deframer_create: bad argument");
+        return QRL_EINVAL;
+    }
+    *out = nullptr;
+    if (qrl_device_count() <= device) { qrl_internal_set_err("qrl_deframer_create: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
+    qrl_deframer* h = new qrl_deframer();
+    h->sync_class = sync_class; h->bit_buf_len = bit_buf_len; h->rx_frame_length = rx_frame_length; h->C = n_channels;
+    h->max_bits = max_bits; h->max_frames = max_frames; h->device = device;
+    h->rec_bytes = (8 + bit_buf_len / 8 + 7) & ~7;
+    auto fail = [&](int rc, const char* what) { qrl_internal_set_err(what); qrl_deframer_destroy(h); return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(QRL_ECUDA, "cudaSetDevice failed");
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(QRL_ECUDA, "stream create failed");
+    h->own_stream = true;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (cudaMalloc(p, std::max<size_t>(bytes, 16)) != cudaSuccess) return false;
+        h->allocs.push_back(*p);
+        return cudaMemsetAsync(*p, 0, std::max<size_t>(bytes, 16), h->stream) == cudaSuccess;
+    };
+    const size_t C = static_cast<size_t>(n_channels);
+    if (!alloc(reinterpret_cast<void**>(&h->d_state), C * sizeof(DeframerState)) ||
+        !alloc(reinterpret_cast<void**>(&h->d_bit_buf), C * bit_buf_len) ||
+        !alloc(reinterpret_cast<void**>(&h->d_records), C * max_frames * h->rec_bytes) ||
+        !alloc(reinterpret_cast<void**>(&h->d_counts), C * sizeof(int)) ||
+        !alloc(reinterpret_cast<void**>(&h->d_stage), C * static_cast<size_t>(max_bits)) ||
+        !alloc(reinterpret_cast<void**>(&h->d_stage_counts), C * sizeof(int)))
+        return fail(QRL_ENOMEM, "qrl_deframer_create: device allocation failed");
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(QRL_ECUDA, "create sync failed");
+    *out = h;
+    return QRL_OK;
+}
+
+int qrl_deframer_set_stream(qrl_deframer* h, void* cuda_stream)
+{
+    if (!h) return QRL_EINVAL;
+    if (!cuda_stream) return QRL_OK;
+    CKD(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = static_cast<cudaStream_t>(cuda_stream); h->own_stream = false;
+    return QRL_OK;
+}
+
+int qrl_deframer_work(qrl_deframer* h, const unsigned char* bits, const int* counts, long stride, int on_device)
+{
+    if (!h || !bits || !counts || stride < 0) { qrl_internal_set_err("qrl_deframer_work: bad argument"); return QRL_EINVAL; }
+    CKD(cudaSetDevice(h->device));
+    const unsigned char* d_bits = bits; const int* d_cnt = counts; long long d_stride = stride;
+    if (!on_device) {
+        if (stride > h->max_bits) { qrl_internal_set_err("qrl_deframer_work: stride exceeds max_bits"); return QRL_ERANGE; }
+        for (int c = 0; c < h->C; c++) if (counts[c] < 0 || counts[c] > stride) { qrl_internal_set_err("qrl_deframer_work: bad count"); return QRL_ERANGE; }
+        CKD(cudaMemcpyAsync(h->d_stage, bits, static_cast<size_t>(h->C) * stride, cudaMemcpyHostToDevice, h->stream));
+        CKD(cudaMemcpyAsync(h->d_stage_counts, counts, sizeof(int) * h->C, cudaMemcpyHostToDevice, h->stream));
+        d_bits = h->d_stage; d_cnt = h->d_stage_counts;
+    }
+    const int warps_per_block = 4;
+    deframer_kernel<<<(h->C + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, h->stream>>>(
+        h->C, h->sync_class, h->bit_buf_len, h->rx_frame_length, d_bits, d_stride, d_cnt, 0,
+        h->d_state, h->d_bit_buf, h->d_records, h->rec_bytes, h->max_frames, h->d_counts);
+    h->launches++;
+    CKD(cudaGetLastError());
+    return QRL_OK;
+}
+
+int qrl_deframer_record_bytes(qrl_deframer* h) { return h ? h->rec_bytes : 0; }
+
+int qrl_deframer_read(qrl_deframer* h, unsigned char* records_host, int* frame_counts_host, int* modem_sync_host)
+{
+    if (!h || !frame_counts_host) return QRL_EINVAL;
+    CKD(cudaSetDevice(h->device));
+    CKD(cudaMemcpyAsync(frame_counts_host, h->d_counts, sizeof(int) * h->C, cudaMemcpyDeviceToHost, h->stream));
+    if (records_host)
+        CKD(cudaMemcpyAsync(records_host, h->d_records, static_cast<size_t>(h->C) * h->max_frames * h->rec_bytes, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<DeframerState> st;
+    if (modem_sync_host) {
+        st.resize(h->C);
+        CKD(cudaMemcpyAsync(st.data(), h->d_state, sizeof(DeframerState) * h->C, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CKD(cudaStreamSynchronize(h->stream));
+    if (modem_sync_host) for (int c = 0; c < h->C; c++) modem_sync_host[c] = st[c].modem_sync;
+    return QRL_OK;
+}
+
+int qrl_deframer_out_device(qrl_deframer* h, void** records, int** frame_counts)
+{
+    if (!h) return QRL_EINVAL;
+    if (records) *records = h->d_records;
+    if (frame_counts) *frame_counts = h->d_counts;
+    return QRL_OK;
+}
+
+int qrl_deframer_sync(qrl_deframer* h)
+{
+    if (!h) return QRL_EINVAL;
+    CKD(cudaStreamSynchronize(h->stream));
+    return QRL_OK;
+}
+
+long qrl_deframer_launch_count(qrl_deframer* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+"""Layer-1 deframer on the device: host-side mirror of gr_modem::synchronize / findSync /
+packBytes (/root/reference/src/gr_modem.cpp:1119-1282, 980-994) for a batch of channels.  The search and the packing
+run in libqrl_b200.so (CUDA); this class only moves buffers and splits the returned records."""
+import ctypes as C
+
+import numpy as np
+
+from .lib import QrlError, check, load_library
+
+SYNC_1K, SYNC_NARROW, SYNC_WIDE = 1, 2, 3
+
+# frame types = sync words (layer1framing.h:8-24)
+FrameTypeVoice, FrameTypeVoice1, FrameTypeText, FrameTypeIP = 0xED89, 0xB5, 0x89EDAA, 0xDE98AA
+FrameTypeVideo, FrameTypeCallsign, FrameTypeProto, FrameTypeEnd = 0x98DEAA, 0x8CC8DD, 0xED77AA, 0x4C8A2B
+
+# (sync_class, bit_buf_len, rx_frame_length) per modem type as gr_modem::toggleRxMode sets them (gr_modem.cpp:203-322)
+MODE_FRAMING = {
+    "BPSK2K": (SYNC_NARROW, 64, 7), "BPSK1K": (SYNC_1K, 32, 4), "2FSK1KFM": (SYNC_1K, 32, 4), "2FSK1K": (SYNC_1K, 32, 4),
+    "QPSK20K": (SYNC_NARROW, 384, 47), "QPSK2K": (SYNC_NARROW, 64, 7), "4FSK10KFM": (SYNC_NARROW, 384, 47),
+    "2FSK10KFM": (SYNC_NARROW, 384, 47), "4FSK2K": (SYNC_NARROW, 64, 7), "4FSK2KFM": (SYNC_NARROW, 64, 7),
+    "4FSK1KFM": (SYNC_1K, 32, 4), "QPSKVideo": (SYNC_WIDE, 3123 * 8, 3122), "2FSK2KFM": (SYNC_NARROW, 64, 7),
+    "2FSK2K": (SYNC_NARROW, 64, 7), "QPSK250K": (SYNC_WIDE, 1517 * 8, 1516), "4FSK100K": (SYNC_WIDE, 623 * 8, 622),
+}
+
+
+class Deframer:
+    def __init__(self, sync_class, bit_buf_len, rx_frame_length, n_channels=1, max_bits=1 << 20, max_frames=None, device=0):
+        self._L = load_library()
+        self.n_channels, self.max_bits = int(n_channels), int(max_bits)
+        self.max_frames = int(max_frames) if max_frames else max(4, self.max_bits // max(8, bit_buf_len - 8) + 2)
+        self._h = C.c_void_p()
+        rc = self._L.qrl_deframer_create(sync_class, bit_buf_len, rx_frame_length, self.n_channels, self.max_bits, self.max_frames,
+                                         device, C.byref(self._h))
+        if rc != 0:
+            raise QrlError("qrl_deframer_create failed (%d): %s" % (rc, (self._L.qrl_last_error(None) or b"").decode()))
+        self.rec_bytes = self._L.qrl_deframer_record_bytes(self._h)
+
+    @classmethod
+    def for_mode(cls, mode, **kw):
+        return cls(*MODE_FRAMING[mode], **kw)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.qrl_deframer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        check(self._L.qrl_deframer_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), self._h, "qrl_deframer_set_stream")
+
+    def _collect(self):
+        rec = np.zeros((self.n_channels, self.max_frames, self.rec_bytes), np.uint8)
+        cnt = np.zeros(self.n_channels, np.int32)
+        self.modem_sync = np.zeros(self.n_channels, np.int32)
+        check(self._L.qrl_deframer_read(self._h, rec.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p),
+                                        self.modem_sync.ctypes.data_as(C.c_void_p)), self._h, "qrl_deframer_read")
+        out = []
+        for c in range(self.n_channels):
+            fr = []
+            for r in rec[c, :cnt[c]]:
+                ty, nb = int(r[:4].view(np.uint32)[0]), int(r[4:8].view(np.uint32)[0])
+                fr.append((ty, r[8:8 + nb].tobytes()))
+            out.append(fr)
+        return out
+
+    def work(self, bits_per_channel):
+        """bits_per_channel: list of uint8 arrays (one decoded bit per byte) -> list (per channel) of (frame_type, payload)."""
+        n = max(1, max(len(b) for b in bits_per_channel))
+        buf = np.zeros((self.n_channels, n), np.uint8)
+        cnt = np.zeros(self.n_channels, np.int32)
+        for c, b in enumerate(bits_per_channel):
+            buf[c, :len(b)] = b; cnt[c] = len(b)
+        check(self._L.qrl_deframer_work(self._h, buf.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), n, 0),
+              self._h, "qrl_deframer_work")
+        return self._collect()
+
+    def work_from_rx(self, rx, port=2):
+        """Deframe what the last rx.work() left on `port` without leaving the GPU (qrl_rx_port_device)."""
+        data, cap, cnts = C.c_void_p(), C.c_long(), C.c_void_p()
+        check(self._L.qrl_rx_port_device(rx._h, port, C.byref(data), C.byref(cap), C.byref(cnts)), rx._h, "qrl_rx_port_device")
+        rx.sync()
+        check(self._L.qrl_deframer_work(self._h, data, cnts, cap.value, 1), self._h, "qrl_deframer_work")
+        return self._collect()
+
+    @property
+    def launches(self):
+        return self._L.qrl_deframer_launch_count(self._h)

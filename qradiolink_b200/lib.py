@@ -66,6 +66,15 @@ SYMBOLS = {
     "qrl_pfb_out_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_l), C.POINTER(_l)]),
     "qrl_pfb_read": (_i, [_vp, _vp, _l]),
     "qrl_pfb_launch_count": (_l, [_vp]),
+    "qrl_deframer_create": (_i, [_i, _i, _i, _i, _l, _i, _i, C.POINTER(_vp)]),
+    "qrl_deframer_destroy": (_i, [_vp]),
+    "qrl_deframer_set_stream": (_i, [_vp, _vp]),
+    "qrl_deframer_work": (_i, [_vp, _vp, _vp, _l, _i]),
+    "qrl_deframer_record_bytes": (_i, [_vp]),
+    "qrl_deframer_read": (_i, [_vp, _vp, _vp, _vp]),
+    "qrl_deframer_out_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "qrl_deframer_sync": (_i, [_vp]),
+    "qrl_deframer_launch_count": (_l, [_vp]),
 }
 
 

@@ -226,3 +226,34 @@ def test_pfb_channelizer_and_synthesizer_against_float64(oracle):
     back = O.PfbChannelizer(M, taps).work(O.PfbSynthesizer(M, st).work(zz))
     p = np.abs(back[:, -1])
     assert abs(p[3] - 1.0) < 0.02 and abs(p[9] - 0.5) < 0.02 and np.all(np.delete(p, [3, 9]) < 0.02)
+
+
+def test_deframer_known_answers(oracle):
+    """gr_modem::synchronize / findSync restated (SURVEY 8f row 2): planted frames come back with type and payload,
+    non-voice frames take 8 bits less, the register is cleared after a frame, chunking is invisible."""
+    O = oracle
+    rng = np.random.default_rng(1)
+    bits_of = lambda bs: np.unpackbits(np.frombuffer(bytes(bs), np.uint8))  # noqa: E731
+    pl = [rng.integers(0, 256, 7, dtype=np.uint8).tobytes() for _ in range(5)]
+    text = rng.integers(0, 256, 7, dtype=np.uint8).tobytes()
+    parts = [bits_of([0xAA] * 8)]
+    for p in pl:
+        parts.append(bits_of([0xED, 0x89, 0xAA] + list(p)))
+    parts.append(bits_of([0x89, 0xED, 0xAA] + list(text)))
+    parts.append(bits_of([0x4C, 0x8A, 0x2B] + [0] * 7))
+    b = np.concatenate(parts)
+    fr = O.Deframer(2, 64, 7).work(b)
+    assert [t for t, _ in fr] == [0xED89] * 5 + [0x89EDAA, 0x4C8A2B]
+    assert [p for _, p in fr[:5]] == [bytes([0xAA]) + p for p in pl]        # reserved byte + 7 payload bytes
+    assert fr[5][1] == text and len(fr[6][1]) == 7
+    d2 = O.Deframer(2, 64, 7)
+    fr2 = []
+    for a in range(0, len(b), 37):
+        fr2 += d2.work(b[a:a + 37])
+    assert fr2 == fr
+    # voice payloads agree with the plain sync search used elsewhere in the tests
+    ff = O.find_frames(b, 0xED89AA, 24, 7)
+    assert [f.tobytes() for f in ff][:5] == pl
+    # class 1: 8-bit sync, 4-byte frames; a sync word inside a frame is not a sync
+    b1 = np.concatenate([bits_of([0x00, 0xB5, 0xB5, 1, 2, 3]), bits_of([0xB5, 9, 8, 7, 6])])
+    assert O.Deframer(1, 32, 4).work(b1) == [(0xB5, bytes([0xB5, 1, 2, 3])), (0xB5, bytes([9, 8, 7, 6]))]
