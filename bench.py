@@ -175,6 +175,11 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     blk.set_stream(stream.cuda_stream)
     L = q.load_library()
+    overlap = not args.no_overlap
+    if overlap:
+        # streaming use: the loop / FEC tail of step k runs under the parallel stages of step k+1 (QRL_PARAM_OVERLAP_CALLS);
+        # qrl_rx_join before the closing event puts every step's tail inside the timed region
+        blk.set_overlap(True)
 
     def step_device():
         blk.work_device(X.data_ptr(), T, T)
@@ -202,6 +207,7 @@ def run_ours(args):
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
+    blk.join()
     e1.record(stream)
     torch.cuda.synchronize()
     sampler.armed = False
@@ -284,6 +290,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "channels_per_gpu": C, "samples_per_channel_per_step": T,
                    "l2": "inputs 2.1 GB/step > 126 MB L2, no flush", "parallelism": "channel-sharded x%d, no data-path collective" % world,
+                   "calls": ("overlapped: tail of step k under step k+1 (QRL_PARAM_OVERLAP_CALLS), joined before the closing event" if overlap else "serialised"),
                    "decoded_bits_per_step": n_bits,
                    "sm_partition": {"loop_fec_sms": sm_a.value, "parallel_sms": sm_b.value}},
         "clocks": sampler.result(),
@@ -309,6 +316,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-overlap", action="store_true", help="serialise qrl_rx_work calls (no QRL_PARAM_OVERLAP_CALLS)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

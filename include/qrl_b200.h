@@ -50,7 +50,11 @@ enum qrl_param {
     QRL_PARAM_CARRIER_OFFSET_HZ = 1,  /* rotator_cc phase increment, gr_demod_base.cpp:1220-1225 */
     QRL_PARAM_SQUELCH_DB = 2,         /* gr_demod_nbfm::set_squelch */
     QRL_PARAM_FILTER_WIDTH = 3,       /* gr_demod_nbfm::set_filter_width */
-    QRL_PARAM_BB_GAIN = 4             /* gr_mod_*::set_bb_gain */
+    QRL_PARAM_BB_GAIN = 4,            /* gr_mod_*::set_bb_gain */
+    QRL_PARAM_OVERLAP_CALLS = 5       /* 1: the loop / FEC tail of qrl_rx_work call k runs under the parallel stages of call
+                                         k+1 (streaming use).  Output ports are double-buffered; the results of a call are
+                                         ordered on the caller's stream only after qrl_rx_join (or qrl_rx_sync /
+                                         qrl_rx_read_port, which wait on the host).  Supported for 4FSK (fm) blocks. */
 };
 
 typedef struct qrl_rx qrl_rx;
@@ -77,6 +81,9 @@ int qrl_rx_reset(qrl_rx* h);
  * the copy to the device is part of the call.  Asynchronous on the handle's stream. */
 int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device);
 /* wait for everything submitted so far */
+/* QRL_PARAM_OVERLAP_CALLS: make the handle's stream wait (on the device, without blocking the host) for everything the
+ * calls so far have started; a no-op otherwise */
+int qrl_rx_join(qrl_rx*);
 int qrl_rx_sync(qrl_rx* h);
 /* number of output ports (2 for analog blocks, 3 for 4FSK/QPSK, 4 for BPSK/2FSK) and item size in bytes */
 int qrl_rx_num_ports(const qrl_rx* h);

@@ -115,6 +115,7 @@ struct qrl_rx : HandleBase {
     float2* d_in_staging = nullptr;
     long long n_in = 0, n1 = 0;       // stage-1 progress (absolute input samples consumed / outputs produced)
     long long n_in_s = 0, n1_s = 0;   // progress of the per-slice stages behind it (equal to the above between calls)
+    bool fir_group_forced = false;     // QRL_FIR_GROUP given: keep it in overlap mode too
     int fir_group = 4;                 // stage-1 launches cover this many slices (bigger launches, same pipeline depth)
     Ring r1;
     // stage 2: channel / shaping filter on the complex stream (port 0)
@@ -159,6 +160,16 @@ struct qrl_rx : HandleBase {
     SymSyncState* d_ss = nullptr;
     float* d_ss_scratch = nullptr; int* d_ss_hdr = nullptr; long long ss_chunk_cap = 0, ss_chunk_off = 0;   // external symbol-sync epilogue
     cudaStream_t s_epi = nullptr;                        // wide-partition stream of the external epilogue
+    // QRL_PARAM_OVERLAP_CALLS: the loop / FEC tail of call k runs under the parallel stages of call k+1.  Output ports
+    // are double-buffered (alt_* = the buffers of the previous call), ring reuse is fenced slice by slice.
+    bool overlap = false;
+    float2* alt_port0 = nullptr; float2* alt_port1 = nullptr; unsigned char* alt_port2 = nullptr; unsigned char* alt_port3 = nullptr;
+    int *alt_port1_cnt = nullptr, *alt_port2_cnt = nullptr, *alt_port3_cnt = nullptr;
+    long alt_port0_n = 0;
+    cudaEvent_t ev_v[16] = { nullptr };                  // Viterbi of slice i done (kMaxSub entries)
+    cudaEvent_t ev_tail[2][3] = { { nullptr } };         // s_loop / s_fec / s_epi at the end of a call, by call parity
+    int call_parity = 0;
+    long long prev_k1[16] = { 0 }, cur_k1[16] = { 0 }; int prev_nsub = 0;      // stage-1 sample index at the end of each slice
     int ss_ch = 256;                                     // rows per symbol-sync window (256 x 3 stages or 512 x 2)
     float2* d_port1 = nullptr; long port1_cap = 0; int* d_port1_cnt = nullptr;
     Ring r5;   // soft bits (u8)
@@ -168,6 +179,7 @@ struct qrl_rx : HandleBase {
     // software pipeline inside one work() call: parallel stages on `stream`, loop stages on s_loop, FEC on s_fec
     static constexpr int kMaxSub = 16;
     int nsub = 12;
+    bool nsub_forced = false;          // QRL_NSUB given
     cudaStream_t s_loop = nullptr, s_loop2 = nullptr, s_fec = nullptr;
     cudaEvent_t ev_start = nullptr, ev_a[kMaxSub] = { nullptr }, ev_b[kMaxSub] = { nullptr }, ev_c[kMaxSub] = { nullptr },
                 ev_loop_done = nullptr, ev_loop2_done = nullptr, ev_fec_done = nullptr;
@@ -603,7 +615,9 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = dev_alloc(h, &h->d_nb, h->C))) return fail(rc);
     } else if (kind == QRL_DEMOD_4FSK || kind == QRL_DEMOD_2FSK) {
         if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + h->ntaps3 + 64))) return fail(rc);
-        if ((rc = make_ring(h, &h->r4, sizeof(float), h->n1max + 600, true))) return fail(rc);
+        // two calls deep when the block may run with overlapped calls (the producer of call k+1 must not wait for the
+        // consumer of call k)
+        if ((rc = make_ring(h, &h->r4, sizeof(float), (flag && kind == QRL_DEMOD_4FSK ? 2 : 1) * h->n1max + 600, true))) return fail(rc);
         if (flag && kind == QRL_DEMOD_4FSK) {
             // scratch of the external symbol-sync epilogue: [groups][chunks][maxs + 2][32] floats + a 128-int header per group
             // window size: 512 rows x 2 stages when the replicated interpolator bank still fits next to it, else 256 x 3
@@ -614,7 +628,7 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
             }
             if (const char* e = getenv("QRL_SS_CH")) { const int v = atoi(e); if (v == 512 || v == 256) h->ss_ch = v; }
             const int maxs = static_cast<int>((h->ss_ch + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
-            h->ss_chunk_cap = h->n1max / (h->ss_ch - 32) + 4 + 3 * qrl_rx::kMaxSub;
+            h->ss_chunk_cap = h->n1max / symsync_stride(h->ss_ch, h->ssp.lookahead) + 4 + 3 * qrl_rx::kMaxSub;
             const size_t groups = (h->C + 31) / 32;
             if ((rc = dev_alloc(h, &h->d_ss_scratch, groups * h->ss_chunk_cap * (maxs + 2) * 32))) return fail(rc);
             if ((rc = dev_alloc(h, &h->d_ss_hdr, groups * 128 * qrl_rx::kMaxSub))) return fail(rc);
@@ -655,6 +669,11 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = dev_alloc(h, &h->d_port3_cnt, h->C))) return fail(rc);
     }
     if ((rc = dev_alloc(h, &h->d_ss, h->C))) return fail(rc);
+    if (h->ssp.lookahead > 0 && symsync_stride(128, h->ssp.lookahead) < 32 &&
+        (kind == QRL_DEMOD_QPSK || kind == QRL_DEMOD_BPSK || (kind == QRL_DEMOD_4FSK && !flag))) {
+        set_err(h, "symbol-sync lookahead does not fit the 128-row window of the complex-symbol kernels");
+        return fail(QRL_EINVAL);
+    }
     if ((rc = dev_alloc(h, &h->d_vs, h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_nsoft, static_cast<size_t>(qrl_rx::kMaxSub) * h->C))) return fail(rc);
     {
@@ -682,11 +701,22 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         for (int i = 0; i < qrl_rx::kMaxSub; i++) { mk(&h->ev_a[i]); mk(&h->ev_b[i]); mk(&h->ev_c[i]); }
         if (!ok) { set_err(h, "stream/event creation failed"); return fail(QRL_ECUDA); }
     }
-    if (const char* e = getenv("QRL_NSUB")) { int v = atoi(e); if (v >= 1 && v <= qrl_rx::kMaxSub) h->nsub = v; }
-    if (const char* e = getenv("QRL_FIR_GROUP")) { int v = atoi(e); if (v >= 1 && v <= qrl_rx::kMaxSub) h->fir_group = v; }
+    if (const char* e = getenv("QRL_NSUB")) { int v = atoi(e); if (v >= 1 && v <= qrl_rx::kMaxSub) { h->nsub = v; h->nsub_forced = true; } }
+    if (const char* e = getenv("QRL_FIR_GROUP")) { int v = atoi(e); if (v >= 1 && v <= qrl_rx::kMaxSub) { h->fir_group = v; h->fir_group_forced = true; } }
     if ((rc = qrl_rx_reset(h))) return fail(rc);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { set_err(h, "create sync failed"); return fail(QRL_ECUDA); }
     *out = h;
+    return QRL_OK;
+}
+
+// host-side wait for everything a handle has in flight on its internal streams
+static int rx_join_host(qrl_rx* h)
+{
+    if (h->s_loop) CK(cudaStreamSynchronize(h->s_loop));
+    if (h->s_fec) CK(cudaStreamSynchronize(h->s_fec));
+    if (h->s_loop2) CK(cudaStreamSynchronize(h->s_loop2));
+    if (h->s_epi) CK(cudaStreamSynchronize(h->s_epi));
+    if (h->s_par) CK(cudaStreamSynchronize(h->s_par));
     return QRL_OK;
 }
 
@@ -735,7 +765,7 @@ int qrl_rx_reset(qrl_rx* h)
     CK(cudaMemsetAsync(h->d_port1_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_port2_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // the staging vectors above go out of scope
-    h->n_in = 0; h->n1 = 0; h->n_in_s = 0; h->n1_s = 0; h->hist_cur = 0; h->port0_n = 0;
+    h->n_in = 0; h->n1 = 0; h->n_in_s = 0; h->n1_s = 0; h->hist_cur = 0; h->port0_n = 0; h->prev_nsub = 0;
     return QRL_OK;
 }
 
@@ -772,6 +802,32 @@ int qrl_rx_set_stream(qrl_rx* h, void* s)
 int qrl_rx_set_param(qrl_rx* h, int channel, int key, double value)
 {
     if (!h) return QRL_EINVAL;
+    if (key == QRL_PARAM_OVERLAP_CALLS) {
+        // only the path whose ring reuse is fenced for it: real-symbol 4FSK (external soft-bit epilogue)
+        if (!(h->kind == QRL_DEMOD_4FSK && h->flag)) { set_err(h, "QRL_PARAM_OVERLAP_CALLS: not supported for this block"); return QRL_EINVAL; }
+        CK(cudaStreamSynchronize(h->stream));
+        { int rc = rx_join_host(h); if (rc) return rc; }
+        const bool on = value != 0.0;
+        if (on && !h->alt_port1) {
+            int rc;
+            if ((rc = dev_alloc(h, &h->alt_port0, static_cast<size_t>(h->port0_cap) * h->C))) return rc;
+            if ((rc = dev_alloc(h, &h->alt_port1, static_cast<size_t>(h->port1_cap) * h->C))) return rc;
+            if ((rc = dev_alloc(h, &h->alt_port2, static_cast<size_t>(h->port2_cap) * h->C))) return rc;
+            if ((rc = dev_alloc(h, &h->alt_port1_cnt, h->C))) return rc;
+            if ((rc = dev_alloc(h, &h->alt_port2_cnt, h->C))) return rc;
+            if (h->d_port3) {
+                if ((rc = dev_alloc(h, &h->alt_port3, static_cast<size_t>(h->port2_cap) * h->C))) return rc;
+                if ((rc = dev_alloc(h, &h->alt_port3_cnt, h->C))) return rc;
+            }
+            for (int q = 0; q < 2; q++) for (int j = 0; j < 3; j++)
+                if (!h->ev_tail[q][j]) CK(cudaEventCreateWithFlags(&h->ev_tail[q][j], cudaEventDisableTiming));
+            for (int i = 0; i < qrl_rx::kMaxSub; i++)
+                if (!h->ev_v[i]) CK(cudaEventCreateWithFlags(&h->ev_v[i], cudaEventDisableTiming));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        h->overlap = on;
+        return QRL_OK;
+    }
     if (key == QRL_PARAM_CARRIER_OFFSET_HZ) {        // gr_demod_base::set_carrier_offset (:1220-1225): phase inc = 2 pi (-offset) / fs
         if (channel >= h->C) { set_err(h, "set_param: channel out of range"); return QRL_EINVAL; }
         if (h->rot.empty()) h->rot.assign(h->C, RotState{ 0u, 0u, 0 });
@@ -787,6 +843,7 @@ int qrl_rx_set_param(qrl_rx* h, int channel, int key, double value)
         for (auto& r : h->rot) if (r.inc != 0 || r.base != 0) h->rot_active = true;
         if (!h->d_rot) { int rc = dev_alloc(h, &h->d_rot, h->C); if (rc) return rc; }
         CK(cudaStreamSynchronize(h->stream));
+        if (h->overlap) { int rc = rx_join_host(h); if (rc) return rc; }
         CK(cudaMemcpy(h->d_rot, h->rot.data(), sizeof(RotState) * h->C, cudaMemcpyHostToDevice));
         return QRL_OK;
     }
@@ -835,6 +892,15 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         h->launches++;
         x = h->d_rot_buf; xstride = h->Tmax;
     }
+    if (h->overlap) {
+        // this call writes the buffers call k-2 used: wait for that call's tail, then they are free
+        h->call_parity ^= 1;
+        for (int j = 0; j < 3; j++) CK(cudaStreamWaitEvent(h->stream, h->ev_tail[h->call_parity][j], 0));
+        std::swap(h->d_port0, h->alt_port0); std::swap(h->d_port1, h->alt_port1); std::swap(h->d_port2, h->alt_port2);
+        std::swap(h->d_port1_cnt, h->alt_port1_cnt); std::swap(h->d_port2_cnt, h->alt_port2_cnt);
+        if (h->d_port3) { std::swap(h->d_port3, h->alt_port3); std::swap(h->d_port3_cnt, h->alt_port3_cnt); }
+        h->d_port1f = reinterpret_cast<float*>(h->d_port1);
+    }
     CK(cudaMemsetAsync(h->d_port1_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_port2_cnt, 0, sizeof(int) * h->C, h->stream));
     if (h->d_port3_cnt) CK(cudaMemsetAsync(h->d_port3_cnt, 0, sizeof(int) * h->C, h->stream));
@@ -848,7 +914,8 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
     CK(cudaStreamWaitEvent(h->s_fec, h->ev_start, 0));
     if (h->s_par) CK(cudaStreamWaitEvent(h->s_par, h->ev_start, 0));
     cudaStream_t sp = h->par();
-    int nsub = h->nsub;
+    // overlapped calls keep the pipeline full across calls: a few big slices (less per-launch overhead) are enough
+    int nsub = (h->overlap && !h->nsub_forced) ? 3 : h->nsub;
     if (T < 32768L * nsub) nsub = static_cast<int>(std::max<long>(1, T / 32768));
     const long long k_call0 = h->n1;
     h->port0_n = 0;
@@ -864,9 +931,10 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         // ---- stage 1: decimating FIR, one launch per group of slices (outputs k with D k <= last absolute input index)
         // stage-1 launch schedule: slice 0 alone (the loop stage starts as early as possible), then fir_group slices
         // per launch (bigger launches run closer to the HBM roofline)
-        const bool fir_here = (i == 0) || ((i - 1) % h->fir_group == 0);
+        // (overlapped calls: the pipeline is already full, one launch for the whole call)
+        const bool fir_here = h->overlap && !h->fir_group_forced ? (i == 0) : ((i == 0) || ((i - 1) % h->fir_group == 0));
         if (fir_here) {
-            const long long tg1 = cut(i == 0 ? 1 : std::min(i + h->fir_group, nsub));
+            const long long tg1 = cut(h->overlap && !h->fir_group_forced ? nsub : (i == 0 ? 1 : std::min(i + h->fir_group, nsub)));
             const long long Tg = tg1 - t0;
             const float2* xg = x + t0;
             const long long Ng = h->n_in + Tg;
@@ -887,6 +955,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         const long long k0 = h->n1_s;
         const long long k1 = (N * h->L1 + h->D1 - 1) / h->D1;
         h->n_in_s = N; h->n1_s = k1;
+        h->cur_k1[i] = k1;
         const long long n_new = k1 - k0;
         h->port0_n += static_cast<long>(n_new);
         long long* nsoft_i = h->d_nsoft + static_cast<size_t>(i) * h->C;
@@ -1038,6 +1107,15 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 h->launches++;
                 h->prof_end(pe);
                 // ---- stage 3: quadrature demod + RRC   |   band-pass bank + discriminator + symbol filter
+                // overlapped calls: this slice overwrites ring slots the previous call's symbol sync (slices i, i+1) read
+                if (h->overlap && h->prev_nsub > 0) {
+                    // the slots [k0, k1) overwrite the samples cap older; the previous call's symbol sync of slice q has
+                    // consumed everything up to prev_k1[q] - lookahead
+                    const long long must = k1 - (static_cast<long long>(h->r4.mask) + 1) + 64;
+                    int q = -1;
+                    for (int j = 0; j < h->prev_nsub; j++) if (h->prev_k1[j] - 64 < must) q = j;      // not yet safe after slice j alone
+                    if (q >= 0) CK(cudaStreamWaitEvent(sp, h->ev_c[std::min(q + 1, h->prev_nsub - 1)], 0));
+                }
                 pe = h->prof_begin(2, sp);
                 if (h->flag) {
                     qdemod_fir_fff_kernel<<<gtile, TB, sizeof(float) * (2 * h->ntaps3 + TB), sp>>>(
@@ -1093,9 +1171,11 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
                     ss_attr[rep] = true;
                 }
+                // overlapped calls: the previous call's Viterbi of slice i still reads d_nsoft[i], its epilogue scratch region i
+                if (h->overlap) CK(cudaStreamWaitEvent(h->s_loop, h->ev_v[i], 0));
                 // every slice of a call gets its own scratch region and header (the epilogue of slice i overlaps symsync i+1)
                 if (i == 0) h->ss_chunk_off = 0;
-                const int chunk_bound = static_cast<int>(std::min<long long>(h->ss_chunk_cap - h->ss_chunk_off, n_new / (CH - 32) + 3));
+                const int chunk_bound = static_cast<int>(std::min<long long>(h->ss_chunk_cap - h->ss_chunk_off, n_new / symsync_stride(CH, h->ssp.lookahead) + 3));
                 float* scratch_i = h->d_ss_scratch + static_cast<size_t>(h->ss_chunk_off) * (maxs + 2) * 32;
                 int* hdr_i = h->d_ss_hdr + static_cast<size_t>(i) * groups * 128;
                 h->ss_chunk_off += chunk_bound;
@@ -1106,7 +1186,8 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                     scratch_i, chunk_bound, static_cast<int>(h->ss_chunk_cap), hdr_i);
                 h->prof_end(pe);
                 cudaStream_t se = h->s_epi ? h->s_epi : h->s_loop;
-                if (se != h->s_loop) { CK(cudaEventRecord(h->ev_c[i], h->s_loop)); CK(cudaStreamWaitEvent(se, h->ev_c[i], 0)); }
+                if (se != h->s_loop || h->overlap) CK(cudaEventRecord(h->ev_c[i], h->s_loop));
+                if (se != h->s_loop) CK(cudaStreamWaitEvent(se, h->ev_c[i], 0));
                 pe = h->prof_begin(5, se);
                 if (chunk_bound > 0)
                     symsync_ext_epilogue_kernel<<<dim3(chunk_bound, groups), dim3(32, 8), 0, se>>>(
@@ -1199,6 +1280,19 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             h->d_port2, h->port2_cap, h->d_port2_cnt, static_cast<int>(h->port2_cap), 0);
         h->launches++;
         h->prof_end(pe);
+        if (h->overlap) CK(cudaEventRecord(h->ev_v[i], h->s_fec));
+    }
+    for (int i = 0; i < nsub; i++) h->prev_k1[i] = h->cur_k1[i];
+    h->prev_nsub = nsub;
+    if (h->overlap) {
+        // the caller's stream only waits for the parallel stages (the input has been consumed); the loop / FEC tail runs
+        // on under the next call and is joined by qrl_rx_join / qrl_rx_sync / qrl_rx_read_port
+        CK(cudaEventRecord(h->ev_tail[h->call_parity][0], h->s_loop));
+        CK(cudaEventRecord(h->ev_tail[h->call_parity][1], h->s_fec));
+        CK(cudaEventRecord(h->ev_tail[h->call_parity][2], h->s_epi ? h->s_epi : h->s_loop));
+        if (h->s_par) { CK(cudaEventRecord(h->ev_par_done, h->s_par)); CK(cudaStreamWaitEvent(h->stream, h->ev_par_done, 0)); }
+        CK(cudaGetLastError());
+        return QRL_OK;
     }
     CK(cudaEventRecord(h->ev_loop_done, h->s_loop));
     CK(cudaEventRecord(h->ev_loop2_done, h->s_loop2));
@@ -1208,6 +1302,14 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
     CK(cudaStreamWaitEvent(h->stream, h->ev_loop_done, 0));
     CK(cudaStreamWaitEvent(h->stream, h->ev_fec_done, 0));
     CK(cudaGetLastError());
+    return QRL_OK;
+}
+
+int qrl_rx_join(qrl_rx* h)
+{
+    if (!h) return QRL_EINVAL;
+    if (!h->overlap) return QRL_OK;
+    for (int j = 0; j < 3; j++) CK(cudaStreamWaitEvent(h->stream, h->ev_tail[h->call_parity][j], 0));
     return QRL_OK;
 }
 
@@ -1225,6 +1327,7 @@ int qrl_rx_profile_read(qrl_rx* h, int stage, double* ms_total, long* n_launches
 {
     if (!h || stage < 0 || stage >= 8) return QRL_EINVAL;
     CK(cudaStreamSynchronize(h->stream));
+    if (h->overlap) { int rc = rx_join_host(h); if (rc) return rc; }
     for (size_t i = 0; i < h->prof_used; i++) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, h->prof_recs[i].a, h->prof_recs[i].b) == cudaSuccess) {
@@ -1241,6 +1344,7 @@ int qrl_rx_sync(qrl_rx* h)
 {
     if (!h) return QRL_EINVAL;
     CK(cudaStreamSynchronize(h->stream));
+    if (h->overlap) return rx_join_host(h);
     return QRL_OK;
 }
 
@@ -1274,6 +1378,7 @@ int qrl_rx_read_port(qrl_rx* h, int port, void* dst, long cap, int* counts, int 
     if (rc) return rc;
     const int isz = qrl_rx_port_itemsize(h, port);
     long maxn = 0;
+    if (h->overlap) { CK(cudaStreamSynchronize(h->stream)); rc = rx_join_host(h); if (rc) return rc; }
     if (dcnt) {
         CK(cudaMemcpyAsync(counts, dcnt, sizeof(int) * h->C, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));

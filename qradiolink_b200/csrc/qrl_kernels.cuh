@@ -446,6 +446,7 @@ struct SymSyncState {
     LoopState costas;            // second Costas loop (EPI_QPSK)
     float dp_r, dp_i;            // diff_phasor memory
 };
+__host__ __device__ inline int symsync_stride(int ch, int lookahead) { return ch - ((lookahead + 31) & ~31); }
 constexpr int SYMSYNC_TAB_FLOATS = 132 * 8 + 129 * 12 + 4;   // tap-major bank + entry-major bank (16-byte pitch multiple)
 struct SymSyncParams {
     float sps, alpha, beta, max_period, min_period;
@@ -737,7 +738,9 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
     constexpr bool EXT = (EPI == EPI_EXT_4FSK_FM);
     static_assert(!EXT || (NEPI == 1 && NCOMP == 1), "external epilogue: one drain warp, real symbols");
     constexpr int ROWF = 32 * NCOMP;                    // floats per row
-    constexpr int STRIDE = CH - 32;                     // window advance per chunk (lookahead <= 32)
+    // window advance per chunk: a lane leaves a window once its position is within `lookahead` rows of the end, so
+    // consecutive windows overlap by the lookahead rounded up to 32 rows (same formula on the host: symsync_stride)
+    const int STRIDE = symsync_stride(CH, p.lookahead);
     extern __shared__ __align__(128) float sm_sync[];   // [NST][CH][ROWF] | mmse[129*8] | sym[2][maxs][ROWF] | cnt[2][32]
     __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[2], bar_empty[2];
     __shared__ volatile int lane_zero[32];

@@ -81,6 +81,14 @@ class RxBlock:
     def sync(self):
         check(self._L.qrl_rx_sync(self._h), self._h, "qrl_rx_sync")
 
+    def set_overlap(self, on=True):
+        """Streaming mode: the loop / FEC tail of work() call k runs under the parallel stages of call k+1; read_port(),
+        sync() or join() wait for it."""
+        self.set_param(PARAM.OVERLAP_CALLS, 1.0 if on else 0.0)
+
+    def join(self):
+        check(self._L.qrl_rx_join(self._h), self._h, "qrl_rx_join")
+
     def read_port(self, port):
         """Returns a list (one entry per channel) of what the last work() produced on `port`."""
         isz = self._itemsize[port]

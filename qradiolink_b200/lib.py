@@ -17,7 +17,7 @@ class KIND:
 
 
 class PARAM:
-    CARRIER_OFFSET_HZ, SQUELCH_DB, FILTER_WIDTH, BB_GAIN = 1, 2, 3, 4
+    CARRIER_OFFSET_HZ, SQUELCH_DB, FILTER_WIDTH, BB_GAIN, OVERLAP_CALLS = 1, 2, 3, 4, 5
 
 
 # every symbol include/qrl_b200.h declares: (restype, argtypes)
@@ -33,6 +33,7 @@ SYMBOLS = {
     "qrl_rx_reset": (_i, [_vp]),
     "qrl_rx_work": (_i, [_vp, _vp, _l, _l, _i]),
     "qrl_rx_sync": (_i, [_vp]),
+    "qrl_rx_join": (_i, [_vp]),
     "qrl_rx_num_ports": (_i, [_vp]),
     "qrl_rx_port_itemsize": (_i, [_vp, _i]),
     "qrl_rx_read_port": (_i, [_vp, _i, _vp, _l, _vp, _i]),
