@@ -315,7 +315,12 @@ bool make_sm_partition(qrl_rx* h, unsigned loop_sms, int prio)
     if (pCreate(&h->g_par, d_par, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
     CUstream a = nullptr, b = nullptr, c = nullptr, d = nullptr;
     if (pStream(&a, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
-    if (pStream(&b, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
+    // FEC (Viterbi) stream: next to the loop kernels by default (measured: 4FSK step 1.23 ms vs 1.28 ms with the decoder
+    // on the wide partition, where it delays the filters feeding the loop; QPSK is bound by the per-sample Costas
+    // recurrence either way).  QRL_FEC_ON_PAR=1 moves it.
+    bool fec_on_par = false;
+    if (const char* e = getenv("QRL_FEC_ON_PAR")) fec_on_par = e[0] == '1';
+    if (pStream(&b, fec_on_par ? h->g_par : h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
     if (pStream(&d, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
     if (pStream(&c, h->g_par, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
     CUstream e2 = nullptr;
@@ -1048,7 +1053,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 {   // agc2_cc (Costas bypassed): r2 -> r3
                     constexpr int CH = 128, NST = 3;
                     const size_t smem = sizeof(float2) * (NST + 2) * CH * 32;
-                    auto kern = agc_costas_kernel<CH, NST>;
+                    auto kern = agc_costas_kernel<CH, NST, 0, 0>;
                     static bool a_attr = false;
                     if (!a_attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a_attr = true; }
                     kern<<<groups, 96, smem, h->s_loop>>>(h->acp, h->d_ac, h->C,
@@ -1236,10 +1241,11 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 pe = h->prof_begin(2, h->s_loop);
                 constexpr int CH = 128, NST = 3;
                 const size_t smem = sizeof(float2) * (NST + 2) * CH * 32;
-                auto kern = agc_costas_kernel<CH, NST>;
+                auto kern = (h->acp.order == 4 && h->acp.use_snr) ? agc_costas_kernel<CH, NST, 4, 1> : agc_costas_kernel<CH, NST>;
                 static bool ac_attr = false;
                 if (!ac_attr) {
-                    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    CK(cudaFuncSetAttribute(agc_costas_kernel<CH, NST, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    CK(cudaFuncSetAttribute(agc_costas_kernel<CH, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     ac_attr = true;
                 }
                 kern<<<groups, 96, smem, h->s_loop>>>(h->acp, h->d_ac, h->C,

@@ -509,6 +509,70 @@ __device__ __forceinline__ void qrl_costas_step(LoopState& st, float alpha, floa
 }
 
 // ------------------------------------------------------------------------------------------------
+// costas_loop_cc(order 4, use_snr) step for the per-sample recurrence of the QPSK chain, restated for a lone warp
+// (same values as qrl_costas_step, bit for bit; no conversion instruction on the chain):
+//   * |phase| < 2*pi + 2 here, so rintf(x * 2/pi) is the magic-number add (exact for |v| < 2^22) and its low
+//     mantissa bits are the quadrant;
+//   * the tanh table index floor(128 + 64 x) is an FADD with round-toward-minus-infinity onto 2^23;
+//   * the 2*pi wrap (exact double subtraction) sits behind one unlikely branch.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void qrl_sincosf_small(float x, float& s, float& c)
+{
+    const float kb = (x * 0.636619772f) + 12582912.0f;       // == rintf(x * 0.636619772f) + 1.5 * 2^23: the product is rounded
+                                                             // first (no fma), the add then rounds to nearest-even integer
+    const float k = kb - 12582912.0f;
+    const int q = __float_as_int(kb);
+    float r = fmaf(k, -1.5703125f, x);
+    r = fmaf(k, -4.837512969970703125e-4f, r);
+    r = fmaf(k, -7.54978995489188216e-8f, r);
+    const float z = r * r;
+    float ps = fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f);
+    ps = fmaf(ps, z, -1.6666654611e-1f);
+    ps = ps * z;
+    const float sn = fmaf(ps, r, r);
+    float pc = fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+    pc = fmaf(pc, z, 4.166664568298827e-2f);
+    pc = pc * z;
+    pc = pc * z;
+    float cs = fmaf(z, -0.5f, 1.0f);
+    cs = cs + pc;
+    const bool swap = q & 1;
+    const float s_ = swap ? cs : sn, c_ = swap ? sn : cs;
+    s = __int_as_float(__float_as_int(s_) ^ ((q & 2) << 30));
+    c = __int_as_float(__float_as_int(c_) ^ (((q + 1) & 2) << 30));
+}
+__device__ __forceinline__ float qrl_tanhf_lut_rd(float x, const float* __restrict__ tab)
+{
+    const float v = 128.0f + 64.0f * fminf(fmaxf(x, -2.0f), 2.0f);          // in [0, 256]
+    int index = __float_as_int(__fadd_rd(v, 8388608.0f)) & 0x1ff;           // floor(v): what static_cast<int>(v) gives
+    index = index > 255 ? 255 : index;
+    const float t = tab[index];
+    return x > 2.0f ? 1.0f : (x <= -2.0f ? -1.0f : t);
+}
+__device__ __forceinline__ void qrl_costas4_snr_step(LoopState& st, float alpha, float beta, float xr, float xi,
+                                                     float& yr, float& yi, const float* __restrict__ tanh_tab)
+{
+    float sn, cs;
+    qrl_sincosf_small(-st.phase, sn, cs);
+    const float orr = xr * cs - xi * sn;
+    const float oi = xr * sn + xi * cs;
+    const float snr = orr * orr + oi * oi;
+    float err = qrl_tanhf_lut_rd(snr * orr, tanh_tab) * oi - qrl_tanhf_lut_rd(snr * oi, tanh_tab) * orr;
+    err = qrl_clip(err, 1.0f);
+    st.freq = st.freq + beta * err;
+    st.phase = st.phase + st.freq + alpha * err;
+    if (__builtin_expect(!(fabsf(st.phase) < 6.2831854820251465f), 0)) {
+        while (st.phase >= 6.2831854820251465f)
+            st.phase = static_cast<float>(static_cast<double>(st.phase) - 2.0 * 3.14159265358979323846);
+        while (st.phase <= -6.2831854820251465f)
+            st.phase = static_cast<float>(static_cast<double>(st.phase) + 2.0 * 3.14159265358979323846);
+    }
+    if (st.freq > 1.0f) st.freq = 1.0f;
+    else if (st.freq < -1.0f) st.freq = -1.0f;
+    yr = orr; yi = oi;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fll_band_edge_cc (BPSK / 2FSK chains): per-sample NCO rotation + two N-tap complex band-edge filters on the
 // rotated stream + second-order loop.  One lane per channel, channel-major rings, rotated-sample window in shared
 // memory ([N][32] complex, bank = lane).  First correct version: the whole dot product sits in the sample loop
@@ -591,7 +655,7 @@ struct AgcCostasParams {
     int order, use_snr;
 };
 
-template <int CH, int NST>
+template <int CH, int NST, int ORDER = -1, int USE_SNR = -1>   // ORDER / USE_SNR >= 0: compile-time loop shape (else p.order / p.use_snr)
 __global__ void __launch_bounds__(96)
 agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
                   const float2* __restrict__ in, unsigned in_mask, long long in_stride, long long avail_total,
@@ -666,28 +730,51 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
         if (active) states[c].gain = gain;
     } else {
         // ---------------------------------------------------------------- Costas warp
+        // works in place on the hand-off block and sends it to the output ring with one TMA bulk store per block
         LoopState pll{ 0.0f, 0.0f };
         if (active) pll = states[c].pll;
-        float2* oring = out + static_cast<long long>(g) * out_stride * 32 + lane;
+        float2* oring = out + static_cast<long long>(g) * out_stride * 32;
+        const long long ocap = static_cast<long long>(out_mask) + 1;
         const float k_a = p.alpha, k_b = p.beta;
+        const int order = ORDER >= 0 ? ORDER : p.order;
+        const bool use_snr = USE_SNR >= 0 ? (USE_SNR != 0) : (p.use_snr != 0);
         for (int m = 0; m < nchunks; m++) {
             const int b = m & 1;
             mbar_wait(&bar_full[b], (m >> 1) & 1);
-            const float2* hb = hand + b * CH * 32 + lane;
+            float2* hb = hand + b * CH * 32 + lane;
             const long long w0 = base + static_cast<long long>(m) * CH;
             const long long rem = total - static_cast<long long>(m) * CH;
             const int n = rem < CH ? static_cast<int>(rem) : CH;
-            if (active) {
-                for (int i = 0; i < n; i++) {
-                    const float2 x = hb[i * 32];
-                    float yr = x.x, yi = x.y;
-                    if (p.order != 0) qrl_costas_step(pll, k_a, k_b, p.order, p.use_snr != 0, x.x, x.y, yr, yi, tanh_s);
-                    oring[((w0 + i) & out_mask) * 32] = make_float2(yr, yi);
+            if (active && order != 0) {
+                if (ORDER == 4 && USE_SNR == 1) {
+                    for (int i = 0; i < n; i++) {
+                        const float2 x = hb[i * 32];
+                        float yr, yi;
+                        qrl_costas4_snr_step(pll, k_a, k_b, x.x, x.y, yr, yi, tanh_s);
+                        hb[i * 32] = make_float2(yr, yi);
+                    }
+                } else {
+                    for (int i = 0; i < n; i++) {
+                        const float2 x = hb[i * 32];
+                        float yr, yi;
+                        qrl_costas_step(pll, k_a, k_b, order, use_snr, x.x, x.y, yr, yi, tanh_s);
+                        hb[i * 32] = make_float2(yr, yi);
+                    }
                 }
             }
+            fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_empty[b]);
+            if (lane == 0) {
+                const float2* src = hand + b * CH * 32;
+                const long long s0 = w0 & out_mask;
+                const long long first = (s0 + n <= ocap) ? n : (ocap - s0);
+                bulk_s2g(oring + s0 * 32, src, static_cast<uint32_t>(first * 256));
+                if (first < n) bulk_s2g(oring, src + first * 32, static_cast<uint32_t>((n - first) * 256));
+                bulk_commit();
+                if (m >= 1) { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); mbar_arrive(&bar_empty[b ^ 1]); }
+            }
         }
+        if (lane == 0) { bulk_wait_all0(); mbar_arrive(&bar_empty[(nchunks - 1) & 1]); }
         if (active) { states[c].pll = pll; states[c].pos = avail_total; }
     }
 }
