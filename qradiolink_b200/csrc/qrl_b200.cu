@@ -1436,6 +1436,10 @@ struct qrl_tx : HandleBase {
     double pe_b0 = 0, pe_b1 = 0, pe_a1 = 0;
     long long n_audio = 0, n_mid = 0;        // audio samples consumed / mid-rate items produced (host mirror of the device counters)
     float* d_audio_in = nullptr;
+    // 4FSK: the three stages (bit chain, pulse shaping + FM scan, x20 interpolator) run slice by slice on three streams
+    static constexpr int kTxSub = 8;
+    cudaStream_t s_bits = nullptr, s_shape = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_bits[kTxSub] = { nullptr }, ev_shape[kTxSub] = { nullptr }, ev_shape_done = nullptr, ev_out_done = nullptr;
 };
 
 static std::vector<float> make_arms(const std::vector<float>& taps, int L, int nt)
@@ -1572,6 +1576,10 @@ int qrl_tx_destroy(qrl_tx* h)
     if (!h) return QRL_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->s_bits) { cudaStreamSynchronize(h->s_bits); cudaStreamDestroy(h->s_bits); }
+    if (h->s_shape) { cudaStreamSynchronize(h->s_shape); cudaStreamDestroy(h->s_shape); }
+    for (cudaEvent_t e : { h->ev_start, h->ev_shape_done, h->ev_out_done }) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < qrl_tx::kTxSub; i++) { if (h->ev_bits[i]) cudaEventDestroy(h->ev_bits[i]); if (h->ev_shape[i]) cudaEventDestroy(h->ev_shape[i]); }
     for (void* p : h->allocs) cudaFree(p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1666,6 +1674,53 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
     const bool cplx = h->kind == QRL_MOD_QPSK || h->kind == QRL_MOD_BPSK;
     const bool one_per_bit = h->kind == QRL_MOD_BPSK || h->kind == QRL_MOD_2FSK;
     const long long sym0 = h->n_sym, nsym = (one_per_bit ? 16LL : 8LL) * n;
+    // 4FSK: bit chain / pulse shaping + FM scan / x20 interpolator are pipelined slice by slice on three streams (the
+    // first two are one-CTA-per-channel recurrences that leave most SMs idle; the interpolator fills them)
+    bool pipelined = h->kind == QRL_MOD_4FSK && h->L2 == 20 && h->nt2 == 35 && n >= 8 * qrl_tx::kTxSub;
+    if (pipelined && !h->s_bits) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        bool ok = cudaStreamCreateWithPriority(&h->s_bits, cudaStreamNonBlocking, hi) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&h->s_shape, cudaStreamNonBlocking, hi) == cudaSuccess;
+        auto mk = [&](cudaEvent_t* e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+        mk(&h->ev_start); mk(&h->ev_shape_done); mk(&h->ev_out_done);
+        for (int i = 0; i < qrl_tx::kTxSub; i++) { mk(&h->ev_bits[i]); mk(&h->ev_shape[i]); }
+        if (!ok) { set_err(h, "qrl_tx_work: stream/event creation failed"); return QRL_ECUDA; }
+    }
+    if (pipelined) {
+        constexpr int S = qrl_tx::kTxSub;
+        CK(cudaEventRecord(h->ev_start, h->stream));
+        CK(cudaStreamWaitEvent(h->s_bits, h->ev_start, 0));
+        CK(cudaStreamWaitEvent(h->s_bits, h->ev_shape_done, 0));      // previous call: symbol ring consumed
+        CK(cudaStreamWaitEvent(h->s_shape, h->ev_out_done, 0));       // previous call: IF ring consumed
+        const long long out_base = sym0 * h->L1 * h->L2;
+        for (int j = 0; j < S; j++) {
+            const long b0 = n * j / S, b1 = n * (j + 1) / S;
+            if (b1 <= b0) continue;
+            const long long symA = sym0 + 8LL * b0, nsym_j = 8LL * (b1 - b0);
+            tx_bits_kernel<TXM_4FSK><<<dim3((h->C + 31) / 32), 32, 0, h->s_bits>>>(h->d_bits, h->C, b + b0, b1 - b0, bstride,
+                                                                                 h->d_sym, h->sym_mask, h->sym_stride, symA);
+            CK(cudaEventRecord(h->ev_bits[j], h->s_bits));
+            CK(cudaStreamWaitEvent(h->s_shape, h->ev_bits[j], 0));
+            tx_shape_fm_kernel<256, 8><<<h->C, 256, 0, h->s_shape>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, symA, nsym_j,
+                h->L1, h->nt1, h->d_arms1, h->repeat_only, h->pulse_scale, h->fm_sens, h->amplif, h->bb_gain,
+                h->d_if, h->if_mask, h->if_stride);
+            CK(cudaEventRecord(h->ev_shape[j], h->s_shape));
+            CK(cudaStreamWaitEvent(h->stream, h->ev_shape[j], 0));
+            constexpr int L = 20, NT = 35, R = 8, G = 16;
+            const long long m0 = symA * h->L1, m1 = (symA + nsym_j) * h->L1;
+            dim3 g(static_cast<unsigned>((m1 - m0 + R * G - 1) / (R * G)), h->C);
+            interp_fir_ccf_rt_kernel<L, NT, R, G><<<g, L * G, 0, h->stream>>>(
+                h->d_if, h->if_mask, h->if_stride, m0, m1, h->d_arms2, 1.0f, 1.0f, 0, h->d_out, h->out_stride, out_base);
+            h->launches += 3;
+        }
+        CK(cudaEventRecord(h->ev_shape_done, h->s_shape));
+        CK(cudaEventRecord(h->ev_out_done, h->stream));
+        h->n_out_last = static_cast<long>(nsym * h->L1 * h->L2);
+        h->n_sym += nsym;
+        CK(cudaGetLastError());
+        return QRL_OK;
+    }
     {
         dim3 g((h->C + 31) / 32);
         if (h->kind == QRL_MOD_QPSK) tx_bits_kernel<TXM_QPSK><<<g, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
@@ -1703,9 +1758,9 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
         h->launches++;
         const long long m0 = sym0 * h->L1, m1 = (sym0 + nsym) * h->L1;
         if (h->L2 == 20 && h->nt2 == 35) {
-            constexpr int L = 20, NT = 35, MB = 8, MLEN = 70;
-            dim3 g(static_cast<unsigned>((m1 - m0 + MB * MLEN - 1) / (MB * MLEN)), h->C);
-            interp_fir_ccf_kernel<L, NT, MB, MLEN><<<g, L * MB, 0, h->stream>>>(
+            constexpr int L = 20, NT = 35, R = 8, G = 16;
+            dim3 g(static_cast<unsigned>((m1 - m0 + R * G - 1) / (R * G)), h->C);
+            interp_fir_ccf_rt_kernel<L, NT, R, G><<<g, L * G, 0, h->stream>>>(
                 h->d_if, h->if_mask, h->if_stride, m0, m1, h->d_arms2, 1.0f, 1.0f, 0, h->d_out, h->out_stride, m0 * L);
             h->launches++;
         } else {
