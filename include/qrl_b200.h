@@ -41,6 +41,7 @@ extern "C" {
 enum qrl_kind {
     QRL_DEMOD_NBFM = 1, QRL_DEMOD_4FSK = 2, QRL_DEMOD_QPSK = 3, QRL_DEMOD_BPSK = 4, QRL_DEMOD_2FSK = 5,
     QRL_DEMOD_SSB = 6,
+    QRL_DEMOD_AM = 7,         /* gr_demod_am.cpp:28-82; ports: IQ, float audio at 8 ksps */
     QRL_MOD_4FSK = 101, QRL_MOD_QPSK = 102, QRL_MOD_NBFM = 103, QRL_MOD_BPSK = 104, QRL_MOD_2FSK = 105,
     QRL_MOD_SSB = 106
 };

@@ -526,6 +526,7 @@ static void resamp_work(resamp_t* r, const float* x, size_t n, qvec* out)
         while (r->ctr >= (unsigned)r->L) { r->ctr -= r->L; r->pos++; }
     }
     size_t keep_from = r->pos - (r->nt - 1);
+    if (keep_from > r->in.n) keep_from = r->in.n;          /* decimation larger than the arm: the next position lies in future input */
     if (keep_from > 0) { qv_drop(&r->in, keep_from); r->pos -= keep_from; }
 }
 
@@ -1141,6 +1142,27 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         qdemod_init(&r->qd, (float)(r->tsr / (4 * M_PI * filter_width)));
         squelch_init(&r->sq, -140, 0.01, 320, 1);
         r->port[1].isz = 4;
+    } else if (kind == QO_DEMOD_AM) {
+        /* /root/reference/src/gr/gr_demod_am.cpp:28-82: /50 (419 taps) -> complex band-pass(-fw, fw) -> [port 0] ->
+         * pwr_squelch_cc(-140, 0.01, 0, gate) -> complex_to_mag -> agc2_ff(.1, .1, 1, 1) -> iir_filter_ffd({1,-1},{0,.9999})
+         * (old style: y = x - x1 + 0.9999 y1, double) -> x0.99 -> rational_resampler_fff(2,5) -> audio low-pass -> [port 1] */
+        r->tsr = 20000;
+        int n0 = qo_firdes_low_pass(1, samp_rate, r->tsr / 2, r->tsr / 2, QO_WIN_BLACKMAN_HARRIS, T0, 4096);
+        r->ntaps_store[0] = n0;
+        resamp_init(&r->resamp, 2, 1, 50, T0, n0);
+        float tc[2 * 4096];
+        int nb = qo_firdes_complex_band_pass_2(1, r->tsr, -filter_width, filter_width, 200, 90, QO_WIN_BLACKMAN_HARRIS, tc, 4096);
+        fircc_init(&r->ssb_bpf, tc, nb);
+        squelch_init(&r->sq, -140, 0.01, 0, 1);
+        agc2_init(&r->agc, 1e-1f, 1e-1f, 1.0f, 1.0f);
+        { const double b[2] = { 1.0, -1.0 }, a[2] = { 1.0, -0.9999 }; iir1_init(&r->deemph, b, a); }
+        int n2 = qo_firdes_low_pass(2, 2 * r->tsr, 3600, 600, QO_WIN_BLACKMAN_HARRIS, T2, 4096);
+        r->ntaps_store[2] = n2;
+        resamp_init(&r->audio_rs, 1, 2, 5, T2, n2);
+        int n3 = qo_firdes_low_pass(1, 8000, 3600, 300, QO_WIN_BLACKMAN_HARRIS, T3, 4096);
+        r->ntaps_store[3] = n3;
+        resamp_init(&r->audio_filt, 1, 1, 1, T3, n3);
+        r->port[1].isz = 4;
     } else if (kind == QO_DEMOD_SSB) {
         /* /root/reference/src/gr/gr_demod_ssb.cpp:31-86; flag = sb (0 = USB, 1 = LSB) */
         r->tsr = 8000;
@@ -1454,6 +1476,30 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
             qv_pushb(&r->s_soft, soft_u8(oi, r->soft_scale));
         }
         rx_fec_tail(r);
+        return 0;
+    }
+    if (r->kind == QO_DEMOD_AM) {
+        r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
+        r->s_filt.n = 0; fircc_work(&r->ssb_bpf, (const float*)r->s_res.d, r->s_res.n, &r->s_filt);
+        qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
+        r->s_tmp.n = 0; squelch_work(&r->sq, (const float*)r->s_filt.d, r->s_filt.n, &r->s_tmp);
+        const float* g = (const float*)r->s_tmp.d;
+        r->s_dem.n = 0;
+        for (size_t i = 0; i < r->s_tmp.n; i++) {
+            /* complex_to_mag, then analog::kernel::agc2_ff::scale */
+            const float mag = sqrtf(g[2 * i] * g[2 * i] + g[2 * i + 1] * g[2 * i + 1]);
+            const float out = mag * r->agc.gain;
+            const float tmp = fabsf(out) - r->agc.ref;
+            float rate = r->agc.decay;
+            if (fabsf(tmp) > r->agc.gain) rate = r->agc.attack;
+            r->agc.gain -= tmp * rate;
+            if (r->agc.gain < 0.0f) r->agc.gain = 10e-5f;
+            if (r->agc.max_gain > 0.0f && r->agc.gain > r->agc.max_gain) r->agc.gain = r->agc.max_gain;
+            qv_pushf(&r->s_dem, out);
+        }
+        r->s_sym.isz = 4; r->s_sym.n = 0; iir1_work(&r->deemph, (const float*)r->s_dem.d, r->s_dem.n, &r->s_sym, 0.99f);
+        r->s_rrc.n = 0; resamp_work(&r->audio_rs, (const float*)r->s_sym.d, r->s_sym.n, &r->s_rrc);
+        resamp_work(&r->audio_filt, (const float*)r->s_rrc.d, r->s_rrc.n, &r->port[1]);
         return 0;
     }
     if (r->kind == QO_DEMOD_NBFM) {

@@ -543,6 +543,13 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         taps2 = flag ? complex_band_pass_2(1, tsr, -filter_width, -200, 200, 90, WIN_BLACKMAN_HARRIS)
                      : complex_band_pass_2(1, tsr, 200, filter_width, 200, 90, WIN_BLACKMAN_HARRIS);
         h->nports = 2;
+    } else if (kind == QRL_DEMOD_AM) {
+        // gr_demod_am.cpp:35-56
+        tsr = 20000; sym_sps = 2;
+        taps1 = low_pass(1, samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
+        h->D1 = 50;
+        taps2 = complex_band_pass_2(1, tsr, -filter_width, filter_width, 200, 90, WIN_BLACKMAN_HARRIS);
+        h->nports = 2;
     } else if (kind == QRL_DEMOD_NBFM) {
         // gr_demod_nbfm.cpp:39-66
         tsr = 20000; sym_sps = 2;
@@ -575,7 +582,7 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     if ((rc = dev_alloc(h, &h->d_hist[1], static_cast<size_t>(h->H) * h->C))) return fail(rc);
     h->n1max = h->Tmax * h->L1 / h->D1 + 2;
     // ---- rings
-    h->ntaps2 = static_cast<int>(taps2.size()) / (kind == QRL_DEMOD_SSB ? 2 : 1);
+    h->ntaps2 = static_cast<int>(taps2.size()) / ((kind == QRL_DEMOD_SSB || kind == QRL_DEMOD_AM) ? 2 : 1);
     h->ntaps3 = static_cast<int>(taps3.size());
     {
         std::vector<float> t2(std::max<size_t>(taps2.size(), 512), 0.0f);     // room for set_filter_width redesigns
@@ -595,6 +602,26 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = make_ring(h, &h->rclip, sizeof(float2), h->n1max + 16))) return fail(rc);
         if ((rc = make_ring(h, &h->rstr, sizeof(float), h->n1max + h->ssbp.nt_audio + 16))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_ssb, h->C))) return fail(rc);
+    } else if (kind == QRL_DEMOD_AM) {
+        // gr_demod_am.cpp:41-70: the NBFM audio kernel in detector mode 1
+        if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + 64))) return fail(rc);
+        std::vector<float> audio_rs = low_pass(2, 2 * tsr, 3600, 600, WIN_BLACKMAN_HARRIS);
+        std::vector<float> audio_f = low_pass(1, 8000, 3600, 300, WIN_BLACKMAN_HARRIS);
+        const int nt_arm = (static_cast<int>(audio_rs.size()) + 1) / 2;
+        std::vector<float> arms(2 * nt_arm, 0.0f);
+        for (int pp = 0; pp < 2; pp++)
+            for (int k = 0; k < nt_arm; k++) { const size_t j = pp + 2 * k; arms[pp * nt_arm + k] = j < audio_rs.size() ? audio_rs[j] : 0.0f; }
+        if ((rc = upload_floats(h, &h->d_arm_taps, arms))) return fail(rc);
+        if ((rc = upload_floats(h, &h->d_audio_taps, audio_f))) return fail(rc);
+        if ((rc = upload_floats(h, &h->d_env, std::vector<float>{ 1.0f, 1.0f }))) return fail(rc);
+        h->nbp.sq_alpha = 0.01; h->nbp.sq_threshold = std::pow(10.0, -140 / 10.0); h->nbp.sq_ramp = 0; h->nbp.sq_gate = 1;
+        h->nbp.qd_gain = 0.0f; h->nbp.nt_arm = nt_arm; h->nbp.nt_audio = static_cast<int>(audio_f.size());
+        h->nbp.b0 = 1.0; h->nbp.b1 = -1.0; h->nbp.a1 = -0.9999; h->nbp.out_gain = 1.0f;      // iir_filter_ffd({1,-1},{0,0.9999}), old style
+        h->nbp.mode = 1; h->nbp.agc_attack = 1e-1f; h->nbp.agc_decay = 1e-1f; h->nbp.agc_ref = 1.0f; h->nbp.agc_max = 65536.0f; h->nbp.am_gain = 0.99f;
+        if ((rc = make_ring(h, &h->rg, sizeof(float2), 64))) return fail(rc);
+        if ((rc = make_ring(h, &h->rd, sizeof(float), h->n1max + nt_arm + 16))) return fail(rc);
+        if ((rc = make_ring(h, &h->rr, sizeof(float), h->n1max * 2 / 5 + h->nbp.nt_audio + 16))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_nb, h->C))) return fail(rc);
     } else if (kind == QRL_DEMOD_NBFM) {
         if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + 64))) return fail(rc);
         std::vector<float> audio_rs = low_pass_2(2, 2 * tsr, 3600, 250, 60, WIN_BLACKMAN_HARRIS);
@@ -758,7 +785,7 @@ int qrl_rx_reset(qrl_rx* h)
     if (h->d_nb) {
         for (int c = 0; c < h->C; c++) {
             std::memset(&nb[c], 0, sizeof(NbfmState));
-            nb[c].sq_state = SQ_MUTED; nb[c].envelope = h->nbp.sq_ramp ? 0.0f : 1.0f;
+            nb[c].sq_state = SQ_MUTED; nb[c].envelope = h->nbp.sq_ramp ? 0.0f : 1.0f; nb[c].agc_gain = 1.0f;
         }
         CK(cudaMemcpyAsync(h->d_nb, nb.data(), sizeof(NbfmState) * h->C, cudaMemcpyHostToDevice, h->stream));
     }
@@ -985,6 +1012,29 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 static_cast<float2*>(h->rclip.d), h->rclip.mask, h->rclip.stride,
                 static_cast<float*>(h->rstr.d), h->rstr.mask, h->rstr.stride,
                 h->d_audio_taps, h->d_port1f, 2 * h->port1_cap, h->d_port1_cnt, static_cast<int>(2 * h->port1_cap));
+            h->launches++;
+            h->prof_end(pe);
+            continue;
+        }
+        if (h->kind == QRL_DEMOD_AM) {
+            if (n_new > 0) {
+                pe = h->prof_begin(1, sp);
+                fir_ccc_ring_kernel<<<gtile, TB, sizeof(float) * 2 * h->ntaps2, sp>>>(
+                    static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
+                    static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                    h->d_taps2, h->ntaps2, 1.0f, k0, k1, h->d_port0, h->port0_cap, k_call0);
+                h->launches++;
+                h->prof_end(pe);
+            }
+            CK(cudaEventRecord(h->ev_a[i], sp));
+            CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
+            pe = h->prof_begin(3, h->s_loop);
+            nbfm_audio_kernel<<<h->C, 128, 0, h->s_loop>>>(h->nbp, h->d_nb,
+                static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, k1, h->d_env,
+                static_cast<float2*>(h->rg.d), h->rg.mask, h->rg.stride,
+                static_cast<float*>(h->rd.d), h->rd.mask, h->rd.stride,
+                static_cast<float*>(h->rr.d), h->rr.mask, h->rr.stride,
+                h->d_arm_taps, h->d_audio_taps, h->d_port1f, 2 * h->port1_cap, h->d_port1_cnt, static_cast<int>(2 * h->port1_cap));
             h->launches++;
             h->prof_end(pe);
             continue;
@@ -1359,7 +1409,7 @@ int qrl_rx_port_itemsize(const qrl_rx* h, int port)
 {
     if (!h || port < 0 || port >= h->nports) return QRL_EINVAL;
     if (port == 0) return 8;
-    if (port == 1) return (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_SSB) ? 4 : 8;
+    if (port == 1) return (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_SSB || h->kind == QRL_DEMOD_AM) ? 4 : 8;
     return 1;
 }
 
@@ -1369,7 +1419,7 @@ int qrl_rx_port_device(qrl_rx* h, int port, void** data, long* cap, int** counts
     if (port == 0) { *data = h->d_port0; *cap = h->port0_cap; *counts = nullptr; }
     else if (port == 1) {
         *data = h->d_port1; *counts = h->d_port1_cnt;
-        *cap = (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_SSB) ? 2 * h->port1_cap : h->port1_cap;      // float view of the same buffer
+        *cap = (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_SSB || h->kind == QRL_DEMOD_AM) ? 2 * h->port1_cap : h->port1_cap;      // float view of the same buffer
     }
     else if (port == 2) { *data = h->d_port2; *cap = h->port2_cap; *counts = h->d_port2_cnt; }
     else { *data = h->d_port3; *cap = h->port2_cap; *counts = h->d_port3_cnt; }
@@ -1829,10 +1879,28 @@ int qrl_design_table(const char* name, float* out, int cap)
 }
 int qrl_design_deemph(int fs, double tau, double* a2, double* b2) { deemph_taps(fs, tau, a2, b2); return QRL_OK; }
 
-int qrl_fir_decim_ccf_device(const float*, int, int, const float*, long, long, float*, long, int, void*)
+int qrl_fir_decim_ccf_device(const float* taps, int ntaps, int D, const float* x_dev, long T, long x_stride,
+                             float* y_dev, long y_stride, int C, void* cuda_stream)
 {
-    set_err(nullptr, "qrl_fir_decim_ccf_device: not built yet");
-    return QRL_EINVAL;
+    if (!taps || ntaps < 1 || ntaps > 65536 || D < 1 || !x_dev || !y_dev || T < 0 || C < 1) { set_err(nullptr, "qrl_fir_decim_ccf_device: bad argument"); return QRL_EINVAL; }
+    if (qrl_device_count() < 1) { set_err(nullptr, "qrl_fir_decim_ccf_device: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
+    const long long nout = (static_cast<long long>(T) + D - 1) / D;
+    if (nout == 0) return QRL_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    float* d_taps = nullptr;
+    HandleBase* h = nullptr;
+    CK(cudaMalloc(&d_taps, sizeof(float) * ntaps));
+    cudaError_t e = cudaMemcpyAsync(d_taps, taps, sizeof(float) * ntaps, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        dim3 g(static_cast<unsigned>(std::min<long long>((nout + 7) / 8, 148LL * 16)), static_cast<unsigned>(C));
+        fir_decim_generic_kernel<<<g, 256, 0, st>>>(d_taps, ntaps, D, reinterpret_cast<const float2*>(x_dev), T, x_stride,
+                                                    reinterpret_cast<float2*>(y_dev), y_stride, nout);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // the tap buffer is released below
+    cudaFree(d_taps);
+    if (e != cudaSuccess) { set_err(nullptr, std::string("qrl_fir_decim_ccf_device: ") + cudaGetErrorString(e)); return QRL_ECUDA; }
+    return QRL_OK;
 }
 
 }  // extern "C"

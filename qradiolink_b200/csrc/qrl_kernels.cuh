@@ -418,6 +418,36 @@ __global__ void qdemod_fir_fff_kernel(const float2* __restrict__ in, unsigned in
     out[(static_cast<long long>(c >> 5) * out_stride + (a & out_mask)) * 32 + (c & 31)] = acc;
 }
 
+// Stand-alone batched decimating FIR for any (ntaps, D), zero history: y[k] = sum_j h[j] x[D k - j] in THE FIR order
+// (branch r = j mod D oldest-first into lane r mod 32, lanes combined 16, 8, 4, 2, 1).  One warp per output; this is the
+// shape-generic entry point behind qrl_fir_decim_ccf_device (the chains use the register-tiled instances above).
+__global__ void __launch_bounds__(256)
+fir_decim_generic_kernel(const float* __restrict__ taps, int ntaps, int D, const float2* __restrict__ x, long long T, long long x_stride,
+                         float2* __restrict__ y, long long y_stride, long long nout)
+{
+    const int lane = threadIdx.x & 31, c = blockIdx.y;
+    const float2* xc = x + static_cast<long long>(c) * x_stride;
+    float2* yc = y + static_cast<long long>(c) * y_stride;
+    const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    for (long long k = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); k < nout; k += warps) {
+        float re = 0.0f, im = 0.0f;
+        for (int r = lane; r < D && r < ntaps; r += 32) {
+            for (int q = (ntaps - 1 - r) / D; q >= 0; q--) {
+                const int j = D * q + r;
+                const long long n = D * k - j;
+                const float2 v = (n >= 0 && n < T) ? xc[n] : make_float2(0.0f, 0.0f);
+                re = fmaf(taps[j], v.x, re); im = fmaf(taps[j], v.y, im);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            re = re + __shfl_down_sync(0xffffffffu, re, off);
+            im = im + __shfl_down_sync(0xffffffffu, im, off);
+        }
+        if (lane == 0) yc[k] = make_float2(re, im);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Sequential loop stage: symbol_sync (PI clock loop, mod. Mueller&Muller TED, 8-tap MMSE interpolator)
 // One lane per channel; a warp stages 32 channels x CH samples in shared memory with coalesced loads,
@@ -1428,6 +1458,7 @@ struct NbfmState {
     int sq_state, ramped;
     float envelope;
     float prev_r, prev_i;     // quadrature demod memory
+    float agc_gain;           // AM: agc2_ff gain
 };
 struct NbfmParams {
     double sq_alpha, sq_threshold;
@@ -1437,6 +1468,10 @@ struct NbfmParams {
     int nt_audio;
     double b0, b1, a1;
     float out_gain;
+    // mode 1 = AM detector (gr_demod_am.cpp:57-71): squelch -> complex_to_mag -> agc2_ff -> iir_filter_ffd (b0, b1, a1) -> x am_gain
+    // on the 20 ksps stream, then resampler 2/5 and audio low-pass straight to port 1 (no de-emphasis behind them)
+    int mode;
+    float agc_attack, agc_decay, agc_ref, agc_max, am_gain;
 };
 enum { SQ_MUTED = 0, SQ_ATTACK = 1, SQ_UNMUTED = 2, SQ_DECAY = 3 };
 
@@ -1470,6 +1505,7 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
         __syncthreads();
         if (threadIdx.x == 0) {
             double pwr = st.pwr; int state = st.sq_state, ramped = st.ramped; float env = st.envelope;
+            float agc = st.agc_gain; double ix1 = st.iir_x1, iy1 = st.iir_y1;
             long long ng = st.n_gate;
             const double one_m_alpha = 1.0 - p.sq_alpha;
             for (int j = 0; j < nt; j++) {
@@ -1489,18 +1525,37 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
                     if (ramped == 0) state = SQ_MUTED;
                     break;
                 }
-                if (state != SQ_MUTED) { gr_[ng & gate_mask] = make_float2(v.x * env, v.y * env); ng++; }
+                if (p.mode == 1) {
+                    if (state != SQ_MUTED) {
+                        const float vr = v.x * env, vi = v.y * env;
+                        const float mag = sqrtf(vr * vr + vi * vi);                    // complex_to_mag
+                        const float outv = mag * agc;                                   // agc2_ff::scale
+                        const float tmp = fabsf(outv) - p.agc_ref;
+                        const float rate = (fabsf(tmp) > agc) ? p.agc_attack : p.agc_decay;
+                        agc = agc - tmp * rate;
+                        if (agc < 0.0f) agc = 10e-5f;
+                        if (p.agc_max > 0.0f && agc > p.agc_max) agc = p.agc_max;
+                        const double xin = static_cast<double>(outv);                   // iir_filter_ffd
+                        double acc = p.b0 * xin;
+                        acc = acc + p.b1 * ix1;
+                        acc = acc - p.a1 * iy1;
+                        ix1 = xin; iy1 = acc;
+                        dr[ng & dem_mask] = static_cast<float>(acc) * p.am_gain;
+                        ng++;
+                    }
+                } else if (state != SQ_MUTED) { gr_[ng & gate_mask] = make_float2(v.x * env, v.y * env); ng++; }
                 else if (!p.sq_gate) { gr_[ng & gate_mask] = make_float2(0.0f, 0.0f); ng++; }
             }
             st.pwr = pwr; st.sq_state = state; st.ramped = ramped; st.envelope = env; st.n_gate = ng;
+            if (p.mode == 1) { st.agc_gain = agc; st.iir_x1 = ix1; st.iir_y1 = iy1; }
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) st.n_in = avail_in;
     __syncthreads();
     const long long gate1 = st.n_gate;
-    // ---- 2. quadrature demod over the gated stream
-    for (long long n = gate0 + threadIdx.x; n < gate1; n += blockDim.x) {
+    // ---- 2. quadrature demod over the gated stream (AM: the detector already wrote the 20 ksps stream)
+    for (long long n = gate0 + threadIdx.x; n < gate1 && p.mode == 0; n += blockDim.x) {
         const float2 cur = gr_[n & gate_mask];
         float2 prev;
         if (n == gate0) prev = make_float2(st.prev_r, st.prev_i);
@@ -1510,7 +1565,7 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
         dr[n & dem_mask] = p.qd_gain * qrl_fast_atan2f(im, re);
     }
     __syncthreads();
-    if (threadIdx.x == 0 && gate1 > gate0) { const float2 l = gr_[(gate1 - 1) & gate_mask]; st.prev_r = l.x; st.prev_i = l.y; }
+    if (threadIdx.x == 0 && gate1 > gate0 && p.mode == 0) { const float2 l = gr_[(gate1 - 1) & gate_mask]; st.prev_r = l.x; st.prev_i = l.y; }
     // ---- 3. rational resampler 2/5: output i uses arm (5 i) mod 2 at input position floor(5 i / 2)
     const long long res0 = st.n_res;
     long long res1 = res0;
@@ -1546,7 +1601,13 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
         }
         __syncthreads();
         // ---- 5. de-emphasis IIR (double) + output gain (sequential)
-        if (threadIdx.x == 0) {
+        if (p.mode == 1) {
+            const int cnt0 = port1_cnt[c];
+            float* o = port1 + static_cast<long long>(c) * port1_stride;
+            for (int j = threadIdx.x; j < nb; j += blockDim.x) if (cnt0 + j < port1_cap) o[cnt0 + j] = aud[j];
+            __syncthreads();
+            if (threadIdx.x == 0) port1_cnt[c] = cnt0 + nb;
+        } else if (threadIdx.x == 0) {
             double x1 = st.iir_x1, y1 = st.iir_y1;
             int cnt = port1_cnt[c];
             float* o = port1 + static_cast<long long>(c) * port1_stride;

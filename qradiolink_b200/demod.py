@@ -136,6 +136,11 @@ def make_gr_demod_ssb(sps, samp_rate, carrier_freq, filter_width, sb, n_channels
     return RxBlock(KIND.DEMOD_SSB, sps, samp_rate, carrier_freq, filter_width, int(sb), n_channels, **kw)
 
 
+def make_gr_demod_am(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
+    """src/gr/gr_demod_am.h (instance gr_demod_base.cpp: make_gr_demod_am(125, 1e6, 1700, 5000)); ports (IQ, float audio)."""
+    return RxBlock(KIND.DEMOD_AM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
+
+
 def make_gr_demod_nbfm(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
     return RxBlock(KIND.DEMOD_NBFM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
 

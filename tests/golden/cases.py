@@ -68,6 +68,16 @@ def _sig_digital(kind):
     return f
 
 
+def _sig_am(O, sg):
+    rng = np.random.default_rng(9650)
+    T = 1 << 18
+    n = np.arange(T)
+    aud = 0.5 * np.sin(2 * np.pi * 900.0 * n / 1e6) + 0.3 * np.sin(2 * np.pi * 2100.0 * n / 1e6)
+    x = 0.4 * (1.0 + 0.8 * aud) * np.exp(2j * np.pi * 150.0 * n / 1e6)
+    x = x + (rng.standard_normal(T) + 1j * rng.standard_normal(T)) * 0.004
+    return x.astype(np.complex64)[None, :]
+
+
 def _sig_ssb(O, sg):
     rng = np.random.default_rng(9600)
     T = 1 << 18
@@ -91,6 +101,8 @@ RX_CASES = {
                     factory="make_gr_demod_bpsk", fargs=(250, 1000000, 1700, 2800)),
     "2fsk_2k_fm": dict(okind=5, args=(25, 1000000, 1700, 4000, 1), nports=4, signal=_sig_digital("2fsk"),
                        factory="make_gr_demod_2fsk", fargs=(25, 1000000, 1700, 4000, True)),
+    "am_5000": dict(okind=7, args=(125, 1000000, 1700, 5000, 0), nports=2, signal=_sig_am,
+                    factory="make_gr_demod_am", fargs=(125, 1000000, 1700, 5000)),
     "ssb_usb": dict(okind=6, args=(125, 1000000, 1700, 2700, 0), nports=2, signal=_sig_ssb,
                     factory="make_gr_demod_ssb", fargs=(125, 1000000, 1700, 2700, 0)),
 }

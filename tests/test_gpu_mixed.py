@@ -54,3 +54,25 @@ def test_channel_counts_not_multiple_of_32(qrl, oracle, C):
     for c in sorted({0, C // 2, C - 1}):
         rx = oracle.Rx(oracle.DEMOD_4FSK, 5, 1000000, 1700, 3000, 1); rx.work(X[c])
         assert np.array_equal(bits[c], rx.port(2)), c
+
+
+@pytest.mark.parametrize("ntaps,D", [(419, 50), (100, 7), (33, 1), (5, 64)])
+def test_standalone_decimating_fir_any_shape(qrl, oracle, ntaps, D):
+    """qrl_fir_decim_ccf_device: shape-generic batched decimating FIR in THE FIR order, bit-identical to the oracle."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(ntaps + D)
+    taps = (rng.standard_normal(ntaps) / ntaps).astype(np.float32)
+    Cn, T = 3, 5003
+    x = (rng.standard_normal((Cn, T)) + 1j * rng.standard_normal((Cn, T))).astype(np.complex64)
+    nout = (T + D - 1) // D
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.zeros((Cn, nout), dtype=torch.complex64, device="cuda")
+    L = qrl.load_library()
+    rc = L.qrl_fir_decim_ccf_device(taps.ctypes.data_as(C.c_void_p), ntaps, D, C.c_void_p(xd.data_ptr()), T, T,
+                                    C.c_void_p(yd.data_ptr()), nout, Cn, None)
+    assert rc == 0
+    got = yd.cpu().numpy()
+    for c in range(Cn):
+        want = oracle.fir_decim_ccf(taps, D, x[c])
+        assert len(want) == nout and np.array_equal(got[c], want)
