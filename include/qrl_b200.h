@@ -42,6 +42,7 @@ enum qrl_kind {
     QRL_DEMOD_NBFM = 1, QRL_DEMOD_4FSK = 2, QRL_DEMOD_QPSK = 3, QRL_DEMOD_BPSK = 4, QRL_DEMOD_2FSK = 5,
     QRL_DEMOD_SSB = 6,
     QRL_DEMOD_AM = 7,         /* gr_demod_am.cpp:28-82; ports: IQ, float audio at 8 ksps */
+    QRL_DEMOD_GMSK = 8,       /* gr_demod_gmsk.cpp:30-134; sps 10 / 5 / 1 = GMSK1K / 2K / 10K; 4 ports like 2FSK */
     QRL_MOD_4FSK = 101, QRL_MOD_QPSK = 102, QRL_MOD_NBFM = 103, QRL_MOD_BPSK = 104, QRL_MOD_2FSK = 105,
     QRL_MOD_SSB = 106
 };
@@ -52,6 +53,7 @@ enum qrl_param {
     QRL_PARAM_SQUELCH_DB = 2,         /* gr_demod_nbfm::set_squelch */
     QRL_PARAM_FILTER_WIDTH = 3,       /* gr_demod_nbfm::set_filter_width */
     QRL_PARAM_BB_GAIN = 4,            /* gr_mod_*::set_bb_gain */
+    QRL_PARAM_RSSI = 6,               /* 1: keep the RSSI tap of rssi_block.cpp:25-45 on port 0 up to date (read with qrl_rx_rssi) */
     QRL_PARAM_OVERLAP_CALLS = 5       /* 1: the loop / FEC tail of qrl_rx_work call k runs under the parallel stages of call
                                          k+1 (streaming use).  Output ports are double-buffered; the results of a call are
                                          ordered on the caller's stream only after qrl_rx_join (or qrl_rx_sync /
@@ -82,6 +84,10 @@ int qrl_rx_reset(qrl_rx* h);
  * the copy to the device is part of the call.  Asynchronous on the handle's stream. */
 int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device);
 /* wait for everything submitted so far */
+/* RSSI tap: per channel the value probe_signal_f holds behind rssi_block (|x|^2 -> moving_average(2000) ->
+ * single_pole_iir(0.04) -> 10 log10 -> + level; /root/reference/src/gr/rssi_block.cpp:25-45, gr_demod_base.cpp:199-200) after the
+ * last qrl_rx_work; rssi_db_host [n_channels]; needs QRL_PARAM_RSSI = 1 */
+int qrl_rx_rssi(qrl_rx*, float level, float* rssi_db_host);
 /* QRL_PARAM_OVERLAP_CALLS: make the handle's stream wait (on the device, without blocking the host) for everything the
  * calls so far have started; a no-op otherwise */
 int qrl_rx_join(qrl_rx*);

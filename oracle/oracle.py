@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 # hier-block kinds (mirror qrl_oracle.h)
-DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB, DEMOD_AM = 1, 2, 3, 4, 5, 6, 7
+DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB, DEMOD_AM, DEMOD_GMSK = 1, 2, 3, 4, 5, 6, 7, 8
 MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB = 101, 102, 103, 104, 105, 106
 WIN_HAMMING, WIN_HANN, WIN_BLACKMAN, WIN_RECT, WIN_KAISER, WIN_BLACKMAN_HARRIS = 0, 1, 2, 3, 4, 5
 
@@ -82,6 +82,11 @@ def lib():
         L.qo_descramble.argtypes = [vp, C.c_long, vp]
         L.qo_find_frames.restype = C.c_long
         L.qo_find_frames.argtypes = [vp, C.c_long, C.c_uint32, C.c_int, C.c_int, vp, C.c_long]
+        L.qo_rssi_create.restype = vp
+        L.qo_rssi_create.argtypes = [C.c_float]
+        L.qo_rssi_destroy.argtypes = [vp]
+        L.qo_rssi_work.restype = C.c_float
+        L.qo_rssi_work.argtypes = [vp, vp, C.c_long]
         L.qo_deframer_create.restype = vp
         L.qo_deframer_create.argtypes = [C.c_int] * 3
         L.qo_deframer_destroy.argtypes = [vp]
@@ -356,3 +361,18 @@ class Deframer:
     @property
     def modem_sync(self):
         return lib().qo_deframer_modem_sync(self._h)
+
+
+class Rssi:
+    """rssi_block.cpp:25-45 on one channel's port-0 stream; work(iq) -> dB value probe_signal_f would hold."""
+
+    def __init__(self, level=0.0):
+        self._h = lib().qo_rssi_create(level)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().qo_rssi_destroy(self._h); self._h = None
+
+    def work(self, iq):
+        iq = np.ascontiguousarray(iq, np.complex64)
+        return float(lib().qo_rssi_work(self._h, _p(iq), len(iq)))

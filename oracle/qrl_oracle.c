@@ -1014,6 +1014,7 @@ void qo_descramble(const uint8_t* in, long n, uint8_t* out) { lfsr_t l; lfsr_ini
 
 /* ------------------------------------------------------------------ RX chains */
 struct qo_rx {
+    int gmsk;               /* 2FSK branch running as gr_demod_gmsk */
     int kind, fm;
     int sym_sps, tsr;
     /* stages (not all used by every kind) */
@@ -1059,6 +1060,10 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
     r->kind = kind;
     rx_common_init(r);
     float* T0 = r->taps_store[0]; float* T1 = r->taps_store[1]; float* T2 = r->taps_store[2]; float* T3 = r->taps_store[3];
+    /* gr_demod_gmsk.cpp:30-134 is the 2FSK (fm) chain without the band-edge FLL, with a plain low-pass as symbol filter and
+     * its own clock-loop constants: restated through the 2FSK branch */
+    const int gmsk = (kind == QO_DEMOD_GMSK);
+    if (gmsk) { kind = QO_DEMOD_2FSK; r->kind = QO_DEMOD_2FSK; r->gmsk = 1; flag = 1; }
     if (kind == QO_DEMOD_4FSK) {
         /* /root/reference/src/gr/gr_demod_4fsk.cpp:32-205 */
         int fm = flag; r->fm = fm;
@@ -1198,7 +1203,8 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         r->ntaps_store[1] = n1;
         resamp_init(&r->filt, 2, 1, 1, T1, n1);
         qdemod_init(&r->qd, (float)(r->sym_sps / (spacing * M_PI / 2)));
-        int n2 = qo_firdes_rrc(1, r->tsr, r->tsr / r->sym_sps, 0.2, nfilts, T2, 4096);
+        int n2 = gmsk ? qo_firdes_low_pass(1, r->tsr, r->tsr / r->sym_sps, r->tsr / r->sym_sps, QO_WIN_HAMMING, T2, 4096)   /* gr_demod_gmsk.cpp:88-90 */
+                      : qo_firdes_rrc(1, r->tsr, r->tsr / r->sym_sps, 0.2, nfilts, T2, 4096);
         r->ntaps_store[2] = n2;
         resamp_init(&r->shaping, 1, 1, 1, T2, n2);
         if (!flag) {
@@ -1214,7 +1220,8 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         }
         float symbol_rate = (float)r->tsr / (float)r->sym_sps;
         float sps_dev = 200.0f / symbol_rate;
-        symsync_init(&r->ss, 1, (float)r->sym_sps, (float)(2 * M_PI / (symbol_rate / 10)), 1.0f, 0.2869f, sps_dev, SL_BPSK);
+        if (gmsk) symsync_init(&r->ss, 1, (float)r->sym_sps, (float)(2 * M_PI / 200.0f), 1.0f, 0.2869f, 0.05f, SL_BPSK);   /* gr_demod_gmsk.cpp:80-84 */
+        else symsync_init(&r->ss, 1, (float)r->sym_sps, (float)(2 * M_PI / (symbol_rate / 10)), 1.0f, 0.2869f, sps_dev, SL_BPSK);
         r->soft_scale = 128.0f;
         ccdec_init(&r->dec); lfsr_init(&r->descr); ccdec_init(&r->dec2); lfsr_init(&r->descr2);
         r->fm = flag;
@@ -1341,7 +1348,7 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
     if (r->kind == QO_DEMOD_2FSK) {
         r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
         float* v = (float*)r->s_res.d;
-        for (size_t i = 0; i < r->s_res.n; i++) fll_step(&r->fll, v[2 * i], v[2 * i + 1], &v[2 * i], &v[2 * i + 1]);
+        if (!r->gmsk) for (size_t i = 0; i < r->s_res.n; i++) fll_step(&r->fll, v[2 * i], v[2 * i + 1], &v[2 * i], &v[2 * i + 1]);
         r->s_filt.n = 0; resamp_work(&r->filt, v, r->s_res.n, &r->s_filt);
         qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
         r->s_rrc.n = 0;
@@ -2023,4 +2030,34 @@ long qo_deframer_work(qo_deframer* d, const uint8_t* bits, long n, uint8_t* reco
         }
     }
     return found;
+}
+
+/* ------------------------------------------------------------------ RSSI tap
+ * /root/reference/src/gr/rssi_block.cpp:25-45 on the demodulators' port 0 (gr_demod_base.cpp:199-200):
+ * complex_to_mag_squared -> moving_average_ff(2000, 1, 2000) -> single_pole_iir_filter_ff(0.04) -> 10 log10 -> + level,
+ * read through probe_signal_f (the latest value).  moving_average_ff: sum += newest; out = sum * scale; sum -= the
+ * sample length-1 older (float running sum, zero history); single_pole_iir<float,float,double>:
+ * y = alpha x + (1 - alpha) y_prev in double, rounded to float.  nlog10_ff clamps its argument at 1e-18; this oracle
+ * uses log10f (VOLK's polynomial log2 is not restated: telemetry value, tolerance 1e-3 dB in the tests). */
+struct qo_rssi { float ring[2000]; int head; float sum; double y_prev; float last_db; float level; long n; };
+typedef struct qo_rssi qo_rssi;
+qo_rssi* qo_rssi_create(float level) { qo_rssi* r = (qo_rssi*)calloc(1, sizeof(qo_rssi)); r->level = level; r->last_db = 10.0f * log10f(1e-18f) + level; return r; }
+void qo_rssi_destroy(qo_rssi* r) { free(r); }
+float qo_rssi_work(qo_rssi* r, const float* iq, long n)
+{
+    for (long i = 0; i < n; i++) {
+        const float m2 = iq[2 * i] * iq[2 * i] + iq[2 * i + 1] * iq[2 * i + 1];
+        /* ring[head] holds the sample 1999 older than the newest once the history is full (zeros before) */
+        r->sum = r->sum + m2;
+        const float out = r->sum * 1.0f;
+        r->ring[(r->head + 1999) % 2000] = m2;           /* slot of the newest */
+        r->sum = r->sum - r->ring[r->head];               /* the sample length-1 = 1999 older than the newest */
+        r->head = (r->head + 1) % 2000;
+        const double y = 0.04 * (double)out + (1.0 - 0.04) * r->y_prev;
+        const float yf = (float)y;
+        r->y_prev = (double)yf;
+        r->last_db = 10.0f * log10f(yf > 1e-18f ? yf : 1e-18f) + r->level;
+        r->n++;
+    }
+    return r->last_db;
 }

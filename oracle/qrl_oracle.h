@@ -27,7 +27,7 @@ enum { QO_WIN_HAMMING = 0, QO_WIN_HANN = 1, QO_WIN_BLACKMAN = 2, QO_WIN_RECT = 3
 
 /* hier-block kinds (one per reference file) */
 enum { QO_DEMOD_NBFM = 1, QO_DEMOD_4FSK = 2, QO_DEMOD_QPSK = 3, QO_DEMOD_BPSK = 4, QO_DEMOD_2FSK = 5,
-       QO_DEMOD_SSB = 6, QO_DEMOD_AM = 7,
+       QO_DEMOD_SSB = 6, QO_DEMOD_AM = 7, QO_DEMOD_GMSK = 8,
        QO_MOD_4FSK = 101, QO_MOD_QPSK = 102, QO_MOD_NBFM = 103, QO_MOD_BPSK = 104, QO_MOD_2FSK = 105,
        QO_MOD_SSB = 106 };
 
@@ -107,6 +107,13 @@ long    qo_pfb_synthesizer_work(qo_pfb*, const float* in, long n, long stride, f
 /* returns number of frames found; frames written back-to-back (frame_len bytes each) */
 long qo_find_frames(const uint8_t* bits, long nbits, uint32_t sync, int sync_bits, int frame_len_bytes,
                     uint8_t* frames, long max_frames);
+
+/* ---- RSSI tap: rssi_block.cpp:25-45 (|x|^2 -> moving_average(2000) -> single_pole_iir(0.04) -> 10 log10 + level) on a
+ *      stream of complex samples; returns the value probe_signal_f would hold after the call ---- */
+typedef struct qo_rssi qo_rssi;
+qo_rssi* qo_rssi_create(float level);
+void  qo_rssi_destroy(qo_rssi*);
+float qo_rssi_work(qo_rssi*, const float* iq, long n);
 
 /* ---- layer-1 deframer: gr_modem::synchronize / findSync / packBytes restated (gr_modem.cpp:1119-1282).
  *      sync_class 1 = "1K" modes (0xB5), 2 = narrow modes (0xED89 + 24-bit words), 3 = wide modes (IP / video / end).

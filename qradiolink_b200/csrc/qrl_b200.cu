@@ -160,6 +160,9 @@ struct qrl_rx : HandleBase {
     SymSyncState* d_ss = nullptr;
     float* d_ss_scratch = nullptr; int* d_ss_hdr = nullptr; long long ss_chunk_cap = 0, ss_chunk_off = 0;   // external symbol-sync epilogue
     cudaStream_t s_epi = nullptr;                        // wide-partition stream of the external epilogue
+    bool gmsk = false;                                   // 2FSK code path running as gr_demod_gmsk (no FLL)
+    // RSSI tap on port 0 (QRL_PARAM_RSSI): ring of |x|^2, carried IIR value, latest dB value per channel
+    bool rssi_on = false; float* d_rssi_ring = nullptr; float* d_rssi_y = nullptr; float* d_rssi_db = nullptr; long long rssi_n = 0;
     // QRL_PARAM_OVERLAP_CALLS: the loop / FEC tail of call k runs under the parallel stages of call k+1.  Output ports
     // are double-buffered (alt_* = the buffers of the previous call), ring reuse is fenced slice by slice.
     bool overlap = false;
@@ -395,9 +398,14 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     if (!out || n_channels <= 0 || max_samples <= 0) { set_err(nullptr, "qrl_rx_create: bad argument"); return QRL_EINVAL; }
     *out = nullptr;
     if (qrl_device_count() <= device) { set_err(nullptr, "qrl_rx_create: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
+    // gr_demod_gmsk.cpp:30-134 is the 2FSK (fm) chain without the band-edge FLL, with a plain low-pass as symbol filter and its
+    // own clock-loop constants: it runs through the 2FSK code path
+    const bool gmsk = (kind == QRL_DEMOD_GMSK);
+    if (gmsk) { kind = QRL_DEMOD_2FSK; flag = 1; }
     qrl_rx* h = new qrl_rx();
     h->kind = kind; h->sps = sps; h->samp_rate = samp_rate; h->carrier_freq = carrier_freq;
     h->filter_width = filter_width; h->flag = flag; h->C = n_channels; h->Tmax = max_samples; h->device = device;
+    h->gmsk = gmsk;
     auto fail = [&](int rc) { std::string e = h->err; qrl_rx_destroy(h); g_err = e; return rc; };
     if (cudaSetDevice(device) != cudaSuccess) { set_err(h, "cudaSetDevice failed"); return fail(QRL_ECUDA); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err(h, "stream create failed"); return fail(QRL_ECUDA); }
@@ -499,11 +507,13 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         taps1 = low_pass(interp, static_cast<double>(interp) * samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
         h->D1 = decim;
         taps2 = low_pass(1, tsr, filter_width, filter_width, WIN_BLACKMAN_HARRIS);
-        taps3 = root_raised_cosine(1, tsr, tsr / sym_sps, 0.2, nfilts);
+        taps3 = gmsk ? low_pass(1, tsr, tsr / sym_sps, tsr / sym_sps, WIN_HAMMING)            // gr_demod_gmsk.cpp:88-90
+                     : root_raised_cosine(1, tsr, tsr / sym_sps, 0.2, nfilts);
         h->qd_gain = static_cast<float>(sym_sps / (1 * kPi / 2));
         const float symbol_rate = static_cast<float>(tsr) / static_cast<float>(sym_sps);
-        const float sps_dev = 200.0f / symbol_rate;
-        clock_loop_gains(static_cast<float>(2 * kPi / (symbol_rate / 10)), 1.0f, 0.2869f, h->ssp.alpha, h->ssp.beta);
+        const float sps_dev = gmsk ? 0.05f : 200.0f / symbol_rate;                                    // gr_demod_gmsk.cpp:79-84
+        clock_loop_gains(gmsk ? static_cast<float>(2 * kPi / 200.0f) : static_cast<float>(2 * kPi / (symbol_rate / 10)), 1.0f, 0.2869f,
+                         h->ssp.alpha, h->ssp.beta);
         h->ssp.sps = static_cast<float>(sym_sps);
         h->ssp.max_period = h->ssp.sps + sps_dev; h->ssp.min_period = h->ssp.sps - sps_dev;
         h->ssp.lookahead = 8 + static_cast<int>(ceilf(h->ssp.max_period)) + 1;
@@ -797,7 +807,7 @@ int qrl_rx_reset(qrl_rx* h)
     CK(cudaMemsetAsync(h->d_port1_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_port2_cnt, 0, sizeof(int) * h->C, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // the staging vectors above go out of scope
-    h->n_in = 0; h->n1 = 0; h->n_in_s = 0; h->n1_s = 0; h->hist_cur = 0; h->port0_n = 0; h->prev_nsub = 0;
+    h->n_in = 0; h->n1 = 0; h->n_in_s = 0; h->n1_s = 0; h->hist_cur = 0; h->port0_n = 0; h->prev_nsub = 0; h->rssi_n = 0;
     return QRL_OK;
 }
 
@@ -834,6 +844,19 @@ int qrl_rx_set_stream(qrl_rx* h, void* s)
 int qrl_rx_set_param(qrl_rx* h, int channel, int key, double value)
 {
     if (!h) return QRL_EINVAL;
+    if (key == QRL_PARAM_RSSI) {
+        if (value != 0.0 && !h->d_rssi_ring) {
+            int rc;
+            if ((rc = dev_alloc(h, &h->d_rssi_ring, static_cast<size_t>(4096) * h->C))) return rc;
+            if ((rc = dev_alloc(h, &h->d_rssi_y, h->C))) return rc;
+            if ((rc = dev_alloc(h, &h->d_rssi_db, h->C))) return rc;
+            h->zero_list.emplace_back(h->d_rssi_ring, sizeof(float) * 4096 * h->C);
+            h->zero_list.emplace_back(h->d_rssi_y, sizeof(float) * h->C);
+            h->rssi_n = 0;
+        }
+        h->rssi_on = value != 0.0;
+        return QRL_OK;
+    }
     if (key == QRL_PARAM_OVERLAP_CALLS) {
         // only the path whose ring reuse is fenced for it: real-symbol 4FSK (external soft-bit epilogue)
         if (!(h->kind == QRL_DEMOD_4FSK && h->flag)) { set_err(h, "QRL_PARAM_OVERLAP_CALLS: not supported for this block"); return QRL_EINVAL; }
@@ -1068,16 +1091,19 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             CK(cudaEventRecord(h->ev_a[i], sp));
             CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
             pe = h->prof_begin(1, h->s_loop);
-            fll_kernel<32><<<groups, 32, 0, h->s_loop>>>(h->fllp, h->d_fll, h->d_fll_hist, h->C, h->d_fll_taps,
-                static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride, k1,
-                static_cast<float2*>(h->rf.d), h->rf.mask, h->rf.stride);
-            h->launches++;
+            if (!h->gmsk) {
+                fll_kernel<32><<<groups, 32, 0, h->s_loop>>>(h->fllp, h->d_fll, h->d_fll_hist, h->C, h->d_fll_taps,
+                    static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride, k1,
+                    static_cast<float2*>(h->rf.d), h->rf.mask, h->rf.stride);
+                h->launches++;
+            }
             h->prof_end(pe);
+            const Ring& fin = h->gmsk ? h->r1 : h->rf;             // GMSK: no FLL in front of the channel filter
             if (n_new > 0) {
                 // ---- channel filter / RRC on the FLL output -> port 0 (+ ring: channel-major for 2FSK, interleaved for BPSK)
                 pe = h->prof_begin(2, h->s_loop);
                 fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->ntaps2, h->s_loop>>>(
-                    static_cast<const float2*>(h->rf.d), h->rf.mask, h->rf.stride,
+                    static_cast<const float2*>(fin.d), fin.mask, fin.stride,
                     static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
                     h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, bpsk ? 1 : 0);
                 h->launches++;
@@ -1338,6 +1364,13 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         h->prof_end(pe);
         if (h->overlap) CK(cudaEventRecord(h->ev_v[i], h->s_fec));
     }
+    if (h->rssi_on && h->port0_n > 0) {
+        // port 0 of this call is complete on the parallel stream: append to the |x|^2 ring, evaluate the latest RSSI value
+        rssi_kernel<<<h->C, 256, 0, sp>>>(h->d_port0, h->port0_cap, static_cast<int>(std::min<long>(h->port0_n, h->port0_cap)),
+                                          h->rssi_n, h->d_rssi_ring, h->d_rssi_y, h->d_rssi_db);
+        h->launches++;
+        h->rssi_n += std::min<long>(h->port0_n, h->port0_cap);
+    }
     for (int i = 0; i < nsub; i++) h->prev_k1[i] = h->cur_k1[i];
     h->prev_nsub = nsub;
     if (h->overlap) {
@@ -1401,6 +1434,17 @@ int qrl_rx_sync(qrl_rx* h)
     if (!h) return QRL_EINVAL;
     CK(cudaStreamSynchronize(h->stream));
     if (h->overlap) return rx_join_host(h);
+    return QRL_OK;
+}
+
+int qrl_rx_rssi(qrl_rx* h, float level, float* rssi_db_host)
+{
+    if (!h || !rssi_db_host) return QRL_EINVAL;
+    if (!h->rssi_on || !h->d_rssi_db) { set_err(h, "qrl_rx_rssi: enable QRL_PARAM_RSSI first"); return QRL_EINVAL; }
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->s_par) CK(cudaStreamSynchronize(h->s_par));
+    CK(cudaMemcpy(rssi_db_host, h->d_rssi_db, sizeof(float) * h->C, cudaMemcpyDeviceToHost));
+    for (int c = 0; c < h->C; c++) rssi_db_host[c] = (h->rssi_n > 0 ? rssi_db_host[c] : -180.0f) + level;      // add_const_ff(level)
     return QRL_OK;
 }
 

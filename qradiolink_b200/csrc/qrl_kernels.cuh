@@ -1289,6 +1289,56 @@ symsync_ext_epilogue_kernel(SymSyncParams p, int C, const float* __restrict__ sc
 }
 
 // ------------------------------------------------------------------------------------------------
+// RSSI tap on port 0 (rssi_block.cpp:25-45 behind gr_demod_base.cpp:199-200): |x|^2 -> moving_average_ff(2000) ->
+// single_pole_iir_filter_ff(0.04) -> 10 log10; only the latest value is observable (probe_signal_f).  The IIR forgets
+// geometrically (0.96^1024 ~ 7e-19), so one CTA per channel evaluates the last min(new, 1024) moving sums directly from
+// a 4096-deep ring of |x|^2 (window sums in a fixed order instead of the reference's drifting running sum: telemetry
+// value, equal to the oracle within 1e-3 dB) and thread 0 runs the IIR over them.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rssi_kernel(const float2* __restrict__ port0, long long port0_stride, int n_new, long long n_before,
+            float* __restrict__ ring /* [C][4096] */, float* __restrict__ y_state /* [C] */, float* __restrict__ out_db /* [C] */)
+{
+    constexpr int RING = 4096, LEN = 2000, KMAX = 1024;
+    __shared__ float w[RING];
+    __shared__ float m[KMAX];
+    const int c = blockIdx.x;
+    float* rg = ring + static_cast<long long>(c) * RING;
+    const float2* x = port0 + static_cast<long long>(c) * port0_stride;
+    for (int i = threadIdx.x; i < n_new; i += blockDim.x) {
+        if (n_new - i > RING) continue;                          // only the last RING samples can matter
+        const float2 v = x[i];
+        rg[(n_before + i) & (RING - 1)] = v.x * v.x + v.y * v.y;
+    }
+    __syncthreads();
+    const long long N = n_before + n_new;
+    for (int k = threadIdx.x; k < RING; k += blockDim.x) {       // w[k] = |x|^2 at absolute index N - RING + k
+        const long long a = N - RING + k;
+        w[k] = a >= 0 ? rg[a & (RING - 1)] : 0.0f;
+    }
+    __syncthreads();
+    const int K = n_new < KMAX ? n_new : KMAX;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {          // output n = N - K + 1 + k (1-based count) ends at w[RING - K + k]
+        const int end = RING - K + k;
+        float acc = 0.0f;
+        for (int j = end - (LEN - 1); j <= end; j++) acc = acc + w[j];
+        m[k] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && K > 0) {
+        double y = (n_new >= KMAX) ? 0.0 : static_cast<double>(y_state[c]);
+        float yf = static_cast<float>(y);
+        for (int k = 0; k < K; k++) {
+            y = 0.04 * static_cast<double>(m[k]) + (1.0 - 0.04) * y;
+            yf = static_cast<float>(y);
+            y = static_cast<double>(yf);
+        }
+        y_state[c] = yf;
+        out_db[c] = 10.0f * log10f(yf > 1e-18f ? yf : 1e-18f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CCSDS K=7 r=1/2 soft Viterbi, fec::decoder(cc_decoder(80,7,2,{109,79}, CC_STREAMING)) stream semantics,
 // + descrambler_bb(0x8A,0x7F,7).  One warp per channel: lane i = butterfly i (states 2i, 2i+1).
 // 32-bit path metrics without renormalisation are decision-equivalent to VOLK's 8-bit generic kernel

@@ -86,6 +86,15 @@ class RxBlock:
         sync() or join() wait for it."""
         self.set_param(PARAM.OVERLAP_CALLS, 1.0 if on else 0.0)
 
+    def enable_rssi(self, on=True):
+        self.set_param(PARAM.RSSI, 1.0 if on else 0.0)
+
+    def rssi(self, level=0.0):
+        """Per-channel RSSI in dB as rssi_block.cpp:25-45 would report it after the last work() (needs enable_rssi())."""
+        out = np.zeros(self.n_channels, np.float32)
+        check(self._L.qrl_rx_rssi(self._h, C.c_float(level), out.ctypes.data_as(C.c_void_p)), self._h, "qrl_rx_rssi")
+        return out
+
     def join(self):
         check(self._L.qrl_rx_join(self._h), self._h, "qrl_rx_join")
 
@@ -134,6 +143,11 @@ def make_gr_demod_2fsk(sps, samp_rate, carrier_freq, filter_width, fm, n_channel
 def make_gr_demod_ssb(sps, samp_rate, carrier_freq, filter_width, sb, n_channels=1, **kw):
     """src/gr/gr_demod_ssb.h: sb = 0 upper side band, 1 lower; ports (IQ, float audio)."""
     return RxBlock(KIND.DEMOD_SSB, sps, samp_rate, carrier_freq, filter_width, int(sb), n_channels, **kw)
+
+
+def make_gr_demod_gmsk(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
+    """src/gr/gr_demod_gmsk.h (instances gr_demod_base.cpp:208-210: sps 5 / 10 / 1 = GMSK2K / 1K / 10K); 4 ports like 2FSK."""
+    return RxBlock(KIND.DEMOD_GMSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
 
 
 def make_gr_demod_am(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):

@@ -12,12 +12,12 @@ class QrlError(RuntimeError):
 
 
 class KIND:
-    DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB, DEMOD_AM = 1, 2, 3, 4, 5, 6, 7
+    DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB, DEMOD_AM, DEMOD_GMSK = 1, 2, 3, 4, 5, 6, 7, 8
     MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB = 101, 102, 103, 104, 105, 106
 
 
 class PARAM:
-    CARRIER_OFFSET_HZ, SQUELCH_DB, FILTER_WIDTH, BB_GAIN, OVERLAP_CALLS = 1, 2, 3, 4, 5
+    CARRIER_OFFSET_HZ, SQUELCH_DB, FILTER_WIDTH, BB_GAIN, OVERLAP_CALLS, RSSI = 1, 2, 3, 4, 5, 6
 
 
 # every symbol include/qrl_b200.h declares: (restype, argtypes)
@@ -34,6 +34,7 @@ SYMBOLS = {
     "qrl_rx_work": (_i, [_vp, _vp, _l, _l, _i]),
     "qrl_rx_sync": (_i, [_vp]),
     "qrl_rx_join": (_i, [_vp]),
+    "qrl_rx_rssi": (_i, [_vp, C.c_float, _vp]),
     "qrl_rx_num_ports": (_i, [_vp]),
     "qrl_rx_port_itemsize": (_i, [_vp, _i]),
     "qrl_rx_read_port": (_i, [_vp, _i, _vp, _l, _vp, _i]),

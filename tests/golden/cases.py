@@ -103,6 +103,8 @@ RX_CASES = {
                        factory="make_gr_demod_2fsk", fargs=(25, 1000000, 1700, 4000, True)),
     "am_5000": dict(okind=7, args=(125, 1000000, 1700, 5000, 0), nports=2, signal=_sig_am,
                     factory="make_gr_demod_am", fargs=(125, 1000000, 1700, 5000)),
+    "gmsk_2k": dict(okind=8, args=(5, 1000000, 1700, 4000, 0), nports=4, signal=_sig_digital("2fsk"),
+                    factory="make_gr_demod_gmsk", fargs=(5, 1000000, 1700, 4000)),
     "ssb_usb": dict(okind=6, args=(125, 1000000, 1700, 2700, 0), nports=2, signal=_sig_ssb,
                     factory="make_gr_demod_ssb", fargs=(125, 1000000, 1700, 2700, 0)),
 }

@@ -74,3 +74,33 @@ def test_2fsk_2k_band_filter_variant(qrl, oracle):
         payloads.append(pl)
     blk = qrl.make_gr_demod_2fsk(5, 1000000, 1700, 4000, False, n_channels=C, max_samples=400000)
     check(qrl, oracle, blk, oracle.DEMOD_2FSK, (5, 1000000, 1700, 4000, 0), X, payloads, [400000, 77777, 5])
+
+
+@pytest.mark.parametrize("sps,fw,tx_sps", [(5, 4000, 25), (10, 2000, 50)])
+def test_gmsk_demod_parity(qrl, oracle, sps, fw, tx_sps):
+    """gr_demod_gmsk (GMSK2K / GMSK1K instances): the 2FSK chain without the FLL, low-pass symbol filter, its own clock loop
+    constants -- all four ports against the oracle, ragged chunks."""
+    C, T = 2, 1 << 18
+    rng = np.random.default_rng(70 + sps)
+    X = np.zeros((C, T), np.complex64)
+    for c in range(C):
+        data, _ = siggen.frames_4fsk(rng, 6)
+        iq = oracle.Tx(oracle.MOD_2FSK, tx_sps, 1000000, 1700, fw, 1).work(data)
+        X[c] = siggen.channel(iq, rng, fo_hz=rng.uniform(-100, 100), phase=rng.uniform(0, 6.28), delay=int(rng.integers(0, 300)),
+                              snr_db=20.0, amp=0.4, total=T)
+    blk = qrl.make_gr_demod_gmsk(sps, 1000000, 1700, fw, n_channels=C, max_samples=100000)
+    acc = [[[] for _ in range(C)] for _ in range(4)]
+    lo, i, sizes = 0, 0, [100000, 49, 50021, 1, 77777]
+    while lo < T:
+        n = min(sizes[i % len(sizes)], T - lo); i += 1
+        blk.work(X[:, lo:lo + n]); lo += n
+        for p in range(4):
+            for c, v in enumerate(blk.read_port(p)):
+                acc[p][c].append(v)
+    for c in range(C):
+        rx = oracle.Rx(oracle.DEMOD_GMSK, sps, 1000000, 1700, fw, 0)
+        rx.work(X[c])
+        for p in range(4):
+            got = np.concatenate(acc[p][c]); want = rx.port(p)
+            assert len(got) == len(want) and len(want) > 100, (p, len(got), len(want))
+            assert np.array_equal(got, want), (c, p)

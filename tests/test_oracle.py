@@ -257,3 +257,44 @@ def test_deframer_known_answers(oracle):
     # class 1: 8-bit sync, 4-byte frames; a sync word inside a frame is not a sync
     b1 = np.concatenate([bits_of([0x00, 0xB5, 0xB5, 1, 2, 3]), bits_of([0xB5, 9, 8, 7, 6])])
     assert O.Deframer(1, 32, 4).work(b1) == [(0xB5, bytes([0xB5, 1, 2, 3])), (0xB5, bytes([9, 8, 7, 6]))]
+
+
+def test_rssi_block_known_answers(oracle):
+    """rssi_block.cpp:25-45 restated: a constant-envelope tone of amplitude a settles at 10 log10(2000 a^2); chunking is
+    invisible; silence reports the nlog10 floor."""
+    n = np.arange(30000)
+    x = (0.1 * np.exp(2j * np.pi * 0.01 * n)).astype(np.complex64)
+    r = oracle.Rssi(0.0)
+    v = r.work(x)
+    assert abs(v - 10 * np.log10(2000 * 0.01)) < 1e-3
+    r2 = oracle.Rssi(0.0)
+    for a in range(0, len(x), 777):
+        v2 = r2.work(x[a:a + 777])
+    assert v2 == v
+    assert oracle.Rssi(-10.0).work(np.zeros(100, np.complex64)) == pytest.approx(-190.0, abs=1e-3)
+
+
+def test_am_and_gmsk_chains_run_and_stream(oracle):
+    """The AM and GMSK receive chains are chunk-size invariant in the oracle, AM audio carries the tone."""
+    O = oracle
+    T = 1 << 17
+    n = np.arange(T)
+    aud = 0.5 * np.sin(2 * np.pi * 1000.0 * n / 1e6)
+    x = (0.4 * (1.0 + 0.8 * aud) * np.exp(2j * np.pi * 200.0 * n / 1e6)).astype(np.complex64)
+    a = O.Rx(O.DEMOD_AM, 125, 1000000, 1700, 5000, 0); a.work(x)
+    b = O.Rx(O.DEMOD_AM, 125, 1000000, 1700, 5000, 0)
+    for lo in range(0, T, 30011):
+        b.work(x[lo:lo + 30011])
+    for p in range(2):
+        assert np.array_equal(a.port(p, clear=False), b.port(p, clear=False))
+    audio = a.port(1)
+    assert len(audio) == pytest.approx(T / 125, abs=40) and np.std(audio[300:]) > 0.05
+    rng = np.random.default_rng(2)
+    y = ((rng.standard_normal(T) + 1j * rng.standard_normal(T)) * 0.1).astype(np.complex64)
+    g = O.Rx(O.DEMOD_GMSK, 5, 1000000, 1700, 4000, 0); g.work(y)
+    g2 = O.Rx(O.DEMOD_GMSK, 5, 1000000, 1700, 4000, 0)
+    for lo in range(0, T, 12345):
+        g2.work(y[lo:lo + 12345])
+    for p in range(4):
+        assert np.array_equal(g.port(p, clear=False), g2.port(p, clear=False))
+    assert len(g.port(2)) > 50
