@@ -4,6 +4,7 @@
 //   make_gr_demod_4fsk(sps, samp_rate, carrier_freq, filter_width, fm)      src/gr/gr_demod_4fsk.h:51-53
 //   make_gr_demod_qpsk(sps, samp_rate, carrier_freq, filter_width)          src/gr/gr_demod_qpsk.h:48-50
 //   make_gr_demod_nbfm(sps, samp_rate, carrier_freq, filter_width)          src/gr/gr_demod_nbfm.h:38-39
+//   make_gr_demod_{bpsk,2fsk,ssb,am,gmsk}(...)                              src/gr/gr_demod_<mode>.h
 //   make_gr_mod_4fsk / make_gr_mod_qpsk                                     src/gr/gr_mod_4fsk.h:46-48
 //   gr_bit_sink / gr_audio_sink / gr_const_sink  get_data() semantics       src/gr/gr_bit_sink.cpp:45-84 ...
 //
@@ -169,6 +170,16 @@ inline gr_demod_b200_sptr make_gr_demod_bpsk(int sps, int samp_rate, int carrier
 inline gr_demod_b200_sptr make_gr_demod_2fsk(int sps, int samp_rate, int carrier_freq, int filter_width, bool fm,
                                              int n_channels = 1, long max_samples = 1 << 20, int device = 0)
 { return std::make_shared<gr_demod_b200>(QRL_DEMOD_2FSK, sps, samp_rate, carrier_freq, filter_width, fm ? 1 : 0, n_channels, max_samples, device); }
+
+inline gr_demod_b200_sptr make_gr_demod_ssb(int sps, int samp_rate, int carrier_freq, int filter_width, int sb,
+                                            int n_channels = 1, long max_samples = 1 << 20, int device = 0)      // src/gr/gr_demod_ssb.h
+{ return std::make_shared<gr_demod_b200>(QRL_DEMOD_SSB, sps, samp_rate, carrier_freq, filter_width, sb, n_channels, max_samples, device); }
+inline gr_demod_b200_sptr make_gr_demod_am(int sps, int samp_rate, int carrier_freq, int filter_width,
+                                           int n_channels = 1, long max_samples = 1 << 20, int device = 0)       // src/gr/gr_demod_am.h
+{ return std::make_shared<gr_demod_b200>(QRL_DEMOD_AM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_samples, device); }
+inline gr_demod_b200_sptr make_gr_demod_gmsk(int sps, int samp_rate, int carrier_freq, int filter_width,
+                                             int n_channels = 1, long max_samples = 1 << 20, int device = 0)     // src/gr/gr_demod_gmsk.h
+{ return std::make_shared<gr_demod_b200>(QRL_DEMOD_GMSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_samples, device); }
 
 // ---- batched modulator
 class gr_mod_b200 {
