@@ -44,7 +44,8 @@ enum qrl_kind {
     QRL_DEMOD_AM = 7,         /* gr_demod_am.cpp:28-82; ports: IQ, float audio at 8 ksps */
     QRL_DEMOD_GMSK = 8,       /* gr_demod_gmsk.cpp:30-134; sps 10 / 5 / 1 = GMSK1K / 2K / 10K; 4 ports like 2FSK */
     QRL_MOD_4FSK = 101, QRL_MOD_QPSK = 102, QRL_MOD_NBFM = 103, QRL_MOD_BPSK = 104, QRL_MOD_2FSK = 105,
-    QRL_MOD_SSB = 106
+    QRL_MOD_SSB = 106,
+    QRL_MOD_GMSK = 107        /* gr_mod_gmsk.cpp:30-100 (sps 50 / 100 / 10 = GMSK2K / 1K / 10K) */
 };
 
 /* runtime parameters (qrl_rx_set_param / qrl_tx_set_param) */
@@ -132,6 +133,7 @@ int qrl_firdes_low_pass_2(double gain, double fs, double fc, double tw, double a
 int qrl_firdes_band_pass(double gain, double fs, double lo, double hi, double tw, int window, float* out, int cap);
 int qrl_firdes_complex_band_pass(double gain, double fs, double lo, double hi, double tw, int window, float* out, int cap);
 int qrl_firdes_root_raised_cosine(double gain, double fs, double symrate, double alpha, int ntaps, float* out, int cap);
+int qrl_firdes_gaussian(double gain, double spb, double bt, int ntaps, float* out, int cap);
 int qrl_design_table(const char* name /* "atan","tanh","mmse","fxpt_sine" */, float* out, int cap);
 int qrl_design_deemph(int fs, double tau, double* a2, double* b2);
 

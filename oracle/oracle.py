@@ -14,7 +14,7 @@ _LIB = None
 
 # hier-block kinds (mirror qrl_oracle.h)
 DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB, DEMOD_AM, DEMOD_GMSK = 1, 2, 3, 4, 5, 6, 7, 8
-MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB = 101, 102, 103, 104, 105, 106
+MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB, MOD_GMSK = 101, 102, 103, 104, 105, 106, 107
 WIN_HAMMING, WIN_HANN, WIN_BLACKMAN, WIN_RECT, WIN_KAISER, WIN_BLACKMAN_HARRIS = 0, 1, 2, 3, 4, 5
 
 
@@ -64,6 +64,7 @@ def lib():
         L.qo_firdes_complex_band_pass.argtypes = [C.c_double] * 5 + [C.c_int, vp, C.c_int]
         L.qo_firdes_complex_band_pass_2.argtypes = [C.c_double] * 6 + [C.c_int, vp, C.c_int]
         L.qo_firdes_rrc.argtypes = [C.c_double] * 4 + [C.c_int, vp, C.c_int]
+        L.qo_firdes_gaussian.argtypes = [C.c_double] * 3 + [C.c_int, vp, C.c_int]
         L.qo_deemph_taps.argtypes = [C.c_int, C.c_double, vp, vp]
         L.qo_preemph_taps.argtypes = [C.c_int, C.c_double, C.c_double, vp, vp]
         L.qo_sincosf.argtypes = [C.c_float, vp, vp]
@@ -146,6 +147,10 @@ def complex_band_pass(gain, fs, lo, hi, tw, win=WIN_HAMMING):
 
 def rrc(gain, fs, symrate, alpha, ntaps):
     return _taps(lib().qo_firdes_rrc, gain, fs, symrate, alpha, ntaps)
+
+
+def gaussian(gain, spb, bt, ntaps):
+    return _taps(lib().qo_firdes_gaussian, gain, spb, bt, ntaps)
 
 
 def deemph_taps(fs, tau):

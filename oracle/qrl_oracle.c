@@ -236,6 +236,24 @@ int qo_firdes_rrc(double gain, double fs, double symrate, double alpha, int ntap
     for (int i = 0; i < ntaps; i++) taps[i] = (float)(taps[i] * gain / scale);
     return ntaps;
 }
+/* gr::filter::firdes::gaussian(gain, spb, bt, ntaps) restated (GNU Radio 3.10 gr-filter firdes.cc; used by
+ * /root/reference/src/gr/gr_mod_gmsk.cpp:77-79) */
+int qo_firdes_gaussian(double gain, double spb, double bt, int ntaps, float* taps, int cap)
+{
+    if (ntaps > cap) return -ntaps;
+    double scale = 0;
+    const double dt = 1.0 / spb;
+    const double s = 1.0 / (sqrt(log(2.0)) / (2 * M_PI * bt));
+    double t0 = -0.5 * ntaps;
+    for (int i = 0; i < ntaps; i++) {
+        t0++;
+        const double ts = s * dt * t0;
+        taps[i] = (float)exp(-0.5 * ts * ts);
+        scale += taps[i];
+    }
+    for (int i = 0; i < ntaps; i++) taps[i] = (float)(taps[i] / scale * gain);
+    return ntaps;
+}
 /* /root/reference/src/gr/emphasis.cpp:16-42 (note the float tanf inside double math) */
 void qo_deemph_taps(int sample_rate, double tau, double* a, double* b)
 {
@@ -1625,6 +1643,22 @@ qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         int n = qo_firdes_rrc(sps, sps, 1, 0.35, 11 * sps, taps, 16384);
         resamp_init(&t->rrc, 2, sps, 1, taps, n);
         t->amplif = 0.6f; t->s_sym.isz = 8;
+    } else if (kind == QO_MOD_GMSK) {
+        /* /root/reference/src/gr/gr_mod_gmsk.cpp:30-100: the 2FSK (fm) modulator path with a Gaussian pulse (BT 0.3),
+         * sensitivity (pi/2)/sps and a x5 (or x1) final interpolation; instances gr_mod_base.cpp:160-162 */
+        t->kind = QO_MOD_2FSK; t->fm = 1;
+        int nfilts = 35, second_interp = 5;
+        if (sps == 10) { sps = 50; second_interp = 1; nfilts = 55; }
+        if (sps == 50) nfilts = 55;
+        if (sps == 100) nfilts = 35;
+        if ((nfilts % 2) == 0) nfilts += 1;
+        t->sps = sps; t->amplif = 0.9f;
+        int n = qo_firdes_gaussian(sps, sps, 0.3, nfilts, taps, 16384);
+        resamp_init(&t->rrc, 1, sps, 1, taps, n);
+        t->fm_sens = (float)((M_PI / 2) / sps);
+        n = qo_firdes_low_pass(second_interp, samp_rate, filter_width, filter_width, QO_WIN_HAMMING, taps, 16384);
+        resamp_init(&t->interp, 2, second_interp, 1, taps, n);
+        t->s_sym.isz = 4;
     } else if (kind == QO_MOD_2FSK) {
         /* /root/reference/src/gr/gr_mod_2fsk.cpp:26-100 */
         int fm = flag; t->fm = fm; t->sps = sps;

@@ -1616,6 +1616,21 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         t1 = root_raised_cosine(sps, sps, 1, 0.35, 11 * sps);
         h->L1 = sps; h->nt1 = (static_cast<int>(t1.size()) + sps - 1) / sps;
         h->amplif = 0.6f;
+    } else if (kind == QRL_MOD_GMSK) {
+        // gr_mod_gmsk.cpp:30-100: the 2FSK (fm) modulator path with a Gaussian pulse (BT 0.3), sensitivity (pi/2)/sps and a
+        // x5 (x1 for the 10k mode) final interpolation; instances gr_mod_base.cpp:160-162
+        int nfilts = 35, second_interp = 5;
+        if (sps == 10) { sps = 50; second_interp = 1; nfilts = 55; }
+        if (sps == 50) nfilts = 55;
+        if (sps == 100) nfilts = 35;
+        if ((nfilts % 2) == 0) nfilts += 1;
+        kind = QRL_MOD_2FSK; h->kind = QRL_MOD_2FSK; h->sps = sps; flag = 1; h->flag = 1;
+        h->amplif = 0.9f; h->repeat_only = 0; h->pulse_scale = 1.0f;
+        t1 = gaussian(sps, sps, 0.3, nfilts);
+        h->L1 = sps; h->nt1 = (static_cast<int>(t1.size()) + sps - 1) / sps;
+        h->fm_sens = static_cast<float>((kPi / 2) / sps);
+        t2 = low_pass(second_interp, samp_rate, filter_width, filter_width, WIN_HAMMING);
+        h->L2 = second_interp; h->nt2 = (static_cast<int>(t2.size()) + second_interp - 1) / second_interp;
     } else if (kind == QRL_MOD_2FSK) {
         // gr_mod_2fsk.cpp:43-76
         int nfilts = 25 * sps, spacing = 2; h->amplif = 0.8f;
@@ -1912,6 +1927,8 @@ int qrl_firdes_complex_band_pass(double gain, double fs, double lo, double hi, d
 { return copy_out(complex_band_pass(gain, fs, lo, hi, tw, window), out, cap, 2); }
 int qrl_firdes_root_raised_cosine(double gain, double fs, double symrate, double alpha, int ntaps, float* out, int cap)
 { return copy_out(root_raised_cosine(gain, fs, symrate, alpha, ntaps), out, cap); }
+int qrl_firdes_gaussian(double gain, double spb, double bt, int ntaps, float* out, int cap)
+{ return copy_out(gaussian(gain, spb, bt, ntaps), out, cap); }
 int qrl_design_table(const char* name, float* out, int cap)
 {
     std::string n(name ? name : "");

@@ -111,6 +111,24 @@ inline std::vector<float> complex_band_pass(double gain, double fs, double lo, d
 inline std::vector<float> complex_band_pass_2(double gain, double fs, double lo, double hi, double tw, double att, int win = WIN_HAMMING)
 { return complex_band_pass_core(gain, fs, lo, hi, ntaps_for_attenuation(fs, tw, att), win); }
 
+// gr::filter::firdes::gaussian (gr_mod_gmsk.cpp:77-79)
+inline std::vector<float> gaussian(double gain, double spb, double bt, int ntaps)
+{
+    std::vector<float> taps(ntaps);
+    double scale = 0;
+    const double dt = 1.0 / spb;
+    const double s = 1.0 / (std::sqrt(std::log(2.0)) / (2 * kPi * bt));
+    double t0 = -0.5 * ntaps;
+    for (int i = 0; i < ntaps; i++) {
+        t0++;
+        const double ts = s * dt * t0;
+        taps[i] = static_cast<float>(std::exp(-0.5 * ts * ts));
+        scale += taps[i];
+    }
+    for (int i = 0; i < ntaps; i++) taps[i] = static_cast<float>(taps[i] / scale * gain);
+    return taps;
+}
+
 inline std::vector<float> root_raised_cosine(double gain, double fs, double symrate, double alpha, int ntaps)
 {
     ntaps |= 1;

@@ -13,7 +13,7 @@ class QrlError(RuntimeError):
 
 class KIND:
     DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB, DEMOD_AM, DEMOD_GMSK = 1, 2, 3, 4, 5, 6, 7, 8
-    MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB = 101, 102, 103, 104, 105, 106
+    MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB, MOD_GMSK = 101, 102, 103, 104, 105, 106, 107
 
 
 class PARAM:
@@ -57,6 +57,7 @@ SYMBOLS = {
     "qrl_firdes_band_pass": (_i, [_d] * 5 + [_i, _vp, _i]),
     "qrl_firdes_complex_band_pass": (_i, [_d] * 5 + [_i, _vp, _i]),
     "qrl_firdes_root_raised_cosine": (_i, [_d] * 4 + [_i, _vp, _i]),
+    "qrl_firdes_gaussian": (_i, [_d] * 3 + [_i, _vp, _i]),
     "qrl_design_table": (_i, [C.c_char_p, _vp, _i]),
     "qrl_design_deemph": (_i, [_i, _d, _vp, _vp]),
     "qrl_fir_decim_ccf_device": (_i, [_vp, _i, _i, _vp, _l, _l, _vp, _l, _i, _vp]),

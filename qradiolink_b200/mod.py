@@ -93,6 +93,11 @@ def make_gr_mod_2fsk(sps, samp_rate, carrier_freq, filter_width, fm, n_channels=
     return TxBlock(KIND.MOD_2FSK, sps, samp_rate, carrier_freq, filter_width, int(bool(fm)), n_channels, **kw)
 
 
+def make_gr_mod_gmsk(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
+    """src/gr/gr_mod_gmsk.h (instances gr_mod_base.cpp:160-162: sps 50 / 100 / 10 = GMSK2K / 1K / 10K)."""
+    return TxBlock(KIND.MOD_GMSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
+
+
 def make_gr_mod_nbfm(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
     """src/gr/gr_mod_nbfm.h (instances gr_mod_base.cpp:171-172); feed with TxBlock.work_audio."""
     return TxBlock(KIND.MOD_NBFM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)

@@ -46,6 +46,8 @@ def test_design_matches_oracle_bitwise(qrl, oracle):
         (_taps(L.qrl_firdes_low_pass_2, 1.0, 1e6, 250000.0, 50000.0, 60.0, BH), O.low_pass_2(1, 1e6, 250000, 50000, 60, BH)),
         (_taps(L.qrl_firdes_root_raised_cosine, 1.5, 20000.0, 2000.0, 0.2, 251), O.rrc(1.5, 20000, 2000, 0.2, 251)),
         (_taps(L.qrl_firdes_root_raised_cosine, 2.0, 2.0, 1.0, 0.35, 22), O.rrc(2, 2, 1, 0.35, 22)),
+        (_taps(L.qrl_firdes_gaussian, 50.0, 50.0, 0.3, 55), O.gaussian(50, 50, 0.3, 55)),
+        (_taps(L.qrl_firdes_gaussian, 100.0, 100.0, 0.3, 35), O.gaussian(100, 100, 0.3, 35)),
         (_taps(L.qrl_firdes_band_pass, 1.0, 8000.0, 300.0, 3500.0, 200.0, BH), O.band_pass(1, 8000, 300, 3500, 200, BH)),
         (_taps(L.qrl_firdes_complex_band_pass, 1.0, 20000.0, -4000.0, -2000.0, 4000.0, BH, per=2),
          O.complex_band_pass(1, 20000, -4000, -2000, 4000, BH).view(np.float32)),

@@ -298,3 +298,19 @@ def test_am_and_gmsk_chains_run_and_stream(oracle):
     for p in range(4):
         assert np.array_equal(g.port(p, clear=False), g2.port(p, clear=False))
     assert len(g.port(2)) > 50
+
+
+def test_gmsk_modem_loops_back_in_the_oracle(oracle):
+    """gr_mod_gmsk -> channel -> gr_demod_gmsk (GMSK2K instances): every transmitted voice frame is recovered by one of the
+    two decoders (the second sits behind delay(1)); ties the two restatements to each other physically."""
+    O = oracle
+    from tests import siggen
+    rng = np.random.default_rng(5)
+    data, pl = siggen.frames_4fsk(rng, 8)
+    iq = O.Tx(O.MOD_GMSK, 50, 1000000, 1700, 4000, 0).work(data)
+    assert len(iq) == len(data) * 16 * 50 * 5
+    x = siggen.channel(iq, rng, fo_hz=30, phase=0.4, delay=123, snr_db=25, amp=0.5, total=len(iq) + 20000)
+    rx = O.Rx(O.DEMOD_GMSK, 5, 1000000, 1700, 4000, 0)
+    rx.work(x)
+    good = max(siggen.count_good_frames(rx.port(p), 0xED89AA, 24, 7, pl)[0] for p in (2, 3))
+    assert good == len(pl)
