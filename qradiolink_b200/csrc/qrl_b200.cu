@@ -1734,7 +1734,7 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
             const long long r0 = h->n_mid, r1 = ((h->n_audio + n) * 25 + 3) / 4;
             static const float one = 1.0f; (void)one;
             // frequency modulator (Q32 scan) on the 50 ksps stream: "RRC" stage degenerated to a pass-through arm {1}
-            tx_shape_fm_kernel<256, 8><<<h->C, 256, 0, h->stream>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, r0, r1 - r0,
+            tx_shape_fm_kernel<1024, 2><<<h->C, 1024, 0, h->stream>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, r0, r1 - r0,
                 1, 1, h->d_arms1, 1, 1.0f, h->fm_sens, 1.0f, 1.0f, h->d_if, h->if_mask, h->if_stride);
             dim3 g(static_cast<unsigned>((r1 - r0 + TB - 1) / TB), h->C);
             if (r1 > r0) {
@@ -1811,7 +1811,7 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
                                                                                  h->d_sym, h->sym_mask, h->sym_stride, symA);
             CK(cudaEventRecord(h->ev_bits[j], h->s_bits));
             CK(cudaStreamWaitEvent(h->s_shape, h->ev_bits[j], 0));
-            tx_shape_fm_kernel<256, 8><<<h->C, 256, 0, h->s_shape>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, symA, nsym_j,
+            tx_shape_fm_kernel<1024, 2><<<h->C, 1024, 0, h->s_shape>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, symA, nsym_j,
                 h->L1, h->nt1, h->d_arms1, h->repeat_only, h->pulse_scale, h->fm_sens, h->amplif, h->bb_gain,
                 h->d_if, h->if_mask, h->if_stride);
             CK(cudaEventRecord(h->ev_shape[j], h->s_shape));
@@ -1861,7 +1861,7 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
         }
         h->n_out_last = static_cast<long>(nsym * h->L1);
     } else {
-        tx_shape_fm_kernel<256, 8><<<h->C, 256, 0, h->stream>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, sym0, nsym,
+        tx_shape_fm_kernel<1024, 2><<<h->C, 1024, 0, h->stream>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, sym0, nsym,
             h->L1, h->nt1, h->d_arms1, h->repeat_only, h->pulse_scale, h->fm_sens, h->amplif, h->bb_gain,
             h->d_if, h->if_mask, h->if_stride);
         h->launches++;
