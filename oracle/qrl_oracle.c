@@ -1165,6 +1165,27 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         qdemod_init(&r->qd, (float)(r->tsr / (4 * M_PI * filter_width)));
         squelch_init(&r->sq, -140, 0.01, 320, 1);
         r->port[1].isz = 4;
+    } else if (kind == QO_DEMOD_WBFM) {
+        /* /root/reference/src/gr/gr_demod_wbfm.cpp:28-70: /5 (low_pass(1, fs, 100k, 100k, BH)) -> low_pass_2(1, 200k, fw, 600, 90, BH)
+         * -> [port 0 at 200 ksps] -> pwr_squelch_cc(-140, 0.01, 0, gate) -> quadrature_demod_cf(200k / (2 pi fw)) -> x0.9 ->
+         * iir_filter_ffd(de-emphasis taps designed for fs = 8000: the reference's own choice, :39-41) -> rational_resampler_fff(1, 25)
+         * with low_pass(1, 200k, 4000, 2000, BH) -> [port 1 at 8 ksps] */
+        r->tsr = 200000;
+        double a[2], b[2];
+        qo_deemph_taps(8000, 50e-6, a, b);
+        iir1_init(&r->deemph, b, a);
+        int n0 = qo_firdes_low_pass(1, samp_rate, r->tsr / 2, r->tsr / 2, QO_WIN_BLACKMAN_HARRIS, T0, 4096);
+        r->ntaps_store[0] = n0;
+        resamp_init(&r->resamp, 2, 1, 5, T0, n0);
+        int n1 = qo_firdes_low_pass_2(1, r->tsr, filter_width, 600, 90, QO_WIN_BLACKMAN_HARRIS, T1, 4096);
+        r->ntaps_store[1] = n1;
+        resamp_init(&r->filt, 2, 1, 1, T1, n1);
+        int n2 = qo_firdes_low_pass(1, r->tsr, 4000, 2000, QO_WIN_BLACKMAN_HARRIS, T2, 4096);
+        r->ntaps_store[2] = n2;
+        resamp_init(&r->audio_rs, 1, 1, 25, T2, n2);
+        qdemod_init(&r->qd, (float)(r->tsr / (2 * M_PI * filter_width)));
+        squelch_init(&r->sq, -140, 0.01, 0, 1);
+        r->port[1].isz = 4;
     } else if (kind == QO_DEMOD_AM) {
         /* /root/reference/src/gr/gr_demod_am.cpp:28-82: /50 (419 taps) -> complex band-pass(-fw, fw) -> [port 0] ->
          * pwr_squelch_cc(-140, 0.01, 0, gate) -> complex_to_mag -> agc2_ff(.1, .1, 1, 1) -> iir_filter_ffd({1,-1},{0,.9999})
@@ -1501,6 +1522,18 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
             qv_pushb(&r->s_soft, soft_u8(oi, r->soft_scale));
         }
         rx_fec_tail(r);
+        return 0;
+    }
+    if (r->kind == QO_DEMOD_WBFM) {
+        r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
+        r->s_filt.n = 0; resamp_work(&r->filt, (const float*)r->s_res.d, r->s_res.n, &r->s_filt);
+        qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
+        r->s_tmp.n = 0; squelch_work(&r->sq, (const float*)r->s_filt.d, r->s_filt.n, &r->s_tmp);
+        r->s_dem.n = 0; qdemod_work(&r->qd, (const float*)r->s_tmp.d, r->s_tmp.n, &r->s_dem);
+        float* d = (float*)r->s_dem.d;
+        for (size_t i = 0; i < r->s_dem.n; i++) d[i] = d[i] * 0.9f;                        /* multiply_const_ff(0.9) */
+        r->s_sym.isz = 4; r->s_sym.n = 0; iir1_work(&r->deemph, d, r->s_dem.n, &r->s_sym, 1.0f);
+        resamp_work(&r->audio_rs, (const float*)r->s_sym.d, r->s_sym.n, &r->port[1]);
         return 0;
     }
     if (r->kind == QO_DEMOD_AM) {

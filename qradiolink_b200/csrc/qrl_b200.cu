@@ -261,8 +261,8 @@ int launch_fir_resamp_2_25(qrl_rx* h, const float2* iq, long long stride, long l
     constexpr int L = 2, M = 25, NT = 105, NOUT = 512;
     constexpr int SPAN = (NOUT * M + L - 1) / L + NT + 1;
     const size_t smem = sizeof(float2) * SPAN;
-    static bool attr_done = false;
-    if (!attr_done) { CK(cudaFuncSetAttribute(fir_resamp_ccf_kernel<L, M, NT, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    static bool attr_done[16] = { false };    // per device: function attributes belong to the device's context
+    if (!attr_done[h->device & 15]) { CK(cudaFuncSetAttribute(fir_resamp_ccf_kernel<L, M, NT, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->device & 15] = true; }
     dim3 grid(static_cast<unsigned>((k1 - k0 + NOUT - 1) / NOUT), h->C);
     fir_resamp_ccf_kernel<L, M, NT, NOUT><<<grid, 256, smem, h->par()>>>(iq, stride, T, h->d_hist[h->hist_cur], h->H, h->d_taps1,
         static_cast<float2*>(h->r1.d), h->r1.mask, h->r1.stride, h->n_in, k0, k1);
@@ -282,7 +282,16 @@ int stage1(qrl_rx* h, const float2* iq, long long stride, long long T, long long
     if (h->D1 == 25 && h->Q1 == 28) return launch_fir_poly<25, 28, 8, 192, 8>(h, iq, stride, T, k0, k1);    // 681 taps (QPSK-20k)
     if (h->D1 == 100 && h->Q1 == 28) return launch_fir_poly<100, 28, 8, 32, 4>(h, iq, stride, T, k0, k1);   // 2727 taps (QPSK-2k)
     if (h->D1 == 2 && h->ntaps1 <= 56) return launch_fir_d2<56, 8, 128>(h, iq, stride, T, k0, k1);
-    set_err(h, "stage-1 resampler shape not built (D=" + std::to_string(h->D1) + ", taps=" + std::to_string(h->ntaps1) + ")");
+    if (h->L1 == 1) {      // no register-tiled instance for this shape: one thread per output, same order, same history
+        const long long nout = k1 - k0;
+        dim3 grid(static_cast<unsigned>((nout + 127) / 128), h->C);
+        fir_decim_hist_generic_kernel<<<grid, 128, 0, h->par()>>>(iq, stride, T, h->d_hist[h->hist_cur], h->H, h->d_taps1, h->ntaps1, h->D1,
+            static_cast<float2*>(h->r1.d), h->r1.mask, h->r1.stride, h->n_in, k0, k1);
+        h->launches++;
+        CK(cudaGetLastError());
+        return QRL_OK;
+    }
+    set_err(h, "stage-1 resampler shape not built (L=" + std::to_string(h->L1) + ", D=" + std::to_string(h->D1) + ", taps=" + std::to_string(h->ntaps1) + ")");
     return QRL_EINVAL;
 }
 
@@ -553,6 +562,14 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         taps2 = flag ? complex_band_pass_2(1, tsr, -filter_width, -200, 200, 90, WIN_BLACKMAN_HARRIS)
                      : complex_band_pass_2(1, tsr, 200, filter_width, 200, 90, WIN_BLACKMAN_HARRIS);
         h->nports = 2;
+    } else if (kind == QRL_DEMOD_WBFM) {
+        // gr_demod_wbfm.cpp:35-54
+        tsr = 200000; sym_sps = 2;
+        taps1 = low_pass(1, samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
+        h->D1 = 5;
+        taps2 = low_pass_2(1, tsr, filter_width, 600, 90, WIN_BLACKMAN_HARRIS);
+        h->qd_gain = static_cast<float>(tsr / (2 * kPi * filter_width));
+        h->nports = 2;
     } else if (kind == QRL_DEMOD_AM) {
         // gr_demod_am.cpp:35-56
         tsr = 20000; sym_sps = 2;
@@ -600,7 +617,7 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = upload_floats(h, &h->d_taps2, t2))) return fail(rc);
     }
     if (!taps3.empty() && (rc = upload_floats(h, &h->d_taps3, taps3))) return fail(rc);
-    if ((rc = make_ring(h, &h->r1, sizeof(float2), h->n1max + 512 + 8))) return fail(rc);
+    if ((rc = make_ring(h, &h->r1, sizeof(float2), h->n1max + std::max(512, static_cast<int>(taps2.size())) + 8))) return fail(rc);
     if (kind == QRL_DEMOD_SSB) {
         if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + 64))) return fail(rc);
         std::vector<float> audio_f = band_pass_2(1, tsr, 200, filter_width, 200, 90, WIN_BLACKMAN_HARRIS);
@@ -612,6 +629,23 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = make_ring(h, &h->rclip, sizeof(float2), h->n1max + 16))) return fail(rc);
         if ((rc = make_ring(h, &h->rstr, sizeof(float), h->n1max + h->ssbp.nt_audio + 16))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_ssb, h->C))) return fail(rc);
+    } else if (kind == QRL_DEMOD_WBFM) {
+        // gr_demod_wbfm.cpp:39-64: the analog audio kernel in mode 2
+        if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + 64))) return fail(rc);
+        std::vector<float> audio_rs = low_pass(1, tsr, 4000, 2000, WIN_BLACKMAN_HARRIS);
+        if ((rc = upload_floats(h, &h->d_audio_taps, audio_rs))) return fail(rc);
+        if ((rc = upload_floats(h, &h->d_arm_taps, std::vector<float>{ 0.0f, 0.0f }))) return fail(rc);
+        if ((rc = upload_floats(h, &h->d_env, std::vector<float>{ 1.0f, 1.0f }))) return fail(rc);
+        double a[2], b[2];
+        deemph_taps(8000, 50e-6, a, b);                        // the reference designs them for 8 kHz (:39) and runs them at 200 ksps
+        h->nbp.sq_alpha = 0.01; h->nbp.sq_threshold = std::pow(10.0, -140 / 10.0); h->nbp.sq_ramp = 0; h->nbp.sq_gate = 1;
+        h->nbp.qd_gain = h->qd_gain; h->nbp.nt_arm = 1; h->nbp.nt_audio = static_cast<int>(audio_rs.size());
+        h->nbp.b0 = b[0]; h->nbp.b1 = b[1]; h->nbp.a1 = a[1]; h->nbp.out_gain = 1.0f;
+        h->nbp.mode = 2; h->nbp.am_gain = 0.9f;
+        if ((rc = make_ring(h, &h->rg, sizeof(float2), h->n1max + 16))) return fail(rc);
+        if ((rc = make_ring(h, &h->rd, sizeof(float), h->n1max + 16))) return fail(rc);
+        if ((rc = make_ring(h, &h->rr, sizeof(float), h->n1max + h->nbp.nt_audio + 16))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_nb, h->C))) return fail(rc);
     } else if (kind == QRL_DEMOD_AM) {
         // gr_demod_am.cpp:41-70: the NBFM audio kernel in detector mode 1
         if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + 64))) return fail(rc);
@@ -1062,7 +1096,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             h->prof_end(pe);
             continue;
         }
-        if (h->kind == QRL_DEMOD_NBFM) {
+        if (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_WBFM) {
             if (n_new > 0) {
                 pe = h->prof_begin(1, sp);
                 fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->ntaps2, sp>>>(
@@ -1130,8 +1164,8 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                     constexpr int CH = 128, NST = 3;
                     const size_t smem = sizeof(float2) * (NST + 2) * CH * 32;
                     auto kern = agc_costas_kernel<CH, NST, 0, 0>;
-                    static bool a_attr = false;
-                    if (!a_attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a_attr = true; }
+                    static bool a_attr[16] = { false };    // per device: function attributes belong to the device's context
+                    if (!a_attr[h->device & 15]) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a_attr[h->device & 15] = true; }
                     kern<<<groups, 96, smem, h->s_loop>>>(h->acp, h->d_ac, h->C,
                         static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, k1,
                         static_cast<float2*>(h->r3.d), h->r3.mask, h->r3.stride);
@@ -1141,8 +1175,8 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period) + 3);
                 const size_t smem = sizeof(float) * (NST * CH * 64 + SYMSYNC_TAB_FLOATS + 2 * maxs * 64) + sizeof(int) * 64;
                 auto kern = symsync_kernel<2, SL_BPSK, EPI_BPSK, CH, NST, NEPI, LOOP_CRMM>;
-                static bool b_attr = false;
-                if (!b_attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); b_attr = true; }
+                static bool b_attr[16] = { false };    // per device: function attributes belong to the device's context
+                if (!b_attr[h->device & 15]) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); b_attr[h->device & 15] = true; }
                 kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop>>>(
                     h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r3.d), h->r3.mask, h->r3.stride, k1,
                     h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
@@ -1153,8 +1187,8 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
                 const size_t smem = sizeof(float) * (NST * CH * 32 + SYMSYNC_TAB_FLOATS + 2 * maxs * 32) + sizeof(int) * 64;
                 auto kern = symsync_kernel<1, SL_BPSK, EPI_REAL1, CH, NST, NEPI>;
-                static bool f_attr = false;
-                if (!f_attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); f_attr = true; }
+                static bool f_attr[16] = { false };    // per device: function attributes belong to the device's context
+                if (!f_attr[h->device & 15]) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); f_attr[h->device & 15] = true; }
                 kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop>>>(
                     h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r4.d), h->r4.mask, h->r4.stride, k1,
                     h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
@@ -1226,8 +1260,8 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
                 const size_t smem = sizeof(float) * (NST * CH * 64 + SYMSYNC_TAB_FLOATS + 2 * maxs * 64) + sizeof(int) * 64;
                 auto kern = symsync_kernel<2, SL_RECT4, EPI_CPLX, CH, NST, NEPI>;
-                static bool sc_attr = false;
-                if (!sc_attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); sc_attr = true; }
+                static bool sc_attr[16] = { false };    // per device: function attributes belong to the device's context
+                if (!sc_attr[h->device & 15]) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); sc_attr[h->device & 15] = true; }
                 kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop>>>(
                     h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r3.d), h->r3.mask, h->r3.stride, k1,
                     h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
@@ -1247,10 +1281,10 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 const size_t smem = rep ? smem_rep : smem_base;
                 auto kern = rep ? symsync_kernel<1, SL_RECT4, EPI_EXT_4FSK_FM, CH, NST, 1, LOOP_SYMSYNC, 2>
                                 : symsync_kernel<1, SL_RECT4, EPI_EXT_4FSK_FM, CH, NST, 1, LOOP_SYMSYNC, 1>;
-                static bool ss_attr[2] = { false, false };   // per (CH, NST) instantiation of this lambda
-                if (!ss_attr[rep]) {
+                static bool ss_attr[2][16] = { { false } };   // per (CH, NST) instantiation of this lambda, per variant, per device
+                if (!ss_attr[rep][h->device & 15]) {
                     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-                    ss_attr[rep] = true;
+                    ss_attr[rep][h->device & 15] = true;
                 }
                 // overlapped calls: the previous call's Viterbi of slice i still reads d_nsoft[i], its epilogue scratch region i
                 if (h->overlap) CK(cudaStreamWaitEvent(h->s_loop, h->ev_v[i], 0));
@@ -1318,11 +1352,11 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 constexpr int CH = 128, NST = 3;
                 const size_t smem = sizeof(float2) * (NST + 2) * CH * 32;
                 auto kern = (h->acp.order == 4 && h->acp.use_snr) ? agc_costas_kernel<CH, NST, 4, 1> : agc_costas_kernel<CH, NST>;
-                static bool ac_attr = false;
-                if (!ac_attr) {
+                static bool ac_attr[16] = { false };    // per device: function attributes belong to the device's context
+                if (!ac_attr[h->device & 15]) {
                     CK(cudaFuncSetAttribute(agc_costas_kernel<CH, NST, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     CK(cudaFuncSetAttribute(agc_costas_kernel<CH, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    ac_attr = true;
+                    ac_attr[h->device & 15] = true;
                 }
                 kern<<<groups, 96, smem, h->s_loop>>>(h->acp, h->d_ac, h->C,
                     static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, k1,
@@ -1339,10 +1373,10 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
                 const size_t smem = sizeof(float) * (NST * CH * 64 + SYMSYNC_TAB_FLOATS + 2 * maxs * 64) + sizeof(int) * 64;
                 auto kern = symsync_kernel<2, SL_DQPSK, EPI_QPSK, CH, NST, NEPI>;
-                static bool sq_attr = false;
-                if (!sq_attr) {
+                static bool sq_attr[16] = { false };    // per device: function attributes belong to the device's context
+                if (!sq_attr[h->device & 15]) {
                     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    sq_attr = true;
+                    sq_attr[h->device & 15] = true;
                 }
                 kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop2>>>(
                     h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r3.d), h->r3.mask, h->r3.stride, k1,
@@ -1453,7 +1487,7 @@ int qrl_rx_port_itemsize(const qrl_rx* h, int port)
 {
     if (!h || port < 0 || port >= h->nports) return QRL_EINVAL;
     if (port == 0) return 8;
-    if (port == 1) return (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_SSB || h->kind == QRL_DEMOD_AM) ? 4 : 8;
+    if (port == 1) return (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_SSB || h->kind == QRL_DEMOD_AM || h->kind == QRL_DEMOD_WBFM) ? 4 : 8;
     return 1;
 }
 
@@ -1463,7 +1497,7 @@ int qrl_rx_port_device(qrl_rx* h, int port, void** data, long* cap, int** counts
     if (port == 0) { *data = h->d_port0; *cap = h->port0_cap; *counts = nullptr; }
     else if (port == 1) {
         *data = h->d_port1; *counts = h->d_port1_cnt;
-        *cap = (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_SSB || h->kind == QRL_DEMOD_AM) ? 2 * h->port1_cap : h->port1_cap;      // float view of the same buffer
+        *cap = (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_SSB || h->kind == QRL_DEMOD_AM || h->kind == QRL_DEMOD_WBFM) ? 2 * h->port1_cap : h->port1_cap;      // float view of the same buffer
     }
     else if (port == 2) { *data = h->d_port2; *cap = h->port2_cap; *counts = h->d_port2_cnt; }
     else { *data = h->d_port3; *cap = h->port2_cap; *counts = h->d_port3_cnt; }

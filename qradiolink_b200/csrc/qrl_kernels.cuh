@@ -418,6 +418,52 @@ __global__ void qdemod_fir_fff_kernel(const float2* __restrict__ in, unsigned in
     out[(static_cast<long long>(c >> 5) * out_stride + (a & out_mask)) * 32 + (c & 31)] = acc;
 }
 
+// THE FIR order for one output inside one thread: 32 partial sums (branch r = j mod D accumulated oldest sample first
+// into slot r mod 32), combined 16, 8, 4, 2, 1 like the warp butterfly.  fetch(j) returns the sample that meets tap j.
+template <class Fetch>
+__device__ __forceinline__ float2 qrl_fir_dot_order_c(const float* __restrict__ taps, int ntaps, int D, Fetch fetch)
+{
+    float sr[32], si[32];
+#pragma unroll
+    for (int l = 0; l < 32; l++) { sr[l] = 0.0f; si[l] = 0.0f; }
+    for (int r = 0; r < D && r < ntaps; r++) {
+        float a = sr[r & 31], b = si[r & 31];
+        for (int q = (ntaps - 1 - r) / D; q >= 0; q--) {
+            const int j = D * q + r;
+            const float2 v = fetch(j);
+            a = fmaf(taps[j], v.x, a); b = fmaf(taps[j], v.y, b);
+        }
+        sr[r & 31] = a; si[r & 31] = b;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+        for (int l = 0; l < off; l++) { sr[l] = sr[l] + sr[l + off]; si[l] = si[l] + si[l + off]; }
+    return make_float2(sr[0], si[0]);
+}
+
+// Shape-generic stage 1 (any decimation / tap count) with the call-to-call history of the tiled instances: one thread per
+// output.  Used for the stage-1 shapes that have no register-tiled instance (WBFM: /5, 41 taps).
+__global__ void __launch_bounds__(128)
+fir_decim_hist_generic_kernel(const float2* __restrict__ iq, long long iq_stride, long long T, const float2* __restrict__ hist, int H,
+                              const float* __restrict__ taps, int ntaps, int D,
+                              float2* __restrict__ out_ring, unsigned ring_mask, long long ring_stride,
+                              long long n_in_before, long long k0, long long k1)
+{
+    const int c = blockIdx.y;
+    const long long k = k0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    const float2* x = iq + static_cast<long long>(c) * iq_stride;
+    const float2* hc = hist + static_cast<long long>(c) * H;
+    const long long newest = static_cast<long long>(D) * k - n_in_before;          // index of x[D k] in this call's input
+    const float2 y = qrl_fir_dot_order_c(taps, ntaps, D, [&](int j) {
+        const long long i = newest - j;
+        if (i >= 0) return i < T ? x[i] : make_float2(0.0f, 0.0f);
+        return (H + i >= 0) ? hc[H + i] : make_float2(0.0f, 0.0f);
+    });
+    out_ring[static_cast<long long>(c) * ring_stride + (k & ring_mask)] = y;
+}
+
 // Stand-alone batched decimating FIR for any (ntaps, D), zero history: y[k] = sum_j h[j] x[D k - j] in THE FIR order
 // (branch r = j mod D oldest-first into lane r mod 32, lanes combined 16, 8, 4, 2, 1).  One warp per output; this is the
 // shape-generic entry point behind qrl_fir_decim_ccf_device (the chains use the register-tiled instances above).
@@ -1518,6 +1564,8 @@ struct NbfmParams {
     int nt_audio;
     double b0, b1, a1;
     float out_gain;
+    // mode 2 = WBFM (gr_demod_wbfm.cpp:56-64): squelch -> quadrature demod -> x am_gain -> de-emphasis iir (b0, b1, a1) on the
+    // 200 ksps stream, then rational_resampler_fff(1, 25) (nt_audio taps, THE FIR order with D = 25) straight to port 1
     // mode 1 = AM detector (gr_demod_am.cpp:57-71): squelch -> complex_to_mag -> agc2_ff -> iir_filter_ffd (b0, b1, a1) -> x am_gain
     // on the 20 ksps stream, then resampler 2/5 and audio low-pass straight to port 1 (no de-emphasis behind them)
     int mode;
@@ -1605,7 +1653,7 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
     __syncthreads();
     const long long gate1 = st.n_gate;
     // ---- 2. quadrature demod over the gated stream (AM: the detector already wrote the 20 ksps stream)
-    for (long long n = gate0 + threadIdx.x; n < gate1 && p.mode == 0; n += blockDim.x) {
+    for (long long n = gate0 + threadIdx.x; n < gate1 && p.mode != 1; n += blockDim.x) {
         const float2 cur = gr_[n & gate_mask];
         float2 prev;
         if (n == gate0) prev = make_float2(st.prev_r, st.prev_i);
@@ -1615,7 +1663,42 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
         dr[n & dem_mask] = p.qd_gain * qrl_fast_atan2f(im, re);
     }
     __syncthreads();
-    if (threadIdx.x == 0 && gate1 > gate0 && p.mode == 0) { const float2 l = gr_[(gate1 - 1) & gate_mask]; st.prev_r = l.x; st.prev_i = l.y; }
+    if (threadIdx.x == 0 && gate1 > gate0 && p.mode != 1) { const float2 l = gr_[(gate1 - 1) & gate_mask]; st.prev_r = l.x; st.prev_i = l.y; }
+    if (p.mode == 2) {
+        // ---- WBFM: x am_gain and de-emphasis IIR over the new demodulated samples (sequential), into the res ring at 200 ksps
+        if (threadIdx.x == 0) {
+            double x1 = st.iir_x1, y1 = st.iir_y1;
+            for (long long n = gate0; n < gate1; n++) {
+                const double xin = static_cast<double>(dr[n & dem_mask] * p.am_gain);
+                double acc = p.b0 * xin;
+                acc = acc + p.b1 * x1;
+                acc = acc - p.a1 * y1;
+                x1 = xin; y1 = acc;
+                rr[n & res_mask] = static_cast<float>(acc);
+            }
+            st.iir_x1 = x1; st.iir_y1 = y1;
+        }
+        __syncthreads();
+        // ---- rational_resampler_fff(1, 25): output i = sum_j h[j] z[25 i - j], outputs with 25 i <= gate1 - 1
+        const long long o0 = st.n_res, o1 = (gate1 + 24) / 25;
+        const int cnt0 = port1_cnt[c];
+        float* o = port1 + static_cast<long long>(c) * port1_stride;
+        for (long long i = o0 + threadIdx.x; i < o1; i += blockDim.x) {
+            const long long newest = 25 * i;
+            const float2 y = qrl_fir_dot_order_c(audio_taps, p.nt_audio, 25, [&](int j) {
+                const long long n = newest - j;
+                return make_float2(n >= 0 ? rr[n & res_mask] : 0.0f, 0.0f);
+            });
+            const long long slot = cnt0 + (i - o0);
+            if (slot < port1_cap) o[slot] = y.x;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (o1 > o0) port1_cnt[c] = cnt0 + static_cast<int>(o1 - o0);
+            st.n_res = o1 > o0 ? o1 : o0; st.n_aud = st.n_res; states[c] = st;
+        }
+        return;
+    }
     // ---- 3. rational resampler 2/5: output i uses arm (5 i) mod 2 at input position floor(5 i / 2)
     const long long res0 = st.n_res;
     long long res1 = res0;

@@ -427,8 +427,8 @@ int qrl_pfb_work(qrl_pfb* h, const void* in, long n_in, long in_stride, int in_o
                 constexpr int TM = kChanR * kChanG, SPAN = (TM + kFastTpf - 1) * kFastM, SPANP = (SPAN + 3) & ~1;
                 const size_t smem = sizeof(float2) * (SPANP + kFastM * (TM + 1));
                 auto kern = pfb_chan_kernel<kFastM, kFastTpf, kChanR, kChanG>;
-                static bool attr = false;
-                if (!attr) { CKP(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = true; }
+                static bool attr[16] = { false };    // per device: function attributes belong to the device's context
+                if (!attr[h->device & 15]) { CKP(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr[h->device & 15] = true; }
                 const int use_tma = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
                 kern<<<static_cast<unsigned>((frames + TM - 1) / TM), kFastM * kChanG, smem, h->stream>>>(
                     h->d_bt, h->d_w, hist, h->hist_len, x, n_in, -static_cast<long long>(h->pend), frames,
@@ -464,8 +464,8 @@ int qrl_pfb_work(qrl_pfb* h, const void* in, long n_in, long in_stride, int in_o
                 constexpr int TN = kSynR * kSynG, COLS = TN + kFastTpf - 1, VP = COLS | 1;
                 const size_t smem = sizeof(float2) * (kFastM * COLS + kFastM * VP);
                 auto kern = pfb_synth_kernel<kFastM, kFastTpf, kSynR, kSynG>;
-                static bool attr = false;
-                if (!attr) { CKP(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = true; }
+                static bool attr[16] = { false };    // per device: function attributes belong to the device's context
+                if (!attr[h->device & 15]) { CKP(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr[h->device & 15] = true; }
                 kern<<<static_cast<unsigned>((n_in + TN - 1) / TN), kFastM * kSynG, smem, h->stream>>>(
                     h->d_bt, h->d_w, hist, x, stride, n_in, h->d_out);
             } else {

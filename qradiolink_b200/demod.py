@@ -150,6 +150,12 @@ def make_gr_demod_gmsk(sps, samp_rate, carrier_freq, filter_width, n_channels=1,
     return RxBlock(KIND.DEMOD_GMSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
 
 
+def make_gr_demod_wbfm(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
+    """src/gr/gr_demod_wbfm.h (instance gr_demod_base.cpp:228: make_gr_demod_wbfm(125, 1e6, 1700, 75000)); ports (IQ at 200 ksps,
+    float audio at 8 ksps)."""
+    return RxBlock(KIND.DEMOD_WBFM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
+
+
 def make_gr_demod_am(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
     """src/gr/gr_demod_am.h (instance gr_demod_base.cpp: make_gr_demod_am(125, 1e6, 1700, 5000)); ports (IQ, float audio)."""
     return RxBlock(KIND.DEMOD_AM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)

@@ -78,6 +78,16 @@ def _sig_am(O, sg):
     return x.astype(np.complex64)[None, :]
 
 
+def _sig_wbfm(O, sg):
+    rng = np.random.default_rng(9660)
+    T = 1 << 17
+    n = np.arange(T)
+    aud = 0.6 * np.sin(2 * np.pi * 1000.0 * n / 1e6) + 0.3 * np.sin(2 * np.pi * 2900.0 * n / 1e6)
+    x = 0.5 * np.exp(1j * 2 * np.pi * 50000.0 * np.cumsum(aud) / 1e6)
+    x = x + (rng.standard_normal(T) + 1j * rng.standard_normal(T)) * 0.005
+    return x.astype(np.complex64)[None, :]
+
+
 def _sig_ssb(O, sg):
     rng = np.random.default_rng(9600)
     T = 1 << 18
@@ -105,6 +115,8 @@ RX_CASES = {
                     factory="make_gr_demod_am", fargs=(125, 1000000, 1700, 5000)),
     "gmsk_2k": dict(okind=8, args=(5, 1000000, 1700, 4000, 0), nports=4, signal=_sig_digital("2fsk"),
                     factory="make_gr_demod_gmsk", fargs=(5, 1000000, 1700, 4000)),
+    "wbfm_75k": dict(okind=9, args=(125, 1000000, 1700, 75000, 0), nports=2, signal=_sig_wbfm,
+                     factory="make_gr_demod_wbfm", fargs=(125, 1000000, 1700, 75000)),
     "ssb_usb": dict(okind=6, args=(125, 1000000, 1700, 2700, 0), nports=2, signal=_sig_ssb,
                     factory="make_gr_demod_ssb", fargs=(125, 1000000, 1700, 2700, 0)),
 }

@@ -314,3 +314,20 @@ def test_gmsk_modem_loops_back_in_the_oracle(oracle):
     rx.work(x)
     good = max(siggen.count_good_frames(rx.port(p), 0xED89AA, 24, 7, pl)[0] for p in (2, 3))
     assert good == len(pl)
+
+
+def test_wbfm_chain_streams_and_recovers_the_tone(oracle):
+    O = oracle
+    T = 1 << 17
+    n = np.arange(T)
+    x = (0.5 * np.exp(1j * 2 * np.pi * 40000.0 * np.cumsum(np.sin(2 * np.pi * 1000.0 * n / 1e6)) / 1e6)).astype(np.complex64)
+    a = O.Rx(O.DEMOD_WBFM, 125, 1000000, 1700, 75000, 0); a.work(x)
+    b = O.Rx(O.DEMOD_WBFM, 125, 1000000, 1700, 75000, 0)
+    for lo in range(0, T, 23456):
+        b.work(x[lo:lo + 23456])
+    for p in range(2):
+        assert np.array_equal(a.port(p, clear=False), b.port(p, clear=False))
+    assert len(a.port(0, clear=False)) == (T + 4) // 5
+    audio = a.port(1)
+    f = np.abs(np.fft.rfft(audio[100:] * np.hanning(len(audio) - 100)))
+    assert abs(np.argmax(f) * 8000.0 / (len(audio) - 100) - 1000.0) < 20.0
