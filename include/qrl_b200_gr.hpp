@@ -181,6 +181,10 @@ inline gr_demod_b200_sptr make_gr_demod_gmsk(int sps, int samp_rate, int carrier
                                              int n_channels = 1, long max_samples = 1 << 20, int device = 0)     // src/gr/gr_demod_gmsk.h
 { return std::make_shared<gr_demod_b200>(QRL_DEMOD_GMSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_samples, device); }
 
+inline gr_demod_b200_sptr make_gr_demod_wbfm(int sps, int samp_rate, int carrier_freq, int filter_width,
+                                             int n_channels = 1, long max_samples = 1 << 20, int device = 0)     // src/gr/gr_demod_wbfm.h
+{ return std::make_shared<gr_demod_b200>(QRL_DEMOD_WBFM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_samples, device); }
+
 // ---- batched modulator
 class gr_mod_b200 {
 public:

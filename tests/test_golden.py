@@ -89,7 +89,7 @@ def test_golden_rx_cuda(qrl, oracle, name):
     assert sha(X) == G["rx"][name]["input_sha256"], "signal generator drifted"
     blk = getattr(qrl, case["factory"])(*case["fargs"], n_channels=X.shape[0], max_samples=X.shape[1])
     # two calls with an odd split: the answer may not depend on chunking
-    cut = 100003
+    cut = min(100003, X.shape[1] // 2 + 3)
     acc = [[[] for _ in range(X.shape[0])] for _ in range(case["nports"])]
     for lo, hi in ((0, cut), (cut, X.shape[1])):
         blk.work(X[:, lo:hi])
