@@ -886,6 +886,8 @@ __device__ __noinline__ float2 symsync_generic_step(float ph)
 //                     reads column `lane` of the window (bank = lane: conflict-free)
 //   warps 2..       : everything that does not feed back (phase modulator / 2nd Costas loop, soft bits, stores),
 //                     fed through a double-buffered shared-memory symbol hand-off (mbarrier full/empty)
+// VAR: 0 = generic recurrence (any NCOMP / slicer); 1 = lean real 4-level recurrence, interpolator bank as 12-float entries
+// (two LDS.128 with bank conflicts); 2 = lean recurrence + 16-fold replicated bank (conflict-free, +66 KB of shared memory)
 template <int NCOMP, int SLICER, int EPI, int CH, int NST, int NEPI, int LOOPK = LOOP_SYMSYNC, int VAR = 0>
 __global__ void __launch_bounds__(64 + 32 * NEPI)
 symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
