@@ -185,6 +185,10 @@ inline gr_demod_b200_sptr make_gr_demod_wbfm(int sps, int samp_rate, int carrier
                                              int n_channels = 1, long max_samples = 1 << 20, int device = 0)     // src/gr/gr_demod_wbfm.h
 { return std::make_shared<gr_demod_b200>(QRL_DEMOD_WBFM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_samples, device); }
 
+inline gr_demod_b200_sptr make_gr_demod_m17(int sps = 125, int samp_rate = 1000000, int carrier_freq = 1700, int filter_width = 9000,
+                                            int n_channels = 1, long max_samples = 1 << 20, int device = 0)      // src/gr/gr_demod_m17.h:41-42
+{ return std::make_shared<gr_demod_b200>(QRL_DEMOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_samples, device); }
+
 // ---- batched modulator
 class gr_mod_b200 {
 public:

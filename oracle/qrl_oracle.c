@@ -1033,6 +1033,7 @@ void qo_descramble(const uint8_t* in, long n, uint8_t* out) { lfsr_t l; lfsr_ini
 /* ------------------------------------------------------------------ RX chains */
 struct qo_rx {
     int gmsk;               /* 2FSK branch running as gr_demod_gmsk */
+    int m17;                /* 4FSK (fm) branch running as gr_demod_m17 */
     int kind, fm;
     int sym_sps, tsr;
     /* stages (not all used by every kind) */
@@ -1082,7 +1083,29 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
      * its own clock-loop constants: restated through the 2FSK branch */
     const int gmsk = (kind == QO_DEMOD_GMSK);
     if (gmsk) { kind = QO_DEMOD_2FSK; r->kind = QO_DEMOD_2FSK; r->gmsk = 1; flag = 1; }
-    if (kind == QO_DEMOD_4FSK) {
+    if (kind == QO_DEMOD_M17) {
+        /* /root/reference/src/gr/gr_demod_m17.cpp:30-113: rational_resampler_ccf(3, 125) to 24 ksps -> low-pass -> quadrature
+         * demod (5 / pi) -> RRC(1.5, 24k, 4800, 0.5, 250) -> symbol_sync_ff (4-level) -> phase_modulator_fc(pi/2) -> [port 1];
+         * re / im -> binary_slicer -> pack 2 -> map {3,1,2,0} -> unpack 2 -> [port 2] (no FEC in this block).  Runs through the
+         * 4FSK (fm) branch with its own constants and bit tail. */
+        r->kind = QO_DEMOD_4FSK; r->fm = 1; r->m17 = 1;
+        r->tsr = 24000; r->sym_sps = 5;
+        int n0 = qo_firdes_low_pass(3, 3.0 * samp_rate, r->tsr / 2, r->tsr / 2, QO_WIN_BLACKMAN_HARRIS, T0, 4096);
+        r->ntaps_store[0] = n0;
+        resamp_init(&r->resamp, 2, 3, 125, T0, n0);
+        int n1 = qo_firdes_low_pass(1, r->tsr, filter_width, filter_width, QO_WIN_BLACKMAN_HARRIS, T1, 4096);
+        r->ntaps_store[1] = n1;
+        resamp_init(&r->filt, 2, 1, 1, T1, n1);
+        qdemod_init(&r->qd, (float)(r->sym_sps / M_PI));
+        int n2 = qo_firdes_rrc(1.5, r->tsr, r->tsr / r->sym_sps, 0.5, 50 * r->sym_sps, T2, 4096);
+        r->ntaps_store[2] = n2;
+        resamp_init(&r->shaping, 1, 1, 1, T2, n2);
+        const float symbol_rate = (float)r->tsr / (float)r->sym_sps;
+        symsync_init(&r->ss, 1, (float)r->sym_sps, (float)(2 * M_PI / (symbol_rate / 50)), 1.0f, 0.2869f, 500.0f / symbol_rate, SL_RECT4);
+        r->pm_sens = (float)(M_PI / 2);
+        r->soft_scale = 128.0f;
+        ccdec_init(&r->dec); lfsr_init(&r->descr);
+    } else if (kind == QO_DEMOD_4FSK) {
         /* /root/reference/src/gr/gr_demod_4fsk.cpp:32-205 */
         int fm = flag; r->fm = fm;
         int rs = 0, bw = 0, decimation = 1, interpolation = 1, nfilts = 0;
@@ -1456,6 +1479,15 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
                 float ph = r->pm_sens * sy[i];
                 float sn, cs; qo_sincosf(ph, &sn, &cs);
                 qv_pushc(&r->port[1], cs, sn);
+                if (r->m17) {
+                    /* gr_demod_m17.cpp:98-107: interleave (real, imag) -> binary_slicer_fb (x >= 0) -> pack_k_bits(2) ->
+                     * map {3,1,2,0} -> unpack_k_bits(2) */
+                    static const int map[4] = { 3, 1, 2, 0 };
+                    const int v = ((cs >= 0.0f) ? 2 : 0) | ((sn >= 0.0f) ? 1 : 0);
+                    qv_pushb(&r->port[2], (unsigned char)((map[v] >> 1) & 1));
+                    qv_pushb(&r->port[2], (unsigned char)(map[v] & 1));
+                    continue;
+                }
                 /* interleave: imag first, then real (gr_demod_4fsk.cpp:186-189) */
                 qv_pushb(&r->s_soft, soft_u8(sn, r->soft_scale));
                 qv_pushb(&r->s_soft, soft_u8(cs, r->soft_scale));
@@ -1485,7 +1517,7 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
                 qv_pushb(&r->s_soft, soft_u8(sy[2 * i + 1], r->soft_scale));
             }
         }
-        rx_fec_tail(r);
+        if (!r->m17) rx_fec_tail(r);
         return 0;
     }
     if (r->kind == QO_DEMOD_QPSK) {

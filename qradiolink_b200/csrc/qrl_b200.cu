@@ -161,6 +161,8 @@ struct qrl_rx : HandleBase {
     float* d_ss_scratch = nullptr; int* d_ss_hdr = nullptr; long long ss_chunk_cap = 0, ss_chunk_off = 0;   // external symbol-sync epilogue
     cudaStream_t s_epi = nullptr;                        // wide-partition stream of the external epilogue
     bool gmsk = false;                                   // 2FSK code path running as gr_demod_gmsk (no FLL)
+    bool m17 = false;                                    // 4FSK (fm) code path running as gr_demod_m17 (x3/125 front end, hard bits)
+    int nt_arm1 = 0;                                     // taps per arm of a generic rational stage 1 (L1 > 1)
     // RSSI tap on port 0 (QRL_PARAM_RSSI): ring of |x|^2, carried IIR value, latest dB value per channel
     bool rssi_on = false; float* d_rssi_ring = nullptr; float* d_rssi_y = nullptr; float* d_rssi_db = nullptr; long long rssi_n = 0;
     // QRL_PARAM_OVERLAP_CALLS: the loop / FEC tail of call k runs under the parallel stages of call k+1.  Output ports
@@ -275,6 +277,16 @@ int stage1(qrl_rx* h, const float2* iq, long long stride, long long T, long long
 {
     if (k1 <= k0) return QRL_OK;
     if (h->L1 == 2 && h->D1 == 25 && h->ntaps1 <= 210) return launch_fir_resamp_2_25(h, iq, stride, T, k0, k1);
+    if (h->L1 > 2) {       // shape-generic rational resampler (M17: x3 / 125)
+        const long long nout = k1 - k0;
+        dim3 grid(static_cast<unsigned>((nout + 127) / 128), h->C);
+        fir_resamp_hist_generic_kernel<<<grid, 128, 0, h->par()>>>(iq, stride, T, h->d_hist[h->hist_cur], h->H, h->d_taps1, h->nt_arm1,
+            h->L1, h->D1, static_cast<float2*>(h->r1.d), h->r1.mask, h->r1.stride, h->n_in, k0, k1);
+        h->launches++;
+        CK(cudaGetLastError());
+        return QRL_OK;
+    }
+    if (h->L1 != 1) { set_err(h, "stage-1 resampler shape not built"); return QRL_EINVAL; }
     if (h->D1 == 50 && h->Q1 == 9) return launch_fir_poly<50, 9, 8, 128, 8>(h, iq, stride, T, k0, k1);
     if (h->D1 == 100 && h->Q1 == 9) return launch_fir_poly<100, 9, 8, 64, 8>(h, iq, stride, T, k0, k1);     // 837 taps (4FSK-1k, QPSK-2k shape)
     if (h->D1 == 25 && h->Q1 == 9) return launch_fir_poly<25, 9, 8, 256, 8>(h, iq, stride, T, k0, k1);      // 209 taps (2FSK-2k)
@@ -411,10 +423,14 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     // own clock-loop constants: it runs through the 2FSK code path
     const bool gmsk = (kind == QRL_DEMOD_GMSK);
     if (gmsk) { kind = QRL_DEMOD_2FSK; flag = 1; }
+    // gr_demod_m17.cpp:30-113 is the 4FSK (fm) chain behind a x3 / 125 rational resampler (24 ksps, 5 samples per symbol) with a
+    // hard-decision bit tail instead of the FEC: it runs through the 4FSK code path
+    const bool m17 = (kind == QRL_DEMOD_M17);
+    if (m17) { kind = QRL_DEMOD_4FSK; flag = 1; }
     qrl_rx* h = new qrl_rx();
     h->kind = kind; h->sps = sps; h->samp_rate = samp_rate; h->carrier_freq = carrier_freq;
     h->filter_width = filter_width; h->flag = flag; h->C = n_channels; h->Tmax = max_samples; h->device = device;
-    h->gmsk = gmsk;
+    h->gmsk = gmsk; h->m17 = m17;
     auto fail = [&](int rc) { std::string e = h->err; qrl_rx_destroy(h); g_err = e; return rc; };
     if (cudaSetDevice(device) != cudaSuccess) { set_err(h, "cudaSetDevice failed"); return fail(QRL_ECUDA); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err(h, "stream create failed"); return fail(QRL_ECUDA); }
@@ -427,7 +443,8 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     if (kind == QRL_DEMOD_4FSK) {
         // gr_demod_4fsk.cpp:46-84 (sps ladder), :98-107 (resampler), :108-109 (filter), :125-131 (demod, RRC, sync)
         int decimation = 1, interpolation = 1, nfilts = 0;
-        if (sps == 1) { tsr = 80000; sym_sps = sps * 8; decimation = 25; interpolation = 2; nfilts = 32 * sym_sps; }
+        if (m17) { tsr = 24000; sym_sps = 5; decimation = 125; interpolation = 3; nfilts = 50 * sym_sps; }      // gr_demod_m17.cpp:37-48
+        else if (sps == 1) { tsr = 80000; sym_sps = sps * 8; decimation = 25; interpolation = 2; nfilts = 32 * sym_sps; }
         else if (sps == 5) { tsr = 20000; sym_sps = sps * 2; decimation = 50; nfilts = 25 * sym_sps; }
         else if (sps == 10) { tsr = 10000; sym_sps = sps; decimation = 100; nfilts = 25 * sym_sps; }
         else if (sps == 2) { decimation = 2; sym_sps = 5; tsr = 500000; nfilts = 50 * sym_sps; }
@@ -435,12 +452,16 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((nfilts % 2) == 0) nfilts += 1;
         taps1 = low_pass(interpolation, static_cast<double>(interpolation) * samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
         h->D1 = decimation; h->L1 = interpolation;
-        taps2 = low_pass(1, tsr, filter_width, filter_width / 2, WIN_BLACKMAN_HARRIS);
-        taps3 = root_raised_cosine(1.5, tsr, tsr / sym_sps, 0.2, nfilts);
+        taps2 = m17 ? low_pass(1, tsr, filter_width, filter_width, WIN_BLACKMAN_HARRIS)                 // gr_demod_m17.cpp:58-59
+                    : low_pass(1, tsr, filter_width, filter_width / 2, WIN_BLACKMAN_HARRIS);
+        taps3 = root_raised_cosine(1.5, tsr, tsr / sym_sps, m17 ? 0.5 : 0.2, nfilts);
         h->qd_gain = static_cast<float>(sym_sps / (1 * kPi));
-        clock_loop_gains(static_cast<float>(2 * kPi / 200.0f), 1.0f, 0.2869f, h->ssp.alpha, h->ssp.beta);
+        const float m17_rate = static_cast<float>(tsr) / static_cast<float>(sym_sps);
+        const float dev = m17 ? 500.0f / m17_rate : 0.05f;                                              // gr_demod_m17.cpp:67-70
+        clock_loop_gains(m17 ? static_cast<float>(2 * kPi / (m17_rate / 50)) : static_cast<float>(2 * kPi / 200.0f), 1.0f, 0.2869f,
+                         h->ssp.alpha, h->ssp.beta);
         h->ssp.sps = static_cast<float>(sym_sps);
-        h->ssp.max_period = h->ssp.sps + 0.05f; h->ssp.min_period = h->ssp.sps - 0.05f;
+        h->ssp.max_period = h->ssp.sps + dev; h->ssp.min_period = h->ssp.sps - dev;
         h->ssp.lookahead = 8 + static_cast<int>(ceilf(h->ssp.max_period)) + 1;
         h->ssp.pm_sens = static_cast<float>(kPi / 2);
         h->ssp.soft_scale = 128.0f;
@@ -602,6 +623,12 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         tp.assign(2 * nt, 0.0f);
         for (int p = 0; p < 2; p++) for (int k = 0; k < nt; k++) { const size_t j = p + 2 * k; if (j < taps1.size()) tp[p * nt + k] = taps1[j]; }
         padded = 128;       // history samples kept
+    } else if (h->L1 > 2) {   // shape-generic rational resampler: arm[p][k] = taps[p + k L]
+        const int nt = (static_cast<int>(taps1.size()) + h->L1 - 1) / h->L1;
+        tp.assign(static_cast<size_t>(h->L1) * nt, 0.0f);
+        for (int p = 0; p < h->L1; p++) for (int k = 0; k < nt; k++) { const size_t j = p + static_cast<size_t>(k) * h->L1; if (j < taps1.size()) tp[p * nt + k] = taps1[j]; }
+        h->nt_arm1 = nt;
+        padded = nt + 8;
     }
     if ((rc = upload_floats(h, &h->d_taps1, tp))) return fail(rc);
     h->H = padded;
@@ -737,7 +764,7 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     if ((rc = dev_alloc(h, &h->d_port1, static_cast<size_t>(h->port1_cap) * h->C))) return fail(rc);
     h->d_port1f = reinterpret_cast<float*>(h->d_port1);
     if ((rc = dev_alloc(h, &h->d_port1_cnt, h->C))) return fail(rc);
-    h->port2_cap = h->port1_cap + 160;
+    h->port2_cap = (h->m17 ? 2 : 1) * h->port1_cap + 160;      // M17: two hard bits per symbol, no rate-1/2 decoder behind them
     if ((rc = dev_alloc(h, &h->d_port2, static_cast<size_t>(h->port2_cap) * h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_port2_cnt, h->C))) return fail(rc);
     if (h->nports == 4) {
@@ -1308,7 +1335,8 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                     symsync_ext_epilogue_kernel<<<dim3(chunk_bound, groups), dim3(32, 8), 0, se>>>(
                         h->ssp, h->C, scratch_i, static_cast<int>(h->ss_chunk_cap), maxs, hdr_i,
                         h->d_port1, h->port1_cap, static_cast<int>(h->port1_cap),
-                        static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride);
+                        static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride,
+                        h->m17 ? h->d_port2 : nullptr, h->port2_cap, static_cast<int>(h->port2_cap), h->d_port2_cnt, h->d_port1_cnt);
                 h->launches++;
                 h->prof_end(pe);
                 CK(cudaEventRecord(h->ev_b[i], se));
@@ -1389,6 +1417,10 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         }
         // ---- stage 5: Viterbi + descrambler on the FEC stream
         CK(cudaStreamWaitEvent(h->s_fec, h->ev_b[i], 0));
+        if (h->m17) {                    // gr_demod_m17 has no FEC: the epilogue wrote the hard bits of port 2 (s_fec joins it at the end)
+            if (h->overlap) CK(cudaEventRecord(h->ev_v[i], h->s_fec));
+            continue;
+        }
         pe = h->prof_begin(4, h->s_fec);
         constexpr int CPB = 4;    // 4 channels (8 warps) per CTA
         viterbi_k7_kernel<CPB><<<(h->C + CPB - 1) / CPB, 64 * CPB, 0, h->s_fec>>>(h->d_vs, nsoft_i, h->C,

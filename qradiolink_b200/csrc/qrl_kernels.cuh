@@ -464,6 +464,35 @@ fir_decim_hist_generic_kernel(const float2* __restrict__ iq, long long iq_stride
     out_ring[static_cast<long long>(c) * ring_stride + (k & ring_mask)] = y;
 }
 
+// Shape-generic rational stage 1 (rational_resampler_ccf(L, M), L > 1): output i takes arm (i M) mod L at input position
+// floor(i M / L); arms[p][k] = taps[p + k L]; plain oldest-first accumulation (the oracle's order for L > 1).  One thread per
+// output; used for the shapes that have no tiled instance (M17: x3 / 125, 349 taps per arm).
+__global__ void __launch_bounds__(128)
+fir_resamp_hist_generic_kernel(const float2* __restrict__ iq, long long iq_stride, long long T, const float2* __restrict__ hist, int H,
+                               const float* __restrict__ arms /* [L][nt] */, int nt, int L, int M,
+                               float2* __restrict__ out_ring, unsigned ring_mask, long long ring_stride,
+                               long long n_in_before, long long k0, long long k1)
+{
+    const int c = blockIdx.y;
+    const long long i = k0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= k1) return;
+    const float2* x = iq + static_cast<long long>(c) * iq_stride;
+    const float2* hc = hist + static_cast<long long>(c) * H;
+    const long long im = i * M;
+    const int p = static_cast<int>(im % L);
+    const long long newest = im / L - n_in_before;                       // index of the newest sample in this call's input
+    const float* h = arms + static_cast<long long>(p) * nt;
+    float re = 0.0f, imv = 0.0f;
+    for (int k = nt - 1; k >= 0; k--) {
+        const long long a = newest - k;
+        float2 v;
+        if (a >= 0) v = a < T ? x[a] : make_float2(0.0f, 0.0f);
+        else v = (H + a >= 0) ? hc[H + a] : make_float2(0.0f, 0.0f);
+        re = fmaf(h[k], v.x, re); imv = fmaf(h[k], v.y, imv);
+    }
+    out_ring[static_cast<long long>(c) * ring_stride + (i & ring_mask)] = make_float2(re, imv);
+}
+
 // Stand-alone batched decimating FIR for any (ntaps, D), zero history: y[k] = sum_j h[j] x[D k - j] in THE FIR order
 // (branch r = j mod D oldest-first into lane r mod 32, lanes combined 16, 8, 4, 2, 1).  One warp per output; this is the
 // shape-generic entry point behind qrl_fir_decim_ccf_device (the chains use the register-tiled instances above).
@@ -1311,7 +1340,9 @@ __global__ void __launch_bounds__(256)
 symsync_ext_epilogue_kernel(SymSyncParams p, int C, const float* __restrict__ scratch, int chunk_stride, int maxs,
                             const int* __restrict__ hdr_all,
                             float2* __restrict__ port1, long long port1_stride, int port1_cap,
-                            unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride)
+                            unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride,
+                            unsigned char* __restrict__ hard_port2 = nullptr /* M17: [C][hard_cap] bits */, long long hard_stride = 0,
+                            int hard_cap = 0, int* __restrict__ hard_cnt = nullptr, const int* __restrict__ port1_cnt = nullptr)
 {
     const int g = blockIdx.y, m = blockIdx.x, lane = threadIdx.x, c = g * 32 + lane;
     const int* hdr = hdr_all + g * 128;
@@ -1330,10 +1361,20 @@ symsync_ext_epilogue_kernel(SymSyncParams p, int C, const float* __restrict__ sc
         qrl_sincosf(p.pm_sens * yr, sn, cs);
         const int idx = sbase + k;
         if (p1cnt0 + idx < port1_cap) p1[p1cnt0 + idx] = make_float2(cs, sn);
+        if (hard_port2) {
+            // gr_demod_m17.cpp:98-107: (re, im) -> binary_slicer_fb -> pack_k_bits(2) -> map {3,1,2,0} -> unpack_k_bits(2)
+            const int v = ((cs >= 0.0f) ? 2 : 0) | ((sn >= 0.0f) ? 1 : 0);
+            const int mp = (0x27 >> (2 * v)) & 3;                     // {3,1,2,0} packed two bits per entry: 0b00'10'01'11
+            const long long b = 2LL * (p1cnt0 + idx);
+            unsigned char* hp = hard_port2 + static_cast<long long>(c) * hard_stride;
+            if (b + 1 < hard_cap) { hp[b] = static_cast<unsigned char>((mp >> 1) & 1); hp[b + 1] = static_cast<unsigned char>(mp & 1); }
+            continue;
+        }
         const long long so = n_soft0 + 2LL * idx;
         sr[so & soft_mask] = qrl_soft_u8(sn, p.soft_scale);          // interleave: imag first, then real
         sr[(so + 1) & soft_mask] = qrl_soft_u8(cs, p.soft_scale);
     }
+    if (hard_port2 && m == 0 && threadIdx.y == 0) hard_cnt[c] = 2 * port1_cnt[c];   // the symbol-sync launch has finished: final count
 }
 
 // ------------------------------------------------------------------------------------------------

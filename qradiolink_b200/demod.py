@@ -150,6 +150,11 @@ def make_gr_demod_gmsk(sps, samp_rate, carrier_freq, filter_width, n_channels=1,
     return RxBlock(KIND.DEMOD_GMSK, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
 
 
+def make_gr_demod_m17(sps=125, samp_rate=1000000, carrier_freq=1700, filter_width=9000, n_channels=1, **kw):
+    """src/gr/gr_demod_m17.h:41-42 (defaults as there); ports (IQ at 24 ksps, symbols, hard bits: 2 per symbol, no FEC)."""
+    return RxBlock(KIND.DEMOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
+
+
 def make_gr_demod_wbfm(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
     """src/gr/gr_demod_wbfm.h (instance gr_demod_base.cpp:228: make_gr_demod_wbfm(125, 1e6, 1700, 75000)); ports (IQ at 200 ksps,
     float audio at 8 ksps)."""

@@ -88,6 +88,19 @@ def _sig_wbfm(O, sg):
     return x.astype(np.complex64)[None, :]
 
 
+def _sig_m17(O, sg):
+    rng = np.random.default_rng(9670)
+    T = 1 << 18
+    nsym = int(T / 1e6 * 4800) + 2
+    sy = np.array([-1.5, -0.5, 0.5, 1.5])[rng.integers(0, 4, nsym)]
+    t = np.arange(T) / 1e6
+    x = sy[np.minimum((t * 4800).astype(int), nsym - 1)]
+    k = np.hanning(400); k /= k.sum()
+    ph = 2 * np.pi * np.cumsum(np.convolve(x, k, mode="same") * 800.0) / 1e6
+    iq = 0.5 * np.exp(1j * ph) + (rng.standard_normal(T) + 1j * rng.standard_normal(T)) * 0.01
+    return iq.astype(np.complex64)[None, :]
+
+
 def _sig_ssb(O, sg):
     rng = np.random.default_rng(9600)
     T = 1 << 18
@@ -117,6 +130,8 @@ RX_CASES = {
                     factory="make_gr_demod_gmsk", fargs=(5, 1000000, 1700, 4000)),
     "wbfm_75k": dict(okind=9, args=(125, 1000000, 1700, 75000, 0), nports=2, signal=_sig_wbfm,
                      factory="make_gr_demod_wbfm", fargs=(125, 1000000, 1700, 75000)),
+    "m17": dict(okind=10, args=(125, 1000000, 1700, 9000, 0), nports=3, signal=_sig_m17,
+                factory="make_gr_demod_m17", fargs=(125, 1000000, 1700, 9000)),
     "ssb_usb": dict(okind=6, args=(125, 1000000, 1700, 2700, 0), nports=2, signal=_sig_ssb,
                     factory="make_gr_demod_ssb", fargs=(125, 1000000, 1700, 2700, 0)),
 }

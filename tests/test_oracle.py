@@ -331,3 +331,18 @@ def test_wbfm_chain_streams_and_recovers_the_tone(oracle):
     audio = a.port(1)
     f = np.abs(np.fft.rfft(audio[100:] * np.hanning(len(audio) - 100)))
     assert abs(np.argmax(f) * 8000.0 / (len(audio) - 100) - 1000.0) < 20.0
+
+
+def test_m17_chain_streams(oracle):
+    """gr_demod_m17 restated (x3/125 to 24 ksps, 4FSK, hard bits): chunk-size invariant, 2 bits per symbol, 3/125 of the input rate."""
+    O = oracle
+    from tests.golden import cases
+    x = cases._sig_m17(O, None)[0][:200000]
+    a = O.Rx(O.DEMOD_M17, 125, 1000000, 1700, 9000, 0); a.work(x)
+    b = O.Rx(O.DEMOD_M17, 125, 1000000, 1700, 9000, 0)
+    for lo in range(0, len(x), 33331):
+        b.work(x[lo:lo + 33331])
+    for p in range(3):
+        assert np.array_equal(a.port(p, clear=False), b.port(p, clear=False))
+    assert len(a.port(0, clear=False)) == (len(x) * 3 + 124) // 125
+    assert len(a.port(2, clear=False)) == 2 * len(a.port(1, clear=False))
