@@ -28,3 +28,19 @@ def test_viterbi_metric_spread_bound():
     """32-bit metrics without renormalisation decide like VOLK's 8-bit kernel iff the 8-bit one never wraps:
     worst case spread over K-1 = 6 steps of branch cost <= 31 plus one add stays below 256."""
     assert 6 * 31 + 31 < 256 and 63 + 5 * 31 + 31 < 256
+
+
+def test_framing_table_and_port_map_match_the_reference_literals():
+    """MODE_FRAMING restates gr_modem::toggleRxMode (gr_modem.cpp:203-322: _bit_buf_len, _rx_frame_length) and the findSync branch
+    each modem type takes (gr_modem.cpp:1208-1274); mmdvm_port_map restates the channel -> port wiring of
+    gr_demod_mmdvm_multi2.cpp:110-124."""
+    from qradiolink_b200 import framing, pfb
+    F = framing.MODE_FRAMING
+    assert F["4FSK2KFM"] == (framing.SYNC_NARROW, 8 * 8, 7) and F["4FSK2K"] == F["4FSK2KFM"] == F["BPSK2K"] == F["QPSK2K"]
+    assert F["QPSK250K"] == (framing.SYNC_WIDE, 1517 * 8, 1516) and F["4FSK100K"] == (framing.SYNC_WIDE, 623 * 8, 622)
+    assert F["QPSKVideo"] == (framing.SYNC_WIDE, 3123 * 8, 3122)
+    assert F["QPSK20K"] == F["4FSK10KFM"] == F["2FSK10KFM"] == (framing.SYNC_NARROW, 48 * 8, 47)
+    for m in ("BPSK1K", "2FSK1KFM", "2FSK1K", "4FSK1KFM"):
+        assert F[m] == (framing.SYNC_1K, 4 * 8, 4)
+    assert (framing.FrameTypeVoice, framing.FrameTypeVoice1, framing.FrameTypeEnd) == (0xED89, 0xB5, 0x4C8A2B)
+    assert pfb.mmdvm_port_map(3) == [0, 1, 2] and pfb.mmdvm_port_map(7) == [0, 1, 2, 3, 9, 8, 7]
