@@ -1664,6 +1664,19 @@ qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         n = qo_firdes_low_pass(second_interp, samp_rate, filter_width, filter_width, QO_WIN_HAMMING, taps, 16384);
         resamp_init(&t->interp, 2, second_interp, 1, taps, n);
         t->s_sym.isz = 4;
+    } else if (kind == QO_MOD_M17) {
+        /* /root/reference/src/gr/gr_mod_m17.cpp:30-95: bits (no scrambler / FEC in this block) -> pack 2 -> map {2,3,1,0} -> levels
+         * -> rational_resampler_fff(5, 1, RRC(5, 5, 1, 0.5, 250)) -> x0.66666666 -> frequency_modulator_fc(pi / 5) -> low_pass(1, 24k,
+         * fw, fw, BH) -> x0.9 -> x bb_gain -> rational_resampler_ccf(sps = 125, 3, low_pass(125, 3 fs, 12k, 12k, BH)) */
+        t->fm = 1; t->sps = 5; t->amplif = 0.9f;
+        int n = qo_firdes_rrc(5, 5, 1, 0.5, 250, taps, 16384);
+        resamp_init(&t->rrc, 1, 5, 1, taps, n);
+        t->fm_sens = (float)(M_PI / 5);
+        n = qo_firdes_low_pass(1, 24000, filter_width, filter_width, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&t->a_if, 2, 1, 1, taps, n);
+        n = qo_firdes_low_pass(sps, 3.0 * samp_rate, 12000, 12000, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&t->interp, 2, sps, 3, taps, n);
+        t->s_sym.isz = 4; qv_init(&t->s_c2, 8);
     } else if (kind == QO_MOD_QPSK) {
         /* /root/reference/src/gr/gr_mod_qpsk.cpp:26-90 */
         int nfilts;
@@ -1783,6 +1796,24 @@ static void fm_mod(qo_tx* t, const float* x, size_t n, qvec* out, float post)
 int qo_tx_work(qo_tx* t, const void* in, long n)
 {
     const uint8_t* bytes = (const uint8_t*)in;
+    if (t->kind == QO_MOD_M17) {
+        static const int map[4] = { 2, 3, 1, 0 };
+        static const float lv[4] = { -1.5f, -0.5f, 0.5f, 1.5f };
+        t->s_sym.n = 0;
+        for (long i = 0; i < n; i++)
+            for (int b = 6; b >= 0; b -= 2) qv_pushf(&t->s_sym, lv[map[(bytes[i] >> b) & 3]]);
+        t->s_shaped.n = 0;
+        resamp_work(&t->rrc, (const float*)t->s_sym.d, t->s_sym.n, &t->s_shaped);
+        float* p = (float*)t->s_shaped.d;
+        for (size_t i = 0; i < t->s_shaped.n; i++) p[i] = p[i] * 0.66666666f;
+        t->s_mod.n = 0;
+        fm_mod(t, p, t->s_shaped.n, &t->s_mod, 1.0f);
+        t->s_c2.n = 0; resamp_work(&t->a_if, (const float*)t->s_mod.d, t->s_mod.n, &t->s_c2);
+        float* m = (float*)t->s_c2.d;
+        for (size_t i = 0; i < 2 * t->s_c2.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
+        resamp_work(&t->interp, m, t->s_c2.n, &t->out);
+        return 0;
+    }
     if (t->kind == QO_MOD_4FSK || t->kind == QO_MOD_QPSK) {
         /* packed_to_unpacked(1, MSB) -> scrambler -> cc_encoder */
         t->s_bits.n = 0;

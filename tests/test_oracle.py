@@ -346,3 +346,23 @@ def test_m17_chain_streams(oracle):
         assert np.array_equal(a.port(p, clear=False), b.port(p, clear=False))
     assert len(a.port(0, clear=False)) == (len(x) * 3 + 124) // 125
     assert len(a.port(2, clear=False)) == 2 * len(a.port(1, clear=False))
+
+
+def test_m17_modem_loops_back_in_the_oracle(oracle):
+    """gr_mod_m17 -> channel -> gr_demod_m17 restated: after acquisition the hard bits of port 2 are the transmitted bits (the
+    TX map {2,3,1,0} and the RX map {3,1,2,0} are inverse through the phase modulator / slicer pair)."""
+    O = oracle
+    from tests import siggen
+    rng = np.random.default_rng(4)
+    data = rng.integers(0, 256, 300, dtype=np.uint8)
+    iq = O.Tx(O.MOD_M17, 125, 1000000, 1700, 9000, 0).work(data)
+    assert len(iq) == len(data) * 4 * 5 * 125 // 3
+    x = siggen.channel(iq, rng, fo_hz=40, phase=0.3, delay=211, snr_db=30, amp=0.5, total=len(iq) + 30000)
+    rx = O.Rx(O.DEMOD_M17, 125, 1000000, 1700, 9000, 0)
+    rx.work(x)
+    bits, tx_bits = rx.port(2), np.unpackbits(data)
+    best = 0.0
+    for off in range(60, 160):
+        n = min(len(bits) - off, len(tx_bits)) - 300
+        best = max(best, float(np.mean(bits[off + 300:off + 300 + n] == tx_bits[300:300 + n])))
+    assert best > 0.999
