@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 # hier-block kinds (mirror qrl_oracle.h)
-DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB, DEMOD_AM, DEMOD_GMSK, DEMOD_WBFM, DEMOD_M17 = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB, DEMOD_AM, DEMOD_GMSK, DEMOD_WBFM, DEMOD_M17, DEMOD_DMR = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
 MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB, MOD_GMSK, MOD_M17 = 101, 102, 103, 104, 105, 106, 107, 108
 WIN_HAMMING, WIN_HANN, WIN_BLACKMAN, WIN_RECT, WIN_KAISER, WIN_BLACKMAN_HARRIS = 0, 1, 2, 3, 4, 5
 
@@ -252,6 +252,8 @@ class Rx:
     def port(self, p, clear=True):
         n = lib().qo_rx_port_items(self.h, p)
         dt = self.PORT_DTYPES.get(p, np.float32 if self.kind in (DEMOD_NBFM, DEMOD_SSB, DEMOD_AM, DEMOD_WBFM) else np.complex64)
+        if self.kind == DEMOD_DMR and p == 3:
+            dt = np.float32                                   # gr_demod_dmr port 3: the symbol filter output
         nbytes = n * np.dtype(dt).itemsize
         if n == 0:
             return np.zeros(0, dt)

@@ -691,6 +691,7 @@ static inline void costas_step(costas_t* c, float xr, float xi, float* yr, float
 enum { SL_RECT4 = 0, SL_DQPSK = 1, SL_BPSK = 2 };
 typedef struct {
     int ncomp, slicer;
+    int ted_plain;          /* 0 = TED_MOD_MUELLER_AND_MULLER (default), 1 = TED_MUELLER_AND_MULLER (gr_demod_dmr.cpp:66) */
     float sps, alpha, beta, max_period, min_period;
     float avg_period, inst_period, mu;
     float xr[3], xi[3], dr[3], di[3];
@@ -755,6 +756,10 @@ static void symsync_work(symsync_t* s, const float* x, size_t n, qvec* out)
             float ar = s->xr[0] - s->xr[2], ai = s->xi[0] - s->xi[2];
             float br = s->dr[0] - s->dr[2], bi = s->di[0] - s->di[2];
             float u = (ar * s->dr[1] + ai * s->di[1]) - (br * s->xr[1] + bi * s->xi[1]);
+            err = clipf(u, 1.0f);
+        } else if (s->ted_plain) {
+            /* TED_MUELLER_AND_MULLER (real input): e = d[n-1] x[n] - d[n] x[n-1], clipped to +-1 (timing_error_detector_type.cc) */
+            float u = s->dr[1] * s->xr[0] - s->dr[0] * s->xr[1];
             err = clipf(u, 1.0f);
         } else {
             float u = (s->xr[0] - s->xr[2]) * s->dr[1] - (s->dr[0] - s->dr[2]) * s->xr[1];
@@ -1083,7 +1088,26 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
      * its own clock-loop constants: restated through the 2FSK branch */
     const int gmsk = (kind == QO_DEMOD_GMSK);
     if (gmsk) { kind = QO_DEMOD_2FSK; r->kind = QO_DEMOD_2FSK; r->gmsk = 1; flag = 1; }
-    if (kind == QO_DEMOD_M17) {
+    if (kind == QO_DEMOD_DMR) {
+        /* /root/reference/src/gr/gr_demod_dmr.cpp:30-112 (oracle only so far: the CUDA path is not built): rational_resampler_ccf(3, 125)
+         * with low_pass_2(3, 3 fs, 5000, 2000, 60, BH) -> [port 0 at 24 ksps] -> quadrature demod (24000 / (pi/2 * 4800)) ->
+         * RRC(1, 24k, 4800, 0.2, 125) -> [port 3, float] -> symbol_sync_ff(TED_MUELLER_AND_MULLER, 5, 2 pi / 100, 1, 0.2869, 0.06, rect4)
+         * -> x0.9 -> phase_modulator_fc(pi/2) -> [port 1]; re / im -> slicer -> pack 2 -> map {3,1,2,0} -> unpack 2 -> [port 2] */
+        r->kind = QO_DEMOD_DMR; r->fm = 1; r->m17 = 1;
+        r->tsr = 24000; r->sym_sps = 5;
+        int n0 = qo_firdes_low_pass_2(3, 3.0 * samp_rate, 5000, 2000, 60, QO_WIN_BLACKMAN_HARRIS, T0, 4096);
+        r->ntaps_store[0] = n0;
+        resamp_init(&r->resamp, 2, 3, 125, T0, n0);
+        const float symbol_rate = (float)r->tsr / (float)r->sym_sps;
+        qdemod_init(&r->qd, (float)(r->tsr / (M_PI / 2 * symbol_rate)));
+        int n2 = qo_firdes_rrc(1, r->tsr, r->tsr / r->sym_sps, 0.2, 25 * r->sym_sps, T2, 4096);
+        r->ntaps_store[2] = n2;
+        resamp_init(&r->shaping, 1, 1, 1, T2, n2);
+        symsync_init(&r->ss, 1, (float)r->sym_sps, (float)(2 * M_PI / 100.0f), 1.0f, 0.2869f, 0.06f, SL_RECT4);
+        r->ss.ted_plain = 1;
+        r->pm_sens = (float)(M_PI / 2);
+        r->port[3].isz = 4;
+    } else if (kind == QO_DEMOD_M17) {
         /* /root/reference/src/gr/gr_demod_m17.cpp:30-113: rational_resampler_ccf(3, 125) to 24 ksps -> low-pass -> quadrature
          * demod (5 / pi) -> RRC(1.5, 24k, 4800, 0.5, 250) -> symbol_sync_ff (4-level) -> phase_modulator_fc(pi/2) -> [port 1];
          * re / im -> binary_slicer -> pack 2 -> map {3,1,2,0} -> unpack 2 -> [port 2] (no FEC in this block).  Runs through the
@@ -1554,6 +1578,26 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
             qv_pushb(&r->s_soft, soft_u8(oi, r->soft_scale));
         }
         rx_fec_tail(r);
+        return 0;
+    }
+    if (r->kind == QO_DEMOD_DMR) {
+        r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
+        qv_push(&r->port[0], r->s_res.d, r->s_res.n);
+        r->s_dem.n = 0; qdemod_work(&r->qd, (const float*)r->s_res.d, r->s_res.n, &r->s_dem);
+        r->s_rrc.n = 0; resamp_work(&r->shaping, (const float*)r->s_dem.d, r->s_dem.n, &r->s_rrc);
+        qv_push(&r->port[3], r->s_rrc.d, r->s_rrc.n);
+        r->s_sym.isz = 4; r->s_sym.n = 0;
+        symsync_work(&r->ss, (const float*)r->s_rrc.d, r->s_rrc.n, &r->s_sym);
+        const float* sy = (const float*)r->s_sym.d;
+        static const int map[4] = { 3, 1, 2, 0 };
+        for (size_t i = 0; i < r->s_sym.n; i++) {
+            const float ph = r->pm_sens * (sy[i] * 0.9f);                 /* multiply_const_ff(0.9) -> phase_modulator_fc(pi/2) */
+            float sn, cs; qo_sincosf(ph, &sn, &cs);
+            qv_pushc(&r->port[1], cs, sn);
+            const int v = ((cs >= 0.0f) ? 2 : 0) | ((sn >= 0.0f) ? 1 : 0);
+            qv_pushb(&r->port[2], (unsigned char)((map[v] >> 1) & 1));
+            qv_pushb(&r->port[2], (unsigned char)(map[v] & 1));
+        }
         return 0;
     }
     if (r->kind == QO_DEMOD_WBFM) {

@@ -366,3 +366,30 @@ def test_m17_modem_loops_back_in_the_oracle(oracle):
         n = min(len(bits) - off, len(tx_bits)) - 100
         best = max(best, float(np.mean(bits[off:off + n] == tx_bits[:n])))
     assert best == 1.0
+
+
+def test_dmr_chain_streams_and_locks(oracle):
+    """gr_demod_dmr restated (oracle only so far: x3/125 to 24 ksps, RRC 0.2, symbol_sync_ff with the PLAIN Mueller & Mueller TED,
+    float port 3): chunk-size invariant, and -- fed the M17 modulator's 4FSK burst, same symbol rate and maps -- its timing
+    loop locks and the hard bits follow the transmitted ones (the 0.5 vs 0.2 roll-off mismatch leaves a little ISI)."""
+    O = oracle
+    from tests import siggen
+    rng = np.random.default_rng(4)
+    data = rng.integers(0, 256, 300, dtype=np.uint8)
+    iq = O.Tx(O.MOD_M17, 125, 1000000, 1700, 9000, 0).work(data)
+    x = siggen.channel(iq, rng, fo_hz=40, phase=0.3, delay=211, snr_db=30, amp=0.5, total=len(iq) + 30000)
+    a = O.Rx(O.DEMOD_DMR, 5, 1000000, 0, 0, 0); a.work(x)
+    b = O.Rx(O.DEMOD_DMR, 5, 1000000, 0, 0, 0)
+    for lo in range(0, len(x), 33331):
+        b.work(x[lo:lo + 33331])
+    for p in range(4):
+        assert np.array_equal(a.port(p, clear=False), b.port(p, clear=False))
+    assert a.port(3, clear=False).dtype == np.float32
+    assert len(a.port(0, clear=False)) == len(a.port(3, clear=False)) == (len(x) * 3 + 124) // 125
+    assert len(a.port(2, clear=False)) == 2 * len(a.port(1, clear=False))
+    bits, tx_bits = a.port(2), np.unpackbits(data)
+    best = 0.0
+    for off in range(40, 200):
+        n = min(len(bits) - off, len(tx_bits)) - 100
+        best = max(best, float(np.mean(bits[off:off + n] == tx_bits[:n])))
+    assert best > 0.97
