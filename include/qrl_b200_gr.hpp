@@ -189,6 +189,10 @@ inline gr_demod_b200_sptr make_gr_demod_m17(int sps = 125, int samp_rate = 10000
                                             int n_channels = 1, long max_samples = 1 << 20, int device = 0)      // src/gr/gr_demod_m17.h:41-42
 { return std::make_shared<gr_demod_b200>(QRL_DEMOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_samples, device); }
 
+inline gr_demod_b200_sptr make_gr_demod_dmr(int sps = 5, int samp_rate = 1000000,
+                                            int n_channels = 1, long max_samples = 1 << 20, int device = 0)      // src/gr/gr_demod_dmr.h:42
+{ return std::make_shared<gr_demod_b200>(QRL_DEMOD_DMR, sps, samp_rate, 0, 5000, 0, n_channels, max_samples, device); }
+
 // ---- batched modulator
 class gr_mod_b200 {
 public:

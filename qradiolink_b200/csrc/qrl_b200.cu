@@ -163,6 +163,8 @@ struct qrl_rx : HandleBase {
     bool gmsk = false;                                   // 2FSK code path running as gr_demod_gmsk (no FLL)
     bool m17 = false;                                    // 4FSK (fm) code path running as gr_demod_m17 (x3/125 front end, hard bits)
     int nt_arm1 = 0;                                     // taps per arm of a generic rational stage 1 (L1 > 1)
+    bool dmr = false;                                    // M17 code path running as gr_demod_dmr (plain M&M detector, x0.9, float port 3)
+    float* d_port3f = nullptr;                           // gr_demod_dmr port 3: symbol filter output, [C][port0_cap] floats
     // RSSI tap on port 0 (QRL_PARAM_RSSI): ring of |x|^2, carried IIR value, latest dB value per channel
     bool rssi_on = false; float* d_rssi_ring = nullptr; float* d_rssi_y = nullptr; float* d_rssi_db = nullptr; long long rssi_n = 0;
     // QRL_PARAM_OVERLAP_CALLS: the loop / FEC tail of call k runs under the parallel stages of call k+1.  Output ports
@@ -425,12 +427,16 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     if (gmsk) { kind = QRL_DEMOD_2FSK; flag = 1; }
     // gr_demod_m17.cpp:30-113 is the 4FSK (fm) chain behind a x3 / 125 rational resampler (24 ksps, 5 samples per symbol) with a
     // hard-decision bit tail instead of the FEC: it runs through the 4FSK code path
-    const bool m17 = (kind == QRL_DEMOD_M17);
+    // gr_demod_dmr.cpp:32-112 is that M17 chain again with its own stage-1 taps, no IF filter, a 0.2 roll-off symbol filter tapped as
+    // (float) port 3, the PLAIN Mueller & Mueller detector in the symbol sync and x0.9 in front of the phase modulator
+    const bool dmr = (kind == QRL_DEMOD_DMR);
+    const bool m17 = (kind == QRL_DEMOD_M17) || dmr;
     if (m17) { kind = QRL_DEMOD_4FSK; flag = 1; }
+    if (dmr) { carrier_freq = 0; filter_width = 5000; }
     qrl_rx* h = new qrl_rx();
     h->kind = kind; h->sps = sps; h->samp_rate = samp_rate; h->carrier_freq = carrier_freq;
     h->filter_width = filter_width; h->flag = flag; h->C = n_channels; h->Tmax = max_samples; h->device = device;
-    h->gmsk = gmsk; h->m17 = m17;
+    h->gmsk = gmsk; h->m17 = m17; h->dmr = dmr;
     auto fail = [&](int rc) { std::string e = h->err; qrl_rx_destroy(h); g_err = e; return rc; };
     if (cudaSetDevice(device) != cudaSuccess) { set_err(h, "cudaSetDevice failed"); return fail(QRL_ECUDA); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err(h, "stream create failed"); return fail(QRL_ECUDA); }
@@ -443,23 +449,30 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     if (kind == QRL_DEMOD_4FSK) {
         // gr_demod_4fsk.cpp:46-84 (sps ladder), :98-107 (resampler), :108-109 (filter), :125-131 (demod, RRC, sync)
         int decimation = 1, interpolation = 1, nfilts = 0;
-        if (m17) { tsr = 24000; sym_sps = 5; decimation = 125; interpolation = 3; nfilts = 50 * sym_sps; }      // gr_demod_m17.cpp:37-48
+        if (dmr) { tsr = 24000; sym_sps = 5; decimation = 125; interpolation = 3; nfilts = 25 * sym_sps; }           // gr_demod_dmr.cpp:38-45
+        else if (m17) { tsr = 24000; sym_sps = 5; decimation = 125; interpolation = 3; nfilts = 50 * sym_sps; }      // gr_demod_m17.cpp:37-48
         else if (sps == 1) { tsr = 80000; sym_sps = sps * 8; decimation = 25; interpolation = 2; nfilts = 32 * sym_sps; }
         else if (sps == 5) { tsr = 20000; sym_sps = sps * 2; decimation = 50; nfilts = 25 * sym_sps; }
         else if (sps == 10) { tsr = 10000; sym_sps = sps; decimation = 100; nfilts = 25 * sym_sps; }
         else if (sps == 2) { decimation = 2; sym_sps = 5; tsr = 500000; nfilts = 50 * sym_sps; }
         else { set_err(h, "make_gr_demod_4fsk: unsupported sps"); return fail(QRL_EINVAL); }
         if ((nfilts % 2) == 0) nfilts += 1;
-        taps1 = low_pass(interpolation, static_cast<double>(interpolation) * samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
+        taps1 = dmr ? low_pass_2(3, 3.0 * samp_rate, 5000, 2000, 60, WIN_BLACKMAN_HARRIS)              // gr_demod_dmr.cpp:54-55
+                    : low_pass(interpolation, static_cast<double>(interpolation) * samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
         h->D1 = decimation; h->L1 = interpolation;
-        taps2 = m17 ? low_pass(1, tsr, filter_width, filter_width, WIN_BLACKMAN_HARRIS)                 // gr_demod_m17.cpp:58-59
+        taps2 = dmr ? std::vector<float>{ 1.0f }                // no IF filter in gr_demod_dmr: the stage runs as a 1-tap pass-through
+              : m17 ? low_pass(1, tsr, filter_width, filter_width, WIN_BLACKMAN_HARRIS)                 // gr_demod_m17.cpp:58-59
                     : low_pass(1, tsr, filter_width, filter_width / 2, WIN_BLACKMAN_HARRIS);
-        taps3 = root_raised_cosine(1.5, tsr, tsr / sym_sps, m17 ? 0.5 : 0.2, nfilts);
-        h->qd_gain = static_cast<float>(sym_sps / (1 * kPi));
+        taps3 = dmr ? root_raised_cosine(1, tsr, tsr / sym_sps, 0.2, nfilts)                            // gr_demod_dmr.cpp:61-62
+                    : root_raised_cosine(1.5, tsr, tsr / sym_sps, m17 ? 0.5 : 0.2, nfilts);
         const float m17_rate = static_cast<float>(tsr) / static_cast<float>(sym_sps);
-        const float dev = m17 ? 500.0f / m17_rate : 0.05f;                                              // gr_demod_m17.cpp:67-70
-        clock_loop_gains(m17 ? static_cast<float>(2 * kPi / (m17_rate / 50)) : static_cast<float>(2 * kPi / 200.0f), 1.0f, 0.2869f,
+        h->qd_gain = dmr ? static_cast<float>(tsr / (kPi / 2 * m17_rate))                               // gr_demod_dmr.cpp:71
+                         : static_cast<float>(sym_sps / (1 * kPi));
+        const float dev = dmr ? 0.06f : (m17 ? 500.0f / m17_rate : 0.05f);                              // gr_demod_m17.cpp:67-70, gr_demod_dmr.cpp:68
+        clock_loop_gains(dmr ? static_cast<float>(2 * kPi / 100.0f)
+                             : (m17 ? static_cast<float>(2 * kPi / (m17_rate / 50)) : static_cast<float>(2 * kPi / 200.0f)), 1.0f, 0.2869f,
                          h->ssp.alpha, h->ssp.beta);
+        if (dmr) h->ssp.sym_scale = 0.9f;                                                               // gr_demod_dmr.cpp:72
         h->ssp.sps = static_cast<float>(sym_sps);
         h->ssp.max_period = h->ssp.sps + dev; h->ssp.min_period = h->ssp.sps - dev;
         h->ssp.lookahead = 8 + static_cast<int>(ceilf(h->ssp.max_period)) + 1;
@@ -467,7 +480,7 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         h->ssp.soft_scale = 128.0f;
         h->ssp.n0 = static_cast<int>(floorf(h->ssp.min_period - fabsf(h->ssp.alpha)));
         h->ssp.fl0 = static_cast<float>(h->ssp.n0);
-        h->nports = 3;
+        h->nports = dmr ? 4 : 3;
         if (!flag) {     // gr_demod_4fsk.cpp:110-124: four complex band-pass filters + discriminator + symbol filter
             int rs = 0, bw = 0;
             if (sps == 1) { rs = 10000; bw = 4000; } else if (sps == 5) { rs = 2000; bw = 4000; } else if (sps == 10) { rs = 1000; bw = 2000; }
@@ -767,7 +780,9 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     h->port2_cap = (h->m17 ? 2 : 1) * h->port1_cap + 160;      // M17: two hard bits per symbol, no rate-1/2 decoder behind them
     if ((rc = dev_alloc(h, &h->d_port2, static_cast<size_t>(h->port2_cap) * h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_port2_cnt, h->C))) return fail(rc);
-    if (h->nports == 4) {
+    if (h->dmr) {
+        if ((rc = dev_alloc(h, &h->d_port3f, static_cast<size_t>(h->port0_cap) * h->C))) return fail(rc);
+    } else if (h->nports == 4) {
         if ((rc = dev_alloc(h, &h->d_port3, static_cast<size_t>(h->port2_cap) * h->C))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_port3_cnt, h->C))) return fail(rc);
     }
@@ -920,7 +935,7 @@ int qrl_rx_set_param(qrl_rx* h, int channel, int key, double value)
     }
     if (key == QRL_PARAM_OVERLAP_CALLS) {
         // only the path whose ring reuse is fenced for it: real-symbol 4FSK (external soft-bit epilogue)
-        if (!(h->kind == QRL_DEMOD_4FSK && h->flag)) { set_err(h, "QRL_PARAM_OVERLAP_CALLS: not supported for this block"); return QRL_EINVAL; }
+        if (!(h->kind == QRL_DEMOD_4FSK && h->flag) || h->dmr) { set_err(h, "QRL_PARAM_OVERLAP_CALLS: not supported for this block"); return QRL_EINVAL; }
         CK(cudaStreamSynchronize(h->stream));
         { int rc = rx_join_host(h); if (rc) return rc; }
         const bool on = value != 0.0;
@@ -1265,6 +1280,12 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                         static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
                         h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
                     h->launches++;
+                    if (h->dmr) {      // gr_demod_dmr.cpp:103: the symbol filter output is port 3
+                        ring_to_port_f32_kernel<<<dim3(static_cast<unsigned>((k1 - k0 + 31) / 32), groups), dim3(32, 8), 0, sp>>>(
+                            static_cast<const float*>(h->r4.d), h->r4.mask, h->r4.stride, h->C, k0, k1,
+                            h->d_port3f, h->port0_cap, k0 - k_call0);
+                        h->launches++;
+                    }
                 } else {
                     fsk_bank_kernel<4><<<gtile, TB, sizeof(float) * 8 * h->nt_bank, sp>>>(
                         static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, h->d_bank_taps, h->nt_bank, k0, k1,
@@ -1304,14 +1325,17 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
                 const size_t smem_base = sizeof(float) * (NST * CH * 32 + SYMSYNC_TAB_FLOATS + 2 * (maxs + 2) * 32) + sizeof(int) * 64;
                 const size_t smem_rep = smem_base + 129 * 512;          // + replicated (conflict-free) interpolator bank
-                const bool rep = smem_rep <= 220 * 1024;
+                const bool rep = smem_rep <= 220 * 1024 && !h->dmr;
                 const size_t smem = rep ? smem_rep : smem_base;
-                auto kern = rep ? symsync_kernel<1, SL_RECT4, EPI_EXT_4FSK_FM, CH, NST, 1, LOOP_SYMSYNC, 2>
+                // gr_demod_dmr: TED_MUELLER_AND_MULLER instead of the modified detector -> generic recurrence, variant 3
+                auto kern = h->dmr ? symsync_kernel<1, SL_RECT4, EPI_EXT_4FSK_FM, CH, NST, 1, LOOP_SYMSYNC, 3>
+                          : rep ? symsync_kernel<1, SL_RECT4, EPI_EXT_4FSK_FM, CH, NST, 1, LOOP_SYMSYNC, 2>
                                 : symsync_kernel<1, SL_RECT4, EPI_EXT_4FSK_FM, CH, NST, 1, LOOP_SYMSYNC, 1>;
-                static bool ss_attr[2][16] = { { false } };   // per (CH, NST) instantiation of this lambda, per variant, per device
-                if (!ss_attr[rep][h->device & 15]) {
+                static bool ss_attr[3][16] = { { false } };   // per (CH, NST) instantiation of this lambda, per variant, per device
+                const int vi = h->dmr ? 2 : (rep ? 1 : 0);
+                if (!ss_attr[vi][h->device & 15]) {
                     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-                    ss_attr[rep][h->device & 15] = true;
+                    ss_attr[vi][h->device & 15] = true;
                 }
                 // overlapped calls: the previous call's Viterbi of slice i still reads d_nsoft[i], its epilogue scratch region i
                 if (h->overlap) CK(cudaStreamWaitEvent(h->s_loop, h->ev_v[i], 0));
@@ -1331,8 +1355,9 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 if (se != h->s_loop || h->overlap) CK(cudaEventRecord(h->ev_c[i], h->s_loop));
                 if (se != h->s_loop) CK(cudaStreamWaitEvent(se, h->ev_c[i], 0));
                 pe = h->prof_begin(5, se);
+                auto epi = h->dmr ? symsync_ext_epilogue_kernel<1> : symsync_ext_epilogue_kernel<0>;
                 if (chunk_bound > 0)
-                    symsync_ext_epilogue_kernel<<<dim3(chunk_bound, groups), dim3(32, 8), 0, se>>>(
+                    epi<<<dim3(chunk_bound, groups), dim3(32, 8), 0, se>>>(
                         h->ssp, h->C, scratch_i, static_cast<int>(h->ss_chunk_cap), maxs, hdr_i,
                         h->d_port1, h->port1_cap, static_cast<int>(h->port1_cap),
                         static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride,
@@ -1520,6 +1545,7 @@ int qrl_rx_port_itemsize(const qrl_rx* h, int port)
     if (!h || port < 0 || port >= h->nports) return QRL_EINVAL;
     if (port == 0) return 8;
     if (port == 1) return (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_SSB || h->kind == QRL_DEMOD_AM || h->kind == QRL_DEMOD_WBFM) ? 4 : 8;
+    if (port == 3 && h->dmr) return 4;
     return 1;
 }
 
@@ -1532,6 +1558,7 @@ int qrl_rx_port_device(qrl_rx* h, int port, void** data, long* cap, int** counts
         *cap = (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_SSB || h->kind == QRL_DEMOD_AM || h->kind == QRL_DEMOD_WBFM) ? 2 * h->port1_cap : h->port1_cap;      // float view of the same buffer
     }
     else if (port == 2) { *data = h->d_port2; *cap = h->port2_cap; *counts = h->d_port2_cnt; }
+    else if (h->dmr) { *data = h->d_port3f; *cap = h->port0_cap; *counts = nullptr; }      // one float per port-0 sample
     else { *data = h->d_port3; *cap = h->port2_cap; *counts = h->d_port3_cnt; }
     return QRL_OK;
 }

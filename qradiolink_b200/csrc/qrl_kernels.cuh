@@ -418,6 +418,28 @@ __global__ void qdemod_fir_fff_kernel(const float2* __restrict__ in, unsigned in
     out[(static_cast<long long>(c >> 5) * out_stride + (a & out_mask)) * 32 + (c & 31)] = acc;
 }
 
+// Channel-interleaved float ring [c / 32][slot][c % 32] -> linear per-channel port buffer [c][a - a0] (gr_demod_dmr's port 3:
+// the symbol filter output, gr_demod_dmr.cpp:103).  grid = (tiles of blockDim.x samples, 32-channel groups), block = (32, ty):
+// reads are whole 128-byte rows of the ring, writes go through a shared-memory transpose so each channel stores runs of 32 floats.
+__global__ void ring_to_port_f32_kernel(const float* __restrict__ ring, unsigned mask, long long stride, int C,
+                                        long long a0, long long a1, float* __restrict__ port, long long port_stride, long long port_off)
+{
+    __shared__ float tile[32][33];
+    const int g = blockIdx.y, lane = threadIdx.x;
+    const long long t0 = a0 + static_cast<long long>(blockIdx.x) * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const long long a = t0 + r;
+        tile[r][lane] = (a < a1) ? ring[(static_cast<long long>(g) * stride + (a & mask)) * 32 + lane] : 0.0f;
+    }
+    __syncthreads();
+    for (int ch = threadIdx.y; ch < 32; ch += blockDim.y) {
+        const int c = g * 32 + ch;
+        const long long a = t0 + lane;
+        if (c < C && a < a1 && port_off + (a - a0) < port_stride)
+            port[static_cast<long long>(c) * port_stride + port_off + (a - a0)] = tile[lane][ch];
+    }
+}
+
 // THE FIR order for one output inside one thread: 32 partial sums (branch r = j mod D accumulated oldest sample first
 // into slot r mod 32), combined 16, 8, 4, 2, 1 like the warp butterfly.  fetch(j) returns the sample that meets tap j.
 template <class Fetch>
@@ -563,6 +585,8 @@ struct SymSyncParams {
     int loop_kind;               // LOOP_SYMSYNC (symbol_sync_xx) or LOOP_CRMM (clock_recovery_mm_cc)
     float gain_omega, gain_mu, omega_mid, omega_lim;      // clock_recovery_mm_cc
     int costas_order;
+    float sym_scale = 1.0f;      // gr_demod_dmr: multiply_const_ff(0.9) between the symbol sync and the phase modulator
+    int reserved_[3] = { 0, 0, 0 };   // keeps the kernel parameters behind this struct on their 16-byte offsets (paired constant loads)
 };
 
 __device__ __forceinline__ void qrl_slice(int slicer, float re, float im, float& dr, float& di)
@@ -917,6 +941,7 @@ __device__ __noinline__ float2 symsync_generic_step(float ph)
 //                     fed through a double-buffered shared-memory symbol hand-off (mbarrier full/empty)
 // VAR: 0 = generic recurrence (any NCOMP / slicer); 1 = lean real 4-level recurrence, interpolator bank as 12-float entries
 // (two LDS.128 with bank conflicts); 2 = lean recurrence + 16-fold replicated bank (conflict-free, +66 KB of shared memory)
+// 3 = generic recurrence with the PLAIN Mueller & Mueller detector (gr_demod_dmr.cpp:66; real symbols only) instead of the modified one
 template <int NCOMP, int SLICER, int EPI, int CH, int NST, int NEPI, int LOOPK = LOOP_SYMSYNC, int VAR = 0>
 __global__ void __launch_bounds__(64 + 32 * NEPI)
 symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
@@ -1091,7 +1116,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                     if (NCOMP == 2) sy[cnt * ROWF + 1] = yi;
                     cnt++;
                 }
-            } else if (active && LOOPK == LOOP_SYMSYNC && NCOMP == 1 && SLICER == SL_RECT4 && VAR >= 1 && lean_ok) {
+            } else if (active && LOOPK == LOOP_SYMSYNC && NCOMP == 1 && SLICER == SL_RECT4 && (VAR == 1 || VAR == 2) && lean_ok) {
                 // Lean restatement of the real 4-level recurrence.  A lone warp pays ~1 cycle per issued instruction
                 // plus ~4 per dependent one, so the loop is written for instruction count.  Every rewrite is exact:
                 //  * err = clip(u/2, +-1) enters only as beta*err and alpha*err, formed as (beta/2)*clip(u, +-2)
@@ -1206,8 +1231,14 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                     } else {
                         if (SLICER == SL_RECT4) d0 = qrl_slice_rect4(yr);
                         else { float ee; qrl_slice(SLICER, yr, yi, d0, ee); }
-                        const float u = (x0 - x2) * d1 - (d0 - d2) * x1;
-                        err = qrl_clip1(u * 0.5f);
+                        if (VAR == 3) {
+                            // TED_MUELLER_AND_MULLER: e = d[n-1] x[n] - d[n] x[n-1], clipped to +-1
+                            const float u = d1 * x0 - d0 * x1;
+                            err = qrl_clip1(u);
+                        } else {
+                            const float u = (x0 - x2) * d1 - (d0 - d2) * x1;
+                            err = qrl_clip1(u * 0.5f);
+                        }
                     }
                     avg_period = avg_period + k_beta * err;
                     avg_period = fminf(fmaxf(avg_period, k_minp), k_maxp);   // == the two-sided clamp (no NaNs here)
@@ -1335,7 +1366,9 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
 
 // External epilogue of symsync_kernel<.., EPI_EXT_4FSK_FM, ..>: phase_modulator_fc(pi/2) -> port 1, soft bits (imag, real)
 // -> soft ring.  One block per (chunk, 32-channel group); x = channel lane (coalesced reads of the hand-off block),
-// y strides over the symbols of the chunk.  Same arithmetic as the in-kernel EPI_4FSK_FM branch.
+// y strides over the symbols of the chunk.  Same arithmetic as the in-kernel EPI_4FSK_FM branch.  SCALE = 1 (gr_demod_dmr): the
+// symbols pass multiply_const_ff(p.sym_scale) before the phase modulator.
+template <int SCALE = 0>
 __global__ void __launch_bounds__(256)
 symsync_ext_epilogue_kernel(SymSyncParams p, int C, const float* __restrict__ scratch, int chunk_stride, int maxs,
                             const int* __restrict__ hdr_all,
@@ -1356,7 +1389,7 @@ symsync_ext_epilogue_kernel(SymSyncParams p, int C, const float* __restrict__ sc
     unsigned char* sr = soft_ring + static_cast<long long>(c) * soft_stride;
     float2* p1 = port1 + static_cast<long long>(c) * port1_stride;
     for (int k = threadIdx.y; k < cnt; k += blockDim.y) {
-        const float yr = blk[k * 32 + lane];
+        const float yr = SCALE ? blk[k * 32 + lane] * p.sym_scale : blk[k * 32 + lane];
         float sn, cs;
         qrl_sincosf(p.pm_sens * yr, sn, cs);
         const int idx = sbase + k;

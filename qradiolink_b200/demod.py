@@ -155,6 +155,12 @@ def make_gr_demod_m17(sps=125, samp_rate=1000000, carrier_freq=1700, filter_widt
     return RxBlock(KIND.DEMOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
 
 
+def make_gr_demod_dmr(sps=5, samp_rate=1000000, n_channels=1, **kw):
+    """src/gr/gr_demod_dmr.h:42 (instance gr_demod_base.cpp:253: make_gr_demod_dmr(5, 1e6)); ports (IQ at 24 ksps, symbols, hard bits:
+    2 per symbol, float symbol-filter output).  Not yet run on a GPU (see include/qrl_b200.h)."""
+    return RxBlock(KIND.DEMOD_DMR, sps, samp_rate, 0, 5000, 0, n_channels, **kw)
+
+
 def make_gr_demod_wbfm(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
     """src/gr/gr_demod_wbfm.h (instance gr_demod_base.cpp:228: make_gr_demod_wbfm(125, 1e6, 1700, 75000)); ports (IQ at 200 ksps,
     float audio at 8 ksps)."""
