@@ -235,4 +235,8 @@ inline gr_mod_b200_sptr make_gr_mod_2fsk(int sps, int samp_rate, int carrier_fre
                                          int n_channels = 1, long max_items = 4096, int device = 0)
 { return std::make_shared<gr_mod_b200>(QRL_MOD_2FSK, sps, samp_rate, carrier_freq, filter_width, fm ? 1 : 0, n_channels, max_items, device); }
 
+inline gr_mod_b200_sptr make_gr_mod_m17(int sps = 125, int samp_rate = 1000000, int carrier_freq = 1700, int filter_width = 9000,
+                                        int n_channels = 1, long max_items = 4096, int device = 0)               // src/gr/gr_mod_m17.h:43-44
+{ return std::make_shared<gr_mod_b200>(QRL_MOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_items, device); }
+
 }  // namespace qrl_gr

@@ -1607,6 +1607,7 @@ struct qrl_tx : HandleBase {
     float* d_arms1 = nullptr; float* d_arms2 = nullptr;
     float fm_sens = 0, amplif = 0, bb_gain = 1.0f, pulse_scale = 0.66666666f;
     int repeat_only = 0;
+    bool m17 = false; int M2 = 1;  // gr_mod_m17: 4 symbols per byte, IF low-pass at 24 ksps, x L2 / M2 rational interpolator
     TxBitState* d_bits = nullptr;
     unsigned char* d_in = nullptr;
     float* d_sym = nullptr; unsigned sym_mask = 0; long long sym_stride = 0;    // float (4FSK) / float2 (QPSK)
@@ -1724,6 +1725,19 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         h->fm_sens = static_cast<float>((kPi / 2) / sps);
         t2 = low_pass(second_interp, samp_rate, filter_width, filter_width, WIN_HAMMING);
         h->L2 = second_interp; h->nt2 = (static_cast<int>(t2.size()) + second_interp - 1) / second_interp;
+    } else if (kind == QRL_MOD_M17) {
+        // gr_mod_m17.cpp:30-95: pulse shaping x5 (RRC 0.5, 250 + 1 taps) -> x0.66666666 -> frequency modulator (pi / 5) -> low-pass at
+        // 24 ksps -> x0.9 -> bb gain -> rational_resampler_ccf(sps = 125, 3)
+        h->m17 = true; h->amplif = 0.9f; h->repeat_only = 0;
+        t1 = root_raised_cosine(5, 5, 1, 0.5, 250);
+        h->L1 = 5; h->nt1 = (static_cast<int>(t1.size()) + 4) / 5;
+        h->fm_sens = static_cast<float>(kPi / 5);
+        std::vector<float> ifl = low_pass(1, 24000, filter_width, filter_width, WIN_BLACKMAN_HARRIS);
+        h->nt_cfilt = static_cast<int>(ifl.size());
+        if ((rc = upload_floats(h, &h->d_cfilt, ifl))) return fail(rc);
+        t2 = low_pass(sps, 3.0 * samp_rate, 12000, 12000, WIN_BLACKMAN_HARRIS);
+        h->L2 = sps; h->M2 = 3; h->nt2 = (static_cast<int>(t2.size()) + sps - 1) / sps;
+        if (sps <= 3 || static_cast<size_t>(h->L2) * h->nt2 * sizeof(float) > 40 * 1024) { set_err(h, "make_gr_mod_m17: unsupported sps"); return fail(QRL_EINVAL); }
     } else if (kind == QRL_MOD_2FSK) {
         // gr_mod_2fsk.cpp:43-76
         int nfilts = 25 * sps, spacing = 2; h->amplif = 0.8f;
@@ -1747,6 +1761,10 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     long long max_sym = (one_per_bit ? 16LL : 8LL) * max_items;
     if (kind == QRL_MOD_NBFM) max_sym = max_items * 25 / 4 + 8;        // 50 ksps items per call
     if (kind == QRL_MOD_SSB) max_sym = max_items + 8;                  // 8 ksps complex items per call
+    if (h->m17) {                                                      // IF ring behind the 24 ksps low-pass: 20 samples per byte
+        unsigned cap2 = pow2_at_least(max_sym * h->L1 + 512 + h->nt2); h->rc_mask = cap2 - 1; h->rc_stride = cap2;
+        if ((rc = dev_alloc(h, &h->d_rc, static_cast<size_t>(cap2) * h->C))) return fail(rc);
+    }
     if (analog) {
         unsigned cap = pow2_at_least(max_items + 512); h->ra_mask = cap - 1; h->ra_stride = cap;
         if ((rc = dev_alloc(h, &h->d_ra, static_cast<size_t>(cap) * h->C))) return fail(rc);
@@ -1765,6 +1783,7 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = dev_alloc(h, &h->d_if, static_cast<size_t>(cap) * h->C))) return fail(rc);
     }
     h->out_stride = analog ? max_sym * h->L2 : max_sym * h->L1 * (qpsk ? 1 : h->L2);
+    if (h->m17) h->out_stride = (4LL * max_items * h->L1 * h->L2 + h->M2 - 1) / h->M2 + 8;
     if ((rc = dev_alloc(h, &h->d_out, static_cast<size_t>(h->out_stride) * h->C, false))) return fail(rc);
     std::vector<TxBitState> st(h->C);
     for (auto& x : st) { x.scr_reg = 0x7F; x.enc_state = 0; x.diff_prev = 0; x.phase_q = 0; }
@@ -1875,7 +1894,7 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
     }
     const bool cplx = h->kind == QRL_MOD_QPSK || h->kind == QRL_MOD_BPSK;
     const bool one_per_bit = h->kind == QRL_MOD_BPSK || h->kind == QRL_MOD_2FSK;
-    const long long sym0 = h->n_sym, nsym = (one_per_bit ? 16LL : 8LL) * n;
+    const long long sym0 = h->n_sym, nsym = (h->m17 ? 4LL : (one_per_bit ? 16LL : 8LL)) * n;
     // 4FSK: bit chain / pulse shaping + FM scan / x20 interpolator are pipelined slice by slice on three streams (the
     // first two are one-CTA-per-channel recurrences that leave most SMs idle; the interpolator fills them)
     bool pipelined = h->kind == QRL_MOD_4FSK && h->L2 == 20 && h->nt2 == 35 && n >= 8 * qrl_tx::kTxSub;
@@ -1925,7 +1944,8 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
     }
     {
         dim3 g((h->C + 31) / 32);
-        if (h->kind == QRL_MOD_QPSK) tx_bits_kernel<TXM_QPSK><<<g, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
+        if (h->m17) tx_bits_kernel<TXM_M17><<<g, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
+        else if (h->kind == QRL_MOD_QPSK) tx_bits_kernel<TXM_QPSK><<<g, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
         else if (h->kind == QRL_MOD_BPSK) tx_bits_kernel<TXM_BPSK><<<g, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
         else if (h->kind == QRL_MOD_2FSK) tx_bits_kernel<TXM_2FSK><<<g, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
         else tx_bits_kernel<TXM_4FSK><<<g, 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
@@ -1940,7 +1960,24 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
                                                                    h->d_out, h->out_stride, m0 * L);
         h->launches++;
     };
-    if (cplx) {
+    if (h->m17) {
+        // pulse shaping + FM scan (gains of 1: x0.9 and the bb gain sit behind the IF filter here), IF low-pass, gains, x125 / 3
+        tx_shape_fm_kernel<1024, 2><<<h->C, 1024, 0, h->stream>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, sym0, nsym,
+            h->L1, h->nt1, h->d_arms1, 0, h->pulse_scale, h->fm_sens, 1.0f, 1.0f, h->d_if, h->if_mask, h->if_stride);
+        const long long m0 = sym0 * h->L1, m1 = (sym0 + nsym) * h->L1;
+        const int TB = 256;
+        dim3 g(static_cast<unsigned>((m1 - m0 + TB - 1) / TB), h->C);
+        fir_ccf_ring_kernel<<<g, TB, sizeof(float) * h->nt_cfilt, h->stream>>>(h->d_if, h->if_mask, h->if_stride,
+            h->d_rc, h->rc_mask, h->rc_stride, h->d_cfilt, h->nt_cfilt, m0, m1, nullptr, 0, 0, 0);
+        scale2_ring_kernel<<<g, TB, 0, h->stream>>>(h->d_rc, h->rc_mask, h->rc_stride, m0, m1, h->amplif, h->bb_gain);
+        const long long o0 = (m0 * h->L2 + h->M2 - 1) / h->M2, o1 = (m1 * h->L2 + h->M2 - 1) / h->M2;   // outputs i with floor(i M / L) < m1
+        if (o1 - o0 > h->out_stride) { set_err(h, "qrl_tx_work: output buffer too small"); return QRL_ERANGE; }
+        dim3 go(static_cast<unsigned>((o1 - o0 + 255) / 256), h->C);
+        resamp_ring_ccf_generic_kernel<<<go, 256, sizeof(float) * h->L2 * h->nt2, h->stream>>>(h->d_rc, h->rc_mask, h->rc_stride,
+            h->d_arms2, h->L2, h->M2, h->nt2, o0, o1, h->d_out, h->out_stride);
+        h->launches += 4;
+        h->n_out_last = static_cast<long>(o1 - o0);
+    } else if (cplx) {
         if (h->L1 == 4 && h->nt1 == 16) {
             constexpr int L = 4, NT = 16, MB = 8, MLEN = 64;
             dim3 g(static_cast<unsigned>((nsym + MB * MLEN - 1) / (MB * MLEN)), h->C);

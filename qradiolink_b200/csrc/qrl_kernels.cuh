@@ -2078,7 +2078,9 @@ struct TxBitState {
 // bytes -> packed_to_unpacked(MSB) -> scrambler -> CC encoder -> pack_k_bits(2) -> map {0,1,3,2}
 //       -> chunks_to_symbols (4FSK: float level, QPSK: diff_encoder(4) + complex point)
 // one thread per channel (the scrambler is a feedback LFSR); 16 symbols per input byte... 8 per byte.
-enum { TXM_4FSK = 0, TXM_QPSK = 1, TXM_BPSK = 2, TXM_2FSK = 3 };
+enum { TXM_4FSK = 0, TXM_QPSK = 1, TXM_BPSK = 2, TXM_2FSK = 3, TXM_M17 = 4 };
+// TXM_M17 (gr_mod_m17.cpp:52-58,79-82): no scrambler / encoder in the block: bytes -> packed_to_unpacked(MSB) -> pack_k_bits(2) ->
+// map {2,3,1,0} -> chunks_to_symbols {-1.5 .. 1.5}: 4 symbols per input byte
 template <int MODE>
 __global__ void tx_bits_kernel(TxBitState* __restrict__ states, int C, const unsigned char* __restrict__ bytes, long long n, long long stride,
                                float* __restrict__ sym_ring /* float or float2 */, unsigned sym_mask, long long sym_stride, long long sym0)
@@ -2090,6 +2092,16 @@ __global__ void tx_bits_kernel(TxBitState* __restrict__ states, int C, const uns
     long long si = sym0;
     for (long long i = 0; i < n; i++) {
         const unsigned byte = b[i];
+        if (MODE == TXM_M17) {
+#pragma unroll
+            for (int k = 3; k >= 0; k--) {
+                const unsigned dibit = (byte >> (2 * k)) & 3u;
+                const unsigned chunk = (0x1Eu >> (2 * dibit)) & 3u;           // map {2,3,1,0}, two bits per entry
+                sym_ring[static_cast<long long>(c) * sym_stride + (si & sym_mask)] = -1.5f + static_cast<float>(chunk);
+                si++;
+            }
+            continue;
+        }
         unsigned coded = 0;                       // 16 coded bits, first emitted = MSB
 #pragma unroll
         for (int k = 7; k >= 0; k--) {
@@ -2335,6 +2347,32 @@ interp_fir_ccf_generic_kernel(const float2* __restrict__ in_ring, unsigned in_ma
         if (apply_gain) { re = re * post_gain1; im = im * post_gain1; re = re * post_gain2; im = im * post_gain2; }
         oc[(m * L + p) - out_base] = make_float2(re, im);
     }
+}
+
+// Shape-generic rational interpolator from a complex ring (rational_resampler_ccf(L, M) with L > M; gr_mod_m17.cpp:70-73: x125 / 3):
+// output i takes arm (i M) mod L at ring position floor(i M / L), arms[p][k] = taps[p + k L], plain oldest-first accumulation (the
+// oracle's order for L > 1).  One thread per output sample, the arm table in shared memory; consecutive outputs share their inputs.
+__global__ void __launch_bounds__(256)
+resamp_ring_ccf_generic_kernel(const float2* __restrict__ in_ring, unsigned in_mask, long long in_stride,
+                               const float* __restrict__ arms /* [L][NT] */, int L, int M, int NT, long long o0, long long o1,
+                               float2* __restrict__ out, long long out_stride)
+{
+    extern __shared__ float sm_rr[];
+    for (int i = threadIdx.x; i < L * NT; i += 256) sm_rr[i] = arms[i];
+    __syncthreads();
+    const int c = blockIdx.y;
+    const long long i = o0 + static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= o1) return;
+    const long long im = i * M;
+    const long long newest = im / L;                                      // absolute index of the newest input sample
+    const float* h = sm_rr + static_cast<int>(im - newest * L) * NT;
+    const float2* x = in_ring + static_cast<long long>(c) * in_stride;
+    float re = 0.0f, imv = 0.0f;
+    for (int k = NT - 1; k >= 0; k--) {
+        const float2 v = x[(newest - k) & in_mask];                       // before the first sample: the zero-initialised top of the ring
+        re = fmaf(h[k], v.x, re); imv = fmaf(h[k], v.y, imv);
+    }
+    out[static_cast<long long>(c) * out_stride + (i - o0)] = make_float2(re, imv);
 }
 
 // ================================================================================================

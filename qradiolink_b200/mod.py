@@ -106,3 +106,9 @@ def make_gr_mod_nbfm(sps, samp_rate, carrier_freq, filter_width, n_channels=1, *
 def make_gr_mod_ssb(sps, samp_rate, carrier_freq, filter_width, sb, n_channels=1, **kw):
     """src/gr/gr_mod_ssb.h (instances gr_mod_base.cpp:178-179); feed with TxBlock.work_audio."""
     return TxBlock(KIND.MOD_SSB, sps, samp_rate, carrier_freq, filter_width, int(sb), n_channels, **kw)
+
+
+def make_gr_mod_m17(sps=125, samp_rate=1000000, carrier_freq=1700, filter_width=9000, n_channels=1, **kw):
+    """src/gr/gr_mod_m17.h:43-44 (defaults as there); items: frame bytes, 4 symbols per byte, 125 / 3 output samples per 24 ksps
+    sample.  Not yet run on a GPU (see include/qrl_b200.h)."""
+    return TxBlock(KIND.MOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
