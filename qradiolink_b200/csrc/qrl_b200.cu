@@ -23,7 +23,8 @@ using namespace qrl;
 namespace {
 
 thread_local std::string g_err;
-std::once_flag g_tables_once[16];
+std::mutex g_tables_mu;
+bool g_tables_done[16] = { false };     // per device ordinal (mod 16): lookup tables uploaded
 
 #define CK(call)                                                                                     \
     do {                                                                                             \
@@ -64,16 +65,16 @@ void set_err(HandleBase* h, const std::string& s)
 
 int upload_tables(HandleBase* h)
 {
-    int rc = QRL_OK;
-    std::call_once(g_tables_once[h->device & 15], [&]() {
-        auto at = atan_table(); auto th = tanh_table(); auto mm = mmse_table(); auto sn = fxpt_sine_table();
-        cudaError_t e = cudaMemcpyToSymbol(d_atan_tab, at.data(), at.size() * 4);
-        if (e == cudaSuccess) e = cudaMemcpyToSymbol(d_tanh_tab, th.data(), th.size() * 4);
-        if (e == cudaSuccess) e = cudaMemcpyToSymbol(d_mmse_tab, mm.data(), mm.size() * 4);
-        if (e == cudaSuccess) e = cudaMemcpyToSymbol(d_sine_tab, sn.data(), sn.size() * 4);
-        if (e != cudaSuccess) { set_err(h, std::string("table upload: ") + cudaGetErrorString(e)); rc = QRL_ECUDA; }
-    });
-    return rc;
+    std::lock_guard<std::mutex> lk(g_tables_mu);
+    if (g_tables_done[h->device & 15]) return QRL_OK;
+    auto at = atan_table(); auto th = tanh_table(); auto mm = mmse_table(); auto sn = fxpt_sine_table();
+    cudaError_t e = cudaMemcpyToSymbol(d_atan_tab, at.data(), at.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(d_tanh_tab, th.data(), th.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(d_mmse_tab, mm.data(), mm.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(d_sine_tab, sn.data(), sn.size() * 4);
+    if (e != cudaSuccess) { set_err(h, std::string("table upload: ") + cudaGetErrorString(e)); return QRL_ECUDA; }   // retried by the next create
+    g_tables_done[h->device & 15] = true;
+    return QRL_OK;
 }
 
 template <class T>
@@ -897,6 +898,12 @@ int qrl_rx_destroy(qrl_rx* h)
     if (h->s_loop2) { cudaStreamSynchronize(h->s_loop2); cudaStreamDestroy(h->s_loop2); }
     if (h->s_epi) { cudaStreamSynchronize(h->s_epi); cudaStreamDestroy(h->s_epi); }
     if (h->s_par) { cudaStreamSynchronize(h->s_par); cudaStreamDestroy(h->s_par); }
+    // every stream is idle now: the events recorded on them can go
+    auto ev_free = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
+    for (cudaEvent_t e : { h->ev_start, h->ev_loop_done, h->ev_loop2_done, h->ev_fec_done, h->ev_par_done }) ev_free(e);
+    for (int i = 0; i < qrl_rx::kMaxSub; i++) { ev_free(h->ev_a[i]); ev_free(h->ev_b[i]); ev_free(h->ev_c[i]); ev_free(h->ev_v[i]); }
+    for (int q = 0; q < 2; q++) for (int j = 0; j < 3; j++) ev_free(h->ev_tail[q][j]);
+    for (auto& r : h->prof_recs) { ev_free(r.a); ev_free(r.b); }
     if (h->g_loop || h->g_par) {
         auto pDestroy = drv<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
         if (pDestroy) { if (h->g_loop) pDestroy(h->g_loop); if (h->g_par) pDestroy(h->g_par); }
