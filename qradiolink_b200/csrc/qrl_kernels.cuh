@@ -1894,6 +1894,7 @@ ssb_audio_kernel(SsbParams p, SsbState* __restrict__ states,
     float2* cr = clip_ring + static_cast<long long>(c) * clip_stride;
     float* sr = str_ring + static_cast<long long>(c) * str_stride;
     const long long gate0 = st.n_gate;
+    __syncthreads();      // every thread holds its copy of gate0 before thread 0 advances st.n_gate at the end of step 1
     // ---- 1. squelch + AGC (sequential); the AGC output is parked in the clip ring, clipped in place in step 2
     if (threadIdx.x == 0) {
         double pwr = st.pwr; int state = st.sq_state; float gain = st.gain; long long ng = st.n_gate;

@@ -22,5 +22,12 @@ def oracle():
 @pytest.fixture(scope="session")
 def qrl():
     import qradiolink_b200 as q
+    # QRL_EMULATED_LIB=<path of a libqrl_b200_emu.so built by tools/emu/build_emulated_lib.py> runs the GPU tier's tests against the
+    # host-thread build of the library (slow; development aid for a container without a GPU, see tools/emu/).  The package itself has
+    # no such switch: the path is patched in here, in the test harness.
+    emu = os.environ.get("QRL_EMULATED_LIB")
+    if emu:
+        from qradiolink_b200 import lib as L
+        L._LIB_PATH, L._LIB = emu, None
     q.load_library()
     return q

@@ -1,18 +1,21 @@
-// cuda_emu.hpp -- a few dozen lines of "CUDA on host threads" for CPU-tier tests of SIMPLE kernels (tests/test_kernel_emulation.py).
+// cuda_emu.hpp -- "CUDA on host threads" for CPU-tier tests (tests/test_kernel_emulation.py, tests/test_emulated_library.py).
 //
 // TEST INFRASTRUCTURE ONLY (like oracle/): nothing under qradiolink_b200/ includes this, and it is no fallback -- it exists so that
-// index arithmetic and accumulation order of kernels that use only plain loads / stores, __syncthreads and warp shuffles can be
-// checked against the oracle in the container that has no GPU.  One OS thread per CUDA thread, blocks run one after the other,
-// __shared__ becomes a function-local static (shared by the block's threads), dynamic shared memory is one heap buffer per block.
-// Not emulated: TMA / mbarrier / inline PTX, cooperative groups, atomics, textures -- kernels using those are out of reach.
+// the library's kernels and host code can be exercised against the oracle in a container that has no GPU.  One OS thread per CUDA
+// thread, the blocks of a grid run one after the other, __shared__ becomes a function-local static (shared by the block's threads),
+// dynamic shared memory is a static arena.  Warp collectives are rendezvous among the lanes named by their mask (lanes that already
+// left the kernel are not waited for); __activemask() returns the lanes of the warp that are at it once every other lane is blocked
+// in a collective or gone.  Not emulated: anything about timing, the memory model, or hardware limits.
 #pragma once
 #include <barrier>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
-#include <functional>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -24,11 +27,82 @@ namespace emu {
 inline thread_local dim3 t_idx, b_idx;
 inline dim3 b_dim, g_dim;
 inline std::barrier<>* blk_bar = nullptr;
-inline std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
-inline unsigned shfl_buf[64][32];
 inline void* dyn_smem = nullptr;
 alignas(128) inline unsigned char smem_arena[256 << 10];     // dynamic shared memory of the running block (static: see qrl_tma_emu.hpp)
 inline unsigned lin_tid() { return t_idx.x + b_dim.x * (t_idx.y + b_dim.y * t_idx.z); }
+
+enum { RUNNING = 0, BLOCKED = 1, EXITED = 2, AT_ACTIVEMASK = 3 };
+struct Rendezvous { unsigned arrived = 0; unsigned long long gen = 0; unsigned long long buf[2][32]; };
+struct WarpCtl {
+    std::mutex m;
+    std::condition_variable cv;
+    unsigned existing = 0, exited = 0;
+    int state[32] = { 0 };
+    std::map<unsigned, Rendezvous> rv;
+    unsigned am_mask = 0; int am_left = 0;                    // a published __activemask() result still being picked up
+};
+inline std::vector<std::unique_ptr<WarpCtl>> warps;
+
+// every lane of `mask` (minus the lanes that have left the kernel) deposits a value; returns the snapshot of all of them
+inline const unsigned long long* gather(unsigned mask, unsigned long long v)
+{
+    const unsigned t = lin_tid(), l = t & 31;
+    WarpCtl& w = *warps[t >> 5];
+    std::unique_lock<std::mutex> lk(w.m);
+    mask &= w.existing;
+    Rendezvous& r = w.rv[mask];
+    const unsigned long long gen = r.gen;
+    r.buf[gen & 1][l] = v;
+    r.arrived |= 1u << l;
+    auto complete = [&] { return (r.arrived & ~w.exited) == (mask & ~w.exited); };
+    if (complete()) { r.arrived = 0; r.gen++; w.cv.notify_all(); }
+    else {
+        w.state[l] = BLOCKED;
+        w.cv.notify_all();
+        w.cv.wait(lk, [&] {
+            if (r.gen != gen) return true;
+            if (complete()) { r.arrived = 0; r.gen++; w.cv.notify_all(); return true; }      // the missing lanes left the kernel meanwhile
+            return false;
+        });
+        w.state[l] = RUNNING;
+    }
+    return r.buf[gen & 1];
+}
+inline unsigned activemask()
+{
+    const unsigned t = lin_tid(), l = t & 31;
+    WarpCtl& w = *warps[t >> 5];
+    std::unique_lock<std::mutex> lk(w.m);
+    w.state[l] = AT_ACTIVEMASK;
+    w.cv.notify_all();
+    for (;;) {
+        if (w.am_left > 0 && (w.am_mask >> l & 1)) break;
+        bool quiet = w.am_left == 0;
+        for (int i = 0; i < 32 && quiet; i++) if ((w.existing >> i & 1) && w.state[i] == RUNNING) quiet = false;
+        if (quiet) {
+            unsigned mk = 0;
+            for (int i = 0; i < 32; i++) if ((w.existing >> i & 1) && w.state[i] == AT_ACTIVEMASK) mk |= 1u << i;
+            w.am_mask = mk; w.am_left = __builtin_popcount(mk);
+            w.cv.notify_all();
+            break;
+        }
+        w.cv.wait(lk);
+    }
+    const unsigned mk = w.am_mask;
+    w.am_left--;
+    w.state[l] = RUNNING;
+    w.cv.notify_all();
+    return mk;
+}
+inline void set_state(int s)
+{
+    const unsigned t = lin_tid();
+    WarpCtl& w = *warps[t >> 5];
+    std::lock_guard<std::mutex> lk(w.m);
+    w.state[t & 31] = s;
+    if (s == EXITED) w.exited |= 1u << (t & 31);
+    w.cv.notify_all();
+}
 
 template <class F>
 void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call)
@@ -40,8 +114,12 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call)
     for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
         std::barrier<> bar(nt);
         blk_bar = &bar;
-        warp_bar.clear();
-        for (unsigned w = 0; w < (nt + 31) / 32; w++) warp_bar.emplace_back(new std::barrier<>(std::min(32u, nt - 32 * w)));
+        warps.clear();
+        for (unsigned w = 0; w < (nt + 31) / 32; w++) {
+            warps.emplace_back(new WarpCtl());
+            const unsigned lanes = std::min(32u, nt - 32 * w);
+            warps.back()->existing = lanes == 32 ? 0xffffffffu : ((1u << lanes) - 1);
+        }
         std::vector<std::thread> th;
         th.reserve(nt);
         for (unsigned t = 0; t < nt; t++)
@@ -49,9 +127,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call)
                 t_idx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
                 b_idx = dim3(bx, by, bz);
                 kernel_call();
-                // a thread that returned early must still release the others at later barriers
+                set_state(EXITED);                   // a thread that returned early must not be waited for at later barriers
                 blk_bar->arrive_and_drop();
-                warp_bar[t >> 5]->arrive_and_drop();
             });
         for (auto& x : th) x.join();
     }
@@ -72,17 +149,40 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call)
 #define __align__(n) __attribute__((aligned(n)))
 #define EMU_DYN_SMEM(type, name) type* name = static_cast<type*>(emu::dyn_smem)
 
-static inline void __syncthreads() { emu::blk_bar->arrive_and_wait(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_bar[emu::lin_tid() >> 5]->arrive_and_wait(); }
-static inline unsigned __shfl_up_sync(unsigned, unsigned v, int off)
+static inline void __syncthreads() { emu::set_state(emu::BLOCKED); emu::blk_bar->arrive_and_wait(); emu::set_state(emu::RUNNING); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::gather(mask, 0); }
+template <class T> static inline unsigned long long emu_raw(T v) { static_assert(sizeof(T) <= 8); unsigned long long r = 0; std::memcpy(&r, &v, sizeof(T)); return r; }
+template <class T> static inline T emu_unraw(unsigned long long r) { T v; std::memcpy(&v, &r, sizeof(T)); return v; }
+template <class T> static inline T __shfl_sync(unsigned mask, T v, int src) { return emu_unraw<T>(emu::gather(mask, emu_raw(v))[src & 31]); }
+template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int off) { return emu_unraw<T>(emu::gather(mask, emu_raw(v))[((emu::lin_tid() & 31) ^ off) & 31]); }
+template <class T> static inline T __shfl_up_sync(unsigned mask, T v, int off)
 {
-    const unsigned t = emu::lin_tid(), w = t >> 5, l = t & 31;
-    emu::shfl_buf[w][l] = v;
-    emu::warp_bar[w]->arrive_and_wait();
-    const unsigned r = (static_cast<int>(l) >= off) ? emu::shfl_buf[w][l - off] : v;
-    emu::warp_bar[w]->arrive_and_wait();
+    const unsigned l = emu::lin_tid() & 31; const unsigned long long* s = emu::gather(mask, emu_raw(v));
+    return static_cast<int>(l) >= off ? emu_unraw<T>(s[l - off]) : v;
+}
+template <class T> static inline T __shfl_down_sync(unsigned mask, T v, int off)
+{
+    const unsigned l = emu::lin_tid() & 31; const unsigned long long* s = emu::gather(mask, emu_raw(v));
+    return l + off < 32 ? emu_unraw<T>(s[l + off]) : v;
+}
+static inline unsigned __ballot_sync(unsigned mask, int pred)
+{
+    const unsigned long long* s = emu::gather(mask, pred ? 1 : 0);
+    const unsigned t = emu::lin_tid(); const unsigned alive = emu::warps[t >> 5]->existing & mask;
+    unsigned m = 0;
+    for (int l = 0; l < 32; l++) if ((alive >> l & 1) && s[l]) m |= 1u << l;
+    return m;
+}
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __reduce_min_sync(unsigned mask, int v)
+{
+    const unsigned long long* s = emu::gather(mask, emu_raw(v));
+    const unsigned t = emu::lin_tid(); const unsigned alive = emu::warps[t >> 5]->existing & mask;
+    int r = v;
+    for (int l = 0; l < 32; l++) if (alive >> l & 1) { const int o = emu_unraw<int>(s[l]); r = o < r ? o : r; }
     return r;
 }
+static inline unsigned __activemask() { return emu::activemask(); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }

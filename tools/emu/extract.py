@@ -36,5 +36,5 @@ def extract(src, names):
             text += ";"
         out.append(text)
     body = "\n\n".join(out)
-    body = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"EMU_DYN_SMEM(\1, \2);", body)
+    body = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];", r"EMU_DYN_SMEM(\1, \2);", body)
     return body

@@ -64,29 +64,3 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity)
 // (a >= b) ? 1.0f : 0.0f  (set.ge.f32.f32 in qrl_kernels.cuh)
 inline float qrl_ge1(float a, float b) { return a >= b ? 1.0f : 0.0f; }
 }  // namespace qrl
-
-// warp collectives on the per-warp barrier of cuda_emu.hpp (all 32 lanes of the warp must take part, as in the kernels under test)
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int off)
-{
-    static unsigned long long buf[64][32];
-    const unsigned t = emu::lin_tid(), w = t >> 5, l = t & 31;
-    unsigned long long raw = 0; std::memcpy(&raw, &v, sizeof(T));
-    buf[w][l] = raw;
-    emu::warp_bar[w]->arrive_and_wait();
-    raw = buf[w][(l ^ off) & 31];
-    emu::warp_bar[w]->arrive_and_wait();
-    T r; std::memcpy(&r, &raw, sizeof(T));
-    return r;
-}
-static inline unsigned __activemask() { return 0xffffffffu; }      // the kernels under test call it with the whole warp converged
-static inline int __reduce_min_sync(unsigned, int v)
-{
-    for (int off = 16; off >= 1; off >>= 1) { const int o = __shfl_xor_sync(0xffffffffu, v, off); v = o < v ? o : v; }
-    return v;
-}
-static inline int __any_sync(unsigned, int pred)
-{
-    int v = pred ? 1 : 0;
-    for (int off = 16; off >= 1; off >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, off);
-    return v;
-}
