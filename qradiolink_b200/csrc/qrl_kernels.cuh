@@ -808,6 +808,7 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
     __syncthreads();
     // all channels of a handle advance in lock step (one output per input): the read position is uniform
     const long long base = states[g * 32 < C ? g * 32 : 0].pos;
+    __syncthreads();      // all 96 threads hold `base` before the Costas warp stores the advanced position at its end
     if (base >= avail_total) return;
     const long long total = avail_total - base;
     const int nchunks = static_cast<int>((total + CH - 1) / CH);
@@ -1019,6 +1020,9 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
             if (active) n_soft_out[c] = ns0;
         }
     } else if (warp == 2 && active) n_soft_out[c] = states[c].n_soft;
+    // every warp has derived its schedule from states[].ii before the loop warp may store the advanced value at its end (with one
+    // or two chunks nothing else orders the drain / epilogue warps' reads before that store)
+    __syncthreads();
     if (nchunks == 0) return;
 
     if (warp == 1) {
