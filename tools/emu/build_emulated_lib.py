@@ -123,6 +123,8 @@ def build(out_dir):
     srcs = [os.path.join(out_dir, f) for f in ("qrl_b200.cpp", "qrl_pfb.cpp", "qrl_deframer.cpp")]
     cmd = ["g++", "-std=c++20", "-O" + os.environ.get("QRL_EMU_OPT", "1"), "-ffp-contract=off", "-fno-fast-math", "-pthread", "-fPIC", "-shared", "-Wno-unknown-pragmas",
            "-I", os.path.join(HERE, "fake_cuda"), "-I", HERE, "-I", out_dir, "-o", lib] + srcs
+    if os.environ.get("QRL_EMU_ASAN"):      # AddressSanitizer build (CPU memcheck): LD_PRELOAD=$(gcc -print-file-name=libasan.so), ASAN_OPTIONS=detect_leaks=0
+        cmd[1:1] = ["-fsanitize=address", "-g"]
     if os.environ.get("QRL_EMU_TSAN"):      # ThreadSanitizer build: load it with LD_PRELOAD=$(gcc -print-file-name=libtsan.so)
         cmd[1:1] = ["-fsanitize=thread", "-g"]
     subprocess.check_call(cmd)

@@ -18,6 +18,9 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/asan_interface.h>
+#endif
 
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { return float2{ x, y }; }
@@ -111,6 +114,11 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call)
     b_dim = block; g_dim = grid;
     if (smem_bytes > sizeof(smem_arena)) std::abort();
     dyn_smem = smem_arena;
+#if defined(__SANITIZE_ADDRESS__)
+    // AddressSanitizer build (QRL_EMU_ASAN=1): everything behind this launch's dynamic shared memory is poisoned
+    __asan_unpoison_memory_region(smem_arena, sizeof(smem_arena));
+    __asan_poison_memory_region(smem_arena + ((smem_bytes + 7) & ~size_t(7)), sizeof(smem_arena) - ((smem_bytes + 7) & ~size_t(7)));
+#endif
     for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
         std::barrier<> bar(nt);
         blk_bar = &bar;
