@@ -63,6 +63,7 @@ deframer_kernel(int C, int sync_class, int bit_buf_len, int rx_frame_length,
     const unsigned char* b = bits + static_cast<long long>(c) * bits_stride;
     const int n = counts ? counts[c] : fixed_count;
     DeframerState st = states[c];
+    __syncwarp();         // all lanes hold the state before lane 0 may store it back (n == 0: no collective in between)
     unsigned char* bb = bit_buf + static_cast<long long>(c) * bit_buf_len;
     unsigned char* rec = records + static_cast<long long>(c) * max_frames * rec_bytes;
     int found = 0;

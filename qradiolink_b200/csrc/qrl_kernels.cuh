@@ -1729,6 +1729,7 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
         }
         __syncthreads();
     }
+    __syncthreads();      // (empty input: no tile barrier above) every thread has read st.n_in for its loop bounds
     if (threadIdx.x == 0) st.n_in = avail_in;
     __syncthreads();
     const long long gate1 = st.n_gate;
@@ -1837,6 +1838,7 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
         }
         __syncthreads();
     }
+    __syncthreads();      // (nothing new: no barrier above) every thread has read st.n_aud
     if (threadIdx.x == 0) { st.n_res = res1; st.n_aud = res1; states[c] = st; }
 }
 
