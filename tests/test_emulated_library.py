@@ -16,6 +16,8 @@ import pytest
 
 from tests.golden import cases
 
+pytestmark = pytest.mark.timeout(900)      # pytest-timeout: a scheduling bug in the emulator must fail, not hang the tier
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 

@@ -10,6 +10,8 @@ import sys
 import numpy as np
 import pytest
 
+pytestmark = pytest.mark.timeout(900)      # pytest-timeout: a scheduling bug in the emulator must fail, not hang the tier
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tools", "emu")
 sys.path.insert(0, EMU)
