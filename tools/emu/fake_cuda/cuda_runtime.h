@@ -26,7 +26,14 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -1; return cudaSuccess; }
-static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::aligned_alloc(256, (n + 255) & ~size_t(255)); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaMalloc(void** p, size_t n)
+{
+    *p = std::aligned_alloc(256, (n + 255) & ~size_t(255));
+    // device memory is not zeroed by cudaMalloc: QRL_EMU_POISON=1 fills it with 0xFF (NaN as float) so that a kernel reading memory
+    // nobody initialised shows up as a mismatch instead of a lucky zero
+    if (*p && std::getenv("QRL_EMU_POISON")) std::memset(*p, 0xFF, (n + 255) & ~size_t(255));
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n); }
 static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* p, int v, size_t n) { std::memset(p, v, n); return cudaSuccess; }
