@@ -44,15 +44,13 @@ enum qrl_kind {
     QRL_DEMOD_AM = 7,         /* gr_demod_am.cpp:28-82; ports: IQ, float audio at 8 ksps */
     QRL_DEMOD_M17 = 10,       /* gr_demod_m17.cpp:30-113; ports: IQ at 24 ksps, symbols, hard bits (2 per symbol) */
     QRL_DEMOD_DMR = 11,       /* gr_demod_dmr.cpp:32-112; qrl_rx_create ignores carrier_freq / filter_width / flag; ports: IQ at
-                                 24 ksps, symbols, hard bits (2 per symbol), FLOAT symbol filter output (one per port-0 sample).  Written after the
-                                 round-1 GPU budget was spent: compiles, NOT yet run on a GPU (tests gated by QRL_RUN_UNVERIFIED=1) */
+                                 24 ksps, symbols, hard bits (2 per symbol), FLOAT symbol filter output (one per port-0 sample) */
     QRL_DEMOD_WBFM = 9,       /* gr_demod_wbfm.cpp:28-70; ports: IQ at 200 ksps, float audio at 8 ksps */
     QRL_DEMOD_GMSK = 8,       /* gr_demod_gmsk.cpp:30-134; sps 10 / 5 / 1 = GMSK1K / 2K / 10K; 4 ports like 2FSK */
     QRL_MOD_4FSK = 101, QRL_MOD_QPSK = 102, QRL_MOD_NBFM = 103, QRL_MOD_BPSK = 104, QRL_MOD_2FSK = 105,
     QRL_MOD_SSB = 106,
     QRL_MOD_GMSK = 107,       /* gr_mod_gmsk.cpp:30-100 (sps 50 / 100 / 10 = GMSK2K / 1K / 10K) */
-    QRL_MOD_M17 = 108         /* gr_mod_m17.cpp:30-95 (sps = 125: x125 / 3 from 24 ksps); items: frame bytes, 4 symbols each.  Like
-                                 QRL_DEMOD_DMR written after the round-1 GPU budget was spent: compiles, NOT yet run on a GPU */
+    QRL_MOD_M17 = 108         /* gr_mod_m17.cpp:30-95 (sps = 125: x125 / 3 from 24 ksps); items: frame bytes, 4 symbols each */
 };
 
 /* runtime parameters (qrl_rx_set_param / qrl_tx_set_param) */

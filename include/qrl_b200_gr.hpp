@@ -17,6 +17,7 @@
 #include <complex>
 #include <cstdint>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -28,26 +29,31 @@ namespace qrl_gr {
 using gr_complex = std::complex<float>;
 static const int WORK_DONE = -1;
 
-// ---- sink blocks: what gr_modem::demodulate()/demodulateAnalog() poll (caller deletes the returned vector)
+// ---- sink blocks: what gr_modem::demodulate()/demodulateAnalog() poll (caller deletes the returned vector).
+// Like the reference's, they are crossed by two threads (the block thread calls work(), the radioop thread polls get_data()):
+// every access to the buffer is under the mutex (gr_bit_sink.cpp:47,70; gr_audio_sink.cpp:51,74; gr_const_sink.cpp:51,80).
 class gr_bit_sink {
 public:
     int work(const unsigned char* in, int n)
     {
         if (n < 1) return n;
+        std::lock_guard<std::mutex> guard(_mutex);
         if (_data.size() > 1048576) return n;                 // reader too slow: drop (gr_bit_sink.cpp:71-76)
         _data.insert(_data.end(), in, in + n);
         return n;
     }
     std::vector<unsigned char>* get_data()
     {
+        std::lock_guard<std::mutex> guard(_mutex);
         if (_data.size() < 32) return nullptr;               // gr_bit_sink.cpp:49-52
         auto* d = new std::vector<unsigned char>(_data);
         _data.clear();
         return d;
     }
-    void flush() { _data.clear(); }
+    void flush() { std::lock_guard<std::mutex> guard(_mutex); _data.clear(); }
 private:
     std::vector<unsigned char> _data;
+    std::mutex _mutex;
 };
 
 class gr_audio_sink {
@@ -55,21 +61,24 @@ public:
     int work(const float* in, int n)
     {
         if (n < 1) return n;
+        std::lock_guard<std::mutex> guard(_mutex);
         if (_data.size() > 8000) { _data.clear(); return n; }  // gr_audio_sink.cpp:77-83
         _data.insert(_data.end(), in, in + n);
         return n;
     }
     std::vector<float>* get_data()
     {
+        std::lock_guard<std::mutex> guard(_mutex);
         const size_t pkt = 640;                               // 40 ms packets, gr_audio_sink.cpp:53
         if (_data.size() < pkt) return nullptr;
         auto* d = new std::vector<float>(_data.begin(), _data.begin() + pkt);
         _data.erase(_data.begin(), _data.begin() + pkt);
         return d;
     }
-    void flush() { _data.clear(); }
+    void flush() { std::lock_guard<std::mutex> guard(_mutex); _data.clear(); }
 private:
     std::vector<float> _data;
+    std::mutex _mutex;
 };
 
 class gr_const_sink {
@@ -77,20 +86,23 @@ public:
     int work(const gr_complex* in, int n)
     {
         if (n < 1) return n;
+        std::lock_guard<std::mutex> guard(_mutex);            // (the reference tests the size before locking: benign there, not copied)
         if (_data.size() > 256) return n;                     // gr_const_sink.cpp:75-79
         _data.insert(_data.end(), in, in + n);
         return n;
     }
     std::vector<gr_complex>* get_data()
     {
+        std::lock_guard<std::mutex> guard(_mutex);
         if (_data.size() < 32) return nullptr;
         auto* d = new std::vector<gr_complex>(_data);
         _data.clear();
         return d;
     }
-    void flush() { _data.clear(); }
+    void flush() { std::lock_guard<std::mutex> guard(_mutex); _data.clear(); }
 private:
     std::vector<gr_complex> _data;
+    std::mutex _mutex;
 };
 
 // ---- batched demodulator: n_channels instances of one reference hier block on one B200

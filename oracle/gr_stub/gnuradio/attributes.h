@@ -1,0 +1,3 @@
+#pragma once
+#define __GR_ATTR_EXPORT
+#define __GR_ATTR_IMPORT

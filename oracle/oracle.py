@@ -103,8 +103,58 @@ def lib():
         L.qo_pfb_channelizer_work.argtypes = [vp, vp, C.c_long, vp, C.c_long, C.c_long]
         L.qo_pfb_synthesizer_work.restype = C.c_long
         L.qo_pfb_synthesizer_work.argtypes = [vp, vp, C.c_long, C.c_long, vp]
+        L.qo_cessb_clipper.argtypes = [vp, C.c_long, C.c_float, vp]
+        L.qo_cessb_stretcher.restype = C.c_long
+        L.qo_cessb_stretcher.argtypes = [vp, C.c_long, vp]
+        L.qo_disc4.argtypes = [vp, vp, vp, vp, C.c_long, vp]
+        L.qo_dfbb_create.restype = vp
+        L.qo_dfbb_create.argtypes = [C.c_int]
+        L.qo_dfbb_destroy.argtypes = [vp]
+        L.qo_dfbb_work.restype = C.c_long
+        L.qo_dfbb_work.argtypes = [vp, vp, C.c_long, vp, C.c_long]
         _LIB = L
     return _LIB
+
+
+_REF = None
+
+
+def ref_blocks():
+    """oracle/_ref/libqrl_ref_blocks.so: the reference's in-tree GNU Radio blocks compiled unmodified (oracle/Makefile `ref`),
+    or None when it was never built (the reference tree exists only in the build container; the built .so travels)."""
+    global _REF
+    if _REF is None:
+        so = os.path.join(_HERE, "_ref", "libqrl_ref_blocks.so")
+        if not os.path.exists(so):
+            return None
+        lib()                                             # libqrl_oracle.so first: the shim resolves two symbols from it
+        R = C.CDLL(so)
+        vp = C.c_void_p
+        R.ref_block_destroy.argtypes = [vp]
+        R.ref_disc4.argtypes = [vp, vp, vp, vp, C.c_long, vp]
+        R.ref_cessb_clipper.restype = C.c_long
+        R.ref_cessb_clipper.argtypes = [vp, C.c_long, C.c_float, vp]
+        R.ref_cessb_stretcher.restype = C.c_long
+        R.ref_cessb_stretcher.argtypes = [vp, C.c_long, C.c_long, vp]
+        R.ref_dfbb_create.restype = vp
+        R.ref_dfbb_create.argtypes = [C.c_int]
+        R.ref_dfbb_work.restype = C.c_long
+        R.ref_dfbb_work.argtypes = [vp, vp, C.c_long, vp, C.c_long]
+        for kind, ty in (("bit", vp), ("audio", vp), ("const", vp)):
+            getattr(R, "ref_%s_sink_create" % kind).restype = vp
+            getattr(R, "ref_%s_sink_work" % kind).argtypes = [vp, ty, C.c_int]
+            getattr(R, "ref_%s_sink_get" % kind).restype = C.c_long
+            getattr(R, "ref_%s_sink_get" % kind).argtypes = [vp, ty, C.c_long]
+        R.ref_dsss_encode.restype = C.c_long
+        R.ref_dsss_encode.argtypes = [vp, C.c_int, vp, C.c_long, vp]
+        R.ref_dsss_decoder_create.restype = vp
+        R.ref_dsss_decoder_create.argtypes = [vp, C.c_int, C.c_float]
+        R.ref_dsss_decoder_taps.argtypes = [vp, vp, C.c_int]
+        R.ref_dsss_decoder_history.argtypes = [vp]
+        R.ref_dsss_decoder_work.restype = C.c_long
+        R.ref_dsss_decoder_work.argtypes = [vp, vp, C.c_int, vp, vp]
+        _REF = R
+    return _REF
 
 
 def _p(a):
@@ -368,6 +418,26 @@ class Deframer:
     @property
     def modem_sync(self):
         return lib().qo_deframer_modem_sync(self._h)
+
+
+class DeframerBB:
+    """gr_deframer_bb (gr_deframer_bb.cpp:83-185), one channel, streaming: work(bits) -> the bits it hands to get_data()."""
+
+    def __init__(self, modem_type):
+        self._h = lib().qo_dfbb_create(modem_type)
+        if not self._h:
+            raise ValueError("gr_deframer_bb: modem_type must be 1, 2 or 3")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().qo_dfbb_destroy(self._h); self._h = None
+
+    def work(self, bits):
+        bits = np.ascontiguousarray(bits, np.uint8)
+        cap = len(bits) + len(bits) // 8 * 3 + 64
+        out = np.zeros(cap, np.uint8)
+        n = lib().qo_dfbb_work(self._h, _p(bits), len(bits), _p(out), cap)
+        return out[:n].copy()
 
 
 class Rssi:

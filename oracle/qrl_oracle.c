@@ -1389,6 +1389,59 @@ static const float* rx_rotate(qo_rx* r, const float* iq, long T)
     return (const float*)r->s_rot.d;
 }
 
+
+/* ---- in-tree reference blocks restated as single-item functions (pinned bit-for-bit against the reference sources compiled
+ *      in oracle/_ref: tests/test_oracle_ref.py) ---- */
+/* cessb::clipper_cc (cessb/clipper_cc_impl.cc:65-95): magnitude limited to `clip`, phase kept (fast_atan2f, then cos / sin) */
+static void cessb_clip_one(float re, float im, float clip, float* orr, float* oi)
+{
+    float mag = sqrtf(re * re + im * im);
+    float ph = qo_fast_atan2f(im, re);
+    float cl = mag < clip ? mag : clip;
+    float sn, cs; qo_sincosf(ph, &sn, &cs);
+    *orr = cs * cl; *oi = sn * cl;
+}
+/* cessb::stretcher_cc (cessb/stretcher_cc_impl.cc:70-110): divisor from the 5-point envelope maximum around the item */
+static float cessb_stretch_div(float e_m2, float e_m1, float e0, float e1, float e2)
+{
+    const float emax = (float)(1 / (sqrt(0.5) / 2));
+    float h = e0;
+    h = fmaxf(h, e_m2); h = fmaxf(h, e_m1); h = fmaxf(h, e1); h = fmaxf(h, e2);
+    h = h * emax; h = fmaxf(h, 1.0f); h = h - 1.0f; h = h * 2.0f; h = h + 1.0f;
+    return h;
+}
+/* gr_4fsk_discriminator::work (gr_4fsk_discriminator.cpp:17-44): strict-greater argmax of four magnitudes */
+static void disc4_one(const float* m, float* orr, float* oi)
+{
+    *orr = 0; *oi = 0;
+    if ((m[0] > m[1]) && (m[0] > m[2]) && (m[0] > m[3])) { *orr = (float)-0.707107; *oi = (float)-0.707107; }
+    else if ((m[1] > m[0]) && (m[1] > m[2]) && (m[1] > m[3])) { *orr = (float)-0.707107; *oi = (float)0.707107; }
+    else if ((m[2] > m[1]) && (m[2] > m[0]) && (m[2] > m[3])) { *orr = (float)0.707107; *oi = (float)0.707107; }
+    else if ((m[3] > m[1]) && (m[3] > m[0]) && (m[3] > m[2])) { *orr = (float)0.707107; *oi = (float)-0.707107; }
+}
+void qo_cessb_clipper(const float* in_c, long n, float clip, float* out_c)
+{
+    for (long i = 0; i < n; i++) cessb_clip_one(in_c[2 * i], in_c[2 * i + 1], clip, &out_c[2 * i], &out_c[2 * i + 1]);
+}
+/* one-shot stretcher over a stream that starts at item 0 (zero envelope history): writes n - 2 items, returns that count */
+long qo_cessb_stretcher(const float* in_c, long n, float* out_c)
+{
+    float em2 = 0.0f, em1 = 0.0f;
+    long k = 0;
+    for (; k + 2 < n; k++) {
+        const float* c = in_c + 2 * k;
+        float e0 = sqrtf(c[0] * c[0] + c[1] * c[1]), e1 = sqrtf(c[2] * c[2] + c[3] * c[3]), e2 = sqrtf(c[4] * c[4] + c[5] * c[5]);
+        float h = cessb_stretch_div(em2, em1, e0, e1, e2);
+        out_c[2 * k] = c[0] / h; out_c[2 * k + 1] = c[1] / h;
+        em2 = em1; em1 = e0;
+    }
+    return k;
+}
+void qo_disc4(const float* m0, const float* m1, const float* m2, const float* m3, long n, float* out_c)
+{
+    for (long i = 0; i < n; i++) { float m[4] = { m0[i], m1[i], m2[i], m3[i] }; disc4_one(m, &out_c[2 * i], &out_c[2 * i + 1]); }
+}
+
 int qo_rx_work(qo_rx* r, const float* iq, long T)
 {
     iq = rx_rotate(r, iq, T);
@@ -1404,14 +1457,11 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
         for (size_t i = 0; i < r->s_tmp.n; i++) {
             float ar, ai;
             agc2_step(&r->agc, g[2 * i], g[2 * i + 1], &ar, &ai);
-            float mag = sqrtf(ar * ar + ai * ai);
-            float ph = qo_fast_atan2f(ai, ar);
-            float cl = mag < 0.95f ? mag : 0.95f;
-            float sn, cs; qo_sincosf(ph, &sn, &cs);
-            qv_pushc(&r->s_clip, cs * cl, sn * cl);
+            float cr, ci;
+            cessb_clip_one(ar, ai, 0.95f, &cr, &ci);
+            qv_pushc(&r->s_clip, cr, ci);
         }
         /* cessb::stretcher_cc (stretcher_cc_impl.cc:70-110): 5-point envelope hold with a 2-sample look-ahead */
-        const float emax = (float)(1 / (sqrt(0.5) / 2));
         const float* c = (const float*)r->s_clip.d;
         r->s_rrc.n = 0;
         while (r->st_pos + 2 < r->s_clip.n) {
@@ -1419,9 +1469,7 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
             float e0 = sqrtf(c[2 * n] * c[2 * n] + c[2 * n + 1] * c[2 * n + 1]);
             float e1 = sqrtf(c[2 * (n + 1)] * c[2 * (n + 1)] + c[2 * (n + 1) + 1] * c[2 * (n + 1) + 1]);
             float e2 = sqrtf(c[2 * (n + 2)] * c[2 * (n + 2)] + c[2 * (n + 2) + 1] * c[2 * (n + 2) + 1]);
-            float h = e0;
-            h = fmaxf(h, r->env_m2); h = fmaxf(h, r->env_m1); h = fmaxf(h, e1); h = fmaxf(h, e2);
-            h = h * emax; h = fmaxf(h, 1.0f); h = h - 1.0f; h = h * 2.0f; h = h + 1.0f;
+            float h = cessb_stretch_div(r->env_m2, r->env_m1, e0, e1, e2);
             float re = c[2 * n] / h;
             qv_pushf(&r->s_rrc, re * 1.333f);                                            /* complex_to_real, x1.333 */
             r->env_m2 = r->env_m1; r->env_m1 = e0;
@@ -1524,11 +1572,8 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
                 float m[4];
                 for (int k = 0; k < 4; k++) { const float* c = (const float*)r->s_bp[k].d + 2 * i; m[k] = sqrtf(c[0] * c[0] + c[1] * c[1]); }
                 /* /root/reference/src/gr/gr_4fsk_discriminator.cpp:17-44 */
-                float orr = 0, oi = 0;
-                if ((m[0] > m[1]) && (m[0] > m[2]) && (m[0] > m[3])) { orr = (float)-0.707107; oi = (float)-0.707107; }
-                else if ((m[1] > m[0]) && (m[1] > m[2]) && (m[1] > m[3])) { orr = (float)-0.707107; oi = (float)0.707107; }
-                else if ((m[2] > m[1]) && (m[2] > m[0]) && (m[2] > m[3])) { orr = (float)0.707107; oi = (float)0.707107; }
-                else if ((m[3] > m[1]) && (m[3] > m[0]) && (m[3] > m[2])) { orr = (float)0.707107; oi = (float)-0.707107; }
+                float orr, oi;
+                disc4_one(m, &orr, &oi);
                 qv_pushc(&r->s_tmp, orr, oi);
             }
             r->s_tmp2.n = 0; resamp_work(&r->symfilt, (const float*)r->s_tmp.d, r->s_tmp.n, &r->s_tmp2);
@@ -1925,13 +1970,10 @@ int qo_tx_work(qo_tx* t, const void* in, long n)
         t->s_aud.n = 0; resamp_work(&t->a_filt, au, (size_t)n, &t->s_aud);
         const float* a1 = (const float*)t->s_aud.d;
         for (size_t i = 0; i < t->s_aud.n; i++) {                                           /* float_to_complex -> clipper_cc(0.95) */
-            float mag = sqrtf(a1[i] * a1[i] + 0.0f * 0.0f);
-            float ph = qo_fast_atan2f(0.0f, a1[i]);
-            float cl = mag < 0.95f ? mag : 0.95f;
-            float sn, cs; qo_sincosf(ph, &sn, &cs);
-            qv_pushc(&t->s_clip, cs * cl, sn * cl);
+            float cr, ci;
+            cessb_clip_one(a1[i], 0.0f, 0.95f, &cr, &ci);
+            qv_pushc(&t->s_clip, cr, ci);
         }
-        const float emax = (float)(1 / (sqrt(0.5) / 2));
         const float* c = (const float*)t->s_clip.d;
         t->s_c2.n = 0;
         while (t->st_pos + 2 < t->s_clip.n) {                                                /* stretcher_cc */
@@ -1939,9 +1981,7 @@ int qo_tx_work(qo_tx* t, const void* in, long n)
             float e0 = sqrtf(c[2 * k] * c[2 * k] + c[2 * k + 1] * c[2 * k + 1]);
             float e1 = sqrtf(c[2 * (k + 1)] * c[2 * (k + 1)] + c[2 * (k + 1) + 1] * c[2 * (k + 1) + 1]);
             float e2 = sqrtf(c[2 * (k + 2)] * c[2 * (k + 2)] + c[2 * (k + 2) + 1] * c[2 * (k + 2) + 1]);
-            float h = e0;
-            h = fmaxf(h, t->env_m2); h = fmaxf(h, t->env_m1); h = fmaxf(h, e1); h = fmaxf(h, e2);
-            h = h * emax; h = fmaxf(h, 1.0f); h = h - 1.0f; h = h * 2.0f; h = h + 1.0f;
+            float h = cessb_stretch_div(t->env_m2, t->env_m1, e0, e1, e2);
             qv_pushc(&t->s_c2, c[2 * k] / h, c[2 * k + 1] / h);
             t->env_m2 = t->env_m1; t->env_m1 = e0;
             t->st_pos++;
@@ -2204,6 +2244,59 @@ long qo_deframer_work(qo_deframer* d, const uint8_t* bits, long n, uint8_t* reco
         }
     }
     return found;
+}
+
+/* ------------------------------------------------------------------ gr_deframer_bb (MMDVM-era bit deframer behind ports 2 / 3 of
+ * the dual-decoder modes: gr_demod_base.cpp wires _deframer1/2 (type 1), _deframer_700_1/2 (type 2), _deframer_10k_1/2 (type 3))
+ * /root/reference/src/gr/gr_deframer_bb.cpp:83-185 restated bit for bit, quirks included: the 8- or 16-bit word under test is
+ * compared against every 16-bit sync word (type 2 masks 8 bits, so only 0xB5 and the 24-bit End word can hit there); on a hit the
+ * block emits the matched word MSB first -- 16 bits, 24 for the End word, 8 for type 2 (the LOW 8 bits of whatever matched) --
+ * then the next bit_buf_len input bits verbatim, then clears its shift register.  Output: a bit stream (one bit per byte). */
+struct qo_dfbb { int type, sync_found, idx, len; uint64_t shift; };
+typedef struct qo_dfbb qo_dfbb;
+qo_dfbb* qo_dfbb_create(int modem_type)
+{
+    if (modem_type < 1 || modem_type > 3) return NULL;          /* the reference leaves _bit_buf_len uninitialised otherwise */
+    qo_dfbb* d = (qo_dfbb*)calloc(1, sizeof(qo_dfbb));
+    d->type = modem_type;
+    d->len = modem_type == 1 ? 8 * 8 : (modem_type == 2 ? 4 * 8 : 48 * 8);
+    return d;
+}
+void qo_dfbb_destroy(qo_dfbb* d) { free(d); }
+static uint32_t dfbb_find_sync(qo_dfbb* d, unsigned bit)
+{
+    d->shift = (d->shift << 1) | (bit & 1u);
+    uint32_t t = (uint32_t)(d->type != 2 ? (d->shift & 0xFFFF) : (d->shift & 0xFF));
+    if (d->type == 2 && t == 0xB5) { d->sync_found = 1; return t; }
+    if (t == 0x89ED || t == 0xED89 || t == 0x98DE || t == 0xED77 || t == 0x8CC8) { d->sync_found = 1; return t; }
+    t = (uint32_t)(d->shift & 0xFFFFFF);
+    if (t == 0x4C8A2B) { d->sync_found = 1; return t; }
+    return 0;
+}
+/* returns the number of output bits appended to out (at most cap; the rest is dropped, state still advances) */
+long qo_dfbb_work(qo_dfbb* d, const uint8_t* bits, long n, uint8_t* out, long cap)
+{
+    long no = 0;
+    for (long i = 0; i < n; i++) {
+        if (!d->sync_found) {
+            const uint32_t ft = dfbb_find_sync(d, bits[i]);
+            if (d->sync_found) {
+                int nb;
+                if ((d->type == 1 || d->type == 3) && ft != 0x4C8A2B) nb = 16;
+                else if ((d->type == 1 || d->type == 3) && ft == 0x4C8A2B) nb = 24;
+                else nb = 8;
+                for (int k = 0; k < nb; k++) { if (no < cap) out[no] = (uint8_t)((ft >> (nb - 1 - k)) & 1u); no++; }
+                d->idx = 0;
+                continue;
+            }
+        }
+        if (d->sync_found) {
+            if (no < cap) out[no] = bits[i] & 1u;
+            no++;
+            if (++d->idx >= d->len) { d->sync_found = 0; d->shift = 0; d->idx = 0; }
+        }
+    }
+    return no < cap ? no : cap;
 }
 
 /* ------------------------------------------------------------------ RSSI tap

@@ -125,6 +125,17 @@ void  qo_deframer_destroy(qo_deframer*);
 long  qo_deframer_work(qo_deframer*, const uint8_t* bits, long n, uint8_t* records, int rec_bytes, long max_frames);
 int   qo_deframer_modem_sync(const qo_deframer*);
 
+/* ---- in-tree reference blocks as stand-alone functions (the chains above call the same code); pinned bit for bit against the
+ *      reference sources compiled into oracle/_ref (tests/test_oracle_ref.py) ---- */
+void qo_cessb_clipper(const float* in_c, long n, float clip, float* out_c);      /* cessb/clipper_cc_impl.cc:65-95 */
+long qo_cessb_stretcher(const float* in_c, long n, float* out_c);                /* cessb/stretcher_cc_impl.cc:70-110, writes n - 2 */
+void qo_disc4(const float* m0, const float* m1, const float* m2, const float* m3, long n, float* out_c);   /* gr_4fsk_discriminator.cpp:17-44 */
+/* gr_deframer_bb.cpp:83-185 (modem_type 1 / 2 / 3): bit stream in, {sync word bits, following bit_buf_len bits} stream out */
+typedef struct qo_dfbb qo_dfbb;
+qo_dfbb* qo_dfbb_create(int modem_type);
+void  qo_dfbb_destroy(qo_dfbb*);
+long  qo_dfbb_work(qo_dfbb*, const uint8_t* bits, long n, uint8_t* out, long cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ and `gr_const_sink` restate the buffering / drop policy of the reference's sink 
 gr_modem::demodulate() polls.  All DSP happens in libqrl_b200.so (CUDA); nothing here computes.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -182,22 +183,26 @@ class gr_bit_sink:
 
     def __init__(self):
         self._data = np.zeros(0, np.uint8)
+        self._mutex = threading.Lock()      # work() and get_data() come from two threads (gr_bit_sink.cpp:47,70)
 
     def flush(self):
-        self._data = np.zeros(0, np.uint8)
+        with self._mutex:
+            self._data = np.zeros(0, np.uint8)
 
     def work(self, items):
         if len(items) < 1:
             return 0
-        if len(self._data) > 1048576:
-            return len(items)          # reader too slow: drop (gr_bit_sink.cpp:71-76)
-        self._data = np.concatenate([self._data, np.asarray(items, np.uint8)])
+        with self._mutex:
+            if len(self._data) > 1048576:
+                return len(items)          # reader too slow: drop (gr_bit_sink.cpp:71-76)
+            self._data = np.concatenate([self._data, np.asarray(items, np.uint8)])
         return len(items)
 
     def get_data(self):
-        if len(self._data) < 32:
-            return None
-        d, self._data = self._data, np.zeros(0, np.uint8)
+        with self._mutex:
+            if len(self._data) < 32:
+                return None
+            d, self._data = self._data, np.zeros(0, np.uint8)
         return d
 
 
@@ -206,23 +211,27 @@ class gr_audio_sink:
 
     def __init__(self):
         self._data = np.zeros(0, np.float32)
+        self._mutex = threading.Lock()
 
     def flush(self):
-        self._data = np.zeros(0, np.float32)
+        with self._mutex:
+            self._data = np.zeros(0, np.float32)
 
     def work(self, items):
         if len(items) < 1:
             return 0
-        if len(self._data) > 8000:
-            self._data = np.zeros(0, np.float32)
-            return len(items)
-        self._data = np.concatenate([self._data, np.asarray(items, np.float32)])
+        with self._mutex:
+            if len(self._data) > 8000:
+                self._data = np.zeros(0, np.float32)
+                return len(items)
+            self._data = np.concatenate([self._data, np.asarray(items, np.float32)])
         return len(items)
 
     def get_data(self):
-        if len(self._data) < 640:
-            return None
-        d, self._data = self._data[:640], self._data[640:]
+        with self._mutex:
+            if len(self._data) < 640:
+                return None
+            d, self._data = self._data[:640], self._data[640:]
         return d
 
 
@@ -231,20 +240,24 @@ class gr_const_sink:
 
     def __init__(self):
         self._data = np.zeros(0, np.complex64)
+        self._mutex = threading.Lock()
 
     def flush(self):
-        self._data = np.zeros(0, np.complex64)
+        with self._mutex:
+            self._data = np.zeros(0, np.complex64)
 
     def work(self, items):
         if len(items) < 1:
             return 0
-        if len(self._data) > 256:
-            return len(items)
-        self._data = np.concatenate([self._data, np.asarray(items, np.complex64)])
+        with self._mutex:
+            if len(self._data) > 256:
+                return len(items)
+            self._data = np.concatenate([self._data, np.asarray(items, np.complex64)])
         return len(items)
 
     def get_data(self):
-        if len(self._data) < 32:
-            return None
-        d, self._data = self._data, np.zeros(0, np.complex64)
+        with self._mutex:
+            if len(self._data) < 32:
+                return None
+            d, self._data = self._data, np.zeros(0, np.complex64)
         return d

@@ -2,16 +2,12 @@
 filter tapped as float port 3, symbol sync with the PLAIN Mueller & Mueller detector, x0.9, phase modulator, hard bits) against the
 CPU oracle: all four ports, ragged chunks.
 
-STATUS: the CUDA side of this chain was written after the round-1 GPU budget was spent.  It compiles for sm_100a but has never run
-on a GPU, so these tests are opt-in (QRL_RUN_UNVERIFIED=1) until a GPU run has confirmed them; nothing else depends on this code
-(the kernels every other chain uses are unchanged instruction for instruction)."""
-import os
-
+STATUS: first run on a B200 at the start of round 2 (tools/gpu_checklist.sh: compute-sanitizer memcheck 0 errors, all tests green,
+profiles/r02_a_checklist_summary.txt); part of the normal GPU tier since."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("QRL_RUN_UNVERIFIED"), reason="DMR CUDA path not yet confirmed on a GPU: set QRL_RUN_UNVERIFIED=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_dmr_parity_chunked(qrl, oracle):

@@ -1,17 +1,14 @@
 """GPU tier: M17 modulator (gr_mod_m17.cpp: bytes -> dibits -> map -> RRC x5 -> x0.66666666 -> frequency modulator -> 24 ksps low-pass
 -> x0.9 -> x125 / 3 rational interpolator) against the CPU oracle, state carried across calls, then CUDA TX -> CUDA M17 RX.
 
-STATUS: written after the round-1 GPU budget was spent.  It compiles for sm_100a but has never run on a GPU, so these tests are
-opt-in (QRL_RUN_UNVERIFIED=1) until a GPU run has confirmed them (see tests/test_gpu_dmr.py)."""
-import os
-
+STATUS: first run on a B200 at the start of round 2 (tools/gpu_checklist.sh: compute-sanitizer memcheck 0 errors, all tests green,
+profiles/r02_a_checklist_summary.txt); part of the normal GPU tier since."""
 import numpy as np
 import pytest
 
 from tests import siggen
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("QRL_RUN_UNVERIFIED"), reason="M17 modulator CUDA path not yet confirmed on a GPU: set QRL_RUN_UNVERIFIED=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("cuts", [(), (100,), (1, 7, 150)])

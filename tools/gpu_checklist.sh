@@ -8,18 +8,18 @@ mkdir -p "$OUT"
 export PYTHONUNBUFFERED=1
 
 # 1. the two chains written without GPU time (DMR receive, M17 modulator): memcheck first -- they have never executed
-QRL_RUN_UNVERIFIED=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 \
+timeout 420 compute-sanitizer --tool memcheck --error-exitcode 9 \
     python -m pytest tests/test_gpu_dmr.py tests/test_gpu_m17_tx.py -m gpu -x -q > "$OUT/1_unverified_memcheck.log" 2>&1
 echo "unverified (memcheck) exit $?" | tee "$OUT/summary.txt"
 
 # 1b. the kernels that gained a barrier after the last GPU run: hardware racecheck on one small case each
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest "tests/test_golden.py::test_golden_rx_cuda[ssb_usb]" \
+timeout 420 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest "tests/test_golden.py::test_golden_rx_cuda[ssb_usb]" \
     "tests/test_golden.py::test_golden_rx_cuda[nbfm_2500]" "tests/test_golden.py::test_golden_rx_cuda[bpsk_2k]" "tests/test_golden.py::test_golden_rx_cuda[m17]" \
     -m gpu -x -q > "$OUT/1b_racecheck.log" 2>&1
 echo "racecheck exit $?" | tee -a "$OUT/summary.txt"
 
 # 2. the same without the sanitizer (parity verdict at full speed)
-QRL_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_dmr.py tests/test_gpu_m17_tx.py -m gpu -q > "$OUT/2_unverified.log" 2>&1
+timeout 300 python -m pytest tests/test_gpu_dmr.py tests/test_gpu_m17_tx.py -m gpu -q > "$OUT/2_unverified.log" 2>&1
 echo "unverified exit $?" | tee -a "$OUT/summary.txt"
 
 # 3. the whole GPU tier as the driver runs it
