@@ -130,6 +130,10 @@ int qrl_tx_sync(qrl_tx* h);
 int qrl_tx_read(qrl_tx* h, float* dst, long cap, long* n_out, int dst_on_device);
 int qrl_tx_out_device(qrl_tx* h, float** data, long* stride, long* n_out);
 long qrl_tx_launch_count(const qrl_tx* h);
+/* per-stage device timing of the modulator (like qrl_rx_profile): stage 0 = bit chain (scrambler / encoder / mapper),
+ * 1 = pulse shaping + frequency modulator, 2 = final interpolating FIR (the HBM-write-bound kernel) */
+int qrl_tx_profile(qrl_tx* h, int enable);
+int qrl_tx_profile_read(qrl_tx* h, int stage, double* ms_total, long* n_launches);
 
 /* ---- design helpers (host only; the gr::filter::firdes calls the reference makes at construction /
  *      in set_filter_width, e.g. gr_demod_nbfm.cpp:82-90).  Return tap count or negative error. ---- */

@@ -1635,6 +1635,27 @@ struct qrl_tx : HandleBase {
     static constexpr int kTxSub = 8;
     cudaStream_t s_bits = nullptr, s_shape = nullptr;
     cudaEvent_t ev_start = nullptr, ev_bits[kTxSub] = { nullptr }, ev_shape[kTxSub] = { nullptr }, ev_shape_done = nullptr, ev_out_done = nullptr;
+    // optional per-stage device timing (qrl_tx_profile): 0 = bit chain, 1 = pulse shaping / FM scan, 2 = final interpolator
+    bool prof = false;
+    struct ProfRec { int stage; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs; size_t prof_used = 0;
+    double prof_ms[4] = { 0 }; long prof_n[4] = { 0 };
+    cudaStream_t prof_stream = nullptr;
+    cudaEvent_t prof_begin(int stage, cudaStream_t on)
+    {
+        prof_stream = on;
+        if (!prof) return nullptr;
+        if (prof_used == prof_recs.size()) {
+            ProfRec r{ stage, nullptr, nullptr };
+            cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+            prof_recs.push_back(r);
+        }
+        ProfRec& r = prof_recs[prof_used];
+        r.stage = stage;
+        cudaEventRecord(r.a, prof_stream);
+        return r.b;
+    }
+    void prof_end(cudaEvent_t b) { if (b) { cudaEventRecord(b, prof_stream); prof_used++; } }
 };
 
 static std::vector<float> make_arms(const std::vector<float>& taps, int L, int nt)
@@ -1808,6 +1829,7 @@ int qrl_tx_destroy(qrl_tx* h)
     if (h->s_shape) { cudaStreamSynchronize(h->s_shape); cudaStreamDestroy(h->s_shape); }
     for (cudaEvent_t e : { h->ev_start, h->ev_shape_done, h->ev_out_done }) if (e) cudaEventDestroy(e);
     for (int i = 0; i < qrl_tx::kTxSub; i++) { if (h->ev_bits[i]) cudaEventDestroy(h->ev_bits[i]); if (h->ev_shape[i]) cudaEventDestroy(h->ev_shape[i]); }
+    for (auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (void* p : h->allocs) cudaFree(p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1926,20 +1948,26 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
             const long b0 = n * j / S, b1 = n * (j + 1) / S;
             if (b1 <= b0) continue;
             const long long symA = sym0 + 8LL * b0, nsym_j = 8LL * (b1 - b0);
+            cudaEvent_t pe = h->prof_begin(0, h->s_bits);
             tx_bits_kernel<TXM_4FSK><<<dim3((h->C + 31) / 32), 32, 0, h->s_bits>>>(h->d_bits, h->C, b + b0, b1 - b0, bstride,
                                                                                  h->d_sym, h->sym_mask, h->sym_stride, symA);
+            h->prof_end(pe);
             CK(cudaEventRecord(h->ev_bits[j], h->s_bits));
             CK(cudaStreamWaitEvent(h->s_shape, h->ev_bits[j], 0));
+            pe = h->prof_begin(1, h->s_shape);
             tx_shape_fm_kernel<1024, 2><<<h->C, 1024, 0, h->s_shape>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, symA, nsym_j,
                 h->L1, h->nt1, h->d_arms1, h->repeat_only, h->pulse_scale, h->fm_sens, h->amplif, h->bb_gain,
                 h->d_if, h->if_mask, h->if_stride);
+            h->prof_end(pe);
             CK(cudaEventRecord(h->ev_shape[j], h->s_shape));
             CK(cudaStreamWaitEvent(h->stream, h->ev_shape[j], 0));
             constexpr int L = 20, NT = 35, R = 8, G = 16;
             const long long m0 = symA * h->L1, m1 = (symA + nsym_j) * h->L1;
             dim3 g(static_cast<unsigned>((m1 - m0 + R * G - 1) / (R * G)), h->C);
+            pe = h->prof_begin(2, h->stream);
             interp_fir_ccf_rt_kernel<L, NT, R, G><<<g, L * G, 0, h->stream>>>(
                 h->d_if, h->if_mask, h->if_stride, m0, m1, h->d_arms2, 1.0f, 1.0f, 0, h->d_out, h->out_stride, out_base);
+            h->prof_end(pe);
             h->launches += 3;
         }
         CK(cudaEventRecord(h->ev_shape_done, h->s_shape));
@@ -2022,6 +2050,30 @@ int qrl_tx_sync(qrl_tx* h)
 {
     if (!h) return QRL_EINVAL;
     CK(cudaStreamSynchronize(h->stream));
+    return QRL_OK;
+}
+int qrl_tx_profile(qrl_tx* h, int enable)
+{
+    if (!h) return QRL_EINVAL;
+    CK(cudaStreamSynchronize(h->stream));
+    h->prof = enable != 0;
+    h->prof_used = 0;
+    for (int i = 0; i < 4; i++) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+    return QRL_OK;
+}
+int qrl_tx_profile_read(qrl_tx* h, int stage, double* ms_total, long* n_launches)
+{
+    if (!h || stage < 0 || stage >= 4) return QRL_EINVAL;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->s_bits) CK(cudaStreamSynchronize(h->s_bits));
+    if (h->s_shape) CK(cudaStreamSynchronize(h->s_shape));
+    for (size_t i = 0; i < h->prof_used; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->prof_recs[i].a, h->prof_recs[i].b) == cudaSuccess) { h->prof_ms[h->prof_recs[i].stage] += ms; h->prof_n[h->prof_recs[i].stage]++; }
+    }
+    h->prof_used = 0;
+    if (ms_total) *ms_total = h->prof_ms[stage];
+    if (n_launches) *n_launches = h->prof_n[stage];
     return QRL_OK;
 }
 int qrl_tx_read(qrl_tx* h, float* dst, long cap, long* n_out, int dst_on_device)

@@ -168,9 +168,9 @@ fir_decim_poly_kernel(const float2* __restrict__ iq, long long iq_stride, long l
 
     float* outc = reinterpret_cast<float*>(out_ring + static_cast<long long>(c) * ring_stride);
     for (int b = warp; b < NOUT / K; b += NWARPS) {
-        float ar[K], ai[K];
+        float2 acc[K];                                // (re, im) pairs: one FFMA2 per tap and output
 #pragma unroll
-        for (int i = 0; i < K; i++) { ar[i] = 0.0f; ai[i] = 0.0f; }
+        for (int i = 0; i < K; i++) acc[i] = make_float2(0.0f, 0.0f);
 #pragma unroll
         for (int rho = 0; rho < R; rho++) {
             int r = lane + 32 * rho;
@@ -182,17 +182,14 @@ fir_decim_poly_kernel(const float2* __restrict__ iq, long long iq_stride, long l
 #pragma unroll
                 for (int i = 0; i < K; i++) {
                     const int q = i + (Q - 1) - ip;
-                    if (q >= 0 && q < Q) {
-                        ar[i] = fmaf(tap[rho][q], x.x, ar[i]);
-                        ai[i] = fmaf(tap[rho][q], x.y, ai[i]);
-                    }
+                    if (q >= 0 && q < Q) ffma2(acc[i], tap[rho][q], x);
                 }
             }
         }
         // transposed butterfly: value v = 2 i + comp; association order == xor-butterfly 16,8,4,2,1
         float a[16];
 #pragma unroll
-        for (int i = 0; i < K; i++) { a[2 * i] = ar[i]; a[2 * i + 1] = ai[i]; }
+        for (int i = 0; i < K; i++) { a[2 * i] = acc[i].x; a[2 * i + 1] = acc[i].y; }
         {
             const bool hi = lane & 16;
 #pragma unroll
@@ -271,9 +268,9 @@ fir_decim2_kernel(const float2* __restrict__ iq, long long iq_stride, long long 
     }
     __syncthreads();
     // thread t: outputs kbase + K t + i ; newest sample of output i at window index (NTP-1) + D (K t + i)
-    float s0r[K], s0i[K], s1r[K], s1i[K];
+    float2 s0[K], s1[K];                                 // branch chains j even / j odd, (re, im) pairs: FFMA2
 #pragma unroll
-    for (int i = 0; i < K; i++) { s0r[i] = s0i[i] = s1r[i] = s1i[i] = 0.0f; }
+    for (int i = 0; i < K; i++) { s0[i] = make_float2(0.0f, 0.0f); s1[i] = make_float2(0.0f, 0.0f); }
     const int t = threadIdx.x;
     // walk window offsets w = 0 .. NTP-1 + D(K-1): sample index = D K t + w ; tap for output i: j = (NTP-1) + D i - w
 #pragma unroll
@@ -285,8 +282,8 @@ fir_decim2_kernel(const float2* __restrict__ iq, long long iq_stride, long long 
             const int j = (NTP - 1) + D * i - w;
             if (j >= 0 && j < NTP) {
                 const float h = hs[j];
-                if ((j & 1) == 0) { s0r[i] = fmaf(h, x.x, s0r[i]); s0i[i] = fmaf(h, x.y, s0i[i]); }
-                else { s1r[i] = fmaf(h, x.x, s1r[i]); s1i[i] = fmaf(h, x.y, s1i[i]); }
+                if ((j & 1) == 0) ffma2(s0[i], h, x);
+                else ffma2(s1[i], h, x);
             }
         }
     }
@@ -294,7 +291,7 @@ fir_decim2_kernel(const float2* __restrict__ iq, long long iq_stride, long long 
 #pragma unroll
     for (int i = 0; i < K; i++) {
         const long long k = kbase + K * t + i;
-        if (k < k1) outc[k & ring_mask] = make_float2(s0r[i] + s1r[i], s0i[i] + s1i[i]);
+        if (k < k1) outc[k & ring_mask] = make_float2(s0[i].x + s1[i].x, s0[i].y + s1[i].y);
     }
 }
 
@@ -367,13 +364,8 @@ __global__ void fir_ccf_ring_kernel(const float2* __restrict__ in, unsigned in_m
     const long long a = a0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (a >= a1) return;
     const float2* x = in + static_cast<long long>(c) * in_stride;
-    float re = 0.0f, im = 0.0f;
-    for (int j = ntaps - 1; j >= 0; j--) {
-        const float2 v = x[(a - j) & in_mask];
-        re = fmaf(hs_dyn[j], v.x, re);
-        im = fmaf(hs_dyn[j], v.y, im);
-    }
-    const float2 y = make_float2(re, im);
+    float2 y = make_float2(0.0f, 0.0f);
+    for (int j = ntaps - 1; j >= 0; j--) ffma2(y, hs_dyn[j], x[(a - j) & in_mask]);
     if (out_interleaved) out[(static_cast<long long>(c >> 5) * out_stride + (a & out_mask)) * 32 + (c & 31)] = y;
     else out[static_cast<long long>(c) * out_stride + (a & out_mask)] = y;
     if (lin) lin[static_cast<long long>(c) * lin_stride + (a - lin_base)] = y;
@@ -2258,13 +2250,10 @@ interp_fir_ccf_kernel(const float2* __restrict__ in_ring, unsigned in_mask, long
         for (int i = 0; i < NT; i++) {
             // window slot (NT-1+i) % NT receives the newest sample; sample m-k sits in slot (NT-1+i-k) % NT
             w[(NT - 1 + i) % NT] = xs[mb * MLEN + g * NT + i + (NT - 1)];
-            float re = 0.0f, im = 0.0f;
+            float2 acc2 = make_float2(0.0f, 0.0f);
 #pragma unroll
-            for (int k = NT - 1; k >= 0; k--) {
-                const float2 v = w[(NT - 1 + i - k + NT) % NT];
-                re = fmaf(h[k], v.x, re);
-                im = fmaf(h[k], v.y, im);
-            }
+            for (int k = NT - 1; k >= 0; k--) ffma2(acc2, h[k], w[(NT - 1 + i - k + NT) % NT]);
+            float re = acc2.x, im = acc2.y;
             if (apply_gain) { re = re * post_gain1; im = im * post_gain1; re = re * post_gain2; im = im * post_gain2; }
             const long long m = tile0 + mb * MLEN + g * NT + i;
             if (m < m1) oc[(m * L + p) - out_base] = make_float2(re, im);
@@ -2297,9 +2286,9 @@ interp_fir_ccf_rt_kernel(const float2* __restrict__ in_ring, unsigned in_mask, l
     float h[NT];
 #pragma unroll
     for (int k = 0; k < NT; k++) h[k] = arms[p * NT + k];
-    float ar[R], ai[R];
+    float2 acc[R];                                              // (re, im) pairs: one FFMA2 per tap and output
 #pragma unroll
-    for (int r = 0; r < R; r++) { ar[r] = 0.0f; ai[r] = 0.0f; }
+    for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f);
     const float2* s = xs + q * R;                               // s[j] = x[tile0 + qR - (NT-1) + j]
 #pragma unroll
     for (int j = 0; j < R + NT - 1; j++) {
@@ -2307,13 +2296,13 @@ interp_fir_ccf_rt_kernel(const float2* __restrict__ in_ring, unsigned in_mask, l
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int k = r + NT - 1 - j;                       // output m = tile0 + qR + r uses x[m - k]
-            if (k >= 0 && k < NT) { ar[r] = fmaf(h[k], v.x, ar[r]); ai[r] = fmaf(h[k], v.y, ai[r]); }
+            if (k >= 0 && k < NT) ffma2(acc[r], h[k], v);
         }
     }
     float2* oc = out + static_cast<long long>(c) * out_stride;
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        float re = ar[r], im = ai[r];
+        float re = acc[r].x, im = acc[r].y;
         if (apply_gain) { re = re * post_gain1; im = im * post_gain1; re = re * post_gain2; im = im * post_gain2; }
         const long long m = tile0 + q * R + r;
         if (m < m1) oc[(m * L + p) - out_base] = make_float2(re, im);

@@ -87,9 +87,9 @@ pfb_chan_kernel(const float* __restrict__ bt /*[M][TPF]*/, const float* __restri
         float h[TPF];
 #pragma unroll
         for (int t = 0; t < TPF; t++) h[t] = bt[k * TPF + t];
-        float ar[R], ai[R];
+        float2 acc[R];                                              // (re, im) pairs: one FFMA2 per tap and output
 #pragma unroll
-        for (int r = 0; r < R; r++) { ar[r] = 0.0f; ai[r] = 0.0f; }
+        for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f);
         const float2* s = win + woff + (q * R) * M + (M - 1 - k);  // s[j*M] = stream sample at time (q*R - (TPF-1) + j)
 #pragma unroll
         for (int j = 0; j < R + TPF - 1; j++) {
@@ -97,11 +97,11 @@ pfb_chan_kernel(const float* __restrict__ bt /*[M][TPF]*/, const float* __restri
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const int t = r + TPF - 1 - j;                      // tap index for output r: sample time = m - t
-                if (t >= 0 && t < TPF) { ar[r] = fmaf(h[t], v.x, ar[r]); ai[r] = fmaf(h[t], v.y, ai[r]); }
+                if (t >= 0 && t < TPF) ffma2(acc[r], h[t], v);
             }
         }
 #pragma unroll
-        for (int r = 0; r < R; r++) ub[k * TMP + q * R + r] = make_float2(ar[r], ai[r]);
+        for (int r = 0; r < R; r++) ub[k * TMP + q * R + r] = acc[r];
     }
     __syncthreads();
     // ---- stage B: warp w owns channel c = w, w + nwarps, ...: its M twiddles stay in registers
@@ -114,14 +114,16 @@ pfb_chan_kernel(const float* __restrict__ bt /*[M][TPF]*/, const float* __restri
             float2* orow = out + c * out_stride + m0;
             for (int m = lane; m < TM; m += 32) {
                 if (m0 + m >= frames) break;
-                float re = 0.0f, im = 0.0f;
+                float2 o = make_float2(0.0f, 0.0f);
 #pragma unroll
                 for (int k = 0; k < M; k++) {
                     const float2 u = ub[k * TMP + m];
-                    re = fmaf(u.x, wr[k], re); re = fmaf(-u.y, wi[k], re);
-                    im = fmaf(u.x, wi[k], im); im = fmaf(u.y, wr[k], im);
+                    // re += u.x wr; re += -u.y wi; im += u.x wi; im += u.y wr  ==  o += u.x (wr, wi); o += u.y (-wi, wr)   (two FFMA2;
+                    // fma(-a, b, c) and fma(a, -b, c) are the same operation)
+                    ffma2_sp(o, u.x, wr[k], wi[k]);
+                    ffma2_sp(o, u.y, -wi[k], wr[k]);
                 }
-                orow[m] = make_float2(re, im);
+                orow[m] = o;
             }
         }
     }
@@ -207,14 +209,14 @@ pfb_synth_kernel(const float* __restrict__ bt, const float* __restrict__ w,
 #pragma unroll
             for (int c = 0; c < M; c++) { const int qd = (br * c) % M; wr[c] = w[2 * qd]; wi[c] = w[2 * qd + 1]; }
             for (int col = lane; col < COLS; col += 32) {
-                float re = 0.0f, im = 0.0f;
+                float2 o = make_float2(0.0f, 0.0f);
 #pragma unroll
                 for (int c = 0; c < M; c++) {
                     const float2 u = xin[c * COLS + col];
-                    re = fmaf(u.x, wr[c], re); re = fmaf(-u.y, wi[c], re);
-                    im = fmaf(u.x, wi[c], im); im = fmaf(u.y, wr[c], im);
+                    ffma2_sp(o, u.x, wr[c], wi[c]);             // re += u.x wr, im += u.x wi
+                    ffma2_sp(o, u.y, -wi[c], wr[c]);            // re += -u.y wi, im += u.y wr
                 }
-                vb[br * VP + col] = make_float2(re, im);
+                vb[br * VP + col] = o;
             }
         }
     }
@@ -224,9 +226,9 @@ pfb_synth_kernel(const float* __restrict__ bt, const float* __restrict__ w,
         float h[TPF];
 #pragma unroll
         for (int t = 0; t < TPF; t++) h[t] = bt[br * TPF + t];
-        float ar[R], ai[R];
+        float2 acc[R];                                              // (re, im) pairs: one FFMA2 per tap and output
 #pragma unroll
-        for (int r = 0; r < R; r++) { ar[r] = 0.0f; ai[r] = 0.0f; }
+        for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f);
         const float2* s = vb + br * VP + q * R;                     // s[j] = v_br[n0 + qR - (TPF-1) + j]
 #pragma unroll
         for (int j = 0; j < R + TPF - 1; j++) {
@@ -234,13 +236,13 @@ pfb_synth_kernel(const float* __restrict__ bt, const float* __restrict__ w,
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const int t = r + TPF - 1 - j;
-                if (t >= 0 && t < TPF) { ar[r] = fmaf(h[t], v.x, ar[r]); ai[r] = fmaf(h[t], v.y, ai[r]); }
+                if (t >= 0 && t < TPF) ffma2(acc[r], h[t], v);
             }
         }
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const long long n = n0 + q * R + r;
-            if (n < n_cols) out[n * M + br] = make_float2(ar[r], ai[r]);
+            if (n < n_cols) out[n * M + br] = acc[r];
         }
     }
 }

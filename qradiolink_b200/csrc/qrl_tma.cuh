@@ -21,6 +21,23 @@ template <int OFF> __device__ __forceinline__ float4 lds_f32x4(uint32_t a)
     return v;
 }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+// Packed FP32 pair FMA (sm_100: FFMA2, one issue slot for two IEEE fma): acc.x = fma(s, v.x, acc.x), acc.y = fma(s, v.y, acc.y).
+// Each half is a correctly rounded single fma, so results are bit-identical to two fmaf() calls; a complex sample times a
+// real tap is exactly this shape (the scalar operand is broadcast by the instruction: FFMA2 Rd, Rs.F32, Rv.F32x2, Rd.F32x2).
+__device__ __forceinline__ void ffma2(float2& acc, float s, float2 v)
+{
+    unsigned long long a, b, c;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(s));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(v.x), "f"(v.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(c));
+}
+// acc.x = fma(s, p.x, acc.x), acc.y = fma(s, p.y, acc.y) with a per-half multiplier pair p (DFT butterflies: s * (wr, wi))
+__device__ __forceinline__ void ffma2_sp(float2& acc, float s, float px, float py)
+{
+    ffma2(acc, s, make_float2(px, py));
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -52,6 +52,8 @@ SYMBOLS = {
     "qrl_tx_read": (_i, [_vp, _vp, _l, C.POINTER(_l), _i]),
     "qrl_tx_out_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_l), C.POINTER(_l)]),
     "qrl_tx_launch_count": (_l, [_vp]),
+    "qrl_tx_profile": (_i, [_vp, _i]),
+    "qrl_tx_profile_read": (_i, [_vp, _i, C.POINTER(_d), C.POINTER(_l)]),
     "qrl_firdes_low_pass": (_i, [_d] * 4 + [_i, _vp, _i]),
     "qrl_firdes_low_pass_2": (_i, [_d] * 5 + [_i, _vp, _i]),
     "qrl_firdes_band_pass": (_i, [_d] * 5 + [_i, _vp, _i]),
