@@ -36,6 +36,7 @@ def lib():
         L.qo_rx_destroy.argtypes = [vp]
         L.qo_rx_work.argtypes = [vp, vp, C.c_long]
         L.qo_rx_set_carrier_offset.argtypes = [vp, C.c_double, C.c_double]
+        L.qo_rx_set_param.argtypes = [vp, C.c_int, C.c_double]
         L.qo_rx_port_items.restype = C.c_long
         L.qo_rx_port_items.argtypes = [vp, C.c_int]
         L.qo_rx_port_data.restype = vp
@@ -295,6 +296,11 @@ class Rx:
         iq = np.ascontiguousarray(iq, np.complex64)
         rc = lib().qo_rx_work(self.h, _p(iq), len(iq))
         assert rc == 0
+
+    def set_param(self, key, value):
+        """analog-block setters (keys = qradiolink_b200.PARAM); raises for a block that has no such setter"""
+        if lib().qo_rx_set_param(self.h, int(key), float(value)) != 0:
+            raise ValueError("oracle: no setter %r for this block" % key)
 
     def set_carrier_offset(self, hz, samp_rate=1e6):
         lib().qo_rx_set_carrier_offset(self.h, float(hz), float(samp_rate))

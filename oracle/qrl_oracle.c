@@ -501,6 +501,7 @@ typedef struct {
     unsigned ctr;
     size_t pos;         /* index in `in` of the newest sample for the next output */
     qvec in;
+    size_t hkeep;       /* history kept beyond the taps' own need (filters whose taps a run-time setter may lengthen) */
 } resamp_t;
 
 static void resamp_init(resamp_t* r, int ncomp, int L, int M, const float* taps, int ntaps)
@@ -520,11 +521,34 @@ static void resamp_init(resamp_t* r, int ncomp, int L, int M, const float* taps,
         }
     }
     r->ctr = 0;
+    r->hkeep = 0;
     qv_init(&r->in, sizeof(float) * ncomp);
     qv_push_zero(&r->in, r->nt - 1);
     r->pos = r->nt - 1;
 }
 static void resamp_free(resamp_t* r) { free(r->arm_store); free(r->arm); qv_free(&r->in); }
+/* set_taps of a running filter (L = M = 1 users only): the new taps meet the true sample history from the next output on
+ * (before the first sample: zeros, like GNU Radio's zero history) */
+static void resamp_retap(resamp_t* r, const float* taps, int ntaps)
+{
+    free(r->arm_store); free(r->arm);
+    const int L = r->L;
+    int padded = ((ntaps + L - 1) / L) * L;
+    r->nt = padded / L;
+    r->arm_store = (float*)calloc(padded, sizeof(float));
+    r->arm = (float**)malloc(sizeof(float*) * L);
+    for (int p = 0; p < L; p++) {
+        r->arm[p] = r->arm_store + (size_t)p * r->nt;
+        for (int k = 0; k < r->nt; k++) { int j = p + k * L; r->arm[p][k] = j < ntaps ? taps[j] : 0.0f; }
+    }
+    if (r->pos < (size_t)(r->nt - 1)) {
+        const size_t add = (size_t)(r->nt - 1) - r->pos, isz = r->in.isz, n0 = r->in.n;
+        qv_push_zero(&r->in, add);
+        memmove(r->in.d + add * isz, r->in.d, n0 * isz);
+        memset(r->in.d, 0, add * isz);
+        r->pos += add;
+    }
+}
 static void resamp_work(resamp_t* r, const float* x, size_t n, qvec* out)
 {
     qv_push(&r->in, x, n);
@@ -543,18 +567,32 @@ static void resamp_work(resamp_t* r, const float* x, size_t n, qvec* out)
         r->ctr += r->M;
         while (r->ctr >= (unsigned)r->L) { r->ctr -= r->L; r->pos++; }
     }
-    size_t keep_from = r->pos - (r->nt - 1);
+    const size_t need = (size_t)(r->nt - 1) > r->hkeep ? (size_t)(r->nt - 1) : r->hkeep;
+    size_t keep_from = r->pos > need ? r->pos - need : 0;
     if (keep_from > r->in.n) keep_from = r->in.n;          /* decimation larger than the arm: the next position lies in future input */
     if (keep_from > 0) { qv_drop(&r->in, keep_from); r->pos -= keep_from; }
 }
 
 /* fft_filter_ccc restated in direct form: complex taps, complex stream */
-typedef struct { int nt; float* h; qvec in; size_t pos; } fircc_t;
+typedef struct { int nt; float* h; qvec in; size_t pos; size_t hkeep; } fircc_t;
 static void fircc_init(fircc_t* f, const float* taps_c, int nt)
 {
     f->nt = nt; f->h = (float*)malloc(sizeof(float) * 2 * nt);
     memcpy(f->h, taps_c, sizeof(float) * 2 * nt);
-    qv_init(&f->in, 8); qv_push_zero(&f->in, nt - 1); f->pos = nt - 1;
+    qv_init(&f->in, 8); qv_push_zero(&f->in, nt - 1); f->pos = nt - 1; f->hkeep = 0;
+}
+static void fircc_retap(fircc_t* f, const float* taps_c, int nt)      /* see resamp_retap */
+{
+    free(f->h);
+    f->nt = nt; f->h = (float*)malloc(sizeof(float) * 2 * nt);
+    memcpy(f->h, taps_c, sizeof(float) * 2 * nt);
+    if (f->pos < (size_t)(nt - 1)) {
+        const size_t add = (size_t)(nt - 1) - f->pos, n0 = f->in.n;
+        qv_push_zero(&f->in, add);
+        memmove(f->in.d + add * 8, f->in.d, n0 * 8);
+        memset(f->in.d, 0, add * 8);
+        f->pos += add;
+    }
 }
 static void fircc_free(fircc_t* f) { free(f->h); qv_free(&f->in); }
 static void fircc_work(fircc_t* f, const float* x, size_t n, qvec* out)
@@ -572,7 +610,8 @@ static void fircc_work(fircc_t* f, const float* x, size_t n, qvec* out)
         qv_pushc(out, re, im);
         f->pos++;
     }
-    size_t keep_from = f->pos - (f->nt - 1);
+    const size_t need = (size_t)(f->nt - 1) > f->hkeep ? (size_t)(f->nt - 1) : f->hkeep;
+    size_t keep_from = f->pos > need ? f->pos - need : 0;
     if (keep_from > 0) { qv_drop(&f->in, keep_from); f->pos -= keep_from; }
 }
 
@@ -1058,6 +1097,8 @@ struct qo_rx {
     fircc_t bp[4]; resamp_t symfilt;
     /* ssb */
     fircc_t ssb_bpf; resamp_t ssb_audio; float env_m2, env_m1; qvec s_clip; size_t st_pos;
+    float if_gain;          /* gr_demod_ssb's multiply_const_cc(0.9) (set_gain) */
+    int filter_width, flag;
     /* bpsk / 2fsk */
     fll_t fll; crmm_t crmm; ccdec_t dec2; lfsr_t descr2; int dec2_started;
     /* front-end rotator (gr_demod_base.cpp:57,180,1220-1225): Q32 NCO, phase = base + inc * (n - n_base) */
@@ -1082,6 +1123,7 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
     tabs_init();
     qo_rx* r = (qo_rx*)calloc(1, sizeof *r);
     r->kind = kind;
+    r->if_gain = 0.9f; r->filter_width = filter_width; r->flag = flag;
     rx_common_init(r);
     float* T0 = r->taps_store[0]; float* T1 = r->taps_store[1]; float* T2 = r->taps_store[2]; float* T3 = r->taps_store[3];
     /* gr_demod_gmsk.cpp:30-134 is the 2FSK (fm) chain without the band-edge FLL, with a plain low-pass as symbol filter and
@@ -1328,6 +1370,9 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         r->soft_scale = 64.0f;
         ccdec_init(&r->dec); lfsr_init(&r->descr); ccdec_init(&r->dec2); lfsr_init(&r->descr2);
     } else { free(r); return NULL; }
+    if (r->kind == QO_DEMOD_NBFM || r->kind == QO_DEMOD_WBFM) { r->filt.hkeep = 2048; r->audio_filt.hkeep = 512; }      /* filters a setter may lengthen */
+    if (r->kind == QO_DEMOD_SSB || r->kind == QO_DEMOD_AM) { r->ssb_bpf.hkeep = 2048; }
+    if (r->kind == QO_DEMOD_SSB) r->ssb_audio.hkeep = 512;
     return r;
 }
 void qo_rx_destroy(qo_rx* r)
@@ -1367,6 +1412,50 @@ static void rx_fec_tail_dual(qo_rx* r)
 /* blocks::rotator_cc restated with an exact Q32 phase (inc = rint(-offset/fs * 2^32)): y[n] = x[n] * exp(j*theta_n),
  * theta_n = phase_n * pi / 2^31 (phase as signed 32-bit), sin/cos from qo_sincosf.  GNU Radio's rotator accumulates a
  * float complex phasor (and renormalises every 512 samples); the two agree to ~1e-6. */
+/* Run-time setters of the analog blocks (gr_demod_nbfm.cpp:82-121, gr_demod_ssb.cpp:89-121, gr_demod_am.cpp:84-107,
+ * gr_demod_wbfm.cpp:77-91).  New taps meet the true sample history from the next output on.  Returns 0, or -1 when the block has
+ * no such setter. */
+int qo_rx_set_param(qo_rx* r, int key, double value)
+{
+    static float T[4096]; static float TC[2 * 4096];
+    const int analog = r->kind == QO_DEMOD_NBFM || r->kind == QO_DEMOD_SSB || r->kind == QO_DEMOD_AM || r->kind == QO_DEMOD_WBFM;
+    if (!analog) return -1;
+    if (key == QO_PARAM_SQUELCH_DB) { r->sq.threshold = pow(10.0, value / 10.0); return 0; }        /* squelch_base::set_threshold */
+    if (key == QO_PARAM_AGC_ATTACK && (r->kind == QO_DEMOD_SSB || r->kind == QO_DEMOD_AM)) { r->agc.attack = (float)value; return 0; }
+    if (key == QO_PARAM_AGC_DECAY && (r->kind == QO_DEMOD_SSB || r->kind == QO_DEMOD_AM)) { r->agc.decay = (float)value; return 0; }
+    if (key == QO_PARAM_GAIN && r->kind == QO_DEMOD_SSB) { r->if_gain = (float)value; return 0; }       /* _if_gain->set_k */
+    if (key == QO_PARAM_CTCSS && r->kind == QO_DEMOD_NBFM && value == 0.0) {
+        int n3 = qo_firdes_low_pass_2(1, 8000, 3500, 200, 35, QO_WIN_BLACKMAN_HARRIS, T, 4096);
+        resamp_retap(&r->audio_filt, T, n3);
+        return 0;
+    }
+    if (key == QO_PARAM_FILTER_WIDTH) {
+        const int fw = (int)value;
+        if (fw <= 0) return -1;
+        r->filter_width = fw;
+        if (r->kind == QO_DEMOD_NBFM) {
+            int n = qo_firdes_low_pass(1, r->tsr, fw, 1200, QO_WIN_BLACKMAN_HARRIS, T, 4096);
+            resamp_retap(&r->filt, T, n);
+            r->qd.gain = (float)(r->tsr / (4 * M_PI * fw));
+        } else if (r->kind == QO_DEMOD_WBFM) {
+            int n = qo_firdes_low_pass(1, r->tsr, fw, 1200, QO_WIN_BLACKMAN_HARRIS, T, 4096);
+            resamp_retap(&r->filt, T, n);
+            r->qd.gain = (float)(r->tsr / (2 * M_PI * fw));
+        } else if (r->kind == QO_DEMOD_AM) {
+            int n = qo_firdes_complex_band_pass(1, r->tsr, -fw, fw, 1200, QO_WIN_BLACKMAN_HARRIS, TC, 4096);
+            fircc_retap(&r->ssb_bpf, TC, n);
+        } else {
+            int n = r->flag ? qo_firdes_complex_band_pass_2(1, r->tsr, -fw, -200, 200, 90, QO_WIN_BLACKMAN_HARRIS, TC, 4096)
+                            : qo_firdes_complex_band_pass_2(1, r->tsr, 200, fw, 200, 90, QO_WIN_BLACKMAN_HARRIS, TC, 4096);
+            fircc_retap(&r->ssb_bpf, TC, n);
+            int n3 = qo_firdes_band_pass_2(2, r->tsr, 200, fw, 200, 90, QO_WIN_BLACKMAN_HARRIS, T, 4096);      /* gain 2 here, 1 in the constructor: the reference's */
+            resamp_retap(&r->ssb_audio, T, n3);
+        }
+        return 0;
+    }
+    return -1;
+}
+
 void qo_rx_set_carrier_offset(qo_rx* r, double offset_hz, double samp_rate)
 {
     r->rot_base = r->rot_base + r->rot_inc * (uint32_t)(r->rot_n - r->rot_nbase);
@@ -1448,7 +1537,7 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
     if (r->kind == QO_DEMOD_SSB) {
         r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
         float* v = (float*)r->s_res.d;
-        for (size_t i = 0; i < 2 * r->s_res.n; i++) v[i] = v[i] * 0.9f;                 /* multiply_const_cc(0.9) */
+        for (size_t i = 0; i < 2 * r->s_res.n; i++) v[i] = v[i] * r->if_gain;           /* multiply_const_cc(0.9) (set_gain) */
         r->s_filt.n = 0; fircc_work(&r->ssb_bpf, v, r->s_res.n, &r->s_filt);
         qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
         r->s_tmp.n = 0; squelch_work(&r->sq, (const float*)r->s_filt.d, r->s_filt.n, &r->s_tmp);

@@ -71,6 +71,10 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
 void   qo_rx_destroy(qo_rx*);
 /* feed T complex samples (interleaved float re,im) of ONE channel */
 int    qo_rx_work(qo_rx*, const float* iq, long T);
+/* run-time setters of the analog blocks (set_squelch, set_filter_width, set_ctcss(0), set_agc_attack / decay, set_gain); keys as in
+ * include/qrl_b200.h; 0 = applied, -1 = this block has no such setter */
+enum { QO_PARAM_SQUELCH_DB = 2, QO_PARAM_FILTER_WIDTH = 3, QO_PARAM_CTCSS = 7, QO_PARAM_AGC_ATTACK = 8, QO_PARAM_AGC_DECAY = 9, QO_PARAM_GAIN = 10 };
+int    qo_rx_set_param(qo_rx*, int key, double value);
 /* gr_demod_base::set_carrier_offset: front-end rotator, phase increment 2*pi*(-offset)/samp_rate */
 void   qo_rx_set_carrier_offset(qo_rx*, double offset_hz, double samp_rate);
 /* ports: 0 = filtered IQ (complex), 1 = constellation (complex) or audio (float), 2 = bits, 3 = delayed bits */

@@ -120,7 +120,8 @@ struct qrl_rx : HandleBase {
     int fir_group = 4;                 // stage-1 launches cover this many slices (bigger launches, same pipeline depth)
     Ring r1;
     // stage 2: channel / shaping filter on the complex stream (port 0)
-    float* d_taps2 = nullptr; int ntaps2 = 0;
+    float* d_taps2 = nullptr; int ntaps2 = 0; size_t taps2_cap = 0;     // floats allocated for d_taps2 (set_filter_width redesigns)
+    float if_gain = 0.9f;              // gr_demod_ssb: multiply_const_cc(0.9) in front of the side-band filter (set_gain)
     Ring r2;
     float2* d_port0 = nullptr; long port0_cap = 0; long port0_n = 0;
     // stage 3: quadrature demod + RRC (4FSK-FM)
@@ -170,6 +171,7 @@ struct qrl_rx : HandleBase {
     bool rssi_on = false; float* d_rssi_ring = nullptr; float* d_rssi_y = nullptr; float* d_rssi_db = nullptr; long long rssi_n = 0;
     // QRL_PARAM_OVERLAP_CALLS: the loop / FEC tail of call k runs under the parallel stages of call k+1.  Output ports
     // are double-buffered (alt_* = the buffers of the previous call), ring reuse is fenced slice by slice.
+    bool many = false;                                   // many-channel geometry of the loop kernels (small windows, no SM partition)
     bool overlap = false;
     float2* alt_port0 = nullptr; float2* alt_port1 = nullptr; unsigned char* alt_port2 = nullptr; unsigned char* alt_port3 = nullptr;
     int *alt_port1_cnt = nullptr, *alt_port2_cnt = nullptr, *alt_port3_cnt = nullptr;
@@ -656,6 +658,7 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         std::vector<float> t2(std::max<size_t>(taps2.size(), 512), 0.0f);     // room for set_filter_width redesigns
         std::copy(taps2.begin(), taps2.end(), t2.begin());
         if ((rc = upload_floats(h, &h->d_taps2, t2))) return fail(rc);
+        h->taps2_cap = t2.size();
     }
     if (!taps3.empty() && (rc = upload_floats(h, &h->d_taps3, taps3))) return fail(rc);
     if ((rc = make_ring(h, &h->r1, sizeof(float2), h->n1max + std::max(512, static_cast<int>(taps2.size())) + 8))) return fail(rc);
@@ -804,7 +807,12 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         const int big_ctas = (kind == QRL_DEMOD_QPSK) ? 2 * groups : groups;
         unsigned loop_sms = static_cast<unsigned>(std::min(48, 8 * ((big_ctas + 4 + 7) / 8)));
         if (const char* e = getenv("QRL_LOOP_SMS")) { int v = atoi(e); if (v >= 8 && v <= 64) loop_sms = static_cast<unsigned>(v); }
-        if (!make_sm_partition(h, loop_sms, hi)) {
+        // Many channels (more loop CTAs than a 48-SM partition holds one per SM): the loop kernels have enough warps in flight to
+        // hide their own latency, a private partition would only serialise them.  They then run with small windows (several CTAs
+        // per SM) on all SMs, next to the parallel stages, on priority streams.
+        h->many = big_ctas > 48;
+        if (const char* e = getenv("QRL_MANY_CHANNELS")) h->many = e[0] == '1';
+        if (h->many || !make_sm_partition(h, loop_sms, hi)) {
             h->s_par = nullptr; h->sm_loop = 0; h->sm_par = 0;
             if (h->s_loop == nullptr)
                 ok = cudaStreamCreateWithPriority(&h->s_loop, cudaStreamNonBlocking, hi) == cudaSuccess;
@@ -985,23 +993,60 @@ int qrl_rx_set_param(qrl_rx* h, int channel, int key, double value)
         CK(cudaMemcpy(h->d_rot, h->rot.data(), sizeof(RotState) * h->C, cudaMemcpyHostToDevice));
         return QRL_OK;
     }
-    if (h->kind == QRL_DEMOD_NBFM && key == QRL_PARAM_SQUELCH_DB) {          // gr_demod_nbfm::set_squelch
-        h->nbp.sq_threshold = std::pow(10.0, value / 10.0);
+    // ---- run-time setters of the analog blocks.  Kernel parameters travel by value with every launch, so a plain host-side update is
+    // enough for scalars; new taps are uploaded after everything in flight has drained and meet the true sample history (the rings)
+    // from the next qrl_rx_work on.
+    const bool nbfm = h->kind == QRL_DEMOD_NBFM, ssb = h->kind == QRL_DEMOD_SSB, am = h->kind == QRL_DEMOD_AM, wbfm = h->kind == QRL_DEMOD_WBFM;
+    auto quiesce = [&]() -> int { CK(cudaStreamSynchronize(h->stream)); return rx_join_host(h); };
+    auto upload = [&](float* dst, const std::vector<float>& t) -> int {
+        int rc = quiesce(); if (rc) return rc;
+        CK(cudaMemcpy(dst, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+        return QRL_OK;
+    };
+    if (key == QRL_PARAM_SQUELCH_DB && (nbfm || ssb || am || wbfm)) {
+        // gr_demod_nbfm::set_squelch (:92-95), gr_demod_ssb.cpp:103-106, gr_demod_am.cpp:104-107, gr_demod_wbfm.cpp:88-91: _squelch->set_threshold(dB)
+        const double thr = std::pow(10.0, value / 10.0);
+        if (ssb) h->ssbp.sq_threshold = thr; else h->nbp.sq_threshold = thr;
         return QRL_OK;
     }
-    if (h->kind == QRL_DEMOD_NBFM && key == QRL_PARAM_FILTER_WIDTH) {        // gr_demod_nbfm::set_filter_width (:82-90)
+    if (key == QRL_PARAM_AGC_ATTACK && (ssb || am)) {    // gr_demod_ssb::set_agc_attack (:108-111), gr_demod_am.cpp:94-97
+        if (ssb) h->ssbp.attack = static_cast<float>(value); else h->nbp.agc_attack = static_cast<float>(value);
+        return QRL_OK;
+    }
+    if (key == QRL_PARAM_AGC_DECAY && (ssb || am)) {     // gr_demod_ssb::set_agc_decay (:113-116), gr_demod_am.cpp:99-102
+        if (ssb) h->ssbp.decay = static_cast<float>(value); else h->nbp.agc_decay = static_cast<float>(value);
+        return QRL_OK;
+    }
+    if (key == QRL_PARAM_GAIN && ssb) { h->if_gain = static_cast<float>(value); return QRL_OK; }      // gr_demod_ssb::set_gain (:118-121): _if_gain->set_k
+    if (key == QRL_PARAM_CTCSS && nbfm) {
+        // gr_demod_nbfm::set_ctcss (:97-121).  0 = no tone squelch: the audio filter gets its low-pass taps back (they are the
+        // constructor's).  A tone frequency inserts analog::ctcss_squelch_ff in front of a band-pass audio filter: not built.
+        if (value != 0.0) { set_err(h, "set_ctcss: the tone squelch (analog::ctcss_squelch_ff) is not built; only set_ctcss(0)"); return QRL_EINVAL; }
+        return upload(h->d_audio_taps, low_pass_2(1, 8000, 3500, 200, 35, WIN_BLACKMAN_HARRIS));
+    }
+    if (key == QRL_PARAM_FILTER_WIDTH && (nbfm || ssb || am || wbfm)) {
         const int fw = static_cast<int>(value);
-        std::vector<float> t = low_pass(1, h->tsr, fw, 1200, WIN_BLACKMAN_HARRIS);
-        if (t.size() > 512 || fw <= 0) { set_err(h, "set_filter_width: out of range"); return QRL_EINVAL; }
-        CK(cudaStreamSynchronize(h->stream));
-        CK(cudaMemcpy(h->d_taps2, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
-        h->ntaps2 = static_cast<int>(t.size());
+        if (fw <= 0) { set_err(h, "set_filter_width: out of range"); return QRL_EINVAL; }
+        std::vector<float> t;
+        if (nbfm || wbfm) t = low_pass(1, h->tsr, fw, 1200, WIN_BLACKMAN_HARRIS);                       // gr_demod_nbfm.cpp:82-90, gr_demod_wbfm.cpp:77-85
+        else if (am) t = complex_band_pass(1, h->tsr, -fw, fw, 1200, WIN_BLACKMAN_HARRIS);              // gr_demod_am.cpp:84-92
+        else t = h->flag ? complex_band_pass_2(1, h->tsr, -fw, -200, 200, 90, WIN_BLACKMAN_HARRIS)      // gr_demod_ssb.cpp:89-101
+                         : complex_band_pass_2(1, h->tsr, 200, fw, 200, 90, WIN_BLACKMAN_HARRIS);
+        if (t.size() > h->taps2_cap) { set_err(h, "set_filter_width: out of range (filter longer than the block was sized for)"); return QRL_EINVAL; }
+        int rc = upload(h->d_taps2, t); if (rc) return rc;
+        h->ntaps2 = static_cast<int>(t.size()) / ((ssb || am) ? 2 : 1);
         h->filter_width = fw;
-        h->qd_gain = static_cast<float>(h->tsr / (4 * kPi * fw));
+        if (nbfm) h->qd_gain = static_cast<float>(h->tsr / (4 * kPi * fw));
+        if (wbfm) h->qd_gain = static_cast<float>(h->tsr / (2 * kPi * fw));
         h->nbp.qd_gain = h->qd_gain;
+        if (ssb) {          // the audio band-pass follows the filter width (gain 2 here, 1 in the constructor: the reference's)
+            std::vector<float> a = band_pass_2(2, h->tsr, 200, fw, 200, 90, WIN_BLACKMAN_HARRIS);
+            if (static_cast<int>(a.size()) != h->ssbp.nt_audio) { set_err(h, "set_filter_width: audio filter length changed"); return QRL_EINVAL; }
+            if ((rc = upload(h->d_audio_taps, a))) return rc;
+        }
         return QRL_OK;
     }
-    set_err(h, "qrl_rx_set_param: key " + std::to_string(key) + " not supported for this block yet");
+    set_err(h, "qrl_rx_set_param: key " + std::to_string(key) + " not supported for this block");
     return QRL_EINVAL;
 }
 
@@ -1106,7 +1151,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 fir_ccc_ring_kernel<<<gtile, TB, sizeof(float) * 2 * h->ntaps2, sp>>>(
                     static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
                     static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-                    h->d_taps2, h->ntaps2, 0.9f, k0, k1, h->d_port0, h->port0_cap, k_call0);
+                    h->d_taps2, h->ntaps2, h->if_gain, k0, k1, h->d_port0, h->port0_cap, k_call0);
                 h->launches++;
                 h->prof_end(pe);
             }
@@ -1211,7 +1256,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             if (bpsk) {
                 {   // agc2_cc (Costas bypassed): r2 -> r3
                     constexpr int CH = 128, NST = 3;
-                    const size_t smem = sizeof(float2) * (NST + 2) * CH * 32;
+                    const size_t smem = sizeof(float2) * ((NST + 2) * CH + 1) * 32;      // + one row of padding behind the hand-off blocks
                     auto kern = agc_costas_kernel<CH, NST, 0, 0>;
                     static bool a_attr[16] = { false };    // per device: function attributes belong to the device's context
                     if (!a_attr[h->device & 15]) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a_attr[h->device & 15] = true; }
@@ -1409,18 +1454,24 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
             {
                 pe = h->prof_begin(2, h->s_loop);
-                constexpr int CH = 128, NST = 3;
-                const size_t smem = sizeof(float2) * (NST + 2) * CH * 32;
-                auto kern = (h->acp.order == 4 && h->acp.use_snr) ? agc_costas_kernel<CH, NST, 4, 1> : agc_costas_kernel<CH, NST>;
-                static bool ac_attr[16] = { false };    // per device: function attributes belong to the device's context
-                if (!ac_attr[h->device & 15]) {
-                    CK(cudaFuncSetAttribute(agc_costas_kernel<CH, NST, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    CK(cudaFuncSetAttribute(agc_costas_kernel<CH, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    ac_attr[h->device & 15] = true;
-                }
-                kern<<<groups, 96, smem, h->s_loop>>>(h->acp, h->d_ac, h->C,
-                    static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, k1,
-                    static_cast<float2*>(h->r3.d), h->r3.mask, h->r3.stride);
+                auto run_ac = [&](auto ch_tag) -> int {
+                    constexpr int CH = decltype(ch_tag)::value, NST = 3;
+                    const size_t smem = sizeof(float2) * ((NST + 2) * CH + 1) * 32;      // + one row of padding behind the hand-off blocks
+                    auto kern = (h->acp.order == 4 && h->acp.use_snr) ? agc_costas_kernel<CH, NST, 4, 1> : agc_costas_kernel<CH, NST>;
+                    static bool ac_attr[16] = { false };    // per CH instantiation, per device: function attributes belong to the device's context
+                    if (!ac_attr[h->device & 15]) {
+                        CK(cudaFuncSetAttribute(agc_costas_kernel<CH, NST, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                        CK(cudaFuncSetAttribute(agc_costas_kernel<CH, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                        ac_attr[h->device & 15] = true;
+                    }
+                    kern<<<groups, 96, smem, h->s_loop>>>(h->acp, h->d_ac, h->C,
+                        static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, k1,
+                        static_cast<float2*>(h->r3.d), h->r3.mask, h->r3.stride);
+                    return QRL_OK;
+                };
+                // many channels: 32-row windows (41 KB of shared memory, five CTAs per SM) instead of 128-row ones (164 KB)
+                const int rc_ac = h->many ? run_ac(std::integral_constant<int, 32>{}) : run_ac(std::integral_constant<int, 128>{});
+                if (rc_ac) return rc_ac;
                 h->launches++;
                 h->prof_end(pe);
             }
@@ -1429,19 +1480,27 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             CK(cudaStreamWaitEvent(h->s_loop2, h->ev_c[i], 0));
             {
                 pe = h->prof_begin(3, h->s_loop2);
-                constexpr int CH = 128, NST = 3, NEPI = 1;
-                const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
-                const size_t smem = sizeof(float) * (NST * CH * 64 + SYMSYNC_TAB_FLOATS + 2 * maxs * 64) + sizeof(int) * 64;
-                auto kern = symsync_kernel<2, SL_DQPSK, EPI_QPSK, CH, NST, NEPI>;
-                static bool sq_attr[16] = { false };    // per device: function attributes belong to the device's context
-                if (!sq_attr[h->device & 15]) {
-                    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    sq_attr[h->device & 15] = true;
-                }
-                kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop2>>>(
-                    h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r3.d), h->r3.mask, h->r3.stride, k1,
-                    h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
-                    static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i, nullptr, 0, 0, nullptr);
+                auto run_sq = [&](auto ch_tag, auto nst_tag) -> int {
+                    constexpr int CH = decltype(ch_tag)::value, NST = decltype(nst_tag)::value, NEPI = 1;
+                    const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
+                    const size_t smem = sizeof(float) * (NST * CH * 64 + SYMSYNC_TAB_FLOATS + 2 * maxs * 64) + sizeof(int) * 64;
+                    auto kern = symsync_kernel<2, SL_DQPSK, EPI_QPSK, CH, NST, NEPI>;
+                    static bool sq_attr[16] = { false };    // per (CH, NST) instantiation, per device
+                    if (!sq_attr[h->device & 15]) {
+                        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                        sq_attr[h->device & 15] = true;
+                    }
+                    kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop2>>>(
+                        h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r3.d), h->r3.mask, h->r3.stride, k1,
+                        h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
+                        static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i, nullptr, 0, 0, nullptr);
+                    return QRL_OK;
+                };
+                // many channels: 64-row windows, two stages (~55 KB, four CTAs per SM) instead of 128 x 3 (143 KB)
+                const bool small_win = h->many && symsync_stride(64, h->ssp.lookahead) >= 32;
+                const int rc_sq = small_win ? run_sq(std::integral_constant<int, 64>{}, std::integral_constant<int, 2>{})
+                                            : run_sq(std::integral_constant<int, 128>{}, std::integral_constant<int, 3>{});
+                if (rc_sq) return rc_sq;
                 h->launches++;
                 h->prof_end(pe);
             }

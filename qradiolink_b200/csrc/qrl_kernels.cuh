@@ -693,6 +693,58 @@ __device__ __forceinline__ void qrl_costas4_snr_step(LoopState& st, float alpha,
     yr = orr; yi = oi;
 }
 
+// Rare path of the Costas phase wrap (exact double subtraction), kept out of line so the common path is one compare + branch.
+__device__ __noinline__ float qrl_phase_wrap_slow(float ph)
+{
+    while (ph >= 6.2831854820251465f) ph = static_cast<float>(static_cast<double>(ph) - 2.0 * 3.14159265358979323846);
+    while (ph <= -6.2831854820251465f) ph = static_cast<float>(static_cast<double>(ph) + 2.0 * 3.14159265358979323846);
+    return ph;
+}
+
+// costas_loop_cc(order 4, use_snr) over `n` complex items that sit in shared memory `row_bytes` apart starting at shared address
+// `addr` (one lane = one channel), IN PLACE.  Same values as qrl_costas_step bit for bit; written for a lone warp, where the
+// loop-carried chain phase -> sincos -> rotate -> snr -> tanh table -> error -> phase is everything:
+//   * items and table are addressed by 32-bit shared addresses (no generic-pointer / S2UR address arithmetic in the loop);
+//   * the next item is loaded before the current one is worked on (the 30-cycle LDS leaves the chain);
+//   * the table index floor(128 + 64 x) never passes through an integer register: the float rounded toward -inf onto 2^23 has
+//     the index in its low mantissa bits, and (bits << 2) + (table - (0x4B000000 << 2)) is the entry's address; the table has a
+//     257th entry (= entry 255) so that x = 2 needs no integer clamp;
+//   * the frequency limit is two FMNMX (exact for non-NaN), the 2*pi wrap one unlikely out-of-line call.
+// tanh_addr_m = smem_u32(table of 257 floats) - (0x4B000000u << 2) + (a zero read from shared memory: to the compiler the sum is then
+// an ordinary register value; a visible constant gets re-derived (S2UR + ULEA) or split into two dependent adds inside the loop).
+__device__ __forceinline__ void qrl_costas4_snr_chunk(LoopState& st, float k_a, float k_b, uint32_t addr, uint32_t row_bytes, int n,
+                                                       uint32_t tanh_addr_m)
+{
+    float phase = st.phase, freq = st.freq;
+    float2 x = lds_f32x2<0>(addr);
+    for (int i = 0; i < n; i++) {
+        const float2 xn = lds_f32x2<0>(addr + row_bytes);            // item i + 1 (the block has one row of padding behind it)
+        float sn, cs;
+        qrl_sincosf_small(-phase, sn, cs);
+        const float orr = x.x * cs - x.y * sn;
+        const float oi = x.x * sn + x.y * cs;
+        const float snr = orr * orr + oi * oi;
+        const float ar = snr * orr, ai = snr * oi;
+        // tanhf_lut: x > 2 -> 1, x <= -2 -> -1, else table[(int)(128 + 64 x)]
+        const float vr = 128.0f + 64.0f * fminf(fmaxf(ar, -2.0f), 2.0f);
+        const float vi = 128.0f + 64.0f * fminf(fmaxf(ai, -2.0f), 2.0f);
+        const float tr_ = lds_f32<0>((__float_as_uint(__fadd_rd(vr, 8388608.0f)) << 2) + tanh_addr_m);
+        const float ti_ = lds_f32<0>((__float_as_uint(__fadd_rd(vi, 8388608.0f)) << 2) + tanh_addr_m);
+        const float tr = ar > 2.0f ? 1.0f : (ar <= -2.0f ? -1.0f : tr_);
+        const float ti = ai > 2.0f ? 1.0f : (ai <= -2.0f ? -1.0f : ti_);
+        float err = tr * oi - ti * orr;
+        err = qrl_clip(err, 1.0f);
+        freq = freq + k_b * err;
+        phase = phase + freq + k_a * err;
+        sts_f32x2(addr, orr, oi);
+        if (__builtin_expect(!(fabsf(phase) < 6.2831854820251465f), 0)) phase = qrl_phase_wrap_slow(phase);
+        freq = fminf(fmaxf(freq, -1.0f), 1.0f);
+        addr += row_bytes;
+        x = xn;
+    }
+    st.phase = phase; st.freq = freq;
+}
+
 // ------------------------------------------------------------------------------------------------
 // fll_band_edge_cc (BPSK / 2FSK chains): per-sample NCO rotation + two N-tap complex band-edge filters on the
 // rotated stream + second-order loop.  One lane per channel, channel-major rings, rotated-sample window in shared
@@ -784,10 +836,12 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
 {
     extern __shared__ __align__(128) float2 sm_ac[];          // [NST][CH][32] | hand-off [2][CH][32]
     __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[2], bar_empty[2];
-    __shared__ float tanh_s[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) tanh_s[i] = d_tanh_tab[i];
+    __shared__ float tanh_s[257];                             // entry 256 = entry 255 (see qrl_costas4_snr_chunk)
+    __shared__ volatile int opaque_zero;
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) tanh_s[i] = d_tanh_tab[i < 256 ? i : 255];
+    if (threadIdx.x == 0) opaque_zero = 0;
     float2* stage0 = sm_ac;
-    float2* hand = sm_ac + NST * CH * 32;
+    float2* hand = sm_ac + NST * CH * 32;                     // [2][CH][32] + one row of padding (prefetch of the item behind a block)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
     const int c = g * 32 + lane;
@@ -858,6 +912,7 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
         float2* oring = out + static_cast<long long>(g) * out_stride * 32;
         const long long ocap = static_cast<long long>(out_mask) + 1;
         const float k_a = p.alpha, k_b = p.beta;
+        const uint32_t tanh_m = smem_u32(tanh_s) - (0x4B000000u << 2) + static_cast<uint32_t>(opaque_zero);
         const int order = ORDER >= 0 ? ORDER : p.order;
         const bool use_snr = USE_SNR >= 0 ? (USE_SNR != 0) : (p.use_snr != 0);
         for (int m = 0; m < nchunks; m++) {
@@ -869,12 +924,7 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
             const int n = rem < CH ? static_cast<int>(rem) : CH;
             if (active && order != 0) {
                 if (ORDER == 4 && USE_SNR == 1) {
-                    for (int i = 0; i < n; i++) {
-                        const float2 x = hb[i * 32];
-                        float yr, yi;
-                        qrl_costas4_snr_step(pll, k_a, k_b, x.x, x.y, yr, yi, tanh_s);
-                        hb[i * 32] = make_float2(yr, yi);
-                    }
+                    qrl_costas4_snr_chunk(pll, k_a, k_b, smem_u32(hb), 256u, n, tanh_m);
                 } else {
                     for (int i = 0; i < n; i++) {
                         const float2 x = hb[i * 32];
@@ -956,6 +1006,10 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
     extern __shared__ __align__(128) float sm_sync[];   // [NST][CH][ROWF] | mmse[129*8] | sym[2][maxs][ROWF] | cnt[2][32]
     __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[2], bar_empty[2];
     __shared__ volatile int lane_zero[32];
+    __shared__ float tanh_s[EPI == EPI_QPSK ? 257 : 1];    // second Costas loop's table (entry 256 = entry 255, see qrl_costas4_snr_chunk)
+    __shared__ volatile int opaque_zero;
+    if (EPI == EPI_QPSK) for (int i = threadIdx.x; i < 257; i += blockDim.x) tanh_s[i] = d_tanh_tab[i < 256 ? i : 255];
+    if (threadIdx.x == 0) opaque_zero = 0;
     float* stage0 = sm_sync;
     float* mm = sm_sync + NST * CH * ROWF;
     float* mm2 = mm + 132 * 8;                          // entry-major copy (12-float pitch), taps reversed: two LDS.128
@@ -1309,6 +1363,12 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
             mbar_wait(&bar_full[b], (m >> 1) & 1);
             const int n = cntbuf[b * 32 + lane];
             const float* sy = symbuf + b * blk_rows * ROWF + lane * NCOMP;
+            if (EPI == EPI_QPSK) {
+                // pass 1: the second Costas loop (the only recurrence here) runs over this lane's symbols in place, lean;
+                // pass 2 below is feed-forward (diff_phasor, rotation, soft bits, stores)
+                qrl_costas4_snr_chunk(costas, p.costas_alpha, p.costas_beta, smem_u32(sy), ROWF * 4, active ? n : 0,
+                                      smem_u32(tanh_s) - (0x4B000000u << 2) + static_cast<uint32_t>(opaque_zero));
+            }
             for (int s = e; s < n; s += NEPI) {
                 const float yr = sy[s * ROWF];
                 const float yi = (NCOMP == 2) ? sy[s * ROWF + 1] : 0.0f;
@@ -1333,8 +1393,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                     sb0 = qrl_soft_u8(yr, p.soft_scale);
                     sb1 = qrl_soft_u8(yi, p.soft_scale);
                 } else {
-                    float cr, ci;
-                    qrl_costas_step(costas, p.costas_alpha, p.costas_beta, 4, true, yr, yi, cr, ci);
+                    const float cr = yr, ci = yi;                  // already through the Costas loop (pass 1)
                     const float dr = cr * dp_r + ci * dp_i;
                     const float di = ci * dp_r - cr * dp_i;
                     dp_r = cr; dp_i = ci;
@@ -1473,6 +1532,16 @@ struct ViterbiState {
 // frame; warp 1 does the 80-step traceback, descrambling and the stores for the previous frame.  Decisions are
 // double buffered in shared memory (mbarrier full/empty); the next frame's soft symbols are prefetched into
 // registers during the current ACS.
+//
+// The ACS step is written for a warp whose only business is the loop-carried metric exchange (round 2; 157 -> ~45 cycles):
+//   * the two path metrics of a lane travel as ONE register (two 16-bit halves: a frame adds at most 86 * 31 to the
+//     start value 63, far below 2^16, so the comparisons are those of the 32-bit form): 2 SHFL per step instead of 4,
+//     the half a lane needs comes out with one PRMT whose selector is a per-lane constant;
+//   * the branch metrics do not depend on the path: at the start of a frame the warp turns its 172 soft symbols into 86
+//     words holding the metric of each of the four branch-label classes (b0, b1) in {0, 255}^2; in the loop a lane takes its
+//     class byte with one PRMT from a word that was loaded four steps earlier (LDS.128 per four steps, off the chain);
+//   * new metric = min(x + m, x' + m') is one VIADDMNMX per state; the two ballots of a step leave with one predicated
+//     STS.64; the last six steps' ballots stay in registers for the tail walk; the best end state is one REDUX.MIN.
 template <int CPB /* channels per CTA */>
 __global__ void __launch_bounds__(64 * CPB)
 viterbi_k7_kernel(ViterbiState* __restrict__ vstates, const long long* __restrict__ n_soft_avail, int C,
@@ -1480,17 +1549,18 @@ viterbi_k7_kernel(ViterbiState* __restrict__ vstates, const long long* __restric
                   unsigned char* __restrict__ port2, long long port2_stride, int* __restrict__ port2_cnt, int port2_cap,
                   int delay /* blocks::delay(1) in front of the second decoder: stream index shifted by `delay` */)
 {
-    __shared__ unsigned char syms_all[CPB][2][176];
-    __shared__ unsigned dec0_all[CPB][2][86], dec1_all[CPB][2][86];
+    __shared__ unsigned char syms_all[CPB][176];
+    __shared__ __align__(16) unsigned mw_all[CPB][88];        // per step: metric of label class (b0 ? 2 : 0) | (b1 ? 1 : 0) in byte `class`
+    __shared__ __align__(8) uint2 dec_all[CPB][2][86];        // per step: ballots of d0 (new state 2 lane) and d1 (new state 2 lane + 1)
     __shared__ unsigned endst_all[CPB][2];
     __shared__ unsigned char obits_all[CPB][80];
     __shared__ __align__(8) uint64_t bar_full_all[CPB][2], bar_empty_all[CPB][2];
     const int slot = threadIdx.x >> 6;                       // channel slot inside the CTA (2 warps each)
     const int c = blockIdx.x * CPB + slot;
     const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 1;
-    unsigned char (*syms)[176] = syms_all[slot];
-    unsigned (*dec0)[86] = dec0_all[slot];
-    unsigned (*dec1)[86] = dec1_all[slot];
+    unsigned char* syms = syms_all[slot];
+    unsigned* mw = mw_all[slot];
+    uint2 (*dec)[86] = dec_all[slot];
     unsigned* endst = endst_all[slot];
     unsigned char* obits = obits_all[slot];
     uint64_t* bar_full = bar_full_all[slot];
@@ -1509,9 +1579,11 @@ viterbi_k7_kernel(ViterbiState* __restrict__ vstates, const long long* __restric
 
     if (warp == 0) {
         // ---------------------------------------------------------------- ACS warp
-        // Branchtab bits of butterfly `lane`: parity((2*lane) & poly)
-        const unsigned b0 = (__popc((2u * lane) & 109u) & 1u) ? 255u : 0u;
-        const unsigned b1 = (__popc((2u * lane) & 79u) & 1u) ? 255u : 0u;
+        // branch labels of butterfly `lane`: parity((2*lane) & poly) -> label class and the PRMT selectors of this lane
+        const unsigned l0 = __popc((2u * lane) & 109u) & 1u, l1 = __popc((2u * lane) & 79u) & 1u;
+        const unsigned sel_m = 0x4440u | (l0 * 2u + l1);                 // byte `class` of the metric word, zero extended
+        const unsigned sel_x = (lane & 1) ? 0x4432u : 0x4410u;           // high / low 16-bit half, zero extended
+        const int src0 = lane >> 1, src1 = (lane >> 1) + 16;
         int start_state = vs0.start_state;
         // soft symbols of a frame: absolute indices [rd - 12, rd + 160); each lane carries bytes i = lane + 32 k
         unsigned char pre[6];
@@ -1527,50 +1599,68 @@ viterbi_k7_kernel(ViterbiState* __restrict__ vstates, const long long* __restric
         for (int f = 0; f < nframes; f++) {
             const int b = f & 1;
 #pragma unroll
-            for (int k = 0; k < 6; k++) { const int i = lane + 32 * k; if (i < 172) syms[b][i] = pre[k]; }
+            for (int k = 0; k < 6; k++) { const int i = lane + 32 * k; if (i < 172) syms[i] = pre[k]; }
             if (f + 1 < nframes) fetch(vs0.rd + 160LL * (f + 1));      // latency hidden behind this frame's ACS
+            __syncwarp();
+            // branch metrics of the frame: (((b0 ^ s0) >> 2) + ((b1 ^ s1) >> 2)) >> 2 for the four label classes
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int st = lane + 32 * k;
+                if (st < 86) {
+                    const unsigned s0 = syms[2 * st], s1 = syms[2 * st + 1];
+                    const unsigned a0 = s0 >> 2, a1 = (255u ^ s0) >> 2, c0 = s1 >> 2, c1 = (255u ^ s1) >> 2;
+                    mw[st] = ((a0 + c0) >> 2) | (((a0 + c1) >> 2) << 8) | (((a1 + c0) >> 2) << 16) | (((a1 + c1) >> 2) << 24);
+                }
+            }
             if (f >= 2) mbar_wait(&bar_empty[b], ((f >> 1) - 1) & 1);  // traceback warp released dec[b]
             __syncwarp();
             unsigned ya = 63, yb = 63;                                  // Y[2 lane], Y[2 lane + 1]
             if ((start_state & 63) == 2 * lane) ya = 0;
             if ((start_state & 63) == 2 * lane + 1) yb = 0;
-            const unsigned char* sy = syms[b];
-#pragma unroll 2
-            for (int s = 0; s < 86; s++) {
-                const unsigned xa0 = __shfl_sync(0xffffffffu, ya, lane >> 1);
-                const unsigned xb0 = __shfl_sync(0xffffffffu, yb, lane >> 1);
-                const unsigned xa1 = __shfl_sync(0xffffffffu, ya, (lane >> 1) + 16);
-                const unsigned xb1 = __shfl_sync(0xffffffffu, yb, (lane >> 1) + 16);
-                const unsigned xi = (lane & 1) ? xb0 : xa0;             // X[lane]
-                const unsigned xj = (lane & 1) ? xb1 : xa1;             // X[lane + 32]
-                const unsigned s0 = sy[2 * s], s1 = sy[2 * s + 1];
-                const unsigned metric = (((b0 ^ s0) >> 2) + ((b1 ^ s1) >> 2)) >> 2;
-                const unsigned m0 = xi + metric, m1 = xj + (31u - metric);
-                const unsigned m2 = xi + (31u - metric), m3 = xj + metric;
-                const bool d0 = m0 > m1, d1 = m2 > m3;
-                ya = d0 ? m1 : m0;
-                yb = d1 ? m3 : m2;
-                const unsigned B0 = __ballot_sync(0xffffffffu, d0);
-                const unsigned B1 = __ballot_sync(0xffffffffu, d1);
-                if (lane == 0) { dec0[b][s] = B0; dec1[b][s] = B1; }
+            unsigned P = ya | (yb << 16);
+            unsigned t0[6], t1[6];                                      // ballots of steps 80..85 (tail walk)
+            auto step = [&](const unsigned W, const int s, unsigned& B0, unsigned& B1) {
+                const unsigned v0 = __shfl_sync(0xffffffffu, P, src0);
+                const unsigned v1 = __shfl_sync(0xffffffffu, P, src1);
+                const unsigned xi = __byte_perm(v0, 0u, sel_x);         // X[lane]
+                const unsigned xj = __byte_perm(v1, 0u, sel_x);         // X[lane + 32]
+                const unsigned m = __byte_perm(W, 0u, sel_m), nm = 31u - m;
+                const unsigned m0 = xi + m, m1 = xj + nm, m2 = xi + nm, m3 = xj + m;
+                const unsigned na = __viaddmin_u32(xi, m, m1);          // min(m0, m1)
+                const unsigned nb = __viaddmin_u32(xi, nm, m3);         // min(m2, m3)
+                B0 = __ballot_sync(0xffffffffu, m0 > m1);
+                B1 = __ballot_sync(0xffffffffu, m2 > m3);
+                P = __byte_perm(na, nb, 0x5410u);                       // na | nb << 16
+                if (lane == 0) dec[b][s] = make_uint2(B0, B1);
+            };
+            const uint4* mw4 = reinterpret_cast<const uint4*>(mw);
+#pragma unroll 1
+            for (int s4 = 0; s4 < 20; s4++) {                           // steps 0..79, four per metric-word load
+                const uint4 W = mw4[s4];
+                unsigned B0, B1;
+                step(W.x, 4 * s4 + 0, B0, B1);
+                step(W.y, 4 * s4 + 1, B0, B1);
+                step(W.z, 4 * s4 + 2, B0, B1);
+                step(W.w, 4 * s4 + 3, B0, B1);
+            }
+            {
+                const uint4 Wa = mw4[20]; const uint2 Wb = reinterpret_cast<const uint2*>(mw)[42];
+                step(Wa.x, 80, t0[0], t1[0]); step(Wa.y, 81, t0[1], t1[1]); step(Wa.z, 82, t0[2], t1[2]); step(Wa.w, 83, t0[3], t1[3]);
+                step(Wb.x, 84, t0[4], t1[4]); step(Wb.y, 85, t0[5], t1[5]);
             }
             // best end state: minimum metric, lowest index on ties
-            unsigned key = (ya <= yb) ? ((ya << 6) | (2u * lane)) : ((yb << 6) | (2u * lane + 1u));
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                const unsigned o = __shfl_xor_sync(0xffffffffu, key, off);
-                key = o < key ? o : key;
-            }
-            __syncwarp();
-            // the first 6 traceback steps (bits 79..74) give the state the next frame starts from
+            ya = P & 0xffffu; yb = P >> 16;
+            const unsigned key_l = (ya <= yb) ? ((ya << 6) | (2u * lane)) : ((yb << 6) | (2u * lane + 1u));
+            const unsigned key = __reduce_min_sync(0xffffffffu, key_l);
+            // the first 6 traceback steps (bits 79..74, trellis steps 85..80) give the state the next frame starts from
             unsigned st = key & 63u;
 #pragma unroll
-            for (int nb = 79; nb >= 74; nb--) {
-                const int s = nb + 6;
-                const unsigned k = (((st & 1u) ? dec1[b][s] : dec0[b][s]) >> (st >> 1)) & 1u;
+            for (int j = 5; j >= 0; j--) {
+                const unsigned k = (((st & 1u) ? t1[j] : t0[j]) >> (st >> 1)) & 1u;
                 st = (st >> 1) | (k << 5);
             }
             start_state = static_cast<int>(st);
+            __syncwarp();                                               // lane 0's dec[b][*] stores are ordered before its arrive
             if (lane == 0) { endst[b] = key & 63u; mbar_arrive(&bar_full[b]); }
         }
         if (lane == 0) { vstates[c].start_state = start_state; vstates[c].rd = vs0.rd + 160LL * nframes; }
@@ -1584,11 +1674,18 @@ viterbi_k7_kernel(ViterbiState* __restrict__ vstates, const long long* __restric
             mbar_wait(&bar_full[b], (f >> 1) & 1);
             if (lane == 0) {
                 unsigned st = endst[b];
-                for (int nb = 79; nb >= 0; nb--) {
-                    const int s = nb + 6;
-                    const unsigned k = (((st & 1u) ? dec1[b][s] : dec0[b][s]) >> (st >> 1)) & 1u;
-                    st = (st >> 1) | (k << 5);
-                    obits[nb] = static_cast<unsigned char>(k);
+                // the decision words do not depend on the state: loaded eight steps ahead of the walk
+#pragma unroll 1
+                for (int nb8 = 72; nb8 >= 0; nb8 -= 8) {
+                    uint2 d[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) d[j] = dec[b][nb8 + j + 6];
+#pragma unroll
+                    for (int j = 7; j >= 0; j--) {
+                        const unsigned k = (((st & 1u) ? d[j].y : d[j].x) >> (st >> 1)) & 1u;
+                        st = (st >> 1) | (k << 5);
+                        obits[nb8 + j] = static_cast<unsigned char>(k);
+                    }
                 }
                 mbar_arrive(&bar_empty[b]);
             }
@@ -1668,17 +1765,44 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
 
     // ---- 1. squelch (sequential on thread 0; input tiles staged in shared memory by the whole CTA so the
     //         recurrence never waits on a global load)
+    // Fast path (round 2): while the squelch sits in a stable state (open, or closed) the only recurrence is the power estimate
+    // pwr = alpha |x|^2 + (1 - alpha) pwr (double, two dependent operations per sample).  Thread 0 runs just that over the
+    // tile's |x|^2 (computed by the whole CTA) until the first sample that would change the state; the samples before it
+    // are passed (or dropped) in bulk by all threads, the rest of the tile goes through the full state machine below.
     __shared__ float2 xin[2048];
+    __shared__ float m2s[2048];
+    __shared__ int fast_n, fast_state;
+    __shared__ long long fast_ng0;
+    __shared__ float fast_env;
     for (long long tile0 = st.n_in; tile0 < avail_in; tile0 += 2048) {
         const int nt = (avail_in - tile0) < 2048 ? static_cast<int>(avail_in - tile0) : 2048;
-        for (int j = threadIdx.x; j < nt; j += blockDim.x) xin[j] = x[(tile0 + j) & in_mask];
+        for (int j = threadIdx.x; j < nt; j += blockDim.x) {
+            const float2 v = x[(tile0 + j) & in_mask];
+            xin[j] = v;
+            m2s[j] = v.x * v.x + v.y * v.y;
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             double pwr = st.pwr; int state = st.sq_state, ramped = st.ramped; float env = st.envelope;
             float agc = st.agc_gain; double ix1 = st.iir_x1, iy1 = st.iir_y1;
             long long ng = st.n_gate;
             const double one_m_alpha = 1.0 - p.sq_alpha;
-            for (int j = 0; j < nt; j++) {
+            int j0 = 0;
+            fast_n = 0;
+            if (p.mode != 1 && (state == SQ_UNMUTED || state == SQ_MUTED)) {
+                const bool want = (state == SQ_MUTED);           // the state holds while every sample's mute flag equals `want`
+                const double k_a = p.sq_alpha, k_thr = p.sq_threshold;
+                int j = 0;
+                for (; j < nt; j++) {
+                    const double pn = k_a * static_cast<double>(m2s[j]) + one_m_alpha * pwr;
+                    if ((pn < k_thr) != want) break;
+                    pwr = pn;
+                }
+                fast_n = j; fast_state = state; fast_ng0 = ng; fast_env = env;
+                if (state == SQ_UNMUTED || !p.sq_gate) ng += j;
+                j0 = j;
+            }
+            for (int j = j0; j < nt; j++) {
                 const float2 v = xin[j];
                 const float mag2 = v.x * v.x + v.y * v.y;
                 pwr = p.sq_alpha * static_cast<double>(mag2) + one_m_alpha * pwr;
@@ -1718,6 +1842,17 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
             }
             st.pwr = pwr; st.sq_state = state; st.ramped = ramped; st.envelope = env; st.n_gate = ng;
             if (p.mode == 1) { st.agc_gain = agc; st.iir_x1 = ix1; st.iir_y1 = iy1; }
+        }
+        __syncthreads();
+        {   // bulk part of the tile: open squelch -> items x envelope, closed and not gating -> zeros, closed and gating -> nothing
+            const int n = fast_n;
+            const long long g0 = fast_ng0;
+            if (fast_state == SQ_UNMUTED) {
+                const float env = fast_env;
+                for (int j = threadIdx.x; j < n; j += blockDim.x) { const float2 v = xin[j]; gr_[(g0 + j) & gate_mask] = make_float2(v.x * env, v.y * env); }
+            } else if (!p.sq_gate) {
+                for (int j = threadIdx.x; j < n; j += blockDim.x) gr_[(g0 + j) & gate_mask] = make_float2(0.0f, 0.0f);
+            }
         }
         __syncthreads();
     }

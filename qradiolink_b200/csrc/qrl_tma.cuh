@@ -21,6 +21,11 @@ template <int OFF> __device__ __forceinline__ float4 lds_f32x4(uint32_t a)
     return v;
 }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+template <int OFF> __device__ __forceinline__ float2 lds_f32x2(uint32_t a)
+{
+    float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF)); return v;
+}
+__device__ __forceinline__ void sts_f32x2(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
 // Packed FP32 pair FMA (sm_100: FFMA2, one issue slot for two IEEE fma): acc.x = fma(s, v.x, acc.x), acc.y = fma(s, v.y, acc.y).
 // Each half is a correctly rounded single fma, so results are bit-identical to two fmaf() calls; a complex sample times a
 // real tap is exactly this shape (the scalar operand is broadcast by the instruction: FFMA2 Rd, Rs.F32, Rv.F32x2, Rd.F32x2).

@@ -55,6 +55,20 @@ class RxBlock:
     def set_filter_width(self, width):
         self.set_param(PARAM.FILTER_WIDTH, width)
 
+    def set_ctcss(self, value):
+        """gr_demod_nbfm::set_ctcss: 0 = no tone squelch (the only value built)"""
+        self.set_param(PARAM.CTCSS, value)
+
+    def set_agc_attack(self, value):
+        self.set_param(PARAM.AGC_ATTACK, value)
+
+    def set_agc_decay(self, value):
+        self.set_param(PARAM.AGC_DECAY, value)
+
+    def set_gain(self, value):
+        """gr_demod_ssb::set_gain (IF gain in front of the side-band filter)"""
+        self.set_param(PARAM.GAIN, value)
+
     def set_carrier_offset(self, hz, channel=-1):
         self.set_param(PARAM.CARRIER_OFFSET_HZ, hz, channel)
 

@@ -17,7 +17,7 @@ class KIND:
 
 
 class PARAM:
-    CARRIER_OFFSET_HZ, SQUELCH_DB, FILTER_WIDTH, BB_GAIN, OVERLAP_CALLS, RSSI = 1, 2, 3, 4, 5, 6
+    CARRIER_OFFSET_HZ, SQUELCH_DB, FILTER_WIDTH, BB_GAIN, OVERLAP_CALLS, RSSI, CTCSS, AGC_ATTACK, AGC_DECAY, GAIN = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 
 
 # every symbol include/qrl_b200.h declares: (restype, argtypes)

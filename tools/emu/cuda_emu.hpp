@@ -23,6 +23,9 @@
 #endif
 
 struct float2 { float x, y; };
+struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{ x, y }; }
 static inline float2 make_float2(float x, float y) { return float2{ x, y }; }
 namespace qrl {
 // qrl_tma.cuh's fma.rn.f32x2 (FFMA2) helpers = two independent correctly rounded fma
@@ -195,7 +198,17 @@ static inline int __reduce_min_sync(unsigned mask, int v)
     for (int l = 0; l < 32; l++) if (alive >> l & 1) { const int o = emu_unraw<int>(s[l]); r = o < r ? o : r; }
     return r;
 }
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) { return static_cast<unsigned>(__reduce_min_sync(mask, static_cast<int>(v))); }   // keys < 2^31
 static inline unsigned __activemask() { return emu::activemask(); }
+// __byte_perm(x, y, s): result byte i = byte (nibble i of s) of the 8-byte value y:x
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)
+{
+    const unsigned long long v = (static_cast<unsigned long long>(y) << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= static_cast<unsigned>((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
+static inline unsigned __viaddmin_u32(unsigned a, unsigned b, unsigned c) { const unsigned t = a + b; return t < c ? t : c; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }

@@ -26,6 +26,8 @@ inline void* smem_ptr(uint32_t a) { return reinterpret_cast<void*>(emu::arena_ba
 template <int OFF> inline float lds_f32(uint32_t a) { return *static_cast<const float*>(smem_ptr(a + OFF)); }
 template <int OFF> inline float4 lds_f32x4(uint32_t a) { return *static_cast<const float4*>(smem_ptr(a + OFF)); }
 inline void sts_f32(uint32_t a, float v) { *static_cast<float*>(smem_ptr(a)) = v; }
+template <int OFF> inline float2 lds_f32x2(uint32_t a) { return *static_cast<const float2*>(smem_ptr(a + OFF)); }
+inline void sts_f32x2(uint32_t a, float x, float y) { *static_cast<float2*>(smem_ptr(a)) = make_float2(x, y); }
 inline void mbar_init(uint64_t* bar, int count)
 {
     std::lock_guard<std::mutex> lk(emu::mbar_mu);
