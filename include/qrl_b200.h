@@ -200,6 +200,28 @@ int  qrl_deframer_read(qrl_deframer*, unsigned char* records_host, int* frame_co
 int  qrl_deframer_out_device(qrl_deframer*, void** records, int** frame_counts);
 int  qrl_deframer_sync(qrl_deframer*);
 long qrl_deframer_launch_count(qrl_deframer*);
+/* two candidate streams per channel (the two gr_deframer_bb outputs of a dual-decoder mode): like gr_modem::demodulate
+ * (/root/reference/src/gr_modem.cpp:1066-1085) the LONGER one of a call is deframed, the first on a tie; same stride for both */
+int  qrl_deframer_work2(qrl_deframer*, const unsigned char* bits_a, const int* counts_a, const unsigned char* bits_b, const int* counts_b,
+                        long stride, int on_device);
+/* frames found beyond max_frames since creation, per channel (they are not stored; frame_counts saturates at max_frames) */
+int  qrl_deframer_dropped(qrl_deframer*, int* dropped_host);
+
+/* ---- gr_deframer_bb on the device (/root/reference/src/gr/gr_deframer_bb.cpp:83-185) --------------------------------------------
+ * The bit deframer behind ports 2 / 3 of the dual-decoder modes (BPSK, 2FSK, GMSK: gr_demod_base wires _deframer1/2 = type 1,
+ * _deframer_700_1/2 = type 2, _deframer_10k_1/2 = type 3).  Input as qrl_deframer_work: one bit per byte, [n_channels][stride] with
+ * per-channel counts -- exactly qrl_rx_port_device(handle, 2 or 3, ...).  Output: the stream get_data() hands to gr_modem: for every
+ * sync word found, the word itself MSB first (16 bits, 24 for the End word, 8 for type 2) and the next 64 / 32 / 384 input bits;
+ * [n_channels][out_stride] with per-channel counts, valid until the next call; feed it to qrl_deframer_work(2) on the device. */
+typedef struct qrl_dfbb qrl_dfbb;
+int  qrl_dfbb_create(int modem_type /* 1, 2, 3 */, int n_channels, long max_bits, int device, qrl_dfbb** out);
+int  qrl_dfbb_destroy(qrl_dfbb*);
+int  qrl_dfbb_set_stream(qrl_dfbb*, void* cuda_stream);
+int  qrl_dfbb_work(qrl_dfbb*, const unsigned char* bits, const int* counts, long stride, int on_device);
+int  qrl_dfbb_out_device(qrl_dfbb*, void** bits, long* stride, int** counts);
+int  qrl_dfbb_read(qrl_dfbb*, unsigned char* out_host /* [n_channels][cap] */, long cap, int* counts_host);
+int  qrl_dfbb_sync(qrl_dfbb*);
+long qrl_dfbb_launch_count(qrl_dfbb*);
 
 /* ---- stand-alone kernels exposed for tests / micro-benchmarks ---- */
 /* batched decimating FIR (stage 1 alone): x [C][T] device, y [C][ceil(T/D)] device; zero history */

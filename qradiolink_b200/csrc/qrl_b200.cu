@@ -8,6 +8,7 @@
 #include "../../include/qrl_b200.h"
 #include "qrl_design.hpp"
 #include "qrl_kernels.cuh"
+#include "qrl_handle.hpp"
 
 #include <cuda.h>
 
@@ -48,14 +49,7 @@ unsigned pow2_at_least(long long n)
     return static_cast<unsigned>(c);
 }
 
-struct HandleBase {
-    std::string err;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    long launches = 0;
-    std::vector<void*> allocs;
-};
+using HandleBase = QrlHandleBase;       // qrl_handle.hpp: shared by every handle type of the library
 
 void set_err(HandleBase* h, const std::string& s)
 {
@@ -804,13 +798,16 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         bool ok = true;
         // loop partition: one SM per big-shared-memory loop CTA (4FSK: symbol sync; QPSK: agc/costas + symbol sync)
         const int groups = (h->C + 31) / 32;
-        const int big_ctas = (kind == QRL_DEMOD_QPSK) ? 2 * groups : groups;
+        // analog blocks: one CTA per channel whose thread 0 runs the double-precision recurrences (squelch power, de-emphasis): they want
+        // an SM (its FP64 pipe) each, up to half the machine
+        const bool analog_kind = kind == QRL_DEMOD_NBFM || kind == QRL_DEMOD_SSB || kind == QRL_DEMOD_AM || kind == QRL_DEMOD_WBFM;
+        const int big_ctas = (kind == QRL_DEMOD_QPSK) ? 2 * groups : (analog_kind ? std::min(h->C, 44) : groups);
         unsigned loop_sms = static_cast<unsigned>(std::min(48, 8 * ((big_ctas + 4 + 7) / 8)));
         if (const char* e = getenv("QRL_LOOP_SMS")) { int v = atoi(e); if (v >= 8 && v <= 64) loop_sms = static_cast<unsigned>(v); }
         // Many channels (more loop CTAs than a 48-SM partition holds one per SM): the loop kernels have enough warps in flight to
         // hide their own latency, a private partition would only serialise them.  They then run with small windows (several CTAs
         // per SM) on all SMs, next to the parallel stages, on priority streams.
-        h->many = big_ctas > 48;
+        h->many = big_ctas > 48 || (analog_kind && h->C > 64);
         if (const char* e = getenv("QRL_MANY_CHANNELS")) h->many = e[0] == '1';
         if (h->many || !make_sm_partition(h, loop_sms, hi)) {
             h->s_par = nullptr; h->sm_loop = 0; h->sm_par = 0;
@@ -1125,6 +1122,13 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             const long long kg1 = (Ng * h->L1 + h->D1 - 1) / h->D1;       // outputs i with floor(i M / L) <= N - 1
             pe = h->prof_begin(0, sp);
             int rc = stage1(h, xg, xstride, Tg, kg0, kg1);
+            if (!rc && h->kind == QRL_DEMOD_SSB && kg1 > kg0) {
+                // gr_demod_ssb's multiply_const_cc(_if_gain) sits between the resampler and the side-band filter: the gain is applied
+                // to the samples as they pass (8 ksps), so after set_gain the filter's history keeps the old gain, like the reference's
+                dim3 gs(static_cast<unsigned>((kg1 - kg0 + 255) / 256), h->C);
+                scale2_ring_kernel<<<gs, 256, 0, sp>>>(static_cast<float2*>(h->r1.d), h->r1.mask, h->r1.stride, kg0, kg1, h->if_gain, 1.0f);
+                h->launches++;
+            }
             h->prof_end(pe);
             if (rc) return rc;
             dim3 g((h->H + 127) / 128, h->C);
@@ -1151,7 +1155,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 fir_ccc_ring_kernel<<<gtile, TB, sizeof(float) * 2 * h->ntaps2, sp>>>(
                     static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
                     static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-                    h->d_taps2, h->ntaps2, h->if_gain, k0, k1, h->d_port0, h->port0_cap, k_call0);
+                    h->d_taps2, h->ntaps2, 1.0f, k0, k1, h->d_port0, h->port0_cap, k_call0);
                 h->launches++;
                 h->prof_end(pe);
             }

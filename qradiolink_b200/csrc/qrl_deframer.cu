@@ -14,6 +14,7 @@
 // One warp per channel: 32 bit positions are tested at once (the lane's shift register is rebuilt from a ballot of
 // the 32 bits and the carried register), frames are packed a byte per lane.  State carries across calls.
 #include "../../include/qrl_b200.h"
+#include "qrl_handle.hpp"
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -54,19 +55,28 @@ __device__ __forceinline__ uint32_t match_sync(int sync_class, uint32_t sr)
 __global__ void __launch_bounds__(128)
 deframer_kernel(int C, int sync_class, int bit_buf_len, int rx_frame_length,
                 const unsigned char* __restrict__ bits, long long bits_stride, const int* __restrict__ counts, int fixed_count,
+                const unsigned char* __restrict__ bits2, const int* __restrict__ counts2,      // optional second stream: the longer one is taken
                 DeframerState* __restrict__ states, unsigned char* __restrict__ bit_buf /*[C][bit_buf_len]*/,
-                unsigned char* __restrict__ records, int rec_bytes, int max_frames, int* __restrict__ frame_counts)
+                unsigned char* __restrict__ records, int rec_bytes, int max_frames, int* __restrict__ frame_counts,
+                int* __restrict__ dropped /* [C], cumulative: frames found beyond max_frames */)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= C) return;
     const int c = warp;
     const unsigned char* b = bits + static_cast<long long>(c) * bits_stride;
-    const int n = counts ? counts[c] : fixed_count;
+    int n = counts ? counts[c] : fixed_count;
+    if (bits2) {
+        // gr_modem::demodulate (gr_modem.cpp:1066-1085): of the two deframed streams of a dual-decoder mode the longer one
+        // goes to synchronize(), the first on a tie
+        const int n2 = counts2[c];
+        if (n2 > n) { n = n2; b = bits2 + static_cast<long long>(c) * bits_stride; }
+    }
+    n = n < 0 ? 0 : (static_cast<long long>(n) > bits_stride ? static_cast<int>(bits_stride) : n);     // a count can never exceed the row
     DeframerState st = states[c];
     __syncwarp();         // all lanes hold the state before lane 0 may store it back (n == 0: no collective in between)
     unsigned char* bb = bit_buf + static_cast<long long>(c) * bit_buf_len;
     unsigned char* rec = records + static_cast<long long>(c) * max_frames * rec_bytes;
-    int found = 0;
+    int found = 0, n_dropped = 0;
     int pos = 0;
     while (pos < n) {
         if (!st.sync_found) {
@@ -124,26 +134,92 @@ deframer_kernel(int C, int sync_class, int bit_buf_len, int rx_frame_length,
             pos += take;
             if (complete) {
                 if (found < max_frames) found++;
+                else n_dropped++;
                 st.sync_found = 0; st.shift_reg = 0; st.bit_idx = 0;
             } else st.bit_idx += take;
         }
     }
-    if (lane == 0) { states[c] = st; frame_counts[c] = found; }
+    if (lane == 0) { states[c] = st; frame_counts[c] = found; if (n_dropped) dropped[c] += n_dropped; }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// gr_deframer_bb (/root/reference/src/gr/gr_deframer_bb.cpp:83-185; behind ports 2 / 3 of the dual-decoder modes, gr_demod_base.cpp:
+// _deframer1/2 type 1, _deframer_700_1/2 type 2, _deframer_10k_1/2 type 3) for a batch of channels, quirks included (oracle:
+// qo_dfbb_work, pinned to the reference source in oracle/_ref): bit stream in, {matched sync word MSB first, the next bit_buf_len
+// bits verbatim} stream out.  One warp per channel, same 32-positions-at-once search as above.
+// ----------------------------------------------------------------------------------------------------------------
+struct DfbbState { uint32_t shift_reg; int sync_found, idx; };
+
+__device__ __forceinline__ uint32_t dfbb_match(int type, uint32_t sr)
+{
+    const uint32_t t = type != 2 ? (sr & 0xFFFFu) : (sr & 0xFFu);
+    if (type == 2 && t == 0xB5u) return t;
+    if (t == 0x89EDu || t == 0xED89u || t == 0x98DEu || t == 0xED77u || t == 0x8CC8u) return t;
+    return (sr & 0xFFFFFFu) == 0x4C8A2Bu ? 0x4C8A2Bu : 0u;
+}
+
+__global__ void __launch_bounds__(128)
+dfbb_kernel(int C, int type, int len, const unsigned char* __restrict__ bits, long long bits_stride, const int* __restrict__ counts,
+            DfbbState* __restrict__ states, unsigned char* __restrict__ out, long long out_stride, int* __restrict__ out_counts)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= C) return;
+    const int c = warp;
+    const unsigned char* b = bits + static_cast<long long>(c) * bits_stride;
+    int n = counts[c];
+    n = n < 0 ? 0 : (static_cast<long long>(n) > bits_stride ? static_cast<int>(bits_stride) : n);
+    DfbbState st = states[c];
+    __syncwarp();
+    unsigned char* o = out + static_cast<long long>(c) * out_stride;
+    long long no = 0;
+    int pos = 0;
+    while (pos < n) {
+        if (!st.sync_found) {
+            const int v = min(32, n - pos);
+            const unsigned bit = (lane < v) ? (b[pos + lane] & 1u) : 0u;
+            const uint32_t wr = __brev(__ballot_sync(0xffffffffu, bit));
+            const uint32_t sr = (lane == 31 ? 0u : (st.shift_reg << (lane + 1))) | (wr >> (31 - lane));
+            const uint32_t ty = (lane < v) ? dfbb_match(type, sr) : 0u;
+            const unsigned hit = __ballot_sync(0xffffffffu, ty != 0u);
+            if (hit == 0u) {
+                st.shift_reg = __shfl_sync(0xffffffffu, sr, v - 1);
+                pos += v;
+            } else {
+                const int f = __ffs(hit) - 1;
+                const uint32_t ft = __shfl_sync(0xffffffffu, ty, f);
+                st.shift_reg = __shfl_sync(0xffffffffu, sr, f);
+                const int nb = (type == 1 || type == 3) ? (ft != 0x4C8A2Bu ? 16 : 24) : 8;
+                if (lane < nb && no + lane < out_stride) o[no + lane] = static_cast<unsigned char>((ft >> (nb - 1 - lane)) & 1u);
+                no += nb;
+                st.sync_found = 1; st.idx = 0;
+                pos += f + 1;
+            }
+        } else {
+            const int take = min(len - st.idx, n - pos);
+            for (int i = lane; i < take; i += 32) if (no + i < out_stride) o[no + i] = b[pos + i] & 1u;
+            no += take; pos += take; st.idx += take;
+            if (st.idx >= len) { st.sync_found = 0; st.shift_reg = 0; st.idx = 0; }
+        }
+    }
+    if (lane == 0) { states[c] = st; out_counts[c] = static_cast<int>(no < out_stride ? no : out_stride); }
 }
 
 }  // namespace
 
-struct qrl_deframer {
-    std::string err;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    long launches = 0;
-    std::vector<void*> allocs;
+struct qrl_deframer : QrlHandleBase {
     int sync_class = 0, bit_buf_len = 0, rx_frame_length = 0, C = 0, max_frames = 0, rec_bytes = 0;
     long max_bits = 0;
     DeframerState* d_state = nullptr;
     unsigned char *d_bit_buf = nullptr, *d_records = nullptr, *d_stage = nullptr;
+    unsigned char* d_stage2 = nullptr;
+    int *d_counts = nullptr, *d_stage_counts = nullptr, *d_stage_counts2 = nullptr, *d_dropped = nullptr;
+};
+
+struct qrl_dfbb : QrlHandleBase {
+    int type = 0, len = 0, C = 0;
+    long max_bits = 0, out_stride = 0;
+    DfbbState* d_state = nullptr;
+    unsigned char *d_out = nullptr, *d_stage = nullptr;
     int *d_counts = nullptr, *d_stage_counts = nullptr;
 };
 
@@ -199,7 +275,8 @@ int qrl_deframer_create(int sync_class, int bit_buf_len, int rx_frame_length, in
         !alloc(reinterpret_cast<void**>(&h->d_records), C * max_frames * h->rec_bytes) ||
         !alloc(reinterpret_cast<void**>(&h->d_counts), C * sizeof(int)) ||
         !alloc(reinterpret_cast<void**>(&h->d_stage), C * static_cast<size_t>(max_bits)) ||
-        !alloc(reinterpret_cast<void**>(&h->d_stage_counts), C * sizeof(int)))
+        !alloc(reinterpret_cast<void**>(&h->d_stage_counts), C * sizeof(int)) ||
+        !alloc(reinterpret_cast<void**>(&h->d_dropped), C * sizeof(int)))
         return fail(QRL_ENOMEM, "qrl_deframer_create: device allocation failed");
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(QRL_ECUDA, "create sync failed");
     *out = h;
@@ -209,10 +286,10 @@ int qrl_deframer_create(int sync_class, int bit_buf_len, int rx_frame_length, in
 int qrl_deframer_set_stream(qrl_deframer* h, void* cuda_stream)
 {
     if (!h) return QRL_EINVAL;
-    if (!cuda_stream) return QRL_OK;
     CKD(cudaStreamSynchronize(h->stream));
-    if (h->own_stream) cudaStreamDestroy(h->stream);
-    h->stream = static_cast<cudaStream_t>(cuda_stream); h->own_stream = false;
+    if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    if (cuda_stream) h->stream = static_cast<cudaStream_t>(cuda_stream);
+    else { CKD(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }     // NULL = back to an own stream
     return QRL_OK;
 }
 
@@ -230,10 +307,49 @@ int qrl_deframer_work(qrl_deframer* h, const unsigned char* bits, const int* cou
     }
     const int warps_per_block = 4;
     deframer_kernel<<<(h->C + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, h->stream>>>(
-        h->C, h->sync_class, h->bit_buf_len, h->rx_frame_length, d_bits, d_stride, d_cnt, 0,
-        h->d_state, h->d_bit_buf, h->d_records, h->rec_bytes, h->max_frames, h->d_counts);
+        h->C, h->sync_class, h->bit_buf_len, h->rx_frame_length, d_bits, d_stride, d_cnt, 0, nullptr, nullptr,
+        h->d_state, h->d_bit_buf, h->d_records, h->rec_bytes, h->max_frames, h->d_counts, h->d_dropped);
     h->launches++;
     CKD(cudaGetLastError());
+    return QRL_OK;
+}
+
+int qrl_deframer_work2(qrl_deframer* h, const unsigned char* bits_a, const int* counts_a, const unsigned char* bits_b, const int* counts_b,
+                       long stride, int on_device)
+{
+    if (!h || !bits_a || !counts_a || !bits_b || !counts_b || stride < 0) { qrl_internal_set_err("qrl_deframer_work2: bad argument"); return QRL_EINVAL; }
+    CKD(cudaSetDevice(h->device));
+    const unsigned char *da = bits_a, *db = bits_b; const int *ca = counts_a, *cb = counts_b;
+    if (!on_device) {
+        if (stride > h->max_bits) { qrl_internal_set_err("qrl_deframer_work2: stride exceeds max_bits"); return QRL_ERANGE; }
+        if (!h->d_stage2) {
+            void* p = nullptr;
+            if (cudaMalloc(&p, static_cast<size_t>(h->C) * h->max_bits) != cudaSuccess) { qrl_internal_set_err("qrl_deframer_work2: allocation failed"); return QRL_ENOMEM; }
+            h->allocs.push_back(p); h->d_stage2 = static_cast<unsigned char*>(p);
+            if (cudaMalloc(&p, sizeof(int) * h->C) != cudaSuccess) { qrl_internal_set_err("qrl_deframer_work2: allocation failed"); return QRL_ENOMEM; }
+            h->allocs.push_back(p); h->d_stage_counts2 = static_cast<int*>(p);
+        }
+        CKD(cudaMemcpyAsync(h->d_stage, bits_a, static_cast<size_t>(h->C) * stride, cudaMemcpyHostToDevice, h->stream));
+        CKD(cudaMemcpyAsync(h->d_stage_counts, counts_a, sizeof(int) * h->C, cudaMemcpyHostToDevice, h->stream));
+        CKD(cudaMemcpyAsync(h->d_stage2, bits_b, static_cast<size_t>(h->C) * stride, cudaMemcpyHostToDevice, h->stream));
+        CKD(cudaMemcpyAsync(h->d_stage_counts2, counts_b, sizeof(int) * h->C, cudaMemcpyHostToDevice, h->stream));
+        da = h->d_stage; ca = h->d_stage_counts; db = h->d_stage2; cb = h->d_stage_counts2;
+    }
+    const int warps_per_block = 4;
+    deframer_kernel<<<(h->C + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, h->stream>>>(
+        h->C, h->sync_class, h->bit_buf_len, h->rx_frame_length, da, stride, ca, 0, db, cb,
+        h->d_state, h->d_bit_buf, h->d_records, h->rec_bytes, h->max_frames, h->d_counts, h->d_dropped);
+    h->launches++;
+    CKD(cudaGetLastError());
+    return QRL_OK;
+}
+
+int qrl_deframer_dropped(qrl_deframer* h, int* dropped_host)
+{
+    if (!h || !dropped_host) return QRL_EINVAL;
+    CKD(cudaSetDevice(h->device));
+    CKD(cudaMemcpyAsync(dropped_host, h->d_dropped, sizeof(int) * h->C, cudaMemcpyDeviceToHost, h->stream));
+    CKD(cudaStreamSynchronize(h->stream));
     return QRL_OK;
 }
 
@@ -272,5 +388,107 @@ int qrl_deframer_sync(qrl_deframer* h)
 }
 
 long qrl_deframer_launch_count(qrl_deframer* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------- gr_deframer_bb
+int qrl_dfbb_destroy(qrl_dfbb* h)
+{
+    if (!h) return QRL_EINVAL;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return QRL_OK;
+}
+
+int qrl_dfbb_create(int modem_type, int n_channels, long max_bits, int device, qrl_dfbb** out)
+{
+    if (!out || modem_type < 1 || modem_type > 3 || n_channels < 1 || max_bits < 1) { qrl_internal_set_err("qrl_dfbb_create: bad argument"); return QRL_EINVAL; }
+    *out = nullptr;
+    if (qrl_device_count() <= device) { qrl_internal_set_err("qrl_dfbb_create: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
+    qrl_dfbb* h = new qrl_dfbb();
+    h->type = modem_type; h->len = modem_type == 1 ? 64 : (modem_type == 2 ? 32 : 384);      // gr_deframer_bb.cpp:36-47
+    h->C = n_channels; h->max_bits = max_bits; h->device = device;
+    h->out_stride = max_bits + 32;          // a call emits at most its input plus one sync word whose last bit just arrived
+    auto fail = [&](int rc, const char* what) { qrl_internal_set_err(what); qrl_dfbb_destroy(h); return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(QRL_ECUDA, "cudaSetDevice failed");
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(QRL_ECUDA, "stream create failed");
+    h->own_stream = true;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (cudaMalloc(p, std::max<size_t>(bytes, 16)) != cudaSuccess) return false;
+        h->allocs.push_back(*p);
+        return cudaMemsetAsync(*p, 0, std::max<size_t>(bytes, 16), h->stream) == cudaSuccess;
+    };
+    const size_t C = static_cast<size_t>(n_channels);
+    if (!alloc(reinterpret_cast<void**>(&h->d_state), C * sizeof(DfbbState)) ||
+        !alloc(reinterpret_cast<void**>(&h->d_out), C * static_cast<size_t>(h->out_stride)) ||
+        !alloc(reinterpret_cast<void**>(&h->d_counts), C * sizeof(int)) ||
+        !alloc(reinterpret_cast<void**>(&h->d_stage), C * static_cast<size_t>(max_bits)) ||
+        !alloc(reinterpret_cast<void**>(&h->d_stage_counts), C * sizeof(int)))
+        return fail(QRL_ENOMEM, "qrl_dfbb_create: device allocation failed");
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(QRL_ECUDA, "create sync failed");
+    *out = h;
+    return QRL_OK;
+}
+
+int qrl_dfbb_set_stream(qrl_dfbb* h, void* cuda_stream)
+{
+    if (!h) return QRL_EINVAL;
+    CKD(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    if (cuda_stream) h->stream = static_cast<cudaStream_t>(cuda_stream);
+    else { CKD(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    return QRL_OK;
+}
+
+int qrl_dfbb_work(qrl_dfbb* h, const unsigned char* bits, const int* counts, long stride, int on_device)
+{
+    if (!h || !bits || !counts || stride < 0) { qrl_internal_set_err("qrl_dfbb_work: bad argument"); return QRL_EINVAL; }
+    CKD(cudaSetDevice(h->device));
+    const unsigned char* d_bits = bits; const int* d_cnt = counts;
+    if (stride > h->max_bits) { qrl_internal_set_err("qrl_dfbb_work: stride exceeds max_bits"); return QRL_ERANGE; }
+    if (!on_device) {
+        for (int c = 0; c < h->C; c++) if (counts[c] < 0 || counts[c] > stride) { qrl_internal_set_err("qrl_dfbb_work: bad count"); return QRL_ERANGE; }
+        CKD(cudaMemcpyAsync(h->d_stage, bits, static_cast<size_t>(h->C) * stride, cudaMemcpyHostToDevice, h->stream));
+        CKD(cudaMemcpyAsync(h->d_stage_counts, counts, sizeof(int) * h->C, cudaMemcpyHostToDevice, h->stream));
+        d_bits = h->d_stage; d_cnt = h->d_stage_counts;
+    }
+    const int warps_per_block = 4;
+    dfbb_kernel<<<(h->C + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, h->stream>>>(
+        h->C, h->type, h->len, d_bits, stride, d_cnt, h->d_state, h->d_out, h->out_stride, h->d_counts);
+    h->launches++;
+    CKD(cudaGetLastError());
+    return QRL_OK;
+}
+
+int qrl_dfbb_out_device(qrl_dfbb* h, void** bits, long* stride, int** counts)
+{
+    if (!h) return QRL_EINVAL;
+    if (bits) *bits = h->d_out;
+    if (stride) *stride = h->out_stride;
+    if (counts) *counts = h->d_counts;
+    return QRL_OK;
+}
+
+int qrl_dfbb_read(qrl_dfbb* h, unsigned char* out_host, long cap, int* counts_host)
+{
+    if (!h || !counts_host) return QRL_EINVAL;
+    CKD(cudaSetDevice(h->device));
+    CKD(cudaMemcpyAsync(counts_host, h->d_counts, sizeof(int) * h->C, cudaMemcpyDeviceToHost, h->stream));
+    if (out_host && cap > 0)
+        CKD(cudaMemcpy2DAsync(out_host, static_cast<size_t>(cap), h->d_out, static_cast<size_t>(h->out_stride), static_cast<size_t>(std::min(cap, h->out_stride)), h->C,
+                              cudaMemcpyDeviceToHost, h->stream));
+    CKD(cudaStreamSynchronize(h->stream));
+    return QRL_OK;
+}
+
+int qrl_dfbb_sync(qrl_dfbb* h)
+{
+    if (!h) return QRL_EINVAL;
+    CKD(cudaStreamSynchronize(h->stream));
+    return QRL_OK;
+}
+
+long qrl_dfbb_launch_count(qrl_dfbb* h) { return h ? h->launches : 0; }
 
 }  // extern "C"

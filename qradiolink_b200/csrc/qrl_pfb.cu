@@ -18,6 +18,7 @@
 // There is NO CPU fallback.
 #include "../../include/qrl_b200.h"
 #include "qrl_tma.cuh"
+#include "qrl_handle.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -307,13 +308,7 @@ __global__ void pfb_synth_tail_kernel(int M, int hl, const float2* __restrict__ 
 
 }  // namespace
 
-struct qrl_pfb {
-    std::string err;                    // first member: qrl_last_error(handle) reads it through the common layout
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    long launches = 0;
-    std::vector<void*> allocs;
+struct qrl_pfb : QrlHandleBase {        // err / device / stream / launches / allocs: qrl_handle.hpp
     int kind = 0, M = 0, tpf = 0;
     long max_in = 0;
     float *d_bt = nullptr, *d_w = nullptr;

@@ -87,6 +87,93 @@ class Deframer:
         check(self._L.qrl_deframer_work(self._h, data, cnts, cap.value, 1), self._h, "qrl_deframer_work")
         return self._collect()
 
+    def work2(self, bits_a, bits_b):
+        """Dual-decoder modes: per channel the LONGER of the two candidate streams of this call is deframed, the first on a tie
+        (gr_modem::demodulate, gr_modem.cpp:1066-1085)."""
+        n = max(1, max(len(b) for b in list(bits_a) + list(bits_b)))
+        bufs, cnts = [], []
+        for src in (bits_a, bits_b):
+            buf = np.zeros((self.n_channels, n), np.uint8)
+            cnt = np.zeros(self.n_channels, np.int32)
+            for c, b in enumerate(src):
+                buf[c, :len(b)] = b; cnt[c] = len(b)
+            bufs.append(buf); cnts.append(cnt)
+        check(self._L.qrl_deframer_work2(self._h, bufs[0].ctypes.data_as(C.c_void_p), cnts[0].ctypes.data_as(C.c_void_p),
+                                         bufs[1].ctypes.data_as(C.c_void_p), cnts[1].ctypes.data_as(C.c_void_p), n, 0), self._h, "qrl_deframer_work2")
+        return self._collect()
+
+    def work2_from_dfbb(self, dfbb_a, dfbb_b):
+        """Same, with both candidates still on the GPU (the outputs of two DeframerBB.work_from_rx calls)."""
+        pa, sa, ca = dfbb_a.out_device()
+        pb, sb, cb = dfbb_b.out_device()
+        if sa != sb:
+            raise ValueError("the two gr_deframer_bb handles must have the same max_bits")
+        dfbb_a.sync(); dfbb_b.sync()
+        check(self._L.qrl_deframer_work2(self._h, pa, ca, pb, cb, sa, 1), self._h, "qrl_deframer_work2")
+        return self._collect()
+
+    def dropped(self):
+        """frames found beyond max_frames since creation, per channel"""
+        d = np.zeros(self.n_channels, np.int32)
+        check(self._L.qrl_deframer_dropped(self._h, d.ctypes.data_as(C.c_void_p)), self._h, "qrl_deframer_dropped")
+        return d
+
     @property
     def launches(self):
         return self._L.qrl_deframer_launch_count(self._h)
+
+
+class DeframerBB:
+    """gr_deframer_bb (src/gr/gr_deframer_bb.cpp:83-185) for a batch of channels: modem_type 1 / 2 / 3 as gr_demod_base creates them
+    (_deframer1/2, _deframer_700_1/2, _deframer_10k_1/2).  work() returns, per channel, the bit stream get_data() would hand to gr_modem."""
+
+    def __init__(self, modem_type, n_channels=1, max_bits=1 << 20, device=0):
+        self._L = load_library()
+        self.n_channels, self.max_bits = int(n_channels), int(max_bits)
+        self._h = C.c_void_p()
+        rc = self._L.qrl_dfbb_create(int(modem_type), self.n_channels, self.max_bits, device, C.byref(self._h))
+        if rc != 0:
+            raise QrlError("qrl_dfbb_create failed (%d): %s" % (rc, (self._L.qrl_last_error(None) or b"").decode()))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.qrl_dfbb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self._L.qrl_dfbb_sync(self._h), self._h, "qrl_dfbb_sync")
+
+    def out_device(self):
+        p, s, c = C.c_void_p(), C.c_long(), C.c_void_p()
+        check(self._L.qrl_dfbb_out_device(self._h, C.byref(p), C.byref(s), C.byref(c)), self._h, "qrl_dfbb_out_device")
+        return p, s.value, c
+
+    def _collect(self):
+        cap = self.max_bits + 32
+        out = np.zeros((self.n_channels, cap), np.uint8)
+        cnt = np.zeros(self.n_channels, np.int32)
+        check(self._L.qrl_dfbb_read(self._h, out.ctypes.data_as(C.c_void_p), cap, cnt.ctypes.data_as(C.c_void_p)), self._h, "qrl_dfbb_read")
+        return [out[c, :cnt[c]].copy() for c in range(self.n_channels)]
+
+    def work(self, bits_per_channel):
+        n = max(1, max(len(b) for b in bits_per_channel))
+        buf = np.zeros((self.n_channels, n), np.uint8)
+        cnt = np.zeros(self.n_channels, np.int32)
+        for c, b in enumerate(bits_per_channel):
+            buf[c, :len(b)] = b; cnt[c] = len(b)
+        check(self._L.qrl_dfbb_work(self._h, buf.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), n, 0), self._h, "qrl_dfbb_work")
+        return self._collect()
+
+    def work_from_rx(self, rx, port, collect=True):
+        """Deframe what the last rx.work() left on bit port 2 / 3 without leaving the GPU."""
+        data, cap, cnts = C.c_void_p(), C.c_long(), C.c_void_p()
+        check(self._L.qrl_rx_port_device(rx._h, port, C.byref(data), C.byref(cap), C.byref(cnts)), rx._h, "qrl_rx_port_device")
+        rx.sync()
+        check(self._L.qrl_dfbb_work(self._h, data, cnts, cap.value, 1), self._h, "qrl_dfbb_work")
+        return self._collect() if collect else None

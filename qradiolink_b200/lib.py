@@ -80,6 +80,16 @@ SYMBOLS = {
     "qrl_deframer_out_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "qrl_deframer_sync": (_i, [_vp]),
     "qrl_deframer_launch_count": (_l, [_vp]),
+    "qrl_deframer_work2": (_i, [_vp, _vp, _vp, _vp, _vp, _l, _i]),
+    "qrl_deframer_dropped": (_i, [_vp, _vp]),
+    "qrl_dfbb_create": (_i, [_i, _i, _l, _i, C.POINTER(_vp)]),
+    "qrl_dfbb_destroy": (_i, [_vp]),
+    "qrl_dfbb_set_stream": (_i, [_vp, _vp]),
+    "qrl_dfbb_work": (_i, [_vp, _vp, _vp, _l, _i]),
+    "qrl_dfbb_out_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_l), C.POINTER(_vp)]),
+    "qrl_dfbb_read": (_i, [_vp, _vp, _l, _vp]),
+    "qrl_dfbb_sync": (_i, [_vp]),
+    "qrl_dfbb_launch_count": (_l, [_vp]),
 }
 
 
