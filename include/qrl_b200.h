@@ -178,7 +178,8 @@ long qrl_pfb_launch_count(qrl_pfb*);
 
 /* ---- layer-1 deframer on the device -------------------------------------------------
  * Replaces gr_modem::synchronize / findSync / packBytes (/root/reference/src/gr_modem.cpp:1119-1282, 980-994) for a
- * batch of channels; sync words /root/reference/src/layer1framing.h:8-24.  sync_class: 1 = "1K" modes (0xB5),
+ * batch of channels; sync words /root/reference/src/layer1framing.h:8-24.  sync_class: 4 = M17 (0x55F7 / 0xFF5D / 32-bit 0x555D555D,
+ * gr_modem.cpp:1187-1207; bit_buf_len 46 * 8, rx_frame_length 46), 1 = "1K" modes (0xB5),
  * 2 = narrow modes (0xED89 voice + 24-bit text / proto / video / callsign / end), 3 = wide modes QPSK250K /
  * QPSKVideo / 4FSK100K (IP / video / end).  bit_buf_len / rx_frame_length as gr_modem::toggleRxMode sets them
  * (gr_modem.cpp:203-322), e.g. 64 / 7 for 4FSK-2k, 1517*8 / 1516 for QPSK-250k.  Input: one decoded bit per byte,
@@ -206,6 +207,14 @@ int  qrl_deframer_work2(qrl_deframer*, const unsigned char* bits_a, const int* c
                         long stride, int on_device);
 /* frames found beyond max_frames since creation, per channel (they are not stored; frame_counts saturates at max_frames) */
 int  qrl_deframer_dropped(qrl_deframer*, int* dropped_host);
+
+/* ---- TX framing: gr_modem::frame (/root/reference/src/gr_modem.cpp:904-961) for a batch of channels -----------------------------------
+ * payload [n_channels][payload_stride] with per-channel lengths and frame types (the sync words of layer1framing.h:8-24) ->
+ * out [n_channels][out_stride] + lengths: [10 x 0xAA for an IP frame when burst_ip] + sync word (voice: 0xB5 when one_k_mode, else 0xED89
+ * + reserved 0xAA; text / video / IP / proto: 24-bit word; other types: none) + payload -- the bytes qrl_tx_work takes.  on_device = 1:
+ * all pointers are device pointers, the call is asynchronous on cuda_stream; 0: host pointers, synchronous. */
+int  qrl_frame_build(int n_channels, const unsigned char* payload, long payload_stride, const int* payload_len, const unsigned* frame_type,
+                     int one_k_mode, int burst_ip, unsigned char* out, long out_stride, int* out_len, int on_device, int device, void* cuda_stream);
 
 /* ---- gr_deframer_bb on the device (/root/reference/src/gr/gr_deframer_bb.cpp:83-185) --------------------------------------------
  * The bit deframer behind ports 2 / 3 of the dual-decoder modes (BPSK, 2FSK, GMSK: gr_demod_base wires _deframer1/2 = type 1,

@@ -95,6 +95,8 @@ def lib():
         L.qo_deframer_work.restype = C.c_long
         L.qo_deframer_work.argtypes = [vp, vp, C.c_long, vp, C.c_int, C.c_long]
         L.qo_deframer_modem_sync.argtypes = [vp]
+        L.qo_frame.restype = C.c_long
+        L.qo_frame.argtypes = [vp, C.c_long, C.c_uint32, C.c_int, C.c_int, vp, C.c_long]
         L.qo_pfb_channelizer_create.restype = vp
         L.qo_pfb_channelizer_create.argtypes = [C.c_int, vp, C.c_int]
         L.qo_pfb_synthesizer_create.restype = vp
@@ -424,6 +426,14 @@ class Deframer:
     @property
     def modem_sync(self):
         return lib().qo_deframer_modem_sync(self._h)
+
+
+def frame(payload, frame_type, one_k_mode=False, burst_ip=False):
+    """gr_modem::frame (gr_modem.cpp:904-961): bytes that go to the modulator for one frame"""
+    payload = np.ascontiguousarray(np.frombuffer(bytes(payload), np.uint8))
+    out = np.zeros(len(payload) + 16, np.uint8)
+    n = lib().qo_frame(_p(payload), len(payload), int(frame_type), int(one_k_mode), int(burst_ip), _p(out), len(out))
+    return out[:n].copy()
 
 
 class DeframerBB:

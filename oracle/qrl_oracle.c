@@ -2254,11 +2254,13 @@ long qo_pfb_synthesizer_work(qo_pfb* p, const float* in, long n, long stride, fl
  * collected, packed MSB first and handed on with the frame type; then the shift register is cleared.
  * sync_class selects the findSync branch: 1 = "1K" modes (8-bit 0xB5 only; gr_modem.cpp:1208-1221),
  * 2 = narrow modes (16-bit voice 0xED89, 24-bit text / proto / video / callsign / end; :1222-1257),
- * 3 = wide modes QPSK250K / QPSKVideo / 4FSK100K (24-bit IP / video / end; :1258-1274).
+ * 3 = wide modes QPSK250K / QPSKVideo / 4FSK100K (24-bit IP / video / end; :1258-1274),
+ * 4 = M17 (16-bit link-setup 0x55F7 / stream 0xFF5D, 32-bit end of transmission 0x555D555D; :1187-1207).
  * Lengths follow synchronize(): for classes 2, 3 a voice frame takes bit_buf_len bits into rx_frame_length + 1 bytes,
  * any other frame bit_buf_len - 8 bits into rx_frame_length bytes; class 1 always bit_buf_len bits (:1146-1167). */
 enum { QO_FT_NONE = 0, QO_FT_VOICE = 0xED89, QO_FT_VOICE1 = 0xB5, QO_FT_TEXT = 0x89EDAA, QO_FT_IP = 0xDE98AA, QO_FT_VIDEO = 0x98DEAA,
-       QO_FT_CALLSIGN = 0x8CC8DD, QO_FT_PROTO = 0xED77AA, QO_FT_END = 0x4C8A2B };
+       QO_FT_CALLSIGN = 0x8CC8DD, QO_FT_PROTO = 0xED77AA, QO_FT_END = 0x4C8A2B,
+       QO_FT_M17_STREAM = 0xFF5D, QO_FT_M17_LSF = 0x55F7, QO_FT_M17_EOT = 0x555D555D };       /* layer1framing.h:21-23 */
 struct qo_deframer {
     int sync_class, bit_buf_len, rx_frame_length;
     uint64_t shift_reg; int sync_found; uint32_t cur_type; int bit_idx; int modem_sync;
@@ -2283,6 +2285,15 @@ static uint32_t deframer_find_sync(qo_deframer* d, unsigned bit)
     if (d->sync_class == 1) {
         t = d->shift_reg & 0xFF;
         if (t == QO_FT_VOICE1) { d->sync_found = 1; return QO_FT_VOICE1; }
+        return QO_FT_NONE;
+    }
+    if (d->sync_class == 4) {
+        /* ModemTypeM17 (gr_modem.cpp:1187-1207): 16-bit link-setup / stream words, else the 32-bit end-of-transmission word */
+        t = d->shift_reg & 0xFFFF;
+        if (t == QO_FT_M17_LSF) { d->sync_found = 1; return QO_FT_M17_LSF; }
+        if (t == QO_FT_M17_STREAM) { d->sync_found = 1; return QO_FT_M17_STREAM; }
+        t = d->shift_reg & 0xFFFFFFFFull;
+        if (t == QO_FT_M17_EOT) { d->sync_found = 1; return QO_FT_M17_EOT; }
         return QO_FT_NONE;
     }
     if (d->sync_class == 2) {
@@ -2311,7 +2322,7 @@ long qo_deframer_work(qo_deframer* d, const uint8_t* bits, long n, uint8_t* reco
         if (d->sync_found) {
             d->bit_buf[d->bit_idx++] = bits[i] & 1;
             int frame_length = d->rx_frame_length, bit_len = d->bit_buf_len;
-            if (d->sync_class != 1) {
+            if (d->sync_class != 1 && d->sync_class != 4) {      /* the "1K" modes and M17 always take bit_buf_len bits (gr_modem.cpp:1146-1167) */
                 if (d->cur_type == QO_FT_VOICE) frame_length++;     /* reserved byte */
                 else bit_len = d->bit_buf_len - 8;
             }
@@ -2386,6 +2397,26 @@ long qo_dfbb_work(qo_dfbb* d, const uint8_t* bits, long n, uint8_t* out, long ca
         }
     }
     return no < cap ? no : cap;
+}
+
+/* ------------------------------------------------------------------ gr_modem::frame (TX framing)
+ * /root/reference/src/gr_modem.cpp:904-961: [10 x 0xAA when an IP frame goes out in burst mode] + the frame type's sync word
+ * (voice: 0xB5 for the "1K" modes, else 0xED89 + the reserved byte 0xAA; text / video / IP / proto: their 24-bit words; any other
+ * type: nothing) + the payload.  Returns the number of bytes written (at most cap). */
+long qo_frame(const uint8_t* payload, long n, uint32_t frame_type, int one_k_mode, int burst_ip, uint8_t* out, long cap)
+{
+    long k = 0;
+#define QO_PUT(v) do { if (k < cap) out[k] = (uint8_t)(v); k++; } while (0)
+    if (frame_type == QO_FT_IP && burst_ip) for (int i = 0; i < 10; i++) QO_PUT(0xAA);
+    if (frame_type == QO_FT_VOICE) {
+        if (one_k_mode) QO_PUT(QO_FT_VOICE1 & 0xFF);
+        else { QO_PUT((QO_FT_VOICE >> 8) & 0xFF); QO_PUT(QO_FT_VOICE & 0xFF); QO_PUT(0xAA); }
+    } else if (frame_type == QO_FT_TEXT || frame_type == QO_FT_VIDEO || frame_type == QO_FT_IP || frame_type == QO_FT_PROTO) {
+        QO_PUT((frame_type >> 16) & 0xFF); QO_PUT((frame_type >> 8) & 0xFF); QO_PUT(frame_type & 0xFF);
+    }
+    for (long i = 0; i < n; i++) QO_PUT(payload[i]);
+#undef QO_PUT
+    return k < cap ? k : cap;
 }
 
 /* ------------------------------------------------------------------ RSSI tap

@@ -128,6 +128,8 @@ qo_deframer* qo_deframer_create(int sync_class, int bit_buf_len, int rx_frame_le
 void  qo_deframer_destroy(qo_deframer*);
 long  qo_deframer_work(qo_deframer*, const uint8_t* bits, long n, uint8_t* records, int rec_bytes, long max_frames);
 int   qo_deframer_modem_sync(const qo_deframer*);
+/* gr_modem::frame (gr_modem.cpp:904-961): sync word (+ burst preamble for IP frames) in front of a payload */
+long  qo_frame(const uint8_t* payload, long n, uint32_t frame_type, int one_k_mode, int burst_ip, uint8_t* out, long cap);
 
 /* ---- in-tree reference blocks as stand-alone functions (the chains above call the same code); pinned bit for bit against the
  *      reference sources compiled into oracle/_ref (tests/test_oracle_ref.py) ---- */

@@ -391,6 +391,46 @@ int make_ring(qrl_rx* h, Ring* r, size_t isz, long long min_items, bool interlea
     return rc;
 }
 
+// low-rate stream filters: register-tiled instances for real calls, the one-thread-per-output kernels for slivers
+int launch_fir_ccf(qrl_rx* h, cudaStream_t st, const float2* in, unsigned in_mask, long long in_stride, float2* out, unsigned out_mask, long long out_stride,
+                   const float* taps, int ntaps, long long a0, long long a1, float2* lin, long long lin_stride, long long lin_base, int interleaved)
+{
+    const long long n = a1 - a0;
+    if (n <= 0) return QRL_OK;
+    constexpr int K = 8, NT = 128, TILE = K * NT;
+    const int span = TILE + ntaps - 1;
+    const size_t smem = sizeof(float) * ((ntaps + 1) & ~1) + sizeof(float2) * (span + (span >> 4) + 2);
+    if (n >= 256 && smem <= 48 * 1024) {
+        dim3 g(static_cast<unsigned>((n + TILE - 1) / TILE), h->C);
+        fir_ccf_ring_tiled_kernel<K, NT><<<g, NT, smem, st>>>(in, in_mask, in_stride, out, out_mask, out_stride, taps, ntaps, a0, a1, lin, lin_stride, lin_base, interleaved);
+    } else {
+        dim3 g(static_cast<unsigned>((n + 255) / 256), h->C);
+        fir_ccf_ring_kernel<<<g, 256, sizeof(float) * ntaps, st>>>(in, in_mask, in_stride, out, out_mask, out_stride, taps, ntaps, a0, a1, lin, lin_stride, lin_base, interleaved);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return QRL_OK;
+}
+int launch_qdemod_fir(qrl_rx* h, cudaStream_t st, const float2* in, unsigned in_mask, long long in_stride, float* out, unsigned out_mask, long long out_stride,
+                      const float* taps, int ntaps, float gain, long long a0, long long a1)
+{
+    const long long n = a1 - a0;
+    if (n <= 0) return QRL_OK;
+    constexpr int K = 8, NT = 128, TILE = K * NT;
+    const int span = TILE + ntaps - 1;
+    const size_t smem = sizeof(float) * (ntaps + span + (span >> 5) + 2);
+    if (n >= 256 && smem <= 48 * 1024) {
+        dim3 g(static_cast<unsigned>((n + TILE - 1) / TILE), h->C);
+        qdemod_fir_fff_tiled_kernel<K, NT><<<g, NT, smem, st>>>(in, in_mask, in_stride, out, out_mask, out_stride, taps, ntaps, gain, a0, a1);
+    } else {
+        dim3 g(static_cast<unsigned>((n + 255) / 256), h->C);
+        qdemod_fir_fff_kernel<<<g, 256, sizeof(float) * (2 * ntaps + 256), st>>>(in, in_mask, in_stride, out, out_mask, out_stride, taps, ntaps, gain, a0, a1, nullptr, 0);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return QRL_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -1197,11 +1237,9 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         if (h->kind == QRL_DEMOD_NBFM || h->kind == QRL_DEMOD_WBFM) {
             if (n_new > 0) {
                 pe = h->prof_begin(1, sp);
-                fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->ntaps2, sp>>>(
-                    static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
-                    static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-                    h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, 0);
-                h->launches++;
+                { int rc = launch_fir_ccf(h, sp, static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
+                                          static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                                          h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, 0); if (rc) return rc; }
                 h->prof_end(pe);
             }
             CK(cudaEventRecord(h->ev_a[i], sp));
@@ -1234,17 +1272,13 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             if (n_new > 0) {
                 // ---- channel filter / RRC on the FLL output -> port 0 (+ ring: channel-major for 2FSK, interleaved for BPSK)
                 pe = h->prof_begin(2, h->s_loop);
-                fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->ntaps2, h->s_loop>>>(
-                    static_cast<const float2*>(fin.d), fin.mask, fin.stride,
-                    static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-                    h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, bpsk ? 1 : 0);
-                h->launches++;
+                { int rc = launch_fir_ccf(h, h->s_loop, static_cast<const float2*>(fin.d), fin.mask, fin.stride,
+                                          static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                                          h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, bpsk ? 1 : 0); if (rc) return rc; }
                 if (!bpsk && h->flag) {
-                    qdemod_fir_fff_kernel<<<gtile, TB, sizeof(float) * (2 * h->ntaps3 + TB), h->s_loop>>>(
-                        static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-                        static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
-                        h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
-                    h->launches++;
+                    { int rc = launch_qdemod_fir(h, h->s_loop, static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                                                 static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
+                                                 h->d_taps3, h->ntaps3, h->qd_gain, k0, k1); if (rc) return rc; }
                 } else if (!bpsk) {
                     fsk_bank_kernel<2><<<gtile, TB, sizeof(float) * 4 * h->nt_bank, h->s_loop>>>(
                         static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, h->d_bank_taps, h->nt_bank, k0, k1,
@@ -1313,11 +1347,9 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             if (n_new > 0) {
                 // ---- stage 2: channel filter -> ring + port 0
                 pe = h->prof_begin(1, sp);
-                fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->ntaps2, sp>>>(
-                    static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
-                    static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-                    h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, 0);
-                h->launches++;
+                { int rc = launch_fir_ccf(h, sp, static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride,
+                                          static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                                          h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, 0); if (rc) return rc; }
                 h->prof_end(pe);
                 // ---- stage 3: quadrature demod + RRC   |   band-pass bank + discriminator + symbol filter
                 // overlapped calls: this slice overwrites ring slots the previous call's symbol sync (slices i, i+1) read
@@ -1331,11 +1363,9 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                 }
                 pe = h->prof_begin(2, sp);
                 if (h->flag) {
-                    qdemod_fir_fff_kernel<<<gtile, TB, sizeof(float) * (2 * h->ntaps3 + TB), sp>>>(
-                        static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-                        static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
-                        h->d_taps3, h->ntaps3, h->qd_gain, k0, k1, nullptr, 0);
-                    h->launches++;
+                    { int rc = launch_qdemod_fir(h, sp, static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                                                 static_cast<float*>(h->r4.d), h->r4.mask, h->r4.stride,
+                                                 h->d_taps3, h->ntaps3, h->qd_gain, k0, k1); if (rc) return rc; }
                     if (h->dmr) {      // gr_demod_dmr.cpp:103: the symbol filter output is port 3
                         ring_to_port_f32_kernel<<<dim3(static_cast<unsigned>((k1 - k0 + 31) / 32), groups), dim3(32, 8), 0, sp>>>(
                             static_cast<const float*>(h->r4.d), h->r4.mask, h->r4.stride, h->C, k0, k1,
@@ -1346,11 +1376,10 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
                     fsk_bank_kernel<4><<<gtile, TB, sizeof(float) * 8 * h->nt_bank, sp>>>(
                         static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, h->d_bank_taps, h->nt_bank, k0, k1,
                         static_cast<float*>(h->rbank.d), h->rbank.mask, h->rbank.stride);
-                    fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->nt_symf, sp>>>(
-                        static_cast<const float2*>(h->rbank.d), h->rbank.mask, h->rbank.stride,
-                        static_cast<float2*>(h->r3.d), h->r3.mask, h->r3.stride,
-                        h->d_symf_taps, h->nt_symf, k0, k1, nullptr, 0, 0, 1);
-                    h->launches += 2;
+                    h->launches++;
+                    { int rc = launch_fir_ccf(h, sp, static_cast<const float2*>(h->rbank.d), h->rbank.mask, h->rbank.stride,
+                                              static_cast<float2*>(h->r3.d), h->r3.mask, h->r3.stride,
+                                              h->d_symf_taps, h->nt_symf, k0, k1, nullptr, 0, 0, 1); if (rc) return rc; }
                 }
                 h->prof_end(pe);
             }
@@ -1446,11 +1475,9 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             if (n_new > 0) {
                 // ---- stage 2: RRC shaping filter -> interleaved ring + port 0
                 pe = h->prof_begin(1, sp);
-                fir_ccf_ring_kernel<<<gtile, TB, sizeof(float) * h->ntaps2, sp>>>(
-                    shaping_in, shaping_mask, shaping_stride,
-                    static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
-                    h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, 1);
-                h->launches++;
+                { int rc = launch_fir_ccf(h, sp, shaping_in, shaping_mask, shaping_stride,
+                                          static_cast<float2*>(h->r2.d), h->r2.mask, h->r2.stride,
+                                          h->d_taps2, h->ntaps2, k0, k1, h->d_port0, h->port0_cap, k_call0, 1); if (rc) return rc; }
                 h->prof_end(pe);
             }
             CK(cudaEventRecord(h->ev_a[i], sp));

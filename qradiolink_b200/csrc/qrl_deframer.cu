@@ -6,7 +6,7 @@
 // { type, length, payload } do.  Semantics are the reference's, bit for bit (oracle: qo_deframer_work):
 //   * a shift register searches for a sync word; class 1 ("1K" modes) 8-bit 0xB5; class 2 (narrow modes) 16-bit 0xED89
 //     first, then the 24-bit text / proto / video / callsign / end words; class 3 (QPSK250K, QPSKVideo, 4FSK100K) the
-//     24-bit IP / video / end words;
+//     24-bit IP / video / end words; class 4 (M17) the 16-bit link-setup / stream words, then the 32-bit end-of-transmission word;
 //   * after a sync the next bit_len bits are collected and packed MSB first; classes 2, 3: voice frames take
 //     bit_buf_len bits into rx_frame_length + 1 bytes, all others bit_buf_len - 8 bits into rx_frame_length bytes;
 //   * then the shift register is cleared (a sync word cannot straddle the end of a frame);
@@ -29,7 +29,8 @@ void qrl_internal_set_err(const std::string& s);
 namespace {
 
 enum : uint32_t { FT_VOICE = 0xED89, FT_VOICE1 = 0xB5, FT_TEXT = 0x89EDAA, FT_IP = 0xDE98AA, FT_VIDEO = 0x98DEAA,
-                  FT_CALLSIGN = 0x8CC8DD, FT_PROTO = 0xED77AA, FT_END = 0x4C8A2B };
+                  FT_CALLSIGN = 0x8CC8DD, FT_PROTO = 0xED77AA, FT_END = 0x4C8A2B,
+                  FT_M17_STREAM = 0xFF5D, FT_M17_LSF = 0x55F7, FT_M17_EOT = 0x555D555D };     // layer1framing.h:21-23
 
 struct DeframerState {
     uint32_t shift_reg;
@@ -42,6 +43,11 @@ struct DeframerState {
 __device__ __forceinline__ uint32_t match_sync(int sync_class, uint32_t sr)
 {
     if (sync_class == 1) return (sr & 0xFFu) == FT_VOICE1 ? FT_VOICE1 : 0u;
+    if (sync_class == 4) {          // ModemTypeM17 (gr_modem.cpp:1187-1207)
+        const uint32_t t16 = sr & 0xFFFFu;
+        if (t16 == FT_M17_LSF || t16 == FT_M17_STREAM) return t16;
+        return sr == FT_M17_EOT ? FT_M17_EOT : 0u;
+    }
     const uint32_t t24 = sr & 0xFFFFFFu;
     if (sync_class == 2) {
         if ((sr & 0xFFFFu) == FT_VOICE) return FT_VOICE;
@@ -102,7 +108,7 @@ deframer_kernel(int C, int sync_class, int bit_buf_len, int rx_frame_length,
             }
         } else {
             int frame_length = rx_frame_length, bit_len = bit_buf_len;
-            if (sync_class != 1) {
+            if (sync_class != 1 && sync_class != 4) {
                 if (st.cur_type == FT_VOICE) frame_length++;
                 else bit_len = bit_buf_len - 8;
             }
@@ -206,6 +212,31 @@ dfbb_kernel(int C, int type, int len, const unsigned char* __restrict__ bits, lo
 
 }  // namespace
 
+// gr_modem::frame (/root/reference/src/gr_modem.cpp:904-961) for a batch of channels: sync word (+ 10 x 0xAA in front of an IP frame in
+// burst mode) + payload -> the byte vector gr_byte_source hands to the modulator.  One CTA per channel.
+__global__ void __launch_bounds__(128)
+frame_build_kernel(int C, const unsigned char* __restrict__ payload, long long payload_stride, const int* __restrict__ payload_len,
+                   const unsigned* __restrict__ frame_type, int one_k_mode, int burst_ip,
+                   unsigned char* __restrict__ out, long long out_stride, int* __restrict__ out_len)
+{
+    const int c = blockIdx.x;
+    if (c >= C) return;
+    const unsigned ft = frame_type[c];
+    const int n = payload_len[c];
+    unsigned char hdr[13]; int nh = 0;
+    if (ft == FT_IP && burst_ip) for (int i = 0; i < 10; i++) hdr[nh++] = 0xAA;
+    if (ft == FT_VOICE) {
+        if (one_k_mode) hdr[nh++] = static_cast<unsigned char>(FT_VOICE1 & 0xFF);
+        else { hdr[nh++] = static_cast<unsigned char>((FT_VOICE >> 8) & 0xFF); hdr[nh++] = static_cast<unsigned char>(FT_VOICE & 0xFF); hdr[nh++] = 0xAA; }
+    } else if (ft == FT_TEXT || ft == FT_VIDEO || ft == FT_IP || ft == FT_PROTO) {
+        hdr[nh++] = static_cast<unsigned char>((ft >> 16) & 0xFF); hdr[nh++] = static_cast<unsigned char>((ft >> 8) & 0xFF); hdr[nh++] = static_cast<unsigned char>(ft & 0xFF);
+    }
+    unsigned char* o = out + static_cast<long long>(c) * out_stride;
+    const unsigned char* p = payload + static_cast<long long>(c) * payload_stride;
+    for (int i = threadIdx.x; i < nh + n; i += blockDim.x) if (i < out_stride) o[i] = i < nh ? hdr[i] : p[i - nh];
+    if (threadIdx.x == 0) out_len[c] = static_cast<int>(nh + n < out_stride ? nh + n : out_stride);
+}
+
 struct qrl_deframer : QrlHandleBase {
     int sync_class = 0, bit_buf_len = 0, rx_frame_length = 0, C = 0, max_frames = 0, rec_bytes = 0;
     long max_bits = 0;
@@ -249,7 +280,7 @@ int qrl_deframer_destroy(qrl_deframer* h)
 int qrl_deframer_create(int sync_class, int bit_buf_len, int rx_frame_length, int n_channels, long max_bits, int max_frames,
                         int device, qrl_deframer** out)
 {
-    if (!out || sync_class < 1 || sync_class > 3 || bit_buf_len < 16 || (bit_buf_len & 7) || rx_frame_length < 1 || n_channels < 1 ||
+    if (!out || sync_class < 1 || sync_class > 4 || bit_buf_len < 16 || (bit_buf_len & 7) || rx_frame_length < 1 || n_channels < 1 ||
         max_bits < 1 || max_frames < 1) {
         qrl_internal_set_err("qrl_deframer_create: bad argument");
         return QRL_EINVAL;
@@ -388,6 +419,36 @@ int qrl_deframer_sync(qrl_deframer* h)
 }
 
 long qrl_deframer_launch_count(qrl_deframer* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------- gr_modem::frame
+int qrl_frame_build(int n_channels, const unsigned char* payload, long payload_stride, const int* payload_len, const unsigned* frame_type,
+                    int one_k_mode, int burst_ip, unsigned char* out, long out_stride, int* out_len, int on_device, int device, void* cuda_stream)
+{
+    if (n_channels < 1 || !payload || !payload_len || !frame_type || !out || !out_len || payload_stride < 0 || out_stride < 1) {
+        qrl_internal_set_err("qrl_frame_build: bad argument"); return QRL_EINVAL;
+    }
+    if (qrl_device_count() <= device) { qrl_internal_set_err("qrl_frame_build: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
+    auto ck = [](cudaError_t e, const char* what) { if (e != cudaSuccess) { qrl_internal_set_err(std::string(what) + ": " + cudaGetErrorString(e)); return false; } return true; };
+    if (!ck(cudaSetDevice(device), "cudaSetDevice")) return QRL_ECUDA;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (on_device) {
+        frame_build_kernel<<<n_channels, 128, 0, st>>>(n_channels, payload, payload_stride, payload_len, frame_type, one_k_mode, burst_ip, out, out_stride, out_len);
+        return ck(cudaGetLastError(), "frame_build_kernel") ? QRL_OK : QRL_ECUDA;
+    }
+    const size_t C = static_cast<size_t>(n_channels);
+    unsigned char *d_p = nullptr, *d_o = nullptr; int *d_l = nullptr, *d_ol = nullptr; unsigned* d_t = nullptr;
+    bool ok = ck(cudaMalloc(&d_p, std::max<size_t>(16, C * payload_stride)), "cudaMalloc") && ck(cudaMalloc(&d_o, C * out_stride), "cudaMalloc") &&
+              ck(cudaMalloc(&d_l, C * 4), "cudaMalloc") && ck(cudaMalloc(&d_ol, C * 4), "cudaMalloc") && ck(cudaMalloc(&d_t, C * 4), "cudaMalloc");
+    if (ok) ok = ck(cudaMemcpyAsync(d_p, payload, C * payload_stride, cudaMemcpyHostToDevice, st), "copy") &&
+                 ck(cudaMemcpyAsync(d_l, payload_len, C * 4, cudaMemcpyHostToDevice, st), "copy") && ck(cudaMemcpyAsync(d_t, frame_type, C * 4, cudaMemcpyHostToDevice, st), "copy");
+    if (ok) {
+        frame_build_kernel<<<n_channels, 128, 0, st>>>(n_channels, d_p, payload_stride, d_l, d_t, one_k_mode, burst_ip, d_o, out_stride, d_ol);
+        ok = ck(cudaGetLastError(), "frame_build_kernel") && ck(cudaMemcpyAsync(out, d_o, C * out_stride, cudaMemcpyDeviceToHost, st), "copy") &&
+             ck(cudaMemcpyAsync(out_len, d_ol, C * 4, cudaMemcpyDeviceToHost, st), "copy") && ck(cudaStreamSynchronize(st), "sync");
+    }
+    cudaFree(d_p); cudaFree(d_o); cudaFree(d_l); cudaFree(d_ol); cudaFree(d_t);
+    return ok ? QRL_OK : QRL_ECUDA;
+}
 
 // ---------------------------------------------------------------------------------------------- gr_deframer_bb
 int qrl_dfbb_destroy(qrl_dfbb* h)

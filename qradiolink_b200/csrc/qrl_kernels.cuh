@@ -371,6 +371,152 @@ __global__ void fir_ccf_ring_kernel(const float2* __restrict__ in, unsigned in_m
     if (lin) lin[static_cast<long long>(c) * lin_stride + (a - lin_base)] = y;
 }
 
+// Register-tiled form of fir_ccf_ring_kernel (round 2): one CTA = NT * K consecutive outputs of one channel.  The tile's samples
+// (+ ntaps - 1 of history) and the taps sit in shared memory; thread t owns K consecutive outputs and walks the samples oldest
+// first, so every sample is loaded once (one LDS.64) and meets K taps that slide through a register window (one broadcast LDS.32
+// per step): 2 LDS per K FFMA2 instead of 2 loads per FFMA2.  Per output the accumulation order is the ring kernel's (tap index
+// descending = oldest sample first): results are bit-identical.  Sample index i lives at i + i / 16 (one pad slot per 16): the K-strided
+// LDS.64 of a half-warp then hit distinct bank pairs.
+template <int K, int NT>
+__global__ void __launch_bounds__(NT)
+fir_ccf_ring_tiled_kernel(const float2* __restrict__ in, unsigned in_mask, long long in_stride,
+                          float2* __restrict__ out, unsigned out_mask, long long out_stride,
+                          const float* __restrict__ taps, int ntaps, long long a0, long long a1,
+                          float2* __restrict__ lin, long long lin_stride, long long lin_base, int out_interleaved)
+{
+    extern __shared__ __align__(16) float sm_tl[];
+    constexpr int TILE = K * NT;
+    float* hs = sm_tl;                                                    // ntaps floats (rounded up to even)
+    float2* xs = reinterpret_cast<float2*>(sm_tl + ((ntaps + 1) & ~1));   // (TILE + ntaps - 1) samples, padded layout
+    const int c = blockIdx.y;
+    const long long tile0 = a0 + static_cast<long long>(blockIdx.x) * TILE;
+    if (tile0 >= a1) return;
+    const float2* x = in + static_cast<long long>(c) * in_stride;
+    for (int i = threadIdx.x; i < ntaps; i += NT) hs[i] = taps[i];
+    const int span = TILE + ntaps - 1;
+    for (int i = threadIdx.x; i < span; i += NT) xs[i + (i >> 4)] = x[(tile0 - (ntaps - 1) + i) & in_mask];
+    __syncthreads();
+    float2 acc[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) acc[i] = make_float2(0.0f, 0.0f);
+    const int base = K * threadIdx.x;                  // xs index of the oldest sample of my output 0
+    // step t meets sample base + t with tap j = i + (ntaps - 1) - t for output i; w[i] holds that tap (slides by one per step)
+    float w[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) w[i] = 0.0f;
+    // head: t = 0 .. K-2, outputs i <= t are inside the filter
+#pragma unroll
+    for (int t = 0; t < K - 1; t++) {
+#pragma unroll
+        for (int i = K - 1; i > 0; i--) w[i] = w[i - 1];
+        w[0] = hs[ntaps - 1 - t];
+        const int idx = base + t;
+        const float2 v = xs[idx + (idx >> 4)];
+#pragma unroll
+        for (int i = 0; i <= t; i++) ffma2(acc[i], w[i], v);
+    }
+    // main: t = K-1 .. ntaps-1, all K outputs
+    for (int t = K - 1; t < ntaps; t++) {
+#pragma unroll
+        for (int i = K - 1; i > 0; i--) w[i] = w[i - 1];
+        w[0] = hs[ntaps - 1 - t];
+        const int idx = base + t;
+        const float2 v = xs[idx + (idx >> 4)];
+#pragma unroll
+        for (int i = 0; i < K; i++) ffma2(acc[i], w[i], v);
+    }
+    // tail: t = ntaps .. ntaps+K-2, outputs i >= t - (ntaps - 1)
+#pragma unroll
+    for (int u = 1; u < K; u++) {
+#pragma unroll
+        for (int i = K - 1; i > 0; i--) w[i] = w[i - 1];
+        const int idx = base + ntaps - 1 + u;
+        const float2 v = xs[idx + (idx >> 4)];
+#pragma unroll
+        for (int i = u; i < K; i++) ffma2(acc[i], w[i], v);
+    }
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        const long long a = tile0 + base + i;
+        if (a >= a1) break;
+        if (out_interleaved) out[(static_cast<long long>(c >> 5) * out_stride + (a & out_mask)) * 32 + (c & 31)] = acc[i];
+        else out[static_cast<long long>(c) * out_stride + (a & out_mask)] = acc[i];
+        if (lin) lin[static_cast<long long>(c) * lin_stride + (a - lin_base)] = acc[i];
+    }
+}
+
+// quadrature_demod_cf + real FIR, register-tiled like the kernel above (K outputs per thread, taps through a register window).
+// The CTA first demodulates its tile + ntaps - 1 of history into shared memory, then filters from there.
+template <int K, int NT>
+__global__ void __launch_bounds__(NT)
+qdemod_fir_fff_tiled_kernel(const float2* __restrict__ in, unsigned in_mask, long long in_stride,
+                            float* __restrict__ out, unsigned out_mask, long long out_stride,
+                            const float* __restrict__ taps, int ntaps, float gain, long long a0, long long a1)
+{
+    extern __shared__ __align__(16) float sm_tl[];
+    constexpr int TILE = K * NT;
+    float* hs = sm_tl;                         // ntaps
+    float* ds = sm_tl + ntaps;                 // TILE + ntaps - 1 demodulated samples, index i at i + i / 32
+    const int c = blockIdx.y;
+    const long long tile0 = a0 + static_cast<long long>(blockIdx.x) * TILE;
+    if (tile0 >= a1) return;
+    const float2* x = in + static_cast<long long>(c) * in_stride;
+    for (int i = threadIdx.x; i < ntaps; i += NT) hs[i] = taps[i];
+    const int span = TILE + ntaps - 1;
+    for (int i = threadIdx.x; i < span; i += NT) {
+        const long long n = tile0 - (ntaps - 1) + i;       // absolute demod index
+        float d = 0.0f;
+        if (n >= 0 && n < a1) {
+            const float2 cur = x[n & in_mask];
+            float2 prev = make_float2(0.0f, 0.0f);
+            if (n >= 1) prev = x[(n - 1) & in_mask];
+            const float re = cur.x * prev.x + cur.y * prev.y;
+            const float im = cur.y * prev.x - cur.x * prev.y;
+            d = gain * qrl_fast_atan2f(im, re);
+        }
+        ds[i + (i >> 5)] = d;
+    }
+    __syncthreads();
+    float acc[K], w[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) { acc[i] = 0.0f; w[i] = 0.0f; }
+    const int base = K * threadIdx.x;
+#pragma unroll
+    for (int t = 0; t < K - 1; t++) {
+#pragma unroll
+        for (int i = K - 1; i > 0; i--) w[i] = w[i - 1];
+        w[0] = hs[ntaps - 1 - t];
+        const int idx = base + t;
+        const float v = ds[idx + (idx >> 5)];
+#pragma unroll
+        for (int i = 0; i <= t; i++) acc[i] = fmaf(w[i], v, acc[i]);
+    }
+    for (int t = K - 1; t < ntaps; t++) {
+#pragma unroll
+        for (int i = K - 1; i > 0; i--) w[i] = w[i - 1];
+        w[0] = hs[ntaps - 1 - t];
+        const int idx = base + t;
+        const float v = ds[idx + (idx >> 5)];
+#pragma unroll
+        for (int i = 0; i < K; i++) acc[i] = fmaf(w[i], v, acc[i]);
+    }
+#pragma unroll
+    for (int u = 1; u < K; u++) {
+#pragma unroll
+        for (int i = K - 1; i > 0; i--) w[i] = w[i - 1];
+        const int idx = base + ntaps - 1 + u;
+        const float v = ds[idx + (idx >> 5)];
+#pragma unroll
+        for (int i = u; i < K; i++) acc[i] = fmaf(w[i], v, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        const long long a = tile0 + base + i;
+        if (a >= a1) break;
+        out[(static_cast<long long>(c >> 5) * out_stride + (a & out_mask)) * 32 + (c & 31)] = acc[i];
+    }
+}
+
 // quadrature_demod_cf fused in front of a real FIR (RRC shaping filter): in = complex ring, out = float ring.
 // Each CTA demodulates its tile (+ntaps-1 halo) into shared memory, then filters from there.
 __global__ void qdemod_fir_fff_kernel(const float2* __restrict__ in, unsigned in_mask, long long in_stride,
@@ -726,8 +872,10 @@ __device__ __forceinline__ void qrl_costas4_snr_chunk(LoopState& st, float k_a, 
         const float snr = orr * orr + oi * oi;
         const float ar = snr * orr, ai = snr * oi;
         // tanhf_lut: x > 2 -> 1, x <= -2 -> -1, else table[(int)(128 + 64 x)]
-        const float vr = 128.0f + 64.0f * fminf(fmaxf(ar, -2.0f), 2.0f);
-        const float vi = 128.0f + 64.0f * fminf(fmaxf(ai, -2.0f), 2.0f);
+        // 128 + 64 clamp(x, -2, 2) == clamp(fma(64, x, 128), 0, 256): 64 x is exact, so the fused form rounds once like the separate add,
+        // and the affine map is monotonic (one dependent operation less)
+        const float vr = fminf(fmaxf(fmaf(64.0f, ar, 128.0f), 0.0f), 256.0f);
+        const float vi = fminf(fmaxf(fmaf(64.0f, ai, 128.0f), 0.0f), 256.0f);
         const float tr_ = lds_f32<0>((__float_as_uint(__fadd_rd(vr, 8388608.0f)) << 2) + tanh_addr_m);
         const float ti_ = lds_f32<0>((__float_as_uint(__fadd_rd(vi, 8388608.0f)) << 2) + tanh_addr_m);
         const float tr = ar > 2.0f ? 1.0f : (ar <= -2.0f ? -1.0f : tr_);
@@ -737,7 +885,15 @@ __device__ __forceinline__ void qrl_costas4_snr_chunk(LoopState& st, float k_a, 
         freq = freq + k_b * err;
         phase = phase + freq + k_a * err;
         sts_f32x2(addr, orr, oi);
-        if (__builtin_expect(!(fabsf(phase) < 6.2831854820251465f), 0)) phase = qrl_phase_wrap_slow(phase);
+        // The 2 pi wrap without a branch (a lone warp pays ~60 cycles per sample for an almost-never-taken one) and without double
+        // precision: for every float a in [C, C + 1.6], C = 6.28318548f (the float just above 2 pi), (float)((double)a - 2 pi) ==
+        // (a - C) + 1.74845553e-7f bit for bit (a - C is exact by Sterbenz, the constant is float(C - 2 pi); checked over ALL 3.4 M
+        // floats of the range in tests/test_host_logic.py); one step moves the phase by at most 1 + alpha, so one wrap is enough.
+        {
+            const float a = fabsf(phase);
+            const float w = (a - 6.2831854820251465f) + 1.7484555314695172e-07f;
+            phase = a >= 6.2831854820251465f ? copysignf(w, phase) : phase;
+        }
         freq = fminf(fmaxf(freq, -1.0f), 1.0f);
         addr += row_bytes;
         x = xn;
@@ -1122,9 +1278,15 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
         const float k_hb = 0.5f * p.beta + zf, k_ha = 0.5f * p.alpha + zf, k128 = 128.0f + zf;
         const float q_minp = p.min_period + zf, q_maxp = p.max_period + zf;
         const float q_f0 = p.fl0 + zf, q_f1 = (p.fl0 + 1.0f) + zf, q_f2 = (p.fl0 + 2.0f) + zf;
-        const uint32_t mm2_b = REP ? smem_u32(mm3) + (lane & 15) * 16 - 0x4B400000u * 512u + static_cast<uint32_t>(zoff)
-                                   : smem_u32(mm2) - 0x4B400000u * 48u + static_cast<uint32_t>(zoff);
+        // the tap-bank base minus the magic-number offset travels through shared memory: as a loaded value it is ONE register to the
+        // compiler; as a visible sum its constant part is re-added behind the index multiply (an extra dependent op per tap load)
+        lane_zero[lane] = static_cast<int>(REP ? smem_u32(mm3) + (lane & 15) * 16 - 0x4B400000u * 512u
+                                               : smem_u32(mm2) - 0x4B400000u * 48u);
+        __syncwarp();
+        const uint32_t mm2_b = static_cast<uint32_t>(lane_zero[lane]);
         const bool lean_ok = p.min_period > fabsf(p.alpha) && p.fl0 >= 1.0f;
+        const bool window_sure = lean_ok && (p.max_period + fabsf(p.alpha) + 1.0f < p.fl0 + 3.0f - 1e-3f) &&
+                                 (p.min_period - fabsf(p.alpha) > p.fl0 + 1e-3f) && p.fl0 == static_cast<float>(p.n0);
         for (int m = 0; m < nchunks; m++) {
             const int st = m % NST, b = m & 1;
             if (m >= 2) mbar_wait(&bar_empty[b], ((m >> 1) - 1) & 1);    // epilogue released this hand-off buffer
@@ -1183,8 +1345,10 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                 uint32_t syp = smem_u32(sy);
                 const uint32_t syp0 = syp;
                 float A = x0, B = x1, Cc = x2, dA = d0, dB = d1, dC = d2;
-                // one symbol; returns true when the lane fell out of the in-lock stride window (generic step taken)
-                auto body = [&](float& n, const float h1, const float h2, float& dn, const float dh1, const float dh2) -> bool {
+                // one symbol; returns true when the lane fell out of the in-lock stride window (generic step taken).
+                // ws_tag = true: the loop constants make that impossible (see window_sure), the check is compiled out.
+                auto body_t = [&](auto ws_tag, float& n, const float h1, const float h2, float& dn, const float dh1, const float dh2) -> bool {
+                    constexpr bool WS = decltype(ws_tag)::value;
                     const uint32_t ta = mm2_b + __float_as_uint(fmaf(mu, k128, 12582912.0f)) * (REP ? 512u : 48u);
                     const uint32_t xa = xb + (__float_as_uint(ofm) << 7);
                     const float ofn = ofm + q_f0;
@@ -1215,11 +1379,13 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                     const float s12 = qrl_ge1(m0, 1.0f) + qrl_ge1(m0, 2.0f);     // == [ph >= n0+1] + [ph >= n0+2] (m0 exact)
                     mu = m0 - s12;
                     ofm = ofn + s12;
-                    if (__builtin_expect(__float_as_uint(m0) >= 0x40400000u, 0)) {    // ph not in [n0, n0+3): generic floor
-                        const float2 g = symsync_generic_step(ph);
-                        mu = g.x;
-                        ofm = (ofn - q_f0) + g.y;
-                        return true;
+                    if (!WS) {
+                        if (__builtin_expect(__float_as_uint(m0) >= 0x40400000u, 0)) {    // ph not in [n0, n0+3): generic floor
+                            const float2 g = symsync_generic_step(ph);
+                            mu = g.x;
+                            ofm = (ofn - q_f0) + g.y;
+                            return true;
+                        }
                     }
                     return false;
                 };
@@ -1228,27 +1394,36 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                 // has a guaranteed symbol left, then each lane finishes under the exact per-lane check.
                 const unsigned amask = __activemask();
                 const float inv_s = 1.0f / static_cast<float>(k_n0 + 2);
-                for (;;) {
-                    const float left = lim - ofm;                      // exact (integers below 2^24)
-                    int ksafe = left >= 0.0f ? static_cast<int>(left * inv_s * 0.999f) + 1 : 0;   // never above the true quotient + 1
-                    ksafe = __reduce_min_sync(amask, ksafe);
-                    if (ksafe == 0) break;
-                    bool fell = false;
-                    for (; ksafe >= 3 && !fell; ksafe -= 3) {
-                        if (body(Cc, A, B, dC, dA, dB)) { const float t = Cc, dt = dC; Cc = B; B = A; A = t; dC = dB; dB = dA; dA = dt; fell = true; }
-                        else if (body(B, Cc, A, dB, dC, dA)) { const float t = B, dt = dB; B = Cc; Cc = A; A = t; dB = dC; dC = dA; dA = dt; fell = true; }
-                        else if (body(A, B, Cc, dA, dB, dC)) fell = true;
+                auto run = [&](auto ws_tag) {
+                    auto body = [&](float& n, const float h1, const float h2, float& dn, const float dh1, const float dh2) -> bool {
+                        return body_t(ws_tag, n, h1, h2, dn, dh1, dh2);
+                    };
+                    for (;;) {
+                        const float left = lim - ofm;                      // exact (integers below 2^24)
+                        int ksafe = left >= 0.0f ? static_cast<int>(left * inv_s * 0.999f) + 1 : 0;   // never above the true quotient + 1
+                        ksafe = __reduce_min_sync(amask, ksafe);
+                        if (ksafe == 0) break;
+                        bool fell = false;
+                        for (; ksafe >= 3 && !fell; ksafe -= 3) {
+                            if (body(Cc, A, B, dC, dA, dB)) { const float t = Cc, dt = dC; Cc = B; B = A; A = t; dC = dB; dB = dA; dA = dt; fell = true; }
+                            else if (body(B, Cc, A, dB, dC, dA)) { const float t = B, dt = dB; B = Cc; Cc = A; A = t; dB = dC; dC = dA; dA = dt; fell = true; }
+                            else if (body(A, B, Cc, dA, dB, dC)) fell = true;
+                        }
+                        for (; ksafe >= 1 && !fell; ksafe--) {
+                            fell = body(Cc, A, B, dC, dA, dB);
+                            const float t = Cc, dt = dC; Cc = B; B = A; A = t; dC = dB; dB = dA; dA = dt;
+                        }
+                        if (__any_sync(amask, fell)) break;
                     }
-                    for (; ksafe >= 1 && !fell; ksafe--) {
-                        fell = body(Cc, A, B, dC, dA, dB);
+                    while (ofm <= lim) {                                   // stragglers (and lanes that fell out of lock)
+                        body(Cc, A, B, dC, dA, dB);
                         const float t = Cc, dt = dC; Cc = B; B = A; A = t; dC = dB; dB = dA; dA = dt;
                     }
-                    if (__any_sync(amask, fell)) break;
-                }
-                while (ofm <= lim) {                                   // stragglers (and lanes that fell out of lock)
-                    body(Cc, A, B, dC, dA, dB);
-                    const float t = Cc, dt = dC; Cc = B; B = A; A = t; dC = dB; dB = dA; dA = dt;
-                }
+                };
+                // With mu in [0, 1) and the instantaneous period in [min_period - |alpha|, max_period + |alpha|], ph = mu + period
+                // lies in [n0, n0 + 3) whenever max_period + |alpha| + 1 < n0 + 3 and min_period - |alpha| > n0 (margins far above
+                // float rounding): the out-of-window test and its branch then leave the per-symbol path altogether.
+                if (window_sure) run(std::true_type{}); else run(std::false_type{});
                 x0 = A; x1 = B; x2 = Cc; d0 = dA; d1 = dB; d2 = dC;
                 o = static_cast<int>(ofm - 8388608.0f);
                 cnt = static_cast<int>((syp - syp0) / (ROWF * 4));

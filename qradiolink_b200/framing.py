@@ -23,6 +23,29 @@ MODE_FRAMING = {
 }
 
 
+SYNC_M17 = 4
+FrameTypeM17Stream, FrameTypeM17LSF, FrameTypeM17EOT = 0xFF5D, 0x55F7, 0x555D555D
+MODE_FRAMING["M17"] = (SYNC_M17, 46 * 8, 46)          # gr_modem.cpp:309-313
+
+
+def frame(payloads, frame_types, one_k_mode=False, burst_ip=False, device=0):
+    """gr_modem::frame (gr_modem.cpp:904-961) for a batch: list of payload bytes + list of frame types -> list of byte arrays for TxBlock.work."""
+    L = load_library()
+    Cn = len(payloads)
+    n = max(1, max(len(p) for p in payloads))
+    buf = np.zeros((Cn, n), np.uint8)
+    lens = np.zeros(Cn, np.int32)
+    for c, p in enumerate(payloads):
+        buf[c, :len(p)] = np.frombuffer(bytes(p), np.uint8); lens[c] = len(p)
+    types = np.asarray(frame_types, np.uint32)
+    out = np.zeros((Cn, n + 16), np.uint8)
+    olen = np.zeros(Cn, np.int32)
+    check(L.qrl_frame_build(Cn, buf.ctypes.data_as(C.c_void_p), n, lens.ctypes.data_as(C.c_void_p), types.ctypes.data_as(C.c_void_p),
+                            int(one_k_mode), int(burst_ip), out.ctypes.data_as(C.c_void_p), n + 16, olen.ctypes.data_as(C.c_void_p), 0, device, None),
+          None, "qrl_frame_build")
+    return [out[c, :olen[c]].copy() for c in range(Cn)]
+
+
 class Deframer:
     def __init__(self, sync_class, bit_buf_len, rx_frame_length, n_channels=1, max_bits=1 << 20, max_frames=None, device=0):
         self._L = load_library()

@@ -82,6 +82,7 @@ SYMBOLS = {
     "qrl_deframer_launch_count": (_l, [_vp]),
     "qrl_deframer_work2": (_i, [_vp, _vp, _vp, _vp, _vp, _l, _i]),
     "qrl_deframer_dropped": (_i, [_vp, _vp]),
+    "qrl_frame_build": (_i, [_i, _vp, _l, _vp, _vp, _i, _i, _vp, _l, _vp, _i, _i, _vp]),
     "qrl_dfbb_create": (_i, [_i, _i, _l, _i, C.POINTER(_vp)]),
     "qrl_dfbb_destroy": (_i, [_vp]),
     "qrl_dfbb_set_stream": (_i, [_vp, _vp]),

@@ -154,3 +154,55 @@ def test_deframer_reports_dropped_frames_and_reverts_streams(qrl):
     assert len(d.work([s])[0]) == 4 and int(d.dropped()[0]) >= 20
     d.set_stream(0)                                   # NULL: back to a stream of its own (include/qrl_b200.h)
     assert len(d.work([s[:10]])[0]) == 0
+
+
+def test_m17_sync_class_matches_oracle(qrl, oracle):
+    """ModemTypeM17 branch of findSync (gr_modem.cpp:1187-1207): link-setup / stream words and the 32-bit end-of-transmission word."""
+    rng = np.random.default_rng(77)
+    C = 3
+    streams = []
+    for c in range(C):
+        parts = [rng.integers(0, 2, 13 + c, dtype=np.uint8)]
+        for k in range(7):
+            w = [[0x55, 0xF7], [0xFF, 0x5D], [0x55, 0x5D, 0x55, 0x5D]][int(rng.integers(0, 3))]
+            parts += [bits_of(w), rng.integers(0, 2, 46 * 8, dtype=np.uint8), rng.integers(0, 2, int(rng.integers(0, 50)), dtype=np.uint8)]
+        streams.append(np.concatenate(parts))
+    want = [oracle.Deframer(4, 46 * 8, 46).work(s) for s in streams]
+    assert sum(len(w) for w in want) >= 15 and {ty for w in want for ty, _ in w} >= {0x55F7, 0xFF5D}
+    d = qrl.Deframer.for_mode("M17", n_channels=C, max_bits=max(len(s) for s in streams))
+    assert d.work(streams) == want
+    d2 = qrl.Deframer.for_mode("M17", n_channels=C, max_bits=512)
+    acc = [[] for _ in range(C)]
+    lo, n = 0, max(len(s) for s in streams)
+    while lo < n:
+        for c, fr in enumerate(d2.work([s[lo:lo + 97] for s in streams])):
+            acc[c] += fr
+        lo += 97
+    assert acc == want
+
+
+def test_tx_frame_matches_oracle_and_round_trips(qrl, oracle):
+    """gr_modem::frame (gr_modem.cpp:904-961) on the device against its oracle restatement, then frame -> CUDA 4FSK TX -> CUDA RX ->
+    device deframer recovers the payloads."""
+    rng = np.random.default_rng(78)
+    types = [0xED89, 0x89EDAA, 0xDE98AA, 0x98DEAA, 0xED77AA, 0x8CC8DD, 0x4C8A2B]
+    payloads = [rng.integers(0, 256, int(rng.integers(1, 60)), dtype=np.uint8).tobytes() for _ in types]
+    for one_k in (False, True):
+        for burst in (False, True):
+            got = qrl.frame(payloads, types, one_k_mode=one_k, burst_ip=burst)
+            for g, p, t in zip(got, payloads, types):
+                assert np.array_equal(g, oracle.frame(p, t, one_k, burst)), (hex(t), one_k, burst)
+    C = 2
+    pl = [[rng.integers(0, 256, 7, dtype=np.uint8).tobytes() for _ in range(20)] for _ in range(C)]
+    data = []
+    for c in range(C):
+        frames = qrl.frame(pl[c], [0xED89] * 20)
+        data.append(np.concatenate([np.full(8, 0xAA, np.uint8)] + frames + [np.full(24, 0xAA, np.uint8)]))
+    tx = qrl.make_gr_mod_4fsk(25, 1000000, 1700, 3500, True, n_channels=C, max_items=len(data[0]))
+    iq = tx.work(np.stack(data)) * 0.8
+    rx = qrl.make_gr_demod_4fsk(5, 1000000, 1700, 3000, True, n_channels=C, max_samples=iq.shape[1])
+    rx.work(iq)
+    fr = qrl.Deframer.for_mode("4FSK2KFM", n_channels=C, max_bits=1 << 16).work_from_rx(rx, port=2)
+    for c in range(C):
+        voice = [p[1:] for ty, p in fr[c] if ty == 0xED89 and len(p) == 8]
+        assert len(set(voice) & set(pl[c])) >= 15

@@ -44,3 +44,21 @@ def test_framing_table_and_port_map_match_the_reference_literals():
         assert F[m] == (framing.SYNC_1K, 4 * 8, 4)
     assert (framing.FrameTypeVoice, framing.FrameTypeVoice1, framing.FrameTypeEnd) == (0xED89, 0xB5, 0x4C8A2B)
     assert pfb.mmdvm_port_map(3) == [0, 1, 2] and pfb.mmdvm_port_map(7) == [0, 1, 2, 3, 9, 8, 7]
+
+
+def test_costas_phase_wrap_in_float_is_exact():
+    """qrl_costas4_snr_chunk wraps the loop phase without double precision: (a - C) + float(C - 2 pi) must equal the oracle's
+    (float)((double)a - 2 pi) for EVERY float a the loop can hold when it wraps (|a| in [C, C + 1 + alpha], C = 6.28318548f)."""
+    C = np.float32(6.2831854820251465)
+    twopi = 2.0 * 3.14159265358979323846
+    n = 3_400_000                                             # all floats from C up to 7.90 (> C + 1.6)
+    a = (np.uint32(C.view(np.uint32)) + np.arange(n, dtype=np.uint32)).view(np.float32)
+    assert a[0] == C and a[-1] > C + np.float32(1.6)
+    want = (a.astype(np.float64) - twopi).astype(np.float32)
+    delta = np.float32(float(C) - twopi)
+    assert delta == np.float32(1.7484555314695172e-07)
+    got = (a - C) + delta
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # the negative side is the mirror image (IEEE rounding is sign-symmetric)
+    want_n = ((-a).astype(np.float64) + twopi).astype(np.float32)
+    assert np.array_equal((-got).view(np.uint32), want_n.view(np.uint32))

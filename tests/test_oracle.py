@@ -393,3 +393,21 @@ def test_dmr_chain_streams_and_locks(oracle):
         n = min(len(bits) - off, len(tx_bits)) - 100
         best = max(best, float(np.mean(bits[off:off + n] == tx_bits[:n])))
     assert best > 0.97
+
+
+def test_frame_and_m17_deframer_restatements(oracle):
+    """gr_modem::frame (gr_modem.cpp:904-961) and the M17 branch of findSync (:1187-1207), oracle level: known answers."""
+    O = oracle
+    assert bytes(O.frame(b"\x01\x02", 0xED89)) == b"\xED\x89\xAA\x01\x02"
+    assert bytes(O.frame(b"\x01\x02", 0xED89, one_k_mode=True)) == b"\xB5\x01\x02"
+    assert bytes(O.frame(b"\x07", 0xDE98AA, burst_ip=True)) == b"\xAA" * 10 + b"\xDE\x98\xAA\x07"
+    assert bytes(O.frame(b"\x07", 0xDE98AA)) == b"\xDE\x98\xAA\x07"
+    assert bytes(O.frame(b"\x09", 0x8CC8DD)) == b"\x09"                      # callsign / end frames get no sync word from frame()
+    rng = np.random.default_rng(5)
+    payload = rng.integers(0, 256, 7, dtype=np.uint8).tobytes()
+    bits = np.unpackbits(np.concatenate([np.full(3, 0xAA, np.uint8), O.frame(payload, 0xED89), np.full(4, 0xAA, np.uint8)]))
+    fr = O.Deframer(2, 64, 7).work(bits)
+    assert fr == [(0xED89, b"\xAA" + payload)]
+    m17 = np.unpackbits(np.array([0x00, 0x55, 0xF7] + list(range(46)) + [0x55, 0x5D, 0x55, 0x5D] + [0xFF] * 46, np.uint8))
+    fr = O.Deframer(4, 46 * 8, 46).work(m17)
+    assert [t for t, _ in fr] == [0x55F7, 0x555D555D] and fr[0][1] == bytes(range(46)) and fr[1][1] == b"\xFF" * 46
