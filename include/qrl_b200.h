@@ -139,6 +139,22 @@ long qrl_tx_launch_count(const qrl_tx* h);
 int qrl_tx_profile(qrl_tx* h, int enable);
 int qrl_tx_profile_read(qrl_tx* h, int stage, double* ms_total, long* n_launches);
 
+/* ---- front end at device rates >= 2 Msps ------------------------------------------------------------------------------------------
+ * gr_demod_base::set_samp_rate (/root/reference/src/gr/gr_demod_base.cpp:1303-1362): when the device delivers samp_rate >= 2 Msps the
+ * reference puts rational_resampler_ccf(1, samp_rate / 1e6, low_pass(1, samp_rate, 480000, 100000, BLACKMAN_HARRIS)) behind the
+ * rotator (which then runs at the device rate, :1220-1225,1358) and in front of the demodulators.  This object is that pair for a batch
+ * of channels: [n_channels][T] gr_complex at samp_rate in, [n_channels][T / N] at 1 Msps out -- the device-resident input layout of
+ * qrl_rx_work.  Streaming (any chunking), phase-continuous retunes. */
+typedef struct qrl_frontend qrl_frontend;
+int  qrl_frontend_create(int samp_rate /* multiple of 1e6, >= 2e6 */, int n_channels, long max_in, int device, qrl_frontend** out);
+int  qrl_frontend_destroy(qrl_frontend*);
+int  qrl_frontend_set_stream(qrl_frontend*, void* cuda_stream);
+int  qrl_frontend_set_carrier_offset(qrl_frontend*, int channel /* -1 = all */, double offset_hz);
+int  qrl_frontend_work(qrl_frontend*, const float* iq, long T, long stride, int on_device, long* n_out);
+int  qrl_frontend_out_device(qrl_frontend*, float** data, long* stride, long* n_out);
+int  qrl_frontend_read(qrl_frontend*, float* dst /* [n_channels][cap] gr_complex */, long cap);
+long qrl_frontend_launch_count(const qrl_frontend*);
+
 /* ---- design helpers (host only; the gr::filter::firdes calls the reference makes at construction /
  *      in set_filter_width, e.g. gr_demod_nbfm.cpp:82-90).  Return tap count or negative error. ---- */
 int qrl_firdes_low_pass(double gain, double fs, double fc, double tw, int window, float* out, int cap);

@@ -129,9 +129,15 @@ public:
 
     int n_channels() const { return _C; }
     int n_ports() const { return _nports; }
-    // runtime setters of the analog blocks (gr_demod_nbfm.h:47-49)
+    // runtime setters of the analog blocks (gr_demod_nbfm.h:47-49, gr_demod_ssb.h:47-51, gr_demod_am.h:47-50, gr_demod_wbfm.h:47-48); like the
+    // reference's they return nothing: a block without the setter ignores it (the shim's QRL_EINVAL stays readable through last_error())
     void set_squelch(int db) { qrl_rx_set_param(_h, -1, QRL_PARAM_SQUELCH_DB, db); }
     void set_filter_width(int w) { qrl_rx_set_param(_h, -1, QRL_PARAM_FILTER_WIDTH, w); }
+    void set_ctcss(float v) { qrl_rx_set_param(_h, -1, QRL_PARAM_CTCSS, v); }
+    void set_agc_attack(float v) { qrl_rx_set_param(_h, -1, QRL_PARAM_AGC_ATTACK, v); }
+    void set_agc_decay(float v) { qrl_rx_set_param(_h, -1, QRL_PARAM_AGC_DECAY, v); }
+    void set_gain(float v) { qrl_rx_set_param(_h, -1, QRL_PARAM_GAIN, v); }
+    void set_carrier_offset(double hz, int channel = -1) { qrl_rx_set_param(_h, channel, QRL_PARAM_CARRIER_OFFSET_HZ, hz); }
 
     // one chunk of the [channels][T] gr_complex stream (host memory); returns T or WORK_DONE on a shim error
     int work(const gr_complex* iq, int T, long stride)

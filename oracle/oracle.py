@@ -95,6 +95,13 @@ def lib():
         L.qo_deframer_work.restype = C.c_long
         L.qo_deframer_work.argtypes = [vp, vp, C.c_long, vp, C.c_int, C.c_long]
         L.qo_deframer_modem_sync.argtypes = [vp]
+        L.qo_frontend_create.restype = vp
+        L.qo_frontend_create.argtypes = [C.c_int]
+        L.qo_frontend_destroy.argtypes = [vp]
+        L.qo_frontend_ntaps.argtypes = [vp]
+        L.qo_frontend_set_carrier_offset.argtypes = [vp, C.c_double]
+        L.qo_frontend_work.restype = C.c_long
+        L.qo_frontend_work.argtypes = [vp, vp, C.c_long, vp, C.c_long]
         L.qo_frame.restype = C.c_long
         L.qo_frame.argtypes = [vp, C.c_long, C.c_uint32, C.c_int, C.c_int, vp, C.c_long]
         L.qo_pfb_channelizer_create.restype = vp
@@ -426,6 +433,34 @@ class Deframer:
     @property
     def modem_sync(self):
         return lib().qo_deframer_modem_sync(self._h)
+
+
+class Frontend:
+    """gr_demod_base front end at a device rate >= 2 Msps (gr_demod_base.cpp:1303-1362): rotator + /N decimator to 1 Msps, one channel."""
+
+    def __init__(self, samp_rate):
+        self._h = lib().qo_frontend_create(int(samp_rate))
+        if not self._h:
+            raise ValueError("front end: samp_rate must be a multiple of 1e6, >= 2e6")
+        self.D = int(samp_rate) // 1000000
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().qo_frontend_destroy(self._h); self._h = None
+
+    @property
+    def ntaps(self):
+        return lib().qo_frontend_ntaps(self._h)
+
+    def set_carrier_offset(self, hz):
+        lib().qo_frontend_set_carrier_offset(self._h, float(hz))
+
+    def work(self, iq):
+        iq = np.ascontiguousarray(iq, np.complex64)
+        cap = len(iq) // self.D + 2
+        out = np.zeros(cap, np.complex64)
+        n = lib().qo_frontend_work(self._h, _p(iq), len(iq), _p(out), cap)
+        return out[:n].copy()
 
 
 def frame(payload, frame_type, one_k_mode=False, burst_ip=False):

@@ -1479,6 +1479,56 @@ static const float* rx_rotate(qo_rx* r, const float* iq, long T)
 }
 
 
+/* ------------------------------------------------------------------ gr_demod_base front end at device rates >= 2 Msps
+ * /root/reference/src/gr/gr_demod_base.cpp:57-63,180,1220-1225,1303-1362: source -> rotator_cc(2 pi (-offset) / samp_rate) ->
+ * rational_resampler_ccf(1, samp_rate / 1e6, low_pass(1, samp_rate, 480000, 100000, BLACKMAN_HARRIS)) -> demodulators at 1 Msps.
+ * (Below 2 Msps the resampler is not in the graph and the rotator feeds the demodulators directly: that case is qo_rx's own rotator.)
+ * Same Q32 NCO as rx_rotate, same FIR order as every decimator here. */
+struct qo_frontend { int samp_rate, D; resamp_t rs; uint32_t inc, base; long long nbase, n; qvec s_rot; };
+typedef struct qo_frontend qo_frontend;
+qo_frontend* qo_frontend_create(int samp_rate)
+{
+    if (samp_rate < 2000000 || samp_rate % 1000000) return NULL;
+    qo_frontend* f = (qo_frontend*)calloc(1, sizeof *f);
+    f->samp_rate = samp_rate; f->D = samp_rate / 1000000;
+    static float T[8192];
+    int n = qo_firdes_low_pass(1, samp_rate, 480000, 100000, QO_WIN_BLACKMAN_HARRIS, T, 8192);
+    resamp_init(&f->rs, 2, 1, f->D, T, n);
+    qv_init(&f->s_rot, 8);
+    return f;
+}
+void qo_frontend_destroy(qo_frontend* f) { if (f) { resamp_free(&f->rs); qv_free(&f->s_rot); free(f); } }
+int qo_frontend_ntaps(const qo_frontend* f) { return f->rs.nt; }
+void qo_frontend_set_carrier_offset(qo_frontend* f, double offset_hz)
+{
+    f->base = f->base + f->inc * (uint32_t)(f->n - f->nbase);
+    f->nbase = f->n;
+    f->inc = (uint32_t)(int32_t)(long long)rint(-offset_hz / f->samp_rate * 4294967296.0);
+}
+/* n input samples at the device rate -> returns the 1 Msps samples written to out (complex interleaved, cap items) */
+long qo_frontend_work(qo_frontend* f, const float* iq, long n, float* out, long cap)
+{
+    const float* x = iq;
+    if (f->inc != 0 || f->base != 0) {
+        f->s_rot.n = 0;
+        for (long i = 0; i < n; i++) {
+            uint32_t ph = f->base + f->inc * (uint32_t)(f->n + i - f->nbase);
+            float ang = (float)((double)(int32_t)ph * (M_PI / 2147483648.0));
+            float sn, cs; qo_sincosf(ang, &sn, &cs);
+            float xr = iq[2 * i], xi = iq[2 * i + 1];
+            qv_pushc(&f->s_rot, xr * cs - xi * sn, xr * sn + xi * cs);
+        }
+        x = (const float*)f->s_rot.d;
+    }
+    f->n += n;
+    qvec o; qv_init(&o, 8);
+    resamp_work(&f->rs, x, (size_t)n, &o);
+    long m = (long)o.n < cap ? (long)o.n : cap;
+    memcpy(out, o.d, (size_t)m * 8);
+    qv_free(&o);
+    return m;
+}
+
 /* ---- in-tree reference blocks restated as single-item functions (pinned bit-for-bit against the reference sources compiled
  *      in oracle/_ref: tests/test_oracle_ref.py) ---- */
 /* cessb::clipper_cc (cessb/clipper_cc_impl.cc:65-95): magnitude limited to `clip`, phase kept (fast_atan2f, then cos / sin) */

@@ -86,6 +86,14 @@ long   qo_rx_dbg_items(qo_rx*, const char* name);
 const void* qo_rx_dbg_data(qo_rx*, const char* name);
 int    qo_rx_ntaps(qo_rx*, int which, float* out, int cap);
 
+/* ---- front end at device rates >= 2 Msps (gr_demod_base.cpp:1303-1362): rotator at the device rate + /N decimator to 1 Msps ---- */
+typedef struct qo_frontend qo_frontend;
+qo_frontend* qo_frontend_create(int samp_rate /* multiple of 1e6, >= 2e6 */);
+void   qo_frontend_destroy(qo_frontend*);
+int    qo_frontend_ntaps(const qo_frontend*);
+void   qo_frontend_set_carrier_offset(qo_frontend*, double offset_hz);
+long   qo_frontend_work(qo_frontend*, const float* iq, long n, float* out, long cap);
+
 /* ---- TX chains ---- */
 typedef struct qo_tx qo_tx;
 qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag);

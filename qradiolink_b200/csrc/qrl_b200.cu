@@ -400,7 +400,7 @@ int launch_fir_ccf(qrl_rx* h, cudaStream_t st, const float2* in, unsigned in_mas
     constexpr int K = 8, NT = 128, TILE = K * NT;
     const int span = TILE + ntaps - 1;
     const size_t smem = sizeof(float) * ((ntaps + 1) & ~1) + sizeof(float2) * (span + (span >> 4) + 2);
-    if (n >= 256 && smem <= 48 * 1024) {
+    if (n >= 256 && smem <= 48 * 1024 && ntaps >= K) {       // (the tiled kernel's head / tail phases assume at least K taps)
         dim3 g(static_cast<unsigned>((n + TILE - 1) / TILE), h->C);
         fir_ccf_ring_tiled_kernel<K, NT><<<g, NT, smem, st>>>(in, in_mask, in_stride, out, out_mask, out_stride, taps, ntaps, a0, a1, lin, lin_stride, lin_base, interleaved);
     } else {
@@ -419,7 +419,7 @@ int launch_qdemod_fir(qrl_rx* h, cudaStream_t st, const float2* in, unsigned in_
     constexpr int K = 8, NT = 128, TILE = K * NT;
     const int span = TILE + ntaps - 1;
     const size_t smem = sizeof(float) * (ntaps + span + (span >> 5) + 2);
-    if (n >= 256 && smem <= 48 * 1024) {
+    if (n >= 256 && smem <= 48 * 1024 && ntaps >= K) {
         dim3 g(static_cast<unsigned>((n + TILE - 1) / TILE), h->C);
         qdemod_fir_fff_tiled_kernel<K, NT><<<g, NT, smem, st>>>(in, in_mask, in_stride, out, out_mask, out_stride, taps, ntaps, gain, a0, a1);
     } else {
@@ -2187,6 +2187,138 @@ int qrl_tx_out_device(qrl_tx* h, float** data, long* stride, long* n_out)
     return QRL_OK;
 }
 long qrl_tx_launch_count(const qrl_tx* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------- front end (device rate >= 2 Msps)
+struct qrl_frontend : HandleBase {
+    int samp_rate = 0, D = 1, C = 0, ntaps = 0, H = 0, hist_cur = 0;
+    long max_in = 0;
+    float* d_taps = nullptr;
+    float2* d_hist[2] = { nullptr, nullptr };
+    float2* d_in = nullptr; float2* d_out = nullptr; long long out_stride = 0; long n_out_last = 0;
+    long long n_in = 0, n1 = 0;
+    std::vector<RotState> rot; RotState* d_rot = nullptr; bool rot_active = false;
+};
+
+int qrl_frontend_destroy(qrl_frontend* h)
+{
+    if (!h) return QRL_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return QRL_OK;
+}
+int qrl_frontend_create(int samp_rate, int n_channels, long max_in, int device, qrl_frontend** out)
+{
+    if (!out || n_channels <= 0 || max_in <= 0 || samp_rate < 2000000 || samp_rate % 1000000) { set_err(nullptr, "qrl_frontend_create: bad argument (samp_rate must be a multiple of 1e6, >= 2e6)"); return QRL_EINVAL; }
+    *out = nullptr;
+    if (qrl_device_count() <= device) { set_err(nullptr, "qrl_frontend_create: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
+    qrl_frontend* h = new qrl_frontend();
+    h->samp_rate = samp_rate; h->D = samp_rate / 1000000; h->C = n_channels; h->max_in = max_in; h->device = device;
+    auto fail = [&](int rc) { std::string e = h->err; qrl_frontend_destroy(h); g_err = e; return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) { set_err(h, "cudaSetDevice failed"); return fail(QRL_ECUDA); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err(h, "stream create failed"); return fail(QRL_ECUDA); }
+    h->own_stream = true;
+    int rc = upload_tables(h);
+    if (rc) return fail(rc);
+    // gr_demod_base.cpp:1329-1333: low_pass(1, samp_rate, 480000, 100000, BLACKMAN_HARRIS) in rational_resampler_ccf(1, samp_rate / 1e6)
+    std::vector<float> taps = low_pass(1, samp_rate, 480000, 100000, WIN_BLACKMAN_HARRIS);
+    h->ntaps = static_cast<int>(taps.size());
+    h->H = h->ntaps + h->D;
+    if ((rc = upload_floats(h, &h->d_taps, taps))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_hist[0], static_cast<size_t>(h->H) * h->C))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_hist[1], static_cast<size_t>(h->H) * h->C))) return fail(rc);
+    h->out_stride = max_in / h->D + 2;
+    if ((rc = dev_alloc(h, &h->d_out, static_cast<size_t>(h->out_stride) * h->C, false))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_rot, h->C))) return fail(rc);
+    h->rot.assign(h->C, RotState{ 0u, 0u, 0 });
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { set_err(h, "create sync failed"); return fail(QRL_ECUDA); }
+    *out = h;
+    return QRL_OK;
+}
+int qrl_frontend_set_stream(qrl_frontend* h, void* s)
+{
+    if (!h) return QRL_EINVAL;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    if (s) h->stream = static_cast<cudaStream_t>(s);
+    else { CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    return QRL_OK;
+}
+int qrl_frontend_set_carrier_offset(qrl_frontend* h, int channel, double offset_hz)
+{
+    // gr_demod_base::set_carrier_offset (:1220-1225): rotator phase increment 2 pi (-offset) / samp_rate at the DEVICE rate
+    if (!h || channel >= h->C) return QRL_EINVAL;
+    const unsigned inc = static_cast<unsigned>(static_cast<int>(static_cast<long long>(std::rint(-offset_hz / h->samp_rate * 4294967296.0))));
+    for (int c = 0; c < h->C; c++) {
+        if (channel >= 0 && c != channel) continue;
+        RotState& r = h->rot[c];
+        r.base = r.base + r.inc * static_cast<unsigned>(h->n_in - r.n_base);
+        r.n_base = h->n_in;
+        r.inc = inc;
+    }
+    h->rot_active = false;
+    for (auto& r : h->rot) if (r.inc != 0 || r.base != 0) h->rot_active = true;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->d_rot, h->rot.data(), sizeof(RotState) * h->C, cudaMemcpyHostToDevice));
+    return QRL_OK;
+}
+int qrl_frontend_work(qrl_frontend* h, const float* iq, long T, long stride, int on_device, long* n_out)
+{
+    if (!h || !iq || T < 0) return QRL_EINVAL;
+    if (T > h->max_in) { set_err(h, "qrl_frontend_work: T exceeds max_in given at create"); return QRL_ERANGE; }
+    h->n_out_last = 0;
+    if (n_out) *n_out = 0;
+    if (T == 0) return QRL_OK;
+    CK(cudaSetDevice(h->device));
+    const float2* x = reinterpret_cast<const float2*>(iq);
+    long long xstride = stride;
+    if (!on_device) {
+        if (!h->d_in) { int rc = dev_alloc(h, &h->d_in, static_cast<size_t>(h->max_in) * h->C, false); if (rc) return rc; }
+        CK(cudaMemcpy2DAsync(h->d_in, sizeof(float2) * h->max_in, iq, sizeof(float2) * stride, sizeof(float2) * T, h->C, cudaMemcpyHostToDevice, h->stream));
+        x = h->d_in; xstride = h->max_in;
+    }
+    const long long N = h->n_in + T;
+    const long long k0 = h->n1, k1 = (N + h->D - 1) / h->D;              // outputs k with D k <= N - 1
+    const RotState* rs = h->rot_active ? h->d_rot : nullptr;
+    if (k1 > k0) {
+        const size_t smem = sizeof(float) * ((h->ntaps + 1) & ~1) + sizeof(float2) * (127 * h->D + h->ntaps);
+        static bool attr[16] = { false };
+        if (!attr[h->device & 15]) { CK(cudaFuncSetAttribute(frontend_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr[h->device & 15] = true; }
+        if (smem > 160 * 1024) { set_err(h, "qrl_frontend_work: device rate too high for this kernel"); return QRL_EINVAL; }
+        dim3 g(static_cast<unsigned>((k1 - k0 + 127) / 128), h->C);
+        frontend_fir_kernel<<<g, 128, smem, h->stream>>>(rs, x, xstride, T, h->n_in, h->d_hist[h->hist_cur], h->H, h->d_taps, h->ntaps, h->D,
+                                                          h->d_out, h->out_stride, k0, k1);
+        h->launches++;
+    }
+    dim3 gh((h->H + 127) / 128, h->C);
+    frontend_hist_kernel<<<gh, 128, 0, h->stream>>>(rs, x, xstride, T, h->n_in, h->d_hist[h->hist_cur], h->d_hist[h->hist_cur ^ 1], h->H);
+    h->launches++;
+    h->hist_cur ^= 1;
+    h->n_in = N; h->n1 = k1;
+    h->n_out_last = static_cast<long>(k1 - k0);
+    if (n_out) *n_out = h->n_out_last;
+    CK(cudaGetLastError());
+    return QRL_OK;
+}
+int qrl_frontend_out_device(qrl_frontend* h, float** data, long* stride, long* n_out)
+{
+    if (!h) return QRL_EINVAL;
+    if (data) *data = reinterpret_cast<float*>(h->d_out);
+    if (stride) *stride = static_cast<long>(h->out_stride);
+    if (n_out) *n_out = h->n_out_last;
+    return QRL_OK;
+}
+int qrl_frontend_read(qrl_frontend* h, float* dst, long cap)
+{
+    if (!h || !dst) return QRL_EINVAL;
+    const long w = std::min(cap, h->n_out_last);
+    if (w > 0) CK(cudaMemcpy2DAsync(dst, static_cast<size_t>(cap) * 8, h->d_out, static_cast<size_t>(h->out_stride) * 8, static_cast<size_t>(w) * 8, h->C, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return QRL_OK;
+}
+long qrl_frontend_launch_count(const qrl_frontend* h) { return h ? h->launches : 0; }
 
 // ---------------------------------------------------------------------------------------------- design helpers
 static int copy_out(const std::vector<float>& v, float* out, int cap, int per_item = 1)

@@ -2360,6 +2360,76 @@ __global__ void rotator_kernel(const RotState* __restrict__ rs, const float2* __
     }
 }
 
+// Front end at device rates >= 2 Msps (gr_demod_base.cpp:1303-1362): rotator_cc at the device rate fused into the /D decimating FIR
+// (83 taps at 2 Msps).  One CTA = 128 outputs of one channel: the window is rotated while it is loaded into shared memory (same Q32
+// phase arithmetic as rotator_kernel), the previous calls' tail comes ALREADY ROTATED from `hist` (a retune must not touch samples that
+// are already inside the filter, like the reference's resampler history); each thread then runs THE FIR order over its window.
+__global__ void __launch_bounds__(128)
+frontend_fir_kernel(const RotState* __restrict__ rs /* nullptr: no rotation */, const float2* __restrict__ in, long long in_stride, long long T,
+                    long long n_abs0 /* absolute index of in[c][0] */, const float2* __restrict__ hist /* [C][H] rotated */, int H,
+                    const float* __restrict__ taps, int ntaps, int D, float2* __restrict__ out, long long out_stride,
+                    long long k0, long long k1 /* absolute output range of this call */)
+{
+    extern __shared__ __align__(16) float sm_fe[];
+    float* hs = sm_fe;                                                  // ntaps (rounded up to even)
+    float2* xs = reinterpret_cast<float2*>(sm_fe + ((ntaps + 1) & ~1));
+    const int c = blockIdx.y;
+    const long long kb = k0 + static_cast<long long>(blockIdx.x) * 128;
+    if (kb >= k1) return;
+    const int nout = (k1 - kb) < 128 ? static_cast<int>(k1 - kb) : 128;
+    const long long a_first = D * kb - (ntaps - 1);                    // absolute index of the oldest sample of the window
+    const int W = (nout - 1) * D + ntaps;
+    for (int i = threadIdx.x; i < ntaps; i += 128) hs[i] = taps[i];
+    const float2* x = in + static_cast<long long>(c) * in_stride;
+    const float2* hc = hist + static_cast<long long>(c) * H;
+    RotState r{ 0u, 0u, 0 };
+    if (rs) r = rs[c];
+    for (int i = threadIdx.x; i < W; i += 128) {
+        const long long a = a_first + i, li = a - n_abs0;               // li: index into this call's input
+        float2 v = make_float2(0.0f, 0.0f);
+        if (li >= 0) {
+            if (li < T) {
+                v = x[li];
+                if (rs) {
+                    const unsigned ph = r.base + r.inc * static_cast<unsigned>(a - r.n_base);
+                    const float ang = static_cast<float>(static_cast<double>(static_cast<int>(ph)) * (3.14159265358979323846 / 2147483648.0));
+                    float sn, cs;
+                    qrl_sincosf(ang, sn, cs);
+                    v = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+                }
+            }
+        } else if (H + li >= 0) v = hc[H + li];
+        xs[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x >= nout) return;
+    const float2* newest = xs + threadIdx.x * D + (ntaps - 1);
+    const float2 y = qrl_fir_dot_order_c(hs, ntaps, D, [&](int j) { return newest[-j]; });
+    out[static_cast<long long>(c) * out_stride + (kb + threadIdx.x - k0)] = y;
+}
+// rotated tail for the next call: new_hist = last H samples of (old_hist ++ rotate(in[0..T)))
+__global__ void frontend_hist_kernel(const RotState* __restrict__ rs, const float2* __restrict__ in, long long in_stride, long long T, long long n_abs0,
+                                     const float2* __restrict__ old_hist, float2* __restrict__ new_hist, int H)
+{
+    const int c = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H) return;
+    const long long li = T - H + i;
+    float2 v;
+    if (li >= 0) {
+        v = in[static_cast<long long>(c) * in_stride + li];
+        if (rs) {
+            const RotState r = rs[c];
+            const unsigned ph = r.base + r.inc * static_cast<unsigned>(n_abs0 + li - r.n_base);
+            const float ang = static_cast<float>(static_cast<double>(static_cast<int>(ph)) * (3.14159265358979323846 / 2147483648.0));
+            float sn, cs;
+            qrl_sincosf(ang, sn, cs);
+            v = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+        }
+    } else v = old_hist[static_cast<long long>(c) * H + (H + li)];
+    new_hist[static_cast<long long>(c) * H + i] = v;
+}
+
 // roll the stage-1 history: new_hist = last H samples of (old_hist ++ iq[0..T))
 __global__ void hist_update_kernel(const float2* __restrict__ iq, long long iq_stride, long long T,
                                    const float2* __restrict__ old_hist, float2* __restrict__ new_hist, int H)

@@ -54,6 +54,14 @@ SYMBOLS = {
     "qrl_tx_launch_count": (_l, [_vp]),
     "qrl_tx_profile": (_i, [_vp, _i]),
     "qrl_tx_profile_read": (_i, [_vp, _i, C.POINTER(_d), C.POINTER(_l)]),
+    "qrl_frontend_create": (_i, [_i, _i, _l, _i, C.POINTER(_vp)]),
+    "qrl_frontend_destroy": (_i, [_vp]),
+    "qrl_frontend_set_stream": (_i, [_vp, _vp]),
+    "qrl_frontend_set_carrier_offset": (_i, [_vp, _i, _d]),
+    "qrl_frontend_work": (_i, [_vp, _vp, _l, _l, _i, C.POINTER(_l)]),
+    "qrl_frontend_out_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_l), C.POINTER(_l)]),
+    "qrl_frontend_read": (_i, [_vp, _vp, _l]),
+    "qrl_frontend_launch_count": (_l, [_vp]),
     "qrl_firdes_low_pass": (_i, [_d] * 4 + [_i, _vp, _i]),
     "qrl_firdes_low_pass_2": (_i, [_d] * 5 + [_i, _vp, _i]),
     "qrl_firdes_band_pass": (_i, [_d] * 5 + [_i, _vp, _i]),
