@@ -134,6 +134,7 @@ struct qrl_rx : HandleBase {
     unsigned char* d_port3 = nullptr; int* d_port3_cnt = nullptr;
     // front-end rotator (carrier offset)
     std::vector<RotState> rot; RotState* d_rot = nullptr; bool rot_active = false; float2* d_rot_buf = nullptr;
+    bool rot_fused = false;            // this call: the rotator runs inside the stage-1 kernel (register-tiled shapes)
     // non-FM FSK detectors: band-pass bank + symbol filter
     float* d_bank_taps = nullptr; int nt_bank = 0;
     float* d_symf_taps = nullptr; int nt_symf = 0;
@@ -235,7 +236,7 @@ int launch_fir_poly(qrl_rx* h, const float2* iq, long long stride, long long T, 
     dim3 grid(static_cast<unsigned>((nout + NOUT - 1) / NOUT), h->C);
     fir_decim_poly_kernel<D, Q, K, NOUT, NWARPS><<<grid, NWARPS * 32, smem, h->par()>>>(
         iq, stride, T, h->d_hist[h->hist_cur], h->H, h->d_taps1,
-        static_cast<float2*>(h->r1.d), h->r1.mask, h->r1.stride, h->n_in, k0, k1);
+        static_cast<float2*>(h->r1.d), h->r1.mask, h->r1.stride, h->n_in, k0, k1, h->rot_fused ? h->d_rot : nullptr);
     h->launches++;
     CK(cudaGetLastError());
     return QRL_OK;
@@ -1105,7 +1106,12 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         x = h->d_in_staging;
         xstride = h->Tmax;
     }
-    if (h->rot_active) {
+    // carrier offset: the register-tiled /50, /100, /25, /125 stage-1 instances rotate their window in shared memory (no extra pass over
+    // HBM); the other stage-1 shapes take the rotator as a separate pass
+    const bool poly_shape = h->L1 == 1 && ((h->D1 == 50 && h->Q1 == 9) || (h->D1 == 100 && (h->Q1 == 9 || h->Q1 == 28)) ||
+                                           (h->D1 == 25 && (h->Q1 == 9 || h->Q1 == 28)) || (h->D1 == 125 && h->Q1 == 9));
+    h->rot_fused = h->rot_active && poly_shape && !getenv("QRL_ROTATOR_PASS");
+    if (h->rot_active && !h->rot_fused) {
         if (!h->d_rot_buf) { int rc = dev_alloc(h, &h->d_rot_buf, static_cast<size_t>(h->Tmax) * h->C, false); if (rc) return rc; }
         dim3 g(static_cast<unsigned>(std::min<long long>((T + 255) / 256, 4096)), h->C);
         rotator_kernel<<<g, 256, 0, h->stream>>>(h->d_rot, x, xstride, h->d_rot_buf, h->Tmax, T, h->n_in);
@@ -1172,7 +1178,8 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
             h->prof_end(pe);
             if (rc) return rc;
             dim3 g((h->H + 127) / 128, h->C);
-            hist_update_kernel<<<g, 128, 0, sp>>>(xg, xstride, Tg, h->d_hist[h->hist_cur], h->d_hist[h->hist_cur ^ 1], h->H);
+            if (h->rot_fused) frontend_hist_kernel<<<g, 128, 0, sp>>>(h->d_rot, xg, xstride, Tg, h->n_in, h->d_hist[h->hist_cur], h->d_hist[h->hist_cur ^ 1], h->H);
+            else hist_update_kernel<<<g, 128, 0, sp>>>(xg, xstride, Tg, h->d_hist[h->hist_cur], h->d_hist[h->hist_cur ^ 1], h->H);
             h->launches++;
             h->hist_cur ^= 1;
             h->n_in = Ng; h->n1 = kg1;

@@ -107,13 +107,19 @@ __device__ __forceinline__ unsigned char qrl_soft_u8(float v, float scale)
 //   Input samples are read once from HBM into shared memory (coalesced 8-byte loads); the previous
 //   call's tail (history) comes from a small per-channel buffer.
 // ------------------------------------------------------------------------------------------------
+// front-end rotator state (gr_demod_base's rotator_cc): exact Q32 phase, phase = base + inc * (n_abs - n_base)
+struct RotState { unsigned inc, base; long long n_base; };
+
+// rot != nullptr: the carrier-offset rotator is applied to the window in shared memory right after the fill (same arithmetic as
+// rotator_kernel, sample by sample), so a non-zero offset costs no extra pass over HBM (8.16 B per input sample instead of 24);
+// the history tail then holds ALREADY ROTATED samples (frontend_hist_kernel), like the reference's resampler history.
 template <int D, int Q, int K, int NOUT, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
 fir_decim_poly_kernel(const float2* __restrict__ iq, long long iq_stride, long long T,
                       const float2* __restrict__ hist, int H,
                       const float* __restrict__ taps_padded,   // Q*D floats, zero padded
                       float2* __restrict__ out_ring, unsigned ring_mask, long long ring_stride,
-                      long long n_in_before, long long k0, long long k1)
+                      long long n_in_before, long long k0, long long k1, const RotState* __restrict__ rot = nullptr)
 {
     static_assert(K == 8, "transposed butterfly below is written for 2K = 16 values");
     constexpr int R = (D + 31) / 32;                 // branch rounds per lane
@@ -162,6 +168,22 @@ fir_decim_poly_kernel(const float2* __restrict__ iq, long long iq_stride, long l
             if (i >= 0) { if (i < T) v = __ldg(iqc + i); }
             else if (H + i >= 0) v = hc[H + i];
             xw[idx] = v;
+        }
+        __syncthreads();
+    }
+    if (rot) {
+        // rotate this call's samples of the window in place (history samples were rotated when they were new)
+        const RotState r = rot[c];
+        float2* xw = xs_raw + shift;
+        for (int idx = threadIdx.x; idx < W; idx += NWARPS * 32) {
+            const long long i = i0 + idx;
+            if (i < 0 || i >= T) continue;
+            const unsigned ph = r.base + r.inc * static_cast<unsigned>(n_in_before + i - r.n_base);
+            const float ang = static_cast<float>(static_cast<double>(static_cast<int>(ph)) * (3.14159265358979323846 / 2147483648.0));
+            float sn, cs;
+            qrl_sincosf(ang, sn, cs);
+            const float2 x = xw[idx];
+            xw[idx] = make_float2(x.x * cs - x.y * sn, x.x * sn + x.y * cs);
         }
         __syncthreads();
     }
@@ -2344,7 +2366,6 @@ __global__ void fir_fff_ring_kernel(const float* __restrict__ in, unsigned in_ma
 // Front-end rotator (gr_demod_base's rotator_cc, carrier offset): out[c][n] = in[c][n] * exp(j theta), exact Q32 phase
 // phase = base[c] + inc[c] * (n_abs - n_base[c]).  Only launched when some channel has a non-zero offset (the
 // reference default is 0); it costs one extra pass over the slab -- fusing it needs complex stage-1 taps (next).
-struct RotState { unsigned inc, base; long long n_base; };
 __global__ void rotator_kernel(const RotState* __restrict__ rs, const float2* __restrict__ in, long long in_stride,
                                float2* __restrict__ out, long long out_stride, long long T, long long n_abs0)
 {
