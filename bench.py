@@ -266,7 +266,7 @@ def qpsk_inputs(q, torch, dev, C, T, seed):
     """[C][T] QPSK-250k bursts made by the product's own modulator on the GPU (x0.5) + AWGN."""
     rng = np.random.default_rng(seed)
     nb = T // 32
-    tx = q.make_gr_mod_qpsk(4, 1000000, 1700, 160000, n_channels=C, max_items=nb)
+    tx = q.make_gr_mod_qpsk(4, 1000000, 1700, 160000, n_channels=C, max_items=nb, device=dev.index)
     d = torch.from_numpy(rng.integers(0, 256, (C, nb), dtype=np.uint8)).to(dev)
     tx.work_device(d.data_ptr(), nb, nb); tx.sync()
     L = q.load_library()
@@ -296,7 +296,7 @@ def rx_config_block(q, torch, dev, name, make, make_args, okind, oargs, X, alg_b
     C, T = X.shape
     peak, _ = peaks()
     stream = torch.cuda.current_stream()
-    blk = make(*make_args, n_channels=C, max_samples=T)
+    blk = make(*make_args, n_channels=C, max_samples=T, device=dev.index)
     blk.set_stream(stream.cuda_stream)
     blk.work_device(X.data_ptr(), T, T)
     torch.cuda.synchronize()
@@ -475,14 +475,14 @@ def mixed_config_block(q, torch, dev, dist, rank, world, synth, k=4):
             continue
         if m == "nbfm":
             X = nbfm_inputs(torch, dev, C, T)
-            blk = q.make_gr_demod_nbfm(125, 1000000, 1700, 2500, n_channels=C, max_samples=T)
+            blk = q.make_gr_demod_nbfm(125, 1000000, 1700, 2500, n_channels=C, max_samples=T, device=dev.index)
         elif m == "4fsk":
             bases = [synth.burst_4fsk(3000 + 97 * rank + i, T) for i in range(4)]
             X = synth.batch_on_device(bases, C, seed=777 + rank, device=dev)
-            blk = q.make_gr_demod_4fsk(5, 1000000, 1700, 3000, True, n_channels=C, max_samples=T)
+            blk = q.make_gr_demod_4fsk(5, 1000000, 1700, 3000, True, n_channels=C, max_samples=T, device=dev.index)
         else:
             X = qpsk_inputs(q, torch, dev, C, T, 3000 + rank)
-            blk = q.make_gr_demod_qpsk(2, 1000000, 1700, 160000, n_channels=C, max_samples=T)
+            blk = q.make_gr_demod_qpsk(2, 1000000, 1700, 160000, n_channels=C, max_samples=T, device=dev.index)
         blk.set_stream(streams[m].cuda_stream)
         blocks[m], inputs[m] = blk, X
     torch.cuda.synchronize()
@@ -600,7 +600,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a rank that dies must not leave the others waiting ten minutes on the box
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local)
     cores, core_info = host_cores()
 

@@ -173,7 +173,14 @@ int qrl_design_deemph(int fs, double tau, double* a2, double* b2);
  * of M stay in the handle, results do not depend on chunking.  Channel c of the channelizer is centred on
  * +c*fs/M (ports M/2.. are the negative frequencies, the order both reference wirings rely on,
  * gr_demod_mmdvm_multi2.cpp:110-124).  The channelizer output [M][stride] gr_complex is exactly the device-resident
- * input layout of qrl_rx_work. */
+ * input layout of qrl_rx_work.
+ * Commutator / timing (GNU Radio itself is not part of /root/reference, so this is restated, not pinned): with oversample rate 1.0
+ * pfb_channelizer_ccf::general_work keeps its filter index at M-1 on every iteration, so stream j (sample x[mM + j] of
+ * stream_to_streams) is filtered by branch M-1-j, taps[(M-1-j) + tM], at in[n] for every j and lands in FFT bin M-1-j of a backward
+ * (e^{+j...}) FFT: u_k[m] = sum_t taps[k + tM] x[(m-t)M + (M-1-k)], out_c[m] = sum_k u_k[m] e^{+j 2 pi k c / M}.  Output column m
+ * therefore needs wideband samples up to mM + M-1: the first column is produced once M samples have arrived.  A caller that
+ * assumes a different commutator phase sees the same channels delayed / advanced by up to M-1 WIDEBAND samples (less than one
+ * channel-rate sample), which the symbol-timing loops downstream absorb. */
 enum { QRL_PFB_CHANNELIZER = 201, QRL_PFB_SYNTHESIZER = 202 };
 typedef struct qrl_pfb qrl_pfb;
 /* max_in: channelizer = wideband samples per call; synthesizer = columns (samples per channel) per call */

@@ -676,7 +676,10 @@ static void iir1_work(iir1_t* f, const float* x, size_t n, qvec* out, float post
         qv_pushf(out, (float)acc * post_gain);
     }
 }
-/* analog::agc2_cc (A7) */
+/* analog::agc2_cc (A7).  GNU Radio's agc2.h is not in /root/reference (parity unpinned for this block): as restated here the COMPLEX
+ * kernel picks the attack rate with a signed compare, `if ((tmp) > _gain)`, while the float kernel agc2_ff (AM chain below) uses
+ * `fabsf(tmp) > _gain`.  The two forms only differ while gain < reference, i.e. for channel input levels above the reference, and
+ * only for blocks whose attack and decay rates differ (QPSK: 1 / 0.1; SSB after set_agc_attack / set_agc_decay). */
 typedef struct { float attack, decay, ref, gain, max_gain; } agc2_t;
 static void agc2_init(agc2_t* a, float attack, float decay, float ref, float gain) { a->attack = attack; a->decay = decay; a->ref = ref; a->gain = gain; a->max_gain = 65536.0f; }
 static inline void agc2_step(agc2_t* a, float xr, float xi, float* yr, float* yi)
@@ -684,7 +687,7 @@ static inline void agc2_step(agc2_t* a, float xr, float xi, float* yr, float* yi
     float orr = xr * a->gain, oi = xi * a->gain;
     float tmp = -a->ref + sqrtf(orr * orr + oi * oi);
     float rate = a->decay;
-    if (fabsf(tmp) > a->gain) rate = a->attack;
+    if (tmp > a->gain) rate = a->attack;
     a->gain -= tmp * rate;
     if (a->gain < 0.0f) a->gain = 10e-5f;
     if (a->max_gain > 0.0f && a->gain > a->max_gain) a->gain = a->max_gain;

@@ -57,6 +57,19 @@ void set_err(HandleBase* h, const std::string& s)
     if (h) h->err = s;
 }
 
+// a device pointer handed to a *_work call must live on the handle's device (a pointer from another GPU would fault inside a kernel
+// long after the call returned)
+int check_device_ptr(HandleBase* h, const void* p, const char* who)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return QRL_OK; }
+    if (a.type == cudaMemoryTypeDevice && a.device != h->device) {
+        set_err(h, std::string(who) + ": the device pointer belongs to GPU " + std::to_string(a.device) + ", the handle to GPU " + std::to_string(h->device));
+        return QRL_EINVAL;
+    }
+    return QRL_OK;
+}
+
 int upload_tables(HandleBase* h)
 {
     std::lock_guard<std::mutex> lk(g_tables_mu);
@@ -174,6 +187,7 @@ struct qrl_rx : HandleBase {
     cudaEvent_t ev_v[16] = { nullptr };                  // Viterbi of slice i done (kMaxSub entries)
     cudaEvent_t ev_tail[2][3] = { { nullptr } };         // s_loop / s_fec / s_epi at the end of a call, by call parity
     int call_parity = 0;
+    long prev_T = -1;                  // length of the previous overlapped call (a change of length joins the tail, see qrl_rx_work)
     long long prev_k1[16] = { 0 }, cur_k1[16] = { 0 }; int prev_nsub = 0;      // stage-1 sample index at the end of each slice
     int ss_ch = 256;                                     // rows per symbol-sync window (256 x 3 stages or 512 x 2)
     float2* d_port1 = nullptr; long port1_cap = 0; int* d_port1_cnt = nullptr;
@@ -1094,6 +1108,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
     if (T > h->Tmax) { set_err(h, "qrl_rx_work: T exceeds max_samples given at create"); return QRL_ERANGE; }
     if (T == 0) return QRL_OK;
     CK(cudaSetDevice(h->device));
+    if (on_device) { int rc = check_device_ptr(h, iq, "qrl_rx_work"); if (rc) return rc; }
     const float2* x = reinterpret_cast<const float2*>(iq);
     long long xstride = stride;
     if (!on_device) {
@@ -1122,6 +1137,11 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
         // this call writes the buffers call k-2 used: wait for that call's tail, then they are free
         h->call_parity ^= 1;
         for (int j = 0; j < 3; j++) CK(cudaStreamWaitEvent(h->stream, h->ev_tail[h->call_parity][j], 0));
+        // The per-slice fences below (ev_v[i], ev_c[q]) pair slice i of this call with slice i of the previous one: that only
+        // holds while both calls are cut the same way.  A call of a different length moves the slice boundaries, the symbol-sync
+        // scratch regions and the number of slices, so it joins the previous call's tail first (no overlap across that one seam).
+        if (h->prev_T != T && h->prev_T >= 0)
+            for (int j = 0; j < 3; j++) CK(cudaStreamWaitEvent(h->stream, h->ev_tail[h->call_parity ^ 1][j], 0));
         std::swap(h->d_port0, h->alt_port0); std::swap(h->d_port1, h->alt_port1); std::swap(h->d_port2, h->alt_port2);
         std::swap(h->d_port1_cnt, h->alt_port1_cnt); std::swap(h->d_port2_cnt, h->alt_port2_cnt);
         if (h->d_port3) { std::swap(h->d_port3, h->alt_port3); std::swap(h->d_port3_cnt, h->alt_port3_cnt); }
@@ -1568,6 +1588,7 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
     }
     for (int i = 0; i < nsub; i++) h->prev_k1[i] = h->cur_k1[i];
     h->prev_nsub = nsub;
+    h->prev_T = T;
     if (h->overlap) {
         // the caller's stream only waits for the parallel stages (the input has been consumed); the loop / FEC tail runs
         // on under the next call and is joined by qrl_rx_join / qrl_rx_sync / qrl_rx_read_port
@@ -1955,6 +1976,7 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
     h->n_out_last = 0;
     if (n == 0) return QRL_OK;
     CK(cudaSetDevice(h->device));
+    if (on_device) { int rc = check_device_ptr(h, in, "qrl_tx_work"); if (rc) return rc; }
     if (h->kind == QRL_MOD_NBFM || h->kind == QRL_MOD_SSB) {
         // `in` = [C][n] float audio at 8 ksps
         const float* au = static_cast<const float*>(in);

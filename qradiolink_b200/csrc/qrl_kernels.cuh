@@ -1071,7 +1071,7 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
                     const float2 x = buf[i * 32];
                     const float orr = x.x * gain, oi = x.y * gain;
                     const float tmp = -k_ref + sqrtf(orr * orr + oi * oi);
-                    const float rate = (fabsf(tmp) > gain) ? k_att : k_dec;
+                    const float rate = (tmp > gain) ? k_att : k_dec;           // agc2_cc: signed compare (agc2_ff takes fabsf), DESIGN.md section 2
                     gain = gain - tmp * rate;
                     if (gain < 0.0f) gain = 10e-5f;
                     if (k_max > 0.0f && gain > k_max) gain = k_max;
@@ -2238,7 +2238,7 @@ ssb_audio_kernel(SsbParams p, SsbState* __restrict__ states,
             if (state != SQ_MUTED) {
                 const float orr = v.x * gain, oi = v.y * gain;          // envelope is 1.0 without a ramp
                 const float tmp = -p.ref + sqrtf(orr * orr + oi * oi);
-                const float rate = (fabsf(tmp) > gain) ? p.attack : p.decay;
+                const float rate = (tmp > gain) ? p.attack : p.decay;      // agc2_cc: signed compare
                 gain = gain - tmp * rate;
                 if (gain < 0.0f) gain = 10e-5f;
                 if (p.max_gain > 0.0f && gain > p.max_gain) gain = p.max_gain;

@@ -213,3 +213,36 @@ def test_overlapped_calls_give_the_same_stream(qrl, oracle):
         rx = oracle.Rx(oracle.DEMOD_4FSK, 5, 1000000, 1700, 3000, 1)
         rx.work(X[c])
         assert np.array_equal(bits[c], rx.port(2))
+
+
+def test_overlapped_calls_with_changing_length(qrl, oracle):
+    """QRL_PARAM_OVERLAP_CALLS with a different T on every call (the per-slice fences pair slice i of a call with slice i of
+    the previous one, which only holds for equal cuts): a call whose length differs joins the previous tail first.  Every call's
+    ports must equal the serialised handle's, with and without a read in between, and the bit stream must equal the oracle's."""
+    C, Tmax = 3, 1 << 18
+    lens = [1 << 18, (1 << 17) + 1234, 1 << 18, 3 << 16, 40000, 1 << 18, 1 << 18, 70001, (1 << 18) - 50]
+    X, _ = siggen.gen_4fsk_channels(C, sum(lens), seed0=1700)
+    ser = qrl.make_gr_demod_4fsk(5, 1000000, 1700, 3000, True, n_channels=C, max_samples=Tmax)
+    want_calls, o = [], 0
+    for T in lens:
+        ser.work(np.ascontiguousarray(X[:, o:o + T]))
+        want_calls.append([ser.read_port(p) for p in range(3)])
+        o += T
+    for read_every in (1, 3, len(lens)):
+        ovl = qrl.make_gr_demod_4fsk(5, 1000000, 1700, 3000, True, n_channels=C, max_samples=Tmax)
+        ovl.set_overlap(True)
+        o = 0
+        for k, T in enumerate(lens):
+            ovl.work(np.ascontiguousarray(X[:, o:o + T]))
+            o += T
+            if (k + 1) % read_every == 0 or k == len(lens) - 1:
+                got = [ovl.read_port(p) for p in range(3)]
+                for p in range(3):
+                    for c in range(C):
+                        assert np.array_equal(got[p][c], want_calls[k][p][c]), (read_every, k, p, c)
+        ovl.close()
+    bits = [np.concatenate([want_calls[k][2][c] for k in range(len(lens))]) for c in range(C)]
+    for c in range(C):
+        rx = oracle.Rx(oracle.DEMOD_4FSK, 5, 1000000, 1700, 3000, 1)
+        rx.work(X[c])
+        assert np.array_equal(bits[c], rx.port(2))

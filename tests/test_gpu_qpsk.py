@@ -92,3 +92,21 @@ def test_qpsk_fll_variants(qrl, oracle, tx_sps, rx_sps, fw):
             assert np.array_equal(got[:n], want[:n]), (c, p)
         good, found = siggen.count_good_frames(np.concatenate(acc[2][c]), 0xED89AA, 24, 7, payloads[c])
         assert good >= 10
+
+
+def test_qpsk_hot_and_fading_input(qrl, oracle):
+    """Channel levels above the AGC reference (gain < 1) with 30 dB dips: the region where the complex AGC's signed rate compare
+    matters (attack 1.0 / decay 0.1, gr_demod_qpsk.cpp:97).  Ports identical to the oracle, frames still recovered."""
+    C, T = 3, 1 << 18
+    X, payloads = siggen.gen_qpsk_channels(C, T, seed0=2400)
+    n = np.arange(T)
+    for c in range(C):
+        level = np.where((n // 37000) % 3 == 2, 0.12, 5.0 + 2.0 * c).astype(np.float32)
+        X[c] *= level
+    want = run_oracle(oracle, X)
+    blk = qrl.make_gr_demod_qpsk(2, 1000000, 1700, 160000, n_channels=C, max_samples=T)
+    blk.work(X)
+    got = [blk.read_port(p) for p in range(3)]
+    for c in range(C):
+        for p in range(3):
+            assert len(got[p][c]) == len(want[c][p]) and np.array_equal(got[p][c], want[c][p]), (c, p)

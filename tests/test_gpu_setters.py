@@ -105,3 +105,19 @@ def test_setters_refused_where_the_reference_has_none(qrl):
         nb.set_param(P.CTCSS, 88.5)          # analog::ctcss_squelch_ff is not built
     with pytest.raises(qrl.QrlError):
         nb.set_param(P.GAIN, 0.5)            # gr_demod_nbfm has no set_gain
+
+
+def test_ssb_agc_with_hot_input(qrl, oracle):
+    """Input levels above the AGC reference drive the gain below it: the one region where agc2_cc's signed rate compare and
+    agc2_ff's fabsf compare differ (oracle/qrl_oracle.c agc2_step), with attack != decay and deep fades."""
+    P = qrl.PARAM
+    T = 700000
+    n = np.arange(T)
+    rng = np.random.default_rng(79)
+    X = np.zeros((2, T), np.complex64)
+    for c in range(2):
+        fade = np.where((n // 90000) % 2 == 0, 1.0, 0.01)
+        x = (3.0 + c) * fade * np.exp(2j * np.pi * (800 + 150 * c) * n / 1e6) * (1 + 0.5 * np.sin(2 * np.pi * 5 * n / 1e6))
+        X[c] = (x + 0.002 * (rng.standard_normal(T) + 1j * rng.standard_normal(T))).astype(np.complex64)
+    run_case(qrl, oracle, qrl.make_gr_demod_ssb, oracle.DEMOD_SSB, (125, 1000000, 1700, 2700, 0), 0, X,
+             [(100000, []), (300000, [(P.AGC_ATTACK, 0.5), (P.AGC_DECAY, 0.01)]), (300000, [(P.AGC_ATTACK, 0.01), (P.AGC_DECAY, 0.6)])])

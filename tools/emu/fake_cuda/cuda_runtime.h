@@ -57,6 +57,13 @@ static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p)
+{
+    *a = cudaPointerAttributes{ cudaMemoryTypeUnregistered, 0, const_cast<void*>(p), const_cast<void*>(p) };
+    return cudaSuccess;
+}
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, int, cudaDriverEntryPointQueryResult* st)
 {
