@@ -50,7 +50,9 @@ enum qrl_kind {
     QRL_MOD_4FSK = 101, QRL_MOD_QPSK = 102, QRL_MOD_NBFM = 103, QRL_MOD_BPSK = 104, QRL_MOD_2FSK = 105,
     QRL_MOD_SSB = 106,
     QRL_MOD_GMSK = 107,       /* gr_mod_gmsk.cpp:30-100 (sps 50 / 100 / 10 = GMSK2K / 1K / 10K) */
-    QRL_MOD_M17 = 108         /* gr_mod_m17.cpp:30-95 (sps = 125: x125 / 3 from 24 ksps); items: frame bytes, 4 symbols each */
+    QRL_MOD_M17 = 108,        /* gr_mod_m17.cpp:30-95 (sps = 125: x125 / 3 from 24 ksps); items: frame bytes, 4 symbols each */
+    QRL_MOD_DMR = 109         /* gr_mod_dmr.cpp:27-93 (the M17 modulator's structure with the DMR pulse, deviation 0.85 and
+                                 gr_zero_idle_bursts in place of the IF low-pass; see qrl_tx_zero_samples) */
 };
 
 /* runtime parameters (qrl_rx_set_param / qrl_tx_set_param) */
@@ -134,6 +136,15 @@ int qrl_tx_sync(qrl_tx* h);
 int qrl_tx_read(qrl_tx* h, float* dst, long cap, long* n_out, int dst_on_device);
 int qrl_tx_out_device(qrl_tx* h, float** data, long* stride, long* n_out);
 long qrl_tx_launch_count(const qrl_tx* h);
+/* QRL_MOD_DMR only: the "zero_samples" stream tag of gr_dmr_source.cpp:148 / gr_mmdvm_source.cpp:264, attached to byte
+ * `byte_offset` (absolute position in the channel's input stream since create) with value n_samples; channel = -1: every channel.
+ * At gr_zero_idle_bursts (gr_zero_idle_bursts.cpp:45-82) the tag sits on 24 ksps item 20 * byte_offset; `delay` = 62 items earlier
+ * the block loads its counter with n_samples and clears one output item per count (a later tag overrides a running count; of two
+ * tags on one item the first registered wins).  The block's history also delays the stream by 2 * 720 - 1 items (60 ms).
+ * Register a tag before the qrl_tx_work call that feeds byte (byte_offset - 4): a tag whose start item has already been produced
+ * clears only what is left of its count.  Deviation from the reference, on purpose: the reference drops a tag that falls into
+ * the first 62 items of a scheduler window (its lookup is bounded by the current window); here results do not depend on chunking. */
+int qrl_tx_zero_samples(qrl_tx* h, int channel, long long byte_offset, long n_samples);
 /* per-stage device timing of the modulator (like qrl_rx_profile): stage 0 = bit chain (scrambler / encoder / mapper),
  * 1 = pulse shaping + frequency modulator, 2 = final interpolating FIR (the HBM-write-bound kernel) */
 int qrl_tx_profile(qrl_tx* h, int enable);

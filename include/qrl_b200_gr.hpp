@@ -224,6 +224,8 @@ public:
     gr_mod_b200(const gr_mod_b200&) = delete;
     gr_mod_b200& operator=(const gr_mod_b200&) = delete;
     void set_bb_gain(float v) { qrl_tx_set_param(_h, -1, QRL_PARAM_BB_GAIN, v); }
+    // gr_mod_dmr: the "zero_samples" tag gr_dmr_source attaches to a byte of the stream (gr_dmr_source.cpp:148)
+    int zero_samples(int channel, long long byte_offset, long n_samples) { return qrl_tx_zero_samples(_h, channel, byte_offset, n_samples); }
     // what gr_byte_source::set_data hands over: [channels][n] frame bytes -> [channels][n_out] gr_complex at 1 Msps
     int work(const unsigned char* bytes, long n, long stride, std::vector<gr_complex>& out, long* n_out)
     {
@@ -256,5 +258,9 @@ inline gr_mod_b200_sptr make_gr_mod_2fsk(int sps, int samp_rate, int carrier_fre
 inline gr_mod_b200_sptr make_gr_mod_m17(int sps = 125, int samp_rate = 1000000, int carrier_freq = 1700, int filter_width = 9000,
                                         int n_channels = 1, long max_items = 4096, int device = 0)               // src/gr/gr_mod_m17.h:43-44
 { return std::make_shared<gr_mod_b200>(QRL_MOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_items, device); }
+
+inline gr_mod_b200_sptr make_gr_mod_dmr(int sps = 125, int samp_rate = 1000000, int carrier_freq = 1700, int filter_width = 5000,
+                                        int n_channels = 1, long max_items = 4096, int device = 0)               // src/gr/gr_mod_dmr.h:37-38
+{ return std::make_shared<gr_mod_b200>(QRL_MOD_DMR, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_items, device); }
 
 }  // namespace qrl_gr

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <time.h>
 #include <sys/types.h>
+#include <gnuradio/tags.h>
 
 typedef std::complex<float> gr_complex;
 typedef std::vector<int> gr_vector_int;
@@ -60,7 +61,20 @@ public:
     long take_consumed() { const long c = d_consumed; d_consumed = 0; return c; }
     void set_thread_priority(int) {}
     const std::string& name() const { return d_name; }
+    // stream tags: the shim places tags (absolute offsets) on input 0 and advances the item counters like the scheduler
+    uint64_t nitems_written(unsigned) const { return d_nitems_written; }
+    uint64_t nitems_read(unsigned) const { return d_nitems_read; }
+    void stub_add_input_tag(const tag_t& t) { d_in_tags.push_back(t); }
+    void stub_advance(uint64_t nread, uint64_t nwritten) { d_nitems_read += nread; d_nitems_written += nwritten; }
+    void get_tags_in_window(std::vector<tag_t>& v, unsigned, uint64_t rel_start, uint64_t rel_end, const pmt::pmt_t& key)
+    {
+        v.clear();
+        for (const auto& t : d_in_tags)
+            if (t.offset >= d_nitems_read + rel_start && t.offset < d_nitems_read + rel_end && pmt::eqv(t.key, key)) v.push_back(t);
+    }
 protected:
+    std::vector<tag_t> d_in_tags;
+    uint64_t d_nitems_read = 0, d_nitems_written = 0;
     std::string d_name;
     io_signature::sptr d_in, d_out;
     unsigned d_history = 1;

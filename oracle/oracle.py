@@ -14,7 +14,7 @@ _LIB = None
 
 # hier-block kinds (mirror qrl_oracle.h)
 DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB, DEMOD_AM, DEMOD_GMSK, DEMOD_WBFM, DEMOD_M17, DEMOD_DMR = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
-MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB, MOD_GMSK, MOD_M17 = 101, 102, 103, 104, 105, 106, 107, 108
+MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB, MOD_GMSK, MOD_M17, MOD_DMR = 101, 102, 103, 104, 105, 106, 107, 108, 109
 WIN_HAMMING, WIN_HANN, WIN_BLACKMAN, WIN_RECT, WIN_KAISER, WIN_BLACKMAN_HARRIS = 0, 1, 2, 3, 4, 5
 
 
@@ -51,6 +51,9 @@ def lib():
         L.qo_tx_create.argtypes = [C.c_int] * 6
         L.qo_tx_destroy.argtypes = [vp]
         L.qo_tx_set_bb_gain.argtypes = [vp, C.c_float]
+        L.qo_tx_zero_samples.argtypes = [vp, C.c_longlong, C.c_long]
+        L.qo_zero_idle_run.argtypes = [vp, C.c_long, C.c_uint, vp, vp, C.c_long, vp]
+        L.qo_zero_idle_run.restype = None
         L.qo_tx_work.argtypes = [vp, vp, C.c_long]
         L.qo_tx_out_items.restype = C.c_long
         L.qo_tx_out_items.argtypes = [vp]
@@ -163,6 +166,8 @@ def ref_blocks():
         R.ref_dsss_decoder_history.argtypes = [vp]
         R.ref_dsss_decoder_work.restype = C.c_long
         R.ref_dsss_decoder_work.argtypes = [vp, vp, C.c_int, vp, vp]
+        R.ref_zero_idle.restype = C.c_long
+        R.ref_zero_idle.argtypes = [vp, C.c_long, C.c_uint, vp, vp, C.c_long, vp, C.c_long, vp]
         _REF = R
     return _REF
 
@@ -356,6 +361,10 @@ class Tx:
     def set_bb_gain(self, g):
         lib().qo_tx_set_bb_gain(self.h, g)
 
+    def zero_samples(self, byte_offset, n_samples):
+        """MOD_DMR: the "zero_samples" stream tag on input byte `byte_offset` (gr_dmr_source.cpp:148)."""
+        return lib().qo_tx_zero_samples(self.h, int(byte_offset), int(n_samples))
+
     def work(self, data):
         data = np.ascontiguousarray(data)
         rc = lib().qo_tx_work(self.h, _p(data), len(data))
@@ -364,6 +373,15 @@ class Tx:
         buf = C.string_at(lib().qo_tx_out_data(self.h), n * 8)
         lib().qo_tx_out_clear(self.h)
         return np.frombuffer(buf, np.complex64).copy()
+
+
+def zero_idle(x, delay, tag_items, tag_vals):
+    """gr_zero_idle_bursts alone (restatement): x complex64 [n], tags on the block's own input items."""
+    x = np.ascontiguousarray(x, np.complex64)
+    to = np.ascontiguousarray(tag_items, np.int64); tv = np.ascontiguousarray(tag_vals, np.int64)
+    out = np.empty_like(x)
+    lib().qo_zero_idle_run(_p(x), len(x), int(delay), _p(to), _p(tv), len(to), _p(out))
+    return out
 
 
 class PfbChannelizer:

@@ -1870,6 +1870,9 @@ struct qo_tx {
     /* analog modulators */
     resamp_t a_filt, a_rs, a_if; iir1_t preemph; fircc_t a_sb; float env_m2, env_m1; size_t st_pos; qvec s_aud, s_clip, s_c2;
     qvec s_bits, s_coded, s_sym, s_shaped, s_mod, out;
+    /* gr_mod_dmr: gr_zero_idle_bursts (a delay line of history-1 items + the "zero_samples" tags) */
+    int dmr; float* zi_line; long zi_len; unsigned zi_delay; uint64_t zi_n, zi_counter;
+    long long* zi_tag_off; uint64_t* zi_tag_val; long zi_ntags, zi_cap;
 };
 qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag)
 {
@@ -1906,6 +1909,24 @@ qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         n = qo_firdes_low_pass(1, 24000, filter_width, filter_width, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
         resamp_init(&t->a_if, 2, 1, 1, taps, n);
         n = qo_firdes_low_pass(sps, 3.0 * samp_rate, 12000, 12000, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&t->interp, 2, sps, 3, taps, n);
+        t->s_sym.isz = 4; qv_init(&t->s_c2, 8);
+    } else if (kind == QO_MOD_DMR) {
+        /* /root/reference/src/gr/gr_mod_dmr.cpp:27-93: the gr_mod_m17 bit chain (pack 2 -> map {2,3,1,0} -> levels) ->
+         * rational_resampler_fff(5, 1, RRC(5, 24000, 4800, 0.2, 125)) -> x0.66666666 -> frequency_modulator_fc(pi*4800*0.85/24000) ->
+         * gr_zero_idle_bursts(delay = (125 - 1) / 2) -> x0.9 -> x bb_gain -> rational_resampler_ccf(sps, 3, low_pass_2(sps, 3 fs, fw,
+         * 2000, 60, BH)).  The fft_filter_ccf the constructor also makes (:72-73) is never connected. */
+        t->fm = 1; t->sps = 5; t->amplif = 0.9f; t->dmr = 1;
+        const float if_samp_rate = 24000, symbol_rate = if_samp_rate / 5.0f;
+        int n = qo_firdes_rrc(5, if_samp_rate, symbol_rate, 0.2, 25 * 5, taps, 16384);
+        resamp_init(&t->rrc, 1, 5, 1, taps, n);
+        t->zi_delay = (unsigned)((n - 1) / 2);
+        t->fm_sens = (float)((M_PI * symbol_rate * 0.85) / if_samp_rate);
+        /* gr_zero_idle_bursts.cpp:35-38: delay > 0 -> set_history(2 * SAMPLES_PER_SLOT), SAMPLES_PER_SLOT = 720 (src/bursttimer.h:30);
+         * the sync block copies in[i] to out[i], and in[0] is the oldest history item: a delay of history - 1 items */
+        t->zi_len = t->zi_delay > 0 ? 2 * 720 - 1 : 0;
+        t->zi_line = (float*)calloc((size_t)(t->zi_len > 0 ? t->zi_len : 1) * 2, sizeof(float));
+        n = qo_firdes_low_pass_2(sps, 3.0 * samp_rate, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
         resamp_init(&t->interp, 2, sps, 3, taps, n);
         t->s_sym.isz = 4; qv_init(&t->s_c2, 8);
     } else if (kind == QO_MOD_QPSK) {
@@ -1988,9 +2009,89 @@ void qo_tx_destroy(qo_tx* t)
 {
     if (!t) return;
     qv_free(&t->s_bits); qv_free(&t->s_coded); qv_free(&t->s_sym); qv_free(&t->s_shaped); qv_free(&t->s_mod); qv_free(&t->out);
+    free(t->zi_line); free(t->zi_tag_off); free(t->zi_tag_val);
     free(t);
 }
 void qo_tx_set_bb_gain(qo_tx* t, float g) { t->bb_gain = g; }
+
+/* The "zero_samples" stream tag of gr_dmr_source.cpp:148 / gr_mmdvm_source.cpp:264, attached to byte `byte_offset` of the modulator's
+ * input with value n_samples.  GNU Radio carries it through packed_to_unpacked (x8), pack_k_bits(2) (/2) and the x5 pulse shaper:
+ * at gr_zero_idle_bursts it sits on item 20 * byte_offset.  gr_zero_idle_bursts.cpp:61-70: at output item (offset - delay) the block
+ * loads its counter with the value (a later tag overrides a running count; of several tags on one item the first registered wins
+ * here, the reference's std::sort leaves that open) and zeroes one output per count.  Deviation, documented: the reference only sees
+ * a tag whose item lies at least `delay` items inside the current work() window (its lookup is get_tags_in_window of the CURRENT
+ * window matched against item + delay), so it drops tags that fall into the first `delay` items of a scheduler chunk; here a tag is
+ * honoured wherever the chunk boundaries are.  A tag registered after its start item has already been produced zeroes what is left
+ * of its count.  Returns 0, or -1 when the block has no zero-idle stage. */
+int qo_tx_zero_samples(qo_tx* t, long long byte_offset, long n_samples)
+{
+    if (!t || !t->dmr || byte_offset < 0 || n_samples < 0) return -1;
+    long long item = byte_offset * 20;
+    if (item < (long long)t->zi_delay) return 0;        /* gr_zero_idle_bursts.cpp:63: offset == nitems + i + delay never holds */
+    long long start = item - (long long)t->zi_delay;
+    uint64_t val = (uint64_t)n_samples;
+    if (start < (long long)t->zi_n) {
+        const uint64_t late = (uint64_t)((long long)t->zi_n - start);
+        if (late >= val) return 0;
+        val -= late; start = (long long)t->zi_n;
+    }
+    for (long i = 0; i < t->zi_ntags; i++) if (t->zi_tag_off[i] == start) return 0;      /* first registered wins */
+    if (t->zi_ntags == t->zi_cap) {
+        t->zi_cap = t->zi_cap ? 2 * t->zi_cap : 16;
+        t->zi_tag_off = (long long*)realloc(t->zi_tag_off, sizeof(long long) * (size_t)t->zi_cap);
+        t->zi_tag_val = (uint64_t*)realloc(t->zi_tag_val, sizeof(uint64_t) * (size_t)t->zi_cap);
+    }
+    t->zi_tag_off[t->zi_ntags] = start; t->zi_tag_val[t->zi_ntags] = val; t->zi_ntags++;
+    return 0;
+}
+/* gr_zero_idle_bursts::work (gr_zero_idle_bursts.cpp:45-82) on n complex items, in place */
+static void zero_idle_work(qo_tx* t, float* x, size_t n);
+/* the block alone (tests/test_oracle_ref.py pins it to the reference's compiled gr_zero_idle_bursts.cpp): tags are given on the
+ * block's own input items */
+void qo_zero_idle_run(const float* in_c, long n, unsigned delay, const long long* tag_item, const long long* tag_val, long ntags, float* out_c)
+{
+    qo_tx t; memset(&t, 0, sizeof t);
+    t.dmr = 1; t.zi_delay = delay; t.zi_len = delay > 0 ? 2 * 720 - 1 : 0;
+    t.zi_line = (float*)calloc((size_t)(t.zi_len > 0 ? t.zi_len : 1) * 2, sizeof(float));
+    for (long i = 0; i < ntags; i++) {
+        if (tag_item[i] < (long long)delay) continue;
+        /* same bookkeeping as qo_tx_zero_samples, on block items */
+        const long long start = tag_item[i] - (long long)delay;
+        int dup = 0;
+        for (long k = 0; k < t.zi_ntags; k++) if (t.zi_tag_off[k] == start) dup = 1;
+        if (dup) continue;
+        if (t.zi_ntags == t.zi_cap) {
+            t.zi_cap = t.zi_cap ? 2 * t.zi_cap : 16;
+            t.zi_tag_off = (long long*)realloc(t.zi_tag_off, sizeof(long long) * (size_t)t.zi_cap);
+            t.zi_tag_val = (uint64_t*)realloc(t.zi_tag_val, sizeof(uint64_t) * (size_t)t.zi_cap);
+        }
+        t.zi_tag_off[t.zi_ntags] = start; t.zi_tag_val[t.zi_ntags] = (uint64_t)tag_val[i]; t.zi_ntags++;
+    }
+    memcpy(out_c, in_c, sizeof(float) * 2 * (size_t)n);
+    zero_idle_work(&t, out_c, (size_t)n);
+    free(t.zi_line); free(t.zi_tag_off); free(t.zi_tag_val);
+}
+static void zero_idle_work(qo_tx* t, float* x, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {
+        float re = x[2 * i], im = x[2 * i + 1];
+        if (t->zi_len > 0) {
+            const size_t slot = (size_t)(t->zi_n % (uint64_t)t->zi_len);
+            const float dr = t->zi_line[2 * slot], di = t->zi_line[2 * slot + 1];
+            t->zi_line[2 * slot] = re; t->zi_line[2 * slot + 1] = im;
+            re = dr; im = di;
+        }
+        for (long k = 0; k < t->zi_ntags; k++)
+            if (t->zi_tag_off[k] == (long long)t->zi_n) {
+                t->zi_counter = t->zi_tag_val[k];
+                t->zi_tag_off[k] = t->zi_tag_off[t->zi_ntags - 1]; t->zi_tag_val[k] = t->zi_tag_val[t->zi_ntags - 1]; t->zi_ntags--;
+                break;
+            }
+        if (t->zi_counter > 0) { re = 0.0f; im = 0.0f; t->zi_counter--; }
+        x[2 * i] = re; x[2 * i + 1] = im;
+        t->zi_n++;
+    }
+}
 
 /* analog::frequency_modulator_fc (A13).  Default: Q32 fixed-point phase accumulator (prefix-sum friendly,
  * documented deviation); literal: float accumulator + fmodf as GNU Radio does. */
@@ -2027,7 +2128,7 @@ static void fm_mod(qo_tx* t, const float* x, size_t n, qvec* out, float post)
 int qo_tx_work(qo_tx* t, const void* in, long n)
 {
     const uint8_t* bytes = (const uint8_t*)in;
-    if (t->kind == QO_MOD_M17) {
+    if (t->kind == QO_MOD_M17 || t->kind == QO_MOD_DMR) {
         static const int map[4] = { 2, 3, 1, 0 };
         static const float lv[4] = { -1.5f, -0.5f, 0.5f, 1.5f };
         t->s_sym.n = 0;
@@ -2039,7 +2140,9 @@ int qo_tx_work(qo_tx* t, const void* in, long n)
         for (size_t i = 0; i < t->s_shaped.n; i++) p[i] = p[i] * 0.66666666f;
         t->s_mod.n = 0;
         fm_mod(t, p, t->s_shaped.n, &t->s_mod, 1.0f);
-        t->s_c2.n = 0; resamp_work(&t->a_if, (const float*)t->s_mod.d, t->s_mod.n, &t->s_c2);
+        t->s_c2.n = 0;
+        if (t->dmr) { zero_idle_work(t, (float*)t->s_mod.d, t->s_mod.n); qv_push(&t->s_c2, t->s_mod.d, t->s_mod.n); }
+        else resamp_work(&t->a_if, (const float*)t->s_mod.d, t->s_mod.n, &t->s_c2);
         float* m = (float*)t->s_c2.d;
         for (size_t i = 0; i < 2 * t->s_c2.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
         resamp_work(&t->interp, m, t->s_c2.n, &t->out);

@@ -175,3 +175,31 @@ long ref_dsss_decoder_work(void* h, const float* in_c, int noutput, float* out_c
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- gr_zero_idle_bursts (sync block with history 2*SAMPLES_PER_SLOT, stream tags)
+// Fed chunk by chunk like the scheduler: every work() sees history()-1 old items in front of the new ones (zeros at the start of
+// the stream) and the "zero_samples" tags whose absolute offset falls into the window.
+#include "gr_zero_idle_bursts.h"
+extern "C" long ref_zero_idle(const float* in_c, long n, unsigned delay, const long long* tag_off, const long long* tag_val, long ntags,
+                              const long* chunks, long nchunks, float* out_c)
+{
+    auto blk = make_gr_zero_idle_bursts(delay);
+    for (long i = 0; i < ntags; i++) {
+        gr::tag_t t; t.offset = static_cast<uint64_t>(tag_off[i]); t.key = pmt::string_to_symbol("zero_samples");
+        t.value = pmt::from_uint64(static_cast<uint64_t>(tag_val[i]));
+        blk->stub_add_input_tag(t);
+    }
+    const long H = static_cast<long>(blk->history()) - 1;
+    std::vector<gr_complex> buf(static_cast<size_t>(H + n), gr_complex(0, 0));
+    std::memcpy(buf.data() + H, in_c, sizeof(gr_complex) * static_cast<size_t>(n));
+    long done = 0;
+    for (long k = 0; k < nchunks && done < n; k++) {
+        const long m = std::min(chunks[k], n - done);
+        gr_vector_const_void_star in = { buf.data() + done };
+        gr_vector_void_star out = { reinterpret_cast<gr_complex*>(out_c) + done };
+        blk->work(static_cast<int>(m), in, out);
+        blk->stub_advance(static_cast<uint64_t>(m), static_cast<uint64_t>(m));
+        done += m;
+    }
+    return done;
+}

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <type_traits>
@@ -1733,6 +1734,11 @@ struct qrl_tx : HandleBase {
     float fm_sens = 0, amplif = 0, bb_gain = 1.0f, pulse_scale = 0.66666666f;
     int repeat_only = 0;
     bool m17 = false; int M2 = 1;  // gr_mod_m17: 4 symbols per byte, IF low-pass at 24 ksps, x L2 / M2 rational interpolator
+    // gr_mod_dmr: the m17 path with gr_zero_idle_bursts in place of the IF low-pass (a delay of history - 1 items + "zero_samples" tags)
+    bool dmr_tx = false; long long zi_delay_items = 0; unsigned zi_tag_delay = 0;
+    std::vector<std::map<long long, unsigned long long>> zi_tags;      // per channel: start item -> count (first registered wins)
+    std::vector<unsigned long long> zi_counter;                       // per channel: count still running at the end of the last call
+    long long* d_zi_ranges = nullptr; size_t zi_ranges_cap = 0;
     TxBitState* d_bits = nullptr;
     unsigned char* d_in = nullptr;
     float* d_sym = nullptr; unsigned sym_mask = 0; long long sym_stride = 0;    // float (4FSK) / float2 (QPSK)
@@ -1884,6 +1890,21 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         t2 = low_pass(sps, 3.0 * samp_rate, 12000, 12000, WIN_BLACKMAN_HARRIS);
         h->L2 = sps; h->M2 = 3; h->nt2 = (static_cast<int>(t2.size()) + sps - 1) / sps;
         if (sps <= 3 || static_cast<size_t>(h->L2) * h->nt2 * sizeof(float) > 40 * 1024) { set_err(h, "make_gr_mod_m17: unsupported sps"); return fail(QRL_EINVAL); }
+    } else if (kind == QRL_MOD_DMR) {
+        // gr_mod_dmr.cpp:27-93: pulse shaping x5 (RRC(5, 24000, 4800, 0.2, 125 taps)) -> x0.66666666 -> frequency modulator
+        // (pi * 4800 * 0.85 / 24000) -> gr_zero_idle_bursts(62) -> x0.9 -> bb gain -> rational_resampler_ccf(sps, 3, low_pass_2(sps, 3 fs,
+        // fw, 2000, 60, BH)); the fft_filter_ccf of :72-73 is never connected
+        h->m17 = true; h->dmr_tx = true; h->amplif = 0.9f; h->repeat_only = 0;
+        const float if_samp_rate = 24000, symbol_rate = if_samp_rate / 5.0f;
+        t1 = root_raised_cosine(5, if_samp_rate, symbol_rate, 0.2, 25 * 5);
+        h->L1 = 5; h->nt1 = (static_cast<int>(t1.size()) + 4) / 5;
+        h->zi_tag_delay = static_cast<unsigned>((t1.size() - 1) / 2);                        // gr_mod_dmr.cpp:58
+        h->zi_delay_items = h->zi_tag_delay > 0 ? 2 * 720 - 1 : 0;                             // gr_zero_idle_bursts.cpp:35-38, bursttimer.h:30
+        h->fm_sens = static_cast<float>((kPi * symbol_rate * 0.85) / if_samp_rate);
+        t2 = low_pass_2(sps, 3.0 * samp_rate, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS);
+        h->L2 = sps; h->M2 = 3; h->nt2 = (static_cast<int>(t2.size()) + sps - 1) / sps;
+        if (sps <= 3 || static_cast<size_t>(h->L2) * h->nt2 * sizeof(float) > 40 * 1024) { set_err(h, "make_gr_mod_dmr: unsupported sps"); return fail(QRL_EINVAL); }
+        h->zi_tags.resize(h->C); h->zi_counter.assign(h->C, 0);
     } else if (kind == QRL_MOD_2FSK) {
         // gr_mod_2fsk.cpp:43-76
         int nfilts = 25 * sps, spacing = 2; h->amplif = 0.8f;
@@ -1925,7 +1946,7 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     { unsigned cap = pow2_at_least(max_sym + 64); h->sym_mask = cap - 1; h->sym_stride = cap;
       if ((rc = dev_alloc(h, &h->d_sym, static_cast<size_t>(cap) * h->C * (qpsk ? 2 : 1)))) return fail(rc); }
     if (!qpsk) {
-        unsigned cap = pow2_at_least(max_sym * (analog ? 1 : h->L1) + 128); h->if_mask = cap - 1; h->if_stride = cap;
+        unsigned cap = pow2_at_least(max_sym * (analog ? 1 : h->L1) + 128 + h->zi_delay_items); h->if_mask = cap - 1; h->if_stride = cap;
         if ((rc = dev_alloc(h, &h->d_if, static_cast<size_t>(cap) * h->C))) return fail(rc);
     }
     h->out_stride = analog ? max_sym * h->L2 : max_sym * h->L1 * (qpsk ? 1 : h->L2);
@@ -1949,6 +1970,7 @@ int qrl_tx_destroy(qrl_tx* h)
     for (int i = 0; i < qrl_tx::kTxSub; i++) { if (h->ev_bits[i]) cudaEventDestroy(h->ev_bits[i]); if (h->ev_shape[i]) cudaEventDestroy(h->ev_shape[i]); }
     for (auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (void* p : h->allocs) cudaFree(p);
+    if (h->d_zi_ranges) cudaFree(h->d_zi_ranges);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return QRL_OK;
@@ -2121,8 +2143,44 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
         const long long m0 = sym0 * h->L1, m1 = (sym0 + nsym) * h->L1;
         const int TB = 256;
         dim3 g(static_cast<unsigned>((m1 - m0 + TB - 1) / TB), h->C);
+        if (h->dmr_tx) {
+            tx_delay_ring_kernel<<<g, TB, 0, h->stream>>>(h->d_if, h->if_mask, h->if_stride, h->d_rc, h->rc_mask, h->rc_stride, m0, m1,
+                                                          h->zi_delay_items);
+            // the "zero_samples" counters of this call as item ranges (gr_zero_idle_bursts.cpp:61-79: a tag loads the counter, a later
+            // one overrides what is left of it, one output is cleared per count)
+            std::vector<long long> ranges;
+            for (int c = 0; c < h->C; c++) {
+                auto& tg = h->zi_tags[c];
+                tg.erase(tg.begin(), tg.lower_bound(m0));
+                unsigned long long cnt = h->zi_counter[c];
+                if (cnt == 0 && (tg.empty() || tg.begin()->first >= m1)) continue;
+                long long cur = m0;
+                auto it = tg.begin();
+                while (true) {
+                    const long long next = (it != tg.end() && it->first < m1) ? it->first : m1;
+                    const long long z_end = cnt >= static_cast<unsigned long long>(next - cur) ? next : cur + static_cast<long long>(cnt);
+                    if (z_end > cur) { ranges.push_back(c); ranges.push_back(cur); ranges.push_back(z_end); }
+                    cnt -= static_cast<unsigned long long>(z_end - cur);
+                    if (next == m1) break;
+                    cnt = it->second; cur = next; it = tg.erase(it);
+                }
+                h->zi_counter[c] = cnt;
+            }
+            if (!ranges.empty()) {
+                if (ranges.size() > h->zi_ranges_cap) {
+                    CK(cudaStreamSynchronize(h->stream));
+                    if (h->d_zi_ranges) CK(cudaFree(h->d_zi_ranges));
+                    h->zi_ranges_cap = 2 * ranges.size() + 48;
+                    CK(cudaMalloc(&h->d_zi_ranges, sizeof(long long) * h->zi_ranges_cap));
+                }
+                CK(cudaMemcpyAsync(h->d_zi_ranges, ranges.data(), sizeof(long long) * ranges.size(), cudaMemcpyHostToDevice, h->stream));
+                tx_zero_ranges_kernel<<<static_cast<unsigned>(ranges.size() / 3), 256, 0, h->stream>>>(h->d_rc, h->rc_mask, h->rc_stride, h->d_zi_ranges);
+                h->launches++;
+            }
+        } else {
         fir_ccf_ring_kernel<<<g, TB, sizeof(float) * h->nt_cfilt, h->stream>>>(h->d_if, h->if_mask, h->if_stride,
             h->d_rc, h->rc_mask, h->rc_stride, h->d_cfilt, h->nt_cfilt, m0, m1, nullptr, 0, 0, 0);
+        }
         scale2_ring_kernel<<<g, TB, 0, h->stream>>>(h->d_rc, h->rc_mask, h->rc_stride, m0, m1, h->amplif, h->bb_gain);
         const long long o0 = (m0 * h->L2 + h->M2 - 1) / h->M2, o1 = (m1 * h->L2 + h->M2 - 1) / h->M2;   // outputs i with floor(i M / L) < m1
         if (o1 - o0 > h->out_stride) { set_err(h, "qrl_tx_work: output buffer too small"); return QRL_ERANGE; }
@@ -2163,6 +2221,24 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
     }
     h->n_sym += nsym;
     CK(cudaGetLastError());
+    return QRL_OK;
+}
+int qrl_tx_zero_samples(qrl_tx* h, int channel, long long byte_offset, long n_samples)
+{
+    if (!h || channel < -1 || channel >= h->C || byte_offset < 0 || n_samples < 0) return QRL_EINVAL;
+    if (!h->dmr_tx) { set_err(h, "qrl_tx_zero_samples: only gr_mod_dmr has a zero-idle stage"); return QRL_EINVAL; }
+    // the tag rides through packed_to_unpacked (x8), pack_k_bits(2) (/2) and the x5 pulse shaper: item 20 * byte_offset at the block
+    const long long item = byte_offset * 4 * h->L1;
+    if (item < static_cast<long long>(h->zi_tag_delay)) return QRL_OK;          // gr_zero_idle_bursts.cpp:63 can never match
+    long long start = item - static_cast<long long>(h->zi_tag_delay);
+    unsigned long long val = static_cast<unsigned long long>(n_samples);
+    const long long produced = h->n_sym * h->L1;
+    if (start < produced) {                                                      // late: clear what is left of the count
+        const unsigned long long late = static_cast<unsigned long long>(produced - start);
+        if (late >= val) return QRL_OK;
+        val -= late; start = produced;
+    }
+    for (int c = (channel < 0 ? 0 : channel); c < (channel < 0 ? h->C : channel + 1); c++) h->zi_tags[c].emplace(start, val);
     return QRL_OK;
 }
 int qrl_tx_sync(qrl_tx* h)

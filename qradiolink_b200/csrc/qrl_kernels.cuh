@@ -2882,4 +2882,25 @@ __global__ void scale2_ring_kernel(float2* __restrict__ ring, unsigned mask, lon
     ring[static_cast<long long>(c) * stride + (a & mask)] = v;
 }
 
+// gr_zero_idle_bursts (gr_zero_idle_bursts.cpp:45-82) as two ring passes.  (1) the sync block's history: out[a] = in[a - delay_items]
+// (zero before the stream began); (2) the "zero_samples" counter: the host has turned the tags of this call into [begin, end) item
+// ranges per channel (qrl_tx_work), one CTA per range clears them.
+__global__ void tx_delay_ring_kernel(const float2* __restrict__ in, unsigned in_mask, long long in_stride,
+                                     float2* __restrict__ out, unsigned out_mask, long long out_stride,
+                                     long long a0, long long a1, long long delay_items)
+{
+    const int c = blockIdx.y;
+    const long long a = a0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (a >= a1) return;
+    const long long s = a - delay_items;
+    float2 v = make_float2(0.0f, 0.0f);
+    if (s >= 0) v = in[static_cast<long long>(c) * in_stride + (s & in_mask)];
+    out[static_cast<long long>(c) * out_stride + (a & out_mask)] = v;
+}
+__global__ void tx_zero_ranges_kernel(float2* __restrict__ ring, unsigned mask, long long stride, const long long* __restrict__ ranges)
+{
+    const long long c = ranges[3 * blockIdx.x], a0 = ranges[3 * blockIdx.x + 1], a1 = ranges[3 * blockIdx.x + 2];
+    for (long long a = a0 + threadIdx.x; a < a1; a += blockDim.x) ring[c * stride + (a & mask)] = make_float2(0.0f, 0.0f);
+}
+
 }  // namespace qrl

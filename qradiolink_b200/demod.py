@@ -172,7 +172,7 @@ def make_gr_demod_m17(sps=125, samp_rate=1000000, carrier_freq=1700, filter_widt
 
 def make_gr_demod_dmr(sps=5, samp_rate=1000000, n_channels=1, **kw):
     """src/gr/gr_demod_dmr.h:42 (instance gr_demod_base.cpp:253: make_gr_demod_dmr(5, 1e6)); ports (IQ at 24 ksps, symbols, hard bits:
-    2 per symbol, float symbol-filter output).  Not yet run on a GPU (see include/qrl_b200.h)."""
+    2 per symbol, float symbol-filter output)."""
     return RxBlock(KIND.DEMOD_DMR, sps, samp_rate, 0, 5000, 0, n_channels, **kw)
 
 

@@ -13,7 +13,7 @@ class QrlError(RuntimeError):
 
 class KIND:
     DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB, DEMOD_AM, DEMOD_GMSK, DEMOD_WBFM, DEMOD_M17, DEMOD_DMR = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
-    MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB, MOD_GMSK, MOD_M17 = 101, 102, 103, 104, 105, 106, 107, 108
+    MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB, MOD_GMSK, MOD_M17, MOD_DMR = 101, 102, 103, 104, 105, 106, 107, 108, 109
 
 
 class PARAM:
@@ -53,6 +53,7 @@ SYMBOLS = {
     "qrl_tx_out_device": (_i, [_vp, C.POINTER(_vp), C.POINTER(_l), C.POINTER(_l)]),
     "qrl_tx_launch_count": (_l, [_vp]),
     "qrl_tx_profile": (_i, [_vp, _i]),
+    "qrl_tx_zero_samples": (_i, [_vp, _i, C.c_longlong, _l]),
     "qrl_tx_profile_read": (_i, [_vp, _i, C.POINTER(_d), C.POINTER(_l)]),
     "qrl_frontend_create": (_i, [_i, _i, _l, _i, C.POINTER(_vp)]),
     "qrl_frontend_destroy": (_i, [_vp]),

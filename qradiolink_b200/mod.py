@@ -30,6 +30,10 @@ class TxBlock:
         except Exception:
             pass
 
+    def zero_samples(self, byte_offset, n_samples, channel=-1):
+        """gr_mod_dmr: the "zero_samples" tag on input byte `byte_offset` of `channel` (-1: all), see qrl_tx_zero_samples."""
+        check(self._L.qrl_tx_zero_samples(self._h, int(channel), int(byte_offset), int(n_samples)), self._h, "zero_samples")
+
     def set_bb_gain(self, value):
         check(self._L.qrl_tx_set_param(self._h, -1, PARAM.BB_GAIN, float(value)), self._h, "set_bb_gain")
 
@@ -110,5 +114,11 @@ def make_gr_mod_ssb(sps, samp_rate, carrier_freq, filter_width, sb, n_channels=1
 
 def make_gr_mod_m17(sps=125, samp_rate=1000000, carrier_freq=1700, filter_width=9000, n_channels=1, **kw):
     """src/gr/gr_mod_m17.h:43-44 (defaults as there); items: frame bytes, 4 symbols per byte, 125 / 3 output samples per 24 ksps
-    sample.  Not yet run on a GPU (see include/qrl_b200.h)."""
+    sample."""
     return TxBlock(KIND.MOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
+
+
+def make_gr_mod_dmr(sps=125, samp_rate=1000000, carrier_freq=1700, filter_width=5000, n_channels=1, **kw):
+    """src/gr/gr_mod_dmr.h:37-38 (defaults as there); items: frame bytes, 4 symbols per byte.  TxBlock.zero_samples is the
+    "zero_samples" stream tag gr_dmr_source attaches to the bytes of an idle burst (gr_zero_idle_bursts)."""
+    return TxBlock(KIND.MOD_DMR, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)

@@ -411,3 +411,42 @@ def test_frame_and_m17_deframer_restatements(oracle):
     m17 = np.unpackbits(np.array([0x00, 0x55, 0xF7] + list(range(46)) + [0x55, 0x5D, 0x55, 0x5D] + [0xFF] * 46, np.uint8))
     fr = O.Deframer(4, 46 * 8, 46).work(m17)
     assert [t for t, _ in fr] == [0x55F7, 0x555D555D] and fr[0][1] == bytes(range(46)) and fr[1][1] == b"\xFF" * 46
+
+
+def test_dmr_modulator_restatement(oracle):
+    """gr_mod_dmr restated (gr_mod_dmr.cpp:27-93): chunk invariant incl. the "zero_samples" tags, 125/3 output items per 24 ksps
+    item, the gr_zero_idle_bursts history shows as 1439 items (60 ms) of silence in front, a tag clears exactly its count `delay`
+    items before the tagged byte's first item, and the burst loops back through the restated DMR receiver (same pulse, 0.2)."""
+    O = oracle
+    from tests import siggen
+    rng = np.random.default_rng(41)
+    data = rng.integers(0, 256, 400, dtype=np.uint8)
+    a = O.Tx(O.MOD_DMR, 125, 1000000, 1700, 5000, 0)
+    a.zero_samples(100, 720); a.zero_samples(110, 100); a.zero_samples(1, 50); a.zero_samples(300, 333)
+    ya = a.work(data)
+    assert len(ya) == (len(data) * 20 * 125 + 2) // 3
+    b = O.Tx(O.MOD_DMR, 125, 1000000, 1700, 5000, 0)
+    b.zero_samples(100, 720); b.zero_samples(110, 100); b.zero_samples(1, 50); b.zero_samples(300, 333)
+    yb = np.concatenate([b.work(data[lo:lo + 37]) for lo in range(0, len(data), 37)])
+    assert np.array_equal(ya.view(np.uint32), yb.view(np.uint32))
+    # where the 24 ksps stream is zero, the x125/3 interpolator's output is zero once its 33-tap arms are flushed
+    up = 125 / 3
+    head = int(1439 * up) - 10
+    assert np.all(ya[:head] == 0) and np.any(ya[head + 40 * 42:head + 80 * 42] != 0)
+    s0, s1 = 100 * 20 - 62, 110 * 20 - 62                    # tag 2 overrides tag 1: zero [s0, s1) then [s1, s1 + 100)
+    z = np.abs(ya[int((s0 + 40) * up):int((s1 + 100 - 5) * up)])
+    assert np.all(z == 0)
+    assert np.all(np.abs(ya[int((s1 + 100 + 40) * up):int((s1 + 100 + 300) * up)]) > 0.5)
+    assert np.all(np.abs(ya[int((1439 + 40) * up):int((1439 + 200) * up)]) > 0.5)      # the tag on byte 1 (item 20 < delay) is ignored
+    # loop-back: no tags
+    iq = O.Tx(O.MOD_DMR, 125, 1000000, 1700, 5000, 0).work(data)
+    x = siggen.channel(iq, rng, fo_hz=30, phase=0.2, delay=97, snr_db=30, amp=0.5, total=len(iq) + 30000)
+    rx = O.Rx(O.DEMOD_DMR, 5, 1000000, 0, 0, 0)
+    rx.work(x)
+    bits, tx_bits = rx.port(2), np.unpackbits(data)
+    best = 0.0
+    for off in range(2 * 1439 // 5 - 200, 2 * 1439 // 5 + 400):
+        n = min(len(bits) - off, len(tx_bits)) - 900           # the last 1439 items (576 bits) are still in the zero-idle delay line, filter tails
+        if n > 1000:
+            best = max(best, float(np.mean(bits[off + 200:off + n] == tx_bits[200:n])))       # first 200 bits: loops pulling in
+    assert best == 1.0, best

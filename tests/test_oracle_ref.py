@@ -124,3 +124,39 @@ def test_sink_restatements_follow_the_reference_sinks(R, kind):
             else:
                 assert m is not None and len(m) == k and np.array_equal(out[:k], m)
     R.ref_block_destroy(h)
+
+
+def test_zero_idle_bursts_is_the_reference_block(R):
+    """gr_zero_idle_bursts.cpp compiled unmodified (stream tags through the stand-in's get_tags_in_window): delay of history-1 items,
+    a counter loaded `delay` items before the tagged one, later tags overriding a running count.  Tags are kept at least `delay`
+    items inside their work() window -- the only place the restatement deviates (it also honours the ones the reference drops)."""
+    rng = np.random.default_rng(31)
+    n, delay = 30000, 62
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    chunks = np.array([4096, 1000, 8192, 5000, 20000], np.int64)
+    edges = np.concatenate([[0], np.cumsum(chunks)])
+    tag_items, tag_vals = [], []
+    for k in range(len(chunks)):
+        lo, hi = edges[k], min(edges[k + 1], n)
+        if hi - lo < 400:
+            continue
+        for j in range(3):
+            tag_items.append(int(lo + delay + rng.integers(0, hi - lo - delay)))
+            tag_vals.append(int(rng.integers(1, 900)))
+    tag_items.append(tag_items[0] + 5); tag_vals.append(3)           # overrides a running count with a short one
+    tag_items.append(30); tag_vals.append(500)                        # item < delay: never matches
+    to = np.array(tag_items, np.int64); tv = np.array(tag_vals, np.int64)
+    ref = np.zeros(n, np.complex64)
+    ch = chunks.astype(np.int64)
+    done = R.ref_zero_idle(_p(x), n, delay, _p(to), _p(tv), len(to), _p(ch.astype(np.dtype("l"))), len(ch), _p(ref))
+    assert done == n
+    got = O.zero_idle(x, delay, to, tv)
+    assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+    assert np.count_nonzero(got == 0) > 1439 + 500 and np.all(got[:1439] == 0)
+    nz = got[1439:] != 0
+    assert np.array_equal(got[1439:][nz], x[:n - 1439][nz])              # what is not zeroed is the input, 1439 items late
+    # delay = 0: no history, pure pass-through + tags at their own item
+    ref0 = np.zeros(n, np.complex64)
+    R.ref_zero_idle(_p(x), n, 0, _p(to), _p(tv), len(to), _p(ch.astype(np.dtype("l"))), len(ch), _p(ref0))
+    got0 = O.zero_idle(x, 0, to, tv)
+    assert np.array_equal(ref0.view(np.uint32), got0.view(np.uint32))
