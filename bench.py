@@ -76,6 +76,30 @@ def host_cores():
     return used, {"sched_affinity": n, "cgroup_quota_cpus": quota, "cpu_count": os.cpu_count()}
 
 
+def bind_to_gpu_numa(torch, local):
+    """Restrict this rank to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) so that the pinned slab of the
+    e2e leg is first-touched on the GPU's NUMA node and the H2D copy does not cross the socket link.  Returns (old affinity, info)."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        old = os.sched_getaffinity(0)
+        use = cpus & old
+        if not use:
+            return None, {"pci": bdf, "numa_node": node, "bound": False, "why": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, use)
+        return old, {"pci": bdf, "numa_node": node, "bound": True, "cpus": len(use)}
+    except Exception as e:  # noqa: BLE001
+        return None, {"bound": False, "why": "%s: %s" % (type(e).__name__, e)}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi style clock / throttle-reason samples during the timed region (pynvml)."""
 
@@ -679,6 +703,7 @@ def run_ours(args):
     value = world * C * T * n_calls / (ms_max * 1e-3) / 1e6
 
     # ---- e2e: the reference-facing call with HOST buffers: H2D of the gr_complex slab + D2H of the decoded bits, every call
+    old_aff, numa = bind_to_gpu_numa(torch, local)
     Xh = torch.empty((C, T), dtype=torch.complex64, pin_memory=True)
     Xh.copy_(X)
     bits_cap = int(blk.read_port_counts(2).max()) + 256
@@ -708,6 +733,43 @@ def run_ours(args):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * C * T * e2e_calls / (float(t2.item()) * 1e-3) / 1e6
     del Xh
+
+    # ---- the same end-to-end call fed with the SDR's wire format (int16 I/Q, 4 B per sample: qrl_rx_work_sc16), reported beside e2e
+    e2e_sc16 = None
+    try:
+        Xq = torch.empty((C, T, 2), dtype=torch.int16, pin_memory=True)
+        Xq.copy_(torch.view_as_real(X).mul(20000.0).round_().clamp_(-32768, 32767).to(torch.int16))
+        sc = Ct.c_float(1.0 / 32767.0)
+
+        def call_host16():
+            rc = L.qrl_rx_work_sc16(blk._h, Ct.c_void_p(Xq.data_ptr()), T, T, sc, 0)
+            assert rc == 0
+            rc = L.qrl_rx_read_port(blk._h, 2, Ct.c_void_p(out_bits.data_ptr()), bits_cap, out_cnt.ctypes.data_as(Ct.c_void_p), 0)
+            assert rc == 0
+
+        call_host16()
+        bits16 = int(out_cnt.sum())
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(e2e_calls):
+            call_host16()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms16 = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+        t3 = torch.tensor([ms16], device=dev, dtype=torch.float64)
+        if dist:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        e2e_sc16 = {"value": world * C * T * e2e_calls / (float(t3.item()) * 1e-3) / 1e6, "unit": "Msamples/s",
+                    "h2d_bytes_per_call": int(C * T * 4), "decoded_bits_per_call": bits16,
+                    "note": "qrl_rx_work_sc16: pinned int16 I/Q slab (x20000, the SDR's wire format) -> device conversion float(v)/32767 -> same chain"}
+        del Xq
+    except Exception as e:  # noqa: BLE001
+        e2e_sc16 = {"error": "%s: %s" % (type(e).__name__, e)}
+    if old_aff is not None:
+        os.sched_setaffinity(0, old_aff)
     blk.close()
 
     # ---- the other BASELINE configurations (config 4 on every rank; the single-GPU ones on rank 0 at N = 1)
@@ -822,7 +884,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(C * T * 8) * CALLS_PER_STEP,
                 "d2h_bytes_per_step": int(C * bits_cap + 4 * C) * CALLS_PER_STEP,
                 "measured_over_calls": e2e_calls, "h2d_bytes_per_call": int(C * T * 8), "d2h_bytes_per_call": int(C * bits_cap + 4 * C),
-                "note": "pinned host slab -> qrl_rx_work (H2D inside the call) -> qrl_rx_read_port of the decoded bits (D2H), every call; PCIe-bound at 8 B/sample"},
+                "note": "pinned host slab -> qrl_rx_work (H2D inside the call) -> qrl_rx_read_port of the decoded bits (D2H), every call; PCIe-bound at 8 B/sample",
+                "numa": numa, "sc16_ingest": e2e_sc16},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "fir_decim_poly_kernel<50,9,8,128,8>", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

@@ -95,6 +95,11 @@ int qrl_rx_reset(qrl_rx* h);
  * on_device != 0: iq is a device pointer (already in HBM). Otherwise host memory (pinned or pageable);
  * the copy to the device is part of the call.  Asynchronous on the handle's stream. */
 int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device);
+/* The same call fed with the SDR's wire format: interleaved int16 I/Q (UHD / SoapySDR "sc16": 4 bytes per sample, half the PCIe
+ * traffic of gr_complex).  Each component becomes float(v) * scale on the device -- one rounding, the arithmetic of the host-side
+ * converter that sits in front of the reference's uhd / osmosdr source blocks (gr_demod_base.cpp:166-196; UHD's sc16 -> fc32
+ * scale is 1 / 32767) -- and the chain then runs exactly as qrl_rx_work on that gr_complex stream.  stride in int16 pairs. */
+int qrl_rx_work_sc16(qrl_rx* h, const short* iq, long T, long stride, float scale, int on_device);
 /* wait for everything submitted so far */
 /* RSSI tap: per channel the value probe_signal_f holds behind rssi_block (|x|^2 -> moving_average(2000) ->
  * single_pole_iir(0.04) -> 10 log10 -> + level; /root/reference/src/gr/rssi_block.cpp:25-45, gr_demod_base.cpp:199-200) after the
@@ -209,6 +214,28 @@ int  qrl_pfb_out_device(qrl_pfb*, void** data, long* stride, long* items);
 /* copy the last call's output to host (channelizer: row c at host_dst + c*dst_stride items) and synchronise */
 int  qrl_pfb_read(qrl_pfb*, void* host_dst, long dst_stride);
 long qrl_pfb_launch_count(qrl_pfb*);
+
+/* ---- display spectrum on the device -----------------------------------------------------------------
+ * rx_fft_c (/root/reference/src/gr/rx_fft.cpp:44-129; gr_demod_base.cpp:166: 32768 points, Blackman-Harris; get_FFT_data :978-986) for
+ * n_streams streams at once (the wideband source of a GPU, or every channel of a batch: [n_streams][stride] gr_complex like
+ * qrl_rx_work).  One qrl_spectrum_work call is one rx_fft_c::work call: while disabled (the initial state) or while a finished spectrum
+ * has not been fetched the whole call is dropped; otherwise samples x window fill the buffer and the first sample AFTER it filled
+ * runs the forward FFT and volk_32fc_s32f_power_spectrum_32f(points, fft, N, N) (dB of |X / N|^2).  qrl_spectrum_get copies the points
+ * fft-shifted (DC in the middle), *fft_size = N, or *fft_size = 0 when no spectrum is ready, and re-arms the block.
+ * The FFT is hand-written (four-step, radix-2 stages in shared memory; no cuFFT).  Float result against the oracle's double-precision
+ * definition: within 2e-4 dB on bins less than 40 dB below the strongest line, every bin's amplitude within 2e-6 of the peak
+ * amplitude (FFTW's rounding cannot be reproduced either way).
+ * fft_size: power of two in [256, 65536]; window_type: gr::fft::window::win_type (0 Hamming, 1 Hann, 2 Blackman, 3 rectangular,
+ * 5 Blackman-Harris; out of range -> Hamming as rx_fft.cpp:176-179; Kaiser / Bartlett / flat-top are not built). */
+typedef struct qrl_spectrum qrl_spectrum;
+int  qrl_spectrum_create(int fft_size, int window_type, int n_streams, long max_samples, int device, qrl_spectrum** out);
+int  qrl_spectrum_destroy(qrl_spectrum*);
+int  qrl_spectrum_set_stream(qrl_spectrum*, void* cuda_stream);
+int  qrl_spectrum_set_enabled(qrl_spectrum*, int enabled);            /* rx_fft_c::set_enabled */
+int  qrl_spectrum_set_fft_size(qrl_spectrum*, int fft_size);          /* rx_fft_c::set_fft_size: buffer and ready flag reset */
+int  qrl_spectrum_work(qrl_spectrum*, const float* iq, long T, long stride, int on_device);
+int  qrl_spectrum_get(qrl_spectrum*, float* dst, long dst_stride, int dst_on_device, unsigned* fft_size);
+long qrl_spectrum_launch_count(qrl_spectrum*);
 
 /* ---- layer-1 deframer on the device -------------------------------------------------
  * Replaces gr_modem::synchronize / findSync / packBytes (/root/reference/src/gr_modem.cpp:1119-1282, 980-994) for a

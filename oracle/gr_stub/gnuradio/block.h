@@ -25,7 +25,7 @@ typedef std::vector<int> gr_vector_int;
 typedef std::vector<const void*> gr_vector_const_void_star;
 typedef std::vector<void*> gr_vector_void_star;
 
-namespace boost { using mutex = std::mutex; }
+namespace boost { struct mutex : std::mutex { typedef std::unique_lock<std::mutex> scoped_lock; }; }
 
 namespace gr {
 namespace thread {

@@ -52,6 +52,13 @@ def lib():
         L.qo_tx_destroy.argtypes = [vp]
         L.qo_tx_set_bb_gain.argtypes = [vp, C.c_float]
         L.qo_tx_zero_samples.argtypes = [vp, C.c_longlong, C.c_long]
+        L.qo_spectrum_create.restype = vp
+        L.qo_spectrum_create.argtypes = [C.c_int, C.c_int]
+        L.qo_spectrum_destroy.argtypes = [vp]
+        L.qo_spectrum_set_enabled.argtypes = [vp, C.c_int]
+        L.qo_spectrum_set_fft_size.argtypes = [vp, C.c_int]
+        L.qo_spectrum_work.argtypes = [vp, vp, C.c_long]
+        L.qo_spectrum_get.argtypes = [vp, vp]
         L.qo_zero_idle_run.argtypes = [vp, C.c_long, C.c_uint, vp, vp, C.c_long, vp]
         L.qo_zero_idle_run.restype = None
         L.qo_tx_work.argtypes = [vp, vp, C.c_long]
@@ -168,6 +175,13 @@ def ref_blocks():
         R.ref_dsss_decoder_work.argtypes = [vp, vp, C.c_int, vp, vp]
         R.ref_zero_idle.restype = C.c_long
         R.ref_zero_idle.argtypes = [vp, C.c_long, C.c_uint, vp, vp, C.c_long, vp, C.c_long, vp]
+        R.ref_rx_fft_create.restype = vp
+        R.ref_rx_fft_create.argtypes = [C.c_uint, C.c_int]
+        R.ref_rx_fft_set_enabled.argtypes = [vp, C.c_int]
+        R.ref_rx_fft_set_fft_size.argtypes = [vp, C.c_uint]
+        R.ref_rx_fft_work.argtypes = [vp, vp, C.c_int]
+        R.ref_rx_fft_get.restype = C.c_uint
+        R.ref_rx_fft_get.argtypes = [vp, vp]
         _REF = R
     return _REF
 
@@ -382,6 +396,34 @@ def zero_idle(x, delay, tag_items, tag_vals):
     out = np.empty_like(x)
     lib().qo_zero_idle_run(_p(x), len(x), int(delay), _p(to), _p(tv), len(to), _p(out))
     return out
+
+
+class Spectrum:
+    """rx_fft_c (rx_fft.cpp:44-129) restated: one work() per call; get() returns the fft-shifted dB points or None."""
+
+    def __init__(self, fft_size=32768, window=WIN_BLACKMAN_HARRIS):
+        self.h = lib().qo_spectrum_create(fft_size, window)
+        if not self.h:
+            raise ValueError("oracle: fft size must be a power of two")
+        self.n = fft_size
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().qo_spectrum_destroy(self.h); self.h = None
+
+    def set_enabled(self, on):
+        lib().qo_spectrum_set_enabled(self.h, int(bool(on)))
+
+    def set_fft_size(self, n):
+        lib().qo_spectrum_set_fft_size(self.h, int(n)); self.n = int(n)
+
+    def work(self, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        lib().qo_spectrum_work(self.h, _p(x), len(x))
+
+    def get(self):
+        out = np.empty(self.n, np.float32)
+        return out if lib().qo_spectrum_get(self.h, _p(out)) else None
 
 
 class PfbChannelizer:

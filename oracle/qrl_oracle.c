@@ -2604,3 +2604,108 @@ float qo_rssi_work(qo_rssi* r, const float* iq, long n)
     }
     return r->last_db;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------------------
+ * rx_fft_c (/root/reference/src/gr/rx_fft.cpp:44-129), the display spectrum: samples x window fill an N-item buffer; when the
+ * buffer is full at the NEXT incoming sample the forward FFT runs, volk_32fc_s32f_power_spectrum_32f(points, fft, N, N) turns it
+ * into dB and the block stops taking input (d_push > 0: whole work() calls are skipped) until get_fft_data has been called, which
+ * hands the points out fft-shifted.  One qo_spectrum_work call = one work() call.
+ * Not reproducible offline, therefore DEFINED here (parity unpinned for the arithmetic, the buffering / drop logic is pinned to
+ * the compiled rx_fft.cpp in tests/test_oracle_ref.py): the DFT is evaluated in double (radix-2, exact twiddles from cos/sin) and
+ * rounded to float once; the power spectrum follows VOLK 2.x's generic kernel: re = x.re * (1/N), im likewise (float),
+ * 3.01029995663981209120f * log2f(re*re + im*im), an infinite log replaced by -/+127. */
+void qo_window_build(int win, int ntaps, float* w) { win_build(win, ntaps, w); }
+static void dft_core(double* wr, double* wi, const float* in_c, int N)
+{
+    int bits = 0; while ((1 << bits) < N) bits++;
+    for (int i = 0; i < N; i++) {
+        unsigned r = 0; for (int b = 0; b < bits; b++) if (i & (1 << b)) r |= 1u << (bits - 1 - b);
+        wr[r] = (double)in_c[2 * i]; wi[r] = (double)in_c[2 * i + 1];
+    }
+    for (int len = 2; len <= N; len <<= 1) {
+        const int half = len / 2;
+        for (int j = 0; j < half; j++) {
+            const double a = -2.0 * M_PI * (double)j / (double)len, cr = cos(a), ci = sin(a);
+            for (int base = 0; base < N; base += len) {
+                const int p = base + j, q = p + half;
+                const double tr = wr[q] * cr - wi[q] * ci, ti = wr[q] * ci + wi[q] * cr;
+                wr[q] = wr[p] - tr; wi[q] = wi[p] - ti;
+                wr[p] += tr; wi[p] += ti;
+            }
+        }
+    }
+}
+/* the forward DFT as defined for this path: double arithmetic, one rounding to float (also the stand-in for FFTW in oracle/gr_stub) */
+void qo_dft_forward(const float* in_c, float* out_c, int n)
+{
+    double* wr = (double*)malloc(sizeof(double) * (size_t)n); double* wi = (double*)malloc(sizeof(double) * (size_t)n);
+    dft_core(wr, wi, in_c, n);
+    for (int k = 0; k < n; k++) { out_c[2 * k] = (float)wr[k]; out_c[2 * k + 1] = (float)wi[k]; }
+    free(wr); free(wi);
+}
+struct qo_spectrum {
+    int N, win, enabled, data_ready, push;
+    unsigned counter;
+    float* window; float* buf; float* points;
+    double* wr; double* wi;
+};
+static void spectrum_alloc(qo_spectrum* s)
+{
+    s->window = (float*)malloc(sizeof(float) * (size_t)s->N); win_build(s->win, s->N, s->window);
+    s->buf = (float*)calloc((size_t)s->N * 2, sizeof(float));
+    s->points = (float*)calloc((size_t)s->N, sizeof(float));
+    s->wr = (double*)malloc(sizeof(double) * (size_t)s->N); s->wi = (double*)malloc(sizeof(double) * (size_t)s->N);
+    s->counter = 0; s->data_ready = 0;
+}
+static void spectrum_free(qo_spectrum* s) { free(s->window); free(s->buf); free(s->points); free(s->wr); free(s->wi); }
+qo_spectrum* qo_spectrum_create(int fft_size, int window_type)
+{
+    if (fft_size < 2 || (fft_size & (fft_size - 1))) return NULL;
+    qo_spectrum* s = (qo_spectrum*)calloc(1, sizeof *s);
+    s->N = fft_size;
+    s->win = (window_type < QO_WIN_HAMMING || window_type > 7) ? QO_WIN_HAMMING : window_type;    /* rx_fft.cpp:176-179 */
+    spectrum_alloc(s);
+    return s;
+}
+void qo_spectrum_destroy(qo_spectrum* s) { if (s) { spectrum_free(s); free(s); } }
+void qo_spectrum_set_enabled(qo_spectrum* s, int on) { s->enabled = on; }
+void qo_spectrum_set_fft_size(qo_spectrum* s, int n)          /* rx_fft.cpp:130-158 */
+{
+    if (n == s->N || n < 2 || (n & (n - 1))) return;
+    spectrum_free(s); s->N = n; spectrum_alloc(s);
+}
+static void spectrum_execute(qo_spectrum* s)
+{
+    const int N = s->N;
+    dft_core(s->wr, s->wi, s->buf, N);
+    const float inorm = 1.0f / (float)N;
+    for (int k = 0; k < N; k++) {
+        const float re = (float)s->wr[k] * inorm, im = (float)s->wi[k] * inorm;
+        float l = log2f(re * re + im * im);
+        if (isinf(l)) l = copysignf(127.0f, l);
+        s->points[k] = 3.01029995663981209120f * l;
+    }
+}
+void qo_spectrum_work(qo_spectrum* s, const float* iq, long n)
+{
+    if (s->push > 0 || !s->enabled) return;                     /* rx_fft.cpp:80-84 */
+    for (long i = 0; i < n; i++) {
+        if (s->counter >= (unsigned)s->N) {
+            s->counter = 0;
+            spectrum_execute(s);
+            s->data_ready = 1; s->push++;
+        }
+        const float w = s->window[s->counter];
+        s->buf[2 * s->counter] = iq[2 * i] * w; s->buf[2 * s->counter + 1] = iq[2 * i + 1] * w;
+        s->counter++;
+    }
+}
+int qo_spectrum_get(qo_spectrum* s, float* out)                 /* rx_fft.cpp:112-128 */
+{
+    s->push = 0;
+    if (!s->data_ready) return 0;
+    memcpy(out + s->N / 2, s->points, sizeof(float) * (size_t)(s->N / 2));
+    memcpy(out, s->points + s->N / 2, sizeof(float) * (size_t)(s->N / 2));
+    s->data_ready = 0;
+    return s->N;
+}

@@ -152,6 +152,17 @@ qo_dfbb* qo_dfbb_create(int modem_type);
 void  qo_dfbb_destroy(qo_dfbb*);
 long  qo_dfbb_work(qo_dfbb*, const uint8_t* bits, long n, uint8_t* out, long cap);
 
+/* rx_fft_c (rx_fft.cpp:44-129): the display spectrum of one stream; one qo_spectrum_work call = one work() call */
+void qo_window_build(int win, int ntaps, float* w);
+void qo_dft_forward(const float* in_c, float* out_c, int n);
+typedef struct qo_spectrum qo_spectrum;
+qo_spectrum* qo_spectrum_create(int fft_size, int window_type);
+void qo_spectrum_destroy(qo_spectrum*);
+void qo_spectrum_set_enabled(qo_spectrum*, int on);
+void qo_spectrum_set_fft_size(qo_spectrum*, int n);
+void qo_spectrum_work(qo_spectrum*, const float* iq, long n);
+int  qo_spectrum_get(qo_spectrum*, float* out);      /* returns fft_size, or 0 when no spectrum is ready */
+
 #ifdef __cplusplus
 }
 #endif

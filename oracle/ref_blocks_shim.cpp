@@ -203,3 +203,18 @@ extern "C" long ref_zero_idle(const float* in_c, long n, unsigned delay, const l
     }
     return done;
 }
+
+// ---------------------------------------------------------------- rx_fft_c (display spectrum; FFTW replaced by the oracle's DFT, see gr_stub/gnuradio/fft/fft.h)
+#include "rx_fft.h"
+extern "C" {
+void* ref_rx_fft_create(unsigned fftsize, int wintype) { auto* a = new Any; a->b = make_rx_fft_c(fftsize, wintype); return a; }
+void ref_rx_fft_set_enabled(void* h, int on) { as<rx_fft_c>(h)->set_enabled(on != 0); }
+void ref_rx_fft_set_fft_size(void* h, unsigned n) { as<rx_fft_c>(h)->set_fft_size(n); }
+void ref_rx_fft_work(void* h, const float* in_c, int n)
+{
+    gr_vector_const_void_star in = { in_c };
+    gr_vector_void_star out;
+    as<rx_fft_c>(h)->work(n, in, out);
+}
+unsigned ref_rx_fft_get(void* h, float* points) { unsigned n = 0; as<rx_fft_c>(h)->get_fft_data(points, n); return n; }
+}

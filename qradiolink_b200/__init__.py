@@ -14,3 +14,4 @@ from .mod import TxBlock, make_gr_mod_4fsk, make_gr_mod_qpsk, make_gr_mod_bpsk, 
 from .pfb import PfbChannelizer, PfbSynthesizer, mmdvm_port_map  # noqa: F401
 from .framing import Deframer, DeframerBB, MODE_FRAMING, SYNC_1K, SYNC_NARROW, SYNC_WIDE, SYNC_M17, frame  # noqa: F401
 from .frontend import Frontend  # noqa: F401
+from .spectrum import Spectrum  # noqa: F401

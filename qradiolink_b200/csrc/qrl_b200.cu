@@ -122,6 +122,7 @@ struct qrl_rx : HandleBase {
     float* d_taps1 = nullptr;
     float2* d_hist[2] = { nullptr, nullptr };
     float2* d_in_staging = nullptr;
+    short2* d_in_sc16 = nullptr;        // qrl_rx_work_sc16 with a host buffer: the int16 slab as it arrived over PCIe
     long long n_in = 0, n1 = 0;       // stage-1 progress (absolute input samples consumed / outputs produced)
     long long n_in_s = 0, n1_s = 0;   // progress of the per-slice stages behind it (equal to the above between calls)
     bool fir_group_forced = false;     // QRL_FIR_GROUP given: keep it in overlap mode too
@@ -1103,8 +1104,20 @@ int qrl_rx_set_param(qrl_rx* h, int channel, int key, double value)
     return QRL_EINVAL;
 }
 
+static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int on_device, bool sc16, float sc16_scale);
+
 int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
 {
+    return rx_work_impl(h, iq, T, stride, on_device, false, 0.0f);
+}
+int qrl_rx_work_sc16(qrl_rx* h, const short* iq, long T, long stride, float scale, int on_device)
+{
+    return rx_work_impl(h, iq, T, stride, on_device, true, scale);
+}
+
+static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int on_device, bool sc16, float sc16_scale)
+{
+    const float* iq = static_cast<const float*>(iq_any);
     if (!h || !iq || T < 0) return QRL_EINVAL;
     if (T > h->Tmax) { set_err(h, "qrl_rx_work: T exceeds max_samples given at create"); return QRL_ERANGE; }
     if (T == 0) return QRL_OK;
@@ -1112,11 +1125,32 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
     if (on_device) { int rc = check_device_ptr(h, iq, "qrl_rx_work"); if (rc) return rc; }
     const float2* x = reinterpret_cast<const float2*>(iq);
     long long xstride = stride;
-    if (!on_device) {
+    if (!on_device || sc16) {
         if (!h->d_in_staging) {
             int rc = dev_alloc(h, &h->d_in_staging, static_cast<size_t>(h->Tmax) * h->C, false);
             if (rc) return rc;
         }
+    }
+    if (sc16) {
+        // the SDR's wire format (interleaved int16 I/Q, 4 B per sample: half the PCIe bytes of gr_complex); converted on the device
+        // exactly like the host converter in front of the reference's source block: float(v) * scale, one rounding
+        const short2* s = static_cast<const short2*>(iq_any);
+        long long sstride = stride;
+        if (!on_device) {
+            if (!h->d_in_sc16) {
+                int rc = dev_alloc(h, &h->d_in_sc16, static_cast<size_t>(h->Tmax) * h->C, false);
+                if (rc) return rc;
+            }
+            CK(cudaMemcpy2DAsync(h->d_in_sc16, sizeof(short2) * h->Tmax, iq_any, sizeof(short2) * stride,
+                                 sizeof(short2) * T, h->C, cudaMemcpyHostToDevice, h->stream));
+            s = h->d_in_sc16; sstride = h->Tmax;
+        }
+        dim3 g(static_cast<unsigned>(std::min<long long>((T + 1023) / 1024, 65535)), h->C);
+        sc16_to_fc32_kernel<<<g, 256, 0, h->stream>>>(s, sstride, h->d_in_staging, h->Tmax, T, sc16_scale);
+        h->launches++;
+        x = h->d_in_staging;
+        xstride = h->Tmax;
+    } else if (!on_device) {
         CK(cudaMemcpy2DAsync(h->d_in_staging, sizeof(float2) * h->Tmax, iq, sizeof(float2) * stride,
                              sizeof(float2) * T, h->C, cudaMemcpyHostToDevice, h->stream));
         x = h->d_in_staging;

@@ -2882,6 +2882,34 @@ __global__ void scale2_ring_kernel(float2* __restrict__ ring, unsigned mask, lon
     ring[static_cast<long long>(c) * stride + (a & mask)] = v;
 }
 
+// interleaved int16 I/Q (the SDR's wire format) -> gr_complex: float(v) * scale, as the host-side converter in front of the reference's
+// source block does.  4 samples per thread: one 16-byte load, two 16-byte stores.
+__global__ void sc16_to_fc32_kernel(const short2* __restrict__ in, long long in_stride, float2* __restrict__ out, long long out_stride,
+                                    long T, float scale)
+{
+    const int c = blockIdx.y;
+    const short2* src = in + static_cast<long long>(c) * in_stride;
+    float2* dst = out + static_cast<long long>(c) * out_stride;
+    const bool al = ((reinterpret_cast<unsigned long long>(src) & 15) == 0) && ((reinterpret_cast<unsigned long long>(dst) & 15) == 0);
+    for (long q = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; q < T; q += static_cast<long>(gridDim.x) * blockDim.x * 4) {
+        if (al && q + 4 <= T) {
+            const uint4 v = *reinterpret_cast<const uint4*>(src + q);
+            const unsigned w[4] = { v.x, v.y, v.z, v.w };
+            float4 o[2];
+            float* of = reinterpret_cast<float*>(o);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                of[2 * k] = static_cast<float>(static_cast<short>(w[k] & 0xFFFFu)) * scale;
+                of[2 * k + 1] = static_cast<float>(static_cast<short>(w[k] >> 16)) * scale;
+            }
+            *reinterpret_cast<float4*>(dst + q) = o[0];
+            *reinterpret_cast<float4*>(dst + q + 2) = o[1];
+        } else {
+            for (long t = q; t < T && t < q + 4; t++) dst[t] = make_float2(static_cast<float>(src[t].x) * scale, static_cast<float>(src[t].y) * scale);
+        }
+    }
+}
+
 // gr_zero_idle_bursts (gr_zero_idle_bursts.cpp:45-82) as two ring passes.  (1) the sync block's history: out[a] = in[a - delay_items]
 // (zero before the stream began); (2) the "zero_samples" counter: the host has turned the tags of this call into [begin, end) item
 // ranges per channel (qrl_tx_work), one CTA per range clears them.

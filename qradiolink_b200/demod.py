@@ -89,6 +89,20 @@ class RxBlock:
         T = iq.shape[1]
         check(self._L.qrl_rx_work(self._h, iq.ctypes.data_as(C.c_void_p), T, T, 0), self._h, "qrl_rx_work")
 
+    def work_sc16(self, iq16, scale=1.0 / 32767.0):
+        """iq16: int16 array [n_channels, T, 2] (interleaved I/Q as the SDR delivers it) in host memory; each component becomes
+        float32(v) * float32(scale) on the device (qrl_rx_work_sc16: half the PCIe bytes of work())."""
+        iq16 = np.ascontiguousarray(iq16, np.int16)
+        if iq16.ndim == 2:
+            iq16 = iq16[None, :, :]
+        if iq16.shape[0] != self.n_channels or iq16.shape[2] != 2:
+            raise ValueError("expected [%d][T][2] int16" % self.n_channels)
+        T = iq16.shape[1]
+        check(self._L.qrl_rx_work_sc16(self._h, iq16.ctypes.data_as(C.c_void_p), T, T, float(scale), 0), self._h, "qrl_rx_work_sc16")
+
+    def work_sc16_device(self, dev_ptr, T, stride, scale=1.0 / 32767.0):
+        check(self._L.qrl_rx_work_sc16(self._h, C.c_void_p(dev_ptr), T, stride, float(scale), 1), self._h, "qrl_rx_work_sc16")
+
     def work_device(self, dev_ptr, T, stride):
         """iq already resident in HBM: dev_ptr = address of [n_channels][stride] complex64."""
         check(self._L.qrl_rx_work(self._h, C.c_void_p(dev_ptr), T, stride, 1), self._h, "qrl_rx_work")

@@ -32,6 +32,7 @@ SYMBOLS = {
     "qrl_rx_set_param": (_i, [_vp, _i, _i, _d]),
     "qrl_rx_reset": (_i, [_vp]),
     "qrl_rx_work": (_i, [_vp, _vp, _l, _l, _i]),
+    "qrl_rx_work_sc16": (_i, [_vp, _vp, _l, _l, C.c_float, _i]),
     "qrl_rx_sync": (_i, [_vp]),
     "qrl_rx_join": (_i, [_vp]),
     "qrl_rx_rssi": (_i, [_vp, C.c_float, _vp]),
@@ -54,6 +55,14 @@ SYMBOLS = {
     "qrl_tx_launch_count": (_l, [_vp]),
     "qrl_tx_profile": (_i, [_vp, _i]),
     "qrl_tx_zero_samples": (_i, [_vp, _i, C.c_longlong, _l]),
+    "qrl_spectrum_create": (_i, [_i, _i, _i, _l, _i, _vp]),
+    "qrl_spectrum_destroy": (_i, [_vp]),
+    "qrl_spectrum_set_stream": (_i, [_vp, _vp]),
+    "qrl_spectrum_set_enabled": (_i, [_vp, _i]),
+    "qrl_spectrum_set_fft_size": (_i, [_vp, _i]),
+    "qrl_spectrum_work": (_i, [_vp, _vp, _l, _l, _i]),
+    "qrl_spectrum_get": (_i, [_vp, _vp, _l, _i, _vp]),
+    "qrl_spectrum_launch_count": (_l, [_vp]),
     "qrl_tx_profile_read": (_i, [_vp, _i, C.POINTER(_d), C.POINTER(_l)]),
     "qrl_frontend_create": (_i, [_i, _i, _l, _i, C.POINTER(_vp)]),
     "qrl_frontend_destroy": (_i, [_vp]),

@@ -246,3 +246,36 @@ def test_overlapped_calls_with_changing_length(qrl, oracle):
         rx = oracle.Rx(oracle.DEMOD_4FSK, 5, 1000000, 1700, 3000, 1)
         rx.work(X[c])
         assert np.array_equal(bits[c], rx.port(2))
+
+
+def test_sc16_ingest_equals_the_float_path(qrl, oracle):
+    """qrl_rx_work_sc16: int16 I/Q converted on the device (float(v) * scale, one rounding) must give exactly the ports of qrl_rx_work
+    fed with the host-converted gr_complex stream, and of the oracle; ragged chunks incl. lengths that break the 16-byte path."""
+    C, T = 3, 200000
+    X, _ = siggen.gen_4fsk_channels(C, T, seed0=1900)
+    q = np.empty((C, T, 2), np.int16)
+    q[..., 0] = np.clip(np.round(X.real * 20000), -32768, 32767)
+    q[..., 1] = np.clip(np.round(X.imag * 20000), -32768, 32767)
+    scale = np.float32(1.0 / 32767.0)
+    Xf = (q[..., 0].astype(np.float32) * scale + 1j * (q[..., 1].astype(np.float32) * scale)).astype(np.complex64)
+    a = qrl.make_gr_demod_4fsk(5, 1000000, 1700, 3000, True, n_channels=C, max_samples=70001)
+    b = qrl.make_gr_demod_4fsk(5, 1000000, 1700, 3000, True, n_channels=C, max_samples=70001)
+    acc_a = [[[] for _ in range(C)] for _ in range(3)]
+    acc_b = [[[] for _ in range(C)] for _ in range(3)]
+    lo = 0
+    for n in [1, 3, 70001, 4096, 2, 65537, 50000, 10360]:
+        a.work_sc16(q[:, lo:lo + n], scale)
+        b.work(Xf[:, lo:lo + n])
+        for p in range(3):
+            for c in range(C):
+                acc_a[p][c].append(a.read_port(p)[c]); acc_b[p][c].append(b.read_port(p)[c])
+        lo += n
+    assert lo == T
+    for c in range(C):
+        rx = oracle.Rx(oracle.DEMOD_4FSK, 5, 1000000, 1700, 3000, 1)
+        rx.work(Xf[c])
+        for p in range(3):
+            ga, gb = np.concatenate(acc_a[p][c]), np.concatenate(acc_b[p][c])
+            assert len(ga) == len(gb) and np.array_equal(ga, gb), (c, p)
+            want = rx.port(p)
+            assert np.array_equal(ga[:len(want)], want[:len(ga)]) and abs(len(ga) - len(want)) <= 80, (c, p)

@@ -450,3 +450,21 @@ def test_dmr_modulator_restatement(oracle):
         if n > 1000:
             best = max(best, float(np.mean(bits[off + 200:off + n] == tx_bits[200:n])))       # first 200 bits: loops pulling in
     assert best == 1.0, best
+
+
+def test_spectrum_restatement_against_numpy(oracle):
+    """The oracle's display spectrum (rx_fft_c restated) against an independent float64 statement: window x fft -> 10 log10 |X / N|^2,
+    fft-shifted; the trigger sits at the first sample AFTER the buffer filled."""
+    O = oracle
+    rng = np.random.default_rng(62)
+    N = 4096
+    x = (rng.standard_normal(3 * N) + 1j * rng.standard_normal(3 * N)).astype(np.complex64) * 0.2
+    s = O.Spectrum(N, O.WIN_BLACKMAN_HARRIS)
+    s.set_enabled(True)
+    s.work(x[:N]); assert s.get() is None                       # full, but the FFT runs with the next sample
+    s.work(x[N:N + 1])
+    g = s.get()
+    w = np.empty(N, np.float32); O.lib().qo_window_build(O.WIN_BLACKMAN_HARRIS, N, w.ctypes.data_as(__import__("ctypes").c_void_p))
+    X = np.fft.fft((x[:N] * w).astype(np.complex64).astype(np.complex128)) / N
+    want = np.fft.fftshift(10 * np.log10(np.abs(X) ** 2))
+    assert np.max(np.abs(g - want)) < 2e-4

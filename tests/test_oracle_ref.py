@@ -160,3 +160,41 @@ def test_zero_idle_bursts_is_the_reference_block(R):
     R.ref_zero_idle(_p(x), n, 0, _p(to), _p(tv), len(to), _p(ch.astype(np.dtype("l"))), len(ch), _p(ref0))
     got0 = O.zero_idle(x, 0, to, tv)
     assert np.array_equal(ref0.view(np.uint32), got0.view(np.uint32))
+
+
+@pytest.mark.parametrize("n_fft", [1024, 32768])
+def test_rx_fft_restatement_follows_the_reference_block(R, n_fft):
+    """rx_fft.cpp compiled unmodified (FFTW replaced by the oracle's own DFT in the stand-in, so this pins the buffering, windowing,
+    d_push drop rule, power-spectrum kernel and fft-shift, not FFTW's rounding): same points after every get, for ragged work()
+    sizes incl. calls longer than the FFT, calls while a spectrum is pending, disable / enable and a change of size."""
+    rng = np.random.default_rng(61)
+    n = n_fft * 9 + 777
+    t = np.arange(n)
+    x = (0.3 * np.exp(2j * np.pi * 0.1234 * t) + 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    x[5000:5050] = 0
+    h = R.ref_rx_fft_create(n_fft, O.WIN_BLACKMAN_HARRIS)
+    s = O.Spectrum(n_fft, O.WIN_BLACKMAN_HARRIS)
+    sizes = [n_fft // 3, 17, n_fft, n_fft // 2 + 5, 2 * n_fft + 9, 100, n_fft - 1, 3 * n_fft]
+    lo, k, got_any = 0, 0, 0
+    pts = np.empty(n_fft, np.float32)
+    for step, m in enumerate(sizes):
+        if step == 0:
+            R.ref_rx_fft_work(h, _p(x[lo:lo + 50]), 50); s.work(x[lo:lo + 50])      # not enabled yet: dropped
+            R.ref_rx_fft_set_enabled(h, 1); s.set_enabled(True)
+        m = min(m, n - lo)
+        R.ref_rx_fft_work(h, _p(x[lo:lo + m]), m); s.work(x[lo:lo + m]); lo += m
+        if step % 2 == 1:
+            nr = R.ref_rx_fft_get(h, _p(pts)); g = s.get()
+            assert (nr == 0) == (g is None), step
+            if g is not None:
+                assert nr == n_fft and np.array_equal(pts.view(np.uint32), g.view(np.uint32)), step
+                got_any += 1
+                peak = int(np.argmax(g))
+                assert abs(peak - (n_fft // 2 + round(0.1234 * n_fft))) <= 1
+    assert got_any >= 3
+    R.ref_rx_fft_set_fft_size(h, n_fft // 2); s.set_fft_size(n_fft // 2)
+    R.ref_rx_fft_get(h, _p(pts)); s.get()
+    R.ref_rx_fft_work(h, _p(x[:n_fft]), n_fft); s.work(x[:n_fft])
+    nr = R.ref_rx_fft_get(h, _p(pts)); g = s.get()
+    assert nr == n_fft // 2 and np.array_equal(pts[:nr].view(np.uint32), g.view(np.uint32))
+    R.ref_block_destroy(h)

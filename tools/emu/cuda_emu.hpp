@@ -24,6 +24,7 @@
 
 struct float2 { float x, y; };
 struct uint2 { unsigned x, y; };
+struct short2 { short x, y; };
 struct uint4 { unsigned x, y, z, w; };
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{ x, y }; }
 static inline float2 make_float2(float x, float y) { return float2{ x, y }; }
@@ -210,6 +211,7 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)
 }
 static inline unsigned __viaddmin_u32(unsigned a, unsigned b, unsigned c) { const unsigned t = a + b; return t < c ? t : c; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline void sincospif(float x, float* s, float* c) { *s = static_cast<float>(std::sin(3.14159265358979323846 * static_cast<double>(x))); *c = static_cast<float>(std::cos(3.14159265358979323846 * static_cast<double>(x))); }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
