@@ -482,6 +482,57 @@ def pfb_config_block(q, torch, dev, cores, cpu_seconds):
     return res
 
 
+def spectrum_config_block(q, torch, dev, cores, cpu_seconds):
+    """rx_fft_c (32768 points, Blackman-Harris) for 64 streams at once, samples resident in HBM.  One call = N + 1 samples
+    per stream after a get: fill, window, FFT, dB, shift.  Algorithmic bytes per spectrum: 8 N read + 4 N written."""
+    from oracle import oracle as O
+    peak, _ = peaks()
+    S, N = 64, 32768
+    stream = torch.cuda.current_stream()
+    x = torch.view_as_complex(torch.randn((S, 2 * N, 2), device=dev) * 0.2)
+    x += 0.3 * torch.polar(torch.ones(2 * N, device=dev), 2 * np.pi * 0.1234 * torch.arange(2 * N, device=dev))
+    sp = q.Spectrum(N, 5, n_streams=S, max_samples=2 * N)
+    sp.set_stream(stream.cuda_stream)
+    sp.set_enabled(True)
+    out = torch.empty((S, N), dtype=torch.float32, device=dev)
+    L = q.load_library()
+    nfft = Ct.c_uint()
+
+    def call():
+        sp.work_device(x.data_ptr(), N + 1, x.shape[1])
+        assert L.qrl_spectrum_get(sp._h, Ct.c_void_p(out.data_ptr()), N, 1, Ct.byref(nfft)) == 0 and nfft.value == N
+
+    call()
+    o = O.Spectrum(N, O.WIN_BLACKMAN_HARRIS); o.set_enabled(True)
+    o.work(x[5, :N + 1].cpu().numpy())
+    want, got = o.get(), out[5].cpu().numpy()
+    ag, aw = 10.0 ** (got.astype(np.float64) / 20), 10.0 ** (want.astype(np.float64) / 20)
+    ms = timed_calls(call, 20, stream, torch, warm=3)
+    alg = 12.0 * N * S
+    res = {"workload": "rx_fft_c(32768, Blackman-Harris) x 64 streams: fill + window + four-step FFT + power spectrum (dB) + fft-shift, and the D2D get",
+           "ms_per_call": ms, "value": S / (ms * 1e-3), "unit": "spectra/s",
+           "roofline": {"kernel": "spectrum_pass_a_kernel + spectrum_pass_b_kernel", "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ms,
+                        "note": "whole call (5 launches + a D2D copy), not one kernel: 25 MB of algorithmic traffic per call is launch-latency territory"},
+           "parity_vs_oracle": {"stream": 5, "max_db_err_within_40db_of_peak": float(np.max(np.abs(got - want)[want > want.max() - 40])),
+                                "amplitude_rms_rel": float(np.sqrt(np.mean((ag - aw) ** 2)) / np.sqrt(np.mean(aw ** 2))), "tolerance_rms": 1e-5}}
+    sp.close()
+    if cpu_seconds > 0:
+        xh = x[0, :N + 1].cpu().numpy()
+
+        def mk(i):
+            c = O.Spectrum(N, O.WIN_BLACKMAN_HARRIS); c.set_enabled(True)
+            buf = np.empty(N, np.float32)
+
+            def it():
+                c.work(xh); c.get()
+            return it
+        v, dt = cpu_rate(mk, cores, min(cpu_seconds, 2.0), 1)
+        res["cpu_baseline"] = {"value": v * 1e6, "unit": "spectra/s", "cores": cores, "kind": "port",
+                               "sample": "%d host threads, one 32768-point spectrum per iteration through the oracle (double-precision radix-2) for %.1f s" % (cores, dt)}
+    return res
+
+
 def mixed_config_block(q, torch, dev, dist, rank, world, synth, k=4):
     """BASELINE config 4: 1024 channels, ch % 3 -> {NBFM, 4FSK-FM, QPSK-250k}, T = 2^21, sharded by mode then by rank
     (qradiolink_b200.sharding): 128 channels per GPU = three handles per rank running concurrently on three streams.  With fewer than
@@ -829,6 +880,10 @@ def run_ours(args):
             configs["pfb_channelizer_m10"] = pfb_config_block(q, torch, dev, cores, cs)
         except Exception as e:  # noqa: BLE001
             configs["pfb_channelizer_m10"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        try:
+            configs["spectrum_32k_64streams"] = spectrum_config_block(q, torch, dev, cores, cs)
+        except Exception as e:  # noqa: BLE001
+            configs["spectrum_32k_64streams"] = {"error": "%s: %s" % (type(e).__name__, e)}
         try:
             # config 2 with more channels per GPU: the 64-channel step is the latency of two loop warps; the machine has room
             sweep = {}
