@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 # hier-block kinds (mirror qrl_oracle.h)
-DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB, DEMOD_AM, DEMOD_GMSK, DEMOD_WBFM, DEMOD_M17, DEMOD_DMR = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
-MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB, MOD_GMSK, MOD_M17, MOD_DMR = 101, 102, 103, 104, 105, 106, 107, 108, 109
+DEMOD_NBFM, DEMOD_4FSK, DEMOD_QPSK, DEMOD_BPSK, DEMOD_2FSK, DEMOD_SSB, DEMOD_AM, DEMOD_GMSK, DEMOD_WBFM, DEMOD_M17, DEMOD_DMR, DEMOD_DSSS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
+MOD_4FSK, MOD_QPSK, MOD_NBFM, MOD_BPSK, MOD_2FSK, MOD_SSB, MOD_GMSK, MOD_M17, MOD_DMR, MOD_DSSS = 101, 102, 103, 104, 105, 106, 107, 108, 109, 110
 WIN_HAMMING, WIN_HANN, WIN_BLACKMAN, WIN_RECT, WIN_KAISER, WIN_BLACKMAN_HARRIS = 0, 1, 2, 3, 4, 5
 
 
@@ -52,6 +52,9 @@ def lib():
         L.qo_tx_destroy.argtypes = [vp]
         L.qo_tx_set_bb_gain.argtypes = [vp, C.c_float]
         L.qo_tx_zero_samples.argtypes = [vp, C.c_longlong, C.c_long]
+        L.qo_dsss_decoder_taps.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.qo_dsss_decoder_run.restype = C.c_long
+        L.qo_dsss_decoder_run.argtypes = [vp, C.c_int, C.c_int, vp, C.c_long, C.c_long, vp, C.c_long]
         L.qo_spectrum_create.restype = vp
         L.qo_spectrum_create.argtypes = [C.c_int, C.c_int]
         L.qo_spectrum_destroy.argtypes = [vp]

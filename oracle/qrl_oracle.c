@@ -1078,6 +1078,86 @@ void qo_scramble(const uint8_t* in, long n, uint8_t* out) { lfsr_t l; lfsr_init(
 void qo_descramble(const uint8_t* in, long n, uint8_t* out) { lfsr_t l; lfsr_init(&l); for (long i = 0; i < n; i++) out[i] = lfsr_descramble(&l, in[i]); }
 
 /* ------------------------------------------------------------------ RX chains */
+/* gr::dsss::dsss_decoder_cc (/root/reference/src/gr/dsss_decoder_cc_impl.cc:45-175): matched filter = the reversed code, `samples`
+ * items per chip, RRC-shaped (:60-96: N + rrc_ntaps taps, rrc_ntaps = 11 * samples); per output symbol m the N = samples * code_len
+ * correlations y_j = fir_filter_ccc(taps).filter(in + (i - 1) N + j), j = 0..N-1, and the strongest one (first strict maximum of
+ * |y|) times 2 / N goes out (:150-166).  With history N the pointer arithmetic reads from item m N - 2 N + 1 + j on: N items
+ * BEFORE the declared history.  In GNU Radio that region is whatever the circular buffer still holds; HERE it is defined as the
+ * stream's own older items (zeros before the stream began), which makes the block a chunk-invariant stream function.
+ * |y| = std::abs(complex<float>) = hypotf, glibc: (float)sqrt((double)re * re + (double)im * im). */
+typedef struct { int N, ntaps; float* tr; qvec in; long long n_in, m_out; } dsssdec_t;
+void qo_dsss_decoder_taps(const int* code, int code_len, int samples, float* taps_c /* [(N + 11 samples)][2] */)
+{
+    const int N = samples * code_len, extra = samples * 11, total = N + 2 * extra;
+    float* cs = (float*)calloc((size_t)total, sizeof(float));
+    for (int i = 0; i < code_len; i++) {
+        const float c = code[code_len - (i + 1)] == 0 ? -1.0f : 1.0f;
+        for (int k = 0; k < samples; k++) cs[extra + i * samples + k] = c;
+    }
+    static float rrc[16384];
+    const int nr = qo_firdes_rrc(1, samples, 1.0, 0.350f, extra, rrc, 16384);
+    /* fir_filter_ccf(rrc).filter(&code_symbols[i]) = sum_k rrc[nr-1-k] * cs[i+k]; code symbols are real: imaginary part 0 */
+    for (int i = 0; i < N + extra; i++) {
+        float acc = 0.0f, acci = 0.0f;
+        for (int k = 0; k < nr; k++) { acc = acc + cs[i + k] * rrc[nr - 1 - k]; acci = acci + 0.0f * rrc[nr - 1 - k]; }
+        taps_c[2 * i] = acc; taps_c[2 * i + 1] = acci;
+    }
+    free(cs);
+}
+static void dsssdec_init(dsssdec_t* d, const int* code, int code_len, int samples)
+{
+    memset(d, 0, sizeof *d);
+    d->N = samples * code_len; d->ntaps = d->N + samples * 11;
+    float* t = (float*)malloc(sizeof(float) * 2 * (size_t)d->ntaps);
+    qo_dsss_decoder_taps(code, code_len, samples, t);
+    d->tr = (float*)malloc(sizeof(float) * 2 * (size_t)d->ntaps);           /* fir_filter_ccc stores the taps reversed */
+    for (int k = 0; k < d->ntaps; k++) { d->tr[2 * k] = t[2 * (d->ntaps - 1 - k)]; d->tr[2 * k + 1] = t[2 * (d->ntaps - 1 - k) + 1]; }
+    free(t);
+    qv_init(&d->in, 8);
+    /* the stream begins with 2 N - 1 zeros in front: in.d[i] is stream item i - (2 N - 1) + (items dropped so far) */
+    float z[2] = { 0.0f, 0.0f };
+    for (int i = 0; i < 2 * d->N - 1; i++) qv_push(&d->in, z, 1);
+}
+static void dsssdec_work(dsssdec_t* d, const float* x, size_t n, qvec* out)
+{
+    qv_push(&d->in, x, n);
+    d->n_in += (long long)n;
+    const int N = d->N;
+    /* output m reads stream items up to m N + (ntaps - N) - 1: produced once they have arrived */
+    while ((d->m_out * N + (d->ntaps - N)) <= d->n_in) {
+        const float* b = (const float*)d->in.d;        /* b[0] = stream item m_out N - (2 N - 1) */
+        float best = 0.0f, br = 0.0f, bi = 0.0f;
+        for (int j = 0; j < N; j++) {
+            const float* w = b + 2 * (size_t)j;
+            float ar = 0.0f, ai = 0.0f;
+            for (int k = 0; k < d->ntaps; k++) {
+                const float xr = w[2 * k], xi = w[2 * k + 1], tr = d->tr[2 * k], ti = d->tr[2 * k + 1];
+                const float pr = xr * tr - xi * ti, pi = xr * ti + xi * tr;
+                ar = ar + pr; ai = ai + pi;
+            }
+            const float mag = (float)sqrt((double)ar * (double)ar + (double)ai * (double)ai);
+            if (mag > best) { best = mag; br = ar; bi = ai; }
+        }
+        const float sc = 2.0f / (float)N;
+        qv_pushc(out, br * sc, bi * sc);
+        /* drop N items: the next symbol's window starts N later */
+        memmove(d->in.d, (char*)d->in.d + 8 * (size_t)N, 8 * (d->in.n - (size_t)N));
+        d->in.n -= (size_t)N;
+        d->m_out++;
+    }
+}
+/* the decoder alone, fed in `chunk`-item pieces (tests: against the compiled reference block, and chunk invariance) */
+long qo_dsss_decoder_run(const int* code, int code_len, int samples, const float* in_c, long n, long chunk, float* out_c, long cap)
+{
+    dsssdec_t d; dsssdec_init(&d, code, code_len, samples);
+    qvec out; qv_init(&out, 8);
+    for (long lo = 0; lo < n; lo += chunk) dsssdec_work(&d, in_c + 2 * lo, (size_t)((n - lo) < chunk ? (n - lo) : chunk), &out);
+    const long m = (long)out.n < cap ? (long)out.n : cap;
+    memcpy(out_c, out.d, 8 * (size_t)m);
+    qv_free(&out); qv_free(&d.in); free(d.tr);
+    return m;
+}
+
 struct qo_rx {
     int gmsk;               /* 2FSK branch running as gr_demod_gmsk */
     int m17;                /* 4FSK (fm) branch running as gr_demod_m17 */
@@ -1104,6 +1184,8 @@ struct qo_rx {
     int filter_width, flag;
     /* bpsk / 2fsk */
     fll_t fll; crmm_t crmm; ccdec_t dec2; lfsr_t descr2; int dec2_started;
+    /* dsss */
+    resamp_t resamp_if; dsssdec_t dsss; qvec s_dsss;
     /* front-end rotator (gr_demod_base.cpp:57,180,1220-1225): Q32 NCO, phase = base + inc * (n - n_base) */
     uint32_t rot_inc, rot_base; long long rot_nbase, rot_n; qvec s_rot;
     /* scratch + ports */
@@ -1372,6 +1454,32 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         costas_init(&r->costas, (float)(2 * M_PI / 200), 2, 0);
         r->soft_scale = 64.0f;
         ccdec_init(&r->dec); lfsr_init(&r->descr); ccdec_init(&r->dec2); lfsr_init(&r->descr2);
+    } else if (kind == QO_DEMOD_DSSS) {
+        /* /root/reference/src/gr/gr_demod_dsss.cpp:32-124 (instance gr_demod_base.cpp:218: make_gr_demod_dsss(25, 1e6, 1700, 150)):
+         * /50 -> rational_resampler_ccf(13, 50) low_pass(1, 20k, 2600, 2600, BH) -> costas_loop_cc(pi/200, 2, snr) -> low_pass(1, 5200,
+         * fw, 1200, BH) [port 0] -> agc2_cc(.1, .1, 1, 10) -> dsss_decoder_cc(barker 13, sps) -> clock_recovery_mm_cc(1, 2.5e-5, .5,
+         * .05, .005) -> costas_loop_cc(2 pi/100, 2) [port 1] -> real -> x64 + 128 -> uchar -> 2 x cc_decoder (second after delay(1))
+         * -> 2 x descrambler [ports 2, 3] */
+        static const int barker_13[13] = { 1, 1, 1, 1, 1, 0, 0, 1, 1, 0, 1, 0, 1 };
+        r->tsr = 5200; r->sym_sps = sps;
+        int n0 = qo_firdes_low_pass(1, samp_rate, 20000 / 2, 20000 / 2, QO_WIN_BLACKMAN_HARRIS, T0, 4096);
+        r->ntaps_store[0] = n0;
+        resamp_init(&r->resamp, 2, 1, 50, T0, n0);
+        int n1 = qo_firdes_low_pass(1, 20000, 5200 / 2, 5200 / 2, QO_WIN_BLACKMAN_HARRIS, T1, 4096);
+        r->ntaps_store[1] = n1;
+        resamp_init(&r->resamp_if, 2, 13, 50, T1, n1);
+        costas_init(&r->pll, (float)(M_PI / 200), 2, 1);
+        int n2 = qo_firdes_low_pass(1, 5200, filter_width, 1200, QO_WIN_BLACKMAN_HARRIS, T2, 4096);
+        r->ntaps_store[2] = n2;
+        resamp_init(&r->shaping, 2, 1, 1, T2, n2);
+        agc2_init(&r->agc, 1e-1f, 1e-1f, 1.0f, 10.0f);
+        dsssdec_init(&r->dsss, barker_13, 13, sps);
+        float gain_mu = 0.05f, gain_omega = 0.005f;
+        crmm_init(&r->crmm, 1.0f, gain_omega * gain_omega, 0.5f, gain_mu, 0.005f);
+        costas_init(&r->costas, (float)(2 * M_PI / 100), 2, 0);
+        r->soft_scale = 64.0f;
+        ccdec_init(&r->dec); lfsr_init(&r->descr); ccdec_init(&r->dec2); lfsr_init(&r->descr2);
+        qv_init(&r->s_dsss, 8);
     } else { free(r); return NULL; }
     if (r->kind == QO_DEMOD_NBFM || r->kind == QO_DEMOD_WBFM) { r->filt.hkeep = 2048; r->audio_filt.hkeep = 512; }      /* filters a setter may lengthen */
     if (r->kind == QO_DEMOD_SSB || r->kind == QO_DEMOD_AM) { r->ssb_bpf.hkeep = 2048; }
@@ -1657,6 +1765,28 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
         rx_fec_tail_dual(r);
         return 0;
     }
+    if (r->kind == QO_DEMOD_DSSS) {
+        r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
+        r->s_tmp.n = 0; resamp_work(&r->resamp_if, (const float*)r->s_res.d, r->s_res.n, &r->s_tmp);
+        float* v = (float*)r->s_tmp.d;
+        for (size_t i = 0; i < r->s_tmp.n; i++) costas_step(&r->pll, v[2 * i], v[2 * i + 1], &v[2 * i], &v[2 * i + 1]);
+        r->s_filt.n = 0; resamp_work(&r->shaping, v, r->s_tmp.n, &r->s_filt);
+        qv_push(&r->port[0], r->s_filt.d, r->s_filt.n);
+        float* f = (float*)r->s_filt.d;
+        for (size_t i = 0; i < r->s_filt.n; i++) agc2_step(&r->agc, f[2 * i], f[2 * i + 1], &f[2 * i], &f[2 * i + 1]);
+        r->s_dsss.n = 0; dsssdec_work(&r->dsss, f, r->s_filt.n, &r->s_dsss);
+        r->s_sym.isz = 8; r->s_sym.n = 0;
+        crmm_work(&r->crmm, (const float*)r->s_dsss.d, r->s_dsss.n, &r->s_sym);
+        const float* sy = (const float*)r->s_sym.d;
+        for (size_t i = 0; i < r->s_sym.n; i++) {
+            float cr, ci;
+            costas_step(&r->costas, sy[2 * i], sy[2 * i + 1], &cr, &ci);
+            qv_pushc(&r->port[1], cr, ci);
+            qv_pushb(&r->s_soft, soft_u8(cr, r->soft_scale));
+        }
+        rx_fec_tail_dual(r);
+        return 0;
+    }
     if (r->kind == QO_DEMOD_BPSK) {
         r->s_res.n = 0; resamp_work(&r->resamp, iq, (size_t)T, &r->s_res);
         float* v = (float*)r->s_res.d;
@@ -1871,6 +2001,7 @@ struct qo_tx {
     resamp_t a_filt, a_rs, a_if; iir1_t preemph; fircc_t a_sb; float env_m2, env_m1; size_t st_pos; qvec s_aud, s_clip, s_c2;
     qvec s_bits, s_coded, s_sym, s_shaped, s_mod, out;
     /* gr_mod_dmr: gr_zero_idle_bursts (a delay line of history-1 items + the "zero_samples" tags) */
+    int dsss;
     int dmr; float* zi_line; long zi_len; unsigned zi_delay; uint64_t zi_n, zi_counter;
     long long* zi_tag_off; uint64_t* zi_tag_val; long zi_ntags, zi_cap;
 };
@@ -1929,6 +2060,19 @@ qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         n = qo_firdes_low_pass_2(sps, 3.0 * samp_rate, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
         resamp_init(&t->interp, 2, sps, 3, taps, n);
         t->s_sym.isz = 4; qv_init(&t->s_c2, 8);
+    } else if (kind == QO_MOD_DSSS) {
+        /* /root/reference/src/gr/gr_mod_dsss.cpp:27-93: bits -> scrambler -> cc_encoder -> unpacked_to_packed(1) -> dsss_encoder_bb(barker
+         * 13) -> chunks_to_symbols_bc{-1, +1} -> rational_resampler_ccf(sps, 1, RRC(sps, sps, 1, 0.35, 11 sps)) -> x0.65 -> x bb_gain ->
+         * rational_resampler_ccf(50, 13, low_pass(50, 5200 * 50, fw, 5 fw)) -> rational_resampler_ccf(50, 1, low_pass(50, fs, fw, 5 fw));
+         * the fft_filter_ccf of :67-69 is never connected */
+        t->sps = sps; t->amplif = 0.65f; t->dsss = 1;
+        int n = qo_firdes_rrc(sps, sps, 1, 0.35, 11 * sps, taps, 16384);
+        resamp_init(&t->rrc, 2, sps, 1, taps, n);
+        n = qo_firdes_low_pass(50.0, 5200.0 * 50, filter_width, filter_width * 5, QO_WIN_HAMMING, taps, 16384);
+        resamp_init(&t->a_if, 2, 50, 13, taps, n);
+        n = qo_firdes_low_pass(50, samp_rate, filter_width, filter_width * 5, QO_WIN_HAMMING, taps, 16384);
+        resamp_init(&t->interp, 2, 50, 1, taps, n);
+        t->s_sym.isz = 8; qv_init(&t->s_c2, 8); qv_init(&t->s_clip, 8);
     } else if (kind == QO_MOD_QPSK) {
         /* /root/reference/src/gr/gr_mod_qpsk.cpp:26-90 */
         int nfilts;
@@ -2128,6 +2272,28 @@ static void fm_mod(qo_tx* t, const float* x, size_t n, qvec* out, float post)
 int qo_tx_work(qo_tx* t, const void* in, long n)
 {
     const uint8_t* bytes = (const uint8_t*)in;
+    if (t->kind == QO_MOD_DSSS) {
+        static const int barker_13[13] = { 1, 1, 1, 1, 1, 0, 0, 1, 1, 0, 1, 0, 1 };
+        t->s_bits.n = 0;
+        for (long i = 0; i < n; i++)
+            for (int b = 7; b >= 0; b--) qv_pushb(&t->s_bits, lfsr_scramble(&t->scr, (bytes[i] >> b) & 1));
+        t->s_coded.n = 0;
+        ccenc_work(&t->enc, t->s_bits.d, t->s_bits.n, &t->s_coded);
+        /* unpacked_to_packed (8 coded bits per byte, MSB first) then dsss_encoder_bb walks the byte MSB first again: per coded bit
+         * 13 chips, the code for a 0 and its complement for a 1 (dsss_encoder_bb_impl.cc:86-97); chips -> {-1, +1} */
+        t->s_sym.n = 0;
+        for (size_t i = 0; i < t->s_coded.n; i++)
+            for (int c = 0; c < 13; c++) {
+                const int chip = t->s_coded.d[i] == 0 ? (1 & barker_13[c]) : (1 & ~barker_13[c]);
+                qv_pushc(&t->s_sym, chip ? 1.0f : -1.0f, 0.0f);
+            }
+        t->s_c2.n = 0; resamp_work(&t->rrc, (const float*)t->s_sym.d, t->s_sym.n, &t->s_c2);
+        float* m = (float*)t->s_c2.d;
+        for (size_t i = 0; i < 2 * t->s_c2.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
+        t->s_clip.n = 0; resamp_work(&t->a_if, m, t->s_c2.n, &t->s_clip);
+        resamp_work(&t->interp, (const float*)t->s_clip.d, t->s_clip.n, &t->out);
+        return 0;
+    }
     if (t->kind == QO_MOD_M17 || t->kind == QO_MOD_DMR) {
         static const int map[4] = { 2, 3, 1, 0 };
         static const float lv[4] = { -1.5f, -0.5f, 0.5f, 1.5f };

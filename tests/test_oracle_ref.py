@@ -198,3 +198,50 @@ def test_rx_fft_restatement_follows_the_reference_block(R, n_fft):
     nr = R.ref_rx_fft_get(h, _p(pts)); g = s.get()
     assert nr == n_fft // 2 and np.array_equal(pts[:nr].view(np.uint32), g.view(np.uint32))
     R.ref_block_destroy(h)
+
+
+BARKER_13 = np.array([1, 1, 1, 1, 1, 0, 0, 1, 1, 0, 1, 0, 1], np.int32)
+
+
+def test_dsss_decoder_restatement_is_the_reference_block(R):
+    """dsss_decoder_cc_impl.cc compiled unmodified: the matched-filter taps its constructor builds, and general_work over a buffer laid
+    out the way the restatement DEFINES the region in front of the declared history (the stream's own older items, zeros at the
+    start): same symbols bit for bit, for several scheduler chunkings of the reference and several of the restatement."""
+    sps, N = 25, 325
+    h = R.ref_dsss_decoder_create(_p(BARKER_13), 13, C.c_float(sps))
+    assert R.ref_dsss_decoder_history(h) == N
+    nt = N + 11 * sps
+    tr = np.zeros(2 * nt, np.float32); tq = np.zeros(2 * nt, np.float32)
+    assert R.ref_dsss_decoder_taps(h, _p(tr), nt) == nt
+    O.lib().qo_dsss_decoder_taps(_p(BARKER_13), 13, sps, _p(tq))
+    assert np.array_equal(tr.view(np.uint32), tq.view(np.uint32))
+    rng = np.random.default_rng(71)
+    n_sym = 40
+    # a spread BPSK stream + noise so that the maximum is well defined, plus a stretch of exact zeros
+    chips = np.repeat(np.where(BARKER_13 > 0, 1.0, -1.0), sps)
+    bits = rng.integers(0, 2, n_sym) * 2 - 1
+    x = np.concatenate([b * chips for b in bits]).astype(np.complex64) * np.exp(0.4j).astype(np.complex64)
+    x = (x + 0.3 * (rng.standard_normal(len(x)) + 1j * rng.standard_normal(len(x)))).astype(np.complex64)
+    x[3000:3400] = 0
+    n = len(x)
+    got = np.zeros(n_sym + 4, np.complex64)
+    for chunk in (n, 1000, 77):
+        m = O.lib().qo_dsss_decoder_run(_p(BARKER_13), 13, sps, _p(x), n, chunk, _p(got), len(got))
+        if chunk == n:
+            first, m0 = got[:m].copy(), m
+        assert m == m0 and np.array_equal(got[:m].view(np.uint32), first.view(np.uint32)), chunk
+    # reference: buffer = [2N - 1 zeros][x][slack]; output m is called with `in` = item m N - (N - 1) (history N), one or more per call
+    buf = np.concatenate([np.zeros(2 * N - 1, np.complex64), x, np.zeros(2 * N, np.complex64)])
+    for per_call in (1, 3, m0):
+        ref = np.zeros(m0, np.complex64)
+        done = 0
+        while done < m0:
+            k = min(per_call, m0 - done)
+            cons = C.c_long()
+            in_ptr = buf[(2 * N - 1) + done * N - (N - 1):]
+            out = np.zeros(k, np.complex64)
+            assert R.ref_dsss_decoder_work(h, _p(in_ptr), k, _p(out), C.byref(cons)) == k and cons.value == k * N
+            ref[done:done + k] = out; done += k
+        assert np.array_equal(ref.view(np.uint32), first.view(np.uint32)), per_call
+    assert m0 >= n_sym - 2
+    R.ref_block_destroy(h)
