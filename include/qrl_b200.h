@@ -45,12 +45,17 @@ enum qrl_kind {
     QRL_DEMOD_M17 = 10,       /* gr_demod_m17.cpp:30-113; ports: IQ at 24 ksps, symbols, hard bits (2 per symbol) */
     QRL_DEMOD_DMR = 11,       /* gr_demod_dmr.cpp:32-112; qrl_rx_create ignores carrier_freq / filter_width / flag; ports: IQ at
                                  24 ksps, symbols, hard bits (2 per symbol), FLOAT symbol filter output (one per port-0 sample) */
+    QRL_DEMOD_DSSS = 12,      /* gr_demod_dsss.cpp:32-124 (make_gr_demod_dsss(25, 1e6, 1700, 150)): Barker-13 BPSK at 16 symbols/s;
+                                 ports: IQ at 5200 sps, symbols, decoded bits of the two decoders (4 ports like BPSK).  The despreader's
+                                 look-back beyond its declared history is DEFINED as the stream's own older items (zeros at the start) */
     QRL_DEMOD_WBFM = 9,       /* gr_demod_wbfm.cpp:28-70; ports: IQ at 200 ksps, float audio at 8 ksps */
     QRL_DEMOD_GMSK = 8,       /* gr_demod_gmsk.cpp:30-134; sps 10 / 5 / 1 = GMSK1K / 2K / 10K; 4 ports like 2FSK */
     QRL_MOD_4FSK = 101, QRL_MOD_QPSK = 102, QRL_MOD_NBFM = 103, QRL_MOD_BPSK = 104, QRL_MOD_2FSK = 105,
     QRL_MOD_SSB = 106,
     QRL_MOD_GMSK = 107,       /* gr_mod_gmsk.cpp:30-100 (sps 50 / 100 / 10 = GMSK2K / 1K / 10K) */
     QRL_MOD_M17 = 108,        /* gr_mod_m17.cpp:30-95 (sps = 125: x125 / 3 from 24 ksps); items: frame bytes, 4 symbols each */
+    QRL_MOD_DSSS = 110,       /* gr_mod_dsss.cpp:27-93 (make_gr_mod_dsss(25, 1e6, 1700, 200), gr_mod_base.cpp:170): one input byte = 208 chips = 10^6 output items, so
+                                 max_items is small (the output buffer holds max_items x 8 MB per channel) */
     QRL_MOD_DMR = 109         /* gr_mod_dmr.cpp:27-93 (the M17 modulator's structure with the DMR pulse, deviation 0.85 and
                                  gr_zero_idle_bursts in place of the IF low-pass; see qrl_tx_zero_samples) */
 };

@@ -207,6 +207,9 @@ inline gr_demod_b200_sptr make_gr_demod_m17(int sps = 125, int samp_rate = 10000
                                             int n_channels = 1, long max_samples = 1 << 20, int device = 0)      // src/gr/gr_demod_m17.h:41-42
 { return std::make_shared<gr_demod_b200>(QRL_DEMOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_samples, device); }
 
+inline gr_demod_b200_sptr make_gr_demod_dsss(int sps = 25, int samp_rate = 1000000, int carrier_freq = 1700, int filter_width = 150,
+                                             int n_channels = 1, long max_samples = 1 << 20, int device = 0)     // instance gr_demod_base.cpp:218
+{ return std::make_shared<gr_demod_b200>(QRL_DEMOD_DSSS, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_samples, device); }
 inline gr_demod_b200_sptr make_gr_demod_dmr(int sps = 5, int samp_rate = 1000000,
                                             int n_channels = 1, long max_samples = 1 << 20, int device = 0)      // src/gr/gr_demod_dmr.h:42
 { return std::make_shared<gr_demod_b200>(QRL_DEMOD_DMR, sps, samp_rate, 0, 5000, 0, n_channels, max_samples, device); }
@@ -259,6 +262,9 @@ inline gr_mod_b200_sptr make_gr_mod_m17(int sps = 125, int samp_rate = 1000000, 
                                         int n_channels = 1, long max_items = 4096, int device = 0)               // src/gr/gr_mod_m17.h:43-44
 { return std::make_shared<gr_mod_b200>(QRL_MOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_items, device); }
 
+inline gr_mod_b200_sptr make_gr_mod_dsss(int sps = 25, int samp_rate = 1000000, int carrier_freq = 1700, int filter_width = 200,
+                                         int n_channels = 1, long max_items = 8, int device = 0)                  // instance gr_mod_base.cpp:170
+{ return std::make_shared<gr_mod_b200>(QRL_MOD_DSSS, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_items, device); }
 inline gr_mod_b200_sptr make_gr_mod_dmr(int sps = 125, int samp_rate = 1000000, int carrier_freq = 1700, int filter_width = 5000,
                                         int n_channels = 1, long max_items = 4096, int device = 0)               // src/gr/gr_mod_dmr.h:37-38
 { return std::make_shared<gr_mod_b200>(QRL_MOD_DMR, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_items, device); }

@@ -65,6 +65,8 @@ public:
     uint64_t nitems_written(unsigned) const { return d_nitems_written; }
     uint64_t nitems_read(unsigned) const { return d_nitems_read; }
     void stub_add_input_tag(const tag_t& t) { d_in_tags.push_back(t); }
+    void add_item_tag(unsigned, uint64_t offset, const pmt::pmt_t& key, const pmt::pmt_t& value) { tag_t t; t.offset = offset; t.key = key; t.value = value; d_out_tags.push_back(t); }
+    std::vector<tag_t>& stub_out_tags() { return d_out_tags; }
     void stub_advance(uint64_t nread, uint64_t nwritten) { d_nitems_read += nread; d_nitems_written += nwritten; }
     void get_tags_in_window(std::vector<tag_t>& v, unsigned, uint64_t rel_start, uint64_t rel_end, const pmt::pmt_t& key)
     {
@@ -73,7 +75,7 @@ public:
             if (t.offset >= d_nitems_read + rel_start && t.offset < d_nitems_read + rel_end && pmt::eqv(t.key, key)) v.push_back(t);
     }
 protected:
-    std::vector<tag_t> d_in_tags;
+    std::vector<tag_t> d_in_tags, d_out_tags;
     uint64_t d_nitems_read = 0, d_nitems_written = 0;
     std::string d_name;
     io_signature::sptr d_in, d_out;

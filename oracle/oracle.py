@@ -55,6 +55,33 @@ def lib():
         L.qo_dsss_decoder_taps.argtypes = [vp, C.c_int, C.c_int, vp]
         L.qo_dsss_decoder_run.restype = C.c_long
         L.qo_dsss_decoder_run.argtypes = [vp, C.c_int, C.c_int, vp, C.c_long, C.c_long, vp, C.c_long]
+        L.qo_mmdvm_rx_create.restype = vp
+        L.qo_mmdvm_rx_create.argtypes = [C.c_int]
+        L.qo_mmdvm_rx_destroy.argtypes = [vp]
+        L.qo_mmdvm_rx_calibrate_rssi.argtypes = [vp, C.c_float]
+        L.qo_mmdvm_rx_work.argtypes = [vp, vp, C.c_long]
+        L.qo_mmdvm_rx_out_items.restype = C.c_long
+        L.qo_mmdvm_rx_out_items.argtypes = [vp]
+        L.qo_mmdvm_rx_out_data.restype = vp
+        L.qo_mmdvm_rx_out_data.argtypes = [vp]
+        L.qo_mmdvm_rx_rssi_items.restype = C.c_long
+        L.qo_mmdvm_rx_rssi_items.argtypes = [vp]
+        L.qo_mmdvm_rx_rssi_db.restype = vp
+        L.qo_mmdvm_rx_rssi_db.argtypes = [vp]
+        L.qo_mmdvm_rx_rssi_at.restype = vp
+        L.qo_mmdvm_rx_rssi_at.argtypes = [vp]
+        L.qo_mmdvm_rx_clear.argtypes = [vp]
+        L.qo_rssi_tags_run.restype = C.c_long
+        L.qo_rssi_tags_run.argtypes = [vp, C.c_long, C.c_float, vp, vp, C.c_long]
+        L.qo_mmdvm_tx_create.restype = vp
+        L.qo_mmdvm_tx_create.argtypes = [C.c_int]
+        L.qo_mmdvm_tx_destroy.argtypes = [vp]
+        L.qo_mmdvm_tx_work.argtypes = [vp, vp, C.c_long]
+        L.qo_mmdvm_tx_out_items.restype = C.c_long
+        L.qo_mmdvm_tx_out_items.argtypes = [vp]
+        L.qo_mmdvm_tx_out_data.restype = vp
+        L.qo_mmdvm_tx_out_data.argtypes = [vp]
+        L.qo_mmdvm_tx_clear.argtypes = [vp]
         L.qo_spectrum_create.restype = vp
         L.qo_spectrum_create.argtypes = [C.c_int, C.c_int]
         L.qo_spectrum_destroy.argtypes = [vp]
@@ -185,6 +212,8 @@ def ref_blocks():
         R.ref_rx_fft_work.argtypes = [vp, vp, C.c_int]
         R.ref_rx_fft_get.restype = C.c_uint
         R.ref_rx_fft_get.argtypes = [vp, vp]
+        R.ref_rssi_tags.restype = C.c_long
+        R.ref_rssi_tags.argtypes = [vp, C.c_long, C.c_float, vp, C.c_long, vp, vp, C.c_long]
         _REF = R
     return _REF
 
@@ -399,6 +428,52 @@ def zero_idle(x, delay, tag_items, tag_vals):
     out = np.empty_like(x)
     lib().qo_zero_idle_run(_p(x), len(x), int(delay), _p(to), _p(tv), len(to), _p(out))
     return out
+
+
+class MmdvmRx:
+    """One channel of gr_demod_mmdvm_multi2 behind the channelizer (gr_demod_mmdvm_multi2.cpp:56-126): complex at 25 ksps -> int16
+    discriminator samples at 24 ksps + the RSSI tags."""
+
+    def __init__(self, filter_width=5000):
+        self.h = lib().qo_mmdvm_rx_create(int(filter_width))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().qo_mmdvm_rx_destroy(self.h); self.h = None
+
+    def calibrate_rssi(self, level):
+        lib().qo_mmdvm_rx_calibrate_rssi(self.h, float(level))
+
+    def work(self, x):
+        """-> (int16 samples, rssi dB values, their item offsets at 24 ksps)"""
+        x = np.ascontiguousarray(x, np.complex64)
+        lib().qo_mmdvm_rx_work(self.h, _p(x), len(x))
+        n, k = lib().qo_mmdvm_rx_out_items(self.h), lib().qo_mmdvm_rx_rssi_items(self.h)
+        out = np.frombuffer(C.string_at(lib().qo_mmdvm_rx_out_data(self.h), 2 * n), np.int16).copy()
+        db = np.frombuffer(C.string_at(lib().qo_mmdvm_rx_rssi_db(self.h), 4 * k), np.float32).copy()
+        at = np.frombuffer(C.string_at(lib().qo_mmdvm_rx_rssi_at(self.h), 8 * k), np.int64).copy()
+        lib().qo_mmdvm_rx_clear(self.h)
+        return out, db, at
+
+
+class MmdvmTx:
+    """One channel of gr_mod_mmdvm_multi2 in front of the synthesizer (gr_mod_mmdvm_multi2.cpp:47-126): int16 at 24 ksps -> complex
+    at 25 ksps."""
+
+    def __init__(self, filter_width=5000):
+        self.h = lib().qo_mmdvm_tx_create(int(filter_width))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().qo_mmdvm_tx_destroy(self.h); self.h = None
+
+    def work(self, s):
+        s = np.ascontiguousarray(s, np.int16)
+        lib().qo_mmdvm_tx_work(self.h, _p(s), len(s))
+        n = lib().qo_mmdvm_tx_out_items(self.h)
+        out = np.frombuffer(C.string_at(lib().qo_mmdvm_tx_out_data(self.h), 8 * n), np.complex64).copy()
+        lib().qo_mmdvm_tx_clear(self.h)
+        return out
 
 
 class Spectrum:

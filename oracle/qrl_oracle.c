@@ -2875,3 +2875,121 @@ int qo_spectrum_get(qo_spectrum* s, float* out)                 /* rx_fft.cpp:11
     s->data_ready = 0;
     return s->N;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------------------
+ * gr_demod_mmdvm_multi2 / gr_mod_mmdvm_multi2 behind / in front of the polyphase channelizer / synthesizer, ONE channel
+ * (/root/reference/src/gr/gr_demod_mmdvm_multi2.cpp:56-126, gr_mod_mmdvm_multi2.cpp:47-126; MMDVM_SAMPLE_RATE = 250000,
+ * src/config_mmdvm.h:4: 25 ksps per channelizer port).
+ * RX: rational_resampler_ccf(24, 25, low_pass_2(1, 600k, fw, 2000, 60, BH)) -> fft_filter_ccf(low_pass_2(1, 24k, fw, 2000, 60, BH)) ->
+ *     rssi_tag_block (an "RSSI" tag every 300 items, rssi_tag_block.cpp:42-63) -> quadrature_demod_cf(24000 / (2 pi 12500)) ->
+ *     x 1.0 -> float_to_short(1, 32767) [to gr_mmdvm_sink].
+ * TX: short_to_float(1, 32767) -> x 1.0 -> frequency_modulator_fc(2 pi 12500 / 24000) -> fft_filter_ccf(low_pass_2(1, 24k, ...)) ->
+ *     x 0.8 -> rational_resampler_ccf(25, 24, low_pass_2(25, 600k, ...)) -> gr_zero_idle_bursts(0) [tags only, not restated here]
+ *     [to the synthesizer; behind it x 1 / num_channels -> x bb_gain].
+ * float_to_short = volk_32f_s32f_convert_16i (x scale, clip to [-32768, 32767], rintf); short_to_float = volk_16i_s32f_convert_32f in
+ * its SIMD form, (float)v * (float)(1.0 / 32767) (the generic kernel divides; an x86 host runs the SIMD one). */
+struct qo_mmdvm_rx { resamp_t rs; resamp_t filt; qdemod_t qd; float sum; int nitems; long long n24; float cal; qvec s_a, s_b, s_f, out, rssi_db, rssi_at; };
+qo_mmdvm_rx* qo_mmdvm_rx_create(int filter_width)
+{
+    static float taps[16384];
+    tabs_init();
+    qo_mmdvm_rx* r = (qo_mmdvm_rx*)calloc(1, sizeof *r);
+    int n = qo_firdes_low_pass_2(1, 600000.0, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+    resamp_init(&r->rs, 2, 24, 25, taps, n);
+    n = qo_firdes_low_pass_2(1, 24000.0, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+    resamp_init(&r->filt, 2, 1, 1, taps, n);
+    qdemod_init(&r->qd, (float)(24000.0f / (2 * M_PI * 12500.0f)));
+    qv_init(&r->s_a, 8); qv_init(&r->s_b, 8); qv_init(&r->s_f, 4); qv_init(&r->out, 2); qv_init(&r->rssi_db, 4); qv_init(&r->rssi_at, 8);
+    return r;
+}
+void qo_mmdvm_rx_destroy(qo_mmdvm_rx* r)
+{
+    if (!r) return;
+    resamp_free(&r->rs); resamp_free(&r->filt);
+    qv_free(&r->s_a); qv_free(&r->s_b); qv_free(&r->s_f); qv_free(&r->out); qv_free(&r->rssi_db); qv_free(&r->rssi_at);
+    free(r);
+}
+void qo_mmdvm_rx_calibrate_rssi(qo_mmdvm_rx* r, float level) { r->cal = level; }
+/* the RSSI tag rule alone (pinned to the compiled rssi_tag_block.cpp in tests/test_oracle_ref.py) */
+static void rssi_tag_step(float re, float im, float* sum, int* nitems, float cal, long long at, qvec* db, qvec* where)
+{
+    const float pwr = re * re + im * im;
+    *sum += pwr * pwr;
+    *nitems += 1;
+    if (*nitems >= 300) {
+        const float level = sqrtf(*sum / (float)(*nitems));
+        const float v = (float)10.0f * log10f((float)(level + 1.0e-20)) + cal;
+        qv_pushf(db, v);
+        qv_push(where, &at, 1);
+        *sum = 0; *nitems = 0;
+    }
+}
+long qo_rssi_tags_run(const float* in_c, long n, float cal, float* db, long long* at, long cap)
+{
+    qvec d, w; qv_init(&d, 4); qv_init(&w, 8);
+    float sum = 0; int ni = 0;
+    for (long i = 0; i < n; i++) rssi_tag_step(in_c[2 * i], in_c[2 * i + 1], &sum, &ni, cal, i, &d, &w);
+    const long m = (long)d.n < cap ? (long)d.n : cap;
+    memcpy(db, d.d, 4 * (size_t)m); memcpy(at, w.d, 8 * (size_t)m);
+    qv_free(&d); qv_free(&w);
+    return m;
+}
+int qo_mmdvm_rx_work(qo_mmdvm_rx* r, const float* iq25k, long n)
+{
+    r->s_a.n = 0; resamp_work(&r->rs, iq25k, (size_t)n, &r->s_a);
+    r->s_b.n = 0; resamp_work(&r->filt, (const float*)r->s_a.d, r->s_a.n, &r->s_b);
+    const float* f = (const float*)r->s_b.d;
+    for (size_t i = 0; i < r->s_b.n; i++) { rssi_tag_step(f[2 * i], f[2 * i + 1], &r->sum, &r->nitems, r->cal, r->n24, &r->rssi_db, &r->rssi_at); r->n24++; }
+    r->s_f.n = 0; qdemod_work(&r->qd, f, r->s_b.n, &r->s_f);
+    const float* d = (const float*)r->s_f.d;
+    for (size_t i = 0; i < r->s_f.n; i++) {
+        float v = d[i] * 1.0f;                       /* multiply_const_ff(1.0) */
+        v = v * 32767.0f;
+        if (v > 32767.0f) v = 32767.0f; else if (v < -32768.0f) v = -32768.0f;
+        const short s = (short)rintf(v);
+        qv_push(&r->out, &s, 1);
+    }
+    return 0;
+}
+long qo_mmdvm_rx_out_items(qo_mmdvm_rx* r) { return (long)r->out.n; }
+const short* qo_mmdvm_rx_out_data(qo_mmdvm_rx* r) { return (const short*)r->out.d; }
+long qo_mmdvm_rx_rssi_items(qo_mmdvm_rx* r) { return (long)r->rssi_db.n; }
+const float* qo_mmdvm_rx_rssi_db(qo_mmdvm_rx* r) { return (const float*)r->rssi_db.d; }
+const long long* qo_mmdvm_rx_rssi_at(qo_mmdvm_rx* r) { return (const long long*)r->rssi_at.d; }
+void qo_mmdvm_rx_clear(qo_mmdvm_rx* r) { r->out.n = 0; r->rssi_db.n = 0; r->rssi_at.n = 0; }
+
+struct qo_mmdvm_tx { qo_tx fm; resamp_t filt; resamp_t rs; qvec s_f, s_m, s_b, out; };
+qo_mmdvm_tx* qo_mmdvm_tx_create(int filter_width)
+{
+    static float taps[16384];
+    tabs_init();
+    qo_mmdvm_tx* t = (qo_mmdvm_tx*)calloc(1, sizeof *t);
+    t->fm.fm_sens = (float)(2 * M_PI * 12500.0f / 24000.0f);
+    int n = qo_firdes_low_pass_2(1, 24000.0, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+    resamp_init(&t->filt, 2, 1, 1, taps, n);
+    n = qo_firdes_low_pass_2(25, 600000.0, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+    resamp_init(&t->rs, 2, 25, 24, taps, n);
+    qv_init(&t->s_f, 4); qv_init(&t->s_m, 8); qv_init(&t->s_b, 8); qv_init(&t->out, 8);
+    return t;
+}
+void qo_mmdvm_tx_destroy(qo_mmdvm_tx* t)
+{
+    if (!t) return;
+    resamp_free(&t->filt); resamp_free(&t->rs); qv_free(&t->s_f); qv_free(&t->s_m); qv_free(&t->s_b); qv_free(&t->out);
+    free(t);
+}
+int qo_mmdvm_tx_work(qo_mmdvm_tx* t, const short* in, long n)
+{
+    const float inv = (float)(1.0 / 32767.0);
+    t->s_f.n = 0;
+    for (long i = 0; i < n; i++) { float v = (float)in[i] * inv; v = v * 1.0f; qv_pushf(&t->s_f, v); }
+    t->s_m.n = 0; fm_mod(&t->fm, (const float*)t->s_f.d, t->s_f.n, &t->s_m, 1.0f);
+    t->s_b.n = 0; resamp_work(&t->filt, (const float*)t->s_m.d, t->s_m.n, &t->s_b);
+    float* m = (float*)t->s_b.d;
+    for (size_t i = 0; i < 2 * t->s_b.n; i++) m[i] = m[i] * 0.8f;                 /* multiply_const_cc(0.8) */
+    resamp_work(&t->rs, m, t->s_b.n, &t->out);
+    return 0;
+}
+long qo_mmdvm_tx_out_items(qo_mmdvm_tx* t) { return (long)t->out.n; }
+const float* qo_mmdvm_tx_out_data(qo_mmdvm_tx* t) { return (const float*)t->out.d; }
+void qo_mmdvm_tx_clear(qo_mmdvm_tx* t) { t->out.n = 0; }

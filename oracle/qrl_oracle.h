@@ -165,6 +165,27 @@ void qo_spectrum_set_fft_size(qo_spectrum*, int n);
 void qo_spectrum_work(qo_spectrum*, const float* iq, long n);
 int  qo_spectrum_get(qo_spectrum*, float* out);      /* returns fft_size, or 0 when no spectrum is ready */
 
+/* gr_demod_mmdvm_multi2 / gr_mod_mmdvm_multi2, one channel behind / in front of the polyphase filter bank (25 ksps <-> int16 at 24 ksps) */
+typedef struct qo_mmdvm_rx qo_mmdvm_rx;
+qo_mmdvm_rx* qo_mmdvm_rx_create(int filter_width);
+void qo_mmdvm_rx_destroy(qo_mmdvm_rx*);
+void qo_mmdvm_rx_calibrate_rssi(qo_mmdvm_rx*, float level);
+int  qo_mmdvm_rx_work(qo_mmdvm_rx*, const float* iq25k, long n);
+long qo_mmdvm_rx_out_items(qo_mmdvm_rx*);
+const short* qo_mmdvm_rx_out_data(qo_mmdvm_rx*);
+long qo_mmdvm_rx_rssi_items(qo_mmdvm_rx*);
+const float* qo_mmdvm_rx_rssi_db(qo_mmdvm_rx*);
+const long long* qo_mmdvm_rx_rssi_at(qo_mmdvm_rx*);
+void qo_mmdvm_rx_clear(qo_mmdvm_rx*);
+long qo_rssi_tags_run(const float* in_c, long n, float cal, float* db, long long* at, long cap);
+typedef struct qo_mmdvm_tx qo_mmdvm_tx;
+qo_mmdvm_tx* qo_mmdvm_tx_create(int filter_width);
+void qo_mmdvm_tx_destroy(qo_mmdvm_tx*);
+int  qo_mmdvm_tx_work(qo_mmdvm_tx*, const short* in, long n);
+long qo_mmdvm_tx_out_items(qo_mmdvm_tx*);
+const float* qo_mmdvm_tx_out_data(qo_mmdvm_tx*);
+void qo_mmdvm_tx_clear(qo_mmdvm_tx*);
+
 #ifdef __cplusplus
 }
 #endif

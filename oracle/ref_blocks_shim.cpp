@@ -218,3 +218,24 @@ void ref_rx_fft_work(void* h, const float* in_c, int n)
 }
 unsigned ref_rx_fft_get(void* h, float* points) { unsigned n = 0; as<rx_fft_c>(h)->get_fft_data(points, n); return n; }
 }
+
+// ---------------------------------------------------------------- rssi_tag_block (an "RSSI" stream tag every 300 items)
+#include "rssi_tag_block.h"
+extern "C" long ref_rssi_tags(const float* in_c, long n, float cal, const long* chunks, long nchunks, float* db, long long* at, long cap)
+{
+    auto blk = make_rssi_tag_block();
+    blk->calibrate_rssi(cal);
+    std::vector<gr_complex> out(static_cast<size_t>(n));
+    long done = 0;
+    for (long k = 0; k < nchunks && done < n; k++) {
+        const long m = std::min(chunks[k], n - done);
+        gr_vector_const_void_star in = { reinterpret_cast<const gr_complex*>(in_c) + done };
+        gr_vector_void_star o = { out.data() + done };
+        blk->work(static_cast<int>(m), in, o);
+        blk->stub_advance(static_cast<uint64_t>(m), static_cast<uint64_t>(m));
+        done += m;
+    }
+    long cnt = 0;
+    for (const auto& t : blk->stub_out_tags()) if (cnt < cap) { db[cnt] = pmt::to_float(t.value); at[cnt] = static_cast<long long>(t.offset); cnt++; }
+    return cnt;
+}

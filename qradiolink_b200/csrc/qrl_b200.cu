@@ -139,6 +139,9 @@ struct qrl_rx : HandleBase {
     // PSK chains: agc2 + costas "PLL" loop stage (per sample), output ring r3 (interleaved)
     AgcCostasParams acp{};
     AgcCostasState* d_ac = nullptr;
+    // gr_demod_dsss: one chain kernel behind stage 1 (dsss_chain_kernel)
+    DsssParams dsp{}; DsssState* d_ds = nullptr; float* d_ds_arms = nullptr; float2* d_ds_taps = nullptr;
+    Ring ds_a, ds_c, ds_d; long long ds_o_call0 = 0;
     Ring r3;
     int sym_sps = 0;
     // BPSK / 2FSK: fll_band_edge_cc + second (delayed) decoder
@@ -642,6 +645,47 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         control_loop_gains(static_cast<float>(8 * kPi / 100), h->fllp.alpha, h->fllp.beta);
         h->fllp.max_freq = static_cast<float>(2.0 * kPi * (2.0 / sps)); h->fllp.min_freq = -h->fllp.max_freq;
         h->nports = 4;
+    } else if (kind == QRL_DEMOD_DSSS) {
+        // gr_demod_dsss.cpp:32-124 (instance gr_demod_base.cpp:218: make_gr_demod_dsss(25, 1e6, 1700, 150)); sps = items per chip at 5200 sps
+        tsr = 20000; sym_sps = 2;
+        taps1 = low_pass(1, samp_rate, tsr / 2, tsr / 2, WIN_BLACKMAN_HARRIS);
+        h->D1 = 50;
+        const std::vector<float> tif = low_pass(1, 20000, 5200 / 2, 5200 / 2, WIN_BLACKMAN_HARRIS);       // rational_resampler_ccf(13, 50)
+        taps2 = low_pass(1, 5200, filter_width, 1200, WIN_BLACKMAN_HARRIS);
+        DsssParams& d = h->dsp;
+        d.nt_arm = (static_cast<int>(tif.size()) + 12) / 13; d.nt2 = static_cast<int>(taps2.size());
+        d.N = sps * 13; d.ntaps = d.N + 11 * sps;
+        if (sps < 1 || d.nt_arm > 8 || d.nt2 > 64 || d.ntaps > 640 || d.N + d.ntaps - 1 > kDsssChunk) {
+            set_err(h, "make_gr_demod_dsss: sps / filter_width outside what the chain kernel holds in shared memory"); return fail(QRL_EINVAL);
+        }
+        std::vector<float> arms(static_cast<size_t>(13) * d.nt_arm, 0.0f);
+        for (int p = 0; p < 13; p++) for (int k = 0; k < d.nt_arm; k++) { const size_t j = p + static_cast<size_t>(k) * 13; if (j < tif.size()) arms[p * d.nt_arm + k] = tif[j]; }
+        if ((rc = upload_floats(h, &h->d_ds_arms, arms))) return fail(rc);
+        {   // dsss_decoder_cc_impl.cc:60-96: reversed Barker-13, `sps` items per chip, shaped by RRC(1, sps, 1, 0.35f, 11 sps); the block's
+            // fir_filter_ccc keeps the taps reversed (what is uploaded)
+            static const int barker_13[13] = { 1, 1, 1, 1, 1, 0, 0, 1, 1, 0, 1, 0, 1 };
+            const int extra = 11 * sps, total = d.N + 2 * extra;
+            std::vector<float> cs(total, 0.0f);
+            for (int i = 0; i < 13; i++) { const float cv = barker_13[13 - (i + 1)] == 0 ? -1.0f : 1.0f; for (int k = 0; k < sps; k++) cs[extra + i * sps + k] = cv; }
+            const std::vector<float> rrc = root_raised_cosine(1, sps, 1.0, static_cast<double>(0.350f), extra);
+            const int nr = static_cast<int>(rrc.size());
+            std::vector<float> t(2 * static_cast<size_t>(d.ntaps));
+            for (int i = 0; i < d.ntaps; i++) {
+                float acc = 0.0f, acci = 0.0f;
+                for (int k = 0; k < nr; k++) { acc = acc + cs[i + k] * rrc[nr - 1 - k]; acci = acci + 0.0f * rrc[nr - 1 - k]; }
+                t[2 * (d.ntaps - 1 - i)] = acc; t[2 * (d.ntaps - 1 - i) + 1] = acci;
+            }
+            float* tp = nullptr;
+            if ((rc = upload_floats(h, &tp, t))) return fail(rc);
+            h->d_ds_taps = reinterpret_cast<float2*>(tp);
+        }
+        control_loop_gains(static_cast<float>(kPi / 200), d.pll_alpha, d.pll_beta);
+        control_loop_gains(static_cast<float>(2 * kPi / 100), d.costas_alpha, d.costas_beta);
+        d.agc_attack = 1e-1f; d.agc_decay = 1e-1f; d.agc_ref = 1.0f; d.agc_max = 65536.0f;
+        const float gain_mu = 0.05f, gain_omega = 0.005f;
+        d.gain_omega = gain_omega * gain_omega; d.gain_mu = gain_mu; d.omega_mid = 1.0f; d.omega_lim = 0.005f * 1.0f; d.soft_scale = 64.0f;
+        h->ssp.lookahead = 0; h->ssp.sps = 2.0f;
+        h->nports = 4;
     } else if (kind == QRL_DEMOD_SSB) {
         // gr_demod_ssb.cpp:37-61; flag = sb (0 USB, 1 LSB); sps = decimation (125)
         tsr = 8000; sym_sps = 2;
@@ -784,6 +828,13 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = make_ring(h, &h->rd, sizeof(float), h->n1max + nt_arm + 16))) return fail(rc);
         if ((rc = make_ring(h, &h->rr, sizeof(float), h->n1max * 2 / 5 + h->nbp.nt_audio + 16))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_nb, h->C))) return fail(rc);
+    } else if (kind == QRL_DEMOD_DSSS) {
+        const long long n5 = h->n1max * 13 / 50 + 8;
+        if ((rc = make_ring(h, &h->ds_a, sizeof(float2), n5 + 2048))) return fail(rc);
+        if ((rc = make_ring(h, &h->ds_c, sizeof(float2), n5 + 2048))) return fail(rc);
+        if ((rc = make_ring(h, &h->ds_d, sizeof(float2), n5 / h->dsp.N + 128))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_ds, h->C))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_vs2, h->C))) return fail(rc);
     } else if (kind == QRL_DEMOD_4FSK || kind == QRL_DEMOD_2FSK) {
         if ((rc = make_ring(h, &h->r2, sizeof(float2), h->n1max + h->ntaps3 + 64))) return fail(rc);
         // two calls deep when the block may run with overlapped calls (the producer of call k+1 must not wait for the
@@ -925,6 +976,17 @@ int qrl_rx_reset(qrl_rx* h)
     CK(cudaMemsetAsync(h->d_hist[0], 0, sizeof(float2) * h->H * h->C, h->stream));
     CK(cudaMemsetAsync(h->d_hist[1], 0, sizeof(float2) * h->H * h->C, h->stream));
     for (auto& z : h->zero_list) CK(cudaMemsetAsync(z.first, 0, z.second, h->stream));
+    if (h->d_ds) {
+        std::vector<DsssState> ds(h->C);
+        for (int c = 0; c < h->C; c++) {
+            std::memset(&ds[c], 0, sizeof(DsssState));
+            ds[c].agc = 10.0f;                        // agc2_cc::make(1e-1, 1e-1, 1, 10): initial gain 10 (gr_demod_dsss.cpp:66)
+            ds[c].omega = 1.0f; ds[c].mu = 0.5f;      // clock_recovery_mm_cc(1, ..., 0.5, ...)
+        }
+        CK(cudaMemcpyAsync(h->d_ds, ds.data(), sizeof(DsssState) * h->C, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->ds_o_call0 = 0;
+    }
     std::vector<SsbState> sb(h->C);
     if (h->d_ssb) {
         for (int c = 0; c < h->C; c++) { std::memset(&sb[c], 0, sizeof(SsbState)); sb[c].sq_state = SQ_MUTED; sb[c].gain = 1.0f; }
@@ -1251,6 +1313,33 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
         const int TB = 256;
         dim3 gtile(static_cast<unsigned>((std::max<long long>(n_new, 1) + TB - 1) / TB), h->C);
         const int groups = (h->C + 31) / 32;
+        if (h->kind == QRL_DEMOD_DSSS) {
+            CK(cudaEventRecord(h->ev_a[i], sp));
+            CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
+            pe = h->prof_begin(3, h->s_loop);
+            dsss_chain_kernel<<<h->C, 256, 0, h->s_loop>>>(h->dsp, h->d_ds, static_cast<const float2*>(h->r1.d), h->r1.mask, h->r1.stride, k1,
+                h->d_ds_arms, h->d_taps2, h->d_ds_taps,
+                static_cast<float2*>(h->ds_a.d), static_cast<float2*>(h->ds_c.d), h->ds_a.mask, h->ds_a.stride,
+                static_cast<float2*>(h->ds_d.d), h->ds_d.mask, h->ds_d.stride,
+                h->d_port0, h->port0_cap, h->ds_o_call0,
+                h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
+                static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, nsoft_i);
+            h->launches++;
+            h->prof_end(pe);
+            CK(cudaEventRecord(h->ev_b[i], h->s_loop));
+            CK(cudaStreamWaitEvent(h->s_fec, h->ev_b[i], 0));
+            pe = h->prof_begin(4, h->s_fec);
+            constexpr int CPB2 = 4;
+            viterbi_k7_kernel<CPB2><<<(h->C + CPB2 - 1) / CPB2, 64 * CPB2, 0, h->s_fec>>>(h->d_vs, nsoft_i, h->C,
+                static_cast<const unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride,
+                h->d_port2, h->port2_cap, h->d_port2_cnt, static_cast<int>(h->port2_cap), 0);
+            viterbi_k7_kernel<CPB2><<<(h->C + CPB2 - 1) / CPB2, 64 * CPB2, 0, h->s_fec>>>(h->d_vs2, nsoft_i, h->C,
+                static_cast<const unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride,
+                h->d_port3, h->port2_cap, h->d_port3_cnt, static_cast<int>(h->port2_cap), 1);
+            h->launches += 2;
+            h->prof_end(pe);
+            continue;
+        }
         if (h->kind == QRL_DEMOD_SSB) {
             if (n_new > 0) {
                 pe = h->prof_begin(1, sp);
@@ -1614,6 +1703,11 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
         h->prof_end(pe);
         if (h->overlap) CK(cudaEventRecord(h->ev_v[i], h->s_fec));
     }
+    if (h->kind == QRL_DEMOD_DSSS) {          // port 0 holds 5200 sps items (13 / 50 of the stage-1 items counted in the loop)
+        const long long o_end = (h->n1_s * 13 + 49) / 50;
+        h->port0_n = static_cast<long>(o_end - h->ds_o_call0);
+        h->ds_o_call0 = o_end;
+    }
     if (h->rssi_on && h->port0_n > 0) {
         // port 0 of this call is complete on the parallel stream: append to the |x|^2 ring, evaluate the latest RSSI value
         rssi_kernel<<<h->C, 256, 0, sp>>>(h->d_port0, h->port0_cap, static_cast<int>(std::min<long>(h->port0_n, h->port0_cap)),
@@ -1768,6 +1862,8 @@ struct qrl_tx : HandleBase {
     float fm_sens = 0, amplif = 0, bb_gain = 1.0f, pulse_scale = 0.66666666f;
     int repeat_only = 0;
     bool m17 = false; int M2 = 1;  // gr_mod_m17: 4 symbols per byte, IF low-pass at 24 ksps, x L2 / M2 rational interpolator
+    // gr_mod_dsss: chips (complex ring d_sym) -> x25 (ring d_if) -> x50 / 13 (ring d_rc, arms in d_cfilt) -> x50 (d_out)
+    bool dsss_tx = false;
     // gr_mod_dmr: the m17 path with gr_zero_idle_bursts in place of the IF low-pass (a delay of history - 1 items + "zero_samples" tags)
     bool dmr_tx = false; long long zi_delay_items = 0; unsigned zi_tag_delay = 0;
     std::vector<std::map<long long, unsigned long long>> zi_tags;      // per channel: start item -> count (first registered wins)
@@ -1896,6 +1992,21 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         t1 = root_raised_cosine(sps, sps, 1, 0.35, 11 * sps);
         h->L1 = sps; h->nt1 = (static_cast<int>(t1.size()) + sps - 1) / sps;
         h->amplif = 0.6f;
+    } else if (kind == QRL_MOD_DSSS) {
+        // gr_mod_dsss.cpp:27-93: scrambler -> cc_encoder -> Barker-13 spreading -> {-1, +1} -> rational_resampler_ccf(sps, 1, RRC(sps, sps, 1,
+        // 0.35, 11 sps)) -> x0.65 -> bb gain -> rational_resampler_ccf(50, 13, low_pass(50, 5200 * 50, fw, 5 fw)) ->
+        // rational_resampler_ccf(50, 1, low_pass(50, fs, fw, 5 fw)); one input byte = 208 chips = 10^6 output samples (sps = 25)
+        h->dsss_tx = true; h->amplif = 0.65f;
+        t1 = root_raised_cosine(sps, sps, 1, 0.35, 11 * sps);
+        h->L1 = sps; h->nt1 = (static_cast<int>(t1.size()) + sps - 1) / sps;
+        const std::vector<float> tif = low_pass(50.0, 5200.0 * 50, filter_width, filter_width * 5, WIN_HAMMING);
+        h->nt_cfilt = (static_cast<int>(tif.size()) + 49) / 50;
+        if ((rc = upload_floats(h, &h->d_cfilt, make_arms(tif, 50, h->nt_cfilt)))) return fail(rc);
+        t2 = low_pass(50, samp_rate, filter_width, filter_width * 5, WIN_HAMMING);
+        h->L2 = 50; h->nt2 = (static_cast<int>(t2.size()) + 49) / 50;
+        if (static_cast<size_t>(50) * std::max(h->nt2, h->nt_cfilt) * sizeof(float) > 40 * 1024 || static_cast<size_t>(h->L1) * h->nt1 * sizeof(float) > 40 * 1024) {
+            set_err(h, "make_gr_mod_dsss: filter_width too small for the shared-memory arm tables"); return fail(QRL_EINVAL);
+        }
     } else if (kind == QRL_MOD_GMSK) {
         // gr_mod_gmsk.cpp:30-100: the 2FSK (fm) modulator path with a Gaussian pulse (BT 0.3), sensitivity (pi/2)/sps and a
         // x5 (x1 for the 10k mode) final interpolation; instances gr_mod_base.cpp:160-162
@@ -1962,6 +2073,14 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     long long max_sym = (one_per_bit ? 16LL : 8LL) * max_items;
     if (kind == QRL_MOD_NBFM) max_sym = max_items * 25 / 4 + 8;        // 50 ksps items per call
     if (kind == QRL_MOD_SSB) max_sym = max_items + 8;                  // 8 ksps complex items per call
+    if (h->dsss_tx) {
+        max_sym = 16LL * 13 * max_items;                               // chips per call
+        unsigned cap1 = pow2_at_least(max_sym * h->L1 + h->nt_cfilt + 128); h->if_mask = cap1 - 1; h->if_stride = cap1;
+        if ((rc = dev_alloc(h, &h->d_if, static_cast<size_t>(cap1) * h->C))) return fail(rc);
+        const long long n20 = (max_sym * h->L1 * 50 + 12) / 13 + 8;
+        unsigned cap2 = pow2_at_least(n20 + h->nt2 + 512); h->rc_mask = cap2 - 1; h->rc_stride = cap2;
+        if ((rc = dev_alloc(h, &h->d_rc, static_cast<size_t>(cap2) * h->C))) return fail(rc);
+    }
     if (h->m17) {                                                      // IF ring behind the 24 ksps low-pass: 20 samples per byte
         unsigned cap2 = pow2_at_least(max_sym * h->L1 + 512 + h->nt2); h->rc_mask = cap2 - 1; h->rc_stride = cap2;
         if ((rc = dev_alloc(h, &h->d_rc, static_cast<size_t>(cap2) * h->C))) return fail(rc);
@@ -1976,7 +2095,7 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = dev_alloc(h, &h->d_an, h->C))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_audio_in, static_cast<size_t>(max_items) * h->C))) return fail(rc);
     }
-    const bool qpsk = kind == QRL_MOD_QPSK || kind == QRL_MOD_BPSK;      // complex symbols, single interpolation stage
+    const bool qpsk = kind == QRL_MOD_QPSK || kind == QRL_MOD_BPSK || h->dsss_tx;      // complex symbols (QPSK / BPSK: single interpolation stage)
     { unsigned cap = pow2_at_least(max_sym + 64); h->sym_mask = cap - 1; h->sym_stride = cap;
       if ((rc = dev_alloc(h, &h->d_sym, static_cast<size_t>(cap) * h->C * (qpsk ? 2 : 1)))) return fail(rc); }
     if (!qpsk) {
@@ -1985,6 +2104,7 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     }
     h->out_stride = analog ? max_sym * h->L2 : max_sym * h->L1 * (qpsk ? 1 : h->L2);
     if (h->m17) h->out_stride = (4LL * max_items * h->L1 * h->L2 + h->M2 - 1) / h->M2 + 8;
+    if (h->dsss_tx) h->out_stride = ((max_sym * h->L1 * 50 + 12) / 13 + 1) * 50;
     if ((rc = dev_alloc(h, &h->d_out, static_cast<size_t>(h->out_stride) * h->C, false))) return fail(rc);
     std::vector<TxBitState> st(h->C);
     for (auto& x : st) { x.scr_reg = 0x7F; x.enc_state = 0; x.diff_prev = 0; x.phase_q = 0; }
@@ -2098,6 +2218,33 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
     }
     const bool cplx = h->kind == QRL_MOD_QPSK || h->kind == QRL_MOD_BPSK;
     const bool one_per_bit = h->kind == QRL_MOD_BPSK || h->kind == QRL_MOD_2FSK;
+    if (h->dsss_tx) {
+        const long long sym0 = h->n_sym, nsym = 16LL * 13 * n;                         // chips
+        tx_bits_kernel<TXM_DSSS><<<dim3((h->C + 31) / 32), 32, 0, h->stream>>>(h->d_bits, h->C, b, n, bstride, h->d_sym, h->sym_mask, h->sym_stride, sym0);
+        // x sps pulse shaping + the two gains -> 5200 sps ring
+        const long long a0 = sym0 * h->L1, a1 = (sym0 + nsym) * h->L1;
+        resamp_ring_to_ring_ccf_kernel<<<dim3(static_cast<unsigned>((a1 - a0 + 255) / 256), h->C), 256, sizeof(float) * h->L1 * h->nt1, h->stream>>>(
+            reinterpret_cast<const float2*>(h->d_sym), h->sym_mask, h->sym_stride, h->d_arms1, h->L1, 1, h->nt1, a0, a1,
+            h->amplif, h->bb_gain, 1, h->d_if, h->if_mask, h->if_stride);
+        // x50 / 13 -> 20 ksps ring: outputs i with floor(13 i / 50) < a1
+        const long long o0 = (a0 * 50 + 12) / 13, o1 = (a1 * 50 + 12) / 13;
+        resamp_ring_to_ring_ccf_kernel<<<dim3(static_cast<unsigned>((o1 - o0 + 255) / 256), h->C), 256, sizeof(float) * 50 * h->nt_cfilt, h->stream>>>(
+            h->d_if, h->if_mask, h->if_stride, h->d_cfilt, 50, 13, h->nt_cfilt, o0, o1, 1.0f, 1.0f, 0, h->d_rc, h->rc_mask, h->rc_stride);
+        // x50 -> output
+        if ((o1 - o0) * 50 > h->out_stride) { set_err(h, "qrl_tx_work: output buffer too small"); return QRL_ERANGE; }
+        {
+            const int L = 50, NT = h->nt2, MT = std::max(1, 4096 / L);
+            const size_t smem = sizeof(float) * ((L * NT + 1) & ~1) + sizeof(float2) * (MT + NT);
+            dim3 g(static_cast<unsigned>((o1 - o0 + MT - 1) / MT), h->C);
+            interp_fir_ccf_generic_kernel<<<g, 256, smem, h->stream>>>(h->d_rc, h->rc_mask, h->rc_stride, o0, o1, h->d_arms2, L, NT, MT, 1.0f, 1.0f, 0,
+                                                                       h->d_out, h->out_stride, o0 * L);
+        }
+        h->launches += 4;
+        h->n_out_last = static_cast<long>((o1 - o0) * 50);
+        h->n_sym += nsym;
+        CK(cudaGetLastError());
+        return QRL_OK;
+    }
     const long long sym0 = h->n_sym, nsym = (h->m17 ? 4LL : (one_per_bit ? 16LL : 8LL)) * n;
     // 4FSK: bit chain / pulse shaping + FM scan / x20 interpolator are pipelined slice by slice on three streams (the
     // first two are one-CTA-per-channel recurrences that leave most SMs idle; the interpolator fills them)

@@ -2478,7 +2478,8 @@ struct TxBitState {
 // bytes -> packed_to_unpacked(MSB) -> scrambler -> CC encoder -> pack_k_bits(2) -> map {0,1,3,2}
 //       -> chunks_to_symbols (4FSK: float level, QPSK: diff_encoder(4) + complex point)
 // one thread per channel (the scrambler is a feedback LFSR); 16 symbols per input byte... 8 per byte.
-enum { TXM_4FSK = 0, TXM_QPSK = 1, TXM_BPSK = 2, TXM_2FSK = 3, TXM_M17 = 4 };
+enum { TXM_4FSK = 0, TXM_QPSK = 1, TXM_BPSK = 2, TXM_2FSK = 3, TXM_M17 = 4, TXM_DSSS = 5 };
+// TXM_DSSS (gr_mod_dsss.cpp:77-82, dsss_encoder_bb_impl.cc:86-97): per coded bit 13 chips, Barker-13 for a 0 and its complement for a 1, chips -> {-1, +1}
 // TXM_M17 (gr_mod_m17.cpp:52-58,79-82): no scrambler / encoder in the block: bytes -> packed_to_unpacked(MSB) -> pack_k_bits(2) ->
 // map {2,3,1,0} -> chunks_to_symbols {-1.5 .. 1.5}: 4 symbols per input byte
 template <int MODE>
@@ -2511,6 +2512,18 @@ __global__ void tx_bits_kernel(TxBitState* __restrict__ states, int C, const uns
             st.scr_reg = ((st.scr_reg >> 1) | (nb << 7)) & 0xffu;
             st.enc_state = ((st.enc_state << 1) | out) & 0x7fu;
             coded = (coded << 2) | ((__popc(st.enc_state & 109u) & 1u) << 1) | (__popc(st.enc_state & 79u) & 1u);
+        }
+        if (MODE == TXM_DSSS) {
+            for (int k = 15; k >= 0; k--) {
+                const unsigned bit = (coded >> k) & 1u;
+#pragma unroll
+                for (int q = 0; q < 13; q++) {
+                    const unsigned chip = ((0x1F35u >> (12 - q)) & 1u) ^ bit;      // {1,1,1,1,1,0,0,1,1,0,1,0,1}, first chip = MSB
+                    reinterpret_cast<float2*>(sym_ring)[static_cast<long long>(c) * sym_stride + (si & sym_mask)] = make_float2(chip ? 1.0f : -1.0f, 0.0f);
+                    si++;
+                }
+            }
+            continue;
         }
         if (MODE == TXM_BPSK || MODE == TXM_2FSK) {
             // one symbol per coded bit: chunks_to_symbols {-1, +1} (complex for BPSK, float for 2FSK)
@@ -2772,6 +2785,33 @@ resamp_ring_ccf_generic_kernel(const float2* __restrict__ in_ring, unsigned in_m
     out[static_cast<long long>(c) * out_stride + (i - o0)] = make_float2(re, imv);
 }
 
+// the same resampler writing a ring (a later stage needs the history across calls), with the two multiply_const_cc gains behind it
+// when apply_gain is set (gr_mod_dsss.cpp:83-86: x25 pulse shaping -> x0.65 -> x bb_gain -> x50 / 13)
+__global__ void __launch_bounds__(256)
+resamp_ring_to_ring_ccf_kernel(const float2* __restrict__ in_ring, unsigned in_mask, long long in_stride,
+                               const float* __restrict__ arms /* [L][NT] */, int L, int M, int NT, long long o0, long long o1,
+                               float g1, float g2, int apply_gain, float2* __restrict__ out_ring, unsigned out_mask, long long out_stride)
+{
+    extern __shared__ float sm_r2r[];
+    for (int i = threadIdx.x; i < L * NT; i += 256) sm_r2r[i] = arms[i];
+    __syncthreads();
+    const int c = blockIdx.y;
+    const long long i = o0 + static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= o1) return;
+    const long long im = i * M;
+    const long long newest = im / L;
+    const float* h = sm_r2r + static_cast<int>(im - newest * L) * NT;
+    const float2* x = in_ring + static_cast<long long>(c) * in_stride;
+    float re = 0.0f, imv = 0.0f;
+    for (int k = NT - 1; k >= 0; k--) {
+        const long long a = newest - k;
+        const float2 v = a >= 0 ? x[a & in_mask] : make_float2(0.0f, 0.0f);
+        re = fmaf(h[k], v.x, re); imv = fmaf(h[k], v.y, imv);
+    }
+    if (apply_gain) { re = re * g1; imv = imv * g1; re = re * g2; imv = imv * g2; }
+    out_ring[static_cast<long long>(c) * out_stride + (i & out_mask)] = make_float2(re, imv);
+}
+
 // ================================================================================================
 // Analog modulators (gr_mod_nbfm.cpp:26-75, gr_mod_ssb.cpp:28-82): 8 ksps float audio in.  One CTA per channel runs
 // the low-rate front part; the FM scan / IF filters / final interpolator reuse the digital TX kernels.
@@ -2880,6 +2920,207 @@ __global__ void scale2_ring_kernel(float2* __restrict__ ring, unsigned mask, lon
     float2 v = ring[static_cast<long long>(c) * stride + (a & mask)];
     v.x = v.x * g1; v.y = v.y * g1; v.x = v.x * g2; v.y = v.y * g2;
     ring[static_cast<long long>(c) * stride + (a & mask)] = v;
+}
+
+// ================================================================================================
+// gr_demod_dsss behind stage 1 (gr_demod_dsss.cpp:89-112): a 16 symbol/s mode -- everything after the /50 FIR runs at 5200 items/s and
+// below, so one CTA per channel walks the whole chain for a call, phase by phase (parallel phases on all threads, the three feedback
+// loops on thread 0 over shared-memory chunks):
+//   A  rational_resampler_ccf(13, 50)  r1 (20 ksps) -> ra          B  costas_loop_cc(pi/200, 2, snr) in place on ra
+//   C  low_pass FIR ra -> rc + port 0                               D  agc2_cc(.1, .1, 1, 10) in place on rc
+//   E  dsss_decoder_cc: per symbol m the N correlations of the N + 11 sps tap matched filter over rc[m N - 2 N + 1 + j ...], first
+//      strict maximum of |y| (|y| = (float)sqrt((double)re re + (double)im im), glibc's hypotf) times 2 / N -> rd
+//   F  clock_recovery_mm_cc(1, 2.5e-5, .5, .05, .005) on rd -> costas_loop_cc(2 pi/100, 2) -> port 1, soft bits (real x64 + 128) -> r5
+// Arithmetic and orders as oracle/qrl_oracle.c (qo_rx_work, QO_DEMOD_DSSS).  Counters are absolute and live in the state.
+// ================================================================================================
+struct DsssState {
+    long long o_n;            // 5200 sps items produced so far (phases A-D)
+    long long m_n;            // despread symbols produced so far
+    long long cr_ii;          // clock recovery: absolute index in rd of the next interpolation window
+    long long n_sym, n_soft;
+    LoopState pll, costas;
+    float agc;
+    float omega, mu, p0r, p0i, p1r, p1i, p2r, p2i, c0r, c0i, c1r, c1i, c2r, c2i;
+};
+struct DsssParams {
+    int nt_arm;               // taps per arm of the 13 / 50 resampler
+    int nt2;                  // low-pass in front of the AGC
+    int N, ntaps;             // despreader: N = sps * 13 correlations per symbol, ntaps = N + 11 sps
+    float pll_alpha, pll_beta, costas_alpha, costas_beta;
+    float agc_attack, agc_decay, agc_ref, agc_max;
+    float gain_omega, gain_mu, omega_mid, omega_lim, soft_scale;
+};
+constexpr int kDsssChunk = 1024;
+
+__global__ void __launch_bounds__(256)
+dsss_chain_kernel(DsssParams p, DsssState* __restrict__ states,
+                  const float2* __restrict__ r1, unsigned r1_mask, long long r1_stride, long long k1,
+                  const float* __restrict__ arms /* [13][nt_arm] */, const float* __restrict__ taps2, const float2* __restrict__ dtaps_rev,
+                  float2* __restrict__ ra, float2* __restrict__ rc, unsigned ring_mask, long long ring_stride,
+                  float2* __restrict__ rd, unsigned rd_mask, long long rd_stride,
+                  float2* __restrict__ port0, long long port0_stride, long long o_call0,
+                  float2* __restrict__ port1, long long port1_stride, int* __restrict__ port1_cnt, int port1_cap,
+                  unsigned char* __restrict__ soft_ring, unsigned soft_mask, long long soft_stride, long long* __restrict__ n_soft_out)
+{
+    __shared__ DsssState st;
+    __shared__ float s_arms[13 * 8], s_t2[64];
+    __shared__ float2 s_dt[640];
+    __shared__ float2 s_buf[kDsssChunk];
+    __shared__ float s_mag[256]; __shared__ int s_idx[256]; __shared__ float2 s_val[256];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) st = states[c];
+    for (int i = tid; i < 13 * p.nt_arm; i += 256) s_arms[i] = arms[i];
+    for (int i = tid; i < p.nt2; i += 256) s_t2[i] = taps2[i];
+    for (int i = tid; i < p.ntaps; i += 256) s_dt[i] = dtaps_rev[i];
+    __syncthreads();
+    const float2* x1 = r1 + static_cast<long long>(c) * r1_stride;
+    float2* xa = ra + static_cast<long long>(c) * ring_stride;
+    float2* xc = rc + static_cast<long long>(c) * ring_stride;
+    float2* xd = rd + static_cast<long long>(c) * rd_stride;
+    const long long o0 = st.o_n;
+    const long long o1 = (k1 * 13 + 49) / 50;                    // outputs o whose newest input floor(50 o / 13) has arrived
+    // ---- A: rational resampler 13 / 50 (arm (50 o) mod 13 at input floor(50 o / 13), oldest tap first)
+    for (long long o = o0 + tid; o < o1; o += 256) {
+        const long long im = o * 50, newest = im / 13;
+        const float* hh = s_arms + static_cast<int>(im - newest * 13) * p.nt_arm;
+        float re = 0.0f, imv = 0.0f;
+        for (int k = p.nt_arm - 1; k >= 0; k--) {
+            const long long a = newest - k;
+            const float2 v = a >= 0 ? x1[a & r1_mask] : make_float2(0.0f, 0.0f);
+            re = fmaf(hh[k], v.x, re); imv = fmaf(hh[k], v.y, imv);
+        }
+        xa[o & ring_mask] = make_float2(re, imv);
+    }
+    __syncthreads();
+    // ---- B: frequency / phase lock (per-item recurrence) over shared-memory chunks
+    for (long long b0 = o0; b0 < o1; b0 += kDsssChunk) {
+        const int n = static_cast<int>(o1 - b0 < kDsssChunk ? o1 - b0 : kDsssChunk);
+        for (int i = tid; i < n; i += 256) s_buf[i] = xa[(b0 + i) & ring_mask];
+        __syncthreads();
+        if (tid == 0) {
+            LoopState pll = st.pll;
+            for (int i = 0; i < n; i++) {
+                float yr, yi;
+                qrl_costas_step(pll, p.pll_alpha, p.pll_beta, 2, true, s_buf[i].x, s_buf[i].y, yr, yi);
+                s_buf[i] = make_float2(yr, yi);
+            }
+            st.pll = pll;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += 256) xa[(b0 + i) & ring_mask] = s_buf[i];
+        __syncthreads();
+    }
+    // ---- C: low-pass -> port 0 and the AGC's input
+    for (long long o = o0 + tid; o < o1; o += 256) {
+        float re = 0.0f, imv = 0.0f;
+        for (int k = p.nt2 - 1; k >= 0; k--) {
+            const long long a = o - k;
+            const float2 v = a >= 0 ? xa[a & ring_mask] : make_float2(0.0f, 0.0f);
+            re = fmaf(s_t2[k], v.x, re); imv = fmaf(s_t2[k], v.y, imv);
+        }
+        xc[o & ring_mask] = make_float2(re, imv);
+        if (o - o_call0 < port0_stride) port0[static_cast<long long>(c) * port0_stride + (o - o_call0)] = make_float2(re, imv);
+    }
+    __syncthreads();
+    // ---- D: agc2_cc::scale (signed rate compare, see agc_costas_kernel)
+    for (long long b0 = o0; b0 < o1; b0 += kDsssChunk) {
+        const int n = static_cast<int>(o1 - b0 < kDsssChunk ? o1 - b0 : kDsssChunk);
+        for (int i = tid; i < n; i += 256) s_buf[i] = xc[(b0 + i) & ring_mask];
+        __syncthreads();
+        if (tid == 0) {
+            float gain = st.agc;
+            for (int i = 0; i < n; i++) {
+                const float orr = s_buf[i].x * gain, oi = s_buf[i].y * gain;
+                const float tmp = -p.agc_ref + sqrtf(orr * orr + oi * oi);
+                const float rate = (tmp > gain) ? p.agc_attack : p.agc_decay;
+                gain = gain - tmp * rate;
+                if (gain < 0.0f) gain = 10e-5f;
+                if (p.agc_max > 0.0f && gain > p.agc_max) gain = p.agc_max;
+                s_buf[i] = make_float2(orr, oi);
+            }
+            st.agc = gain;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += 256) xc[(b0 + i) & ring_mask] = s_buf[i];
+        __syncthreads();
+    }
+    // ---- E: despreader.  Symbol m needs items up to m N + (ntaps - N) - 1.
+    const long long m0 = st.m_n;
+    const long long m1 = o1 >= (p.ntaps - p.N) ? (o1 - (p.ntaps - p.N)) / p.N + 1 : 0;
+    const int wlen = p.N + p.ntaps - 1;                           // items one symbol's correlations touch (<= kDsssChunk, checked at create)
+    for (long long m = m0; m < m1; m++) {
+        const long long w0 = m * p.N - 2LL * p.N + 1;
+        for (int i = tid; i < wlen; i += 256) {
+            const long long a = w0 + i;
+            s_buf[i] = a >= 0 ? xc[a & ring_mask] : make_float2(0.0f, 0.0f);
+        }
+        __syncthreads();
+        float best = 0.0f; int bj = 0x7fffffff; float2 bv = make_float2(0.0f, 0.0f);
+        for (int j = tid; j < p.N; j += 256) {
+            float ar = 0.0f, ai = 0.0f;
+            for (int k = 0; k < p.ntaps; k++) {
+                const float2 v = s_buf[j + k], t = s_dt[k];
+                const float pr = v.x * t.x - v.y * t.y, pi = v.x * t.y + v.y * t.x;
+                ar = ar + pr; ai = ai + pi;
+            }
+            const float mag = static_cast<float>(sqrt(static_cast<double>(ar) * static_cast<double>(ar) + static_cast<double>(ai) * static_cast<double>(ai)));
+            if (mag > best) { best = mag; bj = j; bv = make_float2(ar, ai); }       // ascending j per thread: first strict maximum
+        }
+        s_mag[tid] = best; s_idx[tid] = bj; s_val[tid] = bv;
+        __syncthreads();
+        for (int off = 128; off >= 1; off >>= 1) {
+            if (tid < off) {
+                const float om = s_mag[tid + off]; const int oj = s_idx[tid + off];
+                if (om > s_mag[tid] || (om == s_mag[tid] && oj < s_idx[tid])) { s_mag[tid] = om; s_idx[tid] = oj; s_val[tid] = s_val[tid + off]; }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const float sc = 2.0f / static_cast<float>(p.N);
+            xd[m & rd_mask] = s_mag[0] > 0.0f ? make_float2(s_val[0].x * sc, s_val[0].y * sc) : make_float2(0.0f * sc, 0.0f * sc);
+        }
+        __syncthreads();
+    }
+    // ---- F: symbol clock, carrier phase, soft bits
+    if (tid == 0) {
+        st.o_n = o1; st.m_n = m1 > m0 ? m1 : m0;
+        const long long avail = st.m_n;
+        int cnt = port1_cnt[c];
+        // (each step advances mu by at least omega_min - gain_mu > 0.9, so two steps consume an item; the guard only stops a NaN stream)
+        long long guard = 2 * (avail - st.cr_ii) + 16;
+        while (st.cr_ii + 24 <= avail && guard-- > 0) {                // 8 interpolator taps + the block's 16-item margin (oracle crmm_work)
+            const int imu = static_cast<int>(rintf(st.mu * 128.0f));
+            const float* tt = d_mmse_tab + imu * 8;
+            float yr = 0.0f, yi = 0.0f;
+            for (int i = 0; i < 8; i++) {
+                const float2 v = xd[(st.cr_ii + i) & rd_mask];
+                yr = fmaf(tt[7 - i], v.x, yr); yi = fmaf(tt[7 - i], v.y, yi);
+            }
+            st.p2r = st.p1r; st.p2i = st.p1i; st.p1r = st.p0r; st.p1i = st.p0i; st.p0r = yr; st.p0i = yi;
+            st.c2r = st.c1r; st.c2i = st.c1i; st.c1r = st.c0r; st.c1i = st.c0i;
+            st.c0r = yr > 0.0f ? 1.0f : 0.0f; st.c0i = yi > 0.0f ? 1.0f : 0.0f;
+            const float ar = st.c0r - st.c2r, ai = st.c0i - st.c2i;
+            const float xr_ = ar * st.p1r + ai * st.p1i;
+            const float br = st.p0r - st.p2r, bi = st.p0i - st.p2i;
+            const float yr_ = br * st.c1r + bi * st.c1i;
+            const float mm = qrl_clip(yr_ - xr_, 1.0f);
+            st.omega = st.omega + p.gain_omega * mm;
+            st.omega = p.omega_mid + qrl_clip(st.omega - p.omega_mid, p.omega_lim);
+            st.mu = st.mu + st.omega + p.gain_mu * mm;
+            const float fl = floorf(st.mu);
+            st.cr_ii += static_cast<long long>(static_cast<int>(fl));
+            st.mu = st.mu - fl;
+            float cr, ci;
+            qrl_costas_step(st.costas, p.costas_alpha, p.costas_beta, 2, false, yr, yi, cr, ci);
+            if (cnt < port1_cap) port1[static_cast<long long>(c) * port1_stride + cnt] = make_float2(cr, ci);
+            cnt++;
+            soft_ring[static_cast<long long>(c) * soft_stride + (st.n_soft & soft_mask)] = qrl_soft_u8(cr, p.soft_scale);
+            st.n_soft++; st.n_sym++;
+        }
+        port1_cnt[c] = cnt < port1_cap ? cnt : port1_cap;
+        n_soft_out[c] = st.n_soft;
+        states[c] = st;
+    }
 }
 
 // interleaved int16 I/Q (the SDR's wire format) -> gr_complex: float(v) * scale, as the host-side converter in front of the reference's

@@ -190,6 +190,12 @@ def make_gr_demod_dmr(sps=5, samp_rate=1000000, n_channels=1, **kw):
     return RxBlock(KIND.DEMOD_DMR, sps, samp_rate, 0, 5000, 0, n_channels, **kw)
 
 
+def make_gr_demod_dsss(sps=25, samp_rate=1000000, carrier_freq=1700, filter_width=150, n_channels=1, **kw):
+    """src/gr/gr_demod_dsss.h (instance gr_demod_base.cpp:218: make_gr_demod_dsss(25, 1e6, 1700, 150)); Barker-13 BPSK, 16 symbols/s;
+    ports (IQ at 5200 sps, symbols, decoded bits, decoded bits of the decoder behind delay(1))."""
+    return RxBlock(KIND.DEMOD_DSSS, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
+
+
 def make_gr_demod_wbfm(sps, samp_rate, carrier_freq, filter_width, n_channels=1, **kw):
     """src/gr/gr_demod_wbfm.h (instance gr_demod_base.cpp:228: make_gr_demod_wbfm(125, 1e6, 1700, 75000)); ports (IQ at 200 ksps,
     float audio at 8 ksps)."""

@@ -118,6 +118,12 @@ def make_gr_mod_m17(sps=125, samp_rate=1000000, carrier_freq=1700, filter_width=
     return TxBlock(KIND.MOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
 
 
+def make_gr_mod_dsss(sps=25, samp_rate=1000000, carrier_freq=1700, filter_width=200, n_channels=1, max_items=8, **kw):
+    """src/gr/gr_mod_dsss.h (instance gr_mod_base.cpp:170: make_gr_mod_dsss(25, 1e6, 1700, 200)); items: frame bytes at 1 byte/s: every byte
+    becomes 10^6 output samples, hence the small default max_items."""
+    return TxBlock(KIND.MOD_DSSS, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_items=max_items, **kw)
+
+
 def make_gr_mod_dmr(sps=125, samp_rate=1000000, carrier_freq=1700, filter_width=5000, n_channels=1, **kw):
     """src/gr/gr_mod_dmr.h:37-38 (defaults as there); items: frame bytes, 4 symbols per byte.  TxBlock.zero_samples is the
     "zero_samples" stream tag gr_dmr_source attaches to the bytes of an idle burst (gr_zero_idle_bursts)."""

@@ -501,3 +501,36 @@ def test_dsss_modem_loops_back_in_the_oracle(oracle):
             m = min(len(pa[port]) - off, len(bits))
             best = max(best, float(np.mean(pa[port][off:off + m] == bits[:m])))
     assert best == 1.0
+
+
+def test_mmdvm_channel_chains_restated(oracle):
+    """gr_mod_mmdvm_multi2 -> gr_demod_mmdvm_multi2, one channel each side of the filter bank (25 ksps complex <-> int16 at 24 ksps):
+    rates 25/24 and 24/25, chunk invariance on both sides, RSSI tags every 300 items, and the discriminator returns the modulating
+    samples (the 12.5 kHz deviation maps full-scale int16 onto +-pi/... of phase step; the round trip gain is 1)."""
+    O = oracle
+    rng = np.random.default_rng(91)
+    n = 24000
+    t = np.arange(n)
+    s = (3000 * np.sin(2 * np.pi * 1200 * t / 24000) + 1500 * np.sin(2 * np.pi * 300 * t / 24000 + 0.7)).astype(np.int16)
+    a = O.MmdvmTx(5000); ya = a.work(s)
+    assert len(ya) == n * 25 // 24
+    b = O.MmdvmTx(5000)
+    yb = np.concatenate([b.work(s[lo:lo + 777]) for lo in range(0, n, 777)])
+    assert np.array_equal(ya.view(np.uint32), yb.view(np.uint32))
+    assert 0.6 < np.abs(ya[2000:]).mean() <= 0.81            # x0.8 behind the 5 kHz channel filter (the FM signal is a little wider)
+    r1 = O.MmdvmRx(5000); o1, db1, at1 = r1.work(ya)
+    assert len(o1) == len(ya) * 24 // 25
+    r2 = O.MmdvmRx(5000)
+    parts = [r2.work(ya[lo:lo + 1001]) for lo in range(0, len(ya), 1001)]
+    assert np.array_equal(o1, np.concatenate([p[0] for p in parts]))
+    assert np.array_equal(db1, np.concatenate([p[1] for p in parts])) and np.array_equal(at1, np.concatenate([p[2] for p in parts]))
+    assert len(db1) == len(o1) // 300 and np.array_equal(at1, np.arange(len(db1)) * 300 + 299)
+    # discriminator output against the modulating samples: the chain delay is not a whole number of 24 ksps items (two 819-tap
+    # resamplers at 600 kHz), so compare the two tones' amplitudes (least squares over the steady state) and the residual
+    seg = o1[2000:22000].astype(np.float64)
+    tt = np.arange(len(seg))
+    A = np.stack([np.sin(2 * np.pi * 1200 * tt / 24000), np.cos(2 * np.pi * 1200 * tt / 24000),
+                  np.sin(2 * np.pi * 300 * tt / 24000), np.cos(2 * np.pi * 300 * tt / 24000), np.ones(len(seg))], 1)
+    coef, *_ = np.linalg.lstsq(A, seg, rcond=None)
+    assert abs(np.hypot(coef[0], coef[1]) - 3000) < 30 and abs(np.hypot(coef[2], coef[3]) - 1500) < 15, coef
+    assert np.sqrt(np.mean((seg - A @ coef) ** 2)) < 80          # int16 units (2 % of the signal): FM through two 5 kHz channel filters

@@ -245,3 +245,20 @@ def test_dsss_decoder_restatement_is_the_reference_block(R):
         assert np.array_equal(ref.view(np.uint32), first.view(np.uint32)), per_call
     assert m0 >= n_sym - 2
     R.ref_block_destroy(h)
+
+
+def test_rssi_tag_rule_is_the_reference_block(R):
+    """rssi_tag_block.cpp compiled unmodified (add_item_tag through the stand-in): an "RSSI" tag every 300 items, value and offset, for
+    several scheduler chunkings; the float accumulation order is the block's (sequential)."""
+    rng = np.random.default_rng(81)
+    n = 7000
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * np.repeat(rng.uniform(1e-4, 2.0, n // 100), 100)).astype(np.complex64)
+    db_o = np.zeros(64, np.float32); at_o = np.zeros(64, np.int64)
+    k = O.lib().qo_rssi_tags_run(_p(x), n, -3.5, _p(db_o), _p(at_o), 64)
+    assert k == n // 300
+    for chunks in ([n], [299, 1, 300, 301, 5000, 2000], [7] * 1001):
+        ch = np.array(chunks, np.dtype("l"))
+        db_r = np.zeros(64, np.float32); at_r = np.zeros(64, np.int64)
+        kr = R.ref_rssi_tags(_p(x), n, C.c_float(-3.5), _p(ch), len(ch), _p(db_r), _p(at_r), 64)
+        assert kr == k and np.array_equal(at_r[:k], at_o[:k]) and np.array_equal(db_r[:k].view(np.uint32), db_o[:k].view(np.uint32)), chunks[:3]
+    assert np.array_equal(at_o[:k], np.arange(k) * 300 + 299)
