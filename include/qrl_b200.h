@@ -220,6 +220,45 @@ int  qrl_pfb_out_device(qrl_pfb*, void** data, long* stride, long* items);
 int  qrl_pfb_read(qrl_pfb*, void* host_dst, long dst_stride);
 long qrl_pfb_launch_count(qrl_pfb*);
 
+/* ---- MMDVM multi-channel front end: the per-channel chains either side of the filter bank ------------------------------------------
+ * gr_demod_mmdvm_multi2 (/root/reference/src/gr/gr_demod_mmdvm_multi2.cpp:56-126; MMDVM_SAMPLE_RATE 250000, src/config_mmdvm.h:4) behind
+ * qrl_pfb's channelizer: for channel c, row rows[c] of the [n_rows][stride] gr_complex slab at 25 ksps (NULL rows = identity; the
+ * reference's port map is channels 0..3 on ports 0..3, 4.. on 9, 8, ..) -> rational_resampler_ccf(24, 25, low_pass_2(1, 600k, fw, 2000,
+ * 60, BH)) -> low_pass_2(1, 24k, fw, 2000, 60, BH) -> rssi_tag_block (one dB value per 300 items, rssi_tag_block.cpp:42-63) ->
+ * quadrature_demod_cf(24000 / (2 pi 12500)) -> x1.0 -> float_to_short(1, 32767): int16 [n_channels][*n_out] at 24 ksps, what
+ * gr_mmdvm_sink takes.  No feedback loop anywhere: one thread per item in every stage; results are chunk invariant.
+ * gr_mod_mmdvm_multi2 (gr_mod_mmdvm_multi2.cpp:47-126) in front of the synthesizer: int16 [n_channels][n] at 24 ksps -> short_to_float
+ * (x (float)(1 / 32767): VOLK's SIMD form) -> x1.0 -> frequency_modulator_fc(2 pi 12500 / 24000) (Q32 phase, as the other modulators) ->
+ * low_pass_2(1, 24k, ...) -> x0.8 -> rational_resampler_ccf(25, 24, low_pass_2(25, 600k, ...)) -> rows rows[c] of a zeroed [n_rows][stride]
+ * slab at 25 ksps (the synthesizer's input; unused rows are the reference's null_source).  qrl_mmdvm_tx_finish applies what follows
+ * the synthesizer, multiply_const_cc(1 / n_channels) and multiply_const_cc(bb_gain), in place on the wideband device buffer.
+ * Not built: the "zero_samples" tags of gr_zero_idle_bursts(0) on this path (gr_mod_mmdvm_multi2.cpp:84-87), the MMDVM protocol sink /
+ * source (ZeroMQ, out of scope). */
+typedef struct qrl_mmdvm_rx qrl_mmdvm_rx;
+typedef struct qrl_mmdvm_tx qrl_mmdvm_tx;
+int  qrl_mmdvm_rx_create(int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_rx** out);
+int  qrl_mmdvm_rx_destroy(qrl_mmdvm_rx*);
+int  qrl_mmdvm_rx_set_stream(qrl_mmdvm_rx*, void* cuda_stream);
+int  qrl_mmdvm_rx_calibrate_rssi(qrl_mmdvm_rx*, float level);              /* rssi_tag_block::calibrate_rssi */
+int  qrl_mmdvm_rx_work(qrl_mmdvm_rx*, const float* iq, long n, long stride, int on_device, long* n_out);
+int  qrl_mmdvm_rx_sync(qrl_mmdvm_rx*);
+/* device views of the last call: int16 [n_channels][*stride], RSSI dB [n_channels][*rssi_stride] (*n_rssi values, the first one
+ * belongs to 24 ksps item *first_rssi_item, the next ones follow every 300 items) */
+int  qrl_mmdvm_rx_out_device(qrl_mmdvm_rx*, short** data, long* stride, long* n_out, float** rssi_db, long* rssi_stride, int* n_rssi,
+                             long long* first_rssi_item);
+int  qrl_mmdvm_rx_read(qrl_mmdvm_rx*, short* dst, long dst_stride, float* rssi_db, long rssi_cap, int* n_rssi, long long* first_rssi_item);
+long qrl_mmdvm_rx_launch_count(qrl_mmdvm_rx*);
+int  qrl_mmdvm_tx_create(int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_tx** out);
+int  qrl_mmdvm_tx_destroy(qrl_mmdvm_tx*);
+int  qrl_mmdvm_tx_set_stream(qrl_mmdvm_tx*, void* cuda_stream);
+int  qrl_mmdvm_tx_set_bb_gain(qrl_mmdvm_tx*, float gain);                   /* gr_mod_mmdvm_multi2::set_bb_gain */
+int  qrl_mmdvm_tx_work(qrl_mmdvm_tx*, const short* in, long n, long stride, int on_device, long* n_out);
+int  qrl_mmdvm_tx_sync(qrl_mmdvm_tx*);
+int  qrl_mmdvm_tx_out_device(qrl_mmdvm_tx*, float** data, long* stride, long* n_out);      /* [n_rows][*stride] gr_complex */
+int  qrl_mmdvm_tx_read(qrl_mmdvm_tx*, float* dst, long dst_stride);
+int  qrl_mmdvm_tx_finish(qrl_mmdvm_tx*, float* wideband_dev, long n);
+long qrl_mmdvm_tx_launch_count(qrl_mmdvm_tx*);
+
 /* ---- display spectrum on the device -----------------------------------------------------------------
  * rx_fft_c (/root/reference/src/gr/rx_fft.cpp:44-129; gr_demod_base.cpp:166: 32768 points, Blackman-Harris; get_FFT_data :978-986) for
  * n_streams streams at once (the wideband source of a GPU, or every channel of a batch: [n_streams][stride] gr_complex like

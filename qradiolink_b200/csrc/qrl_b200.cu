@@ -2662,3 +2662,293 @@ int qrl_fir_decim_ccf_device(const float* taps, int ntaps, int D, const float* x
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- MMDVM channel chains
+// gr_demod_mmdvm_multi2.cpp:56-126 behind the channelizer (qrl_pfb): per channel rational_resampler_ccf(24, 25) -> low-pass -> RSSI tags ->
+// quadrature_demod_cf -> x level -> float_to_short; gr_mod_mmdvm_multi2.cpp:47-126 in front of the synthesizer: short_to_float -> x level ->
+// frequency_modulator_fc -> low-pass -> x0.8 -> rational_resampler_ccf(25, 24) [-> synthesizer -> x 1 / num_channels -> x bb_gain].
+struct qrl_mmdvm_rx : HandleBase {
+    int C = 0, n_rows = 0, nt_arm = 0, nt2 = 0;
+    long max_in = 0;
+    int* d_rows = nullptr; float* d_arms = nullptr; float* d_taps2 = nullptr;
+    float2 *d_r25 = nullptr, *d_r24 = nullptr, *d_rf = nullptr, *d_in = nullptr;
+    unsigned m25 = 0, m24 = 0; long long s25 = 0, s24 = 0;
+    short* d_out = nullptr; long long out_stride = 0; long n_out_last = 0;
+    float* d_rssi = nullptr; long long rssi_stride = 0; int n_rssi_last = 0; long long rssi_b0_last = 0;
+    long long n_in = 0, n24 = 0, n_blocks = 0;
+    float qd_gain = 0, level = 1.0f, cal = 0.0f;
+};
+struct qrl_mmdvm_tx : HandleBase {
+    int C = 0, n_rows = 0, num_channels = 0, nt_arm = 0, nt2 = 0;
+    long max_in = 0;
+    int* d_rows = nullptr; float* d_arms = nullptr; float* d_taps2 = nullptr; float* d_one = nullptr;
+    TxBitState* d_bits = nullptr;
+    short* d_in = nullptr;
+    float* d_sym = nullptr; unsigned sym_mask = 0; long long sym_stride = 0;
+    float2 *d_if = nullptr, *d_rf = nullptr; unsigned if_mask = 0; long long if_stride = 0;
+    float2* d_lin = nullptr; long long lin_stride = 0;
+    float2* d_out = nullptr; long long out_stride = 0; long n_out_last = 0;
+    long long n_in = 0, n25 = 0;
+    float fm_sens = 0, level = 1.0f, bb_gain = 1.0f;
+};
+
+template <class H> static int mmdvm_destroy(H* h)
+{
+    if (!h) return QRL_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return QRL_OK;
+}
+template <class H> static int mmdvm_set_stream(H* h, void* s)
+{
+    if (!h) return QRL_EINVAL;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    if (s) h->stream = static_cast<cudaStream_t>(s);
+    else { CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    return QRL_OK;
+}
+static int mmdvm_rows(HandleBase* h, int** d_rows, const int* rows, int C, int n_rows)
+{
+    std::vector<int> r(C);
+    for (int c = 0; c < C; c++) {
+        r[c] = rows ? rows[c] : c;
+        if (r[c] < 0 || r[c] >= n_rows) { set_err(h, "mmdvm: row index outside the slab"); return QRL_EINVAL; }
+    }
+    int rc = dev_alloc(h, d_rows, static_cast<size_t>(C), false);
+    if (rc) return rc;
+    if (cudaMemcpy(*d_rows, r.data(), sizeof(int) * C, cudaMemcpyHostToDevice) != cudaSuccess) { set_err(h, "mmdvm: row upload failed"); return QRL_ECUDA; }
+    return QRL_OK;
+}
+
+extern "C" {
+
+int qrl_mmdvm_rx_destroy(qrl_mmdvm_rx* h) { return mmdvm_destroy(h); }
+int qrl_mmdvm_rx_set_stream(qrl_mmdvm_rx* h, void* s) { return mmdvm_set_stream(h, s); }
+int qrl_mmdvm_rx_create(int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_rx** out)
+{
+    if (!out || n_channels <= 0 || n_rows < n_channels || max_in <= 0 || filter_width <= 0) { set_err(nullptr, "qrl_mmdvm_rx_create: bad argument"); return QRL_EINVAL; }
+    *out = nullptr;
+    if (qrl_device_count() <= device) { set_err(nullptr, "qrl_mmdvm_rx_create: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
+    qrl_mmdvm_rx* h = new qrl_mmdvm_rx();
+    h->C = n_channels; h->n_rows = n_rows; h->max_in = max_in; h->device = device;
+    auto fail = [&](int rc) { std::string e = h->err; qrl_mmdvm_rx_destroy(h); g_err = e; return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) { set_err(h, "cudaSetDevice failed"); return fail(QRL_ECUDA); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err(h, "stream create failed"); return fail(QRL_ECUDA); }
+    h->own_stream = true;
+    int rc = upload_tables(h);
+    if (rc) return fail(rc);
+    if ((rc = mmdvm_rows(h, &h->d_rows, rows, h->C, n_rows))) return fail(rc);
+    // gr_demod_mmdvm_multi2.cpp:58-62,66,71,76
+    const std::vector<float> ti = low_pass_2(1, 600000.0, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS);
+    const std::vector<float> tf = low_pass_2(1, 24000.0, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS);
+    h->nt_arm = (static_cast<int>(ti.size()) + 23) / 24; h->nt2 = static_cast<int>(tf.size());
+    if (static_cast<size_t>(24) * h->nt_arm * sizeof(float) > 40 * 1024 || h->nt2 > kMaxTapsSmem) { set_err(h, "qrl_mmdvm_rx_create: filter_width too small"); return fail(QRL_EINVAL); }
+    if ((rc = upload_floats(h, &h->d_arms, make_arms(ti, 24, h->nt_arm)))) return fail(rc);
+    if ((rc = upload_floats(h, &h->d_taps2, tf))) return fail(rc);
+    h->qd_gain = static_cast<float>(24000.0f / (2 * kPi * 12500.0f));
+    const unsigned c25 = pow2_at_least(max_in + h->nt_arm + 64), c24 = pow2_at_least(max_in + h->nt2 + 400);
+    h->m25 = c25 - 1; h->s25 = c25; h->m24 = c24 - 1; h->s24 = c24;
+    if ((rc = dev_alloc(h, &h->d_r25, static_cast<size_t>(c25) * h->C))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_r24, static_cast<size_t>(c24) * h->C))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_rf, static_cast<size_t>(c24) * h->C))) return fail(rc);
+    h->out_stride = max_in * 24 / 25 + 2;
+    if ((rc = dev_alloc(h, &h->d_out, static_cast<size_t>(h->out_stride) * h->C, false))) return fail(rc);
+    h->rssi_stride = h->out_stride / 300 + 2;
+    if ((rc = dev_alloc(h, &h->d_rssi, static_cast<size_t>(h->rssi_stride) * h->C, false))) return fail(rc);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { set_err(h, "create sync failed"); return fail(QRL_ECUDA); }
+    *out = h;
+    return QRL_OK;
+}
+int qrl_mmdvm_rx_calibrate_rssi(qrl_mmdvm_rx* h, float level) { if (!h) return QRL_EINVAL; h->cal = level; return QRL_OK; }   // rssi_tag_block::calibrate_rssi
+int qrl_mmdvm_rx_work(qrl_mmdvm_rx* h, const float* iq, long n, long stride, int on_device, long* n_out)
+{
+    if (!h || !iq || n < 0) return QRL_EINVAL;
+    if (n > h->max_in) { set_err(h, "qrl_mmdvm_rx_work: n exceeds max_in given at create"); return QRL_ERANGE; }
+    h->n_out_last = 0; h->n_rssi_last = 0;
+    if (n_out) *n_out = 0;
+    if (n == 0) return QRL_OK;
+    CK(cudaSetDevice(h->device));
+    const float2* x = reinterpret_cast<const float2*>(iq);
+    long long xstride = stride;
+    if (on_device) { int rc = check_device_ptr(h, iq, "qrl_mmdvm_rx_work"); if (rc) return rc; }
+    else {
+        if (!h->d_in) { int rc = dev_alloc(h, &h->d_in, static_cast<size_t>(h->max_in) * h->n_rows, false); if (rc) return rc; }
+        CK(cudaMemcpy2DAsync(h->d_in, sizeof(float2) * h->max_in, iq, sizeof(float2) * stride, sizeof(float2) * n, h->n_rows, cudaMemcpyHostToDevice, h->stream));
+        x = h->d_in; xstride = h->max_in;
+    }
+    const int TB = 256;
+    mmdvm_gather_kernel<<<dim3(static_cast<unsigned>(std::min<long long>((n + TB - 1) / TB, 4096)), h->C), TB, 0, h->stream>>>(
+        x, xstride, h->d_rows, n, h->d_r25, h->m25, h->s25, h->n_in);
+    const long long N = h->n_in + n;
+    const long long o0 = h->n24, o1 = (N * 24 + 24) / 25;              // outputs o whose newest input floor(25 o / 24) has arrived
+    h->launches++;
+    if (o1 > o0) {
+        dim3 g(static_cast<unsigned>((o1 - o0 + TB - 1) / TB), h->C);
+        resamp_ring_to_ring_ccf_kernel<<<g, TB, sizeof(float) * 24 * h->nt_arm, h->stream>>>(h->d_r25, h->m25, h->s25, h->d_arms, 24, 25, h->nt_arm, o0, o1,
+                                                                                              1.0f, 1.0f, 0, h->d_r24, h->m24, h->s24);
+        fir_ccf_ring_kernel<<<g, TB, sizeof(float) * h->nt2, h->stream>>>(h->d_r24, h->m24, h->s24, h->d_rf, h->m24, h->s24, h->d_taps2, h->nt2, o0, o1, nullptr, 0, 0, 0);
+        mmdvm_demod_short_kernel<<<g, TB, 0, h->stream>>>(h->d_rf, h->m24, h->s24, o0, o1, h->qd_gain, h->level, h->d_out, h->out_stride);
+        h->launches += 3;
+        const long long b1 = o1 / 300;                                   // complete 300-item blocks so far
+        if (b1 > h->n_blocks) {
+            const int nb = static_cast<int>(b1 - h->n_blocks);
+            mmdvm_rssi_kernel<<<dim3((nb + 63) / 64, h->C), 64, 0, h->stream>>>(h->d_rf, h->m24, h->s24, h->n_blocks, nb, h->cal, h->d_rssi, h->rssi_stride);
+            h->launches++;
+            h->n_rssi_last = nb; h->rssi_b0_last = h->n_blocks; h->n_blocks = b1;
+        }
+    }
+    h->n_in = N; h->n24 = o1;
+    h->n_out_last = static_cast<long>(o1 - o0);
+    if (n_out) *n_out = h->n_out_last;
+    CK(cudaGetLastError());
+    return QRL_OK;
+}
+int qrl_mmdvm_rx_out_device(qrl_mmdvm_rx* h, short** data, long* stride, long* n_out, float** rssi_db, long* rssi_stride, int* n_rssi, long long* first_rssi_item)
+{
+    if (!h) return QRL_EINVAL;
+    if (data) *data = h->d_out;
+    if (stride) *stride = static_cast<long>(h->out_stride);
+    if (n_out) *n_out = h->n_out_last;
+    if (rssi_db) *rssi_db = h->d_rssi;
+    if (rssi_stride) *rssi_stride = static_cast<long>(h->rssi_stride);
+    if (n_rssi) *n_rssi = h->n_rssi_last;
+    if (first_rssi_item) *first_rssi_item = h->rssi_b0_last * 300 + 299;
+    return QRL_OK;
+}
+int qrl_mmdvm_rx_read(qrl_mmdvm_rx* h, short* dst, long dst_stride, float* rssi_db, long rssi_cap, int* n_rssi, long long* first_rssi_item)
+{
+    if (!h || !dst) return QRL_EINVAL;
+    CK(cudaSetDevice(h->device));
+    if (h->n_out_last > 0)
+        CK(cudaMemcpy2DAsync(dst, sizeof(short) * dst_stride, h->d_out, sizeof(short) * h->out_stride, sizeof(short) * h->n_out_last, h->C, cudaMemcpyDeviceToHost, h->stream));
+    const int nr = static_cast<int>(std::min<long>(h->n_rssi_last, rssi_cap));
+    if (rssi_db && nr > 0)
+        CK(cudaMemcpy2DAsync(rssi_db, sizeof(float) * rssi_cap, h->d_rssi, sizeof(float) * h->rssi_stride, sizeof(float) * nr, h->C, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n_rssi) *n_rssi = nr;
+    if (first_rssi_item) *first_rssi_item = h->rssi_b0_last * 300 + 299;
+    return QRL_OK;
+}
+long qrl_mmdvm_rx_launch_count(qrl_mmdvm_rx* h) { return h ? h->launches : 0; }
+
+int qrl_mmdvm_tx_destroy(qrl_mmdvm_tx* h) { return mmdvm_destroy(h); }
+int qrl_mmdvm_tx_set_stream(qrl_mmdvm_tx* h, void* s) { return mmdvm_set_stream(h, s); }
+int qrl_mmdvm_tx_create(int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_tx** out)
+{
+    if (!out || n_channels <= 0 || n_rows < n_channels || max_in <= 0 || filter_width <= 0) { set_err(nullptr, "qrl_mmdvm_tx_create: bad argument"); return QRL_EINVAL; }
+    *out = nullptr;
+    if (qrl_device_count() <= device) { set_err(nullptr, "qrl_mmdvm_tx_create: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
+    qrl_mmdvm_tx* h = new qrl_mmdvm_tx();
+    h->C = n_channels; h->n_rows = n_rows; h->num_channels = n_channels; h->max_in = max_in; h->device = device;
+    auto fail = [&](int rc) { std::string e = h->err; qrl_mmdvm_tx_destroy(h); g_err = e; return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) { set_err(h, "cudaSetDevice failed"); return fail(QRL_ECUDA); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err(h, "stream create failed"); return fail(QRL_ECUDA); }
+    h->own_stream = true;
+    int rc = upload_tables(h);
+    if (rc) return fail(rc);
+    if ((rc = mmdvm_rows(h, &h->d_rows, rows, h->C, n_rows))) return fail(rc);
+    // gr_mod_mmdvm_multi2.cpp:47-50,64,72,80
+    const std::vector<float> ti = low_pass_2(25, 600000.0, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS);
+    const std::vector<float> tf = low_pass_2(1, 24000.0, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS);
+    h->nt_arm = (static_cast<int>(ti.size()) + 24) / 25; h->nt2 = static_cast<int>(tf.size());
+    if (static_cast<size_t>(25) * h->nt_arm * sizeof(float) > 40 * 1024 || h->nt2 > kMaxTapsSmem) { set_err(h, "qrl_mmdvm_tx_create: filter_width too small"); return fail(QRL_EINVAL); }
+    if ((rc = upload_floats(h, &h->d_arms, make_arms(ti, 25, h->nt_arm)))) return fail(rc);
+    if ((rc = upload_floats(h, &h->d_taps2, tf))) return fail(rc);
+    if ((rc = upload_floats(h, &h->d_one, std::vector<float>{ 1.0f }))) return fail(rc);
+    h->fm_sens = static_cast<float>(2 * kPi * 12500.0f / 24000.0f);
+    if ((rc = dev_alloc(h, &h->d_bits, h->C))) return fail(rc);
+    { std::vector<TxBitState> st(h->C); for (auto& x : st) { x.scr_reg = 0x7F; x.enc_state = 0; x.diff_prev = 0; x.phase_q = 0; }
+      if (cudaMemcpy(h->d_bits, st.data(), sizeof(TxBitState) * h->C, cudaMemcpyHostToDevice) != cudaSuccess) { set_err(h, "state upload failed"); return fail(QRL_ECUDA); } }
+    { const unsigned cap = pow2_at_least(max_in + 64); h->sym_mask = cap - 1; h->sym_stride = cap;
+      if ((rc = dev_alloc(h, &h->d_sym, static_cast<size_t>(cap) * h->C))) return fail(rc); }
+    { const unsigned cap = pow2_at_least(max_in + std::max(h->nt2, h->nt_arm) + 128); h->if_mask = cap - 1; h->if_stride = cap;
+      if ((rc = dev_alloc(h, &h->d_if, static_cast<size_t>(cap) * h->C))) return fail(rc);
+      if ((rc = dev_alloc(h, &h->d_rf, static_cast<size_t>(cap) * h->C))) return fail(rc); }
+    h->lin_stride = max_in * 25 / 24 + 4; h->out_stride = h->lin_stride;
+    if ((rc = dev_alloc(h, &h->d_lin, static_cast<size_t>(h->lin_stride) * h->C, false))) return fail(rc);
+    if ((rc = dev_alloc(h, &h->d_out, static_cast<size_t>(h->out_stride) * h->n_rows))) return fail(rc);      // unused rows stay zero (null_source)
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { set_err(h, "create sync failed"); return fail(QRL_ECUDA); }
+    *out = h;
+    return QRL_OK;
+}
+int qrl_mmdvm_tx_set_bb_gain(qrl_mmdvm_tx* h, float g) { if (!h) return QRL_EINVAL; h->bb_gain = g; return QRL_OK; }      // gr_mod_mmdvm_multi2::set_bb_gain
+int qrl_mmdvm_tx_work(qrl_mmdvm_tx* h, const short* in, long n, long stride, int on_device, long* n_out)
+{
+    if (!h || !in || n < 0) return QRL_EINVAL;
+    if (n > h->max_in) { set_err(h, "qrl_mmdvm_tx_work: n exceeds max_in given at create"); return QRL_ERANGE; }
+    h->n_out_last = 0;
+    if (n_out) *n_out = 0;
+    if (n == 0) return QRL_OK;
+    CK(cudaSetDevice(h->device));
+    const short* s = in; long long sstride = stride;
+    if (on_device) { int rc = check_device_ptr(h, in, "qrl_mmdvm_tx_work"); if (rc) return rc; }
+    else {
+        if (!h->d_in) { int rc = dev_alloc(h, &h->d_in, static_cast<size_t>(h->max_in) * h->C, false); if (rc) return rc; }
+        CK(cudaMemcpy2DAsync(h->d_in, sizeof(short) * h->max_in, in, sizeof(short) * stride, sizeof(short) * n, h->C, cudaMemcpyHostToDevice, h->stream));
+        s = h->d_in; sstride = h->max_in;
+    }
+    const int TB = 256;
+    const long long a0 = h->n_in, a1 = h->n_in + n;
+    mmdvm_short_float_kernel<<<dim3(static_cast<unsigned>(std::min<long long>((n + TB - 1) / TB, 4096)), h->C), TB, 0, h->stream>>>(
+        s, sstride, n, h->level, h->d_sym, h->sym_mask, h->sym_stride, a0);
+    // frequency_modulator_fc: the FM scan kernel with a one-tap "pulse" (x * 1.0 is exact), Q32 phase carried in the state
+    tx_shape_fm_kernel<1024, 2><<<h->C, 1024, 0, h->stream>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, a0, n,
+        1, 1, h->d_one, 0, 1.0f, h->fm_sens, 1.0f, 1.0f, h->d_if, h->if_mask, h->if_stride);
+    dim3 g(static_cast<unsigned>((n + TB - 1) / TB), h->C);
+    fir_ccf_ring_kernel<<<g, TB, sizeof(float) * h->nt2, h->stream>>>(h->d_if, h->if_mask, h->if_stride, h->d_rf, h->if_mask, h->if_stride, h->d_taps2, h->nt2, a0, a1, nullptr, 0, 0, 0);
+    scale2_ring_kernel<<<g, TB, 0, h->stream>>>(h->d_rf, h->if_mask, h->if_stride, a0, a1, 0.8f, 1.0f);
+    const long long o0 = h->n25, o1 = (a1 * 25 + 23) / 24;               // outputs i with floor(24 i / 25) < a1
+    if (o1 - o0 > h->lin_stride) { set_err(h, "qrl_mmdvm_tx_work: output buffer too small"); return QRL_ERANGE; }
+    if (o1 > o0) {
+        dim3 go(static_cast<unsigned>((o1 - o0 + 255) / 256), h->C);
+        resamp_ring_ccf_generic_kernel<<<go, 256, sizeof(float) * 25 * h->nt_arm, h->stream>>>(h->d_rf, h->if_mask, h->if_stride, h->d_arms, 25, 24, h->nt_arm, o0, o1,
+                                                                                               h->d_lin, h->lin_stride);
+        mmdvm_scatter_kernel<<<dim3(static_cast<unsigned>(std::min<long long>((o1 - o0 + TB - 1) / TB, 4096)), h->C), TB, 0, h->stream>>>(
+            h->d_lin, h->lin_stride, h->d_rows, o1 - o0, h->d_out, h->out_stride);
+    }
+    h->launches += 6;
+    h->n_in = a1; h->n25 = o1;
+    h->n_out_last = static_cast<long>(o1 - o0);
+    if (n_out) *n_out = h->n_out_last;
+    CK(cudaGetLastError());
+    return QRL_OK;
+}
+int qrl_mmdvm_tx_out_device(qrl_mmdvm_tx* h, float** data, long* stride, long* n_out)
+{
+    if (!h) return QRL_EINVAL;
+    if (data) *data = reinterpret_cast<float*>(h->d_out);
+    if (stride) *stride = static_cast<long>(h->out_stride);
+    if (n_out) *n_out = h->n_out_last;
+    return QRL_OK;
+}
+int qrl_mmdvm_tx_read(qrl_mmdvm_tx* h, float* dst, long dst_stride)
+{
+    if (!h || !dst) return QRL_EINVAL;
+    CK(cudaSetDevice(h->device));
+    if (h->n_out_last > 0)
+        CK(cudaMemcpy2DAsync(dst, sizeof(float2) * dst_stride, h->d_out, sizeof(float2) * h->out_stride, sizeof(float2) * h->n_out_last, h->n_rows, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return QRL_OK;
+}
+// behind the synthesizer (gr_mod_mmdvm_multi2.cpp:94-96,123-125): multiply_const_cc(1 / num_channels) -> multiply_const_cc(bb_gain), in place
+int qrl_mmdvm_tx_finish(qrl_mmdvm_tx* h, float* wideband_dev, long n)
+{
+    if (!h || !wideband_dev || n < 0) return QRL_EINVAL;
+    if (n == 0) return QRL_OK;
+    CK(cudaSetDevice(h->device));
+    int rc = check_device_ptr(h, wideband_dev, "qrl_mmdvm_tx_finish"); if (rc) return rc;
+    scale2_linear_kernel<<<static_cast<unsigned>(std::min<long>((n + 255) / 256, 4096)), 256, 0, h->stream>>>(
+        reinterpret_cast<float2*>(wideband_dev), n, 1.0f / static_cast<float>(h->num_channels), h->bb_gain);
+    h->launches++;
+    CK(cudaGetLastError());
+    return QRL_OK;
+}
+int qrl_mmdvm_rx_sync(qrl_mmdvm_rx* h) { if (!h) return QRL_EINVAL; CK(cudaStreamSynchronize(h->stream)); return QRL_OK; }
+int qrl_mmdvm_tx_sync(qrl_mmdvm_tx* h) { if (!h) return QRL_EINVAL; CK(cudaStreamSynchronize(h->stream)); return QRL_OK; }
+long qrl_mmdvm_tx_launch_count(qrl_mmdvm_tx* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

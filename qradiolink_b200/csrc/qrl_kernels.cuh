@@ -3123,6 +3123,85 @@ dsss_chain_kernel(DsssParams p, DsssState* __restrict__ states,
     }
 }
 
+// ================================================================================================
+// gr_demod_mmdvm_multi2 / gr_mod_mmdvm_multi2 per channel, either side of the polyphase filter bank (gr_demod_mmdvm_multi2.cpp:56-126,
+// gr_mod_mmdvm_multi2.cpp:47-126).  No feedback anywhere: every stage is one thread per output item.
+// ================================================================================================
+// rows of a [n_rows][in_stride] slab (the channelizer's output) -> per-channel input ring (the resampler's history lives there)
+__global__ void mmdvm_gather_kernel(const float2* __restrict__ in, long long in_stride, const int* __restrict__ rows, long long n,
+                                    float2* __restrict__ ring, unsigned mask, long long stride, long long a0)
+{
+    const int c = blockIdx.y;
+    const float2* src = in + static_cast<long long>(rows[c]) * in_stride;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        ring[static_cast<long long>(c) * stride + ((a0 + i) & mask)] = src[i];
+}
+// quadrature_demod_cf(gain) -> x level (multiply_const_ff) -> float_to_short(1, 32767) = volk_32f_s32f_convert_16i: x scale, clip, rintf
+__global__ void mmdvm_demod_short_kernel(const float2* __restrict__ ring, unsigned mask, long long stride, long long o0, long long o1,
+                                         float gain, float level, short* __restrict__ out, long long out_stride)
+{
+    const int c = blockIdx.y;
+    const long long o = o0 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (o >= o1) return;
+    const float2* x = ring + static_cast<long long>(c) * stride;
+    const float2 a = x[o & mask];
+    const float2 p = o > 0 ? x[(o - 1) & mask] : make_float2(0.0f, 0.0f);
+    const float re = a.x * p.x + a.y * p.y;                              // x[n] * conj(x[n-1])
+    const float im = a.y * p.x - a.x * p.y;
+    float v = gain * qrl_fast_atan2f(im, re);
+    v = v * level;
+    v = v * 32767.0f;
+    v = v > 32767.0f ? 32767.0f : (v < -32768.0f ? -32768.0f : v);
+    out[static_cast<long long>(c) * out_stride + (o - o0)] = static_cast<short>(rintf(v));
+}
+// rssi_tag_block (rssi_tag_block.cpp:42-63): one value per 300 items, the block's own sequential float sum of (|x|^2)^2
+__global__ void mmdvm_rssi_kernel(const float2* __restrict__ ring, unsigned mask, long long stride, long long b0, int nblocks, float cal,
+                                  float* __restrict__ db, long long db_stride)
+{
+    const int c = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nblocks) return;
+    const float2* x = ring + static_cast<long long>(c) * stride;
+    const long long base = (b0 + j) * 300;
+    float sum = 0.0f;
+    for (int i = 0; i < 300; i++) {
+        const float2 v = x[(base + i) & mask];
+        const float pwr = v.x * v.x + v.y * v.y;
+        sum = sum + pwr * pwr;
+    }
+    const float lv = sqrtf(sum / 300.0f);
+    db[static_cast<long long>(c) * db_stride + j] = 10.0f * log10f(static_cast<float>(static_cast<double>(lv) + 1.0e-20)) + cal;
+}
+// short_to_float(1, 32767) = volk_16i_s32f_convert_32f (SIMD form: x (float)(1 / 32767)) -> x level -> the FM modulator's input ring
+__global__ void mmdvm_short_float_kernel(const short* __restrict__ in, long long in_stride, long long n, float level,
+                                         float* __restrict__ ring, unsigned mask, long long stride, long long a0)
+{
+    const int c = blockIdx.y;
+    const float inv = static_cast<float>(1.0 / 32767.0);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float v = static_cast<float>(in[static_cast<long long>(c) * in_stride + i]) * inv;
+        v = v * level;
+        ring[static_cast<long long>(c) * stride + ((a0 + i) & mask)] = v;
+    }
+}
+// per-channel linear rows -> rows of the synthesizer's [n_rows][stride] input slab
+__global__ void mmdvm_scatter_kernel(const float2* __restrict__ in, long long in_stride, const int* __restrict__ rows, long long n,
+                                     float2* __restrict__ out, long long out_stride)
+{
+    const int c = blockIdx.y;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[static_cast<long long>(rows[c]) * out_stride + i] = in[static_cast<long long>(c) * in_stride + i];
+}
+// multiply_const_cc twice on a linear buffer (behind the synthesizer: x 1 / num_channels, x bb_gain)
+__global__ void scale2_linear_kernel(float2* __restrict__ x, long long n, float g1, float g2)
+{
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float2 v = x[i];
+        v.x = v.x * g1; v.y = v.y * g1; v.x = v.x * g2; v.y = v.y * g2;
+        x[i] = v;
+    }
+}
+
 // interleaved int16 I/Q (the SDR's wire format) -> gr_complex: float(v) * scale, as the host-side converter in front of the reference's
 // source block does.  4 samples per thread: one 16-byte load, two 16-byte stores.
 __global__ void sc16_to_fc32_kernel(const short2* __restrict__ in, long long in_stride, float2* __restrict__ out, long long out_stride,
