@@ -533,6 +533,75 @@ def spectrum_config_block(q, torch, dev, cores, cpu_seconds):
     return res
 
 
+def mmdvm_config_block(q, torch, dev, cores, cpu_seconds):
+    """gr_demod_mmdvm_multi2 without its protocol sink: 250 ksps wideband -> pfb_channelizer(10) -> 7 x (24/25 resampler, low-pass, RSSI,
+    discriminator, int16), everything resident in HBM.  Batched over `B` independent wideband streams by running B handles back to back
+    would only repeat the number: one stream, long call."""
+    from oracle import oracle as O
+    from qradiolink_b200.mmdvm import _low_pass_2
+    L = q.load_library()
+    peak, _ = peaks()
+    stream = torch.cuda.current_stream()
+    N = 1 << 26
+    x = torch.view_as_complex(torch.randn((N, 2), device=dev) * 0.05)
+    tt = torch.arange(N, device=dev, dtype=torch.float64)
+    for p in (0, 1, 2, 3, 9, 8, 7):
+        f = p * 25000.0 if p < 5 else (p - 10) * 25000.0
+        x += (0.1 * torch.polar(torch.ones(N, device=dev, dtype=torch.float64), 2 * np.pi * ((f + 900.0) * tt / 250000.0 % 1.0))).to(torch.complex64)
+    dem = q.MmdvmDemod(7, 5000, max_in=N)
+    dem.channelizer.set_stream(stream.cuda_stream); dem.channels.set_stream(stream.cuda_stream)
+    cnt = Ct.c_long()
+
+    def call():
+        pf = dem.channelizer
+        assert L.qrl_pfb_work(pf._h, Ct.c_void_p(x.data_ptr()), N, 0, 1, Ct.byref(cnt)) == 0
+        ptr, stride, items = pf.out_device()
+        dem.channels.work_device(ptr, items, stride)
+
+    ms = timed_calls(call, 5, stream, torch, warm=2)
+    # parity on the head of a fresh stream
+    n_chk = 1 << 20
+    d2 = q.MmdvmDemod(7, 5000, max_in=n_chk)
+    xh = x[:n_chk].cpu().numpy()
+    got = d2.work(xh)[0]
+    taps = _low_pass_2(L, 1, 250000, 5000, 2000, 60)
+    chan = O.PfbChannelizer(10, taps).work(xh)
+    ok = True
+    for c, p in enumerate(q.mmdvm_port_map(7)):
+        want = O.MmdvmRx(5000).work(chan[p])[0]
+        m = min(got.shape[1], len(want))
+        ok = ok and bool(np.array_equal(got[c, :m], want[:m]))
+    d2.close()
+    alg = (8.0 + 7 * 0.096 * 2) * N             # 8 B per wideband sample in, 7 x int16 at 24 / 250 of the rate out
+    res = {"workload": "gr_demod_mmdvm_multi2 up to gr_mmdvm_sink: pfb_channelizer_ccf(10, 341 taps) + 7 x (rational_resampler 24/25 (819 taps), 33-tap low-pass, RSSI, quadrature demod, float_to_short), 250 ksps wideband",
+           "wideband_samples_per_call": N, "ms_per_call": ms, "value": N / ms / 1e3, "unit": "Msamples/s (wideband)",
+           "real_time_factor": N / ms / 1e3 * 1e6 / 250000.0,
+           "roofline": {"kernel": "pfb_channelizer_m10_kernel (+ the per-channel kernels)", "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ms,
+                        "note": "whole chain; the channelizer is FP32-pipe bound (see pfb_channelizer_m10)"},
+           "parity_vs_oracle": {"wideband_samples": n_chk, "channels": 7, "int16_equal": ok}}
+    dem.close()
+    if cpu_seconds > 0:
+        xs = x[: 1 << 18].cpu().numpy()
+
+        def mk(i):
+            ch = O.PfbChannelizer(10, taps)
+            rxs = [O.MmdvmRx(5000) for _ in range(7)]
+            ports = q.mmdvm_port_map(7)
+
+            def it():
+                y = ch.work(xs)
+                for r, p in zip(rxs, ports):
+                    r.work(y[p])
+            return it
+        v, dt = cpu_rate(mk, cores, min(cpu_seconds, 3.0), len(xs))
+        res["cpu_baseline"] = {"value": v, "unit": "Msamples/s (wideband)", "cores": cores, "kind": "port",
+                               "sample": "%d host threads x 2^18-sample wideband chunks through the oracle channelizer + 7 channel chains for %.1f s" % (cores, dt)}
+        res["gpu_over_cpu"] = res["value"] / v if v > 0 else None
+    del x
+    return res
+
+
 def mixed_config_block(q, torch, dev, dist, rank, world, synth, k=4):
     """BASELINE config 4: 1024 channels, ch % 3 -> {NBFM, 4FSK-FM, QPSK-250k}, T = 2^21, sharded by mode then by rank
     (qradiolink_b200.sharding): 128 channels per GPU = three handles per rank running concurrently on three streams.  With fewer than
@@ -880,6 +949,10 @@ def run_ours(args):
             configs["pfb_channelizer_m10"] = pfb_config_block(q, torch, dev, cores, cs)
         except Exception as e:  # noqa: BLE001
             configs["pfb_channelizer_m10"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        try:
+            configs["mmdvm_demod_7ch"] = mmdvm_config_block(q, torch, dev, cores, cs)
+        except Exception as e:  # noqa: BLE001
+            configs["mmdvm_demod_7ch"] = {"error": "%s: %s" % (type(e).__name__, e)}
         try:
             configs["spectrum_32k_64streams"] = spectrum_config_block(q, torch, dev, cores, cs)
         except Exception as e:  # noqa: BLE001
