@@ -134,6 +134,8 @@ RX_CASES = {
                 factory="make_gr_demod_m17", fargs=(125, 1000000, 1700, 9000)),
     "ssb_usb": dict(okind=6, args=(125, 1000000, 1700, 2700, 0), nports=2, signal=_sig_ssb,
                     factory="make_gr_demod_ssb", fargs=(125, 1000000, 1700, 2700, 0)),
+    "dmr": dict(okind=11, args=(5, 1000000, 0, 0, 0), nports=4, signal=_sig_m17,
+                factory="make_gr_demod_dmr", fargs=(5, 1000000)),
 }
 
 
@@ -150,4 +152,60 @@ TX_CASES = {
                        factory="make_gr_mod_bpsk", fargs=(250, 1000000, 1700, 2800)),
     "tx_2fsk_2k_fm": dict(okind=105, args=(25, 1000000, 1700, 4000, 1), data=_bytes(9703, 12),
                           factory="make_gr_mod_2fsk", fargs=(25, 1000000, 1700, 4000, True)),
+    "tx_m17": dict(okind=108, args=(125, 1000000, 1700, 9000, 0), data=_bytes(9704, 60),
+                   factory="make_gr_mod_m17", fargs=(125, 1000000, 1700, 9000)),
+    "tx_dmr": dict(okind=109, args=(125, 1000000, 1700, 5000, 0), data=_bytes(9705, 120),
+                   factory="make_gr_mod_dmr", fargs=(125, 1000000, 1700, 5000)),
 }
+
+
+# ---- blocks outside the Rx / Tx factories (added later in round 2): seeded inputs and the oracle call that defines the answer
+def mmdvm_rx_input():
+    rng = np.random.default_rng(9800)
+    n = 30000
+    t = np.arange(n)
+    a = 0.4 * np.sin(2 * np.pi * 700 * t / 25000) + 0.2 * np.sin(2 * np.pi * 1900 * t / 25000 + 0.5)
+    x = 0.05 * (1 + 0.7 * np.sin(2 * np.pi * 2 * t / 25000)) * np.exp(1j * 2 * np.pi * 2500 * np.cumsum(a) / 25000)
+    return (x + 0.001 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+
+
+def mmdvm_tx_input():
+    rng = np.random.default_rng(9801)
+    n = 12000
+    t = np.arange(n)
+    return (7000 * np.sin(2 * np.pi * 800 * t / 24000) + rng.integers(-500, 500, n)).astype(np.int16)
+
+
+def spectrum_input():
+    rng = np.random.default_rng(9802)
+    n = 4096 + 100
+    t = np.arange(n)
+    return (0.3 * np.exp(2j * np.pi * 0.2 * t) + 0.02 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+
+
+def dsss_decoder_input():
+    rng = np.random.default_rng(9803)
+    code = np.array([1, 1, 1, 1, 1, 0, 0, 1, 1, 0, 1, 0, 1])
+    chips = np.repeat(np.where(code > 0, 1.0, -1.0), 25)
+    bits = rng.integers(0, 2, 12) * 2 - 1
+    x = np.concatenate([b * chips for b in bits]) * np.exp(0.7j)
+    return (x + 0.4 * (rng.standard_normal(len(x)) + 1j * rng.standard_normal(len(x)))).astype(np.complex64)
+
+
+def extra_outputs(O):
+    """name -> array, the oracle's answers for the inputs above."""
+    import ctypes as C
+    out = {}
+    o, db, at = O.MmdvmRx(5000).work(mmdvm_rx_input())
+    out["mmdvm_rx_int16"] = o
+    out["mmdvm_rx_rssi_db"] = db
+    out["mmdvm_tx_iq"] = O.MmdvmTx(5000).work(mmdvm_tx_input())
+    s = O.Spectrum(4096, O.WIN_BLACKMAN_HARRIS); s.set_enabled(True); s.work(spectrum_input())
+    out["spectrum_4096_db"] = s.get()
+    x = dsss_decoder_input()
+    code = np.array([1, 1, 1, 1, 1, 0, 0, 1, 1, 0, 1, 0, 1], np.int32)
+    got = np.zeros(16, np.complex64)
+    m = O.lib().qo_dsss_decoder_run(code.ctypes.data_as(C.c_void_p), 13, 25, x.ctypes.data_as(C.c_void_p), len(x), len(x),
+                                    got.ctypes.data_as(C.c_void_p), len(got))
+    out["dsss_decoder_symbols"] = got[:m].copy()
+    return out

@@ -37,7 +37,7 @@ def describe(a):
     a = np.asarray(a)
     if a.dtype == np.uint8:
         return {"n": int(len(a)), "hex": np.packbits(a).tobytes().hex() if len(a) and a.max() <= 1 else a.tobytes().hex()}
-    v = a.view(np.float32) if a.dtype == np.complex64 else a.astype(np.float32)
+    v = a.view(np.float32) if a.dtype == np.complex64 else a.astype(np.float32)          # (the hash is over the raw bytes, int16 included)
     return {"n": int(len(a)), "sha256": sha(a), "head": [float(x) for x in v[:8]]}
 
 
@@ -85,6 +85,9 @@ def main():
         tx = O.Tx(case["okind"], *case["args"])
         y = tx.work(data)
         out["tx"][name] = {"input_sha256": sha(data), "out": describe(y)}
+
+    # ---- oracle: blocks outside the Rx / Tx factories (MMDVM channel chains, display spectrum, DSSS despreader)
+    out["extra"] = {name: describe(a) for name, a in cases.extra_outputs(O).items()}
 
     path = os.path.join(ROOT, "tests", "golden", "golden_v1.json")
     with open(path, "w") as f:

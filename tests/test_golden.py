@@ -80,7 +80,26 @@ def test_golden_tx_oracle(oracle):
         check_stream(oracle.Tx(case["okind"], *case["args"]).work(data), G["tx"][name]["out"], name)
 
 
+def test_golden_extra_blocks_oracle(oracle):
+    """MMDVM channel chains, display spectrum, DSSS despreader: the oracle against the committed answers."""
+    for name, a in cases.extra_outputs(oracle).items():
+        check_stream(a, G["extra"][name], name)
+
+
 # ------------------------------------------------------------------------------------------------ GPU tier
+@pytest.mark.gpu
+def test_golden_mmdvm_chains_cuda(qrl):
+    """The MMDVM channel chains through the C ABI against the committed answers (int16 and IQ are bit-exact on the device)."""
+    rx = qrl.MmdvmChannelsRx(1, filter_width=5000, max_in=30000)
+    o, db, at = rx.work(cases.mmdvm_rx_input()[None, :])
+    check_stream(o[0], G["extra"]["mmdvm_rx_int16"], "mmdvm_rx_int16")
+    assert len(db[0]) == G["extra"]["mmdvm_rx_rssi_db"]["n"]
+    assert np.max(np.abs(db[0][:8] - np.array(G["extra"]["mmdvm_rx_rssi_db"]["head"], np.float32)[:len(db[0][:8])])) < 2e-4
+    tx = qrl.MmdvmChannelsTx(1, filter_width=5000, max_in=12000)
+    check_stream(tx.work(cases.mmdvm_tx_input()[None, :])[0], G["extra"]["mmdvm_tx_iq"], "mmdvm_tx_iq")
+
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(cases.RX_CASES))
 def test_golden_rx_cuda(qrl, oracle, name):
