@@ -56,6 +56,7 @@ enum qrl_kind {
     QRL_MOD_M17 = 108,        /* gr_mod_m17.cpp:30-95 (sps = 125: x125 / 3 from 24 ksps); items: frame bytes, 4 symbols each */
     QRL_MOD_DSSS = 110,       /* gr_mod_dsss.cpp:27-93 (make_gr_mod_dsss(25, 1e6, 1700, 200), gr_mod_base.cpp:170): one input byte = 208 chips = 10^6 output items, so
                                  max_items is small (the output buffer holds max_items x 8 MB per channel) */
+    QRL_MOD_AM = 111,         /* gr_mod_am.cpp:25-72 (make_gr_mod_am(125, 1e6, 1700, 5000), gr_mod_base.cpp:167): float audio at 8 ksps in, like NBFM / SSB */
     QRL_MOD_DMR = 109         /* gr_mod_dmr.cpp:27-93 (the M17 modulator's structure with the DMR pulse, deviation 0.85 and
                                  gr_zero_idle_bursts in place of the IF low-pass; see qrl_tx_zero_samples) */
 };

@@ -262,6 +262,9 @@ inline gr_mod_b200_sptr make_gr_mod_m17(int sps = 125, int samp_rate = 1000000, 
                                         int n_channels = 1, long max_items = 4096, int device = 0)               // src/gr/gr_mod_m17.h:43-44
 { return std::make_shared<gr_mod_b200>(QRL_MOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_items, device); }
 
+inline gr_mod_b200_sptr make_gr_mod_am(int sps = 125, int samp_rate = 1000000, int carrier_freq = 1700, int filter_width = 5000,
+                                       int n_channels = 1, long max_items = 4096, int device = 0)                 // instance gr_mod_base.cpp:167
+{ return std::make_shared<gr_mod_b200>(QRL_MOD_AM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_items, device); }
 inline gr_mod_b200_sptr make_gr_mod_dsss(int sps = 25, int samp_rate = 1000000, int carrier_freq = 1700, int filter_width = 200,
                                          int n_channels = 1, long max_items = 8, int device = 0)                  // instance gr_mod_base.cpp:170
 { return std::make_shared<gr_mod_b200>(QRL_MOD_DSSS, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, max_items, device); }

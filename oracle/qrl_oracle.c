@@ -2002,6 +2002,7 @@ struct qo_tx {
     qvec s_bits, s_coded, s_sym, s_shaped, s_mod, out;
     /* gr_mod_dmr: gr_zero_idle_bursts (a delay line of history-1 items + the "zero_samples" tags) */
     int dsss;
+    agc2_t am_agc; float am_dc;      /* gr_mod_am */
     int dmr; float* zi_line; long zi_len; unsigned zi_delay; uint64_t zi_n, zi_counter;
     long long* zi_tag_off; uint64_t* zi_tag_val; long zi_ntags, zi_cap;
 };
@@ -2110,6 +2111,25 @@ qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         n = qo_firdes_low_pass_2(sps, samp_rate, filter_width, filter_width, 90, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
         resamp_init(&t->interp, 2, sps, 1, taps, n);
         t->amplif = 0.9f;
+        qv_init(&t->s_aud, 4); qv_init(&t->s_clip, 8); qv_init(&t->s_c2, 8);
+    } else if (kind == QO_MOD_AM) {
+        /* /root/reference/src/gr/gr_mod_am.cpp:25-72: audio (8 ksps) -> agc2_ff(1e-2, 1e-4, 1, 1; max gain 1) -> rail_ff(-.98, .98) ->
+         * x0.95 -> fft_filter_fff(band_pass_2(1, 8000, 300, 3000, 200, 60, Hamming)) -> + sig_source_f(8000, cos, 0 Hz, 0.5) ->
+         * float_to_complex -> rational_resampler_ccf(sps, 1, low_pass(sps, fs, fw, fw)) -> x0.5 -> x bb_gain ->
+         * fft_filter_ccc(complex_band_pass_2(1, fs, -fw, fw, 1200, 120, BH)); the feedforward_agc_cc of :51 is never connected.
+         * The carrier term: fxpt_nco at phase 0 gives fxpt::cos(0) from the sine table, times the amplitude in double. */
+        float tc[2 * 8192];
+        agc2_init(&t->am_agc, 1e-2f, 1e-4f, 1.0f, 1.0f); t->am_agc.max_gain = 1.0f;
+        int n = qo_firdes_band_pass_2(1, 8000, 300, 3000, 200, 60, QO_WIN_HAMMING, taps, 16384);
+        resamp_init(&t->a_filt, 1, 1, 1, taps, n);
+        n = qo_firdes_low_pass(sps, samp_rate, filter_width, filter_width, QO_WIN_HAMMING, taps, 16384);
+        resamp_init(&t->interp, 2, sps, 1, taps, n);
+        n = qo_firdes_complex_band_pass_2(1, samp_rate, -filter_width, filter_width, 1200, 120, QO_WIN_BLACKMAN_HARRIS, tc, 8192);
+        fircc_init(&t->a_sb, tc, n);
+        { const uint32_t uc = 0x40000000u; const int ci = uc >> 22;
+          const float c0 = g_sine_tab[2 * ci] * (float)(uc >> 1) + g_sine_tab[2 * ci + 1];
+          t->am_dc = (float)((double)c0 * 0.5); }
+        t->amplif = 0.5f;
         qv_init(&t->s_aud, 4); qv_init(&t->s_clip, 8); qv_init(&t->s_c2, 8);
     } else if (kind == QO_MOD_BPSK) {
         /* /root/reference/src/gr/gr_mod_bpsk.cpp:27-69 */
@@ -2374,6 +2394,32 @@ int qo_tx_work(qo_tx* t, const void* in, long n)
         float* m = (float*)t->s_c2.d;
         for (size_t i = 0; i < 2 * t->s_c2.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
         resamp_work(&t->interp, m, t->s_c2.n, &t->out);
+        return 0;
+    }
+    if (t->kind == QO_MOD_AM) {
+        const float* au = (const float*)in;
+        t->s_aud.n = 0;
+        for (long i = 0; i < n; i++) {
+            /* analog::kernel::agc2_ff::scale (fabsf form), then rail_ff, then multiply_const_ff(0.95) */
+            const float out = au[i] * t->am_agc.gain;
+            const float tmp = fabsf(out) - t->am_agc.ref;
+            float rate = t->am_agc.decay;
+            if (fabsf(tmp) > t->am_agc.gain) rate = t->am_agc.attack;
+            t->am_agc.gain -= tmp * rate;
+            if (t->am_agc.gain < 0.0f) t->am_agc.gain = 10e-5f;
+            if (t->am_agc.max_gain > 0.0f && t->am_agc.gain > t->am_agc.max_gain) t->am_agc.gain = t->am_agc.max_gain;
+            float v = out < -0.98f ? -0.98f : (out > 0.98f ? 0.98f : out);
+            v = v * 0.95f;
+            qv_pushf(&t->s_aud, v);
+        }
+        t->s_shaped.n = 0; resamp_work(&t->a_filt, (const float*)t->s_aud.d, t->s_aud.n, &t->s_shaped);
+        const float* f = (const float*)t->s_shaped.d;
+        t->s_clip.n = 0;
+        for (size_t i = 0; i < t->s_shaped.n; i++) qv_pushc(&t->s_clip, f[i] + t->am_dc, 0.0f);       /* add_ff, float_to_complex */
+        t->s_c2.n = 0; resamp_work(&t->interp, (const float*)t->s_clip.d, t->s_clip.n, &t->s_c2);
+        float* m = (float*)t->s_c2.d;
+        for (size_t i = 0; i < 2 * t->s_c2.n; i++) { m[i] = m[i] * t->amplif; m[i] = m[i] * t->bb_gain; }
+        fircc_work(&t->a_sb, m, t->s_c2.n, &t->out);
         return 0;
     }
     if (t->kind == QO_MOD_SSB) {

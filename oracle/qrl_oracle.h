@@ -29,7 +29,7 @@ enum { QO_WIN_HAMMING = 0, QO_WIN_HANN = 1, QO_WIN_BLACKMAN = 2, QO_WIN_RECT = 3
 enum { QO_DEMOD_NBFM = 1, QO_DEMOD_4FSK = 2, QO_DEMOD_QPSK = 3, QO_DEMOD_BPSK = 4, QO_DEMOD_2FSK = 5,
        QO_DEMOD_SSB = 6, QO_DEMOD_AM = 7, QO_DEMOD_GMSK = 8, QO_DEMOD_WBFM = 9, QO_DEMOD_M17 = 10, QO_DEMOD_DMR = 11, QO_DEMOD_DSSS = 12,
        QO_MOD_4FSK = 101, QO_MOD_QPSK = 102, QO_MOD_NBFM = 103, QO_MOD_BPSK = 104, QO_MOD_2FSK = 105,
-       QO_MOD_SSB = 106, QO_MOD_GMSK = 107, QO_MOD_M17 = 108, QO_MOD_DMR = 109, QO_MOD_DSSS = 110 };
+       QO_MOD_SSB = 106, QO_MOD_GMSK = 107, QO_MOD_M17 = 108, QO_MOD_DMR = 109, QO_MOD_DSSS = 110, QO_MOD_AM = 111 };
 
 /* global numerics switches (used by tests to quantify the documented deviations) */
 void qo_set_fir_order(int order);      /* 0 = polyphase/32-lane tree (default, parity order), 1 = sequential oldest-first */

@@ -412,19 +412,31 @@ int make_ring(qrl_rx* h, Ring* r, size_t isz, long long min_items, bool interlea
 }
 
 // low-rate stream filters: register-tiled instances for real calls, the one-thread-per-output kernels for slivers
+int launch_fir_ccf_c(HandleBase* h, int C, cudaStream_t st, const float2* in, unsigned in_mask, long long in_stride, float2* out, unsigned out_mask, long long out_stride,
+                     const float* taps, int ntaps, long long a0, long long a1, float2* lin, long long lin_stride, long long lin_base, int interleaved);
 int launch_fir_ccf(qrl_rx* h, cudaStream_t st, const float2* in, unsigned in_mask, long long in_stride, float2* out, unsigned out_mask, long long out_stride,
                    const float* taps, int ntaps, long long a0, long long a1, float2* lin, long long lin_stride, long long lin_base, int interleaved)
 {
+    return launch_fir_ccf_c(h, h->C, st, in, in_mask, in_stride, out, out_mask, out_stride, taps, ntaps, a0, a1, lin, lin_stride, lin_base, interleaved);
+}
+int launch_fir_ccf_c(HandleBase* h, int C_, cudaStream_t st, const float2* in, unsigned in_mask, long long in_stride, float2* out, unsigned out_mask, long long out_stride,
+                     const float* taps, int ntaps, long long a0, long long a1, float2* lin, long long lin_stride, long long lin_base, int interleaved)
+{
+    struct CShim { int C; } hc{ C_ }; CShim* hC = &hc;
     const long long n = a1 - a0;
     if (n <= 0) return QRL_OK;
     constexpr int K = 8, NT = 128, TILE = K * NT;
     const int span = TILE + ntaps - 1;
     const size_t smem = sizeof(float) * ((ntaps + 1) & ~1) + sizeof(float2) * (span + (span >> 4) + 2);
-    if (n >= 256 && smem <= 48 * 1024 && ntaps >= K) {       // (the tiled kernel's head / tail phases assume at least K taps)
-        dim3 g(static_cast<unsigned>((n + TILE - 1) / TILE), h->C);
+    if (smem > 48 * 1024 && smem <= 100 * 1024) {            // long filters (gr_mod_am's 4545-tap output filter): opt in to the larger window once per device
+        static bool big_attr[16] = { false };
+        if (!big_attr[h->device & 15]) { CK(cudaFuncSetAttribute(fir_ccf_ring_tiled_kernel<K, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); big_attr[h->device & 15] = true; }
+    }
+    if (n >= 256 && smem <= 100 * 1024 && ntaps >= K) {      // (the tiled kernel's head / tail phases assume at least K taps)
+        dim3 g(static_cast<unsigned>((n + TILE - 1) / TILE), hC->C);
         fir_ccf_ring_tiled_kernel<K, NT><<<g, NT, smem, st>>>(in, in_mask, in_stride, out, out_mask, out_stride, taps, ntaps, a0, a1, lin, lin_stride, lin_base, interleaved);
     } else {
-        dim3 g(static_cast<unsigned>((n + 255) / 256), h->C);
+        dim3 g(static_cast<unsigned>((n + 255) / 256), hC->C);
         fir_ccf_ring_kernel<<<g, 256, sizeof(float) * ntaps, st>>>(in, in_mask, in_stride, out, out_mask, out_stride, taps, ntaps, a0, a1, lin, lin_stride, lin_base, interleaved);
     }
     h->launches++;
@@ -1864,6 +1876,8 @@ struct qrl_tx : HandleBase {
     bool m17 = false; int M2 = 1;  // gr_mod_m17: 4 symbols per byte, IF low-pass at 24 ksps, x L2 / M2 rational interpolator
     // gr_mod_dsss: chips (complex ring d_sym) -> x25 (ring d_if) -> x50 / 13 (ring d_rc, arms in d_cfilt) -> x50 (d_out)
     bool dsss_tx = false;
+    // gr_mod_am: audio ring d_ra -> 8 ksps complex ring d_if -> x sps (ring d_rc at the output rate) -> output filter (taps d_cfilt) -> d_out
+    bool am_tx = false; float am_dc = 0.0f;
     // gr_mod_dmr: the m17 path with gr_zero_idle_bursts in place of the IF low-pass (a delay of history - 1 items + "zero_samples" tags)
     bool dmr_tx = false; long long zi_delay_items = 0; unsigned zi_tag_delay = 0;
     std::vector<std::map<long long, unsigned long long>> zi_tags;      // per channel: start item -> count (first registered wins)
@@ -1992,6 +2006,30 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         t1 = root_raised_cosine(sps, sps, 1, 0.35, 11 * sps);
         h->L1 = sps; h->nt1 = (static_cast<int>(t1.size()) + sps - 1) / sps;
         h->amplif = 0.6f;
+    } else if (kind == QRL_MOD_AM) {
+        // gr_mod_am.cpp:25-72: agc2_ff -> rail -> x0.95 -> band_pass_2(1, 8000, 300, 3000, 200, 60, Hamming) -> + 0.5 cos(0) -> float_to_complex ->
+        // rational_resampler_ccf(sps, 1, low_pass(sps, fs, fw, fw)) -> x0.5 -> bb gain -> fft_filter_ccc(complex_band_pass_2(1, fs, -fw, fw, 1200,
+        // 120, BH)).  The band is symmetric, so the complex taps are the low-pass prototype times e^{j0}: imaginary parts exactly 0 and the
+        // filter is the real-tap ring FIR (same accumulation, see oracle fircc_work with hi = 0).
+        h->am_tx = true; h->amplif = 0.5f;
+        const std::vector<float> bp = band_pass_2(1, 8000, 300, 3000, 200, 60, WIN_HAMMING);
+        h->nt_lpf = static_cast<int>(bp.size());
+        if ((rc = upload_floats(h, &h->d_lpf, bp))) return fail(rc);
+        t1 = { 1.0f }; h->L1 = 1; h->nt1 = 1;
+        t2 = low_pass(sps, samp_rate, filter_width, filter_width, WIN_HAMMING);
+        h->L2 = sps; h->nt2 = (static_cast<int>(t2.size()) + sps - 1) / sps;
+        const std::vector<float> cb = complex_band_pass_2(1, samp_rate, -filter_width, filter_width, 1200, 120, WIN_BLACKMAN_HARRIS);
+        std::vector<float> of(cb.size() / 2);
+        for (size_t i = 0; i < of.size(); i++) {
+            if (cb[2 * i + 1] != 0.0f) { set_err(h, "make_gr_mod_am: output filter taps are not real"); return fail(QRL_EINVAL); }
+            of[i] = cb[2 * i];
+        }
+        h->nt_cfilt = static_cast<int>(of.size());
+        if ((rc = upload_floats(h, &h->d_cfilt, of))) return fail(rc);
+        if (static_cast<size_t>(h->L2) * h->nt2 * sizeof(float) > 40 * 1024 || h->nt_cfilt > 8192) { set_err(h, "make_gr_mod_am: unsupported sps / filter_width"); return fail(QRL_EINVAL); }
+        { const std::vector<float> st_ = fxpt_sine_table(); const unsigned uc = 0x40000000u; const int ci = uc >> 22;
+          const float c0 = st_[2 * ci] * static_cast<float>(uc >> 1) + st_[2 * ci + 1];
+          h->am_dc = static_cast<float>(static_cast<double>(c0) * 0.5); }
     } else if (kind == QRL_MOD_DSSS) {
         // gr_mod_dsss.cpp:27-93: scrambler -> cc_encoder -> Barker-13 spreading -> {-1, +1} -> rational_resampler_ccf(sps, 1, RRC(sps, sps, 1,
         // 0.35, 11 sps)) -> x0.65 -> bb gain -> rational_resampler_ccf(50, 13, low_pass(50, 5200 * 50, fw, 5 fw)) ->
@@ -2073,6 +2111,18 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     long long max_sym = (one_per_bit ? 16LL : 8LL) * max_items;
     if (kind == QRL_MOD_NBFM) max_sym = max_items * 25 / 4 + 8;        // 50 ksps items per call
     if (kind == QRL_MOD_SSB) max_sym = max_items + 8;                  // 8 ksps complex items per call
+    if (h->am_tx) {
+        unsigned cap = pow2_at_least(max_items + h->nt_lpf + 64); h->ra_mask = cap - 1; h->ra_stride = cap;
+        if ((rc = dev_alloc(h, &h->d_ra, static_cast<size_t>(cap) * h->C))) return fail(rc);
+        unsigned cap2 = pow2_at_least(static_cast<long long>(max_items) * h->L2 + h->nt_cfilt + 64); h->rc_mask = cap2 - 1; h->rc_stride = cap2;
+        if ((rc = dev_alloc(h, &h->d_rc, static_cast<size_t>(cap2) * h->C))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_rs2, static_cast<size_t>(cap2) * h->C))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_an, h->C))) return fail(rc);
+        if ((rc = dev_alloc(h, &h->d_audio_in, static_cast<size_t>(max_items) * h->C))) return fail(rc);
+        std::vector<TxAnalogState> an(h->C);
+        for (auto& a : an) { std::memset(&a, 0, sizeof a); a.agc = 1.0f; }               // agc2_ff::make(1e-2, 1e-4, 1, 1): initial gain 1
+        if (cudaMemcpy(h->d_an, an.data(), sizeof(TxAnalogState) * h->C, cudaMemcpyHostToDevice) != cudaSuccess) { set_err(h, "state upload failed"); return fail(QRL_ECUDA); }
+    }
     if (h->dsss_tx) {
         max_sym = 16LL * 13 * max_items;                               // chips per call
         unsigned cap1 = pow2_at_least(max_sym * h->L1 + h->nt_cfilt + 128); h->if_mask = cap1 - 1; h->if_stride = cap1;
@@ -2105,6 +2155,7 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
     h->out_stride = analog ? max_sym * h->L2 : max_sym * h->L1 * (qpsk ? 1 : h->L2);
     if (h->m17) h->out_stride = (4LL * max_items * h->L1 * h->L2 + h->M2 - 1) / h->M2 + 8;
     if (h->dsss_tx) h->out_stride = ((max_sym * h->L1 * 50 + 12) / 13 + 1) * 50;
+    if (h->am_tx) h->out_stride = static_cast<long long>(max_items) * h->L2;
     if ((rc = dev_alloc(h, &h->d_out, static_cast<size_t>(h->out_stride) * h->C, false))) return fail(rc);
     std::vector<TxBitState> st(h->C);
     for (auto& x : st) { x.scr_reg = 0x7F; x.enc_state = 0; x.diff_prev = 0; x.phase_q = 0; }
@@ -2153,6 +2204,29 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
     if (n == 0) return QRL_OK;
     CK(cudaSetDevice(h->device));
     if (on_device) { int rc = check_device_ptr(h, in, "qrl_tx_work"); if (rc) return rc; }
+    if (h->am_tx) {
+        // `in` = [C][n] float audio at 8 ksps
+        const float* au = static_cast<const float*>(in);
+        long long astride = stride;
+        if (!on_device) {
+            CK(cudaMemcpy2DAsync(h->d_audio_in, sizeof(float) * h->max_items, in, sizeof(float) * stride, sizeof(float) * n, h->C,
+                                 cudaMemcpyHostToDevice, h->stream));
+            au = h->d_audio_in; astride = h->max_items;
+        }
+        const long long a0 = h->n_audio, a1 = h->n_audio + n;
+        tx_am_front_kernel<<<h->C, 128, 0, h->stream>>>(h->d_an, au, n, astride, 1e-2f, 1e-4f, 1.0f, 1.0f,
+            h->d_ra, h->ra_mask, h->ra_stride, h->d_lpf, h->nt_lpf, h->am_dc, h->d_if, h->if_mask, h->if_stride);
+        const long long o0 = a0 * h->L2, o1 = a1 * h->L2;
+        resamp_ring_to_ring_ccf_kernel<<<dim3(static_cast<unsigned>((o1 - o0 + 255) / 256), h->C), 256, sizeof(float) * h->L2 * h->nt2, h->stream>>>(
+            h->d_if, h->if_mask, h->if_stride, h->d_arms2, h->L2, 1, h->nt2, o0, o1, h->amplif, h->bb_gain, 1, h->d_rc, h->rc_mask, h->rc_stride);
+        h->launches += 2;
+        { int rc = launch_fir_ccf_c(h, h->C, h->stream, h->d_rc, h->rc_mask, h->rc_stride, h->d_rs2, h->rc_mask, h->rc_stride, h->d_cfilt, h->nt_cfilt, o0, o1,
+                                    h->d_out, h->out_stride, o0, 0); if (rc) return rc; }
+        h->n_audio = a1;
+        h->n_out_last = static_cast<long>(o1 - o0);
+        CK(cudaGetLastError());
+        return QRL_OK;
+    }
     if (h->kind == QRL_MOD_NBFM || h->kind == QRL_MOD_SSB) {
         // `in` = [C][n] float audio at 8 ksps
         const float* au = static_cast<const float*>(in);

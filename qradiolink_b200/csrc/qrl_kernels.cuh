@@ -2816,7 +2816,7 @@ resamp_ring_to_ring_ccf_kernel(const float2* __restrict__ in_ring, unsigned in_m
 // Analog modulators (gr_mod_nbfm.cpp:26-75, gr_mod_ssb.cpp:28-82): 8 ksps float audio in.  One CTA per channel runs
 // the low-rate front part; the FM scan / IF filters / final interpolator reuse the digital TX kernels.
 // ================================================================================================
-struct TxAnalogState { long long n_in, n_rs, n_str; double iir_x1, iir_y1; };
+struct TxAnalogState { long long n_in, n_rs, n_str; double iir_x1, iir_y1; float agc; int pad_; };     // agc: gr_mod_am's agc2_ff gain
 
 // NBFM: audio LPF -> x0.99 -> pre-emphasis IIR (double) -> rational_resampler_fff(25,4) -> float ring (FM input)
 __global__ void __launch_bounds__(128)
@@ -2909,6 +2909,47 @@ tx_ssb_front_kernel(TxAnalogState* __restrict__ states, const float* __restrict_
     }
     __syncthreads();
     if (threadIdx.x == 0) { st.n_in = a1n; st.n_str = s1 > s0 ? s1 : s0; states[c] = st; }
+}
+
+// AM (gr_mod_am.cpp:41-62): agc2_ff(1e-2, 1e-4, 1, 1; max gain 1) -> rail_ff(+-0.98) -> x0.95 (thread 0, per-sample recurrence) -> audio ring;
+// band-pass FIR -> + carrier term -> float_to_complex -> complex ring at 8 ksps (all threads)
+__global__ void __launch_bounds__(128)
+tx_am_front_kernel(TxAnalogState* __restrict__ states, const float* __restrict__ audio, long long n, long long a_stride,
+                   float attack, float decay, float ref, float max_gain,
+                   float* __restrict__ ra, unsigned ra_mask, long long ra_stride, const float* __restrict__ bpf, int nt_bpf, float dc,
+                   float2* __restrict__ rsym, unsigned rs_mask, long long rs_stride)
+{
+    const int c = blockIdx.x;
+    __shared__ TxAnalogState st;
+    if (threadIdx.x == 0) st = states[c];
+    __syncthreads();
+    float* A = ra + static_cast<long long>(c) * ra_stride;
+    float2* S = rsym + static_cast<long long>(c) * rs_stride;
+    const long long a0 = st.n_in, a1n = st.n_in + n;
+    if (threadIdx.x == 0) {
+        float gain = st.agc;
+        const float* au = audio + static_cast<long long>(c) * a_stride;
+        for (long long i = 0; i < n; i++) {
+            const float out = au[i] * gain;                         // analog::kernel::agc2_ff::scale
+            const float tmp = fabsf(out) - ref;
+            const float rate = (fabsf(tmp) > gain) ? attack : decay;
+            gain = gain - tmp * rate;
+            if (gain < 0.0f) gain = 10e-5f;
+            if (max_gain > 0.0f && gain > max_gain) gain = max_gain;
+            float v = out < -0.98f ? -0.98f : (out > 0.98f ? 0.98f : out);
+            v = v * 0.95f;
+            A[(a0 + i) & ra_mask] = v;
+        }
+        st.agc = gain;
+    }
+    __syncthreads();
+    for (long long a = a0 + threadIdx.x; a < a1n; a += blockDim.x) {
+        float acc = 0.0f;
+        for (int k = nt_bpf - 1; k >= 0; k--) { const long long m = a - k; acc = fmaf(bpf[k], m >= 0 ? A[m & ra_mask] : 0.0f, acc); }
+        S[a & rs_mask] = make_float2(acc + dc, 0.0f);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { st.n_in = a1n; states[c] = st; }
 }
 
 // in-place x g1 x g2 on a channel-major complex ring segment (multiply_const_cc twice)

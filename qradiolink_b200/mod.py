@@ -118,6 +118,11 @@ def make_gr_mod_m17(sps=125, samp_rate=1000000, carrier_freq=1700, filter_width=
     return TxBlock(KIND.MOD_M17, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
 
 
+def make_gr_mod_am(sps=125, samp_rate=1000000, carrier_freq=1700, filter_width=5000, n_channels=1, **kw):
+    """src/gr/gr_mod_am.h (instance gr_mod_base.cpp:167: make_gr_mod_am(125, 1e6, 1700, 5000)); feed with TxBlock.work_audio."""
+    return TxBlock(KIND.MOD_AM, sps, samp_rate, carrier_freq, filter_width, 0, n_channels, **kw)
+
+
 def make_gr_mod_dsss(sps=25, samp_rate=1000000, carrier_freq=1700, filter_width=200, n_channels=1, max_items=8, **kw):
     """src/gr/gr_mod_dsss.h (instance gr_mod_base.cpp:170: make_gr_mod_dsss(25, 1e6, 1700, 200)); items: frame bytes at 1 byte/s: every byte
     becomes 10^6 output samples, hence the small default max_items."""

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small fixed workloads for `ncu --set full` captures (one case per invocation, a couple of calls, no timing):
-   python tools/ncu_case.py {cfg2|qpsk|nbfm|tx|pfb} [channels] [log2 T]
+   python tools/ncu_case.py {cfg2|qpsk|nbfm|tx|pfb|mmdvm|dsss|amtx} [channels] [log2 T]
 Inputs come from the product's own modulators on the GPU (or torch for the analog case), like bench.py."""
 import os
 import sys
@@ -75,6 +75,37 @@ def main():
         for _ in range(calls):
             sy.work_device(z.data_ptr(), N // M, N // M)
         sy.sync(); sy.close()
+    elif case == "mmdvm":
+        import ctypes as Ct
+        N = 1 << 24
+        x = torch.view_as_complex(torch.randn((N, 2), device=dev) * 0.05)
+        dem = q.MmdvmDemod(7, 5000, max_in=N)
+        dem.channelizer.set_stream(stream.cuda_stream); dem.channels.set_stream(stream.cuda_stream)
+        L = q.load_library()
+        cnt = Ct.c_long()
+        for _ in range(calls):
+            pf = dem.channelizer
+            assert L.qrl_pfb_work(pf._h, Ct.c_void_p(x.data_ptr()), N, 0, 1, Ct.byref(cnt)) == 0
+            ptr, stride, items = pf.out_device()
+            dem.channels.work_device(ptr, items, stride)
+        torch.cuda.synchronize(); dem.close()
+    elif case == "dsss":
+        C = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+        T = 1 << 22
+        X = bench.nbfm_inputs(torch, dev, C, T)            # any band-limited signal: the chain's cost does not depend on lock
+        blk = q.make_gr_demod_dsss(n_channels=C, max_samples=T)
+        blk.set_stream(stream.cuda_stream)
+        for _ in range(calls):
+            blk.work_device(X.data_ptr(), T, T)
+        blk.sync(); blk.close()
+    elif case == "amtx":
+        C, n = 16, 4000
+        tx = q.make_gr_mod_am(125, 1000000, 1700, 5000, n_channels=C, max_items=n)
+        tx.set_stream(stream.cuda_stream)
+        au = (torch.randn((C, n), device=dev) * 0.3).contiguous()
+        for _ in range(calls):
+            tx.work_device(au.data_ptr(), n, n)
+        tx.sync(); tx.close()
     torch.cuda.synchronize()
     print("case %s done" % case)
 
