@@ -65,7 +65,9 @@ enum qrl_kind {
 enum qrl_param {
     QRL_PARAM_CARRIER_OFFSET_HZ = 1,  /* rotator_cc phase increment, gr_demod_base.cpp:1220-1225 */
     QRL_PARAM_SQUELCH_DB = 2,         /* gr_demod_nbfm::set_squelch */
-    QRL_PARAM_FILTER_WIDTH = 3,       /* set_filter_width of gr_demod_nbfm / _ssb / _am / _wbfm (gr_demod_nbfm.cpp:82-90, gr_demod_ssb.cpp:89-101, ...) */
+    QRL_PARAM_FILTER_WIDTH = 3,       /* set_filter_width of gr_demod_nbfm / _ssb / _am / _wbfm (gr_demod_nbfm.cpp:82-90, gr_demod_ssb.cpp:89-101, ...);
+                                         through qrl_tx_set_param: gr_mod_nbfm / _ssb / _am::set_filter_width (gr_mod_nbfm.cpp:78-93, gr_mod_ssb.cpp:85-100,
+                                         gr_mod_am.cpp:75-85), mid-stream */
     QRL_PARAM_BB_GAIN = 4,            /* gr_mod_*::set_bb_gain */
     QRL_PARAM_CTCSS = 7,              /* gr_demod_nbfm::set_ctcss (gr_demod_nbfm.cpp:97-121): 0 = no tone squelch (the only value built) */
     QRL_PARAM_AGC_ATTACK = 8,         /* gr_demod_ssb::set_agc_attack / gr_demod_am::set_agc_attack (gr_demod_ssb.cpp:108-111, gr_demod_am.cpp:94-97) */

@@ -227,6 +227,7 @@ public:
     gr_mod_b200(const gr_mod_b200&) = delete;
     gr_mod_b200& operator=(const gr_mod_b200&) = delete;
     void set_bb_gain(float v) { qrl_tx_set_param(_h, -1, QRL_PARAM_BB_GAIN, v); }
+    void set_filter_width(int fw) { qrl_tx_set_param(_h, -1, QRL_PARAM_FILTER_WIDTH, fw); }     // gr_mod_nbfm / _ssb / _am
     // gr_mod_dmr: the "zero_samples" tag gr_dmr_source attaches to a byte of the stream (gr_dmr_source.cpp:148)
     int zero_samples(int channel, long long byte_offset, long n_samples) { return qrl_tx_zero_samples(_h, channel, byte_offset, n_samples); }
     // what gr_byte_source::set_data hands over: [channels][n] frame bytes -> [channels][n_out] gr_complex at 1 Msps

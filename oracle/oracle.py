@@ -52,6 +52,7 @@ def lib():
         L.qo_tx_destroy.argtypes = [vp]
         L.qo_tx_set_bb_gain.argtypes = [vp, C.c_float]
         L.qo_tx_zero_samples.argtypes = [vp, C.c_longlong, C.c_long]
+        L.qo_tx_set_param.argtypes = [vp, C.c_int, C.c_double]
         L.qo_dsss_decoder_taps.argtypes = [vp, C.c_int, C.c_int, vp]
         L.qo_dsss_decoder_run.restype = C.c_long
         L.qo_dsss_decoder_run.argtypes = [vp, C.c_int, C.c_int, vp, C.c_long, C.c_long, vp, C.c_long]
@@ -406,6 +407,11 @@ class Tx:
 
     def set_bb_gain(self, g):
         lib().qo_tx_set_bb_gain(self.h, g)
+
+    def set_param(self, key, value):
+        rc = lib().qo_tx_set_param(self.h, int(key), float(value))
+        if rc != 0:
+            raise ValueError("oracle: the reference has no such setter on this modulator")
 
     def zero_samples(self, byte_offset, n_samples):
         """MOD_DMR: the "zero_samples" stream tag on input byte `byte_offset` (gr_dmr_source.cpp:148)."""

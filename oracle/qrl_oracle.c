@@ -2002,6 +2002,7 @@ struct qo_tx {
     qvec s_bits, s_coded, s_sym, s_shaped, s_mod, out;
     /* gr_mod_dmr: gr_zero_idle_bursts (a delay line of history-1 items + the "zero_samples" tags) */
     int dsss;
+    int samp_rate, flag;
     agc2_t am_agc; float am_dc;      /* gr_mod_am */
     int dmr; float* zi_line; long zi_len; unsigned zi_delay; uint64_t zi_n, zi_counter;
     long long* zi_tag_off; uint64_t* zi_tag_val; long zi_ntags, zi_cap;
@@ -2099,6 +2100,8 @@ qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         n = qo_firdes_low_pass_2(sps, samp_rate, filter_width, 3500, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
         resamp_init(&t->interp, 2, sps, 1, taps, n);
         t->amplif = 0.8f;
+        t->samp_rate = samp_rate;
+        t->a_rs.hkeep = 64; t->a_if.hkeep = 512; t->interp.hkeep = 256;          /* filters set_filter_width may lengthen */
         qv_init(&t->s_aud, 4); qv_init(&t->s_clip, 8); qv_init(&t->s_c2, 8);
     } else if (kind == QO_MOD_SSB) {
         /* /root/reference/src/gr/gr_mod_ssb.cpp:28-82; flag = sb */
@@ -2112,6 +2115,7 @@ qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         resamp_init(&t->interp, 2, sps, 1, taps, n);
         t->amplif = 0.9f;
         qv_init(&t->s_aud, 4); qv_init(&t->s_clip, 8); qv_init(&t->s_c2, 8);
+        t->samp_rate = samp_rate; t->flag = flag; t->interp.hkeep = 64; t->a_sb.hkeep = 512;
     } else if (kind == QO_MOD_AM) {
         /* /root/reference/src/gr/gr_mod_am.cpp:25-72: audio (8 ksps) -> agc2_ff(1e-2, 1e-4, 1, 1; max gain 1) -> rail_ff(-.98, .98) ->
          * x0.95 -> fft_filter_fff(band_pass_2(1, 8000, 300, 3000, 200, 60, Hamming)) -> + sig_source_f(8000, cos, 0 Hz, 0.5) ->
@@ -2131,6 +2135,7 @@ qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
           t->am_dc = (float)((double)c0 * 0.5); }
         t->amplif = 0.5f;
         qv_init(&t->s_aud, 4); qv_init(&t->s_clip, 8); qv_init(&t->s_c2, 8);
+        t->samp_rate = samp_rate; t->interp.hkeep = 64; t->a_sb.hkeep = 8192;
     } else if (kind == QO_MOD_BPSK) {
         /* /root/reference/src/gr/gr_mod_bpsk.cpp:27-69 */
         t->sps = sps;
@@ -2177,6 +2182,49 @@ void qo_tx_destroy(qo_tx* t)
     free(t);
 }
 void qo_tx_set_bb_gain(qo_tx* t, float g) { t->bb_gain = g; }
+/* run-time setters of the modulators.  gr_mod_nbfm::set_filter_width (gr_mod_nbfm.cpp:78-93): new taps for the 25/4 resampler
+ * (transition width = fw now, not 3500), the 50 ksps filter (transition 1200) and the final interpolator, new modulator
+ * sensitivity; like GNU Radio's set_taps the new taps meet the stream's true history from the next output on. */
+int qo_tx_set_param(qo_tx* t, int key, double value)
+{
+    static float taps[16384];
+    if (!t) return -1;
+    if (key == QO_PARAM_FILTER_WIDTH && t->kind == QO_MOD_NBFM) {
+        const int fw = (int)value;
+        const float if_samp_rate = 50000;
+        int n = qo_firdes_low_pass_2(25, if_samp_rate * 4, fw, fw, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_retap(&t->a_rs, taps, n);
+        n = qo_firdes_low_pass_2(1, if_samp_rate, fw, 1200, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_retap(&t->a_if, taps, n);
+        n = qo_firdes_low_pass_2(t->interp.L, t->samp_rate, fw, fw, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_retap(&t->interp, taps, n);
+        t->fm_sens = (float)(4 * M_PI * fw / if_samp_rate);
+        return 0;
+    }
+    if (key == QO_PARAM_FILTER_WIDTH && t->kind == QO_MOD_SSB) {
+        /* gr_mod_ssb::set_filter_width (gr_mod_ssb.cpp:85-100): interpolator low_pass_2(sps, fs, fw, fw, 90) and the side-band filter, now
+         * 300 .. fw with a 250 Hz transition (the constructor's is 200 .. fw, 200) */
+        static float tc[2 * 4096];
+        const int fw = (int)value;
+        int n = qo_firdes_low_pass_2(t->interp.L, t->samp_rate, fw, fw, 90, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_retap(&t->interp, taps, n);
+        n = t->flag ? qo_firdes_complex_band_pass_2(1, 8000, -fw, -300, 250, 90, QO_WIN_BLACKMAN_HARRIS, tc, 4096)
+                    : qo_firdes_complex_band_pass_2(1, 8000, 300, fw, 250, 90, QO_WIN_BLACKMAN_HARRIS, tc, 4096);
+        fircc_retap(&t->a_sb, tc, n);
+        return 0;
+    }
+    if (key == QO_PARAM_FILTER_WIDTH && t->kind == QO_MOD_AM) {
+        /* gr_mod_am::set_filter_width (gr_mod_am.cpp:75-85) */
+        static float tc[2 * 8192];
+        const int fw = (int)value;
+        int n = qo_firdes_low_pass(t->interp.L, t->samp_rate, fw, fw, QO_WIN_HAMMING, taps, 16384);
+        resamp_retap(&t->interp, taps, n);
+        n = qo_firdes_complex_band_pass_2(1, t->samp_rate, -fw, fw, 1200, 120, QO_WIN_BLACKMAN_HARRIS, tc, 8192);
+        fircc_retap(&t->a_sb, tc, n);
+        return 0;
+    }
+    return -1;
+}
 
 /* The "zero_samples" stream tag of gr_dmr_source.cpp:148 / gr_mmdvm_source.cpp:264, attached to byte `byte_offset` of the modulator's
  * input with value n_samples.  GNU Radio carries it through packed_to_unpacked (x8), pack_k_bits(2) (/2) and the x5 pulse shaper:

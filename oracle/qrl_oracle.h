@@ -99,6 +99,7 @@ typedef struct qo_tx qo_tx;
 qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter_width, int flag);
 void   qo_tx_destroy(qo_tx*);
 void   qo_tx_set_bb_gain(qo_tx*, float g);
+int    qo_tx_set_param(qo_tx*, int key, double value);      /* QO_PARAM_FILTER_WIDTH on QO_MOD_NBFM (gr_mod_nbfm::set_filter_width) */
 void   qo_zero_idle_run(const float* in_c, long n, unsigned delay, const long long* tag_item, const long long* tag_val, long ntags, float* out_c);
 int    qo_tx_zero_samples(qo_tx*, long long byte_offset, long n_samples);   /* QO_MOD_DMR: the "zero_samples" stream tag */
 /* digital: n bytes in; analog (NBFM/SSB): n float audio samples passed as bytes pointer to float */

@@ -2193,6 +2193,60 @@ int qrl_tx_set_param(qrl_tx* h, int, int key, double value)
 {
     if (!h) return QRL_EINVAL;
     if (key == QRL_PARAM_BB_GAIN) { h->bb_gain = static_cast<float>(value); return QRL_OK; }   // gr_mod_4fsk::set_bb_gain
+    if (key == QRL_PARAM_FILTER_WIDTH && h->kind == QRL_MOD_NBFM) {
+        // gr_mod_nbfm::set_filter_width (gr_mod_nbfm.cpp:78-93): new taps for the 25/4 resampler, the 50 ksps filter and the final
+        // interpolator, new sensitivity.  The rings keep the stream's true history, which the longer filters read from their next output on.
+        const int fw = static_cast<int>(value);
+        if (fw <= 0) { set_err(h, "qrl_tx_set_param: filter width must be positive"); return QRL_EINVAL; }
+        const float if_samp_rate = 50000;
+        const std::vector<float> t1 = low_pass_2(25, if_samp_rate * 4, fw, fw, 60, WIN_BLACKMAN_HARRIS);
+        const std::vector<float> tc = low_pass_2(1, if_samp_rate, fw, 1200, 60, WIN_BLACKMAN_HARRIS);
+        const std::vector<float> t2 = low_pass_2(h->L2, h->samp_rate, fw, fw, 60, WIN_BLACKMAN_HARRIS);
+        const int nt1 = (static_cast<int>(t1.size()) + 24) / 25, nt2 = (static_cast<int>(t2.size()) + h->L2 - 1) / h->L2;
+        if (nt1 > 256 || static_cast<int>(tc.size()) > 400 || nt2 > 400 || static_cast<size_t>(h->L2) * nt2 * sizeof(float) > 40 * 1024) {
+            set_err(h, "qrl_tx_set_param: filter width too small for the rings' history"); return QRL_EINVAL;
+        }
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        float *a1 = nullptr, *cf = nullptr, *a2 = nullptr;
+        int rc;
+        if ((rc = upload_floats(h, &a1, make_arms(t1, 25, nt1)))) return rc;
+        if ((rc = upload_floats(h, &cf, tc))) return rc;
+        if ((rc = upload_floats(h, &a2, make_arms(t2, h->L2, nt2)))) return rc;
+        h->d_arms1 = a1; h->nt1 = nt1; h->d_cfilt = cf; h->nt_cfilt = static_cast<int>(tc.size()); h->d_arms2 = a2; h->nt2 = nt2;
+        h->fm_sens = static_cast<float>(4 * kPi * fw / if_samp_rate);
+        h->filter_width = fw;
+        return QRL_OK;
+    }
+    if (key == QRL_PARAM_FILTER_WIDTH && (h->kind == QRL_MOD_SSB || h->am_tx)) {
+        // gr_mod_ssb::set_filter_width (gr_mod_ssb.cpp:85-100) / gr_mod_am::set_filter_width (gr_mod_am.cpp:75-85)
+        const int fw = static_cast<int>(value);
+        if (fw <= 0) { set_err(h, "qrl_tx_set_param: filter width must be positive"); return QRL_EINVAL; }
+        std::vector<float> t2, cf;
+        if (h->am_tx) {
+            t2 = low_pass(h->L2, h->samp_rate, fw, fw, WIN_HAMMING);
+            const std::vector<float> cb = complex_band_pass_2(1, h->samp_rate, -fw, fw, 1200, 120, WIN_BLACKMAN_HARRIS);
+            cf.resize(cb.size() / 2);
+            for (size_t i = 0; i < cf.size(); i++) cf[i] = cb[2 * i];
+        } else {
+            t2 = low_pass_2(h->L2, h->samp_rate, fw, fw, 90, WIN_BLACKMAN_HARRIS);
+            cf = h->flag ? complex_band_pass_2(1, 8000, -fw, -300, 250, 90, WIN_BLACKMAN_HARRIS) : complex_band_pass_2(1, 8000, 300, fw, 250, 90, WIN_BLACKMAN_HARRIS);
+        }
+        const int nt2 = (static_cast<int>(t2.size()) + h->L2 - 1) / h->L2;
+        const int ntc = static_cast<int>(h->am_tx ? cf.size() : cf.size() / 2);
+        if (nt2 > 60 || static_cast<size_t>(h->L2) * nt2 * sizeof(float) > 40 * 1024 || ntc > (h->am_tx ? 8192 : 500)) {
+            set_err(h, "qrl_tx_set_param: filter width too small for the rings' history"); return QRL_EINVAL;
+        }
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        float *a2 = nullptr, *c2 = nullptr;
+        int rc;
+        if ((rc = upload_floats(h, &a2, make_arms(t2, h->L2, nt2)))) return rc;
+        if ((rc = upload_floats(h, &c2, cf))) return rc;
+        h->d_arms2 = a2; h->nt2 = nt2; h->d_cfilt = c2; h->nt_cfilt = ntc;
+        h->filter_width = fw;
+        return QRL_OK;
+    }
     set_err(h, "qrl_tx_set_param: unsupported key");
     return QRL_EINVAL;
 }

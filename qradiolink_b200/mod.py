@@ -34,6 +34,10 @@ class TxBlock:
         """gr_mod_dmr: the "zero_samples" tag on input byte `byte_offset` of `channel` (-1: all), see qrl_tx_zero_samples."""
         check(self._L.qrl_tx_zero_samples(self._h, int(channel), int(byte_offset), int(n_samples)), self._h, "zero_samples")
 
+    def set_filter_width(self, filter_width):
+        """gr_mod_nbfm::set_filter_width (gr_mod_nbfm.cpp:78-93), mid-stream."""
+        check(self._L.qrl_tx_set_param(self._h, -1, PARAM.FILTER_WIDTH, float(filter_width)), self._h, "set_filter_width")
+
     def set_bb_gain(self, value):
         check(self._L.qrl_tx_set_param(self._h, -1, PARAM.BB_GAIN, float(value)), self._h, "set_bb_gain")
 

@@ -169,3 +169,62 @@ def test_tx_am_modulator(qrl, oracle):
     a = rx.read_port(1)[0][500:]
     spec = np.abs(np.fft.rfft(a * np.hanning(len(a))))
     assert abs(np.argmax(spec[3:]) + 3 - 700 * len(a) / 8000) < 2
+
+
+def test_tx_nbfm_set_filter_width_mid_stream(qrl, oracle):
+    """gr_mod_nbfm::set_filter_width (gr_mod_nbfm.cpp:78-93) between calls: new resampler / IF / interpolator taps (longer than the ones the
+    block was made with) and a new sensitivity meet the true history of the stream; IQ bit-identical to the oracle's restatement."""
+    C, n = 2, 3000
+    t = np.arange(n)
+    audio = np.stack([(0.5 * np.sin(2 * np.pi * (600 + 250 * c) * t / 8000) + 0.2 * np.sin(2 * np.pi * 2100 * t / 8000 + c)).astype(np.float32)
+                      for c in range(C)])
+    tx = qrl.make_gr_mod_nbfm(20, 1000000, 1700, 5000, n_channels=C, max_items=n)
+    os_ = [oracle.Tx(oracle.MOD_NBFM, 20, 1000000, 1700, 5000, 0) for _ in range(C)]
+    got, want = [], [[] for _ in range(C)]
+    for a, b, fw in ((0, 1000, None), (1000, 1003, 2500), (1003, 2200, None), (2200, n, 4000)):
+        if fw is not None:
+            tx.set_filter_width(fw)
+            for o in os_:
+                o.set_param(3, fw)
+        got.append(tx.work_audio(audio[:, a:b]))
+        for c in range(C):
+            want[c].append(os_[c].work(audio[c, a:b]))
+    got = np.concatenate(got, axis=1)
+    for c in range(C):
+        w = np.concatenate(want[c])
+        assert got.shape[1] == len(w) and np.array_equal(got[c], w), c
+    with pytest.raises(qrl.QrlError):
+        qrl.make_gr_mod_4fsk(25, 1000000, 1700, 3500, True, n_channels=1, max_items=16).set_filter_width(3000)
+
+
+@pytest.mark.parametrize("kind", ["usb", "lsb", "am"])
+def test_tx_ssb_am_set_filter_width_mid_stream(qrl, oracle, kind):
+    """gr_mod_ssb::set_filter_width (gr_mod_ssb.cpp:85-100; the new side-band filter is 300 .. fw / 250 Hz, not the constructor's 200 .. fw /
+    200 Hz) and gr_mod_am::set_filter_width (gr_mod_am.cpp:75-85) between calls, against the oracle's restatement."""
+    C, n = 2, 900 if kind == "am" else 3000
+    t = np.arange(n)
+    audio = np.stack([(0.5 * np.sin(2 * np.pi * (600 + 250 * c) * t / 8000) + 0.2 * np.sin(2 * np.pi * 2100 * t / 8000 + c)).astype(np.float32)
+                      for c in range(C)])
+    if kind == "am":
+        tx = qrl.make_gr_mod_am(125, 1000000, 1700, 5000, n_channels=C, max_items=n)
+        okind, oargs = oracle.MOD_AM, (125, 1000000, 1700, 5000, 0)
+        steps = ((0, 300, None), (300, 302, 3500), (302, n, None))
+    else:
+        sb = 1 if kind == "lsb" else 0
+        tx = qrl.make_gr_mod_ssb(125, 1000000, 1700, 2700, sb, n_channels=C, max_items=n)
+        okind, oargs = oracle.MOD_SSB, (125, 1000000, 1700, 2700, sb)
+        steps = ((0, 1000, None), (1000, 1003, 2200), (1003, 2200, None), (2200, n, 3000))
+    os_ = [oracle.Tx(okind, *oargs) for _ in range(C)]
+    got, want = [], [[] for _ in range(C)]
+    for a, b, fw in steps:
+        if fw is not None:
+            tx.set_filter_width(fw)
+            for o in os_:
+                o.set_param(3, fw)
+        got.append(tx.work_audio(audio[:, a:b]))
+        for c in range(C):
+            want[c].append(os_[c].work(audio[c, a:b]))
+    got = np.concatenate(got, axis=1)
+    for c in range(C):
+        w = np.concatenate(want[c])
+        assert got.shape[1] == len(w) and np.array_equal(got[c], w), c
