@@ -2003,6 +2003,7 @@ struct qo_tx {
     /* gr_mod_dmr: gr_zero_idle_bursts (a delay line of history-1 items + the "zero_samples" tags) */
     int dsss;
     int samp_rate, flag;
+    float audio_gain; int tone_on; uint32_t tone_inc, tone_phase;      /* gr_mod_nbfm: multiply_const_ff and the CTCSS tone source */
     agc2_t am_agc; float am_dc;      /* gr_mod_am */
     int dmr; float* zi_line; long zi_len; unsigned zi_delay; uint64_t zi_n, zi_counter;
     long long* zi_tag_off; uint64_t* zi_tag_val; long zi_ntags, zi_cap;
@@ -2102,6 +2103,7 @@ qo_tx* qo_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         t->amplif = 0.8f;
         t->samp_rate = samp_rate;
         t->a_rs.hkeep = 64; t->a_if.hkeep = 512; t->interp.hkeep = 256;          /* filters set_filter_width may lengthen */
+        t->audio_gain = 0.99f; t->a_filt.hkeep = 128;
         qv_init(&t->s_aud, 4); qv_init(&t->s_clip, 8); qv_init(&t->s_c2, 8);
     } else if (kind == QO_MOD_SSB) {
         /* /root/reference/src/gr/gr_mod_ssb.cpp:28-82; flag = sb */
@@ -2199,6 +2201,26 @@ int qo_tx_set_param(qo_tx* t, int key, double value)
         n = qo_firdes_low_pass_2(t->interp.L, t->samp_rate, fw, fw, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
         resamp_retap(&t->interp, taps, n);
         t->fm_sens = (float)(4 * M_PI * fw / if_samp_rate);
+        return 0;
+    }
+    if (key == QO_PARAM_CTCSS && t->kind == QO_MOD_NBFM) {
+        /* gr_mod_nbfm::set_ctcss (gr_mod_nbfm.cpp:101-139): 0 -> gain 0.98 (the constructor's is 0.99), low-pass audio filter, tone branch
+         * out; f -> gain 0.85, band_pass_2(1, 8000, 300, 3500, 200, 35, BH), the tone source at f added in front of the pre-emphasis.
+         * The tone source only runs while it is connected: its phase advances per sample produced with the tone on. */
+        int n;
+        if (value == 0) {
+            t->audio_gain = 0.98f; t->tone_on = 0;
+            n = qo_firdes_low_pass_2(1, 8000, 3500, 200, 35, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        } else {
+            t->audio_gain = 0.85f; t->tone_on = 1;
+            n = qo_firdes_band_pass_2(1, 8000, 300, 3500, 200, 35, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+            /* sig_source_f::set_frequency -> fxpt_nco::set_freq((float)(2 pi f / fs)) -> fxpt::float_to_fixed */
+            float x = (float)(2 * M_PI * (double)(float)value / 8000.0);
+            const int d = (int)floor(x / (float)(2.0 * M_PI) + 0.5);
+            x -= d * (float)(2.0 * M_PI);
+            t->tone_inc = (uint32_t)(int32_t)((float)x * 2147483648.0f / (float)M_PI);
+        }
+        resamp_retap(&t->a_filt, taps, n);
         return 0;
     }
     if (key == QO_PARAM_FILTER_WIDTH && t->kind == QO_MOD_SSB) {
@@ -2433,7 +2455,17 @@ int qo_tx_work(qo_tx* t, const void* in, long n)
         const float* au = (const float*)in;
         t->s_aud.n = 0; resamp_work(&t->a_filt, au, (size_t)n, &t->s_aud);
         float* a1 = (float*)t->s_aud.d;
-        for (size_t i = 0; i < t->s_aud.n; i++) a1[i] = a1[i] * 0.99f;                     /* multiply_const_ff(0.99) */
+        for (size_t i = 0; i < t->s_aud.n; i++) {
+            a1[i] = a1[i] * t->audio_gain;                                                   /* multiply_const_ff(0.99 / 0.98 / 0.85) */
+            if (t->tone_on) {
+                /* add_ff with sig_source_f(8000, cos, f, 0.15): fxpt_nco: (float)(fxpt::cos(phase) * ampl), then phase += inc */
+                const uint32_t uc = t->tone_phase + 0x40000000u;
+                const int ci = uc >> 22;
+                const float cs = g_sine_tab[2 * ci] * (float)(uc >> 1) + g_sine_tab[2 * ci + 1];
+                a1[i] = a1[i] + (float)((double)cs * 0.15);
+                t->tone_phase += t->tone_inc;
+            }
+        }
         t->s_shaped.n = 0; iir1_work(&t->preemph, a1, t->s_aud.n, &t->s_shaped, 1.0f);
         t->s_sym.isz = 4; t->s_sym.n = 0;
         resamp_work(&t->a_rs, (const float*)t->s_shaped.d, t->s_shaped.n, &t->s_sym);       /* 8k -> 50k */

@@ -1878,6 +1878,8 @@ struct qrl_tx : HandleBase {
     bool dsss_tx = false;
     // gr_mod_am: audio ring d_ra -> 8 ksps complex ring d_if -> x sps (ring d_rc at the output rate) -> output filter (taps d_cfilt) -> d_out
     bool am_tx = false; float am_dc = 0.0f;
+    // gr_mod_nbfm::set_ctcss: multiply_const_ff gain and the CTCSS tone source (fxpt_nco phase / increment, advanced per sample with the tone on)
+    float audio_gain = 0.99f; bool tone_on = false; unsigned tone_phase = 0, tone_inc = 0;
     // gr_mod_dmr: the m17 path with gr_zero_idle_bursts in place of the IF low-pass (a delay of history - 1 items + "zero_samples" tags)
     bool dmr_tx = false; long long zi_delay_items = 0; unsigned zi_tag_delay = 0;
     std::vector<std::map<long long, unsigned long long>> zi_tags;      // per channel: start item -> count (first registered wins)
@@ -2218,6 +2220,27 @@ int qrl_tx_set_param(qrl_tx* h, int, int key, double value)
         h->filter_width = fw;
         return QRL_OK;
     }
+    if (key == QRL_PARAM_CTCSS && h->kind == QRL_MOD_NBFM) {
+        // gr_mod_nbfm::set_ctcss (gr_mod_nbfm.cpp:101-139)
+        std::vector<float> lp;
+        if (value == 0) { h->audio_gain = 0.98f; h->tone_on = false; lp = low_pass_2(1, 8000, 3500, 200, 35, WIN_BLACKMAN_HARRIS); }
+        else {
+            h->audio_gain = 0.85f; h->tone_on = true;
+            lp = band_pass_2(1, 8000, 300, 3500, 200, 35, WIN_BLACKMAN_HARRIS);
+            float x = static_cast<float>(2 * kPi * static_cast<double>(static_cast<float>(value)) / 8000.0);      // fxpt::float_to_fixed
+            const int d = static_cast<int>(std::floor(x / static_cast<float>(2.0 * kPi) + 0.5));
+            x -= d * static_cast<float>(2.0 * kPi);
+            h->tone_inc = static_cast<unsigned>(static_cast<int>(static_cast<float>(x) * 2147483648.0f / static_cast<float>(kPi)));
+        }
+        if (static_cast<int>(lp.size()) > 400) { set_err(h, "qrl_tx_set_param: audio filter too long"); return QRL_EINVAL; }
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        float* p = nullptr;
+        int rc = upload_floats(h, &p, lp);
+        if (rc) return rc;
+        h->d_lpf = p; h->nt_lpf = static_cast<int>(lp.size());
+        return QRL_OK;
+    }
     if (key == QRL_PARAM_FILTER_WIDTH && (h->kind == QRL_MOD_SSB || h->am_tx)) {
         // gr_mod_ssb::set_filter_width (gr_mod_ssb.cpp:85-100) / gr_mod_am::set_filter_width (gr_mod_am.cpp:75-85)
         const int fw = static_cast<int>(value);
@@ -2294,7 +2317,8 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
         if (h->kind == QRL_MOD_NBFM) {
             tx_nbfm_front_kernel<<<h->C, 128, 0, h->stream>>>(h->d_an, au, n, astride, h->d_ra, h->ra_mask, h->ra_stride,
                 h->d_rb, h->ra_mask, h->ra_stride, h->d_lpf, h->nt_lpf, h->pe_b0, h->pe_b1, h->pe_a1, h->d_arms1, h->nt1,
-                h->d_sym, h->sym_mask, h->sym_stride);
+                h->d_sym, h->sym_mask, h->sym_stride, h->audio_gain, h->tone_on ? 1 : 0, h->tone_phase, h->tone_inc);
+            if (h->tone_on) h->tone_phase += h->tone_inc * static_cast<unsigned>(n);
             const long long r0 = h->n_mid, r1 = ((h->n_audio + n) * 25 + 3) / 4;
             static const float one = 1.0f; (void)one;
             // frequency modulator (Q32 scan) on the 50 ksps stream: "RRC" stage degenerated to a pass-through arm {1}

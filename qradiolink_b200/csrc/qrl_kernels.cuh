@@ -2825,7 +2825,8 @@ tx_nbfm_front_kernel(TxAnalogState* __restrict__ states, const float* __restrict
                      float* __restrict__ rb, unsigned rb_mask, long long rb_stride,      // filtered + pre-emphasised
                      const float* __restrict__ lpf, int nt_lpf, double b0, double b1, double a1,
                      const float* __restrict__ arms /* [25][nt_arm] */, int nt_arm,
-                     float* __restrict__ rs_out, unsigned rs_mask, long long rs_stride)
+                     float* __restrict__ rs_out, unsigned rs_mask, long long rs_stride,
+                     float audio_gain, int tone_on, unsigned tone_phase0, unsigned tone_inc)      // gr_mod_nbfm::set_ctcss: gain + CTCSS tone
 {
     const int c = blockIdx.x;
     __shared__ TxAnalogState st;
@@ -2840,7 +2841,16 @@ tx_nbfm_front_kernel(TxAnalogState* __restrict__ states, const float* __restrict
     for (long long a = a0 + threadIdx.x; a < a1n; a += blockDim.x) {
         float acc = 0.0f;
         for (int k = nt_lpf - 1; k >= 0; k--) { const long long m = a - k; acc = fmaf(lpf[k], m >= 0 ? A[m & ra_mask] : 0.0f, acc); }
-        B[a & rb_mask] = acc * 0.99f;
+        float v = acc * audio_gain;                                   // multiply_const_ff(0.99 / 0.98 / 0.85)
+        if (tone_on) {
+            // add_ff with sig_source_f(8000, cos, f, 0.15) = fxpt_nco: (float)(fxpt::cos(phase) * 0.15); phase of this call's sample j
+            // is tone_phase0 + j * inc (mod 2^32)
+            const unsigned uc = tone_phase0 + tone_inc * static_cast<unsigned>(a - a0) + 0x40000000u;
+            const int ci = static_cast<int>(uc >> 22);
+            const float cs = d_sine_tab[2 * ci] * static_cast<float>(uc >> 1) + d_sine_tab[2 * ci + 1];
+            v = v + static_cast<float>(static_cast<double>(cs) * 0.15);
+        }
+        B[a & rb_mask] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {

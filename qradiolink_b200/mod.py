@@ -38,6 +38,10 @@ class TxBlock:
         """gr_mod_nbfm::set_filter_width (gr_mod_nbfm.cpp:78-93), mid-stream."""
         check(self._L.qrl_tx_set_param(self._h, -1, PARAM.FILTER_WIDTH, float(filter_width)), self._h, "set_filter_width")
 
+    def set_ctcss(self, value):
+        """gr_mod_nbfm::set_ctcss (gr_mod_nbfm.cpp:101-139): 0 = no tone (audio gain 0.98), f = CTCSS tone at f Hz (gain 0.85, 300 Hz high-pass)."""
+        check(self._L.qrl_tx_set_param(self._h, -1, PARAM.CTCSS, float(value)), self._h, "set_ctcss")
+
     def set_bb_gain(self, value):
         check(self._L.qrl_tx_set_param(self._h, -1, PARAM.BB_GAIN, float(value)), self._h, "set_bb_gain")
 

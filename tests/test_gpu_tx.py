@@ -228,3 +228,33 @@ def test_tx_ssb_am_set_filter_width_mid_stream(qrl, oracle, kind):
     for c in range(C):
         w = np.concatenate(want[c])
         assert got.shape[1] == len(w) and np.array_equal(got[c], w), c
+
+
+def test_tx_nbfm_set_ctcss(qrl, oracle):
+    """gr_mod_nbfm::set_ctcss (gr_mod_nbfm.cpp:101-139) mid-stream: tone on (88.5 Hz, then 123 Hz: the tone source keeps its phase), tone
+    off (gain 0.98, not the constructor's 0.99), against the oracle; the tone is in the demodulated audio of the CUDA receiver."""
+    C, n = 2, 6000
+    t = np.arange(n)
+    audio = np.stack([(0.4 * np.sin(2 * np.pi * (900 + 250 * c) * t / 8000)).astype(np.float32) for c in range(C)])
+    tx = qrl.make_gr_mod_nbfm(20, 1000000, 1700, 2500, n_channels=C, max_items=n)
+    os_ = [oracle.Tx(oracle.MOD_NBFM, 20, 1000000, 1700, 2500, 0) for _ in range(C)]
+    got, want = [], [[] for _ in range(C)]
+    for a, b, f in ((0, 700, None), (700, 3200, 88.5), (3200, 3201, 123.0), (3201, 5000, None), (5000, n, 0.0)):
+        if f is not None:
+            tx.set_ctcss(f)
+            for o in os_:
+                o.set_param(7, f)
+        got.append(tx.work_audio(audio[:, a:b]))
+        for c in range(C):
+            want[c].append(os_[c].work(audio[c, a:b]))
+    got = np.concatenate(got, axis=1)
+    for c in range(C):
+        w = np.concatenate(want[c])
+        assert got.shape[1] == len(w) and np.array_equal(got[c], w), c
+    rx = qrl.make_gr_demod_nbfm(125, 1000000, 1700, 2500, n_channels=1, max_samples=got.shape[1])
+    rx.work(got[:1])
+    a = rx.read_port(1)[0]
+    seg = a[1200:3000]                                            # tone at 88.5 Hz on, 8 ksps audio
+    spec = np.abs(np.fft.rfft(seg * np.hanning(len(seg))))
+    fb = np.fft.rfftfreq(len(seg), 1 / 8000.0)
+    assert spec[np.argmin(np.abs(fb - 88.5))] > 20 * np.median(spec[(fb > 200) & (fb < 700)])
