@@ -886,6 +886,36 @@ def run_ours(args):
                     "h2d_bytes_per_call": int(C * T * 4), "decoded_bits_per_call": bits16,
                     "note": "qrl_rx_work_sc16: pinned int16 I/Q slab (x20000, the SDR's wire format) -> device conversion float(v)/32767 -> same chain"}
         del Xq
+        # int8 I/Q (HackRF-class front ends): 2 B per sample
+        X8 = torch.empty((C, T, 2), dtype=torch.int8, pin_memory=True)
+        X8.copy_(torch.view_as_real(X).mul(100.0).round_().clamp_(-128, 127).to(torch.int8))
+        sc8 = Ct.c_float(1.0 / 128.0)
+
+        def call_host8():
+            rc = L.qrl_rx_work_sc8(blk._h, Ct.c_void_p(X8.data_ptr()), T, T, sc8, 0)
+            assert rc == 0
+            rc = L.qrl_rx_read_port(blk._h, 2, Ct.c_void_p(out_bits.data_ptr()), bits_cap, out_cnt.ctypes.data_as(Ct.c_void_p), 0)
+            assert rc == 0
+
+        call_host8()
+        bits8 = int(out_cnt.sum())
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(e2e_calls):
+            call_host8()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms8 = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+        t4 = torch.tensor([ms8], device=dev, dtype=torch.float64)
+        if dist:
+            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        e2e_sc16["sc8"] = {"value": world * C * T * e2e_calls / (float(t4.item()) * 1e-3) / 1e6, "unit": "Msamples/s",
+                           "h2d_bytes_per_call": int(C * T * 2), "decoded_bits_per_call": bits8,
+                           "note": "qrl_rx_work_sc8: pinned int8 I/Q slab (x100) -> float(v)/128 on the device -> same chain"}
+        del X8
     except Exception as e:  # noqa: BLE001
         e2e_sc16 = {"error": "%s: %s" % (type(e).__name__, e)}
     if old_aff is not None:

@@ -108,6 +108,8 @@ int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device);
  * converter that sits in front of the reference's uhd / osmosdr source blocks (gr_demod_base.cpp:166-196; UHD's sc16 -> fc32
  * scale is 1 / 32767) -- and the chain then runs exactly as qrl_rx_work on that gr_complex stream.  stride in int16 pairs. */
 int qrl_rx_work_sc16(qrl_rx* h, const short* iq, long T, long stride, float scale, int on_device);
+/* the same for 8-bit front ends (HackRF and other int8 sources of gr-osmosdr, 2 bytes per sample): float(v) * scale, stride in int8 pairs */
+int qrl_rx_work_sc8(qrl_rx* h, const signed char* iq, long T, long stride, float scale, int on_device);
 /* wait for everything submitted so far */
 /* RSSI tap: per channel the value probe_signal_f holds behind rssi_block (|x|^2 -> moving_average(2000) ->
  * single_pole_iir(0.04) -> 10 log10 -> + level; /root/reference/src/gr/rssi_block.cpp:25-45, gr_demod_base.cpp:199-200) after the

@@ -1178,18 +1178,23 @@ int qrl_rx_set_param(qrl_rx* h, int channel, int key, double value)
     return QRL_EINVAL;
 }
 
-static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int on_device, bool sc16, float sc16_scale);
+static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int on_device, int sc16, float sc16_scale);
 
 int qrl_rx_work(qrl_rx* h, const float* iq, long T, long stride, int on_device)
 {
-    return rx_work_impl(h, iq, T, stride, on_device, false, 0.0f);
+    return rx_work_impl(h, iq, T, stride, on_device, 0, 0.0f);
 }
 int qrl_rx_work_sc16(qrl_rx* h, const short* iq, long T, long stride, float scale, int on_device)
 {
-    return rx_work_impl(h, iq, T, stride, on_device, true, scale);
+    return rx_work_impl(h, iq, T, stride, on_device, 2, scale);
+}
+int qrl_rx_work_sc8(qrl_rx* h, const signed char* iq, long T, long stride, float scale, int on_device)
+{
+    return rx_work_impl(h, iq, T, stride, on_device, 1, scale);
 }
 
-static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int on_device, bool sc16, float sc16_scale)
+// sc16: 0 = gr_complex input, 2 = int16 pairs, 1 = int8 pairs (bytes per component)
+static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int on_device, int sc16, float sc16_scale)
 {
     const float* iq = static_cast<const float*>(iq_any);
     if (!h || !iq || T < 0) return QRL_EINVAL;
@@ -1210,17 +1215,18 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
         // exactly like the host converter in front of the reference's source block: float(v) * scale, one rounding
         const short2* s = static_cast<const short2*>(iq_any);
         long long sstride = stride;
+        const size_t isz = sc16 == 2 ? sizeof(short2) : sizeof(char2);
         if (!on_device) {
             if (!h->d_in_sc16) {
                 int rc = dev_alloc(h, &h->d_in_sc16, static_cast<size_t>(h->Tmax) * h->C, false);
                 if (rc) return rc;
             }
-            CK(cudaMemcpy2DAsync(h->d_in_sc16, sizeof(short2) * h->Tmax, iq_any, sizeof(short2) * stride,
-                                 sizeof(short2) * T, h->C, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpy2DAsync(h->d_in_sc16, isz * h->Tmax, iq_any, isz * stride, isz * T, h->C, cudaMemcpyHostToDevice, h->stream));
             s = h->d_in_sc16; sstride = h->Tmax;
         }
         dim3 g(static_cast<unsigned>(std::min<long long>((T + 1023) / 1024, 65535)), h->C);
-        sc16_to_fc32_kernel<<<g, 256, 0, h->stream>>>(s, sstride, h->d_in_staging, h->Tmax, T, sc16_scale);
+        if (sc16 == 2) sc16_to_fc32_kernel<<<g, 256, 0, h->stream>>>(s, sstride, h->d_in_staging, h->Tmax, T, sc16_scale);
+        else sc8_to_fc32_kernel<<<g, 256, 0, h->stream>>>(reinterpret_cast<const char2*>(s), sstride, h->d_in_staging, h->Tmax, T, sc16_scale);
         h->launches++;
         x = h->d_in_staging;
         xstride = h->Tmax;

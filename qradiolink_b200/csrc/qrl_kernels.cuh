@@ -3281,6 +3281,33 @@ __global__ void sc16_to_fc32_kernel(const short2* __restrict__ in, long long in_
     }
 }
 
+// interleaved int8 I/Q (HackRF / 8-bit front ends through gr-osmosdr: 2 bytes per sample) -> gr_complex: float(v) * scale.  8 samples per
+// thread: one 16-byte load, four 16-byte stores.
+__global__ void sc8_to_fc32_kernel(const char2* __restrict__ in, long long in_stride, float2* __restrict__ out, long long out_stride,
+                                   long T, float scale)
+{
+    const int c = blockIdx.y;
+    const char2* src = in + static_cast<long long>(c) * in_stride;
+    float2* dst = out + static_cast<long long>(c) * out_stride;
+    const bool al = ((reinterpret_cast<unsigned long long>(src) & 15) == 0) && ((reinterpret_cast<unsigned long long>(dst) & 15) == 0);
+    for (long q = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; q < T; q += static_cast<long>(gridDim.x) * blockDim.x * 8) {
+        if (al && q + 8 <= T) {
+            const uint4 v = *reinterpret_cast<const uint4*>(src + q);
+            const unsigned w[4] = { v.x, v.y, v.z, v.w };
+            float4 o[4];
+            float* of = reinterpret_cast<float*>(o);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) of[4 * k + b] = static_cast<float>(static_cast<signed char>((w[k] >> (8 * b)) & 0xFFu)) * scale;
+#pragma unroll
+            for (int k = 0; k < 4; k++) *reinterpret_cast<float4*>(dst + q + 2 * k) = o[k];
+        } else {
+            for (long t = q; t < T && t < q + 8; t++) dst[t] = make_float2(static_cast<float>(src[t].x) * scale, static_cast<float>(src[t].y) * scale);
+        }
+    }
+}
+
 // gr_zero_idle_bursts (gr_zero_idle_bursts.cpp:45-82) as two ring passes.  (1) the sync block's history: out[a] = in[a - delay_items]
 // (zero before the stream began); (2) the "zero_samples" counter: the host has turned the tags of this call into [begin, end) item
 // ranges per channel (qrl_tx_work), one CTA per range clears them.

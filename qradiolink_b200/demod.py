@@ -100,6 +100,16 @@ class RxBlock:
         T = iq16.shape[1]
         check(self._L.qrl_rx_work_sc16(self._h, iq16.ctypes.data_as(C.c_void_p), T, T, float(scale), 0), self._h, "qrl_rx_work_sc16")
 
+    def work_sc8(self, iq8, scale=1.0 / 128.0):
+        """iq8: int8 array [n_channels, T, 2] (HackRF-style interleaved I/Q) in host memory; float32(v) * float32(scale) on the device."""
+        iq8 = np.ascontiguousarray(iq8, np.int8)
+        if iq8.ndim == 2:
+            iq8 = iq8[None, :, :]
+        if iq8.shape[0] != self.n_channels or iq8.shape[2] != 2:
+            raise ValueError("expected [%d][T][2] int8" % self.n_channels)
+        T = iq8.shape[1]
+        check(self._L.qrl_rx_work_sc8(self._h, iq8.ctypes.data_as(C.c_void_p), T, T, float(scale), 0), self._h, "qrl_rx_work_sc8")
+
     def work_sc16_device(self, dev_ptr, T, stride, scale=1.0 / 32767.0):
         check(self._L.qrl_rx_work_sc16(self._h, C.c_void_p(dev_ptr), T, stride, float(scale), 1), self._h, "qrl_rx_work_sc16")
 

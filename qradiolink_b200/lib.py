@@ -33,6 +33,7 @@ SYMBOLS = {
     "qrl_rx_reset": (_i, [_vp]),
     "qrl_rx_work": (_i, [_vp, _vp, _l, _l, _i]),
     "qrl_rx_work_sc16": (_i, [_vp, _vp, _l, _l, C.c_float, _i]),
+    "qrl_rx_work_sc8": (_i, [_vp, _vp, _l, _l, C.c_float, _i]),
     "qrl_rx_sync": (_i, [_vp]),
     "qrl_rx_join": (_i, [_vp]),
     "qrl_rx_rssi": (_i, [_vp, C.c_float, _vp]),

@@ -248,6 +248,28 @@ def test_overlapped_calls_with_changing_length(qrl, oracle):
         assert np.array_equal(bits[c], rx.port(2))
 
 
+def test_sc8_ingest_equals_the_float_path(qrl):
+    """qrl_rx_work_sc8 (int8 I/Q, 2 bytes per sample) against qrl_rx_work on the host-converted stream: identical ports, ragged chunks."""
+    C, T = 2, 150000
+    X, _ = siggen.gen_4fsk_channels(C, T, seed0=1950)
+    q8 = np.empty((C, T, 2), np.int8)
+    q8[..., 0] = np.clip(np.round(X.real * 100), -128, 127)
+    q8[..., 1] = np.clip(np.round(X.imag * 100), -128, 127)
+    scale = np.float32(1.0 / 128.0)
+    Xf = (q8[..., 0].astype(np.float32) * scale + 1j * (q8[..., 1].astype(np.float32) * scale)).astype(np.complex64)
+    a = qrl.make_gr_demod_4fsk(5, 1000000, 1700, 3000, True, n_channels=C, max_samples=70001)
+    b = qrl.make_gr_demod_4fsk(5, 1000000, 1700, 3000, True, n_channels=C, max_samples=70001)
+    lo = 0
+    for n in [1, 7, 70001, 4096, 5, 65537, 10353]:
+        a.work_sc8(q8[:, lo:lo + n], scale)
+        b.work(Xf[:, lo:lo + n])
+        for p in range(3):
+            for c in range(C):
+                assert np.array_equal(a.read_port(p)[c], b.read_port(p)[c]), (lo, p, c)
+        lo += n
+    assert lo == T
+
+
 def test_sc16_ingest_equals_the_float_path(qrl, oracle):
     """qrl_rx_work_sc16: int16 I/Q converted on the device (float(v) * scale, one rounding) must give exactly the ports of qrl_rx_work
     fed with the host-converted gr_complex stream, and of the oracle; ragged chunks incl. lengths that break the 16-byte path."""

@@ -25,6 +25,7 @@
 struct float2 { float x, y; };
 struct uint2 { unsigned x, y; };
 struct short2 { short x, y; };
+struct char2 { signed char x, y; };
 struct uint4 { unsigned x, y, z, w; };
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{ x, y }; }
 static inline float2 make_float2(float x, float y) { return float2{ x, y }; }
