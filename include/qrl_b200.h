@@ -241,7 +241,12 @@ long qrl_pfb_launch_count(qrl_pfb*);
  * source (ZeroMQ, out of scope). */
 typedef struct qrl_mmdvm_rx qrl_mmdvm_rx;
 typedef struct qrl_mmdvm_tx qrl_mmdvm_tx;
-int  qrl_mmdvm_rx_create(int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_rx** out);
+/* variant 0: the per-channel chains of gr_demod_mmdvm_multi2 / gr_mod_mmdvm_multi2 described above (25 ksps <-> 24 ksps).
+ * variant 1: the single-channel blocks gr_demod_mmdvm (gr_demod_mmdvm.cpp:30-64) / gr_mod_mmdvm (gr_mod_mmdvm.cpp:28-70) at
+ * MMDVM_SAMPLE_RATE = 250 ksps: rational_resampler_ccf(12, 125, low_pass_2(12, 3 MHz, fw, 2000, 60, BH)), the RSSI tags taken in FRONT of the
+ * channel filter, quadrature_demod_cf(24000 / (2 pi 10000)); TX: ... -> x0.8 -> x bb_gain -> rational_resampler_ccf(125, 12) (qrl_mmdvm_tx_finish
+ * is not used there); n_channels independent streams are processed at once. */
+int  qrl_mmdvm_rx_create(int variant, int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_rx** out);
 int  qrl_mmdvm_rx_destroy(qrl_mmdvm_rx*);
 int  qrl_mmdvm_rx_set_stream(qrl_mmdvm_rx*, void* cuda_stream);
 int  qrl_mmdvm_rx_calibrate_rssi(qrl_mmdvm_rx*, float level);              /* rssi_tag_block::calibrate_rssi */
@@ -253,7 +258,7 @@ int  qrl_mmdvm_rx_out_device(qrl_mmdvm_rx*, short** data, long* stride, long* n_
                              long long* first_rssi_item);
 int  qrl_mmdvm_rx_read(qrl_mmdvm_rx*, short* dst, long dst_stride, float* rssi_db, long rssi_cap, int* n_rssi, long long* first_rssi_item);
 long qrl_mmdvm_rx_launch_count(qrl_mmdvm_rx*);
-int  qrl_mmdvm_tx_create(int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_tx** out);
+int  qrl_mmdvm_tx_create(int variant, int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_tx** out);
 int  qrl_mmdvm_tx_destroy(qrl_mmdvm_tx*);
 int  qrl_mmdvm_tx_set_stream(qrl_mmdvm_tx*, void* cuda_stream);
 int  qrl_mmdvm_tx_set_bb_gain(qrl_mmdvm_tx*, float gain);                   /* gr_mod_mmdvm_multi2::set_bb_gain */

@@ -59,6 +59,11 @@ def lib():
         L.qo_mmdvm_rx_create.restype = vp
         L.qo_mmdvm_rx_create.argtypes = [C.c_int]
         L.qo_mmdvm_rx_destroy.argtypes = [vp]
+        L.qo_mmdvm_rx_create2.restype = vp
+        L.qo_mmdvm_rx_create2.argtypes = [C.c_int, C.c_int]
+        L.qo_mmdvm_tx_create2.restype = vp
+        L.qo_mmdvm_tx_create2.argtypes = [C.c_int, C.c_int]
+        L.qo_mmdvm_tx_set_bb_gain.argtypes = [vp, C.c_float]
         L.qo_mmdvm_rx_calibrate_rssi.argtypes = [vp, C.c_float]
         L.qo_mmdvm_rx_work.argtypes = [vp, vp, C.c_long]
         L.qo_mmdvm_rx_out_items.restype = C.c_long
@@ -440,8 +445,9 @@ class MmdvmRx:
     """One channel of gr_demod_mmdvm_multi2 behind the channelizer (gr_demod_mmdvm_multi2.cpp:56-126): complex at 25 ksps -> int16
     discriminator samples at 24 ksps + the RSSI tags."""
 
-    def __init__(self, filter_width=5000):
-        self.h = lib().qo_mmdvm_rx_create(int(filter_width))
+    def __init__(self, filter_width=5000, single=False):
+        """single=True: gr_demod_mmdvm (gr_demod_mmdvm.cpp:30-64): complex at 250 ksps in, x12 / 125, RSSI in front of the filter."""
+        self.h = lib().qo_mmdvm_rx_create2(int(filter_width), int(bool(single)))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -466,8 +472,12 @@ class MmdvmTx:
     """One channel of gr_mod_mmdvm_multi2 in front of the synthesizer (gr_mod_mmdvm_multi2.cpp:47-126): int16 at 24 ksps -> complex
     at 25 ksps."""
 
-    def __init__(self, filter_width=5000):
-        self.h = lib().qo_mmdvm_tx_create(int(filter_width))
+    def __init__(self, filter_width=5000, single=False):
+        """single=True: gr_mod_mmdvm (gr_mod_mmdvm.cpp:28-70): x125 / 12 to 250 ksps, bb_gain in front of the resampler."""
+        self.h = lib().qo_mmdvm_tx_create2(int(filter_width), int(bool(single)))
+
+    def set_bb_gain(self, g):
+        lib().qo_mmdvm_tx_set_bb_gain(self.h, float(g))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -3014,20 +3014,32 @@ int qo_spectrum_get(qo_spectrum* s, float* out)                 /* rx_fft.cpp:11
  *     [to the synthesizer; behind it x 1 / num_channels -> x bb_gain].
  * float_to_short = volk_32f_s32f_convert_16i (x scale, clip to [-32768, 32767], rintf); short_to_float = volk_16i_s32f_convert_32f in
  * its SIMD form, (float)v * (float)(1.0 / 32767) (the generic kernel divides; an x86 host runs the SIMD one). */
-struct qo_mmdvm_rx { resamp_t rs; resamp_t filt; qdemod_t qd; float sum; int nitems; long long n24; float cal; qvec s_a, s_b, s_f, out, rssi_db, rssi_at; };
-qo_mmdvm_rx* qo_mmdvm_rx_create(int filter_width)
+struct qo_mmdvm_rx { int single; resamp_t rs; resamp_t filt; qdemod_t qd; float sum; int nitems; long long n24; float cal; qvec s_a, s_b, s_f, out, rssi_db, rssi_at; };
+/* variant 0: one channel of gr_demod_mmdvm_multi2 behind the channelizer (25 ksps in).  variant 1: gr_demod_mmdvm
+ * (/root/reference/src/gr/gr_demod_mmdvm.cpp:30-64), the single-channel block at MMDVM_SAMPLE_RATE = 250 ksps: rational_resampler_ccf(12, 125,
+ * low_pass_2(12, 12 * 250k, fw, 2000, 60, BH)) -> rssi_tag_block -> low_pass_2(1, 24k, ...) -> quadrature_demod_cf(24000 / (2 pi 10000)) ->
+ * x1.0 -> float_to_short: the RSSI tags sit in FRONT of the channel filter there, and the discriminator width is 10 kHz. */
+qo_mmdvm_rx* qo_mmdvm_rx_create2(int filter_width, int variant)
 {
     static float taps[16384];
     tabs_init();
     qo_mmdvm_rx* r = (qo_mmdvm_rx*)calloc(1, sizeof *r);
-    int n = qo_firdes_low_pass_2(1, 600000.0, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
-    resamp_init(&r->rs, 2, 24, 25, taps, n);
+    r->single = variant;
+    int n;
+    if (variant) {
+        n = qo_firdes_low_pass_2(12, 12 * 250000.0, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&r->rs, 2, 12, 125, taps, n);
+    } else {
+        n = qo_firdes_low_pass_2(1, 600000.0, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&r->rs, 2, 24, 25, taps, n);
+    }
     n = qo_firdes_low_pass_2(1, 24000.0, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
     resamp_init(&r->filt, 2, 1, 1, taps, n);
-    qdemod_init(&r->qd, (float)(24000.0f / (2 * M_PI * 12500.0f)));
+    qdemod_init(&r->qd, (float)(24000.0f / (2 * M_PI * (variant ? 10000.0f : 12500.0f))));
     qv_init(&r->s_a, 8); qv_init(&r->s_b, 8); qv_init(&r->s_f, 4); qv_init(&r->out, 2); qv_init(&r->rssi_db, 4); qv_init(&r->rssi_at, 8);
     return r;
 }
+qo_mmdvm_rx* qo_mmdvm_rx_create(int filter_width) { return qo_mmdvm_rx_create2(filter_width, 0); }
 void qo_mmdvm_rx_destroy(qo_mmdvm_rx* r)
 {
     if (!r) return;
@@ -3065,7 +3077,8 @@ int qo_mmdvm_rx_work(qo_mmdvm_rx* r, const float* iq25k, long n)
     r->s_a.n = 0; resamp_work(&r->rs, iq25k, (size_t)n, &r->s_a);
     r->s_b.n = 0; resamp_work(&r->filt, (const float*)r->s_a.d, r->s_a.n, &r->s_b);
     const float* f = (const float*)r->s_b.d;
-    for (size_t i = 0; i < r->s_b.n; i++) { rssi_tag_step(f[2 * i], f[2 * i + 1], &r->sum, &r->nitems, r->cal, r->n24, &r->rssi_db, &r->rssi_at); r->n24++; }
+    const float* g = r->single ? (const float*)r->s_a.d : f;              /* gr_demod_mmdvm tags the resampler's output, multi2 the filter's */
+    for (size_t i = 0; i < r->s_b.n; i++) { rssi_tag_step(g[2 * i], g[2 * i + 1], &r->sum, &r->nitems, r->cal, r->n24, &r->rssi_db, &r->rssi_at); r->n24++; }
     r->s_f.n = 0; qdemod_work(&r->qd, f, r->s_b.n, &r->s_f);
     const float* d = (const float*)r->s_f.d;
     for (size_t i = 0; i < r->s_f.n; i++) {
@@ -3084,20 +3097,31 @@ const float* qo_mmdvm_rx_rssi_db(qo_mmdvm_rx* r) { return (const float*)r->rssi_
 const long long* qo_mmdvm_rx_rssi_at(qo_mmdvm_rx* r) { return (const long long*)r->rssi_at.d; }
 void qo_mmdvm_rx_clear(qo_mmdvm_rx* r) { r->out.n = 0; r->rssi_db.n = 0; r->rssi_at.n = 0; }
 
-struct qo_mmdvm_tx { qo_tx fm; resamp_t filt; resamp_t rs; qvec s_f, s_m, s_b, out; };
-qo_mmdvm_tx* qo_mmdvm_tx_create(int filter_width)
+struct qo_mmdvm_tx { int single; float bb_gain; qo_tx fm; resamp_t filt; resamp_t rs; qvec s_f, s_m, s_b, out; };
+/* variant 1: gr_mod_mmdvm (/root/reference/src/gr/gr_mod_mmdvm.cpp:28-70): the same chain up to x0.8, then x bb_gain, then
+ * rational_resampler_ccf(125, 12, low_pass_2(125, 125 * 24k, fw, 2000, 60, BH)) to 250 ksps (gr_zero_idle_bursts(0) sits in front of the
+ * filter there: tags only, not restated) */
+qo_mmdvm_tx* qo_mmdvm_tx_create2(int filter_width, int variant)
 {
     static float taps[16384];
     tabs_init();
     qo_mmdvm_tx* t = (qo_mmdvm_tx*)calloc(1, sizeof *t);
+    t->single = variant; t->bb_gain = 1.0f;
     t->fm.fm_sens = (float)(2 * M_PI * 12500.0f / 24000.0f);
     int n = qo_firdes_low_pass_2(1, 24000.0, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
     resamp_init(&t->filt, 2, 1, 1, taps, n);
-    n = qo_firdes_low_pass_2(25, 600000.0, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
-    resamp_init(&t->rs, 2, 25, 24, taps, n);
+    if (variant) {
+        n = qo_firdes_low_pass_2(125, 125 * 24000.0, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&t->rs, 2, 125, 12, taps, n);
+    } else {
+        n = qo_firdes_low_pass_2(25, 600000.0, filter_width, 2000, 60, QO_WIN_BLACKMAN_HARRIS, taps, 16384);
+        resamp_init(&t->rs, 2, 25, 24, taps, n);
+    }
     qv_init(&t->s_f, 4); qv_init(&t->s_m, 8); qv_init(&t->s_b, 8); qv_init(&t->out, 8);
     return t;
 }
+qo_mmdvm_tx* qo_mmdvm_tx_create(int filter_width) { return qo_mmdvm_tx_create2(filter_width, 0); }
+void qo_mmdvm_tx_set_bb_gain(qo_mmdvm_tx* t, float g) { t->bb_gain = g; }
 void qo_mmdvm_tx_destroy(qo_mmdvm_tx* t)
 {
     if (!t) return;
@@ -3112,7 +3136,7 @@ int qo_mmdvm_tx_work(qo_mmdvm_tx* t, const short* in, long n)
     t->s_m.n = 0; fm_mod(&t->fm, (const float*)t->s_f.d, t->s_f.n, &t->s_m, 1.0f);
     t->s_b.n = 0; resamp_work(&t->filt, (const float*)t->s_m.d, t->s_m.n, &t->s_b);
     float* m = (float*)t->s_b.d;
-    for (size_t i = 0; i < 2 * t->s_b.n; i++) m[i] = m[i] * 0.8f;                 /* multiply_const_cc(0.8) */
+    for (size_t i = 0; i < 2 * t->s_b.n; i++) { m[i] = m[i] * 0.8f; if (t->single) m[i] = m[i] * t->bb_gain; }   /* multiply_const_cc(0.8) [, bb_gain] */
     resamp_work(&t->rs, m, t->s_b.n, &t->out);
     return 0;
 }

@@ -169,6 +169,7 @@ int  qo_spectrum_get(qo_spectrum*, float* out);      /* returns fft_size, or 0 w
 /* gr_demod_mmdvm_multi2 / gr_mod_mmdvm_multi2, one channel behind / in front of the polyphase filter bank (25 ksps <-> int16 at 24 ksps) */
 typedef struct qo_mmdvm_rx qo_mmdvm_rx;
 qo_mmdvm_rx* qo_mmdvm_rx_create(int filter_width);
+qo_mmdvm_rx* qo_mmdvm_rx_create2(int filter_width, int variant);      /* variant 1: gr_demod_mmdvm (250 ksps in, x12 / 125) */
 void qo_mmdvm_rx_destroy(qo_mmdvm_rx*);
 void qo_mmdvm_rx_calibrate_rssi(qo_mmdvm_rx*, float level);
 int  qo_mmdvm_rx_work(qo_mmdvm_rx*, const float* iq25k, long n);
@@ -181,6 +182,8 @@ void qo_mmdvm_rx_clear(qo_mmdvm_rx*);
 long qo_rssi_tags_run(const float* in_c, long n, float cal, float* db, long long* at, long cap);
 typedef struct qo_mmdvm_tx qo_mmdvm_tx;
 qo_mmdvm_tx* qo_mmdvm_tx_create(int filter_width);
+qo_mmdvm_tx* qo_mmdvm_tx_create2(int filter_width, int variant);      /* variant 1: gr_mod_mmdvm (x125 / 12 to 250 ksps, bb_gain) */
+void qo_mmdvm_tx_set_bb_gain(qo_mmdvm_tx*, float g);
 void qo_mmdvm_tx_destroy(qo_mmdvm_tx*);
 int  qo_mmdvm_tx_work(qo_mmdvm_tx*, const short* in, long n);
 long qo_mmdvm_tx_out_items(qo_mmdvm_tx*);

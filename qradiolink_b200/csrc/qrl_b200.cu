@@ -2835,6 +2835,7 @@ struct qrl_mmdvm_rx : HandleBase {
     float* d_rssi = nullptr; long long rssi_stride = 0; int n_rssi_last = 0; long long rssi_b0_last = 0;
     long long n_in = 0, n24 = 0, n_blocks = 0;
     float qd_gain = 0, level = 1.0f, cal = 0.0f;
+    int L = 24, M = 25; bool single = false;       // single: gr_demod_mmdvm (250 ksps in, x12 / 125, RSSI in front of the filter, 10 kHz discriminator)
 };
 struct qrl_mmdvm_tx : HandleBase {
     int C = 0, n_rows = 0, num_channels = 0, nt_arm = 0, nt2 = 0;
@@ -2848,6 +2849,7 @@ struct qrl_mmdvm_tx : HandleBase {
     float2* d_out = nullptr; long long out_stride = 0; long n_out_last = 0;
     long long n_in = 0, n25 = 0;
     float fm_sens = 0, level = 1.0f, bb_gain = 1.0f;
+    int L = 25, M = 24; bool single = false;       // single: gr_mod_mmdvm (x125 / 12 to 250 ksps, bb_gain in front of the resampler)
 };
 
 template <class H> static int mmdvm_destroy(H* h)
@@ -2886,9 +2888,9 @@ extern "C" {
 
 int qrl_mmdvm_rx_destroy(qrl_mmdvm_rx* h) { return mmdvm_destroy(h); }
 int qrl_mmdvm_rx_set_stream(qrl_mmdvm_rx* h, void* s) { return mmdvm_set_stream(h, s); }
-int qrl_mmdvm_rx_create(int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_rx** out)
+int qrl_mmdvm_rx_create(int variant, int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_rx** out)
 {
-    if (!out || n_channels <= 0 || n_rows < n_channels || max_in <= 0 || filter_width <= 0) { set_err(nullptr, "qrl_mmdvm_rx_create: bad argument"); return QRL_EINVAL; }
+    if (!out || variant < 0 || variant > 1 || n_channels <= 0 || n_rows < n_channels || max_in <= 0 || filter_width <= 0) { set_err(nullptr, "qrl_mmdvm_rx_create: bad argument"); return QRL_EINVAL; }
     *out = nullptr;
     if (qrl_device_count() <= device) { set_err(nullptr, "qrl_mmdvm_rx_create: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
     qrl_mmdvm_rx* h = new qrl_mmdvm_rx();
@@ -2900,20 +2902,23 @@ int qrl_mmdvm_rx_create(int n_channels, const int* rows, int n_rows, int filter_
     int rc = upload_tables(h);
     if (rc) return fail(rc);
     if ((rc = mmdvm_rows(h, &h->d_rows, rows, h->C, n_rows))) return fail(rc);
-    // gr_demod_mmdvm_multi2.cpp:58-62,66,71,76
-    const std::vector<float> ti = low_pass_2(1, 600000.0, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS);
+    // gr_demod_mmdvm_multi2.cpp:58-62,66,71,76 | gr_demod_mmdvm.cpp:43-52
+    h->single = variant == 1;
+    h->L = h->single ? 12 : 24; h->M = h->single ? 125 : 25;
+    const std::vector<float> ti = h->single ? low_pass_2(12, 12 * 250000.0, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS)
+                                            : low_pass_2(1, 600000.0, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS);
     const std::vector<float> tf = low_pass_2(1, 24000.0, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS);
-    h->nt_arm = (static_cast<int>(ti.size()) + 23) / 24; h->nt2 = static_cast<int>(tf.size());
-    if (static_cast<size_t>(24) * h->nt_arm * sizeof(float) > 40 * 1024 || h->nt2 > kMaxTapsSmem) { set_err(h, "qrl_mmdvm_rx_create: filter_width too small"); return fail(QRL_EINVAL); }
-    if ((rc = upload_floats(h, &h->d_arms, make_arms(ti, 24, h->nt_arm)))) return fail(rc);
+    h->nt_arm = (static_cast<int>(ti.size()) + h->L - 1) / h->L; h->nt2 = static_cast<int>(tf.size());
+    if (static_cast<size_t>(h->L) * h->nt_arm * sizeof(float) > 40 * 1024 || h->nt2 > kMaxTapsSmem) { set_err(h, "qrl_mmdvm_rx_create: filter_width too small"); return fail(QRL_EINVAL); }
+    if ((rc = upload_floats(h, &h->d_arms, make_arms(ti, h->L, h->nt_arm)))) return fail(rc);
     if ((rc = upload_floats(h, &h->d_taps2, tf))) return fail(rc);
-    h->qd_gain = static_cast<float>(24000.0f / (2 * kPi * 12500.0f));
+    h->qd_gain = static_cast<float>(24000.0f / (2 * kPi * (h->single ? 10000.0f : 12500.0f)));
     const unsigned c25 = pow2_at_least(max_in + h->nt_arm + 64), c24 = pow2_at_least(max_in + h->nt2 + 400);
     h->m25 = c25 - 1; h->s25 = c25; h->m24 = c24 - 1; h->s24 = c24;
     if ((rc = dev_alloc(h, &h->d_r25, static_cast<size_t>(c25) * h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_r24, static_cast<size_t>(c24) * h->C))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_rf, static_cast<size_t>(c24) * h->C))) return fail(rc);
-    h->out_stride = max_in * 24 / 25 + 2;
+    h->out_stride = max_in * h->L / h->M + 2;
     if ((rc = dev_alloc(h, &h->d_out, static_cast<size_t>(h->out_stride) * h->C, false))) return fail(rc);
     h->rssi_stride = h->out_stride / 300 + 2;
     if ((rc = dev_alloc(h, &h->d_rssi, static_cast<size_t>(h->rssi_stride) * h->C, false))) return fail(rc);
@@ -2942,19 +2947,26 @@ int qrl_mmdvm_rx_work(qrl_mmdvm_rx* h, const float* iq, long n, long stride, int
     mmdvm_gather_kernel<<<dim3(static_cast<unsigned>(std::min<long long>((n + TB - 1) / TB, 4096)), h->C), TB, 0, h->stream>>>(
         x, xstride, h->d_rows, n, h->d_r25, h->m25, h->s25, h->n_in);
     const long long N = h->n_in + n;
-    const long long o0 = h->n24, o1 = (N * 24 + 24) / 25;              // outputs o whose newest input floor(25 o / 24) has arrived
+    const long long o0 = h->n24, o1 = (N * h->L + h->M - 1) / h->M;    // outputs o whose newest input floor(M o / L) has arrived
     h->launches++;
     if (o1 > o0) {
         dim3 g(static_cast<unsigned>((o1 - o0 + TB - 1) / TB), h->C);
-        resamp_ring_to_ring_ccf_kernel<<<g, TB, sizeof(float) * 24 * h->nt_arm, h->stream>>>(h->d_r25, h->m25, h->s25, h->d_arms, 24, 25, h->nt_arm, o0, o1,
-                                                                                              1.0f, 1.0f, 0, h->d_r24, h->m24, h->s24);
-        fir_ccf_ring_kernel<<<g, TB, sizeof(float) * h->nt2, h->stream>>>(h->d_r24, h->m24, h->s24, h->d_rf, h->m24, h->s24, h->d_taps2, h->nt2, o0, o1, nullptr, 0, 0, 0);
+        if (!h->single && h->nt_arm == 35) {       // the reference's filter width (5000 Hz: 819 taps): tiled instance
+            const int span_cap = 256 * 25 / 24 + 35 + 4;
+            const size_t smem = sizeof(float) * ((24 * 35 + 1) & ~1) + sizeof(float2) * span_cap;
+            resamp_ring_to_ring_tiled_kernel<35><<<g, 256, smem, h->stream>>>(h->d_r25, h->m25, h->s25, h->d_arms, 24, 25, o0, o1, h->d_r24, h->m24, h->s24, span_cap);
+        } else {
+            resamp_ring_to_ring_ccf_kernel<<<g, TB, sizeof(float) * h->L * h->nt_arm, h->stream>>>(h->d_r25, h->m25, h->s25, h->d_arms, h->L, h->M, h->nt_arm, o0, o1,
+                                                                                                    1.0f, 1.0f, 0, h->d_r24, h->m24, h->s24);
+        }
+        { int rc = launch_fir_ccf_c(h, h->C, h->stream, h->d_r24, h->m24, h->s24, h->d_rf, h->m24, h->s24, h->d_taps2, h->nt2, o0, o1, nullptr, 0, 0, 0); if (rc) return rc; h->launches--; }
         mmdvm_demod_short_kernel<<<g, TB, 0, h->stream>>>(h->d_rf, h->m24, h->s24, o0, o1, h->qd_gain, h->level, h->d_out, h->out_stride);
         h->launches += 3;
         const long long b1 = o1 / 300;                                   // complete 300-item blocks so far
         if (b1 > h->n_blocks) {
             const int nb = static_cast<int>(b1 - h->n_blocks);
-            mmdvm_rssi_kernel<<<dim3((nb + 63) / 64, h->C), 64, 0, h->stream>>>(h->d_rf, h->m24, h->s24, h->n_blocks, nb, h->cal, h->d_rssi, h->rssi_stride);
+            // gr_demod_mmdvm tags the resampler's output, gr_demod_mmdvm_multi2 the channel filter's
+            mmdvm_rssi_kernel<<<dim3((nb + 63) / 64, h->C), 64, 0, h->stream>>>(h->single ? h->d_r24 : h->d_rf, h->m24, h->s24, h->n_blocks, nb, h->cal, h->d_rssi, h->rssi_stride);
             h->launches++;
             h->n_rssi_last = nb; h->rssi_b0_last = h->n_blocks; h->n_blocks = b1;
         }
@@ -2995,9 +3007,9 @@ long qrl_mmdvm_rx_launch_count(qrl_mmdvm_rx* h) { return h ? h->launches : 0; }
 
 int qrl_mmdvm_tx_destroy(qrl_mmdvm_tx* h) { return mmdvm_destroy(h); }
 int qrl_mmdvm_tx_set_stream(qrl_mmdvm_tx* h, void* s) { return mmdvm_set_stream(h, s); }
-int qrl_mmdvm_tx_create(int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_tx** out)
+int qrl_mmdvm_tx_create(int variant, int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_tx** out)
 {
-    if (!out || n_channels <= 0 || n_rows < n_channels || max_in <= 0 || filter_width <= 0) { set_err(nullptr, "qrl_mmdvm_tx_create: bad argument"); return QRL_EINVAL; }
+    if (!out || variant < 0 || variant > 1 || n_channels <= 0 || n_rows < n_channels || max_in <= 0 || filter_width <= 0) { set_err(nullptr, "qrl_mmdvm_tx_create: bad argument"); return QRL_EINVAL; }
     *out = nullptr;
     if (qrl_device_count() <= device) { set_err(nullptr, "qrl_mmdvm_tx_create: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
     qrl_mmdvm_tx* h = new qrl_mmdvm_tx();
@@ -3009,12 +3021,15 @@ int qrl_mmdvm_tx_create(int n_channels, const int* rows, int n_rows, int filter_
     int rc = upload_tables(h);
     if (rc) return fail(rc);
     if ((rc = mmdvm_rows(h, &h->d_rows, rows, h->C, n_rows))) return fail(rc);
-    // gr_mod_mmdvm_multi2.cpp:47-50,64,72,80
-    const std::vector<float> ti = low_pass_2(25, 600000.0, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS);
+    // gr_mod_mmdvm_multi2.cpp:47-50,64,72,80 | gr_mod_mmdvm.cpp:36-45
+    h->single = variant == 1;
+    h->L = h->single ? 125 : 25; h->M = h->single ? 12 : 24;
+    const std::vector<float> ti = h->single ? low_pass_2(125, 125 * 24000.0, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS)
+                                            : low_pass_2(25, 600000.0, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS);
     const std::vector<float> tf = low_pass_2(1, 24000.0, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS);
-    h->nt_arm = (static_cast<int>(ti.size()) + 24) / 25; h->nt2 = static_cast<int>(tf.size());
-    if (static_cast<size_t>(25) * h->nt_arm * sizeof(float) > 40 * 1024 || h->nt2 > kMaxTapsSmem) { set_err(h, "qrl_mmdvm_tx_create: filter_width too small"); return fail(QRL_EINVAL); }
-    if ((rc = upload_floats(h, &h->d_arms, make_arms(ti, 25, h->nt_arm)))) return fail(rc);
+    h->nt_arm = (static_cast<int>(ti.size()) + h->L - 1) / h->L; h->nt2 = static_cast<int>(tf.size());
+    if (static_cast<size_t>(h->L) * h->nt_arm * sizeof(float) > 40 * 1024 || h->nt2 > kMaxTapsSmem) { set_err(h, "qrl_mmdvm_tx_create: filter_width too small"); return fail(QRL_EINVAL); }
+    if ((rc = upload_floats(h, &h->d_arms, make_arms(ti, h->L, h->nt_arm)))) return fail(rc);
     if ((rc = upload_floats(h, &h->d_taps2, tf))) return fail(rc);
     if ((rc = upload_floats(h, &h->d_one, std::vector<float>{ 1.0f }))) return fail(rc);
     h->fm_sens = static_cast<float>(2 * kPi * 12500.0f / 24000.0f);
@@ -3026,7 +3041,7 @@ int qrl_mmdvm_tx_create(int n_channels, const int* rows, int n_rows, int filter_
     { const unsigned cap = pow2_at_least(max_in + std::max(h->nt2, h->nt_arm) + 128); h->if_mask = cap - 1; h->if_stride = cap;
       if ((rc = dev_alloc(h, &h->d_if, static_cast<size_t>(cap) * h->C))) return fail(rc);
       if ((rc = dev_alloc(h, &h->d_rf, static_cast<size_t>(cap) * h->C))) return fail(rc); }
-    h->lin_stride = max_in * 25 / 24 + 4; h->out_stride = h->lin_stride;
+    h->lin_stride = max_in * h->L / h->M + 4; h->out_stride = h->lin_stride;
     if ((rc = dev_alloc(h, &h->d_lin, static_cast<size_t>(h->lin_stride) * h->C, false))) return fail(rc);
     if ((rc = dev_alloc(h, &h->d_out, static_cast<size_t>(h->out_stride) * h->n_rows))) return fail(rc);      // unused rows stay zero (null_source)
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { set_err(h, "create sync failed"); return fail(QRL_ECUDA); }
@@ -3058,12 +3073,12 @@ int qrl_mmdvm_tx_work(qrl_mmdvm_tx* h, const short* in, long n, long stride, int
         1, 1, h->d_one, 0, 1.0f, h->fm_sens, 1.0f, 1.0f, h->d_if, h->if_mask, h->if_stride);
     dim3 g(static_cast<unsigned>((n + TB - 1) / TB), h->C);
     fir_ccf_ring_kernel<<<g, TB, sizeof(float) * h->nt2, h->stream>>>(h->d_if, h->if_mask, h->if_stride, h->d_rf, h->if_mask, h->if_stride, h->d_taps2, h->nt2, a0, a1, nullptr, 0, 0, 0);
-    scale2_ring_kernel<<<g, TB, 0, h->stream>>>(h->d_rf, h->if_mask, h->if_stride, a0, a1, 0.8f, 1.0f);
-    const long long o0 = h->n25, o1 = (a1 * 25 + 23) / 24;               // outputs i with floor(24 i / 25) < a1
+    scale2_ring_kernel<<<g, TB, 0, h->stream>>>(h->d_rf, h->if_mask, h->if_stride, a0, a1, 0.8f, h->single ? h->bb_gain : 1.0f);   // gr_mod_mmdvm: bb_gain here
+    const long long o0 = h->n25, o1 = (a1 * h->L + h->M - 1) / h->M;     // outputs i with floor(M i / L) < a1
     if (o1 - o0 > h->lin_stride) { set_err(h, "qrl_mmdvm_tx_work: output buffer too small"); return QRL_ERANGE; }
     if (o1 > o0) {
         dim3 go(static_cast<unsigned>((o1 - o0 + 255) / 256), h->C);
-        resamp_ring_ccf_generic_kernel<<<go, 256, sizeof(float) * 25 * h->nt_arm, h->stream>>>(h->d_rf, h->if_mask, h->if_stride, h->d_arms, 25, 24, h->nt_arm, o0, o1,
+        resamp_ring_ccf_generic_kernel<<<go, 256, sizeof(float) * h->L * h->nt_arm, h->stream>>>(h->d_rf, h->if_mask, h->if_stride, h->d_arms, h->L, h->M, h->nt_arm, o0, o1,
                                                                                                h->d_lin, h->lin_stride);
         mmdvm_scatter_kernel<<<dim3(static_cast<unsigned>(std::min<long long>((o1 - o0 + TB - 1) / TB, 4096)), h->C), TB, 0, h->stream>>>(
             h->d_lin, h->lin_stride, h->d_rows, o1 - o0, h->d_out, h->out_stride);

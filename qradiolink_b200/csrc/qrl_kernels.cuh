@@ -2812,6 +2812,43 @@ resamp_ring_to_ring_ccf_kernel(const float2* __restrict__ in_ring, unsigned in_m
     out_ring[static_cast<long long>(c) * out_stride + (i & out_mask)] = make_float2(re, imv);
 }
 
+// Tiled form of resamp_ring_to_ring_ccf_kernel for M >= L (a decimating rational resampler, gr_demod_mmdvm_multi2's 24 / 25): a CTA takes
+// 256 consecutive outputs, stages the input span they touch (256 M / L + NT items) and the arm table in shared memory once, and every
+// thread walks its NT taps over shared memory with the loop fully unrolled (independent loads in flight instead of one L1 round trip
+// per tap).  Same taps, same order (oldest first) as the generic kernel: bit-identical.
+template <int NT>
+__global__ void __launch_bounds__(256)
+resamp_ring_to_ring_tiled_kernel(const float2* __restrict__ in_ring, unsigned in_mask, long long in_stride,
+                                 const float* __restrict__ arms /* [L][NT] */, int L, int M, long long o0, long long o1,
+                                 float2* __restrict__ out_ring, unsigned out_mask, long long out_stride, int span_cap)
+{
+    extern __shared__ float sm_rt[];
+    float* hs = sm_rt;                                               // L * NT
+    float2* xs = reinterpret_cast<float2*>(sm_rt + ((L * NT + 1) & ~1));
+    const int c = blockIdx.y;
+    const long long ob = o0 + static_cast<long long>(blockIdx.x) * 256;
+    if (ob >= o1) return;
+    const long long oe = ob + 256 < o1 ? ob + 256 : o1;
+    const long long first = (ob * M) / L - (NT - 1), last = ((oe - 1) * M) / L;      // input span of this CTA
+    const int span = static_cast<int>(last - first + 1);
+    for (int i = threadIdx.x; i < L * NT; i += 256) hs[i] = arms[i];
+    const float2* x = in_ring + static_cast<long long>(c) * in_stride;
+    for (int i = threadIdx.x; i < span && i < span_cap; i += 256) {
+        const long long a = first + i;
+        xs[i] = a >= 0 ? x[a & in_mask] : make_float2(0.0f, 0.0f);
+    }
+    __syncthreads();
+    const long long o = ob + threadIdx.x;
+    if (o >= oe) return;
+    const long long im = o * M, newest = im / L;
+    const float* h = hs + static_cast<int>(im - newest * L) * NT;
+    const float2* w = xs + static_cast<int>(newest - first);          // newest item of this output
+    float re = 0.0f, imv = 0.0f;
+#pragma unroll
+    for (int k = NT - 1; k >= 0; k--) { const float2 v = w[-k]; re = fmaf(h[k], v.x, re); imv = fmaf(h[k], v.y, imv); }
+    out_ring[static_cast<long long>(c) * out_stride + (o & out_mask)] = make_float2(re, imv);
+}
+
 // ================================================================================================
 // Analog modulators (gr_mod_nbfm.cpp:26-75, gr_mod_ssb.cpp:28-82): 8 ksps float audio in.  One CTA per channel runs
 // the low-rate front part; the FM scan / IF filters / final interpolator reuse the digital TX kernels.

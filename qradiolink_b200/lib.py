@@ -56,7 +56,7 @@ SYMBOLS = {
     "qrl_tx_launch_count": (_l, [_vp]),
     "qrl_tx_profile": (_i, [_vp, _i]),
     "qrl_tx_zero_samples": (_i, [_vp, _i, C.c_longlong, _l]),
-    "qrl_mmdvm_rx_create": (_i, [_i, _vp, _i, _i, _l, _i, _vp]),
+    "qrl_mmdvm_rx_create": (_i, [_i, _i, _vp, _i, _i, _l, _i, _vp]),
     "qrl_mmdvm_rx_destroy": (_i, [_vp]),
     "qrl_mmdvm_rx_set_stream": (_i, [_vp, _vp]),
     "qrl_mmdvm_rx_calibrate_rssi": (_i, [_vp, C.c_float]),
@@ -65,7 +65,7 @@ SYMBOLS = {
     "qrl_mmdvm_rx_out_device": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qrl_mmdvm_rx_read": (_i, [_vp, _vp, _l, _vp, _l, _vp, _vp]),
     "qrl_mmdvm_rx_launch_count": (_l, [_vp]),
-    "qrl_mmdvm_tx_create": (_i, [_i, _vp, _i, _i, _l, _i, _vp]),
+    "qrl_mmdvm_tx_create": (_i, [_i, _i, _vp, _i, _i, _l, _i, _vp]),
     "qrl_mmdvm_tx_destroy": (_i, [_vp]),
     "qrl_mmdvm_tx_set_stream": (_i, [_vp, _vp]),
     "qrl_mmdvm_tx_set_bb_gain": (_i, [_vp, C.c_float]),

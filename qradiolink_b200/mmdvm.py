@@ -25,14 +25,15 @@ def _low_pass_2(L, gain, fs, fc, tw, att):
 class MmdvmChannelsRx:
     """The per-channel part alone (qrl_mmdvm_rx_*): rows of a [n_rows][stride] gr_complex slab at 25 ksps -> int16 at 24 ksps + RSSI."""
 
-    def __init__(self, n_channels, rows=None, n_rows=None, filter_width=5000, max_in=1 << 16, device=0):
+    def __init__(self, n_channels, rows=None, n_rows=None, filter_width=5000, max_in=1 << 16, device=0, single=False):
+        """single=True: make_gr_demod_mmdvm (gr_demod_mmdvm.cpp:30-64) for n_channels independent 250 ksps streams."""
         self._L = load_library()
         self.n_channels = int(n_channels)
         self.n_rows = int(n_rows if n_rows is not None else n_channels)
         self.max_in = int(max_in)
         r = None if rows is None else np.ascontiguousarray(rows, np.int32)
         self._h = C.c_void_p()
-        rc = self._L.qrl_mmdvm_rx_create(self.n_channels, None if r is None else r.ctypes.data_as(C.c_void_p), self.n_rows, int(filter_width),
+        rc = self._L.qrl_mmdvm_rx_create(int(bool(single)), self.n_channels, None if r is None else r.ctypes.data_as(C.c_void_p), self.n_rows, int(filter_width),
                                          self.max_in, device, C.byref(self._h))
         if rc != 0:
             raise QrlError("qrl_mmdvm_rx_create failed (%d): %s" % (rc, (self._L.qrl_last_error(None) or b"").decode()))
@@ -85,14 +86,15 @@ class MmdvmChannelsRx:
 class MmdvmChannelsTx:
     """The per-channel part alone (qrl_mmdvm_tx_*): int16 [n_channels][n] at 24 ksps -> rows of a [n_rows][stride] slab at 25 ksps."""
 
-    def __init__(self, n_channels, rows=None, n_rows=None, filter_width=5000, max_in=1 << 16, device=0):
+    def __init__(self, n_channels, rows=None, n_rows=None, filter_width=5000, max_in=1 << 16, device=0, single=False):
+        """single=True: make_gr_mod_mmdvm (gr_mod_mmdvm.cpp:28-70) for n_channels independent streams, 250 ksps out."""
         self._L = load_library()
         self.n_channels = int(n_channels)
         self.n_rows = int(n_rows if n_rows is not None else n_channels)
         self.max_in = int(max_in)
         r = None if rows is None else np.ascontiguousarray(rows, np.int32)
         self._h = C.c_void_p()
-        rc = self._L.qrl_mmdvm_tx_create(self.n_channels, None if r is None else r.ctypes.data_as(C.c_void_p), self.n_rows, int(filter_width),
+        rc = self._L.qrl_mmdvm_tx_create(int(bool(single)), self.n_channels, None if r is None else r.ctypes.data_as(C.c_void_p), self.n_rows, int(filter_width),
                                          self.max_in, device, C.byref(self._h))
         if rc != 0:
             raise QrlError("qrl_mmdvm_tx_create failed (%d): %s" % (rc, (self._L.qrl_last_error(None) or b"").decode()))

@@ -127,3 +127,35 @@ def test_modulator_to_demodulator_loop_back(qrl):
         coef, *_ = np.linalg.lstsq(A, seg, rcond=None)
         assert abs(np.hypot(coef[0], coef[1]) - 4000) < 60, (c, coef)
         assert np.sqrt(np.mean((seg - A @ coef) ** 2)) < 120, c
+
+
+def test_single_channel_mmdvm_blocks(qrl, oracle):
+    """gr_mod_mmdvm / gr_demod_mmdvm (gr_mod_mmdvm.cpp:28-70, gr_demod_mmdvm.cpp:30-64; 250 ksps, x125/12 and x12/125, bb_gain in front of the
+    resampler, RSSI tags in front of the channel filter, 10 kHz discriminator) for a batch of independent streams, ragged calls."""
+    C, n = 3, 9000
+    rng = np.random.default_rng(9700)
+    t = np.arange(n)
+    S = np.stack([(5000 * np.sin(2 * np.pi * (400 + 210 * c) * t / 24000) + rng.integers(-200, 200, n)).astype(np.int16) for c in range(C)])
+    tx = qrl.MmdvmChannelsTx(C, filter_width=5000, max_in=5000, single=True)
+    tx.set_bb_gain(0.7)
+    parts, lo = [], 0
+    for m in (1, 11, 12, 5000, 3976):
+        parts.append(tx.work(S[:, lo:lo + m])); lo += m
+    iq = np.concatenate(parts, 1)
+    assert iq.shape == (C, n * 125 // 12)
+    for c in range(C):
+        o = oracle.MmdvmTx(5000, single=True); o.set_bb_gain(0.7)
+        assert np.array_equal(iq[c].view(np.uint32), o.work(S[c]).view(np.uint32)), c
+    rx = qrl.MmdvmChannelsRx(C, filter_width=5000, max_in=40000, single=True)
+    rx.calibrate_rssi(3.0)
+    outs, dbs, ats, lo = [], [], [], 0
+    for m in (1, 124, 125, 40000, 20000, 33500):
+        o, db, at = rx.work(iq[:, lo:lo + m]); lo += m
+        outs.append(o); dbs.append(db); ats.append(at)
+    assert lo == iq.shape[1]
+    got, gdb, gat = np.concatenate(outs, 1), np.concatenate(dbs, 1), np.concatenate(ats)
+    for c in range(C):
+        o = oracle.MmdvmRx(5000, single=True); o.calibrate_rssi(3.0)
+        want, wdb, wat = o.work(iq[c])
+        assert got.shape[1] == len(want) == n and np.array_equal(got[c], want), c
+        assert np.array_equal(gat, wat) and np.max(np.abs(gdb[c] - wdb)) < 2e-4, c

@@ -12,6 +12,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
+#include <cfenv>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -211,6 +212,21 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)
     return r;
 }
 static inline unsigned __viaddmin_u32(unsigned a, unsigned b, unsigned c) { const unsigned t = a + b; return t < c ? t : c; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline unsigned __brev(unsigned v)
+{
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1); v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4); v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+    return (v >> 16) | (v << 16);
+}
+static inline float __fadd_rd(float a, float b)
+{
+    const int old = std::fegetround(); std::fesetround(FE_DOWNWARD);
+    volatile float x = a, y = b; volatile float r = x + y;
+    std::fesetround(old);
+    return r;
+}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline void sincospif(float x, float* s, float* c) { *s = static_cast<float>(std::sin(3.14159265358979323846 * static_cast<double>(x))); *c = static_cast<float>(std::cos(3.14159265358979323846 * static_cast<double>(x))); }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }

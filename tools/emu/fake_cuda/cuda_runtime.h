@@ -71,21 +71,7 @@ static inline cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, int, c
 }
 
 // ---- device intrinsics beyond cuda_emu.hpp / qrl_tma_emu.hpp
-template <class T> static inline T __ldg(const T* p) { return *p; }
-static inline int __ffs(int v) { return __builtin_ffs(v); }
-static inline unsigned __brev(unsigned v)
-{
-    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1); v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
-    v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4); v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
-    return (v >> 16) | (v << 16);
-}
-static inline float __fadd_rd(float a, float b)
-{
-    const int old = std::fegetround(); std::fesetround(FE_DOWNWARD);
-    volatile float x = a, y = b; volatile float r = x + y;
-    std::fesetround(old);
-    return r;
-}
+// (__ldg, __ffs, __brev, __fadd_rd live in cuda_emu.hpp: the kernel-extraction harnesses need them too)
 static inline size_t __cvta_generic_to_shared(const void* p) { return qrl::smem_u32(p); }
 // CUDA's global min / max overloads
 static inline int min(int a, int b) { return a < b ? a : b; }

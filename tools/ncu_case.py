@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small fixed workloads for `ncu --set full` captures (one case per invocation, a couple of calls, no timing):
-   python tools/ncu_case.py {cfg2|qpsk|nbfm|tx|pfb|mmdvm|dsss|amtx} [channels] [log2 T]
+   python tools/ncu_case.py {cfg2|qpsk|nbfm|tx|pfb|spectrum|mmdvm|dsss|amtx} [channels] [log2 T]
 Inputs come from the product's own modulators on the GPU (or torch for the analog case), like bench.py."""
 import os
 import sys
@@ -75,6 +75,15 @@ def main():
         for _ in range(calls):
             sy.work_device(z.data_ptr(), N // M, N // M)
         sy.sync(); sy.close()
+    elif case == "spectrum":
+        S, N = 64, 32768
+        x = torch.view_as_complex(torch.randn((S, 2 * N, 2), device=dev) * 0.2)
+        sp = q.Spectrum(N, 5, n_streams=S, max_samples=2 * N)
+        sp.set_stream(stream.cuda_stream); sp.set_enabled(True)
+        for _ in range(calls):
+            sp.work_device(x.data_ptr(), N + 1, x.shape[1])
+            assert sp.get_fft_data() is not None
+        sp.close()
     elif case == "mmdvm":
         import ctypes as Ct
         N = 1 << 24
