@@ -14,6 +14,7 @@
 // catches, radiocontroller.cpp:1975-1984), work() never throws (returns WORK_DONE = -1 on a shim error).
 // INTEGRATION.md shows the 30-line gr::block adapter that wraps exactly this class inside GNU Radio.
 #pragma once
+#include <algorithm>
 #include <complex>
 #include <cstdint>
 #include <memory>
@@ -102,6 +103,36 @@ public:
     void flush() { std::lock_guard<std::mutex> guard(_mutex); _data.clear(); }
 private:
     std::vector<gr_complex> _data;
+    std::mutex _mutex;
+};
+
+class gr_sample_sink {      // src/gr/gr_sample_sink.cpp: time-domain display tap behind gr_demod_base::get_sample_data (gr_demod_base.cpp:988-1006)
+public:
+    int work(const gr_complex* in, int n)
+    {
+        std::lock_guard<std::mutex> guard(_mutex);
+        if (n < 1 || !_enabled) return n;
+        if (_data.size() > 524288) return n;                  // gr_sample_sink.cpp:77-82
+        _data.insert(_data.end(), in, in + n);
+        return n;
+    }
+    std::vector<gr_complex>* get_data()
+    {
+        std::lock_guard<std::mutex> guard(_mutex);
+        if (_data.size() < 2) return nullptr;
+        unsigned size = std::min(static_cast<unsigned>(_data.size()), _window_size);
+        if (size % 2 != 0) size = size - 1;
+        auto* d = new std::vector<gr_complex>(_data.begin(), _data.begin() + size);
+        _data.erase(_data.begin(), _data.begin() + size);
+        return d;
+    }
+    void set_sample_window(unsigned size) { std::lock_guard<std::mutex> guard(_mutex); if (size % 2 != 0) size = size + 1; _window_size = size; }
+    void set_enabled(bool v) { std::lock_guard<std::mutex> guard(_mutex); _enabled = v; }
+    void flush() { std::lock_guard<std::mutex> guard(_mutex); _data.clear(); }
+private:
+    std::vector<gr_complex> _data;
+    unsigned _window_size = 8096;
+    bool _enabled = false;
     std::mutex _mutex;
 };
 

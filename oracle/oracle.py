@@ -218,6 +218,12 @@ def ref_blocks():
         R.ref_rx_fft_work.argtypes = [vp, vp, C.c_int]
         R.ref_rx_fft_get.restype = C.c_uint
         R.ref_rx_fft_get.argtypes = [vp, vp]
+        R.ref_sample_sink_create.restype = vp
+        R.ref_sample_sink_set_enabled.argtypes = [vp, C.c_int]
+        R.ref_sample_sink_set_window.argtypes = [vp, C.c_uint]
+        R.ref_sample_sink_work.argtypes = [vp, vp, C.c_int]
+        R.ref_sample_sink_get.restype = C.c_long
+        R.ref_sample_sink_get.argtypes = [vp, vp, C.c_long]
         R.ref_rssi_tags.restype = C.c_long
         R.ref_rssi_tags.argtypes = [vp, C.c_long, C.c_float, vp, C.c_long, vp, vp, C.c_long]
         _REF = R

@@ -219,6 +219,28 @@ void ref_rx_fft_work(void* h, const float* in_c, int n)
 unsigned ref_rx_fft_get(void* h, float* points) { unsigned n = 0; as<rx_fft_c>(h)->get_fft_data(points, n); return n; }
 }
 
+// ---------------------------------------------------------------- gr_sample_sink (time-domain display tap: window, enable, 524288-item drop rule)
+#include "gr_sample_sink.h"
+extern "C" {
+void* ref_sample_sink_create() { return new Any{ make_gr_sample_sink() }; }
+void ref_sample_sink_set_enabled(void* h, int on) { as<gr_sample_sink>(h)->set_enabled(on != 0); }
+void ref_sample_sink_set_window(void* h, unsigned n) { as<gr_sample_sink>(h)->set_sample_window(n); }
+int ref_sample_sink_work(void* h, const float* in_c, int n)
+{
+    gr_vector_const_void_star iv = { in_c }; gr_vector_void_star ov;
+    return as<gr_sample_sink>(h)->work(n, iv, ov);
+}
+long ref_sample_sink_get(void* h, float* out_c, long cap)
+{
+    std::vector<gr_complex>* v = as<gr_sample_sink>(h)->get_data();
+    if (!v) return -1;
+    const long m = static_cast<long>(v->size());
+    for (long i = 0; i < m && i < cap; i++) { out_c[2 * i] = (*v)[i].real(); out_c[2 * i + 1] = (*v)[i].imag(); }
+    delete v;
+    return m;
+}
+}
+
 // ---------------------------------------------------------------- rssi_tag_block (an "RSSI" stream tag every 300 items)
 #include "rssi_tag_block.h"
 extern "C" long ref_rssi_tags(const float* in_c, long n, float cal, const long* chunks, long nchunks, float* db, long long* at, long cap)

@@ -305,3 +305,44 @@ class gr_const_sink:
                 return None
             d, self._data = self._data, np.zeros(0, np.complex64)
         return d
+
+
+class gr_sample_sink:
+    """src/gr/gr_sample_sink.cpp: time-domain display tap (gr_demod_base::get_sample_data, gr_demod_base.cpp:988-1006): disabled at
+    start; keeps samples until more than 524288 wait; get_data hands out at most `window` of them (even count), None below 2."""
+
+    def __init__(self):
+        self._data = np.zeros(0, np.complex64)
+        self._window = 8096
+        self._enabled = False
+        self._mutex = threading.Lock()
+
+    def flush(self):
+        with self._mutex:
+            self._data = np.zeros(0, np.complex64)
+
+    def set_sample_window(self, size):
+        with self._mutex:
+            self._window = int(size) + (int(size) % 2)
+
+    def set_enabled(self, value):
+        with self._mutex:
+            self._enabled = bool(value)
+
+    def work(self, items):
+        if len(items) < 1 or not self._enabled:
+            return len(items)
+        with self._mutex:
+            if len(self._data) > 524288:
+                return len(items)
+            self._data = np.concatenate([self._data, np.asarray(items, np.complex64)])
+        return len(items)
+
+    def get_data(self):
+        with self._mutex:
+            if len(self._data) < 2:
+                return None
+            size = min(len(self._data), self._window)
+            size -= size % 2
+            d, self._data = self._data[:size].copy(), self._data[size:]
+        return d

@@ -126,6 +126,36 @@ def test_sink_restatements_follow_the_reference_sinks(R, kind):
     R.ref_block_destroy(h)
 
 
+def test_sample_sink_restatement_follows_the_reference_sink(R):
+    """qradiolink_b200.demod.gr_sample_sink against the compiled gr_sample_sink.cpp: enable, window changes (odd sizes), the 524288-item
+    drop rule, random schedules."""
+    import importlib
+    demod = importlib.import_module("qradiolink_b200.demod")
+    rng = np.random.default_rng(34)
+    mine = demod.gr_sample_sink()
+    h = R.ref_sample_sink_create()
+    out = np.zeros(1 << 20, np.complex64)
+    for step in range(300):
+        r = rng.random()
+        if step == 5:
+            R.ref_sample_sink_set_enabled(h, 1); mine.set_enabled(True)
+        if r < 0.55:
+            n = int(rng.integers(0, 200000))
+            x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+            assert R.ref_sample_sink_work(h, _p(x), n) == mine.work(x)
+        elif r < 0.65:
+            w = int(rng.integers(1, 30000))
+            R.ref_sample_sink_set_window(h, w); mine.set_sample_window(w)
+        else:
+            k = R.ref_sample_sink_get(h, _p(out), len(out))
+            m = mine.get_data()
+            if k < 0:
+                assert m is None
+            else:
+                assert m is not None and len(m) == k and np.array_equal(out[:k], m)
+    R.ref_block_destroy(h)
+
+
 def test_zero_idle_bursts_is_the_reference_block(R):
     """gr_zero_idle_bursts.cpp compiled unmodified (stream tags through the stand-in's get_tags_in_window): delay of history-1 items,
     a counter loaded `delay` items before the tagged one, later tags overriding a running count.  Tags are kept at least `delay`
