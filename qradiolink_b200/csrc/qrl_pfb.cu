@@ -84,7 +84,12 @@ pfb_chan_kernel(const float* __restrict__ bt /*[M][TPF]*/, const float* __restri
     __syncthreads();
     // ---- stage A
     {
-        const int k = tid % M, q = tid / M;
+        // thread -> (branch k, output group q).  The LDS.64 below touch float2 index R M q + (M - 1 - k) + const: a half-warp (16 consecutive
+        // tids) is conflict-free when those are distinct mod 16.  With q = tid / M the group stride R M = 90 = 10 (mod 16) collides with
+        // the k run of the neighbouring group (2-way conflicts on every load, ncu r02_b: 4 wavefronts instead of 2); visiting the groups
+        // in the order 7 q' makes the stride 630 = 6 = -10 (mod 16), i.e. the index is 9 - tid (mod 16): distinct for any 16 consecutive tids.
+        const int k = tid % M, qlin = tid / M;
+        const int q = (M == 10 && R == 9 && G == 32) ? ((7 * qlin) & 31) : qlin;
         float h[TPF];
 #pragma unroll
         for (int t = 0; t < TPF; t++) h[t] = bt[k * TPF + t];
