@@ -2441,11 +2441,11 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
             h->prof_end(pe);
             CK(cudaEventRecord(h->ev_shape[j], h->s_shape));
             CK(cudaStreamWaitEvent(h->stream, h->ev_shape[j], 0));
-            constexpr int L = 20, NT = 35, R = 8, G = 16, TPC = 4;
+            constexpr int L = 20, NT = 35, R = 8, G = 16;
             const long long m0 = symA * h->L1, m1 = (symA + nsym_j) * h->L1;
-            dim3 g(static_cast<unsigned>((m1 - m0 + R * G * TPC - 1) / (R * G * TPC)), h->C);
+            dim3 g(static_cast<unsigned>((m1 - m0 + R * G - 1) / (R * G)), h->C);
             pe = h->prof_begin(2, h->stream);
-            interp_fir_ccf_rt_kernel<L, NT, R, G, TPC><<<g, L * G, 0, h->stream>>>(
+            interp_fir_ccf_rt_kernel<L, NT, R, G><<<g, L * G, 0, h->stream>>>(
                 h->d_if, h->if_mask, h->if_stride, m0, m1, h->d_arms2, 1.0f, 1.0f, 0, h->d_out, h->out_stride, out_base);
             h->prof_end(pe);
             h->launches += 3;
@@ -2548,9 +2548,9 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
         h->launches++;
         const long long m0 = sym0 * h->L1, m1 = (sym0 + nsym) * h->L1;
         if (h->L2 == 20 && h->nt2 == 35) {
-            constexpr int L = 20, NT = 35, R = 8, G = 16, TPC = 4;
-            dim3 g(static_cast<unsigned>((m1 - m0 + R * G * TPC - 1) / (R * G * TPC)), h->C);
-            interp_fir_ccf_rt_kernel<L, NT, R, G, TPC><<<g, L * G, 0, h->stream>>>(
+            constexpr int L = 20, NT = 35, R = 8, G = 16;
+            dim3 g(static_cast<unsigned>((m1 - m0 + R * G - 1) / (R * G)), h->C);
+            interp_fir_ccf_rt_kernel<L, NT, R, G><<<g, L * G, 0, h->stream>>>(
                 h->d_if, h->if_mask, h->if_stride, m0, m1, h->d_arms2, 1.0f, 1.0f, 0, h->d_out, h->out_stride, m0 * L);
             h->launches++;
         } else {

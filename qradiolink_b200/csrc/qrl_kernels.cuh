@@ -2679,62 +2679,50 @@ interp_fir_ccf_kernel(const float2* __restrict__ in_ring, unsigned in_mask, long
 // at once.  Each input sample is loaded once (a broadcast LDS: the lanes of a group read the same address) and feeds
 // R accumulators, so consecutive FFMAs share an operand (register reuse) instead of streaming 2 new operands each:
 // 2 NT FFMA per output as before, about twice the FP32 issue rate.  Same accumulation order (oldest sample first).
-template <int L, int NT, int R, int G, int TPC = 1>
-__global__ void __launch_bounds__(L * G, 4)
+// (round 2 experiment, profiles/README.md: several tiles per CTA with a double-buffered window measured 8 % SLOWER on B200 -- 131.6 vs
+// 121.9 us per launch, the window fill competes with the FFMA stream for the LSU -- and keeping the taps resident across tiles costs
+// an occupancy step (64 registers); the one-tile form below stays)
+template <int L, int NT, int R, int G>
+__global__ void __launch_bounds__(L * G)
 interp_fir_ccf_rt_kernel(const float2* __restrict__ in_ring, unsigned in_mask, long long in_stride, long long m0, long long m1,
                          const float* __restrict__ arms /* [L][NT] */, float post_gain1, float post_gain2, int apply_gain,
                          float2* __restrict__ out, long long out_stride, long long out_base)
 {
-    // TPC consecutive tiles per CTA, the input window double-buffered: the fill of tile t+1 is issued before the FFMAs of tile t, so the
-    // one barrier per tile no longer waits for global loads
     constexpr int TM = G * R;
-    __shared__ float2 xs[2][TM + NT];
+    __shared__ float2 xs[TM + NT];
     const int c = blockIdx.y;
-    const long long cta0 = m0 + static_cast<long long>(blockIdx.x) * TM * TPC;
-    if (cta0 >= m1) return;
+    const long long tile0 = m0 + static_cast<long long>(blockIdx.x) * TM;
+    if (tile0 >= m1) return;
     const float2* x = in_ring + static_cast<long long>(c) * in_stride;
-    auto fill = [&](int b, long long tile0) {
-        for (int i = threadIdx.x; i < TM + NT - 1; i += L * G) {
-            const long long m = tile0 - (NT - 1) + i;
-            xs[b][i] = (m < m1) ? x[m & in_mask] : make_float2(0.0f, 0.0f);
-        }
-    };
-    fill(0, cta0);
-    const int p = threadIdx.x % L, q = threadIdx.x / L;
-    const float* hp = arms + p * NT;
-    // 32-bit bookkeeping inside the tile loop: outputs left in this CTA's span, one running output pointer
-    const long long span = m1 - cta0;
-    int left = static_cast<int>(span < static_cast<long long>(TM) * TPC ? span : static_cast<long long>(TM) * TPC) - q * R;      // outputs m with index >= q R
-    float2* optr = out + static_cast<long long>(c) * out_stride + ((cta0 + q * R) * L + p - out_base);
+    for (int i = threadIdx.x; i < TM + NT - 1; i += L * G) {
+        const long long m = tile0 - (NT - 1) + i;
+        xs[i] = (m < m1) ? x[m & in_mask] : make_float2(0.0f, 0.0f);
+    }
     __syncthreads();
-#pragma unroll 1
-    for (int t = 0; t < TPC; t++) {
-        if (t * TM >= static_cast<int>(span < static_cast<long long>(TM) * TPC ? span : static_cast<long long>(TM) * TPC)) break;
-        if (TPC > 1 && t + 1 < TPC) fill((t + 1) & 1, cta0 + static_cast<long long>(t + 1) * TM);
-        float h[NT];                                                // re-read per tile (L1 hits, each tap is live for R steps only): keeping
-#pragma unroll                                                      // all NT in registers across tiles costs occupancy (64 registers, spills at 48)
-        for (int k = 0; k < NT; k++) h[k] = __ldg(hp + k);
-        float2 acc[R];                                              // (re, im) pairs: one FFMA2 per tap and output
+    const int p = threadIdx.x % L, q = threadIdx.x / L;
+    float h[NT];
 #pragma unroll
-        for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f);
-        const float2* s = xs[t & 1] + q * R;                        // s[j] = x[tile0 + qR - (NT-1) + j]
+    for (int k = 0; k < NT; k++) h[k] = arms[p * NT + k];
+    float2 acc[R];                                              // (re, im) pairs: one FFMA2 per tap and output
 #pragma unroll
-        for (int j = 0; j < R + NT - 1; j++) {
-            const float2 v = s[j];
+    for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f);
+    const float2* s = xs + q * R;                               // s[j] = x[tile0 + qR - (NT-1) + j]
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int k = r + NT - 1 - j;                       // output m = tile0 + qR + r uses x[m - k]
-                if (k >= 0 && k < NT) ffma2(acc[r], h[k], v);
-            }
-        }
+    for (int j = 0; j < R + NT - 1; j++) {
+        const float2 v = s[j];
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            float re = acc[r].x, im = acc[r].y;
-            if (apply_gain) { re = re * post_gain1; im = im * post_gain1; re = re * post_gain2; im = im * post_gain2; }
-            if (r < left) optr[r * L] = make_float2(re, im);
+            const int k = r + NT - 1 - j;                       // output m = tile0 + qR + r uses x[m - k]
+            if (k >= 0 && k < NT) ffma2(acc[r], h[k], v);
         }
-        optr += TM * L; left -= TM;
-        if (TPC > 1) __syncthreads();                               // tile t+1's window is complete; tile t's may be overwritten next round
+    }
+    float2* oc = out + static_cast<long long>(c) * out_stride;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        float re = acc[r].x, im = acc[r].y;
+        if (apply_gain) { re = re * post_gain1; im = im * post_gain1; re = re * post_gain2; im = im * post_gain2; }
+        const long long m = tile0 + q * R + r;
+        if (m < m1) oc[(m * L + p) - out_base] = make_float2(re, im);
     }
 }
 

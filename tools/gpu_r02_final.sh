@@ -13,7 +13,7 @@ echo "reference arm exit $?" | tee -a "$OUT/summary.txt"
 timeout 1200 python bench.py --steps 20 --warmup 5 > "$OUT/3_bench.json" 2> "$OUT/3_bench.err"
 echo "bench exit $?" | tee -a "$OUT/summary.txt"
 tail -3 "$OUT/3_bench.err" | tee -a "$OUT/summary.txt"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$OUT/4_launches_step.csv" \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"fir_|symsync|viterbi|qdemod|hist_|frontend" -c 3000 --csv --log-file "$OUT/4_launches_step.csv" \
     python bench.py --steps 2 --warmup 3 --headline-only --no-cpu --no-parity > "$OUT/4_launches_step.log" 2>&1
 echo "launch list exit $?" | tee -a "$OUT/summary.txt"
 NCU="ncu --set full --clock-control none --import-source on -f"
