@@ -139,6 +139,8 @@ struct qrl_rx : HandleBase {
     // PSK chains: agc2 + costas "PLL" loop stage (per sample), output ring r3 (interleaved)
     AgcCostasParams acp{};
     AgcCostasState* d_ac = nullptr;
+    // NBFM: de-emphasis recurrence in its own kernel on s_loop2 (overlaps the next slice's squelch recurrence)
+    NbfmDeemphState* d_nb2 = nullptr; Ring raud; bool nbfm_split = false;
     // gr_demod_dsss: one chain kernel behind stage 1 (dsss_chain_kernel)
     DsssParams dsp{}; DsssState* d_ds = nullptr; float* d_ds_arms = nullptr; float2* d_ds_taps = nullptr;
     Ring ds_a, ds_c, ds_d; long long ds_o_call0 = 0;
@@ -840,6 +842,12 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = make_ring(h, &h->rd, sizeof(float), h->n1max + nt_arm + 16))) return fail(rc);
         if ((rc = make_ring(h, &h->rr, sizeof(float), h->n1max * 2 / 5 + h->nbp.nt_audio + 16))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_nb, h->C))) return fail(rc);
+        if (kind == QRL_DEMOD_NBFM && !getenv("QRL_NBFM_NO_SPLIT")) {
+            if ((rc = make_ring(h, &h->raud, sizeof(float), h->n1max * 2 / 5 + 64))) return fail(rc);
+            if ((rc = dev_alloc(h, &h->d_nb2, h->C))) return fail(rc);
+            h->zero_list.emplace_back(h->d_nb2, sizeof(NbfmDeemphState) * h->C);
+            h->nbfm_split = true;
+        }
     } else if (kind == QRL_DEMOD_DSSS) {
         const long long n5 = h->n1max * 13 / 50 + 8;
         if ((rc = make_ring(h, &h->ds_a, sizeof(float2), n5 + 2048))) return fail(rc);
@@ -1419,9 +1427,20 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
                 static_cast<float2*>(h->rg.d), h->rg.mask, h->rg.stride,
                 static_cast<float*>(h->rd.d), h->rd.mask, h->rd.stride,
                 static_cast<float*>(h->rr.d), h->rr.mask, h->rr.stride,
-                h->d_arm_taps, h->d_audio_taps, h->d_port1f, 2 * h->port1_cap, h->d_port1_cnt, static_cast<int>(2 * h->port1_cap));
+                h->d_arm_taps, h->d_audio_taps, h->d_port1f, 2 * h->port1_cap, h->d_port1_cnt, static_cast<int>(2 * h->port1_cap),
+                h->nbfm_split ? static_cast<float*>(h->raud.d) : nullptr, h->raud.mask, h->raud.stride, h->nbfm_split ? nsoft_i : nullptr);
             h->launches++;
             h->prof_end(pe);
+            if (h->nbfm_split) {
+                CK(cudaEventRecord(h->ev_b[i], h->s_loop));
+                CK(cudaStreamWaitEvent(h->s_loop2, h->ev_b[i], 0));
+                pe = h->prof_begin(5, h->s_loop2);
+                nbfm_deemph_kernel<<<h->C, 128, 0, h->s_loop2>>>(h->nbp.b0, h->nbp.b1, h->nbp.a1, h->nbp.out_gain, h->d_nb2,
+                    static_cast<const float*>(h->raud.d), h->raud.mask, h->raud.stride, nsoft_i,
+                    h->d_port1f, 2 * h->port1_cap, h->d_port1_cnt, static_cast<int>(2 * h->port1_cap));
+                h->launches++;
+                h->prof_end(pe);
+            }
             continue;
         }
         if (h->kind == QRL_DEMOD_2FSK || h->kind == QRL_DEMOD_BPSK) {

@@ -1948,7 +1948,11 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
                   float* __restrict__ res_ring, unsigned res_mask, long long res_stride,
                   const float* __restrict__ arm_taps,           // [2][nt_arm]
                   const float* __restrict__ audio_taps,
-                  float* __restrict__ port1, long long port1_stride, int* __restrict__ port1_cnt, int port1_cap)
+                  float* __restrict__ port1, long long port1_stride, int* __restrict__ port1_cnt, int port1_cap,
+                  // NBFM (mode 0) only: when given, the audio filter's output goes to this ring and the de-emphasis runs in
+                  // nbfm_deemph_kernel on another stream (its recurrence then overlaps the next slice's squelch recurrence);
+                  // aud_snap[c] = audio items produced so far
+                  float* __restrict__ aud_ring = nullptr, unsigned aud_mask = 0, long long aud_stride = 0, long long* __restrict__ aud_snap = nullptr)
 {
     const int c = blockIdx.x;
     __shared__ NbfmState st;
@@ -2136,10 +2140,13 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
                 acc = fmaf(audio_taps[k], v, acc);
             }
             aud[j] = acc;
+            if (aud_ring && p.mode == 0) aud_ring[static_cast<long long>(c) * aud_stride + (a & aud_mask)] = acc;
         }
         __syncthreads();
         // ---- 5. de-emphasis IIR (double) + output gain (sequential)
-        if (p.mode == 1) {
+        if (aud_ring && p.mode == 0) {
+            // split form: nbfm_deemph_kernel does it
+        } else if (p.mode == 1) {
             const int cnt0 = port1_cnt[c];
             float* o = port1 + static_cast<long long>(c) * port1_stride;
             for (int j = threadIdx.x; j < nb; j += blockDim.x) if (cnt0 + j < port1_cap) o[cnt0 + j] = aud[j];
@@ -2163,7 +2170,47 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
         __syncthreads();
     }
     __syncthreads();      // (nothing new: no barrier above) every thread has read st.n_aud
-    if (threadIdx.x == 0) { st.n_res = res1; st.n_aud = res1; states[c] = st; }
+    if (threadIdx.x == 0) { st.n_res = res1; st.n_aud = res1; states[c] = st; if (aud_snap) aud_snap[c] = res1; }
+}
+
+// The de-emphasis recurrence of the NBFM chain (iir_filter_ffd, double: two dependent FP64 operations per audio item) in a kernel of
+// its own: launched on a second stream behind the slice's nbfm_audio_kernel, it runs while the NEXT slice's squelch recurrence does.
+// One CTA per channel; the audio items are staged through shared memory so the recurrence never waits on a global load.
+struct NbfmDeemphState { double iir_x1, iir_y1; long long n_done; };
+__global__ void __launch_bounds__(128)
+nbfm_deemph_kernel(double b0, double b1, double a1, float out_gain, NbfmDeemphState* __restrict__ states,
+                   const float* __restrict__ aud_ring, unsigned aud_mask, long long aud_stride, const long long* __restrict__ aud_snap,
+                   float* __restrict__ port1, long long port1_stride, int* __restrict__ port1_cnt, int port1_cap)
+{
+    const int c = blockIdx.x;
+    __shared__ float aud[2048];
+    __shared__ NbfmDeemphState st;
+    if (threadIdx.x == 0) st = states[c];
+    __syncthreads();
+    const long long a0 = st.n_done, a1n = aud_snap[c];
+    const float* ar = aud_ring + static_cast<long long>(c) * aud_stride;
+    float* o = port1 + static_cast<long long>(c) * port1_stride;
+    for (long long base = a0; base < a1n; base += 2048) {
+        const int nb = (a1n - base) < 2048 ? static_cast<int>(a1n - base) : 2048;
+        for (int j = threadIdx.x; j < nb; j += blockDim.x) aud[j] = ar[(base + j) & aud_mask];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double x1 = st.iir_x1, y1 = st.iir_y1;
+            int cnt = port1_cnt[c];
+            for (int j = 0; j < nb; j++) {
+                const double xin = static_cast<double>(aud[j]);
+                double acc = b0 * xin;
+                acc = acc + b1 * x1;
+                acc = acc - a1 * y1;
+                x1 = xin; y1 = acc;
+                if (cnt < port1_cap) o[cnt] = static_cast<float>(acc) * out_gain;
+                cnt++;
+            }
+            st.iir_x1 = x1; st.iir_y1 = y1; port1_cnt[c] = cnt;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { st.n_done = a1n > a0 ? a1n : a0; states[c] = st; }
 }
 
 // complex stream, COMPLEX taps (fft_filter_ccc restated in direct form), optional input gain (multiply_const_cc in front)
