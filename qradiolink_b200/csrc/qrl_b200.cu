@@ -842,7 +842,10 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = make_ring(h, &h->rd, sizeof(float), h->n1max + nt_arm + 16))) return fail(rc);
         if ((rc = make_ring(h, &h->rr, sizeof(float), h->n1max * 2 / 5 + h->nbp.nt_audio + 16))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_nb, h->C))) return fail(rc);
-        if (kind == QRL_DEMOD_NBFM && !getenv("QRL_NBFM_NO_SPLIT")) {
+        // (an FP64 instruction occupies an SM's FP64 pipe for ~64 cycles whatever its lane count, so two recurrences only overlap on
+        // DIFFERENT SMs: both kernels then ask for more than half an SM's shared memory, which keeps their CTAs one per SM and apart, and
+        // the split is used while 2 C CTAs fit the machine)
+        if (kind == QRL_DEMOD_NBFM && 2 * h->C <= 140 && !getenv("QRL_NBFM_NO_SPLIT")) {
             if ((rc = make_ring(h, &h->raud, sizeof(float), h->n1max * 2 / 5 + 64))) return fail(rc);
             if ((rc = dev_alloc(h, &h->d_nb2, h->C))) return fail(rc);
             h->zero_list.emplace_back(h->d_nb2, sizeof(NbfmDeemphState) * h->C);
@@ -929,13 +932,13 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         // analog blocks: one CTA per channel whose thread 0 runs the double-precision recurrences (squelch power, de-emphasis): they want
         // an SM (its FP64 pipe) each, up to half the machine
         const bool analog_kind = kind == QRL_DEMOD_NBFM || kind == QRL_DEMOD_SSB || kind == QRL_DEMOD_AM || kind == QRL_DEMOD_WBFM;
-        const int big_ctas = (kind == QRL_DEMOD_QPSK) ? 2 * groups : (analog_kind ? std::min(h->C, 44) : groups);
+        const int big_ctas = (kind == QRL_DEMOD_QPSK) ? 2 * groups : (analog_kind ? (h->nbfm_split ? 2 * h->C : std::min(h->C, 44)) : groups);
         unsigned loop_sms = static_cast<unsigned>(std::min(48, 8 * ((big_ctas + 4 + 7) / 8)));
         if (const char* e = getenv("QRL_LOOP_SMS")) { int v = atoi(e); if (v >= 8 && v <= 64) loop_sms = static_cast<unsigned>(v); }
         // Many channels (more loop CTAs than a 48-SM partition holds one per SM): the loop kernels have enough warps in flight to
         // hide their own latency, a private partition would only serialise them.  They then run with small windows (several CTAs
         // per SM) on all SMs, next to the parallel stages, on priority streams.
-        h->many = big_ctas > 48 || (analog_kind && h->C > 64);
+        h->many = big_ctas > 44 || (analog_kind && h->C > 64);
         if (const char* e = getenv("QRL_MANY_CHANNELS")) h->many = e[0] == '1';
         if (h->many || !make_sm_partition(h, loop_sms, hi)) {
             h->s_par = nullptr; h->sm_loop = 0; h->sm_par = 0;
@@ -1422,7 +1425,16 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
             CK(cudaEventRecord(h->ev_a[i], sp));
             CK(cudaStreamWaitEvent(h->s_loop, h->ev_a[i], 0));
             pe = h->prof_begin(3, h->s_loop);
-            nbfm_audio_kernel<<<h->C, 128, 0, h->s_loop>>>(h->nbp, h->d_nb,
+            const size_t fat = h->nbfm_split ? 120 * 1024 : 0;       // one CTA per SM, and never next to a de-emphasis CTA
+            if (h->nbfm_split) {
+                static bool f_attr[16] = { false };
+                if (!f_attr[h->device & 15]) {
+                    CK(cudaFuncSetAttribute(nbfm_audio_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+                    CK(cudaFuncSetAttribute(nbfm_deemph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+                    f_attr[h->device & 15] = true;
+                }
+            }
+            nbfm_audio_kernel<<<h->C, 128, fat, h->s_loop>>>(h->nbp, h->d_nb,
                 static_cast<const float2*>(h->r2.d), h->r2.mask, h->r2.stride, k1, h->d_env,
                 static_cast<float2*>(h->rg.d), h->rg.mask, h->rg.stride,
                 static_cast<float*>(h->rd.d), h->rd.mask, h->rd.stride,
@@ -1435,7 +1447,7 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
                 CK(cudaEventRecord(h->ev_b[i], h->s_loop));
                 CK(cudaStreamWaitEvent(h->s_loop2, h->ev_b[i], 0));
                 pe = h->prof_begin(5, h->s_loop2);
-                nbfm_deemph_kernel<<<h->C, 128, 0, h->s_loop2>>>(h->nbp.b0, h->nbp.b1, h->nbp.a1, h->nbp.out_gain, h->d_nb2,
+                nbfm_deemph_kernel<<<h->C, 128, fat, h->s_loop2>>>(h->nbp.b0, h->nbp.b1, h->nbp.a1, h->nbp.out_gain, h->d_nb2,
                     static_cast<const float*>(h->raud.d), h->raud.mask, h->raud.stride, nsoft_i,
                     h->d_port1f, 2 * h->port1_cap, h->d_port1_cnt, static_cast<int>(2 * h->port1_cap));
                 h->launches++;
