@@ -69,7 +69,9 @@ enum qrl_param {
                                          through qrl_tx_set_param: gr_mod_nbfm / _ssb / _am::set_filter_width (gr_mod_nbfm.cpp:78-93, gr_mod_ssb.cpp:85-100,
                                          gr_mod_am.cpp:75-85), mid-stream */
     QRL_PARAM_BB_GAIN = 4,            /* gr_mod_*::set_bb_gain */
-    QRL_PARAM_CTCSS = 7,              /* gr_demod_nbfm::set_ctcss (gr_demod_nbfm.cpp:97-121): 0 = no tone squelch (the only value built) */
+    QRL_PARAM_CTCSS = 7,              /* gr_demod_nbfm::set_ctcss (gr_demod_nbfm.cpp:97-121): 0 = no tone squelch; f = analog::ctcss_squelch_ff(8000, f, 0.01,
+                                         8000, 160, gate) in front of the audio filter (the audio stream shrinks while the tone is absent);
+                                         through qrl_tx_set_param: gr_mod_nbfm::set_ctcss (gr_mod_nbfm.cpp:101-139) */
     QRL_PARAM_AGC_ATTACK = 8,         /* gr_demod_ssb::set_agc_attack / gr_demod_am::set_agc_attack (gr_demod_ssb.cpp:108-111, gr_demod_am.cpp:94-97) */
     QRL_PARAM_AGC_DECAY = 9,          /* gr_demod_ssb::set_agc_decay / gr_demod_am::set_agc_decay */
     QRL_PARAM_GAIN = 10,              /* gr_demod_ssb::set_gain (gr_demod_ssb.cpp:118-121): the IF gain in front of the side-band filter */

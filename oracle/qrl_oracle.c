@@ -662,6 +662,75 @@ static void squelch_work(squelch_t* s, const float* x, size_t n, qvec* out)
         } else if (!s->gate) qv_pushc(out, 0.0f, 0.0f);
     }
 }
+/* analog::ctcss_squelch_ff (gr_demod_nbfm.cpp:60: make(8000, 88.5, 0.01, 8000, 160, true), switched in by set_ctcss(f != 0), :97-121).
+ * GNU Radio's own block (gr-analog ctcss_squelch_ff_impl.cc + gr-fft goertzel.cc, not in /root/reference: restated, parity unpinned):
+ * three Goertzel filters (float state) at the tone and its neighbours -- the adjacent entries of the standard CTCSS table, or
+ * -/+2 % for a non-standard or edge tone -- over blocks of `len` items; at the end of a block the three magnitudes (rounded down to
+ * 1e-5) decide: mute unless the tone's is at least `level` and not below either neighbour's; squelch_base_ff then gates / ramps. */
+static const float ctcss_tones[38] = { 67.0f, 71.9f, 74.4f, 77.0f, 79.7f, 82.5f, 85.4f, 88.5f, 91.5f, 94.8f, 97.4f, 100.0f, 103.5f, 107.2f,
+                                       110.9f, 114.8f, 118.8f, 123.0f, 127.3f, 131.8f, 136.5f, 141.3f, 146.2f, 151.4f, 156.7f, 162.2f, 167.9f,
+                                       173.8f, 179.9f, 186.2f, 192.8f, 203.5f, 210.7f, 218.1f, 225.7f, 233.6f, 241.8f, 250.3f };
+typedef struct { float wr, wi, d1, d2; int processed; } goertzel_t;
+static void goertzel_init(goertzel_t* g, int rate, float freq)
+{
+    const float w = (float)(2.0 * M_PI * freq / rate);
+    g->wr = (float)(2.0 * cosf(w)); g->wi = sinf(w); g->d1 = g->d2 = 0.0f; g->processed = 0;      /* std::cos / std::sin of a float */
+}
+static inline void goertzel_in(goertzel_t* g, float x)
+{
+    float y = x + g->wr * g->d1;
+    y = y - g->d2;
+    g->d2 = g->d1; g->d1 = y; g->processed++;
+}
+static inline float goertzel_mag(goertzel_t* g, int len)       /* |output()|, state reset */
+{
+    const float re = (float)((0.5 * g->wr * g->d1 - g->d2) / len), im = (g->wi * g->d1) / len;
+    g->d1 = g->d2 = 0.0f; g->processed = 0;
+    return (float)sqrt((double)re * re + (double)im * im);        /* std::abs(complex<float>) = hypotf */
+}
+typedef struct { int rate, len, ramp, ramped, state, gate, mute; float freq, level; double envelope; goertzel_t gl, gc, gr; } ctcss_t;
+static void ctcss_set_frequency(ctcss_t* s, float freq)
+{
+    int idx = -1;
+    for (int i = 0; i < 38; i++) if (ctcss_tones[i] == freq) idx = i;
+    const float fl = (idx == -1 || idx == 0) ? (float)(freq * 0.98) : ctcss_tones[idx - 1];
+    const float fr = (idx == -1 || idx == 37) ? (float)(freq * 1.02) : ctcss_tones[idx + 1];
+    s->freq = freq;
+    goertzel_init(&s->gl, s->rate, fl); goertzel_init(&s->gc, s->rate, freq); goertzel_init(&s->gr, s->rate, fr);
+}
+static void ctcss_init(ctcss_t* s, int rate, float freq, float level, int len, int ramp, int gate)
+{
+    memset(s, 0, sizeof *s);
+    s->rate = rate; s->level = level; s->len = len; s->ramp = ramp; s->gate = gate; s->mute = 1;
+    s->state = SQ_MUTED; s->envelope = ramp ? 0.0 : 1.0;
+    ctcss_set_frequency(s, freq);
+}
+static void ctcss_work(ctcss_t* s, const float* x, size_t n, qvec* out)
+{
+    for (size_t i = 0; i < n; i++) {
+        goertzel_in(&s->gl, x[i]); goertzel_in(&s->gc, x[i]); goertzel_in(&s->gr, x[i]);
+        if (s->gc.processed == s->len) {
+            const float rounder = 100000;
+            float ml = goertzel_mag(&s->gl, s->len), mc = goertzel_mag(&s->gc, s->len), mr = goertzel_mag(&s->gr, s->len);
+            ml = floorf(rounder * ml) / rounder; mc = floorf(rounder * mc) / rounder; mr = floorf(rounder * mr) / rounder;
+            s->mute = (mc < s->level || mc < ml || mc < mr);
+        }
+        switch (s->state) {
+        case SQ_MUTED: if (!s->mute) s->state = s->ramp ? SQ_ATTACK : SQ_UNMUTED; break;
+        case SQ_UNMUTED: if (s->mute) s->state = s->ramp ? SQ_DECAY : SQ_MUTED; break;
+        case SQ_ATTACK:
+            s->envelope = 0.5 - cos(M_PI * (++s->ramped) / s->ramp) / 2.0;
+            if (s->ramped >= s->ramp) { s->state = SQ_UNMUTED; s->envelope = 1.0; }
+            break;
+        case SQ_DECAY:
+            s->envelope = 0.5 - cos(M_PI * (--s->ramped) / s->ramp) / 2.0;
+            if (s->ramped == 0) s->state = SQ_MUTED;
+            break;
+        }
+        if (s->state != SQ_MUTED) qv_pushf(out, (float)((double)x[i] * s->envelope));
+        else if (!s->gate) qv_pushf(out, 0.0f);
+    }
+}
 /* filter::iir_filter_ffd, 2-tap ff / 2-tap fb, oldstyle=false (A6) */
 typedef struct { double b0, b1, a1; double x1, y1; } iir1_t;
 static void iir1_init(iir1_t* f, const double* b, const double* a) { f->b0 = b[0]; f->b1 = b[1]; f->a1 = a[1]; f->x1 = 0; f->y1 = 0; }
@@ -1184,6 +1253,8 @@ struct qo_rx {
     int filter_width, flag;
     /* bpsk / 2fsk */
     fll_t fll; crmm_t crmm; ccdec_t dec2; lfsr_t descr2; int dec2_started;
+    /* nbfm tone squelch */
+    ctcss_t ctcss; int ctcss_on;
     /* dsss */
     resamp_t resamp_if; dsssdec_t dsss; qvec s_dsss;
     /* front-end rotator (gr_demod_base.cpp:57,180,1220-1225): Q32 NCO, phase = base + inc * (n - n_base) */
@@ -1338,6 +1409,7 @@ qo_rx* qo_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filt
         resamp_init(&r->audio_filt, 1, 1, 1, T3, n3);
         qdemod_init(&r->qd, (float)(r->tsr / (4 * M_PI * filter_width)));
         squelch_init(&r->sq, -140, 0.01, 320, 1);
+        ctcss_init(&r->ctcss, 8000, 88.5f, 0.01f, 8000, 160, 1);                    /* gr_demod_nbfm.cpp:60 */
         r->port[1].isz = 4;
     } else if (kind == QO_DEMOD_WBFM) {
         /* /root/reference/src/gr/gr_demod_wbfm.cpp:28-70: /5 (low_pass(1, fs, 100k, 100k, BH)) -> low_pass_2(1, 200k, fw, 600, 90, BH)
@@ -1536,8 +1608,22 @@ int qo_rx_set_param(qo_rx* r, int key, double value)
     if (key == QO_PARAM_AGC_DECAY && (r->kind == QO_DEMOD_SSB || r->kind == QO_DEMOD_AM)) { r->agc.decay = (float)value; return 0; }
     if (key == QO_PARAM_GAIN && r->kind == QO_DEMOD_SSB) { r->if_gain = (float)value; return 0; }       /* _if_gain->set_k */
     if (key == QO_PARAM_CTCSS && r->kind == QO_DEMOD_NBFM && value == 0.0) {
-        int n3 = qo_firdes_low_pass_2(1, 8000, 3500, 200, 35, QO_WIN_BLACKMAN_HARRIS, T, 4096);
-        resamp_retap(&r->audio_filt, T, n3);
+        /* gr_demod_nbfm.cpp:99-111: the first disconnect throws when the tone squelch is not in the graph and the rest is skipped */
+        if (r->ctcss_on) {
+            int n3 = qo_firdes_low_pass_2(1, 8000, 3500, 200, 35, QO_WIN_BLACKMAN_HARRIS, T, 4096);
+            resamp_retap(&r->audio_filt, T, n3);
+            r->ctcss_on = 0;
+        }
+        return 0;
+    }
+    if (key == QO_PARAM_CTCSS && r->kind == QO_DEMOD_NBFM) {
+        /* :112-125: set_frequency always (new Goertzel filters, block state kept); graph and audio filter only on the first switch */
+        ctcss_set_frequency(&r->ctcss, (float)value);
+        if (!r->ctcss_on) {
+            int n3 = qo_firdes_band_pass_2(1, 8000, 300, 3500, 200, 35, QO_WIN_BLACKMAN_HARRIS, T, 4096);
+            resamp_retap(&r->audio_filt, T, n3);
+            r->ctcss_on = 1;
+        }
         return 0;
     }
     if (key == QO_PARAM_FILTER_WIDTH) {
@@ -1960,7 +2046,12 @@ int qo_rx_work(qo_rx* r, const float* iq, long T)
         r->s_tmp.n = 0; squelch_work(&r->sq, (const float*)r->s_filt.d, r->s_filt.n, &r->s_tmp);
         r->s_dem.n = 0; qdemod_work(&r->qd, (const float*)r->s_tmp.d, r->s_tmp.n, &r->s_dem);
         r->s_rrc.n = 0; resamp_work(&r->audio_rs, (const float*)r->s_dem.d, r->s_dem.n, &r->s_rrc);
-        r->s_sym.isz = 4; r->s_sym.n = 0; resamp_work(&r->audio_filt, (const float*)r->s_rrc.d, r->s_rrc.n, &r->s_sym);
+        if (r->ctcss_on && r->kind == QO_DEMOD_NBFM) {
+            r->s_tmp2.isz = 4; r->s_tmp2.n = 0; ctcss_work(&r->ctcss, (const float*)r->s_rrc.d, r->s_rrc.n, &r->s_tmp2);
+            r->s_sym.isz = 4; r->s_sym.n = 0; resamp_work(&r->audio_filt, (const float*)r->s_tmp2.d, r->s_tmp2.n, &r->s_sym);
+        } else {
+            r->s_sym.isz = 4; r->s_sym.n = 0; resamp_work(&r->audio_filt, (const float*)r->s_rrc.d, r->s_rrc.n, &r->s_sym);
+        }
         iir1_work(&r->deemph, (const float*)r->s_sym.d, r->s_sym.n, &r->port[1], 2.0f);
         return 0;
     }

@@ -141,6 +141,8 @@ struct qrl_rx : HandleBase {
     AgcCostasState* d_ac = nullptr;
     // NBFM: de-emphasis recurrence in its own kernel on s_loop2 (overlaps the next slice's squelch recurrence)
     NbfmDeemphState* d_nb2 = nullptr; Ring raud; bool nbfm_split = false;
+    // NBFM: stream between the 2/5 resampler and the audio filter (copy, or ctcss_squelch_ff after set_ctcss(f))
+    Ring rq; NbfmCtcss ctc{}; double* d_cenv = nullptr;
     // gr_demod_dsss: one chain kernel behind stage 1 (dsss_chain_kernel)
     DsssParams dsp{}; DsssState* d_ds = nullptr; float* d_ds_arms = nullptr; float2* d_ds_taps = nullptr;
     Ring ds_a, ds_c, ds_d; long long ds_o_call0 = 0;
@@ -842,6 +844,15 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         if ((rc = make_ring(h, &h->rd, sizeof(float), h->n1max + nt_arm + 16))) return fail(rc);
         if ((rc = make_ring(h, &h->rr, sizeof(float), h->n1max * 2 / 5 + h->nbp.nt_audio + 16))) return fail(rc);
         if ((rc = dev_alloc(h, &h->d_nb, h->C))) return fail(rc);
+        if (kind == QRL_DEMOD_NBFM) {
+            // analog::ctcss_squelch_ff::make(8000, 88.5, 0.01, 8000, 160, true) (gr_demod_nbfm.cpp:60), out of the graph until set_ctcss(f)
+            if ((rc = make_ring(h, &h->rq, sizeof(float), h->n1max * 2 / 5 + h->nbp.nt_audio + 64))) return fail(rc);
+            h->ctc.on = 0; h->ctc.len = 8000; h->ctc.ramp = 160; h->ctc.gate = 1; h->ctc.level = 0.01f;
+            std::vector<double> ce(h->ctc.ramp + 1);
+            for (int k = 0; k <= h->ctc.ramp; k++) ce[k] = 0.5 - std::cos(kPi * k / h->ctc.ramp) / 2.0;       // squelch_base_ff envelope (double)
+            if ((rc = dev_alloc(h, &h->d_cenv, ce.size(), false))) return fail(rc);
+            if (cudaMemcpy(h->d_cenv, ce.data(), sizeof(double) * ce.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_err(h, "envelope upload failed"); return fail(QRL_ECUDA); }
+        }
         // (an FP64 instruction occupies an SM's FP64 pipe for ~64 cycles whatever its lane count, so two recurrences only overlap on
         // DIFFERENT SMs: both kernels then ask for more than half an SM's shared memory, which keeps their CTAs one per SM and apart, and
         // the split is used while 2 C CTAs fit the machine)
@@ -1020,6 +1031,7 @@ int qrl_rx_reset(qrl_rx* h)
         for (int c = 0; c < h->C; c++) {
             std::memset(&nb[c], 0, sizeof(NbfmState));
             nb[c].sq_state = SQ_MUTED; nb[c].envelope = h->nbp.sq_ramp ? 0.0f : 1.0f; nb[c].agc_gain = 1.0f;
+            nb[c].c_mute = 1; nb[c].c_state = SQ_MUTED; nb[c].c_env = h->ctc.ramp ? 0.0 : 1.0;      // ctcss_squelch_ff: d_mute(true), squelch_base_ff starts muted
         }
         CK(cudaMemcpyAsync(h->d_nb, nb.data(), sizeof(NbfmState) * h->C, cudaMemcpyHostToDevice, h->stream));
     }
@@ -1158,10 +1170,37 @@ int qrl_rx_set_param(qrl_rx* h, int channel, int key, double value)
     }
     if (key == QRL_PARAM_GAIN && ssb) { h->if_gain = static_cast<float>(value); return QRL_OK; }      // gr_demod_ssb::set_gain (:118-121): _if_gain->set_k
     if (key == QRL_PARAM_CTCSS && nbfm) {
-        // gr_demod_nbfm::set_ctcss (:97-121).  0 = no tone squelch: the audio filter gets its low-pass taps back (they are the
-        // constructor's).  A tone frequency inserts analog::ctcss_squelch_ff in front of a band-pass audio filter: not built.
-        if (value != 0.0) { set_err(h, "set_ctcss: the tone squelch (analog::ctcss_squelch_ff) is not built; only set_ctcss(0)"); return QRL_EINVAL; }
-        return upload(h->d_audio_taps, low_pass_2(1, 8000, 3500, 200, 35, WIN_BLACKMAN_HARRIS));
+        // gr_demod_nbfm::set_ctcss (:97-121).  0: tone squelch out of the graph, low-pass audio filter (only when it was in: the first
+        // disconnect of :101 throws otherwise and the rest is skipped).  f: ctcss_squelch_ff::set_frequency(f) (new Goertzel filters at
+        // the tone and its table neighbours, the block's squelch state is kept), and on the first switch the block goes in front of a
+        // band-pass audio filter.
+        if (value == 0.0) {
+            if (!h->ctc.on) return QRL_OK;
+            h->ctc.on = 0;
+            return upload(h->d_audio_taps, low_pass_2(1, 8000, 3500, 200, 35, WIN_BLACKMAN_HARRIS));
+        }
+        static const float tones[38] = { 67.0f, 71.9f, 74.4f, 77.0f, 79.7f, 82.5f, 85.4f, 88.5f, 91.5f, 94.8f, 97.4f, 100.0f, 103.5f, 107.2f,
+                                         110.9f, 114.8f, 118.8f, 123.0f, 127.3f, 131.8f, 136.5f, 141.3f, 146.2f, 151.4f, 156.7f, 162.2f, 167.9f,
+                                         173.8f, 179.9f, 186.2f, 192.8f, 203.5f, 210.7f, 218.1f, 225.7f, 233.6f, 241.8f, 250.3f };
+        const float freq = static_cast<float>(value);
+        int idx = -1;
+        for (int i = 0; i < 38; i++) if (tones[i] == freq) idx = i;
+        const float fl = (idx == -1 || idx == 0) ? static_cast<float>(freq * 0.98) : tones[idx - 1];
+        const float fr = (idx == -1 || idx == 37) ? static_cast<float>(freq * 1.02) : tones[idx + 1];
+        auto gz = [](float f, float& wr, float& wi) { const float w = static_cast<float>(2.0 * kPi * f / 8000); wr = static_cast<float>(2.0 * std::cos(w)); wi = std::sin(w); };
+        gz(fl, h->ctc.wr_l, h->ctc.wi_l); gz(freq, h->ctc.wr_c, h->ctc.wi_c); gz(fr, h->ctc.wr_r, h->ctc.wi_r);
+        int rc = quiesce(); if (rc) return rc;
+        {   // set_frequency makes new Goertzel objects: their running sums restart (the squelch state machine keeps its state)
+            std::vector<NbfmState> stv(h->C);
+            CK(cudaMemcpy(stv.data(), h->d_nb, sizeof(NbfmState) * h->C, cudaMemcpyDeviceToHost));
+            for (auto& x : stv) { x.gl1 = x.gl2 = x.gc1 = x.gc2 = x.gr1 = x.gr2 = 0.0f; x.g_processed = 0; }
+            CK(cudaMemcpy(h->d_nb, stv.data(), sizeof(NbfmState) * h->C, cudaMemcpyHostToDevice));
+        }
+        if (!h->ctc.on) {
+            h->ctc.on = 1;
+            return upload(h->d_audio_taps, band_pass_2(1, 8000, 300, 3500, 200, 35, WIN_BLACKMAN_HARRIS));
+        }
+        return QRL_OK;
     }
     if (key == QRL_PARAM_FILTER_WIDTH && (nbfm || ssb || am || wbfm)) {
         const int fw = static_cast<int>(value);
@@ -1440,7 +1479,8 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
                 static_cast<float*>(h->rd.d), h->rd.mask, h->rd.stride,
                 static_cast<float*>(h->rr.d), h->rr.mask, h->rr.stride,
                 h->d_arm_taps, h->d_audio_taps, h->d_port1f, 2 * h->port1_cap, h->d_port1_cnt, static_cast<int>(2 * h->port1_cap),
-                h->nbfm_split ? static_cast<float*>(h->raud.d) : nullptr, h->raud.mask, h->raud.stride, h->nbfm_split ? nsoft_i : nullptr);
+                h->nbfm_split ? static_cast<float*>(h->raud.d) : nullptr, h->raud.mask, h->raud.stride, h->nbfm_split ? nsoft_i : nullptr,
+                static_cast<float*>(h->rq.d), h->rq.mask, h->rq.stride, h->ctc, h->d_cenv);
             h->launches++;
             h->prof_end(pe);
             if (h->nbfm_split) {

@@ -1921,7 +1921,13 @@ struct NbfmState {
     float envelope;
     float prev_r, prev_i;     // quadrature demod memory
     float agc_gain;           // AM: agc2_ff gain
+    // NBFM tone squelch (ctcss_squelch_ff): gated audio items written so far, three Goertzel filters, squelch_base_ff state
+    long long n_q;
+    float gl1, gl2, gc1, gc2, gr1, gr2;
+    int g_processed, c_mute, c_state, c_ramped;
+    double c_env;
 };
+struct NbfmCtcss { int on, len, ramp, gate; float level, wr_l, wi_l, wr_c, wi_c, wr_r, wi_r; };
 struct NbfmParams {
     double sq_alpha, sq_threshold;
     int sq_ramp, sq_gate;
@@ -1952,7 +1958,11 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
                   // NBFM (mode 0) only: when given, the audio filter's output goes to this ring and the de-emphasis runs in
                   // nbfm_deemph_kernel on another stream (its recurrence then overlaps the next slice's squelch recurrence);
                   // aud_snap[c] = audio items produced so far
-                  float* __restrict__ aud_ring = nullptr, unsigned aud_mask = 0, long long aud_stride = 0, long long* __restrict__ aud_snap = nullptr)
+                  float* __restrict__ aud_ring = nullptr, unsigned aud_mask = 0, long long aud_stride = 0, long long* __restrict__ aud_snap = nullptr,
+                  // NBFM only: the stream between the 2/5 resampler and the audio filter goes through this ring: a plain copy, or
+                  // ctcss_squelch_ff (gate: the stream shrinks while the tone is absent) when ct.on (gr_demod_nbfm::set_ctcss)
+                  float* __restrict__ q_ring = nullptr, unsigned q_mask = 0, long long q_stride = 0, NbfmCtcss ct = NbfmCtcss{},
+                  const double* __restrict__ c_env_tab = nullptr)
 {
     const int c = blockIdx.x;
     __shared__ NbfmState st;
@@ -1971,7 +1981,9 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
     // tile's |x|^2 (computed by the whole CTA) until the first sample that would change the state; the samples before it
     // are passed (or dropped) in bulk by all threads, the rest of the tile goes through the full state machine below.
     __shared__ float2 xin[2048];
-    __shared__ float m2s[2048];
+    __shared__ double t1s[2048];          // alpha * |x|^2 in double, computed by the whole CTA: an FP64 instruction occupies the SM's FP64
+                                          // pipe for ~64 cycles whatever its lane count, so the recurrence thread keeps only the two
+                                          // operations that are on the chain
     __shared__ int fast_n, fast_state;
     __shared__ long long fast_ng0;
     __shared__ float fast_env;
@@ -1980,7 +1992,7 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
         for (int j = threadIdx.x; j < nt; j += blockDim.x) {
             const float2 v = x[(tile0 + j) & in_mask];
             xin[j] = v;
-            m2s[j] = v.x * v.x + v.y * v.y;
+            t1s[j] = p.sq_alpha * static_cast<double>(v.x * v.x + v.y * v.y);
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -1992,11 +2004,13 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
             fast_n = 0;
             if (p.mode != 1 && (state == SQ_UNMUTED || state == SQ_MUTED)) {
                 const bool want = (state == SQ_MUTED);           // the state holds while every sample's mute flag equals `want`
-                const double k_a = p.sq_alpha, k_thr = p.sq_threshold;
+                // pn and the threshold are non-negative doubles: pn < thr is the same comparison on their bit patterns (an integer
+                // compare instead of a third FP64-pipe instruction per sample)
+                const long long thr_bits = __double_as_longlong(p.sq_threshold);
                 int j = 0;
                 for (; j < nt; j++) {
-                    const double pn = k_a * static_cast<double>(m2s[j]) + one_m_alpha * pwr;
-                    if ((pn < k_thr) != want) break;
+                    const double pn = t1s[j] + one_m_alpha * pwr;
+                    if ((__double_as_longlong(pn) < thr_bits) != want) break;
                     pwr = pn;
                 }
                 fast_n = j; fast_state = state; fast_ng0 = ng; fast_env = env;
@@ -2125,10 +2139,64 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
         rr[i & res_mask] = acc;
     }
     __syncthreads();
-    // ---- 4. audio low-pass (direct form), into shared staging for the IIR
     __shared__ float aud[2048];
+    // ---- 3b. NBFM: copy, or tone squelch, into the audio filter's input ring
+    float* qr = q_ring ? q_ring + static_cast<long long>(c) * q_stride : nullptr;
+    if (qr) {
+        const long long q0 = st.n_q;
+        if (!ct.on) {
+            for (long long i = res0 + threadIdx.x; i < res1; i += blockDim.x) qr[(q0 + (i - res0)) & q_mask] = rr[i & res_mask];
+            __syncthreads();
+            if (threadIdx.x == 0) st.n_q = q0 + (res1 - res0);
+        } else {
+            for (long long base = res0; base < res1; base += 2048) {
+                const int nb = (res1 - base) < 2048 ? static_cast<int>(res1 - base) : 2048;
+                for (int j = threadIdx.x; j < nb; j += blockDim.x) aud[j] = rr[(base + j) & res_mask];
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    float gl1 = st.gl1, gl2 = st.gl2, gc1 = st.gc1, gc2 = st.gc2, gr1 = st.gr1, gr2 = st.gr2;
+                    int proc = st.g_processed, mute = st.c_mute, state = st.c_state, ramped = st.c_ramped;
+                    double env = st.c_env;
+                    long long nq = st.n_q;
+                    for (int j = 0; j < nb; j++) {
+                        const float xv = aud[j];
+                        float y = xv + ct.wr_l * gl1; y = y - gl2; gl2 = gl1; gl1 = y;              // fft::goertzel::input
+                        y = xv + ct.wr_c * gc1; y = y - gc2; gc2 = gc1; gc1 = y;
+                        y = xv + ct.wr_r * gr1; y = y - gr2; gr2 = gr1; gr1 = y;
+                        proc++;
+                        if (proc == ct.len) {
+                            auto mag = [&](float wr, float wi, float d1, float d2) -> float {
+                                const float re = static_cast<float>((0.5 * wr * d1 - d2) / ct.len), im = (wi * d1) / ct.len;
+                                const float m = static_cast<float>(sqrt(static_cast<double>(re) * re + static_cast<double>(im) * im));
+                                return floorf(100000.0f * m) / 100000.0f;
+                            };
+                            const float ml = mag(ct.wr_l, ct.wi_l, gl1, gl2), mc = mag(ct.wr_c, ct.wi_c, gc1, gc2), mr = mag(ct.wr_r, ct.wi_r, gr1, gr2);
+                            gl1 = gl2 = gc1 = gc2 = gr1 = gr2 = 0.0f; proc = 0;
+                            mute = (mc < ct.level || mc < ml || mc < mr) ? 1 : 0;
+                        }
+                        switch (state) {                                                                // squelch_base_ff
+                        case SQ_MUTED: if (!mute) state = ct.ramp ? SQ_ATTACK : SQ_UNMUTED; break;
+                        case SQ_UNMUTED: if (mute) state = ct.ramp ? SQ_DECAY : SQ_MUTED; break;
+                        case SQ_ATTACK: env = c_env_tab[++ramped]; if (ramped >= ct.ramp) { state = SQ_UNMUTED; env = 1.0; } break;
+                        case SQ_DECAY: env = c_env_tab[--ramped]; if (ramped == 0) state = SQ_MUTED; break;
+                        }
+                        if (state != SQ_MUTED) { qr[nq & q_mask] = static_cast<float>(static_cast<double>(xv) * env); nq++; }
+                        else if (!ct.gate) { qr[nq & q_mask] = 0.0f; nq++; }
+                    }
+                    st.gl1 = gl1; st.gl2 = gl2; st.gc1 = gc1; st.gc2 = gc2; st.gr1 = gr1; st.gr2 = gr2;
+                    st.g_processed = proc; st.c_mute = mute; st.c_state = state; st.c_ramped = ramped; st.c_env = env; st.n_q = nq;
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+    }
+    // ---- 4. audio low-pass (direct form), into shared staging for the IIR
+    const float* fsrc = qr ? qr : rr;                               // the filter's input stream and its length so far
+    const unsigned fmask = qr ? q_mask : res_mask;
+    const long long fend = qr ? st.n_q : res1;
     const long long aud0 = st.n_aud;
-    const int n_aud = static_cast<int>(res1 - aud0);               // one output per resampler output
+    const int n_aud = static_cast<int>(fend - aud0);                // one output per input item
     for (int base = 0; base < n_aud; base += 2048) {
         const int nb = (n_aud - base) < 2048 ? (n_aud - base) : 2048;
         for (int j = threadIdx.x; j < nb; j += blockDim.x) {
@@ -2136,7 +2204,7 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
             float acc = 0.0f;
             for (int k = p.nt_audio - 1; k >= 0; k--) {
                 const long long n = a - k;
-                const float v = n >= 0 ? rr[n & res_mask] : 0.0f;
+                const float v = n >= 0 ? fsrc[n & fmask] : 0.0f;
                 acc = fmaf(audio_taps[k], v, acc);
             }
             aud[j] = acc;
@@ -2170,7 +2238,7 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
         __syncthreads();
     }
     __syncthreads();      // (nothing new: no barrier above) every thread has read st.n_aud
-    if (threadIdx.x == 0) { st.n_res = res1; st.n_aud = res1; states[c] = st; if (aud_snap) aud_snap[c] = res1; }
+    if (threadIdx.x == 0) { st.n_res = res1; st.n_aud = fend; states[c] = st; if (aud_snap) aud_snap[c] = fend; }
 }
 
 // The de-emphasis recurrence of the NBFM chain (iir_filter_ffd, double: two dependent FP64 operations per audio item) in a kernel of
@@ -2184,6 +2252,7 @@ nbfm_deemph_kernel(double b0, double b1, double a1, float out_gain, NbfmDeemphSt
 {
     const int c = blockIdx.x;
     __shared__ float aud[2048];
+    __shared__ double u[2048];            // b0 x[n] + b1 x[n-1] from all threads (does not depend on the recurrence), then y[n] in place
     __shared__ NbfmDeemphState st;
     if (threadIdx.x == 0) st = states[c];
     __syncthreads();
@@ -2194,20 +2263,25 @@ nbfm_deemph_kernel(double b0, double b1, double a1, float out_gain, NbfmDeemphSt
         const int nb = (a1n - base) < 2048 ? static_cast<int>(a1n - base) : 2048;
         for (int j = threadIdx.x; j < nb; j += blockDim.x) aud[j] = ar[(base + j) & aud_mask];
         __syncthreads();
-        if (threadIdx.x == 0) {
-            double x1 = st.iir_x1, y1 = st.iir_y1;
-            int cnt = port1_cnt[c];
-            for (int j = 0; j < nb; j++) {
-                const double xin = static_cast<double>(aud[j]);
-                double acc = b0 * xin;
-                acc = acc + b1 * x1;
-                acc = acc - a1 * y1;
-                x1 = xin; y1 = acc;
-                if (cnt < port1_cap) o[cnt] = static_cast<float>(acc) * out_gain;
-                cnt++;
-            }
-            st.iir_x1 = x1; st.iir_y1 = y1; port1_cnt[c] = cnt;
+        const double x1c = st.iir_x1;
+        for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+            const double xin = static_cast<double>(aud[j]);
+            const double x1 = j > 0 ? static_cast<double>(aud[j - 1]) : x1c;
+            double acc = b0 * xin;
+            acc = acc + b1 * x1;
+            u[j] = acc;
         }
+        __syncthreads();
+        const int cnt0 = port1_cnt[c];
+        if (threadIdx.x == 0) {
+            double y1 = st.iir_y1;
+            for (int j = 0; j < nb; j++) { const double acc = u[j] - a1 * y1; y1 = acc; u[j] = acc; }      // the two operations on the chain
+            st.iir_y1 = y1; st.iir_x1 = static_cast<double>(aud[nb - 1]);
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < nb; j += blockDim.x) if (cnt0 + j < port1_cap) o[cnt0 + j] = static_cast<float>(u[j]) * out_gain;
+        __syncthreads();
+        if (threadIdx.x == 0) port1_cnt[c] = cnt0 + nb;
         __syncthreads();
     }
     if (threadIdx.x == 0) { st.n_done = a1n > a0 ? a1n : a0; states[c] = st; }

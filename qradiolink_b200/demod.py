@@ -56,7 +56,7 @@ class RxBlock:
         self.set_param(PARAM.FILTER_WIDTH, width)
 
     def set_ctcss(self, value):
-        """gr_demod_nbfm::set_ctcss: 0 = no tone squelch (the only value built)"""
+        """gr_demod_nbfm::set_ctcss (gr_demod_nbfm.cpp:97-121): 0 = no tone squelch; f = the CTCSS tone squelch at f Hz (audio gated)"""
         self.set_param(PARAM.CTCSS, value)
 
     def set_agc_attack(self, value):

@@ -121,3 +121,45 @@ def test_ssb_agc_with_hot_input(qrl, oracle):
         X[c] = (x + 0.002 * (rng.standard_normal(T) + 1j * rng.standard_normal(T))).astype(np.complex64)
     run_case(qrl, oracle, qrl.make_gr_demod_ssb, oracle.DEMOD_SSB, (125, 1000000, 1700, 2700, 0), 0, X,
              [(100000, []), (300000, [(P.AGC_ATTACK, 0.5), (P.AGC_DECAY, 0.01)]), (300000, [(P.AGC_ATTACK, 0.01), (P.AGC_DECAY, 0.6)])])
+
+
+def test_nbfm_tone_squelch(qrl, oracle):
+    """gr_demod_nbfm::set_ctcss(f) (gr_demod_nbfm.cpp:97-121): analog::ctcss_squelch_ff in front of a band-pass audio filter, gating: the
+    audio port only carries items while the 88.5 Hz tone is present (decision once per 8000-item block, 160-item ramps); then a change of
+    tone mid-stream (new Goertzel filters, state kept), then set_ctcss(0).  Channel 0 carries the tone, channel 1 a wrong one, channel 2
+    none.  Ports identical to the oracle's restatement for every call."""
+    P = qrl.PARAM
+    n_aud = 8000 * 5
+    t = np.arange(n_aud)
+    iqs = []
+    for c, tone in enumerate((88.5, 100.0, 0.0)):
+        m = oracle.Tx(oracle.MOD_NBFM, 20, 1000000, 1700, 2500, 0)
+        if tone:
+            m.set_param(7, tone)
+        au = (0.4 * np.sin(2 * np.pi * (800 + 150 * c) * t / 8000)).astype(np.float32)
+        iqs.append(m.work(au))
+    X = np.stack(iqs)
+    X = (X * 0.5 + 0.002 * (np.random.default_rng(75).standard_normal(X.shape) + 1j * np.random.default_rng(76).standard_normal(X.shape))).astype(np.complex64)
+    steps = [(1000000, [(P.CTCSS, 88.5)]), (1500000, []), (700001, [(P.CTCSS, 100.0)]), (1299999, []), (500000, [(P.CTCSS, 0.0)])]
+    assert sum(n for n, _ in steps) == X.shape[1]
+    C = X.shape[0]
+    blk = qrl.make_gr_demod_nbfm(125, 1000000, 1700, 2500, n_channels=C, max_samples=1500000)
+    rxs = [oracle.Rx(oracle.DEMOD_NBFM, 125, 1000000, 1700, 2500, 0) for _ in range(C)]
+    lo, total = 0, np.zeros(C, int)
+    for n, sets in steps:
+        for key, value in sets:
+            blk.set_param(key, value)
+            for rx in rxs:
+                rx.set_param(key, value)
+        blk.work(X[:, lo:lo + n])
+        got = [blk.read_port(p) for p in range(2)]
+        for c in range(C):
+            rxs[c].work(X[c, lo:lo + n])
+            for p in range(2):
+                want = rxs[c].port(p)
+                assert len(got[p][c]) == len(want), (lo, c, p, len(got[p][c]), len(want))
+                assert np.array_equal(got[p][c], want), (lo, c, p)
+            total[c] += len(got[1][c])
+        lo += n
+    # 88.5 Hz on channel 0 opens during the first 2.5 s; the 100 Hz phase opens channel 1 instead; the last call passes everything
+    assert total[0] > 8000 and total[1] > 8000 and total[2] == 500000 * 8 // 1000, total

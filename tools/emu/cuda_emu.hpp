@@ -230,5 +230,6 @@ static inline float __fadd_rd(float a, float b)
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline void sincospif(float x, float* s, float* c) { *s = static_cast<float>(std::sin(3.14159265358979323846 * static_cast<double>(x))); *c = static_cast<float>(std::cos(3.14159265358979323846 * static_cast<double>(x))); }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
