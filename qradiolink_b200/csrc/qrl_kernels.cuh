@@ -2220,20 +2220,29 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
             for (int j = threadIdx.x; j < nb; j += blockDim.x) if (cnt0 + j < port1_cap) o[cnt0 + j] = aud[j];
             __syncthreads();
             if (threadIdx.x == 0) port1_cnt[c] = cnt0 + nb;
-        } else if (threadIdx.x == 0) {
-            double x1 = st.iir_x1, y1 = st.iir_y1;
-            int cnt = port1_cnt[c];
-            float* o = port1 + static_cast<long long>(c) * port1_stride;
-            for (int j = 0; j < nb; j++) {
+        } else {
+            // b0 x[n] + b1 x[n-1] does not depend on the recurrence: all threads (t1s is free by now); thread 0 keeps y[n] = u[n] - a1 y[n-1]
+            double* u = t1s;
+            const double x1c = st.iir_x1;
+            for (int j = threadIdx.x; j < nb; j += blockDim.x) {
                 const double xin = static_cast<double>(aud[j]);
+                const double x1 = j > 0 ? static_cast<double>(aud[j - 1]) : x1c;
                 double acc = p.b0 * xin;
                 acc = acc + p.b1 * x1;
-                acc = acc - p.a1 * y1;
-                x1 = xin; y1 = acc;
-                if (cnt < port1_cap) o[cnt] = static_cast<float>(acc) * p.out_gain;
-                cnt++;
+                u[j] = acc;
             }
-            st.iir_x1 = x1; st.iir_y1 = y1; port1_cnt[c] = cnt;
+            __syncthreads();
+            const int cnt0 = port1_cnt[c];
+            if (threadIdx.x == 0) {
+                double y1 = st.iir_y1;
+                for (int j = 0; j < nb; j++) { const double acc = u[j] - p.a1 * y1; y1 = acc; u[j] = acc; }
+                st.iir_y1 = y1; st.iir_x1 = static_cast<double>(aud[nb - 1]);
+            }
+            __syncthreads();
+            float* o = port1 + static_cast<long long>(c) * port1_stride;
+            for (int j = threadIdx.x; j < nb; j += blockDim.x) if (cnt0 + j < port1_cap) o[cnt0 + j] = static_cast<float>(u[j]) * p.out_gain;
+            __syncthreads();
+            if (threadIdx.x == 0) port1_cnt[c] = cnt0 + nb;
         }
         __syncthreads();
     }

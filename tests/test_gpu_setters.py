@@ -102,9 +102,10 @@ def test_setters_refused_where_the_reference_has_none(qrl):
             blk.set_param(key, 1.0)
     nb = qrl.make_gr_demod_nbfm(125, 1000000, 1700, 2500, n_channels=1, max_samples=65536)
     with pytest.raises(qrl.QrlError):
-        nb.set_param(P.CTCSS, 88.5)          # analog::ctcss_squelch_ff is not built
-    with pytest.raises(qrl.QrlError):
         nb.set_param(P.GAIN, 0.5)            # gr_demod_nbfm has no set_gain
+    am = qrl.make_gr_demod_am(125, 1000000, 1700, 5000, n_channels=1, max_samples=65536)
+    with pytest.raises(qrl.QrlError):
+        am.set_param(P.CTCSS, 88.5)          # only gr_demod_nbfm has a tone squelch
 
 
 def test_ssb_agc_with_hot_input(qrl, oracle):
