@@ -1984,6 +1984,7 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
     __shared__ double t1s[2048];          // alpha * |x|^2 in double, computed by the whole CTA: an FP64 instruction occupies the SM's FP64
                                           // pipe for ~64 cycles whatever its lane count, so the recurrence thread keeps only the two
                                           // operations that are on the chain
+    __shared__ float aud[2048];           // staging of the audio-rate (WBFM: 200 ksps) recurrences
     __shared__ int fast_n, fast_state;
     __shared__ long long fast_ng0;
     __shared__ float fast_env;
@@ -2089,17 +2090,32 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
     if (threadIdx.x == 0 && gate1 > gate0 && p.mode != 1) { const float2 l = gr_[(gate1 - 1) & gate_mask]; st.prev_r = l.x; st.prev_i = l.y; }
     if (p.mode == 2) {
         // ---- WBFM: x am_gain and de-emphasis IIR over the new demodulated samples (sequential), into the res ring at 200 ksps
-        if (threadIdx.x == 0) {
-            double x1 = st.iir_x1, y1 = st.iir_y1;
-            for (long long n = gate0; n < gate1; n++) {
-                const double xin = static_cast<double>(dr[n & dem_mask] * p.am_gain);
-                double acc = p.b0 * xin;
-                acc = acc + p.b1 * x1;
-                acc = acc - p.a1 * y1;
-                x1 = xin; y1 = acc;
-                rr[n & res_mask] = static_cast<float>(acc);
+        // (tiles through shared memory; b0 x[n] + b1 x[n-1] by all threads, thread 0 keeps the two FP64 operations on the chain)
+        {
+            float* wx = aud;
+            double* u = t1s;
+            for (long long base = gate0; base < gate1; base += 2048) {
+                const int nb = (gate1 - base) < 2048 ? static_cast<int>(gate1 - base) : 2048;
+                for (int j = threadIdx.x; j < nb; j += blockDim.x) wx[j] = dr[(base + j) & dem_mask] * p.am_gain;
+                __syncthreads();
+                const double x1c = st.iir_x1;
+                for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+                    const double xin = static_cast<double>(wx[j]);
+                    const double x1 = j > 0 ? static_cast<double>(wx[j - 1]) : x1c;
+                    double acc = p.b0 * xin;
+                    acc = acc + p.b1 * x1;
+                    u[j] = acc;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double y1 = st.iir_y1;
+                    for (int j = 0; j < nb; j++) { const double acc = u[j] - p.a1 * y1; y1 = acc; u[j] = acc; }
+                    st.iir_y1 = y1; st.iir_x1 = static_cast<double>(wx[nb - 1]);
+                }
+                __syncthreads();
+                for (int j = threadIdx.x; j < nb; j += blockDim.x) rr[(base + j) & res_mask] = static_cast<float>(u[j]);
+                __syncthreads();
             }
-            st.iir_x1 = x1; st.iir_y1 = y1;
         }
         __syncthreads();
         // ---- rational_resampler_fff(1, 25): output i = sum_j h[j] z[25 i - j], outputs with 25 i <= gate1 - 1
@@ -2139,7 +2155,6 @@ nbfm_audio_kernel(NbfmParams p, NbfmState* __restrict__ states,
         rr[i & res_mask] = acc;
     }
     __syncthreads();
-    __shared__ float aud[2048];
     // ---- 3b. NBFM: copy, or tone squelch, into the audio filter's input ring
     float* qr = q_ring ? q_ring + static_cast<long long>(c) * q_stride : nullptr;
     if (qr) {
