@@ -1533,8 +1533,8 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
             pe = h->prof_begin(3, h->s_loop);
             if (bpsk) {
                 {   // agc2_cc (Costas bypassed): r2 -> r3
-                    constexpr int CH = 128, NST = 3;
-                    const size_t smem = sizeof(float2) * ((NST + 2) * CH + 1) * 32;      // + one row of padding behind the hand-off blocks
+                    constexpr int CH = 128, NST = 2;
+                    const size_t smem = sizeof(float2) * ((NST + AC_NHB) * CH + 1) * 32;      // + one row of padding behind the hand-off blocks
                     auto kern = agc_costas_kernel<CH, NST, 0, 0>;
                     static bool a_attr[16] = { false };    // per device: function attributes belong to the device's context
                     if (!a_attr[h->device & 15]) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a_attr[h->device & 15] = true; }
@@ -1726,8 +1726,8 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
             {
                 pe = h->prof_begin(2, h->s_loop);
                 auto run_ac = [&](auto ch_tag) -> int {
-                    constexpr int CH = decltype(ch_tag)::value, NST = 3;
-                    const size_t smem = sizeof(float2) * ((NST + 2) * CH + 1) * 32;      // + one row of padding behind the hand-off blocks
+                    constexpr int CH = decltype(ch_tag)::value, NST = 2;      // input stages (2) + hand-off blocks (3): 164 KB at CH = 128
+                    const size_t smem = sizeof(float2) * ((NST + AC_NHB) * CH + 1) * 32;      // + one row of padding behind the hand-off blocks
                     auto kern = (h->acp.order == 4 && h->acp.use_snr) ? agc_costas_kernel<CH, NST, 4, 1> : agc_costas_kernel<CH, NST>;
                     static bool ac_attr[16] = { false };    // per CH instantiation, per device: function attributes belong to the device's context
                     if (!ac_attr[h->device & 15]) {
@@ -3196,3 +3196,13 @@ int qrl_mmdvm_tx_sync(qrl_mmdvm_tx* h) { if (!h) return QRL_EINVAL; CK(cudaStrea
 long qrl_mmdvm_tx_launch_count(qrl_mmdvm_tx* h) { return h ? h->launches : 0; }
 
 }  // extern "C"
+
+#ifdef QRL_SS_PROF
+// profiling build only (tools/ss_prof.py): read and clear the symbol-sync loop warp's cycle counters
+extern "C" int qrl_debug_ss_prof(long long* out16)
+{
+    if (cudaMemcpyFromSymbol(out16, qrl::d_ss_prof, sizeof(long long) * 16) != cudaSuccess) return -1;
+    long long z[16] = { 0 };
+    return cudaMemcpyToSymbol(qrl::d_ss_prof, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif

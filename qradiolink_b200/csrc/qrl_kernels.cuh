@@ -21,6 +21,14 @@ __device__ float d_atan_tab[257];
 __device__ float d_tanh_tab[256];
 __device__ float d_mmse_tab[129 * 8];
 __device__ float d_sine_tab[2048];
+#ifdef QRL_SS_PROF
+// -DQRL_SS_PROF (tools/ss_prof.py): where the symbol-sync loop warp of CTA 0 spends its cycles (clock64 deltas, summed per launch)
+// [0] wait for the hand-off block  [1] wait for the window  [2] uniform rounds  [3] stragglers  [4] hand-off  [5] windows  [6] symbols  [7] rounds
+__device__ long long d_ss_prof[16];
+#define SSP(...) __VA_ARGS__
+#else
+#define SSP(...)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // elementary functions shared by all loop kernels
@@ -992,8 +1000,13 @@ fll_kernel(FllParams p, FllState* __restrict__ states, float2* __restrict__ hist
 // ------------------------------------------------------------------------------------------------
 // Sequential loop stage of the PSK chains: agc2_cc -> costas_loop_cc ("PLL" in gr_demod_qpsk.cpp:108-118), one
 // lane per channel, per SAMPLE.  The two recurrences are independent of each other, so they run in two warps:
-// warp 0 = AGC (gain recurrence), warp 2 = Costas (phase/frequency recurrence), connected by a double-buffered
-// shared-memory hand-off; warp 1 lane 0 = TMA producer.  Input and output rings are channel-interleaved.
+// warp 0 = AGC (gain recurrence), warp 2 = Costas (phase/frequency recurrence), connected by a shared-memory
+// hand-off ring; warp 1 lane 0 = TMA producer.  Input and output rings are channel-interleaved.
+// The hand-off ring is NHB = 3 blocks deep because a block has three owners in turn: the AGC warp fills it, the Costas
+// warp works on it in place, the bulk store drains it -- and the Costas warp learns that block m-1 has been drained
+// only while it closes block m.  With two blocks the AGC warp could not start block m+1 before the Costas warp had
+// finished block m: the two recurrences ran one after the other (398 cycles per item for a 209-cycle Costas chain,
+// tools/microbench/lone_warp.cu); with three they overlap.
 // ------------------------------------------------------------------------------------------------
 struct AgcCostasState {
     long long pos;            // absolute index of the next input sample
@@ -1006,27 +1019,29 @@ struct AgcCostasParams {
     int order, use_snr;
 };
 
+constexpr int AC_NHB = 3;      // hand-off blocks between the AGC and the Costas warp (see above)
 template <int CH, int NST, int ORDER = -1, int USE_SNR = -1>   // ORDER / USE_SNR >= 0: compile-time loop shape (else p.order / p.use_snr)
 __global__ void __launch_bounds__(96)
 agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
                   const float2* __restrict__ in, unsigned in_mask, long long in_stride, long long avail_total,
                   float2* __restrict__ out, unsigned out_mask, long long out_stride)
 {
-    extern __shared__ __align__(128) float2 sm_ac[];          // [NST][CH][32] | hand-off [2][CH][32]
-    __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[2], bar_empty[2];
+    constexpr int NHB = AC_NHB;
+    extern __shared__ __align__(128) float2 sm_ac[];          // [NST][CH][32] | hand-off [NHB][CH][32]
+    __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[NHB], bar_empty[NHB];
     __shared__ float tanh_s[257];                             // entry 256 = entry 255 (see qrl_costas4_snr_chunk)
     __shared__ volatile int opaque_zero;
     for (int i = threadIdx.x; i < 257; i += blockDim.x) tanh_s[i] = d_tanh_tab[i < 256 ? i : 255];
     if (threadIdx.x == 0) opaque_zero = 0;
     float2* stage0 = sm_ac;
-    float2* hand = sm_ac + NST * CH * 32;                     // [2][CH][32] + one row of padding (prefetch of the item behind a block)
+    float2* hand = sm_ac + NST * CH * 32;                     // [NHB][CH][32] + one row of padding (prefetch of the item behind a block)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
     const int c = g * 32 + lane;
     const bool active = c < C;
     if (threadIdx.x == 0) {
         for (int b = 0; b < NST; b++) { mbar_init(&bar_in[b], 1); mbar_init(&bar_free[b], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&bar_full[b], 1); mbar_init(&bar_empty[b], 1); }
+        for (int b = 0; b < NHB; b++) { mbar_init(&bar_full[b], 1); mbar_init(&bar_empty[b], 1); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -1059,8 +1074,8 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
         float gain = active ? states[c].gain : 1.0f;
         const float k_att = p.attack, k_dec = p.decay, k_ref = p.ref, k_max = p.max_gain;
         for (int m = 0; m < nchunks; m++) {
-            const int st = m % NST, b = m & 1;
-            if (m >= 2) mbar_wait(&bar_empty[b], ((m >> 1) - 1) & 1);
+            const int st = m % NST, b = m % NHB;
+            if (m >= NHB) mbar_wait(&bar_empty[b], ((m / NHB) - 1) & 1);
             mbar_wait(&bar_in[st], (m / NST) & 1);
             const float2* buf = stage0 + st * CH * 32 + lane;
             float2* hb = hand + b * CH * 32 + lane;
@@ -1094,8 +1109,8 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
         const int order = ORDER >= 0 ? ORDER : p.order;
         const bool use_snr = USE_SNR >= 0 ? (USE_SNR != 0) : (p.use_snr != 0);
         for (int m = 0; m < nchunks; m++) {
-            const int b = m & 1;
-            mbar_wait(&bar_full[b], (m >> 1) & 1);
+            const int b = m % NHB;
+            mbar_wait(&bar_full[b], (m / NHB) & 1);
             float2* hb = hand + b * CH * 32 + lane;
             const long long w0 = base + static_cast<long long>(m) * CH;
             const long long rem = total - static_cast<long long>(m) * CH;
@@ -1121,10 +1136,10 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
                 bulk_s2g(oring + s0 * 32, src, static_cast<uint32_t>(first * 256));
                 if (first < n) bulk_s2g(oring, src + first * 32, static_cast<uint32_t>((n - first) * 256));
                 bulk_commit();
-                if (m >= 1) { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); mbar_arrive(&bar_empty[b ^ 1]); }
+                if (m >= 1) { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); mbar_arrive(&bar_empty[(m - 1) % NHB]); }
             }
         }
-        if (lane == 0) { bulk_wait_all0(); mbar_arrive(&bar_empty[(nchunks - 1) & 1]); }
+        if (lane == 0) { bulk_wait_all0(); mbar_arrive(&bar_empty[(nchunks - 1) % NHB]); }
         if (active) { states[c].pll = pll; states[c].pos = avail_total; }
     }
 }
@@ -1309,10 +1324,14 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
         const bool lean_ok = p.min_period > fabsf(p.alpha) && p.fl0 >= 1.0f;
         const bool window_sure = lean_ok && (p.max_period + fabsf(p.alpha) + 1.0f < p.fl0 + 3.0f - 1e-3f) &&
                                  (p.min_period - fabsf(p.alpha) > p.fl0 + 1e-3f) && p.fl0 == static_cast<float>(p.n0);
+        SSP(long long pf_we = 0; long long pf_wi = 0; long long pf_run = 0; long long pf_str = 0; long long pf_ho = 0; long long pf_rounds = 0; long long pf_sym = 0;)
         for (int m = 0; m < nchunks; m++) {
             const int st = m % NST, b = m & 1;
+            SSP(const long long pt0 = clock64();)
             if (m >= 2) mbar_wait(&bar_empty[b], ((m >> 1) - 1) & 1);    // epilogue released this hand-off buffer
+            SSP(const long long pt1 = clock64();)
             mbar_wait(&bar_in[st], (m / NST) & 1);
+            SSP(const long long pt2 = clock64(); pf_we += pt1 - pt0; pf_wi += pt2 - pt1; long long pt3 = pt2;)
             const float* buf = stp + st * CH * ROWF;
             float* sy = symbuf + b * blk_rows * ROWF + lane * NCOMP;
             const long long w0 = base + static_cast<long long>(m) * STRIDE;
@@ -1421,6 +1440,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                         return body_t(ws_tag, n, h1, h2, dn, dh1, dh2);
                     };
                     for (;;) {
+                        SSP(pf_rounds++;)
                         const float left = lim - ofm;                      // exact (integers below 2^24)
                         int ksafe = left >= 0.0f ? static_cast<int>(left * inv_s * 0.999f) + 1 : 0;   // never above the true quotient + 1
                         ksafe = __reduce_min_sync(amask, ksafe);
@@ -1437,6 +1457,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                         }
                         if (__any_sync(amask, fell)) break;
                     }
+                    SSP(pt3 = clock64();)
                     while (ofm <= lim) {                                   // stragglers (and lanes that fell out of lock)
                         body(Cc, A, B, dC, dA, dB);
                         const float t = Cc, dt = dC; Cc = B; B = A; A = t; dC = dB; dB = dA; dA = dt;
@@ -1505,6 +1526,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                     cnt++;
                 }
             }
+            SSP(const long long pt4 = clock64(); pf_run += pt3 - pt2; pf_str += pt4 - pt3; pf_sym += cnt;)
             o -= STRIDE;                                   // next window starts STRIDE rows later
             if (EXT) {
                 float* blk = symbuf + b * blk_rows * ROWF;
@@ -1515,7 +1537,10 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
             } else cntbuf[b * 32 + lane] = cnt;
             __syncwarp();
             if (lane == 0) { mbar_arrive(&bar_free[st]); mbar_arrive(&bar_full[b]); }
+            SSP(pf_ho += clock64() - pt4;)
         }
+        SSP(if (g == 0 && lane == 0) { d_ss_prof[0] += pf_we; d_ss_prof[1] += pf_wi; d_ss_prof[2] += pf_run; d_ss_prof[3] += pf_str; d_ss_prof[4] += pf_ho;
+                                       d_ss_prof[5] += nchunks; d_ss_prof[6] += pf_sym; d_ss_prof[7] += pf_rounds; })
         if (active) {
             SymSyncState& st = states[c];
             st.ii = base + static_cast<long long>(nchunks) * STRIDE + o;
