@@ -362,9 +362,9 @@ bool make_sm_partition(qrl_rx* h, unsigned loop_sms, int prio)
     if (pCreate(&h->g_par, d_par, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
     CUstream a = nullptr, b = nullptr, c = nullptr, d = nullptr;
     if (pStream(&a, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
-    // FEC (Viterbi) stream: next to the loop kernels by default (measured: 4FSK step 1.23 ms vs 1.28 ms with the decoder
-    // on the wide partition, where it delays the filters feeding the loop; QPSK is bound by the per-sample Costas
-    // recurrence either way).  QRL_FEC_ON_PAR=1 moves it.
+    // FEC (Viterbi) stream: next to the loop kernels by default.  Measured at the end of round 2 (profiles/r02_u_fec_partition_ab.txt):
+    // 4FSK step 0.959 ms next to the loop kernels, 0.954 ms on the wide partition (QRL_FEC_ON_PAR=1) -- the decoder's warps are not
+    // what slows the lone recurrence warps down.
     bool fec_on_par = false;
     if (const char* e = getenv("QRL_FEC_ON_PAR")) fec_on_par = e[0] == '1';
     if (pStream(&b, fec_on_par ? h->g_par : h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
@@ -951,7 +951,12 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         // per SM) on all SMs, next to the parallel stages, on priority streams.
         h->many = big_ctas > 44 || (analog_kind && h->C > 64);
         if (const char* e = getenv("QRL_MANY_CHANNELS")) h->many = e[0] == '1';
-        if (h->many || !make_sm_partition(h, loop_sms, hi)) {
+        // QPSK (per-sample loops, 2 loop CTAs per 32 channels + a heavy Viterbi load): measured faster WITHOUT a private partition
+        // (256 channels: 62.3 ms per 2^20-sample call on priority streams, 66.8 ms with a 24-SM partition -- the decoder gets the whole
+        // machine (38.9 -> 12.9 ms) and the loop CTAs spread over more SMs); QRL_QPSK_PARTITION=1 brings the partition back.
+        bool want_partition = kind != QRL_DEMOD_QPSK;
+        if (const char* e = getenv("QRL_QPSK_PARTITION")) { if (kind == QRL_DEMOD_QPSK) want_partition = e[0] == '1'; }
+        if (h->many || !want_partition || !make_sm_partition(h, loop_sms, hi)) {
             h->s_par = nullptr; h->sm_loop = 0; h->sm_par = 0;
             if (h->s_loop == nullptr)
                 ok = cudaStreamCreateWithPriority(&h->s_loop, cudaStreamNonBlocking, hi) == cudaSuccess;
@@ -1325,8 +1330,9 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
     CK(cudaStreamWaitEvent(h->s_fec, h->ev_start, 0));
     if (h->s_par) CK(cudaStreamWaitEvent(h->s_par, h->ev_start, 0));
     cudaStream_t sp = h->par();
-    // overlapped calls keep the pipeline full across calls: a few big slices (less per-launch overhead) are enough
-    int nsub = (h->overlap && !h->nsub_forced) ? 3 : h->nsub;
+    // overlapped calls keep the pipeline full across calls: two big slices are enough and cost least (a symbol-sync launch has
+    // ~20 us of start-up: measured 0.941 ms per 64 x 2^22 call with 2 slices, 0.963 with 3, 0.988 with 4, 1.45 with 1)
+    int nsub = (h->overlap && !h->nsub_forced) ? 2 : h->nsub;
     if (T < 32768L * nsub) nsub = static_cast<int>(std::max<long>(1, T / 32768));
     const long long k_call0 = h->n1;
     h->port0_n = 0;

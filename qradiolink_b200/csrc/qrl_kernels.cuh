@@ -869,6 +869,14 @@ __device__ __forceinline__ void qrl_costas4_snr_step(LoopState& st, float alpha,
     yr = orr; yi = oi;
 }
 
+// Shared-memory copy of the tanh table as qrl_costas4_snr_chunk reads it: 256 entries, entry 256 = entry 255 (x = 2 exactly), entry
+// 257 = 1.0f (x > 2), entry 258 = -1.0f (x <= -2, NaN).  Called by all threads of the block.
+__device__ __forceinline__ void qrl_fill_tanh_s(float* tanh_s)
+{
+    for (int i = threadIdx.x; i < 259; i += blockDim.x)
+        tanh_s[i] = i < 256 ? d_tanh_tab[i] : (i == 256 ? d_tanh_tab[255] : (i == 257 ? 1.0f : -1.0f));
+}
+
 // Rare path of the Costas phase wrap (exact double subtraction), kept out of line so the common path is one compare + branch.
 __device__ __noinline__ float qrl_phase_wrap_slow(float ph)
 {
@@ -884,9 +892,9 @@ __device__ __noinline__ float qrl_phase_wrap_slow(float ph)
 //   * the next item is loaded before the current one is worked on (the 30-cycle LDS leaves the chain);
 //   * the table index floor(128 + 64 x) never passes through an integer register: the float rounded toward -inf onto 2^23 has
 //     the index in its low mantissa bits, and (bits << 2) + (table - (0x4B000000 << 2)) is the entry's address; the table has a
-//     257th entry (= entry 255) so that x = 2 needs no integer clamp;
+//     257th entry (= entry 255) so that x = 2 needs no integer clamp, and entries 257 / 258 = +1 / -1 for the saturated ranges;
 //   * the frequency limit is two FMNMX (exact for non-NaN), the 2*pi wrap one unlikely out-of-line call.
-// tanh_addr_m = smem_u32(table of 257 floats) - (0x4B000000u << 2) + (a zero read from shared memory: to the compiler the sum is then
+// tanh_addr_m = smem_u32(table of 259 floats: qrl_fill_tanh_s) - (0x4B000000u << 2) + (a zero read from shared memory: to the compiler the sum is then
 // an ordinary register value; a visible constant gets re-derived (S2UR + ULEA) or split into two dependent adds inside the loop).
 __device__ __forceinline__ void qrl_costas4_snr_chunk(LoopState& st, float k_a, float k_b, uint32_t addr, uint32_t row_bytes, int n,
                                                        uint32_t tanh_addr_m)
@@ -902,14 +910,15 @@ __device__ __forceinline__ void qrl_costas4_snr_chunk(LoopState& st, float k_a, 
         const float snr = orr * orr + oi * oi;
         const float ar = snr * orr, ai = snr * oi;
         // tanhf_lut: x > 2 -> 1, x <= -2 -> -1, else table[(int)(128 + 64 x)]
-        // 128 + 64 clamp(x, -2, 2) == clamp(fma(64, x, 128), 0, 256): 64 x is exact, so the fused form rounds once like the separate add,
-        // and the affine map is monotonic (one dependent operation less)
-        const float vr = fminf(fmaxf(fmaf(64.0f, ar, 128.0f), 0.0f), 256.0f);
-        const float vi = fminf(fmaxf(fmaf(64.0f, ai, 128.0f), 0.0f), 256.0f);
-        const float tr_ = lds_f32<0>((__float_as_uint(__fadd_rd(vr, 8388608.0f)) << 2) + tanh_addr_m);
-        const float ti_ = lds_f32<0>((__float_as_uint(__fadd_rd(vi, 8388608.0f)) << 2) + tanh_addr_m);
-        const float tr = ar > 2.0f ? 1.0f : (ar <= -2.0f ? -1.0f : tr_);
-        const float ti = ai > 2.0f ? 1.0f : (ai <= -2.0f ? -1.0f : ti_);
+        // 128 + 64 x == fma(64, x, 128): 64 x is exact, so the fused form rounds once like the separate add (one dependent operation less),
+        // and for -2 < x <= 2 it lies in (0, 256] by itself.  The two saturated ranges are table entries too (257 = 1.0f, 258 = -1.0f),
+        // picked by two selects IN FRONT of the load (they take the place of the two clamps), so nothing but the multiply stands
+        // behind the 25-cycle LDS.  A NaN fails "x > -2" and reads entry 258: the load address is always inside the table.
+        const float vr_ = fmaf(64.0f, ar, 128.0f), vi_ = fmaf(64.0f, ai, 128.0f);
+        const float vr = ar > 2.0f ? 257.0f : (ar > -2.0f ? vr_ : 258.0f);
+        const float vi = ai > 2.0f ? 257.0f : (ai > -2.0f ? vi_ : 258.0f);
+        const float tr = lds_f32<0>((__float_as_uint(__fadd_rd(vr, 8388608.0f)) << 2) + tanh_addr_m);
+        const float ti = lds_f32<0>((__float_as_uint(__fadd_rd(vi, 8388608.0f)) << 2) + tanh_addr_m);
         float err = tr * oi - ti * orr;
         err = qrl_clip(err, 1.0f);
         freq = freq + k_b * err;
@@ -1029,9 +1038,9 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
     constexpr int NHB = AC_NHB;
     extern __shared__ __align__(128) float2 sm_ac[];          // [NST][CH][32] | hand-off [NHB][CH][32]
     __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[NHB], bar_empty[NHB];
-    __shared__ float tanh_s[257];                             // entry 256 = entry 255 (see qrl_costas4_snr_chunk)
+    __shared__ float tanh_s[259];                             // entries 256 .. 258: see qrl_fill_tanh_s
     __shared__ volatile int opaque_zero;
-    for (int i = threadIdx.x; i < 257; i += blockDim.x) tanh_s[i] = d_tanh_tab[i < 256 ? i : 255];
+    qrl_fill_tanh_s(tanh_s);
     if (threadIdx.x == 0) opaque_zero = 0;
     float2* stage0 = sm_ac;
     float2* hand = sm_ac + NST * CH * 32;                     // [NHB][CH][32] + one row of padding (prefetch of the item behind a block)
@@ -1199,9 +1208,9 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
     extern __shared__ __align__(128) float sm_sync[];   // [NST][CH][ROWF] | mmse[129*8] | sym[2][maxs][ROWF] | cnt[2][32]
     __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[2], bar_empty[2];
     __shared__ volatile int lane_zero[32];
-    __shared__ float tanh_s[EPI == EPI_QPSK ? 257 : 1];    // second Costas loop's table (entry 256 = entry 255, see qrl_costas4_snr_chunk)
+    __shared__ float tanh_s[EPI == EPI_QPSK ? 259 : 1];    // second Costas loop's table (entries 256 .. 258: see qrl_fill_tanh_s)
     __shared__ volatile int opaque_zero;
-    if (EPI == EPI_QPSK) for (int i = threadIdx.x; i < 257; i += blockDim.x) tanh_s[i] = d_tanh_tab[i < 256 ? i : 255];
+    if (EPI == EPI_QPSK) qrl_fill_tanh_s(tanh_s);
     if (threadIdx.x == 0) opaque_zero = 0;
     float* stage0 = sm_sync;
     float* mm = sm_sync + NST * CH * ROWF;
@@ -1386,23 +1395,38 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                 uint32_t syp = smem_u32(sy);
                 const uint32_t syp0 = syp;
                 float A = x0, B = x1, Cc = x2, dA = d0, dB = d1, dC = d2;
+                // The 8 input rows of a symbol are in registers BEFORE its position is known: the next position is ofn + s12 with
+                // ofn = ofm + n0 known at the start of a symbol and s12 in {0, 1, 2} known at its end, so the ten rows ofn .. ofn + 9
+                // are loaded in the shadow of the current symbol's chain and the eight that count are picked by two selects each.
+                // Same values as loading at the final position (exact); what leaves the loop-carried chain is the shared-memory
+                // latency of the sample loads (the tap load, which depends on mu, stays).
+                float xs0 = 0.0f, xs1 = 0.0f, xs2 = 0.0f, xs3 = 0.0f, xs4 = 0.0f, xs5 = 0.0f, xs6 = 0.0f, xs7 = 0.0f;
+                auto load_xs = [&]() {
+                    const uint32_t xa = xb + (__float_as_uint(ofm) << 7);
+                    xs0 = lds_f32<0>(xa); xs1 = lds_f32<ROWF * 4>(xa); xs2 = lds_f32<ROWF * 8>(xa); xs3 = lds_f32<ROWF * 12>(xa);
+                    xs4 = lds_f32<ROWF * 16>(xa); xs5 = lds_f32<ROWF * 20>(xa); xs6 = lds_f32<ROWF * 24>(xa); xs7 = lds_f32<ROWF * 28>(xa);
+                };
+                if (ofm <= lim) load_xs();
                 // one symbol; returns true when the lane fell out of the in-lock stride window (generic step taken).
                 // ws_tag = true: the loop constants make that impossible (see window_sure), the check is compiled out.
                 auto body_t = [&](auto ws_tag, float& n, const float h1, const float h2, float& dn, const float dh1, const float dh2) -> bool {
                     constexpr bool WS = decltype(ws_tag)::value;
                     const uint32_t ta = mm2_b + __float_as_uint(fmaf(mu, k128, 12582912.0f)) * (REP ? 512u : 48u);
-                    const uint32_t xa = xb + (__float_as_uint(ofm) << 7);
                     const float ofn = ofm + q_f0;
+                    const uint32_t xn = xb + (__float_as_uint(ofn) << 7);
+                    const float r0 = lds_f32<0>(xn), r1 = lds_f32<ROWF * 4>(xn), r2 = lds_f32<ROWF * 8>(xn), r3 = lds_f32<ROWF * 12>(xn),
+                                r4 = lds_f32<ROWF * 16>(xn), r5 = lds_f32<ROWF * 20>(xn), r6 = lds_f32<ROWF * 24>(xn), r7 = lds_f32<ROWF * 28>(xn),
+                                r8 = lds_f32<ROWF * 32>(xn), r9 = lds_f32<ROWF * 36>(xn);
                     const float kd = -1.5f - dh2;
                     const float4 ta0 = lds_f32x4<0>(ta), ta1 = lds_f32x4<REP ? 256 : 16>(ta);   // taps[7..4], taps[3..0]
-                    float yr = fmaf(ta0.x, lds_f32<0>(xa), 0.0f);                 // oldest sample first
-                    yr = fmaf(ta0.y, lds_f32<ROWF * 4>(xa), yr);
-                    yr = fmaf(ta0.z, lds_f32<ROWF * 8>(xa), yr);
-                    yr = fmaf(ta0.w, lds_f32<ROWF * 12>(xa), yr);
-                    yr = fmaf(ta1.x, lds_f32<ROWF * 16>(xa), yr);
-                    yr = fmaf(ta1.y, lds_f32<ROWF * 20>(xa), yr);
-                    yr = fmaf(ta1.z, lds_f32<ROWF * 24>(xa), yr);
-                    yr = fmaf(ta1.w, lds_f32<ROWF * 28>(xa), yr);
+                    float yr = fmaf(ta0.x, xs0, 0.0f);                            // oldest sample first
+                    yr = fmaf(ta0.y, xs1, yr);
+                    yr = fmaf(ta0.z, xs2, yr);
+                    yr = fmaf(ta0.w, xs3, yr);
+                    yr = fmaf(ta1.x, xs4, yr);
+                    yr = fmaf(ta1.y, xs5, yr);
+                    yr = fmaf(ta1.z, xs6, yr);
+                    yr = fmaf(ta1.w, xs7, yr);
                     n = yr;
                     // slicer levels are +-0.5, +-1.5: the sums below are exact in any order (two-level tree)
                     const float s1 = qrl_ge1(yr, -1.0f), s23 = qrl_ge1(yr, -5.9604644775390625e-8f) + qrl_ge1(yr, 0.99999988079071044921875f);
@@ -1418,13 +1442,17 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                     sts_f32(syp, yr);
                     syp += ROWF * 4;
                     const float s12 = qrl_ge1(m0, 1.0f) + qrl_ge1(m0, 2.0f);     // == [ph >= n0+1] + [ph >= n0+2] (m0 exact)
+                    const bool g1 = m0 >= 1.0f, g2 = m0 >= 2.0f;
                     mu = m0 - s12;
                     ofm = ofn + s12;
+                    xs0 = g2 ? r2 : (g1 ? r1 : r0); xs1 = g2 ? r3 : (g1 ? r2 : r1); xs2 = g2 ? r4 : (g1 ? r3 : r2); xs3 = g2 ? r5 : (g1 ? r4 : r3);
+                    xs4 = g2 ? r6 : (g1 ? r5 : r4); xs5 = g2 ? r7 : (g1 ? r6 : r5); xs6 = g2 ? r8 : (g1 ? r7 : r6); xs7 = g2 ? r9 : (g1 ? r8 : r7);
                     if (!WS) {
                         if (__builtin_expect(__float_as_uint(m0) >= 0x40400000u, 0)) {    // ph not in [n0, n0+3): generic floor
                             const float2 g = symsync_generic_step(ph);
                             mu = g.x;
                             ofm = (ofn - q_f0) + g.y;
+                            if (ofm <= lim) load_xs();
                             return true;
                         }
                     }

@@ -52,9 +52,9 @@ __global__ void chain_kernel(float a0, float b0, int iters, long long* __restric
 __global__ void costas_kernel(int n, int passes, long long* __restrict__ cyc, float* __restrict__ sink, unsigned warp_mask)
 {
     extern __shared__ __align__(128) float2 items[];          // [warps][n + 1][32]
-    __shared__ float tanh_s[257];
+    __shared__ float tanh_s[259];
     __shared__ volatile int opaque_zero;
-    for (int i = threadIdx.x; i < 257; i += blockDim.x) tanh_s[i] = tanhf((i < 256 ? i : 255) / 64.0f - 2.0f);
+    for (int i = threadIdx.x; i < 259; i += blockDim.x) tanh_s[i] = i < 257 ? tanhf((i < 256 ? i : 255) / 64.0f - 2.0f) : (i == 257 ? 1.0f : -1.0f);
     if (threadIdx.x == 0) opaque_zero = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* mine = items + static_cast<size_t>(warp) * (n + 1) * 32;
