@@ -972,6 +972,9 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         for (int i = 0; i < qrl_rx::kMaxSub; i++) { mk(&h->ev_a[i]); mk(&h->ev_b[i]); mk(&h->ev_c[i]); }
         if (!ok) { set_err(h, "stream/event creation failed"); return fail(QRL_ECUDA); }
     }
+    // QPSK: the call ends with the symbol sync + Viterbi of the last slice behind the per-sample loop (no overlapped calls for this
+    // chain): the finest slicing the event arrays allow keeps that tail short
+    if (kind == QRL_DEMOD_QPSK) h->nsub = qrl_rx::kMaxSub;
     if (const char* e = getenv("QRL_NSUB")) { int v = atoi(e); if (v >= 1 && v <= qrl_rx::kMaxSub) { h->nsub = v; h->nsub_forced = true; } }
     if (const char* e = getenv("QRL_FIR_GROUP")) { int v = atoi(e); if (v >= 1 && v <= qrl_rx::kMaxSub) { h->fir_group = v; h->fir_group_forced = true; } }
     if ((rc = qrl_rx_reset(h))) return fail(rc);

@@ -24,6 +24,7 @@ __device__ float d_sine_tab[2048];
 #ifdef QRL_SS_PROF
 // -DQRL_SS_PROF (tools/ss_prof.py): where the symbol-sync loop warp of CTA 0 spends its cycles (clock64 deltas, summed per launch)
 // [0] wait for the hand-off block  [1] wait for the window  [2] uniform rounds  [3] stragglers  [4] hand-off  [5] windows  [6] symbols  [7] rounds
+// [8] ns entry -> loop warp starts  [9] ns entry -> first window there  [10] ns entry -> loop warp done  [11] launches (globaltimer)
 __device__ long long d_ss_prof[16];
 #define SSP(...) __VA_ARGS__
 #else
@@ -1202,6 +1203,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
     constexpr bool EXT = (EPI == EPI_EXT_4FSK_FM);
     static_assert(!EXT || (NEPI == 1 && NCOMP == 1), "external epilogue: one drain warp, real symbols");
     constexpr int ROWF = 32 * NCOMP;                    // floats per row
+    SSP(const unsigned long long pg0 = globaltimer_ns();)
     // window advance per chunk: a lane leaves a window once its position is within `lookahead` rows of the end, so
     // consecutive windows overlap by the lookahead rounded up to 32 rows (same formula on the host: symsync_stride)
     const int STRIDE = symsync_stride(CH, p.lookahead);
@@ -1228,8 +1230,17 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
     const bool active = c < C;
     // tap-major copy of the MMSE bank: mm[k * 132 + imu] (a lane's 8 taps are 8 scalar loads in the order the
     // oldest-first FMA chain consumes them; random imu across lanes spreads over all 32 banks)
-    for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) {
-        const float t = d_mmse_tab[i];
+    // (all of a thread's table entries are loaded before the first store: one L2 latency per launch instead of one per entry -- the
+    // fill used to be 6 us of every launch, profiles/r02_w_symsync_launch_phases.txt)
+    constexpr int NT = 64 + 32 * NEPI, TPT = (129 * 8 + NT - 1) / NT;
+    float tv[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; k++) { const int i = threadIdx.x + k * NT; tv[k] = i < 129 * 8 ? d_mmse_tab[i] : 0.0f; }
+#pragma unroll
+    for (int k = 0; k < TPT; k++) {
+        const int i = threadIdx.x + k * NT;
+        if (i >= 129 * 8) break;
+        const float t = tv[k];
         mm[(i & 7) * 132 + (i >> 3)] = t;
         mm2[(i >> 3) * 12 + (7 - (i & 7))] = t;
         if (REP) {
@@ -1334,6 +1345,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
         const bool window_sure = lean_ok && (p.max_period + fabsf(p.alpha) + 1.0f < p.fl0 + 3.0f - 1e-3f) &&
                                  (p.min_period - fabsf(p.alpha) > p.fl0 + 1e-3f) && p.fl0 == static_cast<float>(p.n0);
         SSP(long long pf_we = 0; long long pf_wi = 0; long long pf_run = 0; long long pf_str = 0; long long pf_ho = 0; long long pf_rounds = 0; long long pf_sym = 0;)
+        SSP(const unsigned long long pg1 = globaltimer_ns(); unsigned long long pg2 = pg1;)
         for (int m = 0; m < nchunks; m++) {
             const int st = m % NST, b = m & 1;
             SSP(const long long pt0 = clock64();)
@@ -1341,6 +1353,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
             SSP(const long long pt1 = clock64();)
             mbar_wait(&bar_in[st], (m / NST) & 1);
             SSP(const long long pt2 = clock64(); pf_we += pt1 - pt0; pf_wi += pt2 - pt1; long long pt3 = pt2;)
+            SSP(if (m == 0) pg2 = globaltimer_ns();)
             const float* buf = stp + st * CH * ROWF;
             float* sy = symbuf + b * blk_rows * ROWF + lane * NCOMP;
             const long long w0 = base + static_cast<long long>(m) * STRIDE;
@@ -1458,11 +1471,14 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                     }
                     return false;
                 };
-                // Trip counts are warp-uniform: in lock the stride is at most n0 + 2, so every lane can take
-                // floor(rows left / (n0 + 2)) + 1 symbols without looking at the window end; recomputed until no lane
-                // has a guaranteed symbol left, then each lane finishes under the exact per-lane check.
+                // Trip counts are warp-uniform.  Positions telescope: o_j + mu_j = o_0 + mu_0 + sum of the instantaneous periods, each at
+                // most max_period + |alpha| (the average is clamped to max_period, the proportional term is |alpha| |err| <= |alpha|),
+                // so symbol j starts below o_0 + 1 + j pmax and every lane can take floor((rows left - 1) / pmax) + 1 symbols without
+                // looking at the window end (the 0.9999 covers the float roundings of ph, ~5e-7 rows per symbol); recomputed until no
+                // lane has a guaranteed symbol left, then each lane finishes under the exact per-lane check.  (The first version
+                // divided by the largest possible stride n0 + 2 and needed ~3.9 rounds per window; this one needs 2.)
                 const unsigned amask = __activemask();
-                const float inv_s = 1.0f / static_cast<float>(k_n0 + 2);
+                const float inv_s = 0.9999f / (p.max_period + fabsf(p.alpha));
                 auto run = [&](auto ws_tag) {
                     auto body = [&](float& n, const float h1, const float h2, float& dn, const float dh1, const float dh2) -> bool {
                         return body_t(ws_tag, n, h1, h2, dn, dh1, dh2);
@@ -1470,7 +1486,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                     for (;;) {
                         SSP(pf_rounds++;)
                         const float left = lim - ofm;                      // exact (integers below 2^24)
-                        int ksafe = left >= 0.0f ? static_cast<int>(left * inv_s * 0.999f) + 1 : 0;   // never above the true quotient + 1
+                        int ksafe = left >= 0.0f ? static_cast<int>(fmaxf(left - 1.0f, 0.0f) * inv_s) + 1 : 0;
                         ksafe = __reduce_min_sync(amask, ksafe);
                         if (ksafe == 0) break;
                         bool fell = false;
@@ -1567,6 +1583,8 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
             if (lane == 0) { mbar_arrive(&bar_free[st]); mbar_arrive(&bar_full[b]); }
             SSP(pf_ho += clock64() - pt4;)
         }
+        SSP(const unsigned long long pg3 = globaltimer_ns();)
+        SSP(if (g == 0 && lane == 0) { d_ss_prof[8] += pg1 - pg0; d_ss_prof[9] += pg2 - pg0; d_ss_prof[10] += pg3 - pg0; d_ss_prof[11] += 1; })
         SSP(if (g == 0 && lane == 0) { d_ss_prof[0] += pf_we; d_ss_prof[1] += pf_wi; d_ss_prof[2] += pf_run; d_ss_prof[3] += pf_str; d_ss_prof[4] += pf_ho;
                                        d_ss_prof[5] += nchunks; d_ss_prof[6] += pf_sym; d_ss_prof[7] += pf_rounds; })
         if (active) {

@@ -80,5 +80,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     } while (!done);
 }
 
+// nanosecond wall clock of the device (profiling build only: tools/ss_prof.py)
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 }  // namespace qrl

@@ -52,6 +52,9 @@ def main():
         print("%s call %d: windows %d, symbols %d (%.1f per window), uniform rounds %.2f per window; cycles per window: "
               "wait hand-off %.0f, wait window %.0f, uniform rounds %.0f, stragglers %.0f, hand-off %.0f, total %.0f (%.1f per symbol)"
               % (case, it, v[5], v[6], v[6] / w, v[7] / w, v[0] / w, v[1] / w, v[2] / w, v[3] / w, v[4] / w, tot / w, tot / max(v[6], 1)))
+        nl = max(v[11], 1)
+        print("    launches %d; per launch (globaltimer, us): entry -> loop warp starts %.2f, entry -> first window there %.2f, entry -> loop warp done %.2f"
+              % (v[11], v[8] / nl / 1e3, v[9] / nl / 1e3, v[10] / nl / 1e3))
     blk.close()
 
 
