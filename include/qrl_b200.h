@@ -239,8 +239,8 @@ long qrl_pfb_launch_count(qrl_pfb*);
  * low_pass_2(1, 24k, ...) -> x0.8 -> rational_resampler_ccf(25, 24, low_pass_2(25, 600k, ...)) -> rows rows[c] of a zeroed [n_rows][stride]
  * slab at 25 ksps (the synthesizer's input; unused rows are the reference's null_source).  qrl_mmdvm_tx_finish applies what follows
  * the synthesizer, multiply_const_cc(1 / n_channels) and multiply_const_cc(bb_gain), in place on the wideband device buffer.
- * Not built: the "zero_samples" tags of gr_zero_idle_bursts(0) on this path (gr_mod_mmdvm_multi2.cpp:84-87), the MMDVM protocol sink /
- * source (ZeroMQ, out of scope). */
+ * gr_zero_idle_bursts(0) (gr_mod_mmdvm_multi2.cpp:88,108-117; gr_mod_mmdvm.cpp:51-58) = qrl_mmdvm_tx_zero_samples below.
+ * Not built: the MMDVM protocol sink / source (ZeroMQ, out of scope). */
 typedef struct qrl_mmdvm_rx qrl_mmdvm_rx;
 typedef struct qrl_mmdvm_tx qrl_mmdvm_tx;
 /* variant 0: the per-channel chains of gr_demod_mmdvm_multi2 / gr_mod_mmdvm_multi2 described above (25 ksps <-> 24 ksps).
@@ -264,6 +264,14 @@ int  qrl_mmdvm_tx_create(int variant, int n_channels, const int* rows, int n_row
 int  qrl_mmdvm_tx_destroy(qrl_mmdvm_tx*);
 int  qrl_mmdvm_tx_set_stream(qrl_mmdvm_tx*, void* cuda_stream);
 int  qrl_mmdvm_tx_set_bb_gain(qrl_mmdvm_tx*, float gain);                   /* gr_mod_mmdvm_multi2::set_bb_gain */
+/* The "zero_samples" stream tag of gr_mmdvm_source.cpp:264 as gr_zero_idle_bursts(0) consumes it (gr_zero_idle_bursts.cpp:47-86): from item
+ * `item_offset` of the zero-idle block's OWN stream on, n_samples outputs of `channel` (-1: all) are cleared; a later tag overrides what is
+ * left of a running count; counts carry across calls.  The block's stream is the 24 ksps stream behind the FM modulator for variant 1
+ * (gr_mod_mmdvm: every block in front of it is 1:1, so item_offset is the index of the tagged int16 sample) and the 25 ksps stream behind
+ * the x25/24 resampler for variant 0 (gr_mod_mmdvm_multi2: GNU Radio's scheduler moves a tag on input sample k across the resampler to item
+ * floor(k * 25 / 24 + 1/2); the adapter applies that mapping, qradiolink_b200.mmdvm_tag_item does).  Register a tag before the
+ * qrl_mmdvm_tx_work call that produces its item; one registered later clears what is left of its count. */
+int  qrl_mmdvm_tx_zero_samples(qrl_mmdvm_tx*, int channel, long long item_offset, long n_samples);
 int  qrl_mmdvm_tx_work(qrl_mmdvm_tx*, const short* in, long n, long stride, int on_device, long* n_out);
 int  qrl_mmdvm_tx_sync(qrl_mmdvm_tx*);
 int  qrl_mmdvm_tx_out_device(qrl_mmdvm_tx*, float** data, long* stride, long* n_out);      /* [n_rows][*stride] gr_complex */

@@ -64,6 +64,7 @@ def lib():
         L.qo_mmdvm_tx_create2.restype = vp
         L.qo_mmdvm_tx_create2.argtypes = [C.c_int, C.c_int]
         L.qo_mmdvm_tx_set_bb_gain.argtypes = [vp, C.c_float]
+        L.qo_mmdvm_tx_zero_samples.argtypes = [vp, C.c_longlong, C.c_long]
         L.qo_mmdvm_rx_calibrate_rssi.argtypes = [vp, C.c_float]
         L.qo_mmdvm_rx_work.argtypes = [vp, vp, C.c_long]
         L.qo_mmdvm_rx_out_items.restype = C.c_long
@@ -484,6 +485,10 @@ class MmdvmTx:
 
     def set_bb_gain(self, g):
         lib().qo_mmdvm_tx_set_bb_gain(self.h, float(g))
+
+    def zero_samples(self, item_offset, n_samples):
+        """the "zero_samples" tag on item `item_offset` of gr_zero_idle_bursts(0)'s own stream (qo_mmdvm_tx_zero_samples)"""
+        return lib().qo_mmdvm_tx_zero_samples(self.h, int(item_offset), int(n_samples))
 
     def __del__(self):
         if getattr(self, "h", None):

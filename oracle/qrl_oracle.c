@@ -3190,8 +3190,8 @@ void qo_mmdvm_rx_clear(qo_mmdvm_rx* r) { r->out.n = 0; r->rssi_db.n = 0; r->rssi
 
 struct qo_mmdvm_tx { int single; float bb_gain; qo_tx fm; resamp_t filt; resamp_t rs; qvec s_f, s_m, s_b, out; };
 /* variant 1: gr_mod_mmdvm (/root/reference/src/gr/gr_mod_mmdvm.cpp:28-70): the same chain up to x0.8, then x bb_gain, then
- * rational_resampler_ccf(125, 12, low_pass_2(125, 125 * 24k, fw, 2000, 60, BH)) to 250 ksps (gr_zero_idle_bursts(0) sits in front of the
- * filter there: tags only, not restated) */
+ * rational_resampler_ccf(125, 12, low_pass_2(125, 125 * 24k, fw, 2000, 60, BH)) to 250 ksps; gr_zero_idle_bursts(0) sits in front of the
+ * filter there (behind the resampler in the multi-channel block): qo_mmdvm_tx_zero_samples */
 qo_mmdvm_tx* qo_mmdvm_tx_create2(int filter_width, int variant)
 {
     static float taps[16384];
@@ -3217,6 +3217,7 @@ void qo_mmdvm_tx_destroy(qo_mmdvm_tx* t)
 {
     if (!t) return;
     resamp_free(&t->filt); resamp_free(&t->rs); qv_free(&t->s_f); qv_free(&t->s_m); qv_free(&t->s_b); qv_free(&t->out);
+    free(t->fm.zi_tag_off); free(t->fm.zi_tag_val);
     free(t);
 }
 int qo_mmdvm_tx_work(qo_mmdvm_tx* t, const short* in, long n)
@@ -3225,10 +3226,38 @@ int qo_mmdvm_tx_work(qo_mmdvm_tx* t, const short* in, long n)
     t->s_f.n = 0;
     for (long i = 0; i < n; i++) { float v = (float)in[i] * inv; v = v * 1.0f; qv_pushf(&t->s_f, v); }
     t->s_m.n = 0; fm_mod(&t->fm, (const float*)t->s_f.d, t->s_f.n, &t->s_m, 1.0f);
+    if (t->single) zero_idle_work(&t->fm, (float*)t->s_m.d, t->s_m.n);        /* gr_mod_mmdvm.cpp:51-58: gr_zero_idle_bursts(0) */
     t->s_b.n = 0; resamp_work(&t->filt, (const float*)t->s_m.d, t->s_m.n, &t->s_b);
     float* m = (float*)t->s_b.d;
     for (size_t i = 0; i < 2 * t->s_b.n; i++) { m[i] = m[i] * 0.8f; if (t->single) m[i] = m[i] * t->bb_gain; }   /* multiply_const_cc(0.8) [, bb_gain] */
+    const size_t n_before = t->out.n;
     resamp_work(&t->rs, m, t->s_b.n, &t->out);
+    if (!t->single) zero_idle_work(&t->fm, (float*)t->out.d + 2 * n_before, t->out.n - n_before);   /* gr_mod_mmdvm_multi2.cpp:88,108 */
+    return 0;
+}
+/* The "zero_samples" tag (gr_mmdvm_source.cpp:264) as gr_zero_idle_bursts(0) sees it: on item `item_offset` of the block's OWN stream
+ * -- the 24 ksps stream behind the FM modulator for gr_mod_mmdvm (every block in front of it is 1:1), the 25 ksps stream behind the
+ * x25/24 resampler for gr_mod_mmdvm_multi2 (GNU Radio's scheduler moves a tag across a rate-changing block to
+ * floor(offset * 25 / 24 + 1/2); that is runtime behaviour outside /root/reference, so the caller applies it: oracle.mmdvm_tag_item).
+ * Same bookkeeping as qo_tx_zero_samples with delay 0. */
+int qo_mmdvm_tx_zero_samples(qo_mmdvm_tx* t, long long item_offset, long n_samples)
+{
+    if (!t || item_offset < 0 || n_samples < 0) return -1;
+    qo_tx* z = &t->fm;
+    long long start = item_offset;
+    uint64_t val = (uint64_t)n_samples;
+    if (start < (long long)z->zi_n) {
+        const uint64_t late = (uint64_t)((long long)z->zi_n - start);
+        if (late >= val) return 0;
+        val -= late; start = (long long)z->zi_n;
+    }
+    for (long i = 0; i < z->zi_ntags; i++) if (z->zi_tag_off[i] == start) return 0;      /* first registered wins */
+    if (z->zi_ntags == z->zi_cap) {
+        z->zi_cap = z->zi_cap ? 2 * z->zi_cap : 16;
+        z->zi_tag_off = (long long*)realloc(z->zi_tag_off, sizeof(long long) * (size_t)z->zi_cap);
+        z->zi_tag_val = (uint64_t*)realloc(z->zi_tag_val, sizeof(uint64_t) * (size_t)z->zi_cap);
+    }
+    z->zi_tag_off[z->zi_ntags] = start; z->zi_tag_val[z->zi_ntags] = val; z->zi_ntags++;
     return 0;
 }
 long qo_mmdvm_tx_out_items(qo_mmdvm_tx* t) { return (long)t->out.n; }

@@ -15,4 +15,4 @@ from .pfb import PfbChannelizer, PfbSynthesizer, mmdvm_port_map  # noqa: F401
 from .framing import Deframer, DeframerBB, MODE_FRAMING, SYNC_1K, SYNC_NARROW, SYNC_WIDE, SYNC_M17, frame  # noqa: F401
 from .frontend import Frontend  # noqa: F401
 from .spectrum import Spectrum  # noqa: F401
-from .mmdvm import MmdvmDemod, MmdvmMod, MmdvmChannelsRx, MmdvmChannelsTx  # noqa: F401
+from .mmdvm import MmdvmDemod, MmdvmMod, MmdvmChannelsRx, MmdvmChannelsTx, mmdvm_tag_item  # noqa: F401

@@ -1951,6 +1951,60 @@ int qrl_rx_sm_partition(const qrl_rx* h, int* loop_sms, int* parallel_sms)
 }
 
 // ---------------------------------------------------------------------------------------------- TX
+// gr_zero_idle_bursts (gr_zero_idle_bursts.cpp:47-86) as host-side bookkeeping: the "zero_samples" tags waiting per channel and the count
+// still running at the end of the last call; a call turns them into {channel, first item, end item} ranges that one kernel clears
+// (a tag loads the counter, a later one overrides what is left of it, one output is cleared per count).  Shared by gr_mod_dmr (delay
+// 62) and the MMDVM modulators (delay 0).
+struct ZeroIdle {
+    std::vector<std::map<long long, unsigned long long>> tags;      // per channel: start item -> count (first registered wins)
+    std::vector<unsigned long long> counter;                       // per channel: count still running at the end of the last call
+    long long* d_ranges = nullptr; size_t ranges_cap = 0;
+    void init(int C) { tags.assign(C, {}); counter.assign(C, 0); }
+    // tag for item `start` (already corrected for the block's delay); `produced` = items the block has put out so far
+    void add(int channel, int C, long long start, unsigned long long val, long long produced)
+    {
+        if (start < produced) {                                                  // late: clear what is left of the count
+            const unsigned long long late = static_cast<unsigned long long>(produced - start);
+            if (late >= val) return;
+            val -= late; start = produced;
+        }
+        for (int c = (channel < 0 ? 0 : channel); c < (channel < 0 ? C : channel + 1); c++) tags[c].emplace(start, val);
+    }
+    // ranges of the items [m0, m1) this call produces, as {c, a0 - base, a1 - base} triples
+    void collect(int C, long long m0, long long m1, long long base, std::vector<long long>& ranges)
+    {
+        for (int c = 0; c < C; c++) {
+            auto& tg = tags[c];
+            tg.erase(tg.begin(), tg.lower_bound(m0));
+            unsigned long long cnt = counter[c];
+            if (cnt == 0 && (tg.empty() || tg.begin()->first >= m1)) continue;
+            long long cur = m0;
+            auto it = tg.begin();
+            while (true) {
+                const long long next = (it != tg.end() && it->first < m1) ? it->first : m1;
+                const long long z_end = cnt >= static_cast<unsigned long long>(next - cur) ? next : cur + static_cast<long long>(cnt);
+                if (z_end > cur) { ranges.push_back(c); ranges.push_back(cur - base); ranges.push_back(z_end - base); }
+                cnt -= static_cast<unsigned long long>(z_end - cur);
+                if (next == m1) break;
+                cnt = it->second; cur = next; it = tg.erase(it);
+            }
+            counter[c] = cnt;
+        }
+    }
+    // upload the triples (growing the device buffer if needed); returns a CUDA error code
+    cudaError_t upload(const std::vector<long long>& ranges, cudaStream_t stream)
+    {
+        if (ranges.size() > ranges_cap) {
+            cudaError_t e = cudaStreamSynchronize(stream); if (e != cudaSuccess) return e;
+            if (d_ranges) { e = cudaFree(d_ranges); if (e != cudaSuccess) return e; d_ranges = nullptr; }
+            ranges_cap = 2 * ranges.size() + 48;
+            e = cudaMalloc(&d_ranges, sizeof(long long) * ranges_cap); if (e != cudaSuccess) return e;
+        }
+        return cudaMemcpyAsync(d_ranges, ranges.data(), sizeof(long long) * ranges.size(), cudaMemcpyHostToDevice, stream);
+    }
+    void release() { if (d_ranges) cudaFree(d_ranges); d_ranges = nullptr; }
+};
+
 struct qrl_tx : HandleBase {
     int kind = 0, sps = 0, samp_rate = 0, filter_width = 0, flag = 0, C = 0;
     long max_items = 0;
@@ -1968,9 +2022,7 @@ struct qrl_tx : HandleBase {
     float audio_gain = 0.99f; bool tone_on = false; unsigned tone_phase = 0, tone_inc = 0;
     // gr_mod_dmr: the m17 path with gr_zero_idle_bursts in place of the IF low-pass (a delay of history - 1 items + "zero_samples" tags)
     bool dmr_tx = false; long long zi_delay_items = 0; unsigned zi_tag_delay = 0;
-    std::vector<std::map<long long, unsigned long long>> zi_tags;      // per channel: start item -> count (first registered wins)
-    std::vector<unsigned long long> zi_counter;                       // per channel: count still running at the end of the last call
-    long long* d_zi_ranges = nullptr; size_t zi_ranges_cap = 0;
+    ZeroIdle zi;                                                      // gr_mod_dmr: gr_zero_idle_bursts(62)
     TxBitState* d_bits = nullptr;
     unsigned char* d_in = nullptr;
     float* d_sym = nullptr; unsigned sym_mask = 0; long long sym_stride = 0;    // float (4FSK) / float2 (QPSK)
@@ -2175,7 +2227,7 @@ int qrl_tx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         t2 = low_pass_2(sps, 3.0 * samp_rate, filter_width, 2000, 60, WIN_BLACKMAN_HARRIS);
         h->L2 = sps; h->M2 = 3; h->nt2 = (static_cast<int>(t2.size()) + sps - 1) / sps;
         if (sps <= 3 || static_cast<size_t>(h->L2) * h->nt2 * sizeof(float) > 40 * 1024) { set_err(h, "make_gr_mod_dmr: unsupported sps"); return fail(QRL_EINVAL); }
-        h->zi_tags.resize(h->C); h->zi_counter.assign(h->C, 0);
+        h->zi.init(h->C);
     } else if (kind == QRL_MOD_2FSK) {
         // gr_mod_2fsk.cpp:43-76
         int nfilts = 25 * sps, spacing = 2; h->amplif = 0.8f;
@@ -2263,7 +2315,7 @@ int qrl_tx_destroy(qrl_tx* h)
     for (int i = 0; i < qrl_tx::kTxSub; i++) { if (h->ev_bits[i]) cudaEventDestroy(h->ev_bits[i]); if (h->ev_shape[i]) cudaEventDestroy(h->ev_shape[i]); }
     for (auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (void* p : h->allocs) cudaFree(p);
-    if (h->d_zi_ranges) cudaFree(h->d_zi_ranges);
+    h->zi.release();
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return QRL_OK;
@@ -2568,32 +2620,10 @@ int qrl_tx_work(qrl_tx* h, const void* in, long n, long stride, int on_device)
             // the "zero_samples" counters of this call as item ranges (gr_zero_idle_bursts.cpp:61-79: a tag loads the counter, a later
             // one overrides what is left of it, one output is cleared per count)
             std::vector<long long> ranges;
-            for (int c = 0; c < h->C; c++) {
-                auto& tg = h->zi_tags[c];
-                tg.erase(tg.begin(), tg.lower_bound(m0));
-                unsigned long long cnt = h->zi_counter[c];
-                if (cnt == 0 && (tg.empty() || tg.begin()->first >= m1)) continue;
-                long long cur = m0;
-                auto it = tg.begin();
-                while (true) {
-                    const long long next = (it != tg.end() && it->first < m1) ? it->first : m1;
-                    const long long z_end = cnt >= static_cast<unsigned long long>(next - cur) ? next : cur + static_cast<long long>(cnt);
-                    if (z_end > cur) { ranges.push_back(c); ranges.push_back(cur); ranges.push_back(z_end); }
-                    cnt -= static_cast<unsigned long long>(z_end - cur);
-                    if (next == m1) break;
-                    cnt = it->second; cur = next; it = tg.erase(it);
-                }
-                h->zi_counter[c] = cnt;
-            }
+            h->zi.collect(h->C, m0, m1, 0, ranges);
             if (!ranges.empty()) {
-                if (ranges.size() > h->zi_ranges_cap) {
-                    CK(cudaStreamSynchronize(h->stream));
-                    if (h->d_zi_ranges) CK(cudaFree(h->d_zi_ranges));
-                    h->zi_ranges_cap = 2 * ranges.size() + 48;
-                    CK(cudaMalloc(&h->d_zi_ranges, sizeof(long long) * h->zi_ranges_cap));
-                }
-                CK(cudaMemcpyAsync(h->d_zi_ranges, ranges.data(), sizeof(long long) * ranges.size(), cudaMemcpyHostToDevice, h->stream));
-                tx_zero_ranges_kernel<<<static_cast<unsigned>(ranges.size() / 3), 256, 0, h->stream>>>(h->d_rc, h->rc_mask, h->rc_stride, h->d_zi_ranges);
+                CK(h->zi.upload(ranges, h->stream));
+                tx_zero_ranges_kernel<<<static_cast<unsigned>(ranges.size() / 3), 256, 0, h->stream>>>(h->d_rc, h->rc_mask, h->rc_stride, h->zi.d_ranges);
                 h->launches++;
             }
         } else {
@@ -2649,15 +2679,7 @@ int qrl_tx_zero_samples(qrl_tx* h, int channel, long long byte_offset, long n_sa
     // the tag rides through packed_to_unpacked (x8), pack_k_bits(2) (/2) and the x5 pulse shaper: item 20 * byte_offset at the block
     const long long item = byte_offset * 4 * h->L1;
     if (item < static_cast<long long>(h->zi_tag_delay)) return QRL_OK;          // gr_zero_idle_bursts.cpp:63 can never match
-    long long start = item - static_cast<long long>(h->zi_tag_delay);
-    unsigned long long val = static_cast<unsigned long long>(n_samples);
-    const long long produced = h->n_sym * h->L1;
-    if (start < produced) {                                                      // late: clear what is left of the count
-        const unsigned long long late = static_cast<unsigned long long>(produced - start);
-        if (late >= val) return QRL_OK;
-        val -= late; start = produced;
-    }
-    for (int c = (channel < 0 ? 0 : channel); c < (channel < 0 ? h->C : channel + 1); c++) h->zi_tags[c].emplace(start, val);
+    h->zi.add(channel, h->C, item - static_cast<long long>(h->zi_tag_delay), static_cast<unsigned long long>(n_samples), h->n_sym * h->L1);
     return QRL_OK;
 }
 int qrl_tx_sync(qrl_tx* h)
@@ -2930,6 +2952,7 @@ struct qrl_mmdvm_tx : HandleBase {
     long long n_in = 0, n25 = 0;
     float fm_sens = 0, level = 1.0f, bb_gain = 1.0f;
     int L = 25, M = 24; bool single = false;       // single: gr_mod_mmdvm (x125 / 12 to 250 ksps, bb_gain in front of the resampler)
+    ZeroIdle zi;                                   // gr_zero_idle_bursts(0): behind the FM modulator (single) / behind the resampler (multi2)
 };
 
 template <class H> static int mmdvm_destroy(H* h)
@@ -3085,7 +3108,7 @@ int qrl_mmdvm_rx_read(qrl_mmdvm_rx* h, short* dst, long dst_stride, float* rssi_
 }
 long qrl_mmdvm_rx_launch_count(qrl_mmdvm_rx* h) { return h ? h->launches : 0; }
 
-int qrl_mmdvm_tx_destroy(qrl_mmdvm_tx* h) { return mmdvm_destroy(h); }
+int qrl_mmdvm_tx_destroy(qrl_mmdvm_tx* h) { if (h) { cudaSetDevice(h->device); if (h->stream) cudaStreamSynchronize(h->stream); h->zi.release(); } return mmdvm_destroy(h); }
 int qrl_mmdvm_tx_set_stream(qrl_mmdvm_tx* h, void* s) { return mmdvm_set_stream(h, s); }
 int qrl_mmdvm_tx_create(int variant, int n_channels, const int* rows, int n_rows, int filter_width, long max_in, int device, qrl_mmdvm_tx** out)
 {
@@ -3094,6 +3117,7 @@ int qrl_mmdvm_tx_create(int variant, int n_channels, const int* rows, int n_rows
     if (qrl_device_count() <= device) { set_err(nullptr, "qrl_mmdvm_tx_create: no CUDA device (this library has no CPU fallback)"); return QRL_ENODEV; }
     qrl_mmdvm_tx* h = new qrl_mmdvm_tx();
     h->C = n_channels; h->n_rows = n_rows; h->num_channels = n_channels; h->max_in = max_in; h->device = device;
+    h->zi.init(h->C);
     auto fail = [&](int rc) { std::string e = h->err; qrl_mmdvm_tx_destroy(h); g_err = e; return rc; };
     if (cudaSetDevice(device) != cudaSuccess) { set_err(h, "cudaSetDevice failed"); return fail(QRL_ECUDA); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_err(h, "stream create failed"); return fail(QRL_ECUDA); }
@@ -3129,6 +3153,12 @@ int qrl_mmdvm_tx_create(int variant, int n_channels, const int* rows, int n_rows
     return QRL_OK;
 }
 int qrl_mmdvm_tx_set_bb_gain(qrl_mmdvm_tx* h, float g) { if (!h) return QRL_EINVAL; h->bb_gain = g; return QRL_OK; }      // gr_mod_mmdvm_multi2::set_bb_gain
+int qrl_mmdvm_tx_zero_samples(qrl_mmdvm_tx* h, int channel, long long item_offset, long n_samples)
+{
+    if (!h || channel < -1 || channel >= h->C || item_offset < 0 || n_samples < 0) return QRL_EINVAL;
+    h->zi.add(channel, h->C, item_offset, static_cast<unsigned long long>(n_samples), h->single ? h->n_in : h->n25);
+    return QRL_OK;
+}
 int qrl_mmdvm_tx_work(qrl_mmdvm_tx* h, const short* in, long n, long stride, int on_device, long* n_out)
 {
     if (!h || !in || n < 0) return QRL_EINVAL;
@@ -3151,6 +3181,16 @@ int qrl_mmdvm_tx_work(qrl_mmdvm_tx* h, const short* in, long n, long stride, int
     // frequency_modulator_fc: the FM scan kernel with a one-tap "pulse" (x * 1.0 is exact), Q32 phase carried in the state
     tx_shape_fm_kernel<1024, 2><<<h->C, 1024, 0, h->stream>>>(h->d_bits, h->d_sym, h->sym_mask, h->sym_stride, a0, n,
         1, 1, h->d_one, 0, 1.0f, h->fm_sens, 1.0f, 1.0f, h->d_if, h->if_mask, h->if_stride);
+    if (h->single) {
+        // gr_mod_mmdvm.cpp:51-58: gr_zero_idle_bursts(0) between the FM modulator and the filter (items of the 24 ksps stream)
+        std::vector<long long> ranges;
+        h->zi.collect(h->C, a0, a1, 0, ranges);
+        if (!ranges.empty()) {
+            CK(h->zi.upload(ranges, h->stream));
+            tx_zero_ranges_kernel<<<static_cast<unsigned>(ranges.size() / 3), 256, 0, h->stream>>>(h->d_if, h->if_mask, h->if_stride, h->zi.d_ranges);
+            h->launches++;
+        }
+    }
     dim3 g(static_cast<unsigned>((n + TB - 1) / TB), h->C);
     { int rc = launch_fir_ccf_c(h, h->C, h->stream, h->d_if, h->if_mask, h->if_stride, h->d_rf, h->if_mask, h->if_stride, h->d_taps2, h->nt2, a0, a1, nullptr, 0, 0, 0); if (rc) return rc; h->launches--; }
     scale2_ring_kernel<<<g, TB, 0, h->stream>>>(h->d_rf, h->if_mask, h->if_stride, a0, a1, 0.8f, h->single ? h->bb_gain : 1.0f);   // gr_mod_mmdvm: bb_gain here
@@ -3160,6 +3200,17 @@ int qrl_mmdvm_tx_work(qrl_mmdvm_tx* h, const short* in, long n, long stride, int
         dim3 go(static_cast<unsigned>((o1 - o0 + 255) / 256), h->C);
         resamp_ring_ccf_generic_kernel<<<go, 256, sizeof(float) * h->L * h->nt_arm, h->stream>>>(h->d_rf, h->if_mask, h->if_stride, h->d_arms, h->L, h->M, h->nt_arm, o0, o1,
                                                                                                h->d_lin, h->lin_stride);
+        if (!h->single) {
+            // gr_mod_mmdvm_multi2.cpp:88,108-117: gr_zero_idle_bursts(0) between the x25/24 resampler and the synthesizer (items of the
+            // 25 ksps stream; the linear buffer holds items o0 .. o1 of this call)
+            std::vector<long long> ranges;
+            h->zi.collect(h->C, o0, o1, o0, ranges);
+            if (!ranges.empty()) {
+                CK(h->zi.upload(ranges, h->stream));
+                tx_zero_ranges_kernel<<<static_cast<unsigned>(ranges.size() / 3), 256, 0, h->stream>>>(h->d_lin, 0xffffffffu, h->lin_stride, h->zi.d_ranges);
+                h->launches++;
+            }
+        }
         mmdvm_scatter_kernel<<<dim3(static_cast<unsigned>(std::min<long long>((o1 - o0 + TB - 1) / TB, 4096)), h->C), TB, 0, h->stream>>>(
             h->d_lin, h->lin_stride, h->d_rows, o1 - o0, h->d_out, h->out_stride);
     }

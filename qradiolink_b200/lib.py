@@ -69,6 +69,7 @@ SYMBOLS = {
     "qrl_mmdvm_tx_destroy": (_i, [_vp]),
     "qrl_mmdvm_tx_set_stream": (_i, [_vp, _vp]),
     "qrl_mmdvm_tx_set_bb_gain": (_i, [_vp, C.c_float]),
+    "qrl_mmdvm_tx_zero_samples": (_i, [_vp, _i, C.c_longlong, _l]),
     "qrl_mmdvm_tx_work": (_i, [_vp, _vp, _l, _l, _i, _vp]),
     "qrl_mmdvm_tx_sync": (_i, [_vp]),
     "qrl_mmdvm_tx_out_device": (_i, [_vp, _vp, _vp, _vp]),

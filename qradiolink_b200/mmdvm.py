@@ -83,6 +83,14 @@ class MmdvmChannelsRx:
         return int(self._L.qrl_mmdvm_rx_launch_count(self._h))
 
 
+def mmdvm_tag_item(sample_index, single=False):
+    """Item of the zero-idle block's own stream on which a "zero_samples" tag attached to int16 sample `sample_index` arrives: the sample
+    itself for gr_mod_mmdvm (all blocks in front of gr_zero_idle_bursts are 1:1), floor(k * 25 / 24 + 1/2) behind the x25/24 resampler of
+    gr_mod_mmdvm_multi2 (how GNU Radio's scheduler moves a tag across a block of relative rate 25/24)."""
+    k = int(sample_index)
+    return k if single else (2 * k * 25 + 24) // 48
+
+
 class MmdvmChannelsTx:
     """The per-channel part alone (qrl_mmdvm_tx_*): int16 [n_channels][n] at 24 ksps -> rows of a [n_rows][stride] slab at 25 ksps."""
 
@@ -92,6 +100,7 @@ class MmdvmChannelsTx:
         self.n_channels = int(n_channels)
         self.n_rows = int(n_rows if n_rows is not None else n_channels)
         self.max_in = int(max_in)
+        self.single = bool(single)
         r = None if rows is None else np.ascontiguousarray(rows, np.int32)
         self._h = C.c_void_p()
         rc = self._L.qrl_mmdvm_tx_create(int(bool(single)), self.n_channels, None if r is None else r.ctypes.data_as(C.c_void_p), self.n_rows, int(filter_width),
@@ -115,6 +124,12 @@ class MmdvmChannelsTx:
 
     def set_bb_gain(self, g):
         check(self._L.qrl_mmdvm_tx_set_bb_gain(self._h, float(g)), self._h, "qrl_mmdvm_tx_set_bb_gain")
+
+    def zero_samples(self, sample_index, n_samples, channel=-1):
+        """The "zero_samples" tag of gr_mmdvm_source on int16 sample `sample_index` of `channel` (-1: all): gr_zero_idle_bursts(0) clears
+        n_samples items of its stream from where the tag arrives (qrl_mmdvm_tx_zero_samples, mmdvm_tag_item)."""
+        check(self._L.qrl_mmdvm_tx_zero_samples(self._h, int(channel), mmdvm_tag_item(sample_index, self.single), int(n_samples)), self._h,
+              "qrl_mmdvm_tx_zero_samples")
 
     def work(self, samples):
         """samples: int16 [n_channels, n] (host) -> complex64 [n_rows, n_out] (unused rows zero)."""
@@ -180,6 +195,9 @@ class MmdvmMod:
 
     def set_bb_gain(self, g):
         self.channels.set_bb_gain(g)
+
+    def zero_samples(self, sample_index, n_samples, channel=-1):
+        self.channels.zero_samples(sample_index, n_samples, channel)
 
     def work(self, samples):
         samples = np.ascontiguousarray(samples, np.int16)

@@ -97,3 +97,11 @@ def test_channelizer_and_deframer_through_the_emulated_library(emu_qrl, oracle):
     TP.test_channelizer_reference_config_bit_identical_and_chunked(emu_qrl, oracle)
     TP.test_synthesizer_matches_oracle_and_loops_back(emu_qrl, oracle)
     TF.test_deframer_record_overflow_drops_like_the_oracle(emu_qrl, oracle)
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_mmdvm_tx_zero_idle_through_the_emulated_library(emu_qrl, oracle, single):
+    """gr_zero_idle_bursts(0) on the MMDVM modulators (qrl_mmdvm_tx_zero_samples): host bookkeeping of the tags + the clearing kernel
+    between the stages, against the oracle, before GPU time is spent on it."""
+    from tests import test_gpu_mmdvm as TM
+    TM.zero_idle_case(emu_qrl, oracle, single, q=1)

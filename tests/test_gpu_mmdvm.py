@@ -159,3 +159,47 @@ def test_single_channel_mmdvm_blocks(qrl, oracle):
         want, wdb, wat = o.work(iq[c])
         assert got.shape[1] == len(want) == n and np.array_equal(got[c], want), c
         assert np.array_equal(gat, wat) and np.max(np.abs(gdb[c] - wdb)) < 2e-4, c
+
+
+def zero_idle_case(qrl, oracle, single, q=4):
+    """q = 4: the GPU tier's size; q = 1: a quarter of it (the emulated library in the CPU tier)"""
+    C, n = 3, 3000 * q
+    rng = np.random.default_rng(9800)
+    t = np.arange(n)
+    S = np.stack([(7000 * np.sin(2 * np.pi * (450 + 170 * c) * t / 24000) + rng.integers(-250, 250, n)).astype(np.int16) for c in range(C)])
+    sizes = (1, 23, 24, 1000 * q, 750 * q, n - 48 - 1750 * q)
+    # (call index before which the tag is registered, channel (-1: all), tagged int16 sample, count)
+    tags = [(0, 0, 10, 75 * q), (0, 1, 100, 1250 * q), (0, 1, 500 * q, 10 * q), (3, -1, 1025 * q, 180 * q), (4, 2, 1725 * q, 2250 * q), (5, 0, 1250 * q, 750 * q)]
+    tx = qrl.MmdvmChannelsTx(C, filter_width=5000, max_in=max(sizes), single=single)
+    orc = [oracle.MmdvmTx(5000, single=single) for _ in range(C)]
+    got, want, lo = [], [[] for _ in range(C)], 0
+    for i, m in enumerate(sizes):
+        for (at, ch, k, cnt) in tags:
+            if at == i:
+                tx.zero_samples(k, cnt, ch)
+                for c in (range(C) if ch < 0 else [ch]):
+                    orc[c].zero_samples(qrl.mmdvm_tag_item(k, single), cnt)
+        got.append(tx.work(S[:, lo:lo + m]))
+        for c in range(C):
+            want[c].append(orc[c].work(S[c, lo:lo + m]))
+        lo += m
+    assert lo == n
+    got = np.concatenate(got, 1)
+    zeroed = 0
+    for c in range(C):
+        w = np.concatenate(want[c])
+        assert got.shape[1] == len(w)
+        assert np.array_equal(got[c].view(np.uint32), w.view(np.uint32)), c
+        zeroed += int(np.sum(w == 0))
+    assert zeroed > 1250 * q                              # the tags did clear stretches of the output
+    # without tags the same handle type gives the plain chain (nothing is cleared by default)
+    plain = qrl.MmdvmChannelsTx(C, filter_width=5000, max_in=n, single=single).work(S)
+    assert np.sum(plain[0] == 0) < 40 and not np.array_equal(plain[0], got[0])
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_tx_zero_idle_bursts(qrl, oracle, single):
+    """gr_zero_idle_bursts(0) on the MMDVM modulators (gr_mod_mmdvm.cpp:51-58 in front of the filter, gr_mod_mmdvm_multi2.cpp:88,108-117
+    behind the x25/24 resampler): "zero_samples" tags per channel, a later tag overriding a running count, a count running across
+    calls, a tag registered after its item went out -- bit-identical to the oracle's restatement of the same block, ragged calls."""
+    zero_idle_case(qrl, oracle, single)

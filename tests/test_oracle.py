@@ -534,3 +534,38 @@ def test_mmdvm_channel_chains_restated(oracle):
     coef, *_ = np.linalg.lstsq(A, seg, rcond=None)
     assert abs(np.hypot(coef[0], coef[1]) - 3000) < 30 and abs(np.hypot(coef[2], coef[3]) - 1500) < 15, coef
     assert np.sqrt(np.mean((seg - A @ coef) ** 2)) < 80          # int16 units (2 % of the signal): FM through two 5 kHz channel filters
+
+
+def test_mmdvm_tx_zero_idle_restated(oracle):
+    """gr_zero_idle_bursts(0) on the MMDVM modulators (the block itself is pinned to the compiled reference in test_oracle_ref.py):
+    behind the x25/24 resampler of gr_mod_mmdvm_multi2 the tagged stretches of the plain output are cleared and nothing else changes;
+    in front of the filter of gr_mod_mmdvm the output is the plain one away from the cleared stretch and exactly zero deep inside it;
+    results do not depend on the chunking."""
+    n = 6000
+    rng = np.random.default_rng(9810)
+    s = (6000 * np.sin(2 * np.pi * 700 * np.arange(n) / 24000) + rng.integers(-200, 200, n)).astype(np.int16)
+    # multi2: tags on 25 ksps items; the second overrides the first's running count
+    plain = oracle.MmdvmTx(5000).work(s)
+    o = oracle.MmdvmTx(5000)
+    o.zero_samples(1000, 900); o.zero_samples(1500, 100); o.zero_samples(4000, 50)
+    got = np.concatenate([o.work(s[a:b]) for a, b in ((0, 1), (1, 1000), (1000, 1001), (1001, n))])
+    want = plain.copy(); want[1000:1600] = 0; want[4000:4050] = 0
+    assert len(got) == n * 25 // 24 and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # a tag registered after its item has gone out clears what is left of its count
+    o = oracle.MmdvmTx(5000)
+    first = o.work(s[:2400])                                  # 2500 items out
+    o.zero_samples(2400, 300)                                 # 100 of them are gone already
+    got = np.concatenate([first, o.work(s[2400:])])
+    want = plain.copy(); want[2500:2700] = 0
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # single-channel block: the cleared stretch passes the low-pass and the x125/12 resampler
+    plain1 = oracle.MmdvmTx(5000, single=True).work(s)
+    o = oracle.MmdvmTx(5000, single=True)
+    o.zero_samples(2000, 1500)
+    got1 = np.concatenate([o.work(s[a:b]) for a, b in ((0, 777), (777, 2000), (2000, 2001), (2001, n))])
+    assert len(got1) == len(plain1) == n * 125 // 12
+    r = 125 / 12
+    assert np.array_equal(got1[:int(1900 * r)], plain1[:int(1900 * r)])            # before the stretch (minus nothing: the chain is causal)
+    assert np.all(got1[int(2200 * r):int(3450 * r)] == 0)                          # deep inside: filters flushed, exactly zero
+    assert np.array_equal(got1[int(3800 * r):], plain1[int(3800 * r):])            # well behind it the histories hold plain items again
+    assert not np.array_equal(got1, plain1)
