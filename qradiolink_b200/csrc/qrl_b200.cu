@@ -340,7 +340,7 @@ F drv(const char* name)
 }
 
 // split the device into {loop_sms} + {rest} and create the three internal streams; false -> caller falls back
-bool make_sm_partition(qrl_rx* h, unsigned loop_sms, int prio)
+bool make_sm_partition(qrl_rx* h, unsigned loop_sms, int prio, bool fec_on_par_default)
 {
     if (const char* e = getenv("QRL_NO_SM_PARTITION")) { if (e[0] == '1') return false; }
     auto pDeviceGet = drv<CUresult (*)(CUdevice*, int)>("cuDeviceGet");
@@ -362,10 +362,11 @@ bool make_sm_partition(qrl_rx* h, unsigned loop_sms, int prio)
     if (pCreate(&h->g_par, d_par, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
     CUstream a = nullptr, b = nullptr, c = nullptr, d = nullptr;
     if (pStream(&a, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
-    // FEC (Viterbi) stream: next to the loop kernels by default.  Measured at the end of round 2 (profiles/r02_u_fec_partition_ab.txt):
-    // 4FSK step 0.959 ms next to the loop kernels, 0.954 ms on the wide partition (QRL_FEC_ON_PAR=1) -- the decoder's warps are not
-    // what slows the lone recurrence warps down.
-    bool fec_on_par = false;
+    // FEC (Viterbi) stream.  Up to 64 channels the step is the latency of the lone recurrence warps and the decoder runs on the wide
+    // partition, off their SMs (64 ch x 2^22: 0.925 ms per call against 0.941 next to the loop kernels); with more channels the step is
+    // the sum of the parallel stages and the decoder stays in the loop partition, out of their way (256 ch: 2.23 ms against 2.35).
+    // profiles/r02_y_256ch_stage_times.txt; QRL_FEC_ON_PAR=0/1 forces either.
+    bool fec_on_par = fec_on_par_default;
     if (const char* e = getenv("QRL_FEC_ON_PAR")) fec_on_par = e[0] == '1';
     if (pStream(&b, fec_on_par ? h->g_par : h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
     if (pStream(&d, h->g_loop, CU_STREAM_NON_BLOCKING, prio) != CUDA_SUCCESS) return false;
@@ -956,7 +957,7 @@ int qrl_rx_create(int kind, int sps, int samp_rate, int carrier_freq, int filter
         // machine (38.9 -> 12.9 ms) and the loop CTAs spread over more SMs); QRL_QPSK_PARTITION=1 brings the partition back.
         bool want_partition = kind != QRL_DEMOD_QPSK;
         if (const char* e = getenv("QRL_QPSK_PARTITION")) { if (kind == QRL_DEMOD_QPSK) want_partition = e[0] == '1'; }
-        if (h->many || !want_partition || !make_sm_partition(h, loop_sms, hi)) {
+        if (h->many || !want_partition || !make_sm_partition(h, loop_sms, hi, !analog_kind && groups <= 2)) {
             h->s_par = nullptr; h->sm_loop = 0; h->sm_par = 0;
             if (h->s_loop == nullptr)
                 ok = cudaStreamCreateWithPriority(&h->s_loop, cudaStreamNonBlocking, hi) == cudaSuccess;

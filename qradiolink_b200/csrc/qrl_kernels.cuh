@@ -446,16 +446,40 @@ fir_ccf_ring_tiled_kernel(const float2* __restrict__ in, unsigned in_mask, long 
 #pragma unroll
         for (int i = 0; i <= t; i++) ffma2(acc[i], w[i], v);
     }
-    // main: t = K-1 .. ntaps-1, all K outputs
-    for (int t = K - 1; t < ntaps; t++) {
+    // main: t = K-1 .. ntaps-1, all K outputs.  Step K-1 and the last (ntaps mod K) steps shift the window register by register; the rest
+    // runs K steps per iteration with the window ROTATING through the registers (step u of an iteration writes its tap to w[K-1-u] and
+    // output i reads w[K-1 - ((u - i) mod K)]: all indices compile-time, so the K-1 moves per step are gone -- they were 7 of the 20
+    // instructions per 8 FFMA).  After a whole iteration the window is in shifted order again.  Same taps meet the same samples in the
+    // same order: bit-identical.
+    auto shift_steps = [&](int ta, int tb) {
+        for (int t = ta; t < tb; t++) {
 #pragma unroll
-        for (int i = K - 1; i > 0; i--) w[i] = w[i - 1];
-        w[0] = hs[ntaps - 1 - t];
-        const int idx = base + t;
-        const float2 v = xs[idx + (idx >> 4)];
+            for (int i = K - 1; i > 0; i--) w[i] = w[i - 1];
+            w[0] = hs[ntaps - 1 - t];
+            const int idx = base + t;
+            const float2 v = xs[idx + (idx >> 4)];
 #pragma unroll
-        for (int i = 0; i < K; i++) ffma2(acc[i], w[i], v);
+            for (int i = 0; i < K; i++) ffma2(acc[i], w[i], v);
+        }
+    };
+    // rotating iterations start on a multiple of K (= 8): base + t0 is then a multiple of 8 as well, the 8 samples of an iteration sit
+    // in one padding block and are addressed by immediates from one base
+    static_assert(K == 8, "the rotating main phase assumes 8 outputs per thread (one padding block per iteration)");
+    const int t_a = K, t_b = t_a + ((ntaps - t_a) / K) * K;
+    shift_steps(K - 1, t_a < ntaps ? t_a : ntaps);
+    for (int t0 = t_a; t0 < t_b; t0 += K) {
+        const int idx0 = base + t0;
+        const float2* xv = xs + idx0 + (idx0 >> 4);
+        const float* hv = hs + (ntaps - 1 - t0);
+#pragma unroll
+        for (int u = 0; u < K; u++) {
+            w[K - 1 - u] = hv[-u];
+            const float2 v = xv[u];
+#pragma unroll
+            for (int i = 0; i < K; i++) ffma2(acc[i], w[K - 1 - ((u - i + K) % K)], v);
+        }
     }
+    shift_steps(t_b > t_a ? t_b : (t_a < ntaps ? t_a : ntaps), ntaps);
     // tail: t = ntaps .. ntaps+K-2, outputs i >= t - (ntaps - 1)
 #pragma unroll
     for (int u = 1; u < K; u++) {
@@ -522,15 +546,35 @@ qdemod_fir_fff_tiled_kernel(const float2* __restrict__ in, unsigned in_mask, lon
 #pragma unroll
         for (int i = 0; i <= t; i++) acc[i] = fmaf(w[i], v, acc[i]);
     }
-    for (int t = K - 1; t < ntaps; t++) {
+    // (main phase: a few shifting steps, then K steps per iteration with the window rotating through the registers -- see
+    // fir_ccf_ring_tiled_kernel)
+    auto shift_steps = [&](int ta, int tb) {
+        for (int t = ta; t < tb; t++) {
 #pragma unroll
-        for (int i = K - 1; i > 0; i--) w[i] = w[i - 1];
-        w[0] = hs[ntaps - 1 - t];
-        const int idx = base + t;
-        const float v = ds[idx + (idx >> 5)];
+            for (int i = K - 1; i > 0; i--) w[i] = w[i - 1];
+            w[0] = hs[ntaps - 1 - t];
+            const int idx = base + t;
+            const float v = ds[idx + (idx >> 5)];
 #pragma unroll
-        for (int i = 0; i < K; i++) acc[i] = fmaf(w[i], v, acc[i]);
+            for (int i = 0; i < K; i++) acc[i] = fmaf(w[i], v, acc[i]);
+        }
+    };
+    static_assert(K == 8, "the rotating main phase assumes 8 outputs per thread (one padding block per iteration)");
+    const int t_a = K, t_b = t_a + ((ntaps - t_a) / K) * K;
+    shift_steps(K - 1, t_a < ntaps ? t_a : ntaps);
+    for (int t0 = t_a; t0 < t_b; t0 += K) {
+        const int idx0 = base + t0;
+        const float* dv = ds + idx0 + (idx0 >> 5);
+        const float* hv = hs + (ntaps - 1 - t0);
+#pragma unroll
+        for (int u = 0; u < K; u++) {
+            w[K - 1 - u] = hv[-u];
+            const float v = dv[u];
+#pragma unroll
+            for (int i = 0; i < K; i++) acc[i] = fmaf(w[K - 1 - ((u - i + K) % K)], v, acc[i]);
+        }
     }
+    shift_steps(t_b > t_a ? t_b : (t_a < ntaps ? t_a : ntaps), ntaps);
 #pragma unroll
     for (int u = 1; u < K; u++) {
 #pragma unroll

@@ -21,7 +21,7 @@ M17_TX_NAMES = ["d_sine_tab", "TxBitState", "TXM_4FSK", "tx_bits_kernel", "tx_sh
 DMR_RX_NAMES = ["d_atan_tab", "d_tanh_tab", "d_mmse_tab", "qrl_sincosf", "qrl_fast_atan2f", "qrl_tanhf_lut", "qrl_clip", "qrl_soft_u8",
                 "qdemod_fir_fff_kernel", "ring_to_port_f32_kernel", "SL_RECT4", "EPI_4FSK_FM", "LOOP_SYMSYNC", "LoopState", "SymSyncState",
                 "symsync_stride", "SYMSYNC_TAB_FLOATS", "SymSyncParams", "qrl_slice", "qrl_costas_step", "qrl_sincosf_small", "qrl_tanhf_lut_rd",
-                "qrl_costas4_snr_step", "qrl_phase_wrap_slow", "qrl_costas4_snr_chunk", "qrl_slice_rect4", "qrl_clip1",
+                "qrl_costas4_snr_step", "qrl_fill_tanh_s", "qrl_phase_wrap_slow", "qrl_costas4_snr_chunk", "qrl_slice_rect4", "qrl_clip1",
                 "symsync_generic_step", "symsync_kernel", "symsync_ext_epilogue_kernel"]
 
 

@@ -35,6 +35,6 @@ def extract(src, names):
         if text.lstrip().startswith(("struct", "enum")):
             text += ";"
         out.append(text)
-    body = "\n\n".join(out)
+    body = "#ifndef SSP\n#define SSP(...)      /* profiling build only (qrl_kernels.cuh, -DQRL_SS_PROF) */\n#endif\n\n" + "\n\n".join(out)
     body = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];", r"EMU_DYN_SMEM(\1, \2);", body)
     return body
