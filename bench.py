@@ -250,6 +250,21 @@ def timed_calls(fn, k, stream, torch, warm=2):
     return e0.elapsed_time(e1) / k
 
 
+
+def latency_bound_block(kernel, what, stage_ms_per_call, items_per_channel_per_call, clocks, chain_cycles, chain_source):
+    """the loop stages are latency bound -- what is reported for them is cycles of the loop-carried chain per item, live from the
+    stage's CUDA-event time and the SM clock sampled under load, beside the chain's own schedule (the same recurrence alone in a
+    kernel, tools/microbench/lone_warp.cu / ncu of the single launch: it runs at the sum of ptxas' stall counts)."""
+    try:
+        mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965
+        cyc = stage_ms_per_call * 1e-3 * mhz * 1e6 / items_per_channel_per_call
+        return {"kernel": kernel, "bound": "latency (loop-carried dependency chain, one warp per 32 channels)", "what": what,
+                "items_per_channel_per_call": items_per_channel_per_call, "stage_ms_per_call": stage_ms_per_call, "sm_mhz": mhz,
+                "cycles_per_item_in_step": cyc, "chain_cycles_alone": chain_cycles, "frac_of_chain_schedule": chain_cycles / cyc if cyc > 0 else None,
+                "chain_source": chain_source}
+    except Exception as e:  # noqa: BLE001
+        return {"kernel": kernel, "error": "%s: %s" % (type(e).__name__, e)}
+
 def rx_stage_ms(L, blk, names=("stage1_fir", "chan_filter", "demod_or_loop", "symbol_sync_or_audio", "viterbi", "soft_epilogue")):
     out = {}
     for s, name in enumerate(names):
@@ -1054,6 +1069,19 @@ def run_ours(args):
         "parity_vs_oracle": parity,
         "configs": configs,
     }
+    line["latency_bound"] = latency_bound_block(
+        "symsync_kernel<1,SL_RECT4,EPI_EXT_4FSK_FM,512,2,1,LOOP_SYMSYNC,2>", "symbol_sync_ff recurrence (MMSE interpolation -> TED -> loop filter), the stage that IS the step",
+        line["stage_ms_per_call"].get("symbol_sync_or_audio", 0.0), T / 500.0, line["clocks"], 203.0,
+        "ncu --set full of one launch over the whole call, profiles/r02_final2_ncu_full_summary.csv: 891.7 us for 8613 symbols")
+    try:
+        c3 = configs.get("cfg3_qpsk250k_256ch")
+        if isinstance(c3, dict) and "stage_ms_per_call" in c3:
+            c3["latency_bound"] = latency_bound_block(
+                "agc_costas_kernel<128,2,4,1>", "agc2_cc -> costas_loop_cc(order 4, snr) per sample at 500 ksps, the stage that bounds the QPSK chain",
+                c3["stage_ms_per_call"].get("demod_or_loop", 0.0), c3["samples_per_channel_per_call"] / 2.0, line["clocks"], 202.6,
+                "the Costas recurrence alone in a kernel, tools/microbench/lone_warp.cu, profiles/r02_t_symsync_prefetch_costas_select.txt")
+    except Exception:  # noqa: BLE001
+        pass
     if cpu_line:
         line["cpu_baseline"] = cpu_line
     print(json.dumps(line))
