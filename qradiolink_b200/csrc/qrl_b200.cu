@@ -1761,26 +1761,36 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
             CK(cudaStreamWaitEvent(h->s_loop2, h->ev_c[i], 0));
             {
                 pe = h->prof_begin(3, h->s_loop2);
-                auto run_sq = [&](auto ch_tag, auto nst_tag) -> int {
-                    constexpr int CH = decltype(ch_tag)::value, NST = decltype(nst_tag)::value, NEPI = 1;
+                // lean: the prefetching complex recurrence (symbol-sync variant 2, replicated tap bank) with the epilogue split into a
+                // Costas warp and a feed-forward warp over a 3-deep symbol ring (NEPI = 2); else the generic recurrence, one epilogue warp
+                auto run_sq = [&](auto ch_tag, auto nst_tag, auto lean_tag) -> int {
+                    constexpr int CH = decltype(ch_tag)::value, NST = decltype(nst_tag)::value;
+                    constexpr bool LEAN = decltype(lean_tag)::value;
+                    constexpr int NEPI = LEAN ? 2 : 1, NB = LEAN ? 3 : 2;
                     const int maxs = static_cast<int>((CH + 1) / (h->ssp.min_period - fabsf(h->ssp.alpha)) + 3);
-                    const size_t smem = sizeof(float) * (NST * CH * 64 + SYMSYNC_TAB_FLOATS + 2 * maxs * 64) + sizeof(int) * 64;
-                    auto kern = symsync_kernel<2, SL_DQPSK, EPI_QPSK, CH, NST, NEPI>;
-                    static bool sq_attr[16] = { false };    // per (CH, NST) instantiation, per device
+                    const size_t smem = sizeof(float) * (NST * CH * 64 + SYMSYNC_TAB_FLOATS + NB * maxs * 64) + sizeof(int) * 32 * (NB == 2 ? 2 : 4) +
+                                        (LEAN ? 129 * 512 : 0);
+                    auto kern = symsync_kernel<2, SL_DQPSK, EPI_QPSK, CH, NST, NEPI, LOOP_SYMSYNC, LEAN ? 2 : 0>;
+                    static bool sq_attr[16] = { false };    // per (CH, NST, LEAN) instantiation, per device
                     if (!sq_attr[h->device & 15]) {
-                        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
                         sq_attr[h->device & 15] = true;
                     }
+                    if (smem > 224 * 1024) { set_err(h, "QPSK symbol sync: window does not fit shared memory"); return QRL_EINVAL; }
                     kern<<<groups, 64 + 32 * NEPI, smem, h->s_loop2>>>(
                         h->ssp, h->d_ss, h->C, static_cast<const float*>(h->r3.d), h->r3.mask, h->r3.stride, k1,
                         h->d_port1, h->port1_cap, h->d_port1_cnt, static_cast<int>(h->port1_cap),
                         static_cast<unsigned char*>(h->r5.d), h->r5.mask, h->r5.stride, maxs, nsoft_i, nullptr, 0, 0, nullptr);
                     return QRL_OK;
                 };
-                // many channels: 64-row windows, two stages (~55 KB, four CTAs per SM) instead of 128 x 3 (143 KB)
+                // many channels: 64-row windows, two stages (~55 KB, four CTAs per SM) instead of 128-row ones
                 const bool small_win = h->many && symsync_stride(64, h->ssp.lookahead) >= 32;
-                const int rc_sq = small_win ? run_sq(std::integral_constant<int, 64>{}, std::integral_constant<int, 2>{})
-                                            : run_sq(std::integral_constant<int, 128>{}, std::integral_constant<int, 3>{});
+                static const bool lean_env = [] { const char* e = getenv("QRL_QPSK_LEAN_SS"); return !(e && e[0] == '0'); }();
+                // the lean recurrence needs the in-lock window proof (kernel: lean_ok && window_sure) -- true for every QPSK instance of
+                // gr_demod_base.cpp; the kernel itself falls back to the generic loop when it does not hold
+                const int rc_sq = small_win ? run_sq(std::integral_constant<int, 64>{}, std::integral_constant<int, 2>{}, std::false_type{})
+                                : lean_env  ? run_sq(std::integral_constant<int, 128>{}, std::integral_constant<int, 2>{}, std::true_type{})
+                                            : run_sq(std::integral_constant<int, 128>{}, std::integral_constant<int, 3>{}, std::false_type{});
                 if (rc_sq) return rc_sq;
                 h->launches++;
                 h->prof_end(pe);

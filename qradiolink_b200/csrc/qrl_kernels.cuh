@@ -1243,7 +1243,13 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                int ext_chunk_cap = 0 /* chunks this launch may emit */, int ext_chunk_stride = 0 /* chunks per group in the scratch */,
                int* __restrict__ ext_hdr = nullptr /* [groups][128] (EPI_EXT_*) */)
 {
-    static_assert((EPI != EPI_QPSK && EPI != EPI_BPSK) || NEPI == 1, "Costas epilogues carry loop state: one epilogue warp");
+    static_assert(EPI != EPI_BPSK || NEPI == 1, "Costas epilogues carry loop state: one epilogue warp");
+    static_assert(EPI != EPI_QPSK || NEPI == 1 || NEPI == 2, "QPSK: one epilogue warp, or a Costas warp + a feed-forward warp");
+    // QPSK with NEPI == 2: warp 2 runs the second Costas loop in place, warp 3 everything behind it (diff_phasor, rotation, soft bits,
+    // stores).  A symbol block then has three owners in turn (loop warp, Costas warp, feed-forward warp), so the ring is 3 deep (see
+    // agc_costas_kernel) and a third barrier (bar_cdone) hands a block from the Costas warp to the feed-forward warp.
+    constexpr bool SPLIT = (EPI == EPI_QPSK && NEPI == 2);
+    constexpr int NB = SPLIT ? 3 : 2;
     constexpr bool EXT = (EPI == EPI_EXT_4FSK_FM);
     static_assert(!EXT || (NEPI == 1 && NCOMP == 1), "external epilogue: one drain warp, real symbols");
     constexpr int ROWF = 32 * NCOMP;                    // floats per row
@@ -1252,7 +1258,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
     // consecutive windows overlap by the lookahead rounded up to 32 rows (same formula on the host: symsync_stride)
     const int STRIDE = symsync_stride(CH, p.lookahead);
     extern __shared__ __align__(128) float sm_sync[];   // [NST][CH][ROWF] | mmse[129*8] | sym[2][maxs][ROWF] | cnt[2][32]
-    __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[2], bar_empty[2];
+    __shared__ __align__(8) uint64_t bar_in[NST], bar_free[NST], bar_full[NB], bar_empty[NB], bar_cdone[NB];
     __shared__ volatile int lane_zero[32];
     __shared__ float tanh_s[EPI == EPI_QPSK ? 259 : 1];    // second Costas loop's table (entries 256 .. 258: see qrl_fill_tanh_s)
     __shared__ volatile int opaque_zero;
@@ -1263,11 +1269,11 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
     float* mm2 = mm + 132 * 8;                          // entry-major copy (12-float pitch), taps reversed: two LDS.128
     float* symbuf = mm + SYMSYNC_TAB_FLOATS;
     const int blk_rows = EXT ? maxs + 2 : maxs;         // EXT: rows maxs / maxs+1 of a block hold the lane counts / lane bases
-    int* cntbuf = reinterpret_cast<int*>(symbuf + 2 * blk_rows * ROWF);
+    int* cntbuf = reinterpret_cast<int*>(symbuf + NB * blk_rows * ROWF);
     // VAR == 2: 16-fold replicated bank [imu][half][lane & 15][4] (129 * 512 bytes) behind everything else: the 8 lanes
     // of an LDS.128 phase read 128 contiguous bytes, so the two tap loads of a symbol are conflict-free whatever imu is
     constexpr bool REP = (VAR == 2);
-    float* mm3 = reinterpret_cast<float*>(cntbuf + 64);
+    float* mm3 = reinterpret_cast<float*>(cntbuf + 32 * (NB == 2 ? 2 : 4));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
     const int c = g * 32 + lane;
@@ -1296,7 +1302,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
     }
     if (threadIdx.x == 0) {
         for (int b = 0; b < NST; b++) { mbar_init(&bar_in[b], 1); mbar_init(&bar_free[b], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&bar_full[b], 1); mbar_init(&bar_empty[b], NEPI); }
+        for (int b = 0; b < NB; b++) { mbar_init(&bar_full[b], 1); mbar_init(&bar_empty[b], SPLIT ? 1 : NEPI); mbar_init(&bar_cdone[b], 1); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -1391,9 +1397,9 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
         SSP(long long pf_we = 0; long long pf_wi = 0; long long pf_run = 0; long long pf_str = 0; long long pf_ho = 0; long long pf_rounds = 0; long long pf_sym = 0;)
         SSP(const unsigned long long pg1 = globaltimer_ns(); unsigned long long pg2 = pg1;)
         for (int m = 0; m < nchunks; m++) {
-            const int st = m % NST, b = m & 1;
+            const int st = m % NST, b = m % NB;
             SSP(const long long pt0 = clock64();)
-            if (m >= 2) mbar_wait(&bar_empty[b], ((m >> 1) - 1) & 1);    // epilogue released this hand-off buffer
+            if (m >= NB) mbar_wait(&bar_empty[b], ((m / NB) - 1) & 1);   // epilogue released this hand-off buffer
             SSP(const long long pt1 = clock64();)
             mbar_wait(&bar_in[st], (m / NST) & 1);
             SSP(const long long pt2 = clock64(); pf_we += pt1 - pt0; pf_wi += pt2 - pt1; long long pt3 = pt2;)
@@ -1558,6 +1564,110 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
                 x0 = A; x1 = B; x2 = Cc; d0 = dA; d1 = dB; d2 = dC;
                 o = static_cast<int>(ofm - 8388608.0f);
                 cnt = static_cast<int>((syp - syp0) / (ROWF * 4));
+            } else if (active && LOOPK == LOOP_SYMSYNC && NCOMP == 2 && SLICER == SL_DQPSK && VAR == 2 && lean_ok && window_sure) {
+                // Lean restatement of the COMPLEX recurrence (symbol_sync_cc with constellation_dqpsk: the QPSK chain), same construction as the
+                // real one above: position in a float, fractional phase by two exact compares, TED history rotating through registers,
+                // the ten candidate rows of the next symbol prefetched and picked by selects, tap bank replicated 16-fold.  The decision
+                // terms (d0 - d2) x1 of the detector are formed for both signs off the chain and picked by the sign of the new sample.
+                // Same operations in the same order per value as the generic loop below: bit-identical.
+                float ofm = 8388608.0f + static_cast<float>(o);
+                const float lim = 8388608.0f + static_cast<float>(wlen - la);
+                const uint32_t xb = smem_u32(buf) - (0x4B000000u << 8);         // one row = 32 lanes x 8 bytes
+                uint32_t syp = smem_u32(sy);
+                const uint32_t syp0 = syp;
+                float Ar = x0, Ai = y0i, Br = x1, Bi = y1i, Cr = x2, Ci = y2i;
+                float dAr = d0, dAi = e0, dBr = d1, dBi = e1, dCr = d2, dCi = e2;
+                const float k_b = p.beta + zf, k_a = p.alpha + zf, kp = 0.707107f + zf, kn = -0.707107f + zf;
+                float2 xs0 = make_float2(0.0f, 0.0f), xs1 = make_float2(0.0f, 0.0f), xs2 = make_float2(0.0f, 0.0f), xs3 = make_float2(0.0f, 0.0f), xs4 = make_float2(0.0f, 0.0f), xs5 = make_float2(0.0f, 0.0f), xs6 = make_float2(0.0f, 0.0f), xs7 = make_float2(0.0f, 0.0f);
+                auto load_xs = [&]() {
+                    const uint32_t xa = xb + (__float_as_uint(ofm) << 8);
+                    xs0 = lds_f32x2<ROWF * 0>(xa);
+                    xs1 = lds_f32x2<ROWF * 4>(xa);
+                    xs2 = lds_f32x2<ROWF * 8>(xa);
+                    xs3 = lds_f32x2<ROWF * 12>(xa);
+                    xs4 = lds_f32x2<ROWF * 16>(xa);
+                    xs5 = lds_f32x2<ROWF * 20>(xa);
+                    xs6 = lds_f32x2<ROWF * 24>(xa);
+                    xs7 = lds_f32x2<ROWF * 28>(xa);
+                };
+                if (ofm <= lim) load_xs();
+                auto body = [&](float& nr, float& ni, const float h1r, const float h1i, const float h2r, const float h2i,
+                                float& dnr, float& dni, const float dh1r, const float dh1i, const float dh2r, const float dh2i) {
+                    const uint32_t ta = mm2_b + __float_as_uint(fmaf(mu, k128, 12582912.0f)) * 512u;
+                    const float ofn = ofm + q_f0;
+                    const uint32_t xn = xb + (__float_as_uint(ofn) << 8);
+                    const float2 r0 = lds_f32x2<ROWF * 0>(xn);
+                    const float2 r1 = lds_f32x2<ROWF * 4>(xn);
+                    const float2 r2 = lds_f32x2<ROWF * 8>(xn);
+                    const float2 r3 = lds_f32x2<ROWF * 12>(xn);
+                    const float2 r4 = lds_f32x2<ROWF * 16>(xn);
+                    const float2 r5 = lds_f32x2<ROWF * 20>(xn);
+                    const float2 r6 = lds_f32x2<ROWF * 24>(xn);
+                    const float2 r7 = lds_f32x2<ROWF * 28>(xn);
+                    const float2 r8 = lds_f32x2<ROWF * 32>(xn);
+                    const float2 r9 = lds_f32x2<ROWF * 36>(xn);
+                    const float4 ta0 = lds_f32x4<0>(ta), ta1 = lds_f32x4<256>(ta);   // taps[7..4], taps[3..0]
+                    // (d0 - d2) x1 for both decisions of each component
+                    const float prp = (kp - dh2r) * h1r, prn = (kn - dh2r) * h1r, pip = (kp - dh2i) * h1i, pin = (kn - dh2i) * h1i;
+                    float yr = 0.0f, yi = 0.0f;                                   // oldest sample first
+                    yr = fmaf(ta0.x, xs0.x, yr); yi = fmaf(ta0.x, xs0.y, yi);
+                    yr = fmaf(ta0.y, xs1.x, yr); yi = fmaf(ta0.y, xs1.y, yi);
+                    yr = fmaf(ta0.z, xs2.x, yr); yi = fmaf(ta0.z, xs2.y, yi);
+                    yr = fmaf(ta0.w, xs3.x, yr); yi = fmaf(ta0.w, xs3.y, yi);
+                    yr = fmaf(ta1.x, xs4.x, yr); yi = fmaf(ta1.x, xs4.y, yi);
+                    yr = fmaf(ta1.y, xs5.x, yr); yi = fmaf(ta1.y, xs5.y, yi);
+                    yr = fmaf(ta1.z, xs6.x, yr); yi = fmaf(ta1.z, xs6.y, yi);
+                    yr = fmaf(ta1.w, xs7.x, yr); yi = fmaf(ta1.w, xs7.y, yi);
+                    nr = yr; ni = yi;
+                    const bool sr = yr > 0.0f, si = yi > 0.0f;
+                    dnr = sr ? kp : kn; dni = si ? kp : kn;
+                    const float t2 = (sr ? prp : prn) + (si ? pip : pin);         // br x1r + bi x1i
+                    const float t1 = (yr - h2r) * dh1r + (yi - h2i) * dh1i;       // ar d1r + ai d1i
+                    const float err = fminf(fmaxf(t1 - t2, -1.0f), 1.0f);
+                    avg_period = avg_period + k_b * err;
+                    avg_period = fminf(fmaxf(avg_period, q_minp), q_maxp);
+                    inst_period = avg_period + k_a * err;
+                    const float ph = mu + inst_period;
+                    const float m0 = ph - q_f0;
+                    sts_f32x2(syp, yr, yi);
+                    syp += ROWF * 4;
+                    const float s12 = qrl_ge1(m0, 1.0f) + qrl_ge1(m0, 2.0f);     // == [ph >= n0+1] + [ph >= n0+2] (m0 exact)
+                    const bool g1 = m0 >= 1.0f, g2 = m0 >= 2.0f;
+                    mu = m0 - s12;
+                    ofm = ofn + s12;
+                    xs0 = g2 ? r2 : (g1 ? r1 : r0);
+                    xs1 = g2 ? r3 : (g1 ? r2 : r1);
+                    xs2 = g2 ? r4 : (g1 ? r3 : r2);
+                    xs3 = g2 ? r5 : (g1 ? r4 : r3);
+                    xs4 = g2 ? r6 : (g1 ? r5 : r4);
+                    xs5 = g2 ? r7 : (g1 ? r6 : r5);
+                    xs6 = g2 ? r8 : (g1 ? r7 : r6);
+                    xs7 = g2 ? r9 : (g1 ? r8 : r7);
+                };
+                auto rot = [&]() {
+                    const float tr = Cr, ti = Ci, dtr = dCr, dti = dCi;
+                    Cr = Br; Ci = Bi; Br = Ar; Bi = Ai; Ar = tr; Ai = ti;
+                    dCr = dBr; dCi = dBi; dBr = dAr; dBi = dAi; dAr = dtr; dAi = dti;
+                };
+                const unsigned amask = __activemask();
+                const float inv_s = 0.9999f / (p.max_period + fabsf(p.alpha));
+                for (;;) {
+                    const float left = lim - ofm;                              // exact (integers below 2^24)
+                    int ksafe = left >= 0.0f ? static_cast<int>(fmaxf(left - 1.0f, 0.0f) * inv_s) + 1 : 0;
+                    ksafe = __reduce_min_sync(amask, ksafe);
+                    if (ksafe == 0) break;
+                    for (; ksafe >= 3; ksafe -= 3) {
+                        body(Cr, Ci, Ar, Ai, Br, Bi, dCr, dCi, dAr, dAi, dBr, dBi);
+                        body(Br, Bi, Cr, Ci, Ar, Ai, dBr, dBi, dCr, dCi, dAr, dAi);
+                        body(Ar, Ai, Br, Bi, Cr, Ci, dAr, dAi, dBr, dBi, dCr, dCi);
+                    }
+                    for (; ksafe >= 1; ksafe--) { body(Cr, Ci, Ar, Ai, Br, Bi, dCr, dCi, dAr, dAi, dBr, dBi); rot(); }
+                }
+                while (ofm <= lim) { body(Cr, Ci, Ar, Ai, Br, Bi, dCr, dCi, dAr, dAi, dBr, dBi); rot(); }     // stragglers
+                x0 = Ar; y0i = Ai; x1 = Br; y1i = Bi; x2 = Cr; y2i = Ci;
+                d0 = dAr; e0 = dAi; d1 = dBr; e1 = dBi; d2 = dCr; e2 = dCi;
+                o = static_cast<int>(ofm - 8388608.0f);
+                cnt = static_cast<int>((syp - syp0) / (ROWF * 4));
             } else if (active && LOOPK == LOOP_SYMSYNC) {
                 while (o + la <= wlen) {
                     const float* x = buf + o * ROWF;
@@ -1649,8 +1759,8 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
             const size_t blk_floats = static_cast<size_t>(blk_rows) * ROWF;
             float* dst0 = ext_scratch + static_cast<size_t>(g) * ext_chunk_stride * blk_floats;
             for (int m = 0; m < nchunks; m++) {
-                const int b = m & 1;
-                mbar_wait(&bar_full[b], (m >> 1) & 1);
+                const int b = m % NB;
+                mbar_wait(&bar_full[b], (m / NB) & 1);
                 bulk_s2g(dst0 + static_cast<size_t>(m) * blk_floats, symbuf + b * blk_floats, static_cast<uint32_t>(blk_floats * 4));
                 bulk_commit();
                 bulk_wait_read0();                         // the block may be refilled once its bytes have been read
@@ -1660,7 +1770,7 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
         }
     } else {
         // ------------------------------------------------------------------ epilogue warps
-        const int e = warp - 2;
+        const int e = SPLIT ? 0 : warp - 2;
         long long n_sym = 0, n_soft = 0; LoopState costas{ 0.0f, 0.0f }; float dp_r = 0, dp_i = 0;
         int p1cnt = 0;
         if (active) {
@@ -1671,17 +1781,23 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
         unsigned char* sr = soft_ring + static_cast<long long>(c) * soft_stride;
         float2* p1 = port1 + static_cast<long long>(c) * port1_stride;
         for (int m = 0; m < nchunks; m++) {
-            const int b = m & 1;
-            mbar_wait(&bar_full[b], (m >> 1) & 1);
+            const int b = m % NB;
+            if (SPLIT && warp == 3) mbar_wait(&bar_cdone[b], (m / NB) & 1);     // the Costas warp is through with this block
+            else mbar_wait(&bar_full[b], (m / NB) & 1);
             const int n = cntbuf[b * 32 + lane];
             const float* sy = symbuf + b * blk_rows * ROWF + lane * NCOMP;
-            if (EPI == EPI_QPSK) {
+            if (EPI == EPI_QPSK && (!SPLIT || warp == 2)) {
                 // pass 1: the second Costas loop (the only recurrence here) runs over this lane's symbols in place, lean;
                 // pass 2 below is feed-forward (diff_phasor, rotation, soft bits, stores)
                 qrl_costas4_snr_chunk(costas, p.costas_alpha, p.costas_beta, smem_u32(sy), ROWF * 4, active ? n : 0,
                                       smem_u32(tanh_s) - (0x4B000000u << 2) + static_cast<uint32_t>(opaque_zero));
             }
-            for (int s = e; s < n; s += NEPI) {
+            if (SPLIT && warp == 2) {                      // hand the block on to the feed-forward warp
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_cdone[b]);
+                continue;
+            }
+            for (int s = e; s < n; s += (SPLIT ? 1 : NEPI)) {
                 const float yr = sy[s * ROWF];
                 const float yi = (NCOMP == 2) ? sy[s * ROWF + 1] : 0.0f;
                 float o_r, o_i;
@@ -1722,7 +1838,11 @@ symsync_kernel(SymSyncParams p, SymSyncState* __restrict__ states, int C,
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[b]);
         }
-        if (active && e == 0) {
+        if (active && SPLIT) {
+            SymSyncState& st = states[c];
+            if (warp == 2) st.costas = costas;
+            else { st.n_sym = n_sym; st.n_soft = n_soft; st.dp_r = dp_r; st.dp_i = dp_i; port1_cnt[c] = p1cnt; n_soft_out[c] = n_soft; }
+        } else if (active && e == 0) {
             SymSyncState& st = states[c];
             st.n_sym = n_sym; st.n_soft = n_soft; st.costas = costas; st.dp_r = dp_r; st.dp_i = dp_i;
             port1_cnt[c] = p1cnt;
