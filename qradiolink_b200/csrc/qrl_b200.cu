@@ -1544,7 +1544,7 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
             if (bpsk) {
                 {   // agc2_cc (Costas bypassed): r2 -> r3
                     constexpr int CH = 128, NST = 2;
-                    const size_t smem = sizeof(float2) * ((NST + AC_NHB) * CH + 1) * 32;      // + one row of padding behind the hand-off blocks
+                    const size_t smem = sizeof(float2) * (NST * CH + AC_NHB * (CH + 1)) * 32;      // every hand-off block + its padding row
                     auto kern = agc_costas_kernel<CH, NST, 0, 0>;
                     static bool a_attr[16] = { false };    // per device: function attributes belong to the device's context
                     if (!a_attr[h->device & 15]) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a_attr[h->device & 15] = true; }
@@ -1737,7 +1737,7 @@ static int rx_work_impl(qrl_rx* h, const void* iq_any, long T, long stride, int 
                 pe = h->prof_begin(2, h->s_loop);
                 auto run_ac = [&](auto ch_tag) -> int {
                     constexpr int CH = decltype(ch_tag)::value, NST = 2;      // input stages (2) + hand-off blocks (3): 164 KB at CH = 128
-                    const size_t smem = sizeof(float2) * ((NST + AC_NHB) * CH + 1) * 32;      // + one row of padding behind the hand-off blocks
+                    const size_t smem = sizeof(float2) * (NST * CH + AC_NHB * (CH + 1)) * 32;      // every hand-off block + its padding row
                     auto kern = (h->acp.order == 4 && h->acp.use_snr) ? agc_costas_kernel<CH, NST, 4, 1> : agc_costas_kernel<CH, NST>;
                     static bool ac_attr[16] = { false };    // per CH instantiation, per device: function attributes belong to the device's context
                     if (!ac_attr[h->device & 15]) {

@@ -1088,7 +1088,11 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
     qrl_fill_tanh_s(tanh_s);
     if (threadIdx.x == 0) opaque_zero = 0;
     float2* stage0 = sm_ac;
-    float2* hand = sm_ac + NST * CH * 32;                     // [NHB][CH][32] + one row of padding (prefetch of the item behind a block)
+    // [NHB][CH + 1][32]: every block carries its own padding row -- the Costas loop loads the item behind the one it works on, and behind
+    // the last item of a block that must not be the first row of the next block, which the AGC warp may be filling (ThreadSanitizer
+    // on the emulated library reported that read; the value was never used, the load is now inside the block's own storage)
+    float2* hand = sm_ac + NST * CH * 32;
+    constexpr int HB_ROWS = CH + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x;
     const int c = g * 32 + lane;
@@ -1132,7 +1136,7 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
             if (m >= NHB) mbar_wait(&bar_empty[b], ((m / NHB) - 1) & 1);
             mbar_wait(&bar_in[st], (m / NST) & 1);
             const float2* buf = stage0 + st * CH * 32 + lane;
-            float2* hb = hand + b * CH * 32 + lane;
+            float2* hb = hand + b * HB_ROWS * 32 + lane;
             const long long rem = total - static_cast<long long>(m) * CH;
             const int n = rem < CH ? static_cast<int>(rem) : CH;
             if (active) {
@@ -1165,7 +1169,7 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
         for (int m = 0; m < nchunks; m++) {
             const int b = m % NHB;
             mbar_wait(&bar_full[b], (m / NHB) & 1);
-            float2* hb = hand + b * CH * 32 + lane;
+            float2* hb = hand + b * HB_ROWS * 32 + lane;
             const long long w0 = base + static_cast<long long>(m) * CH;
             const long long rem = total - static_cast<long long>(m) * CH;
             const int n = rem < CH ? static_cast<int>(rem) : CH;
@@ -1184,7 +1188,7 @@ agc_costas_kernel(AgcCostasParams p, AgcCostasState* __restrict__ states, int C,
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                const float2* src = hand + b * CH * 32;
+                const float2* src = hand + b * HB_ROWS * 32;
                 const long long s0 = w0 & out_mask;
                 const long long first = (s0 + n <= ocap) ? n : (ocap - s0);
                 bulk_s2g(oring + s0 * 32, src, static_cast<uint32_t>(first * 256));
