@@ -26,7 +26,7 @@ for rep, kern, metric, unit, value in list(csv.reader(open(os.path.join(SRC, "5_
         dur = float(value) * {"us": 1.0, "ms": 1e3, "ns": 1e-3}[unit]
 n = 64 * (1 << 22)
 json.dump({"per_sample": (rd + wr) / n, "dram_bytes_read": rd, "dram_bytes_write": wr, "samples_per_launch": n,
-           "source": "ncu --set full --clock-control none, gpurun_out/r02_final2/ncu_fir_poly.ncu-rep (end of round 2), summary in profiles/r02_final_ncu_full_summary.csv",
+           "source": "ncu --set full --clock-control none, gpurun_out/r02_final2/ncu_fir_poly.ncu-rep (end of round 2), summary in profiles/r02_final2_ncu_full_summary.csv",
            "kernel": "fir_decim_poly_kernel<50,9,8,128,8>", "duration_us_under_ncu": dur},
           open(os.path.join(DST, "fir_traffic_bytes.json"), "w"), indent=1)
 print("traffic per sample", (rd + wr) / n, "duration", dur)
