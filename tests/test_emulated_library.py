@@ -105,3 +105,30 @@ def test_mmdvm_tx_zero_idle_through_the_emulated_library(emu_qrl, oracle, single
     between the stages, against the oracle, before GPU time is spent on it."""
     from tests import test_gpu_mmdvm as TM
     TM.zero_idle_case(emu_qrl, oracle, single, q=1)
+
+
+def test_qpsk_chain_through_the_emulated_library(emu_qrl, oracle):
+    """The QPSK-250k chain's loop kernels hand blocks between warps through 3-deep shared-memory rings (AGC -> Costas -> bulk store;
+    symbol sync -> second Costas -> feed-forward epilogue): a short ragged stream through the real host code and kernels, ports
+    bit-identical to the oracle.  (The golden QPSK case and the GPU tier's QPSK tests also pass under emulation; they take minutes.)"""
+    from tests import siggen
+    C, T = 2, 36000
+    X, _ = siggen.gen_qpsk_channels(C, T, seed0=2300)
+    blk = emu_qrl.make_gr_demod_qpsk(2, 1000000, 1700, 160000, n_channels=C, max_samples=20001)
+    acc = [[[] for _ in range(C)] for _ in range(3)]
+    lo = 0
+    for n in (1, 20001, 3, T - 20005):
+        blk.work(X[:, lo:lo + n]); lo += n
+        for p in range(3):
+            for c, v in enumerate(blk.read_port(p)):
+                acc[p][c].append(v)
+    assert lo == T
+    for c in range(C):
+        rx = oracle.Rx(oracle.DEMOD_QPSK, 2, 1000000, 1700, 160000, 0)
+        rx.work(X[c])
+        for p in range(3):
+            g, w = np.concatenate(acc[p][c]), rx.port(p)
+            n = min(len(g), len(w))
+            assert n >= len(w) - (160 if p == 2 else 8), (c, p, len(g), len(w))
+            assert np.array_equal(g[:n], w[:n]), (c, p)
+        assert len(np.concatenate(acc[2][c])) > 3000           # several Viterbi frames came out
